@@ -1,0 +1,29 @@
+"""Shared helpers for the test-suite (golden loading, oracle construction)."""
+import functools
+import json
+import os
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+EFFECT_NAMES = {1: "EFFECT_ALLOW", 2: "EFFECT_DENY", 3: "EFFECT_NO_MATCH"}
+
+
+def load_golden(name):
+    with open(os.path.join(GOLDEN, name), encoding="utf-8") as f:
+        return json.load(f)
+
+
+@functools.lru_cache(maxsize=None)
+def store_rule_table():
+    from cerbos_b200.policy.compile import build_rule_table
+    docs = [e["policy"] for e in load_golden("store_policies.json")]
+    return build_rule_table(docs)
+
+
+def engine_decisions():
+    """Yields (case_id, lenient, input, action, want_effect_dict) for every golden decision."""
+    for case in load_golden("engine_cases.json"):
+        outs = {(o.get("requestId"), o.get("resourceId")): o for o in case["wantOutputs"]}
+        for inp in case["inputs"]:
+            want = outs[(inp.get("requestId"), inp["resource"]["id"])]
+            yield f"{case['suite']}/{case['file']}", case["lenient"], inp, want
