@@ -1,0 +1,673 @@
+"""CEL condition trees -> device bytecode (host side, at table build).
+
+Replaces, for the GPU path, what the reference does at evaluation time with
+cel-go's tree-walking interpreter: ``SatisfiesCondition`` /
+``evaluateBoolCELExpr`` (internal/ruletable/ruletable.go:1346-1441, 1467-1486)
+over the environment of internal/conditions/cel.go:62-75.
+
+What is lowered
+  * condition trees all/any/none/expr with the reference's leaf rule
+    "error or non-bool => false" (TO_COND);
+  * request paths (``P.attr.x``, ``R.attr.a.b``, ``request.aux_data.jwt.aud`` ...)
+    -> attribute *slots*: the batch encoder extracts the value per request into a
+    NaN-boxed 8-byte column;
+  * ``C.x`` / ``constants.x`` / ``G.x`` / ``globals.x`` folded to literals; ``V.x`` /
+    ``variables.x`` inlined (policy variables are pure; an erroring variable is
+    "unset" in the reference, ruletable.go:1325-1332, and an inlined erroring
+    expression is equally an error; ``has(V.x)`` -> NOERR);
+  * operators, ``in``, index/select, size, startsWith/endsWith/contains,
+    hasIntersection/isSubset, all/exists/exists_one (1- and 2-variable),
+    ternary, numeric/timestamp/duration conversions, now()/timeSince().
+
+Anything else raises :class:`Unsupported` -- table build fails loudly; there is no
+silent per-request divergence and no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+import struct
+
+from ..cel.ast import Call, Const, Ident, ListLit, Macro, MapLit, Node, Select, UInt
+from ..policy.model import Cond, Params
+from . import layout as L
+from .consts import parse_cidr, parse_duration_ns, parse_timestamp_ns
+
+OP = L.OPS
+T = L.TAGS
+
+
+class Unsupported(Exception):
+    """The expression cannot be lowered exactly to device bytecode."""
+
+
+_PRINCIPAL_FIELDS = {"id", "roles", "attr", "policy_version", "scope"}
+_RESOURCE_FIELDS = {"kind", "id", "attr", "policy_version", "scope"}
+_ALIASES = {"policyVersion": "policy_version", "auxData": "aux_data",
+            "effectiveDerivedRoles": "effective_derived_roles"}
+
+
+def f64_bits(d: float) -> int:
+    if math.isnan(d):
+        return L.V64_CANON_NAN
+    return struct.unpack("<Q", struct.pack("<d", d))[0]
+
+
+def box(tag: int, payload: int = 0) -> int:
+    return ((L.V64_BOX_BASE | tag) << 48) | (payload & ((1 << 48) - 1))
+
+
+class StringTable:
+    def __init__(self):
+        self.ids = {}
+        self.items = []
+
+    def intern(self, s: str) -> int:
+        i = self.ids.get(s)
+        if i is None:
+            i = len(self.items)
+            self.ids[s] = i
+            self.items.append(s)
+        return i
+
+    def __len__(self):
+        return len(self.items)
+
+
+class ConstVal:
+    """Compile-time constant: (tag, bits) plus the Python value for further folding."""
+    __slots__ = ("tag", "bits", "py")
+
+    def __init__(self, tag, bits, py=None):
+        self.tag = tag
+        self.bits = bits & 0xFFFFFFFFFFFFFFFF
+        self.py = py
+
+
+class TableBuilderCtx:
+    """Pools shared by every program of one table."""
+
+    def __init__(self, globals_=None):
+        self.strings = StringTable()
+        self.consts: list[ConstVal] = []
+        self._const_ix = {}
+        self.theap: list[int] = []
+        self._heap_ix = {}
+        self.slots: dict[tuple, int] = {}
+        self.globals = globals_ or {}
+        self.uses_pid = False
+        self.uses_now = False
+        self.max_stack = 0
+        self.max_loop_depth = 0
+        self.n_vars = 0
+
+    # -- pools
+    def slot(self, path: tuple) -> int:
+        i = self.slots.get(path)
+        if i is None:
+            i = len(self.slots)
+            self.slots[path] = i
+        return i
+
+    def const_index(self, cv: ConstVal) -> int:
+        k = (cv.tag, cv.bits)
+        i = self._const_ix.get(k)
+        if i is None:
+            i = len(self.consts)
+            self._const_ix[k] = i
+            self.consts.append(cv)
+        return i
+
+    def v64_of(self, v, native_ints: bool) -> int:
+        """Python constant -> NaN-boxed heap element."""
+        if v is None:
+            return box(L.V64_NULL)
+        if isinstance(v, bool):
+            return box(L.V64_BOOL, int(v))
+        if isinstance(v, UInt):
+            raise Unsupported("uint element in constant list/map")
+        if isinstance(v, int):
+            if not native_ints:
+                return f64_bits(float(v))
+            if not (-(1 << 47) <= v < (1 << 47)):
+                raise Unsupported("int constant too large for list element")
+            return box(L.V64_INT, v)
+        if isinstance(v, float):
+            return f64_bits(v)
+        if isinstance(v, str):
+            return box(L.V64_STRING, self.strings.intern(v))
+        if isinstance(v, (list, tuple)):
+            return box(L.V64_LIST, self.heap_list([self.v64_of(x, native_ints) for x in v]))
+        if isinstance(v, dict):
+            return box(L.V64_MAP, self.heap_map(v, native_ints))
+        raise Unsupported(f"constant of type {type(v).__name__}")
+
+    def _heap_put(self, words: list) -> int:
+        k = tuple(words)
+        off = self._heap_ix.get(k)
+        if off is None:
+            off = len(self.theap)
+            self._heap_ix[k] = off
+            self.theap.extend(words)
+        return off
+
+    def heap_list(self, elems_v64: list) -> int:
+        return self._heap_put([len(elems_v64)] + list(elems_v64))
+
+    def heap_map(self, d: dict, native_ints: bool) -> int:
+        keys, vals = [], []
+        for k, v in d.items():
+            if not isinstance(k, str):
+                raise Unsupported("non-string key in constant map")
+            keys.append(box(L.V64_STRING, self.strings.intern(k)))
+            vals.append(self.v64_of(v, native_ints))
+        return self._heap_put([len(keys)] + keys + vals)
+
+    def const_from_py(self, v, native_ints: bool) -> ConstVal:
+        """JSON-ish Python value -> ConstVal. native_ints=False: numbers are doubles
+        (google.protobuf.Value); True: Python ints are CEL ints (CEL literals, Go-native globals)."""
+        if v is None:
+            return ConstVal(T["NULL"], 0, None)
+        if isinstance(v, bool):
+            return ConstVal(T["BOOL"], int(v), v)
+        if isinstance(v, UInt):
+            return ConstVal(T["UINT"], int(v), v)
+        if isinstance(v, int):
+            if native_ints:
+                return ConstVal(T["INT"], v, v)
+            return ConstVal(T["DOUBLE"], f64_bits(float(v)), float(v))
+        if isinstance(v, float):
+            return ConstVal(T["DOUBLE"], f64_bits(v), v)
+        if isinstance(v, str):
+            return ConstVal(T["STRING"], self.strings.intern(v), v)
+        if isinstance(v, bytes):
+            raise Unsupported("bytes constants")
+        if isinstance(v, (list, tuple)):
+            return ConstVal(T["LIST"], self.heap_list([self.v64_of(x, native_ints) for x in v]), list(v))
+        if isinstance(v, dict):
+            return ConstVal(T["MAP"], self.heap_map(v, native_ints), dict(v))
+        raise Unsupported(f"constant of type {type(v).__name__}")
+
+
+class _Static:
+    """Result of static path analysis."""
+    __slots__ = ("kind", "path", "value", "native")
+
+    def __init__(self, kind, path=None, value=None, native=False):
+        self.kind = kind      # 'slot' | 'const' | 'missing' | 'pid'
+        self.path = path
+        self.value = value
+        self.native = native
+
+
+_MISSING = object()
+
+
+class ProgramCompiler:
+    def __init__(self, ctx: TableBuilderCtx, params: Params | None):
+        self.ctx = ctx
+        self.constants = (params.constants if params else {}) or {}
+        self.var_defs = {v.name: v.expr for v in (params.variables if params else [])}
+        self.code: list[list] = []
+        self.sp = 0
+        self.loop_vars: list[dict] = []   # stack of {name: var index}
+        self.inlining: list[str] = []
+
+    # ---------------------------------------------------------------- emit helpers
+    def emit(self, op, a=0, b=0, c=0, delta=0):
+        self.code.append([OP[op], a, b, c])
+        self.sp += delta
+        if self.sp > self.ctx.max_stack:
+            self.ctx.max_stack = self.sp
+        if self.sp > L.MAX_STACK:
+            raise Unsupported("expression needs a deeper evaluation stack than the device provides")
+        return len(self.code) - 1
+
+    def here(self):
+        return len(self.code)
+
+    def patch(self, at, field, val):
+        self.code[at][{"a": 1, "b": 2, "c": 3}[field]] = val
+
+    def push_const(self, cv: ConstVal):
+        self.emit("CONST", c=self.ctx.const_index(cv), delta=1)
+
+    # ---------------------------------------------------------------- conditions
+    def compile_cond(self, cond: Cond):
+        """Leaves a plain BOOL on the stack."""
+        if cond.op == "expr":
+            self.expr(cond.expr.ast)
+            self.emit("TO_COND")
+            return
+        kids = cond.children
+        if not kids:
+            # all[] -> true ; any[] -> false ; none[] -> true
+            self.push_const(ConstVal(T["BOOL"], 0 if cond.op == "any" else 1))
+            return
+        jumps = []
+        for i, ch in enumerate(kids):
+            self.compile_cond(ch)
+            if i > 0:
+                self.emit("AND" if cond.op == "all" else "OR", delta=-1)
+            if i < len(kids) - 1:
+                jumps.append(self.emit("JF_KEEP" if cond.op == "all" else "JT_KEEP"))
+        end = self.here()
+        for j in jumps:
+            self.patch(j, "c", end)
+        if cond.op == "none":
+            self.emit("COND_NOT")
+
+    # ---------------------------------------------------------------- static paths
+    def _lookup_var(self, name):
+        for frame in reversed(self.loop_vars):
+            if name in frame:
+                return frame[name]
+        return None
+
+    def _static(self, n: Node):
+        """Tries to resolve `n` without emitting code. Returns _Static or None."""
+        segs = []
+        cur = n
+        while True:
+            if isinstance(cur, Select) and not cur.test_only:
+                segs.append(cur.field)
+                cur = cur.operand
+            elif (isinstance(cur, Call) and cur.fn == "_[_]" and isinstance(cur.args[1], Const)
+                  and isinstance(cur.args[1].value, str)):
+                segs.append(cur.args[1].value)
+                cur = cur.args[0]
+            else:
+                break
+        if not isinstance(cur, Ident) or self._lookup_var(cur.name) is not None:
+            return None
+        segs.reverse()
+        root = cur.name
+        if root in ("request", "R", "P"):
+            if root == "R":
+                segs = ["resource"] + segs
+            elif root == "P":
+                segs = ["principal"] + segs
+            return self._request_path(segs)
+        if root in ("C", "constants"):
+            return self._const_path(self.constants, segs, native=False, what="constants")
+        if root in ("G", "globals"):
+            return self._const_path(self.ctx.globals, segs, native=True, what="globals")
+        return None
+
+    def _request_path(self, segs):
+        if not segs:
+            raise Unsupported("bare `request` value")
+        first = _ALIASES.get(segs[0], segs[0])
+        if first in ("principal", "resource"):
+            if len(segs) < 2:
+                raise Unsupported(f"bare `request.{first}` message value")
+            fld = _ALIASES.get(segs[1], segs[1])
+            allowed = _PRINCIPAL_FIELDS if first == "principal" else _RESOURCE_FIELDS
+            if fld not in allowed:
+                raise Unsupported(f"unknown field request.{first}.{segs[1]}")
+            path = (first, fld) + tuple(segs[2:])
+            if fld != "attr" and len(segs) > 2:
+                if fld == "roles":
+                    raise Unsupported("field selection on request.principal.roles")
+                raise Unsupported(f"field selection on string request.{first}.{fld}")
+            if path == ("principal", "id"):
+                return _Static("pid")
+            return _Static("slot", path=path)
+        if first == "aux_data":
+            if len(segs) < 2:
+                raise Unsupported("bare `request.aux_data` message value")
+            if segs[1] != "jwt":
+                raise Unsupported(f"unknown field request.aux_data.{segs[1]}")
+            return _Static("slot", path=("aux_data", "jwt") + tuple(segs[2:]))
+        raise Unsupported(f"unknown field request.{segs[0]}")
+
+    def _const_path(self, root, segs, native, what):
+        if not segs:
+            return _Static("const", value=dict(root), native=native)
+        cur = root
+        for s in segs:
+            if isinstance(cur, dict) and s in cur:
+                cur = cur[s]
+            else:
+                return _Static("missing")  # no such key -> CEL error at run time
+        return _Static("const", value=cur, native=native)
+
+    def _push_static(self, st: _Static):
+        if st.kind == "slot":
+            self.emit("SLOT", c=self.ctx.slot(st.path), delta=1)
+        elif st.kind == "pid":
+            self.ctx.uses_pid = True
+            self.emit("PID", delta=1)
+        elif st.kind == "const":
+            self.push_const(self.ctx.const_from_py(st.value, st.native))
+        else:
+            self.push_const(ConstVal(T["ERR"], 0))
+
+    # ---------------------------------------------------------------- expressions
+    def expr(self, n: Node):
+        if isinstance(n, Const):
+            v = n.value
+            if isinstance(v, bytes):
+                raise Unsupported("bytes literal")
+            self.push_const(self.ctx.const_from_py(v, native_ints=True))
+            return
+        if isinstance(n, Ident):
+            vi = self._lookup_var(n.name)
+            if vi is not None:
+                self.emit("VAR", a=vi, delta=1)
+                return
+            if n.name in ("runtime",):
+                raise Unsupported("`runtime` (effectiveDerivedRoles) in conditions")
+            st = self._static(n)
+            if st is not None:
+                self._push_static(st)
+                return
+            raise Unsupported(f"identifier `{n.name}` as a value")
+        if isinstance(n, Select):
+            return self._select(n)
+        if isinstance(n, Call):
+            return self._call(n)
+        if isinstance(n, ListLit):
+            return self._const_literal(n)
+        if isinstance(n, MapLit):
+            return self._const_literal(n)
+        if isinstance(n, Macro):
+            return self._macro(n)
+        raise Unsupported(f"node {type(n).__name__}")
+
+    def _literal_value(self, n: Node):
+        if isinstance(n, Const):
+            if isinstance(n.value, bytes):
+                raise Unsupported("bytes literal")
+            return n.value
+        if isinstance(n, ListLit):
+            return [self._literal_value(e) for e in n.elems]
+        if isinstance(n, MapLit):
+            out = {}
+            for k, v in n.entries:
+                kv = self._literal_value(k)
+                if not isinstance(kv, str):
+                    raise Unsupported("non-string key in map literal")
+                if kv in out:
+                    raise Unsupported("repeated key in map literal")
+                out[kv] = self._literal_value(v)
+            return out
+        st = self._static(n) if isinstance(n, (Select, Ident, Call)) else None
+        if st is not None and st.kind == "const" and st.native:
+            return st.value
+        raise Unsupported("list / map literal with non-constant elements")
+
+    def _const_literal(self, n: Node):
+        self.push_const(self.ctx.const_from_py(self._literal_value(n), native_ints=True))
+
+    def _var_inline(self, name: str):
+        if name not in self.var_defs:
+            # undefined variables are a policy compile error in the reference (compile/variables.go)
+            raise Unsupported(f"undefined variable '{name}'")
+        if name in self.inlining:
+            raise Unsupported(f"cyclic variable '{name}'")
+        self.inlining.append(name)
+        saved, self.loop_vars = self.loop_vars, []   # variable bodies do not see comprehension variables
+        self.expr(self.var_defs[name].ast)
+        self.loop_vars = saved
+        self.inlining.pop()
+
+    def _is_var_ref(self, n: Node):
+        return (isinstance(n, Select) and not n.test_only and isinstance(n.operand, Ident)
+                and n.operand.name in ("V", "variables") and self._lookup_var(n.operand.name) is None)
+
+    def _select(self, n: Select):
+        if n.test_only:
+            return self._has(n)
+        if self._is_var_ref(n):
+            return self._var_inline(n.field)
+        st = self._static(n)
+        if st is not None:
+            return self._push_static(st)
+        if isinstance(n.operand, Ident) and n.operand.name == "runtime":
+            raise Unsupported("`runtime` (effectiveDerivedRoles) in conditions")
+        self.expr(n.operand)
+        self.emit("SELECT", c=self.ctx.strings.intern(n.field))
+
+    def _has(self, n: Select):
+        op = n.operand
+        if isinstance(op, Ident) and op.name in ("V", "variables") and self._lookup_var(op.name) is None:
+            if n.field not in self.var_defs:
+                self.push_const(ConstVal(T["BOOL"], 0))
+                return
+            self._var_inline(n.field)
+            self.emit("NOERR")
+            return
+        full = Select(op, n.field)
+        st = self._static(full)
+        if st is not None:
+            if st.kind == "slot":
+                if len(st.path) <= 2:
+                    raise Unsupported("has() on a request message field")
+                self.emit("HAS_SLOT", c=self.ctx.slot(st.path), delta=1)
+                return
+            if st.kind == "pid":
+                raise Unsupported("has() on a request message field")
+            if st.kind == "const":
+                self.push_const(ConstVal(T["BOOL"], 1))
+                return
+            # missing: has() is false only if the parent exists
+            pst = self._static(op)
+            if pst is not None and pst.kind == "const" and isinstance(pst.value, dict):
+                self.push_const(ConstVal(T["BOOL"], 0))
+            else:
+                self.push_const(ConstVal(T["ERR"], 0))
+            return
+        self.expr(op)
+        self.emit("HAS", c=self.ctx.strings.intern(n.field))
+
+    _BIN = {"_==_": "EQ", "_!=_": "NE", "_<_": "LT", "_<=_": "LE", "_>_": "GT", "_>=_": "GE",
+            "_+_": "ADD", "_-_": "SUB", "_*_": "MUL", "_/_": "DIV", "_%_": "MOD", "@in": "IN", "_[_]": "INDEX"}
+    _STR2 = {"startsWith": "STARTS_WITH", "endsWith": "ENDS_WITH", "contains": "CONTAINS"}
+    _LIST2 = {"hasIntersection": "HAS_INTERSECTION", "has_intersection": "HAS_INTERSECTION",
+              "isSubset": "IS_SUBSET", "is_subset": "IS_SUBSET"}
+    _CONV = {"int": "INT", "uint": "UINT", "double": "DOUBLE", "timestamp": "TIMESTAMP", "duration": "DURATION",
+             "dyn": "DYN", "id": "DYN"}
+
+    def _simple(self, n: Node):
+        """('slot', path) | ('const', ConstVal) | ('pid',) for operands a super-instruction can
+        address; no pool side effects (allocation happens when the fused op is emitted)."""
+        if isinstance(n, Const) and not isinstance(n.value, bytes):
+            return ("const", (n.value, True))
+        if isinstance(n, ListLit):
+            try:
+                return ("const", (self._literal_value(n), True))
+            except Unsupported:
+                return None
+        if isinstance(n, (Select, Ident, Call)) and not (isinstance(n, Select) and n.test_only):
+            if isinstance(n, Call) and n.fn != "_[_]":
+                return None
+            if self._is_var_ref(n):
+                return None
+            try:
+                st = self._static(n)
+            except Unsupported:
+                return None
+            if st is None:
+                return None
+            if st.kind == "slot":
+                return ("slot", st.path)
+            if st.kind == "pid":
+                return ("pid",)
+            if st.kind == "const":
+                return ("const", (st.value, st.native))
+        return None
+
+    def _slot_ix(self, path):
+        s = self.ctx.slot(path)
+        if s > 0xFFFF:
+            raise Unsupported("too many attribute slots")
+        return s
+
+    def _const_ix(self, desc):
+        return self.ctx.const_index(self.ctx.const_from_py(desc[0], desc[1]))
+
+    def _try_fused(self, fn, a, b) -> bool:
+        if fn not in L.CMP_INDEX and fn != "@in":
+            return False
+        sa, sb = self._simple(a), self._simple(b)
+        if sa is None or sb is None:
+            return False
+        ka, kb = sa[0], sb[0]
+        if fn in L.CMP_INDEX:
+            ci = L.CMP_INDEX[fn]
+            swap = {0: 0, 1: 1, 2: 4, 3: 5, 4: 2, 5: 3}
+            if ka == "slot" and kb == "const":
+                self.emit("CMP_SLOT_CONST", a=ci, b=self._slot_ix(sa[1]), c=self._const_ix(sb[1]), delta=1)
+            elif ka == "const" and kb == "slot":
+                self.emit("CMP_SLOT_CONST", a=swap[ci], b=self._slot_ix(sb[1]), c=self._const_ix(sa[1]), delta=1)
+            elif ka == "slot" and kb == "slot":
+                self.emit("CMP_SLOT_SLOT", a=ci, b=self._slot_ix(sa[1]), c=self._slot_ix(sb[1]), delta=1)
+            elif ka == "slot" and kb == "pid":
+                self.ctx.uses_pid = True
+                self.emit("CMP_SLOT_PID", a=ci, b=self._slot_ix(sa[1]), delta=1)
+            elif ka == "pid" and kb == "slot":
+                self.ctx.uses_pid = True
+                self.emit("CMP_SLOT_PID", a=swap[ci], b=self._slot_ix(sb[1]), delta=1)
+            else:
+                return False
+            return True
+        if ka == "slot" and kb == "const":
+            self.emit("IN_SLOT_CONST", b=self._slot_ix(sa[1]), c=self._const_ix(sb[1]), delta=1)
+            return True
+        if ka == "const" and kb == "slot":
+            self.emit("IN_CONST_SLOT", b=self._slot_ix(sb[1]), c=self._const_ix(sa[1]), delta=1)
+            return True
+        return False
+
+    def _call(self, n: Call):
+        fn = n.fn
+        args = ([n.target] if n.target is not None else []) + n.args
+        if fn == "_&&_" or fn == "_||_":
+            self.expr(args[0])
+            j = self.emit("JF_KEEP" if fn == "_&&_" else "JT_KEEP")
+            self.expr(args[1])
+            self.emit("AND" if fn == "_&&_" else "OR", delta=-1)
+            self.patch(j, "c", self.here())
+            return
+        if fn == "_?_:_":
+            self.expr(args[0])
+            t = self.emit("TERN", delta=-1)
+            sp0 = self.sp
+            self.expr(args[1])
+            j = self.emit("JMP")
+            self.patch(t, "c", self.here())
+            self.sp = sp0
+            self.expr(args[2])
+            end = self.here()
+            if end > 0xFFFF:
+                raise Unsupported("program too long")
+            self.patch(t, "b", end)
+            self.patch(j, "c", end)
+            return
+        if fn == "_[_]" or fn in L.CMP_INDEX or fn == "@in":
+            st = self._static(n) if fn == "_[_]" else None
+            if st is not None:
+                return self._push_static(st)
+            if len(args) == 2 and self._try_fused(fn, args[0], args[1]):
+                return
+        if fn in self._BIN and len(args) == 2:
+            self.expr(args[0])
+            self.expr(args[1])
+            self.emit(self._BIN[fn], delta=-1)
+            return
+        if fn == "!_" and len(args) == 1:
+            self.expr(args[0])
+            self.emit("NOT")
+            return
+        if fn == "-_" and len(args) == 1:
+            self.expr(args[0])
+            self.emit("NEG")
+            return
+        if fn == "size" and len(args) == 1:
+            self.expr(args[0])
+            self.emit("SIZE")
+            return
+        if fn in self._STR2 and len(args) == 2:
+            self.expr(args[0])
+            self.expr(args[1])
+            self.emit(self._STR2[fn], delta=-1)
+            return
+        if fn in self._LIST2 and len(args) == 2:
+            self.expr(args[0])
+            self.expr(args[1])
+            self.emit(self._LIST2[fn], delta=-1)
+            return
+        if fn in ("timestamp", "duration") and len(args) == 1 and isinstance(args[0], Const) \
+                and isinstance(args[0].value, str):
+            try:
+                if fn == "timestamp":
+                    self.push_const(ConstVal(T["TS"], parse_timestamp_ns(args[0].value)))
+                else:
+                    self.push_const(ConstVal(T["DUR"], parse_duration_ns(args[0].value)))
+            except ValueError:
+                self.push_const(ConstVal(T["ERR"], 0))
+            return
+        if fn in self._CONV and len(args) == 1:
+            self.expr(args[0])
+            if fn == "duration":
+                raise Unsupported("duration() of a non-constant string")
+            self.emit(self._CONV[fn])
+            return
+        if fn == "inIPAddrRange" and len(args) == 2:
+            if not (isinstance(args[1], Const) and isinstance(args[1].value, str)):
+                raise Unsupported("inIPAddrRange with a non-constant CIDR")
+            cidr = parse_cidr(args[1].value)
+            if cidr is None:
+                # invalid CIDR text is a CEL error whatever the address is (cerbos_lib.go:472-484)
+                self.push_const(ConstVal(T["ERR"], 0))
+                return
+            self.expr(args[0])
+            self.emit("IN_IP_RANGE", c=self.ctx._heap_put(list(cidr)))
+            return
+        if fn == "now" and not args:
+            self.ctx.uses_now = True
+            self.emit("NOW", delta=1)
+            return
+        if fn == "timeSince" and len(args) == 1:
+            self.ctx.uses_now = True
+            self.emit("NOW", delta=1)
+            self.expr(args[0])
+            self.emit("SUB", delta=-1)
+            return
+        raise Unsupported(f"function `{fn}` with {len(args)} argument(s)")
+
+    def _macro(self, n: Macro):
+        kinds = {"all": (L.LOOP_ALL, 1), "exists": (L.LOOP_EXISTS, 1), "exists_one": (L.LOOP_EXISTS_ONE, 1),
+                 "all2": (L.LOOP_ALL, 2), "exists2": (L.LOOP_EXISTS, 2), "exists_one2": (L.LOOP_EXISTS_ONE, 2)}
+        if n.name not in kinds:
+            raise Unsupported(f"macro `{n.name}`")
+        kind, nv = kinds[n.name]
+        depth = len(self.loop_vars)
+        if depth >= L.MAX_LOOP_DEPTH:
+            raise Unsupported("comprehension nesting too deep")
+        self.ctx.max_loop_depth = max(self.ctx.max_loop_depth, depth + 1)
+        base = depth * 2
+        self.ctx.n_vars = max(self.ctx.n_vars, base + 2)
+        self.expr(n.target)
+        init = self.emit("LOOP_INIT", a=base, b=kind | (0x100 if nv == 2 else 0), delta=-1)
+        frame = {n.vars[0]: base} if nv == 1 else {n.vars[0]: base, n.vars[1]: base + 1}
+        self.loop_vars.append(frame)
+        body = self.here()
+        self.expr(n.args[0])
+        self.emit("LOOP_NEXT", a=base, b=kind | (0x100 if nv == 2 else 0), c=body, delta=-1)
+        self.loop_vars.pop()
+        self.sp += 1  # loop result
+        self.patch(init, "c", self.here())
+
+    # ---------------------------------------------------------------- entry
+    def finish(self):
+        self.emit("RET")
+        return self.code
+
+
+def compile_condition(ctx: TableBuilderCtx, cond: Cond, params: Params | None) -> list:
+    """Condition tree -> instruction list [[op, a, b, c], ...] leaving a plain BOOL."""
+    pc = ProgramCompiler(ctx, params)
+    pc.compile_cond(cond)
+    assert pc.sp == 1, pc.sp
+    return pc.finish()

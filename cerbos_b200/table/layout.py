@@ -1,0 +1,232 @@
+"""Binary layout shared by the host flattener, the batch encoder, the CUDA kernels and
+the C oracle: section ids of the table blob, value tags, bytecode opcodes.
+
+This module is the single source of truth; ``python -m cerbos_b200.table.layout``
+regenerates ``include/cerbos_b200_format.h`` (tests check the header is in sync).
+
+Table blob (little endian, every section 16-byte aligned):
+    BlobHeader { u32 magic; u32 version; u32 n_sections; u32 flags; u64 total_bytes; u64 reserved }
+    SectionDesc[n_sections] { u32 id; u32 elem_bytes; u64 offset; u64 n_bytes }
+    sections...
+"""
+from __future__ import annotations
+
+MAGIC = 0x32425243  # 'CRB2'
+VERSION = 3
+ALIGN = 16
+
+NONE32 = 0xFFFFFFFF
+NONE16 = 0xFFFF
+ROLE_ANY = 0xFFFF          # row.role: matches any role ("*")
+ROLE_UNKNOWN = 0xFFFFFFFE  # request role not in the table's role dictionary
+ROLE_PAD = 0xFFFFFFFF      # unused role column entry
+SCOPE_NONE = 0x7FFFFFFF    # request scope that resolves to nothing
+SCOPE_INEXACT_BIT = 0x80000000  # lenient: hdr scope is the nearest known ancestor, not the request's own scope
+
+# ---- sections -----------------------------------------------------------------------------------------
+SECTIONS = {
+    "META": 1,            # u32[META_WORDS]
+    "SCOPE_PARENT": 2,    # u32[n_scopes]   nearest ancestor scope present in the dictionary, or NONE32
+    "SCOPE_FLAGS": 3,     # u32[n_scopes]   bit0 in principalScopeMap, bit1 in resourceScopeMap, bits 4-5 scope permissions
+    "RES_BLOCK_MAP": 4,   # u32[n_versions*n_respats*n_scopes] -> block id | NONE32
+    "RES_EXISTS": 5,      # u8 [n_versions*n_respats*n_scopes] bit0 RESOURCE-kind row exists, bit1 any row exists
+    "PRIN_BLOCK_MAP": 6,  # u32[n_versions*n_principals*n_scopes] -> block id | NONE32
+    "PRIN_EXISTS": 7,     # u8 [n_versions*n_scopes]  any PRINCIPAL-kind row with (version, scope)
+    "PRIN_OF_STRING": 8,  # u32[n_strings] string id -> principal index | NONE32
+    "BLOCKS": 9,          # Block[n_blocks] {u32 row_start, n_rows, cond_base, n_conds}
+    "ROWS": 10,           # Row[n_rows] 16 B
+    "CONDS": 11,          # {u32 code_off, u32 code_len}[n_conds]  (offsets in instructions)
+    "CODE": 12,           # Instr[n_code] 8 B {u8 op; u8 a; u16 b; u32 c}
+    "CONSTS": 13,         # Const[n_consts] 16 B {u32 tag; u32 pad; u64 bits}
+    "THEAP": 14,          # u64[] constant lists / maps (NaN-boxed V64 elements)
+    "STR_OFF": 15,        # u32[n_strings+1]
+    "STR_BYTES": 16,      # u8[]
+    "ROLE_PARENTS_OFF": 17,  # u32[n_scopes*n_roles+1] CSR offsets (only when has_parent_roles)
+    "ROLE_PARENTS": 18,   # u32[] role ids (transitive closure, per (scope, role))
+    "ROLEPOL_OFF": 19,    # u32[n_versions*n_scopes+1] CSR into ROLEPOL_ENTRIES
+    "ROLEPOL_ENTRIES": 20,  # {u32 role; u32 rule_start; u32 n_rules; u32 pad}
+    "ROLEPOL_RULES": 21,  # {u32 respat; u32 cond (global id+1, 0 none); u32 apat_start; u32 n_apats}
+    "ROLEPOL_APATS": 22,  # u32[] action pattern ids
+    "MANIFEST": 100,      # JSON (host only): dictionaries + slot paths for the batch encoder
+}
+
+META_WORDS = 32
+META = {name: i for i, name in enumerate([
+    "n_versions", "n_respats", "n_scopes", "n_principals", "n_roles", "n_apats", "n_blocks", "n_rows",
+    "n_conds", "n_code", "n_consts", "n_slots", "n_strings", "has_role_policies", "has_parent_roles",
+    "has_principal_policies", "max_stack", "max_loop_depth", "n_vars", "theap_words", "uses_pid", "uses_now",
+    "max_scope_depth",
+])}
+
+SCOPE_FLAG_PRINCIPAL = 1
+SCOPE_FLAG_RESOURCE = 2
+SCOPE_PERM_SHIFT = 4
+
+EXISTS_RESOURCE_KIND = 1
+EXISTS_ANY_ROW = 2
+
+ROW_FLAG_PRINCIPAL = 1
+
+EFFECT_ALLOW = 1
+EFFECT_DENY = 2
+
+# ---- 8-byte NaN-boxed values (attribute columns, heap elements) ------------------------------------------
+# doubles are stored raw; everything else is boxed: bits 63..48 = 0xFFF0 | tag, payload = low 48 bits.
+V64_BOX_BASE = 0xFFF0
+V64_NULL = 1
+V64_BOOL = 2
+V64_STRING = 3    # payload = string id
+V64_LIST = 4      # payload = heap word offset (bit 47 set = batch heap, clear = table heap)
+V64_MAP = 5
+V64_ABSENT = 6    # slot only: the last path segment is missing from its (map) parent
+V64_ERROR = 7     # slot only: path traverses a missing / non-map value
+V64_INT = 8       # payload = 48-bit two's complement (constants in the table heap only)
+V64_HEAP_BATCH_BIT = 1 << 47
+V64_CANON_NAN = 0x7FF8000000000000
+
+# ---- interpreter value tags ---------------------------------------------------------------------------------
+TAGS = {name: i for i, name in enumerate([
+    "ERR", "NULL", "BOOL", "INT", "UINT", "DOUBLE", "STRING", "LIST", "MAP", "TS", "DUR", "BYTES", "TYPE",
+])}
+
+# ---- bytecode ---------------------------------------------------------------------------------------------------
+OPS = {name: i for i, name in enumerate([
+    "RET",          # result = TOS
+    "CONST",        # push consts[c]
+    "SLOT",         # push slot[c]            (ABSENT / ERROR -> ERR)
+    "HAS_SLOT",     # push BOOL(slot[c] present) ; ERROR slot -> ERR
+    "PID",          # push STRING(hdr.principal_id)
+    "NOW",          # push TS(batch now)
+    "VAR",          # push loop variable a
+    "SELECT",       # TOS map . key(string id c)
+    "HAS",          # TOS map has key c -> BOOL
+    "INDEX",        # [container, key] -> value
+    "EQ", "NE", "LT", "LE", "GT", "GE",
+    "ADD", "SUB", "MUL", "DIV", "MOD", "NEG", "NOT",
+    "IN",           # [x, container] -> BOOL
+    "SIZE",
+    "STARTS_WITH", "ENDS_WITH", "CONTAINS",   # [s, t] -> BOOL
+    "JF_KEEP",      # if TOS is BOOL false: pc = c (TOS kept)
+    "JT_KEEP",      # if TOS is BOOL true:  pc = c (TOS kept)
+    "AND", "OR",    # [a, b] -> 3-valued combine with cel-go error absorption
+    "JMP",          # pc = c
+    "TERN",         # pop cond: true -> fallthrough ; false -> pc = c ; else push ERR, pc = b (end)
+    "HAS_INTERSECTION", "IS_SUBSET",   # [a, b] lists -> BOOL
+    "LOOP_INIT",    # pop range; a = var slot, b = kind (LOOP_*), c = end pc
+    "LOOP_NEXT",    # pop body result; a = var slot, b = kind, c = body pc
+    "TO_COND",      # TOS -> BOOL(TOS is BOOL true)   (error / non-bool -> false; ruletable.go:1425-1441)
+    "COND_NOT",     # TOS BOOL -> !TOS
+    "NOERR",        # TOS -> BOOL(TOS is not ERR)     (has(V.x) on an inlined variable)
+    "INT", "UINT", "DOUBLE", "TIMESTAMP", "DURATION", "DYN",  # conversions of TOS
+    "TYPE_EQ",      # unused placeholder (reserved)
+    # super-instructions (fused forms of the sequences above; same results)
+    "CMP_SLOT_CONST",   # push cmp(a=EQ..GE as op index)(slot[b], consts[c])
+    "CMP_SLOT_SLOT",    # push cmp(a)(slot[b], slot[c])
+    "CMP_SLOT_PID",     # push cmp(a)(slot[b], P.id)
+    "IN_SLOT_CONST",    # push slot[b] in consts[c]
+    "IN_CONST_SLOT",    # push consts[c] in slot[b]
+    "IN_IP_RANGE",      # TOS string ip -> BOOL(ip in CIDR at theap[c..c+3] = {family 4|6, prefix bits, hi64, lo64})
+])}
+
+LOOP_ALL = 0
+LOOP_EXISTS = 1
+LOOP_EXISTS_ONE = 2
+
+CMP_INDEX = {"_==_": 0, "_!=_": 1, "_<_": 2, "_<=_": 3, "_>_": 4, "_>=_": 5}
+
+MAX_STACK = 16
+MAX_LOOP_DEPTH = 2
+MAX_VARS = 4
+MAX_CHAIN = 8       # scope chain length supported on device (depth+1)
+MAX_ROLE_COLS = 16
+MAX_CLASS_PATS = 8  # resource patterns one request kind may match
+
+# batch flags (cgpu_batch.flags)
+BATCH_FLAG_LENIENT = 1
+
+
+def c_header() -> str:
+    out = ["/* GENERATED by `python -m cerbos_b200.table.layout` -- do not edit. */",
+           "#ifndef CERBOS_B200_FORMAT_H", "#define CERBOS_B200_FORMAT_H", "#include <stdint.h>", ""]
+
+    def d(name, val, hexa=False):
+        if hexa:
+            out.append(f"#define {name} 0x{val:X}u" if val <= 0xFFFFFFFF else f"#define {name} 0x{val:X}ull")
+        else:
+            out.append(f"#define {name} {val}")
+
+    d("CB_MAGIC", MAGIC, True)
+    d("CB_VERSION", VERSION)
+    d("CB_NONE32", NONE32, True)
+    d("CB_NONE16", NONE16, True)
+    d("CB_ROLE_ANY", ROLE_ANY, True)
+    d("CB_ROLE_UNKNOWN", ROLE_UNKNOWN, True)
+    d("CB_ROLE_PAD", ROLE_PAD, True)
+    d("CB_SCOPE_NONE", SCOPE_NONE, True)
+    d("CB_SCOPE_INEXACT_BIT", SCOPE_INEXACT_BIT, True)
+    out.append("")
+    for k, v in SECTIONS.items():
+        d(f"CB_SEC_{k}", v)
+    out.append("")
+    d("CB_META_WORDS", META_WORDS)
+    for k, v in META.items():
+        d(f"CB_META_{k.upper()}", v)
+    out.append("")
+    d("CB_SCOPE_FLAG_PRINCIPAL", SCOPE_FLAG_PRINCIPAL)
+    d("CB_SCOPE_FLAG_RESOURCE", SCOPE_FLAG_RESOURCE)
+    d("CB_SCOPE_PERM_SHIFT", SCOPE_PERM_SHIFT)
+    d("CB_EXISTS_RESOURCE_KIND", EXISTS_RESOURCE_KIND)
+    d("CB_EXISTS_ANY_ROW", EXISTS_ANY_ROW)
+    d("CB_ROW_FLAG_PRINCIPAL", ROW_FLAG_PRINCIPAL)
+    d("CB_EFFECT_ALLOW", EFFECT_ALLOW)
+    d("CB_EFFECT_DENY", EFFECT_DENY)
+    out.append("")
+    d("CB_V64_BOX_BASE", V64_BOX_BASE, True)
+    for k in ("NULL", "BOOL", "STRING", "LIST", "MAP", "ABSENT", "ERROR", "INT"):
+        d(f"CB_V64_{k}", globals()[f"V64_{k}"])
+    d("CB_V64_HEAP_BATCH_BIT", V64_HEAP_BATCH_BIT, True)
+    d("CB_V64_CANON_NAN", V64_CANON_NAN, True)
+    out.append("")
+    for k, v in TAGS.items():
+        d(f"CB_T_{k}", v)
+    out.append("")
+    for k, v in OPS.items():
+        d(f"CB_OP_{k}", v)
+    d("CB_N_OPS", len(OPS))
+    out.append("")
+    d("CB_LOOP_ALL", LOOP_ALL)
+    d("CB_LOOP_EXISTS", LOOP_EXISTS)
+    d("CB_LOOP_EXISTS_ONE", LOOP_EXISTS_ONE)
+    d("CB_MAX_STACK", MAX_STACK)
+    d("CB_MAX_LOOP_DEPTH", MAX_LOOP_DEPTH)
+    d("CB_MAX_VARS", MAX_VARS)
+    d("CB_MAX_CHAIN", MAX_CHAIN)
+    d("CB_MAX_ROLE_COLS", MAX_ROLE_COLS)
+    d("CB_MAX_CLASS_PATS", MAX_CLASS_PATS)
+    d("CB_BATCH_FLAG_LENIENT", BATCH_FLAG_LENIENT)
+    out.append("")
+    out.append("""typedef struct { uint32_t magic, version, n_sections, flags; uint64_t total_bytes, reserved; } cb_blob_header;
+typedef struct { uint32_t id, elem_bytes; uint64_t offset, n_bytes; } cb_section_desc;
+typedef struct { uint32_t row_start, n_rows, cond_base, n_conds; } cb_block;
+typedef struct { uint16_t apat, role, cond, drcond, respat; uint8_t effect, flags; uint32_t pad; } cb_row;
+typedef struct { uint32_t code_off, code_len; } cb_cond;
+typedef struct { uint8_t op, a; uint16_t b; uint32_t c; } cb_instr;
+typedef struct { uint32_t tag, pad; uint64_t bits; } cb_const;
+typedef struct { uint32_t role, rule_start, n_rules, pad; } cb_rolepol_entry;
+typedef struct { uint32_t respat, cond, apat_start, n_apats; } cb_rolepol_rule;
+/* request header columns (SURVEY.md 8(d): 24 B / request) */
+typedef struct { uint32_t principal_id, kind_class, resource_scope, principal_scope; } cb_hdr0;   /* 16 B */
+typedef struct { uint16_t resource_version, principal_version; uint32_t action_set_id; } cb_hdr1;  /*  8 B */
+""")
+    out.append("#endif")
+    return "\n".join(out) + "\n"
+
+
+if __name__ == "__main__":
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    path = os.path.join(root, "include", "cerbos_b200_format.h")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as f:
+        f.write(c_header())
+    print("wrote", path)
