@@ -1,0 +1,156 @@
+"""ctypes binding of the C ABI (include/cerbos_b200.h) -- the same entry points the Go side binds via cgo
+(INTEGRATION.md).  There is no fallback: if the CUDA library is missing or no GPU is present the calls fail.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libcerbos_b200.so")
+
+N_COLUMNS = 11
+OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE = 0, -1, -2, -3, -4
+
+EXPORTS = [
+    "cgpu_init", "cgpu_shutdown", "cgpu_table_load", "cgpu_table_retain", "cgpu_table_release", "cgpu_check",
+    "cgpu_check_device", "cgpu_sync", "cgpu_launch_count", "cgpu_table_info", "cgpu_last_kernel_config",
+    "cgpu_last_error",
+]
+
+
+class CgpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"cerbos_b200 error {code}: {msg}")
+        self.code = code
+
+
+class _Batch(ctypes.Structure):
+    _fields_ = [("n_requests", ctypes.c_uint64), ("max_actions", ctypes.c_uint32),
+                ("now_unix_nanos", ctypes.c_int64), ("flags", ctypes.c_uint32),
+                ("columns", ctypes.POINTER(ctypes.c_void_p)), ("column_bytes", ctypes.POINTER(ctypes.c_size_t)),
+                ("n_columns", ctypes.c_uint32)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads the in-tree CUDA library. Raises if it has not been built (python -m cerbos_b200.csrc.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -m cerbos_b200.csrc.build` "
+                              "(cerbos_b200 has no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        L.cgpu_init.restype = ctypes.c_int
+        L.cgpu_init.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+        L.cgpu_shutdown.restype = None
+        L.cgpu_shutdown.argtypes = [ctypes.c_void_p]
+        L.cgpu_table_load.restype = ctypes.c_int
+        L.cgpu_table_load.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
+        L.cgpu_table_retain.restype = None
+        L.cgpu_table_retain.argtypes = [ctypes.c_void_p]
+        L.cgpu_table_release.restype = None
+        L.cgpu_table_release.argtypes = [ctypes.c_void_p]
+        L.cgpu_check.restype = ctypes.c_int
+        L.cgpu_check.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.c_void_p]
+        L.cgpu_check_device.restype = ctypes.c_int
+        L.cgpu_check_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.c_void_p,
+                                        ctypes.c_void_p]
+        L.cgpu_sync.restype = ctypes.c_int
+        L.cgpu_sync.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.cgpu_launch_count.restype = ctypes.c_uint64
+        L.cgpu_launch_count.argtypes = [ctypes.c_void_p]
+        L.cgpu_table_info.restype = ctypes.c_int
+        L.cgpu_table_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint32), ctypes.c_uint32]
+        L.cgpu_last_kernel_config.restype = ctypes.c_int
+        L.cgpu_last_kernel_config.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_uint32)] * 3
+        L.cgpu_last_error.restype = ctypes.c_char_p
+        L.cgpu_last_error.argtypes = []
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != OK:
+        raise CgpuError(rc, lib().cgpu_last_error().decode("utf-8", "replace"))
+
+
+class Context:
+    """cgpu_ctx: one CUDA device (one process per GPU)."""
+
+    def __init__(self, device: int = 0):
+        self._h = ctypes.c_void_p()
+        ids = (ctypes.c_int * 1)(device)
+        _check(lib().cgpu_init(ids, 1, ctypes.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().cgpu_shutdown(self._h)
+            self._h = ctypes.c_void_p()
+
+    def launch_count(self) -> int:
+        return int(lib().cgpu_launch_count(self._h))
+
+    def last_kernel_config(self):
+        g, b, s = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+        _check(lib().cgpu_last_kernel_config(self._h, ctypes.byref(g), ctypes.byref(b), ctypes.byref(s)))
+        return {"grid": g.value, "block": b.value, "smem_bytes": s.value}
+
+    def load_table(self, blob: bytes) -> "Table":
+        return Table(self, blob)
+
+    def sync(self, stream: int = 0):
+        _check(lib().cgpu_sync(self._h, ctypes.c_void_p(stream)))
+
+
+class Table:
+    """cgpu_table: flattened rule table resident in HBM (reference counted)."""
+
+    def __init__(self, ctx: Context, blob: bytes):
+        self.ctx = ctx
+        self._h = ctypes.c_void_p()
+        buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
+        _check(lib().cgpu_table_load(ctx._h, buf, len(blob), ctypes.byref(self._h)))
+
+    def release(self):
+        if self._h:
+            lib().cgpu_table_release(self._h)
+            self._h = ctypes.c_void_p()
+
+    def meta(self):
+        out = (ctypes.c_uint32 * 32)()
+        _check(lib().cgpu_table_info(self._h, out, 32))
+        return list(out)
+
+    # ---- host-buffer path (engine.Check)
+    def check(self, columns, n: int, max_actions: int, now_ns: int = 0, flags: int = 0) -> np.ndarray:
+        """columns: numpy arrays in host memory (ideally pinned), encode.py order.
+        Returns uint8[n, max_actions]: 1 ALLOW, 2 DENY, 0 padding."""
+        cols = [c if (isinstance(c, np.ndarray) and c.flags["C_CONTIGUOUS"]) else np.ascontiguousarray(c) for c in columns]
+        ptrs = (ctypes.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+        sizes = (ctypes.c_size_t * len(cols))(*[c.nbytes for c in cols])
+        b = _Batch(n, max_actions, now_ns, flags, ptrs, sizes, len(cols))
+        out = np.empty((n, max(max_actions, 1)), dtype=np.uint8)
+        _check(lib().cgpu_check(self.ctx._h, self._h, ctypes.byref(b), out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def check_into(self, ptrs, sizes, n, max_actions, out_ptr, now_ns=0, flags=0):
+        """Zero-overhead variant for timing loops: raw host pointers in, effects written to out_ptr."""
+        p = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        s = (ctypes.c_size_t * len(sizes))(*sizes)
+        b = _Batch(n, max_actions, now_ns, flags, p, s, len(ptrs))
+        _check(lib().cgpu_check(self.ctx._h, self._h, ctypes.byref(b), ctypes.c_void_p(out_ptr)))
+
+    # ---- device-resident path
+    def check_device(self, ptrs, sizes, n, max_actions, bitmap_ptr, now_ns=0, flags=0, stream=0):
+        """ptrs: device pointers (e.g. torch tensor .data_ptr()); asynchronous on `stream` (cudaStream_t value)."""
+        p = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        s = (ctypes.c_size_t * len(sizes))(*sizes)
+        b = _Batch(n, max_actions, now_ns, flags, p, s, len(ptrs))
+        _check(lib().cgpu_check_device(self.ctx._h, self._h, ctypes.byref(b), ctypes.c_void_p(bitmap_ptr),
+                                       ctypes.c_void_p(stream)))

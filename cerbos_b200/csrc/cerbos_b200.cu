@@ -1,0 +1,499 @@
+// cerbos_b200.cu -- sm_100a kernels + C ABI (include/cerbos_b200.h) of the batched CheckResources evaluator.
+//
+// Kernel design (B200):
+//   * persistent grid: (SM count x resident CTAs) CTAs of 256 threads loop over 256-request tiles;
+//   * the flattened rule table image (row blocks, scope tables, bytecode, constants; KBs) is staged ONCE
+//     per CTA into shared memory by the TMA unit: 1-D `cp.async.bulk.shared::cluster.global` copies
+//     completing on an mbarrier, overlapped with the first tile's header loads; tables too large for
+//     shared memory are read through L1/L2 instead;
+//   * request columns are SoA and read exactly once with coalesced 128/64/32-bit `ld.global.nc
+//     .L1::no_allocate` loads (header 16 B + 8 B, roles 4 B, NaN-boxed attribute slots 8 B);
+//   * one thread per request, bit-parallel (action x role) walk + bytecode interpreter (cb_core.h);
+//   * result: 1 bit per decision, coalesced byte stores.
+// Integer / branchy work bounded by HBM bandwidth: no tensor cores are involved.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "cb_core.h"
+#include "cerbos_b200.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr uint32_t kMaxStageBytes = 96 * 1024;   // table images up to this size are TMA-staged into shared memory
+constexpr int kMaxSec = 24;
+
+struct TableDesc {
+    const uint8_t *base;       // device blob image
+    uint32_t image_bytes;      // bytes [0, image_bytes) hold every device section (16-byte multiple)
+    uint32_t off[kMaxSec];     // section offsets by section id
+    uint32_t nV, nRP, nS, nP, nR, nAP, nT, n_slots;
+    uint32_t has_role_policies, has_parent_roles, has_principal_policies;
+};
+
+__device__ __forceinline__ cb::TableView make_view(const uint8_t *base, const TableDesc &d) {
+    cb::TableView t;
+    t.scope_parent = reinterpret_cast<const uint32_t *>(base + d.off[CB_SEC_SCOPE_PARENT]);
+    t.scope_flags = reinterpret_cast<const uint32_t *>(base + d.off[CB_SEC_SCOPE_FLAGS]);
+    t.res_block_map = reinterpret_cast<const uint32_t *>(base + d.off[CB_SEC_RES_BLOCK_MAP]);
+    t.res_exists = base + d.off[CB_SEC_RES_EXISTS];
+    t.prin_block_map = reinterpret_cast<const uint32_t *>(base + d.off[CB_SEC_PRIN_BLOCK_MAP]);
+    t.prin_exists = base + d.off[CB_SEC_PRIN_EXISTS];
+    t.prin_of_string = reinterpret_cast<const uint32_t *>(base + d.off[CB_SEC_PRIN_OF_STRING]);
+    t.blocks = reinterpret_cast<const cb_block *>(base + d.off[CB_SEC_BLOCKS]);
+    t.rows = reinterpret_cast<const cb_row *>(base + d.off[CB_SEC_ROWS]);
+    t.conds = reinterpret_cast<const cb_cond *>(base + d.off[CB_SEC_CONDS]);
+    t.code = reinterpret_cast<const cb_instr *>(base + d.off[CB_SEC_CODE]);
+    t.consts = reinterpret_cast<const cb_const *>(base + d.off[CB_SEC_CONSTS]);
+    t.theap = reinterpret_cast<const uint64_t *>(base + d.off[CB_SEC_THEAP]);
+    t.str_off = reinterpret_cast<const uint32_t *>(base + d.off[CB_SEC_STR_OFF]);
+    t.str_bytes = base + d.off[CB_SEC_STR_BYTES];
+    t.par_off = reinterpret_cast<const uint32_t *>(base + d.off[CB_SEC_ROLE_PARENTS_OFF]);
+    t.par_list = reinterpret_cast<const uint32_t *>(base + d.off[CB_SEC_ROLE_PARENTS]);
+    t.rp_off = reinterpret_cast<const uint32_t *>(base + d.off[CB_SEC_ROLEPOL_OFF]);
+    t.rp_entries = reinterpret_cast<const cb_rolepol_entry *>(base + d.off[CB_SEC_ROLEPOL_ENTRIES]);
+    t.rp_rules = reinterpret_cast<const cb_rolepol_rule *>(base + d.off[CB_SEC_ROLEPOL_RULES]);
+    t.rp_apats = reinterpret_cast<const uint32_t *>(base + d.off[CB_SEC_ROLEPOL_APATS]);
+    t.nV = d.nV; t.nRP = d.nRP; t.nS = d.nS; t.nP = d.nP; t.nR = d.nR; t.nAP = d.nAP; t.nT = d.nT; t.n_slots = d.n_slots;
+    t.has_role_policies = d.has_role_policies; t.has_parent_roles = d.has_parent_roles;
+    t.has_principal_policies = d.has_principal_policies;
+    return t;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Persistent CheckResources kernel. kStage: TMA-stage the table image into dynamic shared memory.
+template <bool kStage>
+__global__ void __launch_bounds__(kThreads, 2) check_kernel(const TableDesc td, const cb::BatchView bv, uint8_t *bitmap,
+                                                          uint32_t *status) {
+    extern __shared__ __align__(128) uint8_t smem_image[];
+    __shared__ __align__(8) uint64_t mbar;
+    const uint8_t *base = td.base;
+    if (kStage) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(td.image_bytes)
+                         : "memory");
+            // 1-D bulk copies (TMA unit), <= 32 KB each, all completing on the same mbarrier
+            for (uint32_t o = 0; o < td.image_bytes; o += 32768) {
+                uint32_t nb = td.image_bytes - o < 32768 ? td.image_bytes - o : 32768;
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                        smem_u32(smem_image + o)),
+                    "l"(td.base + o), "r"(nb), "r"(smem_u32(&mbar))
+                    : "memory");
+            }
+        }
+        base = smem_image;
+    }
+    const cb::TableView tv = make_view(base, td);
+    const uint64_t n_tiles = (bv.count + kThreads - 1) / kThreads;
+    bool staged = !kStage;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint64_t i = tile * kThreads + threadIdx.x;
+        if (!staged) {
+            // every thread waits for the table image (phase 0) before its first table access
+            uint32_t ok = 0;
+            while (!ok) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(ok)
+                    : "r"(smem_u32(&mbar))
+                    : "memory");
+            }
+            staged = true;
+        }
+        if (i < bv.count) cb::eval_request(tv, bv, bv.first + i, bitmap, status);
+    }
+    if (!staged) {
+        // CTA had no tile: still drain the bulk copy before exiting so shared memory is not released under it
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok)
+                : "r"(smem_u32(&mbar))
+                : "memory");
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess) return fail(CGPU_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+struct Slot {   // per in-flight cgpu_check call
+    cudaStream_t stream = nullptr;
+    void *dev = nullptr;
+    size_t dev_cap = 0;
+    uint8_t *pinned = nullptr;   // bitmap staging
+    size_t pinned_cap = 0;
+    uint32_t *d_status = nullptr;
+    bool busy = false;
+};
+
+}  // namespace
+
+struct cgpu_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t *d_status = nullptr;       // for cgpu_check_device / cgpu_sync
+    std::atomic<uint64_t> launches{0};
+    std::mutex mu;
+    std::vector<Slot> slots;
+    uint32_t last_grid = 0, last_block = 0, last_smem = 0;
+    int occ_staged = 0, occ_global = 0;
+    int force_no_stage = 0;
+};
+
+struct cgpu_table {
+    cgpu_ctx *ctx = nullptr;
+    std::atomic<int> refs{1};
+    uint8_t *d_image = nullptr;
+    TableDesc desc{};
+    uint32_t meta[CB_META_WORDS]{};
+};
+
+namespace {
+
+int parse_blob(const void *blob, size_t len, TableDesc *d, uint32_t *meta) {
+    if (!blob || len < sizeof(cb_blob_header)) return fail(CGPU_ERR_INVALID, "table blob too small");
+    const cb_blob_header *h = static_cast<const cb_blob_header *>(blob);
+    if (h->magic != CB_MAGIC) return fail(CGPU_ERR_INVALID, "table blob: bad magic");
+    if (h->version != CB_VERSION) return fail(CGPU_ERR_INVALID, "table blob: version %u, library expects %u", h->version, CB_VERSION);
+    if (h->total_bytes > len || sizeof(cb_blob_header) + (size_t)h->n_sections * sizeof(cb_section_desc) > len)
+        return fail(CGPU_ERR_INVALID, "table blob truncated");
+    const cb_section_desc *sd = reinterpret_cast<const cb_section_desc *>(static_cast<const char *>(blob) + sizeof(cb_blob_header));
+    memset(d, 0, sizeof(*d));
+    uint64_t image_end = 0;
+    bool seen[kMaxSec] = {false};
+    for (uint32_t i = 0; i < h->n_sections; i++) {
+        if (sd[i].offset + sd[i].n_bytes > len || (sd[i].offset & 15)) return fail(CGPU_ERR_INVALID, "table blob: bad section %u", sd[i].id);
+        if (sd[i].id == CB_SEC_MANIFEST) continue;   // host-only
+        if (sd[i].id >= kMaxSec) continue;
+        if (sd[i].offset > 0xFFFFFFF0ull) return fail(CGPU_ERR_INVALID, "table blob too large");
+        d->off[sd[i].id] = (uint32_t)sd[i].offset;
+        seen[sd[i].id] = true;
+        uint64_t end = (sd[i].offset + sd[i].n_bytes + 15) & ~15ull;
+        if (end > image_end) image_end = end;
+        if (sd[i].id == CB_SEC_META) {
+            if (sd[i].n_bytes < CB_META_WORDS * 4) return fail(CGPU_ERR_INVALID, "table blob: short META");
+            memcpy(meta, static_cast<const char *>(blob) + sd[i].offset, CB_META_WORDS * 4);
+        }
+    }
+    for (int id = CB_SEC_META; id <= CB_SEC_ROLEPOL_APATS; id++)
+        if (!seen[id]) return fail(CGPU_ERR_INVALID, "table blob: missing section %d", id);
+    if (image_end > 0xFFFFFFF0ull) return fail(CGPU_ERR_INVALID, "table blob too large");
+    d->image_bytes = (uint32_t)image_end;
+    d->nV = meta[CB_META_N_VERSIONS]; d->nRP = meta[CB_META_N_RESPATS]; d->nS = meta[CB_META_N_SCOPES];
+    d->nP = meta[CB_META_N_PRINCIPALS]; d->nR = meta[CB_META_N_ROLES]; d->nAP = meta[CB_META_N_APATS];
+    d->nT = meta[CB_META_N_STRINGS]; d->n_slots = meta[CB_META_N_SLOTS];
+    d->has_role_policies = meta[CB_META_HAS_ROLE_POLICIES]; d->has_parent_roles = meta[CB_META_HAS_PARENT_ROLES];
+    d->has_principal_policies = meta[CB_META_HAS_PRINCIPAL_POLICIES];
+    if (meta[CB_META_MAX_STACK] > CB_MAX_STACK || meta[CB_META_MAX_LOOP_DEPTH] > CB_MAX_LOOP_DEPTH || meta[CB_META_N_VARS] > CB_MAX_VARS)
+        return fail(CGPU_ERR_INVALID, "table blob needs a deeper interpreter than this build provides");
+    return CGPU_OK;
+}
+
+// Validates the batch against the table and fills the device view (pointers are used as given).
+int make_batch_view(const cgpu_table *t, const cgpu_batch *b, uint64_t first, uint64_t count, cb::BatchView *v) {
+    if (!b || b->n_columns < CGPU_N_COLUMNS || !b->columns || !b->column_bytes) return fail(CGPU_ERR_INVALID, "batch: expected %d columns", CGPU_N_COLUMNS);
+    const uint64_t N = b->n_requests;
+    if (N == 0) return fail(CGPU_ERR_INVALID, "batch: empty");
+    const size_t *cb_ = b->column_bytes;
+    if (cb_[CGPU_COL_HDR0] < N * 16 || cb_[CGPU_COL_HDR1] < N * 8) return fail(CGPU_ERR_INVALID, "batch: header columns too small");
+    if (cb_[CGPU_COL_ROLES] % (4 * N) != 0) return fail(CGPU_ERR_INVALID, "batch: roles column is not a multiple of n_requests");
+    uint32_t role_cols = (uint32_t)(cb_[CGPU_COL_ROLES] / (4 * N));
+    if (role_cols == 0 || role_cols > CB_MAX_ROLE_COLS) return fail(CGPU_ERR_INVALID, "batch: %u role columns (supported 1..%d)", role_cols, CB_MAX_ROLE_COLS);
+    if (cb_[CGPU_COL_SLOTS] < (size_t)8 * t->desc.n_slots * N) return fail(CGPU_ERR_INVALID, "batch: slot columns too small for the table's %u slots", t->desc.n_slots);
+    uint32_t n_asets = (uint32_t)(cb_[CGPU_COL_ASET_K] / 4);
+    if (n_asets == 0) return fail(CGPU_ERR_INVALID, "batch: no action sets");
+    uint32_t km = b->max_actions ? b->max_actions : 1;
+    uint32_t kc = 64 / role_cols;
+    if (kc > km) kc = km;
+    uint32_t n_pass = (km + kc - 1) / kc;
+    uint32_t nAP = t->desc.nAP ? t->desc.nAP : 1;
+    if (cb_[CGPU_COL_ASET_SPREAD] < (size_t)8 * n_pass * n_asets * nAP) return fail(CGPU_ERR_INVALID, "batch: aset_spread too small");
+    if (cb_[CGPU_COL_CLASS_OFF] < 8) return fail(CGPU_ERR_INVALID, "batch: class table too small");
+    for (int i = 0; i < CGPU_N_COLUMNS; i++)
+        if (!b->columns[i]) return fail(CGPU_ERR_INVALID, "batch: column %d is null", i);
+    v->hdr0 = static_cast<const cb_hdr0 *>(b->columns[CGPU_COL_HDR0]);
+    v->hdr1 = static_cast<const cb_hdr1 *>(b->columns[CGPU_COL_HDR1]);
+    v->roles = static_cast<const uint32_t *>(b->columns[CGPU_COL_ROLES]);
+    v->slots = static_cast<const uint64_t *>(b->columns[CGPU_COL_SLOTS]);
+    v->heap = static_cast<const uint64_t *>(b->columns[CGPU_COL_HEAP]);
+    v->bstr_off = static_cast<const uint32_t *>(b->columns[CGPU_COL_BSTR_OFF]);
+    v->bstr_bytes = static_cast<const uint8_t *>(b->columns[CGPU_COL_BSTR_BYTES]);
+    v->class_off = static_cast<const uint32_t *>(b->columns[CGPU_COL_CLASS_OFF]);
+    v->class_pats = static_cast<const uint32_t *>(b->columns[CGPU_COL_CLASS_PATS]);
+    v->aset_k = static_cast<const uint32_t *>(b->columns[CGPU_COL_ASET_K]);
+    v->aset_spread = static_cast<const uint64_t *>(b->columns[CGPU_COL_ASET_SPREAD]);
+    v->stride = N; v->first = first; v->count = count;
+    v->role_cols = role_cols; v->n_asets = n_asets; v->kc = kc; v->n_pass = n_pass; v->max_actions = km;
+    v->kbytes = (km + 7) / 8; v->flags = b->flags; v->now = b->now_unix_nanos;
+    return CGPU_OK;
+}
+
+int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, uint8_t *d_bitmap, uint32_t *d_status,
+                 cudaStream_t stream) {
+    const bool stage = !ctx->force_no_stage && t->desc.image_bytes <= kMaxStageBytes;
+    const uint32_t smem = stage ? t->desc.image_bytes : 0;
+    uint64_t tiles = (bv.count + kThreads - 1) / kThreads;
+    int occ = stage ? ctx->occ_staged : ctx->occ_global;
+    if (stage) {
+        // occupancy depends on the dynamic shared memory size of this table
+        CUDA_TRY(cudaFuncSetAttribute(check_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxStageBytes));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, check_kernel<true>, kThreads, smem));
+    } else if (occ == 0) {
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, check_kernel<false>, kThreads, 0));
+        ctx->occ_global = occ;
+    }
+    if (occ < 1) occ = 1;
+    uint64_t max_ctas = (uint64_t)ctx->sm_count * (uint64_t)occ;
+    uint32_t grid = (uint32_t)(tiles < max_ctas ? tiles : max_ctas);
+    if (grid == 0) grid = 1;
+    if (stage)
+        check_kernel<true><<<grid, kThreads, smem, stream>>>(t->desc, bv, d_bitmap, d_status);
+    else
+        check_kernel<false><<<grid, kThreads, 0, stream>>>(t->desc, bv, d_bitmap, d_status);
+    CUDA_TRY(cudaGetLastError());
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    ctx->last_grid = grid; ctx->last_block = kThreads; ctx->last_smem = smem;
+    return CGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *cgpu_last_error(void) { return g_err.c_str(); }
+
+int cgpu_init(const int *device_ids, int n_devices, cgpu_ctx **out) {
+    if (!out) return fail(CGPU_ERR_INVALID, "cgpu_init: out is null");
+    *out = nullptr;
+    if (n_devices != 1 || !device_ids) return fail(CGPU_ERR_INVALID, "cgpu_init: exactly one device per context (one process per GPU); got %d", n_devices);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return fail(CGPU_ERR_NO_DEVICE, "no CUDA device available (%s); cerbos_b200 has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device_ids[0] < 0 || device_ids[0] >= count) return fail(CGPU_ERR_INVALID, "cgpu_init: device %d out of range (0..%d)", device_ids[0], count - 1);
+    cgpu_ctx *ctx = new (std::nothrow) cgpu_ctx();
+    if (!ctx) return fail(CGPU_ERR_INVALID, "out of memory");
+    ctx->device = device_ids[0];
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, ctx->device));
+    ctx->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc(&ctx->d_status, sizeof(uint32_t)));
+    CUDA_TRY(cudaMemset(ctx->d_status, 0, sizeof(uint32_t)));
+    const char *ns = getenv("CERBOS_B200_NO_STAGE");
+    ctx->force_no_stage = ns && ns[0] == '1';
+    ctx->slots.resize(4);
+    *out = ctx;
+    return CGPU_OK;
+}
+
+void cgpu_shutdown(cgpu_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto &s : ctx->slots) {
+        if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.dev) cudaFree(s.dev);
+        if (s.pinned) cudaFreeHost(s.pinned);
+        if (s.d_status) cudaFree(s.d_status);
+    }
+    if (ctx->d_status) cudaFree(ctx->d_status);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int cgpu_table_load(cgpu_ctx *ctx, const void *blob, size_t len, cgpu_table **out) {
+    if (!ctx || !out) return fail(CGPU_ERR_INVALID, "cgpu_table_load: null argument");
+    *out = nullptr;
+    cgpu_table *t = new (std::nothrow) cgpu_table();
+    if (!t) return fail(CGPU_ERR_INVALID, "out of memory");
+    t->ctx = ctx;
+    int rc = parse_blob(blob, len, &t->desc, t->meta);
+    if (rc != CGPU_OK) { delete t; return rc; }
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&t->d_image), t->desc.image_bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(t->d_image, blob, t->desc.image_bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (t->d_image) cudaFree(t->d_image);
+        delete t;
+        return fail(CGPU_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(e));
+    }
+    t->desc.base = t->d_image;
+    *out = t;
+    return CGPU_OK;
+}
+
+void cgpu_table_retain(cgpu_table *t) { if (t) t->refs.fetch_add(1); }
+
+void cgpu_table_release(cgpu_table *t) {
+    if (!t) return;
+    if (t->refs.fetch_sub(1) == 1) {
+        cudaSetDevice(t->ctx->device);
+        cudaDeviceSynchronize();   // no kernel may still read the image
+        cudaFree(t->d_image);
+        delete t;
+    }
+}
+
+int cgpu_table_info(const cgpu_table *t, uint32_t *meta_out, uint32_t n_words) {
+    if (!t || !meta_out) return fail(CGPU_ERR_INVALID, "cgpu_table_info: null argument");
+    if (n_words > CB_META_WORDS) n_words = CB_META_WORDS;
+    memcpy(meta_out, t->meta, n_words * 4);
+    return CGPU_OK;
+}
+
+uint64_t cgpu_launch_count(const cgpu_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
+
+int cgpu_last_kernel_config(const cgpu_ctx *ctx, uint32_t *grid, uint32_t *block, uint32_t *smem_bytes) {
+    if (!ctx) return fail(CGPU_ERR_INVALID, "null ctx");
+    if (grid) *grid = ctx->last_grid;
+    if (block) *block = ctx->last_block;
+    if (smem_bytes) *smem_bytes = ctx->last_smem;
+    return CGPU_OK;
+}
+
+int cgpu_check_device(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *dev_batch, void *dev_bitmap_out, void *cuda_stream) {
+    if (!ctx || !t || !dev_batch || !dev_bitmap_out) return fail(CGPU_ERR_INVALID, "cgpu_check_device: null argument");
+    if (t->ctx != ctx) return fail(CGPU_ERR_INVALID, "table belongs to another context");
+    cb::BatchView bv;
+    int rc = make_batch_view(t, dev_batch, 0, dev_batch->n_requests, &bv);
+    if (rc != CGPU_OK) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    return launch_check(ctx, t, bv, static_cast<uint8_t *>(dev_bitmap_out), ctx->d_status, s);
+}
+
+int cgpu_sync(cgpu_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return fail(CGPU_ERR_INVALID, "null ctx");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    uint32_t st = 0;
+    CUDA_TRY(cudaMemcpyAsync(&st, ctx->d_status, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (st) {
+        CUDA_TRY(cudaMemsetAsync(ctx->d_status, 0, 4, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        return fail(CGPU_ERR_UNSUPPORTED, "a request produced a run-time value the device cannot represent exactly (e.g. timestamp outside 1678..2262, string->double, concatenation)");
+    }
+    return CGPU_OK;
+}
+
+int cgpu_check(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, uint8_t *effects_out) {
+    if (!ctx || !t || !batch || !effects_out) return fail(CGPU_ERR_INVALID, "cgpu_check: null argument");
+    if (t->ctx != ctx) return fail(CGPU_ERR_INVALID, "table belongs to another context");
+    const uint64_t N = batch->n_requests;
+    const uint32_t km = batch->max_actions ? batch->max_actions : 1;
+    if (N == 0) return CGPU_OK;
+    cb::BatchView hv;
+    int rc = make_batch_view(t, batch, 0, N, &hv);   // validates sizes (pointers here are host pointers)
+    if (rc != CGPU_OK) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+
+    // acquire a slot (stream + scratch); more concurrent callers than slots simply wait
+    Slot *slot = nullptr;
+    for (;;) {
+        {
+            std::lock_guard<std::mutex> g(ctx->mu);
+            for (auto &s : ctx->slots)
+                if (!s.busy) { s.busy = true; slot = &s; break; }
+        }
+        if (slot) break;
+        std::this_thread::yield();
+    }
+    struct Release { cgpu_ctx *c; Slot *s; ~Release() { std::lock_guard<std::mutex> g(c->mu); s->busy = false; } } rel{ctx, slot};
+
+    if (!slot->stream) CUDA_TRY(cudaStreamCreateWithFlags(&slot->stream, cudaStreamNonBlocking));
+    if (!slot->d_status) { CUDA_TRY(cudaMalloc(&slot->d_status, 4)); CUDA_TRY(cudaMemset(slot->d_status, 0, 4)); }
+
+    // device layout: every column 256-byte aligned, then the bitmap
+    size_t offs[CGPU_N_COLUMNS + 1];
+    size_t total = 0;
+    for (int i = 0; i < CGPU_N_COLUMNS; i++) { offs[i] = total; total += (batch->column_bytes[i] + 255) & ~(size_t)255; }
+    const size_t bitmap_bytes = (size_t)N * hv.kbytes;
+    offs[CGPU_N_COLUMNS] = total;
+    total += (bitmap_bytes + 255) & ~(size_t)255;
+    if (slot->dev_cap < total) {
+        if (slot->dev) cudaFree(slot->dev);
+        slot->dev = nullptr; slot->dev_cap = 0;
+        CUDA_TRY(cudaMalloc(&slot->dev, total));
+        slot->dev_cap = total;
+    }
+    if (slot->pinned_cap < bitmap_bytes) {
+        if (slot->pinned) cudaFreeHost(slot->pinned);
+        slot->pinned = nullptr; slot->pinned_cap = 0;
+        CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&slot->pinned), bitmap_bytes));
+        slot->pinned_cap = bitmap_bytes;
+    }
+    uint8_t *dbase = static_cast<uint8_t *>(slot->dev);
+    const void *dcols[CGPU_N_COLUMNS];
+    for (int i = 0; i < CGPU_N_COLUMNS; i++) {
+        dcols[i] = dbase + offs[i];
+        CUDA_TRY(cudaMemcpyAsync(dbase + offs[i], batch->columns[i], batch->column_bytes[i], cudaMemcpyHostToDevice, slot->stream));
+    }
+    cgpu_batch db = *batch;
+    db.columns = dcols;
+    cb::BatchView bv;
+    rc = make_batch_view(t, &db, 0, N, &bv);
+    if (rc != CGPU_OK) return rc;
+    uint8_t *d_bitmap = dbase + offs[CGPU_N_COLUMNS];
+    rc = launch_check(ctx, t, bv, d_bitmap, slot->d_status, slot->stream);
+    if (rc != CGPU_OK) return rc;
+    uint32_t st = 0;
+    CUDA_TRY(cudaMemcpyAsync(slot->pinned, d_bitmap, bitmap_bytes, cudaMemcpyDeviceToHost, slot->stream));
+    CUDA_TRY(cudaMemcpyAsync(&st, slot->d_status, 4, cudaMemcpyDeviceToHost, slot->stream));
+    CUDA_TRY(cudaStreamSynchronize(slot->stream));
+    if (st) {
+        CUDA_TRY(cudaMemset(slot->d_status, 0, 4));
+        return fail(CGPU_ERR_UNSUPPORTED, "a request produced a run-time value the device cannot represent exactly (e.g. timestamp outside 1678..2262, string->double, concatenation)");
+    }
+    // expand 1 bit / decision into effect bytes; slots beyond an input's own action count stay 0
+    const cb_hdr1 *h1 = static_cast<const cb_hdr1 *>(batch->columns[CGPU_COL_HDR1]);
+    const uint32_t *aset_k = static_cast<const uint32_t *>(batch->columns[CGPU_COL_ASET_K]);
+    const uint32_t n_asets = (uint32_t)(batch->column_bytes[CGPU_COL_ASET_K] / 4);
+    for (uint64_t n = 0; n < N; n++) {
+        const uint8_t *bits = slot->pinned + n * hv.kbytes;
+        uint32_t aset = h1[n].action_set_id;
+        uint32_t K = aset < n_asets ? aset_k[aset] : 0;
+        if (K > km) K = km;
+        uint8_t *o = effects_out + n * km;
+        for (uint32_t k = 0; k < K; k++) o[k] = ((bits[k >> 3] >> (k & 7)) & 1) ? CGPU_EFFECT_ALLOW : CGPU_EFFECT_DENY;
+        for (uint32_t k = K; k < km; k++) o[k] = 0;
+    }
+    return CGPU_OK;
+}
+
+}  // extern "C"

@@ -570,6 +570,9 @@ class ProgramCompiler:
                 return self._push_static(st)
             if len(args) == 2 and self._try_fused(fn, args[0], args[1]):
                 return
+        if fn == "_+_" and any(isinstance(a, ListLit) or (isinstance(a, Const) and isinstance(a.value, str))
+                               for a in args):
+            raise Unsupported("string / list concatenation (needs device-side allocation)")
         if fn in self._BIN and len(args) == 2:
             self.expr(args[0])
             self.expr(args[1])

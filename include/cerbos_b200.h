@@ -1,0 +1,114 @@
+/*
+ * cerbos_b200.h -- C ABI of the B200-native batched CheckResources evaluator.
+ *
+ * This is the drop-in boundary for the reference's hot path.  What it replaces (cerbos/cerbos):
+ *
+ *   cgpu_table_load     the in-memory rule index built by ruletable.NewRuleTable / RuleTable.init /
+ *                       indexRules (internal/ruletable/ruletable.go:517-601) and
+ *                       index.Impl.IndexRules (internal/ruletable/index/index.go:353-437); called again
+ *                       from the reload hooks Manager.reload / addPolicy / deletePolicy
+ *                       (internal/ruletable/manager.go:88, 183, 198).
+ *   cgpu_table_release  the RWMutex-guarded table swap of Manager (manager.go:28-35, 52-57): tables are
+ *                       reference counted, release is safe while checks are in flight.
+ *   cgpu_check          the body of Engine.Check -- checkSerial / checkParallel
+ *                       (internal/engine/engine.go:229-235, 295-344) -> Manager.Check (manager.go:52-57)
+ *                       -> RuleTable.check (ruletable.go:785-1155) -> SatisfiesCondition / cel-go
+ *                       (ruletable.go:1346-1486).  Host buffers in, one effect byte per (input, action) out.
+ *   cgpu_check_device   same evaluation for batches already resident in HBM (benchmarks, multi-GPU
+ *                       sharding): no PCIe traffic, packed 1 bit / decision result.
+ *
+ * Conventions kept from the reference: results are index-aligned with the inputs (engine.go:308, 338); any
+ * failure fails the whole call (engine.go:304-306) -- here a negative status plus cgpu_last_error();
+ * `now` is fixed once per call (evaluator_trace_common.go:22-24); unsupported CEL is a *load-time* error
+ * (the host flattener refuses to build the blob), unsupported run-time values (e.g. a timestamp outside
+ * 1678..2262) fail the call with CGPU_ERR_UNSUPPORTED -- never a silent divergence, never a CPU fallback.
+ *
+ * Go owns all Go memory: nothing passed in is retained after a call returns, there are no callbacks.
+ * The reference-side cgo binding is shown in INTEGRATION.md.
+ */
+#ifndef CERBOS_B200_H
+#define CERBOS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cgpu_ctx cgpu_ctx;     /* one device + stream pool; create once per process (one process per GPU) */
+typedef struct cgpu_table cgpu_table; /* immutable flattened rule table resident in HBM */
+
+enum cgpu_status {
+    CGPU_OK = 0,
+    CGPU_ERR_INVALID = -1,      /* bad argument / malformed blob or batch */
+    CGPU_ERR_CUDA = -2,         /* CUDA runtime failure (message in cgpu_last_error) */
+    CGPU_ERR_UNSUPPORTED = -3,  /* a request hit a run-time value the device cannot represent exactly */
+    CGPU_ERR_NO_DEVICE = -4     /* no usable CUDA device: the product never falls back to a CPU path */
+};
+
+/* Effects as in api/public/cerbos/effect/v1/effect.proto */
+#define CGPU_EFFECT_ALLOW 1
+#define CGPU_EFFECT_DENY 2
+
+/* Number of SoA columns in a batch and their order (layout documented in cerbos_b200/encode.py and
+ * include/cerbos_b200_format.h; SURVEY.md 8(d) gives the per-request byte accounting). */
+enum cgpu_column {
+    CGPU_COL_HDR0 = 0,    /* cb_hdr0[N]            16 B / request */
+    CGPU_COL_HDR1,        /* cb_hdr1[N]             8 B / request */
+    CGPU_COL_ROLES,       /* u32[role_cols][N]                    */
+    CGPU_COL_SLOTS,       /* u64[n_slots][N]  NaN-boxed attribute values */
+    CGPU_COL_HEAP,        /* u64[]   lists / maps referenced from slots */
+    CGPU_COL_BSTR_OFF,    /* u32[n_batch_strings + 1] */
+    CGPU_COL_BSTR_BYTES,  /* u8[] */
+    CGPU_COL_CLASS_OFF,   /* u32[n_classes + 1]  resource-kind class -> resource pattern ids */
+    CGPU_COL_CLASS_PATS,  /* u32[] */
+    CGPU_COL_ASET_K,      /* u32[n_asets]  number of actions of each distinct action list */
+    CGPU_COL_ASET_SPREAD, /* u64[n_pass][n_asets][n_apats] */
+    CGPU_N_COLUMNS
+};
+
+typedef struct {
+    uint64_t n_requests;
+    uint32_t max_actions;      /* K: effects_out / bitmap row width */
+    int64_t now_unix_nanos;    /* batch-constant now() */
+    uint32_t flags;            /* bit0: lenient scope search (evaluator.Conf.LenientScopeSearch) */
+    const void *const *columns;   /* CGPU_N_COLUMNS pointers (host memory for cgpu_check, device for *_device) */
+    const size_t *column_bytes;
+    uint32_t n_columns;
+} cgpu_batch;
+
+int cgpu_init(const int *device_ids, int n_devices, cgpu_ctx **out);
+void cgpu_shutdown(cgpu_ctx *ctx);
+
+/* blob = host-built flattened table (cerbos_b200/table/flatten.py; Go: the same writer over runtimev1.RuleTable).
+ * The blob is copied to HBM; the caller may free it when the call returns. */
+int cgpu_table_load(cgpu_ctx *ctx, const void *blob, size_t len, cgpu_table **out);
+void cgpu_table_retain(cgpu_table *t);
+void cgpu_table_release(cgpu_table *t);
+
+/* Host-buffer path (what engine.Check calls).  effects_out: n_requests * max_actions bytes, 1 = ALLOW, 2 = DENY,
+ * 0 for slots beyond an input's own action count.  Re-entrant; blocks until the result is in effects_out. */
+int cgpu_check(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, uint8_t *effects_out);
+
+/* Device-resident path: columns are device pointers on ctx's device.  dev_bitmap_out receives
+ * n_requests * ceil(max_actions / 8) bytes, bit (k % 8) of byte n * ceil(K/8) + k / 8 set <=> ALLOW.
+ * Asynchronous on `cuda_stream` (a cudaStream_t; NULL = the ctx's own stream).  Unsupported run-time values
+ * are reported by the next cgpu_sync(). */
+int cgpu_check_device(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *dev_batch, void *dev_bitmap_out,
+                      void *cuda_stream);
+/* Waits for work queued by cgpu_check_device on `cuda_stream` and returns CGPU_ERR_UNSUPPORTED / CGPU_ERR_CUDA
+ * if any of it failed. */
+int cgpu_sync(cgpu_ctx *ctx, void *cuda_stream);
+
+/* Introspection used by bench.py / tests (not part of the Go surface). */
+uint64_t cgpu_launch_count(const cgpu_ctx *ctx);        /* kernels launched by this library so far */
+int cgpu_table_info(const cgpu_table *t, uint32_t *meta_out, uint32_t n_words);  /* copies META words */
+int cgpu_last_kernel_config(const cgpu_ctx *ctx, uint32_t *grid, uint32_t *block, uint32_t *smem_bytes);
+
+const char *cgpu_last_error(void);   /* thread-local; valid until the next call on this thread */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,42 @@
+"""ctypes driver for the host build of the kernel core (debug aid; see hostsim.cpp)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+_SO = os.path.join(_ROOT, "oracle", "_build", "libhostsim.so")
+_lib = None
+
+
+def build():
+    src = os.path.join(_ROOT, "tests", "hostsim", "hostsim.cpp")
+    deps = [src, os.path.join(_ROOT, "cerbos_b200", "csrc", "cb_core.h"), os.path.join(_ROOT, "include", "cerbos_b200_format.h")]
+    if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(d) for d in deps):
+        os.makedirs(os.path.dirname(_SO), exist_ok=True)
+        subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", f"-I{_ROOT}/include",
+                        f"-I{_ROOT}/cerbos_b200/csrc", "-o", _SO, src], check=True)
+    return _SO
+
+
+def check(blob: bytes, columns, n, max_actions, now_ns=0, flags=0):
+    """Returns uint8[n, max_actions] effects decoded from the packed bitmap (padding slots = DENY-coded 2)."""
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.hostsim_check.restype = ctypes.c_int
+    cols = [np.ascontiguousarray(c) for c in columns]
+    ptrs = (ctypes.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+    sizes = (ctypes.c_uint64 * len(cols))(*[c.nbytes for c in cols])
+    km = max(max_actions, 1)
+    kbytes = (km + 7) // 8
+    bitmap = np.zeros((n, kbytes), dtype=np.uint8)
+    buf = ctypes.create_string_buffer(blob, len(blob))
+    rc = _lib.hostsim_check(buf, ctypes.c_uint64(len(blob)), ctypes.c_uint64(n), ctypes.c_uint32(max_actions),
+                            ctypes.c_int64(now_ns), ctypes.c_uint32(flags), ptrs, sizes,
+                            bitmap.ctypes.data_as(ctypes.c_void_p))
+    if rc != 0:
+        raise RuntimeError(f"hostsim_check failed: {rc}")
+    bits = np.unpackbits(bitmap, axis=1, bitorder="little")[:, :km]
+    return np.where(bits == 1, 1, 2).astype(np.uint8)

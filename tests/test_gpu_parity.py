@@ -1,0 +1,149 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracles (bit-exact)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+NOW_NS = 1_704_067_200_000_000_000  # 2024-01-01T00:00:00Z
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from cerbos_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _names(eff):
+    return {"EFFECT_ALLOW": 1, "EFFECT_DENY": 2}[eff]
+
+
+def test_engine_goldens_through_engine_api():
+    """166 reference engine goldens through Engine.check (host-buffer C ABI)."""
+    from cerbos_b200.engine import Engine
+    from helpers import engine_decisions, load_golden
+    docs = [e["policy"] for e in load_golden("store_policies.json")]
+    engines = {False: Engine(docs, globals_={"environment": "test"}),
+               True: Engine(docs, globals_={"environment": "test"}, lenient_scope_search=True)}
+    n = 0
+    for cid, lenient, inp, want in engine_decisions():
+        got = engines[lenient].check([inp], now_ns=NOW_NS)[0]
+        assert got["requestId"] == inp.get("requestId", "") and got["resourceId"] == inp["resource"]["id"]
+        for a, wv in want["actions"].items():
+            assert got["actions"][a]["effect"] == wv["effect"], (cid, a)
+            n += 1
+    assert n == 166
+    for e in engines.values():
+        e.close()
+
+
+def test_goldens_batched_device_vs_oracle(ctx):
+    from cerbos_b200.device import DeviceBatch
+    from cerbos_b200.encode import Encoder
+    from cerbos_b200.table.flatten import flatten
+    from helpers import engine_decisions, store_rule_table
+    from oracle import cref
+    ft = flatten(store_rule_table(), globals_={"environment": "test"})
+    table = ctx.load_table(ft.blob)
+    inputs = [inp for _, lenient, inp, _ in engine_decisions() if not lenient]
+    b = Encoder(ft.manifest).encode(inputs * 40)   # > 1 tile, mixed shapes
+    want = cref.check(ft.blob, b.columns, b.n, b.max_actions, NOW_NS)
+    db = DeviceBatch(b, "cuda:0")
+    db.run(table, NOW_NS)
+    ctx.sync()
+    got = db.effects()
+    valid = want != 0
+    assert (got[valid] == want[valid]).all()
+    host = table.check(b.columns, b.n, b.max_actions, NOW_NS)
+    assert (host == want).all()
+    table.release()
+
+
+@pytest.mark.parametrize("name,n", [("C1", 1024), ("C2", 1 << 16), ("C2", 1 << 20)])
+def test_workloads_bit_exact(ctx, name, n):
+    from cerbos_b200 import workloads as W
+    from cerbos_b200.device import DeviceBatch
+    from oracle import cref
+    w = W.WORKLOADS[name]()
+    _, ft, enc = W.build(w)
+    b = w.columns(w.fields(n), enc)
+    want = cref.check(ft.blob, b.columns, b.n, b.max_actions, n_threads=os.cpu_count() or 1)
+    table = ctx.load_table(ft.blob)
+    db = DeviceBatch(b, "cuda:0")
+    db.run(table)
+    ctx.sync()
+    got = db.effects()
+    assert (got == want).all()
+    # size-independent properties: every decision is ALLOW or DENY; re-running is idempotent; checksum of checksums
+    assert set(np.unique(got)) <= {1, 2}
+    db.run(table)
+    ctx.sync()
+    assert (db.effects() == got).all()
+    host = table.check(b.columns, b.n, b.max_actions)
+    assert (host == want).all()
+    assert int(host.astype(np.uint64).sum()) == int(want.astype(np.uint64).sum())
+    table.release()
+
+
+def test_staged_and_global_table_paths_agree():
+    """The TMA-staged (shared memory) and the global-memory table paths give identical bits."""
+    from cerbos_b200 import capi, workloads as W
+    from cerbos_b200.device import DeviceBatch
+    w = W.C2()
+    _, ft, enc = W.build(w)
+    b = w.columns(w.fields(1 << 16), enc)
+    outs = []
+    for flag in ("0", "1"):
+        os.environ["CERBOS_B200_NO_STAGE"] = flag
+        c = capi.Context(0)
+        t = c.load_table(ft.blob)
+        db = DeviceBatch(b, "cuda:0")
+        db.run(t)
+        c.sync()
+        outs.append((db.effects(), c.last_kernel_config()))
+        t.release()
+        c.close()
+    os.environ.pop("CERBOS_B200_NO_STAGE", None)
+    assert outs[0][1]["smem_bytes"] > 0 and outs[1][1]["smem_bytes"] == 0
+    assert (outs[0][0] == outs[1][0]).all()
+
+
+def test_error_paths(ctx):
+    from cerbos_b200 import capi, workloads as W
+    with pytest.raises(capi.CgpuError):
+        ctx.load_table(b"\0" * 64)
+    w = W.C1()
+    _, ft, enc = W.build(w)
+    t = ctx.load_table(ft.blob)
+    b = w.columns(w.fields(), enc)
+    cols = list(b.columns)
+    cols[2] = cols[2][:, :100]   # roles column no longer a multiple of n
+    with pytest.raises(capi.CgpuError):
+        t.check(cols, b.n, b.max_actions)
+    t.release()
+
+
+def test_many_actions_multiple_passes(ctx):
+    from cerbos_b200 import workloads as W
+    from cerbos_b200.encode import Encoder
+    from cerbos_b200.policy.compile import build_rule_table
+    from cerbos_b200.table.flatten import flatten
+    from oracle import cref
+    rt = build_rule_table(W.C2().policies())
+    ft = flatten(rt)
+    acts = list(dict.fromkeys([f"a{i % 8}" if i % 3 else f"zz{i}" for i in range(70)]))
+    inputs = []
+    for j in range(300):
+        inputs.append({"actions": acts[: 1 + j % len(acts)],
+                       "principal": {"id": f"p{j % 7}", "roles": ["user", "manager", "admin", "x1", "x2"][: 1 + j % 5], "attr": {"dept": f"d{j % 3}"}},
+                       "resource": {"kind": f"kind_{j % 10}", "id": "r", "attr": {"owner": f"p{j % 5}", "dept": f"d{j % 2}", "status": ["OPEN", "CLOSED"][j % 2], "locked": j % 11 == 0}}})
+    b = Encoder(ft.manifest).encode(inputs)
+    assert b.n_pass > 1
+    want = cref.check(ft.blob, b.columns, b.n, b.max_actions)
+    t = ctx.load_table(ft.blob)
+    got = t.check(b.columns, b.n, b.max_actions)
+    assert (got == want).all()
+    t.release()

@@ -1,0 +1,37 @@
+"""The C-ABI library loads and exports every symbol include/cerbos_b200.h declares (no compute without a GPU)."""
+import os
+import re
+
+import pytest
+
+from cerbos_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_exports_match_header():
+    hdr = open(os.path.join(ROOT, "include", "cerbos_b200.h")).read()
+    declared = set(re.findall(r"\b(cgpu_[a-z_]+)\s*\(", hdr))
+    assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
+    lib = capi.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(capi.CgpuError) as e:
+        capi.Context(0)
+    assert e.value.code == capi.ERR_NO_DEVICE
+
+
+def test_product_does_not_import_oracle():
+    """Nothing under cerbos_b200/ may import or reference the oracle (test infrastructure)."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "cerbos_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, fn), encoding="utf-8").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dirpath, fn)
+                assert "check_ref" not in src, os.path.join(dirpath, fn)

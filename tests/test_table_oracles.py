@@ -1,0 +1,146 @@
+"""Oracle #2 (C interpreter of the flattened table) and the host build of the kernel core against
+oracle #1 (structural Python restatement), on the reference goldens and the synthetic workloads."""
+import numpy as np
+import pytest
+
+from cerbos_b200 import workloads as W
+from cerbos_b200.encode import Encoder
+from cerbos_b200.policy.compile import build_rule_table
+from cerbos_b200.table import layout as L
+from cerbos_b200.table.bytecode import Unsupported
+from cerbos_b200.table.flatten import flatten
+from helpers import engine_decisions, load_golden, store_rule_table
+from hostsim import driver as hostsim
+from oracle import cref
+from oracle.celeval import parse_timestamp
+from oracle.check import CheckOracle
+
+G = {"environment": "test"}
+NOW = parse_timestamp("2024-01-01T00:00:00Z")
+
+
+@pytest.fixture(scope="module")
+def store_flat():
+    return flatten(store_rule_table(), globals_=G)
+
+
+def test_layout_header_in_sync():
+    import os
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "cerbos_b200_format.h")
+    assert open(hdr).read() == L.c_header(), "run `python -m cerbos_b200.table.layout`"
+
+
+def test_c_oracle_and_kernel_core_on_engine_goldens(store_flat):
+    ft = store_flat
+    orc = CheckOracle(store_rule_table(), globals_=G)
+    n = 0
+    for cid, lenient, inp, want in engine_decisions():
+        enc = Encoder(ft.manifest, lenient_scope_search=lenient)
+        b = enc.encode([inp])
+        fl = L.BATCH_FLAG_LENIENT if lenient else 0
+        c_out = cref.check(ft.blob, b.columns, b.n, b.max_actions, NOW.ns, fl)
+        k_out = hostsim.check(ft.blob, b.columns, b.n, b.max_actions, NOW.ns, fl)
+        py = orc.check(inp, NOW, lenient=lenient)
+        for k, a in enumerate(inp["actions"]):
+            assert c_out[0, k] == py["actions"][a]["effect"], (cid, a)
+            assert k_out[0, k] == py["actions"][a]["effect"], (cid, a)
+            n += 1
+    assert n == 166
+
+
+def test_batched_goldens_mixed_shapes(store_flat):
+    """All strict golden inputs in ONE batch: mixed action counts, role counts, scopes, principals."""
+    ft = store_flat
+    inputs = [inp for _, lenient, inp, _ in engine_decisions() if not lenient]
+    b = Encoder(ft.manifest).encode(inputs)
+    c_out = cref.check(ft.blob, b.columns, b.n, b.max_actions, NOW.ns)
+    k_out = hostsim.check(ft.blob, b.columns, b.n, b.max_actions, NOW.ns)
+    valid = c_out != 0
+    assert (c_out[valid] == k_out[valid]).all()
+    one = np.concatenate([cref.check(ft.blob, Encoder(ft.manifest).encode([i]).columns, 1, len(i["actions"]), NOW.ns)[0]
+                          for i in inputs])
+    assert (c_out[valid] == one).all()
+
+
+def _leafs(c):
+    if "expr" in c:
+        yield c["expr"]
+    for k in ("all", "any", "none"):
+        if k in c:
+            for x in c[k]["of"]:
+                yield from _leafs(x)
+
+
+def _cel_cases():
+    for tc in load_golden("cel_eval.json"):
+        for e in _leafs(tc["condition"]):
+            yield tc["file"], e, tc["request"]
+    for tc in load_golden("cerbos_lib_test.json"):
+        yield "cerbos_lib_test", tc["expr"], {"principal": {"id": "x", "roles": ["r"]}, "resource": {"kind": "k", "id": "1"}}
+
+
+def test_bytecode_vs_cel_oracle_on_golden_expressions():
+    """Every golden CEL leaf that lowers to bytecode must evaluate like oracle #1 (the rest must be
+    rejected at table build -- never silently diverge)."""
+    now = parse_timestamp("2021-04-22T10:05:20.021-05:00")
+    lowered = 0
+    for f, e, req in _cel_cases():
+        inp = {"principal": dict(req.get("principal") or {}), "resource": dict(req.get("resource") or {}), "actions": ["a"]}
+        if "auxData" in req:
+            inp["auxData"] = req["auxData"]
+        inp["resource"]["kind"] = "leave_request"
+        inp["principal"].setdefault("roles", ["r"])
+        pol = {"apiVersion": "api.cerbos.dev/v1", "resourcePolicy": {"resource": "leave_request", "version": "default",
+               "rules": [{"actions": ["a"], "effect": "EFFECT_ALLOW", "roles": ["*"], "condition": {"match": {"expr": e}}}]}}
+        try:
+            rt = build_rule_table([pol])
+            ft = flatten(rt)
+        except Unsupported:
+            continue
+        except Exception:
+            continue  # spiffe etc. do not parse into supported calls
+        lowered += 1
+        b = Encoder(ft.manifest).encode([inp])
+        want = CheckOracle(rt).check(inp, now)["actions"]["a"]["effect"]
+        assert cref.check(ft.blob, b.columns, 1, 1, now.ns)[0, 0] == want, (f, e)
+        assert hostsim.check(ft.blob, b.columns, 1, 1, now.ns)[0, 0] == want, (f, e)
+    assert lowered >= 90
+
+
+@pytest.mark.parametrize("cls,n", [(W.C1, 1024), (W.C2, 1 << 14)])
+def test_workloads_three_way(cls, n):
+    w = cls()
+    rt, ft, enc = W.build(w)
+    f = w.fields(n)
+    b = w.columns(f, enc)
+    c_out = cref.check(ft.blob, b.columns, b.n, b.max_actions, n_threads=4)
+    k_out = hostsim.check(ft.blob, b.columns, b.n, b.max_actions)
+    assert (c_out == k_out).all()
+    idx = list(range(0, n, max(1, n // 256)))
+    inputs = w.inputs(f, idx)
+    b2 = enc.encode(inputs)
+    assert (cref.check(ft.blob, b2.columns, b2.n, b2.max_actions) == c_out[idx]).all(), "vectorised columns != encoder"
+    orc = CheckOracle(rt)
+    for j, inp in enumerate(inputs[:64]):
+        g = orc.check(inp)
+        for k, a in enumerate(w.actions):
+            assert g["actions"][a]["effect"] == c_out[idx[j], k]
+
+
+def test_many_actions_and_roles_passes():
+    """K x role_cols > 64 forces several passes of the bit-parallel walk."""
+    docs = W.C2().policies()
+    rt = build_rule_table(docs)
+    ft = flatten(rt)
+    enc = Encoder(ft.manifest)
+    acts = [f"a{i % 8}" if i % 3 else f"zz{i}" for i in range(40)]
+    acts = list(dict.fromkeys(acts)) + ["a0", "a7"]
+    inp = {"actions": acts, "principal": {"id": "p1", "roles": ["user", "manager", "admin", "x1", "x2"], "attr": {"dept": "d1"}},
+           "resource": {"kind": "kind_3", "id": "r", "attr": {"owner": "p1", "dept": "d1", "status": "OPEN", "locked": False}}}
+    b = enc.encode([inp])
+    assert b.n_pass > 1
+    c_out = cref.check(ft.blob, b.columns, 1, b.max_actions)
+    k_out = hostsim.check(ft.blob, b.columns, 1, b.max_actions)
+    py = CheckOracle(rt).check(inp)
+    for k, a in enumerate(acts):
+        assert c_out[0, k] == py["actions"][a]["effect"] == k_out[0, k], a
