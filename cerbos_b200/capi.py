@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libcerbos_b200.so")
 
-N_COLUMNS = 11
+N_COLUMNS = 12
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE = 0, -1, -2, -3, -4
 
 EXPORTS = [
@@ -99,7 +99,7 @@ class Context:
     def last_kernel_config(self):
         g, b, s = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
         _check(lib().cgpu_last_kernel_config(self._h, ctypes.byref(g), ctypes.byref(b), ctypes.byref(s)))
-        return {"grid": g.value, "block": b.value, "smem_bytes": s.value}
+        return {"grid": g.value, "block": b.value, "smem_bytes": s.value & 0x7FFFFFFF, "lean_body": bool(s.value >> 31)}
 
     def load_table(self, blob: bytes) -> "Table":
         return Table(self, blob)
@@ -145,6 +145,21 @@ class Table:
         s = (ctypes.c_size_t * len(sizes))(*sizes)
         b = _Batch(n, max_actions, now_ns, flags, p, s, len(ptrs))
         _check(lib().cgpu_check(self.ctx._h, self._h, ctypes.byref(b), ctypes.c_void_p(out_ptr)))
+
+    def prepared_device_call(self, ptrs, sizes, n, max_actions, bitmap_ptr, now_ns=0, flags=0):
+        """Pre-builds the argument block once; returns f(stream) that only issues cgpu_check_device
+        (keeps per-launch host overhead to the ctypes call itself)."""
+        p = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        s = (ctypes.c_size_t * len(sizes))(*sizes)
+        b = _Batch(n, max_actions, now_ns, flags, p, s, len(ptrs))
+        fn, ctx_h, tab_h, bref, bm = lib().cgpu_check_device, self.ctx._h, self._h, ctypes.byref(b), ctypes.c_void_p(bitmap_ptr)
+        keep = (p, s, b)
+
+        def call(stream=0, _keep=keep):
+            rc = fn(ctx_h, tab_h, bref, bm, ctypes.c_void_p(stream))
+            if rc != OK:
+                _check(rc)
+        return call
 
     # ---- device-resident path
     def check_device(self, ptrs, sizes, n, max_actions, bitmap_ptr, now_ns=0, flags=0, stream=0):

@@ -32,22 +32,45 @@
 namespace cb {
 
 // ---------------------------------------------------------------------------------------------- views
-struct TableView {
-    const uint32_t *scope_parent, *scope_flags, *res_block_map, *prin_block_map, *prin_of_string;
-    const uint8_t *res_exists, *prin_exists;
-    const cb_block *blocks;
-    const cb_row *rows;
-    const cb_cond *conds;
-    const cb_instr *code;
-    const cb_const *consts;
-    const uint64_t *theap;
-    const uint32_t *str_off;
-    const uint8_t *str_bytes;
-    const uint32_t *par_off, *par_list, *rp_off, *rp_apats;
-    const cb_rolepol_entry *rp_entries;
-    const cb_rolepol_rule *rp_rules;
-    uint32_t nV, nRP, nS, nP, nR, nAP, nT, n_slots;
+// Section offsets + dimensions of the table image.  In the kernels this lives in the (grid-constant) kernel
+// parameters, so reading a field is a constant-bank operand and costs no register.
+struct TableLayout {
+    uint32_t off[28];   // by section id (CB_SEC_*)
+    uint32_t nV, nRP, nS, nP, nR, nAP, nT, n_slots, n_rows;
     uint32_t has_role_policies, has_parent_roles, has_principal_policies;
+    uint32_t image_bytes;
+};
+
+// base = start of the table image: shared memory (TMA-staged) or global memory.
+struct TableView {
+    const uint8_t *base;
+    const TableLayout *L;
+    template <typename T>
+    CB_HD const T *sec(int id) const { return reinterpret_cast<const T *>(base + L->off[id]); }
+    CB_HD const uint32_t *scope_parent() const { return sec<uint32_t>(CB_SEC_SCOPE_PARENT); }
+    CB_HD const uint32_t *scope_flags() const { return sec<uint32_t>(CB_SEC_SCOPE_FLAGS); }
+    CB_HD const uint32_t *res_block_map() const { return sec<uint32_t>(CB_SEC_RES_BLOCK_MAP); }
+    CB_HD const uint8_t *res_exists() const { return sec<uint8_t>(CB_SEC_RES_EXISTS); }
+    CB_HD const uint32_t *prin_block_map() const { return sec<uint32_t>(CB_SEC_PRIN_BLOCK_MAP); }
+    CB_HD const uint8_t *prin_exists() const { return sec<uint8_t>(CB_SEC_PRIN_EXISTS); }
+    CB_HD const uint32_t *prin_of_string() const { return sec<uint32_t>(CB_SEC_PRIN_OF_STRING); }
+    CB_HD const cb_block *blocks() const { return sec<cb_block>(CB_SEC_BLOCKS); }
+    CB_HD const cb_row *rows() const { return sec<cb_row>(CB_SEC_ROWS); }
+    CB_HD const cb_cond *conds() const { return sec<cb_cond>(CB_SEC_CONDS); }
+    CB_HD const cb_instr *code() const { return sec<cb_instr>(CB_SEC_CODE); }
+    CB_HD const cb_const *consts() const { return sec<cb_const>(CB_SEC_CONSTS); }
+    CB_HD const uint64_t *consts_v64() const { return sec<uint64_t>(CB_SEC_CONSTS_V64); }
+    CB_HD const uint64_t *theap() const { return sec<uint64_t>(CB_SEC_THEAP); }
+    CB_HD const uint32_t *str_off() const { return sec<uint32_t>(CB_SEC_STR_OFF); }
+    CB_HD const uint8_t *str_bytes() const { return sec<uint8_t>(CB_SEC_STR_BYTES); }
+    CB_HD const uint32_t *par_off() const { return sec<uint32_t>(CB_SEC_ROLE_PARENTS_OFF); }
+    CB_HD const uint32_t *par_list() const { return sec<uint32_t>(CB_SEC_ROLE_PARENTS); }
+    CB_HD const uint32_t *rp_off() const { return sec<uint32_t>(CB_SEC_ROLEPOL_OFF); }
+    CB_HD const cb_rolepol_entry *rp_entries() const { return sec<cb_rolepol_entry>(CB_SEC_ROLEPOL_ENTRIES); }
+    CB_HD const cb_rolepol_rule *rp_rules() const { return sec<cb_rolepol_rule>(CB_SEC_ROLEPOL_RULES); }
+    CB_HD const uint32_t *rp_apats() const { return sec<uint32_t>(CB_SEC_ROLEPOL_APATS); }
+    CB_HD const uint32_t *block_slots_off() const { return sec<uint32_t>(CB_SEC_BLOCK_SLOTS_OFF); }
+    CB_HD const uint32_t *block_slots() const { return sec<uint32_t>(CB_SEC_BLOCK_SLOTS); }
 };
 
 struct BatchView {
@@ -60,6 +83,8 @@ struct BatchView {
     const uint8_t *bstr_bytes;
     const uint32_t *class_off, *class_pats, *aset_k;
     const uint64_t *aset_spread;  // [n_pass][n_asets][nAP]
+    const uint64_t *row_am;       // [n_pass][n_asets][n_rows]
+    uint32_t n_rows;
     uint64_t stride;            // requests per column (N of the whole batch)
     uint64_t first, count;      // sub-range evaluated by this launch
     uint32_t role_cols, n_asets, kc, n_pass, max_actions, kbytes, flags;
@@ -111,8 +136,8 @@ CB_HD cb_hdr1 load_hdr1(const cb_hdr1 *p) {
 CB_HD cb_block load_block(const cb_block *p) { U4 v = ld16(p); cb_block b; b.row_start = v.x; b.n_rows = v.y; b.cond_base = v.z; b.n_conds = v.w; return b; }
 CB_HD cb_row load_row(const cb_row *p) {
     U4 v = ld16(p);
-    cb_row r; r.apat = (uint16_t)(v.x & 0xFFFF); r.role = (uint16_t)(v.x >> 16); r.cond = (uint16_t)(v.y & 0xFFFF); r.drcond = (uint16_t)(v.y >> 16);
-    r.respat = (uint16_t)(v.z & 0xFFFF); r.effect = (uint8_t)((v.z >> 16) & 0xFF); r.flags = (uint8_t)(v.z >> 24); r.pad = v.w; return r;
+    cb_row r; r.role = (uint16_t)(v.x & 0xFFFF); r.cond = (uint16_t)(v.x >> 16); r.drcond = (uint16_t)(v.y & 0xFFFF); r.respat = (uint16_t)(v.y >> 16);
+    r.effect = (uint8_t)(v.z & 0xFF); r.flags = (uint8_t)((v.z >> 8) & 0xFF); r.n_pats = (uint16_t)(v.z >> 16); r.pat_start = v.w; return r;
 }
 CB_HD cb_rolepol_entry load_rp_entry(const cb_rolepol_entry *p) { U4 v = ld16(p); cb_rolepol_entry e; e.role = v.x; e.rule_start = v.y; e.n_rules = v.z; e.pad = v.w; return e; }
 CB_HD cb_rolepol_rule load_rp_rule(const cb_rolepol_rule *p) { U4 v = ld16(p); cb_rolepol_rule e; e.respat = v.x; e.cond = v.y; e.apat_start = v.z; e.n_apats = v.w; return e; }
@@ -181,15 +206,15 @@ struct Ctx {
 };
 
 CB_HD const uint64_t *heap_ptr(const Ctx &c, uint64_t ref) {
-    return (ref & kHeapBatch) ? c.b->heap + (ref & ~kHeapBatch) : c.t->theap + ref;
+    return (ref & kHeapBatch) ? c.b->heap + (ref & ~kHeapBatch) : c.t->theap() + ref;
 }
 CB_HD void str_get(const Ctx &c, uint64_t id, const uint8_t *&p, uint32_t &len) {
-    if (id < c.t->nT) {
-        uint32_t o = ldg(c.t->str_off + id);
-        p = c.t->str_bytes + o;
-        len = ldg(c.t->str_off + id + 1) - o;
+    if (id < c.t->L->nT) {
+        uint32_t o = ldg(c.t->str_off() + id);
+        p = c.t->str_bytes() + o;
+        len = ldg(c.t->str_off() + id + 1) - o;
     } else {
-        uint64_t j = id - c.t->nT;
+        uint64_t j = id - c.t->L->nT;
         uint32_t o = ldg(c.b->bstr_off + j);
         p = c.b->bstr_bytes + o;
         len = ldg(c.b->bstr_off + j + 1) - o;
@@ -784,7 +809,7 @@ CB_HD Val load_slot(const Ctx &c, uint32_t s, int *state) {
     return decode_v64(ldcol64(c.b->slots + (uint64_t)s * c.b->stride + c.req), state);
 }
 CB_HD Val load_const(const Ctx &c, uint32_t k) {
-    const cb_const *p = c.t->consts + k;
+    const cb_const *p = c.t->consts() + k;
     return mk(ldg(&p->tag), ldg(&p->bits));
 }
 
@@ -942,10 +967,129 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
         case CB_OP_CMP_SLOT_PID: { int s; Val a = load_slot(c, ib, &s); st[sp++] = do_cmp(c, (int)ia, a, mk(CB_T_STRING, c.pid)); break; }
         case CB_OP_IN_SLOT_CONST: { int s; Val a = load_slot(c, ib, &s); st[sp++] = do_in(c, a, load_const(c, ic)); break; }
         case CB_OP_IN_CONST_SLOT: { int s; Val a = load_slot(c, ib, &s); st[sp++] = do_in(c, load_const(c, ic), a); break; }
-        case CB_OP_IN_IP_RANGE: st[sp - 1] = st[sp - 1].tag == CB_T_ERR ? mk_err() : do_in_ip_range(c, st[sp - 1], c.t->theap + ic); break;
+        case CB_OP_IN_IP_RANGE: st[sp - 1] = st[sp - 1].tag == CB_T_ERR ? mk_err() : do_in_ip_range(c, st[sp - 1], c.t->theap() + ic); break;
         default: c.unsupported = 1; return false;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------- flat fast path
+// Conditions that are an ALL / ANY of simple terms (layout.FLAT_*, bytecode.FlatCompiler) are evaluated
+// straight on the 8-byte NaN-boxed values: no stack, no tag/payload structs.  Anything unusual (containers,
+// constants without an 8-byte form) drops to the generic helpers above, so results are identical.
+enum { TRI_F = 0, TRI_T = 1, TRI_E = 2 };
+
+CB_HD uint32_t v64_tag(uint64_t b) {   // 0 = double
+    uint32_t top = (uint32_t)(b >> 48);
+    return ((top & 0xFFF0u) == 0xFFF0u) ? (top & 0xFu) : 0u;
+}
+CB_HD int tri_of(const Val &v) { return v.tag == CB_T_BOOL ? (int)v.u : TRI_E; }
+
+CB_HD_NOINLINE int slow_cmp(Ctx &c, int ci, uint64_t x, uint64_t y) {
+    int s;
+    Val a = decode_v64(x, &s), b = decode_v64(y, &s);
+    return tri_of(do_cmp(c, ci, a, b));
+}
+
+// x: slot / P.id value; y: other operand (both NaN-boxed).  ci: 0 EQ, 2 LT, 3 LE, 4 GT, 5 GE
+CB_HD int fast_cmp(Ctx &c, int ci, uint64_t x, uint64_t y) {
+    uint32_t tx = v64_tag(x), ty = v64_tag(y);
+    if (tx == 0 && ty == 0) {
+        double dx = u2d(x), dy = u2d(y);
+        if (ci == 0) return dx == dy;
+        if (dx != dx || dy != dy) return TRI_E;
+        switch (ci) {
+        case 2: return dx < dy;
+        case 3: return dx <= dy;
+        case 4: return dx > dy;
+        default: return dx >= dy;
+        }
+    }
+    if (tx == CB_V64_ABSENT || tx == CB_V64_ERROR || ty == CB_V64_ABSENT || ty == CB_V64_ERROR) return TRI_E;
+    if (tx == CB_V64_INT || ty == CB_V64_INT || tx == 15 || ty == 15) return slow_cmp(c, ci, x, y);
+    if (ci == 0) {
+        if (tx != ty) return TRI_F;
+        if (tx == CB_V64_LIST || tx == CB_V64_MAP) return slow_cmp(c, ci, x, y);
+        return x == y;   // STRING (interned id) / BOOL / NULL
+    }
+    if (tx != ty) return TRI_E;
+    if (tx == CB_V64_STRING) {
+        int r = x == y ? 0 : str_cmp(c, x & 0xFFFFFFFFFFFFull, y & 0xFFFFFFFFFFFFull);
+        switch (ci) {
+        case 2: return r < 0;
+        case 3: return r <= 0;
+        case 4: return r > 0;
+        default: return r >= 0;
+        }
+    }
+    if (tx == CB_V64_BOOL) {
+        uint64_t a = x & 1, b = y & 1;
+        switch (ci) {
+        case 2: return a < b;
+        case 3: return a <= b;
+        case 4: return a > b;
+        default: return a >= b;
+        }
+    }
+    return TRI_E;
+}
+
+// x in container (both NaN-boxed)
+CB_HD_NOINLINE int slow_in(Ctx &c, uint64_t x, uint64_t cont) {
+    int s;
+    Val a = decode_v64(x, &s), b = decode_v64(cont, &s);
+    return tri_of(do_in(c, a, b));
+}
+CB_HD_NOINLINE bool slow_elem_eq(Ctx &c, uint64_t x, uint64_t e) {
+    int s;
+    return val_equal(c, decode_v64(x, &s), decode_v64(e, &s));
+}
+CB_HD int fast_in(Ctx &c, uint64_t x, uint64_t cont) {
+    uint32_t tx = v64_tag(x), tc = v64_tag(cont);
+    if (tx == CB_V64_ABSENT || tx == CB_V64_ERROR || tc == CB_V64_ABSENT || tc == CB_V64_ERROR) return TRI_E;
+    if (tc != CB_V64_LIST || tx == CB_V64_LIST || tx == CB_V64_MAP || tx == 15 || tx == CB_V64_INT) return slow_in(c, x, cont);
+    uint64_t pay = cont & 0xFFFFFFFFFFFFull;
+    const uint64_t *p = (pay & CB_V64_HEAP_BATCH_BIT) ? c.b->heap + (pay & (CB_V64_HEAP_BATCH_BIT - 1)) : c.t->theap() + pay;
+    uint64_t n = ldg(p);
+    for (uint64_t i = 0; i < n; i++) {
+        uint64_t e = ldg(p + 1 + i);
+        uint32_t te = v64_tag(e);
+        if (te == CB_V64_INT || te == CB_V64_LIST || te == CB_V64_MAP) {
+            if (slow_elem_eq(c, x, e)) return TRI_T;
+        } else if (tx == 0 && te == 0) {
+            if (u2d(x) == u2d(e)) return TRI_T;
+        } else if (x == e && tx == te) {
+            return TRI_T;
+        }
+    }
+    return TRI_F;
+}
+
+CB_HD uint64_t slot_bits(const Ctx &c, uint32_t s) { return ldcol64(c.b->slots + (uint64_t)s * c.b->stride + c.req); }
+
+CB_HD bool eval_flat(Ctx &c, const cb_instr *terms, uint32_t info) {
+    const uint32_t n = info & 0xFFFF, kind = (info >> 16) & 0xFF;
+    const bool negate = (info >> 24) & 1;
+    bool res = kind == CB_FLAT_ALL;
+    for (uint32_t i = 0; i < n; i++) {
+        uint64_t raw = ldg(reinterpret_cast<const uint64_t *>(terms + i));
+        uint32_t op = (uint32_t)(raw & 0xFF), ia = (uint32_t)((raw >> 8) & 0xFF), ib = (uint32_t)((raw >> 16) & 0xFFFF);
+        uint32_t ic = (uint32_t)(raw >> 32);
+        int tri;
+        switch (op) {
+        case CB_OP_CMP_SLOT_CONST: tri = fast_cmp(c, (int)(ia & 0x7F), slot_bits(c, ib), ldg(c.t->consts_v64() + ic)); break;
+        case CB_OP_CMP_SLOT_SLOT: tri = fast_cmp(c, (int)(ia & 0x7F), slot_bits(c, ib), slot_bits(c, ic)); break;
+        case CB_OP_CMP_SLOT_PID: tri = fast_cmp(c, (int)(ia & 0x7F), slot_bits(c, ib), ((uint64_t)(CB_V64_BOX_BASE | CB_V64_STRING) << 48) | c.pid); break;
+        case CB_OP_IN_SLOT_CONST: tri = fast_in(c, slot_bits(c, ib), ldg(c.t->consts_v64() + ic)); break;
+        case CB_OP_IN_CONST_SLOT: tri = fast_in(c, ldg(c.t->consts_v64() + ic), slot_bits(c, ib)); break;
+        case CB_OP_HAS_SLOT: { uint32_t ts = v64_tag(slot_bits(c, ic)); tri = ts == CB_V64_ERROR ? TRI_E : (ts != CB_V64_ABSENT); break; }
+        default: c.unsupported = 1; return false;
+        }
+        if ((ia & CB_FLAT_TERM_NEG) && tri != TRI_E) tri ^= 1;
+        if (kind == CB_FLAT_ALL) { if (tri != TRI_T) { res = false; break; } }
+        else if (tri == TRI_T) { res = true; break; }
+    }
+    return res != negate;
 }
 
 // ---------------------------------------------------------------------------------------------- decision walk
@@ -955,215 +1099,585 @@ CB_HD bool in_class(const BatchView &b, uint32_t c0, uint32_t c1, uint32_t pat) 
     return false;
 }
 
+// NOTE on structure: everything the hot path keeps per request lives in plain scalars.  Objects whose address
+// is handed to a non-inlined function are forced into local memory (the first version of this kernel spent most
+// of its time there), so the cold helpers below take their arguments BY VALUE and rebuild what they need.
+
 // is table role `role` in {req_role} U parents(exact resource scope, req_role)   (index.go:805-836)
-CB_HD bool role_in_pr(const TableView &t, uint32_t role, uint32_t req_role, uint32_t rscope) {
+CB_HD bool role_in_pr(const TableView t, uint32_t role, uint32_t req_role, uint32_t rscope) {
     if (req_role == role) return true;
-    if (!t.has_parent_roles || req_role >= t.nR) return false;
-    if (rscope == CB_SCOPE_NONE || (rscope & CB_SCOPE_INEXACT_BIT) || rscope >= t.nS) return false;
-    uint64_t idx = (uint64_t)rscope * t.nR + req_role;
-    for (uint32_t j = ldg(t.par_off + idx), e = ldg(t.par_off + idx + 1); j < e; j++)
-        if (ldg(t.par_list + j) == role) return true;
+    if (!t.L->has_parent_roles || req_role >= t.L->nR) return false;
+    if (rscope == CB_SCOPE_NONE || (rscope & CB_SCOPE_INEXACT_BIT) || rscope >= t.L->nS) return false;
+    uint64_t idx = (uint64_t)rscope * t.L->nR + req_role;
+    for (uint32_t j = ldg(t.par_off() + idx), e = ldg(t.par_off() + idx + 1); j < e; j++)
+        if (ldg(t.par_list() + j) == role) return true;
     return false;
 }
 
-struct Memo {
-    uint64_t done, val;
-};
+// Evaluates condition `gid` (global id) with the generic machinery.  bit0: it yields BOOL true
+// (ruletable.go:1425-1441); bit1: a run-time value the device cannot represent exactly was met.
+// Scalar arguments only: aggregates would travel through local memory under the device ABI.
+CB_HD_NOINLINE uint32_t cond_sat(const uint8_t *base, const TableLayout *L, const BatchView *b, uint64_t req, uint32_t pid, uint32_t gid) {
+    TableView t; t.base = base; t.L = L;
+    Ctx c;
+    c.t = &t; c.b = b; c.req = req; c.pid = pid; c.unsupported = 0;
+    U4 cd = ld16(t.conds() + gid);   // {code_off, code_len, flat_off, flat_info}
+    bool s = cd.w ? eval_flat(c, t.code() + cd.z, cd.w) : run_program(c, t.code() + cd.x);
+    return (s ? 1u : 0u) | (c.unsupported ? 2u : 0u);
+}
 
-CB_HD bool cond_sat(Ctx &c, Memo &m, uint32_t cond_base, uint32_t local /*1-based*/) {
-    uint32_t li = local - 1;
-    if (li < 64 && ((m.done >> li) & 1)) return (m.val >> li) & 1;
-    const cb_cond *cd = c.t->conds + (cond_base + li);
-    bool s = run_program(c, c.t->code + ldg(&cd->code_off));
-    if (li < 64) { m.done |= 1ull << li; m.val |= (uint64_t)s << li; }
-    return s;
+// ---- inline flat evaluator of the hot path: handles doubles and interned scalars in a few instructions and
+// hands everything else (string ordering, containers, int list elements) to the out-of-line helpers ----
+enum { TRI_SLOW = 3 };
+CB_HD_NOINLINE uint32_t slow_term(const uint8_t *base, const TableLayout *L, const BatchView *b, uint64_t req, uint32_t pid,
+                                  uint32_t is_in, uint32_t ci, uint64_t x, uint64_t y) {
+    TableView t; t.base = base; t.L = L;
+    Ctx c;
+    c.t = &t; c.b = b; c.req = req; c.pid = pid; c.unsupported = 0;
+    int tri = is_in ? fast_in(c, x, y) : fast_cmp(c, (int)ci, x, y);
+    return (uint32_t)tri | (c.unsupported ? 4u : 0u);
+}
+CB_HD int cmp_inline(uint32_t ci, uint64_t x, uint64_t y) {
+    uint32_t tx = v64_tag(x), ty = v64_tag(y);
+    if (tx == 0 && ty == 0) {
+        double dx = u2d(x), dy = u2d(y);
+        if (ci == 0) return dx == dy;
+        if (dx != dx || dy != dy) return TRI_E;
+        return ci == 2 ? dx < dy : ci == 3 ? dx <= dy : ci == 4 ? dx > dy : dx >= dy;
+    }
+    if (tx == CB_V64_ABSENT || tx == CB_V64_ERROR || ty == CB_V64_ABSENT || ty == CB_V64_ERROR) return TRI_E;
+    if (ci == 0 && tx <= CB_V64_STRING && ty <= CB_V64_STRING) return x == y;   // double / NULL / BOOL / STRING: equal iff same bits
+    return TRI_SLOW;
+}
+CB_HD int in_inline(const TableView t, const BatchView &b, uint64_t x, uint64_t cont) {
+    uint32_t tx = v64_tag(x);
+    if (v64_tag(cont) != CB_V64_LIST || tx > CB_V64_STRING) return TRI_SLOW;   // errors / containers / maps: out of line
+    uint64_t pay = cont & 0xFFFFFFFFFFFFull;
+    const uint64_t *p = (pay & CB_V64_HEAP_BATCH_BIT) ? b.heap + (pay & (CB_V64_HEAP_BATCH_BIT - 1)) : t.theap() + pay;
+    uint32_t n = (uint32_t)ldg(p);
+    int res = TRI_F;
+    for (uint32_t i = 0; i < n; i++) {
+        uint64_t e = ldg(p + 1 + i);
+        uint32_t te = v64_tag(e);
+        if (te > CB_V64_STRING) return TRI_SLOW;            // int / container elements
+        if (tx == 0 && te == 0 ? u2d(x) == u2d(e) : x == e) { res = TRI_T; break; }
+    }
+    return res;
+}
+// -> bit0 satisfied, bit2: needs the out-of-line general path (no calls are made here)
+CB_HD uint32_t flat_inline(const TableView t, const BatchView &b, uint64_t n, uint32_t pid, uint32_t flat_off, uint32_t info) {
+    const uint32_t nt = info & 0xFFFF, kind = (info >> 16) & 0xFF;
+    const cb_instr *terms = t.code() + flat_off;
+    bool res = kind == CB_FLAT_ALL;
+    uint32_t unsup = 0;
+    for (uint32_t i = 0; i < nt; i++) {
+        uint64_t raw = ldg(reinterpret_cast<const uint64_t *>(terms + i));
+        uint32_t op = (uint32_t)(raw & 0xFF), ia = (uint32_t)((raw >> 8) & 0xFF), ib = (uint32_t)((raw >> 16) & 0xFFFF);
+        uint32_t ic = (uint32_t)(raw >> 32);
+        // operands: x is always a slot (HAS_SLOT keeps it in ic), y a constant, another slot or P.id
+        uint64_t x = ldcol64(b.slots + (uint64_t)(op == CB_OP_HAS_SLOT ? ic : ib) * b.stride + n);
+        uint64_t y;
+        if (op == CB_OP_CMP_SLOT_SLOT) y = ldcol64(b.slots + (uint64_t)ic * b.stride + n);
+        else if (op == CB_OP_CMP_SLOT_PID) y = ((uint64_t)(CB_V64_BOX_BASE | CB_V64_STRING) << 48) | pid;
+        else y = ldg(t.consts_v64() + ic);
+        int tri;
+        const bool is_in = op == CB_OP_IN_SLOT_CONST || op == CB_OP_IN_CONST_SLOT;
+        if (op == CB_OP_HAS_SLOT) { uint32_t ts = v64_tag(x); tri = ts == CB_V64_ERROR ? TRI_E : (ts != CB_V64_ABSENT); }
+        else {
+            if (op == CB_OP_IN_CONST_SLOT) { uint64_t tmp = x; x = y; y = tmp; }
+            tri = is_in ? in_inline(t, b, x, y) : cmp_inline(ia & 0x7F, x, y);
+            if (tri == TRI_SLOW) return 4u;   // not decidable on the 8-byte fast forms: the caller defers the request
+        }
+        if ((ia & CB_FLAT_TERM_NEG) && tri != TRI_E) tri ^= 1;
+        if (kind == CB_FLAT_ALL) { if (tri != TRI_T) { res = false; break; } }
+        else if (tri == TRI_T) { res = true; break; }
+    }
+    return (uint32_t)(res != (bool)((info >> 24) & 1)) | unsup;
+}
+// condition `gid` on the call-free fast path: bit0 satisfied, bit2 = cannot decide here (non-flat condition or an
+// unusual operand): the request is then re-evaluated by the general body
+CB_HD uint32_t cond_eval(const TableView t, const BatchView &b, uint64_t n, uint32_t pid, uint32_t gid) {
+    U4 cd = ld16(t.conds() + gid);
+    if (cd.w) return flat_inline(t, b, n, pid, cd.z, cd.w);
+    return 4u;
 }
 
 // first scope of the chain for `kind_flag`, honouring strict / lenient search (ruletable.go:626-632)
-CB_HD uint32_t chain_start(const TableView &t, uint32_t scope, uint32_t kind_flag, bool lenient) {
+CB_HD uint32_t chain_start(const TableView t, uint32_t scope, uint32_t kind_flag, bool lenient) {
     if (scope == CB_SCOPE_NONE) return CB_NONE32;
     uint32_t s = scope & ~CB_SCOPE_INEXACT_BIT;
-    if (s >= t.nS) return CB_NONE32;
-    if (!(ldg(t.scope_flags + s) & kind_flag)) {
+    if (s >= t.L->nS) return CB_NONE32;
+    if (!(ldg(t.scope_flags() + s) & kind_flag)) {
         if (!lenient) return CB_NONE32;
-        do { s = ldg(t.scope_parent + s); } while (s != CB_NONE32 && !(ldg(t.scope_flags + s) & kind_flag));
+        do { s = ldg(t.scope_parent() + s); } while (s != CB_NONE32 && !(ldg(t.scope_flags() + s) & kind_flag));
     }
     return s;
 }
-CB_HD uint32_t chain_next(const TableView &t, uint32_t s, uint32_t kind_flag) {
-    do { s = ldg(t.scope_parent + s); } while (s != CB_NONE32 && !(ldg(t.scope_flags + s) & kind_flag));
+CB_HD uint32_t chain_next(const TableView t, uint32_t s, uint32_t kind_flag) {
+    do { s = ldg(t.scope_parent() + s); } while (s != CB_NONE32 && !(ldg(t.scope_flags() + s) & kind_flag));
     return s;
 }
 
-// Evaluates request `n` (absolute column index). Writes kbytes bytes of the packed ALLOW bitmap.
-CB_HD void eval_request(const TableView &t, const BatchView &b, uint64_t n, uint8_t *bitmap, uint32_t *status) {
-    Ctx c;
-    c.t = &t; c.b = &b; c.req = n; c.unsupported = 0;
-    uint8_t *out = bitmap + n * b.kbytes;
-    cb_hdr0 h0 = load_hdr0(b.hdr0 + n);
-    cb_hdr1 h1 = load_hdr1(b.hdr1 + n);
-    c.pid = h0.principal_id;
-    // result bits: actions 0..63 accumulate in a register and are stored once; wider action lists
-    // (K > 64, rare) fall back to read-modify-write on the thread's own output bytes
-    uint64_t acc = 0;
-    const bool wide = b.kbytes > 8;
-    if (wide) for (uint32_t q = 0; q < b.kbytes; q++) out[q] = 0;
-    struct Store {
-        uint8_t *out; uint32_t kbytes; bool wide; const uint64_t *acc;
-        CB_HD ~Store() { if (!wide) for (uint32_t q = 0; q < kbytes; q++) out[q] = (uint8_t)(*acc >> (8 * q)); }
-    } store_on_exit{out, b.kbytes, wide, &acc};
+CB_HD void prefetch_l1(const void *p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
 
-    uint32_t roles[CB_MAX_ROLE_COLS];
-    uint32_t n_roles = 0;
-    for (uint32_t i = 0; i < b.role_cols; i++) {
-        uint32_t rr = ldcol32(b.roles + (uint64_t)i * b.stride + n);
-        roles[i] = rr;
-        if (rr != CB_ROLE_PAD) n_roles = i + 1;   // encoder packs roles to the front
+// Issues L1 prefetches for the header / role columns of request `n` (the next tile of this thread).
+CB_HD void prefetch_request(const BatchView &b, uint64_t n) {
+    prefetch_l1(b.hdr0 + n);
+    prefetch_l1(b.hdr1 + n);
+    for (uint32_t i = 0; i < b.role_cols; i++) prefetch_l1(b.roles + (uint64_t)i * b.stride + n);
+}
+
+// The resource patterns a request kind matches; kc is hdr0.kind_class: the pattern id itself when there is exactly
+// one (CB_KIND_NONE: none), else an index into the class CSR.
+CB_HD uint32_t kind_count(const BatchView &b, uint32_t kc) {
+    if (kc == CB_KIND_NONE) return 0;
+    if (!(kc & CB_KIND_CLASS_CSR_BIT)) return 1;
+    uint32_t c = kc & ~CB_KIND_CLASS_CSR_BIT;
+    return ldg(b.class_off + c + 1) - ldg(b.class_off + c);
+}
+CB_HD uint32_t kind_pat_at(const BatchView &b, uint32_t kc, uint32_t j) {
+    if (!(kc & CB_KIND_CLASS_CSR_BIT)) return kc;
+    return ldg(b.class_pats + ldg(b.class_off + (kc & ~CB_KIND_CLASS_CSR_BIT)) + j);
+}
+CB_HD bool kind_has(const BatchView &b, uint32_t kc, uint32_t pat) {
+    if (!(kc & CB_KIND_CLASS_CSR_BIT)) return kc == pat;   // KIND_NONE never equals a pattern id
+    for (uint32_t j = 0, n = kind_count(b, kc); j < n; j++)
+        if (kind_pat_at(b, kc, j) == pat) return true;
+    return false;
+}
+
+// ---- per-request role table: for every table role r, the principal role columns i with r in {role_i} U
+// parents(role_i) (index.go:805-836), RCP bits per role, so a row's role test is one shift (rp0/rp1, 128 bits).
+// Tables with more roles than fit use the slow helper, which re-reads the request's role columns. ----
+template <typename M>
+CB_HD_NOINLINE M role_cols_slow(const uint8_t *base, const TableLayout *L, const BatchView *b, uint64_t n, uint32_t n_roles, uint32_t rscope, uint32_t role) {
+    TableView t; t.base = base; t.L = L;
+    M m = 0;
+    for (uint32_t i = 0; i < n_roles; i++) m |= (M)role_in_pr(t, role, ldcol32(b->roles + (uint64_t)i * b->stride + n), rscope) << i;
+    return m;
+}
+struct U2x64 { uint64_t a, b; };
+CB_HD_NOINLINE U2x64 role_tab_parents(const uint8_t *base, const TableLayout *L, const BatchView *b, uint64_t n, uint32_t n_roles, uint32_t rscope, uint32_t RCP,
+                                     uint64_t rp0, uint64_t rp1) {
+    TableView t; t.base = base; t.L = L;
+    for (uint32_t i = 0; i < n_roles; i++) {
+        uint32_t r = ldcol32(b->roles + (uint64_t)i * b->stride + n);
+        if (r >= t.L->nR) continue;
+        uint64_t idx = (uint64_t)rscope * t.L->nR + r;
+        for (uint32_t j = ldg(t.par_off() + idx), e = ldg(t.par_off() + idx + 1); j < e; j++) {
+            uint32_t pq = ldg(t.par_list() + j) * RCP + i;
+            if (pq < 64) rp0 |= 1ull << pq; else if (pq < 128) rp1 |= 1ull << (pq - 64);
+        }
     }
-    uint32_t aset = h1.action_set_id;
-    uint32_t K = aset < b.n_asets ? ldg(b.aset_k + aset) : 0;
-    if (n_roles == 0 || K == 0) return;
+    U2x64 r; r.a = rp0; r.b = rp1; return r;
+}
 
-    bool lenient = (b.flags & CB_BATCH_FLAG_LENIENT) != 0;
-    uint32_t p0 = chain_start(t, h0.principal_scope, CB_SCOPE_FLAG_PRINCIPAL, lenient);
-    uint32_t r0 = chain_start(t, h0.resource_scope, CB_SCOPE_FLAG_RESOURCE, lenient);
-    if (p0 == CB_NONE32 && r0 == CB_NONE32) return;
-    uint32_t rv = h1.resource_version, pv = h1.principal_version;
-    uint32_t cls0 = ldg(b.class_off + h0.kind_class), cls1 = ldg(b.class_off + h0.kind_class + 1);
+// row record accessors on the raw 16-byte load (cb_row: role u16, cond u16 | drcond u16, respat u16 | effect u8,
+// flags u8, n_pats u16 | pat_start u32)
+CB_HD uint32_t row_role(const U4 &r) { return r.x & 0xFFFF; }
+CB_HD uint32_t row_cond(const U4 &r) { return r.x >> 16; }
+CB_HD uint32_t row_drcond(const U4 &r) { return r.y & 0xFFFF; }
+CB_HD uint32_t row_respat(const U4 &r) { return r.y >> 16; }
+CB_HD uint32_t row_effect(const U4 &r) { return r.z & 0xFF; }
 
-    // existence checks (ruletable.go:852-863)
+// Existence checks (ruletable.go:852-863): false => every action is DENY.  Only reachable when the principal
+// and resource policy versions differ (see eval_request).
+CB_HD_NOINLINE bool exists_check(const uint8_t *base, const TableLayout *L, const BatchView *b, uint32_t kc, uint32_t pscope, uint32_t r0,
+                                 uint32_t pv, uint32_t rv, bool lenient) {
+    TableView t; t.base = base; t.L = L;
     bool p_exists = false, r_exists = false;
     if (pv != CB_NONE16)
-        for (uint32_t s = p0; s != CB_NONE32; s = chain_next(t, s, CB_SCOPE_FLAG_PRINCIPAL))
-            p_exists |= ldg(t.prin_exists + (uint64_t)pv * t.nS + s) != 0;
-    if (rv != CB_NONE16)
-        for (uint32_t s = r0; s != CB_NONE32; s = chain_next(t, s, CB_SCOPE_FLAG_RESOURCE))
-            for (uint32_t j = cls0; j < cls1; j++)
-                r_exists |= (ldg(t.res_exists + ((uint64_t)rv * t.nRP + ldg(b.class_pats + j)) * t.nS + s) & CB_EXISTS_RESOURCE_KIND) != 0;
-    if ((!p_exists && !r_exists) || rv == CB_NONE16) return;
+        for (uint32_t s = chain_start(t, pscope, CB_SCOPE_FLAG_PRINCIPAL, lenient); s != CB_NONE32; s = chain_next(t, s, CB_SCOPE_FLAG_PRINCIPAL))
+            p_exists |= ldg(t.prin_exists() + (uint64_t)pv * t.L->nS + s) != 0;
+    for (uint32_t s = r0; s != CB_NONE32; s = chain_next(t, s, CB_SCOPE_FLAG_RESOURCE))
+        for (uint32_t j = 0, nk = kind_count(*b, kc); j < nk; j++)
+            r_exists |= (ldg(t.res_exists() + ((uint64_t)rv * t.L->nRP + kind_pat_at(*b, kc, j)) * t.L->nS + s) & CB_EXISTS_RESOURCE_KIND) != 0;
+    return p_exists || r_exists;
+}
 
-    uint32_t pidx = (t.has_principal_policies && h0.principal_id < t.nT) ? ldg(t.prin_of_string + h0.principal_id) : CB_NONE32;
+CB_HD void prefetch_block_slots(const TableView t, const BatchView &b, uint32_t bid, uint64_t n) {
+    for (uint32_t q = ldg(t.block_slots_off() + bid), e = ldg(t.block_slots_off() + bid + 1); q < e; q++)
+        prefetch_l1(b.slots + (uint64_t)ldg(t.block_slots() + q) * b.stride + n);
+}
+
+template <typename M>
+struct PairMasks { M deny, allow; uint32_t unsupported; };
+
+// Principal policies: role agnostic, decided per action (state lives on role column 0)  (ruletable.go:905-910).
+// Cold path (few tables have principal policies for the calling principal): self-contained, arguments by value.
+template <typename M>
+CB_HD_NOINLINE PairMasks<M> principal_walk(const uint8_t *base, const TableLayout *L, const BatchView *b, uint64_t n, uint32_t pid, uint32_t kc, uint32_t pidx,
+                                           uint32_t p0, uint32_t rv, M amask, const uint64_t *row_am) {
+    TableView t; t.base = base; t.L = L;
+    PairMasks<M> out; out.deny = 0; out.allow = 0; out.unsupported = 0;
+    M alive = amask;
+    for (uint32_t s = p0; s != CB_NONE32 && alive; s = chain_next(t, s, CB_SCOPE_FLAG_PRINCIPAL)) {
+        uint32_t bid = ldg(t.prin_block_map() + ((uint64_t)rv * t.L->nP + pidx) * t.L->nS + s);
+        if (bid == CB_NONE32) continue;
+        U4 bl = ld16(t.blocks() + bid);   // {row_start, n_rows, cond_base, n_conds}
+        M D = 0, A = 0;
+        for (uint32_t ri = bl.x, re = bl.x + bl.y; ri < re; ri++) {
+            M m = (M)ldg(reinterpret_cast<const M *>(row_am + ri)) & alive;
+            if (!m) continue;
+            U4 row = ld16(t.rows() + ri);
+            if (!kind_has(*b, kc, row_respat(row))) continue;
+            if (row_effect(row) == CB_EFFECT_DENY ? (m & ~D) == 0 : (m & ~A) == 0) continue;   // nothing new to learn
+            bool sat = true;
+            if (row_drcond(row)) { uint32_t r = cond_sat(t.base, t.L, b, n, pid, bl.z + row_drcond(row) - 1); out.unsupported |= r & 2; sat = r & 1; }
+            if (sat && row_cond(row)) { uint32_t r = cond_sat(t.base, t.L, b, n, pid, bl.z + row_cond(row) - 1); out.unsupported |= r & 2; sat = r & 1; }
+            if (!sat) continue;
+            if (row_effect(row) == CB_EFFECT_DENY) D |= m; else A |= m;
+        }
+        out.deny |= D;
+        alive &= ~D;
+        uint32_t perm = (ldg(t.scope_flags() + s) >> CB_SCOPE_PERM_SHIFT) & 3;
+        if (perm == 1) { M a = A & alive; out.allow |= a; alive &= ~a; }
+    }
+    return out;
+}
+
+// Synthesized role-policy DENY rows of one scope (index.go:688-776): returns the pair mask D extended by them.
+template <typename M>
+CB_HD_NOINLINE PairMasks<M> rolepol_denies(const uint8_t *base, const TableLayout *L, const BatchView *b, uint64_t n, uint32_t pid, uint32_t kc, uint32_t n_roles,
+                                           uint32_t rscope, uint32_t RCP, uint64_t rp0, uint64_t rp1, bool packed, uint32_t rv, uint32_t s,
+                                           uint32_t ps, uint32_t aset, M amask, M alive, M D) {
+    TableView t; t.base = base; t.L = L;
+    PairMasks<M> out; out.allow = 0; out.unsupported = 0;
+    const M role_all = (M)(((M)1 << n_roles) - 1);
+    const uint32_t nAP = t.L->nAP ? t.L->nAP : 1;
+    const uint64_t *spread = b->aset_spread + ((uint64_t)ps * b->n_asets + aset) * nAP;
+    uint64_t ro = (uint64_t)rv * t.L->nS + s;
+    for (uint32_t e = ldg(t.rp_off() + ro), ee = ldg(t.rp_off() + ro + 1); e < ee; e++) {
+        U4 en = ld16(t.rp_entries() + e);   // {role, rule_start, n_rules, pad}
+        M rmask;
+        if (packed) { uint32_t pos = en.x * RCP; rmask = (M)(pos < 64 ? rp0 >> pos : rp1 >> (pos - 64)) & role_all; }
+        else rmask = role_cols_slow<M>(t.base, t.L, b, n, n_roles, rscope, en.x);
+        if (!rmask) continue;
+        M matched = 0;   // action bits (role column 0) with at least one matching allow rule
+        for (uint32_t q = 0; q < en.z; q++) {
+            U4 ru = ld16(t.rp_rules() + en.y + q);   // {respat, cond, apat_start, n_apats}
+            if (!kind_has(*b, kc, ru.x)) continue;
+            M am = 0;
+            for (uint32_t a = 0; a < ru.w; a++) am |= (M)ldg(spread + ldg(t.rp_apats() + ru.z + a));
+            if (!am) continue;
+            matched |= am;
+            if (ru.y && ((am * rmask) & alive & ~D)) {
+                uint32_t r = cond_sat(t.base, t.L, b, n, pid, ru.y - 1);
+                out.unsupported |= r & 2;
+                if (!(r & 1)) D |= (am * rmask) & alive;   // DENY none(cond)
+            }
+        }
+        D |= ((amask & ~matched) * rmask) & alive;   // blanket DENY for actions no allow rule matches
+    }
+    out.deny = D;
+    return out;
+}
+
+// Evaluates request `n` (absolute column index).  Output: the packed ALLOW bitmap (kbytes bytes per request), or,
+// if `effects` is non-null, max_actions effect bytes per request (1 ALLOW / 2 DENY / 0 beyond the request's own
+// action count).
+// M is the (action x role-column) pair-mask type: uint32_t when max_actions * role_cols <= 32 (the common
+// CheckResources shape: halves the register and instruction cost of the mask algebra), else uint64_t.
+template <typename M>
+CB_HD void eval_request(const TableView t, const BatchView &b, uint64_t n, uint8_t *bitmap, uint8_t *effects, uint32_t *status) {
+    constexpr M kOne = 1;
+    const U4 h0 = ldcol128(b.hdr0 + n);                                         // principal_id, kind_class, resource_scope, principal_scope
+    const uint64_t h1 = ldcol64(reinterpret_cast<const uint64_t *>(b.hdr1 + n));  // rv u16 | pv u16 | action_set_id u32
+    const uint32_t pid = h0.x, kc = h0.y, rscope = h0.z, pscope = h0.w;
+    const uint32_t rv = (uint32_t)(h1 & 0xFFFF), pv = (uint32_t)((h1 >> 16) & 0xFFFF), aset = (uint32_t)(h1 >> 32);
     const uint32_t RC = b.role_cols;
-    const uint64_t role_all = (n_roles >= 64) ? ~0ull : ((1ull << n_roles) - 1);
-    const uint32_t nAP = t.nAP ? t.nAP : 1;
+    const uint32_t K = aset < b.n_asets ? ldg(b.aset_k + aset) : 0;
+    uint32_t unsupported = 0;
 
-    for (uint32_t ps = 0; ps < b.n_pass; ps++) {
-        uint32_t kbase = ps * b.kc;
-        if (kbase >= K) break;
-        uint32_t kn = K - kbase < b.kc ? K - kbase : b.kc;            // actions in this pass
-        const uint64_t *spread = b.aset_spread + ((uint64_t)ps * b.n_asets + aset) * nAP;
-        // action-only mask: bit kk*RC for every action of this pass
-        uint64_t amask = 0;
-        for (uint32_t kk = 0; kk < kn; kk++) amask |= 1ull << (kk * RC);
-
-        // ---- principal policies: role agnostic, decided per action (state lives on role column 0) ----
-        uint64_t p_allow = 0, p_deny = 0;
-        if (pidx != CB_NONE32) {
-            uint64_t alive = amask;
-            for (uint32_t s = p0; s != CB_NONE32 && alive; s = chain_next(t, s, CB_SCOPE_FLAG_PRINCIPAL)) {
-                uint32_t bid = ldg(t.prin_block_map + ((uint64_t)rv * t.nP + pidx) * t.nS + s);
-                if (bid == CB_NONE32) continue;
-                cb_block bl = load_block(t.blocks + bid);
-                Memo memo; memo.done = 0; memo.val = 0;
-                uint64_t D = 0, A = 0;
-                for (uint32_t ri = 0; ri < bl.n_rows; ri++) {
-                    cb_row row = load_row(t.rows + bl.row_start + ri);
-                    uint64_t m = ldg(spread + row.apat) & alive;
-                    if (!m) continue;
-                    if (!in_class(b, cls0, cls1, row.respat)) continue;
-                    if (row.effect == CB_EFFECT_DENY ? (m & ~D) == 0 : (m & ~A) == 0) continue;   // nothing new to learn
-                    if (row.drcond && !cond_sat(c, memo, bl.cond_base, row.drcond)) continue;
-                    if (row.cond && !cond_sat(c, memo, bl.cond_base, row.cond)) continue;
-                    if (row.effect == CB_EFFECT_DENY) D |= m; else A |= m;
-                }
-                p_deny |= D;
-                alive &= ~D;
-                uint32_t perm = (ldg(t.scope_flags + s) >> CB_SCOPE_PERM_SHIFT) & 3;
-                if (perm == 1) { uint64_t a = A & alive; p_allow |= a; alive &= ~a; }
-            }
-        }
-
-        // ---- resource policies: (action x role) pairs walk the chain together ----
-        uint64_t undecided = amask & ~(p_allow | p_deny);
-        uint64_t r_allow_pairs = 0;
-        if (undecided && r0 != CB_NONE32) {
-            uint64_t alive = undecided * role_all;       // every role column of every undecided action
-            for (uint32_t s = r0; s != CB_NONE32 && alive; s = chain_next(t, s, CB_SCOPE_FLAG_RESOURCE)) {
-                uint64_t D = 0, A = 0;
-                bool any_row = false;
-                for (uint32_t j = cls0; j < cls1; j++) {
-                    uint64_t mi = ((uint64_t)rv * t.nRP + ldg(b.class_pats + j)) * t.nS + s;
-                    any_row |= (ldg(t.res_exists + mi) & CB_EXISTS_ANY_ROW) != 0;
-                    uint32_t bid = ldg(t.res_block_map + mi);
-                    if (bid == CB_NONE32) continue;
-                    cb_block bl = load_block(t.blocks + bid);
-                    Memo memo; memo.done = 0; memo.val = 0;
-                    for (uint32_t ri = 0; ri < bl.n_rows; ri++) {
-                        cb_row row = load_row(t.rows + bl.row_start + ri);
-                        uint64_t am = ldg(spread + row.apat);
-                        if (!am) continue;
-                        uint64_t rmask;
-                        if (row.role == CB_ROLE_ANY) rmask = role_all;
-                        else {
-                            rmask = 0;
-                            for (uint32_t i = 0; i < n_roles; i++)
-                                rmask |= (uint64_t)role_in_pr(t, row.role, roles[i], h0.resource_scope) << i;
-                        }
-                        uint64_t m = (am * rmask) & alive;
-                        if (!m) continue;
-                        if (row.effect == CB_EFFECT_DENY ? (m & ~D) == 0 : (m & ~A) == 0) continue;
-                        if (row.drcond && !cond_sat(c, memo, bl.cond_base, row.drcond)) continue;
-                        if (row.cond && !cond_sat(c, memo, bl.cond_base, row.cond)) continue;
-                        if (row.effect == CB_EFFECT_DENY) D |= m; else A |= m;
-                    }
-                }
-                // synthesized role-policy DENY rows (index.go:688-776)
-                if (t.has_role_policies && any_row) {
-                    uint64_t ro = (uint64_t)rv * t.nS + s;
-                    for (uint32_t e = ldg(t.rp_off + ro), ee = ldg(t.rp_off + ro + 1); e < ee; e++) {
-                        cb_rolepol_entry en = load_rp_entry(t.rp_entries + e);
-                        uint64_t rmask = 0;
-                        for (uint32_t i = 0; i < n_roles; i++)
-                            rmask |= (uint64_t)role_in_pr(t, en.role, roles[i], h0.resource_scope) << i;
-                        if (!rmask) continue;
-                        uint64_t matched = 0;   // action bits (role column 0) with at least one matching allow rule
-                        for (uint32_t q = 0; q < en.n_rules; q++) {
-                            cb_rolepol_rule ru = load_rp_rule(t.rp_rules + en.rule_start + q);
-                            if (!in_class(b, cls0, cls1, ru.respat)) continue;
-                            uint64_t am = 0;
-                            for (uint32_t a = 0; a < ru.n_apats; a++) am |= ldg(spread + ldg(t.rp_apats + ru.apat_start + a));
-                            if (!am) continue;
-                            matched |= am;
-                            if (ru.cond && ((am * rmask) & alive & ~D)) {
-                                Memo none; none.done = 0; none.val = 0;
-                                if (!cond_sat(c, none, ru.cond - 1, 1)) D |= (am * rmask) & alive;   // DENY none(cond)
-                            }
-                        }
-                        D |= ((amask & ~matched) * rmask) & alive;   // blanket DENY for actions no allow rule matches
-                    }
-                }
-                alive &= ~D;
-                uint32_t perm = (ldg(t.scope_flags + s) >> CB_SCOPE_PERM_SHIFT) & 3;
-                if (perm == 1) { uint64_t a = A & alive; r_allow_pairs |= a; alive &= ~a; }
-            }
-        }
-
-        // ---- fold: ALLOW iff principal walk allowed, or undecided there and any role column allowed ----
-        for (uint32_t kk = 0; kk < kn; kk++) {
-            uint64_t abit = 1ull << (kk * RC);
-            bool allow = (p_allow & abit) != 0;
-            if (!allow && (undecided & abit)) allow = ((r_allow_pairs >> (kk * RC)) & role_all) != 0;
-            uint32_t k = kbase + kk;
-            if (allow) { if (wide) out[k >> 3] |= (uint8_t)(1u << (k & 7)); else acc |= 1ull << k; }
+    // role table (see above)
+    uint32_t RCP = 1;
+    while (RCP < RC) RCP <<= 1;
+    const bool packed = (uint64_t)t.L->nR * RCP <= 128;
+    uint64_t rp0 = 0, rp1 = 0;
+    uint32_t n_roles = 0;
+    for (uint32_t i = 0; i < RC; i++) {
+        uint32_t rr = ldcol32(b.roles + (uint64_t)i * b.stride + n);
+        if (rr != CB_ROLE_PAD) n_roles = i + 1;   // the encoder packs roles to the front
+        if (rr < t.L->nR) {
+            uint32_t pos = rr * RCP + i;
+            if (pos < 64) rp0 |= 1ull << pos; else if (pos < 128) rp1 |= 1ull << (pos - 64);
         }
     }
-    if (c.unsupported && status) {
+
+    // result: actions 0..63 accumulate in `acc`; wider action lists (rare) write their bytes directly
+    uint64_t acc = 0;
+    const bool wide = b.kbytes > 8;
+    uint8_t *out = effects ? nullptr : bitmap + n * b.kbytes;
+    uint8_t *eff = effects ? effects + n * (uint64_t)b.max_actions : nullptr;
+    if (wide) {
+        if (eff) for (uint32_t q = 0; q < b.max_actions; q++) eff[q] = (uint8_t)(q < K ? CB_EFFECT_DENY : 0);
+        else for (uint32_t q = 0; q < b.kbytes; q++) out[q] = 0;
+    }
+
+    const bool lenient = (b.flags & CB_BATCH_FLAG_LENIENT) != 0;
+    uint32_t p0 = CB_NONE32, r0 = CB_NONE32;
+    bool live = n_roles != 0 && K != 0 && rv != CB_NONE16;
+    if (live) {
+        if (t.L->has_principal_policies) p0 = chain_start(t, pscope, CB_SCOPE_FLAG_PRINCIPAL, lenient);
+        r0 = chain_start(t, rscope, CB_SCOPE_FLAG_RESOURCE, lenient);
+        // The existence checks can only change a decision when the principal and resource policy versions
+        // differ: with equal versions "no principal row / no resource row" already means the walks find nothing.
+        if (pv != rv && !exists_check(t.base, t.L, &b, kc, pscope, r0, pv, rv, lenient)) live = false;
+        if (p0 == CB_NONE32 && r0 == CB_NONE32) live = false;
+    }
+
+    if (live) {
+        const uint32_t pidx = (t.L->has_principal_policies && pid < t.L->nT) ? ldg(t.prin_of_string() + pid) : CB_NONE32;
+        const M role_all = (M)((kOne << n_roles) - 1);   // n_roles <= 16
+        if (t.L->has_parent_roles && packed && rscope != CB_SCOPE_NONE && !(rscope & CB_SCOPE_INEXACT_BIT) && rscope < t.L->nS) {
+            U2x64 r = role_tab_parents(t.base, t.L, &b, n, n_roles, rscope, RCP, rp0, rp1);
+            rp0 = r.a; rp1 = r.b;
+        }
+        const uint32_t nk = kind_count(b, kc);
+
+        for (uint32_t ps = 0; ps < b.n_pass; ps++) {
+            const uint32_t kbase = ps * b.kc;
+            if (kbase >= K) break;
+            const uint32_t kn = K - kbase < b.kc ? K - kbase : b.kc;            // actions in this pass
+            const uint64_t *row_am = b.row_am + ((uint64_t)ps * b.n_asets + aset) * b.n_rows;
+            M amask = 0;                                                         // bit kk*RC for every action of this pass
+            for (uint32_t kk = 0; kk < kn; kk++) amask |= kOne << (kk * RC);
+
+            M p_allow = 0, p_deny = 0;
+            if (pidx != CB_NONE32 && p0 != CB_NONE32) {
+                PairMasks<M> pm = principal_walk<M>(t.base, t.L, &b, n, pid, kc, pidx, p0, rv, amask, row_am);
+                p_allow = pm.allow; p_deny = pm.deny; unsupported |= pm.unsupported;
+            }
+
+            // ---- resource policies: (action x role) pairs walk the chain together ----
+            const M undecided = amask & ~(p_allow | p_deny);
+            M r_allow_pairs = 0;
+            if (undecided && r0 != CB_NONE32) {
+                M alive = undecided * role_all;              // every role column of every undecided action
+                for (uint32_t s = r0; s != CB_NONE32 && alive; s = chain_next(t, s, CB_SCOPE_FLAG_RESOURCE)) {
+                    M D = 0, A = 0;
+                    bool any_row = false;
+                    for (uint32_t j = 0; j < nk; j++) {
+                        uint64_t mi = ((uint64_t)rv * t.L->nRP + kind_pat_at(b, kc, j)) * t.L->nS + s;
+                        if (t.L->has_role_policies) any_row |= (ldg(t.res_exists() + mi) & CB_EXISTS_ANY_ROW) != 0;
+                        uint32_t bid = ldg(t.res_block_map() + mi);
+                        if (bid == CB_NONE32) continue;
+                        prefetch_block_slots(t, b, bid, n);
+                        const U4 bl = ld16(t.blocks() + bid);   // {row_start, n_rows, cond_base, n_conds}
+                        const uint32_t re = bl.x + bl.y;
+                        // One policy block in three tight phases: (1) which conditions can matter for the pairs
+                        // still alive, (2) evaluate exactly those (the only calls), (3) accumulate DENY / ALLOW.
+                        uint64_t need = 0;
+                        for (uint32_t ri = bl.x; ri < re; ri++) {
+                            M am = (M)ldg(reinterpret_cast<const M *>(row_am + ri));   // little endian: the low half when M is 32-bit
+                            if (!am) continue;
+                            U4 row = ld16(t.rows() + ri);
+                            uint32_t role = row_role(row);
+                            M rc;
+                            if (role == CB_ROLE_ANY) rc = role_all;
+                            else if (packed) { uint32_t pos = role * RCP; rc = (M)(pos < 64 ? rp0 >> pos : rp1 >> (pos - 64)) & role_all; }
+                            else rc = role_cols_slow<M>(t.base, t.L, &b, n, n_roles, rscope, role);
+                            if (!((am * rc) & alive)) continue;
+                            uint32_t c1 = row_cond(row), c2 = row_drcond(row);
+                            if (c1 && c1 <= 64) need |= 1ull << (c1 - 1);
+                            if (c2 && c2 <= 64) need |= 1ull << (c2 - 1);
+                        }
+                        uint64_t val = 0;
+                        for (uint64_t w = need; w;) {
+#if defined(__CUDA_ARCH__)
+                            int li = __ffsll((long long)w) - 1;
+#else
+                            int li = __builtin_ctzll(w);
+#endif
+                            w &= w - 1;
+                            uint32_t r = cond_sat(t.base, t.L, &b, n, pid, bl.z + (uint32_t)li);
+                            unsupported |= r & 2;
+                            val |= (uint64_t)(r & 1) << li;
+                        }
+                        for (uint32_t ri = bl.x; ri < re; ri++) {
+                            M am = (M)ldg(reinterpret_cast<const M *>(row_am + ri));
+                            if (!am) continue;
+                            U4 row = ld16(t.rows() + ri);
+                            uint32_t role = row_role(row);
+                            M rc;
+                            if (role == CB_ROLE_ANY) rc = role_all;
+                            else if (packed) { uint32_t pos = role * RCP; rc = (M)(pos < 64 ? rp0 >> pos : rp1 >> (pos - 64)) & role_all; }
+                            else rc = role_cols_slow<M>(t.base, t.L, &b, n, n_roles, rscope, role);
+                            M m = (am * rc) & alive;
+                            if (!m) continue;
+                            uint32_t c1 = row_cond(row), c2 = row_drcond(row);
+                            bool sat = true;   // blocks with more than 64 distinct conditions evaluate the overflow ones unmemoised
+                            if (c2) { if (c2 <= 64) sat = (val >> (c2 - 1)) & 1; else { uint32_t r = cond_sat(t.base, t.L, &b, n, pid, bl.z + c2 - 1); unsupported |= r & 2; sat = r & 1; } }
+                            if (sat && c1) { if (c1 <= 64) sat = (val >> (c1 - 1)) & 1; else { uint32_t r = cond_sat(t.base, t.L, &b, n, pid, bl.z + c1 - 1); unsupported |= r & 2; sat = r & 1; } }
+                            if (!sat) continue;
+                            if (row_effect(row) == CB_EFFECT_DENY) D |= m; else A |= m;
+                        }
+                    }
+                    if (t.L->has_role_policies && any_row) {
+                        PairMasks<M> pm = rolepol_denies<M>(t.base, t.L, &b, n, pid, kc, n_roles, rscope, RCP, rp0, rp1, packed, rv, s, ps, aset, amask, alive, D);
+                        D = pm.deny; unsupported |= pm.unsupported;
+                    }
+                    alive &= ~D;
+                    uint32_t perm = (ldg(t.scope_flags() + s) >> CB_SCOPE_PERM_SHIFT) & 3;
+                    if (perm == 1) { M a = A & alive; r_allow_pairs |= a; alive &= ~a; }
+                }
+            }
+
+            // ---- fold: ALLOW iff the principal walk allowed, or undecided there and any role column allowed ----
+            M any_role = r_allow_pairs;
+            for (uint32_t j = 1; j < RC; j++) any_role |= r_allow_pairs >> j;      // OR the role columns down to column 0
+            const M allow_bits = p_allow | (undecided & any_role);                // bits at kk * RC
+            for (uint32_t kk = 0; kk < kn; kk++) {
+                if (!((allow_bits >> (kk * RC)) & 1)) continue;
+                uint32_t k = kbase + kk;
+                if (!wide) acc |= 1ull << k; else if (eff) eff[k] = CB_EFFECT_ALLOW; else out[k >> 3] |= (uint8_t)(1u << (k & 7));
+            }
+        }
+    }
+
+    // ---- store ----
+    if (!wide) {
+        if (eff) {
+            if (b.max_actions == 8) {   // one 8-byte store: the common CheckResources shape
+                uint64_t v = 0;
+                for (uint32_t k = 0; k < 8; k++) v |= (uint64_t)(k < K ? (((acc >> k) & 1) ? CB_EFFECT_ALLOW : CB_EFFECT_DENY) : 0) << (8 * k);
+                *reinterpret_cast<uint64_t *>(eff) = v;
+            } else {
+                for (uint32_t k = 0; k < b.max_actions; k++) eff[k] = (uint8_t)(k < K ? (((acc >> k) & 1) ? CB_EFFECT_ALLOW : CB_EFFECT_DENY) : 0);
+            }
+        } else {
+            for (uint32_t q = 0; q < b.kbytes; q++) out[q] = (uint8_t)(acc >> (8 * q));
+        }
+    }
+    if (unsupported && status) {
 #if defined(__CUDA_ARCH__)
         atomicOr(status, 1u);
 #else
         *status |= 1u;
 #endif
     }
+}
+
+// ---------------------------------------------------------------------------------------------- fast kernel body
+// The common deployment shape -- resource policies (+ derived roles, scopes) only: no principal policies, no role
+// policies / parent roles, no resource globs -- with max_actions * role_cols <= 32 and n_roles * RCP <= 64.
+// Same decision semantics as eval_request<M>, stripped of every cold branch so that the whole per-request state
+// is a handful of 32-bit scalars (host code picks this body when table and batch qualify; tests compare both).
+// Returns true if the request must be re-evaluated by the general body (nothing has been written then): a
+// condition without a flat form, an operand the 8-byte fast forms cannot decide, differing policy versions, or
+// a block with more than 64 conditions.  The body itself makes NO calls, so nothing is forced into local memory.
+CB_HD bool eval_request_fast(const TableView t, const BatchView &b, uint64_t n, uint8_t *bitmap, uint8_t *effects) {
+    const U4 h0 = ldcol128(b.hdr0 + n);                                           // principal_id, kind (pattern id), resource_scope, principal_scope
+    const uint64_t h1 = ldcol64(reinterpret_cast<const uint64_t *>(b.hdr1 + n));  // rv u16 | pv u16 | action_set_id u32
+    const uint32_t pid = h0.x, kc = h0.y, rscope = h0.z;
+    const uint32_t rv = (uint32_t)(h1 & 0xFFFF), pv = (uint32_t)((h1 >> 16) & 0xFFFF), aset = (uint32_t)(h1 >> 32);
+    const uint32_t RC = b.role_cols;
+    const uint32_t K = aset < b.n_asets ? ldg(b.aset_k + aset) : 0;
+    uint32_t RCP = 1;
+    while (RCP < RC) RCP <<= 1;
+    uint64_t rp = 0;          // role table: RCP bits per table role
+    uint32_t n_roles = 0;
+    for (uint32_t i = 0; i < RC; i++) {
+        uint32_t rr = ldcol32(b.roles + (uint64_t)i * b.stride + n);
+        if (rr != CB_ROLE_PAD) n_roles = i + 1;
+        if (rr < t.L->nR) rp |= 1ull << (rr * RCP + i);
+    }
+    uint32_t acc = 0;
+    bool live = n_roles != 0 && K != 0 && rv != CB_NONE16 && kc != CB_KIND_NONE;
+    uint32_t r0 = CB_NONE32;
+    if (live) {
+        const bool lenient = (b.flags & CB_BATCH_FLAG_LENIENT) != 0;
+        r0 = chain_start(t, rscope, CB_SCOPE_FLAG_RESOURCE, lenient);
+        if (pv != rv) return true;   // existence checks matter only then (ruletable.go:852-863): general body
+    }
+    if (live && r0 != CB_NONE32) {
+        const uint32_t role_all = (1u << n_roles) - 1;
+        const uint64_t *row_am = b.row_am + (uint64_t)aset * b.n_rows;
+        uint32_t amask = 0;
+        for (uint32_t kk = 0; kk < K; kk++) amask |= 1u << (kk * RC);
+        uint32_t alive = amask * role_all, allow_pairs = 0;
+        for (uint32_t s = r0; s != CB_NONE32 && alive; s = chain_next(t, s, CB_SCOPE_FLAG_RESOURCE)) {
+            const uint32_t bid = ldg(t.res_block_map() + ((uint64_t)rv * t.L->nRP + kc) * t.L->nS + s);
+            if (bid == CB_NONE32) continue;
+            prefetch_block_slots(t, b, bid, n);
+            const U4 bl = ld16(t.blocks() + bid);   // {row_start, n_rows, cond_base, n_conds}
+            const uint32_t re = bl.x + bl.y;
+            uint64_t need = 0;
+            for (uint32_t ri = bl.x; ri < re; ri++) {
+                uint32_t am = ldg(reinterpret_cast<const uint32_t *>(row_am + ri));
+                if (!am) continue;
+                U4 row = ld16(t.rows() + ri);
+                uint32_t role = row_role(row);
+                uint32_t rc = role == CB_ROLE_ANY ? role_all : (uint32_t)(rp >> (role * RCP)) & role_all;
+                if (!((am * rc) & alive)) continue;
+                uint32_t c1 = row_cond(row), c2 = row_drcond(row);
+                if (c1 > 64 || c2 > 64) return true;
+                if (c1) need |= 1ull << (c1 - 1);
+                if (c2) need |= 1ull << (c2 - 1);
+            }
+            uint64_t val = 0;
+            for (uint64_t w = need; w;) {
+#if defined(__CUDA_ARCH__)
+                int li = __ffsll((long long)w) - 1;
+#else
+                int li = __builtin_ctzll(w);
+#endif
+                w &= w - 1;
+                uint32_t r = cond_eval(t, b, n, pid, bl.z + (uint32_t)li);
+                if (r & 4) return true;
+                val |= (uint64_t)(r & 1) << li;
+            }
+            uint32_t D = 0, A = 0;
+            for (uint32_t ri = bl.x; ri < re; ri++) {
+                uint32_t am = ldg(reinterpret_cast<const uint32_t *>(row_am + ri));
+                if (!am) continue;
+                U4 row = ld16(t.rows() + ri);
+                uint32_t role = row_role(row);
+                uint32_t rc = role == CB_ROLE_ANY ? role_all : (uint32_t)(rp >> (role * RCP)) & role_all;
+                uint32_t m = (am * rc) & alive;
+                if (!m) continue;
+                uint32_t c1 = row_cond(row), c2 = row_drcond(row);
+                bool sat = true;
+                if (c2) sat = (val >> (c2 - 1)) & 1;
+                if (sat && c1) sat = (val >> (c1 - 1)) & 1;
+                if (!sat) continue;
+                if (row_effect(row) == CB_EFFECT_DENY) D |= m; else A |= m;
+            }
+            alive &= ~D;
+            if (((ldg(t.scope_flags() + s) >> CB_SCOPE_PERM_SHIFT) & 3) == 1) { uint32_t a = A & alive; allow_pairs |= a; alive &= ~a; }
+        }
+        uint32_t any_role = allow_pairs;
+        for (uint32_t j = 1; j < RC; j++) any_role |= allow_pairs >> j;
+        any_role &= amask;
+        for (uint32_t kk = 0; kk < K; kk++) acc |= ((any_role >> (kk * RC)) & 1) << kk;
+    }
+    if (effects) {
+        uint8_t *eff = effects + n * (uint64_t)b.max_actions;
+        if (b.max_actions == 8) {
+            uint64_t v = 0;
+            for (uint32_t k = 0; k < 8; k++) v |= (uint64_t)(k < K ? (((acc >> k) & 1) ? CB_EFFECT_ALLOW : CB_EFFECT_DENY) : 0) << (8 * k);
+            *reinterpret_cast<uint64_t *>(eff) = v;
+        } else {
+            for (uint32_t k = 0; k < b.max_actions; k++) eff[k] = (uint8_t)(k < K ? (((acc >> k) & 1) ? CB_EFFECT_ALLOW : CB_EFFECT_DENY) : 0);
+        }
+    } else {
+        uint8_t *out = bitmap + n * b.kbytes;
+        for (uint32_t q = 0; q < b.kbytes; q++) out[q] = (uint8_t)(acc >> (8 * q));
+    }
+    return false;
+}
+
+// out-of-line general body for the requests the fast body defers
+CB_HD_NOINLINE void eval_request_general(const uint8_t *base, const TableLayout *L, const BatchView *b, uint64_t n, uint8_t *bitmap,
+                                         uint8_t *effects, uint32_t *status) {
+    TableView t; t.base = base; t.L = L;
+    eval_request<uint64_t>(t, *b, n, bitmap, effects, status);
 }
 
 }  // namespace cb

@@ -30,51 +30,20 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr uint32_t kMaxStageBytes = 96 * 1024;   // table images up to this size are TMA-staged into shared memory
-constexpr int kMaxSec = 24;
+constexpr int kMaxSec = 28;
 
 struct TableDesc {
     const uint8_t *base;       // device blob image
-    uint32_t image_bytes;      // bytes [0, image_bytes) hold every device section (16-byte multiple)
-    uint32_t off[kMaxSec];     // section offsets by section id
-    uint32_t nV, nRP, nS, nP, nR, nAP, nT, n_slots;
-    uint32_t has_role_policies, has_parent_roles, has_principal_policies;
+    cb::TableLayout lay;       // section offsets + dims (image_bytes: bytes [0, image_bytes) hold every device section)
 };
-
-__device__ __forceinline__ cb::TableView make_view(const uint8_t *base, const TableDesc &d) {
-    cb::TableView t;
-    t.scope_parent = reinterpret_cast<const uint32_t *>(base + d.off[CB_SEC_SCOPE_PARENT]);
-    t.scope_flags = reinterpret_cast<const uint32_t *>(base + d.off[CB_SEC_SCOPE_FLAGS]);
-    t.res_block_map = reinterpret_cast<const uint32_t *>(base + d.off[CB_SEC_RES_BLOCK_MAP]);
-    t.res_exists = base + d.off[CB_SEC_RES_EXISTS];
-    t.prin_block_map = reinterpret_cast<const uint32_t *>(base + d.off[CB_SEC_PRIN_BLOCK_MAP]);
-    t.prin_exists = base + d.off[CB_SEC_PRIN_EXISTS];
-    t.prin_of_string = reinterpret_cast<const uint32_t *>(base + d.off[CB_SEC_PRIN_OF_STRING]);
-    t.blocks = reinterpret_cast<const cb_block *>(base + d.off[CB_SEC_BLOCKS]);
-    t.rows = reinterpret_cast<const cb_row *>(base + d.off[CB_SEC_ROWS]);
-    t.conds = reinterpret_cast<const cb_cond *>(base + d.off[CB_SEC_CONDS]);
-    t.code = reinterpret_cast<const cb_instr *>(base + d.off[CB_SEC_CODE]);
-    t.consts = reinterpret_cast<const cb_const *>(base + d.off[CB_SEC_CONSTS]);
-    t.theap = reinterpret_cast<const uint64_t *>(base + d.off[CB_SEC_THEAP]);
-    t.str_off = reinterpret_cast<const uint32_t *>(base + d.off[CB_SEC_STR_OFF]);
-    t.str_bytes = base + d.off[CB_SEC_STR_BYTES];
-    t.par_off = reinterpret_cast<const uint32_t *>(base + d.off[CB_SEC_ROLE_PARENTS_OFF]);
-    t.par_list = reinterpret_cast<const uint32_t *>(base + d.off[CB_SEC_ROLE_PARENTS]);
-    t.rp_off = reinterpret_cast<const uint32_t *>(base + d.off[CB_SEC_ROLEPOL_OFF]);
-    t.rp_entries = reinterpret_cast<const cb_rolepol_entry *>(base + d.off[CB_SEC_ROLEPOL_ENTRIES]);
-    t.rp_rules = reinterpret_cast<const cb_rolepol_rule *>(base + d.off[CB_SEC_ROLEPOL_RULES]);
-    t.rp_apats = reinterpret_cast<const uint32_t *>(base + d.off[CB_SEC_ROLEPOL_APATS]);
-    t.nV = d.nV; t.nRP = d.nRP; t.nS = d.nS; t.nP = d.nP; t.nR = d.nR; t.nAP = d.nAP; t.nT = d.nT; t.n_slots = d.n_slots;
-    t.has_role_policies = d.has_role_policies; t.has_parent_roles = d.has_parent_roles;
-    t.has_principal_policies = d.has_principal_policies;
-    return t;
-}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// Persistent CheckResources kernel. kStage: TMA-stage the table image into dynamic shared memory.
-template <bool kStage>
-__global__ void __launch_bounds__(kThreads, 2) check_kernel(const TableDesc td, const cb::BatchView bv, uint8_t *bitmap,
-                                                          uint32_t *status) {
+// Persistent CheckResources kernel. stage != 0: TMA-stage the table image into dynamic shared memory.
+// kFast: the lean resource-policy-only body (cb::eval_request_fast), else the general body with 64-bit pair masks.
+template <bool kFast>
+__global__ void __launch_bounds__(kThreads, 3) check_kernel(const __grid_constant__ TableDesc td, const __grid_constant__ cb::BatchView bv, uint8_t *bitmap,
+                                                          uint8_t *effects, uint32_t *status, const uint32_t kStage) {
     extern __shared__ __align__(128) uint8_t smem_image[];
     __shared__ __align__(8) uint64_t mbar;
     const uint8_t *base = td.base;
@@ -85,11 +54,11 @@ __global__ void __launch_bounds__(kThreads, 2) check_kernel(const TableDesc td, 
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(td.image_bytes)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(td.lay.image_bytes)
                          : "memory");
             // 1-D bulk copies (TMA unit), <= 32 KB each, all completing on the same mbarrier
-            for (uint32_t o = 0; o < td.image_bytes; o += 32768) {
-                uint32_t nb = td.image_bytes - o < 32768 ? td.image_bytes - o : 32768;
+            for (uint32_t o = 0; o < td.lay.image_bytes; o += 32768) {
+                uint32_t nb = td.lay.image_bytes - o < 32768 ? td.lay.image_bytes - o : 32768;
                 asm volatile(
                     "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                         smem_u32(smem_image + o)),
@@ -99,7 +68,9 @@ __global__ void __launch_bounds__(kThreads, 2) check_kernel(const TableDesc td, 
         }
         base = smem_image;
     }
-    const cb::TableView tv = make_view(base, td);
+    cb::TableView tv;
+    tv.base = base;
+    tv.L = &td.lay;
     const uint64_t n_tiles = (bv.count + kThreads - 1) / kThreads;
     bool staged = !kStage;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -116,7 +87,16 @@ __global__ void __launch_bounds__(kThreads, 2) check_kernel(const TableDesc td, 
             }
             staged = true;
         }
-        if (i < bv.count) cb::eval_request(tv, bv, bv.first + i, bitmap, status);
+        // the next tile of this thread: start pulling its header / role columns towards L1 now
+        uint64_t inext = i + (uint64_t)gridDim.x * kThreads;
+        if (inext < bv.count) cb::prefetch_request(bv, bv.first + inext);
+        if (i < bv.count) {
+            if (kFast) {
+                // call-free lean body; the (rare) requests it cannot decide are redone by the general body
+                if (cb::eval_request_fast(tv, bv, bv.first + i, bitmap, effects))
+                    cb::eval_request_general(tv.base, tv.L, &bv, bv.first + i, bitmap, effects, status);
+            } else cb::eval_request<uint64_t>(tv, bv, bv.first + i, bitmap, effects, status);
+        }
     }
     if (!staged) {
         // CTA had no tile: still drain the bulk copy before exiting so shared memory is not released under it
@@ -153,8 +133,7 @@ struct Slot {   // per in-flight cgpu_check call
     cudaStream_t stream = nullptr;
     void *dev = nullptr;
     size_t dev_cap = 0;
-    uint8_t *pinned = nullptr;   // bitmap staging
-    size_t pinned_cap = 0;
+    uint32_t *h_status = nullptr;   // pinned
     uint32_t *d_status = nullptr;
     bool busy = false;
 };
@@ -169,9 +148,9 @@ struct cgpu_ctx {
     std::atomic<uint64_t> launches{0};
     std::mutex mu;
     std::vector<Slot> slots;
-    uint32_t last_grid = 0, last_block = 0, last_smem = 0;
-    int occ_staged = 0, occ_global = 0;
+    uint32_t last_grid = 0, last_block = 0, last_smem = 0, last_fast = 0;
     int force_no_stage = 0;
+    int force_general = 0;   // CERBOS_B200_FORCE_GENERAL=1: never pick the lean kernel body (tests)
 };
 
 struct cgpu_table {
@@ -180,6 +159,7 @@ struct cgpu_table {
     uint8_t *d_image = nullptr;
     TableDesc desc{};
     uint32_t meta[CB_META_WORDS]{};
+    std::atomic<int> occ[2]{};   // resident CTAs / SM per kernel variant (0 = not queried yet)
 };
 
 namespace {
@@ -200,7 +180,7 @@ int parse_blob(const void *blob, size_t len, TableDesc *d, uint32_t *meta) {
         if (sd[i].id == CB_SEC_MANIFEST) continue;   // host-only
         if (sd[i].id >= kMaxSec) continue;
         if (sd[i].offset > 0xFFFFFFF0ull) return fail(CGPU_ERR_INVALID, "table blob too large");
-        d->off[sd[i].id] = (uint32_t)sd[i].offset;
+        d->lay.off[sd[i].id] = (uint32_t)sd[i].offset;
         seen[sd[i].id] = true;
         uint64_t end = (sd[i].offset + sd[i].n_bytes + 15) & ~15ull;
         if (end > image_end) image_end = end;
@@ -209,15 +189,15 @@ int parse_blob(const void *blob, size_t len, TableDesc *d, uint32_t *meta) {
             memcpy(meta, static_cast<const char *>(blob) + sd[i].offset, CB_META_WORDS * 4);
         }
     }
-    for (int id = CB_SEC_META; id <= CB_SEC_ROLEPOL_APATS; id++)
+    for (int id = CB_SEC_META; id <= CB_SEC_BLOCK_SLOTS; id++)
         if (!seen[id]) return fail(CGPU_ERR_INVALID, "table blob: missing section %d", id);
     if (image_end > 0xFFFFFFF0ull) return fail(CGPU_ERR_INVALID, "table blob too large");
-    d->image_bytes = (uint32_t)image_end;
-    d->nV = meta[CB_META_N_VERSIONS]; d->nRP = meta[CB_META_N_RESPATS]; d->nS = meta[CB_META_N_SCOPES];
-    d->nP = meta[CB_META_N_PRINCIPALS]; d->nR = meta[CB_META_N_ROLES]; d->nAP = meta[CB_META_N_APATS];
-    d->nT = meta[CB_META_N_STRINGS]; d->n_slots = meta[CB_META_N_SLOTS];
-    d->has_role_policies = meta[CB_META_HAS_ROLE_POLICIES]; d->has_parent_roles = meta[CB_META_HAS_PARENT_ROLES];
-    d->has_principal_policies = meta[CB_META_HAS_PRINCIPAL_POLICIES];
+    d->lay.image_bytes = (uint32_t)image_end;
+    d->lay.nV = meta[CB_META_N_VERSIONS]; d->lay.nRP = meta[CB_META_N_RESPATS]; d->lay.nS = meta[CB_META_N_SCOPES];
+    d->lay.nP = meta[CB_META_N_PRINCIPALS]; d->lay.nR = meta[CB_META_N_ROLES]; d->lay.nAP = meta[CB_META_N_APATS];
+    d->lay.nT = meta[CB_META_N_STRINGS]; d->lay.n_slots = meta[CB_META_N_SLOTS]; d->lay.n_rows = meta[CB_META_N_ROWS] ? meta[CB_META_N_ROWS] : 1;
+    d->lay.has_role_policies = meta[CB_META_HAS_ROLE_POLICIES]; d->lay.has_parent_roles = meta[CB_META_HAS_PARENT_ROLES];
+    d->lay.has_principal_policies = meta[CB_META_HAS_PRINCIPAL_POLICIES];
     if (meta[CB_META_MAX_STACK] > CB_MAX_STACK || meta[CB_META_MAX_LOOP_DEPTH] > CB_MAX_LOOP_DEPTH || meta[CB_META_N_VARS] > CB_MAX_VARS)
         return fail(CGPU_ERR_INVALID, "table blob needs a deeper interpreter than this build provides");
     return CGPU_OK;
@@ -233,16 +213,16 @@ int make_batch_view(const cgpu_table *t, const cgpu_batch *b, uint64_t first, ui
     if (cb_[CGPU_COL_ROLES] % (4 * N) != 0) return fail(CGPU_ERR_INVALID, "batch: roles column is not a multiple of n_requests");
     uint32_t role_cols = (uint32_t)(cb_[CGPU_COL_ROLES] / (4 * N));
     if (role_cols == 0 || role_cols > CB_MAX_ROLE_COLS) return fail(CGPU_ERR_INVALID, "batch: %u role columns (supported 1..%d)", role_cols, CB_MAX_ROLE_COLS);
-    if (cb_[CGPU_COL_SLOTS] < (size_t)8 * t->desc.n_slots * N) return fail(CGPU_ERR_INVALID, "batch: slot columns too small for the table's %u slots", t->desc.n_slots);
+    if (cb_[CGPU_COL_SLOTS] < (size_t)8 * t->desc.lay.n_slots * N) return fail(CGPU_ERR_INVALID, "batch: slot columns too small for the table's %u slots", t->desc.lay.n_slots);
     uint32_t n_asets = (uint32_t)(cb_[CGPU_COL_ASET_K] / 4);
     if (n_asets == 0) return fail(CGPU_ERR_INVALID, "batch: no action sets");
     uint32_t km = b->max_actions ? b->max_actions : 1;
     uint32_t kc = 64 / role_cols;
     if (kc > km) kc = km;
     uint32_t n_pass = (km + kc - 1) / kc;
-    uint32_t nAP = t->desc.nAP ? t->desc.nAP : 1;
+    uint32_t nAP = t->desc.lay.nAP ? t->desc.lay.nAP : 1;
     if (cb_[CGPU_COL_ASET_SPREAD] < (size_t)8 * n_pass * n_asets * nAP) return fail(CGPU_ERR_INVALID, "batch: aset_spread too small");
-    if (cb_[CGPU_COL_CLASS_OFF] < 8) return fail(CGPU_ERR_INVALID, "batch: class table too small");
+    if (cb_[CGPU_COL_ROW_AM] < (size_t)8 * n_pass * n_asets * t->desc.lay.n_rows) return fail(CGPU_ERR_INVALID, "batch: row_am too small");
     for (int i = 0; i < CGPU_N_COLUMNS; i++)
         if (!b->columns[i]) return fail(CGPU_ERR_INVALID, "batch: column %d is null", i);
     v->hdr0 = static_cast<const cb_hdr0 *>(b->columns[CGPU_COL_HDR0]);
@@ -256,37 +236,48 @@ int make_batch_view(const cgpu_table *t, const cgpu_batch *b, uint64_t first, ui
     v->class_pats = static_cast<const uint32_t *>(b->columns[CGPU_COL_CLASS_PATS]);
     v->aset_k = static_cast<const uint32_t *>(b->columns[CGPU_COL_ASET_K]);
     v->aset_spread = static_cast<const uint64_t *>(b->columns[CGPU_COL_ASET_SPREAD]);
+    v->row_am = static_cast<const uint64_t *>(b->columns[CGPU_COL_ROW_AM]);
+    v->n_rows = t->desc.lay.n_rows;
     v->stride = N; v->first = first; v->count = count;
     v->role_cols = role_cols; v->n_asets = n_asets; v->kc = kc; v->n_pass = n_pass; v->max_actions = km;
     v->kbytes = (km + 7) / 8; v->flags = b->flags; v->now = b->now_unix_nanos;
     return CGPU_OK;
 }
 
-int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, uint8_t *d_bitmap, uint32_t *d_status,
-                 cudaStream_t stream) {
-    const bool stage = !ctx->force_no_stage && t->desc.image_bytes <= kMaxStageBytes;
-    const uint32_t smem = stage ? t->desc.image_bytes : 0;
+int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, uint8_t *d_bitmap, uint8_t *d_effects,
+                 uint32_t *d_status, cudaStream_t stream) {
+    const bool stage = !ctx->force_no_stage && t->desc.lay.image_bytes <= kMaxStageBytes;
+    const uint32_t smem = stage ? t->desc.lay.image_bytes : 0;
     uint64_t tiles = (bv.count + kThreads - 1) / kThreads;
-    int occ = stage ? ctx->occ_staged : ctx->occ_global;
-    if (stage) {
-        // occupancy depends on the dynamic shared memory size of this table
-        CUDA_TRY(cudaFuncSetAttribute(check_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxStageBytes));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, check_kernel<true>, kThreads, smem));
-    } else if (occ == 0) {
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, check_kernel<false>, kThreads, 0));
-        ctx->occ_global = occ;
+    // The lean body applies to resource-policy-only tables (no principal / role policies, parent roles or
+    // resource globs) when the (action x role column) pair masks fit 32 bits and the role table fits 64 bits.
+    uint32_t rcp = 1;
+    while (rcp < bv.role_cols) rcp <<= 1;
+    const cb::TableLayout &lay = t->desc.lay;
+    const bool narrow = !ctx->force_general && bv.n_pass == 1 && (uint64_t)bv.max_actions * bv.role_cols <= 32 && bv.kbytes <= 4 &&
+                        !lay.has_principal_policies && !lay.has_role_policies && !lay.has_parent_roles &&
+                        t->meta[CB_META_DIRECT_KINDS] && (uint64_t)lay.nR * rcp <= 64;
+    const void *fn = narrow ? (const void *)check_kernel<true> : (const void *)check_kernel<false>;
+    // resident CTAs per SM for this table's shared-memory footprint: queried once per (table, variant)
+    cgpu_table *mt = const_cast<cgpu_table *>(t);
+    int occ = mt->occ[narrow].load(std::memory_order_relaxed);
+    if (occ == 0) {
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxStageBytes));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, smem));
+        if (occ < 1) occ = 1;
+        mt->occ[narrow].store(occ, std::memory_order_relaxed);
     }
-    if (occ < 1) occ = 1;
     uint64_t max_ctas = (uint64_t)ctx->sm_count * (uint64_t)occ;
     uint32_t grid = (uint32_t)(tiles < max_ctas ? tiles : max_ctas);
     if (grid == 0) grid = 1;
-    if (stage)
-        check_kernel<true><<<grid, kThreads, smem, stream>>>(t->desc, bv, d_bitmap, d_status);
-    else
-        check_kernel<false><<<grid, kThreads, 0, stream>>>(t->desc, bv, d_bitmap, d_status);
+    TableDesc td = t->desc;
+    cb::BatchView bvv = bv;
+    uint32_t stage_flag = stage ? 1u : 0u;
+    void *args[] = {&td, &bvv, &d_bitmap, &d_effects, &d_status, &stage_flag};
+    CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(kThreads), args, smem, stream));
     CUDA_TRY(cudaGetLastError());
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
-    ctx->last_grid = grid; ctx->last_block = kThreads; ctx->last_smem = smem;
+    ctx->last_grid = grid; ctx->last_block = kThreads; ctx->last_smem = smem; ctx->last_fast = narrow ? 1 : 0;
     return CGPU_OK;
 }
 
@@ -316,6 +307,8 @@ int cgpu_init(const int *device_ids, int n_devices, cgpu_ctx **out) {
     CUDA_TRY(cudaMemset(ctx->d_status, 0, sizeof(uint32_t)));
     const char *ns = getenv("CERBOS_B200_NO_STAGE");
     ctx->force_no_stage = ns && ns[0] == '1';
+    const char *fg = getenv("CERBOS_B200_FORCE_GENERAL");
+    ctx->force_general = fg && fg[0] == '1';
     ctx->slots.resize(4);
     *out = ctx;
     return CGPU_OK;
@@ -328,7 +321,7 @@ void cgpu_shutdown(cgpu_ctx *ctx) {
     for (auto &s : ctx->slots) {
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.dev) cudaFree(s.dev);
-        if (s.pinned) cudaFreeHost(s.pinned);
+        if (s.h_status) cudaFreeHost(s.h_status);
         if (s.d_status) cudaFree(s.d_status);
     }
     if (ctx->d_status) cudaFree(ctx->d_status);
@@ -345,8 +338,8 @@ int cgpu_table_load(cgpu_ctx *ctx, const void *blob, size_t len, cgpu_table **ou
     int rc = parse_blob(blob, len, &t->desc, t->meta);
     if (rc != CGPU_OK) { delete t; return rc; }
     cudaError_t e = cudaSetDevice(ctx->device);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&t->d_image), t->desc.image_bytes);
-    if (e == cudaSuccess) e = cudaMemcpy(t->d_image, blob, t->desc.image_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&t->d_image), t->desc.lay.image_bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(t->d_image, blob, t->desc.lay.image_bytes, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         if (t->d_image) cudaFree(t->d_image);
         delete t;
@@ -382,7 +375,7 @@ int cgpu_last_kernel_config(const cgpu_ctx *ctx, uint32_t *grid, uint32_t *block
     if (!ctx) return fail(CGPU_ERR_INVALID, "null ctx");
     if (grid) *grid = ctx->last_grid;
     if (block) *block = ctx->last_block;
-    if (smem_bytes) *smem_bytes = ctx->last_smem;
+    if (smem_bytes) *smem_bytes = ctx->last_smem | (ctx->last_fast << 31);   // bit 31: lean kernel body was used
     return CGPU_OK;
 }
 
@@ -393,14 +386,14 @@ int cgpu_check_device(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *dev_
     int rc = make_batch_view(t, dev_batch, 0, dev_batch->n_requests, &bv);
     if (rc != CGPU_OK) return rc;
     CUDA_TRY(cudaSetDevice(ctx->device));
-    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
-    return launch_check(ctx, t, bv, static_cast<uint8_t *>(dev_bitmap_out), ctx->d_status, s);
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);   // NULL = the legacy default stream
+    return launch_check(ctx, t, bv, static_cast<uint8_t *>(dev_bitmap_out), nullptr, ctx->d_status, s);
 }
 
 int cgpu_sync(cgpu_ctx *ctx, void *cuda_stream) {
     if (!ctx) return fail(CGPU_ERR_INVALID, "null ctx");
     CUDA_TRY(cudaSetDevice(ctx->device));
-    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     uint32_t st = 0;
     CUDA_TRY(cudaMemcpyAsync(&st, ctx->d_status, 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -438,25 +431,20 @@ int cgpu_check(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, uint
 
     if (!slot->stream) CUDA_TRY(cudaStreamCreateWithFlags(&slot->stream, cudaStreamNonBlocking));
     if (!slot->d_status) { CUDA_TRY(cudaMalloc(&slot->d_status, 4)); CUDA_TRY(cudaMemset(slot->d_status, 0, 4)); }
+    if (!slot->h_status) CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&slot->h_status), 4));
 
-    // device layout: every column 256-byte aligned, then the bitmap
+    // device layout: every column 256-byte aligned, then the effect bytes
     size_t offs[CGPU_N_COLUMNS + 1];
     size_t total = 0;
     for (int i = 0; i < CGPU_N_COLUMNS; i++) { offs[i] = total; total += (batch->column_bytes[i] + 255) & ~(size_t)255; }
-    const size_t bitmap_bytes = (size_t)N * hv.kbytes;
+    const size_t eff_bytes = (size_t)N * km;
     offs[CGPU_N_COLUMNS] = total;
-    total += (bitmap_bytes + 255) & ~(size_t)255;
+    total += (eff_bytes + 255) & ~(size_t)255;
     if (slot->dev_cap < total) {
         if (slot->dev) cudaFree(slot->dev);
         slot->dev = nullptr; slot->dev_cap = 0;
         CUDA_TRY(cudaMalloc(&slot->dev, total));
         slot->dev_cap = total;
-    }
-    if (slot->pinned_cap < bitmap_bytes) {
-        if (slot->pinned) cudaFreeHost(slot->pinned);
-        slot->pinned = nullptr; slot->pinned_cap = 0;
-        CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&slot->pinned), bitmap_bytes));
-        slot->pinned_cap = bitmap_bytes;
     }
     uint8_t *dbase = static_cast<uint8_t *>(slot->dev);
     const void *dcols[CGPU_N_COLUMNS];
@@ -469,29 +457,16 @@ int cgpu_check(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, uint
     cb::BatchView bv;
     rc = make_batch_view(t, &db, 0, N, &bv);
     if (rc != CGPU_OK) return rc;
-    uint8_t *d_bitmap = dbase + offs[CGPU_N_COLUMNS];
-    rc = launch_check(ctx, t, bv, d_bitmap, slot->d_status, slot->stream);
+    uint8_t *d_effects = dbase + offs[CGPU_N_COLUMNS];
+    // the kernel writes effect bytes directly (1 ALLOW / 2 DENY / 0 padding): one D2H copy, no host post-pass
+    rc = launch_check(ctx, t, bv, nullptr, d_effects, slot->d_status, slot->stream);
     if (rc != CGPU_OK) return rc;
-    uint32_t st = 0;
-    CUDA_TRY(cudaMemcpyAsync(slot->pinned, d_bitmap, bitmap_bytes, cudaMemcpyDeviceToHost, slot->stream));
-    CUDA_TRY(cudaMemcpyAsync(&st, slot->d_status, 4, cudaMemcpyDeviceToHost, slot->stream));
+    CUDA_TRY(cudaMemcpyAsync(effects_out, d_effects, eff_bytes, cudaMemcpyDeviceToHost, slot->stream));
+    CUDA_TRY(cudaMemcpyAsync(slot->h_status, slot->d_status, 4, cudaMemcpyDeviceToHost, slot->stream));
     CUDA_TRY(cudaStreamSynchronize(slot->stream));
-    if (st) {
+    if (*slot->h_status) {
         CUDA_TRY(cudaMemset(slot->d_status, 0, 4));
         return fail(CGPU_ERR_UNSUPPORTED, "a request produced a run-time value the device cannot represent exactly (e.g. timestamp outside 1678..2262, string->double, concatenation)");
-    }
-    // expand 1 bit / decision into effect bytes; slots beyond an input's own action count stay 0
-    const cb_hdr1 *h1 = static_cast<const cb_hdr1 *>(batch->columns[CGPU_COL_HDR1]);
-    const uint32_t *aset_k = static_cast<const uint32_t *>(batch->columns[CGPU_COL_ASET_K]);
-    const uint32_t n_asets = (uint32_t)(batch->column_bytes[CGPU_COL_ASET_K] / 4);
-    for (uint64_t n = 0; n < N; n++) {
-        const uint8_t *bits = slot->pinned + n * hv.kbytes;
-        uint32_t aset = h1[n].action_set_id;
-        uint32_t K = aset < n_asets ? aset_k[aset] : 0;
-        if (K > km) K = km;
-        uint8_t *o = effects_out + n * km;
-        for (uint32_t k = 0; k < K; k++) o[k] = ((bits[k >> 3] >> (k & 7)) & 1) ? CGPU_EFFECT_ALLOW : CGPU_EFFECT_DENY;
-        for (uint32_t k = K; k < km; k++) o[k] = 0;
     }
     return CGPU_OK;
 }

@@ -35,6 +35,11 @@ class DeviceBatch:
         s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
         table.check_device(self.ptrs, self.sizes, self.n, self.max_actions, self.bitmap.data_ptr(), now_ns, flags, s)
 
+    def prepare(self, table, now_ns=0, flags=0):
+        """-> f(stream_handle): launches the check with pre-built arguments (for timing loops / graphs)."""
+        return table.prepared_device_call(self.ptrs, self.sizes, self.n, self.max_actions, self.bitmap.data_ptr(),
+                                          now_ns, flags)
+
     def effects(self) -> np.ndarray:
         """uint8[n, K] 1 = ALLOW, 2 = DENY (synchronises)."""
         bm = self.bitmap[: self.n * self.kbytes].cpu().numpy().reshape(self.n, self.kbytes)

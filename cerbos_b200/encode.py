@@ -20,6 +20,7 @@ Column order (``cgpu_batch.columns``; see include/cerbos_b200.h):
    8 class_pats  u32[]
    9 aset_k      u32[n_asets]           number of actions in each action set
   10 aset_spread u64[n_pass][n_asets][n_apats]   action-pattern -> (action x role-column) bit spread
+  11 row_am      u64[n_pass][n_asets][n_rows]    the same spread OR-ed over the patterns of every table row
 """
 from __future__ import annotations
 
@@ -33,7 +34,7 @@ from .policy import namer
 from .policy.globs import key_matches
 from .table import layout as L
 
-N_COLUMNS = 11
+N_COLUMNS = 12
 
 
 def _f64_bits(d: float) -> int:
@@ -89,6 +90,8 @@ class Encoder:
         self.apats = manifest["apats"]
         self.respats = manifest["respats"]
         self.slots = [tuple(p) for p in manifest["slots"]]
+        self.row_pat_start = np.array(manifest.get("row_pat_start", []), dtype=np.int64)
+        self.row_apats = np.array(manifest.get("row_apats", []), dtype=np.int64)
         self._apat_cache: dict[str, tuple] = {}
         self._class_cache: dict[str, tuple] = {}
 
@@ -200,11 +203,7 @@ class Encoder:
             p_ver = p.get("policyVersion", p.get("policy_version")) or self.default_version
             r_ver = r.get("policyVersion", r.get("policy_version")) or self.default_version
             kp = self.kind_patterns(r.get("kind", ""))
-            cid = classes.get(kp)
-            if cid is None:
-                cid = len(class_list)
-                classes[kp] = cid
-                class_list.append(kp)
+            cid = self.kind_class(kp, classes, class_list)
             acts = tuple(inp.get("actions") or [])
             aid = asets.get(acts)
             if aid is None:
@@ -243,7 +242,7 @@ class Encoder:
         class_off[len(class_list)] = len(cp)
         class_pats = np.array(cp or [0], dtype=np.uint32)
 
-        aset_k, aset_spread = self.build_action_sets(aset_list, role_cols, max_actions)
+        aset_k, aset_spread, row_am = self.build_action_sets(aset_list, role_cols, max_actions)
 
         off = np.zeros(len(bstr_list) + 1, dtype=np.uint32)
         pos = 0
@@ -253,7 +252,7 @@ class Encoder:
         off[len(bstr_list)] = pos
         bbytes = np.frombuffer(b"".join(bstr_list) + b"\0" * 16, dtype=np.uint8)
         cols = [hdr0, hdr1, roles, slots, np.array(heap or [0], dtype=np.uint64), off, bbytes,
-                class_off, class_pats, aset_k, aset_spread]
+                class_off, class_pats, aset_k, aset_spread, row_am]
         return Batch(n, max_actions, role_cols, cols, [list(a.get("actions") or []) for a in inputs], n_pass, kc)
 
     def build_action_sets(self, aset_list, role_cols: int, max_actions: int):
@@ -270,7 +269,33 @@ class Encoder:
                 ps, kk = divmod(k, kc)
                 for ap in self.action_patterns(act):
                     spread[ps, a, ap] |= np.uint64(1 << (kk * role_cols))
-        return aset_k, spread
+        return aset_k, spread, self.row_action_masks(spread)
+
+    def row_action_masks(self, spread: np.ndarray) -> np.ndarray:
+        """row_am[pass][aset][row] = OR of spread[pass][aset][p] over the action patterns p of table row."""
+        n_rows = len(self.row_pat_start)
+        n_pass, n_as, _ = spread.shape
+        if n_rows == 0:
+            return np.zeros((n_pass, n_as, 1), dtype=np.uint64)
+        out = np.zeros((n_pass, n_as, n_rows), dtype=np.uint64)
+        for ps in range(n_pass):
+            for a in range(n_as):
+                out[ps, a] = np.bitwise_or.reduceat(spread[ps, a][self.row_apats], self.row_pat_start)
+        return out
+
+    @staticmethod
+    def kind_class(kp: tuple, classes: dict, class_list: list) -> int:
+        """hdr0.kind_class: the pattern id itself when the kind matches exactly one resource pattern."""
+        if len(kp) == 0:
+            return L.KIND_NONE
+        if len(kp) == 1:
+            return kp[0]
+        cid = classes.get(kp)
+        if cid is None:
+            cid = len(class_list)
+            classes[kp] = cid
+            class_list.append(kp)
+        return cid | L.KIND_CLASS_CSR_BIT
 
 
 def manifest_from_blob(blob: bytes) -> dict:

@@ -482,6 +482,9 @@ class ProgramCompiler:
             if isinstance(n, Call) and n.fn != "_[_]":
                 return None
             if self._is_var_ref(n):
+                d = self.var_defs.get(n.field)
+                if d is not None and isinstance(d.ast, Const) and not isinstance(d.ast.value, bytes):
+                    return ("const", (d.ast.value, True))
                 return None
             try:
                 st = self._static(n)
@@ -666,6 +669,149 @@ class ProgramCompiler:
     def finish(self):
         self.emit("RET")
         return self.code
+
+
+class FlatCompiler:
+    """Recognises conditions that are an ALL / ANY of simple terms (see layout.FLAT_*).
+
+    A term is a fused compare / `in` / has() on slots, constants and P.id; its value is tri-state
+    (true / false / error) and may carry a NEG flag (`!term`, `!=`).  Because a condition leaf only asks
+    "is the result BOOL true" (ruletable.go:1425-1441), cel-go's error absorption collapses:
+        a && b && c   is true  <=> every term is true
+        a || b || c   is true  <=> some term is true
+        !(a && b)     is true  <=> some term is BOOL false      (ANY of negated terms)
+        !(a || b)     is true  <=> every term is BOOL false     (ALL of negated terms)
+    and all/any/none of such leaves compose the same way (none = final negation of an ANY)."""
+
+    def __init__(self, pc: "ProgramCompiler"):
+        self.pc = pc
+
+    def term(self, n: Node, neg: bool):
+        """-> [op, a, b, c] or None"""
+        pc = self.pc
+        if isinstance(n, Call) and n.fn == "!_" and n.target is None and len(n.args) == 1:
+            return self.term(n.args[0], not neg)
+        if isinstance(n, Select) and n.test_only:
+            try:
+                st = pc._static(Select(n.operand, n.field))
+            except Unsupported:
+                return None
+            if st is None or st.kind != "slot" or len(st.path) <= 2:
+                return None
+            return [OP["HAS_SLOT"], L.FLAT_TERM_NEG if neg else 0, 0, pc._slot_ix(st.path)]
+        if isinstance(n, Call) and n.target is None and len(n.args) == 2 and (n.fn in L.CMP_INDEX or n.fn == "@in"):
+            sa, sb = pc._simple(n.args[0]), pc._simple(n.args[1])
+            if sa is None or sb is None:
+                return None
+            ka, kb = sa[0], sb[0]
+            flag = L.FLAT_TERM_NEG if neg else 0
+            if n.fn == "@in":
+                if ka == "slot" and kb == "const":
+                    return [OP["IN_SLOT_CONST"], flag, pc._slot_ix(sa[1]), pc._const_ix(sb[1])]
+                if ka == "const" and kb == "slot":
+                    return [OP["IN_CONST_SLOT"], flag, pc._slot_ix(sb[1]), pc._const_ix(sa[1])]
+                return None
+            ci = L.CMP_INDEX[n.fn]
+            if ci == 1:   # a != b  ==  !(a == b)
+                ci = 0
+                flag ^= L.FLAT_TERM_NEG
+            swap = {0: 0, 2: 4, 3: 5, 4: 2, 5: 3}
+            if ka == "slot" and kb == "const":
+                return [OP["CMP_SLOT_CONST"], ci | flag, pc._slot_ix(sa[1]), pc._const_ix(sb[1])]
+            if ka == "const" and kb == "slot":
+                return [OP["CMP_SLOT_CONST"], swap[ci] | flag, pc._slot_ix(sb[1]), pc._const_ix(sa[1])]
+            if ka == "slot" and kb == "slot":
+                return [OP["CMP_SLOT_SLOT"], ci | flag, pc._slot_ix(sa[1]), pc._slot_ix(sb[1])]
+            if ka == "slot" and kb == "pid":
+                pc.ctx.uses_pid = True
+                return [OP["CMP_SLOT_PID"], ci | flag, pc._slot_ix(sa[1]), 0]
+            if ka == "pid" and kb == "slot":
+                pc.ctx.uses_pid = True
+                return [OP["CMP_SLOT_PID"], swap[ci] | flag, pc._slot_ix(sb[1]), 0]
+            return None
+        if not neg:
+            # a bare boolean attribute: true <=> value == true (only in positive position, see class doc)
+            sa = pc._simple(n) if isinstance(n, (Select, Call)) else None
+            if sa is not None and sa[0] == "slot":
+                return [OP["CMP_SLOT_CONST"], 0, pc._slot_ix(sa[1]), pc._const_ix((True, True))]
+        return None
+
+    def expr(self, n: Node, neg: bool):
+        """-> (kind or None for a single term, [terms]) or None"""
+        if isinstance(n, Call) and n.fn == "!_" and n.target is None and len(n.args) == 1:
+            return self.expr(n.args[0], not neg)
+        if isinstance(n, Call) and n.target is None and n.fn in ("_&&_", "_||_") and len(n.args) == 2:
+            kind = L.FLAT_ALL if n.fn == "_&&_" else L.FLAT_ANY
+            if neg:
+                kind = L.FLAT_ANY if kind == L.FLAT_ALL else L.FLAT_ALL
+            terms = []
+            for a in n.args:
+                sub = self.expr(a, neg)
+                if sub is None:
+                    return None
+                sk, st = sub
+                if sk is not None and sk != kind:
+                    return None
+                terms.extend(st)
+            return kind, terms
+        t = self.term(n, neg)
+        return None if t is None else (None, [t])
+
+    def cond(self, c: Cond):
+        """-> (kind, negate, terms) or None"""
+        if c.op == "expr":
+            r = self.expr(c.expr.ast, False)
+            if r is None:
+                return None
+            kind, terms = r
+            return (kind or L.FLAT_ALL, 0, terms)
+        if not c.children:
+            return None
+        kind = L.FLAT_ALL if c.op == "all" else L.FLAT_ANY
+        terms = []
+        for ch in c.children:
+            r = self.cond(ch)
+            if r is None:
+                return None
+            k, negate, t = r
+            if negate or (len(t) > 1 and k != kind):
+                return None
+            terms.extend(t)
+        return (kind, 1 if c.op == "none" else 0, terms)
+
+
+def compile_flat(ctx: TableBuilderCtx, cond: Cond, params: Params | None):
+    """-> (kind, negate, [[op, a, b, c], ...]) if the condition has a flat fast form, else None."""
+    pc = ProgramCompiler(ctx, params)
+    try:
+        r = FlatCompiler(pc).cond(cond)
+    except Unsupported:
+        return None
+    if r is None or not (1 <= len(r[2]) <= 0xFFFF):
+        return None
+    return r
+
+
+def const_v64(ctx: TableBuilderCtx, cv: ConstVal) -> int:
+    """8-byte fast form of a constant for the flat path (layout.FLAT_NOT_FAST if it has none).
+    INT constants become doubles: cel-go compares int with double by converting the int
+    (types/compare.go compareDoubleInt), so this is exact for comparisons against attribute doubles."""
+    if cv.tag == T["NULL"]:
+        return box(L.V64_NULL)
+    if cv.tag == T["BOOL"]:
+        return box(L.V64_BOOL, cv.bits)
+    if cv.tag == T["STRING"]:
+        return box(L.V64_STRING, cv.bits)
+    if cv.tag == T["DOUBLE"]:
+        return cv.bits
+    if cv.tag == T["INT"]:
+        v = cv.bits - (1 << 64) if cv.bits >> 63 else cv.bits
+        return f64_bits(float(v))
+    if cv.tag == T["LIST"]:
+        return box(L.V64_LIST, cv.bits)
+    if cv.tag == T["MAP"]:
+        return box(L.V64_MAP, cv.bits)
+    return L.FLAT_NOT_FAST
 
 
 def compile_condition(ctx: TableBuilderCtx, cond: Cond, params: Params | None) -> list:

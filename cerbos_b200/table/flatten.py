@@ -30,7 +30,7 @@ from ..policy import namer
 from ..policy.globs import is_glob
 from ..policy.model import KIND_PRINCIPAL, KIND_RESOURCE, RuleTable, SP_UNSPECIFIED
 from . import layout as L
-from .bytecode import TableBuilderCtx, Unsupported, compile_condition
+from .bytecode import TableBuilderCtx, Unsupported, compile_condition, compile_flat, const_v64
 
 
 class _Dict:
@@ -144,19 +144,30 @@ def flatten(rt: RuleTable, globals_=None) -> FlatTable:
         if r.action is not None:
             groups[key].append(r)
 
-    blocks, row_recs, conds, code = [], [], [], []
+    blocks, row_recs, conds, code, row_apats = [], [], [], [], []
     code_ix: dict[tuple, tuple] = {}
 
     def add_program(cond, params) -> int:
         """Compiles and appends to CONDS; returns the global cond id."""
         prog = compile_condition(ctx, cond, params)
-        k = tuple(tuple(i) for i in prog)
-        ent = code_ix.get(k)
-        if ent is None:
-            ent = (len(code), len(prog))
-            code_ix[k] = ent
-            code.extend(prog)
-        conds.append(ent)
+
+        def put(instrs):
+            k = tuple(tuple(i) for i in instrs)
+            ent = code_ix.get(k)
+            if ent is None:
+                ent = (len(code), len(instrs))
+                code_ix[k] = ent
+                code.extend(instrs)
+            return ent
+
+        gen = put(prog)
+        flat = compile_flat(ctx, cond, params)
+        if flat is not None:
+            kind, negate, terms = flat
+            foff, n_terms = put(terms)
+            conds.append((gen[0], gen[1], foff, n_terms | (kind << 16) | (negate << 24)))
+        else:
+            conds.append((gen[0], gen[1], 0, 0))
         return len(conds) - 1
 
     for key, grows in groups.items():
@@ -183,16 +194,22 @@ def flatten(rt: RuleTable, globals_=None) -> FlatTable:
             return li
 
         row_start = len(row_recs)
+        # rows that differ only in their action pattern are merged into one row with a pattern list
+        merged: dict[tuple, list] = {}
         for r in grows:
-            row_recs.append((
-                apats.ids[r.action],
-                L.ROLE_ANY if r.role == "*" else roles.ids[r.role],
-                local_cond(r.condition, r.params),
-                local_cond(r.dr_condition, r.dr_params),
-                respats.ids[r.resource] if kind == "P" else L.NONE16,
-                r.effect,
-                L.ROW_FLAG_PRINCIPAL if kind == "P" else 0,
-            ))
+            key2 = (L.ROLE_ANY if r.role == "*" else roles.ids[r.role],
+                    local_cond(r.condition, r.params), local_cond(r.dr_condition, r.dr_params),
+                    respats.ids[r.resource] if kind == "P" else L.NONE16, r.effect,
+                    L.ROW_FLAG_PRINCIPAL if kind == "P" else 0)
+            pats = merged.setdefault(key2, [])
+            ap = apats.ids[r.action]
+            if ap not in pats:
+                pats.append(ap)
+        for key2, pats in merged.items():
+            if len(pats) > 0xFFFF:
+                raise Unsupported("too many action patterns on one rule")
+            row_recs.append(key2 + (len(pats), len(row_apats)))
+            row_apats.extend(pats)
         blocks.append((row_start, len(row_recs) - row_start, cond_base, len(conds) - cond_base))
 
     # ---- role policies ----------------------------------------------------------------------------------------
@@ -265,16 +282,39 @@ def flatten(rt: RuleTable, globals_=None) -> FlatTable:
         has_parent_roles=int(has_parents), has_principal_policies=int(nP > 0), max_stack=ctx.max_stack,
         max_loop_depth=ctx.max_loop_depth, n_vars=ctx.n_vars, theap_words=len(ctx.theap),
         uses_pid=int(ctx.uses_pid), uses_now=int(ctx.uses_now), max_scope_depth=max_depth,
+        direct_kinds=int(not any(is_glob(p) for p in respats.items)),
     ).items():
         meta[L.META[k]] = val
 
     blocks_a = np.array(blocks or [(0, 0, 0, 0)], dtype=np.uint32).reshape(-1, 4)
     rows_a = np.zeros(max(len(row_recs), 1), dtype=np.dtype([
-        ("apat", "<u2"), ("role", "<u2"), ("cond", "<u2"), ("drcond", "<u2"), ("respat", "<u2"),
-        ("effect", "u1"), ("flags", "u1"), ("pad", "<u4")]))
+        ("role", "<u2"), ("cond", "<u2"), ("drcond", "<u2"), ("respat", "<u2"),
+        ("effect", "u1"), ("flags", "u1"), ("n_pats", "<u2"), ("pat_start", "<u4")]))
     for i, rec in enumerate(row_recs):
-        rows_a[i] = rec + (0,)
-    conds_a = np.array(conds or [(0, 0)], dtype=np.uint32).reshape(-1, 2)
+        rows_a[i] = rec
+    # slots read by the conditions of each block (prefetch list for the kernel)
+    slot_ops_c = {L.OPS["SLOT"], L.OPS["HAS_SLOT"]}
+    slot_ops_b = {L.OPS["CMP_SLOT_CONST"], L.OPS["CMP_SLOT_SLOT"], L.OPS["CMP_SLOT_PID"], L.OPS["IN_SLOT_CONST"],
+                  L.OPS["IN_CONST_SLOT"]}
+    bs_off = np.zeros(len(blocks) + 1, dtype=np.uint32)
+    bs_list = []
+    for bi, (_rs, _nr, cbase, ncond) in enumerate(blocks):
+        bs_off[bi] = len(bs_list)
+        seen = []
+        for ci in range(cbase, cbase + ncond):
+            coff, clen, foff, finfo = conds[ci]
+            spans = [(foff, finfo & 0xFFFF)] if finfo else [(coff, clen)]
+            for off, ln in spans:
+                for ins in code[off:off + ln]:
+                    if ins[0] in slot_ops_c and ins[3] not in seen:
+                        seen.append(ins[3])
+                    if ins[0] in slot_ops_b and ins[2] not in seen:
+                        seen.append(ins[2])
+                    if ins[0] == L.OPS["CMP_SLOT_SLOT"] and ins[3] not in seen:
+                        seen.append(ins[3])
+        bs_list.extend(seen)
+    bs_off[len(blocks)] = len(bs_list)
+    conds_a = np.array(conds or [(0, 0, 0, 0)], dtype=np.uint32).reshape(-1, 4)
     code_a = np.zeros(max(len(code), 1), dtype=np.dtype([("op", "u1"), ("a", "u1"), ("b", "<u2"), ("c", "<u4")]))
     for i, ins in enumerate(code):
         code_a[i] = tuple(ins)
@@ -282,6 +322,7 @@ def flatten(rt: RuleTable, globals_=None) -> FlatTable:
     for i, cv in enumerate(ctx.consts):
         consts_a[i] = (cv.tag, 0, cv.bits)
     theap_a = np.array(ctx.theap or [0], dtype=np.uint64)
+    consts_v64_a = np.array([const_v64(ctx, cv) for cv in ctx.consts] or [0], dtype=np.uint64)
 
     manifest = {
         "versions": versions.items, "scopes": scopes.items, "respats": respats.items, "principals": principals.items,
@@ -291,6 +332,7 @@ def flatten(rt: RuleTable, globals_=None) -> FlatTable:
         "scope_flags": [int(x) for x in scope_flags[:nS]],
         "scope_parent": [int(x) for x in scope_parent[:nS]],
         "parent_role_scopes": sorted(s for s, rmap in rt.scope_parent_roles.items() if any(rmap.values())),
+        "row_pat_start": [int(r[7]) for r in row_recs], "row_apats": [int(x) for x in row_apats],
     }
     man_bytes = json.dumps(manifest, ensure_ascii=False, separators=(",", ":")).encode("utf-8")
 
@@ -299,13 +341,16 @@ def flatten(rt: RuleTable, globals_=None) -> FlatTable:
         ("RES_BLOCK_MAP", res_block_map, 4), ("RES_EXISTS", res_exists, 1),
         ("PRIN_BLOCK_MAP", prin_block_map, 4), ("PRIN_EXISTS", prin_exists, 1),
         ("PRIN_OF_STRING", prin_of_string, 4), ("BLOCKS", blocks_a, 16), ("ROWS", rows_a, 16),
-        ("CONDS", conds_a, 8), ("CODE", code_a, 8), ("CONSTS", consts_a, 16), ("THEAP", theap_a, 8),
+        ("CONDS", conds_a, 16), ("CODE", code_a, 8), ("CONSTS", consts_a, 16), ("THEAP", theap_a, 8),
         ("STR_OFF", str_off, 4), ("STR_BYTES", str_bytes, 1),
         ("ROLE_PARENTS_OFF", par_off, 4), ("ROLE_PARENTS", np.array(par_list or [0], dtype=np.uint32), 4),
         ("ROLEPOL_OFF", rp_off, 4),
         ("ROLEPOL_ENTRIES", np.array(rp_entries or [(0, 0, 0, 0)], dtype=np.uint32).reshape(-1, 4), 16),
         ("ROLEPOL_RULES", np.array(rp_rules or [(0, 0, 0, 0)], dtype=np.uint32).reshape(-1, 4), 16),
         ("ROLEPOL_APATS", np.array(rp_apats or [0], dtype=np.uint32), 4),
+        ("CONSTS_V64", consts_v64_a, 8),
+        ("ROW_APATS", np.array(row_apats or [0], dtype=np.uint32), 4),
+        ("BLOCK_SLOTS_OFF", bs_off, 4), ("BLOCK_SLOTS", np.array(bs_list or [0], dtype=np.uint32), 4),
         ("MANIFEST", np.frombuffer(man_bytes, dtype=np.uint8), 1),
     ]
     assert rows_a.dtype.itemsize == 16 and code_a.dtype.itemsize == 8 and consts_a.dtype.itemsize == 16

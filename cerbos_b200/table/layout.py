@@ -12,7 +12,7 @@ Table blob (little endian, every section 16-byte aligned):
 from __future__ import annotations
 
 MAGIC = 0x32425243  # 'CRB2'
-VERSION = 3
+VERSION = 5
 ALIGN = 16
 
 NONE32 = 0xFFFFFFFF
@@ -22,6 +22,8 @@ ROLE_UNKNOWN = 0xFFFFFFFE  # request role not in the table's role dictionary
 ROLE_PAD = 0xFFFFFFFF      # unused role column entry
 SCOPE_NONE = 0x7FFFFFFF    # request scope that resolves to nothing
 SCOPE_INEXACT_BIT = 0x80000000  # lenient: hdr scope is the nearest known ancestor, not the request's own scope
+KIND_CLASS_CSR_BIT = 0x80000000  # hdr0.kind_class: bit clear = the single matching resource pattern id (KIND_NONE =
+KIND_NONE = 0x7FFFFFFF           # matches nothing); bit set = index into the class_off / class_pats CSR
 
 # ---- sections -----------------------------------------------------------------------------------------
 SECTIONS = {
@@ -34,8 +36,8 @@ SECTIONS = {
     "PRIN_EXISTS": 7,     # u8 [n_versions*n_scopes]  any PRINCIPAL-kind row with (version, scope)
     "PRIN_OF_STRING": 8,  # u32[n_strings] string id -> principal index | NONE32
     "BLOCKS": 9,          # Block[n_blocks] {u32 row_start, n_rows, cond_base, n_conds}
-    "ROWS": 10,           # Row[n_rows] 16 B
-    "CONDS": 11,          # {u32 code_off, u32 code_len}[n_conds]  (offsets in instructions)
+    "ROWS": 10,           # Row[n_rows] 16 B; rows of a block that differ only in their action pattern are merged
+    "CONDS": 11,          # {u32 code_off, code_len, flat_off, flat_info}[n_conds]  (offsets in instructions)
     "CODE": 12,           # Instr[n_code] 8 B {u8 op; u8 a; u16 b; u32 c}
     "CONSTS": 13,         # Const[n_consts] 16 B {u32 tag; u32 pad; u64 bits}
     "THEAP": 14,          # u64[] constant lists / maps (NaN-boxed V64 elements)
@@ -47,6 +49,10 @@ SECTIONS = {
     "ROLEPOL_ENTRIES": 20,  # {u32 role; u32 rule_start; u32 n_rules; u32 pad}
     "ROLEPOL_RULES": 21,  # {u32 respat; u32 cond (global id+1, 0 none); u32 apat_start; u32 n_apats}
     "ROLEPOL_APATS": 22,  # u32[] action pattern ids
+    "ROW_APATS": 24,      # u32[] action pattern ids of the (merged) rows (CSR via row.pat_start / n_pats)
+    "BLOCK_SLOTS_OFF": 25,  # u32[n_blocks+1] CSR: attribute slots read by the conditions of a block (prefetch list)
+    "BLOCK_SLOTS": 26,    # u32[]
+    "CONSTS_V64": 23,     # u64[n_consts] NaN-boxed form of each constant for the flat fast path (FLAT_NOT_FAST if none)
     "MANIFEST": 100,      # JSON (host only): dictionaries + slot paths for the batch encoder
 }
 
@@ -55,7 +61,7 @@ META = {name: i for i, name in enumerate([
     "n_versions", "n_respats", "n_scopes", "n_principals", "n_roles", "n_apats", "n_blocks", "n_rows",
     "n_conds", "n_code", "n_consts", "n_slots", "n_strings", "has_role_policies", "has_parent_roles",
     "has_principal_policies", "max_stack", "max_loop_depth", "n_vars", "theap_words", "uses_pid", "uses_now",
-    "max_scope_depth",
+    "max_scope_depth", "direct_kinds",
 ])}
 
 SCOPE_FLAG_PRINCIPAL = 1
@@ -128,6 +134,14 @@ OPS = {name: i for i, name in enumerate([
     "IN_IP_RANGE",      # TOS string ip -> BOOL(ip in CIDR at theap[c..c+3] = {family 4|6, prefix bits, hi64, lo64})
 ])}
 
+# Flat fast-path conditions: a condition that is an ALL / ANY of "terms" (fused compare / in / has ops on
+# slots, constants and P.id), optionally negated.  flat_info = n_terms | kind << 16 | negate << 24 ; 0 = none.
+# Term = Instr whose `a` field carries the compare index | FLAT_TERM_NEG (term value negated: BOOL false counts).
+FLAT_ALL = 1
+FLAT_ANY = 2
+FLAT_TERM_NEG = 0x80
+FLAT_NOT_FAST = ((V64_BOX_BASE | 15) << 48)   # CONSTS_V64 entry: constant has no 8-byte fast form
+
 LOOP_ALL = 0
 LOOP_EXISTS = 1
 LOOP_EXISTS_ONE = 2
@@ -164,6 +178,8 @@ def c_header() -> str:
     d("CB_ROLE_PAD", ROLE_PAD, True)
     d("CB_SCOPE_NONE", SCOPE_NONE, True)
     d("CB_SCOPE_INEXACT_BIT", SCOPE_INEXACT_BIT, True)
+    d("CB_KIND_CLASS_CSR_BIT", KIND_CLASS_CSR_BIT, True)
+    d("CB_KIND_NONE", KIND_NONE, True)
     out.append("")
     for k, v in SECTIONS.items():
         d(f"CB_SEC_{k}", v)
@@ -194,6 +210,10 @@ def c_header() -> str:
         d(f"CB_OP_{k}", v)
     d("CB_N_OPS", len(OPS))
     out.append("")
+    d("CB_FLAT_ALL", FLAT_ALL)
+    d("CB_FLAT_ANY", FLAT_ANY)
+    d("CB_FLAT_TERM_NEG", FLAT_TERM_NEG, True)
+    d("CB_FLAT_NOT_FAST", FLAT_NOT_FAST, True)
     d("CB_LOOP_ALL", LOOP_ALL)
     d("CB_LOOP_EXISTS", LOOP_EXISTS)
     d("CB_LOOP_EXISTS_ONE", LOOP_EXISTS_ONE)
@@ -208,8 +228,8 @@ def c_header() -> str:
     out.append("""typedef struct { uint32_t magic, version, n_sections, flags; uint64_t total_bytes, reserved; } cb_blob_header;
 typedef struct { uint32_t id, elem_bytes; uint64_t offset, n_bytes; } cb_section_desc;
 typedef struct { uint32_t row_start, n_rows, cond_base, n_conds; } cb_block;
-typedef struct { uint16_t apat, role, cond, drcond, respat; uint8_t effect, flags; uint32_t pad; } cb_row;
-typedef struct { uint32_t code_off, code_len; } cb_cond;
+typedef struct { uint16_t role, cond, drcond, respat; uint8_t effect, flags; uint16_t n_pats; uint32_t pat_start; } cb_row;
+typedef struct { uint32_t code_off, code_len, flat_off, flat_info; } cb_cond;
 typedef struct { uint8_t op, a; uint16_t b; uint32_t c; } cb_instr;
 typedef struct { uint32_t tag, pad; uint64_t bits; } cb_const;
 typedef struct { uint32_t role, rule_start, n_rules, pad; } cb_rolepol_entry;

@@ -65,6 +65,14 @@ def _str_ids(enc: Encoder, strings):
     return np.array(ids, dtype=np.uint64), extra
 
 
+def _kind_classes(enc: Encoder, kinds):
+    """-> (hdr kind_class value per kind, CSR class list) using the encoder's direct / CSR encoding."""
+    classes, class_list, vals = {}, [], []
+    for k in kinds:
+        vals.append(enc.kind_class(enc.kind_patterns(k), classes, class_list))
+    return np.array(vals, dtype=np.uint32), class_list
+
+
 def _finish_batch(enc: Encoder, n, hdr0, hdr1, roles, slots, heap, bstr_list, class_list, aset_list, max_actions):
     role_cols = roles.shape[0]
     class_off = np.zeros(len(class_list) + 1, dtype=np.uint32)
@@ -73,7 +81,7 @@ def _finish_batch(enc: Encoder, n, hdr0, hdr1, roles, slots, heap, bstr_list, cl
         class_off[c] = len(cp)
         cp.extend(pats)
     class_off[len(class_list)] = len(cp)
-    aset_k, aset_spread = enc.build_action_sets(aset_list, role_cols, max_actions)
+    aset_k, aset_spread, row_am = enc.build_action_sets(aset_list, role_cols, max_actions)
     off = np.zeros(len(bstr_list) + 1, dtype=np.uint32)
     pos = 0
     for j, b in enumerate(bstr_list):
@@ -83,7 +91,7 @@ def _finish_batch(enc: Encoder, n, hdr0, hdr1, roles, slots, heap, bstr_list, cl
     bbytes = np.frombuffer(b"".join(bstr_list) + b"\0" * 16, dtype=np.uint8)
     kc, n_pass = passes_for(max_actions, role_cols)
     cols = [hdr0, hdr1, roles, slots, heap, off, bbytes, class_off, np.array(cp or [0], dtype=np.uint32),
-            aset_k, aset_spread]
+            aset_k, aset_spread, row_am]
     return Batch(n, max_actions, role_cols, cols, None, n_pass, kc)
 
 
@@ -132,7 +140,8 @@ class C1:
         pid_ids, extra = _str_ids(enc, [f"user{i}" for i in range(32)])
         hdr0 = np.zeros((n, 4), dtype=np.uint32)
         hdr0[:, 0] = pid_ids[f["pr"]]
-        hdr0[:, 1] = 0
+        kvals, class_list = _kind_classes(enc, ["document"])
+        hdr0[:, 1] = kvals[0]
         hdr0[:, 2] = enc.resolve_scope("")
         hdr0[:, 3] = enc.resolve_scope("")
         hdr1 = np.zeros(n, dtype=np.dtype([("rv", "<u2"), ("pv", "<u2"), ("aset", "<u4")]))
@@ -142,7 +151,7 @@ class C1:
         roles = np.stack([rmap[f["r0"]], rmap[f["r1"]]]).astype(np.uint32)
         slots = np.zeros((1, n), dtype=np.uint64)
         return _finish_batch(enc, n, hdr0, hdr1, roles, slots, np.zeros(1, dtype=np.uint64), extra,
-                             [enc.kind_patterns("document")], [tuple(self.actions)], 3)
+                             class_list, [tuple(self.actions)], 3)
 
     # 24 + 4R + 8A + S + ceil(K/8)
     def bytes_per_request(self):
@@ -233,10 +242,10 @@ class C2:
         st_ids, e3 = _str_ids(enc, self.statuses)
         st_ids = np.where(st_ids >= nts, st_ids + np.uint64(len(extra)), st_ids)
         extra = extra + e3
-        kinds = [enc.kind_patterns(f"kind_{k}") for k in range(self.n_kinds)]
+        kvals, class_list = _kind_classes(enc, [f"kind_{k}" for k in range(self.n_kinds)])
         hdr0 = np.zeros((n, 4), dtype=np.uint32)
         hdr0[:, 0] = pid_ids[f["pid"]]
-        hdr0[:, 1] = f["kind"]
+        hdr0[:, 1] = kvals[f["kind"]]
         hdr0[:, 2] = enc.resolve_scope("")
         hdr0[:, 3] = enc.resolve_scope("")
         hdr1 = np.zeros(n, dtype=np.dtype([("rv", "<u2"), ("pv", "<u2"), ("aset", "<u4")]))
@@ -255,7 +264,7 @@ class C2:
         for s, path in enumerate(enc.slots):
             slots[s] = vals[path]
         return _finish_batch(enc, n, hdr0, hdr1, roles, slots, np.zeros(1, dtype=np.uint64), extra,
-                             kinds, [tuple(self.actions)], 8)
+                             class_list, [tuple(self.actions)], 8)
 
     def bytes_per_request(self):
         return 24 + 4 * 2 + 8 * 5 + 0 + 1   # = 73

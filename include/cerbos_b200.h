@@ -65,6 +65,7 @@ enum cgpu_column {
     CGPU_COL_CLASS_PATS,  /* u32[] */
     CGPU_COL_ASET_K,      /* u32[n_asets]  number of actions of each distinct action list */
     CGPU_COL_ASET_SPREAD, /* u64[n_pass][n_asets][n_apats] */
+    CGPU_COL_ROW_AM,      /* u64[n_pass][n_asets][n_rows]  action mask of every (merged) table row */
     CGPU_N_COLUMNS
 };
 
@@ -93,8 +94,8 @@ int cgpu_check(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, uint
 
 /* Device-resident path: columns are device pointers on ctx's device.  dev_bitmap_out receives
  * n_requests * ceil(max_actions / 8) bytes, bit (k % 8) of byte n * ceil(K/8) + k / 8 set <=> ALLOW.
- * Asynchronous on `cuda_stream` (a cudaStream_t; NULL = the ctx's own stream).  Unsupported run-time values
- * are reported by the next cgpu_sync(). */
+ * Asynchronous on `cuda_stream` (a cudaStream_t, used exactly as given; NULL = the legacy default stream).
+ * Unsupported run-time values are reported by the next cgpu_sync() on the same stream. */
 int cgpu_check_device(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *dev_batch, void *dev_bitmap_out,
                       void *cuda_stream);
 /* Waits for work queued by cgpu_check_device on `cuda_stream` and returns CGPU_ERR_UNSUPPORTED / CGPU_ERR_CUDA

@@ -41,7 +41,7 @@ typedef struct {
 } cref_batch;
 
 enum { COL_HDR0, COL_HDR1, COL_ROLES, COL_SLOTS, COL_HEAP, COL_BSTR_OFF, COL_BSTR_BYTES, COL_CLASS_OFF,
-       COL_CLASS_PATS, COL_ASET_K, COL_ASET_SPREAD, N_COLS };
+       COL_CLASS_PATS, COL_ASET_K, COL_ASET_SPREAD, COL_ROW_AM, N_COLS };
 
 #define CREF_OK 0
 #define CREF_ERR_BLOB (-1)
@@ -60,7 +60,7 @@ typedef struct {
     const uint64_t *theap;
     const uint32_t *str_off;
     const uint8_t *str_bytes;
-    const uint32_t *par_off, *par_list, *rp_off, *rp_apats;
+    const uint32_t *par_off, *par_list, *rp_off, *rp_apats, *row_apats;
     const cb_rolepol_entry *rp_entries;
     const cb_rolepol_rule *rp_rules;
     uint32_t nV, nRP, nS, nP, nR, nAP, nT, n_slots, n_conds;
@@ -111,6 +111,7 @@ static int load_table(const void *blob, size_t len, table_t *t) {
         case CB_SEC_ROLEPOL_ENTRIES: t->rp_entries = p; break;
         case CB_SEC_ROLEPOL_RULES: t->rp_rules = p; break;
         case CB_SEC_ROLEPOL_APATS: t->rp_apats = p; break;
+        case CB_SEC_ROW_APATS: t->row_apats = p; break;
         default: break;
         }
     }
@@ -808,8 +809,20 @@ static int action_matches(const batch_t *b, const table_t *t, uint32_t aset, uin
     return (int)((m >> (kk * b->role_cols)) & 1);
 }
 
-static int in_class(const batch_t *b, uint32_t cls, uint32_t pat) {
-    for (uint32_t j = b->class_off[cls]; j < b->class_off[cls + 1]; j++) if (b->class_pats[j] == pat) return 1;
+/* hdr0.kind_class: direct pattern id, CB_KIND_NONE, or CSR index (CB_KIND_CLASS_CSR_BIT) */
+static uint32_t class_pats(const batch_t *b, uint32_t cls, uint32_t *out) {
+    if (cls == CB_KIND_NONE) return 0;
+    if (!(cls & CB_KIND_CLASS_CSR_BIT)) { out[0] = cls; return 1; }
+    uint32_t c = cls & ~CB_KIND_CLASS_CSR_BIT, n = 0;
+    for (uint32_t j = b->class_off[c]; j < b->class_off[c + 1] && n < CB_MAX_CLASS_PATS; j++) out[n++] = b->class_pats[j];
+    return n;
+}
+static int in_pats(const uint32_t *pats, uint32_t n, uint32_t pat) {
+    for (uint32_t j = 0; j < n; j++) if (pats[j] == pat) return 1;
+    return 0;
+}
+static int row_action_matches(const batch_t *b, const table_t *t, uint32_t aset, uint32_t k, const cb_row *row) {
+    for (uint32_t q = 0; q < row->n_pats; q++) if (action_matches(b, t, aset, k, t->row_apats[row->pat_start + q])) return 1;
     return 0;
 }
 
@@ -840,13 +853,15 @@ static void check_request(rctx_t *r, uint64_t n, uint8_t *out) {
     int np = build_chain(t, h0.principal_scope, CB_SCOPE_FLAG_PRINCIPAL, lenient, pchain);
     int nr = build_chain(t, h0.resource_scope, CB_SCOPE_FLAG_RESOURCE, lenient, rchain);
     if (np == 0 && nr == 0) return;
-    uint32_t rv = h1.resource_version, pv = h1.principal_version, cls = h0.kind_class;
+    uint32_t rv = h1.resource_version, pv = h1.principal_version;
+    uint32_t kpats[CB_MAX_CLASS_PATS];
+    uint32_t n_kp = class_pats(b, h0.kind_class, kpats);
     int p_exists = 0, r_exists = 0;
     if (pv != CB_NONE16) for (int i = 0; i < np; i++) p_exists |= t->prin_exists[(uint64_t)pv * t->nS + pchain[i]];
     if (rv != CB_NONE16)
         for (int i = 0; i < nr; i++)
-            for (uint32_t j = b->class_off[cls]; j < b->class_off[cls + 1]; j++)
-                r_exists |= t->res_exists[((uint64_t)rv * t->nRP + b->class_pats[j]) * t->nS + rchain[i]] & CB_EXISTS_RESOURCE_KIND;
+            for (uint32_t j = 0; j < n_kp; j++)
+                r_exists |= t->res_exists[((uint64_t)rv * t->nRP + kpats[j]) * t->nS + rchain[i]] & CB_EXISTS_RESOURCE_KIND;
     if (!p_exists && !r_exists) return;
     if (rv == CB_NONE16) return;   /* candidate rows are filtered by the resource version (ruletable.go:874) */
     uint32_t pidx = h0.principal_id < t->nT ? t->prin_of_string[h0.principal_id] : CB_NONE32;
@@ -863,8 +878,8 @@ static void check_request(rctx_t *r, uint64_t n, uint8_t *out) {
                 cb_block bl = t->blocks[bid];
                 for (uint32_t ri = 0; ri < bl.n_rows && !deny; ri++) {
                     cb_row row = t->rows[bl.row_start + ri];
-                    if (!in_class(b, cls, row.respat)) continue;
-                    if (!action_matches(b, t, h1.action_set_id, k, row.apat)) continue;
+                    if (!in_pats(kpats, n_kp, row.respat)) continue;
+                    if (!row_action_matches(b, t, h1.action_set_id, k, &row)) continue;
                     if (row.drcond && !cond_sat(r, bl.cond_base + row.drcond - 1)) continue;
                     if (row.cond && !cond_sat(r, bl.cond_base + row.cond - 1)) continue;
                     if (row.effect == CB_EFFECT_DENY) deny = 1; else saw_allow = 1;
@@ -884,8 +899,8 @@ static void check_request(rctx_t *r, uint64_t n, uint8_t *out) {
                 uint32_t s = rchain[si];
                 int saw_allow = 0, deny = 0;
                 int any_row = 0;
-                for (uint32_t j = b->class_off[cls]; j < b->class_off[cls + 1] && !deny; j++) {
-                    uint32_t pat = b->class_pats[j];
+                for (uint32_t j = 0; j < n_kp && !deny; j++) {
+                    uint32_t pat = kpats[j];
                     uint64_t mi = ((uint64_t)rv * t->nRP + pat) * t->nS + s;
                     if (t->res_exists[mi] & CB_EXISTS_ANY_ROW) any_row = 1;
                     uint32_t bid = t->res_block_map[mi];
@@ -893,7 +908,7 @@ static void check_request(rctx_t *r, uint64_t n, uint8_t *out) {
                     cb_block bl = t->blocks[bid];
                     for (uint32_t ri = 0; ri < bl.n_rows && !deny; ri++) {
                         cb_row row = t->rows[bl.row_start + ri];
-                        if (!action_matches(b, t, h1.action_set_id, k, row.apat)) continue;
+                        if (!row_action_matches(b, t, h1.action_set_id, k, &row)) continue;
                         if (row.role != CB_ROLE_ANY && !role_in_pr(t, row.role, roles[i], rscope_exact)) continue;
                         if (row.drcond && !cond_sat(r, bl.cond_base + row.drcond - 1)) continue;
                         if (row.cond && !cond_sat(r, bl.cond_base + row.cond - 1)) continue;
@@ -909,7 +924,7 @@ static void check_request(rctx_t *r, uint64_t n, uint8_t *out) {
                         int matched = 0;
                         for (uint32_t q = 0; q < en.n_rules && !deny; q++) {
                             cb_rolepol_rule ru = t->rp_rules[en.rule_start + q];
-                            if (!in_class(b, cls, ru.respat)) continue;
+                            if (!in_pats(kpats, n_kp, ru.respat)) continue;
                             int am = 0;
                             for (uint32_t a = 0; a < ru.n_apats; a++) if (action_matches(b, t, h1.action_set_id, k, t->rp_apats[ru.apat_start + a])) { am = 1; break; }
                             if (!am) continue;

@@ -20,7 +20,7 @@ def build():
     return _SO
 
 
-def check(blob: bytes, columns, n, max_actions, now_ns=0, flags=0):
+def check(blob: bytes, columns, n, max_actions, now_ns=0, flags=0, mode=0):
     """Returns uint8[n, max_actions] effects decoded from the packed bitmap (padding slots = DENY-coded 2)."""
     global _lib
     if _lib is None:
@@ -35,7 +35,7 @@ def check(blob: bytes, columns, n, max_actions, now_ns=0, flags=0):
     buf = ctypes.create_string_buffer(blob, len(blob))
     rc = _lib.hostsim_check(buf, ctypes.c_uint64(len(blob)), ctypes.c_uint64(n), ctypes.c_uint32(max_actions),
                             ctypes.c_int64(now_ns), ctypes.c_uint32(flags), ptrs, sizes,
-                            bitmap.ctypes.data_as(ctypes.c_void_p))
+                            bitmap.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(mode))
     if rc != 0:
         raise RuntimeError(f"hostsim_check failed: {rc}")
     bits = np.unpackbits(bitmap, axis=1, bitorder="little")[:, :km]

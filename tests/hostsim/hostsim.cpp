@@ -8,7 +8,7 @@
 #include "cb_core.h"
 
 extern "C" int hostsim_check(const void *blob, uint64_t blob_len, uint64_t n, uint32_t max_actions, int64_t now, uint32_t flags,
-                             const void *const *cols, const uint64_t *col_bytes, uint8_t *bitmap) {
+                             const void *const *cols, const uint64_t *col_bytes, uint8_t *bitmap, int mode) {
     const cb_blob_header *h = static_cast<const cb_blob_header *>(blob);
     if (h->magic != CB_MAGIC || h->version != CB_VERSION) return -1;
     const cb_section_desc *sd = reinterpret_cast<const cb_section_desc *>(static_cast<const char *>(blob) + sizeof(cb_blob_header));
@@ -16,32 +16,16 @@ extern "C" int hostsim_check(const void *blob, uint64_t blob_len, uint64_t n, ui
     uint64_t off[128] = {0};
     for (uint32_t i = 0; i < h->n_sections; i++) if (sd[i].id < 128) off[sd[i].id] = sd[i].offset;
     const uint32_t *meta = reinterpret_cast<const uint32_t *>(base + off[CB_SEC_META]);
+    cb::TableLayout lay;
+    memset(&lay, 0, sizeof(lay));
+    for (int i = 0; i < 28; i++) lay.off[i] = (uint32_t)off[i];
+    lay.nV = meta[CB_META_N_VERSIONS]; lay.nRP = meta[CB_META_N_RESPATS]; lay.nS = meta[CB_META_N_SCOPES]; lay.nP = meta[CB_META_N_PRINCIPALS];
+    lay.nR = meta[CB_META_N_ROLES]; lay.nAP = meta[CB_META_N_APATS]; lay.nT = meta[CB_META_N_STRINGS]; lay.n_slots = meta[CB_META_N_SLOTS];
+    lay.n_rows = meta[CB_META_N_ROWS] ? meta[CB_META_N_ROWS] : 1;
+    lay.has_role_policies = meta[CB_META_HAS_ROLE_POLICIES]; lay.has_parent_roles = meta[CB_META_HAS_PARENT_ROLES];
+    lay.has_principal_policies = meta[CB_META_HAS_PRINCIPAL_POLICIES];
     cb::TableView t;
-    t.scope_parent = reinterpret_cast<const uint32_t *>(base + off[CB_SEC_SCOPE_PARENT]);
-    t.scope_flags = reinterpret_cast<const uint32_t *>(base + off[CB_SEC_SCOPE_FLAGS]);
-    t.res_block_map = reinterpret_cast<const uint32_t *>(base + off[CB_SEC_RES_BLOCK_MAP]);
-    t.res_exists = base + off[CB_SEC_RES_EXISTS];
-    t.prin_block_map = reinterpret_cast<const uint32_t *>(base + off[CB_SEC_PRIN_BLOCK_MAP]);
-    t.prin_exists = base + off[CB_SEC_PRIN_EXISTS];
-    t.prin_of_string = reinterpret_cast<const uint32_t *>(base + off[CB_SEC_PRIN_OF_STRING]);
-    t.blocks = reinterpret_cast<const cb_block *>(base + off[CB_SEC_BLOCKS]);
-    t.rows = reinterpret_cast<const cb_row *>(base + off[CB_SEC_ROWS]);
-    t.conds = reinterpret_cast<const cb_cond *>(base + off[CB_SEC_CONDS]);
-    t.code = reinterpret_cast<const cb_instr *>(base + off[CB_SEC_CODE]);
-    t.consts = reinterpret_cast<const cb_const *>(base + off[CB_SEC_CONSTS]);
-    t.theap = reinterpret_cast<const uint64_t *>(base + off[CB_SEC_THEAP]);
-    t.str_off = reinterpret_cast<const uint32_t *>(base + off[CB_SEC_STR_OFF]);
-    t.str_bytes = base + off[CB_SEC_STR_BYTES];
-    t.par_off = reinterpret_cast<const uint32_t *>(base + off[CB_SEC_ROLE_PARENTS_OFF]);
-    t.par_list = reinterpret_cast<const uint32_t *>(base + off[CB_SEC_ROLE_PARENTS]);
-    t.rp_off = reinterpret_cast<const uint32_t *>(base + off[CB_SEC_ROLEPOL_OFF]);
-    t.rp_entries = reinterpret_cast<const cb_rolepol_entry *>(base + off[CB_SEC_ROLEPOL_ENTRIES]);
-    t.rp_rules = reinterpret_cast<const cb_rolepol_rule *>(base + off[CB_SEC_ROLEPOL_RULES]);
-    t.rp_apats = reinterpret_cast<const uint32_t *>(base + off[CB_SEC_ROLEPOL_APATS]);
-    t.nV = meta[CB_META_N_VERSIONS]; t.nRP = meta[CB_META_N_RESPATS]; t.nS = meta[CB_META_N_SCOPES]; t.nP = meta[CB_META_N_PRINCIPALS];
-    t.nR = meta[CB_META_N_ROLES]; t.nAP = meta[CB_META_N_APATS]; t.nT = meta[CB_META_N_STRINGS]; t.n_slots = meta[CB_META_N_SLOTS];
-    t.has_role_policies = meta[CB_META_HAS_ROLE_POLICIES]; t.has_parent_roles = meta[CB_META_HAS_PARENT_ROLES];
-    t.has_principal_policies = meta[CB_META_HAS_PRINCIPAL_POLICIES];
+    t.base = base; t.L = &lay;
 
     cb::BatchView b;
     b.hdr0 = static_cast<const cb_hdr0 *>(cols[0]); b.hdr1 = static_cast<const cb_hdr1 *>(cols[1]);
@@ -50,12 +34,23 @@ extern "C" int hostsim_check(const void *blob, uint64_t blob_len, uint64_t n, ui
     b.bstr_bytes = static_cast<const uint8_t *>(cols[6]); b.class_off = static_cast<const uint32_t *>(cols[7]);
     b.class_pats = static_cast<const uint32_t *>(cols[8]); b.aset_k = static_cast<const uint32_t *>(cols[9]);
     b.aset_spread = static_cast<const uint64_t *>(cols[10]);
+    b.row_am = static_cast<const uint64_t *>(cols[11]);
+    b.n_rows = meta[CB_META_N_ROWS] ? meta[CB_META_N_ROWS] : 1;
     b.stride = n; b.first = 0; b.count = n;
     b.role_cols = (uint32_t)(col_bytes[2] / (4 * n)); b.n_asets = (uint32_t)(col_bytes[9] / 4);
     uint32_t km = max_actions ? max_actions : 1;
     b.kc = 64 / b.role_cols; if (b.kc > km) b.kc = km;
     b.n_pass = (km + b.kc - 1) / b.kc; b.max_actions = km; b.kbytes = (km + 7) / 8; b.flags = flags; b.now = now;
     uint32_t status = 0;
-    for (uint64_t i = 0; i < n; i++) cb::eval_request(t, b, i, bitmap, &status);
+    // mode 0: what the library would pick; 1: force the general 64-bit body; 2: general 32-bit body
+    const bool narrow = b.n_pass == 1 && (uint64_t)km * b.role_cols <= 32;
+    uint32_t rcp = 1; while (rcp < b.role_cols) rcp <<= 1;
+    const bool fast = narrow && !lay.has_principal_policies && !lay.has_role_policies && !lay.has_parent_roles &&
+                      meta[CB_META_DIRECT_KINDS] && (uint64_t)lay.nR * rcp <= 64 && b.kbytes <= 4;
+    for (uint64_t i = 0; i < n; i++) {
+        if (mode == 0 && fast) { if (cb::eval_request_fast(t, b, i, bitmap, nullptr)) cb::eval_request_general(t.base, t.L, &b, i, bitmap, nullptr, &status); }
+        else if (mode == 2 && narrow) cb::eval_request<uint32_t>(t, b, i, bitmap, nullptr, &status);
+        else cb::eval_request<uint64_t>(t, b, i, bitmap, nullptr, &status);
+    }
     return status ? -2 : 0;
 }
