@@ -1155,21 +1155,24 @@ CB_HD int in_inline(const TableView t, const BatchView &b, uint64_t x, uint64_t 
     uint64_t pay = cont & 0xFFFFFFFFFFFFull;
     const uint64_t *p = (pay & CB_V64_HEAP_BATCH_BIT) ? b.heap + (pay & (CB_V64_HEAP_BATCH_BIT - 1)) : t.theap() + pay;
     uint32_t n = (uint32_t)ldg(p);
-    int res = TRI_F;
+    // no early exit: lanes of a warp stay converged (lists are short)
+    bool found = false, slow = false;
     for (uint32_t i = 0; i < n; i++) {
         uint64_t e = ldg(p + 1 + i);
         uint32_t te = v64_tag(e);
-        if (te > CB_V64_STRING) return TRI_SLOW;            // int / container elements
-        if (tx == 0 && te == 0 ? u2d(x) == u2d(e) : x == e) { res = TRI_T; break; }
+        slow |= te > CB_V64_STRING;                        // int / container elements
+        found |= (tx == 0 && te == 0) ? u2d(x) == u2d(e) : x == e;
     }
-    return res;
+    return slow ? TRI_SLOW : (found ? TRI_T : TRI_F);
 }
-// -> bit0 satisfied, bit2: needs the out-of-line general path (no calls are made here)
+// -> bit0 satisfied, bit2: needs the out-of-line general path (no calls are made here).
+// Written without early exits: every lane walks all terms with a predicate, so a warp whose lanes evaluate the
+// same condition shape never diverges here.
 CB_HD uint32_t flat_inline(const TableView t, const BatchView &b, uint64_t n, uint32_t pid, uint32_t flat_off, uint32_t info) {
-    const uint32_t nt = info & 0xFFFF, kind = (info >> 16) & 0xFF;
+    const uint32_t nt = info & 0xFFFF;
+    const bool is_all = ((info >> 16) & 0xFF) == CB_FLAT_ALL;
     const cb_instr *terms = t.code() + flat_off;
-    bool res = kind == CB_FLAT_ALL;
-    uint32_t unsup = 0;
+    bool any_true = false, all_true = true, slow = false;
     for (uint32_t i = 0; i < nt; i++) {
         uint64_t raw = ldg(reinterpret_cast<const uint64_t *>(terms + i));
         uint32_t op = (uint32_t)(raw & 0xFF), ia = (uint32_t)((raw >> 8) & 0xFF), ib = (uint32_t)((raw >> 16) & 0xFFFF);
@@ -1181,18 +1184,18 @@ CB_HD uint32_t flat_inline(const TableView t, const BatchView &b, uint64_t n, ui
         else if (op == CB_OP_CMP_SLOT_PID) y = ((uint64_t)(CB_V64_BOX_BASE | CB_V64_STRING) << 48) | pid;
         else y = ldg(t.consts_v64() + ic);
         int tri;
-        const bool is_in = op == CB_OP_IN_SLOT_CONST || op == CB_OP_IN_CONST_SLOT;
         if (op == CB_OP_HAS_SLOT) { uint32_t ts = v64_tag(x); tri = ts == CB_V64_ERROR ? TRI_E : (ts != CB_V64_ABSENT); }
-        else {
-            if (op == CB_OP_IN_CONST_SLOT) { uint64_t tmp = x; x = y; y = tmp; }
-            tri = is_in ? in_inline(t, b, x, y) : cmp_inline(ia & 0x7F, x, y);
-            if (tri == TRI_SLOW) return 4u;   // not decidable on the 8-byte fast forms: the caller defers the request
-        }
-        if ((ia & CB_FLAT_TERM_NEG) && tri != TRI_E) tri ^= 1;
-        if (kind == CB_FLAT_ALL) { if (tri != TRI_T) { res = false; break; } }
-        else if (tri == TRI_T) { res = true; break; }
+        else if (op == CB_OP_IN_SLOT_CONST) tri = in_inline(t, b, x, y);
+        else if (op == CB_OP_IN_CONST_SLOT) tri = in_inline(t, b, y, x);
+        else tri = cmp_inline(ia & 0x7F, x, y);
+        slow |= tri == TRI_SLOW;
+        if ((ia & CB_FLAT_TERM_NEG) && tri < TRI_E) tri ^= 1;
+        any_true |= tri == TRI_T;
+        all_true &= tri == TRI_T;
     }
-    return (uint32_t)(res != (bool)((info >> 24) & 1)) | unsup;
+    if (slow) return 4u;   // not decidable on the 8-byte fast forms: the caller defers the request
+    bool res = is_all ? all_true : any_true;
+    return (uint32_t)(res != (bool)((info >> 24) & 1));
 }
 // condition `gid` on the call-free fast path: bit0 satisfied, bit2 = cannot decide here (non-flat condition or an
 // unusual operand): the request is then re-evaluated by the general body
@@ -1604,53 +1607,51 @@ CB_HD bool eval_request_fast(const TableView t, const BatchView &b, uint64_t n, 
         uint32_t alive = amask * role_all, allow_pairs = 0;
         for (uint32_t s = r0; s != CB_NONE32 && alive; s = chain_next(t, s, CB_SCOPE_FLAG_RESOURCE)) {
             const uint32_t bid = ldg(t.res_block_map() + ((uint64_t)rv * t.L->nRP + kc) * t.L->nS + s);
-            if (bid == CB_NONE32) continue;
+            if (bid != CB_NONE32) {
             prefetch_block_slots(t, b, bid, n);
             const U4 bl = ld16(t.blocks() + bid);   // {row_start, n_rows, cond_base, n_conds}
             const uint32_t re = bl.x + bl.y;
+            // Three phases per block, each loop body straight-line (selects, no `continue`): lanes that took an
+            // early exit would otherwise stay diverged for the rest of the loop (no reconvergence at a back-edge).
             uint64_t need = 0;
+            bool defer = false;
             for (uint32_t ri = bl.x; ri < re; ri++) {
-                uint32_t am = ldg(reinterpret_cast<const uint32_t *>(row_am + ri));
-                if (!am) continue;
-                U4 row = ld16(t.rows() + ri);
-                uint32_t role = row_role(row);
-                uint32_t rc = role == CB_ROLE_ANY ? role_all : (uint32_t)(rp >> (role * RCP)) & role_all;
-                if (!((am * rc) & alive)) continue;
-                uint32_t c1 = row_cond(row), c2 = row_drcond(row);
-                if (c1 > 64 || c2 > 64) return true;
-                if (c1) need |= 1ull << (c1 - 1);
-                if (c2) need |= 1ull << (c2 - 1);
+                const uint32_t am = ldg(reinterpret_cast<const uint32_t *>(row_am + ri));
+                const U4 row = ld16(t.rows() + ri);
+                const uint32_t role = row_role(row);
+                const uint32_t rc = role == CB_ROLE_ANY ? role_all : (uint32_t)(rp >> (role * RCP)) & role_all;
+                const bool hit = ((am * rc) & alive) != 0;
+                const uint32_t c1 = hit ? row_cond(row) : 0, c2 = hit ? row_drcond(row) : 0;
+                defer |= c1 > 64 || c2 > 64;
+                need |= (c1 ? 1ull << ((c1 - 1) & 63) : 0ull) | (c2 ? 1ull << ((c2 - 1) & 63) : 0ull);
             }
+            if (defer) return true;
             uint64_t val = 0;
-            for (uint64_t w = need; w;) {
-#if defined(__CUDA_ARCH__)
-                int li = __ffsll((long long)w) - 1;
-#else
-                int li = __builtin_ctzll(w);
-#endif
-                w &= w - 1;
-                uint32_t r = cond_eval(t, b, n, pid, bl.z + (uint32_t)li);
-                if (r & 4) return true;
-                val |= (uint64_t)(r & 1) << li;
+            bool slow = false;
+            for (uint32_t li = 0; li < bl.w; li++) {          // uniform order over the block's conditions
+                if ((need >> li) & 1) {
+                    uint32_t r = cond_eval(t, b, n, pid, bl.z + li);
+                    slow |= (r & 4) != 0;
+                    val |= (uint64_t)(r & 1) << li;
+                }
             }
+            if (slow) return true;
             uint32_t D = 0, A = 0;
             for (uint32_t ri = bl.x; ri < re; ri++) {
-                uint32_t am = ldg(reinterpret_cast<const uint32_t *>(row_am + ri));
-                if (!am) continue;
-                U4 row = ld16(t.rows() + ri);
-                uint32_t role = row_role(row);
-                uint32_t rc = role == CB_ROLE_ANY ? role_all : (uint32_t)(rp >> (role * RCP)) & role_all;
-                uint32_t m = (am * rc) & alive;
-                if (!m) continue;
-                uint32_t c1 = row_cond(row), c2 = row_drcond(row);
-                bool sat = true;
-                if (c2) sat = (val >> (c2 - 1)) & 1;
-                if (sat && c1) sat = (val >> (c1 - 1)) & 1;
-                if (!sat) continue;
-                if (row_effect(row) == CB_EFFECT_DENY) D |= m; else A |= m;
+                const uint32_t am = ldg(reinterpret_cast<const uint32_t *>(row_am + ri));
+                const U4 row = ld16(t.rows() + ri);
+                const uint32_t role = row_role(row);
+                const uint32_t rc = role == CB_ROLE_ANY ? role_all : (uint32_t)(rp >> (role * RCP)) & role_all;
+                const uint32_t c1 = row_cond(row), c2 = row_drcond(row);
+                const bool sat = (c1 == 0 || ((val >> ((c1 - 1) & 63)) & 1)) && (c2 == 0 || ((val >> ((c2 - 1) & 63)) & 1));
+                const uint32_t m = sat ? (am * rc) & alive : 0u;
+                const bool deny = row_effect(row) == CB_EFFECT_DENY;
+                D |= deny ? m : 0u;
+                A |= deny ? 0u : m;
             }
             alive &= ~D;
             if (((ldg(t.scope_flags() + s) >> CB_SCOPE_PERM_SHIFT) & 3) == 1) { uint32_t a = A & alive; allow_pairs |= a; alive &= ~a; }
+            }   // block present at this scope
         }
         uint32_t any_role = allow_pairs;
         for (uint32_t j = 1; j < RC; j++) any_role |= allow_pairs >> j;
