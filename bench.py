@@ -218,14 +218,8 @@ def main():
     if rank == 0:
         _, ft, enc = W.build(w)
         blob = ft.blob
-    if world > 1:
-        ln = torch.tensor([len(blob) if rank == 0 else 0], dtype=torch.int64, device=dev)
-        dist.broadcast(ln, 0)
-        t = torch.empty(int(ln.item()), dtype=torch.uint8, device=dev)
-        if rank == 0:
-            t.copy_(torch.frombuffer(bytearray(blob), dtype=torch.uint8))
-        dist.broadcast(t, 0)
-        blob = bytes(t.cpu().numpy().tobytes())
+    from cerbos_b200.dist import all_gather_bitmaps, broadcast_blob
+    blob = broadcast_blob(blob if rank == 0 else None, dev)
     from cerbos_b200.encode import Encoder, manifest_from_blob
     if rank != 0:
         enc = Encoder(manifest_from_blob(blob))
@@ -258,7 +252,7 @@ def main():
     def step(i):
         calls[i % n_buf](stream_h)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, views[i % n_buf])
+            all_gather_bitmaps(views[i % n_buf], gathered)
 
     for i in range(args.warmup):
         step(i)

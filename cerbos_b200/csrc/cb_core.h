@@ -88,12 +88,21 @@ struct BatchView {
     uint64_t stride;            // requests per column (N of the whole batch)
     uint64_t first, count;      // sub-range evaluated by this launch
     uint32_t role_cols, n_asets, kc, n_pass, max_actions, kbytes, flags;
+    uint32_t rcp, stride_pattern;   // set by finish_batch_view(): pow2 >= role_cols; bit j*role_cols for every j (32-bit)
     int64_t now;
 };
 
 // Table data may live in shared memory (TMA-staged image) or in global memory, heap references may point
 // into either the table or the batch: those loads are plain (generic) loads.  Only the big streaming request
 // columns -- read exactly once -- use the read-only, no-L1-allocate path so they do not evict the table.
+// derived BatchView fields (host side, once per launch)
+inline void finish_batch_view(BatchView &b) {
+    b.rcp = 1;
+    while (b.rcp < b.role_cols) b.rcp <<= 1;
+    b.stride_pattern = 0;
+    for (uint32_t j = 0; j * b.role_cols < 32; j++) b.stride_pattern |= 1u << (j * b.role_cols);
+}
+
 template <typename T>
 CB_HD T ldg(const T *p) { return *p; }
 
@@ -1574,89 +1583,84 @@ CB_HD void eval_request(const TableView t, const BatchView &b, uint64_t n, uint8
 // is a handful of 32-bit scalars (host code picks this body when table and batch qualify; tests compare both).
 // Returns true if the request must be re-evaluated by the general body (nothing has been written then): a
 // condition without a flat form, an operand the 8-byte fast forms cannot decide, differing policy versions, or
-// a block with more than 64 conditions.  The body itself makes NO calls, so nothing is forced into local memory.
+// a block with more than 32 conditions.  The body itself makes NO calls, so nothing is forced into local memory,
+// and its loops contain no early exits (`continue` / `break` would leave lanes diverged until the loop ends).
 CB_HD bool eval_request_fast(const TableView t, const BatchView &b, uint64_t n, uint8_t *bitmap, uint8_t *effects) {
     const U4 h0 = ldcol128(b.hdr0 + n);                                           // principal_id, kind (pattern id), resource_scope, principal_scope
     const uint64_t h1 = ldcol64(reinterpret_cast<const uint64_t *>(b.hdr1 + n));  // rv u16 | pv u16 | action_set_id u32
     const uint32_t pid = h0.x, kc = h0.y, rscope = h0.z;
     const uint32_t rv = (uint32_t)(h1 & 0xFFFF), pv = (uint32_t)((h1 >> 16) & 0xFFFF), aset = (uint32_t)(h1 >> 32);
-    const uint32_t RC = b.role_cols;
+    const uint32_t RC = b.role_cols, RCP = b.rcp;
     const uint32_t K = aset < b.n_asets ? ldg(b.aset_k + aset) : 0;
-    uint32_t RCP = 1;
-    while (RCP < RC) RCP <<= 1;
     uint64_t rp = 0;          // role table: RCP bits per table role
     uint32_t n_roles = 0;
     for (uint32_t i = 0; i < RC; i++) {
         uint32_t rr = ldcol32(b.roles + (uint64_t)i * b.stride + n);
-        if (rr != CB_ROLE_PAD) n_roles = i + 1;
-        if (rr < t.L->nR) rp |= 1ull << (rr * RCP + i);
+        n_roles = rr != CB_ROLE_PAD ? i + 1 : n_roles;
+        rp |= rr < t.L->nR ? 1ull << (rr * RCP + i) : 0ull;
     }
+    if (pv != rv) return true;   // existence checks matter only then (ruletable.go:852-863): general body
     uint32_t acc = 0;
-    bool live = n_roles != 0 && K != 0 && rv != CB_NONE16 && kc != CB_KIND_NONE;
-    uint32_t r0 = CB_NONE32;
-    if (live) {
-        const bool lenient = (b.flags & CB_BATCH_FLAG_LENIENT) != 0;
-        r0 = chain_start(t, rscope, CB_SCOPE_FLAG_RESOURCE, lenient);
-        if (pv != rv) return true;   // existence checks matter only then (ruletable.go:852-863): general body
-    }
-    if (live && r0 != CB_NONE32) {
+    const bool live = n_roles != 0 && K != 0 && rv != CB_NONE16 && kc != CB_KIND_NONE;
+    const uint32_t r0 = live ? chain_start(t, rscope, CB_SCOPE_FLAG_RESOURCE, (b.flags & CB_BATCH_FLAG_LENIENT) != 0) : CB_NONE32;
+    if (r0 != CB_NONE32) {
         const uint32_t role_all = (1u << n_roles) - 1;
         const uint64_t *row_am = b.row_am + (uint64_t)aset * b.n_rows;
-        uint32_t amask = 0;
-        for (uint32_t kk = 0; kk < K; kk++) amask |= 1u << (kk * RC);
+        const uint64_t *slots_n = b.slots + n;
+        const uint32_t amask = K * RC >= 32 ? b.stride_pattern : b.stride_pattern & ((1u << (K * RC)) - 1);   // bit kk*RC per action
         uint32_t alive = amask * role_all, allow_pairs = 0;
+        bool defer = false;
         for (uint32_t s = r0; s != CB_NONE32 && alive; s = chain_next(t, s, CB_SCOPE_FLAG_RESOURCE)) {
             const uint32_t bid = ldg(t.res_block_map() + ((uint64_t)rv * t.L->nRP + kc) * t.L->nS + s);
             if (bid != CB_NONE32) {
-            prefetch_block_slots(t, b, bid, n);
-            const U4 bl = ld16(t.blocks() + bid);   // {row_start, n_rows, cond_base, n_conds}
-            const uint32_t re = bl.x + bl.y;
-            // Three phases per block, each loop body straight-line (selects, no `continue`): lanes that took an
-            // early exit would otherwise stay diverged for the rest of the loop (no reconvergence at a back-edge).
-            uint64_t need = 0;
-            bool defer = false;
-            for (uint32_t ri = bl.x; ri < re; ri++) {
-                const uint32_t am = ldg(reinterpret_cast<const uint32_t *>(row_am + ri));
-                const U4 row = ld16(t.rows() + ri);
-                const uint32_t role = row_role(row);
-                const uint32_t rc = role == CB_ROLE_ANY ? role_all : (uint32_t)(rp >> (role * RCP)) & role_all;
-                const bool hit = ((am * rc) & alive) != 0;
-                const uint32_t c1 = hit ? row_cond(row) : 0, c2 = hit ? row_drcond(row) : 0;
-                defer |= c1 > 64 || c2 > 64;
-                need |= (c1 ? 1ull << ((c1 - 1) & 63) : 0ull) | (c2 ? 1ull << ((c2 - 1) & 63) : 0ull);
-            }
-            if (defer) return true;
-            uint64_t val = 0;
-            bool slow = false;
-            for (uint32_t li = 0; li < bl.w; li++) {          // uniform order over the block's conditions
-                if ((need >> li) & 1) {
-                    uint32_t r = cond_eval(t, b, n, pid, bl.z + li);
-                    slow |= (r & 4) != 0;
-                    val |= (uint64_t)(r & 1) << li;
+                // pull the attribute slots this block's conditions read towards L1 so the lazy loads overlap
+                for (uint32_t q = ldg(t.block_slots_off() + bid), e = ldg(t.block_slots_off() + bid + 1); q < e; q++)
+                    prefetch_l1(slots_n + (uint64_t)ldg(t.block_slots() + q) * b.stride);
+                const U4 bl = ld16(t.blocks() + bid);   // {row_start, n_rows, cond_base, n_conds}
+                defer |= bl.w > 32;
+                uint32_t known = 0, val = 0, D = 0, A = 0;   // per-block condition memo + DENY / ALLOW pair masks
+                for (uint32_t ri = bl.x, re = bl.x + bl.y; ri < re; ri++) {
+                    const uint32_t am = ldg(reinterpret_cast<const uint32_t *>(row_am + ri));
+                    const U4 row = ld16(t.rows() + ri);
+                    const uint32_t role = row_role(row);
+                    const uint32_t rc = role == CB_ROLE_ANY ? role_all : (uint32_t)(rp >> (role * RCP)) & role_all;
+                    const uint32_t m = (am * rc) & alive;
+                    // the (at most two) conditions of the row: derived-role condition first, then the rule's own
+                    uint32_t cpair = row.x >> 16 | row.y << 16;   // cond | drcond << 16
+                    bool sat = true;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+                    for (uint32_t h = 0; h < 2; h++) {
+                        const uint32_t ci = (h == 0 ? cpair >> 16 : cpair) & 0xFFFF;   // h = 0: drcond
+                        if (m && sat && ci) {
+                            const uint32_t bit = 1u << ((ci - 1) & 31);
+                            if (!(known & bit)) {
+                                uint32_t r = cond_eval(t, b, n, pid, bl.z + ci - 1);
+                                defer |= (r & 4) != 0;
+                                known |= bit;
+                                val |= (r & 1) ? bit : 0u;
+                            }
+                            sat = (val & bit) != 0;
+                        }
+                    }
+                    const uint32_t ms = sat ? m : 0u;
+                    const bool deny = row_effect(row) == CB_EFFECT_DENY;
+                    D |= deny ? ms : 0u;
+                    A |= deny ? 0u : ms;
                 }
+                alive &= ~D;
+                if (((ldg(t.scope_flags() + s) >> CB_SCOPE_PERM_SHIFT) & 3) == 1) { uint32_t a = A & alive; allow_pairs |= a; alive &= ~a; }
             }
-            if (slow) return true;
-            uint32_t D = 0, A = 0;
-            for (uint32_t ri = bl.x; ri < re; ri++) {
-                const uint32_t am = ldg(reinterpret_cast<const uint32_t *>(row_am + ri));
-                const U4 row = ld16(t.rows() + ri);
-                const uint32_t role = row_role(row);
-                const uint32_t rc = role == CB_ROLE_ANY ? role_all : (uint32_t)(rp >> (role * RCP)) & role_all;
-                const uint32_t c1 = row_cond(row), c2 = row_drcond(row);
-                const bool sat = (c1 == 0 || ((val >> ((c1 - 1) & 63)) & 1)) && (c2 == 0 || ((val >> ((c2 - 1) & 63)) & 1));
-                const uint32_t m = sat ? (am * rc) & alive : 0u;
-                const bool deny = row_effect(row) == CB_EFFECT_DENY;
-                D |= deny ? m : 0u;
-                A |= deny ? 0u : m;
-            }
-            alive &= ~D;
-            if (((ldg(t.scope_flags() + s) >> CB_SCOPE_PERM_SHIFT) & 3) == 1) { uint32_t a = A & alive; allow_pairs |= a; alive &= ~a; }
-            }   // block present at this scope
         }
-        uint32_t any_role = allow_pairs;
-        for (uint32_t j = 1; j < RC; j++) any_role |= allow_pairs >> j;
-        any_role &= amask;
-        for (uint32_t kk = 0; kk < K; kk++) acc |= ((any_role >> (kk * RC)) & 1) << kk;
+        if (defer) return true;
+        // fold: an action is ALLOWed iff some role column allowed it; then pack the stride-RC bits
+        uint32_t x = allow_pairs;
+        for (uint32_t j = 1; j < RC; j++) x |= allow_pairs >> j;
+        x &= amask;
+        if (RC == 1) acc = x;
+        else if (RC == 2) { x = (x | x >> 1) & 0x33333333u; x = (x | x >> 2) & 0x0F0F0F0Fu; x = (x | x >> 4) & 0x00FF00FFu; acc = (x | x >> 8) & 0xFFFFu; }
+        else for (uint32_t kk = 0; kk < K; kk++) acc |= ((x >> (kk * RC)) & 1) << kk;
     }
     if (effects) {
         uint8_t *eff = effects + n * (uint64_t)b.max_actions;

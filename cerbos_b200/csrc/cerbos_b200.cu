@@ -42,7 +42,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 // Persistent CheckResources kernel. stage != 0: TMA-stage the table image into dynamic shared memory.
 // kFast: the lean resource-policy-only body (cb::eval_request_fast), else the general body with 64-bit pair masks.
 template <bool kFast>
-__global__ void __launch_bounds__(kThreads, 3) check_kernel(const __grid_constant__ TableDesc td, const __grid_constant__ cb::BatchView bv, uint8_t *bitmap,
+__global__ void __launch_bounds__(kThreads, 4) check_kernel(const __grid_constant__ TableDesc td, const __grid_constant__ cb::BatchView bv, uint8_t *bitmap,
                                                           uint8_t *effects, uint32_t *status, const uint32_t kStage) {
     extern __shared__ __align__(128) uint8_t smem_image[];
     __shared__ __align__(8) uint64_t mbar;
@@ -241,6 +241,7 @@ int make_batch_view(const cgpu_table *t, const cgpu_batch *b, uint64_t first, ui
     v->stride = N; v->first = first; v->count = count;
     v->role_cols = role_cols; v->n_asets = n_asets; v->kc = kc; v->n_pass = n_pass; v->max_actions = km;
     v->kbytes = (km + 7) / 8; v->flags = b->flags; v->now = b->now_unix_nanos;
+    cb::finish_batch_view(*v);
     return CGPU_OK;
 }
 

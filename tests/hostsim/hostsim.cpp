@@ -41,6 +41,7 @@ extern "C" int hostsim_check(const void *blob, uint64_t blob_len, uint64_t n, ui
     uint32_t km = max_actions ? max_actions : 1;
     b.kc = 64 / b.role_cols; if (b.kc > km) b.kc = km;
     b.n_pass = (km + b.kc - 1) / b.kc; b.max_actions = km; b.kbytes = (km + 7) / 8; b.flags = flags; b.now = now;
+    cb::finish_batch_view(b);
     uint32_t status = 0;
     // mode 0: what the library would pick; 1: force the general 64-bit body; 2: general 32-bit body
     const bool narrow = b.n_pass == 1 && (uint64_t)km * b.role_cols <= 32;
