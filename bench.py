@@ -237,7 +237,6 @@ def main():
         batches.append(DeviceBatch(hb, dev))
     footprint = sum(b.nbytes() for b in batches)
     kbytes = batches[0].kbytes
-    gathered = torch.empty(world * n * kbytes, dtype=torch.uint8, device=dev) if world > 1 else None
 
     calls = [b.prepare(table, NOW_NS) for b in batches]
     views = [b.bitmap[: n * kbytes] for b in batches]
@@ -249,13 +248,25 @@ def main():
     stream_h = stream.cuda_stream
     assert stream_h != 0 and torch.cuda.current_stream().cuda_stream == stream_h
 
+    # one gather buffer per rotating batch: the all-gather of batch i (NCCL stream) overlaps the kernel of batch i+1
+    gathered = [torch.empty(world * n * kbytes, dtype=torch.uint8, device=dev) for _ in range(n_buf)] if world > 1 else None
+    pending = []
+
     def step(i):
         calls[i % n_buf](stream_h)
         if world > 1:
-            all_gather_bitmaps(views[i % n_buf], gathered)
+            if len(pending) >= n_buf - 1:          # buffers are reused after n_buf steps: retire the oldest gather
+                pending.pop(0).wait()
+            _, work = all_gather_bitmaps(views[i % n_buf], gathered[i % n_buf], async_op=True)
+            pending.append(work)
+
+    def drain():
+        while pending:
+            pending.pop(0).wait()
 
     for i in range(args.warmup):
         step(i)
+    drain()
     ctx.sync(stream_h)
     torch.cuda.synchronize()
     if world > 1:
@@ -267,6 +278,8 @@ def main():
         ev[0].record()
         for i in range(args.steps):
             step(i)
+            if i == args.steps - 1:
+                drain()                      # the last gathers are part of the timed work
             ev[i + 1].record()
         torch.cuda.synchronize()
     if world > 1:

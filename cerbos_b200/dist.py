@@ -30,13 +30,14 @@ def broadcast_blob(blob: bytes | None, device) -> bytes:
     return t.cpu().numpy().tobytes()
 
 
-def all_gather_bitmaps(local: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+def all_gather_bitmaps(local: torch.Tensor, out: torch.Tensor | None = None, async_op: bool = False):
     """local: uint8[n_local * kbytes] on this rank (equal sizes on all ranks). Returns uint8[world * n_local * kbytes],
-    rank-major = request-index order for contiguous shards."""
+    rank-major = request-index order for contiguous shards.  With async_op=True returns (out, work): the collective
+    runs on NCCL's own stream and overlaps the next batch's kernel; call work.wait() before reading `out`."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
-        return local
+        return (local, None) if async_op else local
     world = dist.get_world_size()
     if out is None:
         out = torch.empty(world * local.numel(), dtype=torch.uint8, device=local.device)
-    dist.all_gather_into_tensor(out, local)
-    return out
+    work = dist.all_gather_into_tensor(out, local, async_op=async_op)
+    return (out, work) if async_op else out

@@ -270,7 +270,225 @@ class C2:
         return 24 + 4 * 2 + 8 * 5 + 0 + 1   # = 73
 
 
-WORKLOADS = {"C1": C1, "C2": C2}
+# =========================================================================================== C3
+def _ragged_lists(lengths: np.ndarray, elem_fn):
+    """Builds heap words for one variable-length list per request: [len, e0, e1, ...].
+    elem_fn(req_index_array, pos_array) -> uint64 element words. Returns (words, offsets)."""
+    n = len(lengths)
+    sizes = lengths + 1
+    offs = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(sizes, out=offs[1:])
+    words = np.zeros(offs[-1], dtype=np.uint64)
+    words[offs[:-1]] = lengths.astype(np.uint64)
+    req = np.repeat(np.arange(n), lengths)
+    pos = np.arange(lengths.sum()) - np.repeat(offs[:-1] - np.arange(n), lengths)
+    words[np.repeat(offs[:-1] + 1, lengths) + pos] = elem_fn(req, pos)
+    return words, offs[:-1]
+
+
+class C3:
+    """100 resource policies = 20 kinds x 5 scopes (3-level chain), 20 CEL conditions incl. string / list ops on
+    principal.attr, REQUIRE_PARENTAL_CONSENT leaves; batch 2^24 (BASELINE.json configs[2])."""
+    name = "C3"
+    cfg = 3
+    actions = [f"a{i}" for i in range(8)]
+    role_names = ["user", "manager", "admin", "auditor"]
+    scopes = ["", "t0", "t1", "t0.d0", "t1.d0"]
+    req_scopes = ["", "t0", "t1", "t0.d0", "t1.d0", "t0.d9"]
+    tiers = ["gold", "silver", "bronze", "banned"]
+    regions = ["eu", "us", "apac", "latam"]
+    default_n = 1 << 24
+    n_kinds = 20
+    n_principals = 65536
+    role_cols = 3
+    conditions = [
+        'P.attr.email.endsWith("@corp.example")',
+        'P.attr.name.startsWith(R.attr.prefix)',
+        '"eng" in P.attr.groups',
+        'hasIntersection(P.attr.groups, R.attr.allowed_groups)',
+        'P.attr.groups.exists(g, g == R.attr.team)',
+        'size(P.attr.groups) > 2',
+        'P.attr.level >= R.attr.min_level',
+        'P.attr.region in ["eu", "us"]',
+        'P.attr.level > 5 ? R.attr.tier == "gold" : R.attr.public == true',
+        'R.attr.owner == P.id',
+        'R.attr.team in P.attr.groups',
+        'P.attr.name.contains("an")',
+        'R.attr.public == true || P.attr.level >= 8',
+        '!(P.attr.region == "apac")',
+        'P.attr.groups.all(g, g != "g13")',
+        'R.attr.tier in ["gold", "silver"] && P.attr.level > 2',
+        'size(R.attr.allowed_groups) >= 1 && P.attr.groups[0] in R.attr.allowed_groups',
+        'has(R.attr.prefix) && R.attr.prefix != ""',
+        'P.attr.email.contains("@") && R.attr.min_level <= 9',
+        'isSubset(R.attr.allowed_groups, P.attr.groups)',
+    ]
+    groups = ["eng"] + [f"g{i}" for i in range(1, 32)]
+    words = ["".join(chr(97 + (i * 7 + j * 3) % 26) for j in range(3 + i % 6)) + ("an" if i % 5 == 0 else "") for i in range(256)]
+
+    def policies(self):
+        docs = []
+        for k in range(self.n_kinds):
+            for si, sc in enumerate(self.scopes):
+                rules = []
+                for j in range(8):
+                    cond = self.conditions[(k * 8 + j + si * 3) % 20]
+                    role = self.role_names[(j + k + si) % 3]
+                    rule = {"actions": [f"a{j}"], "effect": "EFFECT_ALLOW", "roles": [role, "admin"] if j % 4 == 3 else [role]}
+                    if (j + si) % 4 != 0:       # every fourth rule is unconditional
+                        rule["condition"] = {"match": {"expr": cond}}
+                    rules.append(rule)
+                rules.append({"actions": ["*"], "effect": "EFFECT_DENY", "roles": ["*"],
+                              "condition": {"match": {"expr": 'R.attr.tier == "banned"'}}})
+                rp = {"resource": f"kind_{k}", "version": "default", "rules": rules}
+                if sc:
+                    rp["scope"] = sc
+                if sc.endswith(".d0"):
+                    rp["scopePermissions"] = "SCOPE_PERMISSIONS_REQUIRE_PARENTAL_CONSENT_FOR_ALLOWS"
+                docs.append({"apiVersion": "api.cerbos.dev/v1", "resourcePolicy": rp})
+        return docs
+
+    def fields(self, n=None, start=0):
+        global _START
+        n = n or self.default_n
+        seed = SEED_BASE + self.cfg
+        _START = start
+        try:
+            pid = _uniform(seed, n, 1, self.n_principals)
+            r0 = _uniform(seed, n, 2, 4)
+            nr = 1 + _uniform(seed, n, 3, 3)
+            sc = _uniform(seed, n, 4, 5)
+            f = {
+                "n": n, "kind": _uniform(seed, n, 0, self.n_kinds), "pid": pid,
+                "r0": r0, "r1": np.where(nr >= 2, (r0 + 1) % 4, -1), "r2": np.where(nr >= 3, (r0 + 2) % 4, -1),
+                "scope": np.where(_prob(seed, n, 5, 0.05), 5, sc),
+                "email_w": _uniform(seed, n, 6, 256), "email_corp": _prob(seed, n, 7, 0.5),
+                "name_w": _uniform(seed, n, 8, 256), "prefix_w": _uniform(seed, n, 9, 256),
+                "prefix_same": _prob(seed, n, 10, 0.3), "prefix_len": 1 + _uniform(seed, n, 11, 3),
+                "level": _uniform(seed, n, 12, 10), "min_level": _uniform(seed, n, 13, 10),
+                "region": _uniform(seed, n, 14, 4), "tier": _uniform(seed, n, 15, 4),
+                "public": _prob(seed, n, 16, 0.3), "team": _uniform(seed, n, 17, 32),
+                "owner": np.where(_prob(seed, n, 18, 0.25), pid, _uniform(seed, n, 19, self.n_principals)),
+                "n_groups": 1 + _uniform(seed, n, 20, 6), "g_seed": splitmix(seed, n, 21),
+                "n_allowed": 1 + _uniform(seed, n, 22, 4), "a_seed": splitmix(seed, n, 23),
+            }
+            return f
+        finally:
+            _START = 0
+
+    @staticmethod
+    def _members(seedv, count, pos):
+        """pos-th element of a `count`-element subset of 0..31 drawn from seed: distinct by construction
+        (start + pos * odd step mod 32)."""
+        start = (seedv & np.uint64(31)).astype(np.int64)
+        step = (((seedv >> np.uint64(5)) & np.uint64(15)).astype(np.int64) * 2 + 1)
+        return (start + pos * step) % 32
+
+    def _prefix(self, f, i):
+        w = self.words[f["name_w"][i]] if f["prefix_same"][i] else self.words[f["prefix_w"][i]]
+        return w[: f["prefix_len"][i]]
+
+    def inputs(self, f, idx):
+        out = []
+        for i in idx:
+            roles = [self.role_names[f[k][i]] for k in ("r0", "r1", "r2") if f[k][i] >= 0]
+            ng, na = int(f["n_groups"][i]), int(f["n_allowed"][i])
+            gs = [self.groups[self._members(f["g_seed"][i:i + 1], ng, np.array([p]))[0]] for p in range(ng)]
+            al = [self.groups[self._members(f["a_seed"][i:i + 1], na, np.array([p]))[0]] for p in range(na)]
+            dom = "@corp.example" if f["email_corp"][i] else "@other.example"
+            res = {"kind": f"kind_{f['kind'][i]}", "id": f"r{i}", "attr": {
+                "prefix": self._prefix(f, i), "allowed_groups": al, "team": self.groups[f["team"][i]],
+                "min_level": int(f["min_level"][i]), "tier": self.tiers[f["tier"][i]], "public": bool(f["public"][i]),
+                "owner": f"p{f['owner'][i]}"}}
+            sc = self.req_scopes[f["scope"][i]]
+            if sc:
+                res["scope"] = sc
+            out.append({"requestId": str(i), "actions": list(self.actions),
+                        "principal": {"id": f"p{f['pid'][i]}", "roles": roles, "attr": {
+                            "email": self.words[f["email_w"][i]] + dom, "name": self.words[f["name_w"][i]],
+                            "groups": gs, "level": int(f["level"][i]), "region": self.regions[f["region"][i]]}},
+                        "resource": res})
+        return out
+
+    def columns(self, f, enc: Encoder) -> Batch:
+        n = f["n"]
+        nts = enc.n_table_strings
+        extra: list = []
+
+        def ids_for(strings):
+            nonlocal extra
+            ids, e = _str_ids(enc, strings)
+            # _str_ids numbers new strings from nts; shift by what is already in `extra`, dedupe against it
+            out = []
+            pos = {b: j for j, b in enumerate(extra)}
+            for s_, i_ in zip(strings, ids):
+                if i_ < nts:
+                    out.append(int(i_))
+                else:
+                    bkey = s_.encode("utf-8")
+                    j = pos.get(bkey)
+                    if j is None:
+                        j = len(extra)
+                        pos[bkey] = j
+                        extra.append(bkey)
+                    out.append(nts + j)
+            return np.array(out, dtype=np.uint64)
+
+        pid_ids = ids_for([f"p{i}" for i in range(self.n_principals)])
+        email_ids = ids_for([w + d for d in ("@other.example", "@corp.example") for w in self.words]).reshape(2, 256)
+        name_ids = ids_for(self.words)
+        prefixes = sorted({w[:L_] for w in self.words for L_ in (1, 2, 3)})
+        pre_ix = {p_: j for j, p_ in enumerate(prefixes)}
+        pre_ids = ids_for(prefixes)
+        group_ids = ids_for(self.groups)
+        tier_ids, region_ids = ids_for(self.tiers), ids_for(self.regions)
+        # prefix string per request
+        wsel = np.where(f["prefix_same"], f["name_w"], f["prefix_w"])
+        pre_tab = np.array([[pre_ix[self.words[w][:L_]] for L_ in (1, 2, 3)] for w in range(256)], dtype=np.int64)
+        pre_req = pre_ids[pre_tab[wsel, f["prefix_len"] - 1]]
+
+        kvals, class_list = _kind_classes(enc, [f"kind_{k}" for k in range(self.n_kinds)])
+        hdr0 = np.zeros((n, 4), dtype=np.uint32)
+        hdr0[:, 0] = pid_ids[f["pid"]]
+        hdr0[:, 1] = kvals[f["kind"]]
+        sc_ids = np.array([enc.resolve_scope(s_) for s_ in self.req_scopes], dtype=np.uint32)
+        hdr0[:, 2] = sc_ids[f["scope"]]
+        hdr0[:, 3] = enc.resolve_scope("")
+        hdr1 = np.zeros(n, dtype=np.dtype([("rv", "<u2"), ("pv", "<u2"), ("aset", "<u4")]))
+        hdr1["rv"] = enc.version_ids.get("default", L.NONE16)
+        hdr1["pv"] = hdr1["rv"]
+        rmap = np.array([enc.role_ids.get(r, L.ROLE_UNKNOWN) for r in self.role_names] + [L.ROLE_PAD], dtype=np.uint32)
+        roles = np.stack([rmap[f["r0"]], rmap[f["r1"]], rmap[f["r2"]]]).astype(np.uint32)
+
+        box_s = lambda ids: _box(L.V64_STRING, ids)   # noqa: E731
+        g_words, g_off = _ragged_lists(f["n_groups"], lambda req, pos: box_s(group_ids[self._members(f["g_seed"][req], None, pos)]))
+        a_words, a_off = _ragged_lists(f["n_allowed"], lambda req, pos: box_s(group_ids[self._members(f["a_seed"][req], None, pos)]))
+        heap = np.concatenate([g_words, a_words])
+        batch_bit = np.uint64(L.V64_HEAP_BATCH_BIT)
+        vals = {
+            ("principal", "attr", "email"): box_s(email_ids[f["email_corp"].astype(np.int64), f["email_w"]]),
+            ("principal", "attr", "name"): box_s(name_ids[f["name_w"]]),
+            ("principal", "attr", "groups"): _box(L.V64_LIST, g_off.astype(np.uint64) | batch_bit),
+            ("principal", "attr", "level"): f["level"].astype(np.float64).view(np.uint64),
+            ("principal", "attr", "region"): box_s(region_ids[f["region"]]),
+            ("resource", "attr", "prefix"): box_s(pre_req),
+            ("resource", "attr", "allowed_groups"): _box(L.V64_LIST, (a_off + len(g_words)).astype(np.uint64) | batch_bit),
+            ("resource", "attr", "team"): box_s(group_ids[f["team"]]),
+            ("resource", "attr", "min_level"): f["min_level"].astype(np.float64).view(np.uint64),
+            ("resource", "attr", "tier"): box_s(tier_ids[f["tier"]]),
+            ("resource", "attr", "public"): _box(L.V64_BOOL, f["public"].astype(np.uint64)),
+            ("resource", "attr", "owner"): box_s(pid_ids[f["owner"]]),
+        }
+        slots = np.zeros((max(len(enc.slots), 1), n), dtype=np.uint64)
+        for s_, path in enumerate(enc.slots):
+            slots[s_] = vals[path]
+        return _finish_batch(enc, n, hdr0, hdr1, roles, slots, heap, extra, class_list, [tuple(self.actions)], 8)
+
+    def bytes_per_request(self):
+        return 24 + 4 * 3 + 8 * 12 + 64 + 1   # = 197 (SURVEY.md 8(d))
+
+
+WORKLOADS = {"C1": C1, "C2": C2, "C3": C3}
 
 
 def build(workload, globals_=None):

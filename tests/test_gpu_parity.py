@@ -62,7 +62,7 @@ def test_goldens_batched_device_vs_oracle(ctx):
     table.release()
 
 
-@pytest.mark.parametrize("name,n", [("C1", 1024), ("C2", 1 << 16), ("C2", 1 << 20)])
+@pytest.mark.parametrize("name,n", [("C1", 1024), ("C2", 1 << 16), ("C2", 1 << 20), ("C3", 1 << 16), ("C3", 1 << 20)])
 def test_workloads_bit_exact(ctx, name, n):
     from cerbos_b200 import workloads as W
     from cerbos_b200.device import DeviceBatch
@@ -109,6 +109,30 @@ def test_staged_and_global_table_paths_agree():
     os.environ.pop("CERBOS_B200_NO_STAGE", None)
     assert outs[0][1]["smem_bytes"] > 0 and outs[1][1]["smem_bytes"] == 0
     assert (outs[0][0] == outs[1][0]).all()
+
+
+def test_lean_and_general_kernel_bodies_agree():
+    """CERBOS_B200_FORCE_GENERAL=1 disables the lean body: both must give identical bits."""
+    from cerbos_b200 import capi, workloads as W
+    from cerbos_b200.device import DeviceBatch
+    for name in ("C2", "C3"):
+        w = W.WORKLOADS[name]()
+        _, ft, enc = W.build(w)
+        b = w.columns(w.fields(1 << 15), enc)
+        outs = []
+        for flag in ("0", "1"):
+            os.environ["CERBOS_B200_FORCE_GENERAL"] = flag
+            c = capi.Context(0)
+            t = c.load_table(ft.blob)
+            db = DeviceBatch(b, "cuda:0")
+            db.run(t)
+            c.sync()
+            outs.append((db.effects(), c.last_kernel_config()))
+            t.release()
+            c.close()
+        os.environ.pop("CERBOS_B200_FORCE_GENERAL", None)
+        assert outs[0][1]["lean_body"] and not outs[1][1]["lean_body"]
+        assert (outs[0][0] == outs[1][0]).all(), name
 
 
 def test_error_paths(ctx):

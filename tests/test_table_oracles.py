@@ -107,7 +107,7 @@ def test_bytecode_vs_cel_oracle_on_golden_expressions():
     assert lowered >= 90
 
 
-@pytest.mark.parametrize("cls,n", [(W.C1, 1024), (W.C2, 1 << 14)])
+@pytest.mark.parametrize("cls,n", [(W.C1, 1024), (W.C2, 1 << 14), (W.C3, 1 << 12)])
 def test_workloads_three_way(cls, n):
     w = cls()
     rt, ft, enc = W.build(w)
