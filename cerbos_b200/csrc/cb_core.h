@@ -983,122 +983,11 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
 }
 
 // ---------------------------------------------------------------------------------------------- flat fast path
-// Conditions that are an ALL / ANY of simple terms (layout.FLAT_*, bytecode.FlatCompiler) are evaluated
-// straight on the 8-byte NaN-boxed values: no stack, no tag/payload structs.  Anything unusual (containers,
-// constants without an 8-byte form) drops to the generic helpers above, so results are identical.
-enum { TRI_F = 0, TRI_T = 1, TRI_E = 2 };
+enum { TRI_F = 0, TRI_T = 1, TRI_E = 2, TRI_SLOW = 3 };
 
 CB_HD uint32_t v64_tag(uint64_t b) {   // 0 = double
     uint32_t top = (uint32_t)(b >> 48);
     return ((top & 0xFFF0u) == 0xFFF0u) ? (top & 0xFu) : 0u;
-}
-CB_HD int tri_of(const Val &v) { return v.tag == CB_T_BOOL ? (int)v.u : TRI_E; }
-
-CB_HD_NOINLINE int slow_cmp(Ctx &c, int ci, uint64_t x, uint64_t y) {
-    int s;
-    Val a = decode_v64(x, &s), b = decode_v64(y, &s);
-    return tri_of(do_cmp(c, ci, a, b));
-}
-
-// x: slot / P.id value; y: other operand (both NaN-boxed).  ci: 0 EQ, 2 LT, 3 LE, 4 GT, 5 GE
-CB_HD int fast_cmp(Ctx &c, int ci, uint64_t x, uint64_t y) {
-    uint32_t tx = v64_tag(x), ty = v64_tag(y);
-    if (tx == 0 && ty == 0) {
-        double dx = u2d(x), dy = u2d(y);
-        if (ci == 0) return dx == dy;
-        if (dx != dx || dy != dy) return TRI_E;
-        switch (ci) {
-        case 2: return dx < dy;
-        case 3: return dx <= dy;
-        case 4: return dx > dy;
-        default: return dx >= dy;
-        }
-    }
-    if (tx == CB_V64_ABSENT || tx == CB_V64_ERROR || ty == CB_V64_ABSENT || ty == CB_V64_ERROR) return TRI_E;
-    if (tx == CB_V64_INT || ty == CB_V64_INT || tx == 15 || ty == 15) return slow_cmp(c, ci, x, y);
-    if (ci == 0) {
-        if (tx != ty) return TRI_F;
-        if (tx == CB_V64_LIST || tx == CB_V64_MAP) return slow_cmp(c, ci, x, y);
-        return x == y;   // STRING (interned id) / BOOL / NULL
-    }
-    if (tx != ty) return TRI_E;
-    if (tx == CB_V64_STRING) {
-        int r = x == y ? 0 : str_cmp(c, x & 0xFFFFFFFFFFFFull, y & 0xFFFFFFFFFFFFull);
-        switch (ci) {
-        case 2: return r < 0;
-        case 3: return r <= 0;
-        case 4: return r > 0;
-        default: return r >= 0;
-        }
-    }
-    if (tx == CB_V64_BOOL) {
-        uint64_t a = x & 1, b = y & 1;
-        switch (ci) {
-        case 2: return a < b;
-        case 3: return a <= b;
-        case 4: return a > b;
-        default: return a >= b;
-        }
-    }
-    return TRI_E;
-}
-
-// x in container (both NaN-boxed)
-CB_HD_NOINLINE int slow_in(Ctx &c, uint64_t x, uint64_t cont) {
-    int s;
-    Val a = decode_v64(x, &s), b = decode_v64(cont, &s);
-    return tri_of(do_in(c, a, b));
-}
-CB_HD_NOINLINE bool slow_elem_eq(Ctx &c, uint64_t x, uint64_t e) {
-    int s;
-    return val_equal(c, decode_v64(x, &s), decode_v64(e, &s));
-}
-CB_HD int fast_in(Ctx &c, uint64_t x, uint64_t cont) {
-    uint32_t tx = v64_tag(x), tc = v64_tag(cont);
-    if (tx == CB_V64_ABSENT || tx == CB_V64_ERROR || tc == CB_V64_ABSENT || tc == CB_V64_ERROR) return TRI_E;
-    if (tc != CB_V64_LIST || tx == CB_V64_LIST || tx == CB_V64_MAP || tx == 15 || tx == CB_V64_INT) return slow_in(c, x, cont);
-    uint64_t pay = cont & 0xFFFFFFFFFFFFull;
-    const uint64_t *p = (pay & CB_V64_HEAP_BATCH_BIT) ? c.b->heap + (pay & (CB_V64_HEAP_BATCH_BIT - 1)) : c.t->theap() + pay;
-    uint64_t n = ldg(p);
-    for (uint64_t i = 0; i < n; i++) {
-        uint64_t e = ldg(p + 1 + i);
-        uint32_t te = v64_tag(e);
-        if (te == CB_V64_INT || te == CB_V64_LIST || te == CB_V64_MAP) {
-            if (slow_elem_eq(c, x, e)) return TRI_T;
-        } else if (tx == 0 && te == 0) {
-            if (u2d(x) == u2d(e)) return TRI_T;
-        } else if (x == e && tx == te) {
-            return TRI_T;
-        }
-    }
-    return TRI_F;
-}
-
-CB_HD uint64_t slot_bits(const Ctx &c, uint32_t s) { return ldcol64(c.b->slots + (uint64_t)s * c.b->stride + c.req); }
-
-CB_HD bool eval_flat(Ctx &c, const cb_instr *terms, uint32_t info) {
-    const uint32_t n = info & 0xFFFF, kind = (info >> 16) & 0xFF;
-    const bool negate = (info >> 24) & 1;
-    bool res = kind == CB_FLAT_ALL;
-    for (uint32_t i = 0; i < n; i++) {
-        uint64_t raw = ldg(reinterpret_cast<const uint64_t *>(terms + i));
-        uint32_t op = (uint32_t)(raw & 0xFF), ia = (uint32_t)((raw >> 8) & 0xFF), ib = (uint32_t)((raw >> 16) & 0xFFFF);
-        uint32_t ic = (uint32_t)(raw >> 32);
-        int tri;
-        switch (op) {
-        case CB_OP_CMP_SLOT_CONST: tri = fast_cmp(c, (int)(ia & 0x7F), slot_bits(c, ib), ldg(c.t->consts_v64() + ic)); break;
-        case CB_OP_CMP_SLOT_SLOT: tri = fast_cmp(c, (int)(ia & 0x7F), slot_bits(c, ib), slot_bits(c, ic)); break;
-        case CB_OP_CMP_SLOT_PID: tri = fast_cmp(c, (int)(ia & 0x7F), slot_bits(c, ib), ((uint64_t)(CB_V64_BOX_BASE | CB_V64_STRING) << 48) | c.pid); break;
-        case CB_OP_IN_SLOT_CONST: tri = fast_in(c, slot_bits(c, ib), ldg(c.t->consts_v64() + ic)); break;
-        case CB_OP_IN_CONST_SLOT: tri = fast_in(c, ldg(c.t->consts_v64() + ic), slot_bits(c, ib)); break;
-        case CB_OP_HAS_SLOT: { uint32_t ts = v64_tag(slot_bits(c, ic)); tri = ts == CB_V64_ERROR ? TRI_E : (ts != CB_V64_ABSENT); break; }
-        default: c.unsupported = 1; return false;
-        }
-        if ((ia & CB_FLAT_TERM_NEG) && tri != TRI_E) tri ^= 1;
-        if (kind == CB_FLAT_ALL) { if (tri != TRI_T) { res = false; break; } }
-        else if (tri == TRI_T) { res = true; break; }
-    }
-    return res != negate;
 }
 
 // ---------------------------------------------------------------------------------------------- decision walk
@@ -1123,94 +1012,153 @@ CB_HD bool role_in_pr(const TableView t, uint32_t role, uint32_t req_role, uint3
     return false;
 }
 
-// Evaluates condition `gid` (global id) with the generic machinery.  bit0: it yields BOOL true
+// Evaluates condition `gid` (global id) with the generic stack interpreter.  bit0: it yields BOOL true
 // (ruletable.go:1425-1441); bit1: a run-time value the device cannot represent exactly was met.
 // Scalar arguments only: aggregates would travel through local memory under the device ABI.
 CB_HD_NOINLINE uint32_t cond_sat(const uint8_t *base, const TableLayout *L, const BatchView *b, uint64_t req, uint32_t pid, uint32_t gid) {
     TableView t; t.base = base; t.L = L;
     Ctx c;
     c.t = &t; c.b = b; c.req = req; c.pid = pid; c.unsupported = 0;
-    U4 cd = ld16(t.conds() + gid);   // {code_off, code_len, flat_off, flat_info}
-    bool s = cd.w ? eval_flat(c, t.code() + cd.z, cd.w) : run_program(c, t.code() + cd.x);
+    bool s = run_program(c, t.code() + ldg(&t.conds()[gid].code_off));
     return (s ? 1u : 0u) | (c.unsupported ? 2u : 0u);
 }
 
-// ---- inline flat evaluator of the hot path: handles doubles and interned scalars in a few instructions and
-// hands everything else (string ordering, containers, int list elements) to the out-of-line helpers ----
-enum { TRI_SLOW = 3 };
-CB_HD_NOINLINE uint32_t slow_term(const uint8_t *base, const TableLayout *L, const BatchView *b, uint64_t req, uint32_t pid,
-                                  uint32_t is_in, uint32_t ci, uint64_t x, uint64_t y) {
-    TableView t; t.base = base; t.L = L;
-    Ctx c;
-    c.t = &t; c.b = b; c.req = req; c.pid = pid; c.unsupported = 0;
-    int tri = is_in ? fast_in(c, x, y) : fast_cmp(c, (int)ci, x, y);
-    return (uint32_t)tri | (c.unsupported ? 4u : 0u);
+// ---- inline DNF evaluator of the lean body (layout FLAT_DNF, compiled by bytecode.FlatCompiler) --------------
+// Works directly on the 8-byte NaN-boxed values.  No calls and no early exits: every lane walks every term with
+// predicates, so lanes evaluating the same condition shape stay converged.  Anything it cannot decide exactly
+// (container equality, int list elements, string ordering ...) sets `slow`: the request is then re-evaluated by
+// the general body with the generic interpreter.
+struct StrRef { const uint8_t *p; uint32_t len; };
+CB_HD StrRef str_ref(const TableView t, const BatchView &b, uint64_t v) {   // v: boxed STRING
+    uint32_t id = (uint32_t)(v & 0xFFFFFFFFu);
+    StrRef r;
+    if (id < t.L->nT) { uint32_t o = ldg(t.str_off() + id); r.p = t.str_bytes() + o; r.len = ldg(t.str_off() + id + 1) - o; }
+    else { uint32_t j = id - t.L->nT; uint32_t o = ldg(b.bstr_off + j); r.p = b.bstr_bytes + o; r.len = ldg(b.bstr_off + j + 1) - o; }
+    return r;
 }
-CB_HD int cmp_inline(uint32_t ci, uint64_t x, uint64_t y) {
-    uint32_t tx = v64_tag(x), ty = v64_tag(y);
-    if (tx == 0 && ty == 0) {
-        double dx = u2d(x), dy = u2d(y);
-        if (ci == 0) return dx == dy;
-        if (dx != dx || dy != dy) return TRI_E;
-        return ci == 2 ? dx < dy : ci == 3 ? dx <= dy : ci == 4 ? dx > dy : dx >= dy;
-    }
-    if (tx == CB_V64_ABSENT || tx == CB_V64_ERROR || ty == CB_V64_ABSENT || ty == CB_V64_ERROR) return TRI_E;
-    if (ci == 0 && tx <= CB_V64_STRING && ty <= CB_V64_STRING) return x == y;   // double / NULL / BOOL / STRING: equal iff same bits
-    return TRI_SLOW;
+CB_HD const uint64_t *list_ptr(const TableView t, const BatchView &b, uint64_t v) {   // v: boxed LIST / MAP
+    uint64_t pay = v & 0xFFFFFFFFFFFFull;
+    return (pay & CB_V64_HEAP_BATCH_BIT) ? b.heap + (pay & (CB_V64_HEAP_BATCH_BIT - 1)) : t.theap() + pay;
 }
-CB_HD int in_inline(const TableView t, const BatchView &b, uint64_t x, uint64_t cont) {
+// scalar equality of two NaN-boxed values whose tags are <= STRING (double / null / bool / string)
+CB_HD bool scalar_eq64(uint64_t x, uint64_t y) {
+    return (v64_tag(x) == 0 && v64_tag(y) == 0) ? u2d(x) == u2d(y) : x == y;
+}
+CB_HD uint64_t term_operand(const TableView t, const BatchView &b, uint64_t n, uint32_t pid, uint32_t kind, uint32_t v, uint32_t aux) {
+    const uint64_t kErr = (uint64_t)(CB_V64_BOX_BASE | CB_V64_ERROR) << 48;
+    if (kind == CB_OPK_CONST) return ldg(t.consts_v64() + v);
+    if (kind == CB_OPK_PID) return ((uint64_t)(CB_V64_BOX_BASE | CB_V64_STRING) << 48) | pid;
+    uint64_t x = ldcol64(b.slots + (uint64_t)v * b.stride + n);
+    if (kind == CB_OPK_SLOT) return x;
     uint32_t tx = v64_tag(x);
-    if (v64_tag(cont) != CB_V64_LIST || tx > CB_V64_STRING) return TRI_SLOW;   // errors / containers / maps: out of line
-    uint64_t pay = cont & 0xFFFFFFFFFFFFull;
-    const uint64_t *p = (pay & CB_V64_HEAP_BATCH_BIT) ? b.heap + (pay & (CB_V64_HEAP_BATCH_BIT - 1)) : t.theap() + pay;
-    uint32_t n = (uint32_t)ldg(p);
-    // no early exit: lanes of a warp stay converged (lists are short)
-    bool found = false, slow = false;
-    for (uint32_t i = 0; i < n; i++) {
-        uint64_t e = ldg(p + 1 + i);
-        uint32_t te = v64_tag(e);
-        slow |= te > CB_V64_STRING;                        // int / container elements
-        found |= (tx == 0 && te == 0) ? u2d(x) == u2d(e) : x == e;
+    if (kind == CB_OPK_SLOT_ELEM) {
+        if (tx != CB_V64_LIST) return kErr;                       // map[int] / scalar[int]: no such key / overload
+        const uint64_t *p = list_ptr(t, b, x);
+        return aux < (uint32_t)ldg(p) ? ldg(p + 1 + aux) : kErr;   // index out of bounds is an error
     }
-    return slow ? TRI_SLOW : (found ? TRI_T : TRI_F);
+    // SLOT_SIZE -> double (the compare against an int constant is exact for these magnitudes)
+    if (tx == CB_V64_LIST || tx == CB_V64_MAP) return d2u((double)(uint32_t)ldg(list_ptr(t, b, x)));
+    if (tx == CB_V64_STRING) {
+        StrRef s = str_ref(t, b, x);
+        uint32_t k = 0;
+        for (uint32_t i = 0; i < s.len; i++) k += (ldg(s.p + i) & 0xC0) != 0x80;
+        return d2u((double)k);
+    }
+    return kErr;
 }
-// -> bit0 satisfied, bit2: needs the out-of-line general path (no calls are made here).
-// Written without early exits: every lane walks all terms with a predicate, so a warp whose lanes evaluate the
-// same condition shape never diverges here.
-CB_HD uint32_t flat_inline(const TableView t, const BatchView &b, uint64_t n, uint32_t pid, uint32_t flat_off, uint32_t info) {
+// -> bit0 satisfied, bit2: needs the out-of-line general path
+CB_HD uint32_t flat_dnf_inline(const TableView t, const BatchView &b, uint64_t n, uint32_t pid, uint32_t flat_off, uint32_t info) {
     const uint32_t nt = info & 0xFFFF;
-    const bool is_all = ((info >> 16) & 0xFF) == CB_FLAT_ALL;
     const cb_instr *terms = t.code() + flat_off;
-    bool any_true = false, all_true = true, slow = false;
+    bool any = false, group = true, slow = false;
     for (uint32_t i = 0; i < nt; i++) {
-        uint64_t raw = ldg(reinterpret_cast<const uint64_t *>(terms + i));
-        uint32_t op = (uint32_t)(raw & 0xFF), ia = (uint32_t)((raw >> 8) & 0xFF), ib = (uint32_t)((raw >> 16) & 0xFFFF);
-        uint32_t ic = (uint32_t)(raw >> 32);
-        // operands: x is always a slot (HAS_SLOT keeps it in ic), y a constant, another slot or P.id
-        uint64_t x = ldcol64(b.slots + (uint64_t)(op == CB_OP_HAS_SLOT ? ic : ib) * b.stride + n);
-        uint64_t y;
-        if (op == CB_OP_CMP_SLOT_SLOT) y = ldcol64(b.slots + (uint64_t)ic * b.stride + n);
-        else if (op == CB_OP_CMP_SLOT_PID) y = ((uint64_t)(CB_V64_BOX_BASE | CB_V64_STRING) << 48) | pid;
-        else y = ldg(t.consts_v64() + ic);
-        int tri;
-        if (op == CB_OP_HAS_SLOT) { uint32_t ts = v64_tag(x); tri = ts == CB_V64_ERROR ? TRI_E : (ts != CB_V64_ABSENT); }
-        else if (op == CB_OP_IN_SLOT_CONST) tri = in_inline(t, b, x, y);
-        else if (op == CB_OP_IN_CONST_SLOT) tri = in_inline(t, b, y, x);
-        else tri = cmp_inline(ia & 0x7F, x, y);
-        slow |= tri == TRI_SLOW;
-        if ((ia & CB_FLAT_TERM_NEG) && tri < TRI_E) tri ^= 1;
-        any_true |= tri == TRI_T;
-        all_true &= tri == TRI_T;
+        const U4 w = ld16(terms + 2 * i);   // {op | flags<<8 | xk<<16 | yk<<24, x, y, xa | ya<<16}
+        const uint32_t op = w.x & 0xFF, flags = (w.x >> 8) & 0xFF, xk = (w.x >> 16) & 0xFF, yk = w.x >> 24;
+        const uint64_t x = term_operand(t, b, n, pid, xk, w.y, w.w & 0xFFFF);
+        const uint64_t y = op == CB_TERM_HAS ? 0 : term_operand(t, b, n, pid, yk, w.z, w.w >> 16);
+        const uint32_t tx = v64_tag(x), ty = v64_tag(y);
+        const bool xerr = tx == CB_V64_ABSENT || tx == CB_V64_ERROR, yerr = ty == CB_V64_ABSENT || ty == CB_V64_ERROR;
+        int tri = TRI_E;
+        if (op == CB_TERM_HAS) {
+            tri = tx == CB_V64_ERROR ? TRI_E : (tx != CB_V64_ABSENT);
+        } else if (xerr || yerr) {
+            tri = TRI_E;
+        } else if (op == CB_TERM_CMP) {
+            const uint32_t ci = flags & CB_TERM_CI_MASK;
+            if (tx == 0 && ty == 0) {
+                const double dx = u2d(x), dy = u2d(y);
+                if (ci == 0) tri = dx == dy;
+                else if (dx != dx || dy != dy) tri = TRI_E;
+                else tri = ci == 2 ? dx < dy : ci == 3 ? dx <= dy : ci == 4 ? dx > dy : dx >= dy;
+            } else if (ci == 0 && tx <= CB_V64_STRING && ty <= CB_V64_STRING) tri = x == y;   // null / bool / interned string / mixed
+            else if (ci != 0 && tx != ty) tri = TRI_E;                                         // no ordering across types
+            else slow = true;                                                                  // containers, string ordering, ints
+        } else if (op == CB_TERM_IN) {
+            if (ty != CB_V64_LIST || tx > CB_V64_STRING) slow = true;   // maps, container members: out of line
+            else {
+                const uint64_t *p = list_ptr(t, b, y);
+                const uint32_t ln = (uint32_t)ldg(p);
+                bool found = false;
+                for (uint32_t j = 0; j < ln; j++) {
+                    const uint64_t e = ldg(p + 1 + j);
+                    slow |= v64_tag(e) > CB_V64_STRING;               // int / container elements
+                    found |= scalar_eq64(x, e);
+                }
+                tri = found;
+            }
+        } else if (op == CB_TERM_STARTS || op == CB_TERM_ENDS || op == CB_TERM_CONTAINS) {
+            if (tx != CB_V64_STRING || ty != CB_V64_STRING) tri = TRI_E;
+            else {
+                const StrRef a = str_ref(t, b, x), c = str_ref(t, b, y);
+                if (c.len > a.len) tri = TRI_F;
+                else if (op == CB_TERM_CONTAINS) {
+                    bool hit = false;
+                    for (uint32_t o = 0; o + c.len <= a.len; o++) {
+                        bool eq = true;
+                        for (uint32_t j = 0; j < c.len; j++) eq &= ldg(a.p + o + j) == ldg(c.p + j);
+                        hit |= eq;
+                    }
+                    tri = hit;
+                } else {
+                    const uint8_t *ap = op == CB_TERM_STARTS ? a.p : a.p + (a.len - c.len);
+                    bool eq = true;
+                    for (uint32_t j = 0; j < c.len; j++) eq &= ldg(ap + j) == ldg(c.p + j);
+                    tri = eq;
+                }
+            }
+        } else {   // INTERSECTS / SUBSET on two lists (cerbos_lib.go:323-431)
+            if (tx != CB_V64_LIST || ty != CB_V64_LIST) tri = TRI_E;
+            else {
+                const uint64_t *pa = list_ptr(t, b, x), *pb = list_ptr(t, b, y);
+                const uint32_t na = (uint32_t)ldg(pa), nb = (uint32_t)ldg(pb);
+                bool any_hit = false, all_hit = true;
+                for (uint32_t i2 = 0; i2 < na; i2++) {
+                    const uint64_t ea = ldg(pa + 1 + i2);
+                    slow |= v64_tag(ea) > CB_V64_STRING;
+                    bool hit = false;
+                    for (uint32_t j = 0; j < nb; j++) {
+                        const uint64_t eb = ldg(pb + 1 + j);
+                        slow |= v64_tag(eb) > CB_V64_STRING;       // ints would need the Go-map identity rule
+                        hit |= scalar_eq64(ea, eb);
+                    }
+                    any_hit |= hit;
+                    all_hit &= hit;
+                }
+                tri = op == CB_TERM_INTERSECTS ? any_hit : all_hit;
+            }
+        }
+        const bool lit = (flags & CB_TERM_LIT_F) ? tri == TRI_F : tri == TRI_T;
+        group &= lit;
+        if (flags & CB_TERM_GROUP_END) { any |= group; group = true; }
     }
-    if (slow) return 4u;   // not decidable on the 8-byte fast forms: the caller defers the request
-    bool res = is_all ? all_true : any_true;
-    return (uint32_t)(res != (bool)((info >> 24) & 1));
+    if (slow) return 4u;
+    return (uint32_t)(any != (bool)((info >> 24) & 1));
 }
-// condition `gid` on the call-free fast path: bit0 satisfied, bit2 = cannot decide here (non-flat condition or an
+// condition `gid` on the call-free fast path: bit0 satisfied, bit2 = cannot decide here (no flat form or an
 // unusual operand): the request is then re-evaluated by the general body
 CB_HD uint32_t cond_eval(const TableView t, const BatchView &b, uint64_t n, uint32_t pid, uint32_t gid) {
-    U4 cd = ld16(t.conds() + gid);
-    if (cd.w) return flat_inline(t, b, n, pid, cd.z, cd.w);
+    U4 cd = ld16(t.conds() + gid);   // {code_off, code_len, flat_off, flat_info}
+    if (cd.w) return flat_dnf_inline(t, b, n, pid, cd.z, cd.w);
     return 4u;
 }
 

@@ -672,124 +672,188 @@ class ProgramCompiler:
 
 
 class FlatCompiler:
-    """Recognises conditions that are an ALL / ANY of simple terms (see layout.FLAT_*).
+    """Lowers a condition to disjunctive normal form over simple *terms* (layout.FLAT_DNF) for the kernels'
+    call-free fast path.
 
-    A term is a fused compare / `in` / has() on slots, constants and P.id; its value is tri-state
-    (true / false / error) and may carry a NEG flag (`!term`, `!=`).  Because a condition leaf only asks
-    "is the result BOOL true" (ruletable.go:1425-1441), cel-go's error absorption collapses:
-        a && b && c   is true  <=> every term is true
-        a || b || c   is true  <=> some term is true
-        !(a && b)     is true  <=> some term is BOOL false      (ANY of negated terms)
-        !(a || b)     is true  <=> every term is BOOL false     (ALL of negated terms)
-    and all/any/none of such leaves compose the same way (none = final negation of an ANY)."""
+    A condition leaf only asks "is the result BOOL true" (ruletable.go:1425-1441).  With
+    T(e) = "e is BOOL true" and F(e) = "e is BOOL false", cel-go's error-absorbing logic gives
+        T(a && b) = T(a) & T(b)      F(a && b) = F(a) | F(b)
+        T(a || b) = T(a) | T(b)      F(a || b) = F(a) & F(b)
+        T(!a)     = F(a)             F(!a)     = T(a)
+        T(c ? a : b) = T(c) & T(a) | F(c) & T(b)        F(c ? a : b) = T(c) & F(a) | F(c) & F(b)
+    so any expression over term leaves has an exact DNF over the literals T(term) / F(term); all / any of such
+    leaves compose the same way and a top-level `none` is a final negation.  A term is a compare, `in`, string
+    predicate, set predicate or has() whose operands are attribute slots, constants, P.id, a constant-index list
+    element or size(slot).  `list.exists(x, x == e)` is `e in list`, `list.all(x, x != e)` is F(e in list)
+    (only as positive literals: with an erroring `e` the comprehension and `in` differ in *which* non-true value
+    they produce)."""
+
+    MAX_TERMS = L.FLAT_MAX_TERMS
 
     def __init__(self, pc: "ProgramCompiler"):
         self.pc = pc
 
-    def term(self, n: Node, neg: bool):
-        """-> [op, a, b, c] or None"""
+    # ---- operands
+    def operand(self, n: Node):
+        """-> (kind, value, aux) or None"""
         pc = self.pc
-        if isinstance(n, Call) and n.fn == "!_" and n.target is None and len(n.args) == 1:
-            return self.term(n.args[0], not neg)
+        if isinstance(n, Call) and n.fn == "size" and len(([n.target] if n.target is not None else []) + n.args) == 1:
+            arg = n.target if n.target is not None else n.args[0]
+            s = pc._simple(arg)
+            if s is not None and s[0] == "slot":
+                return (L.OPK["SLOT_SIZE"], pc._slot_ix(s[1]), 0)
+            return None
+        if isinstance(n, Call) and n.fn == "_[_]" and n.target is None and isinstance(n.args[1], Const) \
+                and isinstance(n.args[1].value, int) and not isinstance(n.args[1].value, bool):
+            s = pc._simple(n.args[0])
+            idx = int(n.args[1].value)
+            if s is not None and s[0] == "slot" and 0 <= idx < 0xFFFF:
+                return (L.OPK["SLOT_ELEM"], pc._slot_ix(s[1]), idx)
+            return None
+        s = pc._simple(n)
+        if s is None:
+            return None
+        if s[0] == "slot":
+            return (L.OPK["SLOT"], pc._slot_ix(s[1]), 0)
+        if s[0] == "pid":
+            pc.ctx.uses_pid = True
+            return (L.OPK["PID"], 0, 0)
+        cix = pc._const_ix(s[1])
+        if const_v64(pc.ctx, pc.ctx.consts[cix]) == L.FLAT_NOT_FAST:
+            return None
+        return (L.OPK["CONST"], cix, 0)
+
+    @staticmethod
+    def mk(op, x, y, ci=0):
+        return {"op": L.TERM_OPS[op], "ci": ci, "x": x, "y": y if y is not None else (L.OPK["CONST"], 0, 0)}
+
+    def term(self, n: Node):
+        """-> term dict (value = the expression itself) or None"""
         if isinstance(n, Select) and n.test_only:
             try:
-                st = pc._static(Select(n.operand, n.field))
+                st = self.pc._static(Select(n.operand, n.field))
             except Unsupported:
                 return None
             if st is None or st.kind != "slot" or len(st.path) <= 2:
                 return None
-            return [OP["HAS_SLOT"], L.FLAT_TERM_NEG if neg else 0, 0, pc._slot_ix(st.path)]
-        if isinstance(n, Call) and n.target is None and len(n.args) == 2 and (n.fn in L.CMP_INDEX or n.fn == "@in"):
-            sa, sb = pc._simple(n.args[0]), pc._simple(n.args[1])
-            if sa is None or sb is None:
-                return None
-            ka, kb = sa[0], sb[0]
-            flag = L.FLAT_TERM_NEG if neg else 0
-            if n.fn == "@in":
-                if ka == "slot" and kb == "const":
-                    return [OP["IN_SLOT_CONST"], flag, pc._slot_ix(sa[1]), pc._const_ix(sb[1])]
-                if ka == "const" and kb == "slot":
-                    return [OP["IN_CONST_SLOT"], flag, pc._slot_ix(sb[1]), pc._const_ix(sa[1])]
-                return None
-            ci = L.CMP_INDEX[n.fn]
-            if ci == 1:   # a != b  ==  !(a == b)
-                ci = 0
-                flag ^= L.FLAT_TERM_NEG
-            swap = {0: 0, 2: 4, 3: 5, 4: 2, 5: 3}
-            if ka == "slot" and kb == "const":
-                return [OP["CMP_SLOT_CONST"], ci | flag, pc._slot_ix(sa[1]), pc._const_ix(sb[1])]
-            if ka == "const" and kb == "slot":
-                return [OP["CMP_SLOT_CONST"], swap[ci] | flag, pc._slot_ix(sb[1]), pc._const_ix(sa[1])]
-            if ka == "slot" and kb == "slot":
-                return [OP["CMP_SLOT_SLOT"], ci | flag, pc._slot_ix(sa[1]), pc._slot_ix(sb[1])]
-            if ka == "slot" and kb == "pid":
-                pc.ctx.uses_pid = True
-                return [OP["CMP_SLOT_PID"], ci | flag, pc._slot_ix(sa[1]), 0]
-            if ka == "pid" and kb == "slot":
-                pc.ctx.uses_pid = True
-                return [OP["CMP_SLOT_PID"], swap[ci] | flag, pc._slot_ix(sb[1]), 0]
-            return None
-        if not neg:
-            # a bare boolean attribute: true <=> value == true (only in positive position, see class doc)
-            sa = pc._simple(n) if isinstance(n, (Select, Call)) else None
-            if sa is not None and sa[0] == "slot":
-                return [OP["CMP_SLOT_CONST"], 0, pc._slot_ix(sa[1]), pc._const_ix((True, True))]
+            return self.mk("HAS", (L.OPK["SLOT"], self.pc._slot_ix(st.path), 0), None)
+        if isinstance(n, Call):
+            args = ([n.target] if n.target is not None else []) + n.args
+            if n.target is None and len(args) == 2 and n.fn in L.CMP_INDEX and n.fn != "_!=_":
+                x, y = self.operand(args[0]), self.operand(args[1])
+                if x is None or y is None:
+                    return None
+                return self.mk("CMP", x, y, L.CMP_INDEX[n.fn])
+            if n.target is None and len(args) == 2 and n.fn == "@in":
+                x, y = self.operand(args[0]), self.operand(args[1])
+                if x is None or y is None or x[0] == L.OPK["SLOT_SIZE"] or y[0] not in (L.OPK["SLOT"], L.OPK["CONST"]):
+                    return None
+                return self.mk("IN", x, y)
+            str2 = {"startsWith": "STARTS", "endsWith": "ENDS", "contains": "CONTAINS"}
+            set2 = {"hasIntersection": "INTERSECTS", "has_intersection": "INTERSECTS", "isSubset": "SUBSET", "is_subset": "SUBSET"}
+            if len(args) == 2 and (n.fn in str2 or n.fn in set2):
+                x, y = self.operand(args[0]), self.operand(args[1])
+                ok = (L.OPK["SLOT"], L.OPK["CONST"], L.OPK["PID"], L.OPK["SLOT_ELEM"]) if n.fn in str2 else (L.OPK["SLOT"], L.OPK["CONST"])
+                if x is None or y is None or x[0] not in ok or y[0] not in ok:
+                    return None
+                return self.mk(str2.get(n.fn) or set2[n.fn], x, y)
+        # a bare boolean attribute / constant: true <=> value == true, false <=> value == false
+        if isinstance(n, (Select, Call, Ident, Const)):
+            x = self.operand(n)
+            if x is not None and x[0] in (L.OPK["SLOT"], L.OPK["SLOT_ELEM"]):
+                return None   # a non-bool value would be an *error* as a logical operand but `== true` is false
         return None
 
-    def expr(self, n: Node, neg: bool):
-        """-> (kind or None for a single term, [terms]) or None"""
-        if isinstance(n, Call) and n.fn == "!_" and n.target is None and len(n.args) == 1:
-            return self.expr(n.args[0], not neg)
-        if isinstance(n, Call) and n.target is None and n.fn in ("_&&_", "_||_") and len(n.args) == 2:
-            kind = L.FLAT_ALL if n.fn == "_&&_" else L.FLAT_ANY
-            if neg:
-                kind = L.FLAT_ANY if kind == L.FLAT_ALL else L.FLAT_ALL
-            terms = []
-            for a in n.args:
-                sub = self.expr(a, neg)
-                if sub is None:
+    # ---- DNF: list of groups, each a list of (term, lit_false)
+    def lit(self, n: Node, want_false: bool):
+        if isinstance(n, Call) and n.target is None:
+            if n.fn == "!_" and len(n.args) == 1:
+                return self.lit(n.args[0], not want_false)
+            if n.fn in ("_&&_", "_||_") and len(n.args) == 2:
+                a, b = self.lit(n.args[0], want_false), self.lit(n.args[1], want_false)
+                if a is None or b is None:
                     return None
-                sk, st = sub
-                if sk is not None and sk != kind:
+                conj = (n.fn == "_&&_") != want_false      # T(a&&b), F(a||b) are conjunctions
+                return self._and(a, b) if conj else self._or(a, b)
+            if n.fn == "_!=_" and len(n.args) == 2:
+                return self.lit(Call("_==_", None, n.args), not want_false)
+            if n.fn == "_?_:_" and len(n.args) == 3:
+                ct, cf = self.lit(n.args[0], False), self.lit(n.args[0], True)
+                a, b = self.lit(n.args[1], want_false), self.lit(n.args[2], want_false)
+                if None in (ct, cf, a, b):
                     return None
-                terms.extend(st)
-            return kind, terms
-        t = self.term(n, neg)
-        return None if t is None else (None, [t])
+                l, r = self._and(ct, a), self._and(cf, b)
+                return None if l is None or r is None else self._or(l, r)
+        if isinstance(n, Macro) and not want_false and len(n.vars) == 1 and len(n.args) == 1 and n.name in ("exists", "all"):
+            body, var = n.args[0], n.vars[0]
+            want_fn = "_==_" if n.name == "exists" else "_!=_"
+            if isinstance(body, Call) and body.target is None and body.fn == want_fn and len(body.args) == 2:
+                for a, o in ((body.args[0], body.args[1]), (body.args[1], body.args[0])):
+                    if isinstance(a, Ident) and a.name == var and not any(isinstance(z, Ident) and z.name == var for z in walk_nodes(o)):
+                        return self.lit(Call("@in", None, [o, n.target]), n.name == "all")
+            return None
+        t = self.term(n)
+        if t is None:
+            return None
+        return [[(t, want_false)]]
+
+    def _or(self, a, b):
+        r = a + b
+        return r if sum(len(g) for g in r) <= self.MAX_TERMS else None
+
+    def _and(self, a, b):
+        r = [ga + gb for ga in a for gb in b]
+        return r if sum(len(g) for g in r) <= self.MAX_TERMS else None
 
     def cond(self, c: Cond):
-        """-> (kind, negate, terms) or None"""
+        """-> (negate, dnf) or None"""
         if c.op == "expr":
-            r = self.expr(c.expr.ast, False)
-            if r is None:
-                return None
-            kind, terms = r
-            return (kind or L.FLAT_ALL, 0, terms)
+            d = self.lit(c.expr.ast, False)
+            return None if d is None else (0, d)
         if not c.children:
             return None
-        kind = L.FLAT_ALL if c.op == "all" else L.FLAT_ANY
-        terms = []
+        subs = []
         for ch in c.children:
             r = self.cond(ch)
-            if r is None:
+            if r is None or r[0]:
                 return None
-            k, negate, t = r
-            if negate or (len(t) > 1 and k != kind):
+            subs.append(r[1])
+        d = subs[0]
+        for x in subs[1:]:
+            d = self._and(d, x) if c.op == "all" else self._or(d, x)
+            if d is None:
                 return None
-            terms.extend(t)
-        return (kind, 1 if c.op == "none" else 0, terms)
+        return (1 if c.op == "none" else 0, d)
+
+
+def walk_nodes(n):
+    from ..cel.ast import walk
+    return walk(n)
 
 
 def compile_flat(ctx: TableBuilderCtx, cond: Cond, params: Params | None):
-    """-> (kind, negate, [[op, a, b, c], ...]) if the condition has a flat fast form, else None."""
+    """-> (negate, [term words...]) if the condition has a flat (DNF) fast form, else None.
+    Each term is 16 bytes, returned as two instruction tuples (op, a, b, c) so it fits the CODE section."""
     pc = ProgramCompiler(ctx, params)
     try:
         r = FlatCompiler(pc).cond(cond)
     except Unsupported:
         return None
-    if r is None or not (1 <= len(r[2]) <= 0xFFFF):
+    if r is None:
         return None
-    return r
+    negate, dnf = r
+    n_terms = sum(len(g) for g in dnf)
+    if not (1 <= n_terms <= L.FLAT_MAX_TERMS):
+        return None
+    words = []
+    for g in dnf:
+        for j, (t, lit_false) in enumerate(g):
+            flags = (t["ci"] & L.TERM_CI_MASK) | (L.TERM_LIT_F if lit_false else 0) | (L.TERM_GROUP_END if j == len(g) - 1 else 0)
+            (xk, xv, xa), (yk, yv, ya) = t["x"], t["y"]
+            # {u8 op; u8 flags; u8 xk; u8 yk; u32 x} {u32 y; u16 xa; u16 ya}  as two (op, a, b, c) instruction slots
+            words.append([t["op"], flags, xk | (yk << 8), xv])
+            words.append([yv & 0xFF, (yv >> 8) & 0xFF, (yv >> 16) & 0xFFFF, xa | (ya << 16)])
+    return negate, n_terms, words
 
 
 def const_v64(ctx: TableBuilderCtx, cv: ConstVal) -> int:

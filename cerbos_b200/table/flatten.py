@@ -163,9 +163,12 @@ def flatten(rt: RuleTable, globals_=None) -> FlatTable:
         gen = put(prog)
         flat = compile_flat(ctx, cond, params)
         if flat is not None:
-            kind, negate, terms = flat
-            foff, n_terms = put(terms)
-            conds.append((gen[0], gen[1], foff, n_terms | (kind << 16) | (negate << 24)))
+            negate, n_terms, words = flat
+            if len(code) % 2:
+                code.append([L.OPS["RET"], 0, 0, 0])      # terms are 16 bytes: keep them 16-byte aligned
+            foff = len(code)
+            code.extend(words)
+            conds.append((gen[0], gen[1], foff, n_terms | (L.FLAT_DNF << 16) | (negate << 24)))
         else:
             conds.append((gen[0], gen[1], 0, 0))
         return len(conds) - 1
@@ -303,7 +306,16 @@ def flatten(rt: RuleTable, globals_=None) -> FlatTable:
         seen = []
         for ci in range(cbase, cbase + ncond):
             coff, clen, foff, finfo = conds[ci]
-            spans = [(foff, finfo & 0xFFFF)] if finfo else [(coff, clen)]
+            if finfo:
+                for q in range(finfo & 0xFFFF):
+                    w0, w1 = code[foff + 2 * q], code[foff + 2 * q + 1]
+                    xk, yk = w0[2] & 0xFF, w0[2] >> 8
+                    yv = w1[0] | (w1[1] << 8) | (w1[2] << 16)
+                    for kind_, v_ in ((xk, w0[3]), (yk, yv)):
+                        if kind_ in (L.OPK["SLOT"], L.OPK["SLOT_ELEM"], L.OPK["SLOT_SIZE"]) and v_ not in seen:
+                            seen.append(v_)
+                continue
+            spans = [(coff, clen)]
             for off, ln in spans:
                 for ins in code[off:off + ln]:
                     if ins[0] in slot_ops_c and ins[3] not in seen:

@@ -12,7 +12,7 @@ Table blob (little endian, every section 16-byte aligned):
 from __future__ import annotations
 
 MAGIC = 0x32425243  # 'CRB2'
-VERSION = 5
+VERSION = 6
 ALIGN = 16
 
 NONE32 = 0xFFFFFFFF
@@ -134,13 +134,19 @@ OPS = {name: i for i, name in enumerate([
     "IN_IP_RANGE",      # TOS string ip -> BOOL(ip in CIDR at theap[c..c+3] = {family 4|6, prefix bits, hi64, lo64})
 ])}
 
-# Flat fast-path conditions: a condition that is an ALL / ANY of "terms" (fused compare / in / has ops on
-# slots, constants and P.id), optionally negated.  flat_info = n_terms | kind << 16 | negate << 24 ; 0 = none.
-# Term = Instr whose `a` field carries the compare index | FLAT_TERM_NEG (term value negated: BOOL false counts).
-FLAT_ALL = 1
-FLAT_ANY = 2
-FLAT_TERM_NEG = 0x80
+# Flat fast-path conditions: a condition in disjunctive normal form over "terms".  A term is 16 bytes (two CODE
+# slots): {u8 op; u8 flags; u8 xk; u8 yk; u32 x; u32 y; u16 xa; u16 ya}.  Its value is tri-state (true / false /
+# error); the literal it contributes is selected by flags: T ("is BOOL true"), F ("is BOOL false").  Terms are
+# AND-ed into groups (FLAT_GROUP_END closes a group), groups are OR-ed; CONDS.flat_info = n_terms | FLAT_DNF << 16
+# | negate << 24 (final negation: a top-level `none`); 0 = the condition has no flat form.
+FLAT_DNF = 3
+TERM_OPS = {name: i for i, name in enumerate(["CMP", "IN", "STARTS", "ENDS", "CONTAINS", "HAS", "INTERSECTS", "SUBSET"])}
+TERM_CI_MASK = 0x07        # flags: compare index for CMP (0 EQ, 2 LT, 3 LE, 4 GT, 5 GE)
+TERM_LIT_F = 0x20          # flags: literal is "term is BOOL false" (else "is BOOL true")
+TERM_GROUP_END = 0x40      # flags: last term of its AND-group
+OPK = {name: i for i, name in enumerate(["SLOT", "CONST", "PID", "SLOT_ELEM", "SLOT_SIZE"])}
 FLAT_NOT_FAST = ((V64_BOX_BASE | 15) << 48)   # CONSTS_V64 entry: constant has no 8-byte fast form
+FLAT_MAX_TERMS = 24
 
 LOOP_ALL = 0
 LOOP_EXISTS = 1
@@ -210,9 +216,14 @@ def c_header() -> str:
         d(f"CB_OP_{k}", v)
     d("CB_N_OPS", len(OPS))
     out.append("")
-    d("CB_FLAT_ALL", FLAT_ALL)
-    d("CB_FLAT_ANY", FLAT_ANY)
-    d("CB_FLAT_TERM_NEG", FLAT_TERM_NEG, True)
+    d("CB_FLAT_DNF", FLAT_DNF)
+    for k, v in TERM_OPS.items():
+        d(f"CB_TERM_{k}", v)
+    d("CB_TERM_CI_MASK", TERM_CI_MASK, True)
+    d("CB_TERM_LIT_F", TERM_LIT_F, True)
+    d("CB_TERM_GROUP_END", TERM_GROUP_END, True)
+    for k, v in OPK.items():
+        d(f"CB_OPK_{k}", v)
     d("CB_FLAT_NOT_FAST", FLAT_NOT_FAST, True)
     d("CB_LOOP_ALL", LOOP_ALL)
     d("CB_LOOP_EXISTS", LOOP_EXISTS)
@@ -231,6 +242,7 @@ typedef struct { uint32_t row_start, n_rows, cond_base, n_conds; } cb_block;
 typedef struct { uint16_t role, cond, drcond, respat; uint8_t effect, flags; uint16_t n_pats; uint32_t pat_start; } cb_row;
 typedef struct { uint32_t code_off, code_len, flat_off, flat_info; } cb_cond;
 typedef struct { uint8_t op, a; uint16_t b; uint32_t c; } cb_instr;
+typedef struct { uint8_t op, flags, xk, yk; uint32_t x, y; uint16_t xa, ya; } cb_term;   /* 16 B = two CODE slots */
 typedef struct { uint32_t tag, pad; uint64_t bits; } cb_const;
 typedef struct { uint32_t role, rule_start, n_rules, pad; } cb_rolepol_entry;
 typedef struct { uint32_t respat, cond, apat_start, n_apats; } cb_rolepol_rule;
