@@ -1,0 +1,38 @@
+"""Differential fuzzing: random policy sets x random requests through oracle #1 (structural Python), oracle #2
+(C interpreter of the flattened table) and the kernels' core compiled for the host (lean + general bodies)."""
+import random
+
+import numpy as np
+import pytest
+
+from cerbos_b200.encode import Encoder
+from cerbos_b200.policy.compile import build_rule_table
+from cerbos_b200.table import layout as L
+from cerbos_b200.table.flatten import flatten
+from fuzzgen import rand_policies, rand_request
+from hostsim import driver as hostsim
+from oracle import cref
+from oracle.check import CheckOracle
+
+
+@pytest.mark.parametrize("seed", range(150))
+def test_random_tables(seed):
+    r = random.Random(1000 + seed)
+    docs = rand_policies(r)
+    rt = build_rule_table(docs)
+    ft = flatten(rt)
+    lenient = seed % 4 == 0
+    orc = CheckOracle(rt, lenient_scope_search=lenient)
+    enc = Encoder(ft.manifest, lenient_scope_search=lenient)
+    inputs = [rand_request(r) for _ in range(60)]
+    b = enc.encode(inputs)
+    fl = L.BATCH_FLAG_LENIENT if lenient else 0
+    c_out = cref.check(ft.blob, b.columns, b.n, b.max_actions, 0, fl)
+    for j, inp in enumerate(inputs):
+        py = orc.check(inp)
+        for k, a in enumerate(inp["actions"]):
+            assert c_out[j, k] == py["actions"][a]["effect"], (seed, j, a, inp)
+    valid = c_out != 0
+    for mode in (0, 1, 2):
+        k_out = hostsim.check(ft.blob, b.columns, b.n, b.max_actions, 0, fl, mode=mode)
+        assert (k_out[valid] == c_out[valid]).all(), (seed, mode)
