@@ -17,7 +17,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE = 0, -1, -2, -3, -4
 EXPORTS = [
     "cgpu_init", "cgpu_shutdown", "cgpu_table_load", "cgpu_table_retain", "cgpu_table_release", "cgpu_check",
     "cgpu_check_device", "cgpu_sync", "cgpu_launch_count", "cgpu_table_info", "cgpu_last_kernel_config",
-    "cgpu_last_error",
+    "cgpu_last_cluster_config", "cgpu_profile", "cgpu_last_error",
 ]
 
 
@@ -68,6 +68,10 @@ def lib():
         L.cgpu_table_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint32), ctypes.c_uint32]
         L.cgpu_last_kernel_config.restype = ctypes.c_int
         L.cgpu_last_kernel_config.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_uint32)] * 3
+        L.cgpu_last_cluster_config.restype = ctypes.c_int
+        L.cgpu_last_cluster_config.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_uint32)] * 3
+        L.cgpu_profile.restype = ctypes.c_int
+        L.cgpu_profile.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
         L.cgpu_last_error.restype = ctypes.c_char_p
         L.cgpu_last_error.argtypes = []
         _lib = L
@@ -99,7 +103,20 @@ class Context:
     def last_kernel_config(self):
         g, b, s = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
         _check(lib().cgpu_last_kernel_config(self._h, ctypes.byref(g), ctypes.byref(b), ctypes.byref(s)))
-        return {"grid": g.value, "block": b.value, "smem_bytes": s.value & 0x7FFFFFFF, "lean_body": bool(s.value >> 31)}
+        cfg = {"grid": g.value, "block": b.value, "smem_bytes": s.value & 0x7FFFFFFF, "lean_body": bool(s.value >> 31)}
+        c, w, nb = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+        _check(lib().cgpu_last_cluster_config(self._h, ctypes.byref(c), ctypes.byref(w), ctypes.byref(nb)))
+        cfg["clustered"] = bool(c.value)
+        if c.value:
+            cfg["cluster_window"] = w.value
+            cfg["cluster_buckets"] = nb.value
+        return cfg
+
+    def profile(self, enable: bool):
+        """-> (check-kernel ms summed, launches) since the last call; then turns per-launch events on/off."""
+        ms, n = ctypes.c_double(), ctypes.c_uint64()
+        _check(lib().cgpu_profile(self._h, 1 if enable else 0, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
 
     def load_table(self, blob: bytes) -> "Table":
         return Table(self, blob)

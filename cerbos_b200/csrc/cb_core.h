@@ -90,6 +90,7 @@ struct BatchView {
     uint32_t role_cols, n_asets, kc, n_pass, max_actions, kbytes, flags;
     uint32_t rcp, stride_pattern;   // set by finish_batch_view(): pow2 >= role_cols; bit j*role_cols for every j (32-bit)
     int64_t now;
+    const uint32_t *perm;       // clustered evaluation order (request offsets from `first`), or null = index order
 };
 
 // Table data may live in shared memory (TMA-staged image) or in global memory, heap references may point
@@ -97,6 +98,7 @@ struct BatchView {
 // columns -- read exactly once -- use the read-only, no-L1-allocate path so they do not evict the table.
 // derived BatchView fields (host side, once per launch)
 inline void finish_batch_view(BatchView &b) {
+    b.perm = nullptr;
     b.rcp = 1;
     while (b.rcp < b.role_cols) b.rcp <<= 1;
     b.stride_pattern = 0;

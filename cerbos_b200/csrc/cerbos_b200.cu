@@ -75,6 +75,13 @@ __global__ void __launch_bounds__(kThreads, 4) check_kernel(const __grid_constan
     bool staged = !kStage;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         uint64_t i = tile * kThreads + threadIdx.x;
+        // clustered order: thread i evaluates request perm[i] (cluster kernels below), so that the lanes of a warp
+        // walk the same policy blocks
+        uint64_t req = i, req_next = i + (uint64_t)gridDim.x * kThreads;
+        if (bv.perm) {
+            if (i < bv.count) req = bv.perm[i];
+            if (req_next < bv.count) req_next = bv.perm[req_next]; else req_next = bv.count;
+        }
         if (!staged) {
             // every thread waits for the table image (phase 0) before its first table access
             uint32_t ok = 0;
@@ -88,14 +95,13 @@ __global__ void __launch_bounds__(kThreads, 4) check_kernel(const __grid_constan
             staged = true;
         }
         // the next tile of this thread: start pulling its header / role columns towards L1 now
-        uint64_t inext = i + (uint64_t)gridDim.x * kThreads;
-        if (inext < bv.count) cb::prefetch_request(bv, bv.first + inext);
+        if (req_next < bv.count) cb::prefetch_request(bv, bv.first + req_next);
         if (i < bv.count) {
             if (kFast) {
                 // call-free lean body; the (rare) requests it cannot decide are redone by the general body
-                if (cb::eval_request_fast(tv, bv, bv.first + i, bitmap, effects))
-                    cb::eval_request_general(tv.base, tv.L, &bv, bv.first + i, bitmap, effects, status);
-            } else cb::eval_request<uint64_t>(tv, bv, bv.first + i, bitmap, effects, status);
+                if (cb::eval_request_fast(tv, bv, bv.first + req, bitmap, effects))
+                    cb::eval_request_general(tv.base, tv.L, &bv, bv.first + req, bitmap, effects, status);
+            } else cb::eval_request<uint64_t>(tv, bv, bv.first + req, bitmap, effects, status);
         }
     }
     if (!staged) {
@@ -108,6 +114,102 @@ __global__ void __launch_bounds__(kThreads, 4) check_kernel(const __grid_constan
                 : "r"(smem_u32(&mbar))
                 : "memory");
         }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------ clustering
+// Requests of one batch hit different policy blocks (resource kind x scope x version); evaluated in index order the
+// 32 lanes of a warp would each walk another block and another set of conditions.  Three small kernels build a
+// permutation that groups requests by that key inside windows of `window` requests (a window's columns fit in L2,
+// so the gathers of the check kernel are served from L2 and DRAM traffic stays at the algorithmic bytes):
+//   cluster_count   keys (u16) + per-(window, bucket) histogram      reads hdr0 / hdr1 once, coalesced
+//   cluster_scan    exclusive scan of every window's histogram
+//   cluster_scatter perm[window base + bucket offset + rank] = request offset
+constexpr uint32_t kClusterChunk = 2048;   // requests per CTA (8 per thread)
+constexpr uint32_t kMaxBuckets = 4096;
+
+struct ClusterParams {
+    const cb_hdr0 *hdr0;
+    const cb_hdr1 *hdr1;
+    uint64_t first;
+    uint32_t count, window, nb;   // nb: buckets (power of two <= kMaxBuckets)
+    uint32_t nV, nRP, nS;
+    uint16_t *keys;
+    uint32_t *hist;               // [n_windows][nb]
+    uint32_t *perm;
+};
+
+__device__ __forceinline__ uint32_t cluster_key(const ClusterParams &p, uint64_t n) {
+    const cb::U4 h0 = cb::ldcol128(p.hdr0 + n);
+    const uint64_t h1 = cb::ldcol64(reinterpret_cast<const uint64_t *>(p.hdr1 + n));
+    uint32_t kc = h0.y & ~CB_KIND_CLASS_CSR_BIT, rs = h0.z & ~CB_SCOPE_INEXACT_BIT, rv = (uint32_t)(h1 & 0xFFFF);
+    kc = kc < p.nRP ? kc : p.nRP;
+    rs = rs < p.nS ? rs : p.nS;
+    rv = rv < p.nV ? rv : p.nV;
+    return ((rv * (p.nRP + 1) + kc) * (p.nS + 1) + rs) & (p.nb - 1);
+}
+
+__global__ void __launch_bounds__(kThreads) cluster_count(const __grid_constant__ ClusterParams p) {
+    __shared__ uint32_t hist[kMaxBuckets];
+    for (uint32_t j = threadIdx.x; j < p.nb; j += kThreads) hist[j] = 0;
+    __syncthreads();
+    const uint32_t c0 = blockIdx.x * kClusterChunk;
+    for (uint32_t q = 0; q < kClusterChunk / kThreads; q++) {
+        const uint32_t i = c0 + q * kThreads + threadIdx.x;
+        if (i < p.count) {
+            const uint32_t k = cluster_key(p, p.first + i);
+            p.keys[i] = (uint16_t)k;
+            atomicAdd(&hist[k], 1u);
+        }
+    }
+    __syncthreads();
+    uint32_t *g = p.hist + (uint64_t)(c0 / p.window) * p.nb;
+    for (uint32_t j = threadIdx.x; j < p.nb; j += kThreads)
+        if (hist[j]) atomicAdd(g + j, hist[j]);
+}
+
+__global__ void __launch_bounds__(kThreads) cluster_scan(const __grid_constant__ ClusterParams p) {
+    __shared__ uint32_t part[kThreads];
+    uint32_t *g = p.hist + (uint64_t)blockIdx.x * p.nb;
+    const uint32_t per = (p.nb + kThreads - 1) / kThreads;   // consecutive buckets per thread
+    const uint32_t j0 = threadIdx.x * per;
+    uint32_t sum = 0;
+    for (uint32_t j = j0; j < j0 + per && j < p.nb; j++) sum += g[j];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (uint32_t d = 1; d < kThreads; d <<= 1) {   // Hillis-Steele inclusive scan over the 256 partial sums
+        uint32_t v = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = part[threadIdx.x] - sum;
+    for (uint32_t j = j0; j < j0 + per && j < p.nb; j++) { uint32_t c = g[j]; g[j] = run; run += c; }
+}
+
+__global__ void __launch_bounds__(kThreads) cluster_scatter(const __grid_constant__ ClusterParams p) {
+    __shared__ uint32_t hist[kMaxBuckets];
+    for (uint32_t j = threadIdx.x; j < p.nb; j += kThreads) hist[j] = 0;
+    __syncthreads();
+    const uint32_t c0 = blockIdx.x * kClusterChunk;
+    uint32_t key[kClusterChunk / kThreads], rank[kClusterChunk / kThreads];
+#pragma unroll
+    for (uint32_t q = 0; q < kClusterChunk / kThreads; q++) {
+        const uint32_t i = c0 + q * kThreads + threadIdx.x;
+        key[q] = 0; rank[q] = 0;
+        if (i < p.count) { key[q] = p.keys[i]; rank[q] = atomicAdd(&hist[key[q]], 1u); }
+    }
+    __syncthreads();
+    uint32_t *g = p.hist + (uint64_t)(c0 / p.window) * p.nb;
+    for (uint32_t j = threadIdx.x; j < p.nb; j += kThreads)
+        if (hist[j]) hist[j] = atomicAdd(g + j, hist[j]);   // this CTA's range inside the bucket
+    __syncthreads();
+    const uint32_t wbase = (c0 / p.window) * p.window;
+#pragma unroll
+    for (uint32_t q = 0; q < kClusterChunk / kThreads; q++) {
+        const uint32_t i = c0 + q * kThreads + threadIdx.x;
+        if (i < p.count) p.perm[wbase + hist[key[q]] + rank[q]] = i;
     }
 }
 
@@ -151,6 +253,13 @@ struct cgpu_ctx {
     uint32_t last_grid = 0, last_block = 0, last_smem = 0, last_fast = 0;
     int force_no_stage = 0;
     int force_general = 0;   // CERBOS_B200_FORCE_GENERAL=1: never pick the lean kernel body (tests)
+    int cluster_mode = -1;   // CERBOS_B200_CLUSTER: 0 never, 1 always, unset = batches of >= kClusterMinRequests
+    uint32_t last_clustered = 0, last_window = 0, last_buckets = 0;
+    bool profiling = false;  // cgpu_profile(): CUDA events around the check kernel of every launch
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double prof_ms = 0;
+    uint64_t prof_n = 0;
+    bool prof_pending = false;
 };
 
 struct cgpu_table {
@@ -245,6 +354,45 @@ int make_batch_view(const cgpu_table *t, const cgpu_batch *b, uint64_t first, ui
     return CGPU_OK;
 }
 
+constexpr uint64_t kClusterMinRequests = 32768;
+constexpr uint64_t kClusterWindowBytes = 24u << 20;   // columns of one window: comfortably inside the 126 MB L2
+
+// Builds the clustered evaluation order of `bv` on `stream` (stream-ordered scratch); *perm_out is freed by the caller.
+int launch_cluster(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, uint32_t **perm_out, cudaStream_t stream) {
+    const cb::TableLayout &lay = t->desc.lay;
+    ClusterParams p{};
+    p.hdr0 = bv.hdr0; p.hdr1 = bv.hdr1; p.first = bv.first; p.count = (uint32_t)bv.count;
+    p.nV = lay.nV; p.nRP = lay.nRP; p.nS = lay.nS;
+    const uint64_t nkeys = (uint64_t)(lay.nV + 1) * (lay.nRP + 1) * (lay.nS + 1);
+    p.nb = 32;
+    while (p.nb < nkeys && p.nb < kMaxBuckets) p.nb <<= 1;
+    // window: a power of two number of requests whose header + role + slot columns take about kClusterWindowBytes,
+    // at least 64 requests per bucket
+    const uint64_t per_req = 24 + 4ull * bv.role_cols + 8ull * lay.n_slots + 16;
+    uint64_t w = kClusterChunk;
+    while (w * 2 * per_req <= kClusterWindowBytes) w <<= 1;
+    while (w < 64ull * p.nb && w < (1ull << 22)) w <<= 1;
+    p.window = (uint32_t)w;
+    const uint32_t n_win = (uint32_t)((bv.count + w - 1) / w);
+    const uint32_t n_chunks = (uint32_t)((bv.count + kClusterChunk - 1) / kClusterChunk);
+    const size_t perm_bytes = ((size_t)bv.count * 4 + 255) & ~(size_t)255, keys_bytes = ((size_t)bv.count * 2 + 255) & ~(size_t)255;
+    const size_t hist_bytes = (size_t)n_win * p.nb * 4;
+    uint8_t *scratch = nullptr;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&scratch), perm_bytes + keys_bytes + hist_bytes, stream));
+    p.perm = reinterpret_cast<uint32_t *>(scratch);
+    p.keys = reinterpret_cast<uint16_t *>(scratch + perm_bytes);
+    p.hist = reinterpret_cast<uint32_t *>(scratch + perm_bytes + keys_bytes);
+    CUDA_TRY(cudaMemsetAsync(p.hist, 0, hist_bytes, stream));
+    cluster_count<<<n_chunks, kThreads, 0, stream>>>(p);
+    cluster_scan<<<n_win, kThreads, 0, stream>>>(p);
+    cluster_scatter<<<n_chunks, kThreads, 0, stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    ctx->launches.fetch_add(3, std::memory_order_relaxed);
+    ctx->last_window = p.window; ctx->last_buckets = p.nb;
+    *perm_out = p.perm;
+    return CGPU_OK;
+}
+
 int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, uint8_t *d_bitmap, uint8_t *d_effects,
                  uint32_t *d_status, cudaStream_t stream) {
     const bool stage = !ctx->force_no_stage && t->desc.lay.image_bytes <= kMaxStageBytes;
@@ -273,12 +421,31 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
     if (grid == 0) grid = 1;
     TableDesc td = t->desc;
     cb::BatchView bvv = bv;
+    bvv.perm = nullptr;
+    const bool cluster = bv.count < (1ull << 32) && (ctx->cluster_mode == 1 || (ctx->cluster_mode != 0 && bv.count >= kClusterMinRequests));
+    uint32_t *perm = nullptr;
+    if (cluster) {
+        int rc = launch_cluster(ctx, t, bv, &perm, stream);
+        if (rc != CGPU_OK) return rc;
+        bvv.perm = perm;
+    }
     uint32_t stage_flag = stage ? 1u : 0u;
     void *args[] = {&td, &bvv, &d_bitmap, &d_effects, &d_status, &stage_flag};
+    if (ctx->profiling) {
+        if (ctx->prof_pending && cudaEventSynchronize(ctx->ev1) == cudaSuccess) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) { ctx->prof_ms += ms; ctx->prof_n++; }
+            ctx->prof_pending = false;
+        }
+        CUDA_TRY(cudaEventRecord(ctx->ev0, stream));
+    }
     CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(kThreads), args, smem, stream));
     CUDA_TRY(cudaGetLastError());
+    if (ctx->profiling) { CUDA_TRY(cudaEventRecord(ctx->ev1, stream)); ctx->prof_pending = true; }
+    if (perm) CUDA_TRY(cudaFreeAsync(perm, stream));
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
     ctx->last_grid = grid; ctx->last_block = kThreads; ctx->last_smem = smem; ctx->last_fast = narrow ? 1 : 0;
+    ctx->last_clustered = cluster ? 1 : 0;
     return CGPU_OK;
 }
 
@@ -310,6 +477,14 @@ int cgpu_init(const int *device_ids, int n_devices, cgpu_ctx **out) {
     ctx->force_no_stage = ns && ns[0] == '1';
     const char *fg = getenv("CERBOS_B200_FORCE_GENERAL");
     ctx->force_general = fg && fg[0] == '1';
+    const char *cm = getenv("CERBOS_B200_CLUSTER");
+    ctx->cluster_mode = cm && (cm[0] == '0' || cm[0] == '1') ? cm[0] - '0' : -1;
+    // stream-ordered scratch (clustering): keep freed blocks in the pool instead of returning them to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     ctx->slots.resize(4);
     *out = ctx;
     return CGPU_OK;
@@ -327,6 +502,8 @@ void cgpu_shutdown(cgpu_ctx *ctx) {
     }
     if (ctx->d_status) cudaFree(ctx->d_status);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     delete ctx;
 }
 
@@ -377,6 +554,32 @@ int cgpu_last_kernel_config(const cgpu_ctx *ctx, uint32_t *grid, uint32_t *block
     if (grid) *grid = ctx->last_grid;
     if (block) *block = ctx->last_block;
     if (smem_bytes) *smem_bytes = ctx->last_smem | (ctx->last_fast << 31);   // bit 31: lean kernel body was used
+    return CGPU_OK;
+}
+
+int cgpu_last_cluster_config(const cgpu_ctx *ctx, uint32_t *clustered, uint32_t *window, uint32_t *buckets) {
+    if (!ctx) return fail(CGPU_ERR_INVALID, "null ctx");
+    if (clustered) *clustered = ctx->last_clustered;
+    if (window) *window = ctx->last_window;
+    if (buckets) *buckets = ctx->last_buckets;
+    return CGPU_OK;
+}
+
+int cgpu_profile(cgpu_ctx *ctx, int enable, double *kernel_ms_sum, uint64_t *n_launches) {
+    if (!ctx) return fail(CGPU_ERR_INVALID, "null ctx");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (ctx->prof_pending) {
+        CUDA_TRY(cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->prof_ms += ms; ctx->prof_n++;
+        ctx->prof_pending = false;
+    }
+    if (kernel_ms_sum) *kernel_ms_sum = ctx->prof_ms;
+    if (n_launches) *n_launches = ctx->prof_n;
+    ctx->prof_ms = 0; ctx->prof_n = 0;
+    if (enable && !ctx->ev0) { CUDA_TRY(cudaEventCreate(&ctx->ev0)); CUDA_TRY(cudaEventCreate(&ctx->ev1)); }
+    ctx->profiling = enable != 0;
     return CGPU_OK;
 }
 

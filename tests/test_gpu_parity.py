@@ -171,3 +171,52 @@ def test_many_actions_multiple_passes(ctx):
     got = t.check(b.columns, b.n, b.max_actions)
     assert (got == want).all()
     t.release()
+
+
+@pytest.mark.parametrize("name,n", [("C2", (1 << 16) + 777), ("C3", (1 << 18) + 5), ("C2", 1000)])
+def test_clustered_and_index_order_agree(name, n):
+    """CERBOS_B200_CLUSTER=1 forces the clustering kernels (requests grouped by policy block), =0 disables them:
+    identical bits, host-buffer and device paths, sizes that are not multiples of the chunk / window."""
+    from cerbos_b200 import capi, workloads as W
+    from cerbos_b200.device import DeviceBatch
+    from oracle import cref
+    w = W.WORKLOADS[name]()
+    _, ft, enc = W.build(w)
+    b = w.columns(w.fields(n), enc)
+    want = cref.check(ft.blob, b.columns, b.n, b.max_actions, n_threads=os.cpu_count() or 1)
+    for flag in ("0", "1"):
+        os.environ["CERBOS_B200_CLUSTER"] = flag
+        c = capi.Context(0)
+        t = c.load_table(ft.blob)
+        db = DeviceBatch(b, "cuda:0")
+        db.run(t)
+        c.sync()
+        cfg = c.last_kernel_config()
+        assert cfg["clustered"] == (flag == "1")
+        assert (db.effects() == want).all(), (name, flag)
+        assert (t.check(b.columns, b.n, b.max_actions) == want).all(), (name, flag, "host")
+        t.release()
+        c.close()
+    os.environ.pop("CERBOS_B200_CLUSTER", None)
+
+
+def test_clustered_goldens_mixed_shapes():
+    """The reference goldens (principal / role policies, globs: general body) evaluated in clustered order."""
+    from cerbos_b200 import capi
+    from cerbos_b200.encode import Encoder
+    from cerbos_b200.table.flatten import flatten
+    from helpers import engine_decisions, store_rule_table
+    from oracle import cref
+    ft = flatten(store_rule_table(), globals_={"environment": "test"})
+    inputs = [inp for _, lenient, inp, _ in engine_decisions() if not lenient]
+    b = Encoder(ft.manifest).encode(inputs * 100)
+    want = cref.check(ft.blob, b.columns, b.n, b.max_actions, NOW_NS)
+    os.environ["CERBOS_B200_CLUSTER"] = "1"
+    c = capi.Context(0)
+    t = c.load_table(ft.blob)
+    got = t.check(b.columns, b.n, b.max_actions, NOW_NS)
+    assert c.last_kernel_config()["clustered"]
+    os.environ.pop("CERBOS_B200_CLUSTER", None)
+    assert (got == want).all()
+    t.release()
+    c.close()
