@@ -422,7 +422,10 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
     TableDesc td = t->desc;
     cb::BatchView bvv = bv;
     bvv.perm = nullptr;
-    const bool cluster = bv.count < (1ull << 32) && (ctx->cluster_mode == 1 || (ctx->cluster_mode != 0 && bv.count >= kClusterMinRequests));
+    // Clustering pays when the policy blocks differ in shape (rows / conditions): with a single shape every lane runs
+    // the same control flow in index order already and the coalesced column loads are worth more.
+    const bool cluster = bv.count < (1ull << 32) &&
+                         (ctx->cluster_mode == 1 || (ctx->cluster_mode != 0 && bv.count >= kClusterMinRequests && t->meta[CB_META_BLOCK_SHAPES] > 1));
     uint32_t *perm = nullptr;
     if (cluster) {
         int rc = launch_cluster(ctx, t, bv, &perm, stream);

@@ -145,6 +145,7 @@ def flatten(rt: RuleTable, globals_=None) -> FlatTable:
             groups[key].append(r)
 
     blocks, row_recs, conds, code, row_apats = [], [], [], [], []
+    block_shapes: set = set()
     code_ix: dict[tuple, tuple] = {}
 
     def add_program(cond, params) -> int:
@@ -164,10 +165,15 @@ def flatten(rt: RuleTable, globals_=None) -> FlatTable:
         flat = compile_flat(ctx, cond, params)
         if flat is not None:
             negate, n_terms, words = flat
-            if len(code) % 2:
-                code.append([L.OPS["RET"], 0, 0, 0])      # terms are 16 bytes: keep them 16-byte aligned
-            foff = len(code)
-            code.extend(words)
+            fk = ("flat",) + tuple(tuple(i) for i in words)
+            fent = code_ix.get(fk)
+            if fent is None:
+                if len(code) % 2:
+                    code.append([L.OPS["RET"], 0, 0, 0])      # terms are 16 bytes: keep them 16-byte aligned
+                fent = (len(code), len(words))
+                code_ix[fk] = fent
+                code.extend(words)
+            foff = fent[0]
             conds.append((gen[0], gen[1], foff, n_terms | (L.FLAT_DNF << 16) | (negate << 24)))
         else:
             conds.append((gen[0], gen[1], 0, 0))
@@ -214,6 +220,8 @@ def flatten(rt: RuleTable, globals_=None) -> FlatTable:
             row_recs.append(key2 + (len(pats), len(row_apats)))
             row_apats.extend(pats)
         blocks.append((row_start, len(row_recs) - row_start, cond_base, len(conds) - cond_base))
+        # shape of the block = everything that steers the kernel's control flow through it
+        block_shapes.add((tuple(k2[:3] + k2[4:] + (tuple(p),) for k2, p in merged.items()), tuple(conds[cond_base:])))
 
     # ---- role policies ----------------------------------------------------------------------------------------
     rp_off = np.zeros(nV * nS + 1, dtype=np.uint32)
@@ -285,7 +293,7 @@ def flatten(rt: RuleTable, globals_=None) -> FlatTable:
         has_parent_roles=int(has_parents), has_principal_policies=int(nP > 0), max_stack=ctx.max_stack,
         max_loop_depth=ctx.max_loop_depth, n_vars=ctx.n_vars, theap_words=len(ctx.theap),
         uses_pid=int(ctx.uses_pid), uses_now=int(ctx.uses_now), max_scope_depth=max_depth,
-        direct_kinds=int(not any(is_glob(p) for p in respats.items)),
+        direct_kinds=int(not any(is_glob(p) for p in respats.items)), block_shapes=len(block_shapes),
     ).items():
         meta[L.META[k]] = val
 

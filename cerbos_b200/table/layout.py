@@ -12,7 +12,7 @@ Table blob (little endian, every section 16-byte aligned):
 from __future__ import annotations
 
 MAGIC = 0x32425243  # 'CRB2'
-VERSION = 6
+VERSION = 7
 ALIGN = 16
 
 NONE32 = 0xFFFFFFFF
@@ -61,7 +61,7 @@ META = {name: i for i, name in enumerate([
     "n_versions", "n_respats", "n_scopes", "n_principals", "n_roles", "n_apats", "n_blocks", "n_rows",
     "n_conds", "n_code", "n_consts", "n_slots", "n_strings", "has_role_policies", "has_parent_roles",
     "has_principal_policies", "max_stack", "max_loop_depth", "n_vars", "theap_words", "uses_pid", "uses_now",
-    "max_scope_depth", "direct_kinds",
+    "max_scope_depth", "direct_kinds", "block_shapes",
 ])}
 
 SCOPE_FLAG_PRINCIPAL = 1
