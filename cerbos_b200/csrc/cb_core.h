@@ -1567,34 +1567,25 @@ CB_HD bool eval_request_fast(const TableView t, const BatchView &b, uint64_t n, 
                 for (uint32_t q = ldg(t.block_slots_off() + bid), e = ldg(t.block_slots_off() + bid + 1); q < e; q++)
                     prefetch_l1(slots_n + (uint64_t)ldg(t.block_slots() + q) * b.stride);
                 const U4 bl = ld16(t.blocks() + bid);   // {row_start, n_rows, cond_base, n_conds}
-                defer |= bl.w > 32;
-                uint32_t known = 0, val = 0, D = 0, A = 0;   // per-block condition memo + DENY / ALLOW pair masks
+                defer |= bl.w > 31;
+                // phase 1: every condition of the block, once, into one bit each (bit 0 = "no condition" = true).  The
+                // lanes of a warp evaluate the same condition list together; a row the request does not reach simply
+                // ignores its bit (conditions have no side effects; an operand this path cannot decide defers).
+                uint32_t val = 1;
+                for (uint32_t c = 0, nc = bl.w > 31 ? 0 : bl.w; c < nc; c++) {
+                    const uint32_t r = cond_eval(t, b, n, pid, bl.z + c);
+                    defer |= (r & 4) != 0;
+                    val |= (r & 1) << (c + 1);
+                }
+                // phase 2: rows are pure mask algebra
+                uint32_t D = 0, A = 0;   // DENY / ALLOW pair masks of this scope
                 for (uint32_t ri = bl.x, re = bl.x + bl.y; ri < re; ri++) {
                     const uint32_t am = ldg(reinterpret_cast<const uint32_t *>(row_am + ri));
-                    const U4 row = ld16(t.rows() + ri);
+                    const U4 row = ld16(t.rows() + ri);   // {role | cond << 16, drcond | respat << 16, effect | flags << 8 | n_pats << 16, pat_start}
                     const uint32_t role = row_role(row);
                     const uint32_t rc = role == CB_ROLE_ANY ? role_all : (uint32_t)(rp >> (role * RCP)) & role_all;
-                    const uint32_t m = (am * rc) & alive;
-                    // the (at most two) conditions of the row: derived-role condition first, then the rule's own
-                    uint32_t cpair = row.x >> 16 | row.y << 16;   // cond | drcond << 16
-                    bool sat = true;
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-                    for (uint32_t h = 0; h < 2; h++) {
-                        const uint32_t ci = (h == 0 ? cpair >> 16 : cpair) & 0xFFFF;   // h = 0: drcond
-                        if (m && sat && ci) {
-                            const uint32_t bit = 1u << ((ci - 1) & 31);
-                            if (!(known & bit)) {
-                                uint32_t r = cond_eval(t, b, n, pid, bl.z + ci - 1);
-                                defer |= (r & 4) != 0;
-                                known |= bit;
-                                val |= (r & 1) ? bit : 0u;
-                            }
-                            sat = (val & bit) != 0;
-                        }
-                    }
-                    const uint32_t ms = sat ? m : 0u;
+                    const uint32_t sat = (val >> (row.x >> 16)) & (val >> (row.y & 0xFFFF)) & 1u;   // rule condition AND derived-role condition
+                    const uint32_t ms = (am * rc) & alive & (0u - sat);
                     const bool deny = row_effect(row) == CB_EFFECT_DENY;
                     D |= deny ? ms : 0u;
                     A |= deny ? 0u : ms;

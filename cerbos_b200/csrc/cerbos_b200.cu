@@ -39,13 +39,17 @@ struct TableDesc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// Persistent CheckResources kernel. stage != 0: TMA-stage the table image into dynamic shared memory.
+// Persistent CheckResources kernel. Staged: the table image is TMA-copied into dynamic shared memory.
 // kFast: the lean resource-policy-only body (cb::eval_request_fast), else the general body with 64-bit pair masks.
-template <bool kFast>
+// kStageMode 0: table read from global memory, 1: from the staged shared-memory image (compile-time, so that every
+// table access of the lean body is an LDS with 32-bit address arithmetic instead of a generic load), 2: decided by
+// the `stage_rt` argument (general body: one instantiation keeps the build time down).
+template <bool kFast, int kStageMode>
 __global__ void __launch_bounds__(kThreads, 4) check_kernel(const __grid_constant__ TableDesc td, const __grid_constant__ cb::BatchView bv, uint8_t *bitmap,
-                                                          uint8_t *effects, uint32_t *status, const uint32_t kStage) {
+                                                          uint8_t *effects, uint32_t *status, const uint32_t stage_rt) {
     extern __shared__ __align__(128) uint8_t smem_image[];
     __shared__ __align__(8) uint64_t mbar;
+    const bool kStage = kStageMode == 2 ? stage_rt != 0 : kStageMode == 1;
     const uint8_t *base = td.base;
     if (kStage) {
         if (threadIdx.x == 0) {
@@ -69,7 +73,7 @@ __global__ void __launch_bounds__(kThreads, 4) check_kernel(const __grid_constan
         base = smem_image;
     }
     cb::TableView tv;
-    tv.base = base;
+    tv.base = kStageMode == 1 ? smem_image : kStageMode == 0 ? td.base : base;
     tv.L = &td.lay;
     const uint64_t n_tiles = (bv.count + kThreads - 1) / kThreads;
     bool staged = !kStage;
@@ -268,7 +272,7 @@ struct cgpu_table {
     uint8_t *d_image = nullptr;
     TableDesc desc{};
     uint32_t meta[CB_META_WORDS]{};
-    std::atomic<int> occ[2]{};   // resident CTAs / SM per kernel variant (0 = not queried yet)
+    std::atomic<int> occ[4]{};   // resident CTAs / SM per kernel variant (0 = not queried yet)
 };
 
 namespace {
@@ -406,15 +410,16 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
     const bool narrow = !ctx->force_general && bv.n_pass == 1 && (uint64_t)bv.max_actions * bv.role_cols <= 32 && bv.kbytes <= 4 &&
                         !lay.has_principal_policies && !lay.has_role_policies && !lay.has_parent_roles &&
                         t->meta[CB_META_DIRECT_KINDS] && (uint64_t)lay.nR * rcp <= 64;
-    const void *fn = narrow ? (const void *)check_kernel<true> : (const void *)check_kernel<false>;
+    const void *fn = narrow ? (stage ? (const void *)check_kernel<true, 1> : (const void *)check_kernel<true, 0>) : (const void *)check_kernel<false, 2>;
     // resident CTAs per SM for this table's shared-memory footprint: queried once per (table, variant)
     cgpu_table *mt = const_cast<cgpu_table *>(t);
-    int occ = mt->occ[narrow].load(std::memory_order_relaxed);
+    const int variant = narrow ? (stage ? 1 : 2) : (stage ? 0 : 3);
+    int occ = mt->occ[variant].load(std::memory_order_relaxed);
     if (occ == 0) {
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxStageBytes));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, smem));
         if (occ < 1) occ = 1;
-        mt->occ[narrow].store(occ, std::memory_order_relaxed);
+        mt->occ[variant].store(occ, std::memory_order_relaxed);
     }
     uint64_t max_ctas = (uint64_t)ctx->sm_count * (uint64_t)occ;
     uint32_t grid = (uint32_t)(tiles < max_ctas ? tiles : max_ctas);

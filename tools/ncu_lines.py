@@ -72,3 +72,17 @@ if show_sass:
     print("--- top SASS")
     for a, src, ie, sm, ti, d in sorted(data, key=lambda x: -x[3])[:top]:
         print(f"{a-base:6x} {linemap.get((fn, a-base),'?'):>22} inst {ie:>10} samp {sm:>6} thr {ti/max(ie,1):5.1f}  {src[:90]}")
+if "--regions" in sys.argv:
+    print("--- regions (cb_core.h line ranges)")
+    import bisect
+    regs = collections.defaultdict(lambda: [0, 0, 0])
+    for k, (ie, sm, ti) in agg.items():
+        m = re.match(r"(\S+):(\d+)", k)
+        if not m:
+            regs[k][0] += ie; regs[k][1] += sm; regs[k][2] += ti
+            continue
+        f, l = m.group(1), int(m.group(2))
+        name = f if f != "cb_core.h" else f"cb_core.h:{l // 50 * 50}-{l // 50 * 50 + 49}"
+        regs[name][0] += ie; regs[name][1] += sm; regs[name][2] += ti
+    for k, (ie, sm, ti) in sorted(regs.items(), key=lambda kv: -kv[1][0]):
+        print(f"{k:>28}  inst {ie:>11} ({100*ie/max(tot,1):5.1f}%)  samp {sm:>7} ({100*sm/max(ts,1):5.1f}%)  thr/inst {ti/max(ie,1):5.1f}")
