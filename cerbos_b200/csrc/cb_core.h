@@ -1068,6 +1068,42 @@ CB_HD uint64_t term_operand(const TableView t, const BatchView &b, uint64_t n, u
     }
     return kErr;
 }
+// shape-specialised term kernels (bytecode._specialize_term): straight-line code, same results as the generic term
+CB_HD bool v64_bad(uint64_t x) { return ((uint32_t)(x >> 48) & 0xFFFEu) == (CB_V64_BOX_BASE | CB_V64_ABSENT); }   // ABSENT or ERROR
+CB_HD int eq_tri(uint64_t x, uint64_t y, bool &slow) {
+    const uint32_t tx = v64_tag(x), ty = v64_tag(y);
+    if (v64_bad(x) || v64_bad(y)) return TRI_E;
+    if (tx == 0 && ty == 0) return u2d(x) == u2d(y);
+    if (tx <= CB_V64_STRING && ty <= CB_V64_STRING) return x == y;   // null / bool / interned string / mixed
+    slow = true;                                                       // containers
+    return TRI_E;
+}
+CB_HD int ord_tri(uint32_t ci, uint64_t x, uint64_t y, bool &slow) {
+    const uint32_t tx = v64_tag(x), ty = v64_tag(y);
+    if (v64_bad(x) || v64_bad(y)) return TRI_E;
+    if (tx == 0 && ty == 0) {
+        const double dx = u2d(x), dy = u2d(y);
+        if (dx != dx || dy != dy) return TRI_E;
+        return ci == 2 ? dx < dy : ci == 3 ? dx <= dy : ci == 4 ? dx > dy : dx >= dy;
+    }
+    if (tx != ty) return TRI_E;   // no ordering across types
+    slow = true;                  // strings, bools ...: out of line
+    return TRI_E;
+}
+// x in list(y); elems_scalar: the list is a table constant whose elements are known to be scalars
+CB_HD int in_tri(const TableView t, const BatchView &b, uint64_t x, uint64_t y, bool elems_scalar, bool &slow) {
+    if (v64_bad(x) || v64_bad(y)) return TRI_E;
+    if (v64_tag(y) != CB_V64_LIST || v64_tag(x) > CB_V64_STRING) { slow = true; return TRI_E; }
+    const uint64_t *p = list_ptr(t, b, y);
+    const uint32_t ln = (uint32_t)ldg(p);
+    bool found = false;
+    for (uint32_t j = 0; j < ln; j++) {
+        const uint64_t e = ldg(p + 1 + j);
+        if (!elems_scalar) slow |= v64_tag(e) > CB_V64_STRING;
+        found |= scalar_eq64(x, e);
+    }
+    return found;
+}
 // -> bit0 satisfied, bit2: needs the out-of-line general path
 CB_HD uint32_t flat_dnf_inline(const TableView t, const BatchView &b, uint64_t n, uint32_t pid, uint32_t flat_off, uint32_t info) {
     const uint32_t nt = info & 0xFFFF;
@@ -1076,78 +1112,90 @@ CB_HD uint32_t flat_dnf_inline(const TableView t, const BatchView &b, uint64_t n
     for (uint32_t i = 0; i < nt; i++) {
         const U4 w = ld16(terms + 2 * i);   // {op | flags<<8 | xk<<16 | yk<<24, x, y, xa | ya<<16}
         const uint32_t op = w.x & 0xFF, flags = (w.x >> 8) & 0xFF, xk = (w.x >> 16) & 0xFF, yk = w.x >> 24;
-        const uint64_t x = term_operand(t, b, n, pid, xk, w.y, w.w & 0xFFFF);
-        const uint64_t y = op == CB_TERM_HAS ? 0 : term_operand(t, b, n, pid, yk, w.z, w.w >> 16);
-        const uint32_t tx = v64_tag(x), ty = v64_tag(y);
-        const bool xerr = tx == CB_V64_ABSENT || tx == CB_V64_ERROR, yerr = ty == CB_V64_ABSENT || ty == CB_V64_ERROR;
         int tri = TRI_E;
-        if (op == CB_TERM_HAS) {
-            tri = tx == CB_V64_ERROR ? TRI_E : (tx != CB_V64_ABSENT);
-        } else if (xerr || yerr) {
-            tri = TRI_E;
-        } else if (op == CB_TERM_CMP) {
-            const uint32_t ci = flags & CB_TERM_CI_MASK;
-            if (tx == 0 && ty == 0) {
-                const double dx = u2d(x), dy = u2d(y);
-                if (ci == 0) tri = dx == dy;
-                else if (dx != dx || dy != dy) tri = TRI_E;
-                else tri = ci == 2 ? dx < dy : ci == 3 ? dx <= dy : ci == 4 ? dx > dy : dx >= dy;
-            } else if (ci == 0 && tx <= CB_V64_STRING && ty <= CB_V64_STRING) tri = x == y;   // null / bool / interned string / mixed
-            else if (ci != 0 && tx != ty) tri = TRI_E;                                         // no ordering across types
-            else slow = true;                                                                  // containers, string ordering, ints
-        } else if (op == CB_TERM_IN) {
-            if (ty != CB_V64_LIST || tx > CB_V64_STRING) slow = true;   // maps, container members: out of line
-            else {
-                const uint64_t *p = list_ptr(t, b, y);
-                const uint32_t ln = (uint32_t)ldg(p);
-                bool found = false;
-                for (uint32_t j = 0; j < ln; j++) {
-                    const uint64_t e = ldg(p + 1 + j);
-                    slow |= v64_tag(e) > CB_V64_STRING;               // int / container elements
-                    found |= scalar_eq64(x, e);
+        switch (w.x & 0xFF) {
+        case CB_TERM_EQ_SS: tri = eq_tri(ldcol64(b.slots + (uint64_t)w.y * b.stride + n), ldcol64(b.slots + (uint64_t)w.z * b.stride + n), slow); break;
+        case CB_TERM_EQ_SC: tri = eq_tri(ldcol64(b.slots + (uint64_t)w.y * b.stride + n), ldg(t.consts_v64() + w.z), slow); break;
+        case CB_TERM_EQ_SP: tri = eq_tri(ldcol64(b.slots + (uint64_t)w.y * b.stride + n), ((uint64_t)(CB_V64_BOX_BASE | CB_V64_STRING) << 48) | pid, slow); break;
+        case CB_TERM_ORD_SS: tri = ord_tri(flags & CB_TERM_CI_MASK, ldcol64(b.slots + (uint64_t)w.y * b.stride + n), ldcol64(b.slots + (uint64_t)w.z * b.stride + n), slow); break;
+        case CB_TERM_ORD_SC: tri = ord_tri(flags & CB_TERM_CI_MASK, ldcol64(b.slots + (uint64_t)w.y * b.stride + n), ldg(t.consts_v64() + w.z), slow); break;
+        case CB_TERM_IN_SC: tri = in_tri(t, b, ldcol64(b.slots + (uint64_t)w.y * b.stride + n), ldg(t.consts_v64() + w.z), true, slow); break;
+        case CB_TERM_IN_CS: tri = in_tri(t, b, ldg(t.consts_v64() + w.y), ldcol64(b.slots + (uint64_t)w.z * b.stride + n), false, slow); break;
+        case CB_TERM_IN_SS: tri = in_tri(t, b, ldcol64(b.slots + (uint64_t)w.y * b.stride + n), ldcol64(b.slots + (uint64_t)w.z * b.stride + n), false, slow); break;
+        default: {
+            const uint64_t x = term_operand(t, b, n, pid, xk, w.y, w.w & 0xFFFF);
+            const uint64_t y = op == CB_TERM_HAS ? 0 : term_operand(t, b, n, pid, yk, w.z, w.w >> 16);
+            const uint32_t tx = v64_tag(x), ty = v64_tag(y);
+            const bool xerr = tx == CB_V64_ABSENT || tx == CB_V64_ERROR, yerr = ty == CB_V64_ABSENT || ty == CB_V64_ERROR;
+            if (op == CB_TERM_HAS) {
+                tri = tx == CB_V64_ERROR ? TRI_E : (tx != CB_V64_ABSENT);
+            } else if (xerr || yerr) {
+                tri = TRI_E;
+            } else if (op == CB_TERM_CMP) {
+                const uint32_t ci = flags & CB_TERM_CI_MASK;
+                if (tx == 0 && ty == 0) {
+                    const double dx = u2d(x), dy = u2d(y);
+                    if (ci == 0) tri = dx == dy;
+                    else if (dx != dx || dy != dy) tri = TRI_E;
+                    else tri = ci == 2 ? dx < dy : ci == 3 ? dx <= dy : ci == 4 ? dx > dy : dx >= dy;
+                } else if (ci == 0 && tx <= CB_V64_STRING && ty <= CB_V64_STRING) tri = x == y;   // null / bool / interned string / mixed
+                else if (ci != 0 && tx != ty) tri = TRI_E;                                         // no ordering across types
+                else slow = true;                                                                  // containers, string ordering, ints
+            } else if (op == CB_TERM_IN) {
+                if (ty != CB_V64_LIST || tx > CB_V64_STRING) slow = true;   // maps, container members: out of line
+                else {
+                    const uint64_t *p = list_ptr(t, b, y);
+                    const uint32_t ln = (uint32_t)ldg(p);
+                    bool found = false;
+                    for (uint32_t j = 0; j < ln; j++) {
+                        const uint64_t e = ldg(p + 1 + j);
+                        slow |= v64_tag(e) > CB_V64_STRING;               // int / container elements
+                        found |= scalar_eq64(x, e);
+                    }
+                    tri = found;
                 }
-                tri = found;
-            }
-        } else if (op == CB_TERM_STARTS || op == CB_TERM_ENDS || op == CB_TERM_CONTAINS) {
-            if (tx != CB_V64_STRING || ty != CB_V64_STRING) tri = TRI_E;
-            else {
-                const StrRef a = str_ref(t, b, x), c = str_ref(t, b, y);
-                if (c.len > a.len) tri = TRI_F;
-                else if (op == CB_TERM_CONTAINS) {
-                    bool hit = false;
-                    for (uint32_t o = 0; o + c.len <= a.len; o++) {
+            } else if (op == CB_TERM_STARTS || op == CB_TERM_ENDS || op == CB_TERM_CONTAINS) {
+                if (tx != CB_V64_STRING || ty != CB_V64_STRING) tri = TRI_E;
+                else {
+                    const StrRef a = str_ref(t, b, x), c = str_ref(t, b, y);
+                    if (c.len > a.len) tri = TRI_F;
+                    else if (op == CB_TERM_CONTAINS) {
+                        bool hit = false;
+                        for (uint32_t o = 0; o + c.len <= a.len; o++) {
+                            bool eq = true;
+                            for (uint32_t j = 0; j < c.len; j++) eq &= ldg(a.p + o + j) == ldg(c.p + j);
+                            hit |= eq;
+                        }
+                        tri = hit;
+                    } else {
+                        const uint8_t *ap = op == CB_TERM_STARTS ? a.p : a.p + (a.len - c.len);
                         bool eq = true;
-                        for (uint32_t j = 0; j < c.len; j++) eq &= ldg(a.p + o + j) == ldg(c.p + j);
-                        hit |= eq;
+                        for (uint32_t j = 0; j < c.len; j++) eq &= ldg(ap + j) == ldg(c.p + j);
+                        tri = eq;
                     }
-                    tri = hit;
-                } else {
-                    const uint8_t *ap = op == CB_TERM_STARTS ? a.p : a.p + (a.len - c.len);
-                    bool eq = true;
-                    for (uint32_t j = 0; j < c.len; j++) eq &= ldg(ap + j) == ldg(c.p + j);
-                    tri = eq;
+                }
+            } else {   // INTERSECTS / SUBSET on two lists (cerbos_lib.go:323-431)
+                if (tx != CB_V64_LIST || ty != CB_V64_LIST) tri = TRI_E;
+                else {
+                    const uint64_t *pa = list_ptr(t, b, x), *pb = list_ptr(t, b, y);
+                    const uint32_t na = (uint32_t)ldg(pa), nb = (uint32_t)ldg(pb);
+                    bool any_hit = false, all_hit = true;
+                    for (uint32_t i2 = 0; i2 < na; i2++) {
+                        const uint64_t ea = ldg(pa + 1 + i2);
+                        slow |= v64_tag(ea) > CB_V64_STRING;
+                        bool hit = false;
+                        for (uint32_t j = 0; j < nb; j++) {
+                            const uint64_t eb = ldg(pb + 1 + j);
+                            slow |= v64_tag(eb) > CB_V64_STRING;       // ints would need the Go-map identity rule
+                            hit |= scalar_eq64(ea, eb);
+                        }
+                        any_hit |= hit;
+                        all_hit &= hit;
+                    }
+                    tri = op == CB_TERM_INTERSECTS ? any_hit : all_hit;
                 }
             }
-        } else {   // INTERSECTS / SUBSET on two lists (cerbos_lib.go:323-431)
-            if (tx != CB_V64_LIST || ty != CB_V64_LIST) tri = TRI_E;
-            else {
-                const uint64_t *pa = list_ptr(t, b, x), *pb = list_ptr(t, b, y);
-                const uint32_t na = (uint32_t)ldg(pa), nb = (uint32_t)ldg(pb);
-                bool any_hit = false, all_hit = true;
-                for (uint32_t i2 = 0; i2 < na; i2++) {
-                    const uint64_t ea = ldg(pa + 1 + i2);
-                    slow |= v64_tag(ea) > CB_V64_STRING;
-                    bool hit = false;
-                    for (uint32_t j = 0; j < nb; j++) {
-                        const uint64_t eb = ldg(pb + 1 + j);
-                        slow |= v64_tag(eb) > CB_V64_STRING;       // ints would need the Go-map identity rule
-                        hit |= scalar_eq64(ea, eb);
-                    }
-                    any_hit |= hit;
-                    all_hit &= hit;
-                }
-                tri = op == CB_TERM_INTERSECTS ? any_hit : all_hit;
-            }
+        }
         }
         const bool lit = (flags & CB_TERM_LIT_F) ? tri == TRI_F : tri == TRI_T;
         group &= lit;

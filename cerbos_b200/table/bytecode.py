@@ -848,12 +848,63 @@ def compile_flat(ctx: TableBuilderCtx, cond: Cond, params: Params | None):
     words = []
     for g in dnf:
         for j, (t, lit_false) in enumerate(g):
+            t = _specialize_term(ctx, t)
             flags = (t["ci"] & L.TERM_CI_MASK) | (L.TERM_LIT_F if lit_false else 0) | (L.TERM_GROUP_END if j == len(g) - 1 else 0)
             (xk, xv, xa), (yk, yv, ya) = t["x"], t["y"]
             # {u8 op; u8 flags; u8 xk; u8 yk; u32 x} {u32 y; u16 xa; u16 ya}  as two (op, a, b, c) instruction slots
             words.append([t["op"], flags, xk | (yk << 8), xv])
             words.append([yv & 0xFF, (yv >> 8) & 0xFF, (yv >> 16) & 0xFFFF, xa | (ya << 16)])
     return negate, n_terms, words
+
+
+def _v64_tag(bits: int) -> int:
+    top = bits >> 48
+    return top & 0xF if (top & 0xFFF0) == 0xFFF0 else 0
+
+
+def _specialize_term(ctx: TableBuilderCtx, t: dict) -> dict:
+    """CMP / IN terms whose operand kinds are (slot | scalar constant | P.id) get a shape-specific opcode: the device
+    then runs straight-line code for the shape instead of decoding operand kinds and value classes per request."""
+    S, C, P = L.OPK["SLOT"], L.OPK["CONST"], L.OPK["PID"]
+    op, ci, x, y = t["op"], t["ci"], t["x"], t["y"]
+
+    def ctag(o):
+        return _v64_tag(const_v64(ctx, ctx.consts[o[1]])) if o[0] == C else -1
+
+    def scalar_list(o):   # constant list whose elements are all double / null / bool / string
+        if o[0] != C or ctag(o) != L.V64_LIST:
+            return False
+        off = ctx.consts[o[1]].bits
+        n = ctx.theap[off]
+        return all(_v64_tag(e) <= L.V64_STRING for e in ctx.theap[off + 1: off + 1 + n])
+
+    new = None
+    if op == L.TERM_OPS["CMP"] and ci == 0:
+        if x[0] != S and y[0] == S:
+            x, y = y, x                       # equality is symmetric
+        if x[0] == S and y[0] == S:
+            new = "EQ_SS"
+        elif x[0] == S and y[0] == C and 0 <= ctag(y) <= L.V64_STRING:
+            new = "EQ_SC"
+        elif x[0] == S and y[0] == P:
+            new = "EQ_SP"
+    elif op == L.TERM_OPS["CMP"] and ci in (2, 3, 4, 5):
+        if x[0] == C and y[0] == S:
+            x, y, ci = y, x, {2: 4, 3: 5, 4: 2, 5: 3}[ci]   # c < s  <=>  s > c
+        if x[0] == S and y[0] == S:
+            new = "ORD_SS"
+        elif x[0] == S and y[0] == C and ctag(y) == 0:
+            new = "ORD_SC"
+    elif op == L.TERM_OPS["IN"]:
+        if x[0] == S and scalar_list(y):
+            new = "IN_SC"
+        elif x[0] == C and 0 <= ctag(x) <= L.V64_STRING and y[0] == S:
+            new = "IN_CS"
+        elif x[0] == S and y[0] == S:
+            new = "IN_SS"
+    if new is None:
+        return t
+    return {"op": L.TERM_OPS[new], "ci": ci, "x": x, "y": y}
 
 
 def const_v64(ctx: TableBuilderCtx, cv: ConstVal) -> int:

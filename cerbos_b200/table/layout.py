@@ -12,7 +12,7 @@ Table blob (little endian, every section 16-byte aligned):
 from __future__ import annotations
 
 MAGIC = 0x32425243  # 'CRB2'
-VERSION = 7
+VERSION = 8
 ALIGN = 16
 
 NONE32 = 0xFFFFFFFF
@@ -140,7 +140,12 @@ OPS = {name: i for i, name in enumerate([
 # AND-ed into groups (FLAT_GROUP_END closes a group), groups are OR-ed; CONDS.flat_info = n_terms | FLAT_DNF << 16
 # | negate << 24 (final negation: a top-level `none`); 0 = the condition has no flat form.
 FLAT_DNF = 3
-TERM_OPS = {name: i for i, name in enumerate(["CMP", "IN", "STARTS", "ENDS", "CONTAINS", "HAS", "INTERSECTS", "SUBSET"])}
+TERM_OPS = {name: i for i, name in enumerate([
+    "CMP", "IN", "STARTS", "ENDS", "CONTAINS", "HAS", "INTERSECTS", "SUBSET",
+    # operand-specialised forms of CMP / IN chosen by bytecode.compile_flat (S = attribute slot, C = scalar constant or
+    # constant list of scalars, P = principal id): same semantics, straight-line device code per shape
+    "EQ_SS", "EQ_SC", "EQ_SP", "ORD_SS", "ORD_SC", "IN_SC", "IN_CS", "IN_SS",
+])}
 TERM_CI_MASK = 0x07        # flags: compare index for CMP (0 EQ, 2 LT, 3 LE, 4 GT, 5 GE)
 TERM_LIT_F = 0x20          # flags: literal is "term is BOOL false" (else "is BOOL true")
 TERM_GROUP_END = 0x40      # flags: last term of its AND-group
