@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libcerbos_b200.so")
+LIB_PATH = os.environ.get("CERBOS_B200_LIB") or os.path.join(_HERE, "_lib", "libcerbos_b200.so")   # override: experimental builds
 
 N_COLUMNS = 12
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE = 0, -1, -2, -3, -4
@@ -106,8 +106,9 @@ class Context:
         cfg = {"grid": g.value, "block": b.value, "smem_bytes": s.value & 0x7FFFFFFF, "lean_body": bool(s.value >> 31)}
         c, w, nb = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
         _check(lib().cgpu_last_cluster_config(self._h, ctypes.byref(c), ctypes.byref(w), ctypes.byref(nb)))
-        cfg["clustered"] = bool(c.value)
-        if c.value:
+        cfg["clustered"] = bool(c.value & 1)
+        cfg["tma_column_tiles"] = bool(c.value & 2)
+        if c.value & 1:
             cfg["cluster_window"] = w.value
             cfg["cluster_buckets"] = nb.value
         return cfg

@@ -91,6 +91,7 @@ struct BatchView {
     uint32_t rcp, stride_pattern;   // set by finish_batch_view(): pow2 >= role_cols; bit j*role_cols for every j (32-bit)
     int64_t now;
     const uint32_t *perm;       // clustered evaluation order (request offsets from `first`), or null = index order
+    uint32_t prefetch_slots;    // > 0: the table reads this many slot columns in all (few): prefetch every one per tile
 };
 
 // Table data may live in shared memory (TMA-staged image) or in global memory, heap references may point
@@ -99,6 +100,7 @@ struct BatchView {
 // derived BatchView fields (host side, once per launch)
 inline void finish_batch_view(BatchView &b) {
     b.perm = nullptr;
+    b.prefetch_slots = 0;
     b.rcp = 1;
     while (b.rcp < b.role_cols) b.rcp <<= 1;
     b.stride_pattern = 0;
@@ -984,6 +986,38 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------- column access
+// The lean body reads the per-request columns through one of two accessors: straight from global memory (any
+// evaluation order), or from a tile of the columns that the TMA unit staged in shared memory one tile ahead
+// (index order only).  Layout of a staged tile of CB_TILE requests:
+//   [hdr0 CB_TILE x 16 B][hdr1 CB_TILE x 8 B][roles role_cols x CB_TILE x 4 B][slots n_slots x CB_TILE x 8 B]
+enum { CB_TILE = 256 };
+struct GlobalCols {
+    const BatchView *b;
+    uint64_t n;
+    CB_HD U4 hdr0() const { return ldcol128(b->hdr0 + n); }
+    CB_HD uint64_t hdr1() const { return ldcol64(reinterpret_cast<const uint64_t *>(b->hdr1 + n)); }
+    CB_HD uint32_t role(uint32_t i) const { return ldcol32(b->roles + (uint64_t)i * b->stride + n); }
+    CB_HD uint64_t slot(uint32_t v) const { return ldcol64(b->slots + (uint64_t)v * b->stride + n); }
+    CB_HD void prefetch_slot(uint32_t v) const {
+#if defined(__CUDA_ARCH__)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(b->slots + (uint64_t)v * b->stride + n));
+#endif
+    }
+    CB_HD bool staged() const { return b->prefetch_slots != 0; }   // every slot column was prefetched with the tile
+};
+struct TileCols {
+    const uint8_t *base;   // staged tile (shared memory on the device)
+    uint32_t tid, slots_off;
+    CB_HD U4 hdr0() const { return *reinterpret_cast<const U4 *>(base + tid * 16u); }
+    CB_HD uint64_t hdr1() const { return *reinterpret_cast<const uint64_t *>(base + CB_TILE * 16u + tid * 8u); }
+    CB_HD uint32_t role(uint32_t i) const { return *reinterpret_cast<const uint32_t *>(base + CB_TILE * 24u + i * (CB_TILE * 4u) + tid * 4u); }
+    CB_HD uint64_t slot(uint32_t v) const { return *reinterpret_cast<const uint64_t *>(base + slots_off + v * (CB_TILE * 8u) + tid * 8u); }
+    CB_HD void prefetch_slot(uint32_t) const {}
+    CB_HD bool staged() const { return true; }
+};
+CB_HD uint32_t tile_cols_bytes(uint32_t role_cols, uint32_t n_slots) { return CB_TILE * (24u + 4u * role_cols + 8u * n_slots); }
+
 // ---------------------------------------------------------------------------------------------- flat fast path
 enum { TRI_F = 0, TRI_T = 1, TRI_E = 2, TRI_SLOW = 3 };
 
@@ -1046,11 +1080,12 @@ CB_HD const uint64_t *list_ptr(const TableView t, const BatchView &b, uint64_t v
 CB_HD bool scalar_eq64(uint64_t x, uint64_t y) {
     return (v64_tag(x) == 0 && v64_tag(y) == 0) ? u2d(x) == u2d(y) : x == y;
 }
-CB_HD uint64_t term_operand(const TableView t, const BatchView &b, uint64_t n, uint32_t pid, uint32_t kind, uint32_t v, uint32_t aux) {
+template <typename Cols>
+CB_HD uint64_t term_operand(const TableView t, const BatchView &b, const Cols &cols, uint32_t pid, uint32_t kind, uint32_t v, uint32_t aux) {
     const uint64_t kErr = (uint64_t)(CB_V64_BOX_BASE | CB_V64_ERROR) << 48;
     if (kind == CB_OPK_CONST) return ldg(t.consts_v64() + v);
     if (kind == CB_OPK_PID) return ((uint64_t)(CB_V64_BOX_BASE | CB_V64_STRING) << 48) | pid;
-    uint64_t x = ldcol64(b.slots + (uint64_t)v * b.stride + n);
+    uint64_t x = cols.slot(v);
     if (kind == CB_OPK_SLOT) return x;
     uint32_t tx = v64_tag(x);
     if (kind == CB_OPK_SLOT_ELEM) {
@@ -1105,7 +1140,8 @@ CB_HD int in_tri(const TableView t, const BatchView &b, uint64_t x, uint64_t y, 
     return found;
 }
 // -> bit0 satisfied, bit2: needs the out-of-line general path
-CB_HD uint32_t flat_dnf_inline(const TableView t, const BatchView &b, uint64_t n, uint32_t pid, uint32_t flat_off, uint32_t info) {
+template <typename Cols>
+CB_HD uint32_t flat_dnf_inline(const TableView t, const BatchView &b, const Cols &cols, uint32_t pid, uint32_t flat_off, uint32_t info) {
     const uint32_t nt = info & 0xFFFF;
     const cb_instr *terms = t.code() + flat_off;
     bool any = false, group = true, slow = false;
@@ -1114,17 +1150,17 @@ CB_HD uint32_t flat_dnf_inline(const TableView t, const BatchView &b, uint64_t n
         const uint32_t op = w.x & 0xFF, flags = (w.x >> 8) & 0xFF, xk = (w.x >> 16) & 0xFF, yk = w.x >> 24;
         int tri = TRI_E;
         switch (w.x & 0xFF) {
-        case CB_TERM_EQ_SS: tri = eq_tri(ldcol64(b.slots + (uint64_t)w.y * b.stride + n), ldcol64(b.slots + (uint64_t)w.z * b.stride + n), slow); break;
-        case CB_TERM_EQ_SC: tri = eq_tri(ldcol64(b.slots + (uint64_t)w.y * b.stride + n), ldg(t.consts_v64() + w.z), slow); break;
-        case CB_TERM_EQ_SP: tri = eq_tri(ldcol64(b.slots + (uint64_t)w.y * b.stride + n), ((uint64_t)(CB_V64_BOX_BASE | CB_V64_STRING) << 48) | pid, slow); break;
-        case CB_TERM_ORD_SS: tri = ord_tri(flags & CB_TERM_CI_MASK, ldcol64(b.slots + (uint64_t)w.y * b.stride + n), ldcol64(b.slots + (uint64_t)w.z * b.stride + n), slow); break;
-        case CB_TERM_ORD_SC: tri = ord_tri(flags & CB_TERM_CI_MASK, ldcol64(b.slots + (uint64_t)w.y * b.stride + n), ldg(t.consts_v64() + w.z), slow); break;
-        case CB_TERM_IN_SC: tri = in_tri(t, b, ldcol64(b.slots + (uint64_t)w.y * b.stride + n), ldg(t.consts_v64() + w.z), true, slow); break;
-        case CB_TERM_IN_CS: tri = in_tri(t, b, ldg(t.consts_v64() + w.y), ldcol64(b.slots + (uint64_t)w.z * b.stride + n), false, slow); break;
-        case CB_TERM_IN_SS: tri = in_tri(t, b, ldcol64(b.slots + (uint64_t)w.y * b.stride + n), ldcol64(b.slots + (uint64_t)w.z * b.stride + n), false, slow); break;
+        case CB_TERM_EQ_SS: tri = eq_tri(cols.slot(w.y), cols.slot(w.z), slow); break;
+        case CB_TERM_EQ_SC: tri = eq_tri(cols.slot(w.y), ldg(t.consts_v64() + w.z), slow); break;
+        case CB_TERM_EQ_SP: tri = eq_tri(cols.slot(w.y), ((uint64_t)(CB_V64_BOX_BASE | CB_V64_STRING) << 48) | pid, slow); break;
+        case CB_TERM_ORD_SS: tri = ord_tri(flags & CB_TERM_CI_MASK, cols.slot(w.y), cols.slot(w.z), slow); break;
+        case CB_TERM_ORD_SC: tri = ord_tri(flags & CB_TERM_CI_MASK, cols.slot(w.y), ldg(t.consts_v64() + w.z), slow); break;
+        case CB_TERM_IN_SC: tri = in_tri(t, b, cols.slot(w.y), ldg(t.consts_v64() + w.z), true, slow); break;
+        case CB_TERM_IN_CS: tri = in_tri(t, b, ldg(t.consts_v64() + w.y), cols.slot(w.z), false, slow); break;
+        case CB_TERM_IN_SS: tri = in_tri(t, b, cols.slot(w.y), cols.slot(w.z), false, slow); break;
         default: {
-            const uint64_t x = term_operand(t, b, n, pid, xk, w.y, w.w & 0xFFFF);
-            const uint64_t y = op == CB_TERM_HAS ? 0 : term_operand(t, b, n, pid, yk, w.z, w.w >> 16);
+            const uint64_t x = term_operand(t, b, cols, pid, xk, w.y, w.w & 0xFFFF);
+            const uint64_t y = op == CB_TERM_HAS ? 0 : term_operand(t, b, cols, pid, yk, w.z, w.w >> 16);
             const uint32_t tx = v64_tag(x), ty = v64_tag(y);
             const bool xerr = tx == CB_V64_ABSENT || tx == CB_V64_ERROR, yerr = ty == CB_V64_ABSENT || ty == CB_V64_ERROR;
             if (op == CB_TERM_HAS) {
@@ -1206,9 +1242,10 @@ CB_HD uint32_t flat_dnf_inline(const TableView t, const BatchView &b, uint64_t n
 }
 // condition `gid` on the call-free fast path: bit0 satisfied, bit2 = cannot decide here (no flat form or an
 // unusual operand): the request is then re-evaluated by the general body
-CB_HD uint32_t cond_eval(const TableView t, const BatchView &b, uint64_t n, uint32_t pid, uint32_t gid) {
+template <typename Cols>
+CB_HD uint32_t cond_eval(const TableView t, const BatchView &b, const Cols &cols, uint32_t pid, uint32_t gid) {
     U4 cd = ld16(t.conds() + gid);   // {code_off, code_len, flat_off, flat_info}
-    if (cd.w) return flat_dnf_inline(t, b, n, pid, cd.z, cd.w);
+    if (cd.w) return flat_dnf_inline(t, b, cols, pid, cd.z, cd.w);
     return 4u;
 }
 
@@ -1240,7 +1277,10 @@ CB_HD void prefetch_l1(const void *p) {
 CB_HD void prefetch_request(const BatchView &b, uint64_t n) {
     prefetch_l1(b.hdr0 + n);
     prefetch_l1(b.hdr1 + n);
-    for (uint32_t i = 0; i < b.role_cols; i++) prefetch_l1(b.roles + (uint64_t)i * b.stride + n);
+    const uint32_t *pr = b.roles + n;
+    for (uint32_t i = 0; i < b.role_cols; i++, pr += b.stride) prefetch_l1(pr);
+    const uint64_t *ps = b.slots + n;
+    for (uint32_t q = 0; q < b.prefetch_slots; q++, ps += b.stride) prefetch_l1(ps);
 }
 
 // The resource patterns a request kind matches; kc is hdr0.kind_class: the pattern id itself when there is exactly
@@ -1583,9 +1623,10 @@ CB_HD void eval_request(const TableView t, const BatchView &b, uint64_t n, uint8
 // condition without a flat form, an operand the 8-byte fast forms cannot decide, differing policy versions, or
 // a block with more than 32 conditions.  The body itself makes NO calls, so nothing is forced into local memory,
 // and its loops contain no early exits (`continue` / `break` would leave lanes diverged until the loop ends).
-CB_HD bool eval_request_fast(const TableView t, const BatchView &b, uint64_t n, uint8_t *bitmap, uint8_t *effects) {
-    const U4 h0 = ldcol128(b.hdr0 + n);                                           // principal_id, kind (pattern id), resource_scope, principal_scope
-    const uint64_t h1 = ldcol64(reinterpret_cast<const uint64_t *>(b.hdr1 + n));  // rv u16 | pv u16 | action_set_id u32
+template <typename Cols>
+CB_HD bool eval_request_fast(const TableView t, const BatchView &b, const Cols &cols, uint64_t n, uint8_t *bitmap, uint8_t *effects) {
+    const U4 h0 = cols.hdr0();         // principal_id, kind (pattern id), resource_scope, principal_scope
+    const uint64_t h1 = cols.hdr1();   // rv u16 | pv u16 | action_set_id u32
     const uint32_t pid = h0.x, kc = h0.y, rscope = h0.z;
     const uint32_t rv = (uint32_t)(h1 & 0xFFFF), pv = (uint32_t)((h1 >> 16) & 0xFFFF), aset = (uint32_t)(h1 >> 32);
     const uint32_t RC = b.role_cols, RCP = b.rcp;
@@ -1593,7 +1634,7 @@ CB_HD bool eval_request_fast(const TableView t, const BatchView &b, uint64_t n, 
     uint64_t rp = 0;          // role table: RCP bits per table role
     uint32_t n_roles = 0;
     for (uint32_t i = 0; i < RC; i++) {
-        uint32_t rr = ldcol32(b.roles + (uint64_t)i * b.stride + n);
+        uint32_t rr = cols.role(i);
         n_roles = rr != CB_ROLE_PAD ? i + 1 : n_roles;
         rp |= rr < t.L->nR ? 1ull << (rr * RCP + i) : 0ull;
     }
@@ -1604,7 +1645,6 @@ CB_HD bool eval_request_fast(const TableView t, const BatchView &b, uint64_t n, 
     if (r0 != CB_NONE32) {
         const uint32_t role_all = (1u << n_roles) - 1;
         const uint64_t *row_am = b.row_am + (uint64_t)aset * b.n_rows;
-        const uint64_t *slots_n = b.slots + n;
         const uint32_t amask = K * RC >= 32 ? b.stride_pattern : b.stride_pattern & ((1u << (K * RC)) - 1);   // bit kk*RC per action
         uint32_t alive = amask * role_all, allow_pairs = 0;
         bool defer = false;
@@ -1612,8 +1652,9 @@ CB_HD bool eval_request_fast(const TableView t, const BatchView &b, uint64_t n, 
             const uint32_t bid = ldg(t.res_block_map() + ((uint64_t)rv * t.L->nRP + kc) * t.L->nS + s);
             if (bid != CB_NONE32) {
                 // pull the attribute slots this block's conditions read towards L1 so the lazy loads overlap
-                for (uint32_t q = ldg(t.block_slots_off() + bid), e = ldg(t.block_slots_off() + bid + 1); q < e; q++)
-                    prefetch_l1(slots_n + (uint64_t)ldg(t.block_slots() + q) * b.stride);
+                if (!cols.staged())
+                    for (uint32_t q = ldg(t.block_slots_off() + bid), e = ldg(t.block_slots_off() + bid + 1); q < e; q++)
+                        cols.prefetch_slot(ldg(t.block_slots() + q));
                 const U4 bl = ld16(t.blocks() + bid);   // {row_start, n_rows, cond_base, n_conds}
                 defer |= bl.w > 31;
                 // phase 1: every condition of the block, once, into one bit each (bit 0 = "no condition" = true).  The
@@ -1621,7 +1662,7 @@ CB_HD bool eval_request_fast(const TableView t, const BatchView &b, uint64_t n, 
                 // ignores its bit (conditions have no side effects; an operand this path cannot decide defers).
                 uint32_t val = 1;
                 for (uint32_t c = 0, nc = bl.w > 31 ? 0 : bl.w; c < nc; c++) {
-                    const uint32_t r = cond_eval(t, b, n, pid, bl.z + c);
+                    const uint32_t r = cond_eval(t, b, cols, pid, bl.z + c);
                     defer |= (r & 4) != 0;
                     val |= (r & 1) << (c + 1);
                 }
@@ -1661,8 +1702,11 @@ CB_HD bool eval_request_fast(const TableView t, const BatchView &b, uint64_t n, 
             for (uint32_t k = 0; k < b.max_actions; k++) eff[k] = (uint8_t)(k < K ? (((acc >> k) & 1) ? CB_EFFECT_ALLOW : CB_EFFECT_DENY) : 0);
         }
     } else {
-        uint8_t *out = bitmap + n * b.kbytes;
-        for (uint32_t q = 0; q < b.kbytes; q++) out[q] = (uint8_t)(acc >> (8 * q));
+        if (b.kbytes == 1) bitmap[n] = (uint8_t)acc;
+        else {
+            uint8_t *out = bitmap + n * b.kbytes;
+            for (uint32_t q = 0; q < b.kbytes; q++) out[q] = (uint8_t)(acc >> (8 * q));
+        }
     }
     return false;
 }

@@ -29,8 +29,12 @@
 namespace {
 
 constexpr int kThreads = 256;
+#ifndef CB_MIN_BLOCKS
+#define CB_MIN_BLOCKS 4   // resident CTAs / SM the check kernel is register-budgeted for (64 registers per thread)
+#endif
 constexpr uint32_t kMaxStageBytes = 96 * 1024;   // table images up to this size are TMA-staged into shared memory
 constexpr int kMaxSec = 28;
+constexpr uint32_t kMaxTilesSmem = 56 * 1024;    // image + two column-tile stages: keeps CB_MIN_BLOCKS CTAs resident per SM
 
 struct TableDesc {
     const uint8_t *base;       // device blob image
@@ -45,7 +49,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 // table access of the lean body is an LDS with 32-bit address arithmetic instead of a generic load), 2: decided by
 // the `stage_rt` argument (general body: one instantiation keeps the build time down).
 template <bool kFast, int kStageMode>
-__global__ void __launch_bounds__(kThreads, 4) check_kernel(const __grid_constant__ TableDesc td, const __grid_constant__ cb::BatchView bv, uint8_t *bitmap,
+__global__ void __launch_bounds__(kThreads, CB_MIN_BLOCKS) check_kernel(const __grid_constant__ TableDesc td, const __grid_constant__ cb::BatchView bv, uint8_t *bitmap,
                                                           uint8_t *effects, uint32_t *status, const uint32_t stage_rt) {
     extern __shared__ __align__(128) uint8_t smem_image[];
     __shared__ __align__(8) uint64_t mbar;
@@ -76,6 +80,10 @@ __global__ void __launch_bounds__(kThreads, 4) check_kernel(const __grid_constan
     tv.base = kStageMode == 1 ? smem_image : kStageMode == 0 ? td.base : base;
     tv.L = &td.lay;
     const uint64_t n_tiles = (bv.count + kThreads - 1) / kThreads;
+    {   // columns of this thread's first request: in flight while the table image is still being staged
+        const uint64_t i0 = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+        if (i0 < bv.count) cb::prefetch_request(bv, bv.first + (bv.perm ? bv.perm[i0] : i0));
+    }
     bool staged = !kStage;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         uint64_t i = tile * kThreads + threadIdx.x;
@@ -103,7 +111,9 @@ __global__ void __launch_bounds__(kThreads, 4) check_kernel(const __grid_constan
         if (i < bv.count) {
             if (kFast) {
                 // call-free lean body; the (rare) requests it cannot decide are redone by the general body
-                if (cb::eval_request_fast(tv, bv, bv.first + req, bitmap, effects))
+                cb::GlobalCols gc;
+                gc.b = &bv; gc.n = bv.first + req;
+                if (cb::eval_request_fast(tv, bv, gc, bv.first + req, bitmap, effects))
                     cb::eval_request_general(tv.base, tv.L, &bv, bv.first + req, bitmap, effects, status);
             } else cb::eval_request<uint64_t>(tv, bv, bv.first + req, bitmap, effects, status);
         }
@@ -119,6 +129,86 @@ __global__ void __launch_bounds__(kThreads, 4) check_kernel(const __grid_constan
                 : "memory");
         }
     }
+}
+
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Lean body with BOTH the table image and the request columns staged by the TMA unit.  Index-order batches only
+// (the columns of a tile of 256 requests are contiguous runs: 2 + role_cols + n_slots bulk copies per tile, issued by
+// one thread, double-buffered: tile k+1 streams into shared memory while tile k is evaluated, so no thread ever
+// waits on DRAM and every column read is an LDS).  Shared memory: [image][tile stage 0][tile stage 1].
+__global__ void __launch_bounds__(kThreads, CB_MIN_BLOCKS) check_kernel_tiles(const __grid_constant__ TableDesc td, const __grid_constant__ cb::BatchView bv,
+                                                                            uint8_t *bitmap, uint8_t *effects, uint32_t *status, const uint32_t n_slots) {
+    extern __shared__ __align__(128) uint8_t smem_image[];
+    __shared__ __align__(8) uint64_t mbar_tab, mbar_col[2];
+    const uint32_t image_pad = (td.lay.image_bytes + 127u) & ~127u;
+    const uint32_t tile_bytes = cb::tile_cols_bytes(bv.role_cols, n_slots);
+    const uint32_t slots_off = cb::CB_TILE * (24u + 4u * bv.role_cols);
+    uint8_t *stage0 = smem_image + image_pad;
+    const uint64_t n_tiles = (bv.count + kThreads - 1) / kThreads, n_full = bv.count / kThreads;
+
+    auto issue_tile = [&](uint64_t tile, uint32_t st) {   // one thread: bulk copies of every column run of `tile`
+        uint8_t *dst = stage0 + st * tile_bytes;
+        const uint64_t r0 = bv.first + tile * kThreads;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar_col[st])), "r"(tile_bytes) : "memory");
+        tma_load_1d(dst, bv.hdr0 + r0, kThreads * 16, &mbar_col[st]);
+        tma_load_1d(dst + kThreads * 16, bv.hdr1 + r0, kThreads * 8, &mbar_col[st]);
+        for (uint32_t i = 0; i < bv.role_cols; i++) tma_load_1d(dst + kThreads * 24 + i * (kThreads * 4), bv.roles + i * bv.stride + r0, kThreads * 4, &mbar_col[st]);
+        for (uint32_t v = 0; v < n_slots; v++) tma_load_1d(dst + slots_off + v * (kThreads * 8), bv.slots + v * bv.stride + r0, kThreads * 8, &mbar_col[st]);
+    };
+
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar_tab)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar_col[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar_col[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar_tab)), "r"(td.lay.image_bytes) : "memory");
+        for (uint32_t o = 0; o < td.lay.image_bytes; o += 32768) {
+            uint32_t nb = td.lay.image_bytes - o < 32768 ? td.lay.image_bytes - o : 32768;
+            tma_load_1d(smem_image + o, td.base + o, nb, &mbar_tab);
+        }
+        if (blockIdx.x < n_full) issue_tile(blockIdx.x, 0);
+    }
+    cb::TableView tv;
+    tv.base = smem_image;
+    tv.L = &td.lay;
+    uint32_t k = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, k++) {
+        const uint64_t next = tile + gridDim.x;
+        // stage (k+1)&1 was last read in iteration k-1; the barrier that closed it has been passed by every thread
+        if (threadIdx.x == 0 && next < n_full) issue_tile(next, (k + 1) & 1);
+        if (k == 0) mbar_wait(&mbar_tab, 0);
+        const uint64_t n = bv.first + tile * kThreads + threadIdx.x;
+        if (tile < n_full) {
+            mbar_wait(&mbar_col[k & 1], (k >> 1) & 1);
+            cb::TileCols tc;
+            tc.base = stage0 + (k & 1) * tile_bytes; tc.tid = threadIdx.x; tc.slots_off = slots_off;
+            if (cb::eval_request_fast(tv, bv, tc, n, bitmap, effects)) cb::eval_request_general(tv.base, tv.L, &bv, n, bitmap, effects, status);
+        } else if (tile * kThreads + threadIdx.x < bv.count) {   // the ragged last tile: straight from global memory
+            cb::GlobalCols gc;
+            gc.b = &bv; gc.n = n;
+            if (cb::eval_request_fast(tv, bv, gc, n, bitmap, effects)) cb::eval_request_general(tv.base, tv.L, &bv, n, bitmap, effects, status);
+        }
+        __syncthreads();
+    }
+    if (k == 0) mbar_wait(&mbar_tab, 0);   // no tile: drain the table copy before shared memory is released
 }
 
 
@@ -258,7 +348,8 @@ struct cgpu_ctx {
     int force_no_stage = 0;
     int force_general = 0;   // CERBOS_B200_FORCE_GENERAL=1: never pick the lean kernel body (tests)
     int cluster_mode = -1;   // CERBOS_B200_CLUSTER: 0 never, 1 always, unset = batches of >= kClusterMinRequests
-    uint32_t last_clustered = 0, last_window = 0, last_buckets = 0;
+    uint32_t last_clustered = 0, last_window = 0, last_buckets = 0, last_col_tiles = 0;
+    int force_no_tiles = 0;  // CERBOS_B200_NO_TILES=1: never stage request columns through TMA (tests)
     bool profiling = false;  // cgpu_profile(): CUDA events around the check kernel of every launch
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double prof_ms = 0;
@@ -272,7 +363,8 @@ struct cgpu_table {
     uint8_t *d_image = nullptr;
     TableDesc desc{};
     uint32_t meta[CB_META_WORDS]{};
-    std::atomic<int> occ[4]{};   // resident CTAs / SM per kernel variant (0 = not queried yet)
+    std::atomic<int> occ[5]{};
+    std::atomic<uint32_t> occ_smem[5]{};   // resident CTAs / SM per kernel variant (0 = not queried yet)
 };
 
 namespace {
@@ -399,27 +491,41 @@ int launch_cluster(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, 
 
 int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, uint8_t *d_bitmap, uint8_t *d_effects,
                  uint32_t *d_status, cudaStream_t stream) {
-    const bool stage = !ctx->force_no_stage && t->desc.lay.image_bytes <= kMaxStageBytes;
-    const uint32_t smem = stage ? t->desc.lay.image_bytes : 0;
+    const cb::TableLayout &lay = t->desc.lay;
+    const bool stage = !ctx->force_no_stage && lay.image_bytes <= kMaxStageBytes;
     uint64_t tiles = (bv.count + kThreads - 1) / kThreads;
     // The lean body applies to resource-policy-only tables (no principal / role policies, parent roles or
     // resource globs) when the (action x role column) pair masks fit 32 bits and the role table fits 64 bits.
     uint32_t rcp = 1;
     while (rcp < bv.role_cols) rcp <<= 1;
-    const cb::TableLayout &lay = t->desc.lay;
     const bool narrow = !ctx->force_general && bv.n_pass == 1 && (uint64_t)bv.max_actions * bv.role_cols <= 32 && bv.kbytes <= 4 &&
                         !lay.has_principal_policies && !lay.has_role_policies && !lay.has_parent_roles &&
                         t->meta[CB_META_DIRECT_KINDS] && (uint64_t)lay.nR * rcp <= 64;
-    const void *fn = narrow ? (stage ? (const void *)check_kernel<true, 1> : (const void *)check_kernel<true, 0>) : (const void *)check_kernel<false, 2>;
-    // resident CTAs per SM for this table's shared-memory footprint: queried once per (table, variant)
+    // Clustering pays when the policy blocks differ in shape (rows / conditions): with a single shape every lane runs
+    // the same control flow in index order already and the coalesced column loads are worth more.
+    const bool cluster = bv.count < (1ull << 32) &&
+                         (ctx->cluster_mode == 1 || (ctx->cluster_mode != 0 && bv.count >= kClusterMinRequests && t->meta[CB_META_BLOCK_SHAPES] > 1));
+    // Index-order lean launches stage the request columns through TMA too, when every tile's column runs are
+    // 16-byte aligned and image + two tile stages fit the shared-memory budget of CB_MIN_BLOCKS resident CTAs.
+    const uint32_t tile_bytes = cb::tile_cols_bytes(bv.role_cols, lay.n_slots);
+    const uint32_t tiles_smem = ((lay.image_bytes + 127u) & ~127u) + 2 * tile_bytes;
+    auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const bool col_tiles = narrow && stage && !cluster && !ctx->force_no_tiles && tiles_smem <= kMaxTilesSmem && bv.stride % 4 == 0 &&
+                           bv.first % 4 == 0 && al16(bv.hdr0) && al16(bv.hdr1) && al16(bv.roles) && al16(bv.slots);
+    const uint32_t smem = col_tiles ? tiles_smem : stage ? lay.image_bytes : 0;
+    const void *fn = col_tiles ? (const void *)check_kernel_tiles
+                     : narrow  ? (stage ? (const void *)check_kernel<true, 1> : (const void *)check_kernel<true, 0>)
+                               : (const void *)check_kernel<false, 2>;
+    // resident CTAs per SM for this shared-memory footprint: queried once per (table, variant, footprint)
     cgpu_table *mt = const_cast<cgpu_table *>(t);
-    const int variant = narrow ? (stage ? 1 : 2) : (stage ? 0 : 3);
-    int occ = mt->occ[variant].load(std::memory_order_relaxed);
+    const int variant = col_tiles ? 4 : narrow ? (stage ? 1 : 2) : (stage ? 0 : 3);
+    int occ = mt->occ_smem[variant].load(std::memory_order_relaxed) == smem ? mt->occ[variant].load(std::memory_order_relaxed) : 0;
     if (occ == 0) {
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxStageBytes));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, smem));
         if (occ < 1) occ = 1;
         mt->occ[variant].store(occ, std::memory_order_relaxed);
+        mt->occ_smem[variant].store(smem, std::memory_order_relaxed);
     }
     uint64_t max_ctas = (uint64_t)ctx->sm_count * (uint64_t)occ;
     uint32_t grid = (uint32_t)(tiles < max_ctas ? tiles : max_ctas);
@@ -427,18 +533,17 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
     TableDesc td = t->desc;
     cb::BatchView bvv = bv;
     bvv.perm = nullptr;
-    // Clustering pays when the policy blocks differ in shape (rows / conditions): with a single shape every lane runs
-    // the same control flow in index order already and the coalesced column loads are worth more.
-    const bool cluster = bv.count < (1ull << 32) &&
-                         (ctx->cluster_mode == 1 || (ctx->cluster_mode != 0 && bv.count >= kClusterMinRequests && t->meta[CB_META_BLOCK_SHAPES] > 1));
+    // few slot columns: every tile prefetches all of them one tile ahead (all loads of the tile then hit L1);
+    // otherwise each policy block prefetches the slots its own conditions read
+    bvv.prefetch_slots = lay.n_slots <= 8 ? lay.n_slots : 0;
     uint32_t *perm = nullptr;
     if (cluster) {
         int rc = launch_cluster(ctx, t, bv, &perm, stream);
         if (rc != CGPU_OK) return rc;
         bvv.perm = perm;
     }
-    uint32_t stage_flag = stage ? 1u : 0u;
-    void *args[] = {&td, &bvv, &d_bitmap, &d_effects, &d_status, &stage_flag};
+    uint32_t last_arg = col_tiles ? lay.n_slots : (stage ? 1u : 0u);   // check_kernel: stage_rt; check_kernel_tiles: n_slots
+    void *args[] = {&td, &bvv, &d_bitmap, &d_effects, &d_status, &last_arg};
     if (ctx->profiling) {
         if (ctx->prof_pending && cudaEventSynchronize(ctx->ev1) == cudaSuccess) {
             float ms = 0;
@@ -454,6 +559,7 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
     ctx->last_grid = grid; ctx->last_block = kThreads; ctx->last_smem = smem; ctx->last_fast = narrow ? 1 : 0;
     ctx->last_clustered = cluster ? 1 : 0;
+    ctx->last_col_tiles = col_tiles ? 1 : 0;
     return CGPU_OK;
 }
 
@@ -485,6 +591,8 @@ int cgpu_init(const int *device_ids, int n_devices, cgpu_ctx **out) {
     ctx->force_no_stage = ns && ns[0] == '1';
     const char *fg = getenv("CERBOS_B200_FORCE_GENERAL");
     ctx->force_general = fg && fg[0] == '1';
+    const char *nt = getenv("CERBOS_B200_NO_TILES");
+    ctx->force_no_tiles = nt && nt[0] == '1';
     const char *cm = getenv("CERBOS_B200_CLUSTER");
     ctx->cluster_mode = cm && (cm[0] == '0' || cm[0] == '1') ? cm[0] - '0' : -1;
     // stream-ordered scratch (clustering): keep freed blocks in the pool instead of returning them to the driver
@@ -567,7 +675,7 @@ int cgpu_last_kernel_config(const cgpu_ctx *ctx, uint32_t *grid, uint32_t *block
 
 int cgpu_last_cluster_config(const cgpu_ctx *ctx, uint32_t *clustered, uint32_t *window, uint32_t *buckets) {
     if (!ctx) return fail(CGPU_ERR_INVALID, "null ctx");
-    if (clustered) *clustered = ctx->last_clustered;
+    if (clustered) *clustered = ctx->last_clustered | (ctx->last_col_tiles << 1);   // bit 1: request columns were TMA-staged
     if (window) *window = ctx->last_window;
     if (buckets) *buckets = ctx->last_buckets;
     return CGPU_OK;

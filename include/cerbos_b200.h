@@ -107,7 +107,8 @@ uint64_t cgpu_launch_count(const cgpu_ctx *ctx);        /* kernels launched by t
 int cgpu_table_info(const cgpu_table *t, uint32_t *meta_out, uint32_t n_words);  /* copies META words */
 int cgpu_last_kernel_config(const cgpu_ctx *ctx, uint32_t *grid, uint32_t *block, uint32_t *smem_bytes);
 /* Whether the last launch evaluated in clustered order (requests grouped by policy block inside L2-sized windows by
- * three small kernels ahead of the check kernel; env CERBOS_B200_CLUSTER=0/1 overrides the batch-size rule). */
+ * three small kernels ahead of the check kernel; env CERBOS_B200_CLUSTER=0/1 overrides the batch-size rule).
+ * *clustered bit 0: clustered order; bit 1: the request columns were staged tile by tile through TMA. */
 int cgpu_last_cluster_config(const cgpu_ctx *ctx, uint32_t *clustered, uint32_t *window, uint32_t *buckets);
 /* Returns and resets the CUDA-event time (ms) spent in the check kernel itself over the launches since the last
  * call, then switches the per-launch events on or off. Measurement aid for bench.py; off by default. */

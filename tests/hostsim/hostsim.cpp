@@ -4,6 +4,7 @@
 // library (libcerbos_b200.so) contains no such path: without a CUDA device cgpu_init fails.
 #include <cstdint>
 #include <cstring>
+#include <vector>
 
 #include "cb_core.h"
 
@@ -43,13 +44,34 @@ extern "C" int hostsim_check(const void *blob, uint64_t blob_len, uint64_t n, ui
     b.n_pass = (km + b.kc - 1) / b.kc; b.max_actions = km; b.kbytes = (km + 7) / 8; b.flags = flags; b.now = now;
     cb::finish_batch_view(b);
     uint32_t status = 0;
-    // mode 0: what the library would pick; 1: force the general 64-bit body; 2: general 32-bit body
+    // mode 0: what the library would pick; 1: force the general 64-bit body; 2: general 32-bit body;
+    // 3: the lean body reading a tile of the columns staged the way the kernel's TMA copies lay it out in shared memory
     const bool narrow = b.n_pass == 1 && (uint64_t)km * b.role_cols <= 32;
     uint32_t rcp = 1; while (rcp < b.role_cols) rcp <<= 1;
     const bool fast = narrow && !lay.has_principal_policies && !lay.has_role_policies && !lay.has_parent_roles &&
                       meta[CB_META_DIRECT_KINDS] && (uint64_t)lay.nR * rcp <= 64 && b.kbytes <= 4;
+    if (mode == 3 && fast) {
+        std::vector<uint64_t> tile(cb::tile_cols_bytes(b.role_cols, lay.n_slots) / 8 + 2);
+        uint8_t *tb = reinterpret_cast<uint8_t *>(tile.data());
+        for (uint64_t t0 = 0; t0 < n; t0 += cb::CB_TILE) {
+            const uint64_t cnt = n - t0 < cb::CB_TILE ? n - t0 : cb::CB_TILE;
+            memcpy(tb, b.hdr0 + t0, cnt * 16);
+            memcpy(tb + cb::CB_TILE * 16, b.hdr1 + t0, cnt * 8);
+            for (uint32_t i = 0; i < b.role_cols; i++) memcpy(tb + cb::CB_TILE * 24 + i * cb::CB_TILE * 4, b.roles + i * b.stride + t0, cnt * 4);
+            const uint32_t so = cb::CB_TILE * (24 + 4 * b.role_cols);
+            for (uint32_t v = 0; v < lay.n_slots; v++) memcpy(tb + so + v * cb::CB_TILE * 8, b.slots + v * b.stride + t0, cnt * 8);
+            for (uint32_t j = 0; j < cnt; j++) {
+                cb::TileCols tc; tc.base = tb; tc.tid = j; tc.slots_off = so;
+                if (cb::eval_request_fast(t, b, tc, t0 + j, bitmap, nullptr)) cb::eval_request_general(t.base, t.L, &b, t0 + j, bitmap, nullptr, &status);
+            }
+        }
+        return status ? -2 : 0;
+    }
     for (uint64_t i = 0; i < n; i++) {
-        if (mode == 0 && fast) { if (cb::eval_request_fast(t, b, i, bitmap, nullptr)) cb::eval_request_general(t.base, t.L, &b, i, bitmap, nullptr, &status); }
+        if (mode == 0 && fast) {
+            cb::GlobalCols gc; gc.b = &b; gc.n = i;
+            if (cb::eval_request_fast(t, b, gc, i, bitmap, nullptr)) cb::eval_request_general(t.base, t.L, &b, i, bitmap, nullptr, &status);
+        }
         else if (mode == 2 && narrow) cb::eval_request<uint32_t>(t, b, i, bitmap, nullptr, &status);
         else cb::eval_request<uint64_t>(t, b, i, bitmap, nullptr, &status);
     }

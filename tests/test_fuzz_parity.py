@@ -33,6 +33,6 @@ def test_random_tables(seed):
         for k, a in enumerate(inp["actions"]):
             assert c_out[j, k] == py["actions"][a]["effect"], (seed, j, a, inp)
     valid = c_out != 0
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         k_out = hostsim.check(ft.blob, b.columns, b.n, b.max_actions, 0, fl, mode=mode)
         assert (k_out[valid] == c_out[valid]).all(), (seed, mode)

@@ -220,3 +220,33 @@ def test_clustered_goldens_mixed_shapes():
     assert (got == want).all()
     t.release()
     c.close()
+
+
+@pytest.mark.parametrize("name,n", [("C2", (1 << 16) + 260), ("C2", (1 << 16) + 777), ("C1", 1024), ("C2", 200)])
+def test_tma_column_tiles_and_direct_loads_agree(name, n):
+    """Index-order lean launches stage the request columns through TMA (double-buffered 256-request tiles) when the
+    column runs are 16-byte aligned; CERBOS_B200_NO_TILES=1 forces the per-thread global loads.  Covers a ragged last
+    tile, a batch whose stride is not a multiple of 4 (must fall back) and a batch smaller than one tile."""
+    from cerbos_b200 import capi, workloads as W
+    from cerbos_b200.device import DeviceBatch
+    from oracle import cref
+    w = W.WORKLOADS[name]()
+    _, ft, enc = W.build(w)
+    b = w.columns(w.fields(n), enc)
+    want = cref.check(ft.blob, b.columns, b.n, b.max_actions, n_threads=os.cpu_count() or 1)
+    used = {}
+    for flag in ("0", "1"):
+        os.environ["CERBOS_B200_NO_TILES"] = flag
+        c = capi.Context(0)
+        t = c.load_table(ft.blob)
+        db = DeviceBatch(b, "cuda:0")
+        db.run(t)
+        c.sync()
+        used[flag] = c.last_kernel_config()["tma_column_tiles"]
+        assert (db.effects() == want).all(), (name, n, flag)
+        assert (t.check(b.columns, b.n, b.max_actions) == want).all(), (name, n, flag, "host")
+        t.release()
+        c.close()
+    os.environ.pop("CERBOS_B200_NO_TILES", None)
+    assert used["1"] is False
+    assert used["0"] == (n % 4 == 0)

@@ -114,7 +114,7 @@ def test_workloads_three_way(cls, n):
     f = w.fields(n)
     b = w.columns(f, enc)
     c_out = cref.check(ft.blob, b.columns, b.n, b.max_actions, n_threads=4)
-    for mode in (0, 1, 2):   # fast body / general 64-bit / general 32-bit
+    for mode in (0, 1, 2, 3):   # fast body / general 64-bit / general 32-bit / fast body on staged column tiles
         k_out = hostsim.check(ft.blob, b.columns, b.n, b.max_actions, mode=mode)
         assert (c_out == k_out).all(), mode
     idx = list(range(0, n, max(1, n // 256)))
