@@ -226,6 +226,7 @@ def main():
         enc = Encoder(manifest_from_blob(blob))
     ctx = capi.Context(local_rank)
     table = ctx.load_table(blob)
+    spec_ready, spec_note = table.wait_ready()   # table-specialised kernels (NVRTC, background thread) are in place
 
     n = args.requests or w.default_n
     K = len(w.actions)

@@ -17,7 +17,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE = 0, -1, -2, -3, -4
 EXPORTS = [
     "cgpu_init", "cgpu_shutdown", "cgpu_table_load", "cgpu_table_retain", "cgpu_table_release", "cgpu_check",
     "cgpu_check_device", "cgpu_sync", "cgpu_launch_count", "cgpu_table_info", "cgpu_last_kernel_config",
-    "cgpu_last_cluster_config", "cgpu_profile", "cgpu_last_error",
+    "cgpu_last_cluster_config", "cgpu_profile", "cgpu_table_wait_ready", "cgpu_last_error",
 ]
 
 
@@ -72,6 +72,8 @@ def lib():
         L.cgpu_last_cluster_config.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_uint32)] * 3
         L.cgpu_profile.restype = ctypes.c_int
         L.cgpu_profile.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
+        L.cgpu_table_wait_ready.restype = ctypes.c_int
+        L.cgpu_table_wait_ready.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
         L.cgpu_last_error.restype = ctypes.c_char_p
         L.cgpu_last_error.argtypes = []
         _lib = L
@@ -108,6 +110,7 @@ class Context:
         _check(lib().cgpu_last_cluster_config(self._h, ctypes.byref(c), ctypes.byref(w), ctypes.byref(nb)))
         cfg["clustered"] = bool(c.value & 1)
         cfg["tma_column_tiles"] = bool(c.value & 2)
+        cfg["table_specialised"] = bool(c.value & 4)
         if c.value & 1:
             cfg["cluster_window"] = w.value
             cfg["cluster_buckets"] = nb.value
@@ -139,6 +142,13 @@ class Table:
         if self._h:
             lib().cgpu_table_release(self._h)
             self._h = ctypes.c_void_p()
+
+    def wait_ready(self):
+        """Blocks until the background compilation of the table-specialised kernels has finished.
+        -> (specialised: bool, note: str)"""
+        sp = ctypes.c_int()
+        _check(lib().cgpu_table_wait_ready(self._h, ctypes.byref(sp)))
+        return bool(sp.value), lib().cgpu_last_error().decode("utf-8", "replace")
 
     def meta(self):
         out = (ctypes.c_uint32 * 32)()

@@ -92,20 +92,25 @@ struct BatchView {
     int64_t now;
     const uint32_t *perm;       // clustered evaluation order (request offsets from `first`), or null = index order
     uint32_t prefetch_slots;    // > 0: the table reads this many slot columns in all (few): prefetch every one per tile
+    uint32_t *defer_list, *defer_count;   // run-time specialised lean kernels: requests left to the general kernel
+    const uint32_t *count_dev;            // general kernel draining such a list: its length (device memory), else null
 };
 
 // Table data may live in shared memory (TMA-staged image) or in global memory, heap references may point
 // into either the table or the batch: those loads are plain (generic) loads.  Only the big streaming request
 // columns -- read exactly once -- use the read-only, no-L1-allocate path so they do not evict the table.
 // derived BatchView fields (host side, once per launch)
+#ifndef __CUDACC_RTC__
 inline void finish_batch_view(BatchView &b) {
     b.perm = nullptr;
     b.prefetch_slots = 0;
+    b.defer_list = nullptr; b.defer_count = nullptr; b.count_dev = nullptr;
     b.rcp = 1;
     while (b.rcp < b.role_cols) b.rcp <<= 1;
     b.stride_pattern = 0;
     for (uint32_t j = 0; j * b.role_cols < 32; j++) b.stride_pattern |= 1u << (j * b.role_cols);
 }
+#endif
 
 template <typename T>
 CB_HD T ldg(const T *p) { return *p; }
@@ -155,17 +160,6 @@ CB_HD cb_row load_row(const cb_row *p) {
 CB_HD cb_rolepol_entry load_rp_entry(const cb_rolepol_entry *p) { U4 v = ld16(p); cb_rolepol_entry e; e.role = v.x; e.rule_start = v.y; e.n_rules = v.z; e.pad = v.w; return e; }
 CB_HD cb_rolepol_rule load_rp_rule(const cb_rolepol_rule *p) { U4 v = ld16(p); cb_rolepol_rule e; e.respat = v.x; e.cond = v.y; e.apat_start = v.z; e.n_apats = v.w; return e; }
 
-// ---------------------------------------------------------------------------------------------- values
-struct Val {
-    uint32_t tag;
-    uint64_t u;
-};
-static constexpr uint64_t kHeapBatch = 1ull << 63;
-
-CB_HD Val mk(uint32_t tag, uint64_t u) { Val v; v.tag = tag; v.u = u; return v; }
-CB_HD Val mk_err() { return mk(CB_T_ERR, 0); }
-CB_HD Val mk_bool(bool b) { return mk(CB_T_BOOL, b ? 1u : 0u); }
-CB_HD Val mk_int(int64_t i) { return mk(CB_T_INT, (uint64_t)i); }
 CB_HD double u2d(uint64_t u) {
 #if defined(__CUDA_ARCH__)
     return __longlong_as_double((long long)u);
@@ -180,6 +174,19 @@ CB_HD uint64_t d2u(double d) {
     uint64_t u; __builtin_memcpy(&u, &d, 8); return u;
 #endif
 }
+
+#ifndef CB_LEAN_ONLY   // generic values + stack interpreter: not part of the lean-only (run-time specialised) build
+// ---------------------------------------------------------------------------------------------- values
+struct Val {
+    uint32_t tag;
+    uint64_t u;
+};
+static constexpr uint64_t kHeapBatch = 1ull << 63;
+
+CB_HD Val mk(uint32_t tag, uint64_t u) { Val v; v.tag = tag; v.u = u; return v; }
+CB_HD Val mk_err() { return mk(CB_T_ERR, 0); }
+CB_HD Val mk_bool(bool b) { return mk(CB_T_BOOL, b ? 1u : 0u); }
+CB_HD Val mk_int(int64_t i) { return mk(CB_T_INT, (uint64_t)i); }
 CB_HD Val mk_double(double d) { return mk(CB_T_DOUBLE, d != d ? (uint64_t)CB_V64_CANON_NAN : d2u(d)); }
 
 enum { SLOT_VALUE = 0, SLOT_ABSENT = 1, SLOT_ERROR = 2 };
@@ -986,6 +993,8 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
     }
 }
 
+#endif  // !CB_LEAN_ONLY
+
 // ---------------------------------------------------------------------------------------------- column access
 // The lean body reads the per-request columns through one of two accessors: straight from global memory (any
 // evaluation order), or from a tile of the columns that the TMA unit staged in shared memory one tile ahead
@@ -1027,6 +1036,7 @@ CB_HD uint32_t v64_tag(uint64_t b) {   // 0 = double
 }
 
 // ---------------------------------------------------------------------------------------------- decision walk
+#ifndef CB_LEAN_ONLY
 CB_HD bool in_class(const BatchView &b, uint32_t c0, uint32_t c1, uint32_t pat) {
     for (uint32_t j = c0; j < c1; j++)
         if (ldg(b.class_pats + j) == pat) return true;
@@ -1058,6 +1068,8 @@ CB_HD_NOINLINE uint32_t cond_sat(const uint8_t *base, const TableLayout *L, cons
     bool s = run_program(c, t.code() + ldg(&t.conds()[gid].code_off));
     return (s ? 1u : 0u) | (c.unsupported ? 2u : 0u);
 }
+
+#endif  // !CB_LEAN_ONLY
 
 // ---- inline DNF evaluator of the lean body (layout FLAT_DNF, compiled by bytecode.FlatCompiler) --------------
 // Works directly on the 8-byte NaN-boxed values.  No calls and no early exits: every lane walks every term with
@@ -1139,6 +1151,100 @@ CB_HD int in_tri(const TableView t, const BatchView &b, uint64_t x, uint64_t y, 
     }
     return found;
 }
+// One term {op | flags<<8 | xk<<16 | yk<<24, x, y, xa | ya<<16} -> TRI_T / TRI_F / TRI_E; `slow` is raised for operands
+// this path cannot decide exactly.  Force-inlined: called with a compile-time constant `w` (run-time specialised
+// kernels, cb_specialize.h) the switch, the operand kinds and the slot indices all fold away.
+template <typename Cols>
+CB_HD int term_tri(const TableView t, const BatchView &b, const Cols &cols, uint32_t pid, const U4 w, bool &slow) {
+    const uint32_t op = w.x & 0xFF, flags = (w.x >> 8) & 0xFF, xk = (w.x >> 16) & 0xFF, yk = w.x >> 24;
+    int tri = TRI_E;
+    switch (w.x & 0xFF) {
+    case CB_TERM_EQ_SS: tri = eq_tri(cols.slot(w.y), cols.slot(w.z), slow); break;
+    case CB_TERM_EQ_SC: tri = eq_tri(cols.slot(w.y), ldg(t.consts_v64() + w.z), slow); break;
+    case CB_TERM_EQ_SP: tri = eq_tri(cols.slot(w.y), ((uint64_t)(CB_V64_BOX_BASE | CB_V64_STRING) << 48) | pid, slow); break;
+    case CB_TERM_ORD_SS: tri = ord_tri(flags & CB_TERM_CI_MASK, cols.slot(w.y), cols.slot(w.z), slow); break;
+    case CB_TERM_ORD_SC: tri = ord_tri(flags & CB_TERM_CI_MASK, cols.slot(w.y), ldg(t.consts_v64() + w.z), slow); break;
+    case CB_TERM_IN_SC: tri = in_tri(t, b, cols.slot(w.y), ldg(t.consts_v64() + w.z), true, slow); break;
+    case CB_TERM_IN_CS: tri = in_tri(t, b, ldg(t.consts_v64() + w.y), cols.slot(w.z), false, slow); break;
+    case CB_TERM_IN_SS: tri = in_tri(t, b, cols.slot(w.y), cols.slot(w.z), false, slow); break;
+    default: {
+        const uint64_t x = term_operand(t, b, cols, pid, xk, w.y, w.w & 0xFFFF);
+        const uint64_t y = op == CB_TERM_HAS ? 0 : term_operand(t, b, cols, pid, yk, w.z, w.w >> 16);
+        const uint32_t tx = v64_tag(x), ty = v64_tag(y);
+        const bool xerr = tx == CB_V64_ABSENT || tx == CB_V64_ERROR, yerr = ty == CB_V64_ABSENT || ty == CB_V64_ERROR;
+        if (op == CB_TERM_HAS) {
+            tri = tx == CB_V64_ERROR ? TRI_E : (tx != CB_V64_ABSENT);
+        } else if (xerr || yerr) {
+            tri = TRI_E;
+        } else if (op == CB_TERM_CMP) {
+            const uint32_t ci = flags & CB_TERM_CI_MASK;
+            if (tx == 0 && ty == 0) {
+                const double dx = u2d(x), dy = u2d(y);
+                if (ci == 0) tri = dx == dy;
+                else if (dx != dx || dy != dy) tri = TRI_E;
+                else tri = ci == 2 ? dx < dy : ci == 3 ? dx <= dy : ci == 4 ? dx > dy : dx >= dy;
+            } else if (ci == 0 && tx <= CB_V64_STRING && ty <= CB_V64_STRING) tri = x == y;   // null / bool / interned string / mixed
+            else if (ci != 0 && tx != ty) tri = TRI_E;                                         // no ordering across types
+            else slow = true;                                                                  // containers, string ordering, ints
+        } else if (op == CB_TERM_IN) {
+            if (ty != CB_V64_LIST || tx > CB_V64_STRING) slow = true;   // maps, container members: out of line
+            else {
+                const uint64_t *p = list_ptr(t, b, y);
+                const uint32_t ln = (uint32_t)ldg(p);
+                bool found = false;
+                for (uint32_t j = 0; j < ln; j++) {
+                    const uint64_t e = ldg(p + 1 + j);
+                    slow |= v64_tag(e) > CB_V64_STRING;               // int / container elements
+                    found |= scalar_eq64(x, e);
+                }
+                tri = found;
+            }
+        } else if (op == CB_TERM_STARTS || op == CB_TERM_ENDS || op == CB_TERM_CONTAINS) {
+            if (tx != CB_V64_STRING || ty != CB_V64_STRING) tri = TRI_E;
+            else {
+                const StrRef a = str_ref(t, b, x), c = str_ref(t, b, y);
+                if (c.len > a.len) tri = TRI_F;
+                else if (op == CB_TERM_CONTAINS) {
+                    bool hit = false;
+                    for (uint32_t o = 0; o + c.len <= a.len; o++) {
+                        bool eq = true;
+                        for (uint32_t j = 0; j < c.len; j++) eq &= ldg(a.p + o + j) == ldg(c.p + j);
+                        hit |= eq;
+                    }
+                    tri = hit;
+                } else {
+                    const uint8_t *ap = op == CB_TERM_STARTS ? a.p : a.p + (a.len - c.len);
+                    bool eq = true;
+                    for (uint32_t j = 0; j < c.len; j++) eq &= ldg(ap + j) == ldg(c.p + j);
+                    tri = eq;
+                }
+            }
+        } else {   // INTERSECTS / SUBSET on two lists (cerbos_lib.go:323-431)
+            if (tx != CB_V64_LIST || ty != CB_V64_LIST) tri = TRI_E;
+            else {
+                const uint64_t *pa = list_ptr(t, b, x), *pb = list_ptr(t, b, y);
+                const uint32_t na = (uint32_t)ldg(pa), nb = (uint32_t)ldg(pb);
+                bool any_hit = false, all_hit = true;
+                for (uint32_t i2 = 0; i2 < na; i2++) {
+                    const uint64_t ea = ldg(pa + 1 + i2);
+                    slow |= v64_tag(ea) > CB_V64_STRING;
+                    bool hit = false;
+                    for (uint32_t j = 0; j < nb; j++) {
+                        const uint64_t eb = ldg(pb + 1 + j);
+                        slow |= v64_tag(eb) > CB_V64_STRING;       // ints would need the Go-map identity rule
+                        hit |= scalar_eq64(ea, eb);
+                    }
+                    any_hit |= hit;
+                    all_hit &= hit;
+                }
+                tri = op == CB_TERM_INTERSECTS ? any_hit : all_hit;
+            }
+        }
+    }
+    }
+    return tri;
+}
+CB_HD bool term_lit(int tri, uint32_t flags) { return (flags & CB_TERM_LIT_F) ? tri == TRI_F : tri == TRI_T; }
 // -> bit0 satisfied, bit2: needs the out-of-line general path
 template <typename Cols>
 CB_HD uint32_t flat_dnf_inline(const TableView t, const BatchView &b, const Cols &cols, uint32_t pid, uint32_t flat_off, uint32_t info) {
@@ -1146,95 +1252,9 @@ CB_HD uint32_t flat_dnf_inline(const TableView t, const BatchView &b, const Cols
     const cb_instr *terms = t.code() + flat_off;
     bool any = false, group = true, slow = false;
     for (uint32_t i = 0; i < nt; i++) {
-        const U4 w = ld16(terms + 2 * i);   // {op | flags<<8 | xk<<16 | yk<<24, x, y, xa | ya<<16}
-        const uint32_t op = w.x & 0xFF, flags = (w.x >> 8) & 0xFF, xk = (w.x >> 16) & 0xFF, yk = w.x >> 24;
-        int tri = TRI_E;
-        switch (w.x & 0xFF) {
-        case CB_TERM_EQ_SS: tri = eq_tri(cols.slot(w.y), cols.slot(w.z), slow); break;
-        case CB_TERM_EQ_SC: tri = eq_tri(cols.slot(w.y), ldg(t.consts_v64() + w.z), slow); break;
-        case CB_TERM_EQ_SP: tri = eq_tri(cols.slot(w.y), ((uint64_t)(CB_V64_BOX_BASE | CB_V64_STRING) << 48) | pid, slow); break;
-        case CB_TERM_ORD_SS: tri = ord_tri(flags & CB_TERM_CI_MASK, cols.slot(w.y), cols.slot(w.z), slow); break;
-        case CB_TERM_ORD_SC: tri = ord_tri(flags & CB_TERM_CI_MASK, cols.slot(w.y), ldg(t.consts_v64() + w.z), slow); break;
-        case CB_TERM_IN_SC: tri = in_tri(t, b, cols.slot(w.y), ldg(t.consts_v64() + w.z), true, slow); break;
-        case CB_TERM_IN_CS: tri = in_tri(t, b, ldg(t.consts_v64() + w.y), cols.slot(w.z), false, slow); break;
-        case CB_TERM_IN_SS: tri = in_tri(t, b, cols.slot(w.y), cols.slot(w.z), false, slow); break;
-        default: {
-            const uint64_t x = term_operand(t, b, cols, pid, xk, w.y, w.w & 0xFFFF);
-            const uint64_t y = op == CB_TERM_HAS ? 0 : term_operand(t, b, cols, pid, yk, w.z, w.w >> 16);
-            const uint32_t tx = v64_tag(x), ty = v64_tag(y);
-            const bool xerr = tx == CB_V64_ABSENT || tx == CB_V64_ERROR, yerr = ty == CB_V64_ABSENT || ty == CB_V64_ERROR;
-            if (op == CB_TERM_HAS) {
-                tri = tx == CB_V64_ERROR ? TRI_E : (tx != CB_V64_ABSENT);
-            } else if (xerr || yerr) {
-                tri = TRI_E;
-            } else if (op == CB_TERM_CMP) {
-                const uint32_t ci = flags & CB_TERM_CI_MASK;
-                if (tx == 0 && ty == 0) {
-                    const double dx = u2d(x), dy = u2d(y);
-                    if (ci == 0) tri = dx == dy;
-                    else if (dx != dx || dy != dy) tri = TRI_E;
-                    else tri = ci == 2 ? dx < dy : ci == 3 ? dx <= dy : ci == 4 ? dx > dy : dx >= dy;
-                } else if (ci == 0 && tx <= CB_V64_STRING && ty <= CB_V64_STRING) tri = x == y;   // null / bool / interned string / mixed
-                else if (ci != 0 && tx != ty) tri = TRI_E;                                         // no ordering across types
-                else slow = true;                                                                  // containers, string ordering, ints
-            } else if (op == CB_TERM_IN) {
-                if (ty != CB_V64_LIST || tx > CB_V64_STRING) slow = true;   // maps, container members: out of line
-                else {
-                    const uint64_t *p = list_ptr(t, b, y);
-                    const uint32_t ln = (uint32_t)ldg(p);
-                    bool found = false;
-                    for (uint32_t j = 0; j < ln; j++) {
-                        const uint64_t e = ldg(p + 1 + j);
-                        slow |= v64_tag(e) > CB_V64_STRING;               // int / container elements
-                        found |= scalar_eq64(x, e);
-                    }
-                    tri = found;
-                }
-            } else if (op == CB_TERM_STARTS || op == CB_TERM_ENDS || op == CB_TERM_CONTAINS) {
-                if (tx != CB_V64_STRING || ty != CB_V64_STRING) tri = TRI_E;
-                else {
-                    const StrRef a = str_ref(t, b, x), c = str_ref(t, b, y);
-                    if (c.len > a.len) tri = TRI_F;
-                    else if (op == CB_TERM_CONTAINS) {
-                        bool hit = false;
-                        for (uint32_t o = 0; o + c.len <= a.len; o++) {
-                            bool eq = true;
-                            for (uint32_t j = 0; j < c.len; j++) eq &= ldg(a.p + o + j) == ldg(c.p + j);
-                            hit |= eq;
-                        }
-                        tri = hit;
-                    } else {
-                        const uint8_t *ap = op == CB_TERM_STARTS ? a.p : a.p + (a.len - c.len);
-                        bool eq = true;
-                        for (uint32_t j = 0; j < c.len; j++) eq &= ldg(ap + j) == ldg(c.p + j);
-                        tri = eq;
-                    }
-                }
-            } else {   // INTERSECTS / SUBSET on two lists (cerbos_lib.go:323-431)
-                if (tx != CB_V64_LIST || ty != CB_V64_LIST) tri = TRI_E;
-                else {
-                    const uint64_t *pa = list_ptr(t, b, x), *pb = list_ptr(t, b, y);
-                    const uint32_t na = (uint32_t)ldg(pa), nb = (uint32_t)ldg(pb);
-                    bool any_hit = false, all_hit = true;
-                    for (uint32_t i2 = 0; i2 < na; i2++) {
-                        const uint64_t ea = ldg(pa + 1 + i2);
-                        slow |= v64_tag(ea) > CB_V64_STRING;
-                        bool hit = false;
-                        for (uint32_t j = 0; j < nb; j++) {
-                            const uint64_t eb = ldg(pb + 1 + j);
-                            slow |= v64_tag(eb) > CB_V64_STRING;       // ints would need the Go-map identity rule
-                            hit |= scalar_eq64(ea, eb);
-                        }
-                        any_hit |= hit;
-                        all_hit &= hit;
-                    }
-                    tri = op == CB_TERM_INTERSECTS ? any_hit : all_hit;
-                }
-            }
-        }
-        }
-        const bool lit = (flags & CB_TERM_LIT_F) ? tri == TRI_F : tri == TRI_T;
-        group &= lit;
+        const U4 w = ld16(terms + 2 * i);
+        const uint32_t flags = (w.x >> 8) & 0xFF;
+        group &= term_lit(term_tri(t, b, cols, pid, w, slow), flags);
         if (flags & CB_TERM_GROUP_END) { any |= group; group = true; }
     }
     if (slow) return 4u;
@@ -1283,6 +1303,7 @@ CB_HD void prefetch_request(const BatchView &b, uint64_t n) {
     for (uint32_t q = 0; q < b.prefetch_slots; q++, ps += b.stride) prefetch_l1(ps);
 }
 
+#ifndef CB_LEAN_ONLY
 // The resource patterns a request kind matches; kc is hdr0.kind_class: the pattern id itself when there is exactly
 // one (CB_KIND_NONE: none), else an index into the class CSR.
 CB_HD uint32_t kind_count(const BatchView &b, uint32_t kc) {
@@ -1328,6 +1349,7 @@ CB_HD_NOINLINE U2x64 role_tab_parents(const uint8_t *base, const TableLayout *L,
     U2x64 r; r.a = rp0; r.b = rp1; return r;
 }
 
+#endif  // !CB_LEAN_ONLY
 // row record accessors on the raw 16-byte load (cb_row: role u16, cond u16 | drcond u16, respat u16 | effect u8,
 // flags u8, n_pats u16 | pat_start u32)
 CB_HD uint32_t row_role(const U4 &r) { return r.x & 0xFFFF; }
@@ -1335,6 +1357,7 @@ CB_HD uint32_t row_cond(const U4 &r) { return r.x >> 16; }
 CB_HD uint32_t row_drcond(const U4 &r) { return r.y & 0xFFFF; }
 CB_HD uint32_t row_respat(const U4 &r) { return r.y >> 16; }
 CB_HD uint32_t row_effect(const U4 &r) { return r.z & 0xFF; }
+#ifndef CB_LEAN_ONLY
 
 // Existence checks (ruletable.go:852-863): false => every action is DENY.  Only reachable when the principal
 // and resource policy versions differ (see eval_request).
@@ -1614,6 +1637,8 @@ CB_HD void eval_request(const TableView t, const BatchView &b, uint64_t n, uint8
     }
 }
 
+#endif  // !CB_LEAN_ONLY
+
 // ---------------------------------------------------------------------------------------------- fast kernel body
 // The common deployment shape -- resource policies (+ derived roles, scopes) only: no principal policies, no role
 // policies / parent roles, no resource globs -- with max_actions * role_cols <= 32 and n_roles * RCP <= 64.
@@ -1623,8 +1648,44 @@ CB_HD void eval_request(const TableView t, const BatchView &b, uint64_t n, uint8
 // condition without a flat form, an operand the 8-byte fast forms cannot decide, differing policy versions, or
 // a block with more than 32 conditions.  The body itself makes NO calls, so nothing is forced into local memory,
 // and its loops contain no early exits (`continue` / `break` would leave lanes diverged until the loop ends).
-template <typename Cols>
-CB_HD bool eval_request_fast(const TableView t, const BatchView &b, const Cols &cols, uint64_t n, uint8_t *bitmap, uint8_t *effects) {
+// one row of a block: its (action x role column) pairs, if its conditions hold, join the DENY or the ALLOW mask
+CB_HD void row_apply(uint32_t am, const U4 row, uint64_t rp, uint32_t RCP, uint32_t role_all, uint32_t alive, uint32_t val, uint32_t &D, uint32_t &A) {
+    const uint32_t role = row_role(row);
+    const uint32_t rc = role == CB_ROLE_ANY ? role_all : (uint32_t)(rp >> (role * RCP)) & role_all;
+    const uint32_t sat = (val >> (row.x >> 16)) & (val >> (row.y & 0xFFFF)) & 1u;   // rule condition AND derived-role condition
+    const uint32_t ms = (am * rc) & alive & (0u - sat);
+    const bool deny = row_effect(row) == CB_EFFECT_DENY;
+    D |= deny ? ms : 0u;
+    A |= deny ? 0u : ms;
+}
+// How the lean body evaluates one policy block: this generic walker interprets the block's records; a run-time
+// specialised build (cb_specialize.h) substitutes straight-line code generated from the table.
+struct GenericBlocks {
+    template <typename Cols>
+    CB_HD void operator()(const TableView t, const BatchView &b, const Cols &cols, uint32_t pid, uint32_t bid, uint64_t rp, uint32_t RCP, uint32_t role_all,
+                          uint32_t alive, const uint64_t *row_am, uint32_t &D, uint32_t &A, bool &defer) const {
+        if (!cols.staged())
+            for (uint32_t q = ldg(t.block_slots_off() + bid), e = ldg(t.block_slots_off() + bid + 1); q < e; q++)
+                cols.prefetch_slot(ldg(t.block_slots() + q));
+        const U4 bl = ld16(t.blocks() + bid);   // {row_start, n_rows, cond_base, n_conds}
+        defer |= bl.w > 31;
+        // phase 1: every condition of the block, once, into one bit each (bit 0 = "no condition" = true).  The
+        // lanes of a warp evaluate the same condition list together; a row the request does not reach simply
+        // ignores its bit (conditions have no side effects; an operand this path cannot decide defers).
+        uint32_t val = 1;
+        for (uint32_t c = 0, nc = bl.w > 31 ? 0 : bl.w; c < nc; c++) {
+            const uint32_t r = cond_eval(t, b, cols, pid, bl.z + c);
+            defer |= (r & 4) != 0;
+            val |= (r & 1) << (c + 1);
+        }
+        // phase 2: rows are pure mask algebra
+        for (uint32_t ri = bl.x, re = bl.x + bl.y; ri < re; ri++)
+            row_apply(ldg(reinterpret_cast<const uint32_t *>(row_am + ri)), ld16(t.rows() + ri), rp, RCP, role_all, alive, val, D, A);
+    }
+};
+
+template <typename Cols, typename Blocks = GenericBlocks>
+CB_HD bool eval_request_fast(const TableView t, const BatchView &b, const Cols &cols, uint64_t n, uint8_t *bitmap, uint8_t *effects, const Blocks blocks = Blocks()) {
     const U4 h0 = cols.hdr0();         // principal_id, kind (pattern id), resource_scope, principal_scope
     const uint64_t h1 = cols.hdr1();   // rv u16 | pv u16 | action_set_id u32
     const uint32_t pid = h0.x, kc = h0.y, rscope = h0.z;
@@ -1652,33 +1713,8 @@ CB_HD bool eval_request_fast(const TableView t, const BatchView &b, const Cols &
             const uint32_t bid = ldg(t.res_block_map() + ((uint64_t)rv * t.L->nRP + kc) * t.L->nS + s);
             if (bid != CB_NONE32) {
                 // pull the attribute slots this block's conditions read towards L1 so the lazy loads overlap
-                if (!cols.staged())
-                    for (uint32_t q = ldg(t.block_slots_off() + bid), e = ldg(t.block_slots_off() + bid + 1); q < e; q++)
-                        cols.prefetch_slot(ldg(t.block_slots() + q));
-                const U4 bl = ld16(t.blocks() + bid);   // {row_start, n_rows, cond_base, n_conds}
-                defer |= bl.w > 31;
-                // phase 1: every condition of the block, once, into one bit each (bit 0 = "no condition" = true).  The
-                // lanes of a warp evaluate the same condition list together; a row the request does not reach simply
-                // ignores its bit (conditions have no side effects; an operand this path cannot decide defers).
-                uint32_t val = 1;
-                for (uint32_t c = 0, nc = bl.w > 31 ? 0 : bl.w; c < nc; c++) {
-                    const uint32_t r = cond_eval(t, b, cols, pid, bl.z + c);
-                    defer |= (r & 4) != 0;
-                    val |= (r & 1) << (c + 1);
-                }
-                // phase 2: rows are pure mask algebra
                 uint32_t D = 0, A = 0;   // DENY / ALLOW pair masks of this scope
-                for (uint32_t ri = bl.x, re = bl.x + bl.y; ri < re; ri++) {
-                    const uint32_t am = ldg(reinterpret_cast<const uint32_t *>(row_am + ri));
-                    const U4 row = ld16(t.rows() + ri);   // {role | cond << 16, drcond | respat << 16, effect | flags << 8 | n_pats << 16, pat_start}
-                    const uint32_t role = row_role(row);
-                    const uint32_t rc = role == CB_ROLE_ANY ? role_all : (uint32_t)(rp >> (role * RCP)) & role_all;
-                    const uint32_t sat = (val >> (row.x >> 16)) & (val >> (row.y & 0xFFFF)) & 1u;   // rule condition AND derived-role condition
-                    const uint32_t ms = (am * rc) & alive & (0u - sat);
-                    const bool deny = row_effect(row) == CB_EFFECT_DENY;
-                    D |= deny ? ms : 0u;
-                    A |= deny ? 0u : ms;
-                }
+                blocks(t, b, cols, pid, bid, rp, RCP, role_all, alive, row_am, D, A, defer);
                 alive &= ~D;
                 if (((ldg(t.scope_flags() + s) >> CB_SCOPE_PERM_SHIFT) & 3) == 1) { uint32_t a = A & alive; allow_pairs |= a; alive &= ~a; }
             }
@@ -1711,11 +1747,14 @@ CB_HD bool eval_request_fast(const TableView t, const BatchView &b, const Cols &
     return false;
 }
 
+#ifndef CB_LEAN_ONLY
 // out-of-line general body for the requests the fast body defers
 CB_HD_NOINLINE void eval_request_general(const uint8_t *base, const TableLayout *L, const BatchView *b, uint64_t n, uint8_t *bitmap,
                                          uint8_t *effects, uint32_t *status) {
     TableView t; t.base = base; t.L = L;
     eval_request<uint64_t>(t, *b, n, bitmap, effects, status);
 }
+
+#endif  // !CB_LEAN_ONLY
 
 }  // namespace cb

@@ -1,0 +1,190 @@
+// cb_kernels.h -- device bodies of the CheckResources kernels (sm_100a).
+//
+// Included twice: by cerbos_b200.cu (ahead-of-time build: every body, generic block walker) and, as embedded text,
+// by the translation unit the library compiles with NVRTC when a table is loaded (CB_LEAN_ONLY: lean bodies only,
+// with the straight-line block evaluators cb_specialize.h generates from that table).
+//
+// Kernel design (B200):
+//   * persistent grid: (SM count x resident CTAs) CTAs of 256 threads loop over 256-request tiles;
+//   * the flattened rule table image (row blocks, scope tables, bytecode, constants; KBs) is staged ONCE per CTA
+//     into shared memory by the TMA unit: 1-D `cp.async.bulk.shared::cluster.global` copies completing on an
+//     mbarrier, overlapped with the first tile's loads; tables too large for shared memory are read through L1/L2;
+//   * index-order lean launches stage the REQUEST COLUMNS the same way, tile by tile, double-buffered;
+//   * one thread per request, bit-parallel (action x role) walk + condition evaluation (cb_core.h);
+//   * result: 1 bit per decision (or 1 byte for the host-buffer ABI), coalesced stores.
+// Integer / branchy work bounded by HBM bandwidth: no tensor cores are involved.
+#pragma once
+#include "cb_core.h"
+
+namespace cbk {
+
+constexpr int kThreads = 256;
+
+struct TableDesc {
+    const uint8_t *base;       // device blob image
+    cb::TableLayout lay;       // section offsets + dims (image_bytes: bytes [0, image_bytes) hold every device section)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared by the TMA unit, completing `bytes` on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_image(uint8_t *dst_smem, const TableDesc &td, uint64_t *bar) {   // one thread
+    mbar_expect_tx(bar, td.lay.image_bytes);
+    for (uint32_t o = 0; o < td.lay.image_bytes; o += 32768) {   // <= 32 KB per copy, all completing on the same mbarrier
+        uint32_t nb = td.lay.image_bytes - o < 32768 ? td.lay.image_bytes - o : 32768;
+        tma_load_1d(dst_smem + o, td.base + o, nb, bar);
+    }
+}
+
+// A request the lean body cannot decide (differing policy versions, an operand outside the 8-byte fast forms ...):
+// the ahead-of-time build re-evaluates it on the spot with the out-of-line general body; a run-time specialised
+// module has no general body and appends it to a list that the general kernel drains right after.
+__device__ __forceinline__ void defer_request(const cb::TableView tv, const cb::BatchView &bv, uint64_t n, uint8_t *bitmap, uint8_t *effects, uint32_t *status) {
+#ifdef CB_LEAN_ONLY
+    (void)tv; (void)bitmap; (void)effects; (void)status;
+    const uint32_t k = atomicAdd(bv.defer_count, 1u);
+    bv.defer_list[k] = (uint32_t)(n - bv.first);
+#else
+    cb::eval_request_general(tv.base, tv.L, &bv, n, bitmap, effects, status);
+#endif
+}
+
+// Persistent body, columns read straight from global memory (any evaluation order: bv.perm).
+// kFast: the lean resource-policy-only body (cb::eval_request_fast), else the general body with 64-bit pair masks.
+// kStageMode 0: table read from global memory, 1: from the staged shared-memory image (compile-time, so that every
+// table access of the lean body is an LDS with 32-bit address arithmetic instead of a generic load), 2: decided by
+// the `stage_rt` argument (general body: one instantiation keeps the build time down).
+template <bool kFast, int kStageMode, typename Blocks>
+__device__ __forceinline__ void check_body(const TableDesc &td, const cb::BatchView &bv, uint8_t *bitmap, uint8_t *effects, uint32_t *status, const uint32_t stage_rt,
+                                           uint8_t *smem_image, uint64_t *mbar) {
+    const bool kStage = kStageMode == 2 ? stage_rt != 0 : kStageMode == 1;
+    // deferred mode (drains the list a specialised lean kernel left): the request count lives in device memory
+    const uint64_t count = bv.count_dev ? (uint64_t)*bv.count_dev : bv.count;
+    if (count == 0) return;   // the usual case in deferred mode: nothing was deferred
+    const uint8_t *base = td.base;
+    if (kStage) {
+        if (threadIdx.x == 0) {
+            mbar_init(mbar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) tma_load_image(smem_image, td, mbar);
+        base = smem_image;
+    }
+    cb::TableView tv;
+    tv.base = kStageMode == 1 ? smem_image : kStageMode == 0 ? td.base : base;
+    tv.L = &td.lay;
+    const uint64_t n_tiles = (count + kThreads - 1) / kThreads;
+    {   // columns of this thread's first request: in flight while the table image is still being staged
+        const uint64_t i0 = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+        if (i0 < count) cb::prefetch_request(bv, bv.first + (bv.perm ? bv.perm[i0] : i0));
+    }
+    bool staged = !kStage;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint64_t i = tile * kThreads + threadIdx.x;
+        // clustered order: thread i evaluates request perm[i] (cluster kernels), so that the lanes of a warp walk the
+        // same policy blocks
+        uint64_t req = i, req_next = i + (uint64_t)gridDim.x * kThreads;
+        if (bv.perm) {
+            if (i < count) req = bv.perm[i];
+            if (req_next < count) req_next = bv.perm[req_next]; else req_next = count;
+        }
+        if (!staged) {   // every thread waits for the table image (phase 0) before its first table access
+            mbar_wait(mbar, 0);
+            staged = true;
+        }
+        // the next tile of this thread: start pulling its columns towards L1 now
+        if (req_next < count) cb::prefetch_request(bv, bv.first + req_next);
+        if (i < count) {
+            if (kFast) {
+                cb::GlobalCols gc;
+                gc.b = &bv; gc.n = bv.first + req;
+                if (cb::eval_request_fast(tv, bv, gc, bv.first + req, bitmap, effects, Blocks())) defer_request(tv, bv, bv.first + req, bitmap, effects, status);
+            } else {
+#ifndef CB_LEAN_ONLY
+                cb::eval_request<uint64_t>(tv, bv, bv.first + req, bitmap, effects, status);
+#endif
+            }
+        }
+    }
+    if (!staged) mbar_wait(mbar, 0);   // CTA had no tile: drain the bulk copy before shared memory is released
+}
+
+// Lean body with BOTH the table image and the request columns staged by the TMA unit.  Index-order batches only
+// (the columns of a tile of 256 requests are contiguous runs: 2 + role_cols + n_slots bulk copies per tile, issued by
+// one thread, double-buffered: tile k+1 streams into shared memory while tile k is evaluated, so no thread ever
+// waits on DRAM and every column read is an LDS).  Shared memory: [image][tile stage 0][tile stage 1].
+template <typename Blocks>
+__device__ __forceinline__ void check_tiles_body(const TableDesc &td, const cb::BatchView &bv, uint8_t *bitmap, uint8_t *effects, uint32_t *status, const uint32_t n_slots,
+                                                 uint8_t *smem_image, uint64_t *mbar_tab, uint64_t *mbar_col) {
+    const uint32_t image_pad = (td.lay.image_bytes + 127u) & ~127u;
+    const uint32_t tile_bytes = cb::tile_cols_bytes(bv.role_cols, n_slots);
+    const uint32_t slots_off = cb::CB_TILE * (24u + 4u * bv.role_cols);
+    uint8_t *stage0 = smem_image + image_pad;
+    const uint64_t n_tiles = (bv.count + kThreads - 1) / kThreads, n_full = bv.count / kThreads;
+
+    auto issue_tile = [&](uint64_t tile, uint32_t st) {   // one thread: bulk copies of every column run of `tile`
+        uint8_t *dst = stage0 + st * tile_bytes;
+        const uint64_t r0 = bv.first + tile * kThreads;
+        mbar_expect_tx(&mbar_col[st], tile_bytes);
+        tma_load_1d(dst, bv.hdr0 + r0, kThreads * 16, &mbar_col[st]);
+        tma_load_1d(dst + kThreads * 16, bv.hdr1 + r0, kThreads * 8, &mbar_col[st]);
+        for (uint32_t i = 0; i < bv.role_cols; i++) tma_load_1d(dst + kThreads * 24 + i * (kThreads * 4), bv.roles + i * bv.stride + r0, kThreads * 4, &mbar_col[st]);
+        for (uint32_t v = 0; v < n_slots; v++) tma_load_1d(dst + slots_off + v * (kThreads * 8), bv.slots + v * bv.stride + r0, kThreads * 8, &mbar_col[st]);
+    };
+
+    if (threadIdx.x == 0) {
+        mbar_init(mbar_tab, 1);
+        mbar_init(&mbar_col[0], 1);
+        mbar_init(&mbar_col[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tma_load_image(smem_image, td, mbar_tab);
+        if (blockIdx.x < n_full) issue_tile(blockIdx.x, 0);
+    }
+    cb::TableView tv;
+    tv.base = smem_image;
+    tv.L = &td.lay;
+    uint32_t k = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, k++) {
+        const uint64_t next = tile + gridDim.x;
+        // stage (k+1)&1 was last read in iteration k-1; the barrier that closed it has been passed by every thread
+        if (threadIdx.x == 0 && next < n_full) issue_tile(next, (k + 1) & 1);
+        if (k == 0) mbar_wait(mbar_tab, 0);
+        const uint64_t n = bv.first + tile * kThreads + threadIdx.x;
+        if (tile < n_full) {
+            mbar_wait(&mbar_col[k & 1], (k >> 1) & 1);
+            cb::TileCols tc;
+            tc.base = stage0 + (k & 1) * tile_bytes; tc.tid = threadIdx.x; tc.slots_off = slots_off;
+            if (cb::eval_request_fast(tv, bv, tc, n, bitmap, effects, Blocks())) defer_request(tv, bv, n, bitmap, effects, status);
+        } else if (tile * kThreads + threadIdx.x < bv.count) {   // the ragged last tile: straight from global memory
+            cb::GlobalCols gc;
+            gc.b = &bv; gc.n = n;
+            if (cb::eval_request_fast(tv, bv, gc, n, bitmap, effects, Blocks())) defer_request(tv, bv, n, bitmap, effects, status);
+        }
+        __syncthreads();
+    }
+    if (k == 0) mbar_wait(mbar_tab, 0);   // no tile: drain the table copy before shared memory is released
+}
+
+}  // namespace cbk

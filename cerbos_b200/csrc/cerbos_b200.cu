@@ -1,17 +1,8 @@
 // cerbos_b200.cu -- sm_100a kernels + C ABI (include/cerbos_b200.h) of the batched CheckResources evaluator.
 //
-// Kernel design (B200):
-//   * persistent grid: (SM count x resident CTAs) CTAs of 256 threads loop over 256-request tiles;
-//   * the flattened rule table image (row blocks, scope tables, bytecode, constants; KBs) is staged ONCE
-//     per CTA into shared memory by the TMA unit: 1-D `cp.async.bulk.shared::cluster.global` copies
-//     completing on an mbarrier, overlapped with the first tile's header loads; tables too large for
-//     shared memory are read through L1/L2 instead;
-//   * request columns are SoA and read exactly once with coalesced 128/64/32-bit `ld.global.nc
-//     .L1::no_allocate` loads (header 16 B + 8 B, roles 4 B, NaN-boxed attribute slots 8 B);
-//   * one thread per request, bit-parallel (action x role) walk + bytecode interpreter (cb_core.h);
-//   * result: 1 bit per decision, coalesced byte stores.
-// Integer / branchy work bounded by HBM bandwidth: no tensor cores are involved.
+// Device bodies: cb_kernels.h (+ cb_core.h); this file holds the __global__ wrappers, the clustering kernels and the host side.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <atomic>
 #include <cstdarg>
@@ -24,11 +15,14 @@
 #include <vector>
 
 #include "cb_core.h"
+#include "cb_kernels.h"
+#include "cb_specialize.h"
+#include "cb_embed.inc"
 #include "cerbos_b200.h"
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = cbk::kThreads;
 #ifndef CB_MIN_BLOCKS
 #define CB_MIN_BLOCKS 4   // resident CTAs / SM the check kernel is register-budgeted for (64 registers per thread)
 #endif
@@ -36,181 +30,23 @@ constexpr uint32_t kMaxStageBytes = 96 * 1024;   // table images up to this size
 constexpr int kMaxSec = 28;
 constexpr uint32_t kMaxTilesSmem = 56 * 1024;    // image + two column-tile stages: keeps CB_MIN_BLOCKS CTAs resident per SM
 
-struct TableDesc {
-    const uint8_t *base;       // device blob image
-    cb::TableLayout lay;       // section offsets + dims (image_bytes: bytes [0, image_bytes) hold every device section)
-};
+using cbk::TableDesc;
+using cbk::smem_u32;
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// Persistent CheckResources kernel. Staged: the table image is TMA-copied into dynamic shared memory.
-// kFast: the lean resource-policy-only body (cb::eval_request_fast), else the general body with 64-bit pair masks.
-// kStageMode 0: table read from global memory, 1: from the staged shared-memory image (compile-time, so that every
-// table access of the lean body is an LDS with 32-bit address arithmetic instead of a generic load), 2: decided by
-// the `stage_rt` argument (general body: one instantiation keeps the build time down).
+// Thin __global__ wrappers around the bodies in cb_kernels.h (generic block walker).
 template <bool kFast, int kStageMode>
 __global__ void __launch_bounds__(kThreads, CB_MIN_BLOCKS) check_kernel(const __grid_constant__ TableDesc td, const __grid_constant__ cb::BatchView bv, uint8_t *bitmap,
-                                                          uint8_t *effects, uint32_t *status, const uint32_t stage_rt) {
+                                                                      uint8_t *effects, uint32_t *status, const uint32_t stage_rt) {
     extern __shared__ __align__(128) uint8_t smem_image[];
     __shared__ __align__(8) uint64_t mbar;
-    const bool kStage = kStageMode == 2 ? stage_rt != 0 : kStageMode == 1;
-    const uint8_t *base = td.base;
-    if (kStage) {
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(td.lay.image_bytes)
-                         : "memory");
-            // 1-D bulk copies (TMA unit), <= 32 KB each, all completing on the same mbarrier
-            for (uint32_t o = 0; o < td.lay.image_bytes; o += 32768) {
-                uint32_t nb = td.lay.image_bytes - o < 32768 ? td.lay.image_bytes - o : 32768;
-                asm volatile(
-                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                        smem_u32(smem_image + o)),
-                    "l"(td.base + o), "r"(nb), "r"(smem_u32(&mbar))
-                    : "memory");
-            }
-        }
-        base = smem_image;
-    }
-    cb::TableView tv;
-    tv.base = kStageMode == 1 ? smem_image : kStageMode == 0 ? td.base : base;
-    tv.L = &td.lay;
-    const uint64_t n_tiles = (bv.count + kThreads - 1) / kThreads;
-    {   // columns of this thread's first request: in flight while the table image is still being staged
-        const uint64_t i0 = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
-        if (i0 < bv.count) cb::prefetch_request(bv, bv.first + (bv.perm ? bv.perm[i0] : i0));
-    }
-    bool staged = !kStage;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        uint64_t i = tile * kThreads + threadIdx.x;
-        // clustered order: thread i evaluates request perm[i] (cluster kernels below), so that the lanes of a warp
-        // walk the same policy blocks
-        uint64_t req = i, req_next = i + (uint64_t)gridDim.x * kThreads;
-        if (bv.perm) {
-            if (i < bv.count) req = bv.perm[i];
-            if (req_next < bv.count) req_next = bv.perm[req_next]; else req_next = bv.count;
-        }
-        if (!staged) {
-            // every thread waits for the table image (phase 0) before its first table access
-            uint32_t ok = 0;
-            while (!ok) {
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                    : "=r"(ok)
-                    : "r"(smem_u32(&mbar))
-                    : "memory");
-            }
-            staged = true;
-        }
-        // the next tile of this thread: start pulling its header / role columns towards L1 now
-        if (req_next < bv.count) cb::prefetch_request(bv, bv.first + req_next);
-        if (i < bv.count) {
-            if (kFast) {
-                // call-free lean body; the (rare) requests it cannot decide are redone by the general body
-                cb::GlobalCols gc;
-                gc.b = &bv; gc.n = bv.first + req;
-                if (cb::eval_request_fast(tv, bv, gc, bv.first + req, bitmap, effects))
-                    cb::eval_request_general(tv.base, tv.L, &bv, bv.first + req, bitmap, effects, status);
-            } else cb::eval_request<uint64_t>(tv, bv, bv.first + req, bitmap, effects, status);
-        }
-    }
-    if (!staged) {
-        // CTA had no tile: still drain the bulk copy before exiting so shared memory is not released under it
-        uint32_t ok = 0;
-        while (!ok) {
-            asm volatile(
-                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                : "=r"(ok)
-                : "r"(smem_u32(&mbar))
-                : "memory");
-        }
-    }
+    cbk::check_body<kFast, kStageMode, cb::GenericBlocks>(td, bv, bitmap, effects, status, stage_rt, smem_image, &mbar);
 }
-
-
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t ok = 0;
-    while (!ok) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok)
-                     : "r"(smem_u32(bar)), "r"(parity)
-                     : "memory");
-    }
-}
-__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src),
-                 "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-// Lean body with BOTH the table image and the request columns staged by the TMA unit.  Index-order batches only
-// (the columns of a tile of 256 requests are contiguous runs: 2 + role_cols + n_slots bulk copies per tile, issued by
-// one thread, double-buffered: tile k+1 streams into shared memory while tile k is evaluated, so no thread ever
-// waits on DRAM and every column read is an LDS).  Shared memory: [image][tile stage 0][tile stage 1].
 __global__ void __launch_bounds__(kThreads, CB_MIN_BLOCKS) check_kernel_tiles(const __grid_constant__ TableDesc td, const __grid_constant__ cb::BatchView bv,
                                                                             uint8_t *bitmap, uint8_t *effects, uint32_t *status, const uint32_t n_slots) {
     extern __shared__ __align__(128) uint8_t smem_image[];
     __shared__ __align__(8) uint64_t mbar_tab, mbar_col[2];
-    const uint32_t image_pad = (td.lay.image_bytes + 127u) & ~127u;
-    const uint32_t tile_bytes = cb::tile_cols_bytes(bv.role_cols, n_slots);
-    const uint32_t slots_off = cb::CB_TILE * (24u + 4u * bv.role_cols);
-    uint8_t *stage0 = smem_image + image_pad;
-    const uint64_t n_tiles = (bv.count + kThreads - 1) / kThreads, n_full = bv.count / kThreads;
-
-    auto issue_tile = [&](uint64_t tile, uint32_t st) {   // one thread: bulk copies of every column run of `tile`
-        uint8_t *dst = stage0 + st * tile_bytes;
-        const uint64_t r0 = bv.first + tile * kThreads;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar_col[st])), "r"(tile_bytes) : "memory");
-        tma_load_1d(dst, bv.hdr0 + r0, kThreads * 16, &mbar_col[st]);
-        tma_load_1d(dst + kThreads * 16, bv.hdr1 + r0, kThreads * 8, &mbar_col[st]);
-        for (uint32_t i = 0; i < bv.role_cols; i++) tma_load_1d(dst + kThreads * 24 + i * (kThreads * 4), bv.roles + i * bv.stride + r0, kThreads * 4, &mbar_col[st]);
-        for (uint32_t v = 0; v < n_slots; v++) tma_load_1d(dst + slots_off + v * (kThreads * 8), bv.slots + v * bv.stride + r0, kThreads * 8, &mbar_col[st]);
-    };
-
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar_tab)));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar_col[0])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar_col[1])));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar_tab)), "r"(td.lay.image_bytes) : "memory");
-        for (uint32_t o = 0; o < td.lay.image_bytes; o += 32768) {
-            uint32_t nb = td.lay.image_bytes - o < 32768 ? td.lay.image_bytes - o : 32768;
-            tma_load_1d(smem_image + o, td.base + o, nb, &mbar_tab);
-        }
-        if (blockIdx.x < n_full) issue_tile(blockIdx.x, 0);
-    }
-    cb::TableView tv;
-    tv.base = smem_image;
-    tv.L = &td.lay;
-    uint32_t k = 0;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, k++) {
-        const uint64_t next = tile + gridDim.x;
-        // stage (k+1)&1 was last read in iteration k-1; the barrier that closed it has been passed by every thread
-        if (threadIdx.x == 0 && next < n_full) issue_tile(next, (k + 1) & 1);
-        if (k == 0) mbar_wait(&mbar_tab, 0);
-        const uint64_t n = bv.first + tile * kThreads + threadIdx.x;
-        if (tile < n_full) {
-            mbar_wait(&mbar_col[k & 1], (k >> 1) & 1);
-            cb::TileCols tc;
-            tc.base = stage0 + (k & 1) * tile_bytes; tc.tid = threadIdx.x; tc.slots_off = slots_off;
-            if (cb::eval_request_fast(tv, bv, tc, n, bitmap, effects)) cb::eval_request_general(tv.base, tv.L, &bv, n, bitmap, effects, status);
-        } else if (tile * kThreads + threadIdx.x < bv.count) {   // the ragged last tile: straight from global memory
-            cb::GlobalCols gc;
-            gc.b = &bv; gc.n = n;
-            if (cb::eval_request_fast(tv, bv, gc, n, bitmap, effects)) cb::eval_request_general(tv.base, tv.L, &bv, n, bitmap, effects, status);
-        }
-        __syncthreads();
-    }
-    if (k == 0) mbar_wait(&mbar_tab, 0);   // no tile: drain the table copy before shared memory is released
+    cbk::check_tiles_body<cb::GenericBlocks>(td, bv, bitmap, effects, status, n_slots, smem_image, &mbar_tab, mbar_col);
 }
-
 
 // ------------------------------------------------------------------------------------------------ clustering
 // Requests of one batch hit different policy blocks (resource kind x scope x version); evaluated in index order the
@@ -350,6 +186,8 @@ struct cgpu_ctx {
     int cluster_mode = -1;   // CERBOS_B200_CLUSTER: 0 never, 1 always, unset = batches of >= kClusterMinRequests
     uint32_t last_clustered = 0, last_window = 0, last_buckets = 0, last_col_tiles = 0;
     int force_no_tiles = 0;  // CERBOS_B200_NO_TILES=1: never stage request columns through TMA (tests)
+    int force_no_jit = 0;    // CERBOS_B200_NO_JIT=1: never compile table-specialised kernels (tests)
+    uint32_t last_spec = 0;
     bool profiling = false;  // cgpu_profile(): CUDA events around the check kernel of every launch
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double prof_ms = 0;
@@ -363,8 +201,17 @@ struct cgpu_table {
     uint8_t *d_image = nullptr;
     TableDesc desc{};
     uint32_t meta[CB_META_WORDS]{};
-    std::atomic<int> occ[5]{};
-    std::atomic<uint32_t> occ_smem[5]{};   // resident CTAs / SM per kernel variant (0 = not queried yet)
+    std::atomic<int> occ[7]{};
+    std::atomic<uint32_t> occ_smem[7]{};
+    // table-specialised lean kernels (cb_specialize.h), compiled with NVRTC on first use
+    std::vector<uint8_t> host_image;
+    std::mutex spec_mu;
+    std::atomic<int> spec_state{0};   // 0 not tried, 1 ready, -1 unavailable
+    cudaLibrary_t spec_lib = nullptr;
+    cudaKernel_t spec_tiles = nullptr, spec_direct = nullptr;
+    std::string spec_note;
+    std::thread spec_thread;          // compiles the specialised kernels in the background from cgpu_table_load on
+    std::mutex join_mu;   // resident CTAs / SM per kernel variant (0 = not queried yet)
 };
 
 namespace {
@@ -450,6 +297,109 @@ int make_batch_view(const cgpu_table *t, const cgpu_batch *b, uint64_t first, ui
     return CGPU_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------- run-time specialisation
+// NVRTC is loaded lazily with dlopen: a host without it simply keeps the ahead-of-time (generic) kernels.
+struct Nvrtc {
+    void *h = nullptr;
+    int (*create)(void **, const char *, const char *, int, const char *const *, const char *const *) = nullptr;
+    int (*compile)(void *, int, const char *const *) = nullptr;
+    int (*log_size)(void *, size_t *) = nullptr;
+    int (*log)(void *, char *) = nullptr;
+    int (*cubin_size)(void *, size_t *) = nullptr;
+    int (*cubin)(void *, char *) = nullptr;
+    int (*destroy)(void **) = nullptr;
+    bool ok = false;
+};
+Nvrtc &nvrtc() {
+    static Nvrtc n;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (const char *name : {"libnvrtc.so.12", "libnvrtc.so"}) {
+            n.h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+            if (n.h) break;
+        }
+        if (!n.h) return;
+        n.create = reinterpret_cast<decltype(n.create)>(dlsym(n.h, "nvrtcCreateProgram"));
+        n.compile = reinterpret_cast<decltype(n.compile)>(dlsym(n.h, "nvrtcCompileProgram"));
+        n.log_size = reinterpret_cast<decltype(n.log_size)>(dlsym(n.h, "nvrtcGetProgramLogSize"));
+        n.log = reinterpret_cast<decltype(n.log)>(dlsym(n.h, "nvrtcGetProgramLog"));
+        n.cubin_size = reinterpret_cast<decltype(n.cubin_size)>(dlsym(n.h, "nvrtcGetCUBINSize"));
+        n.cubin = reinterpret_cast<decltype(n.cubin)>(dlsym(n.h, "nvrtcGetCUBIN"));
+        n.destroy = reinterpret_cast<decltype(n.destroy)>(dlsym(n.h, "nvrtcDestroyProgram"));
+        n.ok = n.create && n.compile && n.log_size && n.log && n.cubin_size && n.cubin && n.destroy;
+    });
+    return n;
+}
+
+const char kSpecPrelude[] =
+    "#define CB_LEAN_ONLY 1\n"
+    "typedef unsigned char uint8_t; typedef unsigned short uint16_t; typedef unsigned int uint32_t; typedef unsigned long long uint64_t;\n"
+    "typedef signed char int8_t; typedef short int16_t; typedef int int32_t; typedef long long int64_t; typedef unsigned long long uintptr_t;\n";
+const char kSpecKernels[] =
+    "\nextern \"C\" __global__ void __launch_bounds__(256, 4) cb_spec_tiles(const __grid_constant__ cbk::TableDesc td, const __grid_constant__ cb::BatchView bv,\n"
+    "        uint8_t *bitmap, uint8_t *effects, uint32_t *status, const uint32_t n_slots) {\n"
+    "    extern __shared__ __align__(128) uint8_t smem_image[];\n"
+    "    __shared__ __align__(8) uint64_t mbar_tab, mbar_col[2];\n"
+    "    cbk::check_tiles_body<cb::SpecBlocks>(td, bv, bitmap, effects, status, n_slots, smem_image, &mbar_tab, mbar_col);\n"
+    "}\n"
+    "extern \"C\" __global__ void __launch_bounds__(256, 4) cb_spec_direct(const __grid_constant__ cbk::TableDesc td, const __grid_constant__ cb::BatchView bv,\n"
+    "        uint8_t *bitmap, uint8_t *effects, uint32_t *status, const uint32_t stage_rt) {\n"
+    "    extern __shared__ __align__(128) uint8_t smem_image[];\n"
+    "    __shared__ __align__(8) uint64_t mbar;\n"
+    "    cbk::check_body<true, 1, cb::SpecBlocks>(td, bv, bitmap, effects, status, stage_rt, smem_image, &mbar);\n"
+    "}\n";
+
+// Generates, compiles and loads the table's specialised kernels (once; thread-safe). Returns whether they are usable.
+bool ensure_spec(cgpu_ctx *ctx, cgpu_table *t) {
+    int st = t->spec_state.load(std::memory_order_acquire);
+    if (st != 0) return st > 0;
+    std::lock_guard<std::mutex> g(t->spec_mu);
+    st = t->spec_state.load(std::memory_order_acquire);
+    if (st != 0) return st > 0;
+    auto give_up = [&](const std::string &why) { t->spec_note = why; t->spec_state.store(-1, std::memory_order_release); return false; };
+    if (ctx->force_no_jit) return give_up("disabled (CERBOS_B200_NO_JIT)");
+    if (t->desc.lay.image_bytes > kMaxStageBytes) return give_up("table image too large for shared memory");
+    Nvrtc &n = nvrtc();
+    if (!n.ok) return give_up("libnvrtc not available");
+    const std::string gen = cbspec::generate(t->host_image.data(), t->desc.lay.off, t->meta);
+    if (gen.empty()) return give_up("table does not qualify (a condition without flat form, or too many block shapes)");
+    std::string src = kSpecPrelude;
+    for (const char *const *p = kEmbedFormat; *p; p++) src += *p;
+    for (const char *const *p = kEmbedCore; *p; p++) src += *p;
+    src += gen;
+    for (const char *const *p = kEmbedKernels; *p; p++) src += *p;
+    src += kSpecKernels;
+    void *prog = nullptr;
+    if (n.create(&prog, src.c_str(), "cerbos_b200_spec.cu", 0, nullptr, nullptr) != 0) return give_up("nvrtcCreateProgram failed");
+    const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
+    const int rc = n.compile(prog, 3, opts);
+    if (rc != 0) {
+        size_t ls = 0;
+        n.log_size(prog, &ls);
+        std::string log(ls, '\0');
+        if (ls) n.log(prog, &log[0]);
+        n.destroy(&prog);
+        return give_up("NVRTC compile failed: " + log.substr(0, 400));
+    }
+    size_t cs = 0;
+    n.cubin_size(prog, &cs);
+    std::vector<char> cubin(cs);
+    n.cubin(prog, cubin.data());
+    n.destroy(&prog);
+    if (cudaLibraryLoadData(&t->spec_lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) { cudaGetLastError(); return give_up("cudaLibraryLoadData failed"); }
+    if (cudaLibraryGetKernel(&t->spec_tiles, t->spec_lib, "cb_spec_tiles") != cudaSuccess ||
+        cudaLibraryGetKernel(&t->spec_direct, t->spec_lib, "cb_spec_direct") != cudaSuccess) {
+        cudaGetLastError();
+        cudaLibraryUnload(t->spec_lib);
+        t->spec_lib = nullptr;
+        return give_up("cudaLibraryGetKernel failed");
+    }
+    t->spec_note = "ok";
+    t->spec_state.store(1, std::memory_order_release);
+    return true;
+}
+
 constexpr uint64_t kClusterMinRequests = 32768;
 constexpr uint64_t kClusterWindowBytes = 24u << 20;   // columns of one window: comfortably inside the 126 MB L2
 
@@ -513,19 +463,26 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
     const bool col_tiles = narrow && stage && !cluster && !ctx->force_no_tiles && tiles_smem <= kMaxTilesSmem && bv.stride % 4 == 0 &&
                            bv.first % 4 == 0 && al16(bv.hdr0) && al16(bv.hdr1) && al16(bv.roles) && al16(bv.slots);
     const uint32_t smem = col_tiles ? tiles_smem : stage ? lay.image_bytes : 0;
-    const void *fn = col_tiles ? (const void *)check_kernel_tiles
-                     : narrow  ? (stage ? (const void *)check_kernel<true, 1> : (const void *)check_kernel<true, 0>)
-                               : (const void *)check_kernel<false, 2>;
-    // resident CTAs per SM for this shared-memory footprint: queried once per (table, variant, footprint)
     cgpu_table *mt = const_cast<cgpu_table *>(t);
-    const int variant = col_tiles ? 4 : narrow ? (stage ? 1 : 2) : (stage ? 0 : 3);
-    int occ = mt->occ_smem[variant].load(std::memory_order_relaxed) == smem ? mt->occ[variant].load(std::memory_order_relaxed) : 0;
+    // lean launches with a staged table use the kernels specialised for this table when they exist (NVRTC, first use)
+    const bool spec = narrow && stage && bv.count < (1ull << 32) && mt->spec_state.load(std::memory_order_acquire) == 1;   // never waits for the compile
+    const void *fn = spec        ? (col_tiles ? (const void *)t->spec_tiles : (const void *)t->spec_direct)
+                     : col_tiles ? (const void *)check_kernel_tiles
+                     : narrow    ? (stage ? (const void *)check_kernel<true, 1> : (const void *)check_kernel<true, 0>)
+                                 : (const void *)check_kernel<false, 2>;
+    // resident CTAs per SM for this shared-memory footprint: queried once per (table, variant, footprint)
+    const int variant = spec ? (col_tiles ? 5 : 6) : col_tiles ? 4 : narrow ? (stage ? 1 : 2) : (stage ? 0 : 3);
+    int occ = mt->occ_smem[variant].load(std::memory_order_relaxed) == smem + 1 ? mt->occ[variant].load(std::memory_order_relaxed) : 0;
     if (occ == 0) {
-        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxStageBytes));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, smem));
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxStageBytes) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, smem) != cudaSuccess) {
+            if (!spec) return fail(CGPU_ERR_CUDA, "kernel attribute / occupancy query failed: %s", cudaGetErrorString(cudaGetLastError()));
+            cudaGetLastError();
+            occ = CB_MIN_BLOCKS;   // run-time loaded kernel on a runtime that cannot query it: the launch-bounds minimum
+        }
         if (occ < 1) occ = 1;
         mt->occ[variant].store(occ, std::memory_order_relaxed);
-        mt->occ_smem[variant].store(smem, std::memory_order_relaxed);
+        mt->occ_smem[variant].store(smem + 1, std::memory_order_relaxed);
     }
     uint64_t max_ctas = (uint64_t)ctx->sm_count * (uint64_t)occ;
     uint32_t grid = (uint32_t)(tiles < max_ctas ? tiles : max_ctas);
@@ -543,6 +500,13 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
         bvv.perm = perm;
     }
     uint32_t last_arg = col_tiles ? lay.n_slots : (stage ? 1u : 0u);   // check_kernel: stage_rt; check_kernel_tiles: n_slots
+    uint32_t *defer = nullptr;   // [0] = count, [1 ..] = request offsets the specialised kernel leaves to the general kernel
+    if (spec) {
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&defer), ((size_t)bv.count + 1) * 4, stream));
+        CUDA_TRY(cudaMemsetAsync(defer, 0, 4, stream));
+        bvv.defer_count = defer;
+        bvv.defer_list = defer + 1;
+    }
     void *args[] = {&td, &bvv, &d_bitmap, &d_effects, &d_status, &last_arg};
     if (ctx->profiling) {
         if (ctx->prof_pending && cudaEventSynchronize(ctx->ev1) == cudaSuccess) {
@@ -555,11 +519,37 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
     CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(kThreads), args, smem, stream));
     CUDA_TRY(cudaGetLastError());
     if (ctx->profiling) { CUDA_TRY(cudaEventRecord(ctx->ev1, stream)); ctx->prof_pending = true; }
+    if (spec) {
+        // drain the deferral list with the general body (usually empty: the kernel then exits at once)
+        cb::BatchView dv = bv;
+        dv.perm = defer + 1;
+        dv.count_dev = defer;
+        dv.prefetch_slots = 0;
+        const void *gfn = (const void *)check_kernel<false, 2>;
+        int gocc = mt->occ[0].load(std::memory_order_relaxed);
+        if (gocc == 0 || mt->occ_smem[0].load(std::memory_order_relaxed) != lay.image_bytes + 1) {
+            CUDA_TRY(cudaFuncSetAttribute(gfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxStageBytes));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gocc, gfn, kThreads, lay.image_bytes));
+            if (gocc < 1) gocc = 1;
+            mt->occ[0].store(gocc, std::memory_order_relaxed);
+            mt->occ_smem[0].store(lay.image_bytes + 1, std::memory_order_relaxed);
+        }
+        uint64_t gmax = (uint64_t)ctx->sm_count * (uint64_t)gocc;
+        uint32_t ggrid = (uint32_t)(tiles < gmax ? tiles : gmax);
+        uint32_t one = 1u;
+        uint8_t *gb = d_bitmap, *ge = d_effects;
+        void *gargs[] = {&td, &dv, &gb, &ge, &d_status, &one};
+        CUDA_TRY(cudaLaunchKernel(gfn, dim3(ggrid ? ggrid : 1), dim3(kThreads), gargs, lay.image_bytes, stream));
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaFreeAsync(defer, stream));
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    }
     if (perm) CUDA_TRY(cudaFreeAsync(perm, stream));
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
     ctx->last_grid = grid; ctx->last_block = kThreads; ctx->last_smem = smem; ctx->last_fast = narrow ? 1 : 0;
     ctx->last_clustered = cluster ? 1 : 0;
     ctx->last_col_tiles = col_tiles ? 1 : 0;
+    ctx->last_spec = spec ? 1 : 0;
     return CGPU_OK;
 }
 
@@ -591,6 +581,8 @@ int cgpu_init(const int *device_ids, int n_devices, cgpu_ctx **out) {
     ctx->force_no_stage = ns && ns[0] == '1';
     const char *fg = getenv("CERBOS_B200_FORCE_GENERAL");
     ctx->force_general = fg && fg[0] == '1';
+    const char *nj = getenv("CERBOS_B200_NO_JIT");
+    ctx->force_no_jit = nj && nj[0] == '1';
     const char *nt = getenv("CERBOS_B200_NO_TILES");
     ctx->force_no_tiles = nt && nt[0] == '1';
     const char *cm = getenv("CERBOS_B200_CLUSTER");
@@ -640,6 +632,13 @@ int cgpu_table_load(cgpu_ctx *ctx, const void *blob, size_t len, cgpu_table **ou
         return fail(CGPU_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(e));
     }
     t->desc.base = t->d_image;
+    t->host_image.assign(static_cast<const uint8_t *>(blob), static_cast<const uint8_t *>(blob) + t->desc.lay.image_bytes);
+    // table-specialised kernels are generated + compiled off the caller's thread; launches use the generic kernels
+    // until they are ready (cgpu_table_wait_ready blocks for them)
+    t->spec_thread = std::thread([ctx, t] {
+        cudaSetDevice(ctx->device);
+        ensure_spec(ctx, t);
+    });
     *out = t;
     return CGPU_OK;
 }
@@ -649,11 +648,21 @@ void cgpu_table_retain(cgpu_table *t) { if (t) t->refs.fetch_add(1); }
 void cgpu_table_release(cgpu_table *t) {
     if (!t) return;
     if (t->refs.fetch_sub(1) == 1) {
+        { std::lock_guard<std::mutex> g(t->join_mu); if (t->spec_thread.joinable()) t->spec_thread.join(); }
         cudaSetDevice(t->ctx->device);
         cudaDeviceSynchronize();   // no kernel may still read the image
         cudaFree(t->d_image);
+        if (t->spec_lib) cudaLibraryUnload(t->spec_lib);
         delete t;
     }
+}
+
+int cgpu_table_wait_ready(cgpu_table *t, int *specialised) {
+    if (!t) return fail(CGPU_ERR_INVALID, "cgpu_table_wait_ready: null table");
+    { std::lock_guard<std::mutex> g(t->join_mu); if (t->spec_thread.joinable()) t->spec_thread.join(); }
+    if (specialised) *specialised = t->spec_state.load(std::memory_order_acquire) == 1 ? 1 : 0;
+    g_err = t->spec_note;   // why not, if not (readable through cgpu_last_error)
+    return CGPU_OK;
 }
 
 int cgpu_table_info(const cgpu_table *t, uint32_t *meta_out, uint32_t n_words) {
@@ -675,7 +684,7 @@ int cgpu_last_kernel_config(const cgpu_ctx *ctx, uint32_t *grid, uint32_t *block
 
 int cgpu_last_cluster_config(const cgpu_ctx *ctx, uint32_t *clustered, uint32_t *window, uint32_t *buckets) {
     if (!ctx) return fail(CGPU_ERR_INVALID, "null ctx");
-    if (clustered) *clustered = ctx->last_clustered | (ctx->last_col_tiles << 1);   // bit 1: request columns were TMA-staged
+    if (clustered) *clustered = ctx->last_clustered | (ctx->last_col_tiles << 1) | (ctx->last_spec << 2);   // bit 1: TMA column tiles; bit 2: table-specialised kernel
     if (window) *window = ctx->last_window;
     if (buckets) *buckets = ctx->last_buckets;
     return CGPU_OK;

@@ -102,13 +102,20 @@ int cgpu_check_device(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *dev_
  * if any of it failed. */
 int cgpu_sync(cgpu_ctx *ctx, void *cuda_stream);
 
+/* cgpu_table_load also starts, on a background thread, the generation + NVRTC compilation of kernels specialised for
+ * this table (small tables whose conditions all have a flat form; seconds). Checks never wait for it: they use the
+ * ahead-of-time generic kernels until it is done. This call does wait; *specialised = 1 if such kernels are in use
+ * (otherwise cgpu_last_error() says why not). */
+int cgpu_table_wait_ready(cgpu_table *t, int *specialised);
+
 /* Introspection used by bench.py / tests (not part of the Go surface). */
 uint64_t cgpu_launch_count(const cgpu_ctx *ctx);        /* kernels launched by this library so far */
 int cgpu_table_info(const cgpu_table *t, uint32_t *meta_out, uint32_t n_words);  /* copies META words */
 int cgpu_last_kernel_config(const cgpu_ctx *ctx, uint32_t *grid, uint32_t *block, uint32_t *smem_bytes);
 /* Whether the last launch evaluated in clustered order (requests grouped by policy block inside L2-sized windows by
  * three small kernels ahead of the check kernel; env CERBOS_B200_CLUSTER=0/1 overrides the batch-size rule).
- * *clustered bit 0: clustered order; bit 1: the request columns were staged tile by tile through TMA. */
+ * *clustered bit 0: clustered order; bit 1: the request columns were staged tile by tile through TMA; bit 2: the
+ * kernel was the one compiled for this table at run time (NVRTC; env CERBOS_B200_NO_JIT=1 disables). */
 int cgpu_last_cluster_config(const cgpu_ctx *ctx, uint32_t *clustered, uint32_t *window, uint32_t *buckets);
 /* Returns and resets the CUDA-event time (ms) spent in the check kernel itself over the launches since the last
  * call, then switches the per-launch events on or off. Measurement aid for bench.py; off by default. */

@@ -12,7 +12,8 @@ _lib = None
 
 def build():
     src = os.path.join(_ROOT, "tests", "hostsim", "hostsim.cpp")
-    deps = [src, os.path.join(_ROOT, "cerbos_b200", "csrc", "cb_core.h"), os.path.join(_ROOT, "include", "cerbos_b200_format.h")]
+    deps = [src, os.path.join(_ROOT, "cerbos_b200", "csrc", "cb_core.h"), os.path.join(_ROOT, "cerbos_b200", "csrc", "cb_specialize.h"),
+            os.path.join(_ROOT, "include", "cerbos_b200_format.h")]
     if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(_SO), exist_ok=True)
         subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", f"-I{_ROOT}/include",
@@ -38,5 +39,55 @@ def check(blob: bytes, columns, n, max_actions, now_ns=0, flags=0, mode=0):
                             bitmap.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(mode))
     if rc != 0:
         raise RuntimeError(f"hostsim_check failed: {rc}")
+    return _decode(bitmap, n, km)
+
+
+def _decode(bitmap, n, km):
     bits = np.unpackbits(bitmap, axis=1, bitorder="little")[:, :km]
     return np.where(bits == 1, 1, 2).astype(np.uint8)
+
+
+def generate(blob: bytes) -> str:
+    """Source of the table-specialised block evaluators (cb_specialize.h); "" when the table does not qualify."""
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.hostsim_check.restype = ctypes.c_int
+    _lib.hostsim_generate.restype = ctypes.c_int64
+    cap = 1 << 22
+    out = ctypes.create_string_buffer(cap)
+    n = _lib.hostsim_generate(ctypes.create_string_buffer(blob, len(blob)), ctypes.c_uint64(len(blob)), out, ctypes.c_uint64(cap))
+    if n < 0:
+        raise RuntimeError(f"hostsim_generate failed: {n}")
+    return out.value.decode()
+
+
+def build_spec(blob: bytes, workdir: str):
+    """Host build of the kernel core with the evaluators generated for `blob` -> ctypes library exposing hostsim_check_spec."""
+    src_text = generate(blob)
+    if not src_text:
+        return None
+    with open(os.path.join(workdir, "spec_gen.inc"), "w") as f:
+        f.write(src_text)
+    so = os.path.join(workdir, "libhostsim_spec.so")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DHOSTSIM_SPEC", f"-I{workdir}", f"-I{_ROOT}/include",
+                    f"-I{_ROOT}/cerbos_b200/csrc", "-o", so, os.path.join(_ROOT, "tests", "hostsim", "hostsim.cpp")], check=True)
+    lib = ctypes.CDLL(so)
+    lib.hostsim_check_spec.restype = ctypes.c_int
+    return lib
+
+
+def check_spec(lib, blob: bytes, columns, n, max_actions, now_ns=0, flags=0, mode=0):
+    cols = [np.ascontiguousarray(c) for c in columns]
+    ptrs = (ctypes.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+    sizes = (ctypes.c_uint64 * len(cols))(*[c.nbytes for c in cols])
+    km = max(max_actions, 1)
+    kbytes = (km + 7) // 8
+    bitmap = np.zeros((n, kbytes), dtype=np.uint8)
+    buf = ctypes.create_string_buffer(blob, len(blob))
+    rc = lib.hostsim_check_spec(buf, ctypes.c_uint64(len(blob)), ctypes.c_uint64(n), ctypes.c_uint32(max_actions),
+                                ctypes.c_int64(now_ns), ctypes.c_uint32(flags), ptrs, sizes,
+                                bitmap.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(mode))
+    if rc != 0:
+        raise RuntimeError(f"hostsim_check_spec failed: {rc}")
+    return _decode(bitmap, n, km)

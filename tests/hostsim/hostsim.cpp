@@ -7,8 +7,18 @@
 #include <vector>
 
 #include "cb_core.h"
+#include "cb_specialize.h"
 
-extern "C" int hostsim_check(const void *blob, uint64_t blob_len, uint64_t n, uint32_t max_actions, int64_t now, uint32_t flags,
+#ifdef HOSTSIM_SPEC
+#include "spec_gen.inc"   // generated for one table by hostsim_generate (tests/test_specialize.py)
+typedef cb::SpecBlocks HostBlocks;
+#define HOSTSIM_ENTRY hostsim_check_spec
+#else
+typedef cb::GenericBlocks HostBlocks;
+#define HOSTSIM_ENTRY hostsim_check
+#endif
+
+extern "C" int HOSTSIM_ENTRY(const void *blob, uint64_t blob_len, uint64_t n, uint32_t max_actions, int64_t now, uint32_t flags,
                              const void *const *cols, const uint64_t *col_bytes, uint8_t *bitmap, int mode) {
     const cb_blob_header *h = static_cast<const cb_blob_header *>(blob);
     if (h->magic != CB_MAGIC || h->version != CB_VERSION) return -1;
@@ -62,7 +72,7 @@ extern "C" int hostsim_check(const void *blob, uint64_t blob_len, uint64_t n, ui
             for (uint32_t v = 0; v < lay.n_slots; v++) memcpy(tb + so + v * cb::CB_TILE * 8, b.slots + v * b.stride + t0, cnt * 8);
             for (uint32_t j = 0; j < cnt; j++) {
                 cb::TileCols tc; tc.base = tb; tc.tid = j; tc.slots_off = so;
-                if (cb::eval_request_fast(t, b, tc, t0 + j, bitmap, nullptr)) cb::eval_request_general(t.base, t.L, &b, t0 + j, bitmap, nullptr, &status);
+                if (cb::eval_request_fast(t, b, tc, t0 + j, bitmap, nullptr, HostBlocks())) cb::eval_request_general(t.base, t.L, &b, t0 + j, bitmap, nullptr, &status);
             }
         }
         return status ? -2 : 0;
@@ -70,10 +80,26 @@ extern "C" int hostsim_check(const void *blob, uint64_t blob_len, uint64_t n, ui
     for (uint64_t i = 0; i < n; i++) {
         if (mode == 0 && fast) {
             cb::GlobalCols gc; gc.b = &b; gc.n = i;
-            if (cb::eval_request_fast(t, b, gc, i, bitmap, nullptr)) cb::eval_request_general(t.base, t.L, &b, i, bitmap, nullptr, &status);
+            if (cb::eval_request_fast(t, b, gc, i, bitmap, nullptr, HostBlocks())) cb::eval_request_general(t.base, t.L, &b, i, bitmap, nullptr, &status);
         }
         else if (mode == 2 && narrow) cb::eval_request<uint32_t>(t, b, i, bitmap, nullptr, &status);
         else cb::eval_request<uint64_t>(t, b, i, bitmap, nullptr, &status);
     }
     return status ? -2 : 0;
 }
+
+#ifndef HOSTSIM_SPEC
+// the table-specialised block evaluators the library would hand to NVRTC (source text; "" if the table does not qualify)
+extern "C" int64_t hostsim_generate(const void *blob, uint64_t blob_len, char *out, uint64_t cap) {
+    const cb_blob_header *h = static_cast<const cb_blob_header *>(blob);
+    if (blob_len < sizeof(*h) || h->magic != CB_MAGIC || h->version != CB_VERSION) return -1;
+    const cb_section_desc *sd = reinterpret_cast<const cb_section_desc *>(static_cast<const char *>(blob) + sizeof(cb_blob_header));
+    uint32_t off[128] = {0};
+    for (uint32_t i = 0; i < h->n_sections; i++) if (sd[i].id < 128) off[sd[i].id] = (uint32_t)sd[i].offset;
+    const uint8_t *base = static_cast<const uint8_t *>(blob);
+    std::string src = cbspec::generate(base, off, reinterpret_cast<const uint32_t *>(base + off[CB_SEC_META]));
+    if (src.size() + 1 > cap) return -(int64_t)src.size() - 2;
+    memcpy(out, src.c_str(), src.size() + 1);
+    return (int64_t)src.size();
+}
+#endif

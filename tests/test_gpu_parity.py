@@ -250,3 +250,68 @@ def test_tma_column_tiles_and_direct_loads_agree(name, n):
     os.environ.pop("CERBOS_B200_NO_TILES", None)
     assert used["1"] is False
     assert used["0"] == (n % 4 == 0)
+
+
+@pytest.mark.parametrize("name,n", [("C2", (1 << 16) + 260), ("C2", 4099), ("C1", 1024), ("C3", 1 << 15)])
+def test_table_specialised_and_generic_kernels_agree(name, n):
+    """The kernels compiled for the table at run time (cb_specialize.h + NVRTC) against the ahead-of-time generic
+    ones (CERBOS_B200_NO_JIT=1) and the oracle; tile-staged and direct column paths, clustered and index order."""
+    from cerbos_b200 import capi, workloads as W
+    from cerbos_b200.device import DeviceBatch
+    from oracle import cref
+    w = W.WORKLOADS[name]()
+    _, ft, enc = W.build(w)
+    b = w.columns(w.fields(n), enc)
+    want = cref.check(ft.blob, b.columns, b.n, b.max_actions, n_threads=os.cpu_count() or 1)
+    seen = {}
+    for nojit in ("0", "1"):
+        for cluster in ("0", "1"):
+            os.environ["CERBOS_B200_NO_JIT"] = nojit
+            os.environ["CERBOS_B200_CLUSTER"] = cluster
+            c = capi.Context(0)
+            t = c.load_table(ft.blob)
+            t.wait_ready()
+            db = DeviceBatch(b, "cuda:0")
+            db.run(t)
+            c.sync()
+            cfg = c.last_kernel_config()
+            seen[(nojit, cluster)] = cfg
+            assert (db.effects() == want).all(), (name, n, nojit, cluster)
+            assert (t.check(b.columns, b.n, b.max_actions) == want).all(), (name, n, nojit, cluster, "host")
+            t.release()
+            c.close()
+    os.environ.pop("CERBOS_B200_NO_JIT", None)
+    os.environ.pop("CERBOS_B200_CLUSTER", None)
+    assert seen[("0", "0")]["table_specialised"] == (name != "C3") and not seen[("1", "0")]["table_specialised"]   # C3: too many block shapes
+
+
+def test_specialised_kernel_defers_to_general_kernel():
+    """Requests the lean body cannot decide (principal and resource policy versions differ) travel through the
+    deferral list of the specialised kernel to the general kernel."""
+    from cerbos_b200 import capi, workloads as W
+    from cerbos_b200.device import DeviceBatch
+    from oracle import cref
+    w = W.C2()
+    _, ft, enc = W.build(w)
+    f = w.fields(3000)
+    inputs = w.inputs(f, range(3000))
+    for i in range(0, 3000, 7):
+        inputs[i]["principal"]["policyVersion"] = "v2"
+    for i in range(3, 3000, 11):
+        inputs[i]["resource"]["attr"]["owner"] = ["a", "list"]          # container equality: out of the 8-byte fast forms
+    b = enc.encode(inputs)
+    want = cref.check(ft.blob, b.columns, b.n, b.max_actions)
+    for nojit in ("0", "1"):
+        os.environ["CERBOS_B200_NO_JIT"] = nojit
+        c = capi.Context(0)
+        t = c.load_table(ft.blob)
+        t.wait_ready()
+        db = DeviceBatch(b, "cuda:0")
+        db.run(t)
+        c.sync()
+        assert c.last_kernel_config()["table_specialised"] == (nojit == "0")
+        assert (db.effects() == want).all(), nojit
+        assert (t.check(b.columns, b.n, b.max_actions) == want).all(), nojit
+        t.release()
+        c.close()
+    os.environ.pop("CERBOS_B200_NO_JIT", None)

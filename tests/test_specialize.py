@@ -1,0 +1,63 @@
+"""Table-specialised block evaluators (cerbos_b200/csrc/cb_specialize.h): the source the library hands to NVRTC at
+table load is generated here for the workload / golden / fuzz tables, compiled for the host together with the kernel
+core, and must give the oracles' bits.  (The GPU build of the same text is covered by tests/test_gpu_parity.py.)"""
+import random
+
+import numpy as np
+import pytest
+
+from cerbos_b200 import workloads as W
+from cerbos_b200.encode import Encoder
+from cerbos_b200.policy.compile import build_rule_table
+from cerbos_b200.table.flatten import flatten
+from fuzzgen import rand_policies, rand_request
+from hostsim import driver as hostsim
+from oracle import cref
+
+
+@pytest.mark.parametrize("name,n", [("C1", 1024), ("C2", 1 << 14), ("C3", 1 << 13)])
+def test_workload_tables(name, n, tmp_path):
+    w = W.WORKLOADS[name]()
+    _, ft, enc = W.build(w)
+    src = hostsim.generate(ft.blob)
+    if name == "C3":
+        assert src == "" or "spec_shape_0" in src    # 75 shapes: may exceed the code-size limits
+    else:
+        assert "struct SpecBlocks" in src
+    if not src:
+        pytest.skip("table does not qualify for specialisation")
+    lib = hostsim.build_spec(ft.blob, str(tmp_path))
+    b = w.columns(w.fields(n), enc)
+    want = cref.check(ft.blob, b.columns, b.n, b.max_actions)
+    for mode in (0, 3):   # global columns / staged column tiles
+        got = hostsim.check_spec(lib, ft.blob, b.columns, b.n, b.max_actions, mode=mode)
+        assert (got == want).all(), mode
+
+
+def test_generated_source_is_straight_line_for_c2():
+    w = W.C2()
+    _, ft, _ = W.build(w)
+    src = hostsim.generate(ft.blob)
+    assert src.count("spec_shape_") == 2 * 1 and src.count("term_tri(") == 4 and src.count("row_apply(") == 5   # one shape: 3 conditions / 4 terms, 5 rows
+    assert all(f"case {k}:" in src for k in range(10))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_tables(seed, tmp_path):
+    r = random.Random(7000 + seed)
+    # resource policies only (the lean body's domain): strip what the generator does not cover
+    docs = [d for d in rand_policies(r) if "resourcePolicy" in d or "derivedRoles" in d]
+    rt = build_rule_table(docs)
+    ft = flatten(rt)
+    src = hostsim.generate(ft.blob)
+    if not src:
+        pytest.skip("a condition has no flat form")
+    lib = hostsim.build_spec(ft.blob, str(tmp_path))
+    enc = Encoder(ft.manifest)
+    inputs = [rand_request(r) for _ in range(300)]
+    b = enc.encode(inputs)
+    want = cref.check(ft.blob, b.columns, b.n, b.max_actions, 0, 0)
+    valid = want != 0
+    for mode in (0, 3):
+        got = hostsim.check_spec(lib, ft.blob, b.columns, b.n, b.max_actions, mode=mode)
+        assert (got[valid] == want[valid]).all(), (seed, mode)

@@ -52,6 +52,8 @@ base = min(a for a, *_ in data)
 # pick the function whose name fits the kernel (template arg)
 m = re.search(r"\(bool\)(\d), \(int\)(\d)", kernel or "")
 tag = f"ILb{m.group(1)}ELi{m.group(2)}E" if m else "check_kernel"
+if "check_kernel_tiles" in (kernel or ""):
+    tag = "check_kernel_tiles"
 cands = [f for f in {k[0] for k in linemap} if "check_kernel" in f and "$" not in f and tag in f]
 fn = cands[0]
 # callee functions are laid out after the kernel in the same section group; ncu addresses are relative to kernel start.
