@@ -93,7 +93,7 @@ struct BatchView {
     const uint32_t *perm;       // clustered evaluation order (request offsets from `first`), or null = index order
     uint32_t prefetch_slots;    // > 0: the table reads this many slot columns in all (few): prefetch every one per tile
     uint32_t *defer_list, *defer_count;   // run-time specialised lean kernels: requests left to the general kernel
-    const uint32_t *count_dev;            // general kernel draining such a list: its length (device memory), else null
+    uint32_t *count_dev;                  // general kernel draining such a list: {length, CTAs done} in device memory, else null
 };
 
 // Table data may live in shared memory (TMA-staged image) or in global memory, heap references may point
@@ -1014,6 +1014,8 @@ struct GlobalCols {
 #endif
     }
     CB_HD bool staged() const { return b->prefetch_slots != 0; }   // every slot column was prefetched with the tile
+    CB_HD uint32_t aset_k(uint32_t aset) const { return ldg(b->aset_k + aset); }
+    CB_HD const uint64_t *row_am() const { return b->row_am; }
 };
 struct TileCols {
     const uint8_t *base;   // staged tile (shared memory on the device)
@@ -1024,6 +1026,11 @@ struct TileCols {
     CB_HD uint64_t slot(uint32_t v) const { return *reinterpret_cast<const uint64_t *>(base + slots_off + v * (CB_TILE * 8u) + tid * 8u); }
     CB_HD void prefetch_slot(uint32_t) const {}
     CB_HD bool staged() const { return true; }
+    // small per-batch tables (actions per action set, row x action-set masks): copies in shared memory when they fit
+    const uint32_t *aset_k_s;
+    const uint64_t *row_am_s;
+    CB_HD uint32_t aset_k(uint32_t aset) const { return ldg(aset_k_s + aset); }
+    CB_HD const uint64_t *row_am() const { return row_am_s; }
 };
 CB_HD uint32_t tile_cols_bytes(uint32_t role_cols, uint32_t n_slots) { return CB_TILE * (24u + 4u * role_cols + 8u * n_slots); }
 
@@ -1150,6 +1157,16 @@ CB_HD int in_tri(const TableView t, const BatchView &b, uint64_t x, uint64_t y, 
         found |= scalar_eq64(x, e);
     }
     return found;
+}
+// x in (constant list of scalars) with the elements inlined as arguments (run-time specialised kernels): same outcome
+// as in_tri() with elems_scalar
+template <typename... E>
+CB_HD int in_const_tri(uint64_t x, bool &slow, E... elems) {
+    if (v64_bad(x)) return TRI_E;
+    if (v64_tag(x) > CB_V64_STRING) { slow = true; return TRI_E; }
+    bool found = false;
+    ((found |= scalar_eq64(x, (uint64_t)elems)), ...);
+    return found ? TRI_T : TRI_F;
 }
 // One term {op | flags<<8 | xk<<16 | yk<<24, x, y, xa | ya<<16} -> TRI_T / TRI_F / TRI_E; `slow` is raised for operands
 // this path cannot decide exactly.  Force-inlined: called with a compile-time constant `w` (run-time specialised
@@ -1691,7 +1708,7 @@ CB_HD bool eval_request_fast(const TableView t, const BatchView &b, const Cols &
     const uint32_t pid = h0.x, kc = h0.y, rscope = h0.z;
     const uint32_t rv = (uint32_t)(h1 & 0xFFFF), pv = (uint32_t)((h1 >> 16) & 0xFFFF), aset = (uint32_t)(h1 >> 32);
     const uint32_t RC = b.role_cols, RCP = b.rcp;
-    const uint32_t K = aset < b.n_asets ? ldg(b.aset_k + aset) : 0;
+    const uint32_t K = aset < b.n_asets ? cols.aset_k(aset) : 0;
     uint64_t rp = 0;          // role table: RCP bits per table role
     uint32_t n_roles = 0;
     for (uint32_t i = 0; i < RC; i++) {
@@ -1705,7 +1722,7 @@ CB_HD bool eval_request_fast(const TableView t, const BatchView &b, const Cols &
     const uint32_t r0 = live ? chain_start(t, rscope, CB_SCOPE_FLAG_RESOURCE, (b.flags & CB_BATCH_FLAG_LENIENT) != 0) : CB_NONE32;
     if (r0 != CB_NONE32) {
         const uint32_t role_all = (1u << n_roles) - 1;
-        const uint64_t *row_am = b.row_am + (uint64_t)aset * b.n_rows;
+        const uint64_t *row_am = cols.row_am() + (uint64_t)aset * b.n_rows;
         const uint32_t amask = K * RC >= 32 ? b.stride_pattern : b.stride_pattern & ((1u << (K * RC)) - 1);   // bit kk*RC per action
         uint32_t alive = amask * role_all, allow_pairs = 0;
         bool defer = false;

@@ -126,6 +126,15 @@ __device__ __forceinline__ void check_body(const TableDesc &td, const cb::BatchV
         }
     }
     if (!staged) mbar_wait(mbar, 0);   // CTA had no tile: drain the bulk copy before shared memory is released
+    if (bv.count_dev) {
+        // deferred mode: the last CTA to finish hands the {count, done} cell back zeroed (it comes from a small pool of
+        // pre-zeroed cells, so that a launch needs no memset)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(bv.count_dev + 1, 1u) == gridDim.x - 1) { bv.count_dev[0] = 0; bv.count_dev[1] = 0; }
+        }
+    }
 }
 
 // Lean body with BOTH the table image and the request columns staged by the TMA unit.  Index-order batches only
@@ -134,27 +143,34 @@ __device__ __forceinline__ void check_body(const TableDesc &td, const cb::BatchV
 // waits on DRAM and every column read is an LDS).  Shared memory: [image][tile stage 0][tile stage 1].
 template <typename Blocks>
 __device__ __forceinline__ void check_tiles_body(const TableDesc &td, const cb::BatchView &bv, uint8_t *bitmap, uint8_t *effects, uint32_t *status, const uint32_t n_slots,
-                                                 uint8_t *smem_image, uint64_t *mbar_tab, uint64_t *mbar_col) {
+                                                 uint8_t *smem_image, uint64_t *mbar_tab, uint64_t *mbar_col /* [4]: full[2], empty[2] */) {
     const uint32_t image_pad = (td.lay.image_bytes + 127u) & ~127u;
     const uint32_t tile_bytes = cb::tile_cols_bytes(bv.role_cols, n_slots);
     const uint32_t slots_off = cb::CB_TILE * (24u + 4u * bv.role_cols);
     uint8_t *stage0 = smem_image + image_pad;
     const uint64_t n_tiles = (bv.count + kThreads - 1) / kThreads, n_full = bv.count / kThreads;
+    uint64_t *full = mbar_col, *empty = mbar_col + 2;
+    // small per-batch tables behind the two tile stages: row x action-set masks and actions per action set
+    uint64_t *row_am_s = reinterpret_cast<uint64_t *>(stage0 + 2 * tile_bytes);
+    const uint32_t n_am = bv.n_asets * bv.n_rows;
+    uint32_t *aset_k_s = reinterpret_cast<uint32_t *>(row_am_s + n_am);
 
     auto issue_tile = [&](uint64_t tile, uint32_t st) {   // one thread: bulk copies of every column run of `tile`
         uint8_t *dst = stage0 + st * tile_bytes;
         const uint64_t r0 = bv.first + tile * kThreads;
-        mbar_expect_tx(&mbar_col[st], tile_bytes);
-        tma_load_1d(dst, bv.hdr0 + r0, kThreads * 16, &mbar_col[st]);
-        tma_load_1d(dst + kThreads * 16, bv.hdr1 + r0, kThreads * 8, &mbar_col[st]);
-        for (uint32_t i = 0; i < bv.role_cols; i++) tma_load_1d(dst + kThreads * 24 + i * (kThreads * 4), bv.roles + i * bv.stride + r0, kThreads * 4, &mbar_col[st]);
-        for (uint32_t v = 0; v < n_slots; v++) tma_load_1d(dst + slots_off + v * (kThreads * 8), bv.slots + v * bv.stride + r0, kThreads * 8, &mbar_col[st]);
+        mbar_expect_tx(&full[st], tile_bytes);
+        tma_load_1d(dst, bv.hdr0 + r0, kThreads * 16, &full[st]);
+        tma_load_1d(dst + kThreads * 16, bv.hdr1 + r0, kThreads * 8, &full[st]);
+        for (uint32_t i = 0; i < bv.role_cols; i++) tma_load_1d(dst + kThreads * 24 + i * (kThreads * 4), bv.roles + i * bv.stride + r0, kThreads * 4, &full[st]);
+        for (uint32_t v = 0; v < n_slots; v++) tma_load_1d(dst + slots_off + v * (kThreads * 8), bv.slots + v * bv.stride + r0, kThreads * 8, &full[st]);
     };
 
     if (threadIdx.x == 0) {
         mbar_init(mbar_tab, 1);
-        mbar_init(&mbar_col[0], 1);
-        mbar_init(&mbar_col[1], 1);
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_init(&empty[0], kThreads / 32);   // one arrival per warp
+        mbar_init(&empty[1], kThreads / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -162,27 +178,36 @@ __device__ __forceinline__ void check_tiles_body(const TableDesc &td, const cb::
         tma_load_image(smem_image, td, mbar_tab);
         if (blockIdx.x < n_full) issue_tile(blockIdx.x, 0);
     }
+    for (uint32_t j = threadIdx.x; j < n_am; j += kThreads) row_am_s[j] = bv.row_am[j];
+    for (uint32_t j = threadIdx.x; j < bv.n_asets; j += kThreads) aset_k_s[j] = bv.aset_k[j];
+    __syncthreads();
     cb::TableView tv;
     tv.base = smem_image;
     tv.L = &td.lay;
     uint32_t k = 0;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, k++) {
         const uint64_t next = tile + gridDim.x;
-        // stage (k+1)&1 was last read in iteration k-1; the barrier that closed it has been passed by every thread
-        if (threadIdx.x == 0 && next < n_full) issue_tile(next, (k + 1) & 1);
+        if (threadIdx.x == 0 && next < n_full) {
+            // stage (k+1)&1 was read in iteration k-1: refill it once all eight warps have released it.  No CTA-wide
+            // barrier: only this thread waits, and it is normally released long before
+            if (k >= 1) mbar_wait(&empty[(k + 1) & 1], ((k - 1) >> 1) & 1);
+            issue_tile(next, (k + 1) & 1);
+        }
         if (k == 0) mbar_wait(mbar_tab, 0);
         const uint64_t n = bv.first + tile * kThreads + threadIdx.x;
         if (tile < n_full) {
-            mbar_wait(&mbar_col[k & 1], (k >> 1) & 1);
+            mbar_wait(&full[k & 1], (k >> 1) & 1);
             cb::TileCols tc;
             tc.base = stage0 + (k & 1) * tile_bytes; tc.tid = threadIdx.x; tc.slots_off = slots_off;
+            tc.aset_k_s = aset_k_s; tc.row_am_s = row_am_s;
             if (cb::eval_request_fast(tv, bv, tc, n, bitmap, effects, Blocks())) defer_request(tv, bv, n, bitmap, effects, status);
         } else if (tile * kThreads + threadIdx.x < bv.count) {   // the ragged last tile: straight from global memory
             cb::GlobalCols gc;
             gc.b = &bv; gc.n = n;
             if (cb::eval_request_fast(tv, bv, gc, n, bitmap, effects, Blocks())) defer_request(tv, bv, n, bitmap, effects, status);
         }
-        __syncthreads();
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[k & 1])) : "memory");
     }
     if (k == 0) mbar_wait(mbar_tab, 0);   // no tile: drain the table copy before shared memory is released
 }

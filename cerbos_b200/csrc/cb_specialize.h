@@ -32,6 +32,34 @@ inline std::string hex(uint32_t v) {
     snprintf(buf, sizeof buf, "0x%xu", v);
     return buf;
 }
+inline std::string hex64(uint64_t v) {
+    char buf[32];
+    snprintf(buf, sizeof buf, "0x%llxull", (unsigned long long)v);
+    return buf;
+}
+
+// One DNF term as source text: an expression of type int (TRI_T / TRI_F / TRI_E) that may raise `slow`.
+// Shapes with constant operands get the constants as immediates (no table load, no list walk); everything else
+// goes through term_tri() with the term words as compile-time constants.
+inline std::string term_expr(const uint32_t *w, const uint64_t *consts, const uint64_t *theap) {
+    const uint32_t op = w[0] & 0xFFu, flags = (w[0] >> 8) & 0xFFu;
+    const std::string sx = "cols.slot(" + std::to_string(w[1]) + "u)";
+    switch (op) {
+    case CB_TERM_EQ_SC: return "eq_tri(" + sx + ", " + hex64(consts[w[2]]) + ", slow)";
+    case CB_TERM_ORD_SC: return "ord_tri(" + hex(flags & CB_TERM_CI_MASK) + ", " + sx + ", " + hex64(consts[w[2]]) + ", slow)";
+    case CB_TERM_IN_SC: {
+        const uint64_t lst = consts[w[2]];
+        const uint64_t *p = theap + (lst & 0xFFFFFFFFFFFFull);
+        const uint32_t n = (uint32_t)p[0];
+        if (n > 16) break;
+        std::string e = "in_const_tri(" + sx + ", slow";
+        for (uint32_t j = 0; j < n; j++) e += ", " + hex64(p[1 + j]);
+        return e + ")";
+    }
+    default: break;
+    }
+    return "term_tri(t, b, cols, pid, U4{" + hex(w[0]) + ", " + hex(w[1]) + ", " + hex(w[2]) + ", " + hex(w[3]) + "}, slow)";
+}
 
 // image: host copy of the table image (section offsets in `off`, indexed by CB_SEC_*).  Returns the generated
 // source ("" = the table does not qualify: a condition without flat form, too many shapes ...).
@@ -44,6 +72,8 @@ inline std::string generate(const uint8_t *image, const uint32_t *off, const uin
     const uint32_t *code = reinterpret_cast<const uint32_t *>(image + off[CB_SEC_CODE]);          // 8-byte instruction slots
     const uint32_t *bs_off = reinterpret_cast<const uint32_t *>(image + off[CB_SEC_BLOCK_SLOTS_OFF]);
     const uint32_t *bs = reinterpret_cast<const uint32_t *>(image + off[CB_SEC_BLOCK_SLOTS]);
+    const uint64_t *consts = reinterpret_cast<const uint64_t *>(image + off[CB_SEC_CONSTS_V64]);
+    const uint64_t *theap = reinterpret_cast<const uint64_t *>(image + off[CB_SEC_THEAP]);
 
     std::map<std::vector<uint32_t>, uint32_t> shape_ids;
     std::vector<std::vector<uint32_t>> shape_blocks;     // shape -> block ids
@@ -101,8 +131,7 @@ inline std::string generate(const uint8_t *image, const uint32_t *off, const uin
             for (uint32_t i = 0; i < nt; i++) {
                 const uint32_t *w = code + 2 * (cd[2] + 2 * i);   // a term = two 8-byte instruction slots
                 const uint32_t flags = (w[0] >> 8) & 0xFFu;
-                s += "        group &= term_lit(term_tri(t, b, cols, pid, U4{" + hex(w[0]) + ", " + hex(w[1]) + ", " + hex(w[2]) + ", " + hex(w[3]) + "}, slow), " +
-                     hex(flags) + ");\n";
+                s += "        group &= term_lit(" + term_expr(w, consts, theap) + ", " + hex(flags) + ");\n";
                 if (flags & CB_TERM_GROUP_END) s += "        any |= group; group = true;\n";
             }
             s += std::string("        val |= (uint32_t)(any != ") + (negate ? "true" : "false") + ") << " + std::to_string(c + 1) + ";\n    }\n";

@@ -28,6 +28,7 @@ constexpr int kThreads = cbk::kThreads;
 #endif
 constexpr uint32_t kMaxStageBytes = 96 * 1024;   // table images up to this size are TMA-staged into shared memory
 constexpr int kMaxSec = 28;
+constexpr uint32_t kDeferCells = 256;
 constexpr uint32_t kMaxTilesSmem = 56 * 1024;    // image + two column-tile stages: keeps CB_MIN_BLOCKS CTAs resident per SM
 
 using cbk::TableDesc;
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(kThreads, CB_MIN_BLOCKS) check_kernel(const __
 __global__ void __launch_bounds__(kThreads, CB_MIN_BLOCKS) check_kernel_tiles(const __grid_constant__ TableDesc td, const __grid_constant__ cb::BatchView bv,
                                                                             uint8_t *bitmap, uint8_t *effects, uint32_t *status, const uint32_t n_slots) {
     extern __shared__ __align__(128) uint8_t smem_image[];
-    __shared__ __align__(8) uint64_t mbar_tab, mbar_col[2];
+    __shared__ __align__(8) uint64_t mbar_tab, mbar_col[4];
     cbk::check_tiles_body<cb::GenericBlocks>(td, bv, bitmap, effects, status, n_slots, smem_image, &mbar_tab, mbar_col);
 }
 
@@ -188,6 +189,8 @@ struct cgpu_ctx {
     int force_no_tiles = 0;  // CERBOS_B200_NO_TILES=1: never stage request columns through TMA (tests)
     int force_no_jit = 0;    // CERBOS_B200_NO_JIT=1: never compile table-specialised kernels (tests)
     uint32_t last_spec = 0;
+    uint32_t *d_defer_cells = nullptr;   // kDeferCells x {count, done}, zero between uses (the drain kernel re-zeroes)
+    std::atomic<uint32_t> defer_next{0};
     bool profiling = false;  // cgpu_profile(): CUDA events around the check kernel of every launch
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double prof_ms = 0;
@@ -334,16 +337,17 @@ Nvrtc &nvrtc() {
 
 const char kSpecPrelude[] =
     "#define CB_LEAN_ONLY 1\n"
+    "#ifndef CB_SPEC_MIN_BLOCKS\n#define CB_SPEC_MIN_BLOCKS 5\n#endif\n"
     "typedef unsigned char uint8_t; typedef unsigned short uint16_t; typedef unsigned int uint32_t; typedef unsigned long long uint64_t;\n"
     "typedef signed char int8_t; typedef short int16_t; typedef int int32_t; typedef long long int64_t; typedef unsigned long long uintptr_t;\n";
 const char kSpecKernels[] =
-    "\nextern \"C\" __global__ void __launch_bounds__(256, 4) cb_spec_tiles(const __grid_constant__ cbk::TableDesc td, const __grid_constant__ cb::BatchView bv,\n"
+    "\nextern \"C\" __global__ void __launch_bounds__(256, CB_SPEC_MIN_BLOCKS) cb_spec_tiles(const __grid_constant__ cbk::TableDesc td, const __grid_constant__ cb::BatchView bv,\n"
     "        uint8_t *bitmap, uint8_t *effects, uint32_t *status, const uint32_t n_slots) {\n"
     "    extern __shared__ __align__(128) uint8_t smem_image[];\n"
-    "    __shared__ __align__(8) uint64_t mbar_tab, mbar_col[2];\n"
+    "    __shared__ __align__(8) uint64_t mbar_tab, mbar_col[4];\n"
     "    cbk::check_tiles_body<cb::SpecBlocks>(td, bv, bitmap, effects, status, n_slots, smem_image, &mbar_tab, mbar_col);\n"
     "}\n"
-    "extern \"C\" __global__ void __launch_bounds__(256, 4) cb_spec_direct(const __grid_constant__ cbk::TableDesc td, const __grid_constant__ cb::BatchView bv,\n"
+    "extern \"C\" __global__ void __launch_bounds__(256, CB_SPEC_MIN_BLOCKS) cb_spec_direct(const __grid_constant__ cbk::TableDesc td, const __grid_constant__ cb::BatchView bv,\n"
     "        uint8_t *bitmap, uint8_t *effects, uint32_t *status, const uint32_t stage_rt) {\n"
     "    extern __shared__ __align__(128) uint8_t smem_image[];\n"
     "    __shared__ __align__(8) uint64_t mbar;\n"
@@ -372,8 +376,10 @@ bool ensure_spec(cgpu_ctx *ctx, cgpu_table *t) {
     src += kSpecKernels;
     void *prog = nullptr;
     if (n.create(&prog, src.c_str(), "cerbos_b200_spec.cu", 0, nullptr, nullptr) != 0) return give_up("nvrtcCreateProgram failed");
-    const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
-    const int rc = n.compile(prog, 3, opts);
+    const char *mb = getenv("CERBOS_B200_SPEC_BLOCKS");   // experiments: resident CTAs / SM the specialised kernels are budgeted for
+    const std::string mbopt = std::string("-DCB_SPEC_MIN_BLOCKS=") + (mb && mb[0] >= '1' && mb[0] <= '8' && !mb[1] ? mb : "5");
+    const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", mbopt.c_str()};
+    const int rc = n.compile(prog, 4, opts);
     if (rc != 0) {
         size_t ls = 0;
         n.log_size(prog, &ls);
@@ -458,7 +464,9 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
     // Index-order lean launches stage the request columns through TMA too, when every tile's column runs are
     // 16-byte aligned and image + two tile stages fit the shared-memory budget of CB_MIN_BLOCKS resident CTAs.
     const uint32_t tile_bytes = cb::tile_cols_bytes(bv.role_cols, lay.n_slots);
-    const uint32_t tiles_smem = ((lay.image_bytes + 127u) & ~127u) + 2 * tile_bytes;
+    // [image][tile stage 0][tile stage 1][row_am copy][aset_k copy]
+    const uint64_t small_tabs = (uint64_t)bv.n_asets * lay.n_rows * 8 + (uint64_t)bv.n_asets * 4;
+    const uint32_t tiles_smem = ((lay.image_bytes + 127u) & ~127u) + 2 * tile_bytes + (uint32_t)(small_tabs < 65536 ? small_tabs : 65536);
     auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     const bool col_tiles = narrow && stage && !cluster && !ctx->force_no_tiles && tiles_smem <= kMaxTilesSmem && bv.stride % 4 == 0 &&
                            bv.first % 4 == 0 && al16(bv.hdr0) && al16(bv.hdr1) && al16(bv.roles) && al16(bv.slots);
@@ -500,12 +508,11 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
         bvv.perm = perm;
     }
     uint32_t last_arg = col_tiles ? lay.n_slots : (stage ? 1u : 0u);   // check_kernel: stage_rt; check_kernel_tiles: n_slots
-    uint32_t *defer = nullptr;   // [0] = count, [1 ..] = request offsets the specialised kernel leaves to the general kernel
+    uint32_t *defer = nullptr;   // request offsets the specialised kernel leaves to the general kernel
     if (spec) {
-        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&defer), ((size_t)bv.count + 1) * 4, stream));
-        CUDA_TRY(cudaMemsetAsync(defer, 0, 4, stream));
-        bvv.defer_count = defer;
-        bvv.defer_list = defer + 1;
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&defer), (size_t)bv.count * 4, stream));
+        bvv.defer_count = ctx->d_defer_cells + 2 * (ctx->defer_next.fetch_add(1, std::memory_order_relaxed) % kDeferCells);
+        bvv.defer_list = defer;
     }
     void *args[] = {&td, &bvv, &d_bitmap, &d_effects, &d_status, &last_arg};
     if (ctx->profiling) {
@@ -522,8 +529,8 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
     if (spec) {
         // drain the deferral list with the general body (usually empty: the kernel then exits at once)
         cb::BatchView dv = bv;
-        dv.perm = defer + 1;
-        dv.count_dev = defer;
+        dv.perm = defer;
+        dv.count_dev = bvv.defer_count;
         dv.prefetch_slots = 0;
         const void *gfn = (const void *)check_kernel<false, 2>;
         int gocc = mt->occ[0].load(std::memory_order_relaxed);
@@ -577,6 +584,8 @@ int cgpu_init(const int *device_ids, int n_devices, cgpu_ctx **out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaMalloc(&ctx->d_status, sizeof(uint32_t)));
     CUDA_TRY(cudaMemset(ctx->d_status, 0, sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&ctx->d_defer_cells, kDeferCells * 8));
+    CUDA_TRY(cudaMemset(ctx->d_defer_cells, 0, kDeferCells * 8));
     const char *ns = getenv("CERBOS_B200_NO_STAGE");
     ctx->force_no_stage = ns && ns[0] == '1';
     const char *fg = getenv("CERBOS_B200_FORCE_GENERAL");
@@ -609,6 +618,7 @@ void cgpu_shutdown(cgpu_ctx *ctx) {
         if (s.d_status) cudaFree(s.d_status);
     }
     if (ctx->d_status) cudaFree(ctx->d_status);
+    if (ctx->d_defer_cells) cudaFree(ctx->d_defer_cells);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);

@@ -38,7 +38,8 @@ def test_generated_source_is_straight_line_for_c2():
     w = W.C2()
     _, ft, _ = W.build(w)
     src = hostsim.generate(ft.blob)
-    assert src.count("spec_shape_") == 2 * 1 and src.count("term_tri(") == 4 and src.count("row_apply(") == 5   # one shape: 3 conditions / 4 terms, 5 rows
+    assert src.count("spec_shape_") == 2 * 1 and src.count("term_lit(") == 4 and src.count("row_apply(") == 5   # one shape: 3 conditions / 4 terms, 5 rows
+    assert "in_const_tri(cols.slot(" in src and "eq_tri(cols.slot(" in src                       # constants inlined as immediates
     assert all(f"case {k}:" in src for k in range(10))
 
 
