@@ -93,7 +93,8 @@ struct BatchView {
     const uint32_t *perm;       // clustered evaluation order (request offsets from `first`), or null = index order
     uint32_t prefetch_slots;    // > 0: the table reads this many slot columns in all (few): prefetch every one per tile
     uint32_t *defer_list, *defer_count;   // run-time specialised lean kernels: requests left to the general kernel
-    uint32_t *count_dev;                  // general kernel draining such a list: {length, CTAs done} in device memory, else null
+    uint32_t *count_dev;                  // general kernel draining such a list: {length, CTAs done, tile counter} in device memory, else null
+    uint32_t *tile_counter;               // tile kernel: tiles beyond each CTA's first are claimed from this counter (null: static stride)
 };
 
 // Table data may live in shared memory (TMA-staged image) or in global memory, heap references may point
@@ -104,7 +105,7 @@ struct BatchView {
 inline void finish_batch_view(BatchView &b) {
     b.perm = nullptr;
     b.prefetch_slots = 0;
-    b.defer_list = nullptr; b.defer_count = nullptr; b.count_dev = nullptr;
+    b.defer_list = nullptr; b.defer_count = nullptr; b.count_dev = nullptr; b.tile_counter = nullptr;
     b.rcp = 1;
     while (b.rcp < b.role_cols) b.rcp <<= 1;
     b.stride_pattern = 0;

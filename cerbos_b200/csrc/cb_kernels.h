@@ -76,7 +76,13 @@ template <bool kFast, int kStageMode, typename Blocks>
 __device__ __forceinline__ void check_body(const TableDesc &td, const cb::BatchView &bv, uint8_t *bitmap, uint8_t *effects, uint32_t *status, const uint32_t stage_rt,
                                            uint8_t *smem_image, uint64_t *mbar) {
     const bool kStage = kStageMode == 2 ? stage_rt != 0 : kStageMode == 1;
-    // deferred mode (drains the list a specialised lean kernel left): the request count lives in device memory
+    // deferred mode (drains the list a specialised lean kernel left): the request count lives in device memory.  The
+    // launch is programmatically serialised behind that kernel (its CTAs become resident while the last tiles of the
+    // producer are still running): wait here until the producer has completed and its writes are visible.
+    if (bv.count_dev) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (blockIdx.x == 0 && threadIdx.x == 0) bv.count_dev[2] = 0;   // the producer's tile counter: back to zero for the cell's next user
+    }
     const uint64_t count = bv.count_dev ? (uint64_t)*bv.count_dev : bv.count;
     if (count == 0) return;   // the usual case in deferred mode: nothing was deferred
     const uint8_t *base = td.base;
@@ -89,6 +95,9 @@ __device__ __forceinline__ void check_body(const TableDesc &td, const cb::BatchV
         if (threadIdx.x == 0) tma_load_image(smem_image, td, mbar);
         base = smem_image;
     }
+#ifdef CB_LEAN_ONLY
+    asm volatile("griddepcontrol.launch_dependents;");
+#endif
     cb::TableView tv;
     tv.base = kStageMode == 1 ? smem_image : kStageMode == 0 ? td.base : base;
     tv.L = &td.lay;
@@ -178,25 +187,36 @@ __device__ __forceinline__ void check_tiles_body(const TableDesc &td, const cb::
         tma_load_image(smem_image, td, mbar_tab);
         if (blockIdx.x < n_full) issue_tile(blockIdx.x, 0);
     }
+#ifdef CB_LEAN_ONLY
+    asm volatile("griddepcontrol.launch_dependents;");   // the drain kernel's CTAs may take the slots this grid frees at its tail
+#endif
     for (uint32_t j = threadIdx.x; j < n_am; j += kThreads) row_am_s[j] = bv.row_am[j];
     for (uint32_t j = threadIdx.x; j < bv.n_asets; j += kThreads) aset_k_s[j] = bv.aset_k[j];
     __syncthreads();
     cb::TableView tv;
     tv.base = smem_image;
     tv.L = &td.lay;
+    // Tile order: the first tile of a CTA is its block index; the following ones come from a global counter when the
+    // launch provides one (claimed by thread 0 one tile ahead, published through `tile_s` under the stage's full
+    // barrier), so the tail of the grid stays balanced; else the static grid stride.
+    uint64_t *tile_s = reinterpret_cast<uint64_t *>(aset_k_s + ((bv.n_asets + 1u) & ~1u));   // [2]
     uint32_t k = 0;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, k++) {
-        const uint64_t next = tile + gridDim.x;
-        if (threadIdx.x == 0 && next < n_full) {
-            // stage (k+1)&1 was read in iteration k-1: refill it once all eight warps have released it.  No CTA-wide
-            // barrier: only this thread waits, and it is normally released long before
-            if (k >= 1) mbar_wait(&empty[(k + 1) & 1], ((k - 1) >> 1) & 1);
-            issue_tile(next, (k + 1) & 1);
+    uint64_t tile = blockIdx.x;
+    while (tile < n_tiles) {
+        if (threadIdx.x == 0) {
+            const uint64_t next = bv.tile_counter ? (uint64_t)atomicAdd(bv.tile_counter, 1u) + gridDim.x : tile + gridDim.x;
+            const uint32_t st = (k + 1) & 1;
+            // stage st was read in iteration k-1: refill it once all eight warps have released it.  No CTA-wide barrier:
+            // only this thread waits, and it is normally released long before
+            if (k >= 1) mbar_wait(&empty[st], ((k - 1) >> 1) & 1);
+            tile_s[st] = next;
+            if (next < n_full) issue_tile(next, st);
+            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[st])) : "memory");   // nothing to copy: complete the phase
         }
         if (k == 0) mbar_wait(mbar_tab, 0);
         const uint64_t n = bv.first + tile * kThreads + threadIdx.x;
         if (tile < n_full) {
-            mbar_wait(&full[k & 1], (k >> 1) & 1);
+            if (k == 0) mbar_wait(&full[0], 0);
             cb::TileCols tc;
             tc.base = stage0 + (k & 1) * tile_bytes; tc.tid = threadIdx.x; tc.slots_off = slots_off;
             tc.aset_k_s = aset_k_s; tc.row_am_s = row_am_s;
@@ -208,6 +228,10 @@ __device__ __forceinline__ void check_tiles_body(const TableDesc &td, const cb::
         }
         __syncwarp();
         if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[k & 1])) : "memory");
+        // next tile: its index (and, for a full tile, its columns) are published when stage (k+1)&1 completes
+        k++;
+        mbar_wait(&full[k & 1], (k >> 1) & 1);
+        tile = tile_s[k & 1];
     }
     if (k == 0) mbar_wait(mbar_tab, 0);   // no tile: drain the table copy before shared memory is released
 }

@@ -189,7 +189,7 @@ struct cgpu_ctx {
     int force_no_tiles = 0;  // CERBOS_B200_NO_TILES=1: never stage request columns through TMA (tests)
     int force_no_jit = 0;    // CERBOS_B200_NO_JIT=1: never compile table-specialised kernels (tests)
     uint32_t last_spec = 0;
-    uint32_t *d_defer_cells = nullptr;   // kDeferCells x {count, done}, zero between uses (the drain kernel re-zeroes)
+    uint32_t *d_defer_cells = nullptr;   // kDeferCells x {count, done, tile counter, -}, zero between uses (the drain kernel re-zeroes)
     std::atomic<uint32_t> defer_next{0};
     bool profiling = false;  // cgpu_profile(): CUDA events around the check kernel of every launch
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -465,7 +465,7 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
     // 16-byte aligned and image + two tile stages fit the shared-memory budget of CB_MIN_BLOCKS resident CTAs.
     const uint32_t tile_bytes = cb::tile_cols_bytes(bv.role_cols, lay.n_slots);
     // [image][tile stage 0][tile stage 1][row_am copy][aset_k copy]
-    const uint64_t small_tabs = (uint64_t)bv.n_asets * lay.n_rows * 8 + (uint64_t)bv.n_asets * 4;
+    const uint64_t small_tabs = (uint64_t)bv.n_asets * lay.n_rows * 8 + (((uint64_t)bv.n_asets + 1) & ~1ull) * 4 + 16;   // + tile_s[2]
     const uint32_t tiles_smem = ((lay.image_bytes + 127u) & ~127u) + 2 * tile_bytes + (uint32_t)(small_tabs < 65536 ? small_tabs : 65536);
     auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     const bool col_tiles = narrow && stage && !cluster && !ctx->force_no_tiles && tiles_smem <= kMaxTilesSmem && bv.stride % 4 == 0 &&
@@ -511,7 +511,8 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
     uint32_t *defer = nullptr;   // request offsets the specialised kernel leaves to the general kernel
     if (spec) {
         CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&defer), (size_t)bv.count * 4, stream));
-        bvv.defer_count = ctx->d_defer_cells + 2 * (ctx->defer_next.fetch_add(1, std::memory_order_relaxed) % kDeferCells);
+        bvv.defer_count = ctx->d_defer_cells + 4 * (ctx->defer_next.fetch_add(1, std::memory_order_relaxed) % kDeferCells);   // {count, done, tile counter, -}
+        bvv.tile_counter = col_tiles ? bvv.defer_count + 2 : nullptr;
         bvv.defer_list = defer;
     }
     void *args[] = {&td, &bvv, &d_bitmap, &d_effects, &d_status, &last_arg};
@@ -541,12 +542,19 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
             mt->occ[0].store(gocc, std::memory_order_relaxed);
             mt->occ_smem[0].store(lay.image_bytes + 1, std::memory_order_relaxed);
         }
-        uint64_t gmax = (uint64_t)ctx->sm_count * (uint64_t)gocc;
+        // one CTA per SM: the list is normally empty (every CTA then exits at once), and grid-stride loops otherwise
+        uint64_t gmax = (uint64_t)ctx->sm_count * (uint64_t)(gocc < 1 ? 1 : 1);
         uint32_t ggrid = (uint32_t)(tiles < gmax ? tiles : gmax);
         uint32_t one = 1u;
         uint8_t *gb = d_bitmap, *ge = d_effects;
         void *gargs[] = {&td, &dv, &gb, &ge, &d_status, &one};
-        CUDA_TRY(cudaLaunchKernel(gfn, dim3(ggrid ? ggrid : 1), dim3(kThreads), gargs, lay.image_bytes, stream));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(ggrid ? ggrid : 1); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = lay.image_bytes; cfg.stream = stream;
+        cudaLaunchAttribute pdl[1];
+        pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pdl[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = pdl; cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelExC(&cfg, gfn, gargs));
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaFreeAsync(defer, stream));
         ctx->launches.fetch_add(1, std::memory_order_relaxed);
@@ -584,8 +592,8 @@ int cgpu_init(const int *device_ids, int n_devices, cgpu_ctx **out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaMalloc(&ctx->d_status, sizeof(uint32_t)));
     CUDA_TRY(cudaMemset(ctx->d_status, 0, sizeof(uint32_t)));
-    CUDA_TRY(cudaMalloc(&ctx->d_defer_cells, kDeferCells * 8));
-    CUDA_TRY(cudaMemset(ctx->d_defer_cells, 0, kDeferCells * 8));
+    CUDA_TRY(cudaMalloc(&ctx->d_defer_cells, kDeferCells * 16));
+    CUDA_TRY(cudaMemset(ctx->d_defer_cells, 0, kDeferCells * 16));
     const char *ns = getenv("CERBOS_B200_NO_STAGE");
     ctx->force_no_stage = ns && ns[0] == '1';
     const char *fg = getenv("CERBOS_B200_FORCE_GENERAL");
