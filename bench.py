@@ -262,19 +262,56 @@ def main():
     stream_h = stream.cuda_stream
     assert stream_h != 0 and torch.cuda.current_stream().cuda_stream == stream_h
 
-    # one gather buffer per rotating batch: the all-gather of batch i (NCCL stream) overlaps the kernel of batch i+1
-    gathered = [torch.empty(world * n * kbytes, dtype=torch.uint8, device=dev) for _ in range(n_buf)] if world > 1 else None
+    # Multi-GPU result exchange.  Default: FUSED all-gather -- the check kernels store every result byte straight into
+    # this rank's slice of every rank's gather buffer over NVLink peer memory (cerbos_b200.dist.PeerGather), a flag
+    # release follows, no collective kernel runs.  Fallback (CERBOS_B200_NCCL_GATHER=1, or CUDA IPC unavailable):
+    # asynchronous NCCL all_gather_into_tensor overlapping the next batch's kernel.
+    gather_mode = "none"
+    pg, gcalls = None, None
+    if world > 1:
+        ok = 0
+        no_exchange = os.environ.get("CERBOS_B200_NO_GATHER") == "1"   # diagnosis only: ranks run independently, nothing is exchanged
+        if os.environ.get("CERBOS_B200_NCCL_GATHER") != "1" and kbytes <= 8 and not no_exchange:
+            try:
+                from cerbos_b200.dist import PeerGather
+                pg = PeerGather(ctx, n * kbytes, n_buf)
+                gcalls = [table.prepared_gather_call(b.ptrs, b.sizes, b.n, b.max_actions, pg.bufs[j], pg.flags, rank, n * kbytes, NOW_NS)
+                          for j, b in enumerate(batches)]
+                ok = 1
+            except Exception as e:  # noqa: BLE001 -- any failure here just selects the NCCL path on every rank
+                sys.stderr.write(f"[rank {rank}] peer gather unavailable ({e}); using NCCL\n")
+        t_ok = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        gather_mode = "fused-peer-stores" if int(t_ok.item()) == 1 else "nccl-all-gather"
+        if gather_mode != "fused-peer-stores":
+            pg, gcalls = None, None
+        if no_exchange:
+            gather_mode = "none (diagnosis)"
+    gathered = [torch.empty(world * n * kbytes, dtype=torch.uint8, device=dev) for _ in range(n_buf)] if (world > 1 and pg is None) else None
     pending = []
+    it = [0]          # steps issued so far (warm-up included): numbers the gather steps
 
     def step(i):
-        calls[i % n_buf](stream_h)
-        if world > 1:
+        g = it[0]
+        it[0] += 1
+        j = g % n_buf
+        if pg is not None:
+            # buffers rotate: step g-(n_buf-1) must have landed on this rank before the stream moves on (the wait rides in
+            # the same launch: the kernel that publishes this step's flag also holds the stream for the older one)
+            gcalls[j](g + 1, stream_h, g + 1 - (n_buf - 1) if g >= n_buf - 1 else 0)
+            return
+        calls[j](stream_h)
+        if world > 1 and gather_mode != "none (diagnosis)":
             if len(pending) >= n_buf - 1:          # buffers are reused after n_buf steps: retire the oldest gather
                 pending.pop(0).wait()
-            _, work = all_gather_bitmaps(views[i % n_buf], gathered[i % n_buf], async_op=True)
+            _, work = all_gather_bitmaps(views[j], gathered[j], async_op=True)
             pending.append(work)
 
     def drain():
+        if pg is not None:
+            if it[0]:
+                pg.wait(it[0], stream_h)       # the last step issued (a rank finishes its steps in order)
+            return
         while pending:
             pending.pop(0).wait()
 
@@ -334,7 +371,7 @@ def main():
         "dtype": "u64", "data": "synthetic",
         "config": {"workload": f"{w.name}: {W.C2.__doc__.splitlines()[0] if w.name == 'C2' else w.name}",
                    "requests_per_step_per_gpu": n, "actions_per_request": K, "global_requests_per_step": world * n,
-                   "parallelism": f"dp{world} (requests sharded by index; NCCL table broadcast + bitmap all-gather)",
+                   "parallelism": f"dp{world} (requests sharded by index; NCCL table broadcast; result exchange: {gather_mode})",
                    "l2": f"rotating {n_buf} distinct batches, {footprint / 1e6:.0f} MB of columns > 126 MB L2",
                    "kernel": ctx.last_kernel_config()},
         "gpu_launches": int(launches),

@@ -17,7 +17,8 @@ OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE = 0, -1, -2, -3, -4
 EXPORTS = [
     "cgpu_init", "cgpu_shutdown", "cgpu_table_load", "cgpu_table_retain", "cgpu_table_release", "cgpu_check",
     "cgpu_check_device", "cgpu_sync", "cgpu_launch_count", "cgpu_table_info", "cgpu_last_kernel_config",
-    "cgpu_last_cluster_config", "cgpu_profile", "cgpu_table_wait_ready", "cgpu_last_error",
+    "cgpu_last_cluster_config", "cgpu_profile", "cgpu_table_wait_ready", "cgpu_peer_alloc", "cgpu_peer_open", "cgpu_peer_close",
+    "cgpu_peer_free", "cgpu_peer_read", "cgpu_check_device_gather", "cgpu_gather_wait", "cgpu_last_error",
 ]
 
 
@@ -25,6 +26,11 @@ class CgpuError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"cerbos_b200 error {code}: {msg}")
         self.code = code
+
+
+class _Gather(ctypes.Structure):
+    _fields_ = [("n_ranks", ctypes.c_uint32), ("my_rank", ctypes.c_uint32), ("gather_bufs", ctypes.POINTER(ctypes.c_void_p)),
+                ("slice_bytes", ctypes.c_uint64), ("flags", ctypes.POINTER(ctypes.c_void_p)), ("step", ctypes.c_uint32), ("wait_step", ctypes.c_uint32)]
 
 
 class _Batch(ctypes.Structure):
@@ -74,6 +80,14 @@ def lib():
         L.cgpu_profile.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
         L.cgpu_table_wait_ready.restype = ctypes.c_int
         L.cgpu_table_wait_ready.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
+        for name, args in (("cgpu_peer_alloc", [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
+                           ("cgpu_peer_open", [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+                           ("cgpu_peer_close", [ctypes.c_void_p, ctypes.c_void_p]), ("cgpu_peer_free", [ctypes.c_void_p, ctypes.c_void_p]),
+                           ("cgpu_peer_read", [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+                           ("cgpu_check_device_gather", [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.POINTER(_Gather), ctypes.c_void_p]),
+                           ("cgpu_gather_wait", [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p])):
+            getattr(L, name).restype = ctypes.c_int
+            getattr(L, name).argtypes = args
         L.cgpu_last_error.restype = ctypes.c_char_p
         L.cgpu_last_error.argtypes = []
         _lib = L
@@ -121,6 +135,32 @@ class Context:
         ms, n = ctypes.c_double(), ctypes.c_uint64()
         _check(lib().cgpu_profile(self._h, 1 if enable else 0, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+    # ---- peer memory for the fused all-gather (cerbos_b200/dist.py: PeerGather)
+    def peer_alloc(self, nbytes: int):
+        """-> (device pointer, 64-byte IPC handle)"""
+        ptr, h = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        _check(lib().cgpu_peer_alloc(self._h, nbytes, ctypes.byref(ptr), h))
+        return ptr.value, h.raw
+
+    def peer_open(self, handle: bytes) -> int:
+        ptr = ctypes.c_void_p()
+        _check(lib().cgpu_peer_open(self._h, ctypes.create_string_buffer(handle, 64), ctypes.byref(ptr)))
+        return ptr.value
+
+    def peer_close(self, ptr: int):
+        _check(lib().cgpu_peer_close(self._h, ctypes.c_void_p(ptr)))
+
+    def peer_free(self, ptr: int):
+        _check(lib().cgpu_peer_free(self._h, ctypes.c_void_p(ptr)))
+
+    def peer_read(self, ptr: int, nbytes: int) -> np.ndarray:
+        out = np.empty(nbytes, dtype=np.uint8)
+        _check(lib().cgpu_peer_read(self._h, ctypes.c_void_p(ptr), out.ctypes.data_as(ctypes.c_void_p), nbytes))
+        return out
+
+    def gather_wait(self, local_flags_ptr: int, n_ranks: int, step: int, stream: int = 0):
+        _check(lib().cgpu_gather_wait(self._h, ctypes.c_void_p(local_flags_ptr), n_ranks, step, ctypes.c_void_p(stream)))
 
     def load_table(self, blob: bytes) -> "Table":
         return Table(self, blob)
@@ -185,6 +225,25 @@ class Table:
 
         def call(stream=0, _keep=keep):
             rc = fn(ctx_h, tab_h, bref, bm, ctypes.c_void_p(stream))
+            if rc != OK:
+                _check(rc)
+        return call
+
+    def prepared_gather_call(self, ptrs, sizes, n, max_actions, gather_bufs, flags, my_rank, slice_bytes, now_ns=0, batch_flags=0):
+        """f(step, stream): cgpu_check_device_gather with pre-built arguments (results go straight into every rank's buffer)."""
+        p = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        s = (ctypes.c_size_t * len(sizes))(*sizes)
+        b = _Batch(n, max_actions, now_ns, batch_flags, p, s, len(ptrs))
+        gb = (ctypes.c_void_p * len(gather_bufs))(*gather_bufs)
+        fl = (ctypes.c_void_p * len(flags))(*flags)
+        g = _Gather(len(gather_bufs), my_rank, gb, slice_bytes, fl, 0, 0)
+        fn, ctx_h, tab_h, bref, gref = lib().cgpu_check_device_gather, self.ctx._h, self._h, ctypes.byref(b), ctypes.byref(g)
+        keep = (p, s, b, gb, fl, g)
+
+        def call(step, stream=0, wait_step=0, _keep=keep):
+            g.step = step
+            g.wait_step = wait_step
+            rc = fn(ctx_h, tab_h, bref, gref, ctypes.c_void_p(stream))
             if rc != OK:
                 _check(rc)
         return call

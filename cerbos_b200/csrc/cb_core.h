@@ -73,6 +73,7 @@ struct TableView {
     CB_HD const uint32_t *block_slots() const { return sec<uint32_t>(CB_SEC_BLOCK_SLOTS); }
 };
 
+enum { CB_MAX_GATHER = 8 };
 struct BatchView {
     const cb_hdr0 *hdr0;
     const cb_hdr1 *hdr1;
@@ -95,6 +96,16 @@ struct BatchView {
     uint32_t *defer_list, *defer_count;   // run-time specialised lean kernels: requests left to the general kernel
     uint32_t *count_dev;                  // general kernel draining such a list: {length, CTAs done, tile counter} in device memory, else null
     uint32_t *tile_counter;               // tile kernel: tiles beyond each CTA's first are claimed from this counter (null: static stride)
+    // fused all-gather: n_out > 0 = write every result to this rank's slice of n_out gather buffers (own + peers over
+    // NVLink, peer-mapped pointers already offset to the slice) instead of `bitmap`
+    uint8_t *outs[CB_MAX_GATHER];
+    uint32_t n_out;
+    // ... and, in the general kernel draining a specialised kernel's deferral list (always the last kernel of such a
+    // launch): release `sig_step` into cell sig_rank of every rank's flag array once all results are stored, and
+    // first wait until every rank's `wait_step` has arrived in the local flags (0 = no wait)
+    uint32_t *sig_flags[CB_MAX_GATHER];
+    const uint32_t *wait_flags;
+    uint32_t sig_rank, sig_step, wait_step;
 };
 
 // Table data may live in shared memory (TMA-staged image) or in global memory, heap references may point
@@ -106,6 +117,9 @@ inline void finish_batch_view(BatchView &b) {
     b.perm = nullptr;
     b.prefetch_slots = 0;
     b.defer_list = nullptr; b.defer_count = nullptr; b.count_dev = nullptr; b.tile_counter = nullptr;
+    b.n_out = 0;
+    for (int i = 0; i < CB_MAX_GATHER; i++) { b.outs[i] = nullptr; b.sig_flags[i] = nullptr; }
+    b.wait_flags = nullptr; b.sig_rank = 0; b.sig_step = 0; b.wait_step = 0;
     b.rcp = 1;
     while (b.rcp < b.role_cols) b.rcp <<= 1;
     b.stride_pattern = 0;
@@ -996,6 +1010,20 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
 
 #endif  // !CB_LEAN_ONLY
 
+// Packed decision bits of request n (kbytes <= 8): to `bitmap`, or -- fused all-gather -- to this rank's slice of every
+// rank's gather buffer (plain stores; peer buffers are NVLink-mapped).
+CB_HD void store_bits(const BatchView &b, uint8_t *bitmap, uint64_t n, uint64_t acc) {
+    uint32_t r = 0;
+    do {
+        uint8_t *base = b.n_out ? b.outs[r] : bitmap;
+        if (b.kbytes == 1) base[n] = (uint8_t)acc;
+        else {
+            uint8_t *out = base + n * b.kbytes;
+            for (uint32_t q = 0; q < b.kbytes; q++) out[q] = (uint8_t)(acc >> (8 * q));
+        }
+    } while (++r < b.n_out);
+}
+
 // ---------------------------------------------------------------------------------------------- column access
 // The lean body reads the per-request columns through one of two accessors: straight from global memory (any
 // evaluation order), or from a tile of the columns that the TMA unit staged in shared memory one tile ahead
@@ -1643,7 +1671,7 @@ CB_HD void eval_request(const TableView t, const BatchView &b, uint64_t n, uint8
                 for (uint32_t k = 0; k < b.max_actions; k++) eff[k] = (uint8_t)(k < K ? (((acc >> k) & 1) ? CB_EFFECT_ALLOW : CB_EFFECT_DENY) : 0);
             }
         } else {
-            for (uint32_t q = 0; q < b.kbytes; q++) out[q] = (uint8_t)(acc >> (8 * q));
+            store_bits(b, bitmap, n, acc);
         }
     }
     if (unsupported && status) {
@@ -1756,11 +1784,7 @@ CB_HD bool eval_request_fast(const TableView t, const BatchView &b, const Cols &
             for (uint32_t k = 0; k < b.max_actions; k++) eff[k] = (uint8_t)(k < K ? (((acc >> k) & 1) ? CB_EFFECT_ALLOW : CB_EFFECT_DENY) : 0);
         }
     } else {
-        if (b.kbytes == 1) bitmap[n] = (uint8_t)acc;
-        else {
-            uint8_t *out = bitmap + n * b.kbytes;
-            for (uint32_t q = 0; q < b.kbytes; q++) out[q] = (uint8_t)(acc >> (8 * q));
-        }
+        store_bits(b, bitmap, n, acc);
     }
     return false;
 }

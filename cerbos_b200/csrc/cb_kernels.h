@@ -67,6 +67,20 @@ __device__ __forceinline__ void defer_request(const cb::TableView tv, const cb::
 #endif
 }
 
+// fused all-gather bookkeeping (see BatchView): executed by one warp
+__device__ __forceinline__ void gather_signal_flags(const cb::BatchView &bv) {
+    __threadfence_system();
+    if (threadIdx.x < bv.n_out) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(bv.sig_flags[threadIdx.x] + bv.sig_rank), "r"(bv.sig_step) : "memory");
+}
+__device__ __forceinline__ void gather_wait_flags(const uint32_t *flags, uint32_t n_ranks, uint32_t step) {
+    if (threadIdx.x < n_ranks) {
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+        } while ((int)(v - step) < 0);
+    }
+}
+
 // Persistent body, columns read straight from global memory (any evaluation order: bv.perm).
 // kFast: the lean resource-policy-only body (cb::eval_request_fast), else the general body with 64-bit pair masks.
 // kStageMode 0: table read from global memory, 1: from the staged shared-memory image (compile-time, so that every
@@ -82,9 +96,13 @@ __device__ __forceinline__ void check_body(const TableDesc &td, const cb::BatchV
     if (bv.count_dev) {
         asm volatile("griddepcontrol.wait;" ::: "memory");
         if (blockIdx.x == 0 && threadIdx.x == 0) bv.count_dev[2] = 0;   // the producer's tile counter: back to zero for the cell's next user
+        if (blockIdx.x == 0 && threadIdx.x < 32 && bv.wait_step) gather_wait_flags(bv.wait_flags, bv.n_out, bv.wait_step);
     }
     const uint64_t count = bv.count_dev ? (uint64_t)*bv.count_dev : bv.count;
-    if (count == 0) return;   // the usual case in deferred mode: nothing was deferred
+    if (count == 0) {   // the usual case in deferred mode: nothing was deferred
+        if (bv.count_dev && bv.sig_step && blockIdx.x == 0 && threadIdx.x < 32) gather_signal_flags(bv);
+        return;
+    }
     const uint8_t *base = td.base;
     if (kStage) {
         if (threadIdx.x == 0) {
@@ -141,8 +159,10 @@ __device__ __forceinline__ void check_body(const TableDesc &td, const cb::BatchV
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
-            if (atomicAdd(bv.count_dev + 1, 1u) == gridDim.x - 1) { bv.count_dev[0] = 0; bv.count_dev[1] = 0; }
+            if (atomicAdd(bv.count_dev + 1, 1u) == gridDim.x - 1) { bv.count_dev[0] = 0; bv.count_dev[1] = 0; mbar[0] = 1; } else mbar[0] = 0;
         }
+        __syncthreads();
+        if (bv.sig_step && mbar[0] == 1 && threadIdx.x < 32) gather_signal_flags(bv);   // the last CTA: every result of this launch is stored
     }
 }
 

@@ -49,6 +49,26 @@ __global__ void __launch_bounds__(kThreads, CB_MIN_BLOCKS) check_kernel_tiles(co
     cbk::check_tiles_body<cb::GenericBlocks>(td, bv, bitmap, effects, status, n_slots, smem_image, &mbar_tab, mbar_col);
 }
 
+// ------------------------------------------------------------------------------------------------ fused all-gather
+struct SignalParams { uint32_t *flags[cb::CB_MAX_GATHER]; const uint32_t *wait_flags; uint32_t n_ranks, my_rank, step, wait_step; };
+// After the check kernels of a gather launch: publish `step` into this rank's cell of every rank's flag array.
+// Programmatically serialised behind them; their peer stores are complete (and visible system-wide) once they have.
+__global__ void gather_signal(const __grid_constant__ SignalParams p) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    __threadfence_system();
+    if (threadIdx.x < p.n_ranks) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flags[threadIdx.x] + p.my_rank), "r"(p.step) : "memory");
+    if (p.wait_step) cbk::gather_wait_flags(p.wait_flags, p.n_ranks, p.wait_step);
+}
+// Stream-side wait: until the slice of every rank for `step` has landed in this rank's gather buffer.
+__global__ void gather_wait(const uint32_t *flags, uint32_t n_ranks, uint32_t step) {
+    if (threadIdx.x < n_ranks) {
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+        } while ((int32_t)(v - step) < 0);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ clustering
 // Requests of one batch hit different policy blocks (resource kind x scope x version); evaluated in index order the
 // 32 lanes of a warp would each walk another block and another set of conditions.  Three small kernels build a
@@ -446,8 +466,9 @@ int launch_cluster(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, 
 }
 
 int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, uint8_t *d_bitmap, uint8_t *d_effects,
-                 uint32_t *d_status, cudaStream_t stream) {
+                 uint32_t *d_status, cudaStream_t stream, bool *drained = nullptr) {
     const cb::TableLayout &lay = t->desc.lay;
+    if (drained) *drained = false;
     const bool stage = !ctx->force_no_stage && lay.image_bytes <= kMaxStageBytes;
     uint64_t tiles = (bv.count + kThreads - 1) / kThreads;
     // The lean body applies to resource-policy-only tables (no principal / role policies, parent roles or
@@ -558,6 +579,7 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaFreeAsync(defer, stream));
         ctx->launches.fetch_add(1, std::memory_order_relaxed);
+        if (drained) *drained = true;   // the drain kernel also did the fused-gather signalling (BatchView::sig_*)
     }
     if (perm) CUDA_TRY(cudaFreeAsync(perm, stream));
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
@@ -735,6 +757,101 @@ int cgpu_check_device(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *dev_
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);   // NULL = the legacy default stream
     return launch_check(ctx, t, bv, static_cast<uint8_t *>(dev_bitmap_out), nullptr, ctx->d_status, s);
+}
+
+int cgpu_peer_alloc(cgpu_ctx *ctx, size_t bytes, void **dev_ptr, void *ipc_handle_out) {
+    if (!ctx || !dev_ptr || !ipc_handle_out || bytes == 0) return fail(CGPU_ERR_INVALID, "cgpu_peer_alloc: bad argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    void *p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, bytes));
+    CUDA_TRY(cudaMemset(p, 0, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(CGPU_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e)); }
+    static_assert(sizeof(h) == CGPU_IPC_HANDLE_BYTES, "IPC handle size");
+    memcpy(ipc_handle_out, &h, sizeof(h));
+    *dev_ptr = p;
+    return CGPU_OK;
+}
+
+int cgpu_peer_open(cgpu_ctx *ctx, const void *ipc_handle, void **dev_ptr) {
+    if (!ctx || !ipc_handle || !dev_ptr) return fail(CGPU_ERR_INVALID, "cgpu_peer_open: null argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof(h));
+    CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return CGPU_OK;
+}
+
+int cgpu_peer_close(cgpu_ctx *ctx, void *dev_ptr) {
+    if (!ctx || !dev_ptr) return fail(CGPU_ERR_INVALID, "cgpu_peer_close: null argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+    return CGPU_OK;
+}
+
+int cgpu_peer_free(cgpu_ctx *ctx, void *dev_ptr) {
+    if (!ctx || !dev_ptr) return fail(CGPU_ERR_INVALID, "cgpu_peer_free: null argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaFree(dev_ptr));
+    return CGPU_OK;
+}
+
+int cgpu_peer_read(cgpu_ctx *ctx, const void *dev_ptr, void *host_out, size_t bytes) {
+    if (!ctx || !dev_ptr || !host_out) return fail(CGPU_ERR_INVALID, "cgpu_peer_read: null argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMemcpy(host_out, dev_ptr, bytes, cudaMemcpyDeviceToHost));
+    return CGPU_OK;
+}
+
+int cgpu_check_device_gather(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *dev_batch, const cgpu_gather *g, void *cuda_stream) {
+    if (!ctx || !t || !dev_batch || !g || !g->gather_bufs || !g->flags) return fail(CGPU_ERR_INVALID, "cgpu_check_device_gather: null argument");
+    if (t->ctx != ctx) return fail(CGPU_ERR_INVALID, "table belongs to another context");
+    if (g->n_ranks == 0 || g->n_ranks > cb::CB_MAX_GATHER || g->my_rank >= g->n_ranks || g->step == 0)
+        return fail(CGPU_ERR_INVALID, "cgpu_check_device_gather: 1..%d ranks, my_rank < n_ranks, step > 0", cb::CB_MAX_GATHER);
+    cb::BatchView bv;
+    int rc = make_batch_view(t, dev_batch, 0, dev_batch->n_requests, &bv);
+    if (rc != CGPU_OK) return rc;
+    if (bv.kbytes > 8) return fail(CGPU_ERR_UNSUPPORTED, "fused gather supports up to 64 actions per request");
+    if ((uint64_t)bv.count * bv.kbytes > g->slice_bytes) return fail(CGPU_ERR_INVALID, "gather slice too small");
+    SignalParams sp{};
+    for (uint32_t r = 0; r < g->n_ranks; r++) {
+        if (!g->gather_bufs[r] || !g->flags[r]) return fail(CGPU_ERR_INVALID, "gather buffer / flags of rank %u missing", r);
+        bv.outs[r] = static_cast<uint8_t *>(g->gather_bufs[r]) + (uint64_t)g->my_rank * g->slice_bytes;
+        sp.flags[r] = g->flags[r];
+    }
+    bv.n_out = g->n_ranks;
+    sp.n_ranks = g->n_ranks; sp.my_rank = g->my_rank; sp.step = g->step;
+    sp.wait_flags = g->flags[g->my_rank]; sp.wait_step = g->wait_step;
+    for (uint32_t r = 0; r < g->n_ranks; r++) bv.sig_flags[r] = g->flags[r];
+    bv.sig_rank = g->my_rank; bv.sig_step = g->step;
+    bv.wait_flags = g->flags[g->my_rank]; bv.wait_step = g->wait_step;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    bool drained = false;
+    rc = launch_check(ctx, t, bv, bv.outs[g->my_rank], nullptr, ctx->d_status, s, &drained);
+    if (rc != CGPU_OK) return rc;
+    if (!drained) {   // generic kernels: a one-warp kernel behind them publishes the step (and does the lagged wait)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(1); cfg.blockDim = dim3(32); cfg.stream = s;
+        cudaLaunchAttribute pdl[1];
+        pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pdl[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = pdl; cfg.numAttrs = 1;
+        void *args[] = {&sp};
+        CUDA_TRY(cudaLaunchKernelExC(&cfg, (const void *)gather_signal, args));
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    return CGPU_OK;
+}
+
+int cgpu_gather_wait(cgpu_ctx *ctx, const uint32_t *local_flags, uint32_t n_ranks, uint32_t step, void *cuda_stream) {
+    if (!ctx || !local_flags || n_ranks == 0 || n_ranks > cb::CB_MAX_GATHER) return fail(CGPU_ERR_INVALID, "cgpu_gather_wait: bad argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    gather_wait<<<1, 32, 0, static_cast<cudaStream_t>(cuda_stream)>>>(local_flags, n_ranks, step);
+    CUDA_TRY(cudaGetLastError());
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return CGPU_OK;
 }
 
 int cgpu_sync(cgpu_ctx *ctx, void *cuda_stream) {

@@ -41,3 +41,61 @@ def all_gather_bitmaps(local: torch.Tensor, out: torch.Tensor | None = None, asy
         out = torch.empty(world * local.numel(), dtype=torch.uint8, device=local.device)
     work = dist.all_gather_into_tensor(out, local, async_op=async_op)
     return (out, work) if async_op else out
+
+
+class PeerGather:
+    """Fused all-gather target: one buffer of world * slice_bytes per rank, allocated by the library, exported over
+    CUDA IPC and mapped by every other rank (NVLink / NVSwitch peer memory).  The check kernels of rank r store every
+    result byte into slice r of ALL buffers (cgpu_check_device_gather), then release a step number into every
+    rank's flag array; `wait(step)` makes a stream wait until all slices of that step have landed locally.
+    No NCCL call is involved after construction (the handles travel once through all_gather_object)."""
+
+    def __init__(self, ctx, slice_bytes: int, n_buffers: int = 1):
+        self.ctx = ctx
+        self.world = dist.get_world_size()
+        self.rank = dist.get_rank()
+        self.slice_bytes = int(slice_bytes)
+        self.n_buffers = n_buffers
+        total = self.world * self.slice_bytes
+        self._own = [ctx.peer_alloc(total) for _ in range(n_buffers)]
+        self._own_flags = ctx.peer_alloc(4 * 8)   # uint32[8]: cell r = the latest step rank r has fully stored here
+        mine = {"bufs": [h for _, h in self._own], "flags": self._own_flags[1]}
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine)
+        self._opened = []
+        self.bufs = []      # [buffer][rank] -> device pointer valid here
+        for j in range(n_buffers):
+            row = []
+            for r in range(self.world):
+                if r == self.rank:
+                    row.append(self._own[j][0])
+                else:
+                    ptr = ctx.peer_open(everyone[r]["bufs"][j])
+                    self._opened.append(ptr)
+                    row.append(ptr)
+            self.bufs.append(row)
+        self.flags = []     # [rank] -> that rank's flag array
+        for r in range(self.world):
+            if r == self.rank:
+                self.flags.append(self._own_flags[0])
+            else:
+                ptr = ctx.peer_open(everyone[r]["flags"])
+                self._opened.append(ptr)
+                self.flags.append(ptr)
+        dist.barrier()
+
+    def wait(self, step: int, stream: int = 0):
+        """Steps are numbered 1, 2, 3 ... across all buffers (a rank completes them in order)."""
+        self.ctx.gather_wait(self._own_flags[0], self.world, step, stream)
+
+    def read(self, j: int):
+        return self.ctx.peer_read(self._own[j][0], self.world * self.slice_bytes)
+
+    def close(self):
+        dist.barrier()
+        for p in self._opened:
+            self.ctx.peer_close(p)
+        dist.barrier()
+        for p, _ in self._own:
+            self.ctx.peer_free(p)
+        self.ctx.peer_free(self._own_flags[0])

@@ -108,6 +108,30 @@ int cgpu_sync(cgpu_ctx *ctx, void *cuda_stream);
  * (otherwise cgpu_last_error() says why not). */
 int cgpu_table_wait_ready(cgpu_table *t, int *specialised);
 
+/* ---- Fused all-gather of the decision bitmaps over NVLink peer memory (one process per GPU on one node) --------
+ * Every rank allocates a gather buffer of n_ranks * slice_bytes and a flag array with cgpu_peer_alloc, publishes the
+ * 64-byte handles (any host channel: torch.distributed, MPI ...) and maps the others' with cgpu_peer_open.
+ * cgpu_check_device_gather then makes the check kernels store each result byte straight into this rank's slice of
+ * EVERY rank's buffer (own + peers), followed by a release of `step` into flags[my_rank] of every rank; no separate
+ * collective runs. cgpu_gather_wait enqueues a wait on `stream` until every rank's slice of `step` has landed here. */
+#define CGPU_IPC_HANDLE_BYTES 64
+#define CGPU_MAX_GATHER_RANKS 8
+typedef struct {
+    uint32_t n_ranks, my_rank;
+    void *const *gather_bufs;      /* [n_ranks] device pointers valid in THIS process (own buffer + mapped peers) */
+    uint64_t slice_bytes;          /* bytes per rank slice: n_requests * ceil(max_actions / 8) */
+    uint32_t *const *flags;        /* [n_ranks] each rank's flag array (uint32[n_ranks]), same convention */
+    uint32_t step;                 /* monotonically increasing, > 0 */
+    uint32_t wait_step;            /* 0, or: also hold the stream until every rank's slice of this (earlier) step has landed here */
+} cgpu_gather;
+int cgpu_peer_alloc(cgpu_ctx *ctx, size_t bytes, void **dev_ptr, void *ipc_handle_out);
+int cgpu_peer_open(cgpu_ctx *ctx, const void *ipc_handle, void **dev_ptr);
+int cgpu_peer_close(cgpu_ctx *ctx, void *dev_ptr);
+int cgpu_peer_free(cgpu_ctx *ctx, void *dev_ptr);
+int cgpu_peer_read(cgpu_ctx *ctx, const void *dev_ptr, void *host_out, size_t bytes);   /* tests: synchronous D2H */
+int cgpu_check_device_gather(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *dev_batch, const cgpu_gather *g, void *cuda_stream);
+int cgpu_gather_wait(cgpu_ctx *ctx, const uint32_t *local_flags, uint32_t n_ranks, uint32_t step, void *cuda_stream);
+
 /* Introspection used by bench.py / tests (not part of the Go surface). */
 uint64_t cgpu_launch_count(const cgpu_ctx *ctx);        /* kernels launched by this library so far */
 int cgpu_table_info(const cgpu_table *t, uint32_t *meta_out, uint32_t n_words);  /* copies META words */
