@@ -1045,6 +1045,7 @@ struct GlobalCols {
     CB_HD bool staged() const { return b->prefetch_slots != 0; }   // every slot column was prefetched with the tile
     CB_HD uint32_t aset_k(uint32_t aset) const { return ldg(b->aset_k + aset); }
     CB_HD const uint64_t *row_am() const { return b->row_am; }
+    CB_HD bool stage_result(uint32_t) const { return false; }
 };
 struct TileCols {
     const uint8_t *base;   // staged tile (shared memory on the device)
@@ -1060,6 +1061,10 @@ struct TileCols {
     const uint64_t *row_am_s;
     CB_HD uint32_t aset_k(uint32_t aset) const { return ldg(aset_k_s + aset); }
     CB_HD const uint64_t *row_am() const { return row_am_s; }
+    // fused all-gather: the tile's result bytes are collected in shared memory and leave for the peers as one 256-byte
+    // store per tile and peer (NVLink moves 32-byte writes poorly); the thread then stores its byte locally only
+    uint8_t *res_s;
+    CB_HD bool stage_result(uint32_t acc) const { if (!res_s) return false; res_s[tid] = (uint8_t)acc; return true; }
 };
 CB_HD uint32_t tile_cols_bytes(uint32_t role_cols, uint32_t n_slots) { return CB_TILE * (24u + 4u * role_cols + 8u * n_slots); }
 
@@ -1784,7 +1789,8 @@ CB_HD bool eval_request_fast(const TableView t, const BatchView &b, const Cols &
             for (uint32_t k = 0; k < b.max_actions; k++) eff[k] = (uint8_t)(k < K ? (((acc >> k) & 1) ? CB_EFFECT_ALLOW : CB_EFFECT_DENY) : 0);
         }
     } else {
-        store_bits(b, bitmap, n, acc);
+        if (cols.stage_result(acc)) bitmap[n] = (uint8_t)acc;   // (kbytes == 1; `bitmap` is this rank's own gather slice)
+        else store_bits(b, bitmap, n, acc);
     }
     return false;
 }

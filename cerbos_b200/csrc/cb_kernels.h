@@ -70,7 +70,8 @@ __device__ __forceinline__ void defer_request(const cb::TableView tv, const cb::
 // fused all-gather bookkeeping (see BatchView): executed by one warp
 __device__ __forceinline__ void gather_signal_flags(const cb::BatchView &bv) {
     __threadfence_system();
-    if (threadIdx.x < bv.n_out) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(bv.sig_flags[threadIdx.x] + bv.sig_rank), "r"(bv.sig_step) : "memory");
+    // max, not a plain store: consecutive launches overlap at their tails, the cell must never step backwards
+    if (threadIdx.x < bv.n_out) asm volatile("red.release.sys.global.max.u32 [%0], %1;" ::"l"(bv.sig_flags[threadIdx.x] + bv.sig_rank), "r"(bv.sig_step) : "memory");
 }
 __device__ __forceinline__ void gather_wait_flags(const uint32_t *flags, uint32_t n_ranks, uint32_t step) {
     if (threadIdx.x < n_ranks) {
@@ -94,6 +95,9 @@ __device__ __forceinline__ void check_body(const TableDesc &td, const cb::BatchV
     // launch is programmatically serialised behind that kernel (its CTAs become resident while the last tiles of the
     // producer are still running): wait here until the producer has completed and its writes are visible.
     if (bv.count_dev) {
+        // let the NEXT launch's specialised kernel (programmatically serialised behind this one) take SM slots as the
+        // producer's last tiles retire: it does not depend on anything this launch writes
+        asm volatile("griddepcontrol.launch_dependents;");
         asm volatile("griddepcontrol.wait;" ::: "memory");
         if (blockIdx.x == 0 && threadIdx.x == 0) bv.count_dev[2] = 0;   // the producer's tile counter: back to zero for the cell's next user
         if (blockIdx.x == 0 && threadIdx.x < 32 && bv.wait_step) gather_wait_flags(bv.wait_flags, bv.n_out, bv.wait_step);
@@ -220,18 +224,35 @@ __device__ __forceinline__ void check_tiles_body(const TableDesc &td, const cb::
     // launch provides one (claimed by thread 0 one tile ahead, published through `tile_s` under the stage's full
     // barrier), so the tail of the grid stays balanced; else the static grid stride.
     uint64_t *tile_s = reinterpret_cast<uint64_t *>(aset_k_s + ((bv.n_asets + 1u) & ~1u));   // [2]
+    // fused all-gather: result bytes of a tile, per stage; warp 0 forwards them to the peers once the tile is complete
+    uint8_t *res_s = reinterpret_cast<uint8_t *>(tile_s + 2);                                // [2][kThreads]
+    bool remote = bv.n_out > 1 && bv.kbytes == 1 && (bv.first & 7) == 0;
+    for (uint32_t r = 0; r < bv.n_out; r++) remote = remote && (reinterpret_cast<uintptr_t>(bv.outs[r]) & 7) == 0;   // 8-byte stores per lane
+    auto flush_remote = [&](uint32_t st, uint64_t t) {   // warp 0, all lanes: 256 bytes of tile t to every peer, 8 bytes per lane
+        const uint64_t v = *reinterpret_cast<const uint64_t *>(res_s + st * kThreads + threadIdx.x * 8);
+        for (uint32_t r = 0; r < bv.n_out; r++)
+            if (r != bv.sig_rank) *reinterpret_cast<uint64_t *>(bv.outs[r] + bv.first + t * kThreads + threadIdx.x * 8) = v;
+    };
     uint32_t k = 0;
-    uint64_t tile = blockIdx.x;
+    uint64_t tile = blockIdx.x, prev_tile = 0;
     while (tile < n_tiles) {
-        if (threadIdx.x == 0) {
-            const uint64_t next = bv.tile_counter ? (uint64_t)atomicAdd(bv.tile_counter, 1u) + gridDim.x : tile + gridDim.x;
+        if (threadIdx.x < 32) {
             const uint32_t st = (k + 1) & 1;
-            // stage st was read in iteration k-1: refill it once all eight warps have released it.  No CTA-wide barrier:
-            // only this thread waits, and it is normally released long before
-            if (k >= 1) mbar_wait(&empty[st], ((k - 1) >> 1) & 1);
-            tile_s[st] = next;
-            if (next < n_full) issue_tile(next, st);
-            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[st])) : "memory");   // nothing to copy: complete the phase
+            // stage st was read in iteration k-1: reuse it once all eight warps have released it.  No CTA-wide barrier:
+            // only this warp waits, and it is normally released long before
+            if (k >= 1) {
+                if (threadIdx.x == 0) mbar_wait(&empty[st], ((k - 1) >> 1) & 1);
+                __syncwarp();
+                if (remote && prev_tile < n_full) flush_remote(st, prev_tile);   // before the refill lets anyone overwrite res_s[st]
+                __syncwarp();
+            }
+            if (threadIdx.x == 0) {
+                const uint64_t next = bv.tile_counter ? (uint64_t)atomicAdd(bv.tile_counter, 1u) + gridDim.x : tile + gridDim.x;
+                tile_s[st] = next;
+                if (next < n_full) issue_tile(next, st);
+                else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[st])) : "memory");   // nothing to copy: complete the phase
+            }
+            __syncwarp();
         }
         if (k == 0) mbar_wait(mbar_tab, 0);
         const uint64_t n = bv.first + tile * kThreads + threadIdx.x;
@@ -240,6 +261,7 @@ __device__ __forceinline__ void check_tiles_body(const TableDesc &td, const cb::
             cb::TileCols tc;
             tc.base = stage0 + (k & 1) * tile_bytes; tc.tid = threadIdx.x; tc.slots_off = slots_off;
             tc.aset_k_s = aset_k_s; tc.row_am_s = row_am_s;
+            tc.res_s = remote ? res_s + (k & 1) * kThreads : nullptr;
             if (cb::eval_request_fast(tv, bv, tc, n, bitmap, effects, Blocks())) defer_request(tv, bv, n, bitmap, effects, status);
         } else if (tile * kThreads + threadIdx.x < bv.count) {   // the ragged last tile: straight from global memory
             cb::GlobalCols gc;
@@ -249,9 +271,15 @@ __device__ __forceinline__ void check_tiles_body(const TableDesc &td, const cb::
         __syncwarp();
         if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[k & 1])) : "memory");
         // next tile: its index (and, for a full tile, its columns) are published when stage (k+1)&1 completes
+        prev_tile = tile;
         k++;
         mbar_wait(&full[k & 1], (k >> 1) & 1);
         tile = tile_s[k & 1];
+    }
+    if (remote && k >= 1 && threadIdx.x < 32 && prev_tile < n_full) {   // results of the last tile
+        if (threadIdx.x == 0) mbar_wait(&empty[(k - 1) & 1], ((k - 1) >> 1) & 1);
+        __syncwarp();
+        flush_remote((k - 1) & 1, prev_tile);
     }
     if (k == 0) mbar_wait(mbar_tab, 0);   // no tile: drain the table copy before shared memory is released
 }

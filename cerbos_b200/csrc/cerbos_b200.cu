@@ -56,7 +56,7 @@ struct SignalParams { uint32_t *flags[cb::CB_MAX_GATHER]; const uint32_t *wait_f
 __global__ void gather_signal(const __grid_constant__ SignalParams p) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     __threadfence_system();
-    if (threadIdx.x < p.n_ranks) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flags[threadIdx.x] + p.my_rank), "r"(p.step) : "memory");
+    if (threadIdx.x < p.n_ranks) asm volatile("red.release.sys.global.max.u32 [%0], %1;" ::"l"(p.flags[threadIdx.x] + p.my_rank), "r"(p.step) : "memory");
     if (p.wait_step) cbk::gather_wait_flags(p.wait_flags, p.n_ranks, p.wait_step);
 }
 // Stream-side wait: until the slice of every rank for `step` has landed in this rank's gather buffer.
@@ -211,6 +211,9 @@ struct cgpu_ctx {
     uint32_t last_spec = 0;
     uint32_t *d_defer_cells = nullptr;   // kDeferCells x {count, done, tile counter, -}, zero between uses (the drain kernel re-zeroes)
     std::atomic<uint32_t> defer_next{0};
+    uint32_t *defer_lists[4] = {nullptr, nullptr, nullptr, nullptr};   // rotating deferral lists (grow-only): launches may overlap at their tails
+    size_t defer_cap[4] = {0, 0, 0, 0};
+    std::mutex defer_mu;
     bool profiling = false;  // cgpu_profile(): CUDA events around the check kernel of every launch
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double prof_ms = 0;
@@ -486,7 +489,7 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
     // 16-byte aligned and image + two tile stages fit the shared-memory budget of CB_MIN_BLOCKS resident CTAs.
     const uint32_t tile_bytes = cb::tile_cols_bytes(bv.role_cols, lay.n_slots);
     // [image][tile stage 0][tile stage 1][row_am copy][aset_k copy]
-    const uint64_t small_tabs = (uint64_t)bv.n_asets * lay.n_rows * 8 + (((uint64_t)bv.n_asets + 1) & ~1ull) * 4 + 16;   // + tile_s[2]
+    const uint64_t small_tabs = (uint64_t)bv.n_asets * lay.n_rows * 8 + (((uint64_t)bv.n_asets + 1) & ~1ull) * 4 + 16 + 2 * kThreads;   // + tile_s[2] + res_s[2][256]
     const uint32_t tiles_smem = ((lay.image_bytes + 127u) & ~127u) + 2 * tile_bytes + (uint32_t)(small_tabs < 65536 ? small_tabs : 65536);
     auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     const bool col_tiles = narrow && stage && !cluster && !ctx->force_no_tiles && tiles_smem <= kMaxTilesSmem && bv.stride % 4 == 0 &&
@@ -531,8 +534,18 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
     uint32_t last_arg = col_tiles ? lay.n_slots : (stage ? 1u : 0u);   // check_kernel: stage_rt; check_kernel_tiles: n_slots
     uint32_t *defer = nullptr;   // request offsets the specialised kernel leaves to the general kernel
     if (spec) {
-        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&defer), (size_t)bv.count * 4, stream));
-        bvv.defer_count = ctx->d_defer_cells + 4 * (ctx->defer_next.fetch_add(1, std::memory_order_relaxed) % kDeferCells);   // {count, done, tile counter, -}
+        const uint32_t seq = ctx->defer_next.fetch_add(1, std::memory_order_relaxed);
+        {
+            std::lock_guard<std::mutex> g(ctx->defer_mu);
+            const uint32_t q = seq & 3;
+            if (ctx->defer_cap[q] < (size_t)bv.count) {
+                if (ctx->defer_lists[q]) { CUDA_TRY(cudaStreamSynchronize(stream)); CUDA_TRY(cudaFree(ctx->defer_lists[q])); ctx->defer_lists[q] = nullptr; ctx->defer_cap[q] = 0; }
+                CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&ctx->defer_lists[q]), (size_t)bv.count * 4));
+                ctx->defer_cap[q] = (size_t)bv.count;
+            }
+            defer = ctx->defer_lists[q];
+        }
+        bvv.defer_count = ctx->d_defer_cells + 4 * (seq % kDeferCells);   // {count, done, tile counter, -}
         bvv.tile_counter = col_tiles ? bvv.defer_count + 2 : nullptr;
         bvv.defer_list = defer;
     }
@@ -545,7 +558,20 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
         }
         CUDA_TRY(cudaEventRecord(ctx->ev0, stream));
     }
-    CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(kThreads), args, smem, stream));
+    if (spec && !ctx->profiling) {
+        // programmatically serialised behind the previous launch's drain kernel (which releases its dependents at once):
+        // this kernel's CTAs start as the previous specialised kernel's last tiles retire -- back-to-back launches on one
+        // stream overlap at their tails.  It reads nothing the previous launch writes.
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute pdl[1];
+        pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pdl[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = pdl; cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelExC(&cfg, fn, args));
+    } else {
+        CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(kThreads), args, smem, stream));
+    }
     CUDA_TRY(cudaGetLastError());
     if (ctx->profiling) { CUDA_TRY(cudaEventRecord(ctx->ev1, stream)); ctx->prof_pending = true; }
     if (spec) {
@@ -577,7 +603,6 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
         cfg.attrs = pdl; cfg.numAttrs = 1;
         CUDA_TRY(cudaLaunchKernelExC(&cfg, gfn, gargs));
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaFreeAsync(defer, stream));
         ctx->launches.fetch_add(1, std::memory_order_relaxed);
         if (drained) *drained = true;   // the drain kernel also did the fused-gather signalling (BatchView::sig_*)
     }
@@ -649,6 +674,7 @@ void cgpu_shutdown(cgpu_ctx *ctx) {
     }
     if (ctx->d_status) cudaFree(ctx->d_status);
     if (ctx->d_defer_cells) cudaFree(ctx->d_defer_cells);
+    for (auto p : ctx->defer_lists) if (p) cudaFree(p);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -826,6 +852,11 @@ int cgpu_check_device_gather(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batc
     for (uint32_t r = 0; r < g->n_ranks; r++) bv.sig_flags[r] = g->flags[r];
     bv.sig_rank = g->my_rank; bv.sig_step = g->step;
     bv.wait_flags = g->flags[g->my_rank]; bv.wait_step = g->wait_step;
+    {   // diagnosis switches (measurement only; results are then NOT exchanged correctly)
+        static const int dbg_nowait = getenv("CERBOS_B200_DBG_NOWAIT") != nullptr, dbg_noremote = getenv("CERBOS_B200_DBG_NOREMOTE") != nullptr;
+        if (dbg_nowait) { bv.wait_step = 0; sp.wait_step = 0; }
+        if (dbg_noremote) for (uint32_t r = 0; r < g->n_ranks; r++) bv.outs[r] = bv.outs[g->my_rank];
+    }
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     bool drained = false;

@@ -71,7 +71,7 @@ extern "C" int HOSTSIM_ENTRY(const void *blob, uint64_t blob_len, uint64_t n, ui
             const uint32_t so = cb::CB_TILE * (24 + 4 * b.role_cols);
             for (uint32_t v = 0; v < lay.n_slots; v++) memcpy(tb + so + v * cb::CB_TILE * 8, b.slots + v * b.stride + t0, cnt * 8);
             for (uint32_t j = 0; j < cnt; j++) {
-                cb::TileCols tc; tc.base = tb; tc.tid = j; tc.slots_off = so; tc.aset_k_s = b.aset_k; tc.row_am_s = b.row_am;
+                cb::TileCols tc; tc.base = tb; tc.tid = j; tc.slots_off = so; tc.aset_k_s = b.aset_k; tc.row_am_s = b.row_am; tc.res_s = nullptr;
                 if (cb::eval_request_fast(t, b, tc, t0 + j, bitmap, nullptr, HostBlocks())) cb::eval_request_general(t.base, t.L, &b, t0 + j, bitmap, nullptr, &status);
             }
         }
