@@ -65,7 +65,37 @@ class ClockSampler:
         self._stop = threading.Event()
         self._t = None
 
+    def _run_nvml(self) -> bool:
+        """NVML in-process: ~1 ms per sample (an nvidia-smi process takes ~100 ms, longer than a short timed region)."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self.gpu
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                ids = [x.strip() for x in vis.split(",") if x.strip()]
+                if self.gpu < len(ids) and ids[self.gpu].isdigit():
+                    idx = int(ids[self.gpu])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            mx = str(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = [pynvml.nvmlClocksThrottleReasonHwSlowdown, pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    pynvml.nvmlClocksThrottleReasonSwThermalSlowdown, pynvml.nvmlClocksThrottleReasonSwPowerCap]
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001 -- no NVML: fall back to nvidia-smi
+            return False
+        while not self._stop.is_set():
+            try:
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append([str(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), mx, "0"] +
+                                    ["Active" if r & b else "Not Active" for b in bits])
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.002)
+        return True
+
     def _run(self):
+        if self._run_nvml():
+            return
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
