@@ -233,6 +233,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--requests", type=int, default=0, help="override requests per step per GPU (profiling only)")
+    ap.add_argument("--streams", type=int, default=2, help="CUDA streams the steps are issued on round-robin (independent batches)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -284,13 +285,19 @@ def main():
 
     calls = [b.prepare(table, NOW_NS) for b in batches]
     views = [b.bitmap[: n * kbytes] for b in batches]
-    # everything timed runs on ONE explicit stream: the kernels are launched on it through the C ABI and the
-    # CUDA events are recorded on it (torch.cuda.Event records on the current stream)
     torch.cuda.synchronize()
-    stream = torch.cuda.Stream()
+    # Steps are independent batches: they are issued round-robin on `--streams` explicit streams (the tail of one step's
+    # kernels and its peer-store round trips overlap the next step's kernel).  Everything timed is launched on these
+    # streams through the C ABI and bracketed by CUDA events recorded on them.
+    n_streams = max(1, min(args.streams, n_buf))
+    while n_buf % n_streams:
+        n_streams -= 1
+    streams = [torch.cuda.Stream() for _ in range(n_streams)]
+    stream = streams[0]
     torch.cuda.set_stream(stream)
     stream_h = stream.cuda_stream
-    assert stream_h != 0 and torch.cuda.current_stream().cuda_stream == stream_h
+    stream_hs = [st.cuda_stream for st in streams]
+    assert all(h != 0 for h in stream_hs) and torch.cuda.current_stream().cuda_stream == stream_h
 
     # Multi-GPU result exchange.  Default: FUSED all-gather -- the check kernels store every result byte straight into
     # this rank's slice of every rank's gather buffer over NVLink peer memory (cerbos_b200.dist.PeerGather), a flag
@@ -305,7 +312,7 @@ def main():
             try:
                 from cerbos_b200.dist import PeerGather
                 pg = PeerGather(ctx, n * kbytes, n_buf)
-                gcalls = [table.prepared_gather_call(b.ptrs, b.sizes, b.n, b.max_actions, pg.bufs[j], pg.flags, rank, n * kbytes, NOW_NS)
+                gcalls = [table.prepared_gather_call(b.ptrs, b.sizes, b.n, b.max_actions, pg.bufs[j], pg.lane_flags(j % n_streams), rank, n * kbytes, NOW_NS)
                           for j, b in enumerate(batches)]
                 ok = 1
             except Exception as e:  # noqa: BLE001 -- any failure here just selects the NCCL path on every rank
@@ -317,6 +324,8 @@ def main():
             pg, gcalls = None, None
         if no_exchange:
             gather_mode = "none (diagnosis)"
+        elif pg is None:       # NCCL orders its collective after torch's current stream only: one issuing stream
+            n_streams, streams, stream_hs = 1, streams[:1], stream_hs[:1]
     gathered = [torch.empty(world * n * kbytes, dtype=torch.uint8, device=dev) for _ in range(n_buf)] if (world > 1 and pg is None) else None
     pending = []
     it = [0]          # steps issued so far (warm-up included): numbers the gather steps
@@ -325,12 +334,19 @@ def main():
         g = it[0]
         it[0] += 1
         j = g % n_buf
+        lane = g % n_streams            # == j % n_streams: a buffer always travels on the same stream
+        sh = stream_hs[lane]
         if pg is not None:
-            # buffers rotate: step g-(n_buf-1) must have landed on this rank before the stream moves on (the wait rides in
-            # the same launch: the kernel that publishes this step's flag also holds the stream for the older one)
-            gcalls[j](g + 1, stream_h, g + 1 - (n_buf - 1) if g >= n_buf - 1 else 0)
+            # buffers rotate: step g-(n_buf-1) must have landed on this rank before its stream moves on (the wait rides in
+            # the same launch: the kernel that publishes this step's flag also holds the stream for the older one).
+            # Steps are numbered per stream ("lane"), so that every flag array only ever counts up.
+            k = g - (n_buf - 1)
+            if k >= 0:
+                gcalls[j](g // n_streams + 1, sh, k // n_streams + 1, pg.local_flags(k % n_streams))
+            else:
+                gcalls[j](g // n_streams + 1, sh, 0, None)
             return
-        calls[j](stream_h)
+        calls[j](sh)
         if world > 1 and gather_mode != "none (diagnosis)":
             if len(pending) >= n_buf - 1:          # buffers are reused after n_buf steps: retire the oldest gather
                 pending.pop(0).wait()
@@ -339,35 +355,50 @@ def main():
 
     def drain():
         if pg is not None:
-            if it[0]:
-                pg.wait(it[0], stream_h)       # the last step issued (a rank finishes its steps in order)
+            for lane in range(n_streams):          # the last step issued on every stream (a stream finishes its steps in order)
+                last = [g for g in range(max(0, it[0] - n_streams), it[0]) if g % n_streams == lane]
+                if last:
+                    pg.wait(last[-1] // n_streams + 1, stream_hs[lane], lane)
             return
         while pending:
             pending.pop(0).wait()
 
+    def join_streams():
+        """stream 0 waits for the work issued so far on the other streams"""
+        for st in streams[1:]:
+            e = torch.cuda.Event()
+            e.record(st)
+            stream.wait_event(e)
+
+    if world > 1 and pg is None:
+        assert n_streams == 1 or gather_mode == "none (diagnosis)"
     for i in range(args.warmup):
         step(i)
     drain()
-    ctx.sync(stream_h)
+    for h in stream_hs:
+        ctx.sync(h)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     launches0 = ctx.launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         torch.cuda.synchronize()
-        ev[0].record()
+        ev0.record(stream)
+        for st in streams[1:]:
+            st.wait_event(ev0)               # no stream starts before the start event
         for i in range(args.steps):
             step(i)
-            if i == args.steps - 1:
-                drain()                      # the last gathers are part of the timed work
-            ev[i + 1].record()
+        drain()                              # the last exchanges are part of the timed work
+        join_streams()
+        ev1.record(stream)
         torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    total_ms = ev[0].elapsed_time(ev[args.steps])
+    total_ms = ev0.elapsed_time(ev1)
     launches = ctx.launch_count() - launches0
-    ctx.sync(stream_h)
+    for h in stream_hs:
+        ctx.sync(h)
     if world > 1:
         tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -402,6 +433,7 @@ def main():
         "config": {"workload": f"{w.name}: {W.C2.__doc__.splitlines()[0] if w.name == 'C2' else w.name}",
                    "requests_per_step_per_gpu": n, "actions_per_request": K, "global_requests_per_step": world * n,
                    "parallelism": f"dp{world} (requests sharded by index; NCCL table broadcast; result exchange: {gather_mode})",
+                   "streams": n_streams,
                    "l2": f"rotating {n_buf} distinct batches, {footprint / 1e6:.0f} MB of columns > 126 MB L2",
                    "kernel": ctx.last_kernel_config()},
         "gpu_launches": int(launches),

@@ -30,7 +30,7 @@ class CgpuError(RuntimeError):
 
 class _Gather(ctypes.Structure):
     _fields_ = [("n_ranks", ctypes.c_uint32), ("my_rank", ctypes.c_uint32), ("gather_bufs", ctypes.POINTER(ctypes.c_void_p)),
-                ("slice_bytes", ctypes.c_uint64), ("flags", ctypes.POINTER(ctypes.c_void_p)), ("step", ctypes.c_uint32), ("wait_step", ctypes.c_uint32)]
+                ("slice_bytes", ctypes.c_uint64), ("flags", ctypes.POINTER(ctypes.c_void_p)), ("step", ctypes.c_uint32), ("wait_step", ctypes.c_uint32), ("wait_flags", ctypes.c_void_p)]
 
 
 class _Batch(ctypes.Structure):
@@ -236,13 +236,14 @@ class Table:
         b = _Batch(n, max_actions, now_ns, batch_flags, p, s, len(ptrs))
         gb = (ctypes.c_void_p * len(gather_bufs))(*gather_bufs)
         fl = (ctypes.c_void_p * len(flags))(*flags)
-        g = _Gather(len(gather_bufs), my_rank, gb, slice_bytes, fl, 0, 0)
+        g = _Gather(len(gather_bufs), my_rank, gb, slice_bytes, fl, 0, 0, None)
         fn, ctx_h, tab_h, bref, gref = lib().cgpu_check_device_gather, self.ctx._h, self._h, ctypes.byref(b), ctypes.byref(g)
         keep = (p, s, b, gb, fl, g)
 
-        def call(step, stream=0, wait_step=0, _keep=keep):
+        def call(step, stream=0, wait_step=0, wait_flags=None, _keep=keep):
             g.step = step
             g.wait_step = wait_step
+            g.wait_flags = wait_flags
             rc = fn(ctx_h, tab_h, bref, gref, ctypes.c_void_p(stream))
             if rc != OK:
                 _check(rc)

@@ -848,10 +848,10 @@ int cgpu_check_device_gather(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batc
     }
     bv.n_out = g->n_ranks;
     sp.n_ranks = g->n_ranks; sp.my_rank = g->my_rank; sp.step = g->step;
-    sp.wait_flags = g->flags[g->my_rank]; sp.wait_step = g->wait_step;
+    sp.wait_flags = g->wait_flags ? g->wait_flags : g->flags[g->my_rank]; sp.wait_step = g->wait_step;
     for (uint32_t r = 0; r < g->n_ranks; r++) bv.sig_flags[r] = g->flags[r];
     bv.sig_rank = g->my_rank; bv.sig_step = g->step;
-    bv.wait_flags = g->flags[g->my_rank]; bv.wait_step = g->wait_step;
+    bv.wait_flags = sp.wait_flags; bv.wait_step = g->wait_step;
     {   // diagnosis switches (measurement only; results are then NOT exchanged correctly)
         static const int dbg_nowait = getenv("CERBOS_B200_DBG_NOWAIT") != nullptr, dbg_noremote = getenv("CERBOS_B200_DBG_NOREMOTE") != nullptr;
         if (dbg_nowait) { bv.wait_step = 0; sp.wait_step = 0; }

@@ -58,7 +58,10 @@ class PeerGather:
         self.n_buffers = n_buffers
         total = self.world * self.slice_bytes
         self._own = [ctx.peer_alloc(total) for _ in range(n_buffers)]
-        self._own_flags = ctx.peer_alloc(4 * 8)   # uint32[8]: cell r = the latest step rank r has fully stored here
+        # uint32[n_lanes][8]: cell [l][r] = the latest step of lane l that rank r has fully stored here (a lane = one
+        # CUDA stream of the issuing rank: steps of one lane complete in order, so each array only counts up)
+        self.n_lanes = 4
+        self._own_flags = ctx.peer_alloc(4 * 8 * self.n_lanes)
         mine = {"bufs": [h for _, h in self._own], "flags": self._own_flags[1]}
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine)
@@ -84,9 +87,16 @@ class PeerGather:
                 self.flags.append(ptr)
         dist.barrier()
 
-    def wait(self, step: int, stream: int = 0):
-        """Steps are numbered 1, 2, 3 ... across all buffers (a rank completes them in order)."""
-        self.ctx.gather_wait(self._own_flags[0], self.world, step, stream)
+    def lane_flags(self, lane: int):
+        """flag arrays (one pointer per rank) of `lane`"""
+        return [f + 32 * lane for f in self.flags]
+
+    def local_flags(self, lane: int) -> int:
+        return self._own_flags[0] + 32 * lane
+
+    def wait(self, step: int, stream: int = 0, lane: int = 0):
+        """Steps of one lane are numbered 1, 2, 3 ... (a rank completes them in order)."""
+        self.ctx.gather_wait(self.local_flags(lane), self.world, step, stream)
 
     def read(self, j: int):
         return self.ctx.peer_read(self._own[j][0], self.world * self.slice_bytes)

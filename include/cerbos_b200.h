@@ -123,6 +123,8 @@ typedef struct {
     uint32_t *const *flags;        /* [n_ranks] each rank's flag array (uint32[n_ranks]), same convention */
     uint32_t step;                 /* monotonically increasing, > 0 */
     uint32_t wait_step;            /* 0, or: also hold the stream until every rank's slice of this (earlier) step has landed here */
+    const uint32_t *wait_flags;    /* local flag array watched for wait_step (NULL: flags[my_rank]); callers that issue steps on
+                                      several streams keep one flag array per stream so that each array only ever counts up */
 } cgpu_gather;
 int cgpu_peer_alloc(cgpu_ctx *ctx, size_t bytes, void **dev_ptr, void *ipc_handle_out);
 int cgpu_peer_open(cgpu_ctx *ctx, const void *ipc_handle, void **dev_ptr);

@@ -42,7 +42,7 @@ def main():
         ctx.sync(sh)
         ref = all_gather_bitmaps(db.bitmap[: n]).cpu().numpy()
         j = step % n_buf
-        call = table.prepared_gather_call(db.ptrs, db.sizes, db.n, db.max_actions, pg.bufs[j], pg.flags, rank, n)
+        call = table.prepared_gather_call(db.ptrs, db.sizes, db.n, db.max_actions, pg.bufs[j], pg.lane_flags(0), rank, n)
         call(step + 1, sh, step if step >= 1 else 0)   # also exercises the in-launch wait for the previous step
         pg.wait(step + 1, sh)
         ctx.sync(sh)
