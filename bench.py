@@ -234,6 +234,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--requests", type=int, default=0, help="override requests per step per GPU (profiling only)")
     ap.add_argument("--streams", type=int, default=2, help="CUDA streams the steps are issued on round-robin (independent batches)")
+    ap.add_argument("--no-verify", action="store_true", help="skip the post-run comparison of the result images with the oracle")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -425,7 +426,35 @@ def main():
     algo_bytes = w.bytes_per_request() * n
     achieved = algo_bytes / (kern_ms_mean * 1e-3) / 1e9
 
-    # correctness spot check of what was timed (full compare lives in tests/): checksum vs the C port on rank 0
+    # correctness check of what was timed (the overlapped back-to-back launches included): the result images the timed
+    # loop left behind, every rotating batch, bit for bit against the C port of the reference algorithm (oracle/)
+    verified = None
+    if not args.no_verify and n <= (1 << 21):
+        from oracle import cref as _cref
+        bad = 0
+        for j, hb in enumerate(host_batches):
+            want = _cref.check(blob, hb.columns, hb.n, hb.max_actions, NOW_NS, 0, n_threads=os.cpu_count() or 1)
+            want_bits = np.packbits((want == 1).astype(np.uint8), axis=1, bitorder="little")[:, :kbytes].reshape(-1)
+            if pg is not None:
+                img = pg.read(j)
+                got = img[rank * n * kbytes:(rank + 1) * n * kbytes]
+            else:
+                got = batches[j].bitmap[: n * kbytes].cpu().numpy()
+            bad += int((got != want_bits).sum())
+        if world > 1:
+            tb = torch.tensor([bad], dtype=torch.int64, device=dev)
+            dist.all_reduce(tb)
+            bad = int(tb.item())
+            if pg is not None and bad == 0:
+                # every rank also holds every other rank's slice: compare the whole gathered image across ranks
+                h = torch.tensor([int(np.frombuffer(pg.read(0).tobytes(), dtype=np.uint64).sum() & ((1 << 62) - 1))], dtype=torch.int64, device=dev)
+                hs = [torch.zeros_like(h) for _ in range(world)]
+                dist.all_gather(hs, h)
+                bad = 0 if len({int(x.item()) for x in hs}) == 1 else -1
+        verified = bad == 0
+        if not verified:
+            sys.stderr.write(f"[rank {rank}] VERIFY FAILED: {bad} result bytes differ from the oracle\n")
+
     result = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -444,6 +473,7 @@ def main():
                      "step_achieved": algo_bytes / (statistics.mean(step_ms) * 1e-3) / 1e9,
                      "kernel_share_of_step": kern_ms_mean / statistics.mean(step_ms)},
         "clocks": clocks.summary(),
+        "verified_vs_oracle": verified,
     }
 
     if rank == 0 and not args.no_e2e:
