@@ -157,6 +157,9 @@ __device__ __forceinline__ void check_body(const TableDesc &td, const cb::BatchV
         }
     }
     if (!staged) mbar_wait(mbar, 0);   // CTA had no tile: drain the bulk copy before shared memory is released
+#ifdef CB_LEAN_ONLY
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // see check_tiles_body: complete only after the previous launch has
+#endif
     if (bv.count_dev) {
         // deferred mode: the last CTA to finish hands the {count, done} cell back zeroed (it comes from a small pool of
         // pre-zeroed cells, so that a launch needs no memset)
@@ -282,6 +285,11 @@ __device__ __forceinline__ void check_tiles_body(const TableDesc &td, const cb::
         flush_remote((k - 1) & 1, prev_tile);
     }
     if (k == 0) mbar_wait(mbar_tab, 0);   // no tile: drain the table copy before shared memory is released
+#ifdef CB_LEAN_ONLY
+    // launched programmatically serialised behind the previous launch's drain kernel and never synchronised with it so
+    // far: do not COMPLETE before it has (keeps "this kernel done => everything before it in the stream done")
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
 }
 
 }  // namespace cbk

@@ -852,11 +852,6 @@ int cgpu_check_device_gather(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batc
     for (uint32_t r = 0; r < g->n_ranks; r++) bv.sig_flags[r] = g->flags[r];
     bv.sig_rank = g->my_rank; bv.sig_step = g->step;
     bv.wait_flags = sp.wait_flags; bv.wait_step = g->wait_step;
-    {   // diagnosis switches (measurement only; results are then NOT exchanged correctly)
-        static const int dbg_nowait = getenv("CERBOS_B200_DBG_NOWAIT") != nullptr, dbg_noremote = getenv("CERBOS_B200_DBG_NOREMOTE") != nullptr;
-        if (dbg_nowait) { bv.wait_step = 0; sp.wait_step = 0; }
-        if (dbg_noremote) for (uint32_t r = 0; r < g->n_ranks; r++) bv.outs[r] = bv.outs[g->my_rank];
-    }
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     bool drained = false;
