@@ -569,6 +569,65 @@ CB_HD uint32_t utf8_len(const uint8_t *p, uint32_t n) {
     return k;
 }
 
+// ---- hierarchy(s, delim) (conditions/types/hierarchy.go:146-410): segments = strings.Split(s, delim), never
+// materialised -- the relations walk both strings segment by segment
+struct HierIt { const uint8_t *p; uint32_t n; const uint8_t *d; uint32_t dn; uint32_t pos; bool more; };
+CB_HD HierIt hier_it(const Ctx &c, uint64_t sid, uint32_t delim_id) {
+    HierIt h;
+    str_get(c, sid, h.p, h.n);
+    str_get(c, delim_id, h.d, h.dn);
+    h.pos = 0; h.more = true;
+    return h;
+}
+// next segment -> [*s, *s + *l); false when there is none left
+CB_HD bool hier_next(HierIt &h, uint32_t *s, uint32_t *l) {
+    if (!h.more) return false;
+    *s = h.pos;
+    for (uint32_t i = h.pos; i + h.dn <= h.n; i++) {
+        if (bytes_eq(h.p + i, h.d, h.dn)) { *l = i - h.pos; h.pos = i + h.dn; return true; }
+    }
+    *l = h.n - h.pos;
+    h.more = false;
+    return true;
+}
+CB_HD uint32_t hier_count(HierIt h) {
+    uint32_t k = 0, s, l;
+    while (hier_next(h, &s, &l)) k++;
+    return k;
+}
+// number of equal leading segments of a and b, at most `limit`
+CB_HD uint32_t hier_common(HierIt a, HierIt b, uint32_t limit) {
+    uint32_t k = 0, sa, la, sb, lb;
+    while (k < limit && hier_next(a, &sa, &la) && hier_next(b, &sb, &lb)) {
+        if (la != lb || !bytes_eq(a.p + sa, b.p + sb, la)) break;
+        k++;
+    }
+    return k;
+}
+CB_HD bool hier_rel(uint32_t rel, const HierIt &a, const HierIt &b) {
+    const uint32_t na = hier_count(a), nb = hier_count(b);
+    switch (rel) {
+    case CB_HIER_ANCESTOROF: return nb > na && hier_common(a, b, na) == na;
+    case CB_HIER_DESCENDENTOF: return na > nb && hier_common(a, b, nb) == nb;
+    case CB_HIER_IMMEDIATEPARENTOF: return nb == na + 1 && hier_common(a, b, na) == na;
+    case CB_HIER_IMMEDIATECHILDOF: return na == nb + 1 && hier_common(a, b, nb) == nb;
+    case CB_HIER_SIBLINGOF: return na == nb && hier_common(a, b, na - 1) == na - 1;
+    case CB_HIER_OVERLAPS: { const uint32_t m = na < nb ? na : nb; return hier_common(a, b, m) == m; }
+    default: return na == nb && hier_common(a, b, na) == na;   // CB_HIER_EQUALS
+    }
+}
+CB_HD uint32_t hier_ca_size(const HierIt &a, const HierIt &b) {   // size of a.commonAncestors(b)
+    const uint32_t na = hier_count(a), nb = hier_count(b);
+    uint32_t m = na < nb ? na : nb;
+    if (na == nb) m = na - 1;
+    return hier_common(a, b, m);
+}
+// operand of a hierarchy op: a string, else error (list operands -- hierarchy(list) -- are not representable here)
+CB_HD bool hier_operand(Ctx &c, const Val &v) {
+    if (v.tag == CB_T_LIST) c.unsupported = 1;
+    return v.tag == CB_T_STRING;
+}
+
 // ---- RFC 3339 text -> int64 nanoseconds ----
 CB_HD int64_t days_from_civil(int64_t y, int m, int d) {
     y -= m <= 2;
@@ -1003,6 +1062,28 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
         case CB_OP_IN_SLOT_CONST: { int s; Val a = load_slot(c, ib, &s); st[sp++] = do_in(c, a, load_const(c, ic)); break; }
         case CB_OP_IN_CONST_SLOT: { int s; Val a = load_slot(c, ib, &s); st[sp++] = do_in(c, load_const(c, ic), a); break; }
         case CB_OP_IN_IP_RANGE: st[sp - 1] = st[sp - 1].tag == CB_T_ERR ? mk_err() : do_in_ip_range(c, st[sp - 1], c.t->theap() + ic); break;
+        case CB_OP_HIER_REL: {
+            sp--;
+            const bool ok = hier_operand(c, st[sp - 1]) & hier_operand(c, st[sp]);
+            st[sp - 1] = ok ? mk_bool(hier_rel(ia, hier_it(c, st[sp - 1].u, ib), hier_it(c, st[sp].u, ic))) : mk_err();
+            break;
+        }
+        case CB_OP_HIER_SIZE: st[sp - 1] = hier_operand(c, st[sp - 1]) ? mk_int((int64_t)hier_count(hier_it(c, st[sp - 1].u, ib))) : mk_err(); break;
+        case CB_OP_HIER_CA: {
+            if (ia == 0) {
+                sp--;
+                const bool ok = hier_operand(c, st[sp - 1]) & hier_operand(c, st[sp]);
+                st[sp - 1] = ok ? mk_int((int64_t)hier_ca_size(hier_it(c, st[sp - 1].u, ib), hier_it(c, st[sp].u, ic & 0xFFFF))) : mk_err();
+            } else {
+                sp -= 2;
+                const bool ok = hier_operand(c, st[sp - 1]) & hier_operand(c, st[sp]) & hier_operand(c, st[sp + 1]);
+                if (!ok) { st[sp - 1] = mk_err(); break; }
+                const HierIt a = hier_it(c, st[sp - 1].u, ib), b2 = hier_it(c, st[sp].u, ic & 0xFFFF), z = hier_it(c, st[sp + 1].u, ic >> 16);
+                const uint32_t k = hier_ca_size(a, b2);
+                st[sp - 1] = mk_bool(hier_count(z) == k && hier_common(a, z, k) == k);
+            }
+            break;
+        }
         default: c.unsupported = 1; return false;
         }
     }

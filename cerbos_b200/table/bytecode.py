@@ -567,6 +567,8 @@ class ProgramCompiler:
             self.patch(t, "b", end)
             self.patch(j, "c", end)
             return
+        if self._hier_call(fn, args):
+            return
         if fn == "_[_]" or fn in L.CMP_INDEX or fn == "@in":
             st = self._static(n) if fn == "_[_]" else None
             if st is not None:
@@ -641,6 +643,76 @@ class ProgramCompiler:
             self.emit("SUB", delta=-1)
             return
         raise Unsupported(f"function `{fn}` with {len(args)} argument(s)")
+
+    # ---- hierarchy(s[, delim]) (conditions/types/hierarchy.go): never a run-time value -- the functions over
+    # hierarchies compile to fused ops on the underlying strings
+    def _hier(self, n):
+        """-> (string expression, delimiter string id) if n is hierarchy(expr[, "delim"]), else None"""
+        if not (isinstance(n, Call) and n.fn == "hierarchy" and n.target is None and len(n.args) in (1, 2)):
+            return None
+        delim = "."
+        if len(n.args) == 2:
+            d = n.args[1]
+            if not (isinstance(d, Const) and isinstance(d.value, str) and d.value):
+                raise Unsupported("hierarchy() with a non-constant or empty delimiter")
+            delim = d.value
+        if isinstance(n.args[0], (ListLit, MapLit)):
+            raise Unsupported("hierarchy() of a list")
+        did = self.ctx.strings.intern(delim)
+        if did > 0xFFFF:
+            raise Unsupported("too many table strings for a hierarchy delimiter")
+        return n.args[0], did
+
+    def _hier_ca(self, n):
+        """-> ((s, ds), (t, dt)) if n is hierarchy(..).commonAncestors(hierarchy(..))"""
+        if isinstance(n, Call) and n.fn == "commonAncestors" and n.target is not None and len(n.args) == 1:
+            a, b = self._hier(n.target), self._hier(n.args[0])
+            if a and b:
+                return a, b
+        return None
+
+    def _hier_call(self, fn, args) -> bool:
+        if fn in L.HIER_RELS and fn != "equals" and len(args) == 2:
+            a, b = self._hier(args[0]), self._hier(args[1])
+            if not (a and b):
+                return False
+            self.expr(a[0])
+            self.expr(b[0])
+            self.emit("HIER_REL", a=L.HIER_RELS[fn], b=a[1], c=b[1], delta=-1)
+            return True
+        if fn in ("_==_", "_!=_") and len(args) == 2:
+            for x, y in ((args[0], args[1]), (args[1], args[0])):
+                ca, hz = self._hier_ca(x), self._hier(y)
+                if ca and hz:
+                    self.expr(ca[0][0])
+                    self.expr(ca[1][0])
+                    self.expr(hz[0])
+                    self.emit("HIER_CA", a=1, b=ca[0][1], c=ca[1][1] | (hz[1] << 16), delta=-2)
+                    if fn == "_!=_":
+                        self.emit("NOT")
+                    return True
+            a, b = self._hier(args[0]), self._hier(args[1])
+            if a and b:
+                self.expr(a[0])
+                self.expr(b[0])
+                self.emit("HIER_REL", a=L.HIER_RELS["equals"], b=a[1], c=b[1], delta=-1)
+                if fn == "_!=_":
+                    self.emit("NOT")
+                return True
+            return False
+        if fn == "size" and len(args) == 1:
+            ca = self._hier_ca(args[0])
+            if ca:
+                self.expr(ca[0][0])
+                self.expr(ca[1][0])
+                self.emit("HIER_CA", a=0, b=ca[0][1], c=ca[1][1], delta=-1)
+                return True
+            h = self._hier(args[0])
+            if h:
+                self.expr(h[0])
+                self.emit("HIER_SIZE", b=h[1])
+                return True
+        return False
 
     def _macro(self, n: Macro):
         kinds = {"all": (L.LOOP_ALL, 1), "exists": (L.LOOP_EXISTS, 1), "exists_one": (L.LOOP_EXISTS_ONE, 1),

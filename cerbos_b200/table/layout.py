@@ -12,7 +12,7 @@ Table blob (little endian, every section 16-byte aligned):
 from __future__ import annotations
 
 MAGIC = 0x32425243  # 'CRB2'
-VERSION = 8
+VERSION = 9
 ALIGN = 16
 
 NONE32 = 0xFFFFFFFF
@@ -132,7 +132,13 @@ OPS = {name: i for i, name in enumerate([
     "IN_SLOT_CONST",    # push slot[b] in consts[c]
     "IN_CONST_SLOT",    # push consts[c] in slot[b]
     "IN_IP_RANGE",      # TOS string ip -> BOOL(ip in CIDR at theap[c..c+3] = {family 4|6, prefix bits, hi64, lo64})
+    # hierarchy(s[, delim]) values never materialise: the functions over them are fused (conditions/types/hierarchy.go)
+    "HIER_REL",         # [s, t] strings -> BOOL: a = HIER_* relation of hierarchy(s, delim b) with hierarchy(t, delim c)
+    "HIER_SIZE",        # [s] -> INT segments of hierarchy(s, delim b)
+    "HIER_CA",          # a = 0: [s, t] -> INT size of s.commonAncestors(t); a = 1: [s, t, z] -> BOOL(commonAncestors == hierarchy(z));
+                        #        delimiters b (s), c & 0xFFFF (t), c >> 16 (z)
 ])}
+HIER_RELS = {name: i for i, name in enumerate(["ancestorOf", "descendentOf", "immediateChildOf", "immediateParentOf", "siblingOf", "overlaps", "equals"])}
 
 # Flat fast-path conditions: a condition in disjunctive normal form over "terms".  A term is 16 bytes (two CODE
 # slots): {u8 op; u8 flags; u8 xk; u8 yk; u32 x; u32 y; u16 xa; u16 ya}.  Its value is tri-state (true / false /
@@ -220,6 +226,8 @@ def c_header() -> str:
     for k, v in OPS.items():
         d(f"CB_OP_{k}", v)
     d("CB_N_OPS", len(OPS))
+    for k, v in HIER_RELS.items():
+        d(f"CB_HIER_{k.upper()}", v)
     out.append("")
     d("CB_FLAT_DNF", FLAT_DNF)
     for k, v in TERM_OPS.items():

@@ -442,6 +442,76 @@ static val_t do_str2(ectx_t *c, int op, val_t s, val_t t) {
     return mk_bool(0);
 }
 
+/* ---- hierarchy(s, delim): conditions/types/hierarchy.go:146-410.  Restated the way the reference does it: split into
+ * segments (strings.Split), then compare the segment lists. ---- */
+#define HIER_MAX_SEG 256
+typedef struct { const uint8_t *p[HIER_MAX_SEG]; uint32_t l[HIER_MAX_SEG]; uint32_t n; } hier_t;
+static int hier_split(ectx_t *c, val_t v, uint32_t delim_id, hier_t *h) {
+    if (v.tag != CB_T_STRING) { if (v.tag == CB_T_LIST) c->unsupported = 1; return 0; }   /* hierarchy(list): not lowered */
+    const uint8_t *s, *d; uint32_t ls, ld;
+    str_get(c, v.u, &s, &ls); str_get(c, delim_id, &d, &ld);
+    h->n = 0;
+    uint32_t start = 0, i = 0;
+    while (i + ld <= ls) {
+        if (memcmp(s + i, d, ld) == 0) {
+            if (h->n >= HIER_MAX_SEG - 1) { c->unsupported = 1; return 0; }
+            h->p[h->n] = s + start; h->l[h->n] = i - start; h->n++;
+            i += ld; start = i;
+        } else i++;
+    }
+    h->p[h->n] = s + start; h->l[h->n] = ls - start; h->n++;
+    return 1;
+}
+static int hier_seg_eq(const hier_t *a, uint32_t i, const hier_t *b, uint32_t j) { return a->l[i] == b->l[j] && memcmp(a->p[i], b->p[j], a->l[i]) == 0; }
+static int hier_ancestor_of(const hier_t *h, const hier_t *child) {          /* hierarchy.go:283-299 */
+    if (child->n <= h->n) return 0;
+    for (uint32_t i = 0; i < h->n; i++) if (!hier_seg_eq(child, i, h, i)) return 0;
+    return 1;
+}
+static int hier_immediate_parent_of(const hier_t *h, const hier_t *child) {  /* :343-359 */
+    if (child->n != h->n + 1) return 0;
+    for (uint32_t i = 0; i < h->n; i++) if (!hier_seg_eq(child, i, h, i)) return 0;
+    return 1;
+}
+static uint32_t hier_common_ancestors(const hier_t *h, const hier_t *o) {    /* :301-326 -> number of ancestors (a prefix of either) */
+    const hier_t *sh = h, *lo = o;
+    if (o->n < h->n) { lo = h; sh = o; }
+    uint32_t ns = sh->n, nl = lo->n;
+    if (nl == ns) { nl--; ns--; }
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < ns; i++) { if (!hier_seg_eq(lo, i, sh, i)) break; k++; }
+    (void)nl;
+    return k;
+}
+static val_t do_hier_rel(ectx_t *c, uint32_t rel, val_t x, uint32_t dx, val_t y, uint32_t dy) {
+    static __thread hier_t a, b;
+    int ok = hier_split(c, x, dx, &a);
+    ok &= hier_split(c, y, dy, &b);
+    if (!ok) return mk_err();
+    switch (rel) {
+    case CB_HIER_ANCESTOROF: return mk_bool(hier_ancestor_of(&a, &b));
+    case CB_HIER_DESCENDENTOF: return mk_bool(hier_ancestor_of(&b, &a));                /* :328-335 */
+    case CB_HIER_IMMEDIATEPARENTOF: return mk_bool(hier_immediate_parent_of(&a, &b));
+    case CB_HIER_IMMEDIATECHILDOF: return mk_bool(hier_immediate_parent_of(&b, &a));     /* :337-341 */
+    case CB_HIER_SIBLINGOF: {                                                             /* :361-377 */
+        if (a.n != b.n) return mk_bool(0);
+        for (uint32_t i = 0; i + 1 < a.n; i++) if (!hier_seg_eq(&a, i, &b, i)) return mk_bool(0);
+        return mk_bool(1);
+    }
+    case CB_HIER_OVERLAPS: {                                                              /* :379-397 */
+        const hier_t *sh = &a, *lo = &b;
+        if (b.n < a.n) { lo = &a; sh = &b; }
+        for (uint32_t i = 0; i < sh->n; i++) if (!hier_seg_eq(lo, i, sh, i)) return mk_bool(0);
+        return mk_bool(1);
+    }
+    default: {                                                                            /* Equal, :231-248 */
+        if (a.n != b.n) return mk_bool(0);
+        for (uint32_t i = 0; i < a.n; i++) if (!hier_seg_eq(&a, i, &b, i)) return mk_bool(0);
+        return mk_bool(1);
+    }
+    }
+}
+
 /* ---- RFC 3339 -> ns ---- */
 static int64_t days_from_civil(int64_t y, int m, int d) {
     y -= m <= 2;
@@ -769,6 +839,24 @@ static val_t run_program(ectx_t *c, const cb_instr *code, int64_t now) {
         case CB_OP_IN_SLOT_CONST: { int s; val_t a = load_slot(c, in.b, &s); cb_const k = c->t->consts[in.c]; st[sp++] = do_in(c, a, mk(k.tag, k.bits)); break; }
         case CB_OP_IN_CONST_SLOT: { int s; val_t a = load_slot(c, in.b, &s); cb_const k = c->t->consts[in.c]; st[sp++] = do_in(c, mk(k.tag, k.bits), a); break; }
         case CB_OP_IN_IP_RANGE: st[sp - 1] = st[sp - 1].tag == CB_T_ERR ? mk_err() : do_in_ip_range(c, st[sp - 1], c->t->theap + in.c); break;
+        case CB_OP_HIER_REL: sp--; st[sp - 1] = do_hier_rel(c, in.a, st[sp - 1], in.b, st[sp], in.c); break;
+        case CB_OP_HIER_SIZE: { static __thread hier_t h; st[sp - 1] = hier_split(c, st[sp - 1], in.b, &h) ? mk(CB_T_INT, h.n) : mk_err(); break; }
+        case CB_OP_HIER_CA: {
+            static __thread hier_t a, b, z;
+            if (in.a == 0) {
+                sp--;
+                int ok = hier_split(c, st[sp - 1], in.b, &a); ok &= hier_split(c, st[sp], in.c & 0xFFFF, &b);
+                st[sp - 1] = ok ? mk(CB_T_INT, hier_common_ancestors(&a, &b)) : mk_err();
+            } else {
+                sp -= 2;
+                int ok = hier_split(c, st[sp - 1], in.b, &a); ok &= hier_split(c, st[sp], in.c & 0xFFFF, &b); ok &= hier_split(c, st[sp + 1], in.c >> 16, &z);
+                if (!ok) { st[sp - 1] = mk_err(); break; }
+                uint32_t k = hier_common_ancestors(&a, &b), eq = z.n == k;
+                for (uint32_t i = 0; eq && i < k; i++) eq = hier_seg_eq(&a, i, &z, i);
+                st[sp - 1] = mk_bool(eq);
+            }
+            break;
+        }
         default: c->unsupported = 1; return mk_err();
         }
     }
