@@ -17,7 +17,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE = 0, -1, -2, -3, -4
 EXPORTS = [
     "cgpu_init", "cgpu_shutdown", "cgpu_table_load", "cgpu_table_retain", "cgpu_table_release", "cgpu_check",
     "cgpu_check_device", "cgpu_sync", "cgpu_launch_count", "cgpu_table_info", "cgpu_last_kernel_config",
-    "cgpu_last_cluster_config", "cgpu_profile", "cgpu_table_wait_ready", "cgpu_peer_alloc", "cgpu_peer_open", "cgpu_peer_close",
+    "cgpu_last_cluster_config", "cgpu_profile", "cgpu_table_wait_ready", "cgpu_table_compile_check", "cgpu_peer_alloc", "cgpu_peer_open", "cgpu_peer_close",
     "cgpu_peer_free", "cgpu_peer_read", "cgpu_check_device_gather", "cgpu_gather_wait", "cgpu_last_error",
 ]
 
@@ -78,6 +78,8 @@ def lib():
         L.cgpu_last_cluster_config.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_uint32)] * 3
         L.cgpu_profile.restype = ctypes.c_int
         L.cgpu_profile.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
+        L.cgpu_table_compile_check.restype = ctypes.c_int
+        L.cgpu_table_compile_check.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
         L.cgpu_table_wait_ready.restype = ctypes.c_int
         L.cgpu_table_wait_ready.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
         for name, args in (("cgpu_peer_alloc", [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
@@ -97,6 +99,15 @@ def lib():
 def _check(rc):
     if rc != OK:
         raise CgpuError(rc, lib().cgpu_last_error().decode("utf-8", "replace"))
+
+
+def compile_check(blob: bytes):
+    """Generates and NVRTC-compiles the table-specialised kernels for `blob` without touching a device.
+    -> (cubin bytes, note): 0 bytes when the table does not qualify."""
+    n = ctypes.c_size_t()
+    buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
+    _check(lib().cgpu_table_compile_check(buf, len(blob), ctypes.byref(n)))
+    return n.value, (lib().cgpu_last_error().decode("utf-8", "replace") if n.value == 0 else "ok")
 
 
 class Context:

@@ -377,20 +377,14 @@ const char kSpecKernels[] =
     "    cbk::check_body<true, 1, cb::SpecBlocks>(td, bv, bitmap, effects, status, stage_rt, smem_image, &mbar);\n"
     "}\n";
 
-// Generates, compiles and loads the table's specialised kernels (once; thread-safe). Returns whether they are usable.
-bool ensure_spec(cgpu_ctx *ctx, cgpu_table *t) {
-    int st = t->spec_state.load(std::memory_order_acquire);
-    if (st != 0) return st > 0;
-    std::lock_guard<std::mutex> g(t->spec_mu);
-    st = t->spec_state.load(std::memory_order_acquire);
-    if (st != 0) return st > 0;
-    auto give_up = [&](const std::string &why) { t->spec_note = why; t->spec_state.store(-1, std::memory_order_release); return false; };
-    if (ctx->force_no_jit) return give_up("disabled (CERBOS_B200_NO_JIT)");
-    if (t->desc.lay.image_bytes > kMaxStageBytes) return give_up("table image too large for shared memory");
+// Generates the table's specialised translation unit and compiles it with NVRTC (no CUDA runtime call: also works on
+// a host without a GPU).  false + *why when the table does not qualify or something is unavailable.
+bool spec_compile(const uint8_t *image, const cb::TableLayout &lay, const uint32_t *meta, std::vector<char> *cubin, std::string *why) {
+    if (lay.image_bytes > kMaxStageBytes) { *why = "table image too large for shared memory"; return false; }
     Nvrtc &n = nvrtc();
-    if (!n.ok) return give_up("libnvrtc not available");
-    const std::string gen = cbspec::generate(t->host_image.data(), t->desc.lay.off, t->meta);
-    if (gen.empty()) return give_up("table does not qualify (a condition without flat form, or too many block shapes)");
+    if (!n.ok) { *why = "libnvrtc not available"; return false; }
+    const std::string gen = cbspec::generate(image, lay.off, meta);
+    if (gen.empty()) { *why = "table does not qualify (a condition without flat form, or too many block shapes)"; return false; }
     std::string src = kSpecPrelude;
     for (const char *const *p = kEmbedFormat; *p; p++) src += *p;
     for (const char *const *p = kEmbedCore; *p; p++) src += *p;
@@ -398,7 +392,7 @@ bool ensure_spec(cgpu_ctx *ctx, cgpu_table *t) {
     for (const char *const *p = kEmbedKernels; *p; p++) src += *p;
     src += kSpecKernels;
     void *prog = nullptr;
-    if (n.create(&prog, src.c_str(), "cerbos_b200_spec.cu", 0, nullptr, nullptr) != 0) return give_up("nvrtcCreateProgram failed");
+    if (n.create(&prog, src.c_str(), "cerbos_b200_spec.cu", 0, nullptr, nullptr) != 0) { *why = "nvrtcCreateProgram failed"; return false; }
     const char *mb = getenv("CERBOS_B200_SPEC_BLOCKS");   // experiments: resident CTAs / SM the specialised kernels are budgeted for
     const std::string mbopt = std::string("-DCB_SPEC_MIN_BLOCKS=") + (mb && mb[0] >= '1' && mb[0] <= '8' && !mb[1] ? mb : "5");
     const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", mbopt.c_str()};
@@ -409,13 +403,29 @@ bool ensure_spec(cgpu_ctx *ctx, cgpu_table *t) {
         std::string log(ls, '\0');
         if (ls) n.log(prog, &log[0]);
         n.destroy(&prog);
-        return give_up("NVRTC compile failed: " + log.substr(0, 400));
+        *why = "NVRTC compile failed: " + log.substr(0, 600);
+        return false;
     }
     size_t cs = 0;
     n.cubin_size(prog, &cs);
-    std::vector<char> cubin(cs);
-    n.cubin(prog, cubin.data());
+    cubin->resize(cs);
+    n.cubin(prog, cubin->data());
     n.destroy(&prog);
+    return true;
+}
+
+// Compiles and loads the table's specialised kernels (once; thread-safe). Returns whether they are usable.
+bool ensure_spec(cgpu_ctx *ctx, cgpu_table *t) {
+    int st = t->spec_state.load(std::memory_order_acquire);
+    if (st != 0) return st > 0;
+    std::lock_guard<std::mutex> g(t->spec_mu);
+    st = t->spec_state.load(std::memory_order_acquire);
+    if (st != 0) return st > 0;
+    auto give_up = [&](const std::string &why) { t->spec_note = why; t->spec_state.store(-1, std::memory_order_release); return false; };
+    if (ctx->force_no_jit) return give_up("disabled (CERBOS_B200_NO_JIT)");
+    std::vector<char> cubin;
+    std::string why;
+    if (!spec_compile(t->host_image.data(), t->desc.lay, t->meta, &cubin, &why)) return give_up(why);
     if (cudaLibraryLoadData(&t->spec_lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) { cudaGetLastError(); return give_up("cudaLibraryLoadData failed"); }
     if (cudaLibraryGetKernel(&t->spec_tiles, t->spec_lib, "cb_spec_tiles") != cudaSuccess ||
         cudaLibraryGetKernel(&t->spec_direct, t->spec_lib, "cb_spec_direct") != cudaSuccess) {
@@ -721,6 +731,23 @@ void cgpu_table_release(cgpu_table *t) {
         if (t->spec_lib) cudaLibraryUnload(t->spec_lib);
         delete t;
     }
+}
+
+int cgpu_table_compile_check(const void *blob, size_t len, size_t *cubin_bytes) {
+    if (!blob || !cubin_bytes) return fail(CGPU_ERR_INVALID, "cgpu_table_compile_check: null argument");
+    *cubin_bytes = 0;
+    TableDesc d;
+    uint32_t meta[CB_META_WORDS];
+    int rc = parse_blob(blob, len, &d, meta);
+    if (rc != CGPU_OK) return rc;
+    std::vector<char> cubin;
+    std::string why;
+    if (!spec_compile(static_cast<const uint8_t *>(blob), d.lay, meta, &cubin, &why)) {
+        g_err = why;
+        return why.rfind("NVRTC compile failed", 0) == 0 ? CGPU_ERR_CUDA : CGPU_OK;   // not qualifying is not an error
+    }
+    *cubin_bytes = cubin.size();
+    return CGPU_OK;
 }
 
 int cgpu_table_wait_ready(cgpu_table *t, int *specialised) {

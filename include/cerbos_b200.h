@@ -107,6 +107,9 @@ int cgpu_sync(cgpu_ctx *ctx, void *cuda_stream);
  * ahead-of-time generic kernels until it is done. This call does wait; *specialised = 1 if such kernels are in use
  * (otherwise cgpu_last_error() says why not). */
 int cgpu_table_wait_ready(cgpu_table *t, int *specialised);
+/* Generation + NVRTC compilation only, no device needed (build / CI check of the run-time path): *cubin_bytes = size of
+ * the compiled module, 0 if the table does not qualify (cgpu_last_error() says why). */
+int cgpu_table_compile_check(const void *blob, size_t len, size_t *cubin_bytes);
 
 /* ---- Fused all-gather of the decision bitmaps over NVLink peer memory (one process per GPU on one node) --------
  * Every rank allocates a gather buffer of n_ranks * slice_bytes and a flag array with cgpu_peer_alloc, publishes the

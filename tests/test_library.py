@@ -35,3 +35,16 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, fn), encoding="utf-8").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dirpath, fn)
                 assert "check_ref" not in src, os.path.join(dirpath, fn)
+
+
+def test_runtime_specialisation_compiles_without_a_device():
+    """The table-specialised translation unit the library hands to NVRTC at table load (embedded cb_core.h / cb_kernels.h +
+    generated block evaluators) compiles for sm_100a here, without a GPU; tables that do not qualify say why."""
+    from cerbos_b200 import capi, workloads as W
+    for name, qualifies in (("C1", True), ("C2", True), ("C3", False)):
+        _, ft, _ = W.build(W.WORKLOADS[name]())
+        n, note = capi.compile_check(ft.blob)
+        if qualifies:
+            assert n > 10000 and note == "ok", (name, n, note)
+        else:
+            assert n == 0 and "does not qualify" in note, (name, n, note)
