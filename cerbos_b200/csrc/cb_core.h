@@ -1068,6 +1068,20 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
             st[sp - 1] = ok ? mk_bool(hier_rel(ia, hier_it(c, st[sp - 1].u, ib), hier_it(c, st[sp].u, ic))) : mk_err();
             break;
         }
+        case CB_OP_IN_SPLIT: {   // [x, s]: x in s.split(delim ib)
+            sp--;
+            const Val x = st[sp - 1], sv = st[sp];
+            if (x.tag == CB_T_ERR || sv.tag != CB_T_STRING) { st[sp - 1] = mk_err(); break; }
+            bool found = false;
+            if (x.tag == CB_T_STRING) {
+                const uint8_t *px; uint32_t lx, s0, l0;
+                str_get(c, x.u, px, lx);
+                HierIt it = hier_it(c, sv.u, ib);
+                while (hier_next(it, &s0, &l0)) found |= l0 == lx && bytes_eq(it.p + s0, px, lx);
+            }
+            st[sp - 1] = mk_bool(found);
+            break;
+        }
         case CB_OP_HIER_SIZE: st[sp - 1] = hier_operand(c, st[sp - 1]) ? mk_int((int64_t)hier_count(hier_it(c, st[sp - 1].u, ib))) : mk_err(); break;
         case CB_OP_HIER_CA: {
             if (ia == 0) {

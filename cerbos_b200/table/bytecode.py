@@ -569,6 +569,17 @@ class ProgramCompiler:
             return
         if self._hier_call(fn, args):
             return
+        if fn == "@in" and len(args) == 2 and isinstance(args[1], Call) and args[1].fn == "split" and args[1].target is not None \
+                and len(args[1].args) == 1 and isinstance(args[1].args[0], Const) and isinstance(args[1].args[0].value, str) \
+                and args[1].args[0].value:
+            # x in s.split("sep"): membership among the separated tokens, fused (the list is never built)
+            did = self.ctx.strings.intern(args[1].args[0].value)
+            if did > 0xFFFF:
+                raise Unsupported("too many table strings for a split separator")
+            self.expr(args[0])
+            self.expr(args[1].target)
+            self.emit("IN_SPLIT", b=did, delta=-1)
+            return
         if fn == "_[_]" or fn in L.CMP_INDEX or fn == "@in":
             st = self._static(n) if fn == "_[_]" else None
             if st is not None:

@@ -12,7 +12,7 @@ Table blob (little endian, every section 16-byte aligned):
 from __future__ import annotations
 
 MAGIC = 0x32425243  # 'CRB2'
-VERSION = 9
+VERSION = 10
 ALIGN = 16
 
 NONE32 = 0xFFFFFFFF
@@ -137,6 +137,7 @@ OPS = {name: i for i, name in enumerate([
     "HIER_SIZE",        # [s] -> INT segments of hierarchy(s, delim b)
     "HIER_CA",          # a = 0: [s, t] -> INT size of s.commonAncestors(t); a = 1: [s, t, z] -> BOOL(commonAncestors == hierarchy(z));
                         #        delimiters b (s), c & 0xFFFF (t), c >> 16 (z)
+    "IN_SPLIT",         # [x, s] -> BOOL(x in s.split(delim b)): the token list never materialises (ext strings split)
 ])}
 HIER_RELS = {name: i for i, name in enumerate(["ancestorOf", "descendentOf", "immediateChildOf", "immediateParentOf", "siblingOf", "overlaps", "equals"])}
 

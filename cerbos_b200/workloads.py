@@ -488,7 +488,135 @@ class C3:
         return 24 + 4 * 3 + 8 * 12 + 64 + 1   # = 197
 
 
-WORKLOADS = {"C1": C1, "C2": C2, "C3": C3}
+
+class C5:
+    """Adversarial (BASELINE.json configs[4]): 1000 resource policies = 200 kinds x 5 scopes, 8 actions each, deep CEL --
+    nested all/any/none trees, ternaries, map indexing with a dynamic key, two-variable comprehensions over maps,
+    JWT claims from auxData (list membership, `in ... .split(" ")`, `timestamp(claim) > now()`), variables that
+    reference variables -- Zipf(1.1)-skewed resource kinds.  Parity-test configuration: requests go through the
+    generic encoder (no vectorised column builder), sizes of a few thousand."""
+    name = "C5"
+    cfg = 5
+    actions = [f"a{i}" for i in range(8)]
+    role_names = ["user", "manager", "admin", "auditor"]
+    scopes = ["", "t0", "t1", "t0.d0", "t1.d0"]
+    req_scopes = ["", "t0", "t1", "t0.d0", "t1.d0", "t0.d9"]
+    tiers = ["gold", "silver", "bronze"]
+    n_kinds = 200
+    default_n = 1 << 26
+    role_cols = 4
+    leafs = [
+        'R.attr.meta.tags[P.attr.tier] in ["hot", "warm"]',
+        'P.attr.grants.exists(k, v, k == R.kind && "write" in v)',
+        '"svc" in request.aux_data.jwt.aud',
+        '"deploy" in request.aux_data.jwt.scope.split(" ")',
+        'timestamp(request.aux_data.jwt.exp_ts) > now()',
+        'V.is_internal && V.senior',
+        'P.attr.level > 5 ? R.attr.meta.owner == P.id : R.attr.public == true',
+        'request.aux_data.jwt.tier == P.attr.tier',
+        'R.attr.meta.region in P.attr.regions',
+        'size(P.attr.regions) > 1 || request.aux_data.jwt.iss == "https://issuer.example"',
+        'has(R.attr.meta.owner) && R.attr.meta.owner != ""',
+        'P.attr.level >= R.attr.min_level',
+    ]
+    regions = ["eu", "us", "apac", "latam"]
+
+    def _tree(self, k, j, si):
+        """condition tree of rule j of policy (kind k, scope si): depth-3 nests every third rule"""
+        L_ = self.leafs
+        a, b, c, d = (L_[(k + j * 3 + si + q) % len(L_)] for q in range(4))
+        if j % 3 == 0:
+            return {"all": {"of": [{"any": {"of": [{"expr": a}, {"none": {"of": [{"expr": b}]}}]}}, {"none": {"of": [{"all": {"of": [{"expr": c}, {"expr": d}]}}]}}]}}
+        if j % 3 == 1:
+            return {"any": {"of": [{"expr": a}, {"all": {"of": [{"expr": b}, {"expr": c}]}}]}}
+        return {"expr": a}
+
+    def policies(self):
+        docs = []
+        for k in range(self.n_kinds):
+            for si, sc in enumerate(self.scopes):
+                rules = []
+                for j in range(8):
+                    rule = {"actions": [f"a{j}"], "effect": "EFFECT_ALLOW", "roles": [self.role_names[(j + k + si) % 4]]}
+                    if (j + si + k) % 5 != 0:
+                        rule["condition"] = {"match": self._tree(k, j, si)}
+                    rules.append(rule)
+                rules.append({"actions": ["*"], "effect": "EFFECT_DENY", "roles": ["*"],
+                              "condition": {"match": {"expr": 'request.aux_data.jwt.tier == "banned"'}}})
+                rp = {"resource": f"kind_{k}", "version": "default", "rules": rules,
+                      "variables": {"local": {"is_internal": 'request.aux_data.jwt.iss == "https://issuer.example"',
+                                              "senior": "V.is_internal && P.attr.level >= 7"}}}
+                if sc:
+                    rp["scope"] = sc
+                if sc.endswith(".d0"):
+                    rp["scopePermissions"] = "SCOPE_PERMISSIONS_REQUIRE_PARENTAL_CONSENT_FOR_ALLOWS"
+                docs.append({"apiVersion": "api.cerbos.dev/v1", "resourcePolicy": rp})
+        return docs
+
+    def fields(self, n=None, start=0):
+        global _START
+        n = n or 4096
+        seed = SEED_BASE + self.cfg
+        _START = start
+        try:
+            # Zipf(s = 1.1) over the kinds by inverse CDF on a uniform draw
+            w = 1.0 / np.arange(1, self.n_kinds + 1) ** 1.1
+            cdf = np.cumsum(w) / w.sum()
+            u = (splitmix(seed, n, 0) >> np.uint64(11)).astype(np.float64) * (1.0 / (1 << 53))
+            r0 = _uniform(seed, n, 2, 4)
+            nr = 1 + _uniform(seed, n, 3, 4)
+            return {
+                "n": n, "kind": np.minimum(np.searchsorted(cdf, u), self.n_kinds - 1), "pid": _uniform(seed, n, 1, 4096),
+                "roles": [[self.role_names[(int(r0[i]) + q) % 4] for q in range(int(nr[i]))] for i in range(n)],
+                "scope": np.where(_prob(seed, n, 5, 0.05), 5, _uniform(seed, n, 4, 5)),
+                "tier": _uniform(seed, n, 6, 3), "jtier": _uniform(seed, n, 7, 4), "level": _uniform(seed, n, 8, 10),
+                "min_level": _uniform(seed, n, 9, 10), "nreg": 1 + _uniform(seed, n, 10, 3), "reg0": _uniform(seed, n, 11, 4),
+                "mreg": _uniform(seed, n, 12, 4), "own": _prob(seed, n, 13, 0.3), "public": _prob(seed, n, 14, 0.5),
+                "tagsel": _uniform(seed, n, 15, 4), "grant": _uniform(seed, n, 16, 4), "aud": 1 + _uniform(seed, n, 17, 3),
+                "svc": _prob(seed, n, 18, 0.5), "deploy": _prob(seed, n, 19, 0.5), "expired": _prob(seed, n, 20, 0.3),
+                "iss": _prob(seed, n, 21, 0.7),
+            }
+        finally:
+            _START = 0
+
+    def inputs(self, f, idx):
+        out = []
+        heat = ["hot", "warm", "cold", "frozen"]
+        for i in idx:
+            pid = f"p{f['pid'][i]}"
+            kind = f"kind_{f['kind'][i]}"
+            tier = self.tiers[f["tier"][i]]
+            gk = [kind, f"kind_{(f['kind'][i] + 1) % self.n_kinds}", "other", "misc"][f["grant"][i]]
+            meta = {"tags": {t: heat[(f["tagsel"][i] + q) % 4] for q, t in enumerate(self.tiers[: 1 + f["tagsel"][i] % 3])},
+                    "region": self.regions[f["mreg"][i]]}
+            if f["tagsel"][i] != 3:
+                meta["owner"] = pid if f["own"][i] else "p-someone"
+            aud = (["svc"] if f["svc"][i] else []) + [f"aud{q}" for q in range(f["aud"][i])]
+            jwt = {"iss": "https://issuer.example" if f["iss"][i] else "https://other.example", "aud": aud, "sub": pid,
+                   "scope": " ".join((["deploy"] if f["deploy"][i] else []) + ["read", "list"]),
+                   "tier": (self.tiers + ["banned"])[f["jtier"][i]],
+                   "exp_ts": "2020-01-01T00:00:00Z" if f["expired"][i] else "2031-06-01T12:00:00Z"}
+            req = {"requestId": str(i), "actions": list(self.actions),
+                   "principal": {"id": pid, "roles": list(f["roles"][i]),
+                                 "attr": {"tier": tier, "level": int(f["level"][i]),
+                                          "regions": [self.regions[(f["reg0"][i] + q) % 4] for q in range(f["nreg"][i])],
+                                          "grants": {gk: ["read", "write"] if f["grant"][i] % 2 == 0 else ["read"], "zzz": ["write"]}}},
+                   "resource": {"kind": kind, "id": f"r{i}", "attr": {"meta": meta, "public": bool(f["public"][i]), "min_level": int(f["min_level"][i])}},
+                   "auxData": {"jwt": jwt}}
+            sc = self.req_scopes[f["scope"][i]]
+            if sc:
+                req["resource"]["scope"] = sc
+            out.append(req)
+        return out
+
+    def columns(self, f, enc: Encoder) -> Batch:
+        return enc.encode(self.inputs(f, range(f["n"])))
+
+    def bytes_per_request(self):
+        return 489   # SURVEY.md 8(d): 24 + 4*4 + 8*24 + 256 + 1
+
+
+WORKLOADS = {"C1": C1, "C2": C2, "C3": C3, "C5": C5}
 
 
 def build(workload, globals_=None):

@@ -840,6 +840,20 @@ static val_t run_program(ectx_t *c, const cb_instr *code, int64_t now) {
         case CB_OP_IN_CONST_SLOT: { int s; val_t a = load_slot(c, in.b, &s); cb_const k = c->t->consts[in.c]; st[sp++] = do_in(c, mk(k.tag, k.bits), a); break; }
         case CB_OP_IN_IP_RANGE: st[sp - 1] = st[sp - 1].tag == CB_T_ERR ? mk_err() : do_in_ip_range(c, st[sp - 1], c->t->theap + in.c); break;
         case CB_OP_HIER_REL: sp--; st[sp - 1] = do_hier_rel(c, in.a, st[sp - 1], in.b, st[sp], in.c); break;
+        case CB_OP_IN_SPLIT: {   /* x in s.split(sep): ext strings split + the `in` operator over the token list */
+            static __thread hier_t toks;
+            sp--;
+            val_t x = st[sp - 1], sv = st[sp];
+            if (x.tag == CB_T_ERR || sv.tag != CB_T_STRING || !hier_split(c, sv, in.b, &toks)) { st[sp - 1] = mk_err(); break; }
+            int found = 0;
+            if (x.tag == CB_T_STRING) {
+                const uint8_t *px; uint32_t lx;
+                str_get(c, x.u, &px, &lx);
+                for (uint32_t i = 0; i < toks.n; i++) if (toks.l[i] == lx && memcmp(toks.p[i], px, lx) == 0) found = 1;
+            }
+            st[sp - 1] = mk_bool(found);
+            break;
+        }
         case CB_OP_HIER_SIZE: { static __thread hier_t h; st[sp - 1] = hier_split(c, st[sp - 1], in.b, &h) ? mk(CB_T_INT, h.n) : mk_err(); break; }
         case CB_OP_HIER_CA: {
             static __thread hier_t a, b, z;

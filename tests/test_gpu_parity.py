@@ -315,3 +315,24 @@ def test_specialised_kernel_defers_to_general_kernel():
         t.release()
         c.close()
     os.environ.pop("CERBOS_B200_NO_JIT", None)
+
+
+def test_workload_c5_adversarial(ctx):
+    """BASELINE.json configs[4] (1000 policies, deep CEL, JWT claims, Zipf kinds): table image > 96 KB (read from global
+    memory, not staged), most blocks carry conditions without a flat form (general body), fused hierarchy-free string ops."""
+    from cerbos_b200 import workloads as W
+    from cerbos_b200.device import DeviceBatch
+    from oracle import cref
+    w = W.C5()
+    _, ft, enc = W.build(w)
+    f = w.fields(4096)
+    b = enc.encode(w.inputs(f, range(f["n"])))
+    want = cref.check(ft.blob, b.columns, b.n, b.max_actions, NOW_NS, n_threads=os.cpu_count() or 1)
+    table = ctx.load_table(ft.blob)
+    db = DeviceBatch(b, "cuda:0")
+    db.run(table, NOW_NS)
+    ctx.sync()
+    assert (db.effects() == want).all()
+    assert (table.check(b.columns, b.n, b.max_actions, NOW_NS) == want).all()
+    assert ctx.last_kernel_config()["smem_bytes"] == 0      # too large to stage
+    table.release()

@@ -204,3 +204,22 @@ def test_hierarchy_functions_on_attributes():
     assert allow > 200
     for mode in (0, 1):
         assert (hostsim.check(ft.blob, b.columns, b.n, b.max_actions, mode=mode) == c_out).all(), mode
+
+
+def test_workload_c5_adversarial():
+    """BASELINE.json configs[4]: 1000 policies, deep CEL (nested trees, ternaries, dynamic map keys, 2-variable
+    comprehensions over maps, JWT claims, `in ... .split()`, timestamps vs now(), chained variables), Zipf kinds."""
+    w = W.C5()
+    rt, ft, enc = W.build(w)
+    f = w.fields(1536)
+    inputs = w.inputs(f, range(f["n"]))
+    b = enc.encode(inputs)
+    c_out = cref.check(ft.blob, b.columns, b.n, b.max_actions, NOW.ns, n_threads=4)
+    assert 0.2 < (c_out == 1).mean() < 0.7
+    for mode in (0, 1, 2):
+        assert (hostsim.check(ft.blob, b.columns, b.n, b.max_actions, NOW.ns, mode=mode) == c_out).all(), mode
+    orc = CheckOracle(rt)
+    for j in range(0, f["n"], 8):
+        g = orc.check(inputs[j], NOW)
+        for k, a in enumerate(w.actions):
+            assert g["actions"][a]["effect"] == c_out[j, k], (j, a)
