@@ -213,6 +213,7 @@ struct cgpu_ctx {
     std::atomic<uint32_t> defer_next{0};
     uint32_t *defer_lists[4] = {nullptr, nullptr, nullptr, nullptr};   // rotating deferral lists (grow-only): launches may overlap at their tails
     size_t defer_cap[4] = {0, 0, 0, 0};
+    std::vector<uint32_t *> defer_retired;
     std::mutex defer_mu;
     bool profiling = false;  // cgpu_profile(): CUDA events around the check kernel of every launch
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -549,9 +550,15 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
             std::lock_guard<std::mutex> g(ctx->defer_mu);
             const uint32_t q = seq & 3;
             if (ctx->defer_cap[q] < (size_t)bv.count) {
-                if (ctx->defer_lists[q]) { CUDA_TRY(cudaStreamSynchronize(stream)); CUDA_TRY(cudaFree(ctx->defer_lists[q])); ctx->defer_lists[q] = nullptr; ctx->defer_cap[q] = 0; }
-                CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&ctx->defer_lists[q]), (size_t)bv.count * 4));
-                ctx->defer_cap[q] = (size_t)bv.count;
+                // grow (power-of-two capacities); the old list may still be read by a launch in flight on another stream:
+                // it is retired, not freed, until cgpu_shutdown
+                size_t cap = 1024;
+                while (cap < (size_t)bv.count) cap <<= 1;
+                uint32_t *fresh = nullptr;
+                CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&fresh), cap * 4));
+                if (ctx->defer_lists[q]) ctx->defer_retired.push_back(ctx->defer_lists[q]);
+                ctx->defer_lists[q] = fresh;
+                ctx->defer_cap[q] = cap;
             }
             defer = ctx->defer_lists[q];
         }
@@ -685,6 +692,7 @@ void cgpu_shutdown(cgpu_ctx *ctx) {
     if (ctx->d_status) cudaFree(ctx->d_status);
     if (ctx->d_defer_cells) cudaFree(ctx->d_defer_cells);
     for (auto p : ctx->defer_lists) if (p) cudaFree(p);
+    for (auto p : ctx->defer_retired) cudaFree(p);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
