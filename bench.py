@@ -497,7 +497,7 @@ def main():
         result["e2e"] = {"value": hb.n * K / dt, "unit": UNIT, "h2d_bytes_per_step": int(sum(sizes)),
                          "d2h_bytes_per_step": int(hb.n * kbytes), "ms_per_step": dt * 1e3, "n_gpus": 1,
                          "note": "cgpu_check: pinned host columns -> H2D -> kernel -> D2H bitmap -> effect bytes"}
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:   # the CPU baseline is reported at N = 1 only
         v, threads, passes, ns, dt = cpu_port_rate(w, ft, enc, seconds=args.cpu_seconds)
         result["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                   "sample": f"{passes} passes over {ns} requests x {K} actions ({dt:.1f} s) of the "
