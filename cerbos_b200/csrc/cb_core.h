@@ -569,6 +569,50 @@ CB_HD uint32_t utf8_len(const uint8_t *p, uint32_t n) {
     return k;
 }
 
+// ---- timestamp / duration accessors in UTC (cel-go getFullYear ... getMilliseconds) ----
+CB_HD int64_t days_from_civil(int64_t y, int m, int d);
+CB_HD int64_t floor_div(int64_t a, int64_t b) { int64_t q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
+CB_HD void civil_from_days(int64_t z, int64_t *y, int *m, int *d) {   // days since 1970-01-01 -> proleptic Gregorian date
+    z += 719468;
+    const int64_t era = floor_div(z, 146097);
+    const int64_t doe = z - era * 146097;
+    const int64_t yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+    const int64_t doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+    const int64_t mp = (5 * doy + 2) / 153;
+    *d = (int)(doy - (153 * mp + 2) / 5 + 1);
+    *m = (int)(mp < 10 ? mp + 3 : mp - 9);
+    *y = yoe + era * 400 + (*m <= 2);
+}
+CB_HD Val do_ts_get(uint32_t field, const Val &v) {
+    const int64_t ns = (int64_t)v.u;
+    if (v.tag == CB_T_DUR) {   // total hours / minutes / seconds / milliseconds, truncated toward zero (Go integer division)
+        switch (field) {
+        case CB_TS_GETHOURS: return mk_int(ns / 3600000000000ll);
+        case CB_TS_GETMINUTES: return mk_int(ns / 60000000000ll);
+        case CB_TS_GETSECONDS: return mk_int(ns / 1000000000ll);
+        case CB_TS_GETMILLISECONDS: return mk_int(ns / 1000000ll);
+        default: return mk_err();
+        }
+    }
+    if (v.tag != CB_T_TS) return mk_err();
+    const int64_t s = floor_div(ns, 1000000000ll), sub = ns - s * 1000000000ll;
+    const int64_t days = floor_div(s, 86400), rem = s - days * 86400;
+    int64_t y; int m, d;
+    civil_from_days(days, &y, &m, &d);
+    switch (field) {
+    case CB_TS_GETFULLYEAR: return mk_int(y);
+    case CB_TS_GETMONTH: return mk_int(m - 1);
+    case CB_TS_GETDAYOFYEAR: return mk_int(days - days_from_civil(y, 1, 1));
+    case CB_TS_GETDAYOFMONTH: return mk_int(d - 1);
+    case CB_TS_GETDATE: return mk_int(d);
+    case CB_TS_GETDAYOFWEEK: return mk_int(((days + 4) % 7 + 7) % 7);
+    case CB_TS_GETHOURS: return mk_int(rem / 3600);
+    case CB_TS_GETMINUTES: return mk_int(rem % 3600 / 60);
+    case CB_TS_GETSECONDS: return mk_int(rem % 60);
+    default: return mk_int(sub / 1000000);
+    }
+}
+
 // ---- hierarchy(s, delim) (conditions/types/hierarchy.go:146-410): segments = strings.Split(s, delim), never
 // materialised -- the relations walk both strings segment by segment
 struct HierIt { const uint8_t *p; uint32_t n; const uint8_t *d; uint32_t dn; uint32_t pos; bool more; };
@@ -1068,6 +1112,7 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
             st[sp - 1] = ok ? mk_bool(hier_rel(ia, hier_it(c, st[sp - 1].u, ib), hier_it(c, st[sp].u, ic))) : mk_err();
             break;
         }
+        case CB_OP_TS_GET: st[sp - 1] = do_ts_get(ia, st[sp - 1]); break;
         case CB_OP_IN_SPLIT: {   // [x, s]: x in s.split(delim ib)
             sp--;
             const Val x = st[sp - 1], sv = st[sp];

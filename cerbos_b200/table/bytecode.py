@@ -643,6 +643,10 @@ class ProgramCompiler:
             self.expr(args[0])
             self.emit("IN_IP_RANGE", c=self.ctx._heap_put(list(cidr)))
             return
+        if fn in L.TS_FIELDS and len(args) == 1:      # UTC accessors; the (timestamp, time zone) forms need a tz database
+            self.expr(args[0])
+            self.emit("TS_GET", a=L.TS_FIELDS[fn])
+            return
         if fn == "now" and not args:
             self.ctx.uses_now = True
             self.emit("NOW", delta=1)

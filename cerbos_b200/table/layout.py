@@ -12,7 +12,7 @@ Table blob (little endian, every section 16-byte aligned):
 from __future__ import annotations
 
 MAGIC = 0x32425243  # 'CRB2'
-VERSION = 10
+VERSION = 11
 ALIGN = 16
 
 NONE32 = 0xFFFFFFFF
@@ -138,7 +138,10 @@ OPS = {name: i for i, name in enumerate([
     "HIER_CA",          # a = 0: [s, t] -> INT size of s.commonAncestors(t); a = 1: [s, t, z] -> BOOL(commonAncestors == hierarchy(z));
                         #        delimiters b (s), c & 0xFFFF (t), c >> 16 (z)
     "IN_SPLIT",         # [x, s] -> BOOL(x in s.split(delim b)): the token list never materialises (ext strings split)
+    "TS_GET",           # TOS timestamp / duration -> INT: a = TS_FIELDS getter, UTC (cel-go timestamp / duration accessors)
 ])}
+TS_FIELDS = {name: i for i, name in enumerate(["getFullYear", "getMonth", "getDayOfYear", "getDayOfMonth", "getDate", "getDayOfWeek",
+                                               "getHours", "getMinutes", "getSeconds", "getMilliseconds"])}
 HIER_RELS = {name: i for i, name in enumerate(["ancestorOf", "descendentOf", "immediateChildOf", "immediateParentOf", "siblingOf", "overlaps", "equals"])}
 
 # Flat fast-path conditions: a condition in disjunctive normal form over "terms".  A term is 16 bytes (two CODE
@@ -229,6 +232,8 @@ def c_header() -> str:
     d("CB_N_OPS", len(OPS))
     for k, v in HIER_RELS.items():
         d(f"CB_HIER_{k.upper()}", v)
+    for k, v in TS_FIELDS.items():
+        d(f"CB_TS_{k.upper()}", v)
     out.append("")
     d("CB_FLAT_DNF", FLAT_DNF)
     for k, v in TERM_OPS.items():

@@ -442,6 +442,47 @@ static val_t do_str2(ectx_t *c, int op, val_t s, val_t t) {
     return mk_bool(0);
 }
 
+/* ---- timestamp / duration accessors (UTC): cel-go timestamp.getFullYear() ... duration.getMilliseconds() ---- */
+static int64_t fdiv(int64_t a, int64_t b) { int64_t q = a / b, r = a % b; return (r != 0 && ((r < 0) != (b < 0))) ? q - 1 : q; }
+static val_t do_ts_get(uint32_t field, val_t v) {
+    int64_t ns = (int64_t)v.u;
+    if (v.tag == CB_T_DUR) {
+        if (field == CB_TS_GETHOURS) return mk(CB_T_INT, (uint64_t)(ns / 3600000000000ll));
+        if (field == CB_TS_GETMINUTES) return mk(CB_T_INT, (uint64_t)(ns / 60000000000ll));
+        if (field == CB_TS_GETSECONDS) return mk(CB_T_INT, (uint64_t)(ns / 1000000000ll));
+        if (field == CB_TS_GETMILLISECONDS) return mk(CB_T_INT, (uint64_t)(ns / 1000000ll));
+        return mk_err();
+    }
+    if (v.tag != CB_T_TS) return mk_err();
+    int64_t secs = fdiv(ns, 1000000000ll), sub = ns - secs * 1000000000ll;
+    int64_t days = fdiv(secs, 86400), rem = secs - days * 86400;
+    /* walk years / months from 1970 (independent of the kernels' closed-form civil_from_days) */
+    int64_t y = 1970, dd = days;
+    for (;;) {
+        int leap = (y % 4 == 0 && y % 100 != 0) || y % 400 == 0;
+        int64_t yl = leap ? 366 : 365;
+        if (dd < 0) { y--; leap = (y % 4 == 0 && y % 100 != 0) || y % 400 == 0; dd += leap ? 366 : 365; continue; }
+        if (dd >= yl) { dd -= yl; y++; continue; }
+        break;
+    }
+    int leap = (y % 4 == 0 && y % 100 != 0) || y % 400 == 0;
+    static const int ml[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    int64_t doy = dd; int m = 0;
+    while (m < 12) { int l = ml[m] + (m == 1 && leap); if (dd < l) break; dd -= l; m++; }
+    switch (field) {
+    case CB_TS_GETFULLYEAR: return mk(CB_T_INT, (uint64_t)y);
+    case CB_TS_GETMONTH: return mk(CB_T_INT, (uint64_t)m);
+    case CB_TS_GETDAYOFYEAR: return mk(CB_T_INT, (uint64_t)doy);
+    case CB_TS_GETDAYOFMONTH: return mk(CB_T_INT, (uint64_t)dd);
+    case CB_TS_GETDATE: return mk(CB_T_INT, (uint64_t)(dd + 1));
+    case CB_TS_GETDAYOFWEEK: return mk(CB_T_INT, (uint64_t)(((days + 4) % 7 + 7) % 7));
+    case CB_TS_GETHOURS: return mk(CB_T_INT, (uint64_t)(rem / 3600));
+    case CB_TS_GETMINUTES: return mk(CB_T_INT, (uint64_t)(rem % 3600 / 60));
+    case CB_TS_GETSECONDS: return mk(CB_T_INT, (uint64_t)(rem % 60));
+    default: return mk(CB_T_INT, (uint64_t)(sub / 1000000));
+    }
+}
+
 /* ---- hierarchy(s, delim): conditions/types/hierarchy.go:146-410.  Restated the way the reference does it: split into
  * segments (strings.Split), then compare the segment lists. ---- */
 #define HIER_MAX_SEG 256
@@ -840,6 +881,7 @@ static val_t run_program(ectx_t *c, const cb_instr *code, int64_t now) {
         case CB_OP_IN_CONST_SLOT: { int s; val_t a = load_slot(c, in.b, &s); cb_const k = c->t->consts[in.c]; st[sp++] = do_in(c, mk(k.tag, k.bits), a); break; }
         case CB_OP_IN_IP_RANGE: st[sp - 1] = st[sp - 1].tag == CB_T_ERR ? mk_err() : do_in_ip_range(c, st[sp - 1], c->t->theap + in.c); break;
         case CB_OP_HIER_REL: sp--; st[sp - 1] = do_hier_rel(c, in.a, st[sp - 1], in.b, st[sp], in.c); break;
+        case CB_OP_TS_GET: st[sp - 1] = do_ts_get(in.a, st[sp - 1]); break;
         case CB_OP_IN_SPLIT: {   /* x in s.split(sep): ext strings split + the `in` operator over the token list */
             static __thread hier_t toks;
             sp--;

@@ -223,3 +223,47 @@ def test_workload_c5_adversarial():
         g = orc.check(inputs[j], NOW)
         for k, a in enumerate(w.actions):
             assert g["actions"][a]["effect"] == c_out[j, k], (j, a)
+
+
+def test_timestamp_and_duration_accessors():
+    """getFullYear ... getMilliseconds (UTC) on timestamps from request attributes over 1875-2160, durations incl. negative
+    ones: Python's datetime (expected values travel as attributes), oracle #1, oracle #2 and the kernel core must agree."""
+    import datetime
+    import random
+    fields = ["getFullYear", "getMonth", "getDayOfYear", "getDayOfMonth", "getDate", "getDayOfWeek", "getHours", "getMinutes", "getSeconds",
+              "getMilliseconds"]
+    exprs = [f"timestamp(R.attr.ts).{f}() == int(R.attr.want_{f})" for f in fields] + [
+        "(now() - timestamp(R.attr.ts)).getHours() > 24",
+        'duration("90m").getMinutes() == 90 && duration("-1500ms").getMilliseconds() == -1500 && duration("-1500ms").getSeconds() == -1',
+        "now().getDayOfWeek() == 1 && now().getHours() == 0"]
+    rules = [{"actions": [f"a{i}"], "effect": "EFFECT_ALLOW", "roles": ["*"], "condition": {"match": {"expr": e}}} for i, e in enumerate(exprs)]
+    rt = build_rule_table([{"apiVersion": "api.cerbos.dev/v1", "resourcePolicy": {"resource": "doc", "version": "default", "rules": rules}}])
+    ft = flatten(rt)
+    r = random.Random(3)
+    inputs, perturbed = [], []
+    for _ in range(300):
+        t = datetime.datetime(1970, 1, 1, tzinfo=datetime.timezone.utc) + datetime.timedelta(
+            seconds=r.randrange(-3_000_000_000, 6_000_000_000), milliseconds=r.randrange(0, 1000))
+        iso = t.strftime("%Y-%m-%dT%H:%M:%S.") + f"{t.microsecond // 1000:03d}Z"
+        want = {"getFullYear": t.year, "getMonth": t.month - 1, "getDayOfYear": t.timetuple().tm_yday - 1, "getDayOfMonth": t.day - 1,
+                "getDate": t.day, "getDayOfWeek": (t.weekday() + 1) % 7, "getHours": t.hour, "getMinutes": t.minute, "getSeconds": t.second,
+                "getMilliseconds": t.microsecond // 1000}
+        wrong = r.choice(fields) if r.random() < 0.2 else None
+        if wrong:
+            want[wrong] += 1
+        perturbed.append(wrong)
+        attr = {"ts": iso, **{f"want_{k}": v for k, v in want.items()}}
+        inputs.append({"requestId": "t", "actions": [f"a{i}" for i in range(len(exprs))], "principal": {"id": "u", "roles": ["r"]},
+                       "resource": {"kind": "doc", "id": "d", "attr": attr}})
+    orc = CheckOracle(rt)
+    b = Encoder(ft.manifest).encode(inputs)
+    c_out = cref.check(ft.blob, b.columns, b.n, b.max_actions, NOW.ns)
+    for j, inp in enumerate(inputs):
+        py = orc.check(inp, NOW)
+        for k, a in enumerate(inp["actions"]):
+            assert c_out[j, k] == py["actions"][a]["effect"], (exprs[k], inp["resource"]["attr"]["ts"])
+        for k, f in enumerate(fields):      # datetime's answer: ALLOW unless this field's expectation was perturbed
+            assert c_out[j, k] == (2 if perturbed[j] == f else 1), (f, inp["resource"]["attr"]["ts"])
+    assert (c_out[:, len(fields) + 1] == 1).all() and (c_out[:, len(fields) + 2] == 1).all()     # 2024-01-01T00:00:00Z is a Monday
+    for mode in (0, 1):
+        assert (hostsim.check(ft.blob, b.columns, b.n, b.max_actions, NOW.ns, mode=mode) == c_out).all(), mode
