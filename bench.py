@@ -471,7 +471,11 @@ def main():
                      "kernel": "check_kernel", "kernel_ms_mean": kern_ms_mean,
                      "device_step_ms_mean": statistics.mean(step_ms), "device_step_ms_min": min(step_ms),
                      "step_achieved": algo_bytes / (statistics.mean(step_ms) * 1e-3) / 1e9,
-                     "kernel_share_of_step": kern_ms_mean / statistics.mean(step_ms)},
+                     "kernel_share_of_step": kern_ms_mean / statistics.mean(step_ms),
+                     "note": "kernel_ms_mean: the check kernel alone, CUDA events recorded by the library on the launching stream around "
+                             "that kernel, one call at a time after the timed region; device_step_ms_*: events around one whole "
+                             "call issued alone (includes the launch gaps between its kernels, which back-to-back calls hide: "
+                             "ms_per_step is lower because consecutive calls overlap at their tails)"},
         "clocks": clocks.summary(),
         "verified_vs_oracle": verified,
     }
