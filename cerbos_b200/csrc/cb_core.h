@@ -569,6 +569,59 @@ CB_HD uint32_t utf8_len(const uint8_t *p, uint32_t n) {
     return k;
 }
 
+// ---- Go time.ParseDuration (cel-go duration(string)): [+-] then one or more <digits>[.<digits>]<unit>, or "0" ----
+// -> 0 ok, 1 invalid / out of range (CEL error), 2 more than 25 fraction digits (not representable here)
+CB_HD int parse_duration_text(const uint8_t *p, uint32_t n, int64_t *out) {
+    uint32_t i = 0;
+    bool neg = false;
+    if (n == 0) return 1;
+    if (ldg(p) == '+' || ldg(p) == '-') { neg = ldg(p) == '-'; i = 1; }
+    if (n - i == 1 && ldg(p + i) == '0') { *out = 0; return 0; }
+    if (i == n) return 1;
+    const uint64_t kLimit = 1ull << 63;
+    uint64_t total = 0;
+    bool over = false;
+    while (i < n) {
+        uint64_t whole = 0;
+        bool any = false;
+        while (i < n && ldg(p + i) >= '0' && ldg(p + i) <= '9') {
+            const uint64_t d = ldg(p + i) - '0';
+            if (whole > (kLimit - d) / 10) over = true; else whole = whole * 10 + d;
+            any = true; i++;
+        }
+        unsigned __int128 frac = 0, scale = 1;
+        uint32_t nfrac = 0;
+        if (i < n && ldg(p + i) == '.') {
+            i++;
+            while (i < n && ldg(p + i) >= '0' && ldg(p + i) <= '9') {
+                if (nfrac >= 25) return 2;
+                frac = frac * 10 + (ldg(p + i) - '0'); scale *= 10; nfrac++; i++;
+            }
+        }
+        if (!any && nfrac == 0) return 1;
+        uint64_t unit = 0;
+        const uint32_t rem = n - i;
+        const uint8_t c0 = rem > 0 ? ldg(p + i) : 0, c1 = rem > 1 ? ldg(p + i + 1) : 0, c2 = rem > 2 ? ldg(p + i + 2) : 0;
+        if (c0 == 'n' && c1 == 's') { unit = 1; i += 2; }
+        else if (c0 == 'u' && c1 == 's') { unit = 1000; i += 2; }
+        else if ((c0 == 0xC2 && c1 == 0xB5 && c2 == 's') || (c0 == 0xCE && c1 == 0xBC && c2 == 's')) { unit = 1000; i += 3; }   // U+00B5 / U+03BC
+        else if (c0 == 'm' && c1 == 's') { unit = 1000000; i += 2; }
+        else if (c0 == 's') { unit = 1000000000ull; i += 1; }
+        else if (c0 == 'm') { unit = 60000000000ull; i += 1; }
+        else if (c0 == 'h') { unit = 3600000000000ull; i += 1; }
+        else return 1;
+        if (whole > kLimit / unit) over = true;
+        uint64_t v = over ? 0 : whole * unit;
+        const unsigned __int128 fv = frac * unit / scale;   // < unit
+        if (!over) { v += (uint64_t)fv; if (v > kLimit || total + v > kLimit || total + v < total) over = true; else total += v; }
+    }
+    if (over) return 1;
+    if (neg) { *out = total == kLimit ? (int64_t)0x8000000000000000ull : -(int64_t)total; return 0; }
+    if (total > kLimit - 1) return 1;
+    *out = (int64_t)total;
+    return 0;
+}
+
 // ---- timestamp / duration accessors in UTC (cel-go getFullYear ... getMilliseconds) ----
 CB_HD int64_t days_from_civil(int64_t y, int m, int d);
 CB_HD int64_t floor_div(int64_t a, int64_t b) { int64_t q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
@@ -1095,7 +1148,13 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
             Val v = st[sp - 1];
             if (v.tag == CB_T_DUR) break;
             if (v.tag == CB_T_INT) st[sp - 1] = mk(CB_T_DUR, v.u);
-            else if (v.tag == CB_T_STRING) { c.unsupported = 1; st[sp - 1] = mk_err(); }
+            else if (v.tag == CB_T_STRING) {
+                const uint8_t *p; uint32_t n; int64_t ns = 0;
+                str_get(c, v.u, p, n);
+                const int rc = parse_duration_text(p, n, &ns);
+                if (rc == 2) c.unsupported = 1;
+                st[sp - 1] = rc == 0 ? mk(CB_T_DUR, (uint64_t)ns) : mk_err();
+            }
             else st[sp - 1] = mk_err();
             break;
         }

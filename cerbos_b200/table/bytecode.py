@@ -628,8 +628,6 @@ class ProgramCompiler:
             return
         if fn in self._CONV and len(args) == 1:
             self.expr(args[0])
-            if fn == "duration":
-                raise Unsupported("duration() of a non-constant string")
             self.emit(self._CONV[fn])
             return
         if fn == "inIPAddrRange" and len(args) == 2:

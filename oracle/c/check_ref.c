@@ -442,6 +442,41 @@ static val_t do_str2(ectx_t *c, int op, val_t s, val_t t) {
     return mk_bool(0);
 }
 
+/* ---- Go time.ParseDuration, restated after the standard library's loop (leadingInt / leadingFraction / unit map) ---- */
+static int parse_go_duration(const uint8_t *s, uint32_t n, int64_t *out) {   /* 0 ok, 1 error, 2 not representable here */
+    uint32_t i = 0; int neg = 0;
+    if (n == 0) return 1;
+    if (s[0] == '-' || s[0] == '+') { neg = s[0] == '-'; i++; }
+    if (n - i == 1 && s[i] == '0') { *out = 0; return 0; }
+    if (i == n) return 1;
+    unsigned __int128 d = 0;   /* arbitrary-precision enough: range-checked at the end like the Python oracle */
+    while (i < n) {
+        unsigned __int128 v = 0, f = 0, scale = 1; int pre = 0, post = 0, nd = 0;
+        while (i < n && s[i] >= '0' && s[i] <= '9') { if (v < ((unsigned __int128)1 << 100)) v = v * 10 + (s[i] - '0'); pre = 1; i++; }
+        if (i < n && s[i] == '.') {
+            i++;
+            while (i < n && s[i] >= '0' && s[i] <= '9') { if (++nd > 25) return 2; f = f * 10 + (s[i] - '0'); scale *= 10; post = 1; i++; }
+        }
+        if (!pre && !post) return 1;
+        uint64_t unit;
+        if (i + 1 < n && s[i] == 'n' && s[i + 1] == 's') { unit = 1; i += 2; }
+        else if (i + 1 < n && s[i] == 'u' && s[i + 1] == 's') { unit = 1000; i += 2; }
+        else if (i + 2 < n && ((s[i] == 0xC2 && s[i + 1] == 0xB5) || (s[i] == 0xCE && s[i + 1] == 0xBC)) && s[i + 2] == 's') { unit = 1000; i += 3; }
+        else if (i + 1 < n && s[i] == 'm' && s[i + 1] == 's') { unit = 1000000; i += 2; }
+        else if (i < n && s[i] == 's') { unit = 1000000000ull; i += 1; }
+        else if (i < n && s[i] == 'm') { unit = 60000000000ull; i += 1; }
+        else if (i < n && s[i] == 'h') { unit = 3600000000000ull; i += 1; }
+        else return 1;
+        d += v * unit + f * unit / scale;
+        if (d > ((unsigned __int128)1 << 110)) return 1;
+    }
+    const unsigned __int128 lim = (unsigned __int128)1 << 63;
+    if (neg) { if (d > lim) return 1; *out = d == lim ? INT64_MIN : -(int64_t)(uint64_t)d; return 0; }
+    if (d > lim - 1) return 1;
+    *out = (int64_t)(uint64_t)d;
+    return 0;
+}
+
 /* ---- timestamp / duration accessors (UTC): cel-go timestamp.getFullYear() ... duration.getMilliseconds() ---- */
 static int64_t fdiv(int64_t a, int64_t b) { int64_t q = a / b, r = a % b; return (r != 0 && ((r < 0) != (b < 0))) ? q - 1 : q; }
 static val_t do_ts_get(uint32_t field, val_t v) {
@@ -872,7 +907,7 @@ static val_t run_program(ectx_t *c, const cb_instr *code, int64_t now) {
             } else st[sp - 1] = mk_err();
             break;
         }
-        case CB_OP_DURATION: { val_t v = st[sp - 1]; if (v.tag == CB_T_DUR) break; if (v.tag == CB_T_INT) st[sp - 1] = mk(CB_T_DUR, v.u); else if (v.tag == CB_T_STRING) { c->unsupported = 1; st[sp - 1] = mk_err(); } else st[sp - 1] = mk_err(); break; }
+        case CB_OP_DURATION: { val_t v = st[sp - 1]; if (v.tag == CB_T_DUR) break; if (v.tag == CB_T_INT) st[sp - 1] = mk(CB_T_DUR, v.u); else if (v.tag == CB_T_STRING) { const uint8_t *p; uint32_t n; int64_t ns = 0; str_get(c, v.u, &p, &n); int rc = parse_go_duration(p, n, &ns); if (rc == 2) c->unsupported = 1; st[sp - 1] = rc == 0 ? mk(CB_T_DUR, (uint64_t)ns) : mk_err(); } else st[sp - 1] = mk_err(); break; }
         case CB_OP_DYN: break;
         case CB_OP_CMP_SLOT_CONST: { int s; val_t a = load_slot(c, in.b, &s); cb_const k = c->t->consts[in.c]; st[sp++] = do_cmp(c, in.a, a, mk(k.tag, k.bits)); break; }
         case CB_OP_CMP_SLOT_SLOT: { int s; val_t a = load_slot(c, in.b, &s); val_t b = load_slot(c, in.c, &s); st[sp++] = do_cmp(c, in.a, a, b); break; }
