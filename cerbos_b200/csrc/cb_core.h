@@ -636,9 +636,11 @@ CB_HD void civil_from_days(int64_t z, int64_t *y, int *m, int *d) {   // days si
     *m = (int)(mp < 10 ? mp + 3 : mp - 9);
     *y = yoe + era * 400 + (*m <= 2);
 }
-CB_HD Val do_ts_get(uint32_t field, const Val &v) {
+CB_HD Val do_ts_get(uint32_t field, const Val &v, uint32_t tzform, int32_t offset_s) {
     const int64_t ns = (int64_t)v.u;
-    if (v.tag == CB_T_DUR) {   // total hours / minutes / seconds / milliseconds, truncated toward zero (Go integer division)
+    if (field == 0xFF) return mk_err();
+    if (v.tag == CB_T_DUR) {
+        if (tzform) return mk_err();   // total hours / minutes / seconds / milliseconds, truncated toward zero (Go integer division)
         switch (field) {
         case CB_TS_GETHOURS: return mk_int(ns / 3600000000000ll);
         case CB_TS_GETMINUTES: return mk_int(ns / 60000000000ll);
@@ -648,7 +650,8 @@ CB_HD Val do_ts_get(uint32_t field, const Val &v) {
         }
     }
     if (v.tag != CB_T_TS) return mk_err();
-    const int64_t s = floor_div(ns, 1000000000ll), sub = ns - s * 1000000000ll;
+    const int64_t s0 = floor_div(ns, 1000000000ll), sub = ns - s0 * 1000000000ll;
+    const int64_t s = s0 + offset_s;
     const int64_t days = floor_div(s, 86400), rem = s - days * 86400;
     int64_t y; int m, d;
     civil_from_days(days, &y, &m, &d);
@@ -1171,7 +1174,7 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
             st[sp - 1] = ok ? mk_bool(hier_rel(ia, hier_it(c, st[sp - 1].u, ib), hier_it(c, st[sp].u, ic))) : mk_err();
             break;
         }
-        case CB_OP_TS_GET: st[sp - 1] = do_ts_get(ia, st[sp - 1]); break;
+        case CB_OP_TS_GET: st[sp - 1] = do_ts_get(ia, st[sp - 1], ib, (int32_t)ic); break;
         case CB_OP_IN_SPLIT: {   // [x, s]: x in s.split(delim ib)
             sp--;
             const Val x = st[sp - 1], sv = st[sp];

@@ -641,9 +641,30 @@ class ProgramCompiler:
             self.expr(args[0])
             self.emit("IN_IP_RANGE", c=self.ctx._heap_put(list(cidr)))
             return
-        if fn in L.TS_FIELDS and len(args) == 1:      # UTC accessors; the (timestamp, time zone) forms need a tz database
+        if fn in L.TS_FIELDS and len(args) in (1, 2):
+            off, tzform = 0, 0
+            if len(args) == 2:
+                # a constant fixed offset ("-05:00", "UTC"); IANA zone names would need a tz database on the device
+                tz = args[1]
+                if not (isinstance(tz, Const) and isinstance(tz.value, str)):
+                    raise Unsupported("timestamp accessor with a non-constant time zone")
+                tzs = tz.value
+                if ":" in tzs:
+                    ind = tzs.index(":")
+                    try:
+                        hr, mn = int(tzs[:ind]), int(tzs[ind + 1:])
+                    except ValueError:
+                        self.expr(args[0])          # invalid zone text: a CEL error whatever the timestamp is
+                        self.emit("TS_GET", a=0xFF)
+                        return
+                    off = (hr * 60 - mn if tzs[0] == "-" else hr * 60 + mn) * 60
+                elif tzs not in ("UTC", ""):
+                    raise Unsupported("timestamp accessor with an IANA time zone name")
+                tzform = 1
+                if not -(1 << 31) <= off < (1 << 31):
+                    raise Unsupported("time zone offset out of range")
             self.expr(args[0])
-            self.emit("TS_GET", a=L.TS_FIELDS[fn])
+            self.emit("TS_GET", a=L.TS_FIELDS[fn], b=tzform, c=off & 0xFFFFFFFF)
             return
         if fn == "now" and not args:
             self.ctx.uses_now = True

@@ -12,7 +12,7 @@ Table blob (little endian, every section 16-byte aligned):
 from __future__ import annotations
 
 MAGIC = 0x32425243  # 'CRB2'
-VERSION = 11
+VERSION = 12
 ALIGN = 16
 
 NONE32 = 0xFFFFFFFF
@@ -138,7 +138,8 @@ OPS = {name: i for i, name in enumerate([
     "HIER_CA",          # a = 0: [s, t] -> INT size of s.commonAncestors(t); a = 1: [s, t, z] -> BOOL(commonAncestors == hierarchy(z));
                         #        delimiters b (s), c & 0xFFFF (t), c >> 16 (z)
     "IN_SPLIT",         # [x, s] -> BOOL(x in s.split(delim b)): the token list never materialises (ext strings split)
-    "TS_GET",           # TOS timestamp / duration -> INT: a = TS_FIELDS getter, UTC (cel-go timestamp / duration accessors)
+    "TS_GET",           # TOS timestamp / duration -> INT: a = TS_FIELDS getter (0xFF: always an error), c = fixed offset east of UTC
+                        # in seconds (int32), b = 1 when a zone argument was given (then a duration operand is an error)
 ])}
 TS_FIELDS = {name: i for i, name in enumerate(["getFullYear", "getMonth", "getDayOfYear", "getDayOfMonth", "getDate", "getDayOfWeek",
                                                "getHours", "getMinutes", "getSeconds", "getMilliseconds"])}

@@ -479,9 +479,11 @@ static int parse_go_duration(const uint8_t *s, uint32_t n, int64_t *out) {   /* 
 
 /* ---- timestamp / duration accessors (UTC): cel-go timestamp.getFullYear() ... duration.getMilliseconds() ---- */
 static int64_t fdiv(int64_t a, int64_t b) { int64_t q = a / b, r = a % b; return (r != 0 && ((r < 0) != (b < 0))) ? q - 1 : q; }
-static val_t do_ts_get(uint32_t field, val_t v) {
+static val_t do_ts_get(uint32_t field, val_t v, uint32_t tzform, int32_t offset_s) {
     int64_t ns = (int64_t)v.u;
+    if (field == 0xFF) return mk_err();   /* invalid zone text */
     if (v.tag == CB_T_DUR) {
+        if (tzform) return mk_err();
         if (field == CB_TS_GETHOURS) return mk(CB_T_INT, (uint64_t)(ns / 3600000000000ll));
         if (field == CB_TS_GETMINUTES) return mk(CB_T_INT, (uint64_t)(ns / 60000000000ll));
         if (field == CB_TS_GETSECONDS) return mk(CB_T_INT, (uint64_t)(ns / 1000000000ll));
@@ -490,6 +492,7 @@ static val_t do_ts_get(uint32_t field, val_t v) {
     }
     if (v.tag != CB_T_TS) return mk_err();
     int64_t secs = fdiv(ns, 1000000000ll), sub = ns - secs * 1000000000ll;
+    secs += offset_s;   /* fixed zone offset east of UTC (cel-go timeZone(): "[+-]HH:MM" forms) */
     int64_t days = fdiv(secs, 86400), rem = secs - days * 86400;
     /* walk years / months from 1970 (independent of the kernels' closed-form civil_from_days) */
     int64_t y = 1970, dd = days;
@@ -916,7 +919,7 @@ static val_t run_program(ectx_t *c, const cb_instr *code, int64_t now) {
         case CB_OP_IN_CONST_SLOT: { int s; val_t a = load_slot(c, in.b, &s); cb_const k = c->t->consts[in.c]; st[sp++] = do_in(c, mk(k.tag, k.bits), a); break; }
         case CB_OP_IN_IP_RANGE: st[sp - 1] = st[sp - 1].tag == CB_T_ERR ? mk_err() : do_in_ip_range(c, st[sp - 1], c->t->theap + in.c); break;
         case CB_OP_HIER_REL: sp--; st[sp - 1] = do_hier_rel(c, in.a, st[sp - 1], in.b, st[sp], in.c); break;
-        case CB_OP_TS_GET: st[sp - 1] = do_ts_get(in.a, st[sp - 1]); break;
+        case CB_OP_TS_GET: st[sp - 1] = do_ts_get(in.a, st[sp - 1], in.b, (int32_t)in.c); break;
         case CB_OP_IN_SPLIT: {   /* x in s.split(sep): ext strings split + the `in` operator over the token list */
             static __thread hier_t toks;
             sp--;

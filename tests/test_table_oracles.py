@@ -104,7 +104,7 @@ def test_bytecode_vs_cel_oracle_on_golden_expressions():
         want = CheckOracle(rt).check(inp, now)["actions"]["a"]["effect"]
         assert cref.check(ft.blob, b.columns, 1, 1, now.ns)[0, 0] == want, (f, e)
         assert hostsim.check(ft.blob, b.columns, 1, 1, now.ns)[0, 0] == want, (f, e)
-    assert lowered >= 130
+    assert lowered >= 138
 
 
 @pytest.mark.parametrize("cls,n", [(W.C1, 1024), (W.C2, 1 << 14), (W.C3, 1 << 12)])
@@ -235,7 +235,11 @@ def test_timestamp_and_duration_accessors():
     exprs = [f"timestamp(R.attr.ts).{f}() == int(R.attr.want_{f})" for f in fields] + [
         "(now() - timestamp(R.attr.ts)).getHours() > 24",
         'duration("90m").getMinutes() == 90 && duration("-1500ms").getMilliseconds() == -1500 && duration("-1500ms").getSeconds() == -1',
-        "now().getDayOfWeek() == 1 && now().getHours() == 0"]
+        "now().getDayOfWeek() == 1 && now().getHours() == 0",
+        # fixed-offset zones: -05:30 (east-negative) and +09:00; "UTC"; an invalid zone text is an error => no match
+        'timestamp(R.attr.ts).getHours("-05:30") == int(R.attr.h_m530) && timestamp(R.attr.ts).getDate("-05:30") == int(R.attr.d_m530)',
+        'timestamp(R.attr.ts).getDayOfWeek("+09:00") == int(R.attr.dow_p9) && timestamp(R.attr.ts).getMinutes("UTC") == int(R.attr.want_getMinutes)',
+        '!(timestamp(R.attr.ts).getHours("x:y") >= 0)']
     rules = [{"actions": [f"a{i}"], "effect": "EFFECT_ALLOW", "roles": ["*"], "condition": {"match": {"expr": e}}} for i, e in enumerate(exprs)]
     rt = build_rule_table([{"apiVersion": "api.cerbos.dev/v1", "resourcePolicy": {"resource": "doc", "version": "default", "rules": rules}}])
     ft = flatten(rt)
@@ -252,7 +256,8 @@ def test_timestamp_and_duration_accessors():
         if wrong:
             want[wrong] += 1
         perturbed.append(wrong)
-        attr = {"ts": iso, **{f"want_{k}": v for k, v in want.items()}}
+        t1, t2 = t - datetime.timedelta(minutes=330), t + datetime.timedelta(hours=9)
+        attr = {"ts": iso, **{f"want_{k}": v for k, v in want.items()}, "h_m530": t1.hour, "d_m530": t1.day, "dow_p9": (t2.weekday() + 1) % 7}
         inputs.append({"requestId": "t", "actions": [f"a{i}" for i in range(len(exprs))], "principal": {"id": "u", "roles": ["r"]},
                        "resource": {"kind": "doc", "id": "d", "attr": attr}})
     orc = CheckOracle(rt)
@@ -265,6 +270,8 @@ def test_timestamp_and_duration_accessors():
         for k, f in enumerate(fields):      # datetime's answer: ALLOW unless this field's expectation was perturbed
             assert c_out[j, k] == (2 if perturbed[j] == f else 1), (f, inp["resource"]["attr"]["ts"])
     assert (c_out[:, len(fields) + 1] == 1).all() and (c_out[:, len(fields) + 2] == 1).all()     # 2024-01-01T00:00:00Z is a Monday
+    assert (c_out[:, len(fields) + 3] == 1).all() and (c_out[:, len(fields) + 5] == 2).all()     # zone offsets; invalid zone => error
+    assert ((c_out[:, len(fields) + 4] == 1) == np.array([p != "getMinutes" for p in perturbed])).all()
     for mode in (0, 1):
         assert (hostsim.check(ft.blob, b.columns, b.n, b.max_actions, NOW.ns, mode=mode) == c_out).all(), mode
 
