@@ -27,3 +27,20 @@ def engine_decisions():
         for inp in case["inputs"]:
             want = outs[(inp.get("requestId"), inp["resource"]["id"])]
             yield f"{case['suite']}/{case['file']}", case["lenient"], inp, want
+
+
+def check_resources_api_cases():
+    """The reference's API-shaped CheckResources goldens (internal/test/testdata/server/checks/check_resources/cr_case_0*.yaml,
+    extracted by tests/golden/make_golden.py): one CheckInput per resource entry, the way the service builds them
+    (internal/svc/cerbos_svc.go:249-263), with the decoded JWT claims as auxData.  Yields (file, CheckInput, {action: effect name}).
+    Skipped: request-validation error cases (rejected before the engine) and cr_case_02 (schema enforcement, out of scope)."""
+    for c in load_golden("check_resources_cases.json"):
+        if c.get("wantError") or c["file"] == "cr_case_02.yaml":
+            continue
+        inp = c["input"]
+        for i, entry in enumerate(inp["resources"]):
+            ci = {"requestId": inp.get("requestId", ""), "actions": entry["actions"], "principal": inp["principal"], "resource": entry["resource"]}
+            if c.get("jwtClaims"):
+                ci["auxData"] = {"jwt": c["jwtClaims"]}
+            want = {a: (w if isinstance(w, str) else w.get("effect")) for a, w in c["wantResponse"]["results"][i]["actions"].items()}
+            yield c["file"], ci, want

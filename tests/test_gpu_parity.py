@@ -336,3 +336,19 @@ def test_workload_c5_adversarial(ctx):
     assert (table.check(b.columns, b.n, b.max_actions, NOW_NS) == want).all()
     assert ctx.last_kernel_config()["smem_bytes"] == 0      # too large to stage
     table.release()
+
+
+def test_check_resources_api_goldens_through_engine_api():
+    """The reference's API-level CheckResources goldens (cr_case_00 ... 08, 48 decisions) through Engine.check on the GPU."""
+    from cerbos_b200.engine import Engine
+    from helpers import check_resources_api_cases, load_golden
+    docs = [e["policy"] for e in load_golden("store_policies.json")]
+    eng = Engine(docs, globals_={"environment": "test"})
+    n = 0
+    for f, ci, want in check_resources_api_cases():
+        got = eng.check([ci], now_ns=NOW_NS)[0]
+        for a, w in want.items():
+            assert got["actions"][a]["effect"] == w, (f, a)
+            n += 1
+    assert n == 48
+    eng.close()

@@ -325,3 +325,25 @@ def test_duration_of_request_strings():
     assert (c_out[:, 3] == 1).all() and (c_out[:, 5] == 1).all() and 100 < (c_out[:, 0] == 1).sum() < 500
     for mode in (0, 1):
         assert (hostsim.check(ft.blob, b.columns, b.n, b.max_actions, NOW.ns, mode=mode) == c_out).all(), mode
+
+
+def test_check_resources_api_goldens():
+    """The reference's API-level CheckResources goldens (cr_case_00 ... 08): oracle #1, oracle #2 and the kernel core."""
+    from helpers import check_resources_api_cases
+    rt = store_rule_table()
+    ft = flatten(rt, globals_={"environment": "test"})
+    orc = CheckOracle(rt, globals_={"environment": "test"})
+    enc = Encoder(ft.manifest)
+    names = {"EFFECT_ALLOW": 1, "EFFECT_DENY": 2}
+    n = 0
+    for f, ci, want in check_resources_api_cases():
+        py = orc.check(ci)
+        b = enc.encode([ci])
+        c_out = cref.check(ft.blob, b.columns, 1, b.max_actions)
+        k_out = hostsim.check(ft.blob, b.columns, 1, b.max_actions)
+        for k, a in enumerate(ci["actions"]):
+            assert py["actions"][a]["effect"] == names[want[a]], (f, a, "oracle #1")
+            assert c_out[0, k] == names[want[a]], (f, a, "oracle #2")
+            assert k_out[0, k] == names[want[a]], (f, a, "kernel core")
+            n += 1
+    assert n == 48
