@@ -144,6 +144,82 @@ def check_resources_cases():
     dump("check_resources_cases.json", out)
 
 
+
+def verify_cases():
+    """internal/test/testdata/verify/cases/case_*.yaml{.input,.golden}: policy test suites (txtar archives of fixtures +
+    *_test.yaml files) run by the reference against the `store` policies; the .golden records, per test x principal x
+    resource x action, what the ENGINE answered (success.effect, or failure.actual when the suite's expectation was
+    wrong).  Those engine answers are emitted as (CheckInput, now, lenient, {action: effect}) vectors.
+    Reference: internal/verify/verify_test.go:375-389 (store), internal/verify/test_fixture.go / test_suite_run.go."""
+    import glob
+    base = os.path.join(REF, "test/testdata/verify/cases")
+    out = []
+    for gpath in sorted(glob.glob(os.path.join(base, "*.golden"))):
+        case = os.path.basename(gpath)[: -len(".golden")]
+        try:
+            golden = json.load(open(gpath))
+        except ValueError:
+            continue
+        files, cur = {}, None
+        for line in open(os.path.join(base, case + ".input")).read().split("\n"):
+            if line.startswith("-- ") and line.endswith(" --"):
+                cur = line[3:-3].strip()
+                files[cur] = []
+            elif cur is not None:
+                files[cur].append(line)
+        docs = {}
+        for name, lines in files.items():
+            try:
+                docs[name] = yaml.safe_load("\n".join(lines)) if not name.endswith(".json") else json.loads("\n".join(lines))
+            except Exception:
+                docs[name] = None
+        # fixtures: every testdata/* file may contribute principals / resources / auxData (+ groups)
+        fx = {"principals": {}, "resources": {}, "auxData": {}, "principalGroups": {}, "resourceGroups": {}}
+        for name, d in docs.items():
+            if name.startswith("testdata/") and isinstance(d, dict):
+                for k in fx:
+                    if isinstance(d.get(k), dict):
+                        fx[k].update(d[k])
+        for s in golden.get("suites", []):
+            suite = docs.get(s.get("file"))
+            if not isinstance(suite, dict) or s.get("error"):
+                continue
+            loc = {k: dict(v) for k, v in fx.items()}
+            for k in loc:
+                if isinstance(suite.get(k), dict):
+                    loc[k].update(suite[k])
+            sopt = suite.get("options") or {}
+            tests = {t.get("name"): t for t in (suite.get("tests") or []) if isinstance(t, dict)}
+            for tc in s.get("testCases", []):
+                t = tests.get(tc.get("name"))
+                if t is None:
+                    continue
+                opt = {**sopt, **(t.get("options") or {})}
+                inp = t.get("input") or {}
+                aux = loc["auxData"].get(inp.get("auxData")) if inp.get("auxData") else None
+                for pr in tc.get("principals", []):
+                    principal = loc["principals"].get(pr["name"])
+                    for rs in pr.get("resources", []):
+                        resource = loc["resources"].get(rs["name"])
+                        want = {}
+                        for a in rs.get("actions", []):
+                            det = a.get("details") or {}
+                            eff = (det.get("success") or {}).get("effect") or (det.get("failure") or {}).get("actual")
+                            if eff in ("EFFECT_ALLOW", "EFFECT_DENY"):
+                                want[a["name"]] = eff
+                        if not want or principal is None or resource is None:
+                            continue
+                        ci = {"requestId": f"{case}/{tc.get('name')}", "actions": list(want), "principal": principal, "resource": resource}
+                        if aux:
+                            ci["auxData"] = aux
+                        out.append({"file": case, "suite": s.get("file"), "test": tc.get("name"), "now": opt.get("now"),
+                                    "lenient": bool(opt.get("lenientScopeSearch")), "defaultPolicyVersion": opt.get("defaultPolicyVersion"),
+                                    "defaultScope": opt.get("defaultScope"),
+                                    "globals": opt.get("globals"), "input": ci, "want": want})
+    dump("verify_cases.json", out)
+    print("verify_cases:", len(out), "inputs,", sum(len(o["want"]) for o in out), "decisions")
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("needs /root/reference (authoring container only)")
@@ -152,3 +228,4 @@ if __name__ == "__main__":
     engine_cases()
     store_policies()
     check_resources_cases()
+    verify_cases()

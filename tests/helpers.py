@@ -44,3 +44,15 @@ def check_resources_api_cases():
                 ci["auxData"] = {"jwt": c["jwtClaims"]}
             want = {a: (w if isinstance(w, str) else w.get("effect")) for a, w in c["wantResponse"]["results"][i]["actions"].items()}
             yield c["file"], ci, want
+
+
+def verify_suite_cases():
+    """Engine answers recorded by the reference's policy-test goldens (internal/test/testdata/verify/cases/*.golden, extracted by
+    tests/golden/make_golden.py::verify_cases): grouped by engine configuration.
+    Yields ((globals json, default version, default scope, lenient), [case, ...])."""
+    import json
+    groups = {}
+    for c in load_golden("verify_cases.json"):
+        key = (json.dumps(c["globals"] or {}, sort_keys=True), str(c["defaultPolicyVersion"] or "default"), c["defaultScope"] or "", bool(c["lenient"]))
+        groups.setdefault(key, []).append(c)
+    yield from groups.items()

@@ -352,3 +352,24 @@ def test_check_resources_api_goldens_through_engine_api():
             n += 1
     assert n == 48
     eng.close()
+
+
+def test_verify_suite_goldens_through_engine_api():
+    """145 engine answers recorded by the reference's policy-test goldens (verify/cases) through Engine.check on the GPU, under
+    every engine configuration the suites use (globals, default policy version / scope, lenient scope search, now)."""
+    import json
+    from cerbos_b200.engine import Engine
+    from helpers import load_golden, verify_suite_cases
+    from oracle.celeval import parse_timestamp
+    docs = [e["policy"] for e in load_golden("store_policies.json")]
+    n = 0
+    for (gl, dver, dscope, lenient), cases in verify_suite_cases():
+        eng = Engine(docs, globals_=json.loads(gl), default_policy_version=dver, default_scope=dscope, lenient_scope_search=lenient)
+        for c in cases:
+            now_ns = parse_timestamp(c["now"]).ns if c["now"] else NOW_NS
+            got = eng.check([c["input"]], now_ns=now_ns)[0]
+            for a, w in c["want"].items():
+                assert got["actions"][a]["effect"] == w, (c["file"], c["test"], a)
+                n += 1
+        eng.close()
+    assert n == 145

@@ -347,3 +347,31 @@ def test_check_resources_api_goldens():
             assert k_out[0, k] == names[want[a]], (f, a, "kernel core")
             n += 1
     assert n == 48
+
+
+def test_verify_suite_goldens():
+    """145 engine answers from the reference's policy-test goldens (verify/cases): oracle #1, oracle #2 and the kernel core,
+    under every engine configuration the suites use (globals, default policy version / scope, lenient scope search, now)."""
+    import json
+    from helpers import verify_suite_cases
+    names = {"EFFECT_ALLOW": 1, "EFFECT_DENY": 2}
+    rt = store_rule_table()
+    n = 0
+    for (gl, dver, dscope, lenient), cases in verify_suite_cases():
+        ft = flatten(rt, globals_=json.loads(gl))
+        orc = CheckOracle(rt, globals_=json.loads(gl), default_version=dver, default_scope=dscope, lenient_scope_search=lenient)
+        enc = Encoder(ft.manifest, default_version=dver, default_scope=dscope, lenient_scope_search=lenient)
+        fl = L.BATCH_FLAG_LENIENT if lenient else 0
+        for c in cases:
+            now = parse_timestamp(c["now"]) if c["now"] else NOW
+            py = orc.check(c["input"], now)
+            b = enc.encode([c["input"]])
+            c_out = cref.check(ft.blob, b.columns, 1, b.max_actions, now.ns, fl)
+            k_out = hostsim.check(ft.blob, b.columns, 1, b.max_actions, now.ns, fl)
+            for k, a in enumerate(c["input"]["actions"]):
+                w = names[c["want"][a]]
+                assert py["actions"][a]["effect"] == w, (c["file"], c["test"], a, "oracle #1")
+                assert c_out[0, k] == w, (c["file"], c["test"], a, "oracle #2")
+                assert k_out[0, k] == w, (c["file"], c["test"], a, "kernel core")
+                n += 1
+    assert n == 145
