@@ -136,6 +136,7 @@ class Context:
         cfg["clustered"] = bool(c.value & 1)
         cfg["tma_column_tiles"] = bool(c.value & 2)
         cfg["table_specialised"] = bool(c.value & 4)
+        cfg["unique_conditions"] = bool(c.value & 8)
         if c.value & 1:
             cfg["cluster_window"] = w.value
             cfg["cluster_buckets"] = nb.value

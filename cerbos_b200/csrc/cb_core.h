@@ -39,6 +39,8 @@ struct TableLayout {
     uint32_t nV, nRP, nS, nP, nR, nAP, nT, n_slots, n_rows;
     uint32_t has_role_policies, has_parent_roles, has_principal_policies;
     uint32_t image_bytes;
+    // "unique condition" image (cb_uc.h): offsets of the two derived sections, number of distinct conditions (0 = none)
+    uint32_t uc_conds_off, uc_rows_off, n_uconds;
 };
 
 // base = start of the table image: shared memory (TMA-staged) or global memory.
@@ -71,6 +73,8 @@ struct TableView {
     CB_HD const uint32_t *rp_apats() const { return sec<uint32_t>(CB_SEC_ROLEPOL_APATS); }
     CB_HD const uint32_t *block_slots_off() const { return sec<uint32_t>(CB_SEC_BLOCK_SLOTS_OFF); }
     CB_HD const uint32_t *block_slots() const { return sec<uint32_t>(CB_SEC_BLOCK_SLOTS); }
+    CB_HD const cb_cond *uconds() const { return reinterpret_cast<const cb_cond *>(base + L->uc_conds_off); }     // [n_uconds + 1], entry 0 unused
+    CB_HD const uint32_t *urows() const { return reinterpret_cast<const uint32_t *>(base + L->uc_rows_off); }      // [n_rows] packed (uc_row)
 };
 
 enum { CB_MAX_GATHER = 8 };
@@ -1312,6 +1316,15 @@ CB_HD_NOINLINE uint32_t cond_sat(const uint8_t *base, const TableLayout *L, cons
     return (s ? 1u : 0u) | (c.unsupported ? 2u : 0u);
 }
 
+// same, for a program given by its offset in CODE (the unique-condition image has no CONDS section)
+CB_HD_NOINLINE uint32_t cond_sat_code(const uint8_t *base, const TableLayout *L, const BatchView *b, uint64_t req, uint32_t pid, uint32_t code_off) {
+    TableView t; t.base = base; t.L = L;
+    Ctx c;
+    c.t = &t; c.b = b; c.req = req; c.pid = pid; c.unsupported = 0;
+    bool s = run_program(c, t.code() + code_off);
+    return (s ? 1u : 0u) | (c.unsupported ? 2u : 0u);
+}
+
 #endif  // !CB_LEAN_ONLY
 
 // ---- inline DNF evaluator of the lean body (layout FLAT_DNF, compiled by bytecode.FlatCompiler) --------------
@@ -1937,6 +1950,24 @@ struct GenericBlocks {
     }
 };
 
+// result of one request on the lean bodies: effect bytes (host-buffer ABI) or packed ALLOW bits
+template <typename Cols>
+CB_HD void store_result(const BatchView &b, const Cols &cols, uint64_t n, uint8_t *bitmap, uint8_t *effects, uint32_t K, uint32_t acc) {
+    if (effects) {
+        uint8_t *eff = effects + n * (uint64_t)b.max_actions;
+        if (b.max_actions == 8) {
+            uint64_t v = 0;
+            for (uint32_t k = 0; k < 8; k++) v |= (uint64_t)(k < K ? (((acc >> k) & 1) ? CB_EFFECT_ALLOW : CB_EFFECT_DENY) : 0) << (8 * k);
+            *reinterpret_cast<uint64_t *>(eff) = v;
+        } else {
+            for (uint32_t k = 0; k < b.max_actions; k++) eff[k] = (uint8_t)(k < K ? (((acc >> k) & 1) ? CB_EFFECT_ALLOW : CB_EFFECT_DENY) : 0);
+        }
+    } else {
+        if (cols.stage_result(acc)) bitmap[n] = (uint8_t)acc;   // (kbytes == 1; `bitmap` is this rank's own gather slice)
+        else store_bits(b, bitmap, n, acc);
+    }
+}
+
 template <typename Cols, typename Blocks = GenericBlocks>
 CB_HD bool eval_request_fast(const TableView t, const BatchView &b, const Cols &cols, uint64_t n, uint8_t *bitmap, uint8_t *effects, const Blocks blocks = Blocks()) {
     const U4 h0 = cols.hdr0();         // principal_id, kind (pattern id), resource_scope, principal_scope
@@ -1981,19 +2012,144 @@ CB_HD bool eval_request_fast(const TableView t, const BatchView &b, const Cols &
         else if (RC == 2) { x = (x | x >> 1) & 0x33333333u; x = (x | x >> 2) & 0x0F0F0F0Fu; x = (x | x >> 4) & 0x00FF00FFu; acc = (x | x >> 8) & 0xFFFFu; }
         else for (uint32_t kk = 0; kk < K; kk++) acc |= ((x >> (kk * RC)) & 1) << kk;
     }
-    if (effects) {
-        uint8_t *eff = effects + n * (uint64_t)b.max_actions;
-        if (b.max_actions == 8) {
-            uint64_t v = 0;
-            for (uint32_t k = 0; k < 8; k++) v |= (uint64_t)(k < K ? (((acc >> k) & 1) ? CB_EFFECT_ALLOW : CB_EFFECT_DENY) : 0) << (8 * k);
-            *reinterpret_cast<uint64_t *>(eff) = v;
-        } else {
-            for (uint32_t k = 0; k < b.max_actions; k++) eff[k] = (uint8_t)(k < K ? (((acc >> k) & 1) ? CB_EFFECT_ALLOW : CB_EFFECT_DENY) : 0);
-        }
-    } else {
-        if (cols.stage_result(acc)) bitmap[n] = (uint8_t)acc;   // (kbytes == 1; `bitmap` is this rank's own gather slice)
-        else store_bits(b, bitmap, n, acc);
+    store_result(b, cols, n, bitmap, effects, K, acc);
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------- unique-condition body
+// Tables whose policy blocks differ in shape (many kinds x scopes, each with its own rule list) make the lanes of a
+// warp walk different condition lists in index order.  But real policy sets draw their conditions from a small pool:
+// the same derived-role and rule conditions recur across policies (the reference memoises them per request under their
+// EvaluationKey, ruletable.go:1015, 1050, 1061).  cb_uc.h therefore numbers the DISTINCT conditions of the table
+// (1..U, U <= 63) and rewrites every row to {role, condition bit, derived-role condition bit, effect} (4 bytes).  This
+// body evaluates ALL U conditions of a request once, up front, into one 64-bit word -- every lane runs the same
+// instruction stream over coalesced column loads, whatever block each request hits -- and then walks the request's
+// scope chain with rows that are pure mask algebra on that word.  Conditions have no side effects and an error is
+// "not satisfied" (ruletable.go:1425-1441), so evaluating one that no row of the request needs cannot change a result.
+// Same domain as eval_request_fast (resource policies only, pair masks <= 32 bits); same deferral contract.
+CB_HD uint32_t uc_row(uint32_t role8, uint32_t cond, uint32_t drcond, uint32_t effect) { return role8 | cond << 8 | drcond << 16 | effect << 24; }
+
+// row access of the unique-condition body: {action mask of the request's action set, packed row}
+struct UcRowsGlobal {   // straight from the table image and the batch's row_am column
+    const uint32_t *urows; const uint64_t *row_am;
+    CB_HD void get(uint32_t aset_base, uint32_t ri, uint32_t &am, uint32_t &ur) const { am = (uint32_t)ldg(row_am + aset_base + ri); ur = ldg(urows + ri); }
+};
+struct UcRowsPacked {   // one 8-byte record per (action set, row), merged once per CTA into shared memory
+    const uint64_t *pk;
+    CB_HD void get(uint32_t aset_base, uint32_t ri, uint32_t &am, uint32_t &ur) const { const uint64_t v = ldg(pk + aset_base + ri); am = (uint32_t)v; ur = (uint32_t)(v >> 32); }
+};
+
+// column access with L1 allocation: the eager condition pass reads the same slot from several terms
+struct CachedCols {
+    const BatchView *b;
+    uint64_t n;
+    CB_HD U4 hdr0() const { return ldcol128(b->hdr0 + n); }
+    CB_HD uint64_t hdr1() const { return ldcol64(reinterpret_cast<const uint64_t *>(b->hdr1 + n)); }
+    CB_HD uint32_t role(uint32_t i) const { return ldcol32(b->roles + (uint64_t)i * b->stride + n); }
+    CB_HD uint64_t slot(uint32_t v) const {
+#if defined(__CUDA_ARCH__)
+        uint64_t x;
+        asm("ld.global.nc.u64 %0, [%1];" : "=l"(x) : "l"(b->slots + (uint64_t)v * b->stride + n));
+        return x;
+#else
+        return b->slots[(uint64_t)v * b->stride + n];
+#endif
     }
+    CB_HD void prefetch_slot(uint32_t) const {}
+    CB_HD bool staged() const { return true; }
+    CB_HD uint32_t aset_k(uint32_t aset) const { return ldg(b->aset_k + aset); }
+    CB_HD const uint64_t *row_am() const { return b->row_am; }
+    CB_HD bool stage_result(uint32_t) const { return false; }
+};
+
+// How the unique-condition body gets a request's condition word: this generic evaluator interprets the table's DNF
+// terms (and, in the ahead-of-time build, runs the stack interpreter for conditions without a flat form); a run-time
+// specialised build (cb_specialize.h: generate_uc) substitutes straight-line code over register-resident slots.
+struct GenericConds {
+    template <typename Cols>
+    CB_HD Cols load(const Cols &cols) const { return cols; }
+    template <typename Cols>
+    CB_HD uint64_t operator()(const TableView t, const BatchView &b, const Cols &cols, uint32_t pid, uint64_t n, bool &slow) const {
+        uint64_t val = 1;
+        for (uint32_t u = 1, nu = t.L->n_uconds; u <= nu; u++) {
+            const U4 cd = ld16(t.uconds() + u);   // {code_off, code_len, flat_off, flat_info}
+            uint32_t r;
+            if (cd.w) r = flat_dnf_inline(t, b, cols, pid, cd.z, cd.w);
+            else {
+#ifndef CB_LEAN_ONLY
+                // no flat form: the generic interpreter (an out-of-line call); a value it cannot represent exactly only
+                // matters if a row of the request needs this condition -- the general body decides that
+                const uint32_t q = cond_sat_code(t.base, t.L, &b, n, pid, cd.x);
+                r = (q & 1u) | ((q & 2u) << 1);
+#else
+                r = 4u;
+#endif
+            }
+            slow |= (r & 4u) != 0;
+            val |= (uint64_t)(r & 1u) << u;
+        }
+        return val;
+    }
+};
+
+template <typename Cols, typename Rows, typename Conds = GenericConds>
+CB_HD bool eval_request_uc(const TableView t, const BatchView &b, const Cols &cols, const Rows rows, uint64_t n, uint8_t *bitmap, uint8_t *effects,
+                           const Conds conds = Conds()) {
+    const U4 h0 = cols.hdr0();         // principal_id, kind (pattern id), resource_scope, principal_scope
+    const uint64_t h1 = cols.hdr1();   // rv u16 | pv u16 | action_set_id u32
+    const auto regs = conds.load(cols);   // specialised build: every attribute slot the table reads, in flight at once
+    const uint32_t pid = h0.x, kc = h0.y, rscope = h0.z;
+    const uint32_t rv = (uint32_t)(h1 & 0xFFFF), pv = (uint32_t)((h1 >> 16) & 0xFFFF), aset = (uint32_t)(h1 >> 32);
+    const uint32_t RC = b.role_cols, RCP = b.rcp;
+    const uint32_t K = aset < b.n_asets ? cols.aset_k(aset) : 0;
+    uint64_t rp = 0;          // role table: RCP bits per table role
+    uint32_t n_roles = 0;
+    for (uint32_t i = 0; i < RC; i++) {
+        uint32_t rr = cols.role(i);
+        n_roles = rr != CB_ROLE_PAD ? i + 1 : n_roles;
+        rp |= rr < t.L->nR ? 1ull << (rr * RCP + i) : 0ull;
+    }
+    if (pv != rv) return true;   // existence checks matter only then (ruletable.go:852-863): general body
+    uint32_t acc = 0;
+    const bool live = n_roles != 0 && K != 0 && rv != CB_NONE16 && kc != CB_KIND_NONE;
+    const uint32_t r0 = live ? chain_start(t, rscope, CB_SCOPE_FLAG_RESOURCE, (b.flags & CB_BATCH_FLAG_LENIENT) != 0) : CB_NONE32;
+    if (r0 != CB_NONE32) {
+        bool slow = false;
+        const uint64_t val = conds(t, b, regs, pid, n, slow);   // bit u: distinct condition u holds; bit 0: "no condition"
+        if (slow) return true;
+        const uint32_t role_all = (1u << n_roles) - 1;
+        const uint32_t aset_base = aset * b.n_rows;
+        const uint32_t amask = K * RC >= 32 ? b.stride_pattern : b.stride_pattern & ((1u << (K * RC)) - 1);   // bit kk*RC per action
+        uint32_t alive = amask * role_all, allow_pairs = 0;
+        for (uint32_t s = r0; s != CB_NONE32 && alive; s = chain_next(t, s, CB_SCOPE_FLAG_RESOURCE)) {
+            const uint32_t bid = ldg(t.res_block_map() + ((uint64_t)rv * t.L->nRP + kc) * t.L->nS + s);
+            if (bid != CB_NONE32) {
+                const uint64_t bl = *reinterpret_cast<const uint64_t *>(t.blocks() + bid);   // {row_start, n_rows}
+                uint32_t D = 0, A = 0;   // DENY / ALLOW pair masks of this scope
+                for (uint32_t ri = (uint32_t)bl, re = (uint32_t)bl + (uint32_t)(bl >> 32); ri < re; ri++) {
+                    uint32_t am, ur;
+                    rows.get(aset_base, ri, am, ur);
+                    const uint32_t role = ur & 0xFFu;
+                    const uint32_t rc = role == 0xFFu ? role_all : (uint32_t)(rp >> (role * RCP)) & role_all;
+                    const uint32_t sat = (uint32_t)(val >> ((ur >> 8) & 0xFFu)) & (uint32_t)(val >> ((ur >> 16) & 0xFFu)) & 1u;   // rule AND derived-role condition
+                    const uint32_t ms = (am * rc) & alive & (0u - sat);
+                    const bool deny = (ur >> 24) == CB_EFFECT_DENY;
+                    D |= deny ? ms : 0u;
+                    A |= deny ? 0u : ms;
+                }
+                alive &= ~D;
+                if (((ldg(t.scope_flags() + s) >> CB_SCOPE_PERM_SHIFT) & 3) == 1) { uint32_t a = A & alive; allow_pairs |= a; alive &= ~a; }
+            }
+        }
+        // fold: an action is ALLOWed iff some role column allowed it; then pack the stride-RC bits
+        uint32_t x = allow_pairs;
+        for (uint32_t j = 1; j < RC; j++) x |= allow_pairs >> j;
+        x &= amask;
+        if (RC == 1) acc = x;
+        else if (RC == 2) { x = (x | x >> 1) & 0x33333333u; x = (x | x >> 2) & 0x0F0F0F0Fu; x = (x | x >> 4) & 0x00FF00FFu; acc = (x | x >> 8) & 0xFFFFu; }
+        else for (uint32_t kk = 0; kk < K; kk++) acc |= ((x >> (kk * RC)) & 1) << kk;
+    }
+    store_result(b, cols, n, bitmap, effects, K, acc);
     return false;
 }
 

@@ -292,4 +292,58 @@ __device__ __forceinline__ void check_tiles_body(const TableDesc &td, const cb::
 #endif
 }
 
+// Unique-condition body (cb::eval_request_uc): index order, columns read straight from global memory with coalesced
+// loads (a warp covers 32 consecutive requests: 256 B per slot column), every lane running the same instruction stream
+// whatever policy block its request hits.  No column staging: the specialised build pulls all the slots of a request
+// into registers up front, so each warp keeps ~(3 + role_cols + n_slots) independent loads in flight and the SM's
+// occupancy is bounded by registers only.  kStaged: the compact table image (cb_uc.h; a few KB) is staged once per
+// persistent CTA by the TMA unit and the rows are merged with the batch's row x action-set masks into one 8-byte record
+// per row in shared memory; otherwise both are read from global memory (images too large for shared memory).
+// Work distribution is warp-granular: warp w of the grid takes the 32-request chunks w, w + n_warps, ... -- no
+// CTA-wide barrier in the loop.  Deferred requests (an operand the 8-byte forms cannot decide, differing policy
+// versions) go to the launch's deferral list, drained by the general kernel right behind; they are first written as
+// DENY so that a lost deferral could only fail closed.
+// smem layout (kStaged): [image, 128-byte padded][packed rows: n_asets x n_rows x 8 B]
+template <typename Conds, typename Cols, bool kStaged>
+__device__ __forceinline__ void check_uc_body(const TableDesc &td, const cb::BatchView &bv, uint8_t *bitmap, uint8_t *effects, uint8_t *smem_image, uint64_t *mbar) {
+    cb::TableView tv;
+    tv.L = &td.lay;
+    tv.base = kStaged ? smem_image : td.base;
+    const uint64_t *pk = nullptr;
+    if (kStaged) {
+        if (threadIdx.x == 0) {
+            mbar_init(mbar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) tma_load_image(smem_image, td, mbar);
+        mbar_wait(mbar, 0);
+        uint64_t *pks = reinterpret_cast<uint64_t *>(smem_image + ((td.lay.image_bytes + 127u) & ~127u));
+        const uint32_t n_pk = bv.n_asets * bv.n_rows;
+        const uint32_t *ur = tv.urows();
+        for (uint32_t j = threadIdx.x; j < n_pk; j += kThreads) pks[j] = (uint64_t)(uint32_t)bv.row_am[j] | (uint64_t)ur[j % bv.n_rows] << 32;
+        __syncthreads();
+        pk = pks;
+    }
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t n_chunks = (bv.count + 31) / 32;
+    const uint64_t n_warps = (uint64_t)gridDim.x * (kThreads / 32);
+    for (uint64_t chunk = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); chunk < n_chunks; chunk += n_warps) {
+        const uint64_t i = chunk * 32 + lane;
+        if (i < bv.count) {
+            const uint64_t n = bv.first + i;
+            Cols gc;
+            gc.b = &bv; gc.n = n;
+            bool d;
+            if (kStaged) { cb::UcRowsPacked rows; rows.pk = pk; d = cb::eval_request_uc(tv, bv, gc, rows, n, bitmap, effects, Conds()); }
+            else { cb::UcRowsGlobal rows; rows.urows = tv.urows(); rows.row_am = bv.row_am; d = cb::eval_request_uc(tv, bv, gc, rows, n, bitmap, effects, Conds()); }
+            if (d) {
+                cb::store_result(bv, gc, n, bitmap, effects, bv.max_actions, 0u);
+                const uint32_t k = atomicAdd(bv.defer_count, 1u);
+                bv.defer_list[k] = (uint32_t)i;
+            }
+        }
+    }
+}
+
 }  // namespace cbk

@@ -157,4 +157,77 @@ inline std::string generate(const uint8_t *image, const uint32_t *off, const uin
     return s;
 }
 
+// ---- unique-condition form (cb_uc.h / cb::eval_request_uc) -----------------------------------------------------------
+// For tables whose blocks differ in shape the per-shape inlining above explodes; their DISTINCT conditions are few.
+// generate_uc() emits `SpecConds`: load() pulls every attribute slot the conditions read into registers (all loads in
+// flight at once, coalesced), operator() evaluates every distinct DNF term once (shared between conditions) and
+// combines them into the request's condition word.  Rows stay data (4-byte records walked by the generic loop).
+// uc: the compact image (cb_uc.h) and its layout.  "" = does not qualify (a distinct condition without flat form ...).
+struct UcLimits {
+    uint32_t max_terms = 512;   // distinct terms
+};
+inline std::string generate_uc(const uint8_t *uc_image, const uint32_t *off, uint32_t uc_conds_off, uint32_t n_uconds, uint32_t n_slots, const UcLimits lim = UcLimits()) {
+    if (n_uconds == 0 || n_uconds > 63) return "";
+    const uint32_t *uconds = reinterpret_cast<const uint32_t *>(uc_image + uc_conds_off);    // [n_uconds + 1] x {code_off, code_len, flat_off, flat_info}
+    const uint32_t *code = reinterpret_cast<const uint32_t *>(uc_image + off[CB_SEC_CODE]);
+    const uint64_t *consts = reinterpret_cast<const uint64_t *>(uc_image + off[CB_SEC_CONSTS_V64]);
+    const uint64_t *theap = reinterpret_cast<const uint64_t *>(uc_image + off[CB_SEC_THEAP]);
+    const uint32_t kUseMask = ~((uint32_t)(CB_TERM_LIT_F | CB_TERM_GROUP_END) << 8);
+    std::map<std::vector<uint32_t>, uint32_t> term_ids;
+    std::vector<std::vector<uint32_t>> terms;
+    std::vector<bool> slot_used(n_slots ? n_slots : 1, false);
+    auto use_slot = [&](uint32_t kind, uint32_t v) { if ((kind == CB_OPK_SLOT || kind == CB_OPK_SLOT_ELEM || kind == CB_OPK_SLOT_SIZE) && v < slot_used.size()) slot_used[v] = true; };
+    for (uint32_t u = 1; u <= n_uconds; u++) {
+        const uint32_t *cd = uconds + 4 * u;
+        if (cd[3] == 0 || ((cd[3] >> 16) & 0xFF) != CB_FLAT_DNF) return "";
+        for (uint32_t i = 0, nt = cd[3] & 0xFFFFu; i < nt; i++) {
+            const uint32_t *w = code + 2 * (cd[2] + 2 * i);
+            std::vector<uint32_t> key = {w[0] & kUseMask, w[1], w[2], w[3]};
+            if (term_ids.emplace(key, (uint32_t)terms.size()).second) {
+                terms.push_back(key);
+                const uint32_t op = w[0] & 0xFF;
+                switch (op) {   // which operands are slots (bytecode._specialize_term shapes first)
+                case CB_TERM_EQ_SS: case CB_TERM_ORD_SS: case CB_TERM_IN_SS: use_slot(CB_OPK_SLOT, w[1]); use_slot(CB_OPK_SLOT, w[2]); break;
+                case CB_TERM_EQ_SC: case CB_TERM_EQ_SP: case CB_TERM_ORD_SC: case CB_TERM_IN_SC: use_slot(CB_OPK_SLOT, w[1]); break;
+                case CB_TERM_IN_CS: use_slot(CB_OPK_SLOT, w[2]); break;
+                default: use_slot((w[0] >> 16) & 0xFF, w[1]); if (op != CB_TERM_HAS) use_slot(w[0] >> 24, w[2]); break;
+                }
+            }
+        }
+    }
+    if (terms.size() > lim.max_terms) return "";
+    std::string s;
+    s += "// generated by cb_specialize.h (generate_uc) from the loaded table: every distinct condition, straight-line\n";
+    s += "namespace cb {\nstruct SpecRegs {\n";
+    for (uint32_t v = 0; v < slot_used.size(); v++)
+        if (slot_used[v]) s += "    uint64_t s" + std::to_string(v) + ";\n";
+    s += "    CB_HD uint64_t slot(uint32_t v) const {\n        switch (v) {\n";
+    for (uint32_t v = 0; v < slot_used.size(); v++)
+        if (slot_used[v]) s += "        case " + std::to_string(v) + "u: return s" + std::to_string(v) + ";\n";
+    s += "        default: return (uint64_t)(CB_V64_BOX_BASE | CB_V64_ERROR) << 48;\n        }\n    }\n};\n";
+    s += "struct SpecConds {\n    template <typename Cols>\n    CB_HD SpecRegs load(const Cols &c) const {\n        SpecRegs r;\n";
+    for (uint32_t v = 0; v < slot_used.size(); v++)
+        if (slot_used[v]) s += "        r.s" + std::to_string(v) + " = c.slot(" + std::to_string(v) + "u);\n";
+    s += "        return r;\n    }\n";
+    s += "    CB_HD uint64_t operator()(const TableView t, const BatchView &b, const SpecRegs &cols, uint32_t pid, uint64_t, bool &slow) const {\n";
+    for (uint32_t q = 0; q < terms.size(); q++)
+        s += "        const int q" + std::to_string(q) + " = " + term_expr(terms[q].data(), consts, theap) + ";\n";
+    s += "        uint64_t val = 1ull;\n";
+    for (uint32_t u = 1; u <= n_uconds; u++) {
+        const uint32_t *cd = uconds + 4 * u;
+        const uint32_t nt = cd[3] & 0xFFFFu, negate = (cd[3] >> 24) & 1u;
+        s += "        {   // distinct condition " + std::to_string(u) + "\n            bool any = false, group = true;\n";
+        for (uint32_t i = 0; i < nt; i++) {
+            const uint32_t *w = code + 2 * (cd[2] + 2 * i);
+            const uint32_t flags = (w[0] >> 8) & 0xFFu;
+            const uint32_t q = term_ids[{w[0] & kUseMask, w[1], w[2], w[3]}];
+            s += "            group &= term_lit(q" + std::to_string(q) + ", " + hex(flags) + ");\n";
+            if (flags & CB_TERM_GROUP_END) s += "            any |= group; group = true;\n";
+        }
+        s += std::string("            val |= (uint64_t)(any != ") + (negate ? "true" : "false") + ") << " + std::to_string(u) + ";\n        }\n";
+    }
+    s += "        return val;\n    }\n};\n}  // namespace cb\n";
+    return s;
+}
+
 }  // namespace cbspec

@@ -1,0 +1,105 @@
+// cb_uc.h -- host-side builder of the "unique condition" image of a loaded table.
+//
+// The flattened table (cerbos_b200/table/flatten.py) keeps one condition list per policy block, the way the reference
+// keeps one compiled condition per rule (ruletable.go:105-416).  Across a policy set the same conditions recur: shared
+// derived roles, the same ownership / tenancy test on every resource kind.  This builder
+//   * numbers the DISTINCT conditions of the table 1..U (same DNF term list, or same bytecode program),
+//   * rewrites every row to 4 bytes {role, condition number, derived-role condition number, effect} (cb::uc_row),
+//   * copies only the sections the unique-condition kernels read into a compact image (C3: 49 KB blob -> ~10 KB),
+// so that a kernel can evaluate every distinct condition of a request once, with all lanes in lock step, and walk the
+// rows as mask algebra (cb::eval_request_uc).  Built once per cgpu_table_load; the Python blob format is unchanged.
+//
+// Host-only, no CUDA dependencies: tests/hostsim uses it too.
+#pragma once
+#include <stdint.h>
+
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "cb_core.h"
+
+namespace cbuc {
+
+constexpr uint32_t kMaxUconds = 63;   // bit 0 of the condition word is "no condition"
+
+struct Image {
+    bool ok = false;
+    std::string why;                    // when !ok
+    std::vector<uint8_t> bytes;         // compact image (16-byte aligned sections)
+    cb::TableLayout lay{};              // offsets into `bytes` + the dims of the source layout
+    uint32_t n_uconds = 0, n_flat = 0;  // distinct conditions; how many of them have a flat (DNF) form
+    std::vector<uint32_t> ucond_of_gid; // table condition id -> distinct condition number (1..U)
+};
+
+// image: the table image (blob bytes); off / len: section offset and byte length by section id; lay: its layout
+inline Image build(const uint8_t *image, const uint32_t *off, const uint64_t *len, const uint32_t *meta, const cb::TableLayout &lay) {
+    Image out;
+    const uint32_t n_blocks = meta[CB_META_N_BLOCKS], n_rows = meta[CB_META_N_ROWS], n_conds = meta[CB_META_N_CONDS];
+    if (n_blocks == 0) { out.why = "no policy blocks"; return out; }
+    if (lay.nR > 64) { out.why = "more than 64 roles"; return out; }
+    const uint32_t *blocks = reinterpret_cast<const uint32_t *>(image + off[CB_SEC_BLOCKS]);
+    const uint32_t *rows = reinterpret_cast<const uint32_t *>(image + off[CB_SEC_ROWS]);
+    const uint32_t *conds = reinterpret_cast<const uint32_t *>(image + off[CB_SEC_CONDS]);
+    if (len[CB_SEC_BLOCKS] < (uint64_t)n_blocks * 16 || len[CB_SEC_ROWS] < (uint64_t)n_rows * 16 || len[CB_SEC_CONDS] < (uint64_t)n_conds * 16) {
+        out.why = "section sizes do not match META";
+        return out;
+    }
+    // distinct conditions
+    std::map<std::tuple<uint32_t, uint32_t, uint32_t>, uint32_t> ids;
+    std::vector<uint32_t> ucond_rec;   // 4 words per distinct condition, entry 0 unused
+    ucond_rec.assign(4, 0);
+    out.ucond_of_gid.assign(n_conds, 0);
+    for (uint32_t g = 0; g < n_conds; g++) {
+        const uint32_t *cd = conds + 4 * g;   // {code_off, code_len, flat_off, flat_info}
+        const bool flat = cd[3] != 0 && ((cd[3] >> 16) & 0xFF) == CB_FLAT_DNF;
+        const auto key = flat ? std::make_tuple(1u, cd[2], cd[3]) : std::make_tuple(0u, cd[0], cd[1]);
+        auto it = ids.find(key);
+        if (it == ids.end()) {
+            const uint32_t u = (uint32_t)ids.size() + 1;
+            if (u > kMaxUconds) { out.why = "more than 63 distinct conditions"; return out; }
+            it = ids.emplace(key, u).first;
+            ucond_rec.insert(ucond_rec.end(), {cd[0], cd[1], flat ? cd[2] : 0u, flat ? cd[3] : 0u});
+            out.n_flat += flat;
+        }
+        out.ucond_of_gid[g] = it->second;
+    }
+    out.n_uconds = (uint32_t)ids.size();
+    // rows
+    std::vector<uint32_t> urows(n_rows ? n_rows : 1, 0);
+    for (uint32_t b = 0; b < n_blocks; b++) {
+        const uint32_t *bl = blocks + 4 * b;   // {row_start, n_rows, cond_base, n_conds}
+        if ((uint64_t)bl[0] + bl[1] > n_rows) { out.why = "block rows out of range"; return out; }
+        for (uint32_t r = 0; r < bl[1]; r++) {
+            const uint32_t *row = rows + 4 * (bl[0] + r);
+            const uint32_t role = row[0] & 0xFFFFu, c = row[0] >> 16, dc = row[1] & 0xFFFFu, effect = row[2] & 0xFFu;
+            if ((c && c > bl[3]) || (dc && dc > bl[3]) || (uint64_t)bl[2] + bl[3] > n_conds) { out.why = "row condition out of range"; return out; }
+            if (role != CB_ROLE_ANY && role >= 64) { out.why = "role id out of range"; return out; }
+            const uint32_t uc = c ? out.ucond_of_gid[bl[2] + c - 1] : 0, udc = dc ? out.ucond_of_gid[bl[2] + dc - 1] : 0;
+            urows[bl[0] + r] = cb::uc_row(role == CB_ROLE_ANY ? 0xFFu : role, uc, udc, effect);
+        }
+    }
+    // compact image: the sections the unique-condition kernels (and the interpreter they may call) read
+    out.lay = lay;
+    for (auto &o : out.lay.off) o = 0;
+    auto append = [&](const void *p, uint64_t n) {
+        const uint32_t at = (uint32_t)out.bytes.size();
+        out.bytes.resize((out.bytes.size() + n + 15) & ~(size_t)15, 0);
+        if (n) memcpy(out.bytes.data() + at, p, n);
+        return at;
+    };
+    append("CBUC", 4);   // offset 0 stays unused: a zero offset means "section not present"
+    for (int id : {CB_SEC_SCOPE_PARENT, CB_SEC_SCOPE_FLAGS, CB_SEC_RES_BLOCK_MAP, CB_SEC_BLOCKS, CB_SEC_CODE, CB_SEC_CONSTS, CB_SEC_CONSTS_V64, CB_SEC_THEAP,
+                   CB_SEC_STR_OFF, CB_SEC_STR_BYTES})
+        out.lay.off[id] = append(image + off[id], len[id]);
+    out.lay.uc_conds_off = append(ucond_rec.data(), ucond_rec.size() * 4);
+    out.lay.uc_rows_off = append(urows.data(), urows.size() * 4);
+    out.lay.n_uconds = out.n_uconds;
+    out.lay.image_bytes = (uint32_t)out.bytes.size();
+    out.ok = true;
+    return out;
+}
+
+}  // namespace cbuc

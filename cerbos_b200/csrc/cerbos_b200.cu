@@ -3,11 +3,14 @@
 // Device bodies: cb_kernels.h (+ cb_core.h); this file holds the __global__ wrappers, the clustering kernels and the host side.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <new>
 #include <string>
@@ -17,6 +20,7 @@
 #include "cb_core.h"
 #include "cb_kernels.h"
 #include "cb_specialize.h"
+#include "cb_uc.h"
 #include "cb_embed.inc"
 #include "cerbos_b200.h"
 
@@ -28,7 +32,6 @@ constexpr int kThreads = cbk::kThreads;
 #endif
 constexpr uint32_t kMaxStageBytes = 96 * 1024;   // table images up to this size are TMA-staged into shared memory
 constexpr int kMaxSec = 28;
-constexpr uint32_t kDeferCells = 256;
 constexpr uint32_t kMaxTilesSmem = 56 * 1024;    // image + two column-tile stages: keeps CB_MIN_BLOCKS CTAs resident per SM
 
 using cbk::TableDesc;
@@ -47,6 +50,16 @@ __global__ void __launch_bounds__(kThreads, CB_MIN_BLOCKS) check_kernel_tiles(co
     extern __shared__ __align__(128) uint8_t smem_image[];
     __shared__ __align__(8) uint64_t mbar_tab, mbar_col[4];
     cbk::check_tiles_body<cb::GenericBlocks>(td, bv, bitmap, effects, status, n_slots, smem_image, &mbar_tab, mbar_col);
+}
+
+// unique-condition kernels (cb_uc.h image; generic condition evaluator; deferrals go to the launch's list)
+template <bool kStaged>
+__global__ void __launch_bounds__(kThreads, CB_MIN_BLOCKS) check_uc(const __grid_constant__ TableDesc td, const __grid_constant__ cb::BatchView bv, uint8_t *bitmap,
+                                                                  uint8_t *effects, uint32_t *status, const uint32_t) {
+    extern __shared__ __align__(128) uint8_t smem_image[];
+    __shared__ __align__(8) uint64_t mbar;
+    (void)status;
+    cbk::check_uc_body<cb::GenericConds, cb::CachedCols, kStaged>(td, bv, bitmap, effects, smem_image, &mbar);
 }
 
 // ------------------------------------------------------------------------------------------------ fused all-gather
@@ -209,12 +222,19 @@ struct cgpu_ctx {
     int force_no_tiles = 0;  // CERBOS_B200_NO_TILES=1: never stage request columns through TMA (tests)
     int force_no_jit = 0;    // CERBOS_B200_NO_JIT=1: never compile table-specialised kernels (tests)
     uint32_t last_spec = 0;
-    uint32_t *d_defer_cells = nullptr;   // kDeferCells x {count, done, tile counter, -}, zero between uses (the drain kernel re-zeroes)
-    std::atomic<uint32_t> defer_next{0};
-    uint32_t *defer_lists[4] = {nullptr, nullptr, nullptr, nullptr};   // rotating deferral lists (grow-only): launches may overlap at their tails
-    size_t defer_cap[4] = {0, 0, 0, 0};
-    std::vector<uint32_t *> defer_retired;
+    // Deferral state is owned by the STREAM a launch is issued on (a cgpu_check slot has its own stream): launches on one
+    // stream complete in order, and with programmatic launch chaining at most three consecutive ones are in flight
+    // together (k draining, k+1 running, k+2 starting), so every stream rotates over four lists / counter cells of its own.
+    struct DeferLane {
+        uint32_t seq = 0;
+        uint32_t *lists[4] = {nullptr, nullptr, nullptr, nullptr};
+        size_t cap[4] = {0, 0, 0, 0};
+        uint32_t *cells = nullptr;   // 4 x {count, done, tile counter, -}, zero between uses (the drain kernel re-zeroes)
+    };
+    std::map<cudaStream_t, DeferLane> defer_lanes;
     std::mutex defer_mu;
+    int uc_mode = -1;        // CERBOS_B200_UC: 0 never use the unique-condition kernels, 1 whenever the table allows, unset = tables with > 1 block shape
+    uint32_t last_uc = 0;
     bool profiling = false;  // cgpu_profile(): CUDA events around the check kernel of every launch
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double prof_ms = 0;
@@ -228,22 +248,27 @@ struct cgpu_table {
     uint8_t *d_image = nullptr;
     TableDesc desc{};
     uint32_t meta[CB_META_WORDS]{};
-    std::atomic<int> occ[7]{};
-    std::atomic<uint32_t> occ_smem[7]{};
+    std::atomic<int> occ[10]{};
+    std::atomic<uint32_t> occ_smem[10]{};
     // table-specialised lean kernels (cb_specialize.h), compiled with NVRTC on first use
     std::vector<uint8_t> host_image;
     std::mutex spec_mu;
     std::atomic<int> spec_state{0};   // 0 not tried, 1 ready, -1 unavailable
     cudaLibrary_t spec_lib = nullptr;
-    cudaKernel_t spec_tiles = nullptr, spec_direct = nullptr;
+    cudaKernel_t spec_tiles = nullptr, spec_direct = nullptr, spec_uc = nullptr;
     std::string spec_note;
+    // unique-condition image (cb_uc.h): compact copy of the table for tables whose blocks differ in shape
+    uint64_t sec_len[kMaxSec]{};
+    cbuc::Image uc;
+    uint8_t *d_uc_image = nullptr;
+    TableDesc uc_desc{};
     std::thread spec_thread;          // compiles the specialised kernels in the background from cgpu_table_load on
     std::mutex join_mu;   // resident CTAs / SM per kernel variant (0 = not queried yet)
 };
 
 namespace {
 
-int parse_blob(const void *blob, size_t len, TableDesc *d, uint32_t *meta) {
+int parse_blob(const void *blob, size_t len, TableDesc *d, uint32_t *meta, uint64_t *sec_len = nullptr) {
     if (!blob || len < sizeof(cb_blob_header)) return fail(CGPU_ERR_INVALID, "table blob too small");
     const cb_blob_header *h = static_cast<const cb_blob_header *>(blob);
     if (h->magic != CB_MAGIC) return fail(CGPU_ERR_INVALID, "table blob: bad magic");
@@ -255,11 +280,12 @@ int parse_blob(const void *blob, size_t len, TableDesc *d, uint32_t *meta) {
     uint64_t image_end = 0;
     bool seen[kMaxSec] = {false};
     for (uint32_t i = 0; i < h->n_sections; i++) {
-        if (sd[i].offset + sd[i].n_bytes > len || (sd[i].offset & 15)) return fail(CGPU_ERR_INVALID, "table blob: bad section %u", sd[i].id);
+        if (sd[i].offset > len || sd[i].n_bytes > len - sd[i].offset || (sd[i].offset & 15)) return fail(CGPU_ERR_INVALID, "table blob: bad section %u", sd[i].id);
         if (sd[i].id == CB_SEC_MANIFEST) continue;   // host-only
         if (sd[i].id >= kMaxSec) continue;
         if (sd[i].offset > 0xFFFFFFF0ull) return fail(CGPU_ERR_INVALID, "table blob too large");
         d->lay.off[sd[i].id] = (uint32_t)sd[i].offset;
+        if (sec_len) sec_len[sd[i].id] = sd[i].n_bytes;
         seen[sd[i].id] = true;
         uint64_t end = (sd[i].offset + sd[i].n_bytes + 15) & ~15ull;
         if (end > image_end) image_end = end;
@@ -271,12 +297,26 @@ int parse_blob(const void *blob, size_t len, TableDesc *d, uint32_t *meta) {
     for (int id = CB_SEC_META; id <= CB_SEC_BLOCK_SLOTS; id++)
         if (!seen[id]) return fail(CGPU_ERR_INVALID, "table blob: missing section %d", id);
     if (image_end > 0xFFFFFFF0ull) return fail(CGPU_ERR_INVALID, "table blob too large");
+    if (image_end > len) image_end = len;   // the last device section may end unaligned at the end of the blob (sections themselves are bounds-checked above)
     d->lay.image_bytes = (uint32_t)image_end;
     d->lay.nV = meta[CB_META_N_VERSIONS]; d->lay.nRP = meta[CB_META_N_RESPATS]; d->lay.nS = meta[CB_META_N_SCOPES];
     d->lay.nP = meta[CB_META_N_PRINCIPALS]; d->lay.nR = meta[CB_META_N_ROLES]; d->lay.nAP = meta[CB_META_N_APATS];
     d->lay.nT = meta[CB_META_N_STRINGS]; d->lay.n_slots = meta[CB_META_N_SLOTS]; d->lay.n_rows = meta[CB_META_N_ROWS] ? meta[CB_META_N_ROWS] : 1;
     d->lay.has_role_policies = meta[CB_META_HAS_ROLE_POLICIES]; d->lay.has_parent_roles = meta[CB_META_HAS_PARENT_ROLES];
     d->lay.has_principal_policies = meta[CB_META_HAS_PRINCIPAL_POLICIES];
+    if (sec_len) {
+        struct { int id; uint64_t need; } chk[] = {
+            {CB_SEC_SCOPE_PARENT, 4ull * d->lay.nS}, {CB_SEC_SCOPE_FLAGS, 4ull * d->lay.nS},
+            {CB_SEC_RES_BLOCK_MAP, 4ull * d->lay.nV * d->lay.nRP * d->lay.nS}, {CB_SEC_RES_EXISTS, 1ull * d->lay.nV * d->lay.nRP * d->lay.nS},
+            {CB_SEC_PRIN_BLOCK_MAP, 4ull * d->lay.nV * d->lay.nP * d->lay.nS}, {CB_SEC_PRIN_EXISTS, 1ull * d->lay.nV * d->lay.nS},
+            {CB_SEC_BLOCKS, 16ull * meta[CB_META_N_BLOCKS]}, {CB_SEC_ROWS, 16ull * meta[CB_META_N_ROWS]}, {CB_SEC_CONDS, 16ull * meta[CB_META_N_CONDS]},
+            {CB_SEC_CODE, 8ull * meta[CB_META_N_CODE]}, {CB_SEC_CONSTS, 16ull * meta[CB_META_N_CONSTS]}, {CB_SEC_CONSTS_V64, 8ull * meta[CB_META_N_CONSTS]},
+            {CB_SEC_STR_OFF, 4ull * (d->lay.nT + 1)}, {CB_SEC_THEAP, 8ull * meta[CB_META_THEAP_WORDS]},
+            {CB_SEC_BLOCK_SLOTS_OFF, 4ull * (meta[CB_META_N_BLOCKS] + 1)},
+        };
+        for (const auto &c : chk)
+            if (sec_len[c.id] < c.need) return fail(CGPU_ERR_INVALID, "table blob: section %d holds %llu bytes, META needs %llu", c.id, (unsigned long long)sec_len[c.id], (unsigned long long)c.need);
+    }
     if (meta[CB_META_MAX_STACK] > CB_MAX_STACK || meta[CB_META_MAX_LOOP_DEPTH] > CB_MAX_LOOP_DEPTH || meta[CB_META_N_VARS] > CB_MAX_VARS)
         return fail(CGPU_ERR_INVALID, "table blob needs a deeper interpreter than this build provides");
     return CGPU_OK;
@@ -377,27 +417,100 @@ const char kSpecKernels[] =
     "    __shared__ __align__(8) uint64_t mbar;\n"
     "    cbk::check_body<true, 1, cb::SpecBlocks>(td, bv, bitmap, effects, status, stage_rt, smem_image, &mbar);\n"
     "}\n";
+// unique-condition form: the compact image staged in shared memory, every distinct condition as straight-line code
+const char kSpecUcKernels[] =
+    "\nextern \"C\" __global__ void __launch_bounds__(256, CB_SPEC_UC_MIN_BLOCKS) cb_spec_uc(const __grid_constant__ cbk::TableDesc td, const __grid_constant__ cb::BatchView bv,\n"
+    "        uint8_t *bitmap, uint8_t *effects, uint32_t *status, const uint32_t) {\n"
+    "    extern __shared__ __align__(128) uint8_t smem_image[];\n"
+    "    __shared__ __align__(8) uint64_t mbar;\n"
+    "    cbk::check_uc_body<cb::SpecConds, cb::GlobalCols, true>(td, bv, bitmap, effects, smem_image, &mbar);\n"
+    "}\n";
+
+uint64_t fnv1a(const void *p, size_t n, uint64_t h = 1469598103934665603ull) {
+    const uint8_t *b = static_cast<const uint8_t *>(p);
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+// Compiled modules are cached on disk under their source hash (CERBOS_B200_CACHE_DIR, default ~/.cache/cerbos_b200;
+// CERBOS_B200_CACHE_DIR="" disables): a PDP restarting with the same policy set skips the NVRTC compile.
+std::string cache_path(uint64_t key) {
+    const char *d = getenv("CERBOS_B200_CACHE_DIR");
+    std::string dir;
+    if (d) { if (!d[0]) return ""; dir = d; }
+    else { const char *home = getenv("HOME"); if (!home || !home[0]) return ""; dir = std::string(home) + "/.cache/cerbos_b200"; }
+    char name[64];
+    snprintf(name, sizeof name, "/spec_%016llx.cubin", (unsigned long long)key);
+    return dir + name;
+}
+bool cache_read(const std::string &path, std::vector<char> *out) {
+    if (path.empty()) return false;
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    const long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    bool ok = n > 0;
+    if (ok) { out->resize((size_t)n); ok = fread(out->data(), 1, (size_t)n, f) == (size_t)n; }
+    fclose(f);
+    return ok;
+}
+void cache_write(const std::string &path, const std::vector<char> &data) {
+    if (path.empty()) return;
+    const std::string dir = path.substr(0, path.rfind('/'));
+    for (size_t i = 1; i <= dir.size(); i++)
+        if (i == dir.size() || dir[i] == '/') mkdir(dir.substr(0, i).c_str(), 0755);
+    const std::string tmp = path + ".tmp" + std::to_string((unsigned long long)getpid());
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return;
+    const bool ok = fwrite(data.data(), 1, data.size(), f) == data.size();
+    fclose(f);
+    if (ok) rename(tmp.c_str(), path.c_str()); else remove(tmp.c_str());
+}
+
+// Which specialised form a table gets: per-shape block evaluators when its blocks share (nearly) one shape, else the
+// unique-condition form when every distinct condition has a flat form.  `gen` receives the generated source.
+enum SpecForm { SPEC_NONE = 0, SPEC_SHAPES = 1, SPEC_UC = 2 };
+SpecForm spec_generate(const uint8_t *image, const cb::TableLayout &lay, const uint32_t *meta, const cbuc::Image &uc, std::string *gen, std::string *why) {
+    if (lay.image_bytes <= kMaxStageBytes) {
+        *gen = cbspec::generate(image, lay.off, meta);
+        if (!gen->empty()) return SPEC_SHAPES;
+    }
+    if (uc.ok && uc.lay.image_bytes <= kMaxStageBytes) {
+        *gen = cbspec::generate_uc(uc.bytes.data(), uc.lay.off, uc.lay.uc_conds_off, uc.n_uconds, lay.n_slots);
+        if (!gen->empty()) return SPEC_UC;
+    }
+    *why = "table does not qualify (a condition without flat form, too many block shapes and more than 63 distinct conditions, or an image too large for shared memory)";
+    return SPEC_NONE;
+}
 
 // Generates the table's specialised translation unit and compiles it with NVRTC (no CUDA runtime call: also works on
-// a host without a GPU).  false + *why when the table does not qualify or something is unavailable.
-bool spec_compile(const uint8_t *image, const cb::TableLayout &lay, const uint32_t *meta, std::vector<char> *cubin, std::string *why) {
-    if (lay.image_bytes > kMaxStageBytes) { *why = "table image too large for shared memory"; return false; }
-    Nvrtc &n = nvrtc();
-    if (!n.ok) { *why = "libnvrtc not available"; return false; }
-    const std::string gen = cbspec::generate(image, lay.off, meta);
-    if (gen.empty()) { *why = "table does not qualify (a condition without flat form, or too many block shapes)"; return false; }
+// a host without a GPU).  SPEC_NONE + *why when the table does not qualify or something is unavailable.
+SpecForm spec_compile(const uint8_t *image, const cb::TableLayout &lay, const uint32_t *meta, const cbuc::Image &uc, std::vector<char> *cubin, std::string *why) {
+    std::string gen;
+    const SpecForm form = spec_generate(image, lay, meta, uc, &gen, why);
+    if (form == SPEC_NONE) return SPEC_NONE;
     std::string src = kSpecPrelude;
     for (const char *const *p = kEmbedFormat; *p; p++) src += *p;
     for (const char *const *p = kEmbedCore; *p; p++) src += *p;
     src += gen;
     for (const char *const *p = kEmbedKernels; *p; p++) src += *p;
-    src += kSpecKernels;
-    void *prog = nullptr;
-    if (n.create(&prog, src.c_str(), "cerbos_b200_spec.cu", 0, nullptr, nullptr) != 0) { *why = "nvrtcCreateProgram failed"; return false; }
+    src += form == SPEC_UC ? kSpecUcKernels : kSpecKernels;
     const char *mb = getenv("CERBOS_B200_SPEC_BLOCKS");   // experiments: resident CTAs / SM the specialised kernels are budgeted for
     const std::string mbopt = std::string("-DCB_SPEC_MIN_BLOCKS=") + (mb && mb[0] >= '1' && mb[0] <= '8' && !mb[1] ? mb : "5");
-    const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", mbopt.c_str()};
-    const int rc = n.compile(prog, 4, opts);
+    const char *ub = getenv("CERBOS_B200_SPEC_UC_BLOCKS");
+    const std::string ubopt = std::string("-DCB_SPEC_UC_MIN_BLOCKS=") + (ub && ub[0] >= '1' && ub[0] <= '8' && !ub[1] ? ub : "4");
+    if (const char *dump = getenv("CERBOS_B200_SPEC_DUMP")) {   // profiling aid: the translation unit handed to NVRTC
+        if (FILE *f = fopen(dump, "w")) { fwrite(src.data(), 1, src.size(), f); fclose(f); }
+    }
+    const uint64_t key = fnv1a(ubopt.data(), ubopt.size(), fnv1a(mbopt.data(), mbopt.size(), fnv1a(src.data(), src.size())));
+    const std::string cpath = cache_path(key);
+    if (cache_read(cpath, cubin)) return form;
+    Nvrtc &n = nvrtc();
+    if (!n.ok) { *why = "libnvrtc not available"; return SPEC_NONE; }
+    void *prog = nullptr;
+    if (n.create(&prog, src.c_str(), "cerbos_b200_spec.cu", 0, nullptr, nullptr) != 0) { *why = "nvrtcCreateProgram failed"; return SPEC_NONE; }
+    const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", mbopt.c_str(), ubopt.c_str()};
+    const int rc = n.compile(prog, 5, opts);
     if (rc != 0) {
         size_t ls = 0;
         n.log_size(prog, &ls);
@@ -405,14 +518,15 @@ bool spec_compile(const uint8_t *image, const cb::TableLayout &lay, const uint32
         if (ls) n.log(prog, &log[0]);
         n.destroy(&prog);
         *why = "NVRTC compile failed: " + log.substr(0, 600);
-        return false;
+        return SPEC_NONE;
     }
     size_t cs = 0;
     n.cubin_size(prog, &cs);
     cubin->resize(cs);
     n.cubin(prog, cubin->data());
     n.destroy(&prog);
-    return true;
+    cache_write(cpath, *cubin);
+    return form;
 }
 
 // Compiles and loads the table's specialised kernels (once; thread-safe). Returns whether they are usable.
@@ -426,13 +540,17 @@ bool ensure_spec(cgpu_ctx *ctx, cgpu_table *t) {
     if (ctx->force_no_jit) return give_up("disabled (CERBOS_B200_NO_JIT)");
     std::vector<char> cubin;
     std::string why;
-    if (!spec_compile(t->host_image.data(), t->desc.lay, t->meta, &cubin, &why)) return give_up(why);
+    const SpecForm form = spec_compile(t->host_image.data(), t->desc.lay, t->meta, t->uc, &cubin, &why);
+    if (form == SPEC_NONE) return give_up(why);
     if (cudaLibraryLoadData(&t->spec_lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) { cudaGetLastError(); return give_up("cudaLibraryLoadData failed"); }
-    if (cudaLibraryGetKernel(&t->spec_tiles, t->spec_lib, "cb_spec_tiles") != cudaSuccess ||
-        cudaLibraryGetKernel(&t->spec_direct, t->spec_lib, "cb_spec_direct") != cudaSuccess) {
+    bool got = form == SPEC_UC ? cudaLibraryGetKernel(&t->spec_uc, t->spec_lib, "cb_spec_uc") == cudaSuccess
+                               : cudaLibraryGetKernel(&t->spec_tiles, t->spec_lib, "cb_spec_tiles") == cudaSuccess &&
+                                     cudaLibraryGetKernel(&t->spec_direct, t->spec_lib, "cb_spec_direct") == cudaSuccess;
+    if (!got) {
         cudaGetLastError();
         cudaLibraryUnload(t->spec_lib);
         t->spec_lib = nullptr;
+        t->spec_tiles = t->spec_direct = t->spec_uc = nullptr;
         return give_up("cudaLibraryGetKernel failed");
     }
     t->spec_note = "ok";
@@ -479,6 +597,33 @@ int launch_cluster(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, 
     return CGPU_OK;
 }
 
+// The launch's deferral list + counter cell, owned by the stream it is issued on (see cgpu_ctx::DeferLane).
+int acquire_defer(cgpu_ctx *ctx, cudaStream_t stream, uint64_t count, uint32_t **list, uint32_t **cell) {
+    std::lock_guard<std::mutex> g(ctx->defer_mu);
+    cgpu_ctx::DeferLane &ln = ctx->defer_lanes[stream];
+    if (!ln.cells) {
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&ln.cells), 4 * 16));
+        CUDA_TRY(cudaMemset(ln.cells, 0, 4 * 16));
+    }
+    const uint32_t q = ln.seq++ & 3;
+    if (ln.cap[q] < (size_t)count) {
+        // grow (power-of-two capacities), stream-ordered: the old list is released only after everything queued on this
+        // stream so far -- the only launches that can still read it -- has completed
+        size_t cap = 1024;
+        while (cap < (size_t)count) cap <<= 1;
+        uint32_t *fresh = nullptr;
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&fresh), cap * 4, stream));
+        if (ln.lists[q]) CUDA_TRY(cudaFreeAsync(ln.lists[q], stream));
+        ln.lists[q] = fresh;
+        ln.cap[q] = cap;
+    }
+    *list = ln.lists[q];
+    *cell = ln.cells + 4 * q;   // {count, done, tile counter, -}
+    return CGPU_OK;
+}
+
+constexpr uint32_t kUcMaxSmem = 72 * 1024;   // compact image + merged rows: three CTAs / SM at least
+
 int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, uint8_t *d_bitmap, uint8_t *d_effects,
                  uint32_t *d_status, cudaStream_t stream, bool *drained = nullptr) {
     const cb::TableLayout &lay = t->desc.lay;
@@ -492,9 +637,15 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
     const bool narrow = !ctx->force_general && bv.n_pass == 1 && (uint64_t)bv.max_actions * bv.role_cols <= 32 && bv.kbytes <= 4 &&
                         !lay.has_principal_policies && !lay.has_role_policies && !lay.has_parent_roles &&
                         t->meta[CB_META_DIRECT_KINDS] && (uint64_t)lay.nR * rcp <= 64;
+    cgpu_table *mt = const_cast<cgpu_table *>(t);
+    // Unique-condition kernels: lean-eligible tables with <= 63 distinct conditions whose blocks differ in shape
+    // (with one shape the per-shape specialised tile kernel is the better fit).  Index order, no clustering.
+    const bool uc_spec_ready = mt->spec_state.load(std::memory_order_acquire) == 1 && t->spec_uc != nullptr;
+    const bool uc = narrow && t->uc.ok && t->d_uc_image && bv.count < (1ull << 32) && (uint64_t)bv.n_asets * lay.n_rows < (1ull << 31) &&
+                    (ctx->uc_mode == 1 || (ctx->uc_mode != 0 && t->meta[CB_META_BLOCK_SHAPES] > 1));
     // Clustering pays when the policy blocks differ in shape (rows / conditions): with a single shape every lane runs
     // the same control flow in index order already and the coalesced column loads are worth more.
-    const bool cluster = bv.count < (1ull << 32) &&
+    const bool cluster = !uc && bv.count < (1ull << 32) &&
                          (ctx->cluster_mode == 1 || (ctx->cluster_mode != 0 && bv.count >= kClusterMinRequests && t->meta[CB_META_BLOCK_SHAPES] > 1));
     // Index-order lean launches stage the request columns through TMA too, when every tile's column runs are
     // 16-byte aligned and image + two tile stages fit the shared-memory budget of CB_MIN_BLOCKS resident CTAs.
@@ -503,18 +654,22 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
     const uint64_t small_tabs = (uint64_t)bv.n_asets * lay.n_rows * 8 + (((uint64_t)bv.n_asets + 1) & ~1ull) * 4 + 16 + 2 * kThreads;   // + tile_s[2] + res_s[2][256]
     const uint32_t tiles_smem = ((lay.image_bytes + 127u) & ~127u) + 2 * tile_bytes + (uint32_t)(small_tabs < 65536 ? small_tabs : 65536);
     auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-    const bool col_tiles = narrow && stage && !cluster && !ctx->force_no_tiles && tiles_smem <= kMaxTilesSmem && bv.stride % 4 == 0 &&
+    const bool col_tiles = !uc && narrow && stage && !cluster && !ctx->force_no_tiles && tiles_smem <= kMaxTilesSmem && bv.stride % 4 == 0 &&
                            bv.first % 4 == 0 && al16(bv.hdr0) && al16(bv.hdr1) && al16(bv.roles) && al16(bv.slots);
-    const uint32_t smem = col_tiles ? tiles_smem : stage ? lay.image_bytes : 0;
-    cgpu_table *mt = const_cast<cgpu_table *>(t);
+    // unique-condition launch: staged (compact image + merged rows in shared memory) when that fits
+    const uint64_t uc_smem64 = uc ? ((t->uc.lay.image_bytes + 127u) & ~127u) + (uint64_t)bv.n_asets * lay.n_rows * 8 : 0;
+    const bool uc_staged = uc && !ctx->force_no_stage && uc_smem64 <= kUcMaxSmem;
+    const uint32_t smem = uc ? (uc_staged ? (uint32_t)uc_smem64 : 0) : col_tiles ? tiles_smem : stage ? lay.image_bytes : 0;
     // lean launches with a staged table use the kernels specialised for this table when they exist (NVRTC, first use)
-    const bool spec = narrow && stage && bv.count < (1ull << 32) && mt->spec_state.load(std::memory_order_acquire) == 1;   // never waits for the compile
-    const void *fn = spec        ? (col_tiles ? (const void *)t->spec_tiles : (const void *)t->spec_direct)
+    const bool spec = uc ? (uc_staged && uc_spec_ready)
+                         : narrow && stage && bv.count < (1ull << 32) && mt->spec_state.load(std::memory_order_acquire) == 1 && t->spec_tiles != nullptr;   // never waits for the compile
+    const void *fn = uc          ? (spec ? (const void *)t->spec_uc : uc_staged ? (const void *)check_uc<true> : (const void *)check_uc<false>)
+                     : spec      ? (col_tiles ? (const void *)t->spec_tiles : (const void *)t->spec_direct)
                      : col_tiles ? (const void *)check_kernel_tiles
                      : narrow    ? (stage ? (const void *)check_kernel<true, 1> : (const void *)check_kernel<true, 0>)
                                  : (const void *)check_kernel<false, 2>;
     // resident CTAs per SM for this shared-memory footprint: queried once per (table, variant, footprint)
-    const int variant = spec ? (col_tiles ? 5 : 6) : col_tiles ? 4 : narrow ? (stage ? 1 : 2) : (stage ? 0 : 3);
+    const int variant = uc ? (spec ? 9 : uc_staged ? 7 : 8) : spec ? (col_tiles ? 5 : 6) : col_tiles ? 4 : narrow ? (stage ? 1 : 2) : (stage ? 0 : 3);
     int occ = mt->occ_smem[variant].load(std::memory_order_relaxed) == smem + 1 ? mt->occ[variant].load(std::memory_order_relaxed) : 0;
     if (occ == 0) {
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxStageBytes) != cudaSuccess ||
@@ -530,7 +685,7 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
     uint64_t max_ctas = (uint64_t)ctx->sm_count * (uint64_t)occ;
     uint32_t grid = (uint32_t)(tiles < max_ctas ? tiles : max_ctas);
     if (grid == 0) grid = 1;
-    TableDesc td = t->desc;
+    TableDesc td = uc ? t->uc_desc : t->desc;
     cb::BatchView bvv = bv;
     bvv.perm = nullptr;
     // few slot columns: every tile prefetches all of them one tile ahead (all loads of the tile then hit L1);
@@ -543,27 +698,14 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
         bvv.perm = perm;
     }
     uint32_t last_arg = col_tiles ? lay.n_slots : (stage ? 1u : 0u);   // check_kernel: stage_rt; check_kernel_tiles: n_slots
-    uint32_t *defer = nullptr;   // request offsets the specialised kernel leaves to the general kernel
-    if (spec) {
-        const uint32_t seq = ctx->defer_next.fetch_add(1, std::memory_order_relaxed);
-        {
-            std::lock_guard<std::mutex> g(ctx->defer_mu);
-            const uint32_t q = seq & 3;
-            if (ctx->defer_cap[q] < (size_t)bv.count) {
-                // grow (power-of-two capacities); the old list may still be read by a launch in flight on another stream:
-                // it is retired, not freed, until cgpu_shutdown
-                size_t cap = 1024;
-                while (cap < (size_t)bv.count) cap <<= 1;
-                uint32_t *fresh = nullptr;
-                CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&fresh), cap * 4));
-                if (ctx->defer_lists[q]) ctx->defer_retired.push_back(ctx->defer_lists[q]);
-                ctx->defer_lists[q] = fresh;
-                ctx->defer_cap[q] = cap;
-            }
-            defer = ctx->defer_lists[q];
-        }
-        bvv.defer_count = ctx->d_defer_cells + 4 * (seq % kDeferCells);   // {count, done, tile counter, -}
-        bvv.tile_counter = col_tiles ? bvv.defer_count + 2 : nullptr;
+    const bool lists = spec || uc;   // requests the kernel leaves to the general kernel go to a list drained right behind it
+    uint32_t *defer = nullptr;
+    if (lists) {
+        uint32_t *cell = nullptr;
+        int rc = acquire_defer(ctx, stream, bv.count, &defer, &cell);
+        if (rc != CGPU_OK) return rc;
+        bvv.defer_count = cell;
+        bvv.tile_counter = col_tiles ? cell + 2 : nullptr;
         bvv.defer_list = defer;
     }
     void *args[] = {&td, &bvv, &d_bitmap, &d_effects, &d_status, &last_arg};
@@ -575,7 +717,7 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
         }
         CUDA_TRY(cudaEventRecord(ctx->ev0, stream));
     }
-    if (spec && !ctx->profiling) {
+    if (spec && !uc && !ctx->profiling) {
         // programmatically serialised behind the previous launch's drain kernel (which releases its dependents at once):
         // this kernel's CTAs start as the previous specialised kernel's last tiles retire -- back-to-back launches on one
         // stream overlap at their tails.  It reads nothing the previous launch writes.
@@ -591,29 +733,31 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
     }
     CUDA_TRY(cudaGetLastError());
     if (ctx->profiling) { CUDA_TRY(cudaEventRecord(ctx->ev1, stream)); ctx->prof_pending = true; }
-    if (spec) {
+    if (lists) {
         // drain the deferral list with the general body (usually empty: the kernel then exits at once)
         cb::BatchView dv = bv;
         dv.perm = defer;
         dv.count_dev = bvv.defer_count;
         dv.prefetch_slots = 0;
         const void *gfn = (const void *)check_kernel<false, 2>;
+        const uint32_t gsmem = stage ? lay.image_bytes : 0;
         int gocc = mt->occ[0].load(std::memory_order_relaxed);
-        if (gocc == 0 || mt->occ_smem[0].load(std::memory_order_relaxed) != lay.image_bytes + 1) {
+        if (gocc == 0 || mt->occ_smem[0].load(std::memory_order_relaxed) != gsmem + 1) {
             CUDA_TRY(cudaFuncSetAttribute(gfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxStageBytes));
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gocc, gfn, kThreads, lay.image_bytes));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gocc, gfn, kThreads, gsmem));
             if (gocc < 1) gocc = 1;
             mt->occ[0].store(gocc, std::memory_order_relaxed);
-            mt->occ_smem[0].store(lay.image_bytes + 1, std::memory_order_relaxed);
+            mt->occ_smem[0].store(gsmem + 1, std::memory_order_relaxed);
         }
         // one CTA per SM: the list is normally empty (every CTA then exits at once), and grid-stride loops otherwise
-        uint64_t gmax = (uint64_t)ctx->sm_count * (uint64_t)(gocc < 1 ? 1 : 1);
+        uint64_t gmax = (uint64_t)ctx->sm_count;
         uint32_t ggrid = (uint32_t)(tiles < gmax ? tiles : gmax);
-        uint32_t one = 1u;
+        uint32_t stage_arg = stage ? 1u : 0u;
         uint8_t *gb = d_bitmap, *ge = d_effects;
-        void *gargs[] = {&td, &dv, &gb, &ge, &d_status, &one};
+        TableDesc gtd = t->desc;
+        void *gargs[] = {&gtd, &dv, &gb, &ge, &d_status, &stage_arg};
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(ggrid ? ggrid : 1); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = lay.image_bytes; cfg.stream = stream;
+        cfg.gridDim = dim3(ggrid ? ggrid : 1); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = gsmem; cfg.stream = stream;
         cudaLaunchAttribute pdl[1];
         pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         pdl[0].val.programmaticStreamSerializationAllowed = 1;
@@ -629,6 +773,7 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
     ctx->last_clustered = cluster ? 1 : 0;
     ctx->last_col_tiles = col_tiles ? 1 : 0;
     ctx->last_spec = spec ? 1 : 0;
+    ctx->last_uc = uc ? 1 : 0;
     return CGPU_OK;
 }
 
@@ -649,15 +794,20 @@ int cgpu_init(const int *device_ids, int n_devices, cgpu_ctx **out) {
     cgpu_ctx *ctx = new (std::nothrow) cgpu_ctx();
     if (!ctx) return fail(CGPU_ERR_INVALID, "out of memory");
     ctx->device = device_ids[0];
-    CUDA_TRY(cudaSetDevice(ctx->device));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, ctx->device));
-    ctx->sm_count = prop.multiProcessorCount;
-    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaMalloc(&ctx->d_status, sizeof(uint32_t)));
-    CUDA_TRY(cudaMemset(ctx->d_status, 0, sizeof(uint32_t)));
-    CUDA_TRY(cudaMalloc(&ctx->d_defer_cells, kDeferCells * 16));
-    CUDA_TRY(cudaMemset(ctx->d_defer_cells, 0, kDeferCells * 16));
+    {
+        cudaDeviceProp prop;
+        cudaError_t ie = cudaSetDevice(ctx->device);
+        if (ie == cudaSuccess) ie = cudaGetDeviceProperties(&prop, ctx->device);
+        if (ie == cudaSuccess) { ctx->sm_count = prop.multiProcessorCount; ie = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking); }
+        if (ie == cudaSuccess) ie = cudaMalloc(&ctx->d_status, sizeof(uint32_t));
+        if (ie == cudaSuccess) ie = cudaMemset(ctx->d_status, 0, sizeof(uint32_t));
+        if (ie != cudaSuccess) {   // nothing leaks on a failed init
+            if (ctx->d_status) cudaFree(ctx->d_status);
+            if (ctx->stream) cudaStreamDestroy(ctx->stream);
+            delete ctx;
+            return fail(CGPU_ERR_CUDA, "cgpu_init: %s", cudaGetErrorString(ie));
+        }
+    }
     const char *ns = getenv("CERBOS_B200_NO_STAGE");
     ctx->force_no_stage = ns && ns[0] == '1';
     const char *fg = getenv("CERBOS_B200_FORCE_GENERAL");
@@ -666,6 +816,8 @@ int cgpu_init(const int *device_ids, int n_devices, cgpu_ctx **out) {
     ctx->force_no_jit = nj && nj[0] == '1';
     const char *nt = getenv("CERBOS_B200_NO_TILES");
     ctx->force_no_tiles = nt && nt[0] == '1';
+    const char *um = getenv("CERBOS_B200_UC");
+    ctx->uc_mode = um && (um[0] == '0' || um[0] == '1') ? um[0] - '0' : -1;
     const char *cm = getenv("CERBOS_B200_CLUSTER");
     ctx->cluster_mode = cm && (cm[0] == '0' || cm[0] == '1') ? cm[0] - '0' : -1;
     // stream-ordered scratch (clustering): keep freed blocks in the pool instead of returning them to the driver
@@ -690,9 +842,10 @@ void cgpu_shutdown(cgpu_ctx *ctx) {
         if (s.d_status) cudaFree(s.d_status);
     }
     if (ctx->d_status) cudaFree(ctx->d_status);
-    if (ctx->d_defer_cells) cudaFree(ctx->d_defer_cells);
-    for (auto p : ctx->defer_lists) if (p) cudaFree(p);
-    for (auto p : ctx->defer_retired) cudaFree(p);
+    for (auto &kv : ctx->defer_lanes) {
+        for (auto p : kv.second.lists) if (p) cudaFree(p);
+        if (kv.second.cells) cudaFree(kv.second.cells);
+    }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -705,17 +858,25 @@ int cgpu_table_load(cgpu_ctx *ctx, const void *blob, size_t len, cgpu_table **ou
     cgpu_table *t = new (std::nothrow) cgpu_table();
     if (!t) return fail(CGPU_ERR_INVALID, "out of memory");
     t->ctx = ctx;
-    int rc = parse_blob(blob, len, &t->desc, t->meta);
+    int rc = parse_blob(blob, len, &t->desc, t->meta, t->sec_len);
     if (rc != CGPU_OK) { delete t; return rc; }
+    t->uc = cbuc::build(static_cast<const uint8_t *>(blob), t->desc.lay.off, t->sec_len, t->meta, t->desc.lay);
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&t->d_image), t->desc.lay.image_bytes);
     if (e == cudaSuccess) e = cudaMemcpy(t->d_image, blob, t->desc.lay.image_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && t->uc.ok) {
+        e = cudaMalloc(reinterpret_cast<void **>(&t->d_uc_image), t->uc.bytes.size());
+        if (e == cudaSuccess) e = cudaMemcpy(t->d_uc_image, t->uc.bytes.data(), t->uc.bytes.size(), cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) {
         if (t->d_image) cudaFree(t->d_image);
+        if (t->d_uc_image) cudaFree(t->d_uc_image);
         delete t;
         return fail(CGPU_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(e));
     }
     t->desc.base = t->d_image;
+    t->uc_desc.base = t->d_uc_image;
+    t->uc_desc.lay = t->uc.lay;
     t->host_image.assign(static_cast<const uint8_t *>(blob), static_cast<const uint8_t *>(blob) + t->desc.lay.image_bytes);
     // table-specialised kernels are generated + compiled off the caller's thread; launches use the generic kernels
     // until they are ready (cgpu_table_wait_ready blocks for them)
@@ -736,6 +897,7 @@ void cgpu_table_release(cgpu_table *t) {
         cudaSetDevice(t->ctx->device);
         cudaDeviceSynchronize();   // no kernel may still read the image
         cudaFree(t->d_image);
+        if (t->d_uc_image) cudaFree(t->d_uc_image);
         if (t->spec_lib) cudaLibraryUnload(t->spec_lib);
         delete t;
     }
@@ -746,14 +908,18 @@ int cgpu_table_compile_check(const void *blob, size_t len, size_t *cubin_bytes) 
     *cubin_bytes = 0;
     TableDesc d;
     uint32_t meta[CB_META_WORDS];
-    int rc = parse_blob(blob, len, &d, meta);
+    uint64_t sec_len[kMaxSec] = {0};
+    int rc = parse_blob(blob, len, &d, meta, sec_len);
     if (rc != CGPU_OK) return rc;
+    const cbuc::Image uc = cbuc::build(static_cast<const uint8_t *>(blob), d.lay.off, sec_len, meta, d.lay);
     std::vector<char> cubin;
     std::string why;
-    if (!spec_compile(static_cast<const uint8_t *>(blob), d.lay, meta, &cubin, &why)) {
+    const SpecForm form = spec_compile(static_cast<const uint8_t *>(blob), d.lay, meta, uc, &cubin, &why);
+    if (form == SPEC_NONE) {
         g_err = why;
         return why.rfind("NVRTC compile failed", 0) == 0 ? CGPU_ERR_CUDA : CGPU_OK;   // not qualifying is not an error
     }
+    g_err = form == SPEC_UC ? "unique-condition form" : "block-shape form";
     *cubin_bytes = cubin.size();
     return CGPU_OK;
 }
@@ -785,7 +951,7 @@ int cgpu_last_kernel_config(const cgpu_ctx *ctx, uint32_t *grid, uint32_t *block
 
 int cgpu_last_cluster_config(const cgpu_ctx *ctx, uint32_t *clustered, uint32_t *window, uint32_t *buckets) {
     if (!ctx) return fail(CGPU_ERR_INVALID, "null ctx");
-    if (clustered) *clustered = ctx->last_clustered | (ctx->last_col_tiles << 1) | (ctx->last_spec << 2);   // bit 1: TMA column tiles; bit 2: table-specialised kernel
+    if (clustered) *clustered = ctx->last_clustered | (ctx->last_col_tiles << 1) | (ctx->last_spec << 2) | (ctx->last_uc << 3);   // bit 1: TMA column tiles; bit 2: table-specialised kernel
     if (window) *window = ctx->last_window;
     if (buckets) *buckets = ctx->last_buckets;
     return CGPU_OK;

@@ -13,6 +13,7 @@ _lib = None
 def build():
     src = os.path.join(_ROOT, "tests", "hostsim", "hostsim.cpp")
     deps = [src, os.path.join(_ROOT, "cerbos_b200", "csrc", "cb_core.h"), os.path.join(_ROOT, "cerbos_b200", "csrc", "cb_specialize.h"),
+            os.path.join(_ROOT, "cerbos_b200", "csrc", "cb_uc.h"),
             os.path.join(_ROOT, "include", "cerbos_b200_format.h")]
     if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(_SO), exist_ok=True)
@@ -62,15 +63,33 @@ def generate(blob: bytes) -> str:
     return out.value.decode()
 
 
-def build_spec(blob: bytes, workdir: str):
-    """Host build of the kernel core with the evaluators generated for `blob` -> ctypes library exposing hostsim_check_spec."""
-    src_text = generate(blob)
+def generate_uc(blob: bytes):
+    """(source of the unique-condition specialised evaluator (cb_specialize.h: generate_uc; "" = does not qualify),
+    number of distinct conditions of the table (0 = no unique-condition image))."""
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.hostsim_check.restype = ctypes.c_int
+    _lib.hostsim_generate_uc.restype = ctypes.c_int64
+    cap = 1 << 22
+    out = ctypes.create_string_buffer(cap)
+    nu = ctypes.c_uint32(0)
+    n = _lib.hostsim_generate_uc(ctypes.create_string_buffer(blob, len(blob)), ctypes.c_uint64(len(blob)), out, ctypes.c_uint64(cap), ctypes.byref(nu))
+    if n < 0:
+        raise RuntimeError(f"hostsim_generate_uc failed: {n}")
+    return out.value.decode(), nu.value
+
+
+def build_spec(blob: bytes, workdir: str, uc: bool = False):
+    """Host build of the kernel core with the evaluators generated for `blob` -> ctypes library exposing hostsim_check_spec.
+    uc: the unique-condition form (cb::SpecConds, used by modes 4 / 5) instead of the block-shape form (cb::SpecBlocks)."""
+    src_text = generate_uc(blob)[0] if uc else generate(blob)
     if not src_text:
         return None
     with open(os.path.join(workdir, "spec_gen.inc"), "w") as f:
         f.write(src_text)
-    so = os.path.join(workdir, "libhostsim_spec.so")
-    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DHOSTSIM_SPEC", f"-I{workdir}", f"-I{_ROOT}/include",
+    so = os.path.join(workdir, "libhostsim_spec_uc.so" if uc else "libhostsim_spec.so")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DHOSTSIM_SPEC_UC" if uc else "-DHOSTSIM_SPEC", f"-I{workdir}", f"-I{_ROOT}/include",
                     f"-I{_ROOT}/cerbos_b200/csrc", "-o", so, os.path.join(_ROOT, "tests", "hostsim", "hostsim.cpp")], check=True)
     lib = ctypes.CDLL(so)
     lib.hostsim_check_spec.restype = ctypes.c_int

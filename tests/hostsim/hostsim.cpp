@@ -8,20 +8,36 @@
 
 #include "cb_core.h"
 #include "cb_specialize.h"
+#include "cb_uc.h"
 
-#ifdef HOSTSIM_SPEC
+#if defined(HOSTSIM_SPEC_UC)
+#include "spec_gen.inc"   // generated for one table by hostsim_generate_uc: cb::SpecConds (unique-condition form)
+typedef cb::GenericBlocks HostBlocks;
+typedef cb::SpecConds HostConds;
+#define HOSTSIM_ENTRY hostsim_check_spec
+#elif defined(HOSTSIM_SPEC)
 #include "spec_gen.inc"   // generated for one table by hostsim_generate (tests/test_specialize.py)
 typedef cb::SpecBlocks HostBlocks;
+typedef cb::GenericConds HostConds;
 #define HOSTSIM_ENTRY hostsim_check_spec
 #else
 typedef cb::GenericBlocks HostBlocks;
+typedef cb::GenericConds HostConds;
 #define HOSTSIM_ENTRY hostsim_check
 #endif
+
+static bool parse_sections(const void *blob, uint64_t blob_len, uint32_t *off, uint64_t *len) {
+    const cb_blob_header *h = static_cast<const cb_blob_header *>(blob);
+    if (blob_len < sizeof(*h) || h->magic != CB_MAGIC || h->version != CB_VERSION) return false;
+    const cb_section_desc *sd = reinterpret_cast<const cb_section_desc *>(static_cast<const char *>(blob) + sizeof(cb_blob_header));
+    for (uint32_t i = 0; i < h->n_sections; i++) if (sd[i].id < 128) { off[sd[i].id] = (uint32_t)sd[i].offset; len[sd[i].id] = sd[i].n_bytes; }
+    return true;
+}
 
 extern "C" int HOSTSIM_ENTRY(const void *blob, uint64_t blob_len, uint64_t n, uint32_t max_actions, int64_t now, uint32_t flags,
                              const void *const *cols, const uint64_t *col_bytes, uint8_t *bitmap, int mode) {
     const cb_blob_header *h = static_cast<const cb_blob_header *>(blob);
-    if (h->magic != CB_MAGIC || h->version != CB_VERSION) return -1;
+    if (blob_len < sizeof(*h) || h->magic != CB_MAGIC || h->version != CB_VERSION) return -1;
     const cb_section_desc *sd = reinterpret_cast<const cb_section_desc *>(static_cast<const char *>(blob) + sizeof(cb_blob_header));
     const uint8_t *base = static_cast<const uint8_t *>(blob);
     uint64_t off[128] = {0};
@@ -60,6 +76,26 @@ extern "C" int HOSTSIM_ENTRY(const void *blob, uint64_t blob_len, uint64_t n, ui
     uint32_t rcp = 1; while (rcp < b.role_cols) rcp <<= 1;
     const bool fast = narrow && !lay.has_principal_policies && !lay.has_role_policies && !lay.has_parent_roles &&
                       meta[CB_META_DIRECT_KINDS] && (uint64_t)lay.nR * rcp <= 64 && b.kbytes <= 4;
+    // modes 4 / 5: the unique-condition body (cb_uc.h image) with rows read from the image / from merged 8-byte records
+    if ((mode == 4 || mode == 5) && fast) {
+        uint32_t off32[128] = {0};
+        uint64_t len64[128] = {0};
+        if (!parse_sections(blob, blob_len, off32, len64)) return -1;
+        const cbuc::Image uc = cbuc::build(base, off32, len64, meta, lay);
+        if (!uc.ok) return -3;
+        cb::TableView ut;
+        ut.base = uc.bytes.data(); ut.L = &uc.lay;
+        std::vector<uint64_t> pk((size_t)b.n_asets * b.n_rows);
+        for (size_t j = 0; j < pk.size(); j++) pk[j] = (uint64_t)(uint32_t)b.row_am[j] | (uint64_t)ut.urows()[j % b.n_rows] << 32;
+        for (uint64_t i = 0; i < n; i++) {
+            cb::CachedCols gc; gc.b = &b; gc.n = i;
+            bool d;
+            if (mode == 5) { cb::UcRowsPacked rows; rows.pk = pk.data(); d = cb::eval_request_uc(ut, b, gc, rows, i, bitmap, nullptr, HostConds()); }
+            else { cb::UcRowsGlobal rows; rows.urows = ut.urows(); rows.row_am = b.row_am; d = cb::eval_request_uc(ut, b, gc, rows, i, bitmap, nullptr, HostConds()); }
+            if (d) cb::eval_request_general(t.base, t.L, &b, i, bitmap, nullptr, &status);
+        }
+        return status ? -2 : 0;
+    }
     if (mode == 3 && fast) {
         std::vector<uint64_t> tile(cb::tile_cols_bytes(b.role_cols, lay.n_slots) / 8 + 2);
         uint8_t *tb = reinterpret_cast<uint8_t *>(tile.data());
@@ -88,7 +124,25 @@ extern "C" int HOSTSIM_ENTRY(const void *blob, uint64_t blob_len, uint64_t n, ui
     return status ? -2 : 0;
 }
 
-#ifndef HOSTSIM_SPEC
+#if !defined(HOSTSIM_SPEC) && !defined(HOSTSIM_SPEC_UC)
+// the unique-condition form of the specialised source (cb::SpecConds); "" if the table does not qualify; *n_uconds_out = distinct conditions
+extern "C" int64_t hostsim_generate_uc(const void *blob, uint64_t blob_len, char *out, uint64_t cap, uint32_t *n_uconds_out) {
+    uint32_t off[128] = {0};
+    uint64_t len[128] = {0};
+    if (!parse_sections(blob, blob_len, off, len)) return -1;
+    const uint8_t *base = static_cast<const uint8_t *>(blob);
+    const uint32_t *meta = reinterpret_cast<const uint32_t *>(base + off[CB_SEC_META]);
+    cb::TableLayout lay;
+    memset(&lay, 0, sizeof(lay));
+    for (int i = 0; i < 28; i++) lay.off[i] = off[i];
+    lay.nR = meta[CB_META_N_ROLES]; lay.n_slots = meta[CB_META_N_SLOTS];
+    const cbuc::Image uc = cbuc::build(base, off, len, meta, lay);
+    if (n_uconds_out) *n_uconds_out = uc.ok ? uc.n_uconds : 0;
+    std::string src = uc.ok ? cbspec::generate_uc(uc.bytes.data(), uc.lay.off, uc.lay.uc_conds_off, uc.n_uconds, lay.n_slots) : std::string();
+    if (src.size() + 1 > cap) return -(int64_t)src.size() - 2;
+    memcpy(out, src.c_str(), src.size() + 1);
+    return (int64_t)src.size();
+}
 // the table-specialised block evaluators the library would hand to NVRTC (source text; "" if the table does not qualify)
 extern "C" int64_t hostsim_generate(const void *blob, uint64_t blob_len, char *out, uint64_t cap) {
     const cb_blob_header *h = static_cast<const cb_blob_header *>(blob);

@@ -373,3 +373,75 @@ def test_verify_suite_goldens_through_engine_api():
                 n += 1
         eng.close()
     assert n == 145
+
+
+@pytest.mark.parametrize("name,n", [("C3", (1 << 18) + 77), ("C2", (1 << 16) + 5)])
+def test_unique_condition_kernels(name, n):
+    """Unique-condition kernels (cb_uc.h image, cb::eval_request_uc): the ahead-of-time generic form, the NVRTC-specialised
+    form, staged and global table paths -- all against the oracle; device path and host-buffer path."""
+    from cerbos_b200 import capi, workloads as W
+    from cerbos_b200.device import DeviceBatch
+    from oracle import cref
+    w = W.WORKLOADS[name]()
+    _, ft, enc = W.build(w)
+    b = w.columns(w.fields(n), enc)
+    want = cref.check(ft.blob, b.columns, b.n, b.max_actions, n_threads=os.cpu_count() or 1)
+    seen = set()
+    for env in ({"CERBOS_B200_UC": "1", "CERBOS_B200_NO_JIT": "1"}, {"CERBOS_B200_UC": "1", "CERBOS_B200_NO_JIT": "1", "CERBOS_B200_NO_STAGE": "1"},
+                {"CERBOS_B200_UC": "1"}):
+        os.environ.update(env)
+        try:
+            c = capi.Context(0)
+            t = c.load_table(ft.blob)
+            t.wait_ready()
+            db = DeviceBatch(b, "cuda:0")
+            db.run(t)
+            c.sync()
+            cfg = c.last_kernel_config()
+            assert cfg["unique_conditions"] and not cfg["clustered"], cfg
+            seen.add((cfg["table_specialised"], cfg["smem_bytes"] > 0))
+            assert (db.effects() == want).all(), env
+            assert (t.check(b.columns, b.n, b.max_actions) == want).all(), env
+            t.release()
+            c.close()
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+    if name == "C3":
+        assert (True, True) in seen and (False, True) in seen and (False, False) in seen, seen
+
+
+def test_unique_condition_kernel_deferral_list():
+    """Requests the unique-condition body cannot decide (differing policy versions) travel through the launch's deferral
+    list to the general kernel -- several launches in flight on several streams, each with its own list."""
+    import torch
+    from cerbos_b200 import capi, workloads as W
+    from cerbos_b200.device import DeviceBatch
+    from oracle import cref
+    w = W.C3()
+    _, ft, enc = W.build(w)
+    n = 1 << 16
+    os.environ["CERBOS_B200_UC"] = "1"
+    try:
+        c = capi.Context(0)
+        t = c.load_table(ft.blob)
+        t.wait_ready()
+        batches, wants = [], []
+        for j in range(4):
+            b = w.columns(w.fields(n, start=j * n), enc)
+            hdr1 = b.columns[1].copy()
+            hdr1["pv"][j::7] = 0xFFFF            # no principal policy version: pv != rv -> deferred
+            b.columns[1] = hdr1
+            wants.append(cref.check(ft.blob, b.columns, b.n, b.max_actions, n_threads=os.cpu_count() or 1))
+            batches.append(DeviceBatch(b, "cuda:0"))
+        streams = [torch.cuda.Stream() for _ in range(4)]
+        for rep in range(3):
+            for j, db in enumerate(batches):
+                db.run(t, stream=streams[(j + rep) % 4].cuda_stream)
+        torch.cuda.synchronize()
+        for db, want in zip(batches, wants):
+            assert (db.effects() == want).all()
+        t.release()
+        c.close()
+    finally:
+        os.environ.pop("CERBOS_B200_UC", None)

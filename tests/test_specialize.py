@@ -62,3 +62,69 @@ def test_random_tables(seed, tmp_path):
     for mode in (0, 3):
         got = hostsim.check_spec(lib, ft.blob, b.columns, b.n, b.max_actions, mode=mode)
         assert (got[valid] == want[valid]).all(), (seed, mode)
+
+
+# ---- unique-condition form (cb_uc.h image + cb::eval_request_uc; cb_specialize.h: generate_uc) -------------------------
+@pytest.mark.parametrize("name,n", [("C2", 1 << 13), ("C3", 1 << 13)])
+def test_unique_condition_body_on_workloads(name, n, tmp_path):
+    """Generic condition evaluator (modes 4 / 5: rows from the image / merged records) and the generated straight-line
+    evaluator, both against the oracle."""
+    w = W.WORKLOADS[name]()
+    _, ft, enc = W.build(w)
+    b = w.columns(w.fields(n), enc)
+    want = cref.check(ft.blob, b.columns, b.n, b.max_actions)
+    for mode in (4, 5):
+        assert (hostsim.check(ft.blob, b.columns, b.n, b.max_actions, mode=mode) == want).all(), mode
+    src, nu = hostsim.generate_uc(ft.blob)
+    assert nu == {"C2": 3, "C3": 39}[name] and "struct SpecConds" in src
+    lib = hostsim.build_spec(ft.blob, str(tmp_path), uc=True)
+    for mode in (4, 5):
+        assert (hostsim.check_spec(lib, ft.blob, b.columns, b.n, b.max_actions, mode=mode) == want).all(), mode
+
+
+def test_unique_condition_source_shares_terms_for_c3():
+    w = W.C3()
+    _, ft, _ = W.build(w)
+    src, nu = hostsim.generate_uc(ft.blob)
+    # 39 distinct conditions over 26 distinct terms; every slot the table reads is loaded once into a register
+    assert src.count("const int q") == 26 and src.count("// distinct condition") == 39
+    assert all(f"r.s{v} = c.slot({v}u);" in src for v in range(12))
+
+
+def test_c5_has_too_many_distinct_conditions_for_the_unique_condition_form():
+    w = W.C5()
+    _, ft, _ = W.build(w)
+    src, nu = hostsim.generate_uc(ft.blob)
+    assert src == "" and nu == 0
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_unique_condition_body_on_random_tables(seed, tmp_path):
+    r = random.Random(9100 + seed)
+    docs = [d for d in rand_policies(r) if "resourcePolicy" in d or "derivedRoles" in d]
+    rt = build_rule_table(docs)
+    ft = flatten(rt)
+    enc = Encoder(ft.manifest)
+    inputs = [rand_request(r) for _ in range(300)]
+    b = enc.encode(inputs)
+    try:
+        want = cref.check(ft.blob, b.columns, b.n, b.max_actions, 0, 0)
+    except RuntimeError as e:
+        if "-2" in str(e):
+            pytest.skip("a request produces a run-time value outside the device's exact range (oracle #2 flags it too)")
+        raise
+    valid = want != 0
+    try:
+        got = hostsim.check(ft.blob, b.columns, b.n, b.max_actions, mode=4)
+    except RuntimeError as e:
+        if "-3" in str(e):
+            pytest.skip("no unique-condition image (too many distinct conditions)")
+        raise
+    assert (got[valid] == want[valid]).all(), seed
+    got = hostsim.check(ft.blob, b.columns, b.n, b.max_actions, mode=5)
+    assert (got[valid] == want[valid]).all(), seed
+    src, nu = hostsim.generate_uc(ft.blob)
+    if src:
+        lib = hostsim.build_spec(ft.blob, str(tmp_path), uc=True)
+        got = hostsim.check_spec(lib, ft.blob, b.columns, b.n, b.max_actions, mode=5)
+        assert (got[valid] == want[valid]).all(), seed
