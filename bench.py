@@ -4,17 +4,20 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--impl ours|reference]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...       (N > 1, one rank per GPU)
 
-A *step* is one pass of the hot path (rule-table scan + CEL condition evaluation) over one batch of
-synthetic requests: workload C2 of SURVEY.md 8(d) = BASELINE.json configs[1] (10 resource policies x 8
-actions, 2 derived roles with CEL on request.resource.attr, 2^20 requests = 8 388 608 decisions / step /
-GPU).  Weak scaling: every rank evaluates its own 2^20-request shard (no data-path collective), then the
-packed decision bitmaps are all-gathered over NCCL so every rank holds the whole result.
+A *step* is `batches_per_step` passes of the hot path (rule-table scan + CEL condition evaluation), each over one
+batch of synthetic requests of the workload; the count is chosen once, after warm-up, so that a step is at least
+~10 ms of device work (reported in `config`).  Default workload: C3 of SURVEY.md 8(d) = BASELINE.json configs[2], the
+largest single-GPU configuration (100 scoped resource policies, 3-level scope chains, 20 CEL conditions with string /
+list operations, 2^24 requests x 8 actions per batch).  At --gpus 8 the same command is configs[3] ("C4": the C3 table,
+2^27 requests sharded over 8 GPUs).  Weak scaling: every rank evaluates its own shard of the request stream (no
+data-path collective); the packed decision bitmaps are exchanged over NVLink so that every rank holds the whole result.
+A C2 (configs[1]) measurement rides along as `secondary` at N = 1.
 
   value     whole-job decisions/s with the request columns already resident in HBM (CUDA events, max over
             ranks; successive steps rotate over distinct batches whose total footprint exceeds L2)
   e2e       the same metric through the host-buffer C-ABI call cgpu_check (pinned host columns -> H2D ->
             kernel -> D2H -> effect bytes), i.e. what engine.Check would pay per call
-  roofline  algorithmic bytes / launch (73 B x 2^20) over the mean kernel duration vs the
+  roofline  algorithmic bytes / launch (C3 197 B, C2 73 B per request) over the mean kernel duration vs the
             measured HBM copy bandwidth (MEASURED_PEAKS.json)
   cpu_baseline  oracle/c/check_ref.c (a plain-C port of the reference algorithm) on all host cores
 
@@ -137,9 +140,12 @@ def get_workload(name):
     return W.WORKLOADS[name]()
 
 
-def shard_fields(w, n, shard):
-    """Fields of requests [shard*n, (shard+1)*n) of the workload's stream."""
-    return w.fields(n, start=shard * n)
+def shard_columns(w, n, shard, enc):
+    """Columns of requests [shard*n, (shard+1)*n) of the workload's stream (built in parallel chunks)."""
+    from cerbos_b200 import workloads as W
+    if w.name in ("C2", "C3"):
+        return W.columns_parallel(w, n, shard * n, enc)
+    return w.columns(w.fields(n, start=shard * n), enc)
 
 
 def cpu_port_rate(w, ft, enc, seconds=10.0, n=None, threads=None):
@@ -169,6 +175,15 @@ def cpu_port_rate(w, ft, enc, seconds=10.0, n=None, threads=None):
     return passes * b.n * b.max_actions / dt, threads, passes, b.n, dt
 
 
+def go_probe():
+    """`go version` (the reference's own engine could only be timed with a Go >= 1.25 toolchain and its module cache)."""
+    try:
+        r = subprocess.run(["go", "version"], capture_output=True, text=True, timeout=10)
+        return r.stdout.strip() or "go: no output"
+    except (OSError, subprocess.SubprocessError):
+        return "not found"
+
+
 def run_reference(args):
     """--impl reference: the CPU path alone, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -177,7 +192,7 @@ def run_reference(args):
     w = get_workload(args.workload)
     from cerbos_b200 import workloads as W
     _, ft, enc = W.build(w)
-    # one "step" = a bounded sample: 2^20 requests (C2 full batch) on all host threads
+    # one "step" = a bounded sample: the first 2^20 requests of the workload's stream on all host threads
     n = min(w.default_n, 1 << 20)
     from oracle import cref
     import ctypes
@@ -203,94 +218,87 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": w.name, "requests_per_step": b.n, "actions": b.max_actions,
-                   "note": "CPU port of the reference algorithm (oracle/c/check_ref.c); the reference's Go engine "
-                           "cannot be built in this image (no Go toolchain)"},
+        "config": {"workload": workload_label(w, args.gpus, args.requests or w.default_n), "sample_requests_per_step": b.n, "actions_per_request": b.max_actions,
+                   "go_toolchain": go_probe(),
+                   "note": "CPU port of the reference algorithm (oracle/c/check_ref.c) on all host threads, a 2^20-request prefix of the "
+                           "workload's stream per step; the reference's own Go engine needs a Go toolchain + module cache "
+                           "(baseline/go/ holds the harness source), absent from this image"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 def ncu_traffic(workload: str, n: int):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
-    `ncu --set full` capture of this very command (profiles/; None if there is none for the workload / size)."""
-    if workload != "C2" or n != (1 << 20):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, scaled to n requests, from the
+    committed `ncu --set full` capture of this workload's kernel (profiles/; None if there is none)."""
+    files = {"C2": ("r1_final_check_kernel_ncu_full.json", 1 << 20), "C3": ("r2_C3_check_kernel_ncu_full.json", 1 << 22)}
+    if workload not in files:
         return None
+    name, n_cap = files[workload]
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_final_check_kernel_ncu_full.json")) as f:
-            return float(json.load(f)["_traffic_bytes_per_launch"])
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            d = json.load(f)
+        if "_traffic_bytes_per_launch" in d:
+            per = float(d["_traffic_bytes_per_launch"])
+        else:
+            mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+            per = sum(float(d[k]["value"]) * mult[d[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        return per * (n / n_cap)
     except (OSError, KeyError, ValueError):
         return None
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5000)
-    ap.add_argument("--warmup", type=int, default=50)
-    ap.add_argument("--workload", default="C2")
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=20)
-    ap.add_argument("--cpu-seconds", type=float, default=10.0)
-    ap.add_argument("--requests", type=int, default=0, help="override requests per step per GPU (profiling only)")
-    ap.add_argument("--streams", type=int, default=2, help="CUDA streams the steps are issued on round-robin (independent batches)")
-    ap.add_argument("--no-verify", action="store_true", help="skip the post-run comparison of the result images with the oracle")
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    args = ap.parse_args()
-    if args.warmup < 3:
-        args.warmup = 3
-    if args.impl == "reference":
-        return run_reference(args)
+def verify_images(w, blob, host_batches, images, kbytes):
+    """Result images against the C port of the reference algorithm (oracle/): bit for bit over every request up to 2^24
+    per batch, beyond that over a striped sample (every 16th run of 65 536 requests) as BASELINE.md 2.4 prescribes.
+    -> (mismatching bytes, requests compared)"""
+    from oracle import cref
+    bad = cmp = 0
+    for hb, img in zip(host_batches, images):
+        n = hb.n
+        if n <= (1 << 24):
+            spans = [(0, n)]
+        else:
+            spans = [(s0, min(65536, n - s0)) for s0 in range(0, n, 16 * 65536)]
+        for s0, cnt in spans:
+            if (s0, cnt) == (0, n):
+                cols = hb.columns
+            else:   # a sub-batch: per-request columns sliced, batch-level tables as they are
+                cols = list(hb.columns)
+                cols[0] = np.ascontiguousarray(hb.columns[0][s0:s0 + cnt])
+                cols[1] = np.ascontiguousarray(hb.columns[1][s0:s0 + cnt])
+                cols[2] = np.ascontiguousarray(hb.columns[2][:, s0:s0 + cnt])
+                cols[3] = np.ascontiguousarray(hb.columns[3][:, s0:s0 + cnt])
+            want = cref.check(blob, cols, cnt, hb.max_actions, NOW_NS, 0, n_threads=os.cpu_count() or 1)
+            want_bits = np.packbits((want == 1).astype(np.uint8), axis=1, bitorder="little")[:, :kbytes].reshape(-1)
+            bad += int((img[s0 * kbytes:(s0 + cnt) * kbytes] != want_bits).sum())
+            cmp += cnt
+    return bad, cmp
 
+
+def measure(args, ctx, w, blob, enc, table, dev, rank, world, local_rank, n, primary=True):
+    """Times the device-resident path of one workload; returns the result fragment (see main)."""
     import torch
     import torch.distributed as dist
-    from cerbos_b200 import capi, workloads as W
     from cerbos_b200.device import DeviceBatch
+    from cerbos_b200.dist import all_gather_bitmaps
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: cerbos_b200 has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = f"cuda:{local_rank}"
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(dev))
-
-    w = get_workload(args.workload)
-    # rank 0 flattens the policies; the blob is broadcast over NCCL (SURVEY.md 8(e))
-    if rank == 0:
-        _, ft, enc = W.build(w)
-        blob = ft.blob
-    from cerbos_b200.dist import all_gather_bitmaps, broadcast_blob
-    blob = broadcast_blob(blob if rank == 0 else None, dev)
-    from cerbos_b200.encode import Encoder, manifest_from_blob
-    if rank != 0:
-        enc = Encoder(manifest_from_blob(blob))
-    ctx = capi.Context(local_rank)
-    table = ctx.load_table(blob)
-    spec_ready, spec_note = table.wait_ready()   # table-specialised kernels (NVRTC, background thread) are in place
-
-    n = args.requests or w.default_n
     K = len(w.actions)
-    n_buf = 4 if n >= (1 << 18) else 1
-    # distinct batches: this rank's shard of requests, n_buf consecutive windows of the workload stream
+    n_buf = 2 if n >= (1 << 22) else 4 if n >= (1 << 18) else 1
     batches, host_batches = [], []
-    for j in range(n_buf):
-        hb = w.columns(shard_fields(w, n, rank * n_buf + j), enc)
+    for j in range(n_buf):   # distinct batches: this rank's shard, n_buf consecutive windows of the workload stream
+        hb = shard_columns(w, n, rank * n_buf + j, enc)
         host_batches.append(hb)
         batches.append(DeviceBatch(hb, dev))
     footprint = sum(b.nbytes() for b in batches)
     kbytes = batches[0].kbytes
-
     calls = [b.prepare(table, NOW_NS) for b in batches]
     views = [b.bitmap[: n * kbytes] for b in batches]
     torch.cuda.synchronize()
-    # Steps are independent batches: they are issued round-robin on `--streams` explicit streams (the tail of one step's
-    # kernels and its peer-store round trips overlap the next step's kernel).  Everything timed is launched on these
-    # streams through the C ABI and bracketed by CUDA events recorded on them.
-    n_streams = max(1, min(args.streams, n_buf))
+    # Steps are independent batches.  Small batches (C2: a launch is ~20 us) are issued round-robin on two streams so that
+    # the tail of one launch overlaps the head of the next; a C3-sized launch fills the GPU for milliseconds: one stream.
+    n_streams = args.streams if args.streams else (2 if n < (1 << 22) else 1)
+    n_streams = max(1, min(n_streams, n_buf))
     while n_buf % n_streams:
         n_streams -= 1
     streams = [torch.cuda.Stream() for _ in range(n_streams)]
@@ -300,15 +308,15 @@ def main():
     stream_hs = [st.cuda_stream for st in streams]
     assert all(h != 0 for h in stream_hs) and torch.cuda.current_stream().cuda_stream == stream_h
 
-    # Multi-GPU result exchange.  Default: FUSED all-gather -- the check kernels store every result byte straight into
-    # this rank's slice of every rank's gather buffer over NVLink peer memory (cerbos_b200.dist.PeerGather), a flag
-    # release follows, no collective kernel runs.  Fallback (CERBOS_B200_NCCL_GATHER=1, or CUDA IPC unavailable):
-    # asynchronous NCCL all_gather_into_tensor overlapping the next batch's kernel.
+    # Multi-GPU result exchange (primary workload only).  Default: every rank's results land in every rank's gather
+    # buffer over NVLink peer memory (cerbos_b200.dist.PeerGather): small slices are stored by the check kernels
+    # themselves, large ones are pushed by the copy engines behind the kernel; a flag release follows, no collective
+    # kernel runs.  Fallback (CERBOS_B200_NCCL_GATHER=1, or CUDA IPC unavailable): asynchronous NCCL all-gather.
     gather_mode = "none"
     pg, gcalls = None, None
-    if world > 1:
+    if world > 1 and primary:
         ok = 0
-        no_exchange = os.environ.get("CERBOS_B200_NO_GATHER") == "1"   # diagnosis only: ranks run independently, nothing is exchanged
+        no_exchange = os.environ.get("CERBOS_B200_NO_GATHER") == "1"   # diagnosis only
         if os.environ.get("CERBOS_B200_NCCL_GATHER") != "1" and kbytes <= 8 and not no_exchange:
             try:
                 from cerbos_b200.dist import PeerGather
@@ -320,27 +328,30 @@ def main():
                 sys.stderr.write(f"[rank {rank}] peer gather unavailable ({e}); using NCCL\n")
         t_ok = torch.tensor([ok], dtype=torch.int32, device=dev)
         dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
-        gather_mode = "fused-peer-stores" if int(t_ok.item()) == 1 else "nccl-all-gather"
-        if gather_mode != "fused-peer-stores":
+        gather_mode = "peer-memory" if int(t_ok.item()) == 1 else "nccl-all-gather"
+        if gather_mode != "peer-memory":
             pg, gcalls = None, None
         if no_exchange:
             gather_mode = "none (diagnosis)"
         elif pg is None:       # NCCL orders its collective after torch's current stream only: one issuing stream
             n_streams, streams, stream_hs = 1, streams[:1], stream_hs[:1]
-    gathered = [torch.empty(world * n * kbytes, dtype=torch.uint8, device=dev) for _ in range(n_buf)] if (world > 1 and pg is None) else None
+        elif n * kbytes >= (1 << 20):
+            gather_mode = "peer-memory: copy engines push each rank's slice to every peer behind the kernel"
+        else:
+            gather_mode = "peer-memory: the check kernels store into every peer's buffer"
+    gathered = [torch.empty(world * n * kbytes, dtype=torch.uint8, device=dev) for _ in range(n_buf)] if (world > 1 and primary and pg is None) else None
     pending = []
-    it = [0]          # steps issued so far (warm-up included): numbers the gather steps
+    it = [0]          # launches issued so far (warm-up included): numbers the gather steps
 
-    def step(i):
+    def launch():
         g = it[0]
         it[0] += 1
         j = g % n_buf
         lane = g % n_streams            # == j % n_streams: a buffer always travels on the same stream
         sh = stream_hs[lane]
         if pg is not None:
-            # buffers rotate: step g-(n_buf-1) must have landed on this rank before its stream moves on (the wait rides in
-            # the same launch: the kernel that publishes this step's flag also holds the stream for the older one).
-            # Steps are numbered per stream ("lane"), so that every flag array only ever counts up.
+            # buffers rotate: launch g-(n_buf-1) must have landed on this rank before its stream moves on.  Launches are
+            # numbered per stream ("lane"), so that every flag array only ever counts up.
             k = g - (n_buf - 1)
             if k >= 0:
                 gcalls[j](g // n_streams + 1, sh, k // n_streams + 1, pg.local_flags(k % n_streams))
@@ -348,15 +359,15 @@ def main():
                 gcalls[j](g // n_streams + 1, sh, 0, None)
             return
         calls[j](sh)
-        if world > 1 and gather_mode != "none (diagnosis)":
-            if len(pending) >= n_buf - 1:          # buffers are reused after n_buf steps: retire the oldest gather
+        if gathered is not None and gather_mode != "none (diagnosis)":
+            if len(pending) >= n_buf - 1:          # buffers are reused after n_buf launches: retire the oldest gather
                 pending.pop(0).wait()
             _, work = all_gather_bitmaps(views[j], gathered[j], async_op=True)
             pending.append(work)
 
     def drain():
         if pg is not None:
-            for lane in range(n_streams):          # the last step issued on every stream (a stream finishes its steps in order)
+            for lane in range(n_streams):          # the last launch issued on every stream (a stream finishes in order)
                 last = [g for g in range(max(0, it[0] - n_streams), it[0]) if g % n_streams == lane]
                 if last:
                     pg.wait(last[-1] // n_streams + 1, stream_hs[lane], lane)
@@ -365,22 +376,44 @@ def main():
             pending.pop(0).wait()
 
     def join_streams():
-        """stream 0 waits for the work issued so far on the other streams"""
         for st in streams[1:]:
             e = torch.cuda.Event()
             e.record(st)
             stream.wait_event(e)
 
-    if world > 1 and pg is None:
-        assert n_streams == 1 or gather_mode == "none (diagnosis)"
-    for i in range(args.warmup):
-        step(i)
+    def sync_all():
+        drain()
+        for h in stream_hs:
+            ctx.sync(h)
+        torch.cuda.synchronize()
+        if world > 1 and primary:
+            dist.barrier()
+
+    # warm-up launches, then calibrate batches_per_step so that one step is >= ~10 ms of device work
+    for _ in range(max(3, n_buf)):
+        launch()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(n_buf * n_streams):
+        launch()
     drain()
-    for h in stream_hs:
-        ctx.sync(h)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    join_streams()
+    e1.record(stream)
+    sync_all()
+    t_launch_ms = e0.elapsed_time(e1) / (n_buf * n_streams)
+    m = max(1, int(np.ceil(args.step_ms / max(t_launch_ms, 1e-4))))
+    m = ((m + n_buf - 1) // n_buf) * n_buf if m > 1 else 1
+    if world > 1 and primary:
+        tm = torch.tensor([m], dtype=torch.int64, device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        m = int(tm.item())
+    if args.batches_per_step:
+        m = args.batches_per_step
+    for _ in range(args.warmup):
+        for _ in range(m):
+            launch()
+    sync_all()
     launches0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
@@ -388,127 +421,252 @@ def main():
         ev0.record(stream)
         for st in streams[1:]:
             st.wait_event(ev0)               # no stream starts before the start event
-        for i in range(args.steps):
-            step(i)
+        for _ in range(args.steps * m):
+            launch()
         drain()                              # the last exchanges are part of the timed work
         join_streams()
         ev1.record(stream)
         torch.cuda.synchronize()
-    if world > 1:
+    if world > 1 and primary:
         dist.barrier()
     total_ms = ev0.elapsed_time(ev1)
     launches = ctx.launch_count() - launches0
     for h in stream_hs:
         ctx.sync(h)
-    if world > 1:
+    if world > 1 and primary:
         tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         total_ms = float(tmax.item())
     per_step_ms = total_ms / args.steps
-    value = world * n * K / (per_step_ms * 1e-3)
+    wn = world if primary else 1
+    value = wn * m * n * K / (per_step_ms * 1e-3)
 
-    # kernel-only duration: events around each single launch (no collective), measured after the timed region
-    # (a) the whole device step of one call (clustering kernels + check kernel), (b) the check kernel alone, from
+    # kernel-only duration: (a) the whole device work of one call issued alone, (b) the dominant check kernel alone, from
     # the library's own CUDA events recorded on the launching stream around that kernel (cgpu_profile)
     step_ms = []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ctx.profile(True)
-    for i in range(min(args.steps, 50)):
-        e0.record()
+    for i in range(min(args.steps * m, 30)):
+        p0.record()
         calls[i % n_buf](stream_h)
-        e1.record()
-        e1.synchronize()
-        step_ms.append(e0.elapsed_time(e1))
+        p1.record()
+        p1.synchronize()
+        step_ms.append(p0.elapsed_time(p1))
     k_sum, k_n = ctx.profile(False)
     kern_ms_mean = k_sum / max(k_n, 1)
-    kern_ms = step_ms
+    kcfg = ctx.last_kernel_config()
     peak, peak_src = load_peaks()
     algo_bytes = w.bytes_per_request() * n
     achieved = algo_bytes / (kern_ms_mean * 1e-3) / 1e9
 
-    # correctness check of what was timed (the overlapped back-to-back launches included): the result images the timed
-    # loop left behind, every rotating batch, bit for bit against the C port of the reference algorithm (oracle/)
-    verified = None
-    if not args.no_verify and n <= (1 << 21):
-        from oracle import cref as _cref
-        bad = 0
-        for j, hb in enumerate(host_batches):
-            want = _cref.check(blob, hb.columns, hb.n, hb.max_actions, NOW_NS, 0, n_threads=os.cpu_count() or 1)
-            want_bits = np.packbits((want == 1).astype(np.uint8), axis=1, bitorder="little")[:, :kbytes].reshape(-1)
+    # correctness of what was timed: the result images the timed loop left behind, every rotating batch, against the oracle
+    verified, compared = None, 0
+    if not args.no_verify:
+        for h in stream_hs:
+            ctx.sync(h)
+        torch.cuda.synchronize()
+        images = []
+        for j in range(n_buf):
             if pg is not None:
-                img = pg.read(j)
-                got = img[rank * n * kbytes:(rank + 1) * n * kbytes]
+                images.append(pg.read(j)[rank * n * kbytes:(rank + 1) * n * kbytes])
             else:
-                got = batches[j].bitmap[: n * kbytes].cpu().numpy()
-            bad += int((got != want_bits).sum())
-        if world > 1:
+                images.append(batches[j].bitmap[: n * kbytes].cpu().numpy())
+        bad, compared = verify_images(w, blob, host_batches, images, kbytes)
+        if world > 1 and primary:
             tb = torch.tensor([bad], dtype=torch.int64, device=dev)
             dist.all_reduce(tb)
             bad = int(tb.item())
             if pg is not None and bad == 0:
                 # every rank also holds every other rank's slice: compare the whole gathered image across ranks
-                h = torch.tensor([int(np.frombuffer(pg.read(0).tobytes(), dtype=np.uint64).sum() & ((1 << 62) - 1))], dtype=torch.int64, device=dev)
-                hs = [torch.zeros_like(h) for _ in range(world)]
-                dist.all_gather(hs, h)
+                hsh = torch.tensor([int(np.frombuffer(pg.read(0).tobytes(), dtype=np.uint64).sum() & ((1 << 62) - 1))], dtype=torch.int64, device=dev)
+                hs = [torch.zeros_like(hsh) for _ in range(world)]
+                dist.all_gather(hs, hsh)
                 bad = 0 if len({int(x.item()) for x in hs}) == 1 else -1
         verified = bad == 0
         if not verified:
-            sys.stderr.write(f"[rank {rank}] VERIFY FAILED: {bad} result bytes differ from the oracle\n")
+            sys.stderr.write(f"[rank {rank}] VERIFY FAILED ({w.name}): {bad} result bytes differ from the oracle\n")
 
-    result = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"{w.name}: {W.C2.__doc__.splitlines()[0] if w.name == 'C2' else w.name}",
-                   "requests_per_step_per_gpu": n, "actions_per_request": K, "global_requests_per_step": world * n,
-                   "parallelism": f"dp{world} (requests sharded by index; NCCL table broadcast; result exchange: {gather_mode})",
-                   "streams": n_streams,
-                   "l2": f"rotating {n_buf} distinct batches, {footprint / 1e6:.0f} MB of columns > 126 MB L2",
-                   "kernel": ctx.last_kernel_config()},
+    res = {
+        "value": value, "ms_per_step": per_step_ms, "batches_per_step": m, "requests_per_batch": n, "actions_per_request": K,
+        "ms_per_batch": per_step_ms / m, "streams": n_streams, "gather_mode": gather_mode,
+        "l2": f"rotating {n_buf} distinct batches, {footprint / 1e6:.0f} MB of columns > 126 MB L2", "kernel": kcfg,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(w.name, n), "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
-                     "kernel": "check_kernel", "kernel_ms_mean": kern_ms_mean,
-                     "device_step_ms_mean": statistics.mean(step_ms), "device_step_ms_min": min(step_ms),
-                     "step_achieved": algo_bytes / (statistics.mean(step_ms) * 1e-3) / 1e9,
-                     "kernel_share_of_step": kern_ms_mean / statistics.mean(step_ms),
-                     "note": "kernel_ms_mean: the check kernel alone, CUDA events recorded by the library on the launching stream around "
-                             "that kernel, one call at a time after the timed region; device_step_ms_*: events around one whole "
-                             "call issued alone (includes the launch gaps between its kernels, which back-to-back calls hide: "
-                             "ms_per_step is lower because consecutive calls overlap at their tails)"},
-        "clocks": clocks.summary(),
-        "verified_vs_oracle": verified,
+                     "kernel": "cb_spec_uc" if kcfg.get("unique_conditions") and kcfg.get("table_specialised") else
+                               "cb_spec_tiles" if kcfg.get("table_specialised") else "check_kernel",
+                     "kernel_ms_mean": kern_ms_mean,
+                     "device_call_ms_mean": statistics.mean(step_ms), "device_call_ms_min": min(step_ms),
+                     "call_achieved": algo_bytes / (statistics.mean(step_ms) * 1e-3) / 1e9,
+                     "kernel_share_of_call": kern_ms_mean / statistics.mean(step_ms),
+                     "note": "kernel_ms_mean: the dominant check kernel alone, CUDA events recorded by the library on the launching "
+                             "stream around that kernel, one call at a time after the timed region; device_call_ms_*: events around "
+                             "one whole cgpu_check_device call issued alone (pre-pass + check kernel + drain kernel)"},
+        "clocks": clocks.summary(), "verified_vs_oracle": verified, "verified_requests": compared,
+    }
+    res["_host_batches"] = host_batches
+    res["_kbytes"] = kbytes
+    if pg is not None:
+        torch.cuda.synchronize()
+        dist.barrier()
+        pg.close()
+    del batches, calls, views
+    torch.cuda.empty_cache()
+    return res
+
+
+def measure_e2e(args, table, hb, K, world, dev):
+    """End to end through the host-buffer C ABI on THIS rank's GPU / PCIe link: pinned host columns, H2D + kernels + D2H
+    inside the timing.  Every rank runs it on its own shard; the aggregate is n_gpus x requests over the slowest rank."""
+    import torch
+    import torch.distributed as dist
+    pinned = []
+    for c in hb.columns:
+        a = np.ascontiguousarray(c)
+        t = torch.empty(max(a.nbytes, 1), dtype=torch.uint8).pin_memory()
+        t.numpy()[: a.nbytes] = a.view(np.uint8).reshape(-1)
+        pinned.append((t, a.nbytes))
+    ptrs = [t.data_ptr() for t, _ in pinned]
+    sizes = [nb for _, nb in pinned]
+    out = torch.empty(hb.n * hb.max_actions, dtype=torch.uint8).pin_memory()
+    for _ in range(3):
+        table.check_into(ptrs, sizes, hb.n, hb.max_actions, out.data_ptr(), NOW_NS, 0)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        table.check_into(ptrs, sizes, hb.n, hb.max_actions, out.data_ptr(), NOW_NS, 0)
+    dt = (time.perf_counter() - t0) / args.e2e_steps
+    if world > 1:
+        td = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        dt = float(td.item())
+    return {"value": world * hb.n * K / dt, "unit": UNIT, "h2d_bytes_per_step": int(sum(sizes)),
+            "d2h_bytes_per_step": int(hb.n * hb.max_actions), "ms_per_step": dt * 1e3, "n_gpus": world,
+            "requests_per_step_per_gpu": hb.n,
+            "note": "cgpu_check on every rank (its own PCIe link): pinned host columns -> H2D -> kernels -> D2H effect bytes "
+                    "(1 byte per decision); aggregate = n_gpus x requests / slowest rank"}, out
+
+
+WORKLOAD_DOC = {
+    "C1": "C1: 1 resource policy, 3 actions, role-only rules, 1024 requests (BASELINE.json configs[0])",
+    "C2": "C2: 10 resource policies x 8 actions, 2 derived roles with CEL on request.resource.attr, 2^20 requests (BASELINE.json configs[1])",
+    "C3": "C3: 100 scoped resource policies (3-level scope chains), 20 CEL conditions incl. string / list operations, 2^24 requests (BASELINE.json configs[2])",
+    "C5": "C5: 1000 policies, deep CEL, JWT claims, Zipf-skewed kinds (BASELINE.json configs[4])",
+}
+
+
+def workload_label(w, world, n):
+    """config.workload: the same string on both arms (ours / --impl reference)"""
+    name = WORKLOAD_DOC.get(w.name, w.name)
+    if w.name == "C3" and world > 1:
+        name = f"C4: the C3 table, {world} x 2^{int(np.log2(n))} requests sharded over {world} GPUs (BASELINE.json configs[3]); " + name
+    return name
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="C3")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--requests", type=int, default=0, help="override requests per batch per GPU (profiling only)")
+    ap.add_argument("--streams", type=int, default=0, help="CUDA streams the batches are issued on round-robin (0 = 2 for small batches, 1 for large)")
+    ap.add_argument("--step-ms", type=float, default=10.0, help="a step is as many batches as make at least this much device work")
+    ap.add_argument("--batches-per-step", type=int, default=0, help="override the calibrated number of batches per step")
+    ap.add_argument("--no-verify", action="store_true", help="skip the post-run comparison of the result images with the oracle")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C2 ride-along measurement at N = 1")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from cerbos_b200 import capi, workloads as W
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: cerbos_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    from cerbos_b200.dist import broadcast_blob
+    from cerbos_b200.encode import Encoder, manifest_from_blob
+    ctx = capi.Context(local_rank)
+
+    def load(wname):
+        w = get_workload(wname)
+        blob = None
+        if rank == 0:       # rank 0 flattens the policies; the blob is broadcast over NCCL (SURVEY.md 8(e))
+            _, ft, _ = W.build(w)
+            blob = ft.blob
+        blob = broadcast_blob(blob, dev)
+        enc = Encoder(manifest_from_blob(blob))
+        table = ctx.load_table(blob)
+        spec_ready, spec_note = table.wait_ready()   # table-specialised kernels (NVRTC, background thread) are in place
+        return w, blob, enc, table, spec_ready, spec_note
+
+    w, blob, enc, table, spec_ready, spec_note = load(args.workload)
+    n = args.requests or w.default_n
+    K = len(w.actions)
+    r = measure(args, ctx, w, blob, enc, table, dev, rank, world, local_rank, n, primary=True)
+    host_batches = r.pop("_host_batches")
+    r.pop("_kbytes")
+    wl_name = workload_label(w, world, n)
+    result = {
+        "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": wl_name, "batches_per_step": r["batches_per_step"], "requests_per_batch_per_gpu": n,
+                   "requests_per_step_per_gpu": n * r["batches_per_step"], "actions_per_request": K,
+                   "global_requests_per_step": world * n * r["batches_per_step"], "ms_per_batch": r["ms_per_batch"],
+                   "parallelism": f"dp{world} (requests sharded by index; NCCL table broadcast; result exchange: {r['gather_mode']})",
+                   "streams": r["streams"], "l2": r["l2"], "kernel": r["kernel"],
+                   "specialised_kernels": spec_note if not spec_ready else "compiled for this table at load (NVRTC)"},
+        "gpu_launches": r["gpu_launches"], "roofline": r["roofline"], "clocks": r["clocks"],
+        "verified_vs_oracle": r["verified_vs_oracle"], "verified_requests_per_gpu": r["verified_requests"],
     }
 
-    if rank == 0 and not args.no_e2e:
-        # end to end through the host-buffer C ABI: pinned host columns, H2D + kernel + D2H + decode inside the timing
-        hb = host_batches[0]
-        pinned = []
-        for c in hb.columns:
-            a = np.ascontiguousarray(c)
-            t = torch.empty(a.nbytes, dtype=torch.uint8).pin_memory()
-            t.numpy()[:] = a.view(np.uint8).reshape(-1)
-            pinned.append(t)
-        ptrs = [t.data_ptr() for t in pinned]
-        sizes = [t.numel() for t in pinned]
-        out = torch.empty(hb.n * hb.max_actions, dtype=torch.uint8).pin_memory()
-        for _ in range(3):
-            table.check_into(ptrs, sizes, hb.n, hb.max_actions, out.data_ptr(), NOW_NS, 0)
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            table.check_into(ptrs, sizes, hb.n, hb.max_actions, out.data_ptr(), NOW_NS, 0)
-        dt = (time.perf_counter() - t0) / args.e2e_steps
-        result["e2e"] = {"value": hb.n * K / dt, "unit": UNIT, "h2d_bytes_per_step": int(sum(sizes)),
-                         "d2h_bytes_per_step": int(hb.n * kbytes), "ms_per_step": dt * 1e3, "n_gpus": 1,
-                         "note": "cgpu_check: pinned host columns -> H2D -> kernel -> D2H bitmap -> effect bytes"}
+    if not args.no_e2e:
+        e2e, out = measure_e2e(args, table, host_batches[0], K, world, dev)
+        if not args.no_verify:   # the host-buffer path returns effect bytes: compare them too (first 2^20 requests)
+            from oracle import cref
+            hb = host_batches[0]
+            cnt = min(hb.n, 1 << 20)
+            cols = list(hb.columns)
+            cols[0] = np.ascontiguousarray(hb.columns[0][:cnt]); cols[1] = np.ascontiguousarray(hb.columns[1][:cnt])
+            cols[2] = np.ascontiguousarray(hb.columns[2][:, :cnt]); cols[3] = np.ascontiguousarray(hb.columns[3][:, :cnt])
+            want = cref.check(blob, cols, cnt, hb.max_actions, NOW_NS, 0, n_threads=os.cpu_count() or 1)
+            e2e["verified_vs_oracle"] = bool((out.numpy()[: cnt * hb.max_actions].reshape(cnt, hb.max_actions) == want).all())
+        result["e2e"] = e2e
+    del host_batches
     if rank == 0 and world == 1 and not args.no_cpu:   # the CPU baseline is reported at N = 1 only
-        v, threads, passes, ns, dt = cpu_port_rate(w, ft, enc, seconds=args.cpu_seconds)
+        _, ft0, enc0 = W.build(w)
+        v, threads, passes, ns, dt = cpu_port_rate(w, ft0, enc0, seconds=args.cpu_seconds)
         result["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                   "sample": f"{passes} passes over {ns} requests x {K} actions ({dt:.1f} s) of the "
                                             f"same {w.name} stream, oracle/c/check_ref.c"}
+    table.release()
+    if world == 1 and not args.no_secondary and w.name != "C2":
+        # configs[1] rides along: same measurement on workload C2 (device-resident path only)
+        w2, blob2, enc2, table2, ready2, note2 = load("C2")
+        r2 = measure(args, ctx, w2, blob2, enc2, table2, dev, rank, 1, local_rank, w2.default_n, primary=False)
+        r2.pop("_host_batches"); r2.pop("_kbytes")
+        result["secondary"] = {"workload": WORKLOAD_DOC["C2"], "metric": METRIC, "unit": UNIT, **r2}
+        table2.release()
     if rank == 0:
         print(json.dumps(result))
-    table.release()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

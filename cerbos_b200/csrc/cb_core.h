@@ -31,6 +31,8 @@
 
 namespace cb {
 
+struct alignas(16) U4 { uint32_t x, y, z, w; };
+
 // ---------------------------------------------------------------------------------------------- views
 // Section offsets + dimensions of the table image.  In the kernels this lives in the (grid-constant) kernel
 // parameters, so reading a field is a constant-bank operand and costs no register.
@@ -41,6 +43,7 @@ struct TableLayout {
     uint32_t image_bytes;
     // "unique condition" image (cb_uc.h): offsets of the two derived sections, number of distinct conditions (0 = none)
     uint32_t uc_conds_off, uc_rows_off, n_uconds;
+    uint32_t theap_words;   // 8-byte words in THEAP
 };
 
 // base = start of the table image: shared memory (TMA-staged) or global memory.
@@ -74,7 +77,7 @@ struct TableView {
     CB_HD const uint32_t *block_slots_off() const { return sec<uint32_t>(CB_SEC_BLOCK_SLOTS_OFF); }
     CB_HD const uint32_t *block_slots() const { return sec<uint32_t>(CB_SEC_BLOCK_SLOTS); }
     CB_HD const cb_cond *uconds() const { return reinterpret_cast<const cb_cond *>(base + L->uc_conds_off); }     // [n_uconds + 1], entry 0 unused
-    CB_HD const uint32_t *urows() const { return reinterpret_cast<const uint32_t *>(base + L->uc_rows_off); }      // [n_rows] packed (uc_row)
+    CB_HD const U4 *urows() const { return reinterpret_cast<const U4 *>(base + L->uc_rows_off); }                 // [n_rows] 16-byte rows, DENY first per block
 };
 
 enum { CB_MAX_GATHER = 8 };
@@ -110,6 +113,12 @@ struct BatchView {
     uint32_t *sig_flags[CB_MAX_GATHER];
     const uint32_t *wait_flags;
     uint32_t sig_rank, sig_step, wait_step;
+    // run-time specialised unique-condition kernels: one word per string id (table strings, then batch strings) holding
+    // the outcome of every `attribute.startsWith / endsWith / contains(constant)` predicate of the table, computed once
+    // per distinct string by a pre-pass over the batch's string dictionary (null: none)
+    const uint32_t *strpred;
+    uint32_t n_bstr;            // strings in the batch dictionary
+    uint64_t heap_words;        // 8-byte words in `heap`
 };
 
 // Table data may live in shared memory (TMA-staged image) or in global memory, heap references may point
@@ -124,6 +133,7 @@ inline void finish_batch_view(BatchView &b) {
     b.n_out = 0;
     for (int i = 0; i < CB_MAX_GATHER; i++) { b.outs[i] = nullptr; b.sig_flags[i] = nullptr; }
     b.wait_flags = nullptr; b.sig_rank = 0; b.sig_step = 0; b.wait_step = 0;
+    b.strpred = nullptr;
     b.rcp = 1;
     while (b.rcp < b.role_cols) b.rcp <<= 1;
     b.stride_pattern = 0;
@@ -154,7 +164,6 @@ CB_HD uint32_t ldcol32(const uint32_t *p) {
 }
 
 // 128-bit loads of the 16-byte records (their C structs are only 4-byte aligned, the buffers are 16-byte aligned)
-struct alignas(16) U4 { uint32_t x, y, z, w; };
 CB_HD U4 ld16(const void *p) { return *reinterpret_cast<const U4 *>(p); }
 CB_HD U4 ldcol128(const void *p) {
 #if defined(__CUDA_ARCH__)
@@ -1510,6 +1519,98 @@ CB_HD int term_tri(const TableView t, const BatchView &b, const Cols &cols, uint
     }
     return tri;
 }
+// ---- register-resident lists (run-time specialised unique-condition kernels) ----------------------------------------
+// Several conditions of a table usually read the same list attribute (principal groups, allowed groups ...).  The
+// specialised build loads such a list ONCE per request into registers -- length + up to CB_LC elements, normalised so
+// that scalar equality is plain 64-bit equality (-0.0 -> +0.0; padding = a sentinel that equals nothing) -- and every
+// membership / set predicate over it is a fully unrolled, branch-free run of compares.  Lists the cache cannot hold
+// exactly (longer, container / int / NaN elements) raise `slow`: the request goes to the general body.
+enum { CB_LC = 8 };
+struct ListRegs {
+    uint32_t st, len;        // st 0: cached list; 1: slot ABSENT / ERROR; 2: a list this cache cannot hold exactly; 3: another type
+    uint64_t e[CB_LC];
+};
+static constexpr uint64_t kListPad = 0xFFFE000000000001ull;    // box tag 14: never produced by an encoder
+CB_HD uint64_t norm_scalar(uint64_t v) { return v == 0x8000000000000000ull ? 0ull : v; }
+CB_HD ListRegs list_load(const TableView t, const BatchView &b, uint64_t x) {
+    ListRegs L;
+    L.st = v64_bad(x) ? 1u : v64_tag(x) == CB_V64_LIST ? 0u : 3u;
+    L.len = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < CB_LC; j++) L.e[j] = kListPad;
+    if (L.st == 0) {
+        // length and the first CB_LC element words are requested together (bounded by the end of the heap, not by the
+        // length: one memory round trip instead of two); words beyond the length are discarded below
+        const uint64_t pay = x & 0xFFFFFFFFFFFFull;
+        const bool in_batch = (pay & CB_V64_HEAP_BATCH_BIT) != 0;
+        const uint64_t off = in_batch ? pay & (CB_V64_HEAP_BATCH_BIT - 1) : pay;
+        const uint64_t *p = (in_batch ? b.heap : t.theap()) + off;
+        const uint64_t room = (in_batch ? b.heap_words : (uint64_t)t.L->theap_words) - off;   // words from p to the end of its heap
+        uint64_t w[CB_LC];
+        L.len = (uint32_t)ldg(p);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < CB_LC; j++) w[j] = (uint64_t)(j + 1) < room ? ldg(p + 1 + j) : kListPad;
+        bool odd = L.len > CB_LC;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < CB_LC; j++) {
+            const bool in = (uint32_t)j < L.len;
+            odd |= in && (v64_tag(w[j]) > CB_V64_STRING || w[j] == CB_V64_CANON_NAN);
+            L.e[j] = in ? norm_scalar(w[j]) : kListPad;
+        }
+        L.st = odd ? 2u : 0u;
+    }
+    return L;
+}
+// x in L: the outcome of in_tri() / the IN branch of term_tri() for every input this form decides, `slow` otherwise
+CB_HD int list_in_tri(uint64_t x, const ListRegs &L, bool &slow) {
+    if (v64_bad(x) || L.st == 1) return TRI_E;
+    if (L.st != 0 || v64_tag(x) > CB_V64_STRING || x == CB_V64_CANON_NAN) { slow = true; return TRI_E; }
+    const uint64_t nx = norm_scalar(x);
+    bool found = false;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < CB_LC; j++) found |= nx == L.e[j];
+    return found ? TRI_T : TRI_F;
+}
+// hasIntersection(A, B) / isSubset(A, B): the INTERSECTS / SUBSET branch of term_tri()
+CB_HD int list_set_tri(bool subset, const ListRegs &A, const ListRegs &B, bool &slow) {
+    if (A.st == 1 || B.st == 1) return TRI_E;
+    if (A.st == 3 || B.st == 3) return TRI_E;
+    if (A.st == 2 || B.st == 2) { slow = true; return TRI_E; }
+    bool any_hit = false, all_hit = true;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < CB_LC; i++) {
+        bool hit = false;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < CB_LC; j++) hit |= A.e[i] == B.e[j];
+        const bool valid = (uint32_t)i < A.len;   // padding of A would "hit" the padding of B
+        any_hit |= valid && hit;
+        all_hit &= !valid || hit;
+    }
+    return (subset ? all_hit : any_hit) ? TRI_T : TRI_F;
+}
+// attribute.startsWith / endsWith / contains(constant string) through the per-string predicate word (BatchView::strpred)
+CB_HD int strpred_tri(const BatchView &b, uint64_t x, uint32_t p) {
+    if (v64_bad(x)) return TRI_E;
+    if (v64_tag(x) != CB_V64_STRING) return TRI_E;
+    return (int)((ldg(b.strpred + (uint32_t)(x & 0xFFFFFFFFu)) >> p) & 1u);
+}
+// a one-value column accessor: evaluates a term for a given string (the predicate pre-pass)
+struct OneCols {
+    uint64_t x;
+    CB_HD uint64_t slot(uint32_t) const { return x; }
+};
 CB_HD bool term_lit(int tri, uint32_t flags) { return (flags & CB_TERM_LIT_F) ? tri == TRI_F : tri == TRI_T; }
 // -> bit0 satisfied, bit2: needs the out-of-line general path
 template <typename Cols>
@@ -2027,16 +2128,23 @@ CB_HD bool eval_request_fast(const TableView t, const BatchView &b, const Cols &
 // scope chain with rows that are pure mask algebra on that word.  Conditions have no side effects and an error is
 // "not satisfied" (ruletable.go:1425-1441), so evaluating one that no row of the request needs cannot change a result.
 // Same domain as eval_request_fast (resource policies only, pair masks <= 32 bits); same deferral contract.
-CB_HD uint32_t uc_row(uint32_t role8, uint32_t cond, uint32_t drcond, uint32_t effect) { return role8 | cond << 8 | drcond << 16 | effect << 24; }
-
-// row access of the unique-condition body: {action mask of the request's action set, packed row}
+// Rows of the unique-condition image (cb_uc.h), 16 bytes each, DENY rows first inside every block:
+//   {original row index (for the batch's row x action-set masks), role8 | effect << 8, need_lo, need_hi}
+// need = bit of the rule condition | bit of the derived-role condition | bit 0: the row is satisfied iff
+// (condition word & need) == need.  What the walk consumes is the record merged with the batch:
+//   {action mask of the request's action set, need_lo, need_hi, shift of the row's role field in the role table}
+CB_HD U4 uc_row_record(const U4 ur, uint32_t am, uint32_t RCP, uint32_t nR) {
+    const uint32_t role = ur.y & 0xFFu;
+    U4 r; r.x = am; r.y = ur.z; r.z = ur.w; r.w = (role == 0xFFu ? nR : role) * RCP;   // field nR of the role table = "any role"
+    return r;
+}
 struct UcRowsGlobal {   // straight from the table image and the batch's row_am column
-    const uint32_t *urows; const uint64_t *row_am;
-    CB_HD void get(uint32_t aset_base, uint32_t ri, uint32_t &am, uint32_t &ur) const { am = (uint32_t)ldg(row_am + aset_base + ri); ur = ldg(urows + ri); }
+    const U4 *urows; const uint64_t *row_am; uint32_t RCP, nR;
+    CB_HD U4 get(uint32_t aset_base, uint32_t ri) const { const U4 ur = ld16(urows + ri); return uc_row_record(ur, (uint32_t)ldg(row_am + aset_base + ur.x), RCP, nR); }
 };
-struct UcRowsPacked {   // one 8-byte record per (action set, row), merged once per CTA into shared memory
-    const uint64_t *pk;
-    CB_HD void get(uint32_t aset_base, uint32_t ri, uint32_t &am, uint32_t &ur) const { const uint64_t v = ldg(pk + aset_base + ri); am = (uint32_t)v; ur = (uint32_t)(v >> 32); }
+struct UcRowsPacked {   // one merged record per (action set, row), built once per CTA in shared memory
+    const U4 *pk;
+    CB_HD U4 get(uint32_t aset_base, uint32_t ri) const { return ld16(pk + aset_base + ri); }
 };
 
 // column access with L1 allocation: the eager condition pass reads the same slot from several terms
@@ -2066,8 +2174,9 @@ struct CachedCols {
 // terms (and, in the ahead-of-time build, runs the stack interpreter for conditions without a flat form); a run-time
 // specialised build (cb_specialize.h: generate_uc) substitutes straight-line code over register-resident slots.
 struct GenericConds {
+    static constexpr bool kVal32 = false;   // the condition word may use all 64 bits
     template <typename Cols>
-    CB_HD Cols load(const Cols &cols) const { return cols; }
+    CB_HD Cols load(const TableView, const BatchView &, const Cols &cols) const { return cols; }
     template <typename Cols>
     CB_HD uint64_t operator()(const TableView t, const BatchView &b, const Cols &cols, uint32_t pid, uint64_t n, bool &slow) const {
         uint64_t val = 1;
@@ -2092,12 +2201,49 @@ struct GenericConds {
     }
 };
 
+// (action x role column) pairs of one row if its conditions hold: a needed condition bit that is clear zeroes the role columns
+template <typename RP, bool kVal32>
+CB_HD uint32_t uc_row_pairs(const U4 r, const RP rp, const uint32_t vlo, const uint32_t vhi, const uint32_t role_all) {
+    const uint32_t miss = kVal32 ? r.y & ~vlo : (r.y & ~vlo) | (r.z & ~vhi);
+    const uint32_t rc = miss ? 0u : (uint32_t)(rp >> r.w) & role_all;
+    return r.x * rc;
+}
+// The scope-chain walk of the unique-condition body: per block the DENY rows, then the ALLOW rows, each row three or
+// four ALU operations on registers.  RP: the role table word (32 bits when every role field fits, else 64);
+// kVal32: the condition word has at most 32 bits (known when the kernel is generated for a table).
+template <typename RP, bool kVal32, typename Rows>
+CB_HD uint32_t uc_walk(const TableView t, const BatchView &b, const Rows rows, const RP rp, const uint64_t val, const uint32_t r0, const uint32_t bm_base,
+                       const uint32_t aset_base, const uint32_t role_all, uint32_t alive) {
+    (void)b;
+    uint32_t allow_pairs = 0;
+    const uint32_t vlo = (uint32_t)val, vhi = (uint32_t)(val >> 32);
+    for (uint32_t s = r0; s != CB_NONE32 && alive; s = chain_next(t, s, CB_SCOPE_FLAG_RESOURCE)) {
+        const uint32_t bid = ldg(t.res_block_map() + bm_base + s);
+        if (bid != CB_NONE32) {
+            const U4 bl = ld16(t.blocks() + bid);   // {row_start, n_rows, DENY rows, -}
+            uint32_t D = 0, A = 0;                  // DENY / ALLOW pair masks of this scope
+            uint32_t ri = bl.x;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (const uint32_t re = bl.x + bl.z; ri < re; ri++) D |= uc_row_pairs<RP, kVal32>(rows.get(aset_base, ri), rp, vlo, vhi, role_all) & alive;
+            alive &= ~D;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4
+#endif
+            for (const uint32_t re = bl.x + bl.y; ri < re; ri++) A |= uc_row_pairs<RP, kVal32>(rows.get(aset_base, ri), rp, vlo, vhi, role_all) & alive;
+            if (((ldg(t.scope_flags() + s) >> CB_SCOPE_PERM_SHIFT) & 3) == 1) { allow_pairs |= A; alive &= ~A; }
+        }
+    }
+    return allow_pairs;
+}
+
 template <typename Cols, typename Rows, typename Conds = GenericConds>
 CB_HD bool eval_request_uc(const TableView t, const BatchView &b, const Cols &cols, const Rows rows, uint64_t n, uint8_t *bitmap, uint8_t *effects,
                            const Conds conds = Conds()) {
     const U4 h0 = cols.hdr0();         // principal_id, kind (pattern id), resource_scope, principal_scope
     const uint64_t h1 = cols.hdr1();   // rv u16 | pv u16 | action_set_id u32
-    const auto regs = conds.load(cols);   // specialised build: every attribute slot the table reads, in flight at once
+    const auto regs = conds.load(t, b, cols);   // specialised build: every attribute slot (and list) the table reads, in flight at once
     const uint32_t pid = h0.x, kc = h0.y, rscope = h0.z;
     const uint32_t rv = (uint32_t)(h1 & 0xFFFF), pv = (uint32_t)((h1 >> 16) & 0xFFFF), aset = (uint32_t)(h1 >> 32);
     const uint32_t RC = b.role_cols, RCP = b.rcp;
@@ -2120,33 +2266,23 @@ CB_HD bool eval_request_uc(const TableView t, const BatchView &b, const Cols &co
         const uint32_t role_all = (1u << n_roles) - 1;
         const uint32_t aset_base = aset * b.n_rows;
         const uint32_t amask = K * RC >= 32 ? b.stride_pattern : b.stride_pattern & ((1u << (K * RC)) - 1);   // bit kk*RC per action
-        uint32_t alive = amask * role_all, allow_pairs = 0;
-        for (uint32_t s = r0; s != CB_NONE32 && alive; s = chain_next(t, s, CB_SCOPE_FLAG_RESOURCE)) {
-            const uint32_t bid = ldg(t.res_block_map() + ((uint64_t)rv * t.L->nRP + kc) * t.L->nS + s);
-            if (bid != CB_NONE32) {
-                const uint64_t bl = *reinterpret_cast<const uint64_t *>(t.blocks() + bid);   // {row_start, n_rows}
-                uint32_t D = 0, A = 0;   // DENY / ALLOW pair masks of this scope
-                for (uint32_t ri = (uint32_t)bl, re = (uint32_t)bl + (uint32_t)(bl >> 32); ri < re; ri++) {
-                    uint32_t am, ur;
-                    rows.get(aset_base, ri, am, ur);
-                    const uint32_t role = ur & 0xFFu;
-                    const uint32_t rc = role == 0xFFu ? role_all : (uint32_t)(rp >> (role * RCP)) & role_all;
-                    const uint32_t sat = (uint32_t)(val >> ((ur >> 8) & 0xFFu)) & (uint32_t)(val >> ((ur >> 16) & 0xFFu)) & 1u;   // rule AND derived-role condition
-                    const uint32_t ms = (am * rc) & alive & (0u - sat);
-                    const bool deny = (ur >> 24) == CB_EFFECT_DENY;
-                    D |= deny ? ms : 0u;
-                    A |= deny ? 0u : ms;
-                }
-                alive &= ~D;
-                if (((ldg(t.scope_flags() + s) >> CB_SCOPE_PERM_SHIFT) & 3) == 1) { uint32_t a = A & alive; allow_pairs |= a; alive &= ~a; }
-            }
-        }
+        const uint32_t alive0 = amask * role_all;
+        const uint32_t bm_base = (rv * t.L->nRP + kc) * t.L->nS;
+        uint32_t allow_pairs;
+        // the role table gets one more field, "any role"; when it all fits 32 bits the per-row shift is a single SHF
+        if ((t.L->nR + 1) * RCP <= 32) allow_pairs = uc_walk<uint32_t, Conds::kVal32>(t, b, rows, (uint32_t)rp | role_all << (t.L->nR * RCP), val, r0, bm_base, aset_base, role_all, alive0);
+        else allow_pairs = uc_walk<uint64_t, Conds::kVal32>(t, b, rows, rp | (uint64_t)role_all << (t.L->nR * RCP), val, r0, bm_base, aset_base, role_all, alive0);
         // fold: an action is ALLOWed iff some role column allowed it; then pack the stride-RC bits
         uint32_t x = allow_pairs;
-        for (uint32_t j = 1; j < RC; j++) x |= allow_pairs >> j;
+        x |= RC > 1 ? allow_pairs >> 1 : 0u;
+        x |= RC > 2 ? allow_pairs >> 2 : 0u;
+        x |= RC > 3 ? allow_pairs >> 3 : 0u;
+        for (uint32_t j = 4; j < RC; j++) x |= allow_pairs >> j;
         x &= amask;
         if (RC == 1) acc = x;
         else if (RC == 2) { x = (x | x >> 1) & 0x33333333u; x = (x | x >> 2) & 0x0F0F0F0Fu; x = (x | x >> 4) & 0x00FF00FFu; acc = (x | x >> 8) & 0xFFFFu; }
+        else if (RC == 3) { x = (x | x >> 2) & 0xC30C30C3u; x = (x | x >> 4) & 0x0F00F00Fu; x = (x | x >> 8) & 0xFF0000FFu; acc = (x | x >> 16) & 0x7FFu; }
+        else if (RC == 4) { x = (x | x >> 3) & 0x03030303u; x = (x | x >> 6) & 0x000F000Fu; acc = (x | x >> 12) & 0xFFu; }
         else for (uint32_t kk = 0; kk < K; kk++) acc |= ((x >> (kk * RC)) & 1) << kk;
     }
     store_result(b, cols, n, bitmap, effects, K, acc);

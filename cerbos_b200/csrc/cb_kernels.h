@@ -303,13 +303,13 @@ __device__ __forceinline__ void check_tiles_body(const TableDesc &td, const cb::
 // CTA-wide barrier in the loop.  Deferred requests (an operand the 8-byte forms cannot decide, differing policy
 // versions) go to the launch's deferral list, drained by the general kernel right behind; they are first written as
 // DENY so that a lost deferral could only fail closed.
-// smem layout (kStaged): [image, 128-byte padded][packed rows: n_asets x n_rows x 8 B]
+// smem layout (kStaged): [image, 128-byte padded][merged rows: n_asets x n_rows x 16 B]
 template <typename Conds, typename Cols, bool kStaged>
 __device__ __forceinline__ void check_uc_body(const TableDesc &td, const cb::BatchView &bv, uint8_t *bitmap, uint8_t *effects, uint8_t *smem_image, uint64_t *mbar) {
     cb::TableView tv;
     tv.L = &td.lay;
     tv.base = kStaged ? smem_image : td.base;
-    const uint64_t *pk = nullptr;
+    const cb::U4 *pk = nullptr;
     if (kStaged) {
         if (threadIdx.x == 0) {
             mbar_init(mbar, 1);
@@ -318,10 +318,13 @@ __device__ __forceinline__ void check_uc_body(const TableDesc &td, const cb::Bat
         __syncthreads();
         if (threadIdx.x == 0) tma_load_image(smem_image, td, mbar);
         mbar_wait(mbar, 0);
-        uint64_t *pks = reinterpret_cast<uint64_t *>(smem_image + ((td.lay.image_bytes + 127u) & ~127u));
+        cb::U4 *pks = reinterpret_cast<cb::U4 *>(smem_image + ((td.lay.image_bytes + 127u) & ~127u));
         const uint32_t n_pk = bv.n_asets * bv.n_rows;
-        const uint32_t *ur = tv.urows();
-        for (uint32_t j = threadIdx.x; j < n_pk; j += kThreads) pks[j] = (uint64_t)(uint32_t)bv.row_am[j] | (uint64_t)ur[j % bv.n_rows] << 32;
+        const cb::U4 *ur = tv.urows();
+        for (uint32_t j = threadIdx.x; j < n_pk; j += kThreads) {
+            const cb::U4 u = ur[j % bv.n_rows];
+            pks[j] = cb::uc_row_record(u, (uint32_t)bv.row_am[(j / bv.n_rows) * bv.n_rows + u.x], bv.rcp, td.lay.nR);
+        }
         __syncthreads();
         pk = pks;
     }
@@ -330,13 +333,23 @@ __device__ __forceinline__ void check_uc_body(const TableDesc &td, const cb::Bat
     const uint64_t n_warps = (uint64_t)gridDim.x * (kThreads / 32);
     for (uint64_t chunk = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); chunk < n_chunks; chunk += n_warps) {
         const uint64_t i = chunk * 32 + lane;
+        {   // this warp's next chunk: pull its columns into L2 now (DRAM latency off the critical path of the next iteration)
+            const uint64_t i2 = i + n_warps * 32;
+            if (i2 < bv.count) {
+                const uint64_t n2 = bv.first + i2;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(bv.hdr0 + n2));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(bv.hdr1 + n2));
+                for (uint32_t c = 0; c < bv.role_cols; c++) asm volatile("prefetch.global.L2 [%0];" ::"l"(bv.roles + (uint64_t)c * bv.stride + n2));
+                for (uint32_t v = 0; v < td.lay.n_slots; v++) asm volatile("prefetch.global.L2 [%0];" ::"l"(bv.slots + (uint64_t)v * bv.stride + n2));
+            }
+        }
         if (i < bv.count) {
             const uint64_t n = bv.first + i;
             Cols gc;
             gc.b = &bv; gc.n = n;
             bool d;
             if (kStaged) { cb::UcRowsPacked rows; rows.pk = pk; d = cb::eval_request_uc(tv, bv, gc, rows, n, bitmap, effects, Conds()); }
-            else { cb::UcRowsGlobal rows; rows.urows = tv.urows(); rows.row_am = bv.row_am; d = cb::eval_request_uc(tv, bv, gc, rows, n, bitmap, effects, Conds()); }
+            else { cb::UcRowsGlobal rows; rows.urows = tv.urows(); rows.row_am = bv.row_am; rows.RCP = bv.rcp; rows.nR = td.lay.nR; d = cb::eval_request_uc(tv, bv, gc, rows, n, bitmap, effects, Conds()); }
             if (d) {
                 cb::store_result(bv, gc, n, bitmap, effects, bv.max_actions, 0u);
                 const uint32_t k = atomicAdd(bv.defer_count, 1u);

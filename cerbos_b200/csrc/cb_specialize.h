@@ -166,8 +166,13 @@ inline std::string generate(const uint8_t *image, const uint32_t *off, const uin
 struct UcLimits {
     uint32_t max_terms = 512;   // distinct terms
 };
-inline std::string generate_uc(const uint8_t *uc_image, const uint32_t *off, uint32_t uc_conds_off, uint32_t n_uconds, uint32_t n_slots, const UcLimits lim = UcLimits()) {
-    if (n_uconds == 0 || n_uconds > 63) return "";
+struct UcSource {
+    std::string src;            // "" = does not qualify
+    uint32_t n_strpred = 0;     // string predicates served by the per-string pre-pass (BatchView::strpred)
+};
+inline UcSource generate_uc(const uint8_t *uc_image, const uint32_t *off, uint32_t uc_conds_off, uint32_t n_uconds, uint32_t n_slots, const UcLimits lim = UcLimits()) {
+    UcSource out;
+    if (n_uconds == 0 || n_uconds > 63) return out;
     const uint32_t *uconds = reinterpret_cast<const uint32_t *>(uc_image + uc_conds_off);    // [n_uconds + 1] x {code_off, code_len, flat_off, flat_info}
     const uint32_t *code = reinterpret_cast<const uint32_t *>(uc_image + off[CB_SEC_CODE]);
     const uint64_t *consts = reinterpret_cast<const uint64_t *>(uc_image + off[CB_SEC_CONSTS_V64]);
@@ -175,43 +180,95 @@ inline std::string generate_uc(const uint8_t *uc_image, const uint32_t *off, uin
     const uint32_t kUseMask = ~((uint32_t)(CB_TERM_LIT_F | CB_TERM_GROUP_END) << 8);
     std::map<std::vector<uint32_t>, uint32_t> term_ids;
     std::vector<std::vector<uint32_t>> terms;
-    std::vector<bool> slot_used(n_slots ? n_slots : 1, false);
-    auto use_slot = [&](uint32_t kind, uint32_t v) { if ((kind == CB_OPK_SLOT || kind == CB_OPK_SLOT_ELEM || kind == CB_OPK_SLOT_SIZE) && v < slot_used.size()) slot_used[v] = true; };
+    const uint32_t ns = n_slots ? n_slots : 1;
+    std::vector<bool> slot_used(ns, false), slot_list(ns, false);
+    auto is_slot_kind = [](uint32_t kind) { return kind == CB_OPK_SLOT || kind == CB_OPK_SLOT_ELEM || kind == CB_OPK_SLOT_SIZE; };
+    auto use_slot = [&](uint32_t kind, uint32_t v) { if (is_slot_kind(kind) && v < ns) slot_used[v] = true; };
+    auto v64_tag = [](uint64_t b) { const uint32_t top = (uint32_t)(b >> 48); return (top & 0xFFF0u) == 0xFFF0u ? (top & 0xFu) : 0u; };
     for (uint32_t u = 1; u <= n_uconds; u++) {
         const uint32_t *cd = uconds + 4 * u;
-        if (cd[3] == 0 || ((cd[3] >> 16) & 0xFF) != CB_FLAT_DNF) return "";
+        if (cd[3] == 0 || ((cd[3] >> 16) & 0xFF) != CB_FLAT_DNF) return out;
         for (uint32_t i = 0, nt = cd[3] & 0xFFFFu; i < nt; i++) {
             const uint32_t *w = code + 2 * (cd[2] + 2 * i);
             std::vector<uint32_t> key = {w[0] & kUseMask, w[1], w[2], w[3]};
-            if (term_ids.emplace(key, (uint32_t)terms.size()).second) {
-                terms.push_back(key);
-                const uint32_t op = w[0] & 0xFF;
-                switch (op) {   // which operands are slots (bytecode._specialize_term shapes first)
-                case CB_TERM_EQ_SS: case CB_TERM_ORD_SS: case CB_TERM_IN_SS: use_slot(CB_OPK_SLOT, w[1]); use_slot(CB_OPK_SLOT, w[2]); break;
-                case CB_TERM_EQ_SC: case CB_TERM_EQ_SP: case CB_TERM_ORD_SC: case CB_TERM_IN_SC: use_slot(CB_OPK_SLOT, w[1]); break;
-                case CB_TERM_IN_CS: use_slot(CB_OPK_SLOT, w[2]); break;
-                default: use_slot((w[0] >> 16) & 0xFF, w[1]); if (op != CB_TERM_HAS) use_slot(w[0] >> 24, w[2]); break;
-                }
-            }
+            if (term_ids.emplace(key, (uint32_t)terms.size()).second) terms.push_back(key);
         }
     }
-    if (terms.size() > lim.max_terms) return "";
+    if (terms.size() > lim.max_terms) return out;
+    // per term: which form it takes in the specialised code
+    //   'L' list registers (IN with a slot list, set predicates over two slot lists), 'P' string-predicate word, 'G' generic
+    std::vector<char> form(terms.size(), 'G');
+    std::vector<uint32_t> pred_of(terms.size(), 0);
+    std::vector<uint32_t> pred_terms;   // term index of every string predicate
+    for (uint32_t q = 0; q < terms.size(); q++) {
+        const uint32_t *w = terms[q].data();
+        const uint32_t op = w[0] & 0xFF, xk = (w[0] >> 16) & 0xFF, yk = w[0] >> 24;
+        switch (op) {   // which operands are slots (bytecode._specialize_term shapes first)
+        case CB_TERM_EQ_SS: case CB_TERM_ORD_SS: use_slot(CB_OPK_SLOT, w[1]); use_slot(CB_OPK_SLOT, w[2]); break;
+        case CB_TERM_EQ_SC: case CB_TERM_EQ_SP: case CB_TERM_ORD_SC: case CB_TERM_IN_SC: use_slot(CB_OPK_SLOT, w[1]); break;
+        case CB_TERM_IN_SS: use_slot(CB_OPK_SLOT, w[1]); use_slot(CB_OPK_SLOT, w[2]); if (w[2] < ns) { slot_list[w[2]] = true; form[q] = 'L'; } break;
+        case CB_TERM_IN_CS: use_slot(CB_OPK_SLOT, w[2]); if (w[2] < ns) { slot_list[w[2]] = true; form[q] = 'L'; } break;
+        default:
+            use_slot(xk, w[1]);
+            if (op != CB_TERM_HAS) use_slot(yk, w[2]);
+            if (op == CB_TERM_IN && yk == CB_OPK_SLOT && w[2] < ns) { slot_list[w[2]] = true; form[q] = 'L'; }
+            if ((op == CB_TERM_INTERSECTS || op == CB_TERM_SUBSET) && xk == CB_OPK_SLOT && yk == CB_OPK_SLOT && w[1] < ns && w[2] < ns) {
+                slot_list[w[1]] = slot_list[w[2]] = true;
+                form[q] = 'L';
+            }
+            if ((op == CB_TERM_STARTS || op == CB_TERM_ENDS || op == CB_TERM_CONTAINS) && xk == CB_OPK_SLOT && yk == CB_OPK_CONST &&
+                v64_tag(consts[w[2]]) == CB_V64_STRING && pred_terms.size() < 32) {
+                form[q] = 'P';
+                pred_of[q] = (uint32_t)pred_terms.size();
+                pred_terms.push_back(q);
+            }
+            break;
+        }
+    }
+    auto sl = [](uint32_t v) { return "cols.slot(" + std::to_string(v) + "u)"; };
+    auto term_code = [&](uint32_t q) -> std::string {
+        const uint32_t *w = terms[q].data();
+        const uint32_t op = w[0] & 0xFF, xk = (w[0] >> 16) & 0xFF;
+        if (form[q] == 'P') return "strpred_tri(b, " + sl(w[1]) + ", " + std::to_string(pred_of[q]) + "u)";
+        if (form[q] == 'L') {
+            if (op == CB_TERM_IN_CS) return "list_in_tri(" + hex64(consts[w[1]]) + ", cols.l" + std::to_string(w[2]) + ", slow)";
+            if (op == CB_TERM_IN_SS) return "list_in_tri(" + sl(w[1]) + ", cols.l" + std::to_string(w[2]) + ", slow)";
+            if (op == CB_TERM_IN)
+                return "list_in_tri(term_operand(t, b, cols, pid, " + hex(xk) + ", " + hex(w[1]) + ", " + hex(w[3] & 0xFFFFu) + "), cols.l" + std::to_string(w[2]) + ", slow)";
+            return std::string("list_set_tri(") + (op == CB_TERM_SUBSET ? "true" : "false") + ", cols.l" + std::to_string(w[1]) + ", cols.l" + std::to_string(w[2]) + ", slow)";
+        }
+        return term_expr(w, consts, theap);
+    };
     std::string s;
     s += "// generated by cb_specialize.h (generate_uc) from the loaded table: every distinct condition, straight-line\n";
     s += "namespace cb {\nstruct SpecRegs {\n";
-    for (uint32_t v = 0; v < slot_used.size(); v++)
+    for (uint32_t v = 0; v < ns; v++)
         if (slot_used[v]) s += "    uint64_t s" + std::to_string(v) + ";\n";
+    for (uint32_t v = 0; v < ns; v++)
+        if (slot_list[v]) s += "    ListRegs l" + std::to_string(v) + ";\n";
     s += "    CB_HD uint64_t slot(uint32_t v) const {\n        switch (v) {\n";
-    for (uint32_t v = 0; v < slot_used.size(); v++)
+    for (uint32_t v = 0; v < ns; v++)
         if (slot_used[v]) s += "        case " + std::to_string(v) + "u: return s" + std::to_string(v) + ";\n";
     s += "        default: return (uint64_t)(CB_V64_BOX_BASE | CB_V64_ERROR) << 48;\n        }\n    }\n};\n";
-    s += "struct SpecConds {\n    template <typename Cols>\n    CB_HD SpecRegs load(const Cols &c) const {\n        SpecRegs r;\n";
-    for (uint32_t v = 0; v < slot_used.size(); v++)
+    s += "struct SpecConds {\n    static constexpr uint32_t n_strpred = " + std::to_string(pred_terms.size()) + "u;\n";
+    s += std::string("    static constexpr bool kVal32 = ") + (n_uconds <= 31 ? "true" : "false") + ";   // the condition word fits 32 bits\n";
+    s += "    template <typename Cols>\n    CB_HD SpecRegs load(const TableView t, const BatchView &b, const Cols &c) const {\n        SpecRegs r;\n";
+    for (uint32_t v = 0; v < ns; v++)
         if (slot_used[v]) s += "        r.s" + std::to_string(v) + " = c.slot(" + std::to_string(v) + "u);\n";
+    for (uint32_t v = 0; v < ns; v++)
+        if (slot_list[v]) s += "        r.l" + std::to_string(v) + " = list_load(t, b, r.s" + std::to_string(v) + ");\n";
     s += "        return r;\n    }\n";
+    s += "    // the predicate word of one string (pre-pass over the string dictionary; bit p = predicate p holds)\n";
+    s += "    CB_HD uint32_t strpred(const TableView t, const BatchView &b, uint32_t id) const {\n";
+    s += "        OneCols cols; cols.x = ((uint64_t)(CB_V64_BOX_BASE | CB_V64_STRING) << 48) | id;\n        bool slow = false; uint32_t bits = 0u; const uint32_t pid = 0u;\n";
+    for (uint32_t p = 0; p < pred_terms.size(); p++) {
+        const uint32_t *w = terms[pred_terms[p]].data();
+        s += "        bits |= (uint32_t)(term_tri(t, b, cols, pid, U4{" + hex(w[0]) + ", 0x0u, " + hex(w[2]) + ", " + hex(w[3]) + "}, slow) == TRI_T) << " + std::to_string(p) + ";\n";
+    }
+    s += "        (void)slow; (void)pid;\n        return bits;\n    }\n";
     s += "    CB_HD uint64_t operator()(const TableView t, const BatchView &b, const SpecRegs &cols, uint32_t pid, uint64_t, bool &slow) const {\n";
     for (uint32_t q = 0; q < terms.size(); q++)
-        s += "        const int q" + std::to_string(q) + " = " + term_expr(terms[q].data(), consts, theap) + ";\n";
+        s += "        const int q" + std::to_string(q) + " = " + term_code(q) + ";\n";
     s += "        uint64_t val = 1ull;\n";
     for (uint32_t u = 1; u <= n_uconds; u++) {
         const uint32_t *cd = uconds + 4 * u;
@@ -227,7 +284,9 @@ inline std::string generate_uc(const uint8_t *uc_image, const uint32_t *off, uin
         s += std::string("            val |= (uint64_t)(any != ") + (negate ? "true" : "false") + ") << " + std::to_string(u) + ";\n        }\n";
     }
     s += "        return val;\n    }\n};\n}  // namespace cb\n";
-    return s;
+    out.src = s;
+    out.n_strpred = (uint32_t)pred_terms.size();
+    return out;
 }
 
 }  // namespace cbspec

@@ -4,7 +4,7 @@
 // keeps one compiled condition per rule (ruletable.go:105-416).  Across a policy set the same conditions recur: shared
 // derived roles, the same ownership / tenancy test on every resource kind.  This builder
 //   * numbers the DISTINCT conditions of the table 1..U (same DNF term list, or same bytecode program),
-//   * rewrites every row to 4 bytes {role, condition number, derived-role condition number, effect} (cb::uc_row),
+//   * rewrites every row to {original index, role, effect, mask of the condition bits it needs} (16 bytes, DENY rows first per block),
 //   * copies only the sections the unique-condition kernels read into a compact image (C3: 49 KB blob -> ~10 KB),
 // so that a kernel can evaluate every distinct condition of a request once, with all lanes in lock step, and walk the
 // rows as mask algebra (cb::eval_request_uc).  Built once per cgpu_table_load; the Python blob format is unchanged.
@@ -67,19 +67,33 @@ inline Image build(const uint8_t *image, const uint32_t *off, const uint64_t *le
         out.ucond_of_gid[g] = it->second;
     }
     out.n_uconds = (uint32_t)ids.size();
-    // rows
-    std::vector<uint32_t> urows(n_rows ? n_rows : 1, 0);
+    // rows: DENY rows first inside every block (within a scope every matching row is evaluated and DENY beats ALLOW,
+    // ruletable.go:1083-1118, so the order of rows inside a block is free); 16 bytes each, see cb_core.h
+    std::vector<uint32_t> urows(4 * (size_t)(n_rows ? n_rows : 1), 0);
+    std::vector<uint32_t> ublocks(blocks, blocks + 4 * (size_t)n_blocks);   // {row_start, n_rows, DENY rows, 0}
     for (uint32_t b = 0; b < n_blocks; b++) {
         const uint32_t *bl = blocks + 4 * b;   // {row_start, n_rows, cond_base, n_conds}
-        if ((uint64_t)bl[0] + bl[1] > n_rows) { out.why = "block rows out of range"; return out; }
-        for (uint32_t r = 0; r < bl[1]; r++) {
-            const uint32_t *row = rows + 4 * (bl[0] + r);
-            const uint32_t role = row[0] & 0xFFFFu, c = row[0] >> 16, dc = row[1] & 0xFFFFu, effect = row[2] & 0xFFu;
-            if ((c && c > bl[3]) || (dc && dc > bl[3]) || (uint64_t)bl[2] + bl[3] > n_conds) { out.why = "row condition out of range"; return out; }
-            if (role != CB_ROLE_ANY && role >= 64) { out.why = "role id out of range"; return out; }
-            const uint32_t uc = c ? out.ucond_of_gid[bl[2] + c - 1] : 0, udc = dc ? out.ucond_of_gid[bl[2] + dc - 1] : 0;
-            urows[bl[0] + r] = cb::uc_row(role == CB_ROLE_ANY ? 0xFFu : role, uc, udc, effect);
+        if ((uint64_t)bl[0] + bl[1] > n_rows || (uint64_t)bl[2] + bl[3] > n_conds) { out.why = "block out of range"; return out; }
+        uint32_t at = bl[0], n_deny = 0;
+        for (int pass = 0; pass < 2; pass++) {
+            for (uint32_t r = 0; r < bl[1]; r++) {
+                const uint32_t *row = rows + 4 * (bl[0] + r);
+                const uint32_t role = row[0] & 0xFFFFu, c = row[0] >> 16, dc = row[1] & 0xFFFFu, effect = row[2] & 0xFFu;
+                if ((effect == CB_EFFECT_DENY) != (pass == 0)) continue;
+                if ((c && c > bl[3]) || (dc && dc > bl[3])) { out.why = "row condition out of range"; return out; }
+                if (role != CB_ROLE_ANY && role >= 64) { out.why = "role id out of range"; return out; }
+                const uint32_t uc = c ? out.ucond_of_gid[bl[2] + c - 1] : 0, udc = dc ? out.ucond_of_gid[bl[2] + dc - 1] : 0;
+                const uint64_t need = 1ull | 1ull << uc | 1ull << udc;
+                uint32_t *u = urows.data() + 4 * (size_t)at++;
+                u[0] = bl[0] + r;
+                u[1] = (role == CB_ROLE_ANY ? 0xFFu : role) | effect << 8;
+                u[2] = (uint32_t)need;
+                u[3] = (uint32_t)(need >> 32);
+                n_deny += pass == 0;
+            }
         }
+        ublocks[4 * b + 2] = n_deny;
+        ublocks[4 * b + 3] = 0;
     }
     // compact image: the sections the unique-condition kernels (and the interpreter they may call) read
     out.lay = lay;
@@ -91,12 +105,14 @@ inline Image build(const uint8_t *image, const uint32_t *off, const uint64_t *le
         return at;
     };
     append("CBUC", 4);   // offset 0 stays unused: a zero offset means "section not present"
-    for (int id : {CB_SEC_SCOPE_PARENT, CB_SEC_SCOPE_FLAGS, CB_SEC_RES_BLOCK_MAP, CB_SEC_BLOCKS, CB_SEC_CODE, CB_SEC_CONSTS, CB_SEC_CONSTS_V64, CB_SEC_THEAP,
+    out.lay.off[CB_SEC_BLOCKS] = append(ublocks.data(), ublocks.size() * 4);
+    for (int id : {CB_SEC_SCOPE_PARENT, CB_SEC_SCOPE_FLAGS, CB_SEC_RES_BLOCK_MAP, CB_SEC_CODE, CB_SEC_CONSTS, CB_SEC_CONSTS_V64, CB_SEC_THEAP,
                    CB_SEC_STR_OFF, CB_SEC_STR_BYTES})
         out.lay.off[id] = append(image + off[id], len[id]);
     out.lay.uc_conds_off = append(ucond_rec.data(), ucond_rec.size() * 4);
     out.lay.uc_rows_off = append(urows.data(), urows.size() * 4);
     out.lay.n_uconds = out.n_uconds;
+    out.lay.theap_words = (uint32_t)(len[CB_SEC_THEAP] / 8);
     out.lay.image_bytes = (uint32_t)out.bytes.size();
     out.ok = true;
     return out;

@@ -9,6 +9,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -196,7 +197,9 @@ int fail(int code, const char *fmt, ...) {
     } while (0)
 
 struct Slot {   // per in-flight cgpu_check call
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;                 // kernels
+    cudaStream_t h2d = nullptr, d2h = nullptr;     // column chunks in, effect bytes out (PCIe is full duplex)
+    std::vector<cudaEvent_t> ev;                   // two per chunk: columns landed, results ready
     void *dev = nullptr;
     size_t dev_cap = 0;
     uint32_t *h_status = nullptr;   // pinned
@@ -230,9 +233,18 @@ struct cgpu_ctx {
         uint32_t *lists[4] = {nullptr, nullptr, nullptr, nullptr};
         size_t cap[4] = {0, 0, 0, 0};
         uint32_t *cells = nullptr;   // 4 x {count, done, tile counter, -}, zero between uses (the drain kernel re-zeroes)
+        uint32_t *strpred[4] = {nullptr, nullptr, nullptr, nullptr};   // per-string predicate words of the specialised unique-condition kernels
+        size_t sp_cap[4] = {0, 0, 0, 0};
     };
     std::map<cudaStream_t, DeferLane> defer_lanes;
     std::mutex defer_mu;
+    // copy-engine result exchange (cgpu_check_device_gather, large slices): a side stream + a ring of events
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_ev[16] = {};
+    uint32_t copy_seq = 0;
+    struct SliceUse { const void *ptr; cudaEvent_t done; };
+    std::vector<SliceUse> slice_uses;   // own slices whose last push to the peers may still be in flight
+    std::mutex copy_mu;
     int uc_mode = -1;        // CERBOS_B200_UC: 0 never use the unique-condition kernels, 1 whenever the table allows, unset = tables with > 1 block shape
     uint32_t last_uc = 0;
     bool profiling = false;  // cgpu_profile(): CUDA events around the check kernel of every launch
@@ -255,7 +267,8 @@ struct cgpu_table {
     std::mutex spec_mu;
     std::atomic<int> spec_state{0};   // 0 not tried, 1 ready, -1 unavailable
     cudaLibrary_t spec_lib = nullptr;
-    cudaKernel_t spec_tiles = nullptr, spec_direct = nullptr, spec_uc = nullptr;
+    cudaKernel_t spec_tiles = nullptr, spec_direct = nullptr, spec_uc = nullptr, spec_strpred = nullptr;
+    uint32_t spec_n_strpred = 0;   // string predicates the specialised unique-condition kernel reads from the per-string pre-pass
     std::string spec_note;
     // unique-condition image (cb_uc.h): compact copy of the table for tables whose blocks differ in shape
     uint64_t sec_len[kMaxSec]{};
@@ -361,6 +374,8 @@ int make_batch_view(const cgpu_table *t, const cgpu_batch *b, uint64_t first, ui
     v->role_cols = role_cols; v->n_asets = n_asets; v->kc = kc; v->n_pass = n_pass; v->max_actions = km;
     v->kbytes = (km + 7) / 8; v->flags = b->flags; v->now = b->now_unix_nanos;
     cb::finish_batch_view(*v);
+    v->n_bstr = cb_[CGPU_COL_BSTR_OFF] >= 4 ? (uint32_t)(cb_[CGPU_COL_BSTR_OFF] / 4 - 1) : 0;
+    v->heap_words = cb_[CGPU_COL_HEAP] / 8;
     return CGPU_OK;
 }
 
@@ -424,6 +439,12 @@ const char kSpecUcKernels[] =
     "    extern __shared__ __align__(128) uint8_t smem_image[];\n"
     "    __shared__ __align__(8) uint64_t mbar;\n"
     "    cbk::check_uc_body<cb::SpecConds, cb::GlobalCols, true>(td, bv, bitmap, effects, smem_image, &mbar);\n"
+    "}\n"
+    // pre-pass over the string dictionary (table strings, then the batch's): one predicate word per string
+    "extern \"C\" __global__ void __launch_bounds__(256) cb_spec_strpred(const __grid_constant__ cbk::TableDesc td, const __grid_constant__ cb::BatchView bv, uint32_t *out, const uint32_t n) {\n"
+    "    const uint32_t id = blockIdx.x * 256u + threadIdx.x;\n"
+    "    cb::TableView tv; tv.base = td.base; tv.L = &td.lay;\n"
+    "    if (id < n) out[id] = cb::SpecConds().strpred(tv, bv, id);\n"
     "}\n";
 
 uint64_t fnv1a(const void *p, size_t n, uint64_t h = 1469598103934665603ull) {
@@ -470,13 +491,16 @@ void cache_write(const std::string &path, const std::vector<char> &data) {
 // Which specialised form a table gets: per-shape block evaluators when its blocks share (nearly) one shape, else the
 // unique-condition form when every distinct condition has a flat form.  `gen` receives the generated source.
 enum SpecForm { SPEC_NONE = 0, SPEC_SHAPES = 1, SPEC_UC = 2 };
-SpecForm spec_generate(const uint8_t *image, const cb::TableLayout &lay, const uint32_t *meta, const cbuc::Image &uc, std::string *gen, std::string *why) {
+SpecForm spec_generate(const uint8_t *image, const cb::TableLayout &lay, const uint32_t *meta, const cbuc::Image &uc, std::string *gen, std::string *why, uint32_t *n_strpred) {
+    *n_strpred = 0;
     if (lay.image_bytes <= kMaxStageBytes) {
         *gen = cbspec::generate(image, lay.off, meta);
         if (!gen->empty()) return SPEC_SHAPES;
     }
     if (uc.ok && uc.lay.image_bytes <= kMaxStageBytes) {
-        *gen = cbspec::generate_uc(uc.bytes.data(), uc.lay.off, uc.lay.uc_conds_off, uc.n_uconds, lay.n_slots);
+        cbspec::UcSource us = cbspec::generate_uc(uc.bytes.data(), uc.lay.off, uc.lay.uc_conds_off, uc.n_uconds, lay.n_slots);
+        *gen = us.src;
+        *n_strpred = us.n_strpred;
         if (!gen->empty()) return SPEC_UC;
     }
     *why = "table does not qualify (a condition without flat form, too many block shapes and more than 63 distinct conditions, or an image too large for shared memory)";
@@ -485,9 +509,9 @@ SpecForm spec_generate(const uint8_t *image, const cb::TableLayout &lay, const u
 
 // Generates the table's specialised translation unit and compiles it with NVRTC (no CUDA runtime call: also works on
 // a host without a GPU).  SPEC_NONE + *why when the table does not qualify or something is unavailable.
-SpecForm spec_compile(const uint8_t *image, const cb::TableLayout &lay, const uint32_t *meta, const cbuc::Image &uc, std::vector<char> *cubin, std::string *why) {
+SpecForm spec_compile(const uint8_t *image, const cb::TableLayout &lay, const uint32_t *meta, const cbuc::Image &uc, std::vector<char> *cubin, std::string *why, uint32_t *n_strpred) {
     std::string gen;
-    const SpecForm form = spec_generate(image, lay, meta, uc, &gen, why);
+    const SpecForm form = spec_generate(image, lay, meta, uc, &gen, why, n_strpred);
     if (form == SPEC_NONE) return SPEC_NONE;
     std::string src = kSpecPrelude;
     for (const char *const *p = kEmbedFormat; *p; p++) src += *p;
@@ -540,17 +564,18 @@ bool ensure_spec(cgpu_ctx *ctx, cgpu_table *t) {
     if (ctx->force_no_jit) return give_up("disabled (CERBOS_B200_NO_JIT)");
     std::vector<char> cubin;
     std::string why;
-    const SpecForm form = spec_compile(t->host_image.data(), t->desc.lay, t->meta, t->uc, &cubin, &why);
+    const SpecForm form = spec_compile(t->host_image.data(), t->desc.lay, t->meta, t->uc, &cubin, &why, &t->spec_n_strpred);
     if (form == SPEC_NONE) return give_up(why);
     if (cudaLibraryLoadData(&t->spec_lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) { cudaGetLastError(); return give_up("cudaLibraryLoadData failed"); }
-    bool got = form == SPEC_UC ? cudaLibraryGetKernel(&t->spec_uc, t->spec_lib, "cb_spec_uc") == cudaSuccess
+    bool got = form == SPEC_UC ? cudaLibraryGetKernel(&t->spec_uc, t->spec_lib, "cb_spec_uc") == cudaSuccess &&
+                                     cudaLibraryGetKernel(&t->spec_strpred, t->spec_lib, "cb_spec_strpred") == cudaSuccess
                                : cudaLibraryGetKernel(&t->spec_tiles, t->spec_lib, "cb_spec_tiles") == cudaSuccess &&
                                      cudaLibraryGetKernel(&t->spec_direct, t->spec_lib, "cb_spec_direct") == cudaSuccess;
     if (!got) {
         cudaGetLastError();
         cudaLibraryUnload(t->spec_lib);
         t->spec_lib = nullptr;
-        t->spec_tiles = t->spec_direct = t->spec_uc = nullptr;
+        t->spec_tiles = t->spec_direct = t->spec_uc = t->spec_strpred = nullptr;
         return give_up("cudaLibraryGetKernel failed");
     }
     t->spec_note = "ok";
@@ -598,7 +623,7 @@ int launch_cluster(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, 
 }
 
 // The launch's deferral list + counter cell, owned by the stream it is issued on (see cgpu_ctx::DeferLane).
-int acquire_defer(cgpu_ctx *ctx, cudaStream_t stream, uint64_t count, uint32_t **list, uint32_t **cell) {
+int acquire_defer(cgpu_ctx *ctx, cudaStream_t stream, uint64_t count, uint32_t **list, uint32_t **cell, size_t n_strpred = 0, uint32_t **strpred = nullptr) {
     std::lock_guard<std::mutex> g(ctx->defer_mu);
     cgpu_ctx::DeferLane &ln = ctx->defer_lanes[stream];
     if (!ln.cells) {
@@ -616,6 +641,18 @@ int acquire_defer(cgpu_ctx *ctx, cudaStream_t stream, uint64_t count, uint32_t *
         if (ln.lists[q]) CUDA_TRY(cudaFreeAsync(ln.lists[q], stream));
         ln.lists[q] = fresh;
         ln.cap[q] = cap;
+    }
+    if (strpred) {
+        if (ln.sp_cap[q] < n_strpred) {
+            size_t cap = 4096;
+            while (cap < n_strpred) cap <<= 1;
+            uint32_t *fresh = nullptr;
+            CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&fresh), cap * 4, stream));
+            if (ln.strpred[q]) CUDA_TRY(cudaFreeAsync(ln.strpred[q], stream));
+            ln.strpred[q] = fresh;
+            ln.sp_cap[q] = cap;
+        }
+        *strpred = ln.strpred[q];
     }
     *list = ln.lists[q];
     *cell = ln.cells + 4 * q;   // {count, done, tile counter, -}
@@ -641,7 +678,7 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
     // Unique-condition kernels: lean-eligible tables with <= 63 distinct conditions whose blocks differ in shape
     // (with one shape the per-shape specialised tile kernel is the better fit).  Index order, no clustering.
     const bool uc_spec_ready = mt->spec_state.load(std::memory_order_acquire) == 1 && t->spec_uc != nullptr;
-    const bool uc = narrow && t->uc.ok && t->d_uc_image && bv.count < (1ull << 32) && (uint64_t)bv.n_asets * lay.n_rows < (1ull << 31) &&
+    const bool uc = narrow && t->uc.ok && t->d_uc_image && bv.count < (1ull << 32) && (uint64_t)bv.n_asets * lay.n_rows < (1ull << 31) && (uint64_t)(lay.nR + 1) * rcp <= 64 &&
                     (ctx->uc_mode == 1 || (ctx->uc_mode != 0 && t->meta[CB_META_BLOCK_SHAPES] > 1));
     // Clustering pays when the policy blocks differ in shape (rows / conditions): with a single shape every lane runs
     // the same control flow in index order already and the coalesced column loads are worth more.
@@ -657,7 +694,7 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
     const bool col_tiles = !uc && narrow && stage && !cluster && !ctx->force_no_tiles && tiles_smem <= kMaxTilesSmem && bv.stride % 4 == 0 &&
                            bv.first % 4 == 0 && al16(bv.hdr0) && al16(bv.hdr1) && al16(bv.roles) && al16(bv.slots);
     // unique-condition launch: staged (compact image + merged rows in shared memory) when that fits
-    const uint64_t uc_smem64 = uc ? ((t->uc.lay.image_bytes + 127u) & ~127u) + (uint64_t)bv.n_asets * lay.n_rows * 8 : 0;
+    const uint64_t uc_smem64 = uc ? ((t->uc.lay.image_bytes + 127u) & ~127u) + (uint64_t)bv.n_asets * lay.n_rows * 16 : 0;
     const bool uc_staged = uc && !ctx->force_no_stage && uc_smem64 <= kUcMaxSmem;
     const uint32_t smem = uc ? (uc_staged ? (uint32_t)uc_smem64 : 0) : col_tiles ? tiles_smem : stage ? lay.image_bytes : 0;
     // lean launches with a staged table use the kernels specialised for this table when they exist (NVRTC, first use)
@@ -701,12 +738,23 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
     const bool lists = spec || uc;   // requests the kernel leaves to the general kernel go to a list drained right behind it
     uint32_t *defer = nullptr;
     if (lists) {
-        uint32_t *cell = nullptr;
-        int rc = acquire_defer(ctx, stream, bv.count, &defer, &cell);
+        uint32_t *cell = nullptr, *strpred = nullptr;
+        const bool want_sp = uc && spec && t->spec_n_strpred;
+        const uint32_t n_str = lay.nT + bv.n_bstr;
+        int rc = acquire_defer(ctx, stream, bv.count, &defer, &cell, (size_t)n_str + 1, want_sp ? &strpred : nullptr);
         if (rc != CGPU_OK) return rc;
         bvv.defer_count = cell;
         bvv.tile_counter = col_tiles ? cell + 2 : nullptr;
         bvv.defer_list = defer;
+        if (want_sp && n_str) {
+            // string predicates against constants: evaluated once per distinct string of the dictionary, not once per request
+            TableDesc ptd = t->uc_desc;
+            uint32_t n_arg = n_str;
+            void *pargs[] = {&ptd, &bvv, &strpred, &n_arg};
+            CUDA_TRY(cudaLaunchKernel((const void *)t->spec_strpred, dim3((n_str + 255) / 256), dim3(256), pargs, 0, stream));
+            ctx->launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        bvv.strpred = strpred;
     }
     void *args[] = {&td, &bvv, &d_bitmap, &d_effects, &d_status, &last_arg};
     if (ctx->profiling) {
@@ -837,6 +885,9 @@ void cgpu_shutdown(cgpu_ctx *ctx) {
     cudaDeviceSynchronize();
     for (auto &s : ctx->slots) {
         if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.h2d) cudaStreamDestroy(s.h2d);
+        if (s.d2h) cudaStreamDestroy(s.d2h);
+        for (auto e : s.ev) cudaEventDestroy(e);
         if (s.dev) cudaFree(s.dev);
         if (s.h_status) cudaFreeHost(s.h_status);
         if (s.d_status) cudaFree(s.d_status);
@@ -844,8 +895,12 @@ void cgpu_shutdown(cgpu_ctx *ctx) {
     if (ctx->d_status) cudaFree(ctx->d_status);
     for (auto &kv : ctx->defer_lanes) {
         for (auto p : kv.second.lists) if (p) cudaFree(p);
+        for (auto p : kv.second.strpred) if (p) cudaFree(p);
         if (kv.second.cells) cudaFree(kv.second.cells);
     }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (auto e : ctx->copy_ev) if (e) cudaEventDestroy(e);
+    for (auto &u : ctx->slice_uses) if (u.done) cudaEventDestroy(u.done);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -914,7 +969,8 @@ int cgpu_table_compile_check(const void *blob, size_t len, size_t *cubin_bytes) 
     const cbuc::Image uc = cbuc::build(static_cast<const uint8_t *>(blob), d.lay.off, sec_len, meta, d.lay);
     std::vector<char> cubin;
     std::string why;
-    const SpecForm form = spec_compile(static_cast<const uint8_t *>(blob), d.lay, meta, uc, &cubin, &why);
+    uint32_t n_strpred = 0;
+    const SpecForm form = spec_compile(static_cast<const uint8_t *>(blob), d.lay, meta, uc, &cubin, &why, &n_strpred);
     if (form == SPEC_NONE) {
         g_err = why;
         return why.rfind("NVRTC compile failed", 0) == 0 ? CGPU_ERR_CUDA : CGPU_OK;   // not qualifying is not an error
@@ -1047,14 +1103,55 @@ int cgpu_check_device_gather(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batc
         bv.outs[r] = static_cast<uint8_t *>(g->gather_bufs[r]) + (uint64_t)g->my_rank * g->slice_bytes;
         sp.flags[r] = g->flags[r];
     }
-    bv.n_out = g->n_ranks;
     sp.n_ranks = g->n_ranks; sp.my_rank = g->my_rank; sp.step = g->step;
     sp.wait_flags = g->wait_flags ? g->wait_flags : g->flags[g->my_rank]; sp.wait_step = g->wait_step;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    const uint64_t slice_used = (uint64_t)bv.count * bv.kbytes;
+    const char *ce = getenv("CERBOS_B200_CE_GATHER");
+    const bool ce_gather = g->n_ranks > 1 && (ce ? ce[0] == '1' : slice_used >= (1u << 20));
+    if (ce_gather) {
+        // Large slices: the kernels store this rank's results into its own slice only; the copy engines then push that
+        // slice to every peer over NVLink on a side stream (no SM is involved and the next batch's kernel runs meanwhile),
+        // and a one-warp kernel behind the copies releases the step into every rank's flag array.
+        std::lock_guard<std::mutex> lk(ctx->copy_mu);
+        if (!ctx->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        uint8_t *own = bv.outs[g->my_rank];
+        // the previous push out of this very slice must have drained before the kernel overwrites it
+        cgpu_ctx::SliceUse *use = nullptr;
+        for (auto &u : ctx->slice_uses) if (u.ptr == own) use = &u;
+        if (use) CUDA_TRY(cudaStreamWaitEvent(s, use->done, 0));
+        else {
+            cgpu_ctx::SliceUse nu{own, nullptr};
+            CUDA_TRY(cudaEventCreateWithFlags(&nu.done, cudaEventDisableTiming));
+            ctx->slice_uses.push_back(nu);
+            use = &ctx->slice_uses.back();
+        }
+        rc = launch_check(ctx, t, bv, own, nullptr, ctx->d_status, s);
+        if (rc != CGPU_OK) return rc;
+        cudaEvent_t &ev = ctx->copy_ev[ctx->copy_seq++ & 15];
+        if (!ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(ev, s));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
+        for (uint32_t r = 0; r < g->n_ranks; r++)
+            if (r != g->my_rank) CUDA_TRY(cudaMemcpyAsync(bv.outs[r], own, slice_used, cudaMemcpyDeviceToDevice, ctx->copy_stream));
+        SignalParams sp2 = sp;
+        sp2.wait_step = 0;
+        void *args[] = {&sp2};
+        CUDA_TRY(cudaLaunchKernel((const void *)gather_signal, dim3(1), dim3(32), args, 0, ctx->copy_stream));
+        CUDA_TRY(cudaEventRecord(use->done, ctx->copy_stream));
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+        if (g->wait_step) {   // hold the issuing stream until every rank's slice of the older step has landed here
+            gather_wait<<<1, 32, 0, s>>>(sp.wait_flags, g->n_ranks, g->wait_step);
+            CUDA_TRY(cudaGetLastError());
+            ctx->launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        return CGPU_OK;
+    }
+    bv.n_out = g->n_ranks;
     for (uint32_t r = 0; r < g->n_ranks; r++) bv.sig_flags[r] = g->flags[r];
     bv.sig_rank = g->my_rank; bv.sig_step = g->step;
     bv.wait_flags = sp.wait_flags; bv.wait_step = g->wait_step;
-    CUDA_TRY(cudaSetDevice(ctx->device));
-    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     bool drained = false;
     rc = launch_check(ctx, t, bv, bv.outs[g->my_rank], nullptr, ctx->d_status, s, &drained);
     if (rc != CGPU_OK) return rc;
@@ -1121,8 +1218,12 @@ int cgpu_check(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, uint
     struct Release { cgpu_ctx *c; Slot *s; ~Release() { std::lock_guard<std::mutex> g(c->mu); s->busy = false; } } rel{ctx, slot};
 
     if (!slot->stream) CUDA_TRY(cudaStreamCreateWithFlags(&slot->stream, cudaStreamNonBlocking));
+    if (!slot->h2d) CUDA_TRY(cudaStreamCreateWithFlags(&slot->h2d, cudaStreamNonBlocking));
+    if (!slot->d2h) CUDA_TRY(cudaStreamCreateWithFlags(&slot->d2h, cudaStreamNonBlocking));
     if (!slot->d_status) { CUDA_TRY(cudaMalloc(&slot->d_status, 4)); CUDA_TRY(cudaMemset(slot->d_status, 0, 4)); }
     if (!slot->h_status) CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&slot->h_status), 4));
+    // a failed call must not leave work queued on the slot's streams when the slot goes back to the pool
+    struct Quiesce { Slot *s; bool armed = true; ~Quiesce() { if (armed) { cudaStreamSynchronize(s->h2d); cudaStreamSynchronize(s->stream); cudaStreamSynchronize(s->d2h); } } } quiesce{slot};
 
     // device layout: every column 256-byte aligned, then the effect bytes
     size_t offs[CGPU_N_COLUMNS + 1];
@@ -1139,22 +1240,54 @@ int cgpu_check(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, uint
     }
     uint8_t *dbase = static_cast<uint8_t *>(slot->dev);
     const void *dcols[CGPU_N_COLUMNS];
-    for (int i = 0; i < CGPU_N_COLUMNS; i++) {
-        dcols[i] = dbase + offs[i];
-        CUDA_TRY(cudaMemcpyAsync(dbase + offs[i], batch->columns[i], batch->column_bytes[i], cudaMemcpyHostToDevice, slot->stream));
-    }
+    for (int i = 0; i < CGPU_N_COLUMNS; i++) dcols[i] = dbase + offs[i];
     cgpu_batch db = *batch;
     db.columns = dcols;
     cb::BatchView bv;
     rc = make_batch_view(t, &db, 0, N, &bv);
     if (rc != CGPU_OK) return rc;
     uint8_t *d_effects = dbase + offs[CGPU_N_COLUMNS];
-    // the kernel writes effect bytes directly (1 ALLOW / 2 DENY / 0 padding): one D2H copy, no host post-pass
-    rc = launch_check(ctx, t, bv, nullptr, d_effects, slot->d_status, slot->stream);
-    if (rc != CGPU_OK) return rc;
-    CUDA_TRY(cudaMemcpyAsync(effects_out, d_effects, eff_bytes, cudaMemcpyDeviceToHost, slot->stream));
-    CUDA_TRY(cudaMemcpyAsync(slot->h_status, slot->d_status, 4, cudaMemcpyDeviceToHost, slot->stream));
-    CUDA_TRY(cudaStreamSynchronize(slot->stream));
+
+    // Pipeline: the batch-level tables and the heap go first, then the per-request columns travel in chunks of
+    // `chunk` requests -- while chunk k is evaluated, chunk k+1 is on its way in and the effect bytes of chunk k-1 on
+    // their way out (three streams, PCIe in both directions at once).  The kernels take a sub-range of the batch
+    // (BatchView::first / count over columns of stride N), so nothing is re-packed.  Host buffers should be pinned
+    // (cudaHostAlloc / cudaHostRegister): pageable memory makes every copy synchronous.
+    const char *ce = getenv("CERBOS_B200_CHECK_CHUNK");
+    uint64_t chunk = ce ? strtoull(ce, nullptr, 10) : (1ull << 18);
+    if (chunk < 4096) chunk = 4096;
+    chunk &= ~(uint64_t)255;
+    const uint64_t n_chunks = (N + chunk - 1) / chunk;
+    while (slot->ev.size() < 2 * n_chunks) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        slot->ev.push_back(e);
+    }
+    const uint8_t *const *hc = reinterpret_cast<const uint8_t *const *>(batch->columns);
+    for (int i = CGPU_COL_HEAP; i < CGPU_N_COLUMNS; i++)
+        if (batch->column_bytes[i]) CUDA_TRY(cudaMemcpyAsync(dbase + offs[i], hc[i], batch->column_bytes[i], cudaMemcpyHostToDevice, slot->h2d));
+    for (uint64_t k = 0; k < n_chunks; k++) {
+        const uint64_t c0 = k * chunk, cnt = N - c0 < chunk ? N - c0 : chunk;
+        CUDA_TRY(cudaMemcpyAsync(dbase + offs[CGPU_COL_HDR0] + c0 * 16, hc[CGPU_COL_HDR0] + c0 * 16, cnt * 16, cudaMemcpyHostToDevice, slot->h2d));
+        CUDA_TRY(cudaMemcpyAsync(dbase + offs[CGPU_COL_HDR1] + c0 * 8, hc[CGPU_COL_HDR1] + c0 * 8, cnt * 8, cudaMemcpyHostToDevice, slot->h2d));
+        for (uint32_t i = 0; i < bv.role_cols; i++)
+            CUDA_TRY(cudaMemcpyAsync(dbase + offs[CGPU_COL_ROLES] + ((uint64_t)i * N + c0) * 4, hc[CGPU_COL_ROLES] + ((uint64_t)i * N + c0) * 4, cnt * 4, cudaMemcpyHostToDevice, slot->h2d));
+        for (uint32_t v = 0; v < t->desc.lay.n_slots; v++)
+            CUDA_TRY(cudaMemcpyAsync(dbase + offs[CGPU_COL_SLOTS] + ((uint64_t)v * N + c0) * 8, hc[CGPU_COL_SLOTS] + ((uint64_t)v * N + c0) * 8, cnt * 8, cudaMemcpyHostToDevice, slot->h2d));
+        CUDA_TRY(cudaEventRecord(slot->ev[2 * k], slot->h2d));
+        CUDA_TRY(cudaStreamWaitEvent(slot->stream, slot->ev[2 * k], 0));
+        cb::BatchView cv = bv;
+        cv.first = c0; cv.count = cnt;
+        // the kernel writes effect bytes directly (1 ALLOW / 2 DENY / 0 padding): no host post-pass
+        rc = launch_check(ctx, t, cv, nullptr, d_effects, slot->d_status, slot->stream);
+        if (rc != CGPU_OK) return rc;
+        CUDA_TRY(cudaEventRecord(slot->ev[2 * k + 1], slot->stream));
+        CUDA_TRY(cudaStreamWaitEvent(slot->d2h, slot->ev[2 * k + 1], 0));
+        CUDA_TRY(cudaMemcpyAsync(effects_out + c0 * km, d_effects + c0 * km, cnt * km, cudaMemcpyDeviceToHost, slot->d2h));
+    }
+    CUDA_TRY(cudaMemcpyAsync(slot->h_status, slot->d_status, 4, cudaMemcpyDeviceToHost, slot->d2h));   // behind the last chunk's results
+    CUDA_TRY(cudaStreamSynchronize(slot->d2h));
+    quiesce.armed = false;   // d2h waited for every kernel, every kernel for its columns: all three streams are idle
     if (*slot->h_status) {
         CUDA_TRY(cudaMemset(slot->d_status, 0, 4));
         return fail(CGPU_ERR_UNSUPPORTED, "a request produced a run-time value the device cannot represent exactly (e.g. timestamp outside 1678..2262, string->double, concatenation)");

@@ -23,13 +23,15 @@ _GOLDEN = np.uint64(0x9E3779B97F4A7C15)
 _DRAWS = 32  # draws reserved per request
 
 
-_START = 0  # first request index of the window being generated (set by fields(n, start))
+import threading
+
+_TLS = threading.local()  # .start: first request index of the window being generated (set by fields(n, start)); per thread
 
 
 def splitmix(seed: int, n: int, draw: int) -> np.ndarray:
-    """draw-th SplitMix64 output of the stream of every request _START.._START+n-1."""
+    """draw-th SplitMix64 output of the stream of every request start..start+n-1 (start: see fields(n, start))."""
     with np.errstate(over="ignore"):
-        idx = (np.arange(n, dtype=np.uint64) + np.uint64(_START)) * np.uint64(_DRAWS) + np.uint64(draw + 1)
+        idx = (np.arange(n, dtype=np.uint64) + np.uint64(getattr(_TLS, 'start', 0))) * np.uint64(_DRAWS) + np.uint64(draw + 1)
         z = np.uint64(seed) + idx * _GOLDEN
         z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
         z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
@@ -193,14 +195,13 @@ class C2:
 
     def fields(self, n=None, start=0):
         """Requests [start, start+n) of the workload's stream."""
-        global _START
         n = n or self.default_n
         seed = SEED_BASE + self.cfg
-        _START = start
+        _TLS.start = start
         try:
             return self._fields(n, seed)
         finally:
-            _START = 0
+            _TLS.start = 0
 
     def _fields(self, n, seed):
         pid = _uniform(seed, n, 1, self.n_principals)
@@ -349,10 +350,9 @@ class C3:
         return docs
 
     def fields(self, n=None, start=0):
-        global _START
         n = n or self.default_n
         seed = SEED_BASE + self.cfg
-        _START = start
+        _TLS.start = start
         try:
             pid = _uniform(seed, n, 1, self.n_principals)
             r0 = _uniform(seed, n, 2, 4)
@@ -374,7 +374,7 @@ class C3:
             }
             return f
         finally:
-            _START = 0
+            _TLS.start = 0
 
     @staticmethod
     def _members(seedv, count, pos):
@@ -554,10 +554,9 @@ class C5:
         return docs
 
     def fields(self, n=None, start=0):
-        global _START
         n = n or 4096
         seed = SEED_BASE + self.cfg
-        _START = start
+        _TLS.start = start
         try:
             # Zipf(s = 1.1) over the kinds by inverse CDF on a uniform draw
             w = 1.0 / np.arange(1, self.n_kinds + 1) ** 1.1
@@ -577,7 +576,7 @@ class C5:
                 "iss": _prob(seed, n, 21, 0.7),
             }
         finally:
-            _START = 0
+            _TLS.start = 0
 
     def inputs(self, f, idx):
         out = []
@@ -617,6 +616,45 @@ class C5:
 
 
 WORKLOADS = {"C1": C1, "C2": C2, "C3": C3, "C5": C5}
+
+
+def columns_parallel(w, n, start, enc: Encoder, chunk=1 << 20, threads=None) -> Batch:
+    """w.columns(w.fields(n, start), enc) built chunk by chunk on a thread pool (numpy releases the GIL) and merged: the
+    per-request columns are concatenated, list / map references into the batch heap are rebased.  For workloads whose
+    batch-level tables (string dictionary, kind classes, action sets) do not depend on the requests (C2, C3)."""
+    from concurrent.futures import ThreadPoolExecutor
+    import os
+    if n <= chunk:
+        return w.columns(w.fields(n, start=start), enc)
+    threads = threads or min(32, os.cpu_count() or 1)
+    spans = [(s0, min(chunk, n - s0)) for s0 in range(0, n, chunk)]
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        parts = list(ex.map(lambda sp: w.columns(w.fields(sp[1], start=start + sp[0]), enc), spans))
+    first = parts[0]
+    for p in parts[1:]:
+        for ci in (5, 6, 7, 8, 9, 10, 11):
+            assert np.array_equal(np.asarray(p.columns[ci]), np.asarray(first.columns[ci])), "batch-level tables differ between chunks"
+    batch_bit = np.uint64(L.V64_HEAP_BATCH_BIT)
+    lo48 = np.uint64((1 << 48) - 1)
+
+    def rebase(a, base):
+        """heap references (LIST / MAP boxes with the batch bit) inside `a` move by `base` words"""
+        if base == 0:
+            return a
+        tag = (a >> np.uint64(48)).astype(np.uint32)
+        ref = ((tag == (L.V64_BOX_BASE | L.V64_LIST)) | (tag == (L.V64_BOX_BASE | L.V64_MAP))) & ((a & batch_bit) != 0)
+        out = a.copy()
+        out[ref] = (a[ref] & ~lo48) | ((a[ref] & lo48) + np.uint64(base))
+        return out
+
+    bases = np.cumsum([0] + [len(p.columns[4]) for p in parts[:-1]])
+    hdr0 = np.concatenate([p.columns[0] for p in parts], axis=0)
+    hdr1 = np.concatenate([p.columns[1] for p in parts], axis=0)
+    roles = np.concatenate([p.columns[2] for p in parts], axis=1)
+    slots = np.concatenate([rebase(p.columns[3], int(b)) for p, b in zip(parts, bases)], axis=1)
+    heap = np.concatenate([rebase(np.asarray(p.columns[4]), int(b)) for p, b in zip(parts, bases)])
+    cols = [hdr0, hdr1, roles, slots, heap] + list(first.columns[5:])
+    return Batch(n, first.max_actions, first.role_cols, cols, None, first.n_pass, first.kc)
 
 
 def build(workload, globals_=None):

@@ -69,6 +69,8 @@ extern "C" int HOSTSIM_ENTRY(const void *blob, uint64_t blob_len, uint64_t n, ui
     b.kc = 64 / b.role_cols; if (b.kc > km) b.kc = km;
     b.n_pass = (km + b.kc - 1) / b.kc; b.max_actions = km; b.kbytes = (km + 7) / 8; b.flags = flags; b.now = now;
     cb::finish_batch_view(b);
+    b.n_bstr = col_bytes[5] >= 4 ? (uint32_t)(col_bytes[5] / 4 - 1) : 0;
+    b.heap_words = col_bytes[4] / 8;
     uint32_t status = 0;
     // mode 0: what the library would pick; 1: force the general 64-bit body; 2: general 32-bit body;
     // 3: the lean body reading a tile of the columns staged the way the kernel's TMA copies lay it out in shared memory
@@ -85,13 +87,23 @@ extern "C" int HOSTSIM_ENTRY(const void *blob, uint64_t blob_len, uint64_t n, ui
         if (!uc.ok) return -3;
         cb::TableView ut;
         ut.base = uc.bytes.data(); ut.L = &uc.lay;
-        std::vector<uint64_t> pk((size_t)b.n_asets * b.n_rows);
-        for (size_t j = 0; j < pk.size(); j++) pk[j] = (uint64_t)(uint32_t)b.row_am[j] | (uint64_t)ut.urows()[j % b.n_rows] << 32;
+        std::vector<cb::U4> pk((size_t)b.n_asets * b.n_rows);
+        for (size_t j = 0; j < pk.size(); j++) {
+            const cb::U4 u = ut.urows()[j % b.n_rows];
+            pk[j] = cb::uc_row_record(u, (uint32_t)b.row_am[(j / b.n_rows) * b.n_rows + u.x], b.rcp, lay.nR);
+        }
+#if defined(HOSTSIM_SPEC_UC)
+        // the per-string predicate words the library's pre-pass kernel would compute (one per table / batch string)
+        std::vector<uint32_t> strpred(lay.nT + b.n_bstr + 1, 0);
+        if (HostConds::n_strpred)
+            for (uint32_t id = 0; id < lay.nT + b.n_bstr; id++) strpred[id] = HostConds().strpred(ut, b, id);
+        b.strpred = strpred.data();
+#endif
         for (uint64_t i = 0; i < n; i++) {
             cb::CachedCols gc; gc.b = &b; gc.n = i;
             bool d;
             if (mode == 5) { cb::UcRowsPacked rows; rows.pk = pk.data(); d = cb::eval_request_uc(ut, b, gc, rows, i, bitmap, nullptr, HostConds()); }
-            else { cb::UcRowsGlobal rows; rows.urows = ut.urows(); rows.row_am = b.row_am; d = cb::eval_request_uc(ut, b, gc, rows, i, bitmap, nullptr, HostConds()); }
+            else { cb::UcRowsGlobal rows; rows.urows = ut.urows(); rows.row_am = b.row_am; rows.RCP = b.rcp; rows.nR = lay.nR; d = cb::eval_request_uc(ut, b, gc, rows, i, bitmap, nullptr, HostConds()); }
             if (d) cb::eval_request_general(t.base, t.L, &b, i, bitmap, nullptr, &status);
         }
         return status ? -2 : 0;
@@ -138,7 +150,7 @@ extern "C" int64_t hostsim_generate_uc(const void *blob, uint64_t blob_len, char
     lay.nR = meta[CB_META_N_ROLES]; lay.n_slots = meta[CB_META_N_SLOTS];
     const cbuc::Image uc = cbuc::build(base, off, len, meta, lay);
     if (n_uconds_out) *n_uconds_out = uc.ok ? uc.n_uconds : 0;
-    std::string src = uc.ok ? cbspec::generate_uc(uc.bytes.data(), uc.lay.off, uc.lay.uc_conds_off, uc.n_uconds, lay.n_slots) : std::string();
+    std::string src = uc.ok ? cbspec::generate_uc(uc.bytes.data(), uc.lay.off, uc.lay.uc_conds_off, uc.n_uconds, lay.n_slots).src : std::string();
     if (src.size() + 1 > cap) return -(int64_t)src.size() - 2;
     memcpy(out, src.c_str(), src.size() + 1);
     return (int64_t)src.size();

@@ -445,3 +445,53 @@ def test_unique_condition_kernel_deferral_list():
         c.close()
     finally:
         os.environ.pop("CERBOS_B200_UC", None)
+
+
+def test_cgpu_check_is_reentrant_across_threads():
+    """16 host threads call cgpu_check concurrently (as gRPC goroutines call engine.Check, cerbos_svc.go:156, 205, 265):
+    batches of different sizes, some with requests the lean kernels defer (differing policy versions), pipelined in chunks
+    (CERBOS_B200_CHECK_CHUNK small, so every call is multi-chunk).  Every result must match the oracle."""
+    import threading
+    from cerbos_b200 import capi, workloads as W
+    from oracle import cref
+    os.environ["CERBOS_B200_CHECK_CHUNK"] = "8192"
+    try:
+        c = capi.Context(0)
+        tables, jobs = {}, []
+        for name in ("C2", "C3"):
+            w = W.WORKLOADS[name]()
+            _, ft, enc = W.build(w)
+            t = c.load_table(ft.blob)
+            t.wait_ready()
+            tables[name] = t
+            for j in range(8):
+                n = 20000 + 4099 * j
+                b = w.columns(w.fields(n, start=j * 50000), enc)
+                hdr1 = b.columns[1].copy()
+                hdr1["pv"][j::11] = 0xFFFF            # pv != rv -> deferred to the general kernel
+                b.columns[1] = hdr1
+                want = cref.check(ft.blob, b.columns, b.n, b.max_actions, n_threads=os.cpu_count() or 1)
+                jobs.append((name, b, want))
+        errors = []
+
+        def run(job):
+            name, b, want = job
+            try:
+                for _ in range(3):
+                    got = tables[name].check(b.columns, b.n, b.max_actions)
+                    if not (got == want).all():
+                        errors.append((name, b.n, int((got != want).sum())))
+            except Exception as e:  # noqa: BLE001
+                errors.append((name, b.n, repr(e)))
+
+        threads = [threading.Thread(target=run, args=(j,)) for j in jobs]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        assert not errors, errors
+        for t in tables.values():
+            t.release()
+        c.close()
+    finally:
+        os.environ.pop("CERBOS_B200_CHECK_CHUNK", None)
