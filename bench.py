@@ -112,6 +112,9 @@ class ClockSampler:
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
+        t0 = time.time()
+        while not self.samples and time.time() - t0 < 3.0:   # sampler initialised (NVML / first nvidia-smi) before the timed region starts
+            time.sleep(0.002)
         return self
 
     def __exit__(self, *a):

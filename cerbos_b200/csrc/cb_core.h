@@ -1228,6 +1228,7 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
 // Packed decision bits of request n (kbytes <= 8): to `bitmap`, or -- fused all-gather -- to this rank's slice of every
 // rank's gather buffer (plain stores; peer buffers are NVLink-mapped).
 CB_HD void store_bits(const BatchView &b, uint8_t *bitmap, uint64_t n, uint64_t acc) {
+    if (b.n_out == 0 && b.kbytes == 1) { bitmap[n] = (uint8_t)acc; return; }
     uint32_t r = 0;
     do {
         uint8_t *base = b.n_out ? b.outs[r] : bitmap;

@@ -333,14 +333,17 @@ __device__ __forceinline__ void check_uc_body(const TableDesc &td, const cb::Bat
     const uint64_t n_warps = (uint64_t)gridDim.x * (kThreads / 32);
     for (uint64_t chunk = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); chunk < n_chunks; chunk += n_warps) {
         const uint64_t i = chunk * 32 + lane;
-        {   // this warp's next chunk: pull its columns into L2 now (DRAM latency off the critical path of the next iteration)
+        {   // this warp's next chunk: pull its columns towards L2 now (two lanes cover the chunk's two 128-byte lines per column)
             const uint64_t i2 = i + n_warps * 32;
-            if (i2 < bv.count) {
+            if ((lane & 15u) == 0 && i2 < bv.count) {
                 const uint64_t n2 = bv.first + i2;
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(bv.hdr0 + n2));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(bv.hdr0 + n2 + 8));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(bv.hdr1 + n2));
-                for (uint32_t c = 0; c < bv.role_cols; c++) asm volatile("prefetch.global.L2 [%0];" ::"l"(bv.roles + (uint64_t)c * bv.stride + n2));
-                for (uint32_t v = 0; v < td.lay.n_slots; v++) asm volatile("prefetch.global.L2 [%0];" ::"l"(bv.slots + (uint64_t)v * bv.stride + n2));
+                const uint32_t *pr = bv.roles + n2;
+                for (uint32_t c = 0; c < bv.role_cols; c++, pr += bv.stride) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr));
+                const uint64_t *ps = bv.slots + n2;
+                for (uint32_t v = 0; v < td.lay.n_slots; v++, ps += bv.stride) asm volatile("prefetch.global.L2 [%0];" ::"l"(ps));
             }
         }
         if (i < bv.count) {

@@ -679,7 +679,7 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
     // (with one shape the per-shape specialised tile kernel is the better fit).  Index order, no clustering.
     const bool uc_spec_ready = mt->spec_state.load(std::memory_order_acquire) == 1 && t->spec_uc != nullptr;
     const bool uc = narrow && t->uc.ok && t->d_uc_image && bv.count < (1ull << 32) && (uint64_t)bv.n_asets * lay.n_rows < (1ull << 31) && (uint64_t)(lay.nR + 1) * rcp <= 64 &&
-                    (ctx->uc_mode == 1 || (ctx->uc_mode != 0 && t->meta[CB_META_BLOCK_SHAPES] > 1));
+                    (ctx->uc_mode == 1 || (ctx->uc_mode != 0 && ctx->cluster_mode != 1 && t->meta[CB_META_BLOCK_SHAPES] > 1));   // CERBOS_B200_CLUSTER=1 keeps the clustered path reachable
     // Clustering pays when the policy blocks differ in shape (rows / conditions): with a single shape every lane runs
     // the same control flow in index order already and the coalesced column loads are worth more.
     const bool cluster = !uc && bv.count < (1ull << 32) &&
