@@ -210,6 +210,13 @@ struct Val {
     uint64_t u;
 };
 static constexpr uint64_t kHeapBatch = 1ull << 63;
+// Values made at run time (list / string producing functions, comprehensions that build lists or maps, concatenation)
+// live in a small per-thread scratch arena inside Ctx: lists / maps as [n, elements...] words exactly like the heaps,
+// strings as raw bytes.  A program that outgrows it raises the sticky `unsupported` flag (the call fails loudly).
+static constexpr uint64_t kHeapScratch = 1ull << 62;          // Val.u of a LIST / MAP: word offset into Ctx::scratch
+static constexpr uint64_t kStrDyn = 1ull << 47;               // Val.u / V64 payload of a STRING: byte offset << 16 | byte length
+static constexpr uint64_t kV64ScratchBit = 1ull << 46;        // V64 payload of a LIST / MAP element living in the arena
+enum { CB_SCRATCH_WORDS = 192, CB_T_SKIP = 15 };              // CB_T_SKIP: comprehension iteration filtered out (internal)
 
 CB_HD Val mk(uint32_t tag, uint64_t u) { Val v; v.tag = tag; v.u = u; return v; }
 CB_HD Val mk_err() { return mk(CB_T_ERR, 0); }
@@ -233,6 +240,7 @@ CB_HD Val decode_v64(uint64_t bits, int *state) {
         case CB_V64_MAP: {
             uint64_t off = pay & (CB_V64_HEAP_BATCH_BIT - 1);
             if (pay & CB_V64_HEAP_BATCH_BIT) off |= kHeapBatch;
+            else if (off & kV64ScratchBit) off = (off & ~kV64ScratchBit) | kHeapScratch;
             return mk(tag == CB_V64_LIST ? CB_T_LIST : CB_T_MAP, off);
         }
         case CB_V64_INT: return mk_int((int64_t)(pay << 16) >> 16);
@@ -251,13 +259,18 @@ struct Ctx {
     uint32_t pid;          // hdr0.principal_id
     uint32_t unsupported;  // sticky
     Val vars[CB_MAX_VARS];
+    uint32_t scr_used;     // words of `scratch` in use
+    uint64_t scratch[CB_SCRATCH_WORDS];
 };
 
 CB_HD const uint64_t *heap_ptr(const Ctx &c, uint64_t ref) {
-    return (ref & kHeapBatch) ? c.b->heap + (ref & ~kHeapBatch) : c.t->theap() + ref;
+    return (ref & kHeapBatch) ? c.b->heap + (ref & ~kHeapBatch) : (ref & kHeapScratch) ? c.scratch + (ref & 0xFFFFu) : c.t->theap() + ref;
 }
 CB_HD void str_get(const Ctx &c, uint64_t id, const uint8_t *&p, uint32_t &len) {
-    if (id < c.t->L->nT) {
+    if (id & kStrDyn) {
+        p = reinterpret_cast<const uint8_t *>(c.scratch) + ((id >> 16) & 0xFFFFu);
+        len = (uint32_t)(id & 0xFFFFu);
+    } else if (id < c.t->L->nT) {
         uint32_t o = ldg(c.t->str_off() + id);
         p = c.t->str_bytes() + o;
         len = ldg(c.t->str_off() + id + 1) - o;
@@ -310,22 +323,36 @@ CB_HD int num_cmp(const Val &a, const Val &b) {
     return a.u < (uint64_t)y ? -1 : (a.u > (uint64_t)y ? 1 : 0);
 }
 
+// strings: interned ids are unique per string; one made at run time is compared by its bytes
+CB_HD bool str_equal(const Ctx &c, uint64_t a, uint64_t b) {
+    if (a == b) return true;
+    if (!((a | b) & kStrDyn)) return false;
+    const uint8_t *pa, *pb;
+    uint32_t la, lb;
+    str_get(c, a, pa, la);
+    str_get(c, b, pb, lb);
+    if (la != lb) return false;
+    for (uint32_t i = 0; i < la; i++)
+        if (ldg(pa + i) != ldg(pb + i)) return false;
+    return true;
+}
 // scalar (non-container) equality; containers handled by the callers below
-CB_HD bool scalar_equal(const Val &a, const Val &b) {
+CB_HD bool scalar_equal(const Ctx &c, const Val &a, const Val &b) {
     if (is_num(a) && is_num(b)) return num_cmp(a, b) == 0;
     if (a.tag != b.tag) return false;
     if (a.tag == CB_T_NULL) return true;
-    return a.u == b.u;  // BOOL / STRING (interned ids) / TS / DUR
+    if (a.tag == CB_T_STRING) return str_equal(c, a.u, b.u);
+    return a.u == b.u;  // BOOL / TS / DUR
 }
 CB_HD bool is_container(const Val &v) { return v.tag == CB_T_LIST || v.tag == CB_T_MAP; }
 
 CB_HD bool map_find(const Ctx &c, const Val &m, const Val &key, Val *out) {
-    if (key.tag != CB_T_STRING) return false;  // JSON / constant maps have string keys only
+    if (is_container(key) || key.tag == CB_T_ERR) return false;   // keys are scalars: string (JSON), int / uint / bool (literals, comprehensions)
     const uint64_t *p = heap_ptr(c, m.u);
     uint64_t n = ldg(p);
     for (uint64_t i = 0; i < n; i++) {
         Val k = decode_elem(ldg(p + 1 + i));
-        if (k.tag == CB_T_STRING && k.u == key.u) {
+        if (scalar_equal(c, k, key)) {
             if (out) *out = decode_elem(ldg(p + 1 + n + i));
             return true;
         }
@@ -340,7 +367,7 @@ struct Eq {
     static CB_HD bool eq(Ctx &c, const Val &a, const Val &b) {
         if (!is_container(a) || !is_container(b)) {
             if (is_container(a) != is_container(b)) return false;
-            return scalar_equal(a, b);
+            return scalar_equal(c, a, b);
         }
         if (a.tag != b.tag) return false;
         const uint64_t *pa = heap_ptr(c, a.u), *pb = heap_ptr(c, b.u);
@@ -364,7 +391,7 @@ struct Eq<0> {
     static CB_HD bool eq(Ctx &c, const Val &a, const Val &b) {
         if (is_container(a) && is_container(b)) { c.unsupported = 1; return false; }
         if (is_container(a) != is_container(b)) return false;
-        return scalar_equal(a, b);
+        return scalar_equal(c, a, b);
     }
 };
 CB_HD bool val_equal(Ctx &c, const Val &a, const Val &b) { return Eq<3>::eq(c, a, b); }
@@ -455,9 +482,10 @@ CB_HD bool uses_go_map(const Ctx &c, const Val &b) {
         if (!hashable(decode_elem(ldg(p + 1 + i)))) return false;
     return true;
 }
-CB_HD bool key_identical(const Val &a, const Val &b) {
+CB_HD bool key_identical(const Ctx &c, const Val &a, const Val &b) {
     if (a.tag != b.tag) return false;
     if (a.tag == CB_T_DOUBLE) return u2d(a.u) == u2d(b.u);
+    if (a.tag == CB_T_STRING) return str_equal(c, a.u, b.u);
     return a.u == b.u;
 }
 CB_HD bool list_member(Ctx &c, bool go_map, const Val &b, const Val &x) {
@@ -465,7 +493,7 @@ CB_HD bool list_member(Ctx &c, bool go_map, const Val &b, const Val &x) {
     uint64_t n = ldg(p);
     for (uint64_t i = 0; i < n; i++) {
         Val e = decode_elem(ldg(p + 1 + i));
-        if (go_map ? key_identical(x, e) : val_equal(c, x, e)) return true;
+        if (go_map ? key_identical(c, x, e) : val_equal(c, x, e)) return true;
     }
     return false;
 }
@@ -501,6 +529,7 @@ CB_HD bool mul_ovf(int64_t x, int64_t y, int64_t *r) { return __builtin_mul_over
 CB_HD bool umul_ovf(uint64_t x, uint64_t y, uint64_t *r) { return __builtin_mul_overflow(x, y, r); }
 #endif
 
+CB_HD_NOINLINE Val dyn_concat(Ctx &c, const Val &a, const Val &b);   // defined with the run-time values below
 CB_HD Val do_arith(Ctx &c, int op, const Val &a, const Val &b) {
     if (a.tag == CB_T_ERR || b.tag == CB_T_ERR) return mk_err();
     const int64_t kMin = (int64_t)0x8000000000000000ull;
@@ -541,10 +570,7 @@ CB_HD Val do_arith(Ctx &c, int op, const Val &a, const Val &b) {
             return mk(CB_T_TS, (uint64_t)r);
         }
         if (a.tag == CB_T_DUR && b.tag == CB_T_DUR) return add_ovf(x, y, &r) ? mk_err() : mk(CB_T_DUR, (uint64_t)r);
-        if ((a.tag == CB_T_STRING && b.tag == CB_T_STRING) || (a.tag == CB_T_LIST && b.tag == CB_T_LIST)) {
-            c.unsupported = 1;  // concatenation would need device-side allocation
-            return mk_err();
-        }
+        if ((a.tag == CB_T_STRING && b.tag == CB_T_STRING) || (a.tag == CB_T_LIST && b.tag == CB_T_LIST)) return dyn_concat(c, a, b);
     }
     if (op == CB_OP_SUB) {
         if (a.tag == CB_T_TS && b.tag == CB_T_TS) return sub_ovf(x, y, &r) ? mk_err() : mk(CB_T_DUR, (uint64_t)r);
@@ -1002,6 +1028,387 @@ CB_HD_NOINLINE Val conv_uint(Ctx &c, const Val &v) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------- run-time values
+// List / string producing functions (cel-go ext.Strings / ext.Lists, conditions/cel.go:62-75; Cerbos except /
+// intersect, cerbos_lib.go:287, 433; hierarchy(list), hierarchy[i], types/hierarchy.go).  Results live in Ctx::scratch.
+CB_HD bool scr_alloc(Ctx &c, uint32_t words, uint32_t *off) {
+    if (c.scr_used + words > CB_SCRATCH_WORDS) { c.unsupported = 1; return false; }
+    *off = c.scr_used;
+    c.scr_used += words;
+    return true;
+}
+// NaN-boxed element form of a value (what lists / maps hold); false: not representable (sets `unsupported`)
+CB_HD bool encode_elem(Ctx &c, const Val &v, uint64_t *out) {
+    switch (v.tag) {
+    case CB_T_NULL: *out = (uint64_t)(CB_V64_BOX_BASE | CB_V64_NULL) << 48; return true;
+    case CB_T_BOOL: *out = ((uint64_t)(CB_V64_BOX_BASE | CB_V64_BOOL) << 48) | (v.u & 1); return true;
+    case CB_T_DOUBLE: *out = v.u; return true;
+    case CB_T_STRING: *out = ((uint64_t)(CB_V64_BOX_BASE | CB_V64_STRING) << 48) | (v.u & 0xFFFFFFFFFFFFull); return true;
+    case CB_T_INT: {
+        const int64_t i = (int64_t)v.u;
+        if (i < -(1ll << 47) || i >= (1ll << 47)) { c.unsupported = 1; return false; }
+        *out = ((uint64_t)(CB_V64_BOX_BASE | CB_V64_INT) << 48) | (v.u & 0xFFFFFFFFFFFFull);
+        return true;
+    }
+    case CB_T_LIST:
+    case CB_T_MAP: {
+        uint64_t pay = v.u & ~(kHeapBatch | kHeapScratch);
+        if (v.u & kHeapBatch) pay |= CB_V64_HEAP_BATCH_BIT;
+        else if (v.u & kHeapScratch) pay |= kV64ScratchBit;
+        *out = ((uint64_t)(CB_V64_BOX_BASE | (v.tag == CB_T_LIST ? CB_V64_LIST : CB_V64_MAP)) << 48) | pay;
+        return true;
+    }
+    default: c.unsupported = 1; return false;   // uint / timestamp / duration / bytes elements have no 8-byte form
+    }
+}
+CB_HD Val mk_scratch(uint32_t tag, uint32_t off) { return mk(tag, kHeapScratch | off); }
+// a list of n elements whose words the caller fills at c.scratch[*off + 1 ...]
+CB_HD bool list_new(Ctx &c, uint32_t n, uint32_t *off) {
+    if (!scr_alloc(c, n + 1, off)) return false;
+    c.scratch[*off] = n;
+    return true;
+}
+// string under construction at the top of the arena
+struct StrB {
+    Ctx *c; uint32_t b0, len, cap; bool ok;
+};
+CB_HD StrB strb_begin(Ctx &c) { StrB s; s.c = &c; s.b0 = c.scr_used * 8; s.len = 0; s.cap = (CB_SCRATCH_WORDS - c.scr_used) * 8; s.ok = true; return s; }
+CB_HD void strb_put(StrB &s, uint8_t ch) {
+    if (s.len >= s.cap || s.len >= 0xFFFF) { s.ok = false; return; }
+    reinterpret_cast<uint8_t *>(s.c->scratch)[s.b0 + s.len++] = ch;
+}
+CB_HD void strb_bytes(StrB &s, const uint8_t *p, uint32_t n) { for (uint32_t i = 0; i < n; i++) strb_put(s, ldg(p + i)); }
+CB_HD Val strb_end(StrB &s) {
+    if (!s.ok) { s.c->unsupported = 1; return mk_err(); }
+    s.c->scr_used += (s.len + 7) / 8;
+    return mk(CB_T_STRING, kStrDyn | ((uint64_t)s.b0 << 16) | s.len);
+}
+CB_HD uint32_t rune_len(uint8_t lead) { return lead < 0x80 ? 1u : lead < 0xE0 ? 2u : lead < 0xF0 ? 3u : 4u; }
+// byte offset of rune index r (r <= rune count)
+CB_HD uint32_t rune_off(const uint8_t *p, uint32_t n, uint32_t r) {
+    uint32_t i = 0;
+    while (r > 0 && i < n) { i += rune_len(ldg(p + i)); r--; }
+    return i < n ? i : n;
+}
+CB_HD uint32_t rune_at(const uint8_t *p, uint32_t n, uint32_t i, uint32_t *adv) {
+    const uint8_t b0 = ldg(p + i);
+    uint32_t l = rune_len(b0);
+    if (i + l > n) l = n - i;
+    *adv = l;
+    if (l == 1) return b0;
+    uint32_t cp = b0 & (0xFFu >> (l + 1));
+    for (uint32_t k = 1; k < l; k++) cp = (cp << 6) | (ldg(p + i + k) & 0x3F);
+    return cp;
+}
+CB_HD bool go_space(uint32_t r) {   // unicode.IsSpace (strings.TrimSpace)
+    return r == 0x20 || (r >= 0x09 && r <= 0x0D) || r == 0x85 || r == 0xA0 || r == 0x1680 || (r >= 0x2000 && r <= 0x200A) || r == 0x2028 || r == 0x2029 ||
+           r == 0x202F || r == 0x205F || r == 0x3000;
+}
+// first byte offset >= from where [q, q + m) occurs in [p, p + n), or n + 1
+CB_HD uint32_t bytes_find(const uint8_t *p, uint32_t n, const uint8_t *q, uint32_t m, uint32_t from) {
+    for (uint32_t i = from; i + m <= n; i++)
+        if (bytes_eq(p + i, q, m)) return i;
+    return n + 1;
+}
+struct LView { const uint64_t *p; uint32_t n; };
+CB_HD LView lview(const Ctx &c, const Val &v) { LView l; l.p = heap_ptr(c, v.u); l.n = (uint32_t)ldg(l.p); l.p += 1; return l; }
+CB_HD bool arg_int(const Val &v, int64_t *out) { if (v.tag != CB_T_INT) return false; *out = (int64_t)v.u; return true; }
+
+CB_HD_NOINLINE Val dyn_concat(Ctx &c, const Val &a, const Val &b) {
+    if (a.tag == CB_T_STRING && b.tag == CB_T_STRING) {
+        const uint8_t *pa, *pb; uint32_t la, lb;
+        str_get(c, a.u, pa, la); str_get(c, b.u, pb, lb);
+        StrB s = strb_begin(c);
+        strb_bytes(s, pa, la); strb_bytes(s, pb, lb);
+        return strb_end(s);
+    }
+    if (a.tag == CB_T_LIST && b.tag == CB_T_LIST) {
+        const LView x = lview(c, a), y = lview(c, b);
+        uint32_t off;
+        if (!list_new(c, x.n + y.n, &off)) return mk_err();
+        for (uint32_t i = 0; i < x.n; i++) c.scratch[off + 1 + i] = ldg(x.p + i);
+        for (uint32_t i = 0; i < y.n; i++) c.scratch[off + 1 + x.n + i] = ldg(y.p + i);
+        // elements copied from another heap keep their own references (table / batch / arena bits travel in the word)
+        return mk_scratch(CB_T_LIST, off);
+    }
+    return mk_err();
+}
+
+// string functions of cel-go ext.Strings (indices count code points)
+CB_HD_NOINLINE Val dyn_strfn(Ctx &c, uint32_t fn, const Val *a, uint32_t argc) {
+    for (uint32_t i = 0; i < argc; i++) if (a[i].tag == CB_T_ERR) return mk_err();
+    if (fn == CB_FN_JOIN) {
+        if (a[0].tag != CB_T_LIST || (argc == 2 && a[1].tag != CB_T_STRING)) return mk_err();
+        const LView l = lview(c, a[0]);
+        const uint8_t *ps = nullptr; uint32_t ls = 0;
+        if (argc == 2) str_get(c, a[1].u, ps, ls);
+        for (uint32_t i = 0; i < l.n; i++) if (decode_elem(ldg(l.p + i)).tag != CB_T_STRING) return mk_err();
+        StrB s = strb_begin(c);
+        for (uint32_t i = 0; i < l.n; i++) {
+            const uint8_t *pe; uint32_t le;
+            str_get(c, decode_elem(ldg(l.p + i)).u, pe, le);
+            if (i) strb_bytes(s, ps, ls);
+            strb_bytes(s, pe, le);
+        }
+        return strb_end(s);
+    }
+    if (fn == CB_FN_HIER_JOIN) {   // hierarchy(list of strings): the parts joined by U+001F, which no part may contain
+        if (a[0].tag != CB_T_LIST) return mk_err();
+        const LView l = lview(c, a[0]);
+        for (uint32_t i = 0; i < l.n; i++) if (decode_elem(ldg(l.p + i)).tag != CB_T_STRING) return mk_err();
+        StrB s = strb_begin(c);
+        for (uint32_t i = 0; i < l.n; i++) {
+            const uint8_t *pe; uint32_t le;
+            str_get(c, decode_elem(ldg(l.p + i)).u, pe, le);
+            for (uint32_t j = 0; j < le; j++) if (ldg(pe + j) == 0x1F) c.unsupported = 1;
+            if (i) strb_put(s, 0x1F);
+            strb_bytes(s, pe, le);
+        }
+        return strb_end(s);
+    }
+    if (a[0].tag != CB_T_STRING) return mk_err();
+    const uint8_t *p; uint32_t n;
+    str_get(c, a[0].u, p, n);
+    const uint32_t nr = utf8_len(p, n);
+    switch (fn) {
+    case CB_FN_LOWER: case CB_FN_UPPER: {
+        StrB s = strb_begin(c);
+        for (uint32_t i = 0; i < n; i++) {
+            uint8_t ch = ldg(p + i);
+            if (fn == CB_FN_LOWER && ch >= 'A' && ch <= 'Z') ch += 32;
+            if (fn == CB_FN_UPPER && ch >= 'a' && ch <= 'z') ch -= 32;
+            strb_put(s, ch);
+        }
+        return strb_end(s);
+    }
+    case CB_FN_TRIM: {
+        uint32_t lo = 0, hi = n, adv;
+        while (lo < hi && go_space(rune_at(p, n, lo, &adv))) lo += adv;
+        while (hi > lo) {   // step back one rune
+            uint32_t q = hi - 1;
+            while (q > lo && (ldg(p + q) & 0xC0) == 0x80) q--;
+            if (!go_space(rune_at(p, n, q, &adv))) break;
+            hi = q;
+        }
+        StrB s = strb_begin(c);
+        strb_bytes(s, p + lo, hi - lo);
+        return strb_end(s);
+    }
+    case CB_FN_STR_REVERSE: {
+        StrB s = strb_begin(c);
+        uint32_t hi = n;
+        while (hi > 0) {
+            uint32_t q = hi - 1;
+            while (q > 0 && (ldg(p + q) & 0xC0) == 0x80) q--;
+            strb_bytes(s, p + q, hi - q);
+            hi = q;
+        }
+        return strb_end(s);
+    }
+    case CB_FN_CHARAT: {
+        int64_t i;
+        if (argc != 2 || !arg_int(a[1], &i)) return mk_err();
+        if (i < 0 || i > (int64_t)nr) return mk_err();
+        StrB s = strb_begin(c);
+        if (i < (int64_t)nr) { const uint32_t o = rune_off(p, n, (uint32_t)i); strb_bytes(s, p + o, rune_len(ldg(p + o))); }
+        return strb_end(s);
+    }
+    case CB_FN_INDEXOF: case CB_FN_LASTINDEXOF: {
+        if (argc < 2 || a[1].tag != CB_T_STRING) return mk_err();
+        const uint8_t *q; uint32_t m;
+        str_get(c, a[1].u, q, m);
+        int64_t off = fn == CB_FN_INDEXOF ? 0 : (int64_t)nr;
+        if (argc == 3) { if (!arg_int(a[2], &off) || off < 0 || off > (int64_t)nr) return mk_err(); }
+        if (m == 0) return mk_int(off);
+        if (fn == CB_FN_INDEXOF) {
+            const uint32_t at = bytes_find(p, n, q, m, rune_off(p, n, (uint32_t)off));
+            return mk_int(at > n ? -1 : (int64_t)utf8_len(p, at));
+        }
+        // the last occurrence that starts at or before rune `off`
+        const uint32_t lim = rune_off(p, n, (uint32_t)off);
+        int64_t best = -1;
+        for (uint32_t i = 0; i + m <= n && i <= lim; i++)
+            if ((ldg(p + i) & 0xC0) != 0x80 && bytes_eq(p + i, q, m)) best = (int64_t)utf8_len(p, i);
+        return mk_int(best);
+    }
+    case CB_FN_SUBSTRING: {
+        int64_t st, en = (int64_t)nr;
+        if (argc < 2 || !arg_int(a[1], &st) || (argc == 3 && !arg_int(a[2], &en))) return mk_err();
+        if (st < 0 || st > (int64_t)nr || en < 0 || en > (int64_t)nr || st > en) return mk_err();
+        const uint32_t o0 = rune_off(p, n, (uint32_t)st), o1 = rune_off(p, n, (uint32_t)en);
+        StrB s = strb_begin(c);
+        strb_bytes(s, p + o0, o1 - o0);
+        return strb_end(s);
+    }
+    case CB_FN_REPLACE: {
+        if (argc < 3 || a[1].tag != CB_T_STRING || a[2].tag != CB_T_STRING) return mk_err();
+        int64_t lim = -1;
+        if (argc == 4 && !arg_int(a[3], &lim)) return mk_err();
+        const uint8_t *po, *pn; uint32_t lo, ln;
+        str_get(c, a[1].u, po, lo); str_get(c, a[2].u, pn, ln);
+        StrB s = strb_begin(c);
+        int64_t done = 0;
+        if (lo == 0) {   // Go strings.Replace with an empty `old`: `new` before every rune (and at the end) up to lim times
+            uint32_t i = 0;
+            while (i < n) {
+                if (lim < 0 || done < lim) { strb_bytes(s, pn, ln); done++; }
+                const uint32_t l = rune_len(ldg(p + i));
+                strb_bytes(s, p + i, i + l <= n ? l : n - i);
+                i += l;
+            }
+            if (lim < 0 || done < lim) strb_bytes(s, pn, ln);
+            return strb_end(s);
+        }
+        uint32_t i = 0;
+        while (i < n) {
+            if ((lim < 0 || done < lim) && i + lo <= n && bytes_eq(p + i, po, lo)) { strb_bytes(s, pn, ln); i += lo; done++; }
+            else strb_put(s, ldg(p + i++));
+        }
+        return strb_end(s);
+    }
+    case CB_FN_SPLIT: {
+        if (argc < 2 || a[1].tag != CB_T_STRING) return mk_err();
+        int64_t lim = -1;
+        if (argc == 3 && !arg_int(a[2], &lim)) return mk_err();
+        const uint8_t *q; uint32_t m;
+        str_get(c, a[1].u, q, m);
+        // count the pieces first (Go strings.SplitN)
+        uint32_t pieces = 0;
+        if (lim != 0) {
+            if (m == 0) pieces = nr;
+            else { pieces = 1; for (uint32_t i = 0; i + m <= n;) { if (bytes_eq(p + i, q, m)) { pieces++; i += m; } else i++; } }
+            if (lim > 0 && (int64_t)pieces > lim) pieces = (uint32_t)lim;
+        }
+        uint32_t off;
+        if (!list_new(c, pieces, &off)) return mk_err();
+        uint32_t i = 0;
+        for (uint32_t k = 0; k < pieces; k++) {
+            uint32_t end;
+            if (k + 1 == pieces) end = n;
+            else if (m == 0) end = i + rune_len(ldg(p + i));
+            else end = bytes_find(p, n, q, m, i);
+            StrB s = strb_begin(c);
+            strb_bytes(s, p + i, end - i);
+            const Val piece = strb_end(s);
+            if (piece.tag == CB_T_ERR) return mk_err();
+            encode_elem(c, piece, &c.scratch[off + 1 + k]);
+            i = end + (m == 0 ? 0 : m);
+        }
+        return mk_scratch(CB_T_LIST, off);
+    }
+    case CB_FN_HIER_AT: {   // hierarchy(s, delim a[2])[a[1]]
+        int64_t i;
+        if (argc != 3 || !arg_int(a[1], &i) || a[2].tag != CB_T_STRING) return mk_err();
+        HierIt it = hier_it(c, a[0].u, (uint32_t)a[2].u);
+        uint32_t s0, l0;
+        int64_t k = 0;
+        while (hier_next(it, &s0, &l0)) {
+            if (k++ == i) { StrB s = strb_begin(c); strb_bytes(s, it.p + s0, l0); return strb_end(s); }
+        }
+        return mk_err();   // index out of range
+    }
+    default: c.unsupported = 1; return mk_err();
+    }
+}
+
+// list functions: cel-go ext.Lists (sort, slice, flatten, reverse, distinct, lists.range) and Cerbos except / intersect
+CB_HD_NOINLINE Val dyn_listfn(Ctx &c, uint32_t fn, const Val *a, uint32_t argc) {
+    for (uint32_t i = 0; i < argc; i++) if (a[i].tag == CB_T_ERR) return mk_err();
+    uint32_t off;
+    if (fn == CB_FN_RANGE) {
+        int64_t n;
+        if (!arg_int(a[0], &n)) return mk_err();
+        if (n < 0) n = 0;
+        if (n > CB_SCRATCH_WORDS) { c.unsupported = 1; return mk_err(); }
+        if (!list_new(c, (uint32_t)n, &off)) return mk_err();
+        for (int64_t i = 0; i < n; i++) encode_elem(c, mk_int(i), &c.scratch[off + 1 + i]);
+        return mk_scratch(CB_T_LIST, off);
+    }
+    if (a[0].tag != CB_T_LIST) return mk_err();
+    const LView x = lview(c, a[0]);
+    switch (fn) {
+    case CB_FN_EXCEPT: case CB_FN_INTERSECT: {
+        if (argc != 2 || a[1].tag != CB_T_LIST) return mk_err();
+        Val la = a[0], lb = a[1];
+        if (fn == CB_FN_INTERSECT && x.n > lview(c, lb).n) { la = a[1]; lb = a[0]; }   // cerbos_lib.go:433-470: probe the larger list
+        const LView xa = lview(c, la);
+        const bool gm = uses_go_map(c, lb);
+        if (!list_new(c, xa.n, &off)) return mk_err();
+        uint32_t k = 0;
+        for (uint32_t i = 0; i < xa.n; i++) {
+            const uint64_t w = ldg(xa.p + i);
+            if (list_member(c, gm, lb, decode_elem(w)) == (fn == CB_FN_INTERSECT)) c.scratch[off + 1 + k++] = w;
+        }
+        c.scratch[off] = k;
+        return mk_scratch(CB_T_LIST, off);
+    }
+    case CB_FN_REVERSE: {
+        if (!list_new(c, x.n, &off)) return mk_err();
+        for (uint32_t i = 0; i < x.n; i++) c.scratch[off + 1 + i] = ldg(x.p + (x.n - 1 - i));
+        return mk_scratch(CB_T_LIST, off);
+    }
+    case CB_FN_SLICE: {
+        int64_t s0, e0;
+        if (argc != 3 || !arg_int(a[1], &s0) || !arg_int(a[2], &e0)) return mk_err();
+        if (s0 < 0 || e0 < 0 || s0 > e0 || e0 > (int64_t)x.n) return mk_err();
+        if (!list_new(c, (uint32_t)(e0 - s0), &off)) return mk_err();
+        for (int64_t i = s0; i < e0; i++) c.scratch[off + 1 + (i - s0)] = ldg(x.p + i);
+        return mk_scratch(CB_T_LIST, off);
+    }
+    case CB_FN_FLATTEN: {
+        int64_t depth = 1;
+        if (argc == 2 && !arg_int(a[1], &depth)) return mk_err();
+        if (depth < 0) return mk_err();
+        if (depth > 1) { c.unsupported = 1; return mk_err(); }
+        uint32_t total = 0;
+        for (uint32_t i = 0; i < x.n; i++) { const Val e = decode_elem(ldg(x.p + i)); total += (depth && e.tag == CB_T_LIST) ? lview(c, e).n : 1; }
+        if (!list_new(c, total, &off)) return mk_err();
+        uint32_t k = 0;
+        for (uint32_t i = 0; i < x.n; i++) {
+            const uint64_t w = ldg(x.p + i);
+            const Val e = decode_elem(w);
+            if (depth && e.tag == CB_T_LIST) { const LView y = lview(c, e); for (uint32_t j = 0; j < y.n; j++) c.scratch[off + 1 + k++] = ldg(y.p + j); }
+            else c.scratch[off + 1 + k++] = w;
+        }
+        return mk_scratch(CB_T_LIST, off);
+    }
+    case CB_FN_DISTINCT: {
+        if (!list_new(c, x.n, &off)) return mk_err();
+        uint32_t k = 0;
+        for (uint32_t i = 0; i < x.n; i++) {
+            const Val e = decode_elem(ldg(x.p + i));
+            bool seen = false;
+            for (uint32_t j = 0; j < k && !seen; j++) seen = val_equal(c, e, decode_elem(c.scratch[off + 1 + j]));
+            if (!seen) c.scratch[off + 1 + k++] = ldg(x.p + i);
+        }
+        c.scratch[off] = k;
+        return mk_scratch(CB_T_LIST, off);
+    }
+    case CB_FN_SORT: {
+        if (!list_new(c, x.n, &off)) return mk_err();
+        if (x.n == 0) return mk_scratch(CB_T_LIST, off);
+        const uint32_t t0 = decode_elem(ldg(x.p)).tag;
+        if (!(t0 == CB_T_INT || t0 == CB_T_UINT || t0 == CB_T_DOUBLE || t0 == CB_T_BOOL || t0 == CB_T_STRING || t0 == CB_T_TS || t0 == CB_T_DUR)) return mk_err();
+        for (uint32_t i = 0; i < x.n; i++) {   // stable insertion sort
+            const uint64_t w = ldg(x.p + i);
+            const Val e = decode_elem(w);
+            if (e.tag != t0) return mk_err();   // "list elements must have the same type"
+            uint32_t j = i;
+            while (j > 0) {
+                const int r = val_order(c, decode_elem(c.scratch[off + j]), e);
+                if (r == 3) return mk_err();
+                if (r <= 0) break;
+                c.scratch[off + 1 + j] = c.scratch[off + j];
+                j--;
+            }
+            c.scratch[off + 1 + j] = w;
+        }
+        return mk_scratch(CB_T_LIST, off);
+    }
+    default: c.unsupported = 1; return mk_err();
+    }
+}
+
 // ---- 3-valued && / || with cel-go error absorption ----
 CB_HD Val and_or(bool is_or, const Val &a, const Val &b) {
     bool ab = a.tag == CB_T_BOOL, bb = b.tag == CB_T_BOOL;
@@ -1025,6 +1432,7 @@ struct Loop {
     uint64_t i, n;
     uint32_t any_err;
     int64_t count;
+    uint32_t out;      // collecting comprehensions (map / filter / transform*): result under construction in the arena
 };
 
 CB_HD void loop_bind(Ctx &c, const Loop &L, int var, bool two) {
@@ -1104,8 +1512,15 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
             bool two = (ib >> 8) & 1;
             if (!is_container(r)) { st[sp++] = mk_err(); pc = ic; break; }
             Loop &L = loops[ld];
-            L.range = r; L.i = 0; L.n = ldg(heap_ptr(c, r.u)); L.any_err = 0; L.count = 0;
-            if (L.n == 0) { st[sp++] = mk_bool(kind == CB_LOOP_ALL); pc = ic; break; }
+            L.range = r; L.i = 0; L.n = ldg(heap_ptr(c, r.u)); L.any_err = 0; L.count = 0; L.out = 0;
+            if (kind >= CB_LOOP_MAP) {
+                // result capacity: one element (map entry) per iteration; a list is [n, e...], a map [n, keys..., values...]
+                if (L.n > CB_SCRATCH_WORDS) { c.unsupported = 1; st[sp++] = mk_err(); pc = ic; break; }
+                const bool is_map = kind == CB_LOOP_TMAP || kind == CB_LOOP_TENTRY;
+                if (!scr_alloc(c, 1 + (uint32_t)L.n * (is_map ? 2u : 1u), &L.out)) { st[sp++] = mk_err(); pc = ic; break; }
+                c.scratch[L.out] = 0;
+                if (L.n == 0) { st[sp++] = mk_scratch(is_map ? CB_T_MAP : CB_T_LIST, L.out); pc = ic; break; }
+            } else if (L.n == 0) { st[sp++] = mk_bool(kind == CB_LOOP_ALL); pc = ic; break; }
             ld++;
             loop_bind(c, L, (int)ia, two);
             break;
@@ -1117,6 +1532,53 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
             Loop &L = loops[ld - 1];
             bool done = false;
             Val res = mk_err();
+            if (kind >= CB_LOOP_MAP) {
+                // an erroring body (or predicate) makes the whole comprehension an error; CB_T_SKIP = filtered out
+                const uint32_t cap = (uint32_t)L.n;
+                if (r.tag == CB_T_ERR) { done = true; }
+                else if (r.tag != CB_T_SKIP) {
+                    uint64_t w = 0;
+                    if (kind == CB_LOOP_MAP) {
+                        if (!encode_elem(c, r, &w)) done = true; else c.scratch[L.out + 1 + L.count++] = w;
+                    } else if (kind == CB_LOOP_FILTER) {
+                        if (r.tag != CB_T_BOOL) done = true;
+                        else if (r.u) { if (!encode_elem(c, c.vars[ia], &w)) done = true; else c.scratch[L.out + 1 + L.count++] = w; }
+                    } else if (kind == CB_LOOP_TMAP) {      // key of this iteration -> body value
+                        uint64_t kw = 0;
+                        if (!encode_elem(c, c.vars[ia], &kw) || !encode_elem(c, r, &w)) done = true;
+                        else { c.scratch[L.out + 1 + L.count] = kw; c.scratch[L.out + 1 + cap + L.count] = w; L.count++; }
+                    } else {                                // transformMapEntry: the body yields a map whose entries are merged
+                        if (r.tag != CB_T_MAP) done = true;
+                        else {
+                            const uint64_t *mp = heap_ptr(c, r.u);
+                            const uint64_t mn = ldg(mp);
+                            for (uint64_t q = 0; q < mn && !done; q++) {
+                                const uint64_t kw = ldg(mp + 1 + q), vw = ldg(mp + 1 + mn + q);
+                                Val mv = mk_scratch(CB_T_MAP, L.out);
+                                // look the key up among the entries merged so far (values sit `cap` words behind the keys)
+                                bool dup = false;
+                                for (int64_t z = 0; z < L.count && !dup; z++) dup = scalar_equal(c, decode_elem(c.scratch[L.out + 1 + z]), decode_elem(kw));
+                                (void)mv;
+                                if (dup) done = true;                                   // "insert failed: key already exists"
+                                else if ((uint64_t)L.count >= cap) { c.unsupported = 1; done = true; }
+                                else { c.scratch[L.out + 1 + L.count] = kw; c.scratch[L.out + 1 + cap + L.count] = vw; L.count++; }
+                            }
+                        }
+                    }
+                }
+                const bool failed = done;
+                L.i++;
+                if (!failed && L.i >= L.n) {
+                    done = true;
+                    const bool is_map = kind == CB_LOOP_TMAP || kind == CB_LOOP_TENTRY;
+                    if (is_map) for (int64_t z = 0; z < L.count; z++) c.scratch[L.out + 1 + L.count + z] = c.scratch[L.out + 1 + cap + z];   // values right behind the keys
+                    c.scratch[L.out] = (uint64_t)L.count;
+                    res = mk_scratch(is_map ? CB_T_MAP : CB_T_LIST, L.out);
+                }
+                if (done) { ld--; st[sp++] = res; }
+                else { loop_bind(c, L, (int)ia, two); pc = ic; }
+                break;
+            }
             if (kind == CB_LOOP_EXISTS_ONE) {
                 if (r.tag != CB_T_BOOL) L.any_err = 1; else if (r.u) L.count++;
             } else {
@@ -1216,6 +1678,41 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
                 const uint32_t k = hier_ca_size(a, b2);
                 st[sp - 1] = mk_bool(hier_count(z) == k && hier_common(a, z, k) == k);
             }
+            break;
+        }
+        case CB_OP_FN: {   // ia = function, ib = argument count
+            sp -= (int)ib - 1;
+            if (ia == CB_FN_REVERSE && st[sp - 1].tag == CB_T_STRING) st[sp - 1] = dyn_strfn(c, CB_FN_STR_REVERSE, &st[sp - 1], ib);
+            else st[sp - 1] = ia >= CB_FN_EXCEPT ? dyn_listfn(c, ia, &st[sp - 1], ib) : dyn_strfn(c, ia, &st[sp - 1], ib);
+            break;
+        }
+        case CB_OP_MKLIST: {   // ic elements on the stack -> list
+            sp -= (int)ic;
+            uint32_t off;
+            bool ok = list_new(c, ic, &off);
+            for (uint32_t q = 0; q < ic && ok; q++) ok = st[sp + q].tag != CB_T_ERR && encode_elem(c, st[sp + q], &c.scratch[off + 1 + q]);
+            st[sp++] = ok ? mk_scratch(CB_T_LIST, off) : mk_err();
+            break;
+        }
+        case CB_OP_MKMAP: {    // ic (key, value) pairs on the stack -> map; keys: string / int / double / bool
+            sp -= 2 * (int)ic;
+            uint32_t off;
+            bool ok = scr_alloc(c, 1 + 2 * ic, &off);
+            if (ok) c.scratch[off] = ic;
+            for (uint32_t q = 0; q < ic && ok; q++) {
+                const Val k = st[sp + 2 * q], v = st[sp + 2 * q + 1];
+                ok = k.tag != CB_T_ERR && v.tag != CB_T_ERR && !is_container(k) && k.tag != CB_T_NULL &&
+                     encode_elem(c, k, &c.scratch[off + 1 + q]) && encode_elem(c, v, &c.scratch[off + 1 + ic + q]);
+                for (uint32_t z = 0; z < q && ok; z++) ok = !scalar_equal(c, decode_elem(c.scratch[off + 1 + z]), k);   // repeated key: error
+            }
+            st[sp++] = ok ? mk_scratch(CB_T_MAP, off) : mk_err();
+            break;
+        }
+        case CB_OP_LOOP_PRED: {   // predicate of a filtering map / transform*: false -> this iteration is skipped
+            const Val v = st[sp - 1];
+            if (v.tag != CB_T_BOOL) { st[sp - 1] = mk_err(); pc = ic; }
+            else if (!v.u) { st[sp - 1] = mk(CB_T_SKIP, 0); pc = ic; }
+            else sp--;
             break;
         }
         default: c.unsupported = 1; return false;
@@ -1321,7 +1818,7 @@ CB_HD bool role_in_pr(const TableView t, uint32_t role, uint32_t req_role, uint3
 CB_HD_NOINLINE uint32_t cond_sat(const uint8_t *base, const TableLayout *L, const BatchView *b, uint64_t req, uint32_t pid, uint32_t gid) {
     TableView t; t.base = base; t.L = L;
     Ctx c;
-    c.t = &t; c.b = b; c.req = req; c.pid = pid; c.unsupported = 0;
+    c.t = &t; c.b = b; c.req = req; c.pid = pid; c.unsupported = 0; c.scr_used = 0;
     bool s = run_program(c, t.code() + ldg(&t.conds()[gid].code_off));
     return (s ? 1u : 0u) | (c.unsupported ? 2u : 0u);
 }
@@ -1330,7 +1827,7 @@ CB_HD_NOINLINE uint32_t cond_sat(const uint8_t *base, const TableLayout *L, cons
 CB_HD_NOINLINE uint32_t cond_sat_code(const uint8_t *base, const TableLayout *L, const BatchView *b, uint64_t req, uint32_t pid, uint32_t code_off) {
     TableView t; t.base = base; t.L = L;
     Ctx c;
-    c.t = &t; c.b = b; c.req = req; c.pid = pid; c.unsupported = 0;
+    c.t = &t; c.b = b; c.req = req; c.pid = pid; c.unsupported = 0; c.scr_used = 0;
     bool s = run_program(c, t.code() + code_off);
     return (s ? 1u : 0u) | (c.unsupported ? 2u : 0u);
 }

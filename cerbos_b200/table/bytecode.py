@@ -156,9 +156,12 @@ class TableBuilderCtx:
     def heap_map(self, d: dict, native_ints: bool) -> int:
         keys, vals = [], []
         for k, v in d.items():
-            if not isinstance(k, str):
-                raise Unsupported("non-string key in constant map")
-            keys.append(box(L.V64_STRING, self.strings.intern(k)))
+            if isinstance(k, str):
+                keys.append(box(L.V64_STRING, self.strings.intern(k)))
+            elif isinstance(k, (bool, int, float)) and not isinstance(k, UInt) and native_ints:
+                keys.append(self.v64_of(k, True))       # CEL map literal with bool / int / double keys
+            else:
+                raise Unsupported("map key that is not a string, int, double or bool")
             vals.append(self.v64_of(v, native_ints))
         return self._heap_put([len(keys)] + keys + vals)
 
@@ -366,13 +369,32 @@ class ProgramCompiler:
             return self._select(n)
         if isinstance(n, Call):
             return self._call(n)
-        if isinstance(n, ListLit):
-            return self._const_literal(n)
-        if isinstance(n, MapLit):
-            return self._const_literal(n)
+        if isinstance(n, (ListLit, MapLit)):
+            try:
+                value = self._literal_value(n)
+            except Unsupported:
+                return self._dynamic_literal(n)
+            self.push_const(self.ctx.const_from_py(value, native_ints=True))
+            return
         if isinstance(n, Macro):
             return self._macro(n)
         raise Unsupported(f"node {type(n).__name__}")
+
+    def _dynamic_literal(self, n: Node):
+        """[e0, e1 ...] / {k0: v0 ...} with elements computed at run time: built in the device's scratch arena."""
+        if isinstance(n, ListLit):
+            if len(n.elems) > 12:
+                raise Unsupported("list literal with more than 12 run-time elements")
+            for e in n.elems:
+                self.expr(e)
+            self.emit("MKLIST", c=len(n.elems), delta=1 - len(n.elems))
+            return
+        if len(n.entries) > 6:
+            raise Unsupported("map literal with more than 6 run-time entries")
+        for k, v in n.entries:
+            self.expr(k)
+            self.expr(v)
+        self.emit("MKMAP", c=len(n.entries), delta=1 - 2 * len(n.entries))
 
     def _literal_value(self, n: Node):
         if isinstance(n, Const):
@@ -385,8 +407,8 @@ class ProgramCompiler:
             out = {}
             for k, v in n.entries:
                 kv = self._literal_value(k)
-                if not isinstance(kv, str):
-                    raise Unsupported("non-string key in map literal")
+                if not isinstance(kv, (str, bool, int, float)) or isinstance(kv, UInt):
+                    raise Unsupported("map literal key that is not a string, int, double or bool")
                 if kv in out:
                     raise Unsupported("repeated key in map literal")
                 out[kv] = self._literal_value(v)
@@ -396,8 +418,6 @@ class ProgramCompiler:
             return st.value
         raise Unsupported("list / map literal with non-constant elements")
 
-    def _const_literal(self, n: Node):
-        self.push_const(self.ctx.const_from_py(self._literal_value(n), native_ints=True))
 
     def _var_inline(self, name: str):
         if name not in self.var_defs:
@@ -567,6 +587,18 @@ class ProgramCompiler:
             self.patch(t, "b", end)
             self.patch(j, "c", end)
             return
+        if fn == "@hier_join" and len(args) == 1:
+            self.expr(args[0])
+            self.emit("FN", a=L.FNS["HIER_JOIN"], b=1)
+            return
+        if fn == "_[_]" and len(args) == 2:
+            h = self._hier(args[0])
+            if h:       # hierarchy(..)[i]: the i-th part
+                self.expr(h[0])
+                self.expr(args[1])
+                self.emit("CONST", c=self.ctx.const_index(ConstVal(T["STRING"], h[1])), delta=1)
+                self.emit("FN", a=L.FNS["HIER_AT"], b=3, delta=-2)
+                return
         if self._hier_call(fn, args):
             return
         if fn == "@in" and len(args) == 2 and isinstance(args[1], Call) and args[1].fn == "split" and args[1].target is not None \
@@ -586,9 +618,6 @@ class ProgramCompiler:
                 return self._push_static(st)
             if len(args) == 2 and self._try_fused(fn, args[0], args[1]):
                 return
-        if fn == "_+_" and any(isinstance(a, ListLit) or (isinstance(a, Const) and isinstance(a.value, str))
-                               for a in args):
-            raise Unsupported("string / list concatenation (needs device-side allocation)")
         if fn in self._BIN and len(args) == 2:
             self.expr(args[0])
             self.expr(args[1])
@@ -676,7 +705,20 @@ class ProgramCompiler:
             self.expr(args[0])
             self.emit("SUB", delta=-1)
             return
+        if fn in self._FN and len(args) in self._FN[fn][1]:
+            # string / list producing functions (ext.Strings, ext.Lists, Cerbos except / intersect): results live in the
+            # device's per-thread scratch arena
+            for a in args:
+                self.expr(a)
+            self.emit("FN", a=L.FNS[self._FN[fn][0]], b=len(args), delta=1 - len(args))
+            return
         raise Unsupported(f"function `{fn}` with {len(args)} argument(s)")
+
+    _FN = {"lowerAscii": ("LOWER", (1,)), "upperAscii": ("UPPER", (1,)), "trim": ("TRIM", (1,)), "charAt": ("CHARAT", (2,)),
+           "indexOf": ("INDEXOF", (2, 3)), "lastIndexOf": ("LASTINDEXOF", (2, 3)), "substring": ("SUBSTRING", (2, 3)),
+           "replace": ("REPLACE", (3, 4)), "split": ("SPLIT", (2, 3)), "join": ("JOIN", (1, 2)), "reverse": ("REVERSE", (1,)),
+           "except": ("EXCEPT", (2,)), "intersect": ("INTERSECT", (2,)), "sort": ("SORT", (1,)), "slice": ("SLICE", (3,)),
+           "flatten": ("FLATTEN", (1, 2)), "distinct": ("DISTINCT", (1,)), "lists.range": ("RANGE", (1,))}
 
     # ---- hierarchy(s[, delim]) (conditions/types/hierarchy.go): never a run-time value -- the functions over
     # hierarchies compile to fused ops on the underlying strings
@@ -690,8 +732,17 @@ class ProgramCompiler:
             if not (isinstance(d, Const) and isinstance(d.value, str) and d.value):
                 raise Unsupported("hierarchy() with a non-constant or empty delimiter")
             delim = d.value
-        if isinstance(n.args[0], (ListLit, MapLit)):
-            raise Unsupported("hierarchy() of a list")
+        if isinstance(n.args[0], MapLit):
+            raise Unsupported("hierarchy() of a map")
+        if isinstance(n.args[0], ListLit) or (isinstance(n.args[0], Macro) and n.args[0].name in ("map", "filter", "transformList")) or \
+                (isinstance(n.args[0], Call) and n.args[0].fn in ("split", "except", "intersect", "sort", "slice", "flatten", "distinct")):
+            # hierarchy(list of strings): the parts themselves -- joined on the device by U+001F, the delimiter the fused ops then split on
+            if len(n.args) == 2:
+                raise Unsupported("hierarchy(list, delimiter)")
+            did = self.ctx.strings.intern("\x1f")
+            if did > 0xFFFF:
+                raise Unsupported("too many table strings for a hierarchy delimiter")
+            return Call("@hier_join", None, [n.args[0]]), did
         did = self.ctx.strings.intern(delim)
         if did > 0xFFFF:
             raise Unsupported("too many table strings for a hierarchy delimiter")
@@ -750,7 +801,10 @@ class ProgramCompiler:
 
     def _macro(self, n: Macro):
         kinds = {"all": (L.LOOP_ALL, 1), "exists": (L.LOOP_EXISTS, 1), "exists_one": (L.LOOP_EXISTS_ONE, 1),
-                 "all2": (L.LOOP_ALL, 2), "exists2": (L.LOOP_EXISTS, 2), "exists_one2": (L.LOOP_EXISTS_ONE, 2)}
+                 "all2": (L.LOOP_ALL, 2), "exists2": (L.LOOP_EXISTS, 2), "exists_one2": (L.LOOP_EXISTS_ONE, 2),
+                 # collecting comprehensions: the result is built in the device's scratch arena
+                 "map": (L.LOOP_MAP, 1), "filter": (L.LOOP_FILTER, 1), "transformList": (L.LOOP_MAP, 2),
+                 "transformMap": (L.LOOP_TMAP, 2), "transformMapEntry": (L.LOOP_TENTRY, 2)}
         if n.name not in kinds:
             raise Unsupported(f"macro `{n.name}`")
         kind, nv = kinds[n.name]
@@ -765,8 +819,14 @@ class ProgramCompiler:
         frame = {n.vars[0]: base} if nv == 1 else {n.vars[0]: base, n.vars[1]: base + 1}
         self.loop_vars.append(frame)
         body = self.here()
-        self.expr(n.args[0])
-        self.emit("LOOP_NEXT", a=base, b=kind | (0x100 if nv == 2 else 0), c=body, delta=-1)
+        pred = None
+        if len(n.args) == 2:          # map(x, pred, f) / transform*(k, v, pred, f): iterations whose predicate is false are skipped
+            self.expr(n.args[0])
+            pred = self.emit("LOOP_PRED", delta=-1)
+        self.expr(n.args[-1])
+        nxt = self.emit("LOOP_NEXT", a=base, b=kind | (0x100 if nv == 2 else 0), c=body, delta=-1)
+        if pred is not None:
+            self.patch(pred, "c", nxt)
         self.loop_vars.pop()
         self.sp += 1  # loop result
         self.patch(init, "c", self.here())

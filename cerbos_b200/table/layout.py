@@ -12,7 +12,7 @@ Table blob (little endian, every section 16-byte aligned):
 from __future__ import annotations
 
 MAGIC = 0x32425243  # 'CRB2'
-VERSION = 12
+VERSION = 13
 ALIGN = 16
 
 NONE32 = 0xFFFFFFFF
@@ -140,6 +140,19 @@ OPS = {name: i for i, name in enumerate([
     "IN_SPLIT",         # [x, s] -> BOOL(x in s.split(delim b)): the token list never materialises (ext strings split)
     "TS_GET",           # TOS timestamp / duration -> INT: a = TS_FIELDS getter (0xFF: always an error), c = fixed offset east of UTC
                         # in seconds (int32), b = 1 when a zone argument was given (then a duration operand is an error)
+    # values made at run time (per-thread scratch arena on the device)
+    "FN",               # a = FN id, b = argument count n: [arg0 .. argn-1] -> result (string / list functions below)
+    "MKLIST",           # c = n: [e0 .. en-1] -> list
+    "MKMAP",            # c = n: [k0, v0 .. kn-1, vn-1] -> map
+    "LOOP_PRED",        # TOS = predicate of a filtering map / transformList / transformMap / transformMapEntry: true -> pop and
+                        # fall through to the transform; false -> skip this iteration; else error. c = pc of the LOOP_NEXT
+])}
+# FN ids: string functions first (cel-go ext.Strings), list functions from EXCEPT on (ext.Lists, Cerbos except / intersect)
+FNS = {name: i for i, name in enumerate([
+    "LOWER", "UPPER", "TRIM", "STR_REVERSE", "CHARAT", "INDEXOF", "LASTINDEXOF", "SUBSTRING", "REPLACE", "SPLIT", "JOIN",
+    "HIER_JOIN",        # hierarchy(list of strings): the parts joined by U+001F (the delimiter the fused hierarchy ops then use)
+    "HIER_AT",          # [s, i, delim]: hierarchy(s, delim)[i]
+    "EXCEPT", "INTERSECT", "SORT", "REVERSE", "SLICE", "FLATTEN", "DISTINCT", "RANGE",
 ])}
 TS_FIELDS = {name: i for i, name in enumerate(["getFullYear", "getMonth", "getDayOfYear", "getDayOfMonth", "getDate", "getDayOfWeek",
                                                "getHours", "getMinutes", "getSeconds", "getMilliseconds"])}
@@ -167,6 +180,10 @@ FLAT_MAX_TERMS = 24
 LOOP_ALL = 0
 LOOP_EXISTS = 1
 LOOP_EXISTS_ONE = 2
+LOOP_MAP = 3          # collecting comprehensions: kinds >= LOOP_MAP build a list / map in the scratch arena
+LOOP_FILTER = 4
+LOOP_TMAP = 5         # transformMap: {key of the iteration: transform}
+LOOP_TENTRY = 6       # transformMapEntry: the transform yields a map whose entries are merged
 
 CMP_INDEX = {"_==_": 0, "_!=_": 1, "_<_": 2, "_<=_": 3, "_>_": 4, "_>=_": 5}
 
@@ -248,6 +265,12 @@ def c_header() -> str:
     d("CB_LOOP_ALL", LOOP_ALL)
     d("CB_LOOP_EXISTS", LOOP_EXISTS)
     d("CB_LOOP_EXISTS_ONE", LOOP_EXISTS_ONE)
+    d("CB_LOOP_MAP", LOOP_MAP)
+    d("CB_LOOP_FILTER", LOOP_FILTER)
+    d("CB_LOOP_TMAP", LOOP_TMAP)
+    d("CB_LOOP_TENTRY", LOOP_TENTRY)
+    for k, v in FNS.items():
+        d(f"CB_FN_{k}", v)
     d("CB_MAX_STACK", MAX_STACK)
     d("CB_MAX_LOOP_DEPTH", MAX_LOOP_DEPTH)
     d("CB_MAX_VARS", MAX_VARS)

@@ -860,6 +860,7 @@ static val_t run_program(ectx_t *c, const cb_instr *code, int64_t now) {
         case CB_OP_LOOP_INIT: {
             val_t r = st[--sp];
             int kind = in.b & 0xFF, two = (in.b >> 8) & 1;
+            if (kind > CB_LOOP_EXISTS_ONE) { c->unsupported = 1; return mk_err(); }   /* collecting comprehensions (map / filter / transform*): not in this port */
             if (r.tag != CB_T_LIST && r.tag != CB_T_MAP) { st[sp++] = mk_err(); pc = in.c; break; }
             loop_t *L = &loops[ld];
             L->range = r; L->i = 0; L->n = heap_ptr(c, r.u)[0]; L->any_err = 0; L->count = 0;

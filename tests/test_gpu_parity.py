@@ -497,3 +497,41 @@ def test_cgpu_check_is_reentrant_across_threads():
         c.close()
     finally:
         os.environ.pop("CERBOS_B200_CHECK_CHUNK", None)
+
+
+def test_run_time_values_on_gpu(ctx):
+    """The list / string producing functions, collecting comprehensions, dynamic literals and hierarchy(list) on the
+    device (per-thread scratch arena of the general kernel) against oracle #1 -- same cases as the CPU test of the
+    kernel core -- plus every golden CEL leaf that builds values at run time."""
+    from cerbos_b200.encode import Encoder
+    from oracle.check import CheckOracle
+    from oracle.celeval import parse_timestamp
+    from test_table_oracles import RUN_TIME_VALUE_CASES, RUN_TIME_VALUE_REQUEST, run_time_value_table, _cel_cases
+    from cerbos_b200.table.bytecode import Unsupported
+    now = parse_timestamp("2021-04-22T10:05:20.021-05:00")
+    os.environ["CERBOS_B200_NO_JIT"] = "1"   # one table per expression: skip the background NVRTC compile
+    try:
+        cases = [(e, RUN_TIME_VALUE_REQUEST) for e in RUN_TIME_VALUE_CASES]
+        for f, e, req in _cel_cases():
+            if any(k in e for k in ("except", "intersect", "sort", "transform", ".map(", ".filter(", "split", "replace", "substring", "charAt", "indexOf",
+                                    "Ascii", "trim", "reverse", "slice", "flatten", "lists.range", "hierarchy([", ")[", " + ")):
+                inp = {"principal": dict(req.get("principal") or {}), "resource": dict(req.get("resource") or {}), "actions": ["a"]}
+                inp["resource"]["kind"] = "leave_request"
+                inp["principal"].setdefault("roles", ["r"])
+                cases.append((e, inp))
+        n = 0
+        for e, inp in cases:
+            try:
+                rt, ft = run_time_value_table(e)
+            except Unsupported:
+                continue
+            b = Encoder(ft.manifest).encode([inp])
+            want = CheckOracle(rt).check(inp, now)["actions"]["a"]["effect"]
+            t = ctx.load_table(ft.blob)
+            got = t.check(b.columns, b.n, b.max_actions, now.ns)
+            assert got[0, 0] == want, e
+            t.release()
+            n += 1
+        assert n >= 80, n
+    finally:
+        os.environ.pop("CERBOS_B200_NO_JIT", None)

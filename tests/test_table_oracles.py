@@ -83,7 +83,7 @@ def test_bytecode_vs_cel_oracle_on_golden_expressions():
     """Every golden CEL leaf that lowers to bytecode must evaluate like oracle #1 (the rest must be
     rejected at table build -- never silently diverge)."""
     now = parse_timestamp("2021-04-22T10:05:20.021-05:00")
-    lowered = 0
+    lowered = run_time_values = 0
     for f, e, req in _cel_cases():
         inp = {"principal": dict(req.get("principal") or {}), "resource": dict(req.get("resource") or {}), "actions": ["a"]}
         if "auxData" in req:
@@ -102,9 +102,60 @@ def test_bytecode_vs_cel_oracle_on_golden_expressions():
         lowered += 1
         b = Encoder(ft.manifest).encode([inp])
         want = CheckOracle(rt).check(inp, now)["actions"]["a"]["effect"]
-        assert cref.check(ft.blob, b.columns, 1, 1, now.ns)[0, 0] == want, (f, e)
         assert hostsim.check(ft.blob, b.columns, 1, 1, now.ns)[0, 0] == want, (f, e)
-    assert lowered >= 138
+        try:
+            c_out = cref.check(ft.blob, b.columns, 1, 1, now.ns)[0, 0]
+        except RuntimeError as x:
+            # oracle #2 does not port the functions that build lists / strings at run time (it flags them): those
+            # expressions are pinned by oracle #1 (which the reference goldens pin) against the kernel core only
+            assert "-2" in str(x), (f, e, x)
+            run_time_values += 1
+            continue
+        assert c_out == want, (f, e)
+    assert lowered >= 184 and run_time_values <= 45, (lowered, run_time_values)
+
+
+RUN_TIME_VALUE_CASES = [
+    'P.attr["1-2-3"].transformMapEntry(indexVar, valueVar, {valueVar: indexVar}) == {1: 0, 2: 1, 3: 2}', '{2.0: 5}[2] == 5',
+    'P.attr.s.trim() == "héllo wörld"', 'P.attr.s.charAt(1) == "é"', 'P.attr.s.indexOf("ö") == 7', 'P.attr.s.lastIndexOf("l") == 10',
+    'P.attr.s.substring(1, 5) == "éllo"', 'P.attr.s.upperAscii() == "HéLLO WöRLD  "', 'P.attr.s.replace("l", "L", 2) == "héLLo wörld  "',
+    'P.attr.s.replace("", "-", 3) == "-h-é-llo wörld  "', 'R.attr.csv.split(",") == ["a","b","","c"]', 'R.attr.csv.split(",", 2) == ["a","b,,c"]',
+    'R.attr.csv.split("") == ["a",",","b",",",",","c"]', 'P.attr.e.split(",") == [""]', 'R.attr.csv.split(",").join("-") == "a-b--c"',
+    'P.attr.teams.map(t, t.upperAscii()).sort() == ["COMMERCIAL","COMMUNICATIONS","DESIGN","PRODUCT"]',
+    'P.attr.teams.filter(t, t.startsWith("co")).reverse() == ["commercial","communications"]', 'P.attr.teams.except(["design"]).size() == 3',
+    'P.attr.teams.map(t, t.size() > 7, t + "!") == ["communications!", "commercial!"]', '(P.attr.teams + ["x"]).slice(3, 5) == ["commercial", "x"]',
+    'lists.range(4).map(i, i * i) == [0, 1, 4, 9]', '[[1,2],[3],[4,[5]]].flatten() == [1,2,3,4,[5]]', '[3,1,2,3].distinct().sort() == [1,2,3]',
+    'hierarchy(R.attr.csv.split(",").filter(x, x != "")).ancestorOf(hierarchy("a.b.c.d"))', 'hierarchy("a:b:c", ":")[2] == "c"',
+    'hierarchy(P.attr.department)[0] == "marketing"', 'hierarchy(P.attr.department)[1] == "x"', 'P.attr.s.reverse() == "  dlröw olléh"',
+    'P.attr.teams.transformMap(i, t, i % 2 == 0, t.charAt(0)) == {0: "d", 2: "p"}', '"abc".lastIndexOf("") == 3', '"abc".indexOf("c", 3) == -1',
+    'P.attr.teams.exists(t, t.lowerAscii() == "DESIGN".lowerAscii())', 'intersect(P.attr.teams, ["product","x","design","q","z"]) == ["design","product"]',
+    'P.attr.s.charAt(99) == "x"', '[1, "a"].sort() == []', 'P.attr.teams.map(t, t.nope)  == []', '[P.id, R.attr.owner] == ["john", "john"]',
+    '{P.id: R.attr.csv}.john == "a,b,,c"', '{P.id: 1, R.attr.owner: 2} == {}', 'P.attr.teams.transformList(i, t, t.size() + i).sort() == [6, 9, 12, 15]',
+    '"a,b".split(",", 0) == []', 'P.attr.teams.join() == "designcommunicationsproductcommercial"', '[1, 2].join(",") == "1,2"',
+    'hierarchy(["a", "b"]) == hierarchy("a.b")', 'hierarchy(["a.b", "c"]) == hierarchy("a.b.c")', 'hierarchy(["a", "b"]).siblingOf(hierarchy("a:c", ":"))',
+]
+RUN_TIME_VALUE_REQUEST = {"principal": {"attr": {"1-2-3": [1, 2, 3], "department": "marketing", "teams": ["design", "communications", "product", "commercial"],
+                                                 "s": "héllo wörld  ", "e": ""}, "id": "john", "roles": ["employee"]},
+                          "resource": {"attr": {"owner": "john", "csv": "a,b,,c"}, "id": "test", "kind": "leave_request"}, "actions": ["a"]}
+
+
+def run_time_value_table(e):
+    pol = {"apiVersion": "api.cerbos.dev/v1", "resourcePolicy": {"resource": "leave_request", "version": "default",
+           "rules": [{"actions": ["a"], "effect": "EFFECT_ALLOW", "roles": ["*"], "condition": {"match": {"expr": e}}}]}}
+    rt = build_rule_table([pol])
+    return rt, flatten(rt)
+
+
+def test_run_time_values_vs_cel_oracle():
+    """List / string producing functions, collecting comprehensions, dynamic literals, concatenation, hierarchy(list) and
+    hierarchy[i] (device scratch arena; cerbos_lib.go:287, 433, cel-go ext.Strings / ext.Lists): the kernel core must
+    evaluate every case like oracle #1, including the error cases (index out of range, mixed-type sort, missing field)."""
+    now = parse_timestamp("2021-04-22T10:05:20.021-05:00")
+    for e in RUN_TIME_VALUE_CASES:
+        rt, ft = run_time_value_table(e)
+        b = Encoder(ft.manifest).encode([RUN_TIME_VALUE_REQUEST])
+        want = CheckOracle(rt).check(RUN_TIME_VALUE_REQUEST, now)["actions"]["a"]["effect"]
+        assert hostsim.check(ft.blob, b.columns, 1, 1, now.ns)[0, 0] == want, e
 
 
 @pytest.mark.parametrize("cls,n", [(W.C1, 1024), (W.C2, 1 << 14), (W.C3, 1 << 12)])
