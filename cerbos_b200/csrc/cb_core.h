@@ -341,7 +341,7 @@ CB_HD bool scalar_equal(const Ctx &c, const Val &a, const Val &b) {
     if (is_num(a) && is_num(b)) return num_cmp(a, b) == 0;
     if (a.tag != b.tag) return false;
     if (a.tag == CB_T_NULL) return true;
-    if (a.tag == CB_T_STRING) return str_equal(c, a.u, b.u);
+    if (a.tag == CB_T_STRING || a.tag == CB_T_BYTES) return str_equal(c, a.u, b.u);
     return a.u == b.u;  // BOOL / TS / DUR
 }
 CB_HD bool is_container(const Val &v) { return v.tag == CB_T_LIST || v.tag == CB_T_MAP; }
@@ -1166,6 +1166,46 @@ CB_HD_NOINLINE Val dyn_strfn(Ctx &c, uint32_t fn, const Val *a, uint32_t argc) {
         }
         return strb_end(s);
     }
+    if (fn == CB_FN_TO_BYTES) return (a[0].tag == CB_T_STRING || a[0].tag == CB_T_BYTES) ? mk(CB_T_BYTES, a[0].u) : mk_err();
+    if (fn == CB_FN_B64ENC) {
+        if (a[0].tag != CB_T_BYTES) return mk_err();
+        const uint8_t *q; uint32_t m;
+        str_get(c, a[0].u, q, m);
+        const char *abc = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+        StrB s = strb_begin(c);
+        for (uint32_t i = 0; i < m; i += 3) {
+            const uint32_t b0 = ldg(q + i), b1 = i + 1 < m ? ldg(q + i + 1) : 0, b2 = i + 2 < m ? ldg(q + i + 2) : 0;
+            strb_put(s, (uint8_t)abc[b0 >> 2]);
+            strb_put(s, (uint8_t)abc[((b0 & 3) << 4) | (b1 >> 4)]);
+            strb_put(s, i + 1 < m ? (uint8_t)abc[((b1 & 15) << 2) | (b2 >> 6)] : (uint8_t)'=');
+            strb_put(s, i + 2 < m ? (uint8_t)abc[b2 & 63] : (uint8_t)'=');
+        }
+        return strb_end(s);
+    }
+    if (fn == CB_FN_B64DEC) {   // standard alphabet; the padding may be missing (cel-go tries StdEncoding, then RawStdEncoding)
+        if (a[0].tag != CB_T_STRING) return mk_err();
+        const uint8_t *q; uint32_t m;
+        str_get(c, a[0].u, q, m);
+        uint32_t body = m, pad = 0;
+        while (body > 0 && ldg(q + body - 1) == '=' && pad < 2) { body--; pad++; }
+        if (pad && (m & 3) != 0) return mk_err();
+        if ((body & 3) == 1) return mk_err();
+        if (pad && ((body + pad) & 3) != 0) return mk_err();
+        StrB s = strb_begin(c);
+        uint32_t acc = 0, bits = 0;
+        for (uint32_t i = 0; i < body; i++) {
+            const uint8_t ch = ldg(q + i);
+            uint32_t v;
+            if (ch >= 'A' && ch <= 'Z') v = ch - 'A'; else if (ch >= 'a' && ch <= 'z') v = ch - 'a' + 26;
+            else if (ch >= '0' && ch <= '9') v = ch - '0' + 52; else if (ch == '+') v = 62; else if (ch == '/') v = 63; else return mk_err();
+            acc = (acc << 6) | v; bits += 6;
+            if (bits >= 8) { bits -= 8; strb_put(s, (uint8_t)(acc >> bits)); acc &= (1u << bits) - 1; }
+        }
+        if (acc != 0) return mk_err();   // non-zero trailing bits: illegal base64 data
+        Val r = strb_end(s);
+        if (r.tag == CB_T_STRING) r.tag = CB_T_BYTES;
+        return r;
+    }
     if (a[0].tag != CB_T_STRING) return mk_err();
     const uint8_t *p; uint32_t n;
     str_get(c, a[0].u, p, n);
@@ -1487,6 +1527,7 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
         case CB_OP_SIZE: {
             Val v = st[sp - 1];
             if (v.tag == CB_T_STRING) { const uint8_t *p; uint32_t n; str_get(c, v.u, p, n); st[sp - 1] = mk_int(utf8_len(p, n)); }
+            else if (v.tag == CB_T_BYTES) { const uint8_t *p; uint32_t n; str_get(c, v.u, p, n); st[sp - 1] = mk_int(n); }
             else if (is_container(v)) st[sp - 1] = mk_int((int64_t)ldg(heap_ptr(c, v.u)));
             else st[sp - 1] = mk_err();
             break;
@@ -1516,10 +1557,11 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
             if (kind >= CB_LOOP_MAP) {
                 // result capacity: one element (map entry) per iteration; a list is [n, e...], a map [n, keys..., values...]
                 if (L.n > CB_SCRATCH_WORDS) { c.unsupported = 1; st[sp++] = mk_err(); pc = ic; break; }
-                const bool is_map = kind == CB_LOOP_TMAP || kind == CB_LOOP_TENTRY;
+                const bool is_map = kind == CB_LOOP_TMAP || kind == CB_LOOP_TENTRY || kind == CB_LOOP_SORTBY;   // sortBy: elements + their keys
+                if (kind == CB_LOOP_SORTBY && r.tag != CB_T_LIST) { st[sp++] = mk_err(); pc = ic; break; }
                 if (!scr_alloc(c, 1 + (uint32_t)L.n * (is_map ? 2u : 1u), &L.out)) { st[sp++] = mk_err(); pc = ic; break; }
                 c.scratch[L.out] = 0;
-                if (L.n == 0) { st[sp++] = mk_scratch(is_map ? CB_T_MAP : CB_T_LIST, L.out); pc = ic; break; }
+                if (L.n == 0) { st[sp++] = mk_scratch(is_map && kind != CB_LOOP_SORTBY ? CB_T_MAP : CB_T_LIST, L.out); pc = ic; break; }
             } else if (L.n == 0) { st[sp++] = mk_bool(kind == CB_LOOP_ALL); pc = ic; break; }
             ld++;
             loop_bind(c, L, (int)ia, two);
@@ -1543,6 +1585,22 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
                     } else if (kind == CB_LOOP_FILTER) {
                         if (r.tag != CB_T_BOOL) done = true;
                         else if (r.u) { if (!encode_elem(c, c.vars[ia], &w)) done = true; else c.scratch[L.out + 1 + L.count++] = w; }
+                    } else if (kind == CB_LOOP_SORTBY) {    // insert the element where its key belongs (stable): elements at [1..], keys `cap` behind
+                        uint64_t ew = 0;
+                        const uint32_t t0 = L.count ? decode_elem(c.scratch[L.out + 1 + cap]).tag : r.tag;
+                        const bool cmpable = r.tag == CB_T_INT || r.tag == CB_T_UINT || r.tag == CB_T_DOUBLE || r.tag == CB_T_BOOL || r.tag == CB_T_STRING;
+                        if (!cmpable || r.tag != t0 || !encode_elem(c, c.vars[ia], &ew) || !encode_elem(c, r, &w)) done = true;
+                        else {
+                            int64_t j = L.count;
+                            while (j > 0 && val_order(c, decode_elem(c.scratch[L.out + cap + j]), r) > 0 && val_order(c, decode_elem(c.scratch[L.out + cap + j]), r) != 3) {
+                                c.scratch[L.out + 1 + j] = c.scratch[L.out + j];
+                                c.scratch[L.out + 1 + cap + j] = c.scratch[L.out + cap + j];
+                                j--;
+                            }
+                            c.scratch[L.out + 1 + j] = ew;
+                            c.scratch[L.out + 1 + cap + j] = w;
+                            L.count++;
+                        }
                     } else if (kind == CB_LOOP_TMAP) {      // key of this iteration -> body value
                         uint64_t kw = 0;
                         if (!encode_elem(c, c.vars[ia], &kw) || !encode_elem(c, r, &w)) done = true;
@@ -1570,7 +1628,7 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
                 L.i++;
                 if (!failed && L.i >= L.n) {
                     done = true;
-                    const bool is_map = kind == CB_LOOP_TMAP || kind == CB_LOOP_TENTRY;
+                    const bool is_map = kind == CB_LOOP_TMAP || kind == CB_LOOP_TENTRY;   // (sortBy: the keys behind the elements are simply dropped)
                     if (is_map) for (int64_t z = 0; z < L.count; z++) c.scratch[L.out + 1 + L.count + z] = c.scratch[L.out + 1 + cap + z];   // values right behind the keys
                     c.scratch[L.out] = (uint64_t)L.count;
                     res = mk_scratch(is_map ? CB_T_MAP : CB_T_LIST, L.out);
@@ -1649,7 +1707,21 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
             st[sp - 1] = ok ? mk_bool(hier_rel(ia, hier_it(c, st[sp - 1].u, ib), hier_it(c, st[sp].u, ic))) : mk_err();
             break;
         }
-        case CB_OP_TS_GET: st[sp - 1] = do_ts_get(ia, st[sp - 1], ib, (int32_t)ic); break;
+        case CB_OP_TS_GET: {
+            int32_t off_s = (int32_t)ic;
+            if (ib == 2 && st[sp - 1].tag == CB_T_TS) {
+                // IANA zone: the offset in force at this instant, from the zone's transition table (bytecode.iana_zone_words)
+                const uint64_t *z = c.t->theap() + ic;
+                const int64_t sec = floor_div((int64_t)st[sp - 1].u, 1000000000ll);
+                const uint64_t nz = ldg(z);
+                if (sec < (int64_t)ldg(z + 1) || sec >= (int64_t)ldg(z + 2)) { c.unsupported = 1; st[sp - 1] = mk_err(); break; }
+                uint64_t lo = 0, hi = nz;          // last entry whose start <= sec
+                while (hi - lo > 1) { const uint64_t mid = (lo + hi) / 2; if ((int64_t)ldg(z + 3 + 2 * mid) <= sec) lo = mid; else hi = mid; }
+                off_s = (int32_t)(int64_t)ldg(z + 3 + 2 * lo + 1);
+            }
+            st[sp - 1] = do_ts_get(ia, st[sp - 1], ib, off_s);
+            break;
+        }
         case CB_OP_IN_SPLIT: {   // [x, s]: x in s.split(delim ib)
             sp--;
             const Val x = st[sp - 1], sv = st[sp];
@@ -1706,6 +1778,25 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
                 for (uint32_t z = 0; z < q && ok; z++) ok = !scalar_equal(c, decode_elem(c.scratch[off + 1 + z]), k);   // repeated key: error
             }
             st[sp++] = ok ? mk_scratch(CB_T_MAP, off) : mk_err();
+            break;
+        }
+        case CB_OP_MATCHES: {   // RE2 search by the DFA table at theap[ic]: text = BOT, bytes, EOT (cel/regex_dfa.py)
+            const Val v = st[sp - 1];
+            if (v.tag != CB_T_STRING) { st[sp - 1] = mk_err(); break; }
+            const uint64_t *d = c.t->theap() + ic;
+            const uint64_t h = ldg(d);
+            const uint32_t ns = (uint32_t)(h & 0xFFFF), nc = (uint32_t)((h >> 16) & 0xFFFF);
+            uint32_t state = (uint32_t)(h >> 32) & 0xFFFF;
+            const uint8_t *cm = reinterpret_cast<const uint8_t *>(d + 1);
+            const uint64_t *acc = d + 1 + 33, *tr = acc + (ns + 63) / 64;
+            const uint8_t *p; uint32_t n;
+            str_get(c, v.u, p, n);
+            for (uint32_t i = 0; i < n + 2; i++) {
+                const uint32_t sym = i == 0 ? 256u : i == n + 1 ? 257u : (uint32_t)ldg(p + i - 1);
+                const uint32_t q = state * nc + ldg(cm + sym);
+                state = (uint32_t)(ldg(tr + (q >> 2)) >> (16 * (q & 3))) & 0xFFFFu;
+            }
+            st[sp - 1] = mk_bool((ldg(acc + (state >> 6)) >> (state & 63)) & 1);
             break;
         }
         case CB_OP_LOOP_PRED: {   // predicate of a filtering map / transform*: false -> this iteration is skipped

@@ -191,6 +191,74 @@ class TableBuilderCtx:
         raise Unsupported(f"constant of type {type(v).__name__}")
 
 
+_ZONE_CACHE: dict = {}
+
+
+def iana_zone_words(name: str):
+    """Transition table of an IANA zone for the device: [n, first covered second, last covered second, then n pairs
+    (UTC second from which the offset applies, offset east of UTC in seconds as two's complement)].  Built from the host's
+    tz database (zoneinfo; Go's time.LoadLocation reads the same data); None for an unknown zone.  Instants outside
+    1900-01-01 .. 2100-01-01 are not covered (the device then fails the call loudly)."""
+    if name in _ZONE_CACHE:
+        return _ZONE_CACHE[name]
+    import datetime as _dt
+    import zoneinfo
+    zi = None
+    cand = name
+    for _ in range(3):
+        try:
+            zi = zoneinfo.ZoneInfo(cand)
+            break
+        except Exception:  # noqa: BLE001 -- backward-compatible link names live in tzdata.zi on some hosts
+            link = None
+            try:
+                with open("/usr/share/zoneinfo/tzdata.zi", encoding="utf-8") as f:
+                    for ln in f:
+                        parts = ln.split()
+                        if len(parts) == 3 and parts[0] == "L" and parts[2] == cand:
+                            link = parts[1]
+                            break
+            except OSError:
+                pass
+            if link is None:
+                break
+            cand = link
+    if zi is None:
+        _ZONE_CACHE[name] = None
+        return None
+    utc = _dt.timezone.utc
+
+    def off(sec):
+        return int(_dt.datetime.fromtimestamp(sec, tz=utc).astimezone(zi).utcoffset().total_seconds())
+
+    lo = int(_dt.datetime(1900, 1, 1, tzinfo=utc).timestamp())
+    hi = int(_dt.datetime(2100, 1, 1, tzinfo=utc).timestamp())
+    pairs = [(lo, off(lo))]
+    t, cur = lo, pairs[0][1]
+    step = 86400
+    while t < hi:
+        nt = min(t + step, hi)
+        o = off(nt)
+        if o != cur:
+            a, b = t, nt          # offset(a) == cur, offset(b) != cur: bisect to the first second of the new offset
+            while b - a > 1:
+                m = (a + b) // 2
+                if off(m) == cur:
+                    a = m
+                else:
+                    b = m
+            cur = off(b)
+            pairs.append((b, cur))
+            t = b
+            continue
+        t = nt
+    words = [len(pairs), lo & 0xFFFFFFFFFFFFFFFF, hi & 0xFFFFFFFFFFFFFFFF]
+    for sec, o in pairs:
+        words += [sec & 0xFFFFFFFFFFFFFFFF, o & 0xFFFFFFFFFFFFFFFF]
+    _ZONE_CACHE[name] = words
+    return words
+
+
 class _Static:
     """Result of static path analysis."""
     __slots__ = ("kind", "path", "value", "native")
@@ -350,7 +418,13 @@ class ProgramCompiler:
         if isinstance(n, Const):
             v = n.value
             if isinstance(v, bytes):
-                raise Unsupported("bytes literal")
+                try:        # the string table holds UTF-8 text: a bytes literal that is valid UTF-8 is that string, retagged
+                    text = v.decode("utf-8")
+                except UnicodeDecodeError:
+                    raise Unsupported("bytes literal that is not valid UTF-8") from None
+                self.push_const(self.ctx.const_from_py(text, native_ints=True))
+                self.emit("FN", a=L.FNS["TO_BYTES"], b=1)
+                return
             self.push_const(self.ctx.const_from_py(v, native_ints=True))
             return
         if isinstance(n, Ident):
@@ -688,7 +762,15 @@ class ProgramCompiler:
                         return
                     off = (hr * 60 - mn if tzs[0] == "-" else hr * 60 + mn) * 60
                 elif tzs not in ("UTC", ""):
-                    raise Unsupported("timestamp accessor with an IANA time zone name")
+                    # an IANA zone name: its UTC-offset transitions 1900..2100 go into the table (built from the host's tz database)
+                    words = iana_zone_words(tzs)
+                    if words is None:
+                        self.expr(args[0])          # unknown zone: a CEL error whatever the timestamp is
+                        self.emit("TS_GET", a=0xFF)
+                        return
+                    self.expr(args[0])
+                    self.emit("TS_GET", a=L.TS_FIELDS[fn], b=2, c=self.ctx._heap_put(words))
+                    return
                 tzform = 1
                 if not -(1 << 31) <= off < (1 << 31):
                     raise Unsupported("time zone offset out of range")
@@ -705,6 +787,21 @@ class ProgramCompiler:
             self.expr(args[0])
             self.emit("SUB", delta=-1)
             return
+        if fn == "matches" and len(args) == 2:
+            # RE2 search: a constant pattern becomes a byte-level DFA table at table build (cel/regex_dfa.py)
+            from ..cel.regex_dfa import RegexError, RegexUnsupported, compile_dfa, dfa_words
+            if not (isinstance(args[1], Const) and isinstance(args[1].value, str)):
+                raise Unsupported("matches() with a non-constant pattern")
+            try:
+                words = dfa_words(compile_dfa(args[1].value))
+            except RegexUnsupported as e:
+                raise Unsupported(f"regular expression: {e}") from e
+            except RegexError:
+                self.push_const(ConstVal(T["ERR"], 0))    # an invalid pattern is an error whatever the text is
+                return
+            self.expr(args[0])
+            self.emit("MATCHES", c=self.ctx._heap_put(words))
+            return
         if fn in self._FN and len(args) in self._FN[fn][1]:
             # string / list producing functions (ext.Strings, ext.Lists, Cerbos except / intersect): results live in the
             # device's per-thread scratch arena
@@ -714,7 +811,8 @@ class ProgramCompiler:
             return
         raise Unsupported(f"function `{fn}` with {len(args)} argument(s)")
 
-    _FN = {"lowerAscii": ("LOWER", (1,)), "upperAscii": ("UPPER", (1,)), "trim": ("TRIM", (1,)), "charAt": ("CHARAT", (2,)),
+    _FN = {"bytes": ("TO_BYTES", (1,)), "base64.encode": ("B64ENC", (1,)), "base64.decode": ("B64DEC", (1,)),
+           "lowerAscii": ("LOWER", (1,)), "upperAscii": ("UPPER", (1,)), "trim": ("TRIM", (1,)), "charAt": ("CHARAT", (2,)),
            "indexOf": ("INDEXOF", (2, 3)), "lastIndexOf": ("LASTINDEXOF", (2, 3)), "substring": ("SUBSTRING", (2, 3)),
            "replace": ("REPLACE", (3, 4)), "split": ("SPLIT", (2, 3)), "join": ("JOIN", (1, 2)), "reverse": ("REVERSE", (1,)),
            "except": ("EXCEPT", (2,)), "intersect": ("INTERSECT", (2,)), "sort": ("SORT", (1,)), "slice": ("SLICE", (3,)),
@@ -804,7 +902,7 @@ class ProgramCompiler:
                  "all2": (L.LOOP_ALL, 2), "exists2": (L.LOOP_EXISTS, 2), "exists_one2": (L.LOOP_EXISTS_ONE, 2),
                  # collecting comprehensions: the result is built in the device's scratch arena
                  "map": (L.LOOP_MAP, 1), "filter": (L.LOOP_FILTER, 1), "transformList": (L.LOOP_MAP, 2),
-                 "transformMap": (L.LOOP_TMAP, 2), "transformMapEntry": (L.LOOP_TENTRY, 2)}
+                 "transformMap": (L.LOOP_TMAP, 2), "transformMapEntry": (L.LOOP_TENTRY, 2), "sortBy": (L.LOOP_SORTBY, 1)}
         if n.name not in kinds:
             raise Unsupported(f"macro `{n.name}`")
         kind, nv = kinds[n.name]

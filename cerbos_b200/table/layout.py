@@ -139,19 +139,23 @@ OPS = {name: i for i, name in enumerate([
                         #        delimiters b (s), c & 0xFFFF (t), c >> 16 (z)
     "IN_SPLIT",         # [x, s] -> BOOL(x in s.split(delim b)): the token list never materialises (ext strings split)
     "TS_GET",           # TOS timestamp / duration -> INT: a = TS_FIELDS getter (0xFF: always an error), c = fixed offset east of UTC
-                        # in seconds (int32), b = 1 when a zone argument was given (then a duration operand is an error)
+                        # in seconds (int32), b = 1 when a zone argument was given (then a duration operand is an error);
+                        # b = 2: an IANA zone -- c = theap offset of its transition table [n, first, last, (utc second, offset)...]
     # values made at run time (per-thread scratch arena on the device)
     "FN",               # a = FN id, b = argument count n: [arg0 .. argn-1] -> result (string / list functions below)
     "MKLIST",           # c = n: [e0 .. en-1] -> list
     "MKMAP",            # c = n: [k0, v0 .. kn-1, vn-1] -> map
     "LOOP_PRED",        # TOS = predicate of a filtering map / transformList / transformMap / transformMapEntry: true -> pop and
                         # fall through to the transform; false -> skip this iteration; else error. c = pc of the LOOP_NEXT
+    "MATCHES",          # TOS string -> BOOL: RE2 search with the byte-level DFA at theap[c] (cel/regex_dfa.py)
 ])}
 # FN ids: string functions first (cel-go ext.Strings), list functions from EXCEPT on (ext.Lists, Cerbos except / intersect)
 FNS = {name: i for i, name in enumerate([
     "LOWER", "UPPER", "TRIM", "STR_REVERSE", "CHARAT", "INDEXOF", "LASTINDEXOF", "SUBSTRING", "REPLACE", "SPLIT", "JOIN",
     "HIER_JOIN",        # hierarchy(list of strings): the parts joined by U+001F (the delimiter the fused hierarchy ops then use)
     "HIER_AT",          # [s, i, delim]: hierarchy(s, delim)[i]
+    "TO_BYTES",         # bytes(string | bytes)
+    "B64ENC", "B64DEC", # base64.encode(bytes) -> string, base64.decode(string) -> bytes (std alphabet, padding optional)
     "EXCEPT", "INTERSECT", "SORT", "REVERSE", "SLICE", "FLATTEN", "DISTINCT", "RANGE",
 ])}
 TS_FIELDS = {name: i for i, name in enumerate(["getFullYear", "getMonth", "getDayOfYear", "getDayOfMonth", "getDate", "getDayOfWeek",
@@ -184,6 +188,7 @@ LOOP_MAP = 3          # collecting comprehensions: kinds >= LOOP_MAP build a lis
 LOOP_FILTER = 4
 LOOP_TMAP = 5         # transformMap: {key of the iteration: transform}
 LOOP_TENTRY = 6       # transformMapEntry: the transform yields a map whose entries are merged
+LOOP_SORTBY = 7       # sortBy: the elements ordered by the key the body yields (stable)
 
 CMP_INDEX = {"_==_": 0, "_!=_": 1, "_<_": 2, "_<=_": 3, "_>_": 4, "_>=_": 5}
 
@@ -269,6 +274,7 @@ def c_header() -> str:
     d("CB_LOOP_FILTER", LOOP_FILTER)
     d("CB_LOOP_TMAP", LOOP_TMAP)
     d("CB_LOOP_TENTRY", LOOP_TENTRY)
+    d("CB_LOOP_SORTBY", LOOP_SORTBY)
     for k, v in FNS.items():
         d(f"CB_FN_{k}", v)
     d("CB_MAX_STACK", MAX_STACK)

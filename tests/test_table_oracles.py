@@ -112,7 +112,7 @@ def test_bytecode_vs_cel_oracle_on_golden_expressions():
             run_time_values += 1
             continue
         assert c_out == want, (f, e)
-    assert lowered >= 184 and run_time_values <= 45, (lowered, run_time_values)
+    assert lowered >= 190 and run_time_values <= 52, (lowered, run_time_values)   # everything but the 18 SPIFFE expressions
 
 
 RUN_TIME_VALUE_CASES = [
@@ -133,10 +133,29 @@ RUN_TIME_VALUE_CASES = [
     '{P.id: R.attr.csv}.john == "a,b,,c"', '{P.id: 1, R.attr.owner: 2} == {}', 'P.attr.teams.transformList(i, t, t.size() + i).sort() == [6, 9, 12, 15]',
     '"a,b".split(",", 0) == []', 'P.attr.teams.join() == "designcommunicationsproductcommercial"', '[1, 2].join(",") == "1,2"',
     'hierarchy(["a", "b"]) == hierarchy("a.b")', 'hierarchy(["a.b", "c"]) == hierarchy("a.b.c")', 'hierarchy(["a", "b"]).siblingOf(hierarchy("a:c", ":"))',
+    # RE2 search through a DFA table built at table load (cel/regex_dfa.py)
+    'P.attr.department.matches("^[mM].*g$")', 'size(P.attr.teams.filter(t, t.matches("^comm"))) == 2', 'P.attr.s.matches("^h.llo w.rld\\\\s+$")',
+    'R.attr.csv.matches("^(\\\\w?,)+\\\\w$")', 'P.attr.e.matches("^$")', 'P.attr.teams.all(t, t.matches("^[a-z]+$"))', 'P.attr.department.matches("[")',
+    'R.attr.owner.matches("^jo(hn|e)$") && !R.attr.owner.matches("x")', 'P.attr.teams.matches("a")',
+    # bytes / base64
+    'base64.decode("aGVsbG8=") == bytes("hello")', 'base64.encode(bytes("hello")) == "aGVsbG8="', 'base64.decode(R.attr.b64) == b"hello"',
+    'base64.encode(bytes(P.attr.department)) == "bWFya2V0aW5n"', 'base64.decode("a") == b""', 'base64.decode("aGVsbG8h") == b"hello!"',
+    'size(bytes("héllo")) == 6', 'base64.decode("aGVsbG9=") == b"x"',
+    # IANA zones (transition table built from the host's tz database at table load)
+    'timestamp(R.attr.lastAccessed).getMonth("NZ") == 3', 'timestamp(R.attr.lastAccessed).getHours("NZ") == 3',
+    'timestamp(R.attr.lastAccessed).getHours("America/New_York") == 11', 'timestamp(R.attr.lastAccessed).getDayOfWeek("Asia/Kolkata") == 2',
+    'timestamp(R.attr.lastAccessed).getHours("Mars/Olympus") == 1',
+    'timestamp("2021-12-25T00:30:00Z").getDate("Europe/London") == 25 && timestamp("2021-06-25T23:30:00Z").getDate("Europe/London") == 26',
+    # sortBy
+    'P.attr.people.sortBy(e, e.score).map(e, e.name) == ["bar", "foo", "baz"]', 'P.attr.teams.sortBy(t, t.size()) == ["design", "product", "commercial", "communications"]',
+    'P.attr.teams.sortBy(t, t) == ["commercial", "communications", "design", "product"]', 'P.attr.people.sortBy(e, e.nope) == []',
 ]
 RUN_TIME_VALUE_REQUEST = {"principal": {"attr": {"1-2-3": [1, 2, 3], "department": "marketing", "teams": ["design", "communications", "product", "commercial"],
-                                                 "s": "héllo wörld  ", "e": ""}, "id": "john", "roles": ["employee"]},
-                          "resource": {"attr": {"owner": "john", "csv": "a,b,,c"}, "id": "test", "kind": "leave_request"}, "actions": ["a"]}
+                                                 "s": "héllo wörld  ", "e": "",
+                                                 "people": [{"name": "foo", "score": 0}, {"name": "bar", "score": -10}, {"name": "baz", "score": 1000}]},
+                                        "id": "john", "roles": ["employee"]},
+                          "resource": {"attr": {"owner": "john", "csv": "a,b,,c", "lastAccessed": "2021-04-20T10:00:20.021-05:00", "b64": "aGVsbG8"},
+                                       "id": "test", "kind": "leave_request"}, "actions": ["a"]}
 
 
 def run_time_value_table(e):
