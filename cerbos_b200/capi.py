@@ -15,7 +15,7 @@ N_COLUMNS = 12
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE = 0, -1, -2, -3, -4
 
 EXPORTS = [
-    "cgpu_init", "cgpu_shutdown", "cgpu_table_load", "cgpu_table_retain", "cgpu_table_release", "cgpu_check",
+    "cgpu_init", "cgpu_shutdown", "cgpu_table_load", "cgpu_table_retain", "cgpu_table_release", "cgpu_check", "cgpu_check_meta",
     "cgpu_check_device", "cgpu_sync", "cgpu_launch_count", "cgpu_table_info", "cgpu_last_kernel_config",
     "cgpu_last_cluster_config", "cgpu_profile", "cgpu_table_wait_ready", "cgpu_table_compile_check", "cgpu_peer_alloc", "cgpu_peer_open", "cgpu_peer_close",
     "cgpu_peer_free", "cgpu_peer_read", "cgpu_check_device_gather", "cgpu_gather_wait", "cgpu_last_error",
@@ -63,6 +63,8 @@ def lib():
         L.cgpu_table_release.argtypes = [ctypes.c_void_p]
         L.cgpu_check.restype = ctypes.c_int
         L.cgpu_check.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.c_void_p]
+        L.cgpu_check_meta.restype = ctypes.c_int
+        L.cgpu_check_meta.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.cgpu_check_device.restype = ctypes.c_int
         L.cgpu_check_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.c_void_p,
                                         ctypes.c_void_p]
@@ -218,6 +220,22 @@ class Table:
         out = np.empty((n, max(max_actions, 1)), dtype=np.uint8)
         _check(lib().cgpu_check(self.ctx._h, self._h, ctypes.byref(b), out.ctypes.data_as(ctypes.c_void_p)))
         return out
+
+    def check_meta(self, columns, n: int, max_actions: int, now_ns: int = 0, flags: int = 0):
+        """cgpu_check_meta: -> (effects uint8[n, K], action metadata words uint32[n, K], request metadata records
+        (cerbos_b200.meta.REQUEST_META_DTYPE)); decode with cerbos_b200.meta."""
+        from .meta import REQUEST_META_DTYPE
+        cols = [c if (isinstance(c, np.ndarray) and c.flags["C_CONTIGUOUS"]) else np.ascontiguousarray(c) for c in columns]
+        ptrs = (ctypes.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+        sizes = (ctypes.c_size_t * len(cols))(*[c.nbytes for c in cols])
+        b = _Batch(n, max_actions, now_ns, flags, ptrs, sizes, len(cols))
+        km = max(max_actions, 1)
+        eff = np.empty((n, km), dtype=np.uint8)
+        am = np.empty((n, km), dtype=np.uint32)
+        rm = np.empty(n, dtype=REQUEST_META_DTYPE)
+        _check(lib().cgpu_check_meta(self.ctx._h, self._h, ctypes.byref(b), eff.ctypes.data_as(ctypes.c_void_p),
+                                     am.ctypes.data_as(ctypes.c_void_p), rm.ctypes.data_as(ctypes.c_void_p)))
+        return eff, am, rm
 
     def check_into(self, ptrs, sizes, n, max_actions, out_ptr, now_ns=0, flags=0):
         """Zero-overhead variant for timing loops: raw host pointers in, effects written to out_ptr."""

@@ -37,13 +37,14 @@ struct alignas(16) U4 { uint32_t x, y, z, w; };
 // Section offsets + dimensions of the table image.  In the kernels this lives in the (grid-constant) kernel
 // parameters, so reading a field is a constant-bank operand and costs no register.
 struct TableLayout {
-    uint32_t off[28];   // by section id (CB_SEC_*)
+    uint32_t off[32];   // by section id (CB_SEC_*)
     uint32_t nV, nRP, nS, nP, nR, nAP, nT, n_slots, n_rows;
     uint32_t has_role_policies, has_parent_roles, has_principal_policies;
     uint32_t image_bytes;
     // "unique condition" image (cb_uc.h): offsets of the two derived sections, number of distinct conditions (0 = none)
     uint32_t uc_conds_off, uc_rows_off, n_uconds;
     uint32_t theap_words;   // 8-byte words in THEAP
+    uint32_t uses_runtime;  // a condition reads runtime.effectiveDerivedRoles
 };
 
 // base = start of the table image: shared memory (TMA-staged) or global memory.
@@ -76,6 +77,10 @@ struct TableView {
     CB_HD const uint32_t *rp_apats() const { return sec<uint32_t>(CB_SEC_ROLEPOL_APATS); }
     CB_HD const uint32_t *block_slots_off() const { return sec<uint32_t>(CB_SEC_BLOCK_SLOTS_OFF); }
     CB_HD const uint32_t *block_slots() const { return sec<uint32_t>(CB_SEC_BLOCK_SLOTS); }
+    CB_HD const uint32_t *dr_off() const { return sec<uint32_t>(CB_SEC_DR_OFF); }
+    CB_HD const uint32_t *dr_entries() const { return sec<uint32_t>(CB_SEC_DR_ENTRIES); }   // 4 words each
+    CB_HD const uint32_t *dr_parents() const { return sec<uint32_t>(CB_SEC_DR_PARENTS); }
+    CB_HD const uint32_t *dr_name_str() const { return sec<uint32_t>(CB_SEC_DR_NAME_STR); }
     CB_HD const cb_cond *uconds() const { return reinterpret_cast<const cb_cond *>(base + L->uc_conds_off); }     // [n_uconds + 1], entry 0 unused
     CB_HD const U4 *urows() const { return reinterpret_cast<const U4 *>(base + L->uc_rows_off); }                 // [n_rows] 16-byte rows, DENY first per block
 };
@@ -259,6 +264,7 @@ struct Ctx {
     uint32_t pid;          // hdr0.principal_id
     uint32_t unsupported;  // sticky
     Val vars[CB_MAX_VARS];
+    uint64_t edr;          // runtime.effectiveDerivedRoles of the policy being evaluated: bit set over MANIFEST.derived_roles
     uint32_t scr_used;     // words of `scratch` in use
     uint64_t scratch[CB_SCRATCH_WORDS];
 };
@@ -1780,6 +1786,16 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
             st[sp++] = ok ? mk_scratch(CB_T_MAP, off) : mk_err();
             break;
         }
+        case CB_OP_RUNTIME_EDR: {   // runtime.effectiveDerivedRoles: the names of the set bits, already in sorted order
+            uint32_t cnt = 0, off;
+            for (uint64_t m = c.edr; m; m &= m - 1) cnt++;
+            if (!list_new(c, cnt, &off)) { st[sp++] = mk_err(); break; }
+            uint32_t k = 0;
+            for (uint32_t bit = 0; bit < 64; bit++)
+                if ((c.edr >> bit) & 1) c.scratch[off + 1 + k++] = ((uint64_t)(CB_V64_BOX_BASE | CB_V64_STRING) << 48) | ldg(c.t->dr_name_str() + bit);
+            st[sp++] = mk_scratch(CB_T_LIST, off);
+            break;
+        }
         case CB_OP_MATCHES: {   // RE2 search by the DFA table at theap[ic]: text = BOT, bytes, EOT (cel/regex_dfa.py)
             const Val v = st[sp - 1];
             if (v.tag != CB_T_STRING) { st[sp - 1] = mk_err(); break; }
@@ -1906,10 +1922,10 @@ CB_HD bool role_in_pr(const TableView t, uint32_t role, uint32_t req_role, uint3
 // Evaluates condition `gid` (global id) with the generic stack interpreter.  bit0: it yields BOOL true
 // (ruletable.go:1425-1441); bit1: a run-time value the device cannot represent exactly was met.
 // Scalar arguments only: aggregates would travel through local memory under the device ABI.
-CB_HD_NOINLINE uint32_t cond_sat(const uint8_t *base, const TableLayout *L, const BatchView *b, uint64_t req, uint32_t pid, uint32_t gid) {
+CB_HD_NOINLINE uint32_t cond_sat(const uint8_t *base, const TableLayout *L, const BatchView *b, uint64_t req, uint32_t pid, uint32_t gid, uint64_t edr = 0) {
     TableView t; t.base = base; t.L = L;
     Ctx c;
-    c.t = &t; c.b = b; c.req = req; c.pid = pid; c.unsupported = 0; c.scr_used = 0;
+    c.t = &t; c.b = b; c.req = req; c.pid = pid; c.unsupported = 0; c.scr_used = 0; c.edr = edr;
     bool s = run_program(c, t.code() + ldg(&t.conds()[gid].code_off));
     return (s ? 1u : 0u) | (c.unsupported ? 2u : 0u);
 }
@@ -1918,7 +1934,7 @@ CB_HD_NOINLINE uint32_t cond_sat(const uint8_t *base, const TableLayout *L, cons
 CB_HD_NOINLINE uint32_t cond_sat_code(const uint8_t *base, const TableLayout *L, const BatchView *b, uint64_t req, uint32_t pid, uint32_t code_off) {
     TableView t; t.base = base; t.L = L;
     Ctx c;
-    c.t = &t; c.b = b; c.req = req; c.pid = pid; c.unsupported = 0; c.scr_used = 0;
+    c.t = &t; c.b = b; c.req = req; c.pid = pid; c.unsupported = 0; c.scr_used = 0; c.edr = 0;
     bool s = run_program(c, t.code() + code_off);
     return (s ? 1u : 0u) | (c.unsupported ? 2u : 0u);
 }
@@ -2335,6 +2351,30 @@ CB_HD void prefetch_block_slots(const TableView t, const BatchView &b, uint32_t 
         prefetch_l1(b.slots + (uint64_t)ldg(t.block_slots() + q) * b.stride + n);
 }
 
+// ---- effectiveDerivedRoles (ruletable.go:936-979) ------------------------------------------------------------------
+// The derived roles of resource policy block `bid` whose parent roles intersect the principal's roles (+ parents in the
+// request's resource scope) and whose condition holds: bit set over MANIFEST.derived_roles.  Feeds
+// runtime.effectiveDerivedRoles while that policy's conditions are evaluated and the decision metadata.
+CB_HD_NOINLINE uint64_t compute_edr(const uint8_t *base, const TableLayout *L, const BatchView *b, uint64_t n, uint32_t pid, uint32_t bid, uint32_t n_roles,
+                                    uint32_t rscope, uint32_t *unsupported) {
+    TableView t; t.base = base; t.L = L;
+    uint64_t mask = 0;
+    for (uint32_t e = ldg(t.dr_off() + bid), ee = ldg(t.dr_off() + bid + 1); e < ee; e++) {
+        const U4 en = ld16(t.dr_entries() + 4 * (uint64_t)e);   // {name index, cond + 1, parents start, n parents}
+        bool hit = false;
+        for (uint32_t q = 0; q < en.w && !hit; q++) {
+            const uint32_t pr = ldg(t.dr_parents() + en.z + q);
+            if (pr == CB_ROLE_ANY) { hit = true; break; }
+            for (uint32_t i = 0; i < n_roles && !hit; i++) hit = role_in_pr(t, pr, ldcol32(b->roles + (uint64_t)i * b->stride + n), rscope);
+        }
+        if (!hit) continue;
+        bool sat = true;
+        if (en.y) { const uint32_t r = cond_sat(base, L, b, n, pid, en.y - 1); *unsupported |= r & 2; sat = r & 1; }
+        if (sat) mask |= 1ull << (en.x & 63);
+    }
+    return mask;
+}
+
 template <typename M>
 struct PairMasks { M deny, allow; uint32_t unsupported; };
 
@@ -2517,6 +2557,7 @@ CB_HD void eval_request(const TableView t, const BatchView &b, uint64_t n, uint8
                             if (c1 && c1 <= 64) need |= 1ull << (c1 - 1);
                             if (c2 && c2 <= 64) need |= 1ull << (c2 - 1);
                         }
+                        const uint64_t edr = t.L->uses_runtime ? compute_edr(t.base, t.L, &b, n, pid, bid, n_roles, rscope, &unsupported) : 0ull;
                         uint64_t val = 0;
                         for (uint64_t w = need; w;) {
 #if defined(__CUDA_ARCH__)
@@ -2525,7 +2566,7 @@ CB_HD void eval_request(const TableView t, const BatchView &b, uint64_t n, uint8
                             int li = __builtin_ctzll(w);
 #endif
                             w &= w - 1;
-                            uint32_t r = cond_sat(t.base, t.L, &b, n, pid, bl.z + (uint32_t)li);
+                            uint32_t r = cond_sat(t.base, t.L, &b, n, pid, bl.z + (uint32_t)li, edr);
                             unsupported |= r & 2;
                             val |= (uint64_t)(r & 1) << li;
                         }
@@ -2542,8 +2583,8 @@ CB_HD void eval_request(const TableView t, const BatchView &b, uint64_t n, uint8
                             if (!m) continue;
                             uint32_t c1 = row_cond(row), c2 = row_drcond(row);
                             bool sat = true;   // blocks with more than 64 distinct conditions evaluate the overflow ones unmemoised
-                            if (c2) { if (c2 <= 64) sat = (val >> (c2 - 1)) & 1; else { uint32_t r = cond_sat(t.base, t.L, &b, n, pid, bl.z + c2 - 1); unsupported |= r & 2; sat = r & 1; } }
-                            if (sat && c1) { if (c1 <= 64) sat = (val >> (c1 - 1)) & 1; else { uint32_t r = cond_sat(t.base, t.L, &b, n, pid, bl.z + c1 - 1); unsupported |= r & 2; sat = r & 1; } }
+                            if (c2) { if (c2 <= 64) sat = (val >> (c2 - 1)) & 1; else { uint32_t r = cond_sat(t.base, t.L, &b, n, pid, bl.z + c2 - 1, edr); unsupported |= r & 2; sat = r & 1; } }
+                            if (sat && c1) { if (c1 <= 64) sat = (val >> (c1 - 1)) & 1; else { uint32_t r = cond_sat(t.base, t.L, &b, n, pid, bl.z + c1 - 1, edr); unsupported |= r & 2; sat = r & 1; } }
                             if (!sat) continue;
                             if (row_effect(row) == CB_EFFECT_DENY) D |= m; else A |= m;
                         }
@@ -2584,6 +2625,188 @@ CB_HD void eval_request(const TableView t, const BatchView &b, uint64_t n, uint8
             store_bits(b, bitmap, n, acc);
         }
     }
+    if (unsupported && status) {
+#if defined(__CUDA_ARCH__)
+        atomicOr(status, 1u);
+#else
+        *status |= 1u;
+#endif
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- decision metadata
+// ActionEffect.Policy / Scope and CheckOutput.EffectiveDerivedRoles (ruletable.go:753-782, 913-922, 936-979, 1082-1148)
+// depend on WHICH row decided -- which role column, which scope, whether it came from a role policy -- so this body
+// keeps the reference's own loop order (action -> policy kind -> role -> scope -> candidate rows in index order)
+// instead of the bit-parallel walk.  It is the optional metadata plane (cgpu_check_meta): one thread per request, every
+// condition through the generic interpreter.  The effect it derives is the same decision; tests hold it against both
+// the bit-parallel kernels and the oracle.
+struct MetaInfo { uint32_t effect, src, scope, role; };   // effect 0 = NO_MATCH
+CB_HD uint32_t pack_meta(const MetaInfo &m) { return (m.scope == CB_NONE32 ? 0xFFFFu : (m.scope & 0xFFFFu)) | (m.src & 0xFFu) << 16 | (m.role & 0xFFu) << 24; }
+
+CB_HD bool meta_row_action(const BatchView &b, uint32_t aset, uint32_t n_rows, uint32_t ps, uint32_t kk, uint32_t ri) {
+    return ((ldg(b.row_am + ((uint64_t)ps * b.n_asets + aset) * n_rows + ri) >> (kk * b.role_cols)) & 1) != 0;
+}
+
+CB_HD_NOINLINE void eval_request_meta(const uint8_t *base, const TableLayout *L, const BatchView *bp, uint64_t n, uint8_t *effects, uint32_t *action_meta,
+                                      cb_request_meta *req_meta, uint32_t *status) {
+    TableView t; t.base = base; t.L = L;
+    const BatchView &b = *bp;
+    const U4 h0 = ldcol128(b.hdr0 + n);
+    const uint64_t h1 = ldcol64(reinterpret_cast<const uint64_t *>(b.hdr1 + n));
+    const uint32_t pid = h0.x, kc = h0.y, rscope = h0.z, pscope = h0.w;
+    const uint32_t rv = (uint32_t)(h1 & 0xFFFF), pv = (uint32_t)((h1 >> 16) & 0xFFFF), aset = (uint32_t)(h1 >> 32);
+    const uint32_t K = aset < b.n_asets ? ldg(b.aset_k + aset) : 0;
+    const uint32_t KM = b.max_actions;
+    uint32_t unsupported = 0;
+    uint8_t *eff = effects + n * (uint64_t)KM;
+    uint32_t *am = action_meta + n * (uint64_t)KM;
+    for (uint32_t k = 0; k < KM; k++) { eff[k] = (uint8_t)(k < K ? CB_EFFECT_DENY : 0); am[k] = 0xFFFFu; }
+    cb_request_meta rm; rm.principal_first_scope = 0xFFFF; rm.resource_first_scope = 0xFFFF; rm.flags = 0; rm.effective_derived_roles = 0;
+
+    uint32_t roles[CB_MAX_ROLE_COLS], n_roles = 0;
+    for (uint32_t i = 0; i < b.role_cols; i++) { const uint32_t rr = ldcol32(b.roles + (uint64_t)i * b.stride + n); if (rr != CB_ROLE_PAD) roles[n_roles++] = rr; }
+    const bool lenient = (b.flags & CB_BATCH_FLAG_LENIENT) != 0;
+    uint32_t pchain[CB_MAX_CHAIN], rchain[CB_MAX_CHAIN], np = 0, nr = 0;
+    for (uint32_t s = chain_start(t, pscope, CB_SCOPE_FLAG_PRINCIPAL, lenient); s != CB_NONE32 && np < CB_MAX_CHAIN; s = chain_next(t, s, CB_SCOPE_FLAG_PRINCIPAL)) pchain[np++] = s;
+    for (uint32_t s = chain_start(t, rscope, CB_SCOPE_FLAG_RESOURCE, lenient); s != CB_NONE32 && nr < CB_MAX_CHAIN; s = chain_next(t, s, CB_SCOPE_FLAG_RESOURCE)) rchain[nr++] = s;
+    if (np) rm.principal_first_scope = (uint16_t)pchain[0];
+    if (nr) rm.resource_first_scope = (uint16_t)rchain[0];
+    req_meta[n] = rm;
+    if ((np == 0 && nr == 0) || K == 0) return;
+
+    const uint32_t nk = kind_count(b, kc);
+    bool p_exists = false, r_exists = false;
+    if (pv != CB_NONE16) for (uint32_t i = 0; i < np; i++) p_exists |= ldg(t.prin_exists() + (uint64_t)pv * L->nS + pchain[i]) != 0;
+    if (rv != CB_NONE16)
+        for (uint32_t i = 0; i < nr; i++)
+            for (uint32_t j = 0; j < nk; j++)
+                r_exists |= (ldg(t.res_exists() + ((uint64_t)rv * L->nRP + kind_pat_at(b, kc, j)) * L->nS + rchain[i]) & CB_EXISTS_RESOURCE_KIND) != 0;
+    if (!p_exists && !r_exists) return;
+    const uint32_t pidx = (L->has_principal_policies && pid < L->nT) ? ldg(t.prin_of_string() + pid) : CB_NONE32;
+    const bool rows_ok = rv != CB_NONE16;   // candidate rows are those of the resource policy version (ruletable.go:874)
+    // allRoles = the principal's roles, then their parents in the resource scope (index.go:805-836): the order candidate
+    // rows come in (index.go:564-801); duplicates add nothing
+    uint32_t all_roles[CB_MAX_ROLE_COLS * 3], n_all = 0;
+    for (uint32_t i = 0; i < n_roles; i++) all_roles[n_all++] = roles[i];
+    if (L->has_parent_roles && rscope != CB_SCOPE_NONE && !(rscope & CB_SCOPE_INEXACT_BIT) && rscope < L->nS)
+        for (uint32_t i = 0; i < n_roles; i++) {
+            if (roles[i] >= L->nR) continue;
+            const uint64_t idx = (uint64_t)rscope * L->nR + roles[i];
+            for (uint32_t j = ldg(t.par_off() + idx), e = ldg(t.par_off() + idx + 1); j < e && n_all < CB_MAX_ROLE_COLS * 3; j++) all_roles[n_all++] = ldg(t.par_list() + j);
+        }
+    const uint32_t nAP = L->nAP ? L->nAP : 1;
+    uint32_t processed = 0;      // resource chain positions whose derived roles have been evaluated
+    uint64_t cur_edr = 0, all_edr = 0;
+
+    for (uint32_t k = 0; k < K; k++) {
+        const uint32_t ps = k / b.kc, kk = k % b.kc;
+        const uint64_t *spread = b.aset_spread + ((uint64_t)ps * b.n_asets + aset) * nAP;
+        MetaInfo info; info.effect = 0; info.src = CB_META_SRC_NO_MATCH; info.scope = CB_NONE32; info.role = 0;
+        for (uint32_t pt = 0; pt < 2; pt++) {        // principal policies, then resource policies
+            const bool principal = pt == 0;
+            const uint32_t *chain = principal ? pchain : rchain;
+            const uint32_t nc = principal ? np : nr;
+            info.effect = 0;
+            for (uint32_t i = 0; i < n_roles; i++) {
+                if (i > 0 && principal) break;       // principal policies are role agnostic
+                MetaInfo ri; ri.effect = 0; ri.scope = CB_NONE32; ri.role = 0;
+                ri.src = (principal ? p_exists : r_exists) ? (principal ? CB_META_SRC_PRINCIPAL_POLICY : CB_META_SRC_RESOURCE_POLICY) : CB_META_SRC_NO_MATCH;
+                for (uint32_t si = 0; si < nc; si++) {
+                    const uint32_t s = chain[si];
+                    if (!principal && !((processed >> si) & 1)) {
+                        uint64_t edr = 0;
+                        if (rows_ok)
+                            for (uint32_t j = 0; j < nk; j++) {
+                                const uint32_t bid = ldg(t.res_block_map() + ((uint64_t)rv * L->nRP + kind_pat_at(b, kc, j)) * L->nS + s);
+                                if (bid != CB_NONE32) edr |= compute_edr(base, L, bp, n, pid, bid, n_roles, rscope, &unsupported);
+                            }
+                        cur_edr = edr;
+                        all_edr |= edr;
+                        processed |= 1u << si;
+                    }
+                    if (ri.effect) break;
+                    bool saw_allow = false, deny = false, deny_rp = false;
+                    uint32_t deny_role = 0;
+                    if (principal) {
+                        const uint32_t bid = (pidx != CB_NONE32 && rows_ok) ? ldg(t.prin_block_map() + ((uint64_t)rv * L->nP + pidx) * L->nS + s) : CB_NONE32;
+                        if (bid != CB_NONE32) {
+                            const U4 bl = ld16(t.blocks() + bid);
+                            for (uint32_t q = 0; q < bl.y && !deny; q++) {
+                                const uint32_t rix = bl.x + q;
+                                const U4 row = ld16(t.rows() + rix);
+                                if (!kind_has(b, kc, row_respat(row)) || !meta_row_action(b, aset, L->n_rows, ps, kk, rix)) continue;
+                                if (row_drcond(row)) { const uint32_t r = cond_sat(base, L, bp, n, pid, bl.z + row_drcond(row) - 1, cur_edr); unsupported |= r & 2; if (!(r & 1)) continue; }
+                                if (row_cond(row)) { const uint32_t r = cond_sat(base, L, bp, n, pid, bl.z + row_cond(row) - 1, cur_edr); unsupported |= r & 2; if (!(r & 1)) continue; }
+                                if (row_effect(row) == CB_EFFECT_DENY) deny = true; else saw_allow = true;
+                            }
+                        }
+                    } else if (rows_ok) {
+                        bool any_row = false;
+                        for (uint32_t j = 0; j < nk; j++) any_row |= (ldg(t.res_exists() + ((uint64_t)rv * L->nRP + kind_pat_at(b, kc, j)) * L->nS + s) & CB_EXISTS_ANY_ROW) != 0;
+                        // candidate rows in index order: for every role R of allRoles, the role policy of R (synthesised
+                        // DENY rows) and then the resource policy rows naming R ("*" rows travel with the first role)
+                        for (uint32_t a = 0; a < n_all && !deny; a++) {
+                            const uint32_t R = all_roles[a];
+                            bool dup = false;
+                            for (uint32_t z = 0; z < a; z++) dup |= all_roles[z] == R;
+                            if (dup) continue;
+                            const bool in_pr = role_in_pr(t, R, roles[i], rscope);
+                            if (in_pr && any_row && L->has_role_policies) {
+                                const uint64_t ro = (uint64_t)rv * L->nS + s;
+                                for (uint32_t e = ldg(t.rp_off() + ro), ee = ldg(t.rp_off() + ro + 1); e < ee && !deny; e++) {
+                                    const U4 en = ld16(t.rp_entries() + e);   // {role, rule_start, n_rules, pad}
+                                    if (en.x != R) continue;
+                                    bool matched = false;
+                                    for (uint32_t q = 0; q < en.z && !deny; q++) {
+                                        const U4 ru = ld16(t.rp_rules() + en.y + q);   // {respat, cond, apat_start, n_apats}
+                                        if (!kind_has(b, kc, ru.x)) continue;
+                                        bool amatch = false;
+                                        for (uint32_t x = 0; x < ru.w && !amatch; x++) amatch = ((ldg(spread + ldg(t.rp_apats() + ru.z + x)) >> (kk * b.role_cols)) & 1) != 0;
+                                        if (!amatch) continue;
+                                        matched = true;
+                                        if (ru.y) { const uint32_t r = cond_sat(base, L, bp, n, pid, ru.y - 1, cur_edr); unsupported |= r & 2; if (!(r & 1)) deny = true; }   // DENY none(cond)
+                                    }
+                                    if (!matched) deny = true;   // no allow rule of the role policy covers the action
+                                    if (deny) { deny_rp = true; deny_role = R; }
+                                }
+                            }
+                            if (deny) break;
+                            for (uint32_t j = 0; j < nk && !deny; j++) {
+                                const uint32_t bid = ldg(t.res_block_map() + ((uint64_t)rv * L->nRP + kind_pat_at(b, kc, j)) * L->nS + s);
+                                if (bid == CB_NONE32) continue;
+                                const U4 bl = ld16(t.blocks() + bid);
+                                for (uint32_t q = 0; q < bl.y && !deny; q++) {
+                                    const uint32_t rix = bl.x + q;
+                                    const U4 row = ld16(t.rows() + rix);
+                                    const uint32_t rr = row_role(row);
+                                    if (!(rr == CB_ROLE_ANY ? a == 0 : (rr == R && in_pr))) continue;
+                                    if (!meta_row_action(b, aset, L->n_rows, ps, kk, rix)) continue;
+                                    if (row_drcond(row)) { const uint32_t r = cond_sat(base, L, bp, n, pid, bl.z + row_drcond(row) - 1, cur_edr); unsupported |= r & 2; if (!(r & 1)) continue; }
+                                    if (row_cond(row)) { const uint32_t r = cond_sat(base, L, bp, n, pid, bl.z + row_cond(row) - 1, cur_edr); unsupported |= r & 2; if (!(r & 1)) continue; }
+                                    if (row_effect(row) == CB_EFFECT_DENY) deny = true; else saw_allow = true;
+                                }
+                            }
+                        }
+                    }
+                    if (deny) {
+                        ri.effect = CB_EFFECT_DENY; ri.scope = s;
+                        if (deny_rp) { ri.src = CB_META_SRC_ROLE_POLICY; ri.role = deny_role; }
+                        break;
+                    }
+                    if (saw_allow && ((ldg(t.scope_flags() + s) >> CB_SCOPE_PERM_SHIFT) & 3) == 1) { ri.effect = CB_EFFECT_ALLOW; ri.scope = s; break; }
+                }
+                if (info.effect == 0) info = ri;
+                if (ri.effect == CB_EFFECT_ALLOW) { info = ri; break; }
+                else if (ri.effect == CB_EFFECT_DENY && info.src == CB_META_SRC_NO_MATCH_FOR_SCOPE_PERMISSIONS && ri.src != CB_META_SRC_NO_MATCH_FOR_SCOPE_PERMISSIONS) info = ri;
+            }
+            if (info.effect) break;
+        }
+        eff[k] = (uint8_t)(info.effect == CB_EFFECT_ALLOW ? CB_EFFECT_ALLOW : CB_EFFECT_DENY);
+        am[k] = pack_meta(info);
+    }
+    rm.effective_derived_roles = all_edr;
+    req_meta[n] = rm;
     if (unsupported && status) {
 #if defined(__CUDA_ARCH__)
         atomicOr(status, 1u);
@@ -2760,7 +2983,7 @@ struct CachedCols {
 };
 
 // How the unique-condition body gets a request's condition word: this generic evaluator interprets the table's DNF
-// terms (and, in the ahead-of-time build, runs the stack interpreter for conditions without a flat form); a run-time
+// terms; a run-time
 // specialised build (cb_specialize.h: generate_uc) substitutes straight-line code over register-resident slots.
 struct GenericConds {
     static constexpr bool kVal32 = false;   // the condition word may use all 64 bits
@@ -2773,16 +2996,7 @@ struct GenericConds {
             const U4 cd = ld16(t.uconds() + u);   // {code_off, code_len, flat_off, flat_info}
             uint32_t r;
             if (cd.w) r = flat_dnf_inline(t, b, cols, pid, cd.z, cd.w);
-            else {
-#ifndef CB_LEAN_ONLY
-                // no flat form: the generic interpreter (an out-of-line call); a value it cannot represent exactly only
-                // matters if a row of the request needs this condition -- the general body decides that
-                const uint32_t q = cond_sat_code(t.base, t.L, &b, n, pid, cd.x);
-                r = (q & 1u) | ((q & 2u) << 1);
-#else
-                r = 4u;
-#endif
-            }
+            else r = 4u;   // no flat form: the request goes to the general kernel (cb_uc.h only builds images whose conditions are all flat)
             slow |= (r & 4u) != 0;
             val |= (uint64_t)(r & 1u) << u;
         }

@@ -54,17 +54,13 @@ __device__ __forceinline__ void tma_load_image(uint8_t *dst_smem, const TableDes
     }
 }
 
-// A request the lean body cannot decide (differing policy versions, an operand outside the 8-byte fast forms ...):
-// the ahead-of-time build re-evaluates it on the spot with the out-of-line general body; a run-time specialised
-// module has no general body and appends it to a list that the general kernel drains right after.
+// A request the lean body cannot decide (differing policy versions, an operand outside the 8-byte fast forms ...) is
+// appended to the launch's deferral list, which the general kernel drains right behind this one.  (Only the general
+// and the metadata kernels carry the generic interpreter: it is compiled once per kernel that can reach it.)
 __device__ __forceinline__ void defer_request(const cb::TableView tv, const cb::BatchView &bv, uint64_t n, uint8_t *bitmap, uint8_t *effects, uint32_t *status) {
-#ifdef CB_LEAN_ONLY
     (void)tv; (void)bitmap; (void)effects; (void)status;
     const uint32_t k = atomicAdd(bv.defer_count, 1u);
     bv.defer_list[k] = (uint32_t)(n - bv.first);
-#else
-    cb::eval_request_general(tv.base, tv.L, &bv, n, bitmap, effects, status);
-#endif
 }
 
 // fused all-gather bookkeeping (see BatchView): executed by one warp

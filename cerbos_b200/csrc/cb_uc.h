@@ -67,6 +67,7 @@ inline Image build(const uint8_t *image, const uint32_t *off, const uint64_t *le
         out.ucond_of_gid[g] = it->second;
     }
     out.n_uconds = (uint32_t)ids.size();
+    if (out.n_flat != out.n_uconds) { out.why = "a condition has no flat (DNF) form"; return out; }
     // rows: DENY rows first inside every block (within a scope every matching row is evaluated and DENY beats ALLOW,
     // ruletable.go:1083-1118, so the order of rows inside a block is free); 16 bytes each, see cb_core.h
     std::vector<uint32_t> urows(4 * (size_t)(n_rows ? n_rows : 1), 0);

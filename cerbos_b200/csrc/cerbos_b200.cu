@@ -32,7 +32,7 @@ constexpr int kThreads = cbk::kThreads;
 #define CB_MIN_BLOCKS 4   // resident CTAs / SM the check kernel is register-budgeted for (64 registers per thread)
 #endif
 constexpr uint32_t kMaxStageBytes = 96 * 1024;   // table images up to this size are TMA-staged into shared memory
-constexpr int kMaxSec = 28;
+constexpr int kMaxSec = 32;
 constexpr uint32_t kMaxTilesSmem = 56 * 1024;    // image + two column-tile stages: keeps CB_MIN_BLOCKS CTAs resident per SM
 
 using cbk::TableDesc;
@@ -51,6 +51,13 @@ __global__ void __launch_bounds__(kThreads, CB_MIN_BLOCKS) check_kernel_tiles(co
     extern __shared__ __align__(128) uint8_t smem_image[];
     __shared__ __align__(8) uint64_t mbar_tab, mbar_col[4];
     cbk::check_tiles_body<cb::GenericBlocks>(td, bv, bitmap, effects, status, n_slots, smem_image, &mbar_tab, mbar_col);
+}
+
+// decision-metadata kernel (cgpu_check_meta): one thread per request, the reference's own loop order (cb::eval_request_meta)
+__global__ void __launch_bounds__(kThreads) check_meta_kernel(const __grid_constant__ TableDesc td, const __grid_constant__ cb::BatchView bv, uint8_t *effects,
+                                                             uint32_t *action_meta, cb_request_meta *req_meta, uint32_t *status) {
+    for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < bv.count; i += (uint64_t)gridDim.x * kThreads)
+        cb::eval_request_meta(td.base, &td.lay, &bv, bv.first + i, effects, action_meta, req_meta, status);
 }
 
 // unique-condition kernels (cb_uc.h image; generic condition evaluator; deferrals go to the launch's list)
@@ -245,6 +252,7 @@ struct cgpu_ctx {
     struct SliceUse { const void *ptr; cudaEvent_t done; };
     std::vector<SliceUse> slice_uses;   // own slices whose last push to the peers may still be in flight
     std::mutex copy_mu;
+    std::mutex meta_mu;      // cgpu_check_meta calls share ctx->stream
     int uc_mode = -1;        // CERBOS_B200_UC: 0 never use the unique-condition kernels, 1 whenever the table allows, unset = tables with > 1 block shape
     uint32_t last_uc = 0;
     bool profiling = false;  // cgpu_profile(): CUDA events around the check kernel of every launch
@@ -307,7 +315,7 @@ int parse_blob(const void *blob, size_t len, TableDesc *d, uint32_t *meta, uint6
             memcpy(meta, static_cast<const char *>(blob) + sd[i].offset, CB_META_WORDS * 4);
         }
     }
-    for (int id = CB_SEC_META; id <= CB_SEC_BLOCK_SLOTS; id++)
+    for (int id = CB_SEC_META; id <= CB_SEC_DR_NAME_STR; id++)
         if (!seen[id]) return fail(CGPU_ERR_INVALID, "table blob: missing section %d", id);
     if (image_end > 0xFFFFFFF0ull) return fail(CGPU_ERR_INVALID, "table blob too large");
     if (image_end > len) image_end = len;   // the last device section may end unaligned at the end of the blob (sections themselves are bounds-checked above)
@@ -317,6 +325,7 @@ int parse_blob(const void *blob, size_t len, TableDesc *d, uint32_t *meta, uint6
     d->lay.nT = meta[CB_META_N_STRINGS]; d->lay.n_slots = meta[CB_META_N_SLOTS]; d->lay.n_rows = meta[CB_META_N_ROWS] ? meta[CB_META_N_ROWS] : 1;
     d->lay.has_role_policies = meta[CB_META_HAS_ROLE_POLICIES]; d->lay.has_parent_roles = meta[CB_META_HAS_PARENT_ROLES];
     d->lay.has_principal_policies = meta[CB_META_HAS_PRINCIPAL_POLICIES];
+    d->lay.uses_runtime = meta[CB_META_USES_RUNTIME];
     if (sec_len) {
         struct { int id; uint64_t need; } chk[] = {
             {CB_SEC_SCOPE_PARENT, 4ull * d->lay.nS}, {CB_SEC_SCOPE_FLAGS, 4ull * d->lay.nS},
@@ -325,7 +334,8 @@ int parse_blob(const void *blob, size_t len, TableDesc *d, uint32_t *meta, uint6
             {CB_SEC_BLOCKS, 16ull * meta[CB_META_N_BLOCKS]}, {CB_SEC_ROWS, 16ull * meta[CB_META_N_ROWS]}, {CB_SEC_CONDS, 16ull * meta[CB_META_N_CONDS]},
             {CB_SEC_CODE, 8ull * meta[CB_META_N_CODE]}, {CB_SEC_CONSTS, 16ull * meta[CB_META_N_CONSTS]}, {CB_SEC_CONSTS_V64, 8ull * meta[CB_META_N_CONSTS]},
             {CB_SEC_STR_OFF, 4ull * (d->lay.nT + 1)}, {CB_SEC_THEAP, 8ull * meta[CB_META_THEAP_WORDS]},
-            {CB_SEC_BLOCK_SLOTS_OFF, 4ull * (meta[CB_META_N_BLOCKS] + 1)},
+            {CB_SEC_BLOCK_SLOTS_OFF, 4ull * (meta[CB_META_N_BLOCKS] + 1)}, {CB_SEC_DR_OFF, 4ull * (meta[CB_META_N_BLOCKS] + 1)},
+            {CB_SEC_DR_NAME_STR, 4ull * meta[CB_META_N_DR_NAMES]},
         };
         for (const auto &c : chk)
             if (sec_len[c.id] < c.need) return fail(CGPU_ERR_INVALID, "table blob: section %d holds %llu bytes, META needs %llu", c.id, (unsigned long long)sec_len[c.id], (unsigned long long)c.need);
@@ -735,7 +745,7 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
         bvv.perm = perm;
     }
     uint32_t last_arg = col_tiles ? lay.n_slots : (stage ? 1u : 0u);   // check_kernel: stage_rt; check_kernel_tiles: n_slots
-    const bool lists = spec || uc;   // requests the kernel leaves to the general kernel go to a list drained right behind it
+    const bool lists = narrow;       // requests a lean kernel leaves to the general kernel go to a list drained right behind it
     uint32_t *defer = nullptr;
     if (lists) {
         uint32_t *cell = nullptr, *strpred = nullptr;
@@ -1190,6 +1200,59 @@ int cgpu_sync(cgpu_ctx *ctx, void *cuda_stream) {
         CUDA_TRY(cudaStreamSynchronize(s));
         return fail(CGPU_ERR_UNSUPPORTED, "a request produced a run-time value the device cannot represent exactly (e.g. timestamp outside 1678..2262, string->double, concatenation)");
     }
+    return CGPU_OK;
+}
+
+int cgpu_check_meta(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, uint8_t *effects_out, uint32_t *action_meta_out, void *request_meta_out_v) {
+    cb_request_meta *request_meta_out = static_cast<cb_request_meta *>(request_meta_out_v);
+    if (!ctx || !t || !batch || !effects_out || !action_meta_out || !request_meta_out) return fail(CGPU_ERR_INVALID, "cgpu_check_meta: null argument");
+    if (t->ctx != ctx) return fail(CGPU_ERR_INVALID, "table belongs to another context");
+    const uint64_t N = batch->n_requests;
+    const uint32_t km = batch->max_actions ? batch->max_actions : 1;
+    if (N == 0) return CGPU_OK;
+    cb::BatchView hv;
+    int rc = make_batch_view(t, batch, 0, N, &hv);
+    if (rc != CGPU_OK) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    // the metadata plane is the cold path (IncludeMeta requests, audit): plain stream-ordered scratch, one launch
+    cudaStream_t s = ctx->stream;
+    std::lock_guard<std::mutex> lk(ctx->meta_mu);
+    size_t offs[CGPU_N_COLUMNS + 3], total = 0;
+    for (int i = 0; i < CGPU_N_COLUMNS; i++) { offs[i] = total; total += (batch->column_bytes[i] + 255) & ~(size_t)255; }
+    offs[CGPU_N_COLUMNS] = total; total += ((size_t)N * km + 255) & ~(size_t)255;
+    offs[CGPU_N_COLUMNS + 1] = total; total += ((size_t)N * km * 4 + 255) & ~(size_t)255;
+    offs[CGPU_N_COLUMNS + 2] = total; total += ((size_t)N * sizeof(cb_request_meta) + 255) & ~(size_t)255;
+    uint8_t *dbase = nullptr;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&dbase), total + 4, s));
+    struct Free { uint8_t *p; cudaStream_t s; ~Free() { cudaFreeAsync(p, s); cudaStreamSynchronize(s); } } fr{dbase, s};
+    const void *dcols[CGPU_N_COLUMNS];
+    for (int i = 0; i < CGPU_N_COLUMNS; i++) {
+        dcols[i] = dbase + offs[i];
+        if (batch->column_bytes[i]) CUDA_TRY(cudaMemcpyAsync(dbase + offs[i], batch->columns[i], batch->column_bytes[i], cudaMemcpyHostToDevice, s));
+    }
+    uint32_t *d_status = reinterpret_cast<uint32_t *>(dbase + total);
+    CUDA_TRY(cudaMemsetAsync(d_status, 0, 4, s));
+    cgpu_batch db = *batch;
+    db.columns = dcols;
+    cb::BatchView bv;
+    rc = make_batch_view(t, &db, 0, N, &bv);
+    if (rc != CGPU_OK) return rc;
+    uint8_t *d_eff = dbase + offs[CGPU_N_COLUMNS];
+    uint32_t *d_am = reinterpret_cast<uint32_t *>(dbase + offs[CGPU_N_COLUMNS + 1]);
+    cb_request_meta *d_rm = reinterpret_cast<cb_request_meta *>(dbase + offs[CGPU_N_COLUMNS + 2]);
+    TableDesc td = t->desc;
+    const uint64_t tiles = (N + kThreads - 1) / kThreads;
+    const uint32_t grid = (uint32_t)(tiles < (uint64_t)ctx->sm_count * 4 ? tiles : (uint64_t)ctx->sm_count * 4);
+    check_meta_kernel<<<grid, kThreads, 0, s>>>(td, bv, d_eff, d_am, d_rm, d_status);
+    CUDA_TRY(cudaGetLastError());
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    uint32_t st = 0;
+    CUDA_TRY(cudaMemcpyAsync(effects_out, d_eff, (size_t)N * km, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(action_meta_out, d_am, (size_t)N * km * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(request_meta_out, d_rm, (size_t)N * sizeof(cb_request_meta), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (st) return fail(CGPU_ERR_UNSUPPORTED, "a request produced a run-time value the device cannot represent exactly (e.g. timestamp outside 1678..2262, string->double, a list longer than the scratch arena)");
     return CGPU_OK;
 }
 

@@ -8,8 +8,9 @@ reference's engine golden files).  Conventions kept: outputs are index-aligned w
 an input appears in its output with EFFECT_ALLOW or EFFECT_DENY; any failure raises (fails the whole call);
 ``now`` is fixed once per call.
 
-What is *not* produced: ``policy`` / ``scope`` attribution, effectiveDerivedRoles,
-outputs, validation errors, audit trail.
+``check(..., include_meta=True)`` also fills ``policy`` / ``scope`` of every action and ``effectiveDerivedRoles`` (the
+reference's IncludeMeta responses, cerbos_svc.go:291-311) from the device's metadata plane (cgpu_check_meta).
+Not produced: rule outputs, validation errors, audit trail.
 """
 from __future__ import annotations
 
@@ -57,10 +58,13 @@ class Engine:
         eff = self.table.check(batch.columns, batch.n, batch.max_actions, now_ns, flags)
         return batch, eff
 
-    def check(self, inputs, now_ns=None):
-        """-> list of CheckOutput dicts, index-aligned with `inputs`."""
+    def check(self, inputs, now_ns=None, include_meta=False):
+        """-> list of CheckOutput dicts, index-aligned with `inputs`.  include_meta: also `policy` / `scope` per action
+        and `effectiveDerivedRoles` (ruletable.go:753-782), through the metadata plane of the device."""
         if not inputs:
             return []
+        if include_meta:
+            return self._check_with_meta(inputs, now_ns)
         batch, eff = self.check_effects(inputs, now_ns)
         outs = []
         for i, inp in enumerate(inputs):
@@ -69,6 +73,27 @@ class Engine:
                 actions[a] = {"effect": EFFECT_NAMES[int(eff[i, k])]}
             outs.append({"requestId": inp.get("requestId", ""), "resourceId": (inp.get("resource") or {}).get("id", ""),
                          "actions": actions})
+        return outs
+
+    def _check_with_meta(self, inputs, now_ns=None):
+        from . import meta as M
+        if now_ns is None:
+            now_ns = time.time_ns()
+        batch = self.encoder.encode(inputs)
+        flags = L.BATCH_FLAG_LENIENT if self.conf["lenient_scope_search"] else 0
+        eff, am, rm = self.table.check_meta(batch.columns, batch.n, batch.max_actions, now_ns, flags)
+        man = self.flat.manifest
+        outs = []
+        for i, inp in enumerate(inputs):
+            p, r = inp.get("principal") or {}, inp.get("resource") or {}
+            p_ver = p.get("policyVersion") or self.conf["default_policy_version"]
+            r_ver = r.get("policyVersion") or self.conf["default_policy_version"]
+            actions = {}
+            for k, a in enumerate(inp.get("actions") or []):
+                policy, scope = M.decode_action(int(am[i, k]), rm[i], man, p.get("id", ""), r.get("kind", ""), p_ver, r_ver)
+                actions[a] = {"effect": EFFECT_NAMES[int(eff[i, k])], "policy": policy, "scope": scope}
+            outs.append({"requestId": inp.get("requestId", ""), "resourceId": r.get("id", ""), "actions": actions,
+                         "effectiveDerivedRoles": M.decode_edr(int(rm[i]["effective_derived_roles"]), man)})
         return outs
 
     def close(self):

@@ -99,6 +99,7 @@ class TableBuilderCtx:
         self.max_stack = 0
         self.max_loop_depth = 0
         self.n_vars = 0
+        self.uses_runtime = False
 
     # -- pools
     def slot(self, path: tuple) -> int:
@@ -517,8 +518,12 @@ class ProgramCompiler:
         st = self._static(n)
         if st is not None:
             return self._push_static(st)
-        if isinstance(n.operand, Ident) and n.operand.name == "runtime":
-            raise Unsupported("`runtime` (effectiveDerivedRoles) in conditions")
+        if isinstance(n.operand, Ident) and n.operand.name == "runtime" and self._lookup_var("runtime") is None:
+            if n.field not in ("effectiveDerivedRoles", "effective_derived_roles"):
+                raise Unsupported(f"unknown field runtime.{n.field}")
+            self.ctx.uses_runtime = True
+            self.emit("RUNTIME_EDR", delta=1)
+            return
         self.expr(n.operand)
         self.emit("SELECT", c=self.ctx.strings.intern(n.field))
 

@@ -86,6 +86,15 @@ def flatten(rt: RuleTable, globals_=None) -> FlatTable:
             roles.add(role)
             for p in parents:
                 roles.add(p)
+    for drs in rt.policy_derived_roles.values():
+        for dr in drs.values():
+            for pr in dr.parent_roles:
+                if pr != "*":
+                    roles.add(pr)
+    dr_names = sorted({name for drs in rt.policy_derived_roles.values() for name in drs})
+    if len(dr_names) > 64:
+        raise Unsupported(f"more than 64 derived role names ({len(dr_names)})")
+    dr_name_ix = {nm: i for i, nm in enumerate(dr_names)}
     for name, lim in (("roles", len(roles)), ("action patterns", len(apats)), ("resource patterns", len(respats))):
         if lim >= 0xFFFF:
             raise Unsupported(f"too many {name} ({lim})")
@@ -145,6 +154,7 @@ def flatten(rt: RuleTable, globals_=None) -> FlatTable:
             groups[key].append(r)
 
     blocks, row_recs, conds, code, row_apats = [], [], [], [], []
+    dr_off, dr_entries, dr_parents = [], [], []
     block_shapes: set = set()
     code_ix: dict[tuple, tuple] = {}
 
@@ -222,6 +232,15 @@ def flatten(rt: RuleTable, globals_=None) -> FlatTable:
         blocks.append((row_start, len(row_recs) - row_start, cond_base, len(conds) - cond_base))
         # shape of the block = everything that steers the kernel's control flow through it
         block_shapes.add((tuple(k2[:3] + k2[4:] + (tuple(p),) for k2, p in merged.items()), tuple(conds[cond_base:])))
+        # derived roles of this resource policy (evaluated once per scope for effectiveDerivedRoles, ruletable.go:936-979);
+        # the reference looks them up under the request's own kind, so only exact-name policies carry any
+        dr_off.append(len(dr_entries))
+        if kind == "R" and not is_glob(respats.items[ent]):
+            fqn = namer.resource_policy_fqn(respats.items[ent], versions.items[v], scopes.items[s])
+            for nm, dr in sorted((rt.policy_derived_roles.get(fqn) or {}).items()):
+                cid = 0 if dr.condition is None else add_program(dr.condition, dr.params) + 1
+                dr_entries.append((dr_name_ix[nm], cid, len(dr_parents), len(dr.parent_roles)))
+                dr_parents.extend(L.ROLE_ANY if pr == "*" else roles.ids[pr] for pr in dr.parent_roles)
 
     # ---- role policies ----------------------------------------------------------------------------------------
     rp_off = np.zeros(nV * nS + 1, dtype=np.uint32)
@@ -269,6 +288,7 @@ def flatten(rt: RuleTable, globals_=None) -> FlatTable:
     # ---- strings: everything the kernels may compare against request strings ---------------------------------------
     # principals must be table strings so that hdr.principal_id (a string id) can be mapped to a principal index
     prin_str = [ctx.strings.intern(p) for p in principals.items]
+    dr_name_str = [ctx.strings.intern(nm) for nm in dr_names]
     n_strings = len(ctx.strings)
     prin_of_string = np.full(max(n_strings, 1), L.NONE32, dtype=np.uint32)
     for pi, sid in enumerate(prin_str):
@@ -294,6 +314,7 @@ def flatten(rt: RuleTable, globals_=None) -> FlatTable:
         max_loop_depth=ctx.max_loop_depth, n_vars=ctx.n_vars, theap_words=len(ctx.theap),
         uses_pid=int(ctx.uses_pid), uses_now=int(ctx.uses_now), max_scope_depth=max_depth,
         direct_kinds=int(not any(is_glob(p) for p in respats.items)), block_shapes=len(block_shapes),
+        uses_runtime=int(ctx.uses_runtime), n_dr_names=len(dr_names),
     ).items():
         meta[L.META[k]] = val
 
@@ -353,6 +374,7 @@ def flatten(rt: RuleTable, globals_=None) -> FlatTable:
         "scope_parent": [int(x) for x in scope_parent[:nS]],
         "parent_role_scopes": sorted(s for s, rmap in rt.scope_parent_roles.items() if any(rmap.values())),
         "row_pat_start": [int(r[7]) for r in row_recs], "row_apats": [int(x) for x in row_apats],
+        "derived_roles": dr_names,
     }
     man_bytes = json.dumps(manifest, ensure_ascii=False, separators=(",", ":")).encode("utf-8")
 
@@ -371,6 +393,10 @@ def flatten(rt: RuleTable, globals_=None) -> FlatTable:
         ("CONSTS_V64", consts_v64_a, 8),
         ("ROW_APATS", np.array(row_apats or [0], dtype=np.uint32), 4),
         ("BLOCK_SLOTS_OFF", bs_off, 4), ("BLOCK_SLOTS", np.array(bs_list or [0], dtype=np.uint32), 4),
+        ("DR_OFF", np.array(dr_off + [len(dr_entries)], dtype=np.uint32), 4),
+        ("DR_ENTRIES", np.array(dr_entries or [(0, 0, 0, 0)], dtype=np.uint32).reshape(-1, 4), 16),
+        ("DR_PARENTS", np.array(dr_parents or [0], dtype=np.uint32), 4),
+        ("DR_NAME_STR", np.array(dr_name_str or [0], dtype=np.uint32), 4),
         ("MANIFEST", np.frombuffer(man_bytes, dtype=np.uint8), 1),
     ]
     assert rows_a.dtype.itemsize == 16 and code_a.dtype.itemsize == 8 and consts_a.dtype.itemsize == 16

@@ -12,7 +12,7 @@ Table blob (little endian, every section 16-byte aligned):
 from __future__ import annotations
 
 MAGIC = 0x32425243  # 'CRB2'
-VERSION = 13
+VERSION = 14
 ALIGN = 16
 
 NONE32 = 0xFFFFFFFF
@@ -53,6 +53,11 @@ SECTIONS = {
     "BLOCK_SLOTS_OFF": 25,  # u32[n_blocks+1] CSR: attribute slots read by the conditions of a block (prefetch list)
     "BLOCK_SLOTS": 26,    # u32[]
     "CONSTS_V64": 23,     # u64[n_consts] NaN-boxed form of each constant for the flat fast path (FLAT_NOT_FAST if none)
+    # derived roles of every resource policy block (effectiveDerivedRoles bookkeeping, ruletable.go:936-979)
+    "DR_OFF": 27,         # u32[n_blocks+1] CSR into DR_ENTRIES
+    "DR_ENTRIES": 28,     # {u32 name index (MANIFEST derived_roles, sorted); cond (global id + 1, 0 none); parents start; n parents}
+    "DR_PARENTS": 29,     # u32[] parent role ids (ROLE_ANY for "*")
+    "DR_NAME_STR": 30,    # u32[n derived role names] string id of each name (runtime.effectiveDerivedRoles in conditions)
     "MANIFEST": 100,      # JSON (host only): dictionaries + slot paths for the batch encoder
 }
 
@@ -61,7 +66,7 @@ META = {name: i for i, name in enumerate([
     "n_versions", "n_respats", "n_scopes", "n_principals", "n_roles", "n_apats", "n_blocks", "n_rows",
     "n_conds", "n_code", "n_consts", "n_slots", "n_strings", "has_role_policies", "has_parent_roles",
     "has_principal_policies", "max_stack", "max_loop_depth", "n_vars", "theap_words", "uses_pid", "uses_now",
-    "max_scope_depth", "direct_kinds", "block_shapes",
+    "max_scope_depth", "direct_kinds", "block_shapes", "uses_runtime", "n_dr_names",
 ])}
 
 SCOPE_FLAG_PRINCIPAL = 1
@@ -148,6 +153,7 @@ OPS = {name: i for i, name in enumerate([
     "LOOP_PRED",        # TOS = predicate of a filtering map / transformList / transformMap / transformMapEntry: true -> pop and
                         # fall through to the transform; false -> skip this iteration; else error. c = pc of the LOOP_NEXT
     "MATCHES",          # TOS string -> BOOL: RE2 search with the byte-level DFA at theap[c] (cel/regex_dfa.py)
+    "RUNTIME_EDR",      # push runtime.effectiveDerivedRoles: the derived roles in force for the policy being evaluated (list of strings)
 ])}
 # FN ids: string functions first (cel-go ext.Strings), list functions from EXCEPT on (ext.Lists, Cerbos except / intersect)
 FNS = {name: i for i, name in enumerate([
@@ -198,6 +204,9 @@ MAX_VARS = 4
 MAX_CHAIN = 8       # scope chain length supported on device (depth+1)
 MAX_ROLE_COLS = 16
 MAX_CLASS_PATS = 8  # resource patterns one request kind may match
+
+# decision metadata: where ActionEffect.Policy comes from (ruletable.go:913-922, 1082-1095)
+META_SRC = {"NO_MATCH": 0, "PRINCIPAL_POLICY": 1, "RESOURCE_POLICY": 2, "NO_MATCH_FOR_SCOPE_PERMISSIONS": 3, "ROLE_POLICY": 4}
 
 # batch flags (cgpu_batch.flags)
 BATCH_FLAG_LENIENT = 1
@@ -284,6 +293,8 @@ def c_header() -> str:
     d("CB_MAX_ROLE_COLS", MAX_ROLE_COLS)
     d("CB_MAX_CLASS_PATS", MAX_CLASS_PATS)
     d("CB_BATCH_FLAG_LENIENT", BATCH_FLAG_LENIENT)
+    for k, v in META_SRC.items():
+        d(f"CB_META_SRC_{k}", v)
     out.append("")
     out.append("""typedef struct { uint32_t magic, version, n_sections, flags; uint64_t total_bytes, reserved; } cb_blob_header;
 typedef struct { uint32_t id, elem_bytes; uint64_t offset, n_bytes; } cb_section_desc;
@@ -295,6 +306,10 @@ typedef struct { uint8_t op, flags, xk, yk; uint32_t x, y; uint16_t xa, ya; } cb
 typedef struct { uint32_t tag, pad; uint64_t bits; } cb_const;
 typedef struct { uint32_t role, rule_start, n_rules, pad; } cb_rolepol_entry;
 typedef struct { uint32_t respat, cond, apat_start, n_apats; } cb_rolepol_rule;
+/* decision metadata plane (cgpu_check_meta): per (request, action) one word -- scope id of the deciding scope (0xFFFF: none) |
+ * source << 16 | role id << 24 (source CB_META_SRC_ROLE_POLICY) -- and per request the first scope of each chain + the
+ * effective derived roles as a bit set over MANIFEST.derived_roles */
+typedef struct { uint16_t principal_first_scope, resource_first_scope; uint32_t flags; uint64_t effective_derived_roles; } cb_request_meta;
 /* request header columns (SURVEY.md 8(d): 24 B / request) */
 typedef struct { uint32_t principal_id, kind_class, resource_scope, principal_scope; } cb_hdr0;   /* 16 B */
 typedef struct { uint16_t resource_version, principal_version; uint32_t action_set_id; } cb_hdr1;  /*  8 B */

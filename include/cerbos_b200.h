@@ -92,6 +92,18 @@ void cgpu_table_release(cgpu_table *t);
  * 0 for slots beyond an input's own action count.  Re-entrant; blocks until the result is in effects_out. */
 int cgpu_check(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, uint8_t *effects_out);
 
+/* Decision metadata (the reference's IncludeMeta responses and audit entries: ActionEffect.Policy / Scope and
+ * CheckOutput.EffectiveDerivedRoles -- internal/ruletable/ruletable.go:753-782, 913-922, 936-979, 1082-1148;
+ * internal/svc/cerbos_svc.go:291-311).  Same inputs as cgpu_check; besides the effect bytes it returns
+ *   action_meta_out   n_requests * max_actions words: scope id of the deciding scope (0xFFFF none) | source << 16
+ *                     (CB_META_SRC_*, cerbos_b200_format.h) | role id << 24 (role policies)
+ *   request_meta_out  n_requests records: first scope of the principal / resource chain (the policy key's scope) and
+ *                     the effective derived roles as a bit set over the table's derived-role names
+ * ids index the dictionaries the host encoder already holds (table MANIFEST); the host assembles the strings
+ * (cerbos_b200/meta.py; Go: namer.PolicyKeyFromFQN over the same ids).  An optional plane: cgpu_check moves no extra byte. */
+int cgpu_check_meta(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, uint8_t *effects_out,
+                    uint32_t *action_meta_out, void *request_meta_out /* cb_request_meta[n_requests] */);
+
 /* Device-resident path: columns are device pointers on ctx's device.  dev_bitmap_out receives
  * n_requests * ceil(max_actions / 8) bytes, bit (k % 8) of byte n * ceil(K/8) + k / 8 set <=> ALLOW.
  * Asynchronous on `cuda_stream` (a cudaStream_t, used exactly as given; NULL = the legacy default stream).

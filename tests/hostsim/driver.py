@@ -110,3 +110,27 @@ def check_spec(lib, blob: bytes, columns, n, max_actions, now_ns=0, flags=0, mod
     if rc != 0:
         raise RuntimeError(f"hostsim_check_spec failed: {rc}")
     return _decode(bitmap, n, km)
+
+
+def check_meta(blob: bytes, columns, n, max_actions, now_ns=0, flags=0):
+    """The decision-metadata body: -> (effects uint8[n, K], action words uint32[n, K], request records (cerbos_b200.meta dtype))."""
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.hostsim_check.restype = ctypes.c_int
+    from cerbos_b200.meta import REQUEST_META_DTYPE
+    _lib.hostsim_check_meta.restype = ctypes.c_int
+    cols = [np.ascontiguousarray(c) for c in columns]
+    ptrs = (ctypes.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+    sizes = (ctypes.c_uint64 * len(cols))(*[c.nbytes for c in cols])
+    km = max(max_actions, 1)
+    eff = np.zeros((n, km), dtype=np.uint8)
+    am = np.zeros((n, km), dtype=np.uint32)
+    rm = np.zeros(n, dtype=REQUEST_META_DTYPE)
+    buf = ctypes.create_string_buffer(blob, len(blob))
+    rc = _lib.hostsim_check_meta(buf, ctypes.c_uint64(len(blob)), ctypes.c_uint64(n), ctypes.c_uint32(max_actions), ctypes.c_int64(now_ns),
+                                 ctypes.c_uint32(flags), ptrs, sizes, eff.ctypes.data_as(ctypes.c_void_p), am.ctypes.data_as(ctypes.c_void_p),
+                                 rm.ctypes.data_as(ctypes.c_void_p))
+    if rc != 0:
+        raise RuntimeError(f"hostsim_check_meta failed: {rc}")
+    return eff, am, rm

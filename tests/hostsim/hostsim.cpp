@@ -45,7 +45,8 @@ extern "C" int HOSTSIM_ENTRY(const void *blob, uint64_t blob_len, uint64_t n, ui
     const uint32_t *meta = reinterpret_cast<const uint32_t *>(base + off[CB_SEC_META]);
     cb::TableLayout lay;
     memset(&lay, 0, sizeof(lay));
-    for (int i = 0; i < 28; i++) lay.off[i] = (uint32_t)off[i];
+    for (int i = 0; i < 32; i++) lay.off[i] = (uint32_t)off[i];
+    lay.uses_runtime = meta[CB_META_USES_RUNTIME];
     lay.nV = meta[CB_META_N_VERSIONS]; lay.nRP = meta[CB_META_N_RESPATS]; lay.nS = meta[CB_META_N_SCOPES]; lay.nP = meta[CB_META_N_PRINCIPALS];
     lay.nR = meta[CB_META_N_ROLES]; lay.nAP = meta[CB_META_N_APATS]; lay.nT = meta[CB_META_N_STRINGS]; lay.n_slots = meta[CB_META_N_SLOTS];
     lay.n_rows = meta[CB_META_N_ROWS] ? meta[CB_META_N_ROWS] : 1;
@@ -137,6 +138,43 @@ extern "C" int HOSTSIM_ENTRY(const void *blob, uint64_t blob_len, uint64_t n, ui
 }
 
 #if !defined(HOSTSIM_SPEC) && !defined(HOSTSIM_SPEC_UC)
+// the decision-metadata body (cb::eval_request_meta): effects + per-action metadata words + per-request metadata
+extern "C" int hostsim_check_meta(const void *blob, uint64_t blob_len, uint64_t n, uint32_t max_actions, int64_t now, uint32_t flags,
+                                  const void *const *cols, const uint64_t *col_bytes, uint8_t *effects, uint32_t *action_meta, cb_request_meta *req_meta) {
+    const cb_blob_header *h = static_cast<const cb_blob_header *>(blob);
+    if (blob_len < sizeof(*h) || h->magic != CB_MAGIC || h->version != CB_VERSION) return -1;
+    const cb_section_desc *sd = reinterpret_cast<const cb_section_desc *>(static_cast<const char *>(blob) + sizeof(cb_blob_header));
+    const uint8_t *base = static_cast<const uint8_t *>(blob);
+    uint64_t off[128] = {0};
+    for (uint32_t i = 0; i < h->n_sections; i++) if (sd[i].id < 128) off[sd[i].id] = sd[i].offset;
+    const uint32_t *meta = reinterpret_cast<const uint32_t *>(base + off[CB_SEC_META]);
+    cb::TableLayout lay;
+    memset(&lay, 0, sizeof(lay));
+    for (int i = 0; i < 32; i++) lay.off[i] = (uint32_t)off[i];
+    lay.nV = meta[CB_META_N_VERSIONS]; lay.nRP = meta[CB_META_N_RESPATS]; lay.nS = meta[CB_META_N_SCOPES]; lay.nP = meta[CB_META_N_PRINCIPALS];
+    lay.nR = meta[CB_META_N_ROLES]; lay.nAP = meta[CB_META_N_APATS]; lay.nT = meta[CB_META_N_STRINGS]; lay.n_slots = meta[CB_META_N_SLOTS];
+    lay.n_rows = meta[CB_META_N_ROWS] ? meta[CB_META_N_ROWS] : 1;
+    lay.has_role_policies = meta[CB_META_HAS_ROLE_POLICIES]; lay.has_parent_roles = meta[CB_META_HAS_PARENT_ROLES];
+    lay.has_principal_policies = meta[CB_META_HAS_PRINCIPAL_POLICIES]; lay.uses_runtime = meta[CB_META_USES_RUNTIME];
+    cb::BatchView b;
+    b.hdr0 = static_cast<const cb_hdr0 *>(cols[0]); b.hdr1 = static_cast<const cb_hdr1 *>(cols[1]);
+    b.roles = static_cast<const uint32_t *>(cols[2]); b.slots = static_cast<const uint64_t *>(cols[3]);
+    b.heap = static_cast<const uint64_t *>(cols[4]); b.bstr_off = static_cast<const uint32_t *>(cols[5]);
+    b.bstr_bytes = static_cast<const uint8_t *>(cols[6]); b.class_off = static_cast<const uint32_t *>(cols[7]);
+    b.class_pats = static_cast<const uint32_t *>(cols[8]); b.aset_k = static_cast<const uint32_t *>(cols[9]);
+    b.aset_spread = static_cast<const uint64_t *>(cols[10]); b.row_am = static_cast<const uint64_t *>(cols[11]);
+    b.n_rows = lay.n_rows; b.stride = n; b.first = 0; b.count = n;
+    b.role_cols = (uint32_t)(col_bytes[2] / (4 * n)); b.n_asets = (uint32_t)(col_bytes[9] / 4);
+    uint32_t km = max_actions ? max_actions : 1;
+    b.kc = 64 / b.role_cols; if (b.kc > km) b.kc = km;
+    b.n_pass = (km + b.kc - 1) / b.kc; b.max_actions = km; b.kbytes = (km + 7) / 8; b.flags = flags; b.now = now;
+    cb::finish_batch_view(b);
+    b.n_bstr = col_bytes[5] >= 4 ? (uint32_t)(col_bytes[5] / 4 - 1) : 0;
+    b.heap_words = col_bytes[4] / 8;
+    uint32_t status = 0;
+    for (uint64_t i = 0; i < n; i++) cb::eval_request_meta(base, &lay, &b, i, effects, action_meta, req_meta, &status);
+    return status ? -2 : 0;
+}
 // the unique-condition form of the specialised source (cb::SpecConds); "" if the table does not qualify; *n_uconds_out = distinct conditions
 extern "C" int64_t hostsim_generate_uc(const void *blob, uint64_t blob_len, char *out, uint64_t cap, uint32_t *n_uconds_out) {
     uint32_t off[128] = {0};
@@ -146,7 +184,7 @@ extern "C" int64_t hostsim_generate_uc(const void *blob, uint64_t blob_len, char
     const uint32_t *meta = reinterpret_cast<const uint32_t *>(base + off[CB_SEC_META]);
     cb::TableLayout lay;
     memset(&lay, 0, sizeof(lay));
-    for (int i = 0; i < 28; i++) lay.off[i] = off[i];
+    for (int i = 0; i < 32; i++) lay.off[i] = off[i];
     lay.nR = meta[CB_META_N_ROLES]; lay.n_slots = meta[CB_META_N_SLOTS];
     const cbuc::Image uc = cbuc::build(base, off, len, meta, lay);
     if (n_uconds_out) *n_uconds_out = uc.ok ? uc.n_uconds : 0;

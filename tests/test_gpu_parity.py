@@ -535,3 +535,28 @@ def test_run_time_values_on_gpu(ctx):
         assert n >= 80, n
     finally:
         os.environ.pop("CERBOS_B200_NO_JIT", None)
+
+
+def test_decision_metadata_on_gpu():
+    """cgpu_check_meta through Engine.check(include_meta=True): effect, policy, scope of all 166 reference decisions and the
+    effectiveDerivedRoles of every output, against the reference's own recorded answers (engine goldens)."""
+    from cerbos_b200.engine import Engine
+    from helpers import engine_decisions, load_golden
+    docs = [e["policy"] for e in load_golden("store_policies.json")]
+    engines = {False: Engine(docs, globals_={"environment": "test"}),
+               True: Engine(docs, globals_={"environment": "test"}, lenient_scope_search=True)}
+    n = n_edr = 0
+    for cid, lenient, inp, want in engine_decisions():
+        got = engines[lenient].check([inp], now_ns=NOW_NS, include_meta=True)[0]
+        plain = engines[lenient].check([inp], now_ns=NOW_NS)[0]
+        for a, wv in want["actions"].items():
+            g = got["actions"][a]
+            assert (g["effect"], g["policy"], g["scope"]) == (wv["effect"], wv.get("policy", ""), wv.get("scope", "")), (cid, a)
+            assert plain["actions"][a]["effect"] == g["effect"], (cid, a)
+            n += 1
+        wedr = sorted(want.get("effectiveDerivedRoles", want.get("effective_derived_roles")) or [])
+        assert got["effectiveDerivedRoles"] == wedr, cid
+        n_edr += bool(wedr)
+    assert n == 166 and n_edr >= 20
+    for e in engines.values():
+        e.close()

@@ -445,3 +445,36 @@ def test_verify_suite_goldens():
                 assert k_out[0, k] == w, (c["file"], c["test"], a, "kernel core")
                 n += 1
     assert n == 145
+
+
+def test_decision_metadata_on_engine_goldens(store_flat):
+    """ActionEffect.Policy / Scope and EffectiveDerivedRoles (ruletable.go:753-782, 913-922, 936-979, 1082-1148): the
+    metadata body of the kernel core (cb::eval_request_meta, the optional plane behind cgpu_check_meta) against oracle #1
+    on all 166 reference decisions -- and its effects against the bit-parallel body."""
+    from cerbos_b200 import meta as M
+    ft = store_flat
+    orc = CheckOracle(store_rule_table(), globals_=G)
+    n = n_edr = 0
+    for cid, lenient, inp, want in engine_decisions():
+        enc = Encoder(ft.manifest, lenient_scope_search=lenient)
+        b = enc.encode([inp])
+        fl = L.BATCH_FLAG_LENIENT if lenient else 0
+        eff, am, rm = hostsim.check_meta(ft.blob, b.columns, b.n, b.max_actions, NOW.ns, fl)
+        k_out = hostsim.check(ft.blob, b.columns, b.n, b.max_actions, NOW.ns, fl)
+        py = orc.check(inp, NOW, lenient=lenient)
+        p, r = inp.get("principal") or {}, inp.get("resource") or {}
+        for k, a in enumerate(inp["actions"]):
+            pol, sc = M.decode_action(int(am[0, k]), rm[0], ft.manifest, p.get("id", ""), r.get("kind", ""),
+                                      p.get("policyVersion") or "default", r.get("policyVersion") or "default")
+            w = py["actions"][a]
+            assert (int(eff[0, k]), pol, sc) == (w["effect"], w["policy"], w["scope"]), (cid, a)
+            assert eff[0, k] == k_out[0, k], (cid, a)
+            # ... and the reference's own recorded answer
+            names = {"EFFECT_ALLOW": 1, "EFFECT_DENY": 2}
+            wa = want["actions"][a]
+            assert (names[wa["effect"]], wa.get("policy", ""), wa.get("scope", "")) == (int(eff[0, k]), pol, sc), (cid, a)
+            n += 1
+        edr = M.decode_edr(int(rm[0]["effective_derived_roles"]), ft.manifest)
+        assert edr == py["effectiveDerivedRoles"] == sorted(want.get("effectiveDerivedRoles", want.get("effective_derived_roles")) or []), cid
+        n_edr += bool(edr)
+    assert n == 166 and n_edr >= 20
