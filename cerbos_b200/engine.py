@@ -35,10 +35,25 @@ class Engine:
         self.encoder = None
         self.reload(policies)
 
+    @classmethod
+    def from_rule_table_bundle(cls, bundle: bytes, **conf):
+        """An engine over a serialized runtimev1.RuleTable (rule-table bundle, storage/hub/ruletable_bundle.go:36-87)."""
+        from .table.ruletable_pb import decode_rule_table
+        self = cls.__new__(cls)
+        self.conf = dict(globals_=conf.get("globals_") or {}, default_policy_version=conf.get("default_policy_version", "default"),
+                         default_scope=conf.get("default_scope", ""), lenient_scope_search=conf.get("lenient_scope_search", False))
+        self.ctx = capi.Context(conf.get("device", 0))
+        self.table = None
+        self.encoder = None
+        self._install(decode_rule_table(bundle))
+        return self
+
     def reload(self, policies):
         """Build-then-swap, like Manager.reload (internal/ruletable/manager.go:88-124): on failure the
         previous table stays in place."""
-        rt = build_rule_table(policies)
+        self._install(build_rule_table(policies))
+
+    def _install(self, rt):
         ft = flatten(rt, globals_=self.conf["globals_"])
         new_table = self.ctx.load_table(ft.blob)
         old, self.table = self.table, new_table

@@ -410,7 +410,7 @@ class PolicySet:
             rows.append(Row(origin_fqn=fqn, role=role, resource=resource,
                             allow_actions=list(dict.fromkeys(rule.get("allowActions") or [])), condition=cond,
                             scope=scope, version=version,
-                            evaluation_key=f"{namer.policy_key_from_fqn(fqn)}#{role}_rule-{idx:03d}/{resource}",
+                            evaluation_key=f"{namer.policy_key_from_fqn(fqn)}#{role}_rule-{idx:03d}",   # ruletable.go:398 (index within the resource's rule list)
                             policy_kind=KIND_RESOURCE, from_role_policy=True))
         rt.scope_parent_roles.setdefault(scope, {})[role] = list(rp.get("parentRoles") or [])
         return rows

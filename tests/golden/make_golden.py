@@ -220,6 +220,17 @@ def verify_cases():
     print("verify_cases:", len(out), "inputs,", sum(len(o["want"]) for o in out), "decisions")
 
 
+def ruletable_bundle():
+    """internal/test/testdata/bundle/v2_ruletable/bundle_unencrypted.crrt: the reference compiler's own output for the
+    `store` policies as a serialized runtimev1.RuleTable (what OpenRuleTableBundle unmarshals,
+    internal/storage/hub/ruletable_bundle.go:36-87).  Kept verbatim: it pins cerbos_b200/table/ruletable_pb.py (bundle
+    ingestion) and, row for row, cerbos_b200/policy/compile.py."""
+    import shutil
+    src = os.path.join(REF, "test/testdata/bundle/v2_ruletable/bundle_unencrypted.crrt")
+    shutil.copyfile(src, os.path.join(OUT, "ruletable_bundle_unencrypted.crrt"))
+    print("ruletable bundle:", os.path.getsize(src), "bytes")
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("needs /root/reference (authoring container only)")
@@ -229,3 +240,4 @@ if __name__ == "__main__":
     store_policies()
     check_resources_cases()
     verify_cases()
+    ruletable_bundle()
