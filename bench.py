@@ -551,6 +551,41 @@ def measure_e2e(args, table, hb, K, world, dev):
                     "(1 byte per decision); aggregate = n_gpus x requests / slowest rank"}, out
 
 
+def measure_host_encode(w, blob, table, K, n=1 << 16):
+    """The host stage a PDP adds in front of cgpu_check: serialized enginev1.CheckInput messages -> columns (native encoder,
+    cgpu_encode, all host threads), alone and followed by cgpu_check -- reported separately from `e2e`, whose inputs are
+    already encoded."""
+    import ctypes
+    from cerbos_b200 import capi, wire
+    inputs = w.inputs(w.fields(n), range(n))
+    msgs = [wire.check_input(i) for i in inputs]
+    keep = [ctypes.create_string_buffer(m, len(m)) for m in msgs]
+    ptrs = (ctypes.c_void_p * n)(*[ctypes.addressof(b) for b in keep])
+    lens = (ctypes.c_size_t * n)(*[len(m) for m in msgs])
+    ne = capi.NativeEncoder(blob)
+    eb = ne.encode_raw(ptrs, lens, n)
+    col_bytes = sum(int(eb.batch().column_bytes[i]) for i in range(capi.N_COLUMNS))
+    table.check_encoded(eb, NOW_NS)
+    eb.free()
+    reps = 5
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        eb = ne.encode_raw(ptrs, lens, n)
+        eb.free()
+    t_enc = (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        eb = ne.encode_raw(ptrs, lens, n)
+        table.check_encoded(eb, NOW_NS)
+        eb.free()
+    t_both = (time.perf_counter() - t0) / reps
+    ne.close()
+    threads = int(os.environ.get("CERBOS_B200_ENCODE_THREADS", "0")) or min(32, os.cpu_count() or 1)
+    return {"requests_per_s": n / t_enc, "column_gb_per_s": col_bytes / t_enc / 1e9, "wire_bytes_per_request": sum(len(m) for m in msgs) / n,
+            "threads": threads, "encode_plus_check_decisions_per_s": n * K / t_both,
+            "sample": f"{n} serialized CheckInput messages of the workload per call (cgpu_encode, then cgpu_encode + cgpu_check)"}
+
+
 WORKLOAD_DOC = {
     "C1": "C1: 1 resource policy, 3 actions, role-only rules, 1024 requests (BASELINE.json configs[0])",
     "C2": "C2: 10 resource policies x 8 actions, 2 derived roles with CEL on request.resource.attr, 2^20 requests (BASELINE.json configs[1])",
@@ -654,6 +689,8 @@ def main():
             e2e["verified_vs_oracle"] = bool((out.numpy()[: cnt * hb.max_actions].reshape(cnt, hb.max_actions) == want).all())
         result["e2e"] = e2e
     del host_batches
+    if rank == 0 and world == 1 and not args.no_e2e:
+        result["host_encode"] = measure_host_encode(w, blob, table, K)
     if rank == 0 and world == 1 and not args.no_cpu:   # the CPU baseline is reported at N = 1 only
         _, ft0, enc0 = W.build(w)
         v, threads, passes, ns, dt = cpu_port_rate(w, ft0, enc0, seconds=args.cpu_seconds)

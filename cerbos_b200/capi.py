@@ -19,6 +19,7 @@ EXPORTS = [
     "cgpu_check_device", "cgpu_sync", "cgpu_launch_count", "cgpu_table_info", "cgpu_last_kernel_config",
     "cgpu_last_cluster_config", "cgpu_profile", "cgpu_table_wait_ready", "cgpu_table_compile_check", "cgpu_peer_alloc", "cgpu_peer_open", "cgpu_peer_close",
     "cgpu_peer_free", "cgpu_peer_read", "cgpu_check_device_gather", "cgpu_gather_wait", "cgpu_last_error",
+    "cgpu_encoder_create", "cgpu_encoder_destroy", "cgpu_encode", "cgpu_encoded_batch", "cgpu_encoded_free",
 ]
 
 
@@ -92,6 +93,16 @@ def lib():
                            ("cgpu_gather_wait", [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p])):
             getattr(L, name).restype = ctypes.c_int
             getattr(L, name).argtypes = args
+        L.cgpu_encoder_create.restype = ctypes.c_int
+        L.cgpu_encoder_create.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+        L.cgpu_encoder_destroy.restype = None
+        L.cgpu_encoder_destroy.argtypes = [ctypes.c_void_p]
+        L.cgpu_encode.restype = ctypes.c_int
+        L.cgpu_encode.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t), ctypes.c_uint64, ctypes.POINTER(ctypes.c_void_p)]
+        L.cgpu_encoded_batch.restype = ctypes.c_int
+        L.cgpu_encoded_batch.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(_Batch)]
+        L.cgpu_encoded_free.restype = None
+        L.cgpu_encoded_free.argtypes = [ctypes.c_void_p]
         L.cgpu_last_error.restype = ctypes.c_char_p
         L.cgpu_last_error.argtypes = []
         _lib = L
@@ -110,6 +121,55 @@ def compile_check(blob: bytes):
     buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
     _check(lib().cgpu_table_compile_check(buf, len(blob), ctypes.byref(n)))
     return n.value, (lib().cgpu_last_error().decode("utf-8", "replace") if n.value == 0 else "ok")
+
+
+class NativeEncoder:
+    """cgpu_encoder: serialized enginev1.CheckInput messages -> column batch, in C++ (cb_encode.h)."""
+
+    def __init__(self, blob: bytes, default_version="default", default_scope="", lenient_scope_search=False):
+        self._h = ctypes.c_void_p()
+        buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
+        _check(lib().cgpu_encoder_create(buf, len(blob), default_version.encode(), default_scope.encode(), 1 if lenient_scope_search else 0,
+                                         ctypes.byref(self._h)))
+
+    def encode(self, messages) -> "EncodedBatch":
+        n = len(messages)
+        keep = [ctypes.create_string_buffer(m, len(m)) for m in messages]
+        ptrs = (ctypes.c_void_p * n)(*[ctypes.addressof(b) for b in keep])
+        lens = (ctypes.c_size_t * n)(*[len(m) for m in messages])
+        return self.encode_raw(ptrs, lens, n)
+
+    def encode_raw(self, ptrs, lens, n) -> "EncodedBatch":
+        out = ctypes.c_void_p()
+        _check(lib().cgpu_encode(self._h, ptrs, lens, n, ctypes.byref(out)))
+        return EncodedBatch(out)
+
+    def close(self):
+        if self._h:
+            lib().cgpu_encoder_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+
+class EncodedBatch:
+    """cgpu_encoded: the columns of one batch in page-locked memory, owned by the library."""
+
+    def __init__(self, h):
+        self._h = h
+
+    def batch(self, now_ns: int = 0) -> _Batch:
+        b = _Batch()
+        _check(lib().cgpu_encoded_batch(self._h, now_ns, ctypes.byref(b)))
+        return b
+
+    def columns(self):
+        """copies of the twelve columns as uint8 arrays (tests)"""
+        b = self.batch()
+        return [np.frombuffer(ctypes.string_at(b.columns[i], b.column_bytes[i]), dtype=np.uint8).copy() for i in range(N_COLUMNS)]
+
+    def free(self):
+        if self._h:
+            lib().cgpu_encoded_free(self._h)
+            self._h = None
 
 
 class Context:
@@ -218,6 +278,13 @@ class Table:
         sizes = (ctypes.c_size_t * len(cols))(*[c.nbytes for c in cols])
         b = _Batch(n, max_actions, now_ns, flags, ptrs, sizes, len(cols))
         out = np.empty((n, max(max_actions, 1)), dtype=np.uint8)
+        _check(lib().cgpu_check(self.ctx._h, self._h, ctypes.byref(b), out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def check_encoded(self, enc: "EncodedBatch", now_ns: int = 0) -> np.ndarray:
+        """cgpu_check on a batch produced by the native encoder -> uint8[n, K] effects."""
+        b = enc.batch(now_ns)
+        out = np.empty((b.n_requests, max(b.max_actions, 1)), dtype=np.uint8)
         _check(lib().cgpu_check(self.ctx._h, self._h, ctypes.byref(b), out.ctypes.data_as(ctypes.c_void_p)))
         return out
 

@@ -22,6 +22,7 @@
 #include "cb_kernels.h"
 #include "cb_specialize.h"
 #include "cb_uc.h"
+#include "cb_encode.h"
 #include "cb_embed.inc"
 #include "cerbos_b200.h"
 
@@ -260,6 +261,15 @@ struct cgpu_ctx {
     double prof_ms = 0;
     uint64_t prof_n = 0;
     bool prof_pending = false;
+};
+
+struct cgpu_encoder { cbenc::Encoder enc; };
+struct cgpu_encoded {
+    cbenc::Columns cols;
+    void *pinned = nullptr;              // one page-locked block holding all twelve columns (null: no CUDA device, columns stay in `cols`)
+    const void *ptrs[CGPU_N_COLUMNS] = {};
+    size_t bytes[CGPU_N_COLUMNS] = {};
+    uint32_t flags = 0;
 };
 
 struct cgpu_table {
@@ -1201,6 +1211,74 @@ int cgpu_sync(cgpu_ctx *ctx, void *cuda_stream) {
         return fail(CGPU_ERR_UNSUPPORTED, "a request produced a run-time value the device cannot represent exactly (e.g. timestamp outside 1678..2262, string->double, concatenation)");
     }
     return CGPU_OK;
+}
+
+// ---- native batch encoder (cb_encode.h) ----------------------------------------------------------------------------
+int cgpu_encoder_create(const void *blob, size_t len, const char *default_version, const char *default_scope, int lenient_scope_search, cgpu_encoder **out) {
+    if (!blob || !out) return fail(CGPU_ERR_INVALID, "cgpu_encoder_create: null argument");
+    *out = nullptr;
+    cgpu_encoder *e = new (std::nothrow) cgpu_encoder();
+    if (!e) return fail(CGPU_ERR_INVALID, "out of memory");
+    cbenc::Conf conf;
+    if (default_version && default_version[0]) conf.default_version = default_version;
+    if (default_scope) conf.default_scope = default_scope;
+    conf.lenient = lenient_scope_search != 0;
+    if (!e->enc.init(blob, len, conf)) { const std::string why = e->enc.error; delete e; return fail(CGPU_ERR_INVALID, "%s", why.c_str()); }
+    *out = e;
+    return CGPU_OK;
+}
+void cgpu_encoder_destroy(cgpu_encoder *e) { delete e; }
+
+int cgpu_encode(const cgpu_encoder *e, const void *const *inputs, const size_t *input_bytes, uint64_t n, cgpu_encoded **out) {
+    if (!e || !inputs || !input_bytes || !out || n == 0) return fail(CGPU_ERR_INVALID, "cgpu_encode: null argument or empty batch");
+    *out = nullptr;
+    cgpu_encoded *r = new (std::nothrow) cgpu_encoded();
+    if (!r) return fail(CGPU_ERR_INVALID, "out of memory");
+    cbenc::Encoder local = e->enc;     // the dictionaries are read-only; only `error` is per call
+    // shards of the batch are encoded on host threads and merged in order (CERBOS_B200_ENCODE_THREADS, default: the cores, at most 32)
+    unsigned threads = std::thread::hardware_concurrency();
+    if (threads > 32) threads = 32;
+    if (const char *et = getenv("CERBOS_B200_ENCODE_THREADS")) { const long v = strtol(et, nullptr, 10); if (v >= 1 && v <= 256) threads = (unsigned)v; }
+    if (!local.encode(inputs, input_bytes, n, &r->cols, threads ? threads : 1)) { const std::string why = local.error; delete r; return fail(CGPU_ERR_INVALID, "cgpu_encode: %s", why.c_str()); }
+    r->flags = e->enc.conf.lenient ? CB_BATCH_FLAG_LENIENT : 0;
+    size_t total = 0, offs[CGPU_N_COLUMNS];
+    for (int i = 0; i < CGPU_N_COLUMNS; i++) { offs[i] = total; r->bytes[i] = r->cols.bytes(i); total += (r->bytes[i] + 255) & ~(size_t)255; }
+    // page-locked staging so that cgpu_check's chunked H2D copies run asynchronously; without a CUDA device the columns
+    // simply stay where they were built (host memory either way: this is data marshalling, not evaluation)
+    if (cudaHostAlloc(&r->pinned, total ? total : 256, cudaHostAllocDefault) == cudaSuccess) {
+        for (int i = 0; i < CGPU_N_COLUMNS; i++) {
+            if (r->bytes[i]) memcpy(static_cast<uint8_t *>(r->pinned) + offs[i], r->cols.ptr(i), r->bytes[i]);
+            r->ptrs[i] = static_cast<uint8_t *>(r->pinned) + offs[i];
+        }
+        const uint64_t nreq = r->cols.n;
+        const uint32_t ma = r->cols.max_actions;
+        r->cols = cbenc::Columns();
+        r->cols.n = nreq; r->cols.max_actions = ma;
+    } else {
+        cudaGetLastError();
+        r->pinned = nullptr;
+        for (int i = 0; i < CGPU_N_COLUMNS; i++) r->ptrs[i] = r->cols.ptr(i);
+    }
+    *out = r;
+    return CGPU_OK;
+}
+
+int cgpu_encoded_batch(const cgpu_encoded *r, int64_t now_unix_nanos, cgpu_batch *out) {
+    if (!r || !out) return fail(CGPU_ERR_INVALID, "cgpu_encoded_batch: null argument");
+    out->n_requests = r->cols.n;
+    out->max_actions = r->cols.max_actions;
+    out->now_unix_nanos = now_unix_nanos;
+    out->flags = r->flags;
+    out->columns = r->ptrs;
+    out->column_bytes = r->bytes;
+    out->n_columns = CGPU_N_COLUMNS;
+    return CGPU_OK;
+}
+
+void cgpu_encoded_free(cgpu_encoded *r) {
+    if (!r) return;
+    if (r->pinned) cudaFreeHost(r->pinned);
+    delete r;
 }
 
 int cgpu_check_meta(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, uint8_t *effects_out, uint32_t *action_meta_out, void *request_meta_out_v) {

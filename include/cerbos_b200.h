@@ -92,6 +92,22 @@ void cgpu_table_release(cgpu_table *t);
  * 0 for slots beyond an input's own action count.  Re-entrant; blocks until the result is in effects_out. */
 int cgpu_check(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, uint8_t *effects_out);
 
+/* ---- Native batch encoder: serialized enginev1.CheckInput messages -> the column batch cgpu_check takes ----------------
+ * Replaces, on the host, the per-input string / map work of RuleTable.check (internal/ruletable/ruletable.go:785-884) and
+ * the glob lookups over actions and resource kinds (internal/util/globs_common.go; glob_map.go:138-186).  The Go side
+ * passes proto.Marshal of every enginev1.CheckInput it assembled (internal/svc/cerbos_svc.go:249-265); nothing is retained
+ * after cgpu_encode returns.  An encoder belongs to one table blob (its dictionaries) and is immutable: share it freely
+ * between goroutines, rebuild it when the table is reloaded.  The columns come back in page-locked memory. */
+typedef struct cgpu_encoder cgpu_encoder;
+typedef struct cgpu_encoded cgpu_encoded;
+int cgpu_encoder_create(const void *blob, size_t len, const char *default_policy_version /* evaluator.Conf, NULL = "default" */,
+                        const char *default_scope /* NULL = "" */, int lenient_scope_search, cgpu_encoder **out);
+void cgpu_encoder_destroy(cgpu_encoder *e);
+int cgpu_encode(const cgpu_encoder *e, const void *const *inputs, const size_t *input_bytes, uint64_t n, cgpu_encoded **out);
+/* fills `out` so that it can be handed to cgpu_check / cgpu_check_meta; valid until cgpu_encoded_free */
+int cgpu_encoded_batch(const cgpu_encoded *r, int64_t now_unix_nanos, cgpu_batch *out);
+void cgpu_encoded_free(cgpu_encoded *r);
+
 /* Decision metadata (the reference's IncludeMeta responses and audit entries: ActionEffect.Policy / Scope and
  * CheckOutput.EffectiveDerivedRoles -- internal/ruletable/ruletable.go:753-782, 913-922, 936-979, 1082-1148;
  * internal/svc/cerbos_svc.go:291-311).  Same inputs as cgpu_check; besides the effect bytes it returns

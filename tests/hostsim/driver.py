@@ -13,7 +13,7 @@ _lib = None
 def build():
     src = os.path.join(_ROOT, "tests", "hostsim", "hostsim.cpp")
     deps = [src, os.path.join(_ROOT, "cerbos_b200", "csrc", "cb_core.h"), os.path.join(_ROOT, "cerbos_b200", "csrc", "cb_specialize.h"),
-            os.path.join(_ROOT, "cerbos_b200", "csrc", "cb_uc.h"),
+            os.path.join(_ROOT, "cerbos_b200", "csrc", "cb_uc.h"), os.path.join(_ROOT, "cerbos_b200", "csrc", "cb_encode.h"),
             os.path.join(_ROOT, "include", "cerbos_b200_format.h")]
     if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(_SO), exist_ok=True)
@@ -134,3 +134,29 @@ def check_meta(blob: bytes, columns, n, max_actions, now_ns=0, flags=0):
     if rc != 0:
         raise RuntimeError(f"hostsim_check_meta failed: {rc}")
     return eff, am, rm
+
+
+def native_encode(blob: bytes, messages, default_version="default", default_scope="", lenient=False, threads=1):
+    """The native batch encoder (cb_encode.h) on serialized CheckInput messages -> (list of 12 uint8 arrays, dims)."""
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.hostsim_check.restype = ctypes.c_int
+    _lib.hostsim_encode.restype = ctypes.c_void_p
+    _lib.hostsim_encoded_column.restype = ctypes.c_void_p
+    n = len(messages)
+    bufs = [ctypes.create_string_buffer(m, len(m)) for m in messages]
+    ptrs = (ctypes.c_void_p * n)(*[ctypes.addressof(b) for b in bufs])
+    lens = (ctypes.c_uint64 * n)(*[len(m) for m in messages])
+    dims = (ctypes.c_uint32 * 4)()
+    h = _lib.hostsim_encode(ctypes.create_string_buffer(blob, len(blob)), ctypes.c_uint64(len(blob)), default_version.encode(), default_scope.encode(),
+                            ctypes.c_int(1 if lenient else 0), ptrs, lens, ctypes.c_uint64(n), dims, ctypes.c_uint32(threads))
+    if not h:
+        raise RuntimeError("native encoder failed")
+    cols = []
+    for i in range(12):
+        nb = ctypes.c_uint64()
+        p = _lib.hostsim_encoded_column(ctypes.c_void_p(h), ctypes.c_int(i), ctypes.byref(nb))
+        cols.append(np.frombuffer(ctypes.string_at(p, nb.value), dtype=np.uint8).copy())
+    _lib.hostsim_encoded_free(ctypes.c_void_p(h))
+    return cols, list(dims)

@@ -9,6 +9,7 @@
 #include "cb_core.h"
 #include "cb_specialize.h"
 #include "cb_uc.h"
+#include "cb_encode.h"
 
 #if defined(HOSTSIM_SPEC_UC)
 #include "spec_gen.inc"   // generated for one table by hostsim_generate_uc: cb::SpecConds (unique-condition form)
@@ -138,6 +139,28 @@ extern "C" int HOSTSIM_ENTRY(const void *blob, uint64_t blob_len, uint64_t n, ui
 }
 
 #if !defined(HOSTSIM_SPEC) && !defined(HOSTSIM_SPEC_UC)
+// the native batch encoder (cb_encode.h): n serialized CheckInput messages -> the twelve columns; the caller reads them
+// back through hostsim_encoded_column() and releases with hostsim_encoded_free()
+struct HostEncoded { cbenc::Columns cols; };
+extern "C" void *hostsim_encode(const void *blob, uint64_t blob_len, const char *default_version, const char *default_scope, int lenient,
+                                const void *const *inputs, const uint64_t *lens, uint64_t n, uint32_t *dims /* max_actions, role_cols, kc, n_pass */, uint32_t n_threads) {
+    cbenc::Encoder enc;
+    cbenc::Conf conf;
+    conf.default_version = default_version; conf.default_scope = default_scope; conf.lenient = lenient != 0;
+    if (!enc.init(blob, blob_len, conf)) return nullptr;
+    std::vector<size_t> ls(lens, lens + n);
+    HostEncoded *he = new HostEncoded();
+    if (!enc.encode(inputs, ls.data(), n, &he->cols, n_threads)) { delete he; return nullptr; }
+    dims[0] = he->cols.max_actions; dims[1] = he->cols.role_cols; dims[2] = he->cols.kc; dims[3] = he->cols.n_pass;
+    return he;
+}
+extern "C" const void *hostsim_encoded_column(const void *h, int i, uint64_t *bytes) {
+    const HostEncoded *he = static_cast<const HostEncoded *>(h);
+    *bytes = he->cols.bytes(i);
+    return he->cols.ptr(i);
+}
+extern "C" void hostsim_encoded_free(void *h) { delete static_cast<HostEncoded *>(h); }
+
 // the decision-metadata body (cb::eval_request_meta): effects + per-action metadata words + per-request metadata
 extern "C" int hostsim_check_meta(const void *blob, uint64_t blob_len, uint64_t n, uint32_t max_actions, int64_t now, uint32_t flags,
                                   const void *const *cols, const uint64_t *col_bytes, uint8_t *effects, uint32_t *action_meta, cb_request_meta *req_meta) {
