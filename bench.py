@@ -187,12 +187,49 @@ def go_probe():
         return "not found"
 
 
+def run_go_reference(args, w):
+    """The reference's own Go engine through baseline/go/engine_gpubaseline_test.go, when a Go toolchain and a cerbos
+    checkout with its module cache are present (CERBOS_B200_REF_CHECKOUT or baseline/_ref/cerbos); None otherwise."""
+    import shutil
+    import tempfile
+    if go_probe() == "not found":
+        return None
+    checkout = os.environ.get("CERBOS_B200_REF_CHECKOUT") or os.path.join(ROOT, "baseline", "_ref", "cerbos")
+    if not os.path.isdir(os.path.join(checkout, "internal", "engine")):
+        return None
+    try:
+        work = tempfile.mkdtemp(prefix="cerbos_b200_ref_")
+        subprocess.run([sys.executable, os.path.join(ROOT, "tools", "export_workload.py"), "--workload", w.name, "--out", work, "--requests", str(1 << 20),
+                        "--want"], check=True, capture_output=True, timeout=1200)
+        shutil.copy(os.path.join(ROOT, "baseline", "go", "engine_gpubaseline_test.go"), os.path.join(checkout, "internal", "engine"))
+        env = dict(os.environ, CERBOS_B200_WORKLOAD_DIR=work, CERBOS_B200_SECONDS=str(max(10.0, args.cpu_seconds)), GOFLAGS="-mod=mod")
+        r = subprocess.run(["go", "test", "./internal/engine", "-run", "TestGPUBaseline", "-v", "-count=1"], cwd=checkout, env=env, capture_output=True,
+                           text=True, timeout=1800)
+        for ln in r.stdout.splitlines():
+            if "GPU_BASELINE_RESULT " in ln:
+                return json.loads(ln.split("GPU_BASELINE_RESULT ", 1)[1])
+    except Exception as e:  # noqa: BLE001 -- any failure means "not available": the port is timed instead
+        sys.stderr.write(f"go reference arm unavailable: {e}\n")
+    return None
+
+
 def run_reference(args):
     """--impl reference: the CPU path alone, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     w = get_workload(args.workload)
+    go = run_go_reference(args, w)
+    if go is not None:
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": go["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_label(w, args.gpus, args.requests or w.default_n), "go_toolchain": go.get("go"),
+                       "note": "the reference's own engine.Check (baseline/go/engine_gpubaseline_test.go), GOMAXPROCS client goroutines, batches of 1024"},
+            "cpu_baseline": {"value": go["value"], "unit": UNIT, "cores": go["cores"], "kind": "reference",
+                             "sample": f"{go['inputs']} inputs of the workload stream for {go['seconds']:.1f} s"},
+            "e2e": {"value": go["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
     from cerbos_b200 import workloads as W
     _, ft, enc = W.build(w)
     # one "step" = a bounded sample: the first 2^20 requests of the workload's stream on all host threads
