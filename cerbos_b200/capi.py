@@ -19,7 +19,7 @@ EXPORTS = [
     "cgpu_check_device", "cgpu_sync", "cgpu_launch_count", "cgpu_table_info", "cgpu_last_kernel_config",
     "cgpu_last_cluster_config", "cgpu_profile", "cgpu_table_wait_ready", "cgpu_table_compile_check", "cgpu_peer_alloc", "cgpu_peer_open", "cgpu_peer_close",
     "cgpu_peer_free", "cgpu_peer_read", "cgpu_check_device_gather", "cgpu_gather_wait", "cgpu_last_error",
-    "cgpu_encoder_create", "cgpu_encoder_destroy", "cgpu_encode", "cgpu_encoded_batch", "cgpu_encoded_free",
+    "cgpu_device_count", "cgpu_encoder_create", "cgpu_encoder_destroy", "cgpu_encode", "cgpu_encoded_batch", "cgpu_encoded_free",
 ]
 
 
@@ -175,11 +175,14 @@ class EncodedBatch:
 class Context:
     """cgpu_ctx: one CUDA device (one process per GPU)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
+        """device: an index, or a list of indices for one context over several GPUs (cgpu_check then shards every batch)."""
         self._h = ctypes.c_void_p()
-        ids = (ctypes.c_int * 1)(device)
-        _check(lib().cgpu_init(ids, 1, ctypes.byref(self._h)))
-        self.device = device
+        devs = list(device) if isinstance(device, (list, tuple)) else [device]
+        ids = (ctypes.c_int * len(devs))(*devs)
+        _check(lib().cgpu_init(ids, len(devs), ctypes.byref(self._h)))
+        self.device = devs[0]
+        self.devices = devs
 
     def close(self):
         if self._h:

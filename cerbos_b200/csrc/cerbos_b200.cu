@@ -254,6 +254,7 @@ struct cgpu_ctx {
     std::vector<SliceUse> slice_uses;   // own slices whose last push to the peers may still be in flight
     std::mutex copy_mu;
     std::mutex meta_mu;      // cgpu_check_meta calls share ctx->stream
+    std::vector<cgpu_ctx *> peers;   // cgpu_init with n_devices > 1: the contexts of devices 1..n-1 (owned)
     int uc_mode = -1;        // CERBOS_B200_UC: 0 never use the unique-condition kernels, 1 whenever the table allows, unset = tables with > 1 block shape
     uint32_t last_uc = 0;
     bool profiling = false;  // cgpu_profile(): CUDA events around the check kernel of every launch
@@ -290,6 +291,7 @@ struct cgpu_table {
     std::string spec_note;
     // unique-condition image (cb_uc.h): compact copy of the table for tables whose blocks differ in shape
     uint64_t sec_len[kMaxSec]{};
+    std::vector<cgpu_table *> peer_tables;   // the same table on the other devices of a multi-device context (owned)
     cbuc::Image uc;
     uint8_t *d_uc_image = nullptr;
     TableDesc uc_desc{};
@@ -854,7 +856,24 @@ const char *cgpu_last_error(void) { return g_err.c_str(); }
 int cgpu_init(const int *device_ids, int n_devices, cgpu_ctx **out) {
     if (!out) return fail(CGPU_ERR_INVALID, "cgpu_init: out is null");
     *out = nullptr;
-    if (n_devices != 1 || !device_ids) return fail(CGPU_ERR_INVALID, "cgpu_init: exactly one device per context (one process per GPU); got %d", n_devices);
+    if (n_devices < 1 || !device_ids) return fail(CGPU_ERR_INVALID, "cgpu_init: at least one device; got %d", n_devices);
+    if (n_devices > 1) {
+        // one context per device; the first one is the handle, the others hang off it (a Go PDP is one process)
+        for (int i = 0; i < n_devices; i++)
+            for (int j = 0; j < i; j++)
+                if (device_ids[i] == device_ids[j]) return fail(CGPU_ERR_INVALID, "cgpu_init: device %d listed twice", device_ids[i]);
+        cgpu_ctx *head = nullptr;
+        int rc = cgpu_init(device_ids, 1, &head);
+        if (rc != CGPU_OK) return rc;
+        for (int i = 1; i < n_devices; i++) {
+            cgpu_ctx *c = nullptr;
+            rc = cgpu_init(device_ids + i, 1, &c);
+            if (rc != CGPU_OK) { const std::string why = g_err; cgpu_shutdown(head); return fail(rc, "%s", why.c_str()); }
+            head->peers.push_back(c);
+        }
+        *out = head;
+        return CGPU_OK;
+    }
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) return fail(CGPU_ERR_NO_DEVICE, "no CUDA device available (%s); cerbos_b200 has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
@@ -901,6 +920,8 @@ int cgpu_init(const int *device_ids, int n_devices, cgpu_ctx **out) {
 
 void cgpu_shutdown(cgpu_ctx *ctx) {
     if (!ctx) return;
+    for (cgpu_ctx *p : ctx->peers) cgpu_shutdown(p);
+    ctx->peers.clear();
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (auto &s : ctx->slots) {
@@ -959,15 +980,25 @@ int cgpu_table_load(cgpu_ctx *ctx, const void *blob, size_t len, cgpu_table **ou
         cudaSetDevice(ctx->device);
         ensure_spec(ctx, t);
     });
+    // a multi-device context holds the table on every device ("broadcast" of the blob: one process, so a copy per device)
+    for (cgpu_ctx *p : ctx->peers) {
+        cgpu_table *pt = nullptr;
+        rc = cgpu_table_load(p, blob, len, &pt);
+        if (rc != CGPU_OK) { const std::string why = g_err; cgpu_table_release(t); return fail(rc, "%s", why.c_str()); }
+        t->peer_tables.push_back(pt);
+    }
     *out = t;
     return CGPU_OK;
 }
 
 void cgpu_table_retain(cgpu_table *t) { if (t) t->refs.fetch_add(1); }
+int cgpu_device_count(const cgpu_ctx *ctx) { return ctx ? 1 + (int)ctx->peers.size() : 0; }
 
 void cgpu_table_release(cgpu_table *t) {
     if (!t) return;
     if (t->refs.fetch_sub(1) == 1) {
+        for (cgpu_table *pt : t->peer_tables) cgpu_table_release(pt);
+        t->peer_tables.clear();
         { std::lock_guard<std::mutex> g(t->join_mu); if (t->spec_thread.joinable()) t->spec_thread.join(); }
         cudaSetDevice(t->ctx->device);
         cudaDeviceSynchronize();   // no kernel may still read the image
@@ -1002,6 +1033,7 @@ int cgpu_table_compile_check(const void *blob, size_t len, size_t *cubin_bytes) 
 
 int cgpu_table_wait_ready(cgpu_table *t, int *specialised) {
     if (!t) return fail(CGPU_ERR_INVALID, "cgpu_table_wait_ready: null table");
+    for (cgpu_table *pt : t->peer_tables) cgpu_table_wait_ready(pt, nullptr);
     { std::lock_guard<std::mutex> g(t->join_mu); if (t->spec_thread.joinable()) t->spec_thread.join(); }
     if (specialised) *specialised = t->spec_state.load(std::memory_order_acquire) == 1 ? 1 : 0;
     g_err = t->spec_note;   // why not, if not (readable through cgpu_last_error)
@@ -1334,12 +1366,10 @@ int cgpu_check_meta(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch,
     return CGPU_OK;
 }
 
-int cgpu_check(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, uint8_t *effects_out) {
-    if (!ctx || !t || !batch || !effects_out) return fail(CGPU_ERR_INVALID, "cgpu_check: null argument");
-    if (t->ctx != ctx) return fail(CGPU_ERR_INVALID, "table belongs to another context");
+// requests [lo, hi) of `batch` on ctx's device: pipelined H2D / kernels / D2H (see below); effects_out covers the whole batch
+static int check_range(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, uint64_t lo, uint64_t hi, uint8_t *effects_out) {
     const uint64_t N = batch->n_requests;
     const uint32_t km = batch->max_actions ? batch->max_actions : 1;
-    if (N == 0) return CGPU_OK;
     cb::BatchView hv;
     int rc = make_batch_view(t, batch, 0, N, &hv);   // validates sizes (pointers here are host pointers)
     if (rc != CGPU_OK) return rc;
@@ -1398,7 +1428,7 @@ int cgpu_check(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, uint
     uint64_t chunk = ce ? strtoull(ce, nullptr, 10) : (1ull << 18);
     if (chunk < 4096) chunk = 4096;
     chunk &= ~(uint64_t)255;
-    const uint64_t n_chunks = (N + chunk - 1) / chunk;
+    const uint64_t n_chunks = (hi - lo + chunk - 1) / chunk;
     while (slot->ev.size() < 2 * n_chunks) {
         cudaEvent_t e;
         CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1408,7 +1438,7 @@ int cgpu_check(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, uint
     for (int i = CGPU_COL_HEAP; i < CGPU_N_COLUMNS; i++)
         if (batch->column_bytes[i]) CUDA_TRY(cudaMemcpyAsync(dbase + offs[i], hc[i], batch->column_bytes[i], cudaMemcpyHostToDevice, slot->h2d));
     for (uint64_t k = 0; k < n_chunks; k++) {
-        const uint64_t c0 = k * chunk, cnt = N - c0 < chunk ? N - c0 : chunk;
+        const uint64_t c0 = lo + k * chunk, cnt = hi - c0 < chunk ? hi - c0 : chunk;
         CUDA_TRY(cudaMemcpyAsync(dbase + offs[CGPU_COL_HDR0] + c0 * 16, hc[CGPU_COL_HDR0] + c0 * 16, cnt * 16, cudaMemcpyHostToDevice, slot->h2d));
         CUDA_TRY(cudaMemcpyAsync(dbase + offs[CGPU_COL_HDR1] + c0 * 8, hc[CGPU_COL_HDR1] + c0 * 8, cnt * 8, cudaMemcpyHostToDevice, slot->h2d));
         for (uint32_t i = 0; i < bv.role_cols; i++)
@@ -1433,6 +1463,35 @@ int cgpu_check(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, uint
         CUDA_TRY(cudaMemset(slot->d_status, 0, 4));
         return fail(CGPU_ERR_UNSUPPORTED, "a request produced a run-time value the device cannot represent exactly (e.g. timestamp outside 1678..2262, string->double, concatenation)");
     }
+    return CGPU_OK;
+}
+
+int cgpu_check(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, uint8_t *effects_out) {
+    if (!ctx || !t || !batch || !effects_out) return fail(CGPU_ERR_INVALID, "cgpu_check: null argument");
+    if (t->ctx != ctx) return fail(CGPU_ERR_INVALID, "table belongs to another context");
+    const uint64_t N = batch->n_requests;
+    if (N == 0) return CGPU_OK;
+    const size_t n_dev = 1 + ctx->peers.size();
+    if (n_dev == 1 || N < 2 * 4096) return check_range(ctx, t, batch, 0, N, effects_out);
+    // a context over several devices (cgpu_init with n_devices > 1): the requests are independent (engine.go:302-310), so
+    // the batch is cut into one contiguous index range per device, each range travels over that device's own PCIe link
+    // and is evaluated there; results land index-aligned in effects_out.  One host thread per device.
+    if (t->peer_tables.size() != ctx->peers.size()) return fail(CGPU_ERR_INVALID, "table was not loaded on every device of the context");
+    std::vector<int> rcs(n_dev, CGPU_OK);
+    std::vector<std::string> errs(n_dev);
+    const uint64_t per = (((N + n_dev - 1) / n_dev) + 255) & ~(uint64_t)255;
+    std::vector<std::thread> th;
+    auto work = [&](size_t d) {
+        const uint64_t lo = d * per < N ? d * per : N, hi = lo + per < N ? lo + per : N;
+        if (lo >= hi) return;
+        rcs[d] = d == 0 ? check_range(ctx, t, batch, lo, hi, effects_out) : check_range(ctx->peers[d - 1], t->peer_tables[d - 1], batch, lo, hi, effects_out);
+        if (rcs[d] != CGPU_OK) errs[d] = g_err;
+    };
+    for (size_t d = 1; d < n_dev; d++) th.emplace_back(work, d);
+    work(0);
+    for (auto &x : th) x.join();
+    for (size_t d = 0; d < n_dev; d++)
+        if (rcs[d] != CGPU_OK) return fail(rcs[d], "device %zu: %s", d, errs[d].c_str());
     return CGPU_OK;
 }
 

@@ -36,7 +36,10 @@
 extern "C" {
 #endif
 
-typedef struct cgpu_ctx cgpu_ctx;     /* one device + stream pool; create once per process (one process per GPU) */
+typedef struct cgpu_ctx cgpu_ctx;     /* devices + stream pools; create once per process.  n_devices = 1: one GPU (one process
+                                       * per GPU under torchrun / MPI); n_devices > 1: one process drives several GPUs --
+                                       * cgpu_table_load places the table on every device, cgpu_check cuts a batch into one
+                                       * index range per device (each over its own PCIe link), results stay index-aligned */
 typedef struct cgpu_table cgpu_table; /* immutable flattened rule table resident in HBM */
 
 enum cgpu_status {
@@ -80,6 +83,7 @@ typedef struct {
 } cgpu_batch;
 
 int cgpu_init(const int *device_ids, int n_devices, cgpu_ctx **out);
+int cgpu_device_count(const cgpu_ctx *ctx);
 void cgpu_shutdown(cgpu_ctx *ctx);
 
 /* blob = host-built flattened table (cerbos_b200/table/flatten.py; Go: the same writer over runtimev1.RuleTable).

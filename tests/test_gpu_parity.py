@@ -560,3 +560,26 @@ def test_decision_metadata_on_gpu():
     assert n == 166 and n_edr >= 20
     for e in engines.values():
         e.close()
+
+
+def test_multi_device_context_shards_a_batch():
+    """cgpu_init with several devices in ONE process: the table lives on every device, cgpu_check cuts the batch
+    into one index range per device; results index-aligned and equal to the oracle.  Needs >= 2 GPUs (gpurun --gpus 2)."""
+    import torch
+    from cerbos_b200 import capi, workloads as W
+    from oracle import cref
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs at least two GPUs")
+    for name, n in (("C2", (1 << 18) + 999), ("C3", (1 << 17) + 3)):
+        w = W.WORKLOADS[name]()
+        _, ft, enc = W.build(w)
+        b = w.columns(w.fields(n), enc)
+        want = cref.check(ft.blob, b.columns, b.n, b.max_actions, n_threads=os.cpu_count() or 1)
+        c = capi.Context(list(range(min(n_dev, 4))))
+        t = c.load_table(ft.blob)
+        t.wait_ready()
+        for _ in range(2):
+            assert (t.check(b.columns, b.n, b.max_actions) == want).all(), name
+        t.release()
+        c.close()
