@@ -555,37 +555,57 @@ def measure(args, ctx, w, blob, enc, table, dev, rank, world, local_rank, n, pri
     return res
 
 
-def measure_e2e(args, table, hb, K, world, dev):
+def measure_e2e(args, table, hb, K, world, dev, n_slots):
     """End to end through the host-buffer C ABI on THIS rank's GPU / PCIe link: pinned host columns, H2D + kernels + D2H
-    inside the timing.  Every rank runs it on its own shard; the aggregate is n_gpus x requests over the slowest rank."""
+    inside the timing.  Every rank runs it on its own shard; the aggregate is n_gpus x requests over the slowest rank.
+    Headline: cgpu_check_narrow (the batch in its narrow wire form, widened on the device); cgpu_check on the canonical
+    8-byte columns is timed beside it (`wide`)."""
     import torch
     import torch.distributed as dist
-    pinned = []
-    for c in hb.columns:
-        a = np.ascontiguousarray(c)
+    from cerbos_b200 import narrow as NW
+
+    def pin(a):
+        a = np.ascontiguousarray(a)
         t = torch.empty(max(a.nbytes, 1), dtype=torch.uint8).pin_memory()
         t.numpy()[: a.nbytes] = a.view(np.uint8).reshape(-1)
-        pinned.append((t, a.nbytes))
-    ptrs = [t.data_ptr() for t, _ in pinned]
-    sizes = [nb for _, nb in pinned]
+        return t.data_ptr(), t
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            fn()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        if world > 1:
+            td = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+            dt = float(td.item())
+        return dt
+
+    pinned = [pin(c) for c in hb.columns]
+    ptrs = [p for p, _ in pinned]
+    sizes = [int(np.ascontiguousarray(c).nbytes) for c in hb.columns]
     out = torch.empty(hb.n * hb.max_actions, dtype=torch.uint8).pin_memory()
-    for _ in range(3):
-        table.check_into(ptrs, sizes, hb.n, hb.max_actions, out.data_ptr(), NOW_NS, 0)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        table.check_into(ptrs, sizes, hb.n, hb.max_actions, out.data_ptr(), NOW_NS, 0)
-    dt = (time.perf_counter() - t0) / args.e2e_steps
-    if world > 1:
-        td = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(td, op=dist.ReduceOp.MAX)
-        dt = float(td.item())
-    return {"value": world * hb.n * K / dt, "unit": UNIT, "h2d_bytes_per_step": int(sum(sizes)),
-            "d2h_bytes_per_step": int(hb.n * hb.max_actions), "ms_per_step": dt * 1e3, "n_gpus": world,
-            "requests_per_step_per_gpu": hb.n,
-            "note": "cgpu_check on every rank (its own PCIe link): pinned host columns -> H2D -> kernels -> D2H effect bytes "
-                    "(1 byte per decision); aggregate = n_gpus x requests / slowest rank"}, out
+    dt_wide = timed(lambda: table.check_into(ptrs, sizes, hb.n, hb.max_actions, out.data_ptr(), NOW_NS, 0))
+    wide = {"value": world * hb.n * K / dt_wide, "unit": UNIT, "h2d_bytes_per_step": int(sum(sizes)), "d2h_bytes_per_step": int(hb.n * hb.max_actions),
+            "ms_per_step": dt_wide * 1e3, "call": "cgpu_check (canonical 8-byte columns)"}
+    nb = NW.narrow_batch(hb, n_slots)
+    if nb is None:
+        res = dict(wide)
+    else:
+        out.zero_()
+        b, nr, keep = table.prepare_narrow(nb, NOW_NS, 0, pin=pin)
+        dt = timed(lambda: table.check_narrow_into(b, nr, out.data_ptr()))
+        res = {"value": world * hb.n * K / dt, "unit": UNIT, "h2d_bytes_per_step": nb.wire_bytes(), "d2h_bytes_per_step": int(hb.n * hb.max_actions),
+               "ms_per_step": dt * 1e3, "call": "cgpu_check_narrow (narrow wire form: 16-bit ids, u32 / f32 / u8 slot columns, 32-bit string heap; widened on the device)",
+               "wire_bytes_per_request": nb.wire_bytes() / hb.n, "wide": wide}
+    res.update({"n_gpus": world, "requests_per_step_per_gpu": hb.n,
+                "note": "every rank calls it on its own shard over its own PCIe link: pinned host columns -> H2D (chunked, overlapped) -> kernels "
+                        "-> D2H effect bytes (1 byte per decision); aggregate = n_gpus x requests / slowest rank"})
+    return res, out
 
 
 def measure_host_encode(w, blob, table, K, n=1 << 16):
@@ -714,7 +734,7 @@ def main():
     }
 
     if not args.no_e2e:
-        e2e, out = measure_e2e(args, table, host_batches[0], K, world, dev)
+        e2e, out = measure_e2e(args, table, host_batches[0], K, world, dev, len(enc.slots))
         if not args.no_verify:   # the host-buffer path returns effect bytes: compare them too (first 2^20 requests)
             from oracle import cref
             hb = host_batches[0]

@@ -15,7 +15,7 @@ N_COLUMNS = 12
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE = 0, -1, -2, -3, -4
 
 EXPORTS = [
-    "cgpu_init", "cgpu_shutdown", "cgpu_table_load", "cgpu_table_retain", "cgpu_table_release", "cgpu_check", "cgpu_check_meta",
+    "cgpu_init", "cgpu_shutdown", "cgpu_table_load", "cgpu_table_retain", "cgpu_table_release", "cgpu_check", "cgpu_check_meta", "cgpu_check_narrow",
     "cgpu_check_device", "cgpu_sync", "cgpu_launch_count", "cgpu_table_info", "cgpu_last_kernel_config",
     "cgpu_last_cluster_config", "cgpu_profile", "cgpu_table_wait_ready", "cgpu_table_compile_check", "cgpu_peer_alloc", "cgpu_peer_open", "cgpu_peer_close",
     "cgpu_peer_free", "cgpu_peer_read", "cgpu_check_device_gather", "cgpu_gather_wait", "cgpu_last_error",
@@ -32,6 +32,11 @@ class CgpuError(RuntimeError):
 class _Gather(ctypes.Structure):
     _fields_ = [("n_ranks", ctypes.c_uint32), ("my_rank", ctypes.c_uint32), ("gather_bufs", ctypes.POINTER(ctypes.c_void_p)),
                 ("slice_bytes", ctypes.c_uint64), ("flags", ctypes.POINTER(ctypes.c_void_p)), ("step", ctypes.c_uint32), ("wait_step", ctypes.c_uint32), ("wait_flags", ctypes.c_void_p)]
+
+
+class _Narrow(ctypes.Structure):
+    _fields_ = [("principal_id", ctypes.c_void_p), ("hdr16", ctypes.c_void_p), ("versions", ctypes.c_void_p), ("roles", ctypes.c_void_p),
+                ("role_cols", ctypes.c_uint32), ("slot_class", ctypes.c_void_p), ("slot_cols", ctypes.POINTER(ctypes.c_void_p)), ("heap_u32", ctypes.c_uint32)]
 
 
 class _Batch(ctypes.Structure):
@@ -64,6 +69,8 @@ def lib():
         L.cgpu_table_release.argtypes = [ctypes.c_void_p]
         L.cgpu_check.restype = ctypes.c_int
         L.cgpu_check.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.c_void_p]
+        L.cgpu_check_narrow.restype = ctypes.c_int
+        L.cgpu_check_narrow.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.POINTER(_Narrow), ctypes.c_void_p]
         L.cgpu_check_meta.restype = ctypes.c_int
         L.cgpu_check_meta.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.cgpu_check_device.restype = ctypes.c_int
@@ -289,6 +296,39 @@ class Table:
         b = enc.batch(now_ns)
         out = np.empty((b.n_requests, max(b.max_actions, 1)), dtype=np.uint8)
         _check(lib().cgpu_check(self.ctx._h, self._h, ctypes.byref(b), out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def prepare_narrow(self, nb, now_ns: int = 0, flags: int = 0, pin=None):
+        """Argument block for cgpu_check_narrow from a cerbos_b200.narrow.NarrowBatch.  pin(array) -> (pointer, keepalive)
+        lets the caller place the columns in page-locked memory; default: the numpy buffers themselves."""
+        keep = []
+
+        def ptr(a):
+            a = np.ascontiguousarray(a)
+            if pin is not None:
+                p, k = pin(a)
+                keep.append(k)
+                return p
+            keep.append(a)
+            return a.ctypes.data
+
+        tabs = [ptr(t) for t in nb.tables]
+        sizes = [0, 0, 0, 0] + [int(np.asarray(t).nbytes) for t in nb.tables]
+        cols = (ctypes.c_void_p * N_COLUMNS)(*([None] * 4 + tabs))
+        csz = (ctypes.c_size_t * N_COLUMNS)(*sizes)
+        b = _Batch(nb.n, nb.max_actions, now_ns, flags, cols, csz, N_COLUMNS)
+        scols = (ctypes.c_void_p * max(len(nb.slot_cols), 1))(*[ptr(c) for c in nb.slot_cols])
+        nr = _Narrow(ptr(nb.principal_id), ptr(nb.hdr16), ptr(nb.versions), ptr(nb.roles), nb.role_cols, ptr(nb.slot_class), scols, 1 if nb.heap_u32 else 0)
+        keep += [cols, csz, scols]
+        return b, nr, keep
+
+    def check_narrow_into(self, b, nr, out_ptr):
+        _check(lib().cgpu_check_narrow(self.ctx._h, self._h, ctypes.byref(b), ctypes.byref(nr), ctypes.c_void_p(out_ptr)))
+
+    def check_narrow(self, nb, now_ns: int = 0, flags: int = 0) -> np.ndarray:
+        b, nr, keep = self.prepare_narrow(nb, now_ns, flags)
+        out = np.empty((nb.n, max(nb.max_actions, 1)), dtype=np.uint8)
+        self.check_narrow_into(b, nr, out.ctypes.data)
         return out
 
     def check_meta(self, columns, n: int, max_actions: int, now_ns: int = 0, flags: int = 0):

@@ -61,6 +61,81 @@ __global__ void __launch_bounds__(kThreads) check_meta_kernel(const __grid_const
         cb::eval_request_meta(td.base, &td.lay, &bv, bv.first + i, effects, action_meta, req_meta, status);
 }
 
+// ---- narrow wire format (cgpu_check_narrow): the per-request columns travel over PCIe in their narrowest exact form and are
+// widened to the canonical columns here, in HBM, right before the check kernels read them
+constexpr uint32_t kMaxNarrowSlots = 64;
+struct WidenParams {
+    const uint32_t *pid; const uint16_t *hdr16; const uint8_t *versions; const uint8_t *roles;
+    const void *slot_src[kMaxNarrowSlots];
+    uint8_t slot_class[kMaxNarrowSlots];
+    cb_hdr0 *hdr0; cb_hdr1 *hdr1; uint32_t *roles_out; uint64_t *slots_out;
+    uint64_t first, count, stride;
+    uint32_t role_cols, n_slots;
+};
+__device__ __forceinline__ uint64_t widen_special(uint32_t code) {   // 0 absent, 1 error, 2 null
+    return (uint64_t)(CB_V64_BOX_BASE | (code == 0 ? CB_V64_ABSENT : code == 1 ? CB_V64_ERROR : CB_V64_NULL)) << 48;
+}
+__global__ void __launch_bounds__(kThreads) widen_kernel(const __grid_constant__ WidenParams p) {
+    for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < p.count; i += (uint64_t)gridDim.x * kThreads) {
+        const uint64_t n = p.first + i;
+        const uint2 h = reinterpret_cast<const uint2 *>(p.hdr16)[n];   // kind, resource scope | principal scope, action set
+        const uint32_t k16 = h.x & 0xFFFF, rs16 = h.x >> 16, ps16 = h.y & 0xFFFF, aset = h.y >> 16;
+        cb_hdr0 h0;
+        h0.principal_id = p.pid[n];
+        h0.kind_class = k16 == 0xFFFF ? CB_KIND_NONE : (k16 & 0x8000) ? ((k16 & 0x7FFF) | CB_KIND_CLASS_CSR_BIT) : k16;
+        h0.resource_scope = rs16 == 0xFFFF ? CB_SCOPE_NONE : (rs16 & 0x8000) ? ((rs16 & 0x7FFF) | CB_SCOPE_INEXACT_BIT) : rs16;
+        h0.principal_scope = ps16 == 0xFFFF ? CB_SCOPE_NONE : (ps16 & 0x8000) ? ((ps16 & 0x7FFF) | CB_SCOPE_INEXACT_BIT) : ps16;
+        p.hdr0[n] = h0;
+        const uint32_t rv = p.versions[2 * n], pv = p.versions[2 * n + 1];
+        cb_hdr1 h1;
+        h1.resource_version = (uint16_t)(rv == 0xFF ? CB_NONE16 : rv); h1.principal_version = (uint16_t)(pv == 0xFF ? CB_NONE16 : pv); h1.action_set_id = aset;
+        p.hdr1[n] = h1;
+        for (uint32_t c = 0; c < p.role_cols; c++) {
+            const uint32_t r = p.roles[(uint64_t)c * p.stride + n];
+            p.roles_out[(uint64_t)c * p.stride + n] = r == 0xFF ? CB_ROLE_PAD : r == 0xFE ? CB_ROLE_UNKNOWN : r;
+        }
+        for (uint32_t v = 0; v < p.n_slots; v++) {
+            uint64_t out;
+            switch (p.slot_class[v]) {
+            case CGPU_SLOT_U32_ID: {      // string id | specials | bool
+                const uint32_t w = static_cast<const uint32_t *>(p.slot_src[v])[n];
+                if (w < 0xFFFFFFF0u) out = ((uint64_t)(CB_V64_BOX_BASE | CB_V64_STRING) << 48) | w;
+                else if (w >= 0xFFFFFFFDu) out = widen_special(0xFFFFFFFFu - w);
+                else out = ((uint64_t)(CB_V64_BOX_BASE | CB_V64_BOOL) << 48) | (w == 0xFFFFFFFBu ? 1u : 0u);
+                break;
+            }
+            case CGPU_SLOT_U32_HEAP: {    // list / map in the batch heap | specials
+                const uint32_t w = static_cast<const uint32_t *>(p.slot_src[v])[n];
+                if (w >= 0xFFFFFFFDu) out = widen_special(0xFFFFFFFFu - w);
+                else out = ((uint64_t)(CB_V64_BOX_BASE | ((w & 0x80000000u) ? CB_V64_MAP : CB_V64_LIST)) << 48) | CB_V64_HEAP_BATCH_BIT | (w & 0x7FFFFFFFu);
+                break;
+            }
+            case CGPU_SLOT_F32: {         // a double that float32 holds exactly | specials as NaN payloads
+                const uint32_t w = static_cast<const uint32_t *>(p.slot_src[v])[n];
+                if ((w & 0x7FC00000u) == 0x7FC00000u && (w & 0x3FFFFFu)) out = widen_special((w & 3u) - 1u);
+                else if (w == 0x7FC00000u) out = CB_V64_CANON_NAN;
+                else out = (uint64_t)__double_as_longlong((double)__uint_as_float(w));
+                break;
+            }
+            case CGPU_SLOT_U8: {          // 0 false, 1 true, 2 null, 3 absent, 4 error
+                const uint32_t w = static_cast<const uint8_t *>(p.slot_src[v])[n];
+                out = w <= 1 ? (((uint64_t)(CB_V64_BOX_BASE | CB_V64_BOOL) << 48) | w) : widen_special(w == 3 ? 0u : w == 4 ? 1u : 2u);
+                break;
+            }
+            default: out = static_cast<const uint64_t *>(p.slot_src[v])[n]; break;
+            }
+            p.slots_out[(uint64_t)v * p.stride + n] = out;
+        }
+    }
+}
+// heap words in 32 bits: bit 31 clear = the word itself (counts, zero-extended), set = a string id (boxed STRING)
+__global__ void __launch_bounds__(kThreads) widen_heap_kernel(const uint32_t *src, uint64_t *dst, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kThreads) {
+        const uint32_t w = src[i];
+        dst[i] = (w & 0x80000000u) ? (((uint64_t)(CB_V64_BOX_BASE | CB_V64_STRING) << 48) | (w & 0x7FFFFFFFu)) : (uint64_t)w;
+    }
+}
+
 // unique-condition kernels (cb_uc.h image; generic condition evaluator; deferrals go to the launch's list)
 template <bool kStaged>
 __global__ void __launch_bounds__(kThreads, CB_MIN_BLOCKS) check_uc(const __grid_constant__ TableDesc td, const __grid_constant__ cb::BatchView bv, uint8_t *bitmap,
@@ -1367,7 +1442,23 @@ int cgpu_check_meta(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch,
 }
 
 // requests [lo, hi) of `batch` on ctx's device: pipelined H2D / kernels / D2H (see below); effects_out covers the whole batch
-static int check_range(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, uint64_t lo, uint64_t hi, uint8_t *effects_out) {
+static int check_range(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch_in, uint64_t lo, uint64_t hi, uint8_t *effects_out, const cgpu_narrow *nb = nullptr) {
+    // narrow form: the canonical sizes of the per-request columns (and of a 32-bit heap) are implied, not passed
+    cgpu_batch batch_c = *batch_in;
+    size_t cbytes[CGPU_N_COLUMNS];
+    const void *ccols[CGPU_N_COLUMNS];
+    uint32_t n_role_cols_narrow = 0;
+    if (nb) {
+        for (int i = 0; i < CGPU_N_COLUMNS; i++) { cbytes[i] = batch_in->column_bytes[i]; ccols[i] = batch_in->columns[i] ? batch_in->columns[i] : static_cast<const void *>(""); }
+        n_role_cols_narrow = nb->role_cols;
+        cbytes[CGPU_COL_HDR0] = batch_in->n_requests * 16; cbytes[CGPU_COL_HDR1] = batch_in->n_requests * 8;
+        cbytes[CGPU_COL_ROLES] = (size_t)nb->role_cols * batch_in->n_requests * 4;
+        cbytes[CGPU_COL_SLOTS] = (size_t)(t->desc.lay.n_slots ? t->desc.lay.n_slots : 1) * batch_in->n_requests * 8;
+        if (nb->heap_u32) cbytes[CGPU_COL_HEAP] = batch_in->column_bytes[CGPU_COL_HEAP] * 2;
+        batch_c.columns = ccols; batch_c.column_bytes = cbytes;
+    }
+    const cgpu_batch *batch = &batch_c;
+    (void)n_role_cols_narrow;
     const uint64_t N = batch->n_requests;
     const uint32_t km = batch->max_actions ? batch->max_actions : 1;
     cb::BatchView hv;
@@ -1403,6 +1494,20 @@ static int check_range(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *bat
     const size_t eff_bytes = (size_t)N * km;
     offs[CGPU_N_COLUMNS] = total;
     total += (eff_bytes + 255) & ~(size_t)255;
+    // narrow form: staging for the narrow columns (and the 32-bit heap) behind the canonical region
+    size_t n_pid = 0, n_h16 = 0, n_ver = 0, n_roles = 0, n_heap32 = 0, n_slot[kMaxNarrowSlots] = {0};
+    const uint32_t n_slots_t = t->desc.lay.n_slots;
+    if (nb) {
+        if (n_slots_t > kMaxNarrowSlots) return fail(CGPU_ERR_INVALID, "cgpu_check_narrow: more than %u attribute slots", kMaxNarrowSlots);
+        auto take = [&](size_t bytes) { const size_t at = total; total += (bytes + 255) & ~(size_t)255; return at; };
+        n_pid = take(N * 4); n_h16 = take(N * 8); n_ver = take(N * 2); n_roles = take((size_t)nb->role_cols * N);
+        for (uint32_t v = 0; v < n_slots_t; v++) {
+            const uint32_t cl = nb->slot_class[v];
+            if (cl > CGPU_SLOT_U8) return fail(CGPU_ERR_INVALID, "cgpu_check_narrow: slot class %u", cl);
+            n_slot[v] = take(N * (cl == CGPU_SLOT_U64 ? 8 : cl == CGPU_SLOT_U8 ? 1 : 4));
+        }
+        if (nb->heap_u32) n_heap32 = take(batch_in->column_bytes[CGPU_COL_HEAP]);
+    }
     if (slot->dev_cap < total) {
         if (slot->dev) cudaFree(slot->dev);
         slot->dev = nullptr; slot->dev_cap = 0;
@@ -1435,10 +1540,48 @@ static int check_range(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *bat
         slot->ev.push_back(e);
     }
     const uint8_t *const *hc = reinterpret_cast<const uint8_t *const *>(batch->columns);
-    for (int i = CGPU_COL_HEAP; i < CGPU_N_COLUMNS; i++)
+    for (int i = CGPU_COL_HEAP; i < CGPU_N_COLUMNS; i++) {
+        if (nb && nb->heap_u32 && i == CGPU_COL_HEAP) {
+            const size_t nb32 = batch_in->column_bytes[CGPU_COL_HEAP];
+            if (nb32) {
+                CUDA_TRY(cudaMemcpyAsync(dbase + n_heap32, hc[i], nb32, cudaMemcpyHostToDevice, slot->h2d));
+                const uint64_t words = nb32 / 4;
+                widen_heap_kernel<<<(unsigned)((words + kThreads - 1) / kThreads < 1184 ? (words + kThreads - 1) / kThreads : 1184), kThreads, 0, slot->h2d>>>(
+                    reinterpret_cast<const uint32_t *>(dbase + n_heap32), reinterpret_cast<uint64_t *>(dbase + offs[i]), words);
+                CUDA_TRY(cudaGetLastError());
+                ctx->launches.fetch_add(1, std::memory_order_relaxed);
+            }
+            continue;
+        }
         if (batch->column_bytes[i]) CUDA_TRY(cudaMemcpyAsync(dbase + offs[i], hc[i], batch->column_bytes[i], cudaMemcpyHostToDevice, slot->h2d));
+    }
     for (uint64_t k = 0; k < n_chunks; k++) {
         const uint64_t c0 = lo + k * chunk, cnt = hi - c0 < chunk ? hi - c0 : chunk;
+        if (nb) {
+            CUDA_TRY(cudaMemcpyAsync(dbase + n_pid + c0 * 4, nb->principal_id + c0, cnt * 4, cudaMemcpyHostToDevice, slot->h2d));
+            CUDA_TRY(cudaMemcpyAsync(dbase + n_h16 + c0 * 8, nb->hdr16 + c0 * 4, cnt * 8, cudaMemcpyHostToDevice, slot->h2d));
+            CUDA_TRY(cudaMemcpyAsync(dbase + n_ver + c0 * 2, nb->versions + c0 * 2, cnt * 2, cudaMemcpyHostToDevice, slot->h2d));
+            for (uint32_t i = 0; i < nb->role_cols; i++)
+                CUDA_TRY(cudaMemcpyAsync(dbase + n_roles + (uint64_t)i * N + c0, nb->roles + (uint64_t)i * N + c0, cnt, cudaMemcpyHostToDevice, slot->h2d));
+            WidenParams wp{};
+            for (uint32_t v = 0; v < n_slots_t; v++) {
+                const uint32_t cl = nb->slot_class[v], es = cl == CGPU_SLOT_U64 ? 8 : cl == CGPU_SLOT_U8 ? 1 : 4;
+                CUDA_TRY(cudaMemcpyAsync(dbase + n_slot[v] + c0 * es, static_cast<const uint8_t *>(nb->slot_cols[v]) + c0 * es, cnt * es, cudaMemcpyHostToDevice, slot->h2d));
+                wp.slot_src[v] = dbase + n_slot[v];
+                wp.slot_class[v] = (uint8_t)cl;
+            }
+            wp.pid = reinterpret_cast<const uint32_t *>(dbase + n_pid); wp.hdr16 = reinterpret_cast<const uint16_t *>(dbase + n_h16);
+            wp.versions = dbase + n_ver; wp.roles = dbase + n_roles;
+            wp.hdr0 = reinterpret_cast<cb_hdr0 *>(dbase + offs[CGPU_COL_HDR0]); wp.hdr1 = reinterpret_cast<cb_hdr1 *>(dbase + offs[CGPU_COL_HDR1]);
+            wp.roles_out = reinterpret_cast<uint32_t *>(dbase + offs[CGPU_COL_ROLES]); wp.slots_out = reinterpret_cast<uint64_t *>(dbase + offs[CGPU_COL_SLOTS]);
+            wp.first = c0; wp.count = cnt; wp.stride = N; wp.role_cols = nb->role_cols; wp.n_slots = n_slots_t;
+            CUDA_TRY(cudaEventRecord(slot->ev[2 * k], slot->h2d));
+            CUDA_TRY(cudaStreamWaitEvent(slot->stream, slot->ev[2 * k], 0));
+            const uint64_t wt = (cnt + kThreads - 1) / kThreads;
+            widen_kernel<<<(unsigned)(wt < 1184 ? wt : 1184), kThreads, 0, slot->stream>>>(wp);
+            CUDA_TRY(cudaGetLastError());
+            ctx->launches.fetch_add(1, std::memory_order_relaxed);
+        } else {
         CUDA_TRY(cudaMemcpyAsync(dbase + offs[CGPU_COL_HDR0] + c0 * 16, hc[CGPU_COL_HDR0] + c0 * 16, cnt * 16, cudaMemcpyHostToDevice, slot->h2d));
         CUDA_TRY(cudaMemcpyAsync(dbase + offs[CGPU_COL_HDR1] + c0 * 8, hc[CGPU_COL_HDR1] + c0 * 8, cnt * 8, cudaMemcpyHostToDevice, slot->h2d));
         for (uint32_t i = 0; i < bv.role_cols; i++)
@@ -1447,6 +1590,7 @@ static int check_range(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *bat
             CUDA_TRY(cudaMemcpyAsync(dbase + offs[CGPU_COL_SLOTS] + ((uint64_t)v * N + c0) * 8, hc[CGPU_COL_SLOTS] + ((uint64_t)v * N + c0) * 8, cnt * 8, cudaMemcpyHostToDevice, slot->h2d));
         CUDA_TRY(cudaEventRecord(slot->ev[2 * k], slot->h2d));
         CUDA_TRY(cudaStreamWaitEvent(slot->stream, slot->ev[2 * k], 0));
+        }
         cb::BatchView cv = bv;
         cv.first = c0; cv.count = cnt;
         // the kernel writes effect bytes directly (1 ALLOW / 2 DENY / 0 padding): no host post-pass
@@ -1464,6 +1608,15 @@ static int check_range(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *bat
         return fail(CGPU_ERR_UNSUPPORTED, "a request produced a run-time value the device cannot represent exactly (e.g. timestamp outside 1678..2262, string->double, concatenation)");
     }
     return CGPU_OK;
+}
+
+int cgpu_check_narrow(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, const cgpu_narrow *narrow, uint8_t *effects_out) {
+    if (!ctx || !t || !batch || !narrow || !effects_out) return fail(CGPU_ERR_INVALID, "cgpu_check_narrow: null argument");
+    if (t->ctx != ctx) return fail(CGPU_ERR_INVALID, "table belongs to another context");
+    if (!narrow->principal_id || !narrow->hdr16 || !narrow->versions || !narrow->roles || !narrow->slot_class || !narrow->slot_cols || narrow->role_cols == 0)
+        return fail(CGPU_ERR_INVALID, "cgpu_check_narrow: missing narrow column");
+    if (batch->n_requests == 0) return CGPU_OK;
+    return check_range(ctx, t, batch, 0, batch->n_requests, effects_out, narrow);
 }
 
 int cgpu_check(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, uint8_t *effects_out) {

@@ -96,6 +96,34 @@ void cgpu_table_release(cgpu_table *t);
  * 0 for slots beyond an input's own action count.  Re-entrant; blocks until the result is in effects_out. */
 int cgpu_check(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, uint8_t *effects_out);
 
+/* ---- Narrow wire format: the same batch with its per-request columns in their narrowest exact form ---------------------
+ * cgpu_check is bound by the PCIe link (the kernels take a few percent of a call), so what crosses it is what counts.
+ * A host encoder that knows its dictionaries are small can send
+ *   principal_id  u32[N]
+ *   hdr16         u16[N][4]  kind class, resource scope, principal scope, action set: 0xFFFF = none, bit 15 = the CSR /
+ *                            inexact flag of the 32-bit form (needs < 32767 patterns / scopes, < 65536 action sets)
+ *   versions      u8[N][2]   resource, principal policy version id; 0xFF = none
+ *   roles         u8[role_cols][N]   0xFF pad, 0xFE unknown role
+ *   slot columns  per attribute slot one of CGPU_SLOT_*: u64 as is; u32 string id (0xFFFFFFFF absent, ..FE error, ..FD null,
+ *                 ..FC false, ..FB true); u32 heap reference (bit 31 = map; specials as before); float32 when every number of
+ *                 the column is exactly a float32 (specials = quiet NaNs with payload 1 absent, 2 error, 3 null); u8 (0 false,
+ *                 1 true, 2 null, 3 absent, 4 error)
+ *   heap          optionally u32 words: bit 31 clear = the word (element counts), set = string id (lists / maps of strings)
+ * and a widening kernel rebuilds the canonical columns in HBM (1/100 of the PCIe cost).  `batch` carries the batch-level
+ * tables (columns 4..11; column 4 = the u32 heap when heap_u32) and the scalars; its columns 0..3 are ignored. */
+enum cgpu_slot_class { CGPU_SLOT_U64 = 0, CGPU_SLOT_U32_ID = 1, CGPU_SLOT_U32_HEAP = 2, CGPU_SLOT_F32 = 3, CGPU_SLOT_U8 = 4 };
+typedef struct {
+    const uint32_t *principal_id;
+    const uint16_t *hdr16;
+    const uint8_t *versions;
+    const uint8_t *roles;
+    uint32_t role_cols;
+    const uint8_t *slot_class;        /* [table n_slots] */
+    const void *const *slot_cols;     /* [table n_slots] */
+    uint32_t heap_u32;
+} cgpu_narrow;
+int cgpu_check_narrow(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, const cgpu_narrow *narrow, uint8_t *effects_out);
+
 /* ---- Native batch encoder: serialized enginev1.CheckInput messages -> the column batch cgpu_check takes ----------------
  * Replaces, on the host, the per-input string / map work of RuleTable.check (internal/ruletable/ruletable.go:785-884) and
  * the glob lookups over actions and resource kinds (internal/util/globs_common.go; glob_map.go:138-186).  The Go side
