@@ -2131,6 +2131,65 @@ CB_HD int term_tri(const TableView t, const BatchView &b, const Cols &cols, uint
 // membership / set predicate over it is a fully unrolled, branch-free run of compares.  Lists the cache cannot hold
 // exactly (longer, container / int / NaN elements) raise `slow`: the request goes to the general body.
 enum { CB_LC = 8 };
+#ifndef CB_LIST_KEYS64
+// Lists of interned strings (what set / membership conditions over attributes hold in practice) are cached as their
+// 32-bit string ids: half the registers and compares of the boxed words.  Any other element (number, bool, null,
+// container) makes the list one "this cache cannot hold": the general body decides.
+struct ListRegs {
+    uint32_t st, len;        // st 0: cached list; 1: slot ABSENT / ERROR; 2: a list this cache cannot hold exactly; 3: another type
+    uint32_t e[CB_LC];
+};
+static constexpr uint32_t kListPad = 0xFFFFFFFEu;      // never a string id
+static constexpr uint32_t kListNoKey = 0xFFFFFFFFu;    // a scalar that is not a string: equal to no element of a cached list
+static constexpr uint32_t kStringTop = CB_V64_BOX_BASE | CB_V64_STRING;
+CB_HD ListRegs list_load(const TableView t, const BatchView &b, uint64_t x) {
+    ListRegs L;
+    L.st = v64_bad(x) ? 1u : v64_tag(x) == CB_V64_LIST ? 0u : 3u;
+    L.len = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < CB_LC; j++) L.e[j] = kListPad;
+    if (L.st == 0) {
+        // length and the first CB_LC element words are requested together (bounded by the end of the heap, not by the
+        // length: one memory round trip instead of two); words beyond the length are discarded below
+        const uint64_t pay = x & 0xFFFFFFFFFFFFull;
+        const bool in_batch = (pay & CB_V64_HEAP_BATCH_BIT) != 0;
+        const uint64_t off = in_batch ? pay & (CB_V64_HEAP_BATCH_BIT - 1) : pay;
+        const uint64_t *p = (in_batch ? b.heap : t.theap()) + off;
+        const uint64_t room = (in_batch ? b.heap_words : (uint64_t)t.L->theap_words) - off;   // words from p to the end of its heap
+        uint64_t w[CB_LC];
+        L.len = (uint32_t)ldg(p);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < CB_LC; j++) w[j] = (uint64_t)(j + 1) < room ? ldg(p + 1 + j) : 0ull;
+        bool odd = L.len > CB_LC;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < CB_LC; j++) {
+            const bool in = (uint32_t)j < L.len;
+            odd |= in && (uint32_t)(w[j] >> 48) != kStringTop;
+            L.e[j] = in ? (uint32_t)w[j] : kListPad;
+        }
+        L.st = odd ? 2u : 0u;
+    }
+    return L;
+}
+// x in L: the outcome of in_tri() / the IN branch of term_tri() for every input this form decides, `slow` otherwise
+CB_HD int list_in_tri(uint64_t x, const ListRegs &L, bool &slow) {
+    if (v64_bad(x) || L.st == 1) return TRI_E;
+    if (L.st != 0 || v64_tag(x) > CB_V64_STRING || x == CB_V64_CANON_NAN) { slow = true; return TRI_E; }
+    const uint32_t nx = (uint32_t)(x >> 48) == kStringTop ? (uint32_t)x : kListNoKey;   // number / bool / null: in no list of strings
+    bool found = false;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < CB_LC; j++) found |= nx == L.e[j];
+    return found ? TRI_T : TRI_F;
+}
+#else
 struct ListRegs {
     uint32_t st, len;        // st 0: cached list; 1: slot ABSENT / ERROR; 2: a list this cache cannot hold exactly; 3: another type
     uint64_t e[CB_LC];
@@ -2146,8 +2205,6 @@ CB_HD ListRegs list_load(const TableView t, const BatchView &b, uint64_t x) {
 #endif
     for (int j = 0; j < CB_LC; j++) L.e[j] = kListPad;
     if (L.st == 0) {
-        // length and the first CB_LC element words are requested together (bounded by the end of the heap, not by the
-        // length: one memory round trip instead of two); words beyond the length are discarded below
         const uint64_t pay = x & 0xFFFFFFFFFFFFull;
         const bool in_batch = (pay & CB_V64_HEAP_BATCH_BIT) != 0;
         const uint64_t off = in_batch ? pay & (CB_V64_HEAP_BATCH_BIT - 1) : pay;
@@ -2172,7 +2229,6 @@ CB_HD ListRegs list_load(const TableView t, const BatchView &b, uint64_t x) {
     }
     return L;
 }
-// x in L: the outcome of in_tri() / the IN branch of term_tri() for every input this form decides, `slow` otherwise
 CB_HD int list_in_tri(uint64_t x, const ListRegs &L, bool &slow) {
     if (v64_bad(x) || L.st == 1) return TRI_E;
     if (L.st != 0 || v64_tag(x) > CB_V64_STRING || x == CB_V64_CANON_NAN) { slow = true; return TRI_E; }
@@ -2184,6 +2240,7 @@ CB_HD int list_in_tri(uint64_t x, const ListRegs &L, bool &slow) {
     for (int j = 0; j < CB_LC; j++) found |= nx == L.e[j];
     return found ? TRI_T : TRI_F;
 }
+#endif
 // hasIntersection(A, B) / isSubset(A, B): the INTERSECTS / SUBSET branch of term_tri()
 CB_HD int list_set_tri(bool subset, const ListRegs &A, const ListRegs &B, bool &slow) {
     if (A.st == 1 || B.st == 1) return TRI_E;

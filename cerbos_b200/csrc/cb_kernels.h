@@ -306,6 +306,22 @@ __device__ __forceinline__ void check_uc_body(const TableDesc &td, const cb::Bat
     tv.L = &td.lay;
     tv.base = kStaged ? smem_image : td.base;
     const cb::U4 *pk = nullptr;
+    // prefetch table: the 128-byte lines the columns of 32 consecutive requests span (hdr0 4, hdr1 2, a role column 1, a slot
+    // column 2), as column base + offset of the line and the shift that turns a request index into a byte offset
+    __shared__ unsigned long long pf_base[64];
+    __shared__ uint32_t pf_shift[64];
+    const uint32_t n_pf = min(64u, 6u + bv.role_cols + 2u * td.lay.n_slots);
+    for (uint32_t q = threadIdx.x; q < n_pf; q += kThreads) {
+        unsigned long long p;
+        uint32_t sh;
+        if (q < 4) { p = (unsigned long long)bv.hdr0 + q * 128u; sh = 4; }
+        else if (q < 6) { p = (unsigned long long)bv.hdr1 + (q - 4) * 128u; sh = 3; }
+        else if (q < 6 + bv.role_cols) { p = (unsigned long long)(bv.roles + (uint64_t)(q - 6) * bv.stride); sh = 2; }
+        else { const uint32_t v = q - 6 - bv.role_cols; p = (unsigned long long)(bv.slots + (uint64_t)(v >> 1) * bv.stride) + (v & 1u) * 128u; sh = 3; }
+        pf_base[q] = p;
+        pf_shift[q] = sh;
+    }
+    if (!kStaged) __syncthreads();
     if (kStaged) {
         if (threadIdx.x == 0) {
             mbar_init(mbar, 1);
@@ -329,17 +345,11 @@ __device__ __forceinline__ void check_uc_body(const TableDesc &td, const cb::Bat
     const uint64_t n_warps = (uint64_t)gridDim.x * (kThreads / 32);
     for (uint64_t chunk = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); chunk < n_chunks; chunk += n_warps) {
         const uint64_t i = chunk * 32 + lane;
-        {   // this warp's next chunk: pull its columns towards L2 now (two lanes cover the chunk's two 128-byte lines per column)
-            const uint64_t i2 = i + n_warps * 32;
-            if ((lane & 15u) == 0 && i2 < bv.count) {
-                const uint64_t n2 = bv.first + i2;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(bv.hdr0 + n2));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(bv.hdr0 + n2 + 8));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(bv.hdr1 + n2));
-                const uint32_t *pr = bv.roles + n2;
-                for (uint32_t c = 0; c < bv.role_cols; c++, pr += bv.stride) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr));
-                const uint64_t *ps = bv.slots + n2;
-                for (uint32_t v = 0; v < td.lay.n_slots; v++, ps += bv.stride) asm volatile("prefetch.global.L2 [%0];" ::"l"(ps));
+        {   // this warp's next chunk: pull its columns towards L2 now, one lane per 128-byte line (table built above)
+            const uint64_t c2 = chunk + n_warps;
+            if (c2 * 32 + 32 <= bv.count) {
+                const uint64_t n2 = bv.first + c2 * 32;
+                for (uint32_t q = lane; q < n_pf; q += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_base[q] + (n2 << pf_shift[q])));
             }
         }
         if (i < bv.count) {

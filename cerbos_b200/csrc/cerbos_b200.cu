@@ -623,15 +623,25 @@ SpecForm spec_compile(const uint8_t *image, const cb::TableLayout &lay, const ui
     if (const char *dump = getenv("CERBOS_B200_SPEC_DUMP")) {   // profiling aid: the translation unit handed to NVRTC
         if (FILE *f = fopen(dump, "w")) { fwrite(src.data(), 1, src.size(), f); fclose(f); }
     }
-    const uint64_t key = fnv1a(ubopt.data(), ubopt.size(), fnv1a(mbopt.data(), mbopt.size(), fnv1a(src.data(), src.size())));
+    std::vector<std::string> defs;   // experiments: extra -D options for the generated translation unit, space separated
+    if (const char *xd = getenv("CERBOS_B200_SPEC_DEFS")) {
+        std::string cur;
+        for (const char *c = xd;; c++) {
+            if (*c == ' ' || *c == 0) { if (!cur.empty()) defs.push_back(cur); cur.clear(); if (!*c) break; }
+            else cur += *c;
+        }
+    }
+    uint64_t key = fnv1a(ubopt.data(), ubopt.size(), fnv1a(mbopt.data(), mbopt.size(), fnv1a(src.data(), src.size())));
+    for (const std::string &d : defs) key = fnv1a(d.data(), d.size(), key);
     const std::string cpath = cache_path(key);
     if (cache_read(cpath, cubin)) return form;
     Nvrtc &n = nvrtc();
     if (!n.ok) { *why = "libnvrtc not available"; return SPEC_NONE; }
     void *prog = nullptr;
     if (n.create(&prog, src.c_str(), "cerbos_b200_spec.cu", 0, nullptr, nullptr) != 0) { *why = "nvrtcCreateProgram failed"; return SPEC_NONE; }
-    const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", mbopt.c_str(), ubopt.c_str()};
-    const int rc = n.compile(prog, 5, opts);
+    std::vector<const char *> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", mbopt.c_str(), ubopt.c_str()};
+    for (const std::string &d : defs) opts.push_back(d.c_str());
+    const int rc = n.compile(prog, (int)opts.size(), opts.data());
     if (rc != 0) {
         size_t ls = 0;
         n.log_size(prog, &ls);
