@@ -139,15 +139,56 @@ class ClockSampler:
 
 
 def get_workload(name):
-    from cerbos_b200 import workloads as W
+    import workloads as W
     return W.WORKLOADS[name]()
 
 
-def shard_columns(w, n, shard, enc):
+def _serialized_chunk(job):
+    """(worker process) serialized enginev1.CheckInput messages of requests [start, start + n) of a workload's stream"""
+    name, n, start = job
+    from cerbos_b200 import wire
+    import workloads as W
+    w = W.WORKLOADS[name]()
+    return [wire.check_input(x) for x in w.inputs(w.fields(n, start=start), range(n))]
+
+
+def native_columns(w, n, start, blob):
+    """Columns of a workload without a vectorised column builder (C5), at bench scale: worker processes generate and
+    serialize the requests (the Python part), the native encoder (cgpu_encode, host threads) builds the batch."""
+    import multiprocessing as mp
+    from concurrent.futures import ProcessPoolExecutor
+    from cerbos_b200 import capi
+    from cerbos_b200.encode import Batch, passes_for
+    chunk = 4096
+    jobs = [(w.name, min(chunk, n - o), start + o) for o in range(0, n, chunk)]
+    if len(jobs) > 1:
+        with ProcessPoolExecutor(max_workers=min(48, os.cpu_count() or 1, len(jobs)), mp_context=mp.get_context("spawn")) as pool:
+            parts = list(pool.map(_serialized_chunk, jobs))
+    else:
+        parts = [_serialized_chunk(j) for j in jobs]
+    msgs = [m for p in parts for m in p]
+    ne = capi.NativeEncoder(blob)
+    eb = ne.encode(msgs)
+    raw = eb.columns()
+    K = int(eb.batch().max_actions)
+    eb.free()
+    ne.close()
+    hdr1_t = np.dtype([("rv", "<u2"), ("pv", "<u2"), ("aset", "<u4")])
+    rc = raw[2].nbytes // (4 * n)
+    cols = [raw[0].view(np.uint32).reshape(n, 4), raw[1].view(hdr1_t), raw[2].view(np.uint32).reshape(rc, n), raw[3].view(np.uint64).reshape(-1, n),
+            raw[4].view(np.uint64), raw[5].view(np.uint32), raw[6], raw[7].view(np.uint32), raw[8].view(np.uint32), raw[9].view(np.uint32),
+            raw[10].view(np.uint64), raw[11].view(np.uint64)]
+    kc, n_pass = passes_for(K, rc)
+    return Batch(n, K, rc, cols, None, n_pass, kc)
+
+
+def shard_columns(w, n, shard, enc, blob=None):
     """Columns of requests [shard*n, (shard+1)*n) of the workload's stream (built in parallel chunks)."""
-    from cerbos_b200 import workloads as W
+    import workloads as W
     if w.name in ("C2", "C3"):
         return W.columns_parallel(w, n, shard * n, enc)
+    if blob is not None and n > 8192:
+        return native_columns(w, n, shard * n, blob)
     return w.columns(w.fields(n, start=shard * n), enc)
 
 
@@ -157,7 +198,7 @@ def cpu_port_rate(w, ft, enc, seconds=10.0, n=None, threads=None):
     import ctypes
     n = n or min(w.default_n, 1 << 20)
     threads = threads or (os.cpu_count() or 1)
-    b = w.columns(w.fields(n), enc)
+    b = shard_columns(w, n, 0, enc, ft.blob)
     cols = [np.ascontiguousarray(c) for c in b.columns]
     ptrs = (ctypes.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
     sizes = (ctypes.c_size_t * len(cols))(*[c.nbytes for c in cols])
@@ -230,14 +271,14 @@ def run_reference(args):
                              "sample": f"{go['inputs']} inputs of the workload stream for {go['seconds']:.1f} s"},
             "e2e": {"value": go["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
-    from cerbos_b200 import workloads as W
+    import workloads as W
     _, ft, enc = W.build(w)
     # one "step" = a bounded sample: the first 2^20 requests of the workload's stream on all host threads
     n = min(w.default_n, 1 << 20)
     from oracle import cref
     import ctypes
     threads = os.cpu_count() or 1
-    b = w.columns(w.fields(n), enc)
+    b = shard_columns(w, n, 0, enc, ft.blob)
     cols = [np.ascontiguousarray(c) for c in b.columns]
     ptrs = (ctypes.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
     sizes = (ctypes.c_size_t * len(cols))(*[c.nbytes for c in cols])
@@ -327,7 +368,7 @@ def measure(args, ctx, w, blob, enc, table, dev, rank, world, local_rank, n, pri
     n_buf = 2 if n >= (1 << 22) else 4 if n >= (1 << 18) else 1
     batches, host_batches = [], []
     for j in range(n_buf):   # distinct batches: this rank's shard, n_buf consecutive windows of the workload stream
-        hb = shard_columns(w, n, rank * n_buf + j, enc)
+        hb = shard_columns(w, n, rank * n_buf + j, enc, blob)
         host_batches.append(hb)
         batches.append(DeviceBatch(hb, dev))
     footprint = sum(b.nbytes() for b in batches)
@@ -684,7 +725,8 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from cerbos_b200 import capi, workloads as W
+    from cerbos_b200 import capi
+    import workloads as W
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

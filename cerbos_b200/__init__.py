@@ -10,6 +10,7 @@ Layout
   encode.py  CheckInput batch -> SoA request columns
   policy/    policy documents -> rule rows (stand-in for the reference's Go compile + AddPolicy)
   cel/       CEL parser (stand-in for cel-go's parser: produces what CheckedExpr carries)
-  workloads.py  synthetic configurations C1..C3 of BASELINE.json
+  narrow.py  the narrow wire format of cgpu_check_narrow;  meta.py  decoding of the metadata plane;  wire.py  CheckInput protobuf bytes
+(the synthetic configurations C1..C5 of BASELINE.json are bench / test infrastructure: /workloads.py at the repository root)
 """
-__all__ = ["capi", "engine", "encode", "workloads"]
+__all__ = ["capi", "engine", "encode"]

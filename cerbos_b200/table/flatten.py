@@ -216,8 +216,16 @@ def flatten(rt: RuleTable, globals_=None) -> FlatTable:
         # rows that differ only in their action pattern are merged into one row with a pattern list
         merged: dict[tuple, list] = {}
         for r in grows:
-            key2 = (L.ROLE_ANY if r.role == "*" else roles.ids[r.role],
-                    local_cond(r.condition, r.params), local_cond(r.dr_condition, r.dr_params),
+            try:
+                c_ix, dc_ix = local_cond(r.condition, r.params), local_cond(r.dr_condition, r.dr_params)
+            except Unsupported as e:     # name the policy (and rule / derived role) the construct came from
+                where = r.origin_fqn or "?"
+                if getattr(r, "name", ""):
+                    where += f" rule {r.name!r}"
+                if r.origin_derived_role:
+                    where += f" (derived role {r.origin_derived_role!r})"
+                raise Unsupported(f"{where}: {e}") from e
+            key2 = (L.ROLE_ANY if r.role == "*" else roles.ids[r.role], c_ix, dc_ix,
                     respats.ids[r.resource] if kind == "P" else L.NONE16, r.effect,
                     L.ROW_FLAG_PRINCIPAL if kind == "P" else 0)
             pats = merged.setdefault(key2, [])
@@ -253,7 +261,10 @@ def flatten(rt: RuleTable, globals_=None) -> FlatTable:
                 for r in rrows:
                     cid = 0
                     if r.condition is not None:
-                        cid = add_program(r.condition, None) + 1
+                        try:
+                            cid = add_program(r.condition, None) + 1
+                        except Unsupported as e:
+                            raise Unsupported(f"{r.origin_fqn or '?'}: {e}") from e
                     rp_rules.append((respats.ids[r.resource], cid, len(rp_apats), len(r.allow_actions)))
                     rp_apats.extend(apats.ids[a] for a in r.allow_actions)
                 rp_entries.append((roles.ids[role], rule_start, len(rp_rules) - rule_start, 0))

@@ -14,7 +14,8 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-from cerbos_b200 import capi, workloads as W  # noqa: E402
+from cerbos_b200 import capi  # noqa: E402
+import workloads as W
 from cerbos_b200.device import DeviceBatch  # noqa: E402
 from cerbos_b200.dist import PeerGather, all_gather_bitmaps  # noqa: E402
 

@@ -64,7 +64,7 @@ def test_goldens_batched_device_vs_oracle(ctx):
 
 @pytest.mark.parametrize("name,n", [("C1", 1024), ("C2", 1 << 16), ("C2", 1 << 20), ("C3", 1 << 16), ("C3", 1 << 20)])
 def test_workloads_bit_exact(ctx, name, n):
-    from cerbos_b200 import workloads as W
+    import workloads as W
     from cerbos_b200.device import DeviceBatch
     from oracle import cref
     w = W.WORKLOADS[name]()
@@ -90,7 +90,8 @@ def test_workloads_bit_exact(ctx, name, n):
 
 def test_staged_and_global_table_paths_agree():
     """The TMA-staged (shared memory) and the global-memory table paths give identical bits."""
-    from cerbos_b200 import capi, workloads as W
+    from cerbos_b200 import capi
+    import workloads as W
     from cerbos_b200.device import DeviceBatch
     w = W.C2()
     _, ft, enc = W.build(w)
@@ -113,7 +114,8 @@ def test_staged_and_global_table_paths_agree():
 
 def test_lean_and_general_kernel_bodies_agree():
     """CERBOS_B200_FORCE_GENERAL=1 disables the lean body: both must give identical bits."""
-    from cerbos_b200 import capi, workloads as W
+    from cerbos_b200 import capi
+    import workloads as W
     from cerbos_b200.device import DeviceBatch
     for name in ("C2", "C3"):
         w = W.WORKLOADS[name]()
@@ -136,7 +138,8 @@ def test_lean_and_general_kernel_bodies_agree():
 
 
 def test_error_paths(ctx):
-    from cerbos_b200 import capi, workloads as W
+    from cerbos_b200 import capi
+    import workloads as W
     with pytest.raises(capi.CgpuError):
         ctx.load_table(b"\0" * 64)
     w = W.C1()
@@ -151,7 +154,7 @@ def test_error_paths(ctx):
 
 
 def test_many_actions_multiple_passes(ctx):
-    from cerbos_b200 import workloads as W
+    import workloads as W
     from cerbos_b200.encode import Encoder
     from cerbos_b200.policy.compile import build_rule_table
     from cerbos_b200.table.flatten import flatten
@@ -177,7 +180,8 @@ def test_many_actions_multiple_passes(ctx):
 def test_clustered_and_index_order_agree(name, n):
     """CERBOS_B200_CLUSTER=1 forces the clustering kernels (requests grouped by policy block), =0 disables them:
     identical bits, host-buffer and device paths, sizes that are not multiples of the chunk / window."""
-    from cerbos_b200 import capi, workloads as W
+    from cerbos_b200 import capi
+    import workloads as W
     from cerbos_b200.device import DeviceBatch
     from oracle import cref
     w = W.WORKLOADS[name]()
@@ -227,7 +231,8 @@ def test_tma_column_tiles_and_direct_loads_agree(name, n):
     """Index-order lean launches stage the request columns through TMA (double-buffered 256-request tiles) when the
     column runs are 16-byte aligned; CERBOS_B200_NO_TILES=1 forces the per-thread global loads.  Covers a ragged last
     tile, a batch whose stride is not a multiple of 4 (must fall back) and a batch smaller than one tile."""
-    from cerbos_b200 import capi, workloads as W
+    from cerbos_b200 import capi
+    import workloads as W
     from cerbos_b200.device import DeviceBatch
     from oracle import cref
     w = W.WORKLOADS[name]()
@@ -256,7 +261,8 @@ def test_tma_column_tiles_and_direct_loads_agree(name, n):
 def test_table_specialised_and_generic_kernels_agree(name, n):
     """The kernels compiled for the table at run time (cb_specialize.h + NVRTC) against the ahead-of-time generic
     ones (CERBOS_B200_NO_JIT=1) and the oracle; tile-staged and direct column paths, clustered and index order."""
-    from cerbos_b200 import capi, workloads as W
+    from cerbos_b200 import capi
+    import workloads as W
     from cerbos_b200.device import DeviceBatch
     from oracle import cref
     w = W.WORKLOADS[name]()
@@ -290,7 +296,8 @@ def test_table_specialised_and_generic_kernels_agree(name, n):
 def test_specialised_kernel_defers_to_general_kernel():
     """Requests the lean body cannot decide (principal and resource policy versions differ) travel through the
     deferral list of the specialised kernel to the general kernel."""
-    from cerbos_b200 import capi, workloads as W
+    from cerbos_b200 import capi
+    import workloads as W
     from cerbos_b200.device import DeviceBatch
     from oracle import cref
     w = W.C2()
@@ -322,7 +329,7 @@ def test_specialised_kernel_defers_to_general_kernel():
 def test_workload_c5_adversarial(ctx):
     """BASELINE.json configs[4] (1000 policies, deep CEL, JWT claims, Zipf kinds): table image > 96 KB (read from global
     memory, not staged), most blocks carry conditions without a flat form (general body), fused hierarchy-free string ops."""
-    from cerbos_b200 import workloads as W
+    import workloads as W
     from cerbos_b200.device import DeviceBatch
     from oracle import cref
     w = W.C5()
@@ -381,7 +388,8 @@ def test_verify_suite_goldens_through_engine_api():
 def test_unique_condition_kernels(name, n):
     """Unique-condition kernels (cb_uc.h image, cb::eval_request_uc): the ahead-of-time generic form, the NVRTC-specialised
     form, staged and global table paths -- all against the oracle; device path and host-buffer path."""
-    from cerbos_b200 import capi, workloads as W
+    from cerbos_b200 import capi
+    import workloads as W
     from cerbos_b200.device import DeviceBatch
     from oracle import cref
     w = W.WORKLOADS[name]()
@@ -417,7 +425,8 @@ def test_unique_condition_kernel_deferral_list():
     """Requests the unique-condition body cannot decide (differing policy versions) travel through the launch's deferral
     list to the general kernel -- several launches in flight on several streams, each with its own list."""
     import torch
-    from cerbos_b200 import capi, workloads as W
+    from cerbos_b200 import capi
+    import workloads as W
     from cerbos_b200.device import DeviceBatch
     from oracle import cref
     w = W.C3()
@@ -454,7 +463,8 @@ def test_cgpu_check_is_reentrant_across_threads():
     batches of different sizes, some with requests the lean kernels defer (differing policy versions), pipelined in chunks
     (CERBOS_B200_CHECK_CHUNK small, so every call is multi-chunk).  Every result must match the oracle."""
     import threading
-    from cerbos_b200 import capi, workloads as W
+    from cerbos_b200 import capi
+    import workloads as W
     from oracle import cref
     os.environ["CERBOS_B200_CHECK_CHUNK"] = "8192"
     try:
@@ -566,7 +576,8 @@ def test_multi_device_context_shards_a_batch():
     """cgpu_init with several devices in ONE process: the table lives on every device, cgpu_check cuts the batch
     into one index range per device; results index-aligned and equal to the oracle.  Needs >= 2 GPUs (gpurun --gpus 2)."""
     import torch
-    from cerbos_b200 import capi, workloads as W
+    from cerbos_b200 import capi
+    import workloads as W
     from oracle import cref
     n_dev = torch.cuda.device_count()
     if n_dev < 2:

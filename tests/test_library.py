@@ -41,7 +41,8 @@ def test_runtime_specialisation_compiles_without_a_device():
     """The table-specialised translation unit the library hands to NVRTC at table load (embedded cb_core.h / cb_kernels.h +
     generated block evaluators, or -- tables with many block shapes -- the unique-condition evaluator) compiles for sm_100a
     here, without a GPU; tables that do not qualify say why (C5: 73 distinct conditions, most without a flat form)."""
-    from cerbos_b200 import capi, workloads as W
+    from cerbos_b200 import capi
+    import workloads as W
     for name, qualifies in (("C1", True), ("C2", True), ("C3", True), ("C5", False)):
         _, ft, _ = W.build(W.WORKLOADS[name]())
         n, note = capi.compile_check(ft.blob)

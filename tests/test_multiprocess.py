@@ -23,7 +23,7 @@ def _worker(rank, world, port, n_total, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from cerbos_b200 import workloads as W
+    import workloads as W
     from cerbos_b200.dist import all_gather_bitmaps, broadcast_blob, shard_range
     from cerbos_b200.encode import Encoder, manifest_from_blob
     from oracle import cref
@@ -46,7 +46,7 @@ def _worker(rank, world, port, n_total, out_dir):
 def test_sharded_evaluation_matches_single_process(tmp_path):
     n_total, world = 4096, 2
     mp.spawn(_worker, args=(world, _free_port(), n_total, str(tmp_path)), nprocs=world, join=True)
-    from cerbos_b200 import workloads as W
+    import workloads as W
     from oracle import cref
     w = W.C2()
     _, ft, enc = W.build(w)

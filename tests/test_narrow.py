@@ -5,7 +5,8 @@ import os
 import numpy as np
 import pytest
 
-from cerbos_b200 import narrow as NW, workloads as W
+from cerbos_b200 import narrow as NW
+import workloads as W
 from cerbos_b200.encode import Encoder
 from cerbos_b200.table import layout as L
 from cerbos_b200.table.flatten import flatten

@@ -4,7 +4,8 @@ encoder (cerbos_b200/encode.py) on the same inputs: all twelve columns byte for 
 import numpy as np
 import pytest
 
-from cerbos_b200 import wire, workloads as W
+from cerbos_b200 import wire
+import workloads as W
 from cerbos_b200.encode import Encoder
 from cerbos_b200.table.flatten import flatten
 from helpers import engine_decisions, store_rule_table

@@ -6,7 +6,7 @@ import random
 import numpy as np
 import pytest
 
-from cerbos_b200 import workloads as W
+import workloads as W
 from cerbos_b200.encode import Encoder
 from cerbos_b200.policy.compile import build_rule_table
 from cerbos_b200.table.flatten import flatten

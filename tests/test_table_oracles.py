@@ -3,7 +3,7 @@ oracle #1 (structural Python restatement), on the reference goldens and the synt
 import numpy as np
 import pytest
 
-from cerbos_b200 import workloads as W
+import workloads as W
 from cerbos_b200.encode import Encoder
 from cerbos_b200.policy.compile import build_rule_table
 from cerbos_b200.table import layout as L

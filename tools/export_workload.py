@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--want", action="store_true")
     args = ap.parse_args()
     import yaml
-    from cerbos_b200 import workloads as W
+    import workloads as W
     w = W.WORKLOADS[args.workload]()
     os.makedirs(os.path.join(args.out, "policies"), exist_ok=True)
     for i, doc in enumerate(w.policies()):

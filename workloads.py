@@ -15,8 +15,8 @@ from __future__ import annotations
 
 import numpy as np
 
-from .encode import Batch, Encoder, passes_for
-from .table import layout as L
+from cerbos_b200.encode import Batch, Encoder, passes_for
+from cerbos_b200.table import layout as L
 
 SEED_BASE = 0xCE4B05
 _GOLDEN = np.uint64(0x9E3779B97F4A7C15)
@@ -659,8 +659,8 @@ def columns_parallel(w, n, start, enc: Encoder, chunk=1 << 20, threads=None) -> 
 
 def build(workload, globals_=None):
     """-> (rule table, FlatTable, Encoder)"""
-    from .policy.compile import build_rule_table
-    from .table.flatten import flatten
+    from cerbos_b200.policy.compile import build_rule_table
+    from cerbos_b200.table.flatten import flatten
     rt = build_rule_table(workload.policies())
     ft = flatten(rt, globals_=globals_)
     return rt, ft, Encoder(ft.manifest)
