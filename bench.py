@@ -538,7 +538,11 @@ def measure(args, ctx, w, blob, enc, table, dev, rank, world, local_rank, n, pri
     kcfg = ctx.last_kernel_config()
     peak, peak_src = load_peaks()
     algo_bytes = w.bytes_per_request() * n
-    achieved = algo_bytes / (kern_ms_mean * 1e-3) / 1e9
+    # The library's events bracket the first check kernel of a call.  When that kernel is not where the time goes (a table
+    # whose requests are deferred to the general kernel behind it), the roofline is taken on the whole call instead.
+    kernel_dominates = kern_ms_mean >= 0.5 * statistics.mean(step_ms)
+    dominant_ms = kern_ms_mean if kernel_dominates else statistics.mean(step_ms)
+    achieved = algo_bytes / (dominant_ms * 1e-3) / 1e9
 
     # correctness of what was timed: the result images the timed loop left behind, every rotating batch, against the oracle
     verified, compared = None, 0
@@ -574,8 +578,9 @@ def measure(args, ctx, w, blob, enc, table, dev, rank, world, local_rank, n, pri
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(w.name, n), "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
-                     "kernel": "cb_spec_uc" if kcfg.get("unique_conditions") and kcfg.get("table_specialised") else
-                               "cb_spec_tiles" if kcfg.get("table_specialised") else "check_kernel",
+                     "kernel": ("check_kernel<false,2> (general body draining the deferral list; timed as the whole call)" if not kernel_dominates else
+                                ("cb_spec_uc" if kcfg.get("smem_bytes") else "cb_spec_uc_global") if kcfg.get("unique_conditions") and kcfg.get("table_specialised") else
+                                "cb_spec_tiles" if kcfg.get("table_specialised") else "check_kernel"),
                      "kernel_ms_mean": kern_ms_mean,
                      "device_call_ms_mean": statistics.mean(step_ms), "device_call_ms_min": min(step_ms),
                      "call_achieved": algo_bytes / (statistics.mean(step_ms) * 1e-3) / 1e9,
@@ -688,7 +693,7 @@ WORKLOAD_DOC = {
     "C1": "C1: 1 resource policy, 3 actions, role-only rules, 1024 requests (BASELINE.json configs[0])",
     "C2": "C2: 10 resource policies x 8 actions, 2 derived roles with CEL on request.resource.attr, 2^20 requests (BASELINE.json configs[1])",
     "C3": "C3: 100 scoped resource policies (3-level scope chains), 20 CEL conditions incl. string / list operations, 2^24 requests (BASELINE.json configs[2])",
-    "C5": "C5: 1000 policies, deep CEL, JWT claims, Zipf-skewed kinds (BASELINE.json configs[4])",
+    "C5": "C5: 1000 policies, deep CEL, JWT claims, Zipf-skewed kinds (BASELINE.json configs[4]); batches of 2^20 requests per GPU (bounded by the Python request generator)",
 }
 
 
@@ -755,7 +760,9 @@ def main():
         return w, blob, enc, table, spec_ready, spec_note
 
     w, blob, enc, table, spec_ready, spec_note = load(args.workload)
-    n = args.requests or w.default_n
+    # C5 has no vectorised column builder: its requests are generated and serialized by Python worker processes and encoded
+    # by the native encoder, which bounds a batch at 2^20 requests per GPU (four distinct batches rotate)
+    n = args.requests or (w.default_n if w.name in ("C1", "C2", "C3") else min(w.default_n, 1 << 20))
     K = len(w.actions)
     r = measure(args, ctx, w, blob, enc, table, dev, rank, world, local_rank, n, primary=True)
     host_batches = r.pop("_host_batches")

@@ -208,7 +208,9 @@ CB_HD uint64_t d2u(double d) {
 #endif
 }
 
-#ifndef CB_LEAN_ONLY   // generic values + stack interpreter: not part of the lean-only (run-time specialised) build
+// generic values + the helpers behind every bytecode instruction: not part of the lean-only (run-time specialised) build
+// unless the table's specialised code contains leaf programs (cb_specialize.h: CB_SPEC_PROGRAMS)
+#if !defined(CB_LEAN_ONLY) || defined(CB_SPEC_PROGRAMS)
 // ---------------------------------------------------------------------------------------------- values
 struct Val {
     uint32_t tag;
@@ -400,7 +402,13 @@ struct Eq<0> {
         return scalar_equal(c, a, b);
     }
 };
-CB_HD bool val_equal(Ctx &c, const Val &a, const Val &b) { return Eq<3>::eq(c, a, b); }
+// Container equality stays out of line: inlined into every compare of a generated leaf program (cb_specialize.h) the
+// nested loops made NVRTC spend ~2 s per call site; scalars -- nearly every compare -- take the short inline path.
+CB_HD_NOINLINE bool container_equal(Ctx &c, const Val &a, const Val &b) { return Eq<3>::eq(c, a, b); }
+CB_HD bool val_equal(Ctx &c, const Val &a, const Val &b) {
+    if (!is_container(a) || !is_container(b)) { if (is_container(a) != is_container(b)) return false; return scalar_equal(c, a, b); }
+    return container_equal(c, a, b);
+}
 
 CB_HD int str_cmp(const Ctx &c, uint64_t ia, uint64_t ib) {
     const uint8_t *pa, *pb;
@@ -1492,6 +1500,152 @@ CB_HD void loop_bind(Ctx &c, const Loop &L, int var, bool two) {
     }
 }
 
+// ---- single-instruction bodies: shared by the interpreter below and by the straight-line code that
+// cb_specialize.h (generate_uc) emits from a condition's program for the run-time specialised kernels
+CB_HD Val op_select(Ctx &c, const Val &m, uint32_t key) { Val o; return (m.tag == CB_T_MAP && map_find(c, m, mk(CB_T_STRING, key), &o)) ? o : mk_err(); }
+CB_HD Val op_has(Ctx &c, const Val &m, uint32_t key) { return m.tag == CB_T_MAP ? mk_bool(map_find(c, m, mk(CB_T_STRING, key), nullptr)) : mk_err(); }
+CB_HD Val op_has_slot(int s) { return s == SLOT_ERROR ? mk_err() : mk_bool(s == SLOT_VALUE); }
+CB_HD Val op_neg(const Val &v) {
+    const int64_t kMin = (int64_t)0x8000000000000000ull;
+    if (v.tag == CB_T_INT) return (int64_t)v.u == kMin ? mk_err() : mk_int(-(int64_t)v.u);
+    if (v.tag == CB_T_DOUBLE) return mk_double(-u2d(v.u));
+    if (v.tag == CB_T_DUR) return (int64_t)v.u == kMin ? mk_err() : mk(CB_T_DUR, (uint64_t)(-(int64_t)v.u));
+    return mk_err();
+}
+CB_HD Val op_not(const Val &v) { return v.tag == CB_T_BOOL ? mk_bool(!v.u) : mk_err(); }
+CB_HD Val op_size(Ctx &c, const Val &v) {
+    if (v.tag == CB_T_STRING) { const uint8_t *p; uint32_t n; str_get(c, v.u, p, n); return mk_int(utf8_len(p, n)); }
+    if (v.tag == CB_T_BYTES) { const uint8_t *p; uint32_t n; str_get(c, v.u, p, n); return mk_int(n); }
+    if (is_container(v)) return mk_int((int64_t)ldg(heap_ptr(c, v.u)));
+    return mk_err();
+}
+CB_HD Val op_double(Ctx &c, const Val &v) {
+    if (v.tag == CB_T_INT) return mk_double((double)(int64_t)v.u);
+    if (v.tag == CB_T_UINT) return mk_double((double)v.u);
+    if (v.tag == CB_T_STRING) { c.unsupported = 1; return mk_err(); }  // strconv.ParseFloat at run time
+    if (v.tag != CB_T_DOUBLE) return mk_err();
+    return v;
+}
+CB_HD Val op_timestamp(Ctx &c, const Val &v) {
+    if (v.tag == CB_T_TS) return v;
+    if (v.tag == CB_T_STRING) return parse_ts(c, v);
+    if (v.tag == CB_T_INT) {
+        int64_t s = (int64_t)v.u, ns;
+        if (s < -62135596800ll || s > 253402300799ll) return mk_err();
+        if (mul_ovf(s, 1000000000ll, &ns)) { c.unsupported = 1; return mk_err(); }
+        return mk(CB_T_TS, (uint64_t)ns);
+    }
+    return mk_err();
+}
+CB_HD Val op_duration(Ctx &c, const Val &v) {
+    if (v.tag == CB_T_DUR) return v;
+    if (v.tag == CB_T_INT) return mk(CB_T_DUR, v.u);
+    if (v.tag == CB_T_STRING) {
+        const uint8_t *p; uint32_t n; int64_t ns = 0;
+        str_get(c, v.u, p, n);
+        const int rc = parse_duration_text(p, n, &ns);
+        if (rc == 2) c.unsupported = 1;
+        return rc == 0 ? mk(CB_T_DUR, (uint64_t)ns) : mk_err();
+    }
+    return mk_err();
+}
+CB_HD Val op_hier_rel(Ctx &c, uint32_t rel, uint32_t da, uint32_t db, const Val &a, const Val &b) {
+    const bool ok = hier_operand(c, a) & hier_operand(c, b);
+    return ok ? mk_bool(hier_rel(rel, hier_it(c, a.u, da), hier_it(c, b.u, db))) : mk_err();
+}
+CB_HD Val op_ts_get(Ctx &c, const Val &v, uint32_t ia, uint32_t ib, uint32_t ic) {
+    int32_t off_s = (int32_t)ic;
+    if (ib == 2 && v.tag == CB_T_TS) {
+        // IANA zone: the offset in force at this instant, from the zone's transition table (bytecode.iana_zone_words)
+        const uint64_t *z = c.t->theap() + ic;
+        const int64_t sec = floor_div((int64_t)v.u, 1000000000ll);
+        const uint64_t nz = ldg(z);
+        if (sec < (int64_t)ldg(z + 1) || sec >= (int64_t)ldg(z + 2)) { c.unsupported = 1; return mk_err(); }
+        uint64_t lo = 0, hi = nz;          // last entry whose start <= sec
+        while (hi - lo > 1) { const uint64_t mid = (lo + hi) / 2; if ((int64_t)ldg(z + 3 + 2 * mid) <= sec) lo = mid; else hi = mid; }
+        off_s = (int32_t)(int64_t)ldg(z + 3 + 2 * lo + 1);
+    }
+    return do_ts_get(ia, v, ib, off_s);
+}
+CB_HD Val op_in_split(Ctx &c, const Val &x, const Val &sv, uint32_t delim) {   // x in s.split(delim)
+    if (x.tag == CB_T_ERR || sv.tag != CB_T_STRING) return mk_err();
+    bool found = false;
+    if (x.tag == CB_T_STRING) {
+        const uint8_t *px; uint32_t lx, s0, l0;
+        str_get(c, x.u, px, lx);
+        HierIt it = hier_it(c, sv.u, delim);
+        while (hier_next(it, &s0, &l0)) found |= l0 == lx && bytes_eq(it.p + s0, px, lx);
+    }
+    return mk_bool(found);
+}
+CB_HD Val op_hier_size(Ctx &c, const Val &v, uint32_t delim) { return hier_operand(c, v) ? mk_int((int64_t)hier_count(hier_it(c, v.u, delim))) : mk_err(); }
+CB_HD Val op_hier_ca2(Ctx &c, const Val &a, const Val &b, uint32_t ib, uint32_t ic) {
+    const bool ok = hier_operand(c, a) & hier_operand(c, b);
+    return ok ? mk_int((int64_t)hier_ca_size(hier_it(c, a.u, ib), hier_it(c, b.u, ic & 0xFFFF))) : mk_err();
+}
+CB_HD Val op_hier_ca3(Ctx &c, const Val &a0, const Val &b0, const Val &z0, uint32_t ib, uint32_t ic) {
+    const bool ok = hier_operand(c, a0) & hier_operand(c, b0) & hier_operand(c, z0);
+    if (!ok) return mk_err();
+    const HierIt a = hier_it(c, a0.u, ib), b2 = hier_it(c, b0.u, ic & 0xFFFF), z = hier_it(c, z0.u, ic >> 16);
+    const uint32_t k = hier_ca_size(a, b2);
+    return mk_bool(hier_count(z) == k && hier_common(a, z, k) == k);
+}
+CB_HD Val op_fn(Ctx &c, uint32_t fn, uint32_t argc, Val *a) {   // a[0..argc): arguments (target first)
+    if (fn == CB_FN_REVERSE && a[0].tag == CB_T_STRING) return dyn_strfn(c, CB_FN_STR_REVERSE, a, argc);
+    return fn >= CB_FN_EXCEPT ? dyn_listfn(c, fn, a, argc) : dyn_strfn(c, fn, a, argc);
+}
+CB_HD Val op_matches(Ctx &c, const Val &v, uint32_t ic) {   // RE2 search by the DFA table at theap[ic]: text = BOT, bytes, EOT (cel/regex_dfa.py)
+    if (v.tag != CB_T_STRING) return mk_err();
+    const uint64_t *d = c.t->theap() + ic;
+    const uint64_t h = ldg(d);
+    const uint32_t ns = (uint32_t)(h & 0xFFFF), nc = (uint32_t)((h >> 16) & 0xFFFF);
+    uint32_t state = (uint32_t)(h >> 32) & 0xFFFF;
+    const uint8_t *cm = reinterpret_cast<const uint8_t *>(d + 1);
+    const uint64_t *acc = d + 1 + 33, *tr = acc + (ns + 63) / 64;
+    const uint8_t *p; uint32_t n;
+    str_get(c, v.u, p, n);
+    for (uint32_t i = 0; i < n + 2; i++) {
+        const uint32_t sym = i == 0 ? 256u : i == n + 1 ? 257u : (uint32_t)ldg(p + i - 1);
+        const uint32_t q = state * nc + ldg(cm + sym);
+        state = (uint32_t)(ldg(tr + (q >> 2)) >> (16 * (q & 3))) & 0xFFFFu;
+    }
+    return mk_bool((ldg(acc + (state >> 6)) >> (state & 63)) & 1);
+}
+// Quantifier comprehensions (all / exists / exists_one).  qloop_init: true = entered, the first element is bound;
+// false = *res is the comprehension's value.  qloop_next (r = the body's value): true = finished with *res,
+// false = the next element is bound.
+CB_HD bool qloop_init(Ctx &c, Loop &L, const Val &r, int kind, bool two, int var, Val *res) {
+    if (!is_container(r)) { *res = mk_err(); return false; }
+    L.range = r; L.i = 0; L.n = ldg(heap_ptr(c, r.u)); L.any_err = 0; L.count = 0; L.out = 0;
+    if (L.n == 0) { *res = mk_bool(kind == CB_LOOP_ALL); return false; }
+    loop_bind(c, L, var, two);
+    return true;
+}
+CB_HD bool qloop_next(Ctx &c, Loop &L, const Val &r, int kind, bool two, int var, Val *res) {
+    bool done = false;
+    *res = mk_err();
+    if (kind == CB_LOOP_EXISTS_ONE) {
+        if (r.tag != CB_T_BOOL) L.any_err = 1; else if (r.u) L.count++;
+    } else {
+        uint64_t dom = kind == CB_LOOP_EXISTS ? 1 : 0;
+        if (r.tag == CB_T_BOOL) { if (r.u == dom) { done = true; *res = mk_bool(dom != 0); } }
+        else L.any_err = 1;
+    }
+    L.i++;
+    if (!done && L.i >= L.n) {
+        done = true;
+        if (L.any_err) *res = mk_err();
+        else if (kind == CB_LOOP_EXISTS_ONE) *res = mk_bool(L.count == 1);
+        else *res = mk_bool(kind == CB_LOOP_ALL);
+    }
+    if (!done) loop_bind(c, L, var, two);
+    return done;
+}
+CB_HD bool cond_true(const Val &v) { return v.tag == CB_T_BOOL && v.u == 1; }
+
+#endif  // !CB_LEAN_ONLY || CB_SPEC_PROGRAMS
+
+#ifndef CB_LEAN_ONLY   // the stack interpreter
 // Runs one condition program; returns true iff it yields BOOL true (ruletable.go:1425-1441).
 CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
     Val st[CB_MAX_STACK + 1];
@@ -1505,39 +1659,24 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
         uint32_t op = (uint32_t)(raw & 0xFF), ia = (uint32_t)((raw >> 8) & 0xFF), ib = (uint32_t)((raw >> 16) & 0xFFFF);
         uint32_t ic = (uint32_t)(raw >> 32);
         switch (op) {
-        case CB_OP_RET: return st[sp - 1].tag == CB_T_BOOL && st[sp - 1].u == 1;
+        case CB_OP_RET: return cond_true(st[sp - 1]);
         case CB_OP_CONST: st[sp++] = load_const(c, ic); break;
         case CB_OP_SLOT: { int s; st[sp++] = load_slot(c, ic, &s); break; }
-        case CB_OP_HAS_SLOT: { int s; load_slot(c, ic, &s); st[sp++] = s == SLOT_ERROR ? mk_err() : mk_bool(s == SLOT_VALUE); break; }
+        case CB_OP_HAS_SLOT: { int s; load_slot(c, ic, &s); st[sp++] = op_has_slot(s); break; }
         case CB_OP_PID: st[sp++] = mk(CB_T_STRING, c.pid); break;
         case CB_OP_NOW: st[sp++] = mk(CB_T_TS, (uint64_t)c.b->now); break;
         case CB_OP_VAR: st[sp++] = c.vars[ia]; break;
-        case CB_OP_SELECT: { Val m = st[sp - 1]; Val o; st[sp - 1] = (m.tag == CB_T_MAP && map_find(c, m, mk(CB_T_STRING, ic), &o)) ? o : mk_err(); break; }
-        case CB_OP_HAS: { Val m = st[sp - 1]; st[sp - 1] = m.tag == CB_T_MAP ? mk_bool(map_find(c, m, mk(CB_T_STRING, ic), nullptr)) : mk_err(); break; }
+        case CB_OP_SELECT: st[sp - 1] = op_select(c, st[sp - 1], ic); break;
+        case CB_OP_HAS: st[sp - 1] = op_has(c, st[sp - 1], ic); break;
         case CB_OP_INDEX: sp--; st[sp - 1] = do_index(c, st[sp - 1], st[sp]); break;
         case CB_OP_EQ: case CB_OP_NE: case CB_OP_LT: case CB_OP_LE: case CB_OP_GT: case CB_OP_GE:
             sp--; st[sp - 1] = do_cmp(c, (int)op - CB_OP_EQ, st[sp - 1], st[sp]); break;
         case CB_OP_ADD: case CB_OP_SUB: case CB_OP_MUL: case CB_OP_DIV: case CB_OP_MOD:
             sp--; st[sp - 1] = do_arith(c, (int)op, st[sp - 1], st[sp]); break;
-        case CB_OP_NEG: {
-            Val v = st[sp - 1];
-            const int64_t kMin = (int64_t)0x8000000000000000ull;
-            if (v.tag == CB_T_INT) st[sp - 1] = (int64_t)v.u == kMin ? mk_err() : mk_int(-(int64_t)v.u);
-            else if (v.tag == CB_T_DOUBLE) st[sp - 1] = mk_double(-u2d(v.u));
-            else if (v.tag == CB_T_DUR) st[sp - 1] = (int64_t)v.u == kMin ? mk_err() : mk(CB_T_DUR, (uint64_t)(-(int64_t)v.u));
-            else st[sp - 1] = mk_err();
-            break;
-        }
-        case CB_OP_NOT: { Val v = st[sp - 1]; st[sp - 1] = v.tag == CB_T_BOOL ? mk_bool(!v.u) : mk_err(); break; }
+        case CB_OP_NEG: st[sp - 1] = op_neg(st[sp - 1]); break;
+        case CB_OP_NOT: st[sp - 1] = op_not(st[sp - 1]); break;
         case CB_OP_IN: sp--; st[sp - 1] = do_in(c, st[sp - 1], st[sp]); break;
-        case CB_OP_SIZE: {
-            Val v = st[sp - 1];
-            if (v.tag == CB_T_STRING) { const uint8_t *p; uint32_t n; str_get(c, v.u, p, n); st[sp - 1] = mk_int(utf8_len(p, n)); }
-            else if (v.tag == CB_T_BYTES) { const uint8_t *p; uint32_t n; str_get(c, v.u, p, n); st[sp - 1] = mk_int(n); }
-            else if (is_container(v)) st[sp - 1] = mk_int((int64_t)ldg(heap_ptr(c, v.u)));
-            else st[sp - 1] = mk_err();
-            break;
-        }
+        case CB_OP_SIZE: st[sp - 1] = op_size(c, st[sp - 1]); break;
         case CB_OP_STARTS_WITH: case CB_OP_ENDS_WITH: case CB_OP_CONTAINS:
             sp--; st[sp - 1] = do_str2(c, (int)op, st[sp - 1], st[sp]); break;
         case CB_OP_JF_KEEP: if (st[sp - 1].tag == CB_T_BOOL && st[sp - 1].u == 0) pc = ic; break;
@@ -1643,22 +1782,8 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
                 else { loop_bind(c, L, (int)ia, two); pc = ic; }
                 break;
             }
-            if (kind == CB_LOOP_EXISTS_ONE) {
-                if (r.tag != CB_T_BOOL) L.any_err = 1; else if (r.u) L.count++;
-            } else {
-                uint64_t dom = kind == CB_LOOP_EXISTS ? 1 : 0;
-                if (r.tag == CB_T_BOOL) { if (r.u == dom) { done = true; res = mk_bool(dom != 0); } }
-                else L.any_err = 1;
-            }
-            L.i++;
-            if (!done && L.i >= L.n) {
-                done = true;
-                if (L.any_err) res = mk_err();
-                else if (kind == CB_LOOP_EXISTS_ONE) res = mk_bool(L.count == 1);
-                else res = mk_bool(kind == CB_LOOP_ALL);
-            }
-            if (done) { ld--; st[sp++] = res; }
-            else { loop_bind(c, L, (int)ia, two); pc = ic; }
+            if (qloop_next(c, L, r, kind, two, (int)ia, &res)) { ld--; st[sp++] = res; }
+            else pc = ic;
             break;
         }
         case CB_OP_TO_COND: { Val v = st[sp - 1]; st[sp - 1] = mk_bool(v.tag == CB_T_BOOL && v.u == 1); break; }
@@ -1666,40 +1791,9 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
         case CB_OP_NOERR: st[sp - 1] = mk_bool(st[sp - 1].tag != CB_T_ERR); break;
         case CB_OP_INT: st[sp - 1] = conv_int(c, st[sp - 1]); break;
         case CB_OP_UINT: st[sp - 1] = conv_uint(c, st[sp - 1]); break;
-        case CB_OP_DOUBLE: {
-            Val v = st[sp - 1];
-            if (v.tag == CB_T_INT) st[sp - 1] = mk_double((double)(int64_t)v.u);
-            else if (v.tag == CB_T_UINT) st[sp - 1] = mk_double((double)v.u);
-            else if (v.tag == CB_T_STRING) { c.unsupported = 1; st[sp - 1] = mk_err(); }  // strconv.ParseFloat at run time
-            else if (v.tag != CB_T_DOUBLE) st[sp - 1] = mk_err();
-            break;
-        }
-        case CB_OP_TIMESTAMP: {
-            Val v = st[sp - 1];
-            if (v.tag == CB_T_TS) break;
-            if (v.tag == CB_T_STRING) st[sp - 1] = parse_ts(c, v);
-            else if (v.tag == CB_T_INT) {
-                int64_t s = (int64_t)v.u, ns;
-                if (s < -62135596800ll || s > 253402300799ll) st[sp - 1] = mk_err();
-                else if (mul_ovf(s, 1000000000ll, &ns)) { c.unsupported = 1; st[sp - 1] = mk_err(); }
-                else st[sp - 1] = mk(CB_T_TS, (uint64_t)ns);
-            } else st[sp - 1] = mk_err();
-            break;
-        }
-        case CB_OP_DURATION: {
-            Val v = st[sp - 1];
-            if (v.tag == CB_T_DUR) break;
-            if (v.tag == CB_T_INT) st[sp - 1] = mk(CB_T_DUR, v.u);
-            else if (v.tag == CB_T_STRING) {
-                const uint8_t *p; uint32_t n; int64_t ns = 0;
-                str_get(c, v.u, p, n);
-                const int rc = parse_duration_text(p, n, &ns);
-                if (rc == 2) c.unsupported = 1;
-                st[sp - 1] = rc == 0 ? mk(CB_T_DUR, (uint64_t)ns) : mk_err();
-            }
-            else st[sp - 1] = mk_err();
-            break;
-        }
+        case CB_OP_DOUBLE: st[sp - 1] = op_double(c, st[sp - 1]); break;
+        case CB_OP_TIMESTAMP: st[sp - 1] = op_timestamp(c, st[sp - 1]); break;
+        case CB_OP_DURATION: st[sp - 1] = op_duration(c, st[sp - 1]); break;
         case CB_OP_DYN: break;
         case CB_OP_CMP_SLOT_CONST: { int s; Val a = load_slot(c, ib, &s); st[sp++] = do_cmp(c, (int)ia, a, load_const(c, ic)); break; }
         case CB_OP_CMP_SLOT_SLOT: { int s; Val a = load_slot(c, ib, &s); Val b = load_slot(c, ic, &s); st[sp++] = do_cmp(c, (int)ia, a, b); break; }
@@ -1707,63 +1801,15 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
         case CB_OP_IN_SLOT_CONST: { int s; Val a = load_slot(c, ib, &s); st[sp++] = do_in(c, a, load_const(c, ic)); break; }
         case CB_OP_IN_CONST_SLOT: { int s; Val a = load_slot(c, ib, &s); st[sp++] = do_in(c, load_const(c, ic), a); break; }
         case CB_OP_IN_IP_RANGE: st[sp - 1] = st[sp - 1].tag == CB_T_ERR ? mk_err() : do_in_ip_range(c, st[sp - 1], c.t->theap() + ic); break;
-        case CB_OP_HIER_REL: {
-            sp--;
-            const bool ok = hier_operand(c, st[sp - 1]) & hier_operand(c, st[sp]);
-            st[sp - 1] = ok ? mk_bool(hier_rel(ia, hier_it(c, st[sp - 1].u, ib), hier_it(c, st[sp].u, ic))) : mk_err();
+        case CB_OP_HIER_REL: sp--; st[sp - 1] = op_hier_rel(c, ia, ib, ic, st[sp - 1], st[sp]); break;
+        case CB_OP_TS_GET: st[sp - 1] = op_ts_get(c, st[sp - 1], ia, ib, ic); break;
+        case CB_OP_IN_SPLIT: sp--; st[sp - 1] = op_in_split(c, st[sp - 1], st[sp], ib); break;   // [x, s]: x in s.split(delim ib)
+        case CB_OP_HIER_SIZE: st[sp - 1] = op_hier_size(c, st[sp - 1], ib); break;
+        case CB_OP_HIER_CA:
+            if (ia == 0) { sp--; st[sp - 1] = op_hier_ca2(c, st[sp - 1], st[sp], ib, ic); }
+            else { sp -= 2; st[sp - 1] = op_hier_ca3(c, st[sp - 1], st[sp], st[sp + 1], ib, ic); }
             break;
-        }
-        case CB_OP_TS_GET: {
-            int32_t off_s = (int32_t)ic;
-            if (ib == 2 && st[sp - 1].tag == CB_T_TS) {
-                // IANA zone: the offset in force at this instant, from the zone's transition table (bytecode.iana_zone_words)
-                const uint64_t *z = c.t->theap() + ic;
-                const int64_t sec = floor_div((int64_t)st[sp - 1].u, 1000000000ll);
-                const uint64_t nz = ldg(z);
-                if (sec < (int64_t)ldg(z + 1) || sec >= (int64_t)ldg(z + 2)) { c.unsupported = 1; st[sp - 1] = mk_err(); break; }
-                uint64_t lo = 0, hi = nz;          // last entry whose start <= sec
-                while (hi - lo > 1) { const uint64_t mid = (lo + hi) / 2; if ((int64_t)ldg(z + 3 + 2 * mid) <= sec) lo = mid; else hi = mid; }
-                off_s = (int32_t)(int64_t)ldg(z + 3 + 2 * lo + 1);
-            }
-            st[sp - 1] = do_ts_get(ia, st[sp - 1], ib, off_s);
-            break;
-        }
-        case CB_OP_IN_SPLIT: {   // [x, s]: x in s.split(delim ib)
-            sp--;
-            const Val x = st[sp - 1], sv = st[sp];
-            if (x.tag == CB_T_ERR || sv.tag != CB_T_STRING) { st[sp - 1] = mk_err(); break; }
-            bool found = false;
-            if (x.tag == CB_T_STRING) {
-                const uint8_t *px; uint32_t lx, s0, l0;
-                str_get(c, x.u, px, lx);
-                HierIt it = hier_it(c, sv.u, ib);
-                while (hier_next(it, &s0, &l0)) found |= l0 == lx && bytes_eq(it.p + s0, px, lx);
-            }
-            st[sp - 1] = mk_bool(found);
-            break;
-        }
-        case CB_OP_HIER_SIZE: st[sp - 1] = hier_operand(c, st[sp - 1]) ? mk_int((int64_t)hier_count(hier_it(c, st[sp - 1].u, ib))) : mk_err(); break;
-        case CB_OP_HIER_CA: {
-            if (ia == 0) {
-                sp--;
-                const bool ok = hier_operand(c, st[sp - 1]) & hier_operand(c, st[sp]);
-                st[sp - 1] = ok ? mk_int((int64_t)hier_ca_size(hier_it(c, st[sp - 1].u, ib), hier_it(c, st[sp].u, ic & 0xFFFF))) : mk_err();
-            } else {
-                sp -= 2;
-                const bool ok = hier_operand(c, st[sp - 1]) & hier_operand(c, st[sp]) & hier_operand(c, st[sp + 1]);
-                if (!ok) { st[sp - 1] = mk_err(); break; }
-                const HierIt a = hier_it(c, st[sp - 1].u, ib), b2 = hier_it(c, st[sp].u, ic & 0xFFFF), z = hier_it(c, st[sp + 1].u, ic >> 16);
-                const uint32_t k = hier_ca_size(a, b2);
-                st[sp - 1] = mk_bool(hier_count(z) == k && hier_common(a, z, k) == k);
-            }
-            break;
-        }
-        case CB_OP_FN: {   // ia = function, ib = argument count
-            sp -= (int)ib - 1;
-            if (ia == CB_FN_REVERSE && st[sp - 1].tag == CB_T_STRING) st[sp - 1] = dyn_strfn(c, CB_FN_STR_REVERSE, &st[sp - 1], ib);
-            else st[sp - 1] = ia >= CB_FN_EXCEPT ? dyn_listfn(c, ia, &st[sp - 1], ib) : dyn_strfn(c, ia, &st[sp - 1], ib);
-            break;
-        }
+        case CB_OP_FN: sp -= (int)ib - 1; st[sp - 1] = op_fn(c, ia, ib, &st[sp - 1]); break;   // ia = function, ib = argument count
         case CB_OP_MKLIST: {   // ic elements on the stack -> list
             sp -= (int)ic;
             uint32_t off;
@@ -1796,25 +1842,7 @@ CB_HD_NOINLINE bool run_program(Ctx &c, const cb_instr *code) {
             st[sp++] = mk_scratch(CB_T_LIST, off);
             break;
         }
-        case CB_OP_MATCHES: {   // RE2 search by the DFA table at theap[ic]: text = BOT, bytes, EOT (cel/regex_dfa.py)
-            const Val v = st[sp - 1];
-            if (v.tag != CB_T_STRING) { st[sp - 1] = mk_err(); break; }
-            const uint64_t *d = c.t->theap() + ic;
-            const uint64_t h = ldg(d);
-            const uint32_t ns = (uint32_t)(h & 0xFFFF), nc = (uint32_t)((h >> 16) & 0xFFFF);
-            uint32_t state = (uint32_t)(h >> 32) & 0xFFFF;
-            const uint8_t *cm = reinterpret_cast<const uint8_t *>(d + 1);
-            const uint64_t *acc = d + 1 + 33, *tr = acc + (ns + 63) / 64;
-            const uint8_t *p; uint32_t n;
-            str_get(c, v.u, p, n);
-            for (uint32_t i = 0; i < n + 2; i++) {
-                const uint32_t sym = i == 0 ? 256u : i == n + 1 ? 257u : (uint32_t)ldg(p + i - 1);
-                const uint32_t q = state * nc + ldg(cm + sym);
-                state = (uint32_t)(ldg(tr + (q >> 2)) >> (16 * (q & 3))) & 0xFFFFu;
-            }
-            st[sp - 1] = mk_bool((ldg(acc + (state >> 6)) >> (state & 63)) & 1);
-            break;
-        }
+        case CB_OP_MATCHES: st[sp - 1] = op_matches(c, st[sp - 1], ic); break;
         case CB_OP_LOOP_PRED: {   // predicate of a filtering map / transform*: false -> this iteration is skipped
             const Val v = st[sp - 1];
             if (v.tag != CB_T_BOOL) { st[sp - 1] = mk_err(); pc = ic; }
@@ -3042,12 +3070,18 @@ struct CachedCols {
 // How the unique-condition body gets a request's condition word: this generic evaluator interprets the table's DNF
 // terms; a run-time
 // specialised build (cb_specialize.h: generate_uc) substitutes straight-line code over register-resident slots.
+// The condition word: bit u = distinct condition u holds, bit 0 = "no condition".  Form 0: at most 32 bits, rows carry a
+// 32-bit need mask; form 1: 64 bits, 64-bit need masks; form 2 (64..127 distinct conditions, run-time specialised
+// kernels only): rows carry the two condition NUMBERS they need instead of a mask.
+struct CondWord { uint64_t lo, hi; };
+enum { CB_UC_FORM_MASK32 = 0, CB_UC_FORM_MASK64 = 1, CB_UC_FORM_INDEX = 2 };
 struct GenericConds {
-    static constexpr bool kVal32 = false;   // the condition word may use all 64 bits
+    static constexpr int kForm = CB_UC_FORM_MASK64;   // the condition word may use all 64 bits
     template <typename Cols>
     CB_HD Cols load(const TableView, const BatchView &, const Cols &cols) const { return cols; }
     template <typename Cols>
-    CB_HD uint64_t operator()(const TableView t, const BatchView &b, const Cols &cols, uint32_t pid, uint64_t n, bool &slow) const {
+    CB_HD CondWord operator()(const TableView t, const BatchView &b, const Cols &cols, uint32_t pid, uint64_t n, bool &slow) const {
+        if (t.L->n_uconds > 63) { slow = true; CondWord w; w.lo = 1; w.hi = 0; return w; }   // index-form image: specialised kernels only
         uint64_t val = 1;
         for (uint32_t u = 1, nu = t.L->n_uconds; u <= nu; u++) {
             const U4 cd = ld16(t.uconds() + u);   // {code_off, code_len, flat_off, flat_info}
@@ -3057,26 +3091,30 @@ struct GenericConds {
             slow |= (r & 4u) != 0;
             val |= (uint64_t)(r & 1u) << u;
         }
-        return val;
+        CondWord w; w.lo = val; w.hi = 0;
+        return w;
     }
 };
 
 // (action x role column) pairs of one row if its conditions hold: a needed condition bit that is clear zeroes the role columns
-template <typename RP, bool kVal32>
-CB_HD uint32_t uc_row_pairs(const U4 r, const RP rp, const uint32_t vlo, const uint32_t vhi, const uint32_t role_all) {
-    const uint32_t miss = kVal32 ? r.y & ~vlo : (r.y & ~vlo) | (r.z & ~vhi);
+CB_HD uint32_t cond_bit(const CondWord v, uint32_t u) { return (uint32_t)(((u & 64u) ? v.hi : v.lo) >> (u & 63u)) & 1u; }
+template <typename RP, int kForm>
+CB_HD uint32_t uc_row_pairs(const U4 r, const RP rp, const CondWord v, const uint32_t role_all) {
+    const uint32_t vlo = (uint32_t)v.lo, vhi = (uint32_t)(v.lo >> 32);
+    const uint32_t miss = kForm == CB_UC_FORM_MASK32   ? r.y & ~vlo
+                          : kForm == CB_UC_FORM_MASK64 ? (r.y & ~vlo) | (r.z & ~vhi)
+                                                       : (cond_bit(v, r.y & 0xFFu) & cond_bit(v, (r.y >> 8) & 0xFFu)) ^ 1u;
     const uint32_t rc = miss ? 0u : (uint32_t)(rp >> r.w) & role_all;
     return r.x * rc;
 }
 // The scope-chain walk of the unique-condition body: per block the DENY rows, then the ALLOW rows, each row three or
 // four ALU operations on registers.  RP: the role table word (32 bits when every role field fits, else 64);
-// kVal32: the condition word has at most 32 bits (known when the kernel is generated for a table).
-template <typename RP, bool kVal32, typename Rows>
-CB_HD uint32_t uc_walk(const TableView t, const BatchView &b, const Rows rows, const RP rp, const uint64_t val, const uint32_t r0, const uint32_t bm_base,
+// kForm: how the rows name their conditions (known when the kernel is generated for a table).
+template <typename RP, int kForm, typename Rows>
+CB_HD uint32_t uc_walk(const TableView t, const BatchView &b, const Rows rows, const RP rp, const CondWord val, const uint32_t r0, const uint32_t bm_base,
                        const uint32_t aset_base, const uint32_t role_all, uint32_t alive) {
     (void)b;
     uint32_t allow_pairs = 0;
-    const uint32_t vlo = (uint32_t)val, vhi = (uint32_t)(val >> 32);
     for (uint32_t s = r0; s != CB_NONE32 && alive; s = chain_next(t, s, CB_SCOPE_FLAG_RESOURCE)) {
         const uint32_t bid = ldg(t.res_block_map() + bm_base + s);
         if (bid != CB_NONE32) {
@@ -3086,12 +3124,12 @@ CB_HD uint32_t uc_walk(const TableView t, const BatchView &b, const Rows rows, c
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-            for (const uint32_t re = bl.x + bl.z; ri < re; ri++) D |= uc_row_pairs<RP, kVal32>(rows.get(aset_base, ri), rp, vlo, vhi, role_all) & alive;
+            for (const uint32_t re = bl.x + bl.z; ri < re; ri++) D |= uc_row_pairs<RP, kForm>(rows.get(aset_base, ri), rp, val, role_all) & alive;
             alive &= ~D;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 4
 #endif
-            for (const uint32_t re = bl.x + bl.y; ri < re; ri++) A |= uc_row_pairs<RP, kVal32>(rows.get(aset_base, ri), rp, vlo, vhi, role_all) & alive;
+            for (const uint32_t re = bl.x + bl.y; ri < re; ri++) A |= uc_row_pairs<RP, kForm>(rows.get(aset_base, ri), rp, val, role_all) & alive;
             if (((ldg(t.scope_flags() + s) >> CB_SCOPE_PERM_SHIFT) & 3) == 1) { allow_pairs |= A; alive &= ~A; }
         }
     }
@@ -3121,7 +3159,7 @@ CB_HD bool eval_request_uc(const TableView t, const BatchView &b, const Cols &co
     const uint32_t r0 = live ? chain_start(t, rscope, CB_SCOPE_FLAG_RESOURCE, (b.flags & CB_BATCH_FLAG_LENIENT) != 0) : CB_NONE32;
     if (r0 != CB_NONE32) {
         bool slow = false;
-        const uint64_t val = conds(t, b, regs, pid, n, slow);   // bit u: distinct condition u holds; bit 0: "no condition"
+        const CondWord val = conds(t, b, regs, pid, n, slow);   // bit u: distinct condition u holds; bit 0: "no condition"
         if (slow) return true;
         const uint32_t role_all = (1u << n_roles) - 1;
         const uint32_t aset_base = aset * b.n_rows;
@@ -3130,8 +3168,8 @@ CB_HD bool eval_request_uc(const TableView t, const BatchView &b, const Cols &co
         const uint32_t bm_base = (rv * t.L->nRP + kc) * t.L->nS;
         uint32_t allow_pairs;
         // the role table gets one more field, "any role"; when it all fits 32 bits the per-row shift is a single SHF
-        if ((t.L->nR + 1) * RCP <= 32) allow_pairs = uc_walk<uint32_t, Conds::kVal32>(t, b, rows, (uint32_t)rp | role_all << (t.L->nR * RCP), val, r0, bm_base, aset_base, role_all, alive0);
-        else allow_pairs = uc_walk<uint64_t, Conds::kVal32>(t, b, rows, rp | (uint64_t)role_all << (t.L->nR * RCP), val, r0, bm_base, aset_base, role_all, alive0);
+        if ((t.L->nR + 1) * RCP <= 32) allow_pairs = uc_walk<uint32_t, Conds::kForm>(t, b, rows, (uint32_t)rp | role_all << (t.L->nR * RCP), val, r0, bm_base, aset_base, role_all, alive0);
+        else allow_pairs = uc_walk<uint64_t, Conds::kForm>(t, b, rows, rp | (uint64_t)role_all << (t.L->nR * RCP), val, r0, bm_base, aset_base, role_all, alive0);
         // fold: an action is ALLOWed iff some role column allowed it; then pack the stride-RC bits
         uint32_t x = allow_pairs;
         x |= RC > 1 ? allow_pairs >> 1 : 0u;

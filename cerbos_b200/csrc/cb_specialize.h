@@ -157,6 +157,262 @@ inline std::string generate(const uint8_t *image, const uint32_t *off, const uin
     return s;
 }
 
+// ---- conditions without a flat form: their bytecode programs as straight-line code ------------------------------------
+// A condition program (table/bytecode.py: compile_cond) is a condition TREE (all / any / none) over CEL leaf expressions:
+//   leaf ... TO_COND [JF_KEEP | JT_KEEP] leaf ... TO_COND (AND | OR) ... [COND_NOT] RET
+// A leaf only asks "is the value BOOL true" (errors are plain false: ruletable.go:1467-1486 drops CEL errors), it has no
+// side effect, so the tree is a boolean formula over its leaves.  translate_program() splits a program into its leaves
+// (ATOMS; the same leaf in several conditions is one atom, evaluated once per request) and the formula; atom_source()
+// turns a leaf's instructions into C++ that calls the interpreter's own per-instruction helpers (cb_core.h: op_*,
+// do_cmp, do_in ...) with the operand stack as named locals and jumps as gotos -- same helpers, same order, so the
+// semantics are the interpreter's by construction; NVRTC then folds constant tags and keeps the stack in registers.
+// Programs using instructions outside the supported set (values built in the arena by collecting comprehensions,
+// list / map literals, runtime.effectiveDerivedRoles) make the table "not qualify", as before.
+struct Ins { uint32_t op, ia, ib, ic; };
+struct Atoms {
+    std::map<std::vector<uint32_t>, uint32_t> ids;    // normalised instruction list -> atom number
+    std::vector<std::string> src;                     // one function per atom
+    std::vector<bool> slot_used;
+};
+
+inline bool is_jump(uint32_t op) {
+    return op == CB_OP_JF_KEEP || op == CB_OP_JT_KEEP || op == CB_OP_JMP || op == CB_OP_TERN || op == CB_OP_LOOP_INIT || op == CB_OP_LOOP_NEXT || op == CB_OP_LOOP_PRED;
+}
+
+// One leaf P[lo, hi) (hi = its TO_COND) -> the body of `template <typename Cols> CB_HD bool uc_atom_K(Ctx &c, const Cols &cols)`.
+// "" = an unsupported instruction or a malformed program.
+inline std::string atom_source(const std::vector<Ins> &P, uint32_t lo, uint32_t hi, const uint32_t *consts /* cb_const words */, uint32_t n_consts, uint32_t n_slots,
+                               std::vector<bool> &slot_used) {
+    const uint32_t n = hi - lo;
+    const int kUnset = -1000;
+    std::vector<int> depth(n + 1, kUnset), ldep(n + 1, kUnset);
+    std::vector<bool> target(n + 1, false);
+    bool bad = false;
+    auto set = [&](uint32_t k, int d, int l) {
+        if (k > n) { bad = true; return; }
+        if (depth[k] == kUnset) { depth[k] = d; ldep[k] = l; }
+        else if (depth[k] != d || ldep[k] != l) bad = true;
+    };
+    auto rel = [&](uint32_t abs) -> uint32_t { if (abs < lo || abs > hi) { bad = true; return 0; } return abs - lo; };
+    set(0, 0, 0);
+    for (uint32_t k = 0; k < n && !bad; k++) {
+        if (depth[k] == kUnset) { bad = true; break; }   // unreachable instruction: not something compile_cond emits
+        const Ins &I = P[lo + k];
+        const int d = depth[k], l = ldep[k];
+        int nd = d;
+        bool falls = true;
+        switch (I.op) {
+        case CB_OP_CONST: case CB_OP_SLOT: case CB_OP_HAS_SLOT: case CB_OP_PID: case CB_OP_NOW: case CB_OP_VAR:
+        case CB_OP_CMP_SLOT_CONST: case CB_OP_CMP_SLOT_SLOT: case CB_OP_CMP_SLOT_PID: case CB_OP_IN_SLOT_CONST: case CB_OP_IN_CONST_SLOT:
+            nd = d + 1; break;
+        case CB_OP_SELECT: case CB_OP_HAS: case CB_OP_NEG: case CB_OP_NOT: case CB_OP_SIZE: case CB_OP_NOERR: case CB_OP_INT: case CB_OP_UINT:
+        case CB_OP_DOUBLE: case CB_OP_TIMESTAMP: case CB_OP_DURATION: case CB_OP_DYN: case CB_OP_IN_IP_RANGE: case CB_OP_HIER_SIZE: case CB_OP_TS_GET:
+        case CB_OP_MATCHES:
+            if (d < 1) bad = true;
+            break;
+        case CB_OP_INDEX: case CB_OP_EQ: case CB_OP_NE: case CB_OP_LT: case CB_OP_LE: case CB_OP_GT: case CB_OP_GE:
+        case CB_OP_ADD: case CB_OP_SUB: case CB_OP_MUL: case CB_OP_DIV: case CB_OP_MOD: case CB_OP_IN:
+        case CB_OP_STARTS_WITH: case CB_OP_ENDS_WITH: case CB_OP_CONTAINS: case CB_OP_AND: case CB_OP_OR:
+        case CB_OP_HAS_INTERSECTION: case CB_OP_IS_SUBSET: case CB_OP_HIER_REL: case CB_OP_IN_SPLIT:
+            if (d < 2) bad = true;
+            nd = d - 1; break;
+        case CB_OP_HIER_CA: nd = d - (I.ia == 0 ? 1 : 2); if (nd < 1) bad = true; break;
+        case CB_OP_FN: if (I.ib < 1 || I.ib > 4 || d < (int)I.ib) bad = true; nd = d - ((int)I.ib - 1); break;
+        case CB_OP_JF_KEEP: case CB_OP_JT_KEEP: if (d < 1) bad = true; set(rel(I.ic), d, l); target[rel(I.ic)] = true; break;
+        case CB_OP_JMP: set(rel(I.ic), d, l); target[rel(I.ic)] = true; falls = false; break;
+        case CB_OP_TERN:
+            if (d < 1) bad = true;
+            nd = d - 1;
+            set(rel(I.ic), d - 1, l); target[rel(I.ic)] = true;
+            set(rel(I.ib), d, l); target[rel(I.ib)] = true;
+            break;
+        case CB_OP_LOOP_INIT:
+            if (d < 1 || (I.ib & 0xFF) >= CB_LOOP_MAP || l >= CB_MAX_LOOP_DEPTH) bad = true;
+            set(rel(I.ic), d, l); target[rel(I.ic)] = true;      // not entered: the comprehension's value is pushed
+            set(k + 1, d - 1, l + 1);
+            falls = false;
+            break;
+        case CB_OP_LOOP_NEXT:
+            if (d < 1 || (I.ib & 0xFF) >= CB_LOOP_MAP || l < 1) bad = true;
+            set(rel(I.ic), d - 1, l); target[rel(I.ic)] = true;  // next element: back to the body
+            set(k + 1, d, l - 1);
+            falls = false;
+            break;
+        default: bad = true; break;   // TO_COND / COND_NOT inside a leaf, MKLIST, MKMAP, LOOP_PRED, RUNTIME_EDR, unknown
+        }
+        if (nd > CB_MAX_STACK) bad = true;
+        if (falls && !bad) set(k + 1, nd, l);
+    }
+    if (bad || depth[n] != 1 || ldep[n] != 0) return "";
+    auto S = [](int i) { return "s" + std::to_string(i); };
+    auto lab = [](uint32_t k) { return "P" + std::to_string(k); };
+    auto cst = [&](uint32_t k) -> std::string {
+        if (k >= n_consts) { bad = true; return "mk_err()"; }
+        const uint32_t *w = consts + 4 * k;    // {tag, pad, bits lo, bits hi}
+        return "mk(" + hex(w[0]) + ", " + hex64((uint64_t)w[2] | (uint64_t)w[3] << 32) + ")";
+    };
+    auto slot = [&](uint32_t v) -> std::string {
+        if (v >= n_slots) { bad = true; return "0ull"; }
+        slot_used[v] = true;
+        return "cols.slot(" + std::to_string(v) + "u)";
+    };
+    int maxd = 1;
+    for (uint32_t k = 0; k <= n; k++) if (depth[k] > maxd) maxd = depth[k];
+    std::string s = "    Val";
+    for (int i = 0; i < maxd; i++) s += std::string(i ? ", " : " ") + S(i);
+    s += ";\n    Loop L0, L1; int st_; (void)st_; (void)L0; (void)L1;\n";
+    for (uint32_t k = 0; k < n; k++) {
+        const Ins &I = P[lo + k];
+        const int d = depth[k], l = ldep[k];
+        if (target[k]) s += lab(k) + ":;\n";
+        const std::string a = S(d - 1), a2 = S(d - 2), top = S(d);   // a: top of stack, a2: below it, top: next free
+        s += "    ";
+        switch (I.op) {
+        case CB_OP_CONST: s += top + " = " + cst(I.ic) + ";"; break;
+        case CB_OP_SLOT: s += top + " = decode_v64(" + slot(I.ic) + ", &st_);"; break;
+        case CB_OP_HAS_SLOT: s += "decode_v64(" + slot(I.ic) + ", &st_); " + top + " = op_has_slot(st_);"; break;
+        case CB_OP_PID: s += top + " = mk(CB_T_STRING, c.pid);"; break;
+        case CB_OP_NOW: s += top + " = mk(CB_T_TS, (uint64_t)c.b->now);"; break;
+        case CB_OP_VAR: if (I.ia >= CB_MAX_VARS) bad = true; s += top + " = c.vars[" + std::to_string(I.ia) + "];"; break;
+        case CB_OP_SELECT: s += a + " = op_select(c, " + a + ", " + hex(I.ic) + ");"; break;
+        case CB_OP_HAS: s += a + " = op_has(c, " + a + ", " + hex(I.ic) + ");"; break;
+        case CB_OP_INDEX: s += a2 + " = do_index(c, " + a2 + ", " + a + ");"; break;
+        case CB_OP_EQ: case CB_OP_NE: case CB_OP_LT: case CB_OP_LE: case CB_OP_GT: case CB_OP_GE:
+            s += a2 + " = do_cmp(c, " + std::to_string(I.op - CB_OP_EQ) + ", " + a2 + ", " + a + ");"; break;
+        case CB_OP_ADD: case CB_OP_SUB: case CB_OP_MUL: case CB_OP_DIV: case CB_OP_MOD:
+            s += a2 + " = do_arith(c, " + std::to_string(I.op) + ", " + a2 + ", " + a + ");"; break;
+        case CB_OP_NEG: s += a + " = op_neg(" + a + ");"; break;
+        case CB_OP_NOT: s += a + " = op_not(" + a + ");"; break;
+        case CB_OP_IN: s += a2 + " = do_in(c, " + a2 + ", " + a + ");"; break;
+        case CB_OP_SIZE: s += a + " = op_size(c, " + a + ");"; break;
+        case CB_OP_STARTS_WITH: case CB_OP_ENDS_WITH: case CB_OP_CONTAINS:
+            s += a2 + " = do_str2(c, " + std::to_string(I.op) + ", " + a2 + ", " + a + ");"; break;
+        case CB_OP_JF_KEEP: s += "if (" + a + ".tag == CB_T_BOOL && " + a + ".u == 0) goto " + lab(I.ic - lo) + ";"; break;
+        case CB_OP_JT_KEEP: s += "if (" + a + ".tag == CB_T_BOOL && " + a + ".u == 1) goto " + lab(I.ic - lo) + ";"; break;
+        case CB_OP_AND: s += a2 + " = and_or(false, " + a2 + ", " + a + ");"; break;
+        case CB_OP_OR: s += a2 + " = and_or(true, " + a2 + ", " + a + ");"; break;
+        case CB_OP_JMP: s += "goto " + lab(I.ic - lo) + ";"; break;
+        case CB_OP_TERN:
+            s += "if (" + a + ".tag == CB_T_BOOL) { if (!" + a + ".u) goto " + lab(I.ic - lo) + "; } else { " + a + " = mk_err(); goto " + lab(I.ib - lo) + "; }";
+            break;
+        case CB_OP_HAS_INTERSECTION: s += a2 + " = do_set_pred(c, false, " + a2 + ", " + a + ");"; break;
+        case CB_OP_IS_SUBSET: s += a2 + " = do_set_pred(c, true, " + a2 + ", " + a + ");"; break;
+        case CB_OP_LOOP_INIT:
+            s += "{ const Val r_ = " + a + "; if (!qloop_init(c, L" + std::to_string(l) + ", r_, " + std::to_string(I.ib & 0xFF) + ", " + (((I.ib >> 8) & 1) ? "true" : "false") +
+                 ", " + std::to_string(I.ia) + ", &" + a + ")) goto " + lab(I.ic - lo) + "; }";
+            break;
+        case CB_OP_LOOP_NEXT:
+            s += "{ const Val r_ = " + a + "; if (!qloop_next(c, L" + std::to_string(l - 1) + ", r_, " + std::to_string(I.ib & 0xFF) + ", " + (((I.ib >> 8) & 1) ? "true" : "false") +
+                 ", " + std::to_string(I.ia) + ", &" + a + ")) goto " + lab(I.ic - lo) + "; }";
+            break;
+        case CB_OP_NOERR: s += a + " = mk_bool(" + a + ".tag != CB_T_ERR);"; break;
+        case CB_OP_INT: s += a + " = conv_int(c, " + a + ");"; break;
+        case CB_OP_UINT: s += a + " = conv_uint(c, " + a + ");"; break;
+        case CB_OP_DOUBLE: s += a + " = op_double(c, " + a + ");"; break;
+        case CB_OP_TIMESTAMP: s += a + " = op_timestamp(c, " + a + ");"; break;
+        case CB_OP_DURATION: s += a + " = op_duration(c, " + a + ");"; break;
+        case CB_OP_DYN: s += ";"; break;
+        case CB_OP_CMP_SLOT_CONST: s += top + " = do_cmp(c, " + std::to_string(I.ia) + ", decode_v64(" + slot(I.ib) + ", &st_), " + cst(I.ic) + ");"; break;
+        case CB_OP_CMP_SLOT_SLOT: s += "{ const Val x_ = decode_v64(" + slot(I.ib) + ", &st_); " + top + " = do_cmp(c, " + std::to_string(I.ia) + ", x_, decode_v64(" + slot(I.ic) + ", &st_)); }"; break;
+        case CB_OP_CMP_SLOT_PID: s += top + " = do_cmp(c, " + std::to_string(I.ia) + ", decode_v64(" + slot(I.ib) + ", &st_), mk(CB_T_STRING, c.pid));"; break;
+        case CB_OP_IN_SLOT_CONST: s += top + " = do_in(c, decode_v64(" + slot(I.ib) + ", &st_), " + cst(I.ic) + ");"; break;
+        case CB_OP_IN_CONST_SLOT: s += top + " = do_in(c, " + cst(I.ic) + ", decode_v64(" + slot(I.ib) + ", &st_));"; break;
+        case CB_OP_IN_IP_RANGE: s += a + " = " + a + ".tag == CB_T_ERR ? mk_err() : do_in_ip_range(c, " + a + ", c.t->theap() + " + hex(I.ic) + ");"; break;
+        case CB_OP_HIER_REL: s += a2 + " = op_hier_rel(c, " + hex(I.ia) + ", " + hex(I.ib) + ", " + hex(I.ic) + ", " + a2 + ", " + a + ");"; break;
+        case CB_OP_TS_GET: s += a + " = op_ts_get(c, " + a + ", " + hex(I.ia) + ", " + hex(I.ib) + ", " + hex(I.ic) + ");"; break;
+        case CB_OP_IN_SPLIT: s += a2 + " = op_in_split(c, " + a2 + ", " + a + ", " + hex(I.ib) + ");"; break;
+        case CB_OP_HIER_SIZE: s += a + " = op_hier_size(c, " + a + ", " + hex(I.ib) + ");"; break;
+        case CB_OP_HIER_CA:
+            if (I.ia == 0) s += a2 + " = op_hier_ca2(c, " + a2 + ", " + a + ", " + hex(I.ib) + ", " + hex(I.ic) + ");";
+            else s += S(d - 3) + " = op_hier_ca3(c, " + S(d - 3) + ", " + a2 + ", " + a + ", " + hex(I.ib) + ", " + hex(I.ic) + ");";
+            break;
+        case CB_OP_FN: {
+            const int base = d - (int)I.ib;
+            s += "{ Val a_[" + std::to_string(I.ib) + "] = {";
+            for (uint32_t q = 0; q < I.ib; q++) s += std::string(q ? ", " : "") + S(base + (int)q);
+            s += "}; " + S(base) + " = op_fn(c, " + hex(I.ia) + ", " + hex(I.ib) + ", a_); }";
+            break;
+        }
+        case CB_OP_MATCHES: s += a + " = op_matches(c, " + a + ", " + hex(I.ic) + ");"; break;
+        default: bad = true; break;
+        }
+        s += "\n";
+    }
+    if (target[n]) s += lab(n) + ":;\n";
+    s += "    return cond_true(s0);\n";
+    return bad ? std::string() : s;
+}
+
+// A whole condition program -> boolean formula over atoms ("" = does not qualify).  New atoms are appended to `at`.
+inline std::string translate_program(const uint32_t *code_words, uint32_t code_off, uint32_t code_len, const uint32_t *consts, uint32_t n_consts, uint32_t n_slots, Atoms &at) {
+    if (code_len == 0 || code_len > 4096) return "";
+    std::vector<Ins> P(code_len);
+    for (uint32_t i = 0; i < code_len; i++) {
+        const uint32_t w0 = code_words[2 * (code_off + i)], w1 = code_words[2 * (code_off + i) + 1];
+        P[i] = Ins{w0 & 0xFFu, (w0 >> 8) & 0xFFu, w0 >> 16, w1};
+    }
+    std::vector<std::string> st;    // the condition-level stack, symbolically
+    uint32_t i = 0;
+    bool ret = false;
+    while (i < code_len && !ret) {
+        const Ins &I = P[i];
+        auto cond_level = [&](uint32_t op) { return op == CB_OP_AND || op == CB_OP_OR || op == CB_OP_COND_NOT || op == CB_OP_RET; };
+        switch (I.op) {
+        case CB_OP_RET: ret = true; continue;
+        case CB_OP_AND: case CB_OP_OR: {
+            if (st.size() < 2) return "";
+            const std::string b = st.back(); st.pop_back();
+            st.back() = "(" + st.back() + (I.op == CB_OP_AND ? " & " : " | ") + b + ")";
+            i++;
+            continue;
+        }
+        case CB_OP_COND_NOT: if (st.empty()) return ""; st.back() = "!" + st.back(); i++; continue;
+        case CB_OP_JF_KEEP: case CB_OP_JT_KEEP:
+            // condition-level short circuit: every leaf is evaluated anyway (no side effects), the formula is what matters
+            if (st.empty() || I.ic <= i || I.ic > code_len) return "";
+            i++;
+            continue;
+        default: break;
+        }
+        // a leaf starts here: it ends at the next TO_COND
+        uint32_t e = i;
+        while (e < code_len && P[e].op != CB_OP_TO_COND) e++;
+        bool literal = false;
+        if (I.op == CB_OP_CONST && i + 1 < code_len) {   // all[] / any[] / none[]: a bare constant at condition level
+            const uint32_t nx = P[i + 1].op;
+            if (cond_level(nx)) literal = true;
+            if ((nx == CB_OP_JF_KEEP || nx == CB_OP_JT_KEEP) && (e >= code_len || P[i + 1].ic > e)) literal = true;
+        }
+        if (literal) {
+            if (I.ic >= n_consts || consts[4 * I.ic] != CB_T_BOOL) return "";
+            st.push_back(consts[4 * I.ic + 2] ? "true" : "false");
+            i++;
+            continue;
+        }
+        if (e >= code_len) return "";
+        std::vector<uint32_t> key;
+        for (uint32_t k = i; k < e; k++) {
+            const Ins &J = P[k];
+            const bool j = is_jump(J.op);
+            key.push_back(J.op | J.ia << 8 | (J.op == CB_OP_TERN ? (J.ib - i) : J.ib) << 16);
+            key.push_back(j ? J.ic - i : J.ic);
+        }
+        auto it = at.ids.find(key);
+        if (it == at.ids.end()) {
+            if (at.slot_used.size() < n_slots) at.slot_used.resize(n_slots, false);
+            const std::string body = atom_source(P, i, e, consts, n_consts, n_slots, at.slot_used);
+            if (body.empty()) return "";
+            const uint32_t id = (uint32_t)at.src.size();
+            at.src.push_back("template <typename Cols>\nCB_HD bool uc_atom_" + std::to_string(id) + "(Ctx &c, const Cols &cols) {\n" + body + "}\n");
+            it = at.ids.emplace(key, id).first;
+        }
+        st.push_back("a" + std::to_string(it->second));
+        i = e + 1;
+    }
+    if (!ret || st.size() != 1) return "";
+    return st[0];
+}
+
 // ---- unique-condition form (cb_uc.h / cb::eval_request_uc) -----------------------------------------------------------
 // For tables whose blocks differ in shape the per-shape inlining above explodes; their DISTINCT conditions are few.
 // generate_uc() emits `SpecConds`: load() pulls every attribute slot the conditions read into registers (all loads in
@@ -169,10 +425,15 @@ struct UcLimits {
 struct UcSource {
     std::string src;            // "" = does not qualify
     uint32_t n_strpred = 0;     // string predicates served by the per-string pre-pass (BatchView::strpred)
+    uint32_t n_atoms = 0;       // leaf programs translated to straight-line code (conditions without a flat form)
 };
-inline UcSource generate_uc(const uint8_t *uc_image, const uint32_t *off, uint32_t uc_conds_off, uint32_t n_uconds, uint32_t n_slots, const UcLimits lim = UcLimits()) {
+inline UcSource generate_uc(const uint8_t *uc_image, const uint32_t *off, uint32_t uc_conds_off, uint32_t n_uconds, uint32_t n_slots, uint32_t n_consts = 0,
+                            const UcLimits lim = UcLimits()) {
     UcSource out;
-    if (n_uconds == 0 || n_uconds > 63) return out;
+    if (n_uconds == 0 || n_uconds > 127) return out;
+    const uint32_t *const_words = reinterpret_cast<const uint32_t *>(uc_image + off[CB_SEC_CONSTS]);   // cb_const: {tag, pad, bits}
+    Atoms atoms;
+    std::vector<std::string> formula(n_uconds + 1);   // per distinct condition without flat form: boolean formula over atoms
     const uint32_t *uconds = reinterpret_cast<const uint32_t *>(uc_image + uc_conds_off);    // [n_uconds + 1] x {code_off, code_len, flat_off, flat_info}
     const uint32_t *code = reinterpret_cast<const uint32_t *>(uc_image + off[CB_SEC_CODE]);
     const uint64_t *consts = reinterpret_cast<const uint64_t *>(uc_image + off[CB_SEC_CONSTS_V64]);
@@ -187,7 +448,11 @@ inline UcSource generate_uc(const uint8_t *uc_image, const uint32_t *off, uint32
     auto v64_tag = [](uint64_t b) { const uint32_t top = (uint32_t)(b >> 48); return (top & 0xFFF0u) == 0xFFF0u ? (top & 0xFu) : 0u; };
     for (uint32_t u = 1; u <= n_uconds; u++) {
         const uint32_t *cd = uconds + 4 * u;
-        if (cd[3] == 0 || ((cd[3] >> 16) & 0xFF) != CB_FLAT_DNF) return out;
+        if (cd[3] == 0 || ((cd[3] >> 16) & 0xFF) != CB_FLAT_DNF) {
+            formula[u] = translate_program(code, cd[0], cd[1], const_words, n_consts, ns, atoms);
+            if (formula[u].empty()) return out;
+            continue;
+        }
         for (uint32_t i = 0, nt = cd[3] & 0xFFFFu; i < nt; i++) {
             const uint32_t *w = code + 2 * (cd[2] + 2 * i);
             std::vector<uint32_t> key = {w[0] & kUseMask, w[1], w[2], w[3]};
@@ -239,22 +504,34 @@ inline UcSource generate_uc(const uint8_t *uc_image, const uint32_t *off, uint32
         }
         return term_expr(w, consts, theap);
     };
+    // Slots read by the flat terms live in registers (all loads in flight at once); slots only the leaf programs read --
+    // and every slot once the table reads more than kMaxRegSlots of them -- are loaded where they are used (L1-allocating loads).
+    const uint32_t kMaxRegSlots = 16;
+    const bool have_atoms = !atoms.src.empty();
+    atoms.slot_used.resize(ns, false);
+    uint32_t n_reg = 0;
+    for (uint32_t v = 0; v < ns; v++) n_reg += slot_used[v] || slot_list[v];
+    if (n_reg > kMaxRegSlots)
+        for (uint32_t v = 0; v < ns; v++) if (!slot_list[v]) slot_used[v] = false;
     std::string s;
     s += "// generated by cb_specialize.h (generate_uc) from the loaded table: every distinct condition, straight-line\n";
-    s += "namespace cb {\nstruct SpecRegs {\n";
+    s += "namespace cb {\n";
+    for (const std::string &a : atoms.src) s += a;
+    s += "struct SpecRegs {\n    CachedCols g;\n";
     for (uint32_t v = 0; v < ns; v++)
-        if (slot_used[v]) s += "    uint64_t s" + std::to_string(v) + ";\n";
+        if (slot_used[v] || slot_list[v]) s += "    uint64_t s" + std::to_string(v) + ";\n";
     for (uint32_t v = 0; v < ns; v++)
         if (slot_list[v]) s += "    ListRegs l" + std::to_string(v) + ";\n";
     s += "    CB_HD uint64_t slot(uint32_t v) const {\n        switch (v) {\n";
     for (uint32_t v = 0; v < ns; v++)
-        if (slot_used[v]) s += "        case " + std::to_string(v) + "u: return s" + std::to_string(v) + ";\n";
-    s += "        default: return (uint64_t)(CB_V64_BOX_BASE | CB_V64_ERROR) << 48;\n        }\n    }\n};\n";
+        if (slot_used[v] || slot_list[v]) s += "        case " + std::to_string(v) + "u: return s" + std::to_string(v) + ";\n";
+    s += "        default: return v < " + std::to_string(ns) + "u ? g.slot(v) : (uint64_t)(CB_V64_BOX_BASE | CB_V64_ERROR) << 48;\n        }\n    }\n};\n";
     s += "struct SpecConds {\n    static constexpr uint32_t n_strpred = " + std::to_string(pred_terms.size()) + "u;\n";
-    s += std::string("    static constexpr bool kVal32 = ") + (n_uconds <= 31 ? "true" : "false") + ";   // the condition word fits 32 bits\n";
-    s += "    template <typename Cols>\n    CB_HD SpecRegs load(const TableView t, const BatchView &b, const Cols &c) const {\n        SpecRegs r;\n";
+    s += std::string("    static constexpr int kForm = ") + (n_uconds <= 31 ? "CB_UC_FORM_MASK32" : n_uconds <= 63 ? "CB_UC_FORM_MASK64" : "CB_UC_FORM_INDEX") + ";   // how the rows name their conditions\n";
+    s += std::string("    static constexpr bool kPrograms = ") + (have_atoms ? "true" : "false") + ";   // leaf programs: needs the value helpers of cb_core.h\n";
+    s += "    template <typename Cols>\n    CB_HD SpecRegs load(const TableView t, const BatchView &b, const Cols &c) const {\n        SpecRegs r;\n        r.g.b = c.b; r.g.n = c.n;\n";
     for (uint32_t v = 0; v < ns; v++)
-        if (slot_used[v]) s += "        r.s" + std::to_string(v) + " = c.slot(" + std::to_string(v) + "u);\n";
+        if (slot_used[v] || slot_list[v]) s += "        r.s" + std::to_string(v) + " = c.slot(" + std::to_string(v) + "u);\n";
     for (uint32_t v = 0; v < ns; v++)
         if (slot_list[v]) s += "        r.l" + std::to_string(v) + " = list_load(t, b, r.s" + std::to_string(v) + ");\n";
     s += "        return r;\n    }\n";
@@ -266,12 +543,23 @@ inline UcSource generate_uc(const uint8_t *uc_image, const uint32_t *off, uint32
         s += "        bits |= (uint32_t)(term_tri(t, b, cols, pid, U4{" + hex(w[0]) + ", 0x0u, " + hex(w[2]) + ", " + hex(w[3]) + "}, slow) == TRI_T) << " + std::to_string(p) + ";\n";
     }
     s += "        (void)slow; (void)pid;\n        return bits;\n    }\n";
-    s += "    CB_HD uint64_t operator()(const TableView t, const BatchView &b, const SpecRegs &cols, uint32_t pid, uint64_t, bool &slow) const {\n";
+    s += "    CB_HD CondWord operator()(const TableView t, const BatchView &b, const SpecRegs &cols, uint32_t pid, uint64_t n, bool &slow) const {\n";
     for (uint32_t q = 0; q < terms.size(); q++)
         s += "        const int q" + std::to_string(q) + " = " + term_code(q) + ";\n";
-    s += "        uint64_t val = 1ull;\n";
+    if (have_atoms) {
+        s += "        Ctx c; c.t = &t; c.b = &b; c.req = n; c.pid = pid; c.unsupported = 0; c.edr = 0; c.scr_used = 0;\n";
+        for (uint32_t a = 0; a < atoms.src.size(); a++)
+            s += "        c.scr_used = 0; const bool a" + std::to_string(a) + " = uc_atom_" + std::to_string(a) + "(c, cols);\n";
+        s += "        slow |= c.unsupported != 0;   // a value the device forms cannot hold: the general kernel reports it\n";
+    } else s += "        (void)n;\n";
+    s += "        CondWord val; val.lo = 1ull; val.hi = 0ull;\n";
     for (uint32_t u = 1; u <= n_uconds; u++) {
         const uint32_t *cd = uconds + 4 * u;
+        const std::string word = u < 64 ? "val.lo" : "val.hi", sh = std::to_string(u & 63u);
+        if (!formula[u].empty()) {
+            s += "        " + word + " |= (uint64_t)(" + formula[u] + ") << " + sh + ";   // distinct condition " + std::to_string(u) + " (program)\n";
+            continue;
+        }
         const uint32_t nt = cd[3] & 0xFFFFu, negate = (cd[3] >> 24) & 1u;
         s += "        {   // distinct condition " + std::to_string(u) + "\n            bool any = false, group = true;\n";
         for (uint32_t i = 0; i < nt; i++) {
@@ -281,11 +569,12 @@ inline UcSource generate_uc(const uint8_t *uc_image, const uint32_t *off, uint32
             s += "            group &= term_lit(q" + std::to_string(q) + ", " + hex(flags) + ");\n";
             if (flags & CB_TERM_GROUP_END) s += "            any |= group; group = true;\n";
         }
-        s += std::string("            val |= (uint64_t)(any != ") + (negate ? "true" : "false") + ") << " + std::to_string(u) + ";\n        }\n";
+        s += "            " + word + std::string(" |= (uint64_t)(any != ") + (negate ? "true" : "false") + ") << " + sh + ";\n        }\n";
     }
     s += "        return val;\n    }\n};\n}  // namespace cb\n";
     out.src = s;
     out.n_strpred = (uint32_t)pred_terms.size();
+    out.n_atoms = (uint32_t)atoms.src.size();
     return out;
 }
 

@@ -3,7 +3,7 @@
 // The flattened table (cerbos_b200/table/flatten.py) keeps one condition list per policy block, the way the reference
 // keeps one compiled condition per rule (ruletable.go:105-416).  Across a policy set the same conditions recur: shared
 // derived roles, the same ownership / tenancy test on every resource kind.  This builder
-//   * numbers the DISTINCT conditions of the table 1..U (same DNF term list, or same bytecode program),
+//   * numbers the DISTINCT conditions of the table 1..U (same DNF term list, or -- no flat form -- same bytecode program),
 //   * rewrites every row to {original index, role, effect, mask of the condition bits it needs} (16 bytes, DENY rows first per block),
 //   * copies only the sections the unique-condition kernels read into a compact image (C3: 49 KB blob -> ~10 KB),
 // so that a kernel can evaluate every distinct condition of a request once, with all lanes in lock step, and walk the
@@ -23,7 +23,8 @@
 
 namespace cbuc {
 
-constexpr uint32_t kMaxUconds = 63;   // bit 0 of the condition word is "no condition"
+constexpr uint32_t kMaxUconds = 127;      // bit 0 of the condition word is "no condition"
+constexpr uint32_t kMaxMaskUconds = 63;   // up to here rows carry need MASKS; above, the two condition NUMBERS (cb_core.h: CB_UC_FORM_INDEX)
 
 struct Image {
     bool ok = false;
@@ -31,6 +32,9 @@ struct Image {
     std::vector<uint8_t> bytes;         // compact image (16-byte aligned sections)
     cb::TableLayout lay{};              // offsets into `bytes` + the dims of the source layout
     uint32_t n_uconds = 0, n_flat = 0;  // distinct conditions; how many of them have a flat (DNF) form
+    // programs among the conditions, or rows in index form: only the run-time specialised kernel can evaluate the image
+    bool needs_spec() const { return n_flat != n_uconds || n_uconds > kMaxMaskUconds; }
+    uint32_t n_gids = 0, n_gids_flat = 0;   // table conditions (per-block lists), and how many of them have a flat form
     std::vector<uint32_t> ucond_of_gid; // table condition id -> distinct condition number (1..U)
 };
 
@@ -59,19 +63,24 @@ inline Image build(const uint8_t *image, const uint32_t *off, const uint64_t *le
         auto it = ids.find(key);
         if (it == ids.end()) {
             const uint32_t u = (uint32_t)ids.size() + 1;
-            if (u > kMaxUconds) { out.why = "more than 63 distinct conditions"; return out; }
+            if (u > kMaxUconds) { out.why = "more than 127 distinct conditions"; return out; }
             it = ids.emplace(key, u).first;
             ucond_rec.insert(ucond_rec.end(), {cd[0], cd[1], flat ? cd[2] : 0u, flat ? cd[3] : 0u});
             out.n_flat += flat;
         }
         out.ucond_of_gid[g] = it->second;
+        out.n_gids++;
+        out.n_gids_flat += flat;
     }
     out.n_uconds = (uint32_t)ids.size();
-    if (out.n_flat != out.n_uconds) { out.why = "a condition has no flat (DNF) form"; return out; }
+    // Conditions without a flat form stay in the image as programs: only the run-time specialised kernel evaluates them
+    // (cb_specialize.h turns their bytecode into straight-line code); the generic unique-condition kernels defer such
+    // requests, so the library uses the image of a table with programs only once its specialised kernel is loaded.
     // rows: DENY rows first inside every block (within a scope every matching row is evaluated and DENY beats ALLOW,
     // ruletable.go:1083-1118, so the order of rows inside a block is free); 16 bytes each, see cb_core.h
     std::vector<uint32_t> urows(4 * (size_t)(n_rows ? n_rows : 1), 0);
     std::vector<uint32_t> ublocks(blocks, blocks + 4 * (size_t)n_blocks);   // {row_start, n_rows, DENY rows, 0}
+    const bool index_form = out.n_uconds > kMaxMaskUconds;
     for (uint32_t b = 0; b < n_blocks; b++) {
         const uint32_t *bl = blocks + 4 * b;   // {row_start, n_rows, cond_base, n_conds}
         if ((uint64_t)bl[0] + bl[1] > n_rows || (uint64_t)bl[2] + bl[3] > n_conds) { out.why = "block out of range"; return out; }
@@ -84,12 +93,12 @@ inline Image build(const uint8_t *image, const uint32_t *off, const uint64_t *le
                 if ((c && c > bl[3]) || (dc && dc > bl[3])) { out.why = "row condition out of range"; return out; }
                 if (role != CB_ROLE_ANY && role >= 64) { out.why = "role id out of range"; return out; }
                 const uint32_t uc = c ? out.ucond_of_gid[bl[2] + c - 1] : 0, udc = dc ? out.ucond_of_gid[bl[2] + dc - 1] : 0;
-                const uint64_t need = 1ull | 1ull << uc | 1ull << udc;
+                const uint64_t need = index_form ? 0ull : (1ull | 1ull << uc | 1ull << udc);
                 uint32_t *u = urows.data() + 4 * (size_t)at++;
                 u[0] = bl[0] + r;
                 u[1] = (role == CB_ROLE_ANY ? 0xFFu : role) | effect << 8;
-                u[2] = (uint32_t)need;
-                u[3] = (uint32_t)(need >> 32);
+                u[2] = index_form ? (uc | udc << 8) : (uint32_t)need;
+                u[3] = index_form ? 0u : (uint32_t)(need >> 32);
                 n_deny += pass == 0;
             }
         }

@@ -354,14 +354,14 @@ struct cgpu_table {
     uint8_t *d_image = nullptr;
     TableDesc desc{};
     uint32_t meta[CB_META_WORDS]{};
-    std::atomic<int> occ[10]{};
-    std::atomic<uint32_t> occ_smem[10]{};
+    std::atomic<int> occ[11]{};
+    std::atomic<uint32_t> occ_smem[11]{};
     // table-specialised lean kernels (cb_specialize.h), compiled with NVRTC on first use
     std::vector<uint8_t> host_image;
     std::mutex spec_mu;
     std::atomic<int> spec_state{0};   // 0 not tried, 1 ready, -1 unavailable
     cudaLibrary_t spec_lib = nullptr;
-    cudaKernel_t spec_tiles = nullptr, spec_direct = nullptr, spec_uc = nullptr, spec_strpred = nullptr;
+    cudaKernel_t spec_tiles = nullptr, spec_direct = nullptr, spec_uc = nullptr, spec_uc_global = nullptr, spec_strpred = nullptr;
     uint32_t spec_n_strpred = 0;   // string predicates the specialised unique-condition kernel reads from the per-string pre-pass
     std::string spec_note;
     // unique-condition image (cb_uc.h): compact copy of the table for tables whose blocks differ in shape
@@ -530,15 +530,22 @@ const char kSpecKernels[] =
     "    cbk::check_body<true, 1, cb::SpecBlocks>(td, bv, bitmap, effects, status, stage_rt, smem_image, &mbar);\n"
     "}\n";
 // unique-condition form: the compact image staged in shared memory, every distinct condition as straight-line code
-const char kSpecUcKernels[] =
+const char kSpecUcStaged[] =
     "\nextern \"C\" __global__ void __launch_bounds__(256, CB_SPEC_UC_MIN_BLOCKS) cb_spec_uc(const __grid_constant__ cbk::TableDesc td, const __grid_constant__ cb::BatchView bv,\n"
     "        uint8_t *bitmap, uint8_t *effects, uint32_t *status, const uint32_t) {\n"
     "    extern __shared__ __align__(128) uint8_t smem_image[];\n"
     "    __shared__ __align__(8) uint64_t mbar;\n"
     "    cbk::check_uc_body<cb::SpecConds, cb::GlobalCols, true>(td, bv, bitmap, effects, smem_image, &mbar);\n"
-    "}\n"
-    // pre-pass over the string dictionary (table strings, then the batch's): one predicate word per string
-    "extern \"C\" __global__ void __launch_bounds__(256) cb_spec_strpred(const __grid_constant__ cbk::TableDesc td, const __grid_constant__ cb::BatchView bv, uint32_t *out, const uint32_t n) {\n"
+    "}\n";
+// the same body with the image and the rows read from global memory (L2 / L1): images too large for shared memory
+const char kSpecUcGlobal[] =
+    "\nextern \"C\" __global__ void __launch_bounds__(256, CB_SPEC_UC_MIN_BLOCKS) cb_spec_uc_global(const __grid_constant__ cbk::TableDesc td, const __grid_constant__ cb::BatchView bv,\n"
+    "        uint8_t *bitmap, uint8_t *effects, uint32_t *status, const uint32_t) {\n"
+    "    cbk::check_uc_body<cb::SpecConds, cb::GlobalCols, false>(td, bv, bitmap, effects, nullptr, nullptr);\n"
+    "}\n";
+// pre-pass over the string dictionary (table strings, then the batch's): one predicate word per string
+const char kSpecUcStrpred[] =
+    "\nextern \"C\" __global__ void __launch_bounds__(256) cb_spec_strpred(const __grid_constant__ cbk::TableDesc td, const __grid_constant__ cb::BatchView bv, uint32_t *out, const uint32_t n) {\n"
     "    const uint32_t id = blockIdx.x * 256u + threadIdx.x;\n"
     "    cb::TableView tv; tv.base = td.base; tv.L = &td.lay;\n"
     "    if (id < n) out[id] = cb::SpecConds().strpred(tv, bv, id);\n"
@@ -588,19 +595,29 @@ void cache_write(const std::string &path, const std::vector<char> &data) {
 // Which specialised form a table gets: per-shape block evaluators when its blocks share (nearly) one shape, else the
 // unique-condition form when every distinct condition has a flat form.  `gen` receives the generated source.
 enum SpecForm { SPEC_NONE = 0, SPEC_SHAPES = 1, SPEC_UC = 2 };
-SpecForm spec_generate(const uint8_t *image, const cb::TableLayout &lay, const uint32_t *meta, const cbuc::Image &uc, std::string *gen, std::string *why, uint32_t *n_strpred) {
+constexpr uint32_t kUcMaxSmem = 72 * 1024;   // compact image + merged rows: three CTAs / SM at least
+SpecForm spec_generate(const uint8_t *image, const cb::TableLayout &lay, const uint32_t *meta, const cbuc::Image &uc, std::string *gen, std::string *why, uint32_t *n_strpred,
+                       uint32_t *n_atoms = nullptr) {
     *n_strpred = 0;
+    if (n_atoms) *n_atoms = 0;
+    // the specialised kernels are lean bodies: a table launch_check can never route to a lean kernel needs none
+    if (lay.has_principal_policies || lay.has_role_policies || lay.has_parent_roles || !meta[CB_META_DIRECT_KINDS]) {
+        *why = "table is not lean-eligible (principal / role policies, parent roles or resource globs): general kernel only";
+        return SPEC_NONE;
+    }
     if (lay.image_bytes <= kMaxStageBytes) {
         *gen = cbspec::generate(image, lay.off, meta);
         if (!gen->empty()) return SPEC_SHAPES;
     }
-    if (uc.ok && uc.lay.image_bytes <= kMaxStageBytes) {
-        cbspec::UcSource us = cbspec::generate_uc(uc.bytes.data(), uc.lay.off, uc.lay.uc_conds_off, uc.n_uconds, lay.n_slots);
+    if (uc.ok) {   // any image size: cb_spec_uc stages the image in shared memory, cb_spec_uc_global reads it through L2 / L1
+        cbspec::UcSource us = cbspec::generate_uc(uc.bytes.data(), uc.lay.off, uc.lay.uc_conds_off, uc.n_uconds, lay.n_slots, meta[CB_META_N_CONSTS]);
         *gen = us.src;
         *n_strpred = us.n_strpred;
+        if (n_atoms) *n_atoms = us.n_atoms;
         if (!gen->empty()) return SPEC_UC;
     }
-    *why = "table does not qualify (a condition without flat form, too many block shapes and more than 63 distinct conditions, or an image too large for shared memory)";
+    *why = "table does not qualify (too many block shapes and: more than 127 distinct conditions, or a condition program the translator does not take -- "
+           "list / map literals, collecting comprehensions, runtime.effectiveDerivedRoles)";
     return SPEC_NONE;
 }
 
@@ -608,18 +625,27 @@ SpecForm spec_generate(const uint8_t *image, const cb::TableLayout &lay, const u
 // a host without a GPU).  SPEC_NONE + *why when the table does not qualify or something is unavailable.
 SpecForm spec_compile(const uint8_t *image, const cb::TableLayout &lay, const uint32_t *meta, const cbuc::Image &uc, std::vector<char> *cubin, std::string *why, uint32_t *n_strpred) {
     std::string gen;
-    const SpecForm form = spec_generate(image, lay, meta, uc, &gen, why, n_strpred);
+    uint32_t n_atoms = 0;
+    const SpecForm form = spec_generate(image, lay, meta, uc, &gen, why, n_strpred, &n_atoms);
     if (form == SPEC_NONE) return SPEC_NONE;
     std::string src = kSpecPrelude;
+    if (n_atoms) src += "#define CB_SPEC_PROGRAMS 1\n";   // leaf programs call the value helpers of cb_core.h
     for (const char *const *p = kEmbedFormat; *p; p++) src += *p;
     for (const char *const *p = kEmbedCore; *p; p++) src += *p;
     src += gen;
     for (const char *const *p = kEmbedKernels; *p; p++) src += *p;
-    src += form == SPEC_UC ? kSpecUcKernels : kSpecKernels;
+    if (form == SPEC_UC) {
+        // an image that can never be staged (larger than the shared-memory budget of the staged kernel) gets the global
+        // variant only, a small one both: which of the two a launch takes also depends on the batch's action sets
+        if (uc.lay.image_bytes + 128u <= kUcMaxSmem) src += kSpecUcStaged;
+        src += kSpecUcGlobal;
+        src += kSpecUcStrpred;
+    } else src += kSpecKernels;
     const char *mb = getenv("CERBOS_B200_SPEC_BLOCKS");   // experiments: resident CTAs / SM the specialised kernels are budgeted for
     const std::string mbopt = std::string("-DCB_SPEC_MIN_BLOCKS=") + (mb && mb[0] >= '1' && mb[0] <= '8' && !mb[1] ? mb : "5");
     const char *ub = getenv("CERBOS_B200_SPEC_UC_BLOCKS");
-    const std::string ubopt = std::string("-DCB_SPEC_UC_MIN_BLOCKS=") + (ub && ub[0] >= '1' && ub[0] <= '8' && !ub[1] ? ub : "4");
+    // leaf programs keep whole values (tag + payload) in registers: budget 128 registers / thread for them, 64 otherwise
+    const std::string ubopt = std::string("-DCB_SPEC_UC_MIN_BLOCKS=") + (ub && ub[0] >= '1' && ub[0] <= '8' && !ub[1] ? ub : n_atoms ? "2" : "4");
     if (const char *dump = getenv("CERBOS_B200_SPEC_DUMP")) {   // profiling aid: the translation unit handed to NVRTC
         if (FILE *f = fopen(dump, "w")) { fwrite(src.data(), 1, src.size(), f); fclose(f); }
     }
@@ -641,6 +667,7 @@ SpecForm spec_compile(const uint8_t *image, const cb::TableLayout &lay, const ui
     if (n.create(&prog, src.c_str(), "cerbos_b200_spec.cu", 0, nullptr, nullptr) != 0) { *why = "nvrtcCreateProgram failed"; return SPEC_NONE; }
     std::vector<const char *> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", mbopt.c_str(), ubopt.c_str()};
     for (const std::string &d : defs) opts.push_back(d.c_str());
+    if (n_atoms) opts.push_back("--device-int128");   // parse_duration_text (cb_core.h) scales fractions in 128 bits
     const int rc = n.compile(prog, (int)opts.size(), opts.data());
     if (rc != 0) {
         size_t ls = 0;
@@ -674,7 +701,9 @@ bool ensure_spec(cgpu_ctx *ctx, cgpu_table *t) {
     const SpecForm form = spec_compile(t->host_image.data(), t->desc.lay, t->meta, t->uc, &cubin, &why, &t->spec_n_strpred);
     if (form == SPEC_NONE) return give_up(why);
     if (cudaLibraryLoadData(&t->spec_lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) { cudaGetLastError(); return give_up("cudaLibraryLoadData failed"); }
-    bool got = form == SPEC_UC ? cudaLibraryGetKernel(&t->spec_uc, t->spec_lib, "cb_spec_uc") == cudaSuccess &&
+    const bool staged_variant = t->uc.lay.image_bytes + 128u <= kUcMaxSmem;
+    bool got = form == SPEC_UC ? (!staged_variant || cudaLibraryGetKernel(&t->spec_uc, t->spec_lib, "cb_spec_uc") == cudaSuccess) &&
+                                     cudaLibraryGetKernel(&t->spec_uc_global, t->spec_lib, "cb_spec_uc_global") == cudaSuccess &&
                                      cudaLibraryGetKernel(&t->spec_strpred, t->spec_lib, "cb_spec_strpred") == cudaSuccess
                                : cudaLibraryGetKernel(&t->spec_tiles, t->spec_lib, "cb_spec_tiles") == cudaSuccess &&
                                      cudaLibraryGetKernel(&t->spec_direct, t->spec_lib, "cb_spec_direct") == cudaSuccess;
@@ -682,7 +711,7 @@ bool ensure_spec(cgpu_ctx *ctx, cgpu_table *t) {
         cudaGetLastError();
         cudaLibraryUnload(t->spec_lib);
         t->spec_lib = nullptr;
-        t->spec_tiles = t->spec_direct = t->spec_uc = t->spec_strpred = nullptr;
+        t->spec_tiles = t->spec_direct = t->spec_uc = t->spec_uc_global = t->spec_strpred = nullptr;
         return give_up("cudaLibraryGetKernel failed");
     }
     t->spec_note = "ok";
@@ -766,8 +795,6 @@ int acquire_defer(cgpu_ctx *ctx, cudaStream_t stream, uint64_t count, uint32_t *
     return CGPU_OK;
 }
 
-constexpr uint32_t kUcMaxSmem = 72 * 1024;   // compact image + merged rows: three CTAs / SM at least
-
 int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, uint8_t *d_bitmap, uint8_t *d_effects,
                  uint32_t *d_status, cudaStream_t stream, bool *drained = nullptr) {
     const cb::TableLayout &lay = t->desc.lay;
@@ -778,14 +805,19 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
     // resource globs) when the (action x role column) pair masks fit 32 bits and the role table fits 64 bits.
     uint32_t rcp = 1;
     while (rcp < bv.role_cols) rcp <<= 1;
-    const bool narrow = !ctx->force_general && bv.n_pass == 1 && (uint64_t)bv.max_actions * bv.role_cols <= 32 && bv.kbytes <= 4 &&
+    cgpu_table *mt = const_cast<cgpu_table *>(t);
+    const bool uc_spec_ready = mt->spec_state.load(std::memory_order_acquire) == 1 && t->spec_uc_global != nullptr;
+    // A table most of whose conditions have no flat form gains nothing from a lean kernel until its specialised kernel
+    // (leaf programs as straight-line code) is loaded: the lean body would defer nearly every request to the one-CTA-per-SM
+    // drain launch.  Such launches go to the general kernel at full occupancy instead.
+    const bool mostly_programs = t->uc.ok && !uc_spec_ready && 2 * (uint64_t)t->uc.n_gids_flat < t->uc.n_gids;
+    const bool narrow = !ctx->force_general && !mostly_programs && bv.n_pass == 1 && (uint64_t)bv.max_actions * bv.role_cols <= 32 && bv.kbytes <= 4 &&
                         !lay.has_principal_policies && !lay.has_role_policies && !lay.has_parent_roles &&
                         t->meta[CB_META_DIRECT_KINDS] && (uint64_t)lay.nR * rcp <= 64;
-    cgpu_table *mt = const_cast<cgpu_table *>(t);
     // Unique-condition kernels: lean-eligible tables with <= 63 distinct conditions whose blocks differ in shape
     // (with one shape the per-shape specialised tile kernel is the better fit).  Index order, no clustering.
-    const bool uc_spec_ready = mt->spec_state.load(std::memory_order_acquire) == 1 && t->spec_uc != nullptr;
-    const bool uc = narrow && t->uc.ok && t->d_uc_image && bv.count < (1ull << 32) && (uint64_t)bv.n_asets * lay.n_rows < (1ull << 31) && (uint64_t)(lay.nR + 1) * rcp <= 64 &&
+    // (an image with condition programs or index-form rows is only good for the specialised kernel: cbuc::Image::needs_spec)
+    const bool uc = narrow && t->uc.ok && (uc_spec_ready || !t->uc.needs_spec()) && t->d_uc_image && bv.count < (1ull << 32) && (uint64_t)bv.n_asets * lay.n_rows < (1ull << 31) && (uint64_t)(lay.nR + 1) * rcp <= 64 &&
                     (ctx->uc_mode == 1 || (ctx->uc_mode != 0 && ctx->cluster_mode != 1 && t->meta[CB_META_BLOCK_SHAPES] > 1));   // CERBOS_B200_CLUSTER=1 keeps the clustered path reachable
     // Clustering pays when the policy blocks differ in shape (rows / conditions): with a single shape every lane runs
     // the same control flow in index order already and the coalesced column loads are worth more.
@@ -802,18 +834,18 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
                            bv.first % 4 == 0 && al16(bv.hdr0) && al16(bv.hdr1) && al16(bv.roles) && al16(bv.slots);
     // unique-condition launch: staged (compact image + merged rows in shared memory) when that fits
     const uint64_t uc_smem64 = uc ? ((t->uc.lay.image_bytes + 127u) & ~127u) + (uint64_t)bv.n_asets * lay.n_rows * 16 : 0;
-    const bool uc_staged = uc && !ctx->force_no_stage && uc_smem64 <= kUcMaxSmem;
+    const bool uc_staged = uc && !ctx->force_no_stage && uc_smem64 <= kUcMaxSmem && (!uc_spec_ready || t->spec_uc != nullptr);
     const uint32_t smem = uc ? (uc_staged ? (uint32_t)uc_smem64 : 0) : col_tiles ? tiles_smem : stage ? lay.image_bytes : 0;
     // lean launches with a staged table use the kernels specialised for this table when they exist (NVRTC, first use)
-    const bool spec = uc ? (uc_staged && uc_spec_ready)
+    const bool spec = uc ? uc_spec_ready
                          : narrow && stage && bv.count < (1ull << 32) && mt->spec_state.load(std::memory_order_acquire) == 1 && t->spec_tiles != nullptr;   // never waits for the compile
-    const void *fn = uc          ? (spec ? (const void *)t->spec_uc : uc_staged ? (const void *)check_uc<true> : (const void *)check_uc<false>)
+    const void *fn = uc          ? (spec ? (uc_staged ? (const void *)t->spec_uc : (const void *)t->spec_uc_global) : uc_staged ? (const void *)check_uc<true> : (const void *)check_uc<false>)
                      : spec      ? (col_tiles ? (const void *)t->spec_tiles : (const void *)t->spec_direct)
                      : col_tiles ? (const void *)check_kernel_tiles
                      : narrow    ? (stage ? (const void *)check_kernel<true, 1> : (const void *)check_kernel<true, 0>)
                                  : (const void *)check_kernel<false, 2>;
     // resident CTAs per SM for this shared-memory footprint: queried once per (table, variant, footprint)
-    const int variant = uc ? (spec ? 9 : uc_staged ? 7 : 8) : spec ? (col_tiles ? 5 : 6) : col_tiles ? 4 : narrow ? (stage ? 1 : 2) : (stage ? 0 : 3);
+    const int variant = uc ? (spec ? (uc_staged ? 9 : 10) : uc_staged ? 7 : 8) : spec ? (col_tiles ? 5 : 6) : col_tiles ? 4 : narrow ? (stage ? 1 : 2) : (stage ? 0 : 3);
     int occ = mt->occ_smem[variant].load(std::memory_order_relaxed) == smem + 1 ? mt->occ[variant].load(std::memory_order_relaxed) : 0;
     if (occ == 0) {
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxStageBytes) != cudaSuccess ||

@@ -17,8 +17,10 @@ def build():
             os.path.join(_ROOT, "include", "cerbos_b200_format.h")]
     if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(_SO), exist_ok=True)
+        tmp = f"{_SO}.{os.getpid()}.tmp"     # parallel test workers may build at once: write aside, then rename
         subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", f"-I{_ROOT}/include",
-                        f"-I{_ROOT}/cerbos_b200/csrc", "-o", _SO, src], check=True)
+                        f"-I{_ROOT}/cerbos_b200/csrc", "-o", tmp, src], check=True)
+        os.replace(tmp, _SO)
     return _SO
 
 
@@ -78,6 +80,12 @@ def generate_uc(blob: bytes):
     if n < 0:
         raise RuntimeError(f"hostsim_generate_uc failed: {n}")
     return out.value.decode(), nu.value
+
+
+def deferred(lib=None) -> int:
+    """Requests the lean / unique-condition body left to the general body in the last call through `lib` (default: the plain build)."""
+    import ctypes as ct
+    return int(ct.c_uint64.in_dll(lib if lib is not None else _lib, "hostsim_deferred").value)
 
 
 def build_spec(blob: bytes, workdir: str, uc: bool = False):

@@ -27,6 +27,7 @@ typedef cb::GenericConds HostConds;
 #define HOSTSIM_ENTRY hostsim_check
 #endif
 
+extern "C" { uint64_t hostsim_deferred = 0; }   // requests the lean / unique-condition body left to the general body in the last call
 static bool parse_sections(const void *blob, uint64_t blob_len, uint32_t *off, uint64_t *len) {
     const cb_blob_header *h = static_cast<const cb_blob_header *>(blob);
     if (blob_len < sizeof(*h) || h->magic != CB_MAGIC || h->version != CB_VERSION) return false;
@@ -74,6 +75,7 @@ extern "C" int HOSTSIM_ENTRY(const void *blob, uint64_t blob_len, uint64_t n, ui
     b.n_bstr = col_bytes[5] >= 4 ? (uint32_t)(col_bytes[5] / 4 - 1) : 0;
     b.heap_words = col_bytes[4] / 8;
     uint32_t status = 0;
+    hostsim_deferred = 0;
     // mode 0: what the library would pick; 1: force the general 64-bit body; 2: general 32-bit body;
     // 3: the lean body reading a tile of the columns staged the way the kernel's TMA copies lay it out in shared memory
     const bool narrow = b.n_pass == 1 && (uint64_t)km * b.role_cols <= 32;
@@ -106,7 +108,7 @@ extern "C" int HOSTSIM_ENTRY(const void *blob, uint64_t blob_len, uint64_t n, ui
             bool d;
             if (mode == 5) { cb::UcRowsPacked rows; rows.pk = pk.data(); d = cb::eval_request_uc(ut, b, gc, rows, i, bitmap, nullptr, HostConds()); }
             else { cb::UcRowsGlobal rows; rows.urows = ut.urows(); rows.row_am = b.row_am; rows.RCP = b.rcp; rows.nR = lay.nR; d = cb::eval_request_uc(ut, b, gc, rows, i, bitmap, nullptr, HostConds()); }
-            if (d) cb::eval_request_general(t.base, t.L, &b, i, bitmap, nullptr, &status);
+            if (d) { hostsim_deferred++; cb::eval_request_general(t.base, t.L, &b, i, bitmap, nullptr, &status); }
         }
         return status ? -2 : 0;
     }
@@ -211,7 +213,7 @@ extern "C" int64_t hostsim_generate_uc(const void *blob, uint64_t blob_len, char
     lay.nR = meta[CB_META_N_ROLES]; lay.n_slots = meta[CB_META_N_SLOTS];
     const cbuc::Image uc = cbuc::build(base, off, len, meta, lay);
     if (n_uconds_out) *n_uconds_out = uc.ok ? uc.n_uconds : 0;
-    std::string src = uc.ok ? cbspec::generate_uc(uc.bytes.data(), uc.lay.off, uc.lay.uc_conds_off, uc.n_uconds, lay.n_slots).src : std::string();
+    std::string src = uc.ok ? cbspec::generate_uc(uc.bytes.data(), uc.lay.off, uc.lay.uc_conds_off, uc.n_uconds, lay.n_slots, meta[CB_META_N_CONSTS]).src : std::string();
     if (src.size() + 1 > cap) return -(int64_t)src.size() - 2;
     memcpy(out, src.c_str(), src.size() + 1);
     return (int64_t)src.size();

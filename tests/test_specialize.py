@@ -91,11 +91,24 @@ def test_unique_condition_source_shares_terms_for_c3():
     assert all(f"r.s{v} = c.slot({v}u);" in src for v in range(12))
 
 
-def test_c5_has_too_many_distinct_conditions_for_the_unique_condition_form():
+def test_c5_conditions_become_leaf_programs(tmp_path):
+    """C5: 73 distinct conditions (the REQUIRE_PARENTAL_CONSENT leaves double the 37 trees as none(...)), 50 of them
+    without a flat form.  Their bytecode is translated to straight-line code: 12 distinct leaves (atoms) shared by all
+    the trees, rows in index form (more than 63 conditions).  Bit-exact against the oracle, and the specialised body
+    decides the requests itself (nothing but the differing-version / unsupported cases may defer)."""
     w = W.C5()
-    _, ft, _ = W.build(w)
+    _, ft, enc = W.build(w)
     src, nu = hostsim.generate_uc(ft.blob)
-    assert src == "" and nu == 0
+    assert nu == 73 and src.count("CB_HD bool uc_atom_") == 12 and "kForm = CB_UC_FORM_INDEX" in src and "kPrograms = true" in src
+    lib = hostsim.build_spec(ft.blob, str(tmp_path), uc=True)
+    b = w.columns(w.fields(4096), enc)
+    want = cref.check(ft.blob, b.columns, b.n, b.max_actions)
+    for mode in (4, 5):
+        assert (hostsim.check_spec(lib, ft.blob, b.columns, b.n, b.max_actions, mode=mode) == want).all(), mode
+        assert hostsim.deferred(lib) == 0
+    # the generic unique-condition body cannot evaluate programs: it defers, the general body answers
+    assert (hostsim.check(ft.blob, b.columns, b.n, b.max_actions, mode=4) == want).all()
+    assert hostsim.deferred() > b.n // 2
 
 
 @pytest.mark.parametrize("seed", range(10))
@@ -128,3 +141,66 @@ def test_unique_condition_body_on_random_tables(seed, tmp_path):
         lib = hostsim.build_spec(ft.blob, str(tmp_path), uc=True)
         got = hostsim.check_spec(lib, ft.blob, b.columns, b.n, b.max_actions, mode=5)
         assert (got[valid] == want[valid]).all(), seed
+
+
+# ---- leaf programs (cb_specialize.h: translate_program / atom_source) on the reference's golden CEL expressions -----------
+def _golden_leaf_cases():
+    from test_table_oracles import _cel_cases
+    groups = {}
+    for f, e, req in _cel_cases():
+        groups.setdefault(f, (req, []))[1].append(e)
+    return groups
+
+
+def test_leaf_programs_on_golden_expressions(tmp_path):
+    """Every golden CEL leaf whose program the translator accepts (all but the ones building lists / maps in the arena)
+    is evaluated by the generated straight-line code, inside tables of up to 16 rules, and must give oracle #1's
+    answer -- the same bar the interpreter is held to in test_table_oracles.py."""
+    from cerbos_b200.table.bytecode import Unsupported
+    from oracle.celeval import parse_timestamp
+    from oracle.check import CheckOracle
+    now = parse_timestamp("2021-04-22T10:05:20.021-05:00")
+    translated = checked = 0
+    for gi, (f, (req, exprs)) in enumerate(sorted(_golden_leaf_cases().items())):
+        inp = {"principal": dict(req.get("principal") or {}), "resource": dict(req.get("resource") or {})}
+        if "auxData" in req:
+            inp["auxData"] = req["auxData"]
+        inp["resource"]["kind"] = "leave_request"
+        inp["principal"].setdefault("roles", ["r"])
+
+        def table(es):
+            rules = [{"actions": [f"a{i}"], "effect": "EFFECT_ALLOW", "roles": ["*"], "condition": {"match": {"expr": e}}} for i, e in enumerate(es)]
+            pol = {"apiVersion": "api.cerbos.dev/v1", "resourcePolicy": {"resource": "leave_request", "version": "default", "rules": rules}}
+            rt = build_rule_table([pol])
+            return rt, flatten(rt)
+
+        ok = []
+        for e in dict.fromkeys(exprs):
+            try:
+                _, ft1 = table([e])
+            except Exception:
+                continue          # not lowered at all (SPIFFE ...): rejected at table build
+            src, _ = hostsim.generate_uc(ft1.blob)
+            if "CB_HD bool uc_atom_" in src:
+                ok.append(e)      # no flat form, and the translator takes its program
+        translated += len(ok)
+        for c0 in range(0, len(ok), 16):
+            es = ok[c0:c0 + 16]
+            rt, ft = table(es)
+            src, _ = hostsim.generate_uc(ft.blob)
+            assert src.count("CB_HD bool uc_atom_") >= 1
+            d = tmp_path / f"g{gi}_{c0}"
+            d.mkdir()
+            lib = hostsim.build_spec(ft.blob, str(d), uc=True)
+            one = dict(inp, actions=[f"a{i}" for i in range(len(es))])
+            b = Encoder(ft.manifest).encode([one])
+            want = CheckOracle(rt).check(one, now)["actions"]
+            try:
+                got = hostsim.check_spec(lib, ft.blob, b.columns, 1, b.max_actions, now.ns, mode=4)
+            except RuntimeError as x:
+                assert "-2" in str(x), (f, x)     # a run-time value outside the device's exact range: flagged, never wrong
+                continue
+            for i, e in enumerate(es):
+                assert got[0, i] == want[f"a{i}"]["effect"], (f, e)
+                checked += 1
+    assert translated >= 60 and checked >= 50, (translated, checked)
