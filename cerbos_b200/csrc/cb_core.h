@@ -122,6 +122,9 @@ struct BatchView {
     // the outcome of every `attribute.startsWith / endsWith / contains(constant)` predicate of the table, computed once
     // per distinct string by a pre-pass over the batch's string dictionary (null: none)
     const uint32_t *strpred;
+    // ... launched with the table image in global memory: the image's rows merged with this batch's row x action-set
+    // masks (cb::uc_row_record), one 16-byte record per (action set, row), built by a pre-pass (null: merge on the fly)
+    const U4 *uc_rows_pk;
     uint32_t n_bstr;            // strings in the batch dictionary
     uint64_t heap_words;        // 8-byte words in `heap`
 };
@@ -139,6 +142,7 @@ inline void finish_batch_view(BatchView &b) {
     for (int i = 0; i < CB_MAX_GATHER; i++) { b.outs[i] = nullptr; b.sig_flags[i] = nullptr; }
     b.wait_flags = nullptr; b.sig_rank = 0; b.sig_step = 0; b.wait_step = 0;
     b.strpred = nullptr;
+    b.uc_rows_pk = nullptr;
     b.rcp = 1;
     while (b.rcp < b.role_cols) b.rcp <<= 1;
     b.stride_pattern = 0;
@@ -234,28 +238,25 @@ CB_HD Val mk_double(double d) { return mk(CB_T_DOUBLE, d != d ? (uint64_t)CB_V64
 enum { SLOT_VALUE = 0, SLOT_ABSENT = 1, SLOT_ERROR = 2 };
 
 CB_HD Val decode_v64(uint64_t bits, int *state) {
-    *state = SLOT_VALUE;
-    uint32_t top = (uint32_t)(bits >> 48);
-    if ((top & 0xFFF0u) == 0xFFF0u && (top & 0xFu) != 0) {
-        uint32_t tag = top & 0xFu;
-        uint64_t pay = bits & 0xFFFFFFFFFFFFull;
-        switch (tag) {
-        case CB_V64_NULL: return mk(CB_T_NULL, 0);
-        case CB_V64_BOOL: return mk_bool(pay != 0);
-        case CB_V64_STRING: return mk(CB_T_STRING, pay);
-        case CB_V64_LIST:
-        case CB_V64_MAP: {
-            uint64_t off = pay & (CB_V64_HEAP_BATCH_BIT - 1);
-            if (pay & CB_V64_HEAP_BATCH_BIT) off |= kHeapBatch;
-            else if (off & kV64ScratchBit) off = (off & ~kV64ScratchBit) | kHeapScratch;
-            return mk(tag == CB_V64_LIST ? CB_T_LIST : CB_T_MAP, off);
-        }
-        case CB_V64_INT: return mk_int((int64_t)(pay << 16) >> 16);
-        case CB_V64_ABSENT: *state = SLOT_ABSENT; return mk_err();
-        default: *state = SLOT_ERROR; return mk_err();
-        }
-    }
-    return mk(CB_T_DOUBLE, bits);
+    // branch-free: lanes of a warp hold values of different classes (a switch here was an indirect branch per decode)
+    const uint32_t top = (uint32_t)(bits >> 48);
+    const bool boxed = (top & 0xFFF0u) == 0xFFF0u && (top & 0xFu) != 0;
+    const uint32_t vt = top & 0xFu;
+    const uint64_t pay = bits & 0xFFFFFFFFFFFFull;
+    // value class by box tag: NULL 1 -> NULL, BOOL 2 -> BOOL, STRING 3 -> STRING, LIST 4 -> LIST, MAP 5 -> MAP, INT 8 -> INT, the rest -> ERR
+    const uint64_t kTagOf = (uint64_t)CB_T_NULL << 4 | (uint64_t)CB_T_BOOL << 8 | (uint64_t)CB_T_STRING << 12 | (uint64_t)CB_T_LIST << 16 |
+                            (uint64_t)CB_T_MAP << 20 | (uint64_t)CB_T_INT << 32;
+    const uint32_t tag = boxed ? (uint32_t)(kTagOf >> (4 * vt)) & 0xFu : (uint32_t)CB_T_DOUBLE;
+    uint64_t off = pay & (CB_V64_HEAP_BATCH_BIT - 1);
+    off = (pay & CB_V64_HEAP_BATCH_BIT) ? off | kHeapBatch : (off & kV64ScratchBit) ? (off & ~kV64ScratchBit) | kHeapScratch : off;
+    const uint64_t u = !boxed                                  ? bits
+                       : vt == CB_V64_BOOL                     ? (uint64_t)(pay != 0)
+                       : vt == CB_V64_STRING                   ? pay
+                       : (vt == CB_V64_LIST || vt == CB_V64_MAP) ? off
+                       : vt == CB_V64_INT                      ? (uint64_t)((int64_t)(pay << 16) >> 16)
+                                                               : 0ull;
+    *state = !boxed || tag != CB_T_ERR ? SLOT_VALUE : vt == CB_V64_ABSENT ? SLOT_ABSENT : SLOT_ERROR;
+    return mk(tag, u);
 }
 CB_HD Val decode_elem(uint64_t bits) { int s; return decode_v64(bits, &s); }
 

@@ -305,7 +305,7 @@ __device__ __forceinline__ void check_uc_body(const TableDesc &td, const cb::Bat
     cb::TableView tv;
     tv.L = &td.lay;
     tv.base = kStaged ? smem_image : td.base;
-    const cb::U4 *pk = nullptr;
+    const cb::U4 *pk = kStaged ? nullptr : bv.uc_rows_pk;   // global image: the rows merged by the launch's pre-pass, if any
     // prefetch table: the 128-byte lines the columns of 32 consecutive requests span (hdr0 4, hdr1 2, a role column 1, a slot
     // column 2), as column base + offset of the line and the shift that turns a request index into a byte offset
     __shared__ unsigned long long pf_base[64];
@@ -357,7 +357,7 @@ __device__ __forceinline__ void check_uc_body(const TableDesc &td, const cb::Bat
             Cols gc;
             gc.b = &bv; gc.n = n;
             bool d;
-            if (kStaged) { cb::UcRowsPacked rows; rows.pk = pk; d = cb::eval_request_uc(tv, bv, gc, rows, n, bitmap, effects, Conds()); }
+            if (kStaged || pk) { cb::UcRowsPacked rows; rows.pk = pk; d = cb::eval_request_uc(tv, bv, gc, rows, n, bitmap, effects, Conds()); }
             else { cb::UcRowsGlobal rows; rows.urows = tv.urows(); rows.row_am = bv.row_am; rows.RCP = bv.rcp; rows.nR = td.lay.nR; d = cb::eval_request_uc(tv, bv, gc, rows, n, bitmap, effects, Conds()); }
             if (d) {
                 cb::store_result(bv, gc, n, bitmap, effects, bv.max_actions, 0u);

@@ -150,6 +150,18 @@ __global__ void __launch_bounds__(kThreads, CB_MIN_BLOCKS) check_uc(const __grid
 struct SignalParams { uint32_t *flags[cb::CB_MAX_GATHER]; const uint32_t *wait_flags; uint32_t n_ranks, my_rank, step, wait_step; };
 // After the check kernels of a gather launch: publish `step` into this rank's cell of every rank's flag array.
 // Programmatically serialised behind them; their peer stores are complete (and visible system-wide) once they have.
+// Pre-pass of a unique-condition launch that reads its table image from global memory: the image's rows merged with the
+// batch's row x action-set masks into one 16-byte record per (action set, row) -- what the staged kernels build in
+// shared memory per CTA.  One load per row in the walk instead of two dependent ones.
+__global__ void __launch_bounds__(kThreads) uc_merge_rows(const __grid_constant__ TableDesc td, const __grid_constant__ cb::BatchView bv, cb::U4 *out, const uint32_t n_pk) {
+    const uint32_t j = blockIdx.x * kThreads + threadIdx.x;
+    if (j >= n_pk) return;
+    cb::TableView tv;
+    tv.base = td.base; tv.L = &td.lay;
+    const cb::U4 u = tv.urows()[j % bv.n_rows];
+    out[j] = cb::uc_row_record(u, (uint32_t)bv.row_am[(j / bv.n_rows) * bv.n_rows + u.x], bv.rcp, td.lay.nR);
+}
+
 __global__ void gather_signal(const __grid_constant__ SignalParams p) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     __threadfence_system();
@@ -318,6 +330,8 @@ struct cgpu_ctx {
         uint32_t *cells = nullptr;   // 4 x {count, done, tile counter, -}, zero between uses (the drain kernel re-zeroes)
         uint32_t *strpred[4] = {nullptr, nullptr, nullptr, nullptr};   // per-string predicate words of the specialised unique-condition kernels
         size_t sp_cap[4] = {0, 0, 0, 0};
+        cb::U4 *pk[4] = {nullptr, nullptr, nullptr, nullptr};          // merged row records of unique-condition launches on a global image
+        size_t pk_cap[4] = {0, 0, 0, 0};
     };
     std::map<cudaStream_t, DeferLane> defer_lanes;
     std::mutex defer_mu;
@@ -759,7 +773,8 @@ int launch_cluster(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, 
 }
 
 // The launch's deferral list + counter cell, owned by the stream it is issued on (see cgpu_ctx::DeferLane).
-int acquire_defer(cgpu_ctx *ctx, cudaStream_t stream, uint64_t count, uint32_t **list, uint32_t **cell, size_t n_strpred = 0, uint32_t **strpred = nullptr) {
+int acquire_defer(cgpu_ctx *ctx, cudaStream_t stream, uint64_t count, uint32_t **list, uint32_t **cell, size_t n_strpred = 0, uint32_t **strpred = nullptr,
+                  size_t n_pk = 0, cb::U4 **pk = nullptr) {
     std::lock_guard<std::mutex> g(ctx->defer_mu);
     cgpu_ctx::DeferLane &ln = ctx->defer_lanes[stream];
     if (!ln.cells) {
@@ -789,6 +804,18 @@ int acquire_defer(cgpu_ctx *ctx, cudaStream_t stream, uint64_t count, uint32_t *
             ln.sp_cap[q] = cap;
         }
         *strpred = ln.strpred[q];
+    }
+    if (pk) {
+        if (ln.pk_cap[q] < n_pk) {
+            size_t cap = 4096;
+            while (cap < n_pk) cap <<= 1;
+            cb::U4 *fresh = nullptr;
+            CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&fresh), cap * 16, stream));
+            if (ln.pk[q]) CUDA_TRY(cudaFreeAsync(ln.pk[q], stream));
+            ln.pk[q] = fresh;
+            ln.pk_cap[q] = cap;
+        }
+        *pk = ln.pk[q];
     }
     *list = ln.lists[q];
     *cell = ln.cells + 4 * q;   // {count, done, tile counter, -}
@@ -880,8 +907,18 @@ int launch_check(cgpu_ctx *ctx, const cgpu_table *t, const cb::BatchView &bv, ui
         uint32_t *cell = nullptr, *strpred = nullptr;
         const bool want_sp = uc && spec && t->spec_n_strpred;
         const uint32_t n_str = lay.nT + bv.n_bstr;
-        int rc = acquire_defer(ctx, stream, bv.count, &defer, &cell, (size_t)n_str + 1, want_sp ? &strpred : nullptr);
+        // unique-condition launch on a global image: merge the rows with the batch's action-set masks once, up front
+        const uint64_t n_pk = (uint64_t)bv.n_asets * lay.n_rows;
+        const bool want_pk = uc && !uc_staged && n_pk <= (1u << 19);
+        cb::U4 *pk = nullptr;
+        int rc = acquire_defer(ctx, stream, bv.count, &defer, &cell, (size_t)n_str + 1, want_sp ? &strpred : nullptr, (size_t)n_pk, want_pk ? &pk : nullptr);
         if (rc != CGPU_OK) return rc;
+        if (want_pk) {
+            uc_merge_rows<<<(unsigned)((n_pk + kThreads - 1) / kThreads), kThreads, 0, stream>>>(t->uc_desc, bvv, pk, (uint32_t)n_pk);
+            CUDA_TRY(cudaGetLastError());
+            ctx->launches.fetch_add(1, std::memory_order_relaxed);
+            bvv.uc_rows_pk = pk;
+        }
         bvv.defer_count = cell;
         bvv.tile_counter = col_tiles ? cell + 2 : nullptr;
         bvv.defer_list = defer;
@@ -1054,6 +1091,7 @@ void cgpu_shutdown(cgpu_ctx *ctx) {
     for (auto &kv : ctx->defer_lanes) {
         for (auto p : kv.second.lists) if (p) cudaFree(p);
         for (auto p : kv.second.strpred) if (p) cudaFree(p);
+        for (auto p : kv.second.pk) if (p) cudaFree(p);
         if (kv.second.cells) cudaFree(kv.second.cells);
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

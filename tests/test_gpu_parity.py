@@ -529,7 +529,7 @@ def test_cgpu_check_is_reentrant_across_threads():
         os.environ.pop("CERBOS_B200_CHECK_CHUNK", None)
 
 
-def test_run_time_values_on_gpu(ctx):
+def test_run_time_values_on_gpu():
     """The list / string producing functions, collecting comprehensions, dynamic literals and hierarchy(list) on the
     device (per-thread scratch arena of the general kernel) against oracle #1 -- same cases as the CPU test of the
     kernel core -- plus every golden CEL leaf that builds values at run time."""
@@ -539,7 +539,9 @@ def test_run_time_values_on_gpu(ctx):
     from test_table_oracles import RUN_TIME_VALUE_CASES, RUN_TIME_VALUE_REQUEST, run_time_value_table, _cel_cases
     from cerbos_b200.table.bytecode import Unsupported
     now = parse_timestamp("2021-04-22T10:05:20.021-05:00")
-    os.environ["CERBOS_B200_NO_JIT"] = "1"   # one table per expression: skip the background NVRTC compile
+    os.environ["CERBOS_B200_NO_JIT"] = "1"   # one table per expression: skip the background NVRTC compile (read at cgpu_init)
+    from cerbos_b200 import capi
+    ctx = capi.Context(0)
     try:
         cases = [(e, RUN_TIME_VALUE_REQUEST) for e in RUN_TIME_VALUE_CASES]
         for f, e, req in _cel_cases():
@@ -565,6 +567,7 @@ def test_run_time_values_on_gpu(ctx):
         assert n >= 80, n
     finally:
         os.environ.pop("CERBOS_B200_NO_JIT", None)
+        ctx.close()
 
 
 def test_decision_metadata_on_gpu():
