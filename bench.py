@@ -395,15 +395,19 @@ def measure(args, ctx, w, blob, enc, table, dev, rank, world, local_rank, n, pri
     # kernel runs.  Fallback (CERBOS_B200_NCCL_GATHER=1, or CUDA IPC unavailable): asynchronous NCCL all-gather.
     gather_mode = "none"
     pg, gcalls = None, None
+    n_gbuf = n_buf if n_buf >= 4 else 4     # gather buffers (a multiple of n_buf and of n_streams)
     if world > 1 and primary:
         ok = 0
         no_exchange = os.environ.get("CERBOS_B200_NO_GATHER") == "1"   # diagnosis only
         if os.environ.get("CERBOS_B200_NCCL_GATHER") != "1" and kbytes <= 8 and not no_exchange:
             try:
                 from cerbos_b200.dist import PeerGather
-                pg = PeerGather(ctx, n * kbytes, n_buf)
-                gcalls = [table.prepared_gather_call(b.ptrs, b.sizes, b.n, b.max_actions, pg.bufs[j], pg.lane_flags(j % n_streams), rank, n * kbytes, NOW_NS)
-                          for j, b in enumerate(batches)]
+                # more gather buffers than batches: a buffer is reused n_gbuf launches later, so a rank only ever waits for
+                # what its peers finished n_gbuf - 1 launches ago (ranks drift apart by a few percent per launch)
+                pg = PeerGather(ctx, n * kbytes, n_gbuf)
+                gcalls = [table.prepared_gather_call(batches[i % n_buf].ptrs, batches[i % n_buf].sizes, batches[i % n_buf].n, batches[i % n_buf].max_actions,
+                                                     pg.bufs[i], pg.lane_flags(i % n_streams), rank, n * kbytes, NOW_NS)
+                          for i in range(n_gbuf)]
                 ok = 1
             except Exception as e:  # noqa: BLE001 -- any failure here just selects the NCCL path on every rank
                 sys.stderr.write(f"[rank {rank}] peer gather unavailable ({e}); using NCCL\n")
@@ -431,13 +435,13 @@ def measure(args, ctx, w, blob, enc, table, dev, rank, world, local_rank, n, pri
         lane = g % n_streams            # == j % n_streams: a buffer always travels on the same stream
         sh = stream_hs[lane]
         if pg is not None:
-            # buffers rotate: launch g-(n_buf-1) must have landed on this rank before its stream moves on.  Launches are
-            # numbered per stream ("lane"), so that every flag array only ever counts up.
-            k = g - (n_buf - 1)
+            # gather buffers rotate: launch g-(n_gbuf-1) must have landed on this rank before its stream moves on.  Launches
+            # are numbered per stream ("lane"), so that every flag array only ever counts up.
+            k = g - (n_gbuf - 1)
             if k >= 0:
-                gcalls[j](g // n_streams + 1, sh, k // n_streams + 1, pg.local_flags(k % n_streams))
+                gcalls[g % n_gbuf](g // n_streams + 1, sh, k // n_streams + 1, pg.local_flags(k % n_streams))
             else:
-                gcalls[j](g // n_streams + 1, sh, 0, None)
+                gcalls[g % n_gbuf](g // n_streams + 1, sh, 0, None)
             return
         calls[j](sh)
         if gathered is not None and gather_mode != "none (diagnosis)":
@@ -471,7 +475,7 @@ def measure(args, ctx, w, blob, enc, table, dev, rank, world, local_rank, n, pri
             dist.barrier()
 
     # warm-up launches, then calibrate batches_per_step so that one step is >= ~10 ms of device work
-    for _ in range(max(3, n_buf)):
+    for _ in range(max(3, n_gbuf if pg is not None else n_buf)):
         launch()
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -502,8 +506,10 @@ def measure(args, ctx, w, blob, enc, table, dev, rank, world, local_rank, n, pri
         ev0.record(stream)
         for st in streams[1:]:
             st.wait_event(ev0)               # no stream starts before the start event
+        t_host0 = time.perf_counter()
         for _ in range(args.steps * m):
             launch()
+        host_issue_ms = (time.perf_counter() - t_host0) * 1e3 / (args.steps * m)   # host time to enqueue one batch
         drain()                              # the last exchanges are part of the timed work
         join_streams()
         ev1.record(stream)
@@ -573,7 +579,7 @@ def measure(args, ctx, w, blob, enc, table, dev, rank, world, local_rank, n, pri
 
     res = {
         "value": value, "ms_per_step": per_step_ms, "batches_per_step": m, "requests_per_batch": n, "actions_per_request": K,
-        "ms_per_batch": per_step_ms / m, "streams": n_streams, "gather_mode": gather_mode,
+        "ms_per_batch": per_step_ms / m, "host_issue_ms_per_batch": host_issue_ms, "streams": n_streams, "gather_mode": gather_mode,
         "l2": f"rotating {n_buf} distinct batches, {footprint / 1e6:.0f} MB of columns > 126 MB L2", "kernel": kcfg,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -775,6 +781,7 @@ def main():
         "config": {"workload": wl_name, "batches_per_step": r["batches_per_step"], "requests_per_batch_per_gpu": n,
                    "requests_per_step_per_gpu": n * r["batches_per_step"], "actions_per_request": K,
                    "global_requests_per_step": world * n * r["batches_per_step"], "ms_per_batch": r["ms_per_batch"],
+                   "host_issue_ms_per_batch": r["host_issue_ms_per_batch"],
                    "parallelism": f"dp{world} (requests sharded by index; NCCL table broadcast; result exchange: {r['gather_mode']})",
                    "streams": r["streams"], "l2": r["l2"], "kernel": r["kernel"],
                    "specialised_kernels": spec_note if not spec_ready else "compiled for this table at load (NVRTC)"},
