@@ -312,7 +312,8 @@ def run_reference(args):
 def ncu_traffic(workload: str, n: int):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, scaled to n requests, from the
     committed `ncu --set full` capture of this workload's kernel (profiles/; None if there is none)."""
-    files = {"C2": ("r1_final_check_kernel_ncu_full.json", 1 << 20), "C3": ("r2_C3_check_kernel_ncu_full.json", 1 << 22)}
+    files = {"C2": ("r1_final_check_kernel_ncu_full.json", 1 << 20), "C3": ("r2_C3_check_kernel_ncu_full.json", 1 << 22),
+             "C5": ("r2_C5_cb_spec_uc_global_ncu_full.json", 1 << 18)}
     if workload not in files:
         return None
     name, n_cap = files[workload]
