@@ -36,7 +36,10 @@ class _Gather(ctypes.Structure):
 
 class _Narrow(ctypes.Structure):
     _fields_ = [("principal_id", ctypes.c_void_p), ("hdr16", ctypes.c_void_p), ("versions", ctypes.c_void_p), ("roles", ctypes.c_void_p),
-                ("role_cols", ctypes.c_uint32), ("slot_class", ctypes.c_void_p), ("slot_cols", ctypes.POINTER(ctypes.c_void_p)), ("heap_u32", ctypes.c_uint32)]
+                ("role_cols", ctypes.c_uint32), ("slot_class", ctypes.c_void_p), ("slot_cols", ctypes.POINTER(ctypes.c_void_p)), ("heap_u32", ctypes.c_uint32),
+                ("slot_base", ctypes.c_void_p), ("slot_base2", ctypes.c_void_p), ("principal_id16", ctypes.c_void_p), ("principal_base", ctypes.c_uint32), ("hdr_const_mask", ctypes.c_uint32),
+                ("hdr_const", ctypes.c_uint16 * 4), ("versions_const", ctypes.c_uint32), ("versions_value", ctypes.c_uint8 * 2),
+                ("heap_bits", ctypes.c_uint32), ("heap_base", ctypes.c_uint32), ("heap_base2", ctypes.c_uint32)]
 
 
 class _Batch(ctypes.Structure):
@@ -318,7 +321,12 @@ class Table:
         csz = (ctypes.c_size_t * N_COLUMNS)(*sizes)
         b = _Batch(nb.n, nb.max_actions, now_ns, flags, cols, csz, N_COLUMNS)
         scols = (ctypes.c_void_p * max(len(nb.slot_cols), 1))(*[ptr(c) for c in nb.slot_cols])
-        nr = _Narrow(ptr(nb.principal_id), ptr(nb.hdr16), ptr(nb.versions), ptr(nb.roles), nb.role_cols, ptr(nb.slot_class), scols, 1 if nb.heap_u32 else 0)
+        p16 = nb.principal_base is not None
+        nr = _Narrow(None if p16 else ptr(nb.principal_id), ptr(nb.hdr16) if nb.hdr16.size else None, ptr(nb.versions) if nb.versions is not None else None,
+                     ptr(nb.roles), nb.role_cols, ptr(nb.slot_class), scols, 1 if nb.heap_u32 else 0,
+                     ptr(nb.slot_base), ptr(nb.slot_base2), ptr(nb.principal_id) if p16 else None, int(nb.principal_base or 0), int(nb.hdr_const_mask),
+                     (ctypes.c_uint16 * 4)(*nb.hdr_const), 1 if nb.versions_value is not None else 0,
+                     (ctypes.c_uint8 * 2)(*(nb.versions_value or (0, 0))), int(nb.heap_bits), int(nb.heap_base), int(nb.heap_base2))
         keep += [cols, csz, scols]
         return b, nr, keep
 

@@ -71,6 +71,12 @@ struct WidenParams {
     cb_hdr0 *hdr0; cb_hdr1 *hdr1; uint32_t *roles_out; uint64_t *slots_out;
     uint64_t first, count, stride;
     uint32_t role_cols, n_slots;
+    // the narrower forms (cgpu_narrow, second half): per-slot base of the 16-bit string ids, 16-bit principal ids, header
+    // fields / versions that are constant over the batch
+    uint32_t slot_base[kMaxNarrowSlots], slot_base2[kMaxNarrowSlots];
+    const uint16_t *pid16; uint32_t pid_base;
+    uint32_t hdr_const_mask, hdr_w; uint16_t hdr_const[4];
+    uint32_t versions_const; uint8_t versions_value[2];
 };
 __device__ __forceinline__ uint64_t widen_special(uint32_t code) {   // 0 absent, 1 error, 2 null
     return (uint64_t)(CB_V64_BOX_BASE | (code == 0 ? CB_V64_ABSENT : code == 1 ? CB_V64_ERROR : CB_V64_NULL)) << 48;
@@ -78,15 +84,23 @@ __device__ __forceinline__ uint64_t widen_special(uint32_t code) {   // 0 absent
 __global__ void __launch_bounds__(kThreads) widen_kernel(const __grid_constant__ WidenParams p) {
     for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < p.count; i += (uint64_t)gridDim.x * kThreads) {
         const uint64_t n = p.first + i;
-        const uint2 h = reinterpret_cast<const uint2 *>(p.hdr16)[n];   // kind, resource scope | principal scope, action set
-        const uint32_t k16 = h.x & 0xFFFF, rs16 = h.x >> 16, ps16 = h.y & 0xFFFF, aset = h.y >> 16;
+        uint32_t f16[4];   // kind, resource scope, principal scope, action set
+        if (p.hdr_const_mask == 0) {
+            const uint2 h = reinterpret_cast<const uint2 *>(p.hdr16)[n];
+            f16[0] = h.x & 0xFFFF; f16[1] = h.x >> 16; f16[2] = h.y & 0xFFFF; f16[3] = h.y >> 16;
+        } else {
+            const uint16_t *hp = p.hdr16 + n * p.hdr_w;
+            uint32_t q = 0;
+            for (uint32_t f = 0; f < 4; f++) f16[f] = (p.hdr_const_mask >> f) & 1u ? p.hdr_const[f] : hp[q++];
+        }
+        const uint32_t k16 = f16[0], rs16 = f16[1], ps16 = f16[2], aset = f16[3];
         cb_hdr0 h0;
-        h0.principal_id = p.pid[n];
+        h0.principal_id = p.pid16 ? p.pid_base + p.pid16[n] : p.pid[n];
         h0.kind_class = k16 == 0xFFFF ? CB_KIND_NONE : (k16 & 0x8000) ? ((k16 & 0x7FFF) | CB_KIND_CLASS_CSR_BIT) : k16;
         h0.resource_scope = rs16 == 0xFFFF ? CB_SCOPE_NONE : (rs16 & 0x8000) ? ((rs16 & 0x7FFF) | CB_SCOPE_INEXACT_BIT) : rs16;
         h0.principal_scope = ps16 == 0xFFFF ? CB_SCOPE_NONE : (ps16 & 0x8000) ? ((ps16 & 0x7FFF) | CB_SCOPE_INEXACT_BIT) : ps16;
         p.hdr0[n] = h0;
-        const uint32_t rv = p.versions[2 * n], pv = p.versions[2 * n + 1];
+        const uint32_t rv = p.versions_const ? p.versions_value[0] : p.versions[2 * n], pv = p.versions_const ? p.versions_value[1] : p.versions[2 * n + 1];
         cb_hdr1 h1;
         h1.resource_version = (uint16_t)(rv == 0xFF ? CB_NONE16 : rv); h1.principal_version = (uint16_t)(pv == 0xFF ? CB_NONE16 : pv); h1.action_set_id = aset;
         p.hdr1[n] = h1;
@@ -122,6 +136,18 @@ __global__ void __launch_bounds__(kThreads) widen_kernel(const __grid_constant__
                 out = w <= 1 ? (((uint64_t)(CB_V64_BOX_BASE | CB_V64_BOOL) << 48) | w) : widen_special(w == 3 ? 0u : w == 4 ? 1u : 2u);
                 break;
             }
+            case CGPU_SLOT_U16_ID: {      // string id - base | specials | bool
+                const uint32_t w = static_cast<const uint16_t *>(p.slot_src[v])[n];
+                if (w < 0xFFF0u) out = ((uint64_t)(CB_V64_BOX_BASE | CB_V64_STRING) << 48) | (uint64_t)(w < 0x8000u ? p.slot_base[v] + w : p.slot_base2[v] + (w - 0x8000u));
+                else if (w >= 0xFFFDu) out = widen_special(0xFFFFu - w);
+                else out = ((uint64_t)(CB_V64_BOX_BASE | CB_V64_BOOL) << 48) | (w == 0xFFFBu ? 1u : 0u);
+                break;
+            }
+            case CGPU_SLOT_U8_NUM: {      // a small non-negative integer (as the double it is) | specials
+                const uint32_t w = static_cast<const uint8_t *>(p.slot_src[v])[n];
+                out = w >= 0xFDu ? widen_special(0xFFu - w) : (uint64_t)__double_as_longlong((double)w);
+                break;
+            }
             default: out = static_cast<const uint64_t *>(p.slot_src[v])[n]; break;
             }
             p.slots_out[(uint64_t)v * p.stride + n] = out;
@@ -133,6 +159,14 @@ __global__ void __launch_bounds__(kThreads) widen_heap_kernel(const uint32_t *sr
     for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kThreads) {
         const uint32_t w = src[i];
         dst[i] = (w & 0x80000000u) ? (((uint64_t)(CB_V64_BOX_BASE | CB_V64_STRING) << 48) | (w & 0x7FFFFFFFu)) : (uint64_t)w;
+    }
+}
+
+// heap words in 16 bits: bit 15 clear = the word itself, set = a string id in one of two windows (bit 14)
+__global__ void __launch_bounds__(kThreads) widen_heap16_kernel(const uint16_t *src, uint64_t *dst, uint64_t n, uint32_t base, uint32_t base2) {
+    for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kThreads) {
+        const uint32_t w = src[i];
+        dst[i] = (w & 0x8000u) ? (((uint64_t)(CB_V64_BOX_BASE | CB_V64_STRING) << 48) | (uint64_t)(((w & 0x4000u) ? base2 : base) + (w & 0x3FFFu))) : (uint64_t)w;
     }
 }
 
@@ -1532,6 +1566,9 @@ int cgpu_check_meta(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch,
 }
 
 // requests [lo, hi) of `batch` on ctx's device: pipelined H2D / kernels / D2H (see below); effects_out covers the whole batch
+static inline uint32_t narrow_elem_bytes(uint32_t cl) {
+    return cl == CGPU_SLOT_U64 ? 8u : (cl == CGPU_SLOT_U8 || cl == CGPU_SLOT_U8_NUM) ? 1u : cl == CGPU_SLOT_U16_ID ? 2u : 4u;
+}
 static int check_range(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch_in, uint64_t lo, uint64_t hi, uint8_t *effects_out, const cgpu_narrow *nb = nullptr) {
     // narrow form: the canonical sizes of the per-request columns (and of a 32-bit heap) are implied, not passed
     cgpu_batch batch_c = *batch_in;
@@ -1544,7 +1581,9 @@ static int check_range(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *bat
         cbytes[CGPU_COL_HDR0] = batch_in->n_requests * 16; cbytes[CGPU_COL_HDR1] = batch_in->n_requests * 8;
         cbytes[CGPU_COL_ROLES] = (size_t)nb->role_cols * batch_in->n_requests * 4;
         cbytes[CGPU_COL_SLOTS] = (size_t)(t->desc.lay.n_slots ? t->desc.lay.n_slots : 1) * batch_in->n_requests * 8;
-        if (nb->heap_u32) cbytes[CGPU_COL_HEAP] = batch_in->column_bytes[CGPU_COL_HEAP] * 2;
+        if (nb->heap_bits == 16) cbytes[CGPU_COL_HEAP] = batch_in->column_bytes[CGPU_COL_HEAP] * 4;
+        else if (nb->heap_bits != 0) return fail(CGPU_ERR_INVALID, "cgpu_check_narrow: heap_bits %u (0 or 16)", nb->heap_bits);
+        else if (nb->heap_u32) cbytes[CGPU_COL_HEAP] = batch_in->column_bytes[CGPU_COL_HEAP] * 2;
         batch_c.columns = ccols; batch_c.column_bytes = cbytes;
     }
     const cgpu_batch *batch = &batch_c;
@@ -1587,16 +1626,20 @@ static int check_range(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *bat
     // narrow form: staging for the narrow columns (and the 32-bit heap) behind the canonical region
     size_t n_pid = 0, n_h16 = 0, n_ver = 0, n_roles = 0, n_heap32 = 0, n_slot[kMaxNarrowSlots] = {0};
     const uint32_t n_slots_t = t->desc.lay.n_slots;
+    const uint32_t hdr_w = nb ? 4u - (uint32_t)__builtin_popcount(nb->hdr_const_mask & 15u) : 4u;   // header fields that travel
     if (nb) {
         if (n_slots_t > kMaxNarrowSlots) return fail(CGPU_ERR_INVALID, "cgpu_check_narrow: more than %u attribute slots", kMaxNarrowSlots);
         auto take = [&](size_t bytes) { const size_t at = total; total += (bytes + 255) & ~(size_t)255; return at; };
-        n_pid = take(N * 4); n_h16 = take(N * 8); n_ver = take(N * 2); n_roles = take((size_t)nb->role_cols * N);
+        if ((nb->hdr_const_mask & ~15u) || (hdr_w && !nb->hdr16) || (!nb->versions_const && !nb->versions) || (!nb->principal_id16 && !nb->principal_id))
+            return fail(CGPU_ERR_INVALID, "cgpu_check_narrow: missing narrow column");
+        n_pid = take(N * (nb->principal_id16 ? 2 : 4)); n_h16 = take(N * 2 * hdr_w); n_ver = take(nb->versions_const ? 0 : N * 2); n_roles = take((size_t)nb->role_cols * N);
         for (uint32_t v = 0; v < n_slots_t; v++) {
             const uint32_t cl = nb->slot_class[v];
-            if (cl > CGPU_SLOT_U8) return fail(CGPU_ERR_INVALID, "cgpu_check_narrow: slot class %u", cl);
-            n_slot[v] = take(N * (cl == CGPU_SLOT_U64 ? 8 : cl == CGPU_SLOT_U8 ? 1 : 4));
+            if (cl > CGPU_SLOT_U8_NUM) return fail(CGPU_ERR_INVALID, "cgpu_check_narrow: slot class %u", cl);
+            if (cl == CGPU_SLOT_U16_ID && !nb->slot_base) return fail(CGPU_ERR_INVALID, "cgpu_check_narrow: CGPU_SLOT_U16_ID needs slot_base");
+            n_slot[v] = take(N * narrow_elem_bytes(cl));
         }
-        if (nb->heap_u32) n_heap32 = take(batch_in->column_bytes[CGPU_COL_HEAP]);
+        if (nb->heap_u32 || nb->heap_bits) n_heap32 = take(batch_in->column_bytes[CGPU_COL_HEAP]);
     }
     if (slot->dev_cap < total) {
         if (slot->dev) cudaFree(slot->dev);
@@ -1631,12 +1674,16 @@ static int check_range(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *bat
     }
     const uint8_t *const *hc = reinterpret_cast<const uint8_t *const *>(batch->columns);
     for (int i = CGPU_COL_HEAP; i < CGPU_N_COLUMNS; i++) {
-        if (nb && nb->heap_u32 && i == CGPU_COL_HEAP) {
+        if (nb && (nb->heap_u32 || nb->heap_bits) && i == CGPU_COL_HEAP) {
             const size_t nb32 = batch_in->column_bytes[CGPU_COL_HEAP];
             if (nb32) {
                 CUDA_TRY(cudaMemcpyAsync(dbase + n_heap32, hc[i], nb32, cudaMemcpyHostToDevice, slot->h2d));
-                const uint64_t words = nb32 / 4;
-                widen_heap_kernel<<<(unsigned)((words + kThreads - 1) / kThreads < 1184 ? (words + kThreads - 1) / kThreads : 1184), kThreads, 0, slot->h2d>>>(
+                const uint64_t words = nb32 / (nb->heap_bits == 16 ? 2 : 4);
+                const unsigned hgrid = (unsigned)((words + kThreads - 1) / kThreads < 1184 ? (words + kThreads - 1) / kThreads : 1184);
+                if (nb->heap_bits == 16)
+                    widen_heap16_kernel<<<hgrid, kThreads, 0, slot->h2d>>>(reinterpret_cast<const uint16_t *>(dbase + n_heap32), reinterpret_cast<uint64_t *>(dbase + offs[i]), words, nb->heap_base, nb->heap_base2);
+                else
+                widen_heap_kernel<<<hgrid, kThreads, 0, slot->h2d>>>(
                     reinterpret_cast<const uint32_t *>(dbase + n_heap32), reinterpret_cast<uint64_t *>(dbase + offs[i]), words);
                 CUDA_TRY(cudaGetLastError());
                 ctx->launches.fetch_add(1, std::memory_order_relaxed);
@@ -1648,18 +1695,25 @@ static int check_range(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *bat
     for (uint64_t k = 0; k < n_chunks; k++) {
         const uint64_t c0 = lo + k * chunk, cnt = hi - c0 < chunk ? hi - c0 : chunk;
         if (nb) {
-            CUDA_TRY(cudaMemcpyAsync(dbase + n_pid + c0 * 4, nb->principal_id + c0, cnt * 4, cudaMemcpyHostToDevice, slot->h2d));
-            CUDA_TRY(cudaMemcpyAsync(dbase + n_h16 + c0 * 8, nb->hdr16 + c0 * 4, cnt * 8, cudaMemcpyHostToDevice, slot->h2d));
-            CUDA_TRY(cudaMemcpyAsync(dbase + n_ver + c0 * 2, nb->versions + c0 * 2, cnt * 2, cudaMemcpyHostToDevice, slot->h2d));
+            if (nb->principal_id16) CUDA_TRY(cudaMemcpyAsync(dbase + n_pid + c0 * 2, nb->principal_id16 + c0, cnt * 2, cudaMemcpyHostToDevice, slot->h2d));
+            else CUDA_TRY(cudaMemcpyAsync(dbase + n_pid + c0 * 4, nb->principal_id + c0, cnt * 4, cudaMemcpyHostToDevice, slot->h2d));
+            if (hdr_w) CUDA_TRY(cudaMemcpyAsync(dbase + n_h16 + c0 * 2 * hdr_w, nb->hdr16 + c0 * hdr_w, cnt * 2 * hdr_w, cudaMemcpyHostToDevice, slot->h2d));
+            if (!nb->versions_const) CUDA_TRY(cudaMemcpyAsync(dbase + n_ver + c0 * 2, nb->versions + c0 * 2, cnt * 2, cudaMemcpyHostToDevice, slot->h2d));
             for (uint32_t i = 0; i < nb->role_cols; i++)
                 CUDA_TRY(cudaMemcpyAsync(dbase + n_roles + (uint64_t)i * N + c0, nb->roles + (uint64_t)i * N + c0, cnt, cudaMemcpyHostToDevice, slot->h2d));
             WidenParams wp{};
             for (uint32_t v = 0; v < n_slots_t; v++) {
-                const uint32_t cl = nb->slot_class[v], es = cl == CGPU_SLOT_U64 ? 8 : cl == CGPU_SLOT_U8 ? 1 : 4;
+                const uint32_t cl = nb->slot_class[v], es = narrow_elem_bytes(cl);
                 CUDA_TRY(cudaMemcpyAsync(dbase + n_slot[v] + c0 * es, static_cast<const uint8_t *>(nb->slot_cols[v]) + c0 * es, cnt * es, cudaMemcpyHostToDevice, slot->h2d));
                 wp.slot_src[v] = dbase + n_slot[v];
                 wp.slot_class[v] = (uint8_t)cl;
+                wp.slot_base[v] = nb->slot_base ? nb->slot_base[v] : 0u;
+                wp.slot_base2[v] = nb->slot_base2 ? nb->slot_base2[v] : 0u;
             }
+            wp.pid16 = nb->principal_id16 ? reinterpret_cast<const uint16_t *>(dbase + n_pid) : nullptr; wp.pid_base = nb->principal_base;
+            wp.hdr_const_mask = nb->hdr_const_mask & 15u; wp.hdr_w = hdr_w;
+            for (int f = 0; f < 4; f++) wp.hdr_const[f] = nb->hdr_const[f];
+            wp.versions_const = nb->versions_const; wp.versions_value[0] = nb->versions_value[0]; wp.versions_value[1] = nb->versions_value[1];
             wp.pid = reinterpret_cast<const uint32_t *>(dbase + n_pid); wp.hdr16 = reinterpret_cast<const uint16_t *>(dbase + n_h16);
             wp.versions = dbase + n_ver; wp.roles = dbase + n_roles;
             wp.hdr0 = reinterpret_cast<cb_hdr0 *>(dbase + offs[CGPU_COL_HDR0]); wp.hdr1 = reinterpret_cast<cb_hdr1 *>(dbase + offs[CGPU_COL_HDR1]);
@@ -1703,7 +1757,7 @@ static int check_range(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *bat
 int cgpu_check_narrow(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, const cgpu_narrow *narrow, uint8_t *effects_out) {
     if (!ctx || !t || !batch || !narrow || !effects_out) return fail(CGPU_ERR_INVALID, "cgpu_check_narrow: null argument");
     if (t->ctx != ctx) return fail(CGPU_ERR_INVALID, "table belongs to another context");
-    if (!narrow->principal_id || !narrow->hdr16 || !narrow->versions || !narrow->roles || !narrow->slot_class || !narrow->slot_cols || narrow->role_cols == 0)
+    if (!narrow->roles || !narrow->slot_class || !narrow->slot_cols || narrow->role_cols == 0)
         return fail(CGPU_ERR_INVALID, "cgpu_check_narrow: missing narrow column");
     if (batch->n_requests == 0) return CGPU_OK;
     return check_range(ctx, t, batch, 0, batch->n_requests, effects_out, narrow);

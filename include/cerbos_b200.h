@@ -111,7 +111,8 @@ int cgpu_check(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, uint
  *   heap          optionally u32 words: bit 31 clear = the word (element counts), set = string id (lists / maps of strings)
  * and a widening kernel rebuilds the canonical columns in HBM (1/100 of the PCIe cost).  `batch` carries the batch-level
  * tables (columns 4..11; column 4 = the u32 heap when heap_u32) and the scalars; its columns 0..3 are ignored. */
-enum cgpu_slot_class { CGPU_SLOT_U64 = 0, CGPU_SLOT_U32_ID = 1, CGPU_SLOT_U32_HEAP = 2, CGPU_SLOT_F32 = 3, CGPU_SLOT_U8 = 4 };
+enum cgpu_slot_class { CGPU_SLOT_U64 = 0, CGPU_SLOT_U32_ID = 1, CGPU_SLOT_U32_HEAP = 2, CGPU_SLOT_F32 = 3, CGPU_SLOT_U8 = 4,
+                       CGPU_SLOT_U16_ID = 5, CGPU_SLOT_U8_NUM = 6 };
 typedef struct {
     const uint32_t *principal_id;
     const uint16_t *hdr16;
@@ -121,6 +122,30 @@ typedef struct {
     const uint8_t *slot_class;        /* [table n_slots] */
     const void *const *slot_cols;     /* [table n_slots] */
     uint32_t heap_u32;
+    /* Narrower still -- every field below is optional (zero / NULL = not used; a caller of the first form zero-fills them):
+     *   CGPU_SLOT_U16_ID   u16 per request: w < 0x8000 = string id slot_base[v] + w, 0x8000 <= w < 0xFFF0 = string id slot_base2[v] +
+     *                      (w - 0x8000); 0xFFFF absent, ..FE error, ..FD null, ..FC false, ..FB true.  Two windows because an
+     *                      attribute's strings come from two dictionaries: the table's (constants the policies name, low ids)
+     *                      and the batch's (numbered from n_table_strings in order of first appearance)
+     *   CGPU_SLOT_U8_NUM   u8 per request = a number that is an integer in 0 .. 0xEF (0xFF absent, 0xFE error, 0xFD null)
+     *   principal_id16     u16 = principal string id - principal_base, instead of principal_id
+     *   hdr_const_mask     bit f set: header field f (0 kind class, 1 resource scope, 2 principal scope, 3 action set) has the same
+     *                      16-bit value hdr_const[f] in every request; hdr16 then holds only the other fields, in order:
+     *                      u16[N][4 - popcount(mask)] (NULL when all four are constant)
+     *   versions_const     1: both policy version ids are the same in every request (versions_value); `versions` is ignored
+     *   heap_bits          16: the heap as u16 words -- bit 15 clear = the word (element counts < 32768); set = a string id, bit 14
+     *                      choosing the window: heap_base + (w & 0x3FFF) or heap_base2 + (w & 0x3FFF)
+     *                      (overrides heap_u32; column 4 of `batch` is the u16 heap) */
+    const uint32_t *slot_base;        /* [table n_slots] */
+    const uint32_t *slot_base2;       /* [table n_slots] */
+    const uint16_t *principal_id16;
+    uint32_t principal_base;
+    uint32_t hdr_const_mask;
+    uint16_t hdr_const[4];
+    uint32_t versions_const;
+    uint8_t versions_value[2];
+    uint32_t heap_bits;
+    uint32_t heap_base, heap_base2;
 } cgpu_narrow;
 int cgpu_check_narrow(cgpu_ctx *ctx, const cgpu_table *t, const cgpu_batch *batch, const cgpu_narrow *narrow, uint8_t *effects_out);
 
