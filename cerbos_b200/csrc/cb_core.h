@@ -437,8 +437,13 @@ CB_HD int val_order(const Ctx &c, const Val &a, const Val &b) {
     }
 }
 
+CB_HD_NOINLINE int spiffe_equal(Ctx &c, const Val &a, const Val &b);   // with the SPIFFE functions below
 CB_HD Val do_cmp(Ctx &c, int ci, const Val &a, const Val &b) {
     if (a.tag == CB_T_ERR || b.tag == CB_T_ERR) return mk_err();
+    if (ci <= 1 && (a.tag == CB_T_SPIFFE_ID || a.tag == CB_T_SPIFFE_TD)) {   // the left operand's Equal decides (spiffe.go)
+        const int r = spiffe_equal(c, a, b);
+        return r == 2 ? mk_err() : mk_bool((r == 1) == (ci == 0));
+    }
     if (ci == 0) return mk_bool(val_equal(c, a, b));
     if (ci == 1) return mk_bool(!val_equal(c, a, b));
     int r = val_order(c, a, b);
@@ -1501,6 +1506,150 @@ CB_HD void loop_bind(Ctx &c, const Loop &L, int var, bool two) {
     }
 }
 
+// ---- SPIFFE ids and trust domains (conditions/types/spiffe.go over go-spiffe's spiffeid package) ------------------------
+// A SPIFFE id is its validated string (tag CB_T_SPIFFE_ID, payload = the string reference), a trust domain its name (tag
+// CB_T_SPIFFE_TD); a matcher never exists as a value: spiffeMatchX(arg).matchesID(x) is one fused function.
+CB_HD bool spiffe_td_char(uint8_t ch) { return (ch >= 'a' && ch <= 'z') || (ch >= '0' && ch <= '9') || ch == '-' || ch == '.' || ch == '_'; }
+CB_HD bool spiffe_seg_char(uint8_t ch) { return spiffe_td_char(ch) || (ch >= 'A' && ch <= 'Z'); }
+// spiffeid.FromString: "spiffe://" + trust domain (lower case, digits, - . _; not empty) + path of non-empty segments
+// (letters, digits, - . _; no "." / ".." segment, no trailing slash).  *pathidx = where the path starts.
+CB_HD_NOINLINE bool spiffe_parse_id(const uint8_t *p, uint32_t n, uint32_t *pathidx) {
+    const uint8_t pre[9] = {'s', 'p', 'i', 'f', 'f', 'e', ':', '/', '/'};
+    if (n < 9) return false;
+    for (uint32_t i = 0; i < 9; i++) if (ldg(p + i) != pre[i]) return false;
+    uint32_t i = 9;
+    while (i < n && ldg(p + i) != '/') { if (!spiffe_td_char(ldg(p + i))) return false; i++; }
+    if (i == 9) return false;
+    *pathidx = i;
+    uint32_t seg = i + 1;
+    for (uint32_t k = i + 1; k <= n && i < n; k++) {
+        if (k == n || ldg(p + k) == '/') {
+            const uint32_t len = k - seg;
+            if (len == 0) return false;
+            if (len == 1 && ldg(p + seg) == '.') return false;
+            if (len == 2 && ldg(p + seg) == '.' && ldg(p + seg + 1) == '.') return false;
+            seg = k + 1;
+        } else if (!spiffe_seg_char(ldg(p + k))) return false;
+    }
+    return true;
+}
+// bytes [from, to) of string `ref` as a string of its own (the whole string: the reference itself)
+CB_HD Val spiffe_substr(Ctx &c, uint64_t ref, const uint8_t *p, uint32_t n, uint32_t from, uint32_t to) {
+    if (from == 0 && to == n) return mk(CB_T_STRING, ref);
+    StrB s = strb_begin(c);
+    strb_bytes(s, p + from, to - from);
+    return strb_end(s);
+}
+// spiffeid.TrustDomainFromString: an id (anything containing ":/") gives its trust domain, else the text must be a name
+CB_HD_NOINLINE Val spiffe_td_from_string(Ctx &c, uint64_t ref) {
+    const uint8_t *p; uint32_t n;
+    str_get(c, ref, p, n);
+    if (n == 0) return mk_err();
+    bool looks_like_id = false;
+    for (uint32_t i = 0; i + 1 < n; i++) looks_like_id |= ldg(p + i) == ':' && ldg(p + i + 1) == '/';
+    if (looks_like_id) {
+        uint32_t px;
+        if (!spiffe_parse_id(p, n, &px)) return mk_err();
+        Val v = spiffe_substr(c, ref, p, n, 9, px);
+        if (v.tag == CB_T_STRING) v.tag = CB_T_SPIFFE_TD;
+        return v;
+    }
+    for (uint32_t i = 0; i < n; i++) if (!spiffe_td_char(ldg(p + i))) return mk_err();
+    return mk(CB_T_SPIFFE_TD, ref);
+}
+CB_HD Val spiffe_id_of(Ctx &c, const Val &v) {   // spiffeID(string | id); also how matchesID takes its argument
+    if (v.tag == CB_T_SPIFFE_ID) return v;
+    if (v.tag != CB_T_STRING) return mk_err();
+    const uint8_t *p; uint32_t n, px;
+    str_get(c, v.u, p, n);
+    return spiffe_parse_id(p, n, &px) ? mk(CB_T_SPIFFE_ID, v.u) : mk_err();
+}
+CB_HD Val spiffe_td_of_id(Ctx &c, const Val &id) {
+    const uint8_t *p; uint32_t n, px = 9;
+    str_get(c, id.u, p, n);
+    spiffe_parse_id(p, n, &px);
+    Val v = spiffe_substr(c, id.u, p, n, 9, px);
+    if (v.tag == CB_T_STRING) v.tag = CB_T_SPIFFE_TD;
+    return v;
+}
+CB_HD Val spiffe_td_of(Ctx &c, const Val &v) {   // spiffeTrustDomain(string | id | trust domain); spiffeMatchTrustDomain's argument
+    if (v.tag == CB_T_SPIFFE_TD) return v;
+    if (v.tag == CB_T_SPIFFE_ID) return spiffe_td_of_id(c, v);
+    if (v.tag == CB_T_STRING) return spiffe_td_from_string(c, v.u);
+    return mk_err();
+}
+CB_HD_NOINLINE Val spiffe_fn(Ctx &c, uint32_t fn, const Val *a, uint32_t argc) {
+    for (uint32_t i = 0; i < argc; i++) if (a[i].tag == CB_T_ERR) return mk_err();
+    switch (fn) {
+    case CB_FN_SPIFFE_ID: return spiffe_id_of(c, a[0]);
+    case CB_FN_SPIFFE_IDSTR: { Val v = spiffe_id_of(c, a[0]); if (v.tag == CB_T_SPIFFE_ID) v.tag = CB_T_STRING; return v; }
+    case CB_FN_SPIFFE_TD: return spiffe_td_of(c, a[0]);
+    case CB_FN_SPIFFE_TD_OF: return a[0].tag == CB_T_SPIFFE_ID ? spiffe_td_of_id(c, a[0]) : mk_err();
+    case CB_FN_SPIFFE_PATH: {
+        if (a[0].tag != CB_T_SPIFFE_ID) return mk_err();
+        const uint8_t *p; uint32_t n, px = 0;
+        str_get(c, a[0].u, p, n);
+        spiffe_parse_id(p, n, &px);
+        if (px == n) { StrB s = strb_begin(c); return strb_end(s); }   // no path: the empty string
+        return spiffe_substr(c, a[0].u, p, n, px, n);
+    }
+    case CB_FN_SPIFFE_MEMBER: {
+        if (a[0].tag != CB_T_SPIFFE_ID || a[1].tag != CB_T_SPIFFE_TD) return mk_err();
+        const Val td = spiffe_td_of_id(c, a[0]);
+        return td.tag == CB_T_SPIFFE_TD ? mk_bool(str_equal(c, td.u, a[1].u)) : mk_err();
+    }
+    case CB_FN_SPIFFE_TD_NAME: return a[0].tag == CB_T_SPIFFE_TD ? mk(CB_T_STRING, a[0].u) : mk_err();
+    case CB_FN_SPIFFE_TD_ID: {      // "spiffe://" + name; id(x) of any other value is x (cerbos_lib.go)
+        if (a[0].tag != CB_T_SPIFFE_TD) return a[0];
+        const uint8_t pre[9] = {'s', 'p', 'i', 'f', 'f', 'e', ':', '/', '/'};
+        const uint8_t *p; uint32_t n;
+        str_get(c, a[0].u, p, n);
+        StrB s = strb_begin(c);
+        for (uint32_t i = 0; i < 9; i++) strb_put(s, pre[i]);
+        strb_bytes(s, p, n);
+        return strb_end(s);
+    }
+    case CB_FN_SPIFFE_MATCH_ANY: return spiffe_id_of(c, a[0]).tag == CB_T_SPIFFE_ID ? mk_bool(true) : mk_err();
+    case CB_FN_SPIFFE_MATCH_EXACT: {
+        const Val want = spiffe_id_of(c, a[0]), got = spiffe_id_of(c, a[1]);
+        if (want.tag != CB_T_SPIFFE_ID || got.tag != CB_T_SPIFFE_ID) return mk_err();
+        return mk_bool(str_equal(c, want.u, got.u));
+    }
+    case CB_FN_SPIFFE_MATCH_ONEOF: {   // every element must be (the string of) a valid id, else no such overload
+        if (a[0].tag != CB_T_LIST) return mk_err();
+        const LView l = lview(c, a[0]);
+        for (uint32_t i = 0; i < l.n; i++) if (spiffe_id_of(c, decode_elem(ldg(l.p + i))).tag != CB_T_SPIFFE_ID) return mk_err();
+        const Val got = spiffe_id_of(c, a[1]);
+        if (got.tag != CB_T_SPIFFE_ID) return mk_err();
+        bool found = false;
+        for (uint32_t i = 0; i < l.n; i++) found |= str_equal(c, decode_elem(ldg(l.p + i)).u, got.u);
+        return mk_bool(found);
+    }
+    case CB_FN_SPIFFE_MATCH_TD: {
+        const Val td = spiffe_td_of(c, a[0]);
+        if (td.tag != CB_T_SPIFFE_TD || a[0].tag == CB_T_SPIFFE_ID) return mk_err();   // (an id is no argument of spiffeMatchTrustDomain)
+        const Val got = spiffe_id_of(c, a[1]);
+        if (got.tag != CB_T_SPIFFE_ID) return mk_err();
+        const Val gtd = spiffe_td_of_id(c, got);
+        return gtd.tag == CB_T_SPIFFE_TD ? mk_bool(str_equal(c, gtd.u, td.u)) : mk_err();
+    }
+    default: c.unsupported = 1; return mk_err();
+    }
+}
+// `==` with a SPIFFE value on the left (spiffe.go:346-360, 443-461); 0 false, 1 true, 2 no such overload
+CB_HD_NOINLINE int spiffe_equal(Ctx &c, const Val &a, const Val &b) {
+    if (a.tag == CB_T_SPIFFE_ID) {
+        if (b.tag == CB_T_SPIFFE_ID || b.tag == CB_T_STRING) return str_equal(c, a.u, b.u) ? 1 : 0;
+        return 2;
+    }
+    if (b.tag == CB_T_SPIFFE_TD) return str_equal(c, a.u, b.u) ? 1 : 0;
+    if (b.tag == CB_T_STRING) {   // a string that is no trust domain is simply unequal
+        const Val t = spiffe_td_from_string(c, b.u);
+        return t.tag == CB_T_SPIFFE_TD && str_equal(c, a.u, t.u) ? 1 : 0;
+    }
+    return 2;
+}
+
 // ---- single-instruction bodies: shared by the interpreter below and by the straight-line code that
 // cb_specialize.h (generate_uc) emits from a condition's program for the run-time specialised kernels
 CB_HD Val op_select(Ctx &c, const Val &m, uint32_t key) { Val o; return (m.tag == CB_T_MAP && map_find(c, m, mk(CB_T_STRING, key), &o)) ? o : mk_err(); }
@@ -1592,6 +1741,7 @@ CB_HD Val op_hier_ca3(Ctx &c, const Val &a0, const Val &b0, const Val &z0, uint3
     return mk_bool(hier_count(z) == k && hier_common(a, z, k) == k);
 }
 CB_HD Val op_fn(Ctx &c, uint32_t fn, uint32_t argc, Val *a) {   // a[0..argc): arguments (target first)
+    if (fn >= CB_FN_SPIFFE_ID) return spiffe_fn(c, fn, a, argc);
     if (fn == CB_FN_REVERSE && a[0].tag == CB_T_STRING) return dyn_strfn(c, CB_FN_STR_REVERSE, a, argc);
     return fn >= CB_FN_EXCEPT ? dyn_listfn(c, fn, a, argc) : dyn_strfn(c, fn, a, argc);
 }

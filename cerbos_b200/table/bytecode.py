@@ -807,6 +807,8 @@ class ProgramCompiler:
             self.expr(args[0])
             self.emit("MATCHES", c=self.ctx._heap_put(words))
             return
+        if self._spiffe_call(n, fn, args):
+            return
         if fn in self._FN and len(args) in self._FN[fn][1]:
             # string / list producing functions (ext.Strings, ext.Lists, Cerbos except / intersect): results live in the
             # device's per-thread scratch arena
@@ -822,6 +824,62 @@ class ProgramCompiler:
            "replace": ("REPLACE", (3, 4)), "split": ("SPLIT", (2, 3)), "join": ("JOIN", (1, 2)), "reverse": ("REVERSE", (1,)),
            "except": ("EXCEPT", (2,)), "intersect": ("INTERSECT", (2,)), "sort": ("SORT", (1,)), "slice": ("SLICE", (3,)),
            "flatten": ("FLATTEN", (1, 2)), "distinct": ("DISTINCT", (1,)), "lists.range": ("RANGE", (1,))}
+
+    # ---- SPIFFE (conditions/types/spiffe.go): ids and trust domains are strings of a validated shape (tags SPIFFE_ID /
+    # SPIFFE_TD); a matcher is never a run-time value -- spiffeMatchX(arg).matchesID(x) compiles to one fused function
+    _SPIFFE1 = {"spiffeID": "SPIFFE_ID", "spiffeTrustDomain": "SPIFFE_TD"}
+    _SPIFFE_RECV = {"path": "SPIFFE_PATH", "trustDomain": "SPIFFE_TD_OF", "name": "SPIFFE_TD_NAME"}
+    _SPIFFE_MATCH = {"spiffeMatchExact": "SPIFFE_MATCH_EXACT", "spiffeMatchOneOf": "SPIFFE_MATCH_ONEOF", "spiffeMatchTrustDomain": "SPIFFE_MATCH_TD"}
+
+    def _fn(self, name, argc):
+        self.emit("FN", a=L.FNS[name], b=argc, delta=1 - argc)
+
+    def _spiffe_call(self, n: Call, fn, args) -> bool:
+        if fn in self._SPIFFE1 and n.target is None and len(args) == 1:
+            self.expr(args[0])
+            self._fn(self._SPIFFE1[fn], 1)
+            return True
+        if fn in self._SPIFFE_RECV and n.target is not None and len(args) == 1:
+            self.expr(args[0])
+            self._fn(self._SPIFFE_RECV[fn], 1)
+            return True
+        if fn == "id" and n.target is not None and len(args) == 1:      # spiffeTrustDomain(..).id(); id(x) of any other value is x
+            self.expr(args[0])
+            self._fn("SPIFFE_TD_ID", 1)
+            return True
+        if fn == "isMemberOf" and n.target is not None and len(args) == 2:
+            self.expr(args[0])
+            self.expr(args[1])
+            self._fn("SPIFFE_MEMBER", 2)
+            return True
+        if fn == "matchesID" and n.target is not None and len(args) == 2:
+            m = n.target
+            if not (isinstance(m, Call) and m.target is None):
+                raise Unsupported("matchesID on a matcher that is not built in place")
+            if m.fn == "spiffeMatchAny" and not m.args:
+                self.expr(args[1])
+                self._fn("SPIFFE_MATCH_ANY", 1)
+                return True
+            if m.fn in self._SPIFFE_MATCH and len(m.args) == 1:
+                a = m.args[0]
+                if m.fn == "spiffeMatchOneOf" and isinstance(a, ListLit):
+                    # a literal list of ids: spiffeID(e) elements are validated where they stand and travel as their id strings
+                    for e in a.elems:
+                        if isinstance(e, Call) and e.fn == "spiffeID" and e.target is None and len(e.args) == 1:
+                            self.expr(e.args[0])
+                            self._fn("SPIFFE_IDSTR", 1)
+                        else:
+                            self.expr(e)
+                    self.emit("MKLIST", c=len(a.elems), delta=1 - len(a.elems))
+                else:
+                    self.expr(a)
+                self.expr(args[1])
+                self._fn(self._SPIFFE_MATCH[m.fn], 2)
+                return True
+            raise Unsupported("matchesID on a matcher that is not built in place")
+        if fn in self._SPIFFE_MATCH or fn == "spiffeMatchAny":
+            raise Unsupported("a SPIFFE matcher used as a value")
+        return False
 
     # ---- hierarchy(s[, delim]) (conditions/types/hierarchy.go): never a run-time value -- the functions over
     # hierarchies compile to fused ops on the underlying strings

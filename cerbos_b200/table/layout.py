@@ -12,7 +12,7 @@ Table blob (little endian, every section 16-byte aligned):
 from __future__ import annotations
 
 MAGIC = 0x32425243  # 'CRB2'
-VERSION = 14
+VERSION = 15
 ALIGN = 16
 
 NONE32 = 0xFFFFFFFF
@@ -98,6 +98,7 @@ V64_CANON_NAN = 0x7FF8000000000000
 # ---- interpreter value tags ---------------------------------------------------------------------------------
 TAGS = {name: i for i, name in enumerate([
     "ERR", "NULL", "BOOL", "INT", "UINT", "DOUBLE", "STRING", "LIST", "MAP", "TS", "DUR", "BYTES", "TYPE",
+    "SPIFFE_ID", "SPIFFE_TD",     # conditions/types/spiffe.go: a validated SPIFFE id string; a trust domain name (payload: a string reference)
 ])}
 
 # ---- bytecode ---------------------------------------------------------------------------------------------------
@@ -163,6 +164,9 @@ FNS = {name: i for i, name in enumerate([
     "TO_BYTES",         # bytes(string | bytes)
     "B64ENC", "B64DEC", # base64.encode(bytes) -> string, base64.decode(string) -> bytes (std alphabet, padding optional)
     "EXCEPT", "INTERSECT", "SORT", "REVERSE", "SLICE", "FLATTEN", "DISTINCT", "RANGE",
+    # SPIFFE (conditions/types/spiffe.go); a matcher never exists as a value: matcher(arg).matchesID(x) is one fused function
+    "SPIFFE_ID", "SPIFFE_TD", "SPIFFE_PATH", "SPIFFE_TD_OF", "SPIFFE_MEMBER", "SPIFFE_TD_ID", "SPIFFE_TD_NAME", "SPIFFE_IDSTR",
+    "SPIFFE_MATCH_ANY", "SPIFFE_MATCH_EXACT", "SPIFFE_MATCH_ONEOF", "SPIFFE_MATCH_TD",
 ])}
 TS_FIELDS = {name: i for i, name in enumerate(["getFullYear", "getMonth", "getDayOfYear", "getDayOfMonth", "getDate", "getDayOfWeek",
                                                "getHours", "getMinutes", "getSeconds", "getMilliseconds"])}

@@ -100,6 +100,84 @@ class Hierarchy:
         return f"hierarchy({'.'.join(self.parts)})"
 
 
+# ---- SPIFFE types (internal/conditions/types/spiffe.go over github.com/spiffe/go-spiffe/v2 v2.x, go.mod -- a third-party
+# dependency that is not under /root/reference: its spiffeid.FromString / TrustDomainFromString / ValidatePath rules are
+# restated here from the library's published source and pinned by the reference's TestCerbosLib rows and cel_eval goldens)
+_TD_CHARS = set("abcdefghijklmnopqrstuvwxyz0123456789-._")
+_SEG_CHARS = _TD_CHARS | set("ABCDEFGHIJKLMNOPQRSTUVWXYZ")
+
+
+def spiffe_parse_id(s: str):
+    """spiffeid.FromString -> (id string, index where the path starts) or raises CelError"""
+    if s == "":
+        raise CelError("failed to parse SPIFFE ID: cannot be empty")
+    if not s.startswith("spiffe://"):
+        raise CelError("failed to parse SPIFFE ID: scheme is missing or invalid")
+    i = 9
+    while i < len(s) and s[i] != "/":
+        if s[i] not in _TD_CHARS:
+            raise CelError("failed to parse SPIFFE ID: trust domain characters are limited to lowercase letters, numbers, dots, dashes, and underscores")
+        i += 1
+    if i == 9:
+        raise CelError("failed to parse SPIFFE ID: trust domain is missing")
+    path = s[i:]
+    if path:                                   # spiffeid.ValidatePath
+        for seg in path[1:].split("/"):
+            if seg == "":
+                raise CelError("failed to parse SPIFFE ID: path cannot contain empty segments / have a trailing slash")
+            if seg in (".", ".."):
+                raise CelError("failed to parse SPIFFE ID: path cannot contain dot segments")
+            if any(ch not in _SEG_CHARS for ch in seg):
+                raise CelError("failed to parse SPIFFE ID: path segment characters are limited to letters, numbers, dots, dashes, and underscores")
+    return s, i
+
+
+def spiffe_parse_td(s: str) -> str:
+    """spiffeid.TrustDomainFromString -> trust domain name"""
+    if s == "":
+        raise CelError("failed to parse SPIFFE trust domain: trust domain is missing")
+    if ":/" in s:
+        sid, i = spiffe_parse_id(s)
+        return sid[9:i]
+    if any(ch not in _TD_CHARS for ch in s):
+        raise CelError("failed to parse SPIFFE trust domain: trust domain characters are limited to lowercase letters, numbers, dots, dashes, and underscores")
+    return s
+
+
+class SpiffeID:
+    __slots__ = ("id", "pathidx")
+
+    def __init__(self, s):
+        self.id, self.pathidx = spiffe_parse_id(s)
+
+    @property
+    def td(self):
+        return self.id[9:self.pathidx]
+
+
+class SpiffeTD:
+    __slots__ = ("name",)
+
+    def __init__(self, name):
+        self.name = name
+
+
+class SpiffeMatcher:
+    __slots__ = ("kind", "arg")     # "any" | "exact" (id string) | "oneof" (set of id strings) | "td" (name)
+
+    def __init__(self, kind, arg=None):
+        self.kind, self.arg = kind, arg
+
+    def matches(self, sid: SpiffeID) -> bool:
+        if self.kind == "any":
+            return True
+        if self.kind == "exact":
+            return sid.id == self.arg
+        if self.kind == "oneof":
+            return sid.id in self.arg
+        return sid.td == self.arg
+
+
 class CelMap:
     """Insertion-ordered CEL map with type-aware key lookup."""
     __slots__ = ("keys", "vals", "_sidx")
@@ -314,6 +392,23 @@ def cel_equal(a, b) -> bool:
         if not isinstance(b, Hierarchy):
             raise no_overload("_==_", a, b)
         return a.parts == b.parts
+    if isinstance(a, SpiffeID):                      # spiffe.go:346-360
+        if isinstance(b, SpiffeID):
+            return a.id == b.id
+        if isinstance(b, str):
+            return a.id == b
+        raise no_overload("_==_", a, b)
+    if isinstance(a, SpiffeTD):                      # spiffe.go:443-461: a string that is no trust domain is simply unequal
+        if isinstance(b, SpiffeTD):
+            return a.name == b.name
+        if isinstance(b, str):
+            try:
+                return spiffe_parse_td(b) == a.name
+            except CelError:
+                return False
+        raise no_overload("_==_", a, b)
+    if isinstance(a, SpiffeMatcher):                 # spiffe.go:538-540
+        return False
     if isinstance(a, Msg):
         return isinstance(b, Msg) and a.type_name == b.type_name and all(
             cel_equal(a.fields[k], b.fields[k]) for k in a.fields)
@@ -1882,8 +1977,90 @@ def _lib2(fn):
     return f
 
 
+def _f_spiffe_id(ev, a):
+    if len(a) == 1 and isinstance(a[0], SpiffeID):
+        return a[0]
+    if len(a) == 1 and isinstance(a[0], str):
+        return SpiffeID(a[0])
+    raise no_overload("spiffeID", *a)
+
+
+def _f_spiffe_td(ev, a):
+    if len(a) == 1 and isinstance(a[0], SpiffeTD):
+        return a[0]
+    if len(a) == 1 and isinstance(a[0], SpiffeID):
+        return SpiffeTD(a[0].td)
+    if len(a) == 1 and isinstance(a[0], str):
+        return SpiffeTD(spiffe_parse_td(a[0]))
+    raise no_overload("spiffeTrustDomain", *a)
+
+
+def _f_spiffe_match_exact(ev, a):
+    if len(a) == 1 and isinstance(a[0], SpiffeID):
+        return SpiffeMatcher("exact", a[0].id)
+    if len(a) == 1 and isinstance(a[0], str):
+        return SpiffeMatcher("exact", SpiffeID(a[0]).id)
+    raise no_overload("spiffeMatchExact", *a)
+
+
+def _f_spiffe_match_one_of(ev, a):
+    if len(a) != 1 or not isinstance(a[0], list):
+        raise no_overload("spiffeMatchOneOf", *a)
+    if all(isinstance(x, SpiffeID) for x in a[0]):
+        return SpiffeMatcher("oneof", {x.id for x in a[0]})
+    if all(isinstance(x, str) for x in a[0]):
+        try:
+            return SpiffeMatcher("oneof", {SpiffeID(x).id for x in a[0]})
+        except CelError:
+            pass
+    raise no_overload("spiffeMatchOneOf", *a)
+
+
+def _f_spiffe_match_td(ev, a):
+    if len(a) == 1 and isinstance(a[0], SpiffeTD):
+        return SpiffeMatcher("td", a[0].name)
+    if len(a) == 1 and isinstance(a[0], str):
+        return SpiffeMatcher("td", spiffe_parse_td(a[0]))
+    raise no_overload("spiffeMatchTrustDomain", *a)
+
+
+def _f_spiffe_matches_id(ev, a):
+    if len(a) != 2 or not isinstance(a[0], SpiffeMatcher):
+        raise no_overload("matchesID", *a)
+    if isinstance(a[1], SpiffeID):
+        return a[0].matches(a[1])
+    if isinstance(a[1], str):
+        return a[0].matches(SpiffeID(a[1]))
+    raise no_overload("matchesID", *a)
+
+
+def _f_spiffe_member_of(ev, a):
+    if len(a) != 2 or not isinstance(a[0], SpiffeID) or not isinstance(a[1], SpiffeTD):
+        raise no_overload("isMemberOf", *a)
+    return a[0].td == a[1].name
+
+
+def _spiffe_recv(fn, cls, f):
+    def g(ev, a):
+        if len(a) != 1 or not isinstance(a[0], cls):
+            raise no_overload(fn, *a)
+        return f(a[0])
+    return g
+
+
+def _f_id(ev, a):
+    if len(a) == 1 and isinstance(a[0], SpiffeTD):   # spiffeTrustDomain.id(): the fully qualified trust domain id
+        return "spiffe://" + a[0].name
+    return a[0]                                        # cerbos_lib.go: id(x) = x
+
+
 _FUNCS = {
     "_==_": _f_eq, "_!=_": _f_ne,
+    "spiffeID": _f_spiffe_id, "spiffeTrustDomain": _f_spiffe_td, "spiffeMatchAny": lambda ev, a: SpiffeMatcher("any") if not a else (_ for _ in ()).throw(no_overload("spiffeMatchAny", *a)),
+    "spiffeMatchExact": _f_spiffe_match_exact, "spiffeMatchOneOf": _f_spiffe_match_one_of, "spiffeMatchTrustDomain": _f_spiffe_match_td,
+    "matchesID": _f_spiffe_matches_id, "isMemberOf": _f_spiffe_member_of,
+    "path": _spiffe_recv("path", SpiffeID, lambda s: s.id[s.pathidx:]), "trustDomain": _spiffe_recv("trustDomain", SpiffeID, lambda s: SpiffeTD(s.td)),
+    "name": _spiffe_recv("name", SpiffeTD, lambda t: t.name),
     "_<_": _rel("_<_", lambda c: c < 0), "_<=_": _rel("_<=_", lambda c: c <= 0),
     "_>_": _rel("_>_", lambda c: c > 0), "_>=_": _rel("_>=_", lambda c: c >= 0),
     "_+_": lambda ev, a: op_add(*a), "_-_": lambda ev, a: op_sub(*a), "_*_": lambda ev, a: op_mul(*a),
@@ -1891,7 +2068,7 @@ _FUNCS = {
     "!_": _f_not, "@in": _f_in, "_[_]": _f_index, "size": _f_size,
     "int": _conv(conv_int), "uint": _conv(conv_uint), "double": _conv(conv_double), "string": _conv(conv_string),
     "bool": _conv(conv_bool), "bytes": _conv(conv_bytes), "timestamp": _conv(conv_timestamp),
-    "duration": _conv(conv_duration), "dyn": lambda ev, a: a[0], "type": _f_type, "id": lambda ev, a: a[0],
+    "duration": _conv(conv_duration), "dyn": lambda ev, a: a[0], "type": _f_type, "id": _f_id,
     "contains": _str2("contains", lambda s, t: t in s), "startsWith": _str2("startsWith", lambda s, t: s.startswith(t)),
     "endsWith": _str2("endsWith", lambda s, t: s.endswith(t)), "matches": _f_matches,
     "charAt": _f_char_at, "indexOf": _f_index_of, "lastIndexOf": _f_last_index_of,

@@ -41,8 +41,6 @@ _LIB = [tc for tc in load_golden("cerbos_lib_test.json")]
 def test_cerbos_lib_table(tc):
     """internal/conditions/cerbos_lib_test.go:26-134 -- every expression is true (or errors).
     The reference runs it with the real wall clock, so `now` only has to be later than 2021-05-01."""
-    if "spiffe" in tc["expr"]:
-        pytest.skip("SPIFFE types are SURVEY §8(f) 'next' (conditions/types/spiffe.go)")
     now = parse_timestamp("2026-01-01T00:00:00Z")
     act = build_activation(build_request({}))
     try:
