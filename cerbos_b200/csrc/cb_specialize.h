@@ -173,6 +173,10 @@ struct Atoms {
     std::map<std::vector<uint32_t>, uint32_t> ids;    // normalised instruction list -> atom number
     std::vector<std::string> src;                     // one function per atom
     std::vector<bool> slot_used;
+    // per atom: the one slot it reads (CB_NONE32: none or several) and whether it reads anything else of the request
+    // (P.id) -- an atom over one slot is a function of that slot's value alone (and of the batch's `now`)
+    std::vector<uint32_t> only_slot;
+    std::vector<bool> reads_pid;
 };
 
 inline bool is_jump(uint32_t op) {
@@ -182,7 +186,9 @@ inline bool is_jump(uint32_t op) {
 // One leaf P[lo, hi) (hi = its TO_COND) -> the body of `template <typename Cols> CB_HD bool uc_atom_K(Ctx &c, const Cols &cols)`.
 // "" = an unsupported instruction or a malformed program.
 inline std::string atom_source(const std::vector<Ins> &P, uint32_t lo, uint32_t hi, const uint32_t *consts /* cb_const words */, uint32_t n_consts, uint32_t n_slots,
-                               std::vector<bool> &slot_used) {
+                               std::vector<bool> &slot_used, uint32_t *only_slot = nullptr, bool *reads_pid = nullptr) {
+    std::vector<uint32_t> my_slots;
+    bool my_pid = false;
     const uint32_t n = hi - lo;
     const int kUnset = -1000;
     std::vector<int> depth(n + 1, kUnset), ldep(n + 1, kUnset);
@@ -254,6 +260,9 @@ inline std::string atom_source(const std::vector<Ins> &P, uint32_t lo, uint32_t 
     auto slot = [&](uint32_t v) -> std::string {
         if (v >= n_slots) { bad = true; return "0ull"; }
         slot_used[v] = true;
+        bool seen = false;
+        for (uint32_t q : my_slots) seen |= q == v;
+        if (!seen) my_slots.push_back(v);
         return "cols.slot(" + std::to_string(v) + "u)";
     };
     int maxd = 1;
@@ -271,7 +280,7 @@ inline std::string atom_source(const std::vector<Ins> &P, uint32_t lo, uint32_t 
         case CB_OP_CONST: s += top + " = " + cst(I.ic) + ";"; break;
         case CB_OP_SLOT: s += top + " = decode_v64(" + slot(I.ic) + ", &st_);"; break;
         case CB_OP_HAS_SLOT: s += "decode_v64(" + slot(I.ic) + ", &st_); " + top + " = op_has_slot(st_);"; break;
-        case CB_OP_PID: s += top + " = mk(CB_T_STRING, c.pid);"; break;
+        case CB_OP_PID: my_pid = true; s += top + " = mk(CB_T_STRING, c.pid);"; break;
         case CB_OP_NOW: s += top + " = mk(CB_T_TS, (uint64_t)c.b->now);"; break;
         case CB_OP_VAR: if (I.ia >= CB_MAX_VARS) bad = true; s += top + " = c.vars[" + std::to_string(I.ia) + "];"; break;
         case CB_OP_SELECT: s += a + " = op_select(c, " + a + ", " + hex(I.ic) + ");"; break;
@@ -314,7 +323,7 @@ inline std::string atom_source(const std::vector<Ins> &P, uint32_t lo, uint32_t 
         case CB_OP_DYN: s += ";"; break;
         case CB_OP_CMP_SLOT_CONST: s += top + " = do_cmp(c, " + std::to_string(I.ia) + ", decode_v64(" + slot(I.ib) + ", &st_), " + cst(I.ic) + ");"; break;
         case CB_OP_CMP_SLOT_SLOT: s += "{ const Val x_ = decode_v64(" + slot(I.ib) + ", &st_); " + top + " = do_cmp(c, " + std::to_string(I.ia) + ", x_, decode_v64(" + slot(I.ic) + ", &st_)); }"; break;
-        case CB_OP_CMP_SLOT_PID: s += top + " = do_cmp(c, " + std::to_string(I.ia) + ", decode_v64(" + slot(I.ib) + ", &st_), mk(CB_T_STRING, c.pid));"; break;
+        case CB_OP_CMP_SLOT_PID: my_pid = true; s += top + " = do_cmp(c, " + std::to_string(I.ia) + ", decode_v64(" + slot(I.ib) + ", &st_), mk(CB_T_STRING, c.pid));"; break;
         case CB_OP_IN_SLOT_CONST: s += top + " = do_in(c, decode_v64(" + slot(I.ib) + ", &st_), " + cst(I.ic) + ");"; break;
         case CB_OP_IN_CONST_SLOT: s += top + " = do_in(c, " + cst(I.ic) + ", decode_v64(" + slot(I.ib) + ", &st_));"; break;
         case CB_OP_IN_IP_RANGE: s += a + " = " + a + ".tag == CB_T_ERR ? mk_err() : do_in_ip_range(c, " + a + ", c.t->theap() + " + hex(I.ic) + ");"; break;
@@ -340,6 +349,8 @@ inline std::string atom_source(const std::vector<Ins> &P, uint32_t lo, uint32_t 
     }
     if (target[n]) s += lab(n) + ":;\n";
     s += "    return cond_true(s0);\n";
+    if (only_slot) *only_slot = my_slots.size() == 1 ? my_slots[0] : CB_NONE32;
+    if (reads_pid) *reads_pid = my_pid;
     return bad ? std::string() : s;
 }
 
@@ -400,9 +411,13 @@ inline std::string translate_program(const uint32_t *code_words, uint32_t code_o
         auto it = at.ids.find(key);
         if (it == at.ids.end()) {
             if (at.slot_used.size() < n_slots) at.slot_used.resize(n_slots, false);
-            const std::string body = atom_source(P, i, e, consts, n_consts, n_slots, at.slot_used);
+            uint32_t one = CB_NONE32;
+            bool pid = false;
+            const std::string body = atom_source(P, i, e, consts, n_consts, n_slots, at.slot_used, &one, &pid);
             if (body.empty()) return "";
             const uint32_t id = (uint32_t)at.src.size();
+            at.only_slot.push_back(one);
+            at.reads_pid.push_back(pid);
             at.src.push_back("template <typename Cols>\nCB_HD bool uc_atom_" + std::to_string(id) + "(Ctx &c, const Cols &cols) {\n" + body + "}\n");
             it = at.ids.emplace(key, id).first;
         }
@@ -490,6 +505,14 @@ inline UcSource generate_uc(const uint8_t *uc_image, const uint32_t *off, uint32
             break;
         }
     }
+    // Leaf programs over ONE attribute slot (and nothing else of the request) are functions of that slot's value: for a
+    // string value the pre-pass evaluates them once per distinct dictionary string -- timestamp(<claim>) > now(),
+    // "x" in <claim>.split(" ") ... -- and the request kernel reads two bits: the value, and "evaluate in place" (the
+    // pre-pass met a value the device forms cannot hold: the in-place evaluation then raises it for this request).
+    std::vector<int> atom_pred(atoms.src.size(), -1);
+    uint32_t n_pred_bits = (uint32_t)pred_terms.size();
+    for (uint32_t a = 0; a < atoms.src.size(); a++)
+        if (atoms.only_slot[a] != CB_NONE32 && !atoms.reads_pid[a] && n_pred_bits + 2 <= 32) { atom_pred[a] = (int)n_pred_bits; n_pred_bits += 2; }
     auto sl = [](uint32_t v) { return "cols.slot(" + std::to_string(v) + "u)"; };
     auto term_code = [&](uint32_t q) -> std::string {
         const uint32_t *w = terms[q].data();
@@ -526,7 +549,7 @@ inline UcSource generate_uc(const uint8_t *uc_image, const uint32_t *off, uint32
     for (uint32_t v = 0; v < ns; v++)
         if (slot_used[v] || slot_list[v]) s += "        case " + std::to_string(v) + "u: return s" + std::to_string(v) + ";\n";
     s += "        default: return v < " + std::to_string(ns) + "u ? g.slot(v) : (uint64_t)(CB_V64_BOX_BASE | CB_V64_ERROR) << 48;\n        }\n    }\n};\n";
-    s += "struct SpecConds {\n    static constexpr uint32_t n_strpred = " + std::to_string(pred_terms.size()) + "u;\n";
+    s += "struct SpecConds {\n    static constexpr uint32_t n_strpred = " + std::to_string(n_pred_bits) + "u;\n";
     s += std::string("    static constexpr int kForm = ") + (n_uconds <= 31 ? "CB_UC_FORM_MASK32" : n_uconds <= 63 ? "CB_UC_FORM_MASK64" : "CB_UC_FORM_INDEX") + ";   // how the rows name their conditions\n";
     s += std::string("    static constexpr bool kPrograms = ") + (have_atoms ? "true" : "false") + ";   // leaf programs: needs the value helpers of cb_core.h\n";
     s += "    template <typename Cols>\n    CB_HD SpecRegs load(const TableView t, const BatchView &b, const Cols &c) const {\n        SpecRegs r;\n        r.g.b = c.b; r.g.n = c.n;\n";
@@ -542,14 +565,33 @@ inline UcSource generate_uc(const uint8_t *uc_image, const uint32_t *off, uint32
         const uint32_t *w = terms[pred_terms[p]].data();
         s += "        bits |= (uint32_t)(term_tri(t, b, cols, pid, U4{" + hex(w[0]) + ", 0x0u, " + hex(w[2]) + ", " + hex(w[3]) + "}, slow) == TRI_T) << " + std::to_string(p) + ";\n";
     }
+    {
+        bool any = false;
+        for (int p : atom_pred) any |= p >= 0;
+        if (any) {
+            s += "        Ctx c; c.t = &t; c.b = &b; c.req = 0; c.pid = 0; c.edr = 0;\n";
+            for (uint32_t a = 0; a < atoms.src.size(); a++)
+                if (atom_pred[a] >= 0)
+                    s += "        c.unsupported = 0; c.scr_used = 0; bits |= (uint32_t)uc_atom_" + std::to_string(a) + "(c, cols) << " + std::to_string(atom_pred[a]) +
+                         "; bits |= (uint32_t)(c.unsupported != 0) << " + std::to_string(atom_pred[a] + 1) + ";\n";
+        }
+    }
     s += "        (void)slow; (void)pid;\n        return bits;\n    }\n";
     s += "    CB_HD CondWord operator()(const TableView t, const BatchView &b, const SpecRegs &cols, uint32_t pid, uint64_t n, bool &slow) const {\n";
     for (uint32_t q = 0; q < terms.size(); q++)
         s += "        const int q" + std::to_string(q) + " = " + term_code(q) + ";\n";
     if (have_atoms) {
         s += "        Ctx c; c.t = &t; c.b = &b; c.req = n; c.pid = pid; c.unsupported = 0; c.edr = 0; c.scr_used = 0;\n";
-        for (uint32_t a = 0; a < atoms.src.size(); a++)
-            s += "        c.scr_used = 0; const bool a" + std::to_string(a) + " = uc_atom_" + std::to_string(a) + "(c, cols);\n";
+        for (uint32_t a = 0; a < atoms.src.size(); a++) {
+            const std::string A = std::to_string(a);
+            if (atom_pred[a] >= 0) {
+                const std::string P = std::to_string(atom_pred[a]), V = sl(atoms.only_slot[a]);
+                s += "        bool a" + A + ";\n        {\n            const uint64_t x = " + V + ";\n            const uint32_t w = v64_tag(x) == CB_V64_STRING && !v64_bad(x) ? ldg(b.strpred + (uint32_t)(x & 0xFFFFFFFFu)) >> " + P + " : 2u;\n";
+                s += "            if (w & 2u) { c.scr_used = 0; a" + A + " = uc_atom_" + A + "(c, cols); } else a" + A + " = (w & 1u) != 0;\n        }\n";
+            } else {
+                s += "        c.scr_used = 0; const bool a" + A + " = uc_atom_" + A + "(c, cols);\n";
+            }
+        }
         s += "        slow |= c.unsupported != 0;   // a value the device forms cannot hold: the general kernel reports it\n";
     } else s += "        (void)n;\n";
     s += "        CondWord val; val.lo = 1ull; val.hi = 0ull;\n";
@@ -573,7 +615,7 @@ inline UcSource generate_uc(const uint8_t *uc_image, const uint32_t *off, uint32
     }
     s += "        return val;\n    }\n};\n}  // namespace cb\n";
     out.src = s;
-    out.n_strpred = (uint32_t)pred_terms.size();
+    out.n_strpred = n_pred_bits;
     out.n_atoms = (uint32_t)atoms.src.size();
     return out;
 }
