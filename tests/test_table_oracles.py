@@ -177,6 +177,27 @@ def test_run_time_values_vs_cel_oracle():
         assert hostsim.check(ft.blob, b.columns, 1, 1, now.ns)[0, 0] == want, e
 
 
+def test_c5_vectorised_columns_answer_like_the_generic_encoder():
+    """workloads.C5.columns (numpy, what the bench generates 2^23 requests per GPU with) against the generic encoder over the
+    same requests as protojson dicts: same headers and roles, same heap volume, and -- the heap and the batch dictionary
+    are laid out in another order -- the same 8 decisions per request from oracle #2; chunked generation (columns_parallel,
+    heap references rebased incl. the lists nested in the grants maps) gives the same answers again."""
+    w = W.C5()
+    _, ft, enc = W.build(w)
+    n = 5000
+    f = w.fields(n, start=777)
+    b = w.columns(f, enc)
+    b2 = enc.encode(w.inputs(f, range(n)))
+    assert (np.asarray(b.columns[0])[:, 1:] == np.asarray(b2.columns[0])[:, 1:]).all() and (np.asarray(b.columns[2]) == np.asarray(b2.columns[2])).all()
+    assert len(b.columns[4]) == len(b2.columns[4])
+    want = cref.check(ft.blob, b2.columns, b2.n, b2.max_actions, n_threads=4)
+    assert (cref.check(ft.blob, b.columns, b.n, b.max_actions, n_threads=4) == want).all()
+    assert 0.3 < (want == 1).mean() < 0.5
+    b3 = W.columns_parallel(w, n, 777, enc, chunk=1024)
+    assert (cref.check(ft.blob, b3.columns, b3.n, b3.max_actions, n_threads=4) == want).all()
+    assert (hostsim.check(ft.blob, b3.columns, b3.n, b3.max_actions, mode=1)[:512] == want[:512]).all()
+
+
 SPIFFE_IDS = ["spiffe://cerbos.dev/ns/privileged/sa/curl", "spiffe://cerbos.dev", "spiffe://example.com/a", "spiffe://Cerbos.dev/x", "spiffe://cerbos.dev/",
               "spiffe://cerbos.dev//a", "spiffe://cerbos.dev/./a", "spiffe://cerbos.dev/a/..", "spiffe://cerbos.dev/a b", "http://cerbos.dev/x", "", "spiffe:///x",
               "spiffe://cerbos.dev/A_b-c.d/e", "spiffe://a_b-c.1/x", "cerbos.dev"]

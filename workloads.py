@@ -272,15 +272,16 @@ class C2:
 
 
 # =========================================================================================== C3
-def _ragged_lists(lengths: np.ndarray, elem_fn):
+def _ragged_lists(lengths: np.ndarray, elem_fn, head=None):
     """Builds heap words for one variable-length list per request: [len, e0, e1, ...].
-    elem_fn(req_index_array, pos_array) -> uint64 element words. Returns (words, offsets)."""
+    elem_fn(req_index_array, pos_array) -> uint64 element words. Returns (words, offsets).
+    head: the first word of every record if it is not the number of elements (a map's [n, keys..., values...] has 2n)."""
     n = len(lengths)
     sizes = lengths + 1
     offs = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(sizes, out=offs[1:])
     words = np.zeros(offs[-1], dtype=np.uint64)
-    words[offs[:-1]] = lengths.astype(np.uint64)
+    words[offs[:-1]] = (lengths if head is None else head).astype(np.uint64)
     req = np.repeat(np.arange(n), lengths)
     pos = np.arange(lengths.sum()) - np.repeat(offs[:-1] - np.arange(n), lengths)
     words[np.repeat(offs[:-1] + 1, lengths) + pos] = elem_fn(req, pos)
@@ -566,7 +567,7 @@ class C5:
             nr = 1 + _uniform(seed, n, 3, 4)
             return {
                 "n": n, "kind": np.minimum(np.searchsorted(cdf, u), self.n_kinds - 1), "pid": _uniform(seed, n, 1, 4096),
-                "roles": [[self.role_names[(int(r0[i]) + q) % 4] for q in range(int(nr[i]))] for i in range(n)],
+                "r0": r0, "nr": nr,     # roles: role_names[(r0 + q) % 4] for q < nr
                 "scope": np.where(_prob(seed, n, 5, 0.05), 5, _uniform(seed, n, 4, 5)),
                 "tier": _uniform(seed, n, 6, 3), "jtier": _uniform(seed, n, 7, 4), "level": _uniform(seed, n, 8, 10),
                 "min_level": _uniform(seed, n, 9, 10), "nreg": 1 + _uniform(seed, n, 10, 3), "reg0": _uniform(seed, n, 11, 4),
@@ -596,7 +597,7 @@ class C5:
                    "tier": (self.tiers + ["banned"])[f["jtier"][i]],
                    "exp_ts": "2020-01-01T00:00:00Z" if f["expired"][i] else "2031-06-01T12:00:00Z"}
             req = {"requestId": str(i), "actions": list(self.actions),
-                   "principal": {"id": pid, "roles": list(f["roles"][i]),
+                   "principal": {"id": pid, "roles": [self.role_names[(int(f["r0"][i]) + q) % 4] for q in range(int(f["nr"][i]))],
                                  "attr": {"tier": tier, "level": int(f["level"][i]),
                                           "regions": [self.regions[(f["reg0"][i] + q) % 4] for q in range(f["nreg"][i])],
                                           "grants": {gk: ["read", "write"] if f["grant"][i] % 2 == 0 else ["read"], "zzz": ["write"]}}},
@@ -609,7 +610,105 @@ class C5:
         return out
 
     def columns(self, f, enc: Encoder) -> Batch:
-        return enc.encode(self.inputs(f, range(f["n"])))
+        """Vectorised column builder (numpy): what the generic encoder makes of inputs(f, ...), without the per-request Python.
+        Every request gets its own heap records (its lists, its two maps and the nested lists), as an encoder would write them."""
+        n = f["n"]
+        nts = enc.n_table_strings
+        extra: list = []
+        pos_of: dict = {}
+
+        def ids_for(strings):
+            out = []
+            for s_ in strings:
+                i_ = enc.table_strings.get(s_)
+                if i_ is None:
+                    bkey = s_.encode("utf-8")
+                    j = pos_of.get(bkey)
+                    if j is None:
+                        j = len(extra)
+                        pos_of[bkey] = j
+                        extra.append(bkey)
+                    i_ = nts + j
+                out.append(int(i_))
+            return np.array(out, dtype=np.uint64)
+
+        heat = ["hot", "warm", "cold", "frozen"]
+        pid_ids = ids_for([f"p{i}" for i in range(4096)])
+        someone = ids_for(["p-someone"])[0]
+        kind_ids = ids_for([f"kind_{k}" for k in range(self.n_kinds)])
+        other_misc = ids_for(["other", "misc"])
+        zzz, read, write, svc = (ids_for([x])[0] for x in ("zzz", "read", "write", "svc"))
+        tier_ids, heat_ids, region_ids = ids_for(self.tiers), ids_for(heat), ids_for(self.regions)
+        jtier_ids = ids_for(self.tiers + ["banned"])
+        aud_ids = ids_for([f"aud{q}" for q in range(3)])
+        iss_ids = ids_for(["https://other.example", "https://issuer.example"])
+        scope_ids = ids_for(["read list", "deploy read list"])
+        exp_ids = ids_for(["2031-06-01T12:00:00Z", "2020-01-01T00:00:00Z"])
+
+        kvals, class_list = _kind_classes(enc, [f"kind_{k}" for k in range(self.n_kinds)])
+        hdr0 = np.zeros((n, 4), dtype=np.uint32)
+        hdr0[:, 0] = pid_ids[f["pid"]]
+        hdr0[:, 1] = kvals[f["kind"]]
+        sc_ids = np.array([enc.resolve_scope(s_) for s_ in self.req_scopes], dtype=np.uint32)
+        hdr0[:, 2] = sc_ids[f["scope"]]
+        hdr0[:, 3] = enc.resolve_scope("")
+        hdr1 = np.zeros(n, dtype=np.dtype([("rv", "<u2"), ("pv", "<u2"), ("aset", "<u4")]))
+        hdr1["rv"] = enc.version_ids.get("default", L.NONE16)
+        hdr1["pv"] = hdr1["rv"]
+        rmap = np.array([enc.role_ids.get(r, L.ROLE_UNKNOWN) for r in self.role_names], dtype=np.uint32)
+        roles = np.stack([np.where(q < f["nr"], rmap[(f["r0"] + q) % 4], np.uint32(L.ROLE_PAD)) for q in range(4)]).astype(np.uint32)
+
+        box_s = lambda ids: _box(L.V64_STRING, ids)   # noqa: E731
+        batch_bit = np.uint64(L.V64_HEAP_BATCH_BIT)
+        svc_i = f["svc"].astype(np.int64)
+        # principal.attr.regions; jwt.aud = (["svc"]) + aud0 ..
+        reg_w, reg_off = _ragged_lists(f["nreg"], lambda req, pos: box_s(region_ids[(f["reg0"][req] + pos) % 4]))
+        aud_w, aud_off = _ragged_lists(svc_i + f["aud"], lambda req, pos: box_s(np.where((svc_i[req] == 1) & (pos == 0), svc, aud_ids[np.maximum(pos - svc_i[req], 0)])))
+        # resource.attr.meta.tags = {tiers[q]: heat[(tagsel + q) % 4] for q < 1 + tagsel % 3}: [m, keys.., values..]
+        m = 1 + f["tagsel"] % 3
+        tag_w, tag_off = _ragged_lists(2 * m, lambda req, pos: box_s(np.where(pos < m[req], tier_ids[np.minimum(pos, 2)],
+                                                                                heat_ids[(f["tagsel"][req] + pos - m[req]) % 4])), head=m)
+        # principal.attr.grants = {gk: ["read", "write"] | ["read"], "zzz": ["write"]}: two nested lists, then [2, gk, zzz, ref, ref]
+        rw = (f["grant"] % 2 == 0)
+        l1_w, l1_off = _ragged_lists(np.where(rw, 2, 1), lambda req, pos: box_s(np.where(pos == 0, read, write)))
+        l2_w = np.empty((n, 2), dtype=np.uint64)
+        l2_w[:, 0] = 1
+        l2_w[:, 1] = box_s(np.full(n, write, dtype=np.uint64))
+        gk = np.where(f["grant"] == 0, kind_ids[f["kind"]], np.where(f["grant"] == 1, kind_ids[(f["kind"] + 1) % self.n_kinds], other_misc[np.maximum(f["grant"] - 2, 0)]))
+        base_reg, base_aud = 0, len(reg_w)
+        base_tag = base_aud + len(aud_w)
+        base_l1 = base_tag + len(tag_w)
+        base_l2 = base_l1 + len(l1_w)
+        base_map = base_l2 + 2 * n
+        gm = np.empty((n, 5), dtype=np.uint64)
+        gm[:, 0] = 2
+        gm[:, 1] = box_s(gk)
+        gm[:, 2] = box_s(np.full(n, zzz, dtype=np.uint64))
+        gm[:, 3] = _box(L.V64_LIST, (l1_off + base_l1).astype(np.uint64) | batch_bit)
+        gm[:, 4] = _box(L.V64_LIST, (np.arange(n, dtype=np.int64) * 2 + base_l2).astype(np.uint64) | batch_bit)
+        heap = np.concatenate([reg_w, aud_w, tag_w, l1_w, l2_w.reshape(-1), gm.reshape(-1)])
+        absent = np.uint64((L.V64_BOX_BASE | L.V64_ABSENT) << 48)
+        vals = {
+            ("aux_data", "jwt", "scope"): box_s(scope_ids[f["deploy"].astype(np.int64)]),
+            ("aux_data", "jwt", "exp_ts"): box_s(exp_ids[f["expired"].astype(np.int64)]),
+            ("aux_data", "jwt", "iss"): box_s(iss_ids[f["iss"].astype(np.int64)]),
+            ("aux_data", "jwt", "aud"): _box(L.V64_LIST, (aud_off + base_aud).astype(np.uint64) | batch_bit),
+            ("aux_data", "jwt", "tier"): box_s(jtier_ids[f["jtier"]]),
+            ("principal", "attr", "level"): f["level"].astype(np.float64).view(np.uint64),
+            ("principal", "attr", "tier"): box_s(tier_ids[f["tier"]]),
+            ("principal", "attr", "regions"): _box(L.V64_LIST, (reg_off + base_reg).astype(np.uint64) | batch_bit),
+            ("principal", "attr", "grants"): _box(L.V64_MAP, (np.arange(n, dtype=np.int64) * 5 + base_map).astype(np.uint64) | batch_bit),
+            ("resource", "kind"): box_s(kind_ids[f["kind"]]),
+            ("resource", "attr", "public"): _box(L.V64_BOOL, f["public"].astype(np.uint64)),
+            ("resource", "attr", "min_level"): f["min_level"].astype(np.float64).view(np.uint64),
+            ("resource", "attr", "meta", "owner"): np.where(f["tagsel"] == 3, absent, box_s(np.where(f["own"], pid_ids[f["pid"]], someone))),
+            ("resource", "attr", "meta", "tags"): _box(L.V64_MAP, (tag_off + base_tag).astype(np.uint64) | batch_bit),
+            ("resource", "attr", "meta", "region"): box_s(region_ids[f["mreg"]]),
+        }
+        slots = np.zeros((max(len(enc.slots), 1), n), dtype=np.uint64)
+        for s_, path in enumerate(enc.slots):
+            slots[s_] = vals[path]
+        return _finish_batch(enc, n, hdr0, hdr1, roles, slots, heap, extra, class_list, [tuple(self.actions)], 8)
 
     def bytes_per_request(self):
         return 489   # SURVEY.md 8(d): 24 + 4*4 + 8*24 + 256 + 1
