@@ -36,9 +36,13 @@ class Engine:
         self.reload(policies)
 
     @classmethod
-    def from_rule_table_bundle(cls, bundle: bytes, **conf):
-        """An engine over a serialized runtimev1.RuleTable (rule-table bundle, storage/hub/ruletable_bundle.go:36-87)."""
+    def from_rule_table_bundle(cls, bundle: bytes, key=None, **conf):
+        """An engine over a serialized runtimev1.RuleTable (rule-table bundle, storage/hub/ruletable_bundle.go:36-87).
+        key: the bundle's encryption key (32 bytes or 64 hex digits) for an encrypted bundle (`*.crrts`), None for a plain one."""
         from .table.ruletable_pb import decode_rule_table
+        if key is not None:
+            from .table.bundle_crypto import decrypt_stream
+            bundle = decrypt_stream(key, bundle)
         self = cls.__new__(cls)
         self.conf = dict(globals_=conf.get("globals_") or {}, default_policy_version=conf.get("default_policy_version", "default"),
                          default_scope=conf.get("default_scope", ""), lenient_scope_search=conf.get("lenient_scope_search", False))

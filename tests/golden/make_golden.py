@@ -229,6 +229,10 @@ def ruletable_bundle():
     src = os.path.join(REF, "test/testdata/bundle/v2_ruletable/bundle_unencrypted.crrt")
     shutil.copyfile(src, os.path.join(OUT, "ruletable_bundle_unencrypted.crrt"))
     print("ruletable bundle:", os.path.getsize(src), "bytes")
+    # the same rule table as the PDP receives it from Cerbos Hub: encrypted (bundle.crrts) + its key (encryption_key.txt);
+    # pins cerbos_b200/table/bundle_crypto.py (crypto.DecryptChaCha20Poly1305Stream of github.com/cerbos/cloud-api)
+    for name, out in (("bundle.crrts", "ruletable_bundle_encrypted.crrts"), ("encryption_key.txt", "ruletable_bundle_encryption_key.txt")):
+        shutil.copyfile(os.path.join(REF, "test/testdata/bundle/v2_ruletable", name), os.path.join(OUT, out))
 
 
 if __name__ == "__main__":
