@@ -617,3 +617,17 @@ def test_multi_device_context_shards_a_batch():
             assert (t.check(b.columns, b.n, b.max_actions) == want).all(), name
         t.release()
         c.close()
+
+
+def test_fused_gather_against_nccl_under_torchrun():
+    """tests/mgpu_gather_check.py (two ranks, one per GPU): the image gathered through cgpu_check_device_gather -- peer stores
+    fused into the kernels -- must equal an NCCL all-gather of the plain path on every rank.  Needs two GPUs."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", os.path.join(root, "tests", "mgpu_gather_check.py")], capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0 and "MGPU_GATHER_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])

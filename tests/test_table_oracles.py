@@ -255,7 +255,7 @@ def test_workloads_three_way(cls, n):
     b2 = enc.encode(inputs)
     assert (cref.check(ft.blob, b2.columns, b2.n, b2.max_actions) == c_out[idx]).all(), "vectorised columns != encoder"
     orc = CheckOracle(rt)
-    for j, inp in enumerate(inputs[:64]):
+    for j, inp in enumerate(inputs[:256]):
         g = orc.check(inp)
         for k, a in enumerate(w.actions):
             assert g["actions"][a]["effect"] == c_out[idx[j], k]
@@ -352,7 +352,7 @@ def test_workload_c5_adversarial():
     for mode in (0, 1, 2):
         assert (hostsim.check(ft.blob, b.columns, b.n, b.max_actions, NOW.ns, mode=mode) == c_out).all(), mode
     orc = CheckOracle(rt)
-    for j in range(0, f["n"], 8):
+    for j in range(0, f["n"], 3):
         g = orc.check(inputs[j], NOW)
         for k, a in enumerate(w.actions):
             assert g["actions"][a]["effect"] == c_out[j, k], (j, a)
