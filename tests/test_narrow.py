@@ -111,6 +111,23 @@ def test_goldens_narrow_exactly():
         roundtrip(enc.encode(inputs), len(enc.slots), v2=False)
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_random_batches_narrow_exactly(seed):
+    """Random policy sets x random requests (tests/fuzzgen.py: missing attributes, nulls, mixed-type columns, nested lists and
+    maps, unknown roles, odd scopes): both narrow forms must widen back to the canonical columns bit for bit -- or decline
+    the batch (None) -- whatever classes the columns fall into."""
+    import random
+    from cerbos_b200.policy.compile import build_rule_table
+    from fuzzgen import rand_policies, rand_request
+    r = random.Random(4200 + seed)
+    ft = flatten(build_rule_table(rand_policies(r)))
+    enc = Encoder(ft.manifest)
+    b = enc.encode([rand_request(r) for _ in range(400)])
+    for v2 in (True, False):
+        if NW.narrow_batch(b, len(enc.slots), v2=v2) is not None:
+            roundtrip(b, len(enc.slots), v2=v2)
+
+
 def test_slot_classes():
     f = lambda xs: np.array(xs, dtype=np.float64).view(np.uint64)   # noqa: E731
     assert NW.narrow_slot(f([1.0, 7.0, 0.0, 239.0]))[0] == NW.SLOT_U8_NUM and NW.narrow_slot(f([1.0, 240.0]))[0] == NW.SLOT_F32
