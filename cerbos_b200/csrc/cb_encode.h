@@ -273,6 +273,55 @@ inline bool map_entry(Span ent, Span *key, Span *val) {
     return !it.bad;
 }
 
+// ---------------------------------------------------------------------------------------------- byte-keyed dictionary
+// string -> u32 keyed by raw bytes (no std::string temporaries on the lookup path): open addressing, keys copied into one arena
+inline uint64_t hash_bytes(const uint8_t *p, size_t n) {
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (n * 0xD6E8FEB86659FD93ull);
+    while (n >= 8) { uint64_t w; memcpy(&w, p, 8); h = (h ^ w) * 0x9FB21C651E98DF25ull; h ^= h >> 29; p += 8; n -= 8; }
+    uint64_t w = 0;
+    if (n) { memcpy(&w, p, n); h = (h ^ w) * 0x9FB21C651E98DF25ull; }
+    h ^= h >> 32;
+    return h * 0xD6E8FEB86659FD93ull;
+}
+struct BytesMap {
+    struct Ent { uint64_t h; uint32_t off, len, val; };
+    std::vector<uint32_t> tab;    // entry index + 1, 0 = empty
+    std::vector<Ent> ents;
+    std::vector<uint8_t> arena;
+    BytesMap() { tab.assign(64, 0); }
+    size_t size() const { return ents.size(); }
+    const uint8_t *key(size_t i) const { return arena.data() + ents[i].off; }
+    const uint32_t *find(const uint8_t *p, size_t n, uint64_t h) const {
+        const size_t mask = tab.size() - 1;
+        for (size_t i = (size_t)(h >> 7) & mask;; i = (i + 1) & mask) {
+            const uint32_t e = tab[i];
+            if (!e) return nullptr;
+            const Ent &x = ents[e - 1];
+            if (x.h == h && x.len == n && !memcmp(arena.data() + x.off, p, n)) return &x.val;
+        }
+    }
+    const uint32_t *find(const uint8_t *p, size_t n) const { return find(p, n, hash_bytes(p, n)); }
+    void insert(const uint8_t *p, size_t n, uint64_t h, uint32_t val) {   // the key must not be present
+        if ((ents.size() + 1) * 2 > tab.size()) {
+            std::vector<uint32_t> nt(tab.size() * 2, 0);
+            const size_t mask = nt.size() - 1;
+            for (size_t e = 0; e < ents.size(); e++) {
+                size_t i = (size_t)(ents[e].h >> 7) & mask;
+                while (nt[i]) i = (i + 1) & mask;
+                nt[i] = (uint32_t)e + 1;
+            }
+            tab.swap(nt);
+        }
+        ents.push_back(Ent{h, (uint32_t)arena.size(), (uint32_t)n, val});
+        arena.insert(arena.end(), p, p + n);
+        const size_t mask = tab.size() - 1;
+        size_t i = (size_t)(h >> 7) & mask;
+        while (tab[i]) i = (i + 1) & mask;
+        tab[i] = (uint32_t)ents.size();
+    }
+};
+inline bool span_eq(Span a, Span b) { return a.n == b.n && (a.n == 0 || !memcmp(a.p, b.p, a.n)); }
+
 // ---------------------------------------------------------------------------------------------- encoder
 constexpr uint64_t box(uint32_t tag, uint64_t payload = 0) { return ((uint64_t)(CB_V64_BOX_BASE | tag) << 48) | (payload & 0xFFFFFFFFFFFFull); }
 constexpr uint64_t V_ABSENT = box(CB_V64_ABSENT), V_ERROR = box(CB_V64_ERROR), V_NULL = box(CB_V64_NULL);
@@ -312,7 +361,14 @@ struct Columns {   // the twelve cgpu_batch columns, in order; buffers owned her
 
 struct PrincipalView { Span id, version, scope; std::vector<Span> roles; std::vector<std::pair<Span, Span>> attr; };
 struct ResourceView { Span kind, version, id, scope; std::vector<std::pair<Span, Span>> attr; };
-struct InputView { PrincipalView p; ResourceView r; std::vector<Span> actions; std::vector<std::pair<Span, Span>> jwt; bool has_aux = false; };
+struct InputView {
+    PrincipalView p; ResourceView r; std::vector<Span> actions; std::vector<std::pair<Span, Span>> jwt; bool has_aux = false;
+    void clear() {   // keeps the vectors' capacity: one view per thread is reused for every message of its shard
+        p.id = p.version = p.scope = Span{}; p.roles.clear(); p.attr.clear();
+        r.kind = r.version = r.id = r.scope = Span{}; r.attr.clear();
+        actions.clear(); jwt.clear(); has_aux = false;
+    }
+};
 
 class Encoder {
   public:
@@ -321,7 +377,12 @@ class Encoder {
     std::vector<std::string> versions, scopes, respats, roles, apats, strings;
     std::vector<std::vector<std::string>> slots;
     std::vector<uint32_t> row_pat_start, row_apats;
-    std::unordered_map<std::string, uint32_t> version_ids, scope_ids, role_ids, table_strings;
+    std::unordered_map<std::string, uint32_t> version_ids, scope_ids, role_ids;
+    BytesMap table_strings, role_map;
+    // where a slot's value comes from, decided once: [0] of the path and, for attribute paths, where the walk starts
+    enum SlotSrc { SRC_ERROR, SRC_AUX, SRC_P_ATTR, SRC_R_ATTR, SRC_P_ROLES, SRC_R_ROLES, SRC_P_SCOPE, SRC_R_SCOPE, SRC_P_VERSION, SRC_R_VERSION, SRC_P_ID, SRC_R_ID,
+                   SRC_P_KIND, SRC_R_KIND, SRC_EMPTY };
+    std::vector<SlotSrc> slot_src;
 
     // blob: the table blob (its MANIFEST section carries the dictionaries)
     bool init(const void *blob, size_t len, const Conf &c) {
@@ -348,16 +409,40 @@ class Encoder {
         for (uint32_t i = 0; i < versions.size(); i++) version_ids[versions[i]] = i;
         for (uint32_t i = 0; i < scopes.size(); i++) scope_ids[scopes[i]] = i;
         for (uint32_t i = 0; i < roles.size(); i++) role_ids[roles[i]] = i;
-        for (uint32_t i = 0; i < strings.size(); i++) table_strings[strings[i]] = i;
+        for (uint32_t i = 0; i < strings.size(); i++) {
+            const uint8_t *sp = reinterpret_cast<const uint8_t *>(strings[i].data());
+            const uint64_t hh = hash_bytes(sp, strings[i].size());
+            if (!table_strings.find(sp, strings[i].size(), hh)) table_strings.insert(sp, strings[i].size(), hh, i);
+        }
+        for (uint32_t i = 0; i < roles.size(); i++) {
+            const uint8_t *sp = reinterpret_cast<const uint8_t *>(roles[i].data());
+            const uint64_t hh = hash_bytes(sp, roles[i].size());
+            if (const uint32_t *old = role_map.find(sp, roles[i].size(), hh)) *const_cast<uint32_t *>(old) = i; else role_map.insert(sp, roles[i].size(), hh, i);
+        }
+        for (const auto &path : slots) {
+            SlotSrc src = SRC_ERROR;
+            if (!path.empty()) {
+                if (path[0] == "aux_data") src = SRC_AUX;
+                else {
+                    const bool principal = path[0] == "principal";
+                    const std::string &fld = path.size() > 1 ? path[1] : path[0];
+                    src = fld == "attr" ? (principal ? SRC_P_ATTR : SRC_R_ATTR) : fld == "roles" ? (principal ? SRC_P_ROLES : SRC_R_ROLES)
+                          : fld == "scope" ? (principal ? SRC_P_SCOPE : SRC_R_SCOPE) : fld == "policy_version" ? (principal ? SRC_P_VERSION : SRC_R_VERSION)
+                          : fld == "id" ? (principal ? SRC_P_ID : SRC_R_ID) : fld == "kind" ? (principal ? SRC_P_KIND : SRC_R_KIND) : SRC_EMPTY;
+                }
+            }
+            slot_src.push_back(src);
+        }
         return true;
     }
 
     // inputs: n serialized enginev1.CheckInput messages.  n_threads > 1: contiguous shards are encoded concurrently with
     // shard-local dictionaries / heaps, then merged in shard order -- the result is byte for byte what one thread produces
     // (first-appearance order of strings, classes, action sets and heap records is the sequential order).
-    bool encode(const void *const *inputs, const size_t *lens, uint64_t n, Columns *out, unsigned n_threads = 1) const {
-        Encoder *self = const_cast<Encoder *>(this);
-        std::vector<InputView> views(n);
+    // Read-only on the encoder (safe from any number of threads at once); *err receives the reason when it returns false.
+    bool encode(const void *const *inputs, const size_t *lens, uint64_t n, Columns *out, unsigned n_threads = 1, std::string *err = nullptr) const {
+        std::string err_local;
+        std::string *self_error = err ? err : &err_local;
         if (n_threads < 1) n_threads = 1;
         if ((uint64_t)n_threads > (n + 255) / 256) n_threads = (unsigned)((n + 255) / 256);
         const uint64_t per = (n + n_threads - 1) / n_threads;
@@ -367,19 +452,22 @@ class Encoder {
         run(n_threads, [&](unsigned t) {
             uint64_t lo, hi;
             span_of(t, &lo, &hi);
+            // first pass: only what sizes the columns (roles per principal, actions per input); the messages are parsed for
+            // real in the second pass, into one reusable view per thread
             for (uint64_t i = lo; i < hi; i++) {
-                if (!parse_input(Span{static_cast<const uint8_t *>(inputs[i]), lens[i]}, &views[i])) { bad[t] = 1; return; }
-                if (views[i].p.roles.size() > mr[t]) mr[t] = (uint32_t)views[i].p.roles.size();
-                if (views[i].actions.size() > ma[t]) ma[t] = (uint32_t)views[i].actions.size();
+                uint32_t nr = 0, na = 0;
+                if (!scan_counts(Span{static_cast<const uint8_t *>(inputs[i]), lens[i]}, &nr, &na)) { bad[t] = 1; return; }
+                if (nr > mr[t]) mr[t] = nr;
+                if (na > ma[t]) ma[t] = na;
             }
         });
         uint32_t max_roles = 1, max_actions = 1;
         for (unsigned t = 0; t < n_threads; t++) {
-            if (bad[t]) { self->error = "malformed CheckInput message"; return false; }
+            if (bad[t]) { *self_error = "malformed CheckInput message"; return false; }
             if (mr[t] > max_roles) max_roles = mr[t];
             if (ma[t] > max_actions) max_actions = ma[t];
         }
-        if (max_roles > CB_MAX_ROLE_COLS) { self->error = "more than 16 roles on one principal is not supported"; return false; }
+        if (max_roles > CB_MAX_ROLE_COLS) { *self_error = "more than 16 roles on one principal is not supported"; return false; }
         Columns &c = *out;
         c.n = n; c.role_cols = max_roles; c.max_actions = max_actions;
         c.kc = 64 / max_roles; if (c.kc > max_actions) c.kc = max_actions; if (c.kc < 1) c.kc = 1;
@@ -399,29 +487,40 @@ class Encoder {
             uint64_t lo, hi;
             span_of(t, &lo, &hi);
             State &st = shards[t];
+            // Header fields repeat from one request to the next (a CheckResources call shares its principal and actions, a
+            // batch its kinds and scopes): each is resolved again only when its bytes differ from the previous request's.
+            Span m_kind{}, m_rscope{}, m_pscope{}, m_rver{}, m_pver{};
+            bool have = false;
+            uint32_t cid = CB_KIND_NONE, rs_id = CB_SCOPE_NONE, ps_id = CB_SCOPE_NONE, aid = 0;
+            uint16_t rv = (uint16_t)CB_NONE16, pv = (uint16_t)CB_NONE16;
+            std::vector<Span> m_actions;
+            bool have_actions = false;
+            InputView v;
             for (uint64_t i = lo; i < hi; i++) {
-                const InputView &v = views[i];
-                const std::string p_scope = scope_value(v.p.scope.n ? str_of(v.p.scope) : conf.default_scope);
-                const std::string r_scope = scope_value(v.r.scope.n ? str_of(v.r.scope) : conf.default_scope);
-                const std::string p_ver = v.p.version.n ? str_of(v.p.version) : conf.default_version;
-                const std::string r_ver = v.r.version.n ? str_of(v.r.version) : conf.default_version;
-                const uint32_t cid = st.kind_class(str_of(v.r.kind), &errs[t]);
-                if (!errs[t].empty()) return;
-                const uint32_t aid = st.action_set(v.actions);
+                v.clear();
+                if (!parse_input(Span{static_cast<const uint8_t *>(inputs[i]), lens[i]}, &v)) { errs[t] = "malformed CheckInput message"; return; }
+                if (!have || !span_eq(v.r.kind, m_kind)) { cid = st.kind_class(str_of(v.r.kind), &errs[t]); m_kind = v.r.kind; if (!errs[t].empty()) return; }
+                if (!have || !span_eq(v.r.scope, m_rscope)) { rs_id = resolve_scope(scope_value(v.r.scope.n ? str_of(v.r.scope) : conf.default_scope)); m_rscope = v.r.scope; }
+                if (!have || !span_eq(v.p.scope, m_pscope)) { ps_id = resolve_scope(scope_value(v.p.scope.n ? str_of(v.p.scope) : conf.default_scope)); m_pscope = v.p.scope; }
+                if (!have || !span_eq(v.r.version, m_rver)) { rv = version_id(v.r.version.n ? str_of(v.r.version) : conf.default_version); m_rver = v.r.version; }
+                if (!have || !span_eq(v.p.version, m_pver)) { pv = version_id(v.p.version.n ? str_of(v.p.version) : conf.default_version); m_pver = v.p.version; }
+                bool same_actions = have_actions && m_actions.size() == v.actions.size();
+                for (size_t k = 0; same_actions && k < v.actions.size(); k++) same_actions = span_eq(v.actions[k], m_actions[k]);
+                if (!same_actions) { aid = st.action_set(v.actions); m_actions = v.actions; have_actions = true; }
+                have = true;
                 c.hdr0[i * 4 + 0] = st.sid(v.p.id);
                 c.hdr0[i * 4 + 1] = cid;
-                c.hdr0[i * 4 + 2] = resolve_scope(r_scope);
-                c.hdr0[i * 4 + 3] = resolve_scope(p_scope);
-                const uint16_t rv = version_id(r_ver), pv = version_id(p_ver);
+                c.hdr0[i * 4 + 2] = rs_id;
+                c.hdr0[i * 4 + 3] = ps_id;
                 memcpy(&c.hdr1[i * 8], &rv, 2); memcpy(&c.hdr1[i * 8 + 2], &pv, 2); memcpy(&c.hdr1[i * 8 + 4], &aid, 4);
                 for (size_t j = 0; j < v.p.roles.size(); j++) {
-                    auto it = role_ids.find(str_of(v.p.roles[j]));
-                    c.roles[j * n + i] = it == role_ids.end() ? CB_ROLE_UNKNOWN : it->second;
+                    const uint32_t *rid = role_map.find(v.p.roles[j].p, v.p.roles[j].n);
+                    c.roles[j * n + i] = rid ? *rid : CB_ROLE_UNKNOWN;
                 }
-                for (size_t s = 0; s < n_slots; s++) c.slots[s * n + i] = st.slot_value(v, slots[s]);
+                for (size_t s = 0; s < n_slots; s++) c.slots[s * n + i] = st.slot_value(v, slots[s], slot_src[s]);
             }
         });
-        for (unsigned t = 0; t < n_threads; t++) if (!errs[t].empty()) { self->error = errs[t]; return false; }
+        for (unsigned t = 0; t < n_threads; t++) if (!errs[t].empty()) { *self_error = errs[t]; return false; }
         if (n_threads > 1) {
             // merge the shard-local tables into shard 0's, in order; remember how every local id maps
             State &g = shards[0];
@@ -430,11 +529,13 @@ class Encoder {
             c.heap = std::move(heaps[0]);
             for (unsigned t = 1; t < n_threads; t++) {
                 State &st = shards[t];
-                str_map[t].resize(st.bstr_list.size());
-                for (size_t j = 0; j < st.bstr_list.size(); j++) {
-                    auto it = g.bstr.find(st.bstr_list[j]);
-                    if (it == g.bstr.end()) { it = g.bstr.emplace(st.bstr_list[j], (uint32_t)g.bstr_list.size()).first; g.bstr_list.push_back(st.bstr_list[j]); }
-                    str_map[t][j] = it->second;
+                str_map[t].resize(st.bstr.size());
+                for (size_t j = 0; j < st.bstr.size(); j++) {
+                    const BytesMap::Ent &e = st.bstr.ents[j];       // entry j holds batch string j of the shard (values are assigned in order)
+                    const uint8_t *kp = st.bstr.key(j);
+                    const uint32_t *hit = g.bstr.find(kp, e.len, e.h);
+                    if (hit) str_map[t][j] = *hit;
+                    else { str_map[t][j] = (uint32_t)g.bstr.size(); g.bstr.insert(kp, e.len, e.h, (uint32_t)g.bstr.size()); }
                 }
                 class_map[t].resize(st.class_list.size());
                 for (size_t j = 0; j < st.class_list.size(); j++) {
@@ -514,6 +615,19 @@ class Encoder {
         attr->emplace_back(k, v);
         return true;
     }
+    // roles of the principal and actions of one CheckInput message, without building a view
+    static bool scan_counts(Span msg, uint32_t *n_roles, uint32_t *n_actions) {
+        WireIt it(msg);
+        while (it.next()) {
+            if (it.wt != 2) continue;
+            if (it.fno == 3) {
+                WireIt p(it.s);
+                while (p.next()) if (p.wt == 2 && p.fno == 3) (*n_roles)++;
+                if (p.bad) return false;
+            } else if (it.fno == 4) (*n_actions)++;
+        }
+        return !it.bad;
+    }
     static bool parse_input(Span msg, InputView *out) {
         WireIt it(msg);
         while (it.next()) {
@@ -550,8 +664,7 @@ class Encoder {
         const Encoder *E;
         Columns *c;
         std::vector<uint64_t> *heap;     // where lists / maps go: the batch heap itself, or a shard-local one merged later
-        std::unordered_map<std::string, uint32_t> bstr;
-        std::vector<std::string> bstr_list;
+        BytesMap bstr;                   // the batch string dictionary: entry j = batch string j (first appearance order)
         std::unordered_map<std::string, std::vector<uint32_t>> class_cache;
         std::map<std::vector<uint32_t>, uint32_t> classes;
         std::vector<std::vector<uint32_t>> class_list;
@@ -559,17 +672,16 @@ class Encoder {
         std::vector<std::vector<std::string>> aset_list;
         State(const Encoder *e, Columns *cc) : E(e), c(cc), heap(&cc->heap) {}
 
-        uint32_t sid(const std::string &s) {
-            auto t = E->table_strings.find(s);
-            if (t != E->table_strings.end()) return t->second;
-            auto b = bstr.find(s);
-            if (b != bstr.end()) return (uint32_t)E->strings.size() + b->second;
-            const uint32_t i = (uint32_t)bstr_list.size();
-            bstr.emplace(s, i);
-            bstr_list.push_back(s);
+        uint32_t sid(const uint8_t *p, size_t n) {
+            const uint64_t h = hash_bytes(p, n);
+            if (const uint32_t *t = E->table_strings.find(p, n, h)) return *t;
+            if (const uint32_t *b = bstr.find(p, n, h)) return (uint32_t)E->strings.size() + *b;
+            const uint32_t i = (uint32_t)bstr.size();
+            bstr.insert(p, n, h, i);
             return (uint32_t)E->strings.size() + i;
         }
-        uint32_t sid(Span s) { return sid(str_of(s)); }
+        uint32_t sid(const std::string &s) { return sid(reinterpret_cast<const uint8_t *>(s.data()), s.size()); }
+        uint32_t sid(Span s) { return sid(s.p, s.n); }
 
         uint32_t kind_class(const std::string &kind, std::string *err) {
             auto it = class_cache.find(kind);
@@ -607,13 +719,19 @@ class Encoder {
                 case 3: out = box(CB_V64_STRING, sid(it.s)); break;
                 case 4: out = box(CB_V64_BOOL, it.u ? 1 : 0); break;
                 case 5: out = v64_struct(it.s); break;
-                case 6: {
-                    std::vector<uint64_t> elems;
+                case 6: {   // (children are written to the heap before their parent: the elements are collected first)
+                    uint64_t small[16];
+                    std::vector<uint64_t> big;
+                    size_t ne = 0;
                     WireIt l(it.s);
-                    while (l.next()) if (l.fno == 1 && l.wt == 2) elems.push_back(v64(l.s));
+                    while (l.next()) if (l.fno == 1 && l.wt == 2) {
+                        const uint64_t w = v64(l.s);
+                        if (ne < 16) small[ne] = w; else { if (ne == 16) big.assign(small, small + 16); big.push_back(w); }
+                        ne++;
+                    }
                     const uint64_t off = heap->size();
-                    heap->push_back(elems.size());
-                    heap->insert(heap->end(), elems.begin(), elems.end());
+                    heap->push_back(ne);
+                    if (ne <= 16) heap->insert(heap->end(), small, small + ne); else heap->insert(heap->end(), big.begin(), big.end());
                     out = box(CB_V64_LIST, off | CB_V64_HEAP_BATCH_BIT);
                     break;
                 }
@@ -623,26 +741,49 @@ class Encoder {
             return out;
         }
         uint64_t v64_struct(Span st) {     // google.protobuf.Struct { map<string, Value> fields = 1 }
-            std::vector<std::pair<Span, Span>> ents;
+            std::pair<Span, Span> small[12];
+            size_t ne = 0;
             WireIt f(st);
-            while (f.next()) if (f.fno == 1 && f.wt == 2) { Span k, v; if (map_entry(f.s, &k, &v)) ents.emplace_back(k, v); }
-            return v64_map(ents);
-        }
-        uint64_t v64_map(const std::vector<std::pair<Span, Span>> &ents_in) {
-            // a repeated key keeps its first position and its last value (dict semantics of the JSON path)
-            std::vector<std::pair<Span, Span>> ents;
-            for (const auto &e : ents_in) {
-                bool dup = false;
-                for (auto &x : ents) if (x.first.n == e.first.n && !memcmp(x.first.p, e.first.p, e.first.n)) { x.second = e.second; dup = true; break; }
-                if (!dup) ents.push_back(e);
+            while (f.next()) if (f.fno == 1 && f.wt == 2) {
+                Span k, v;
+                if (!map_entry(f.s, &k, &v)) continue;
+                if (ne == 12) {     // a larger object: the general path
+                    std::vector<std::pair<Span, Span>> ents(small, small + 12);
+                    ents.emplace_back(k, v);
+                    while (f.next()) if (f.fno == 1 && f.wt == 2) { Span k2, v2; if (map_entry(f.s, &k2, &v2)) ents.emplace_back(k2, v2); }
+                    return v64_map(ents.data(), ents.size());
+                }
+                small[ne++] = std::make_pair(k, v);
             }
-            std::vector<uint64_t> keys, vals;
-            for (const auto &e : ents) keys.push_back(box(CB_V64_STRING, sid(e.first)));
-            for (const auto &e : ents) vals.push_back(e.second.p ? v64(e.second) : V_NULL);
+            return v64_map(small, ne);
+        }
+        uint64_t v64_map(const std::vector<std::pair<Span, Span>> &ents_in) { return v64_map(ents_in.data(), ents_in.size()); }
+        uint64_t v64_map(const std::pair<Span, Span> *ents_in, size_t n_in) {
+            // a repeated key keeps its first position and its last value (dict semantics of the JSON path)
+            std::pair<Span, Span> small[12];
+            std::vector<std::pair<Span, Span>> big;
+            if (n_in > 12) big.reserve(n_in);
+            std::pair<Span, Span> *ents = n_in > 12 ? nullptr : small;
+            size_t ne = 0;
+            for (size_t q = 0; q < n_in; q++) {
+                const auto &e = ents_in[q];
+                std::pair<Span, Span> *cur = n_in > 12 ? big.data() : small;
+                bool dup = false;
+                for (size_t z = 0; z < ne; z++) if (cur[z].first.n == e.first.n && !memcmp(cur[z].first.p, e.first.p, e.first.n)) { cur[z].second = e.second; dup = true; break; }
+                if (!dup) { if (n_in > 12) big.push_back(e); else small[ne] = e; ne++; }
+            }
+            ents = n_in > 12 ? big.data() : small;
+            // keys are interned in order, then the values are encoded (their heap records precede the map's own)
+            uint64_t ksmall[12], vsmall[12];
+            std::vector<uint64_t> kbig, vbig;
+            uint64_t *keys = ksmall, *vals = vsmall;
+            if (ne > 12) { kbig.resize(ne); vbig.resize(ne); keys = kbig.data(); vals = vbig.data(); }
+            for (size_t z = 0; z < ne; z++) keys[z] = box(CB_V64_STRING, sid(ents[z].first));
+            for (size_t z = 0; z < ne; z++) vals[z] = ents[z].second.p ? v64(ents[z].second) : V_NULL;
             const uint64_t off = heap->size();
-            heap->push_back(keys.size());
-            heap->insert(heap->end(), keys.begin(), keys.end());
-            heap->insert(heap->end(), vals.begin(), vals.end());
+            heap->push_back(ne);
+            heap->insert(heap->end(), keys, keys + ne);
+            heap->insert(heap->end(), vals, vals + ne);
             return box(CB_V64_MAP, off | CB_V64_HEAP_BATCH_BIT);
         }
         uint64_t v64_string(const std::string &s) { return box(CB_V64_STRING, sid(s)); }
@@ -673,28 +814,26 @@ class Encoder {
             }
             return val.p ? v64(val) : V_NULL;
         }
-        uint64_t slot_value(const InputView &v, const std::vector<std::string> &path) {
-            if (path.empty()) return V_ERROR;
-            if (path[0] == "aux_data") return path.size() > 2 ? walk(v.jwt, path, 2) : v64_map(v.jwt);
-            const bool principal = path[0] == "principal";
-            const std::string &fld = path.size() > 1 ? path[1] : path[0];
-            if (fld == "attr") {
-                const auto &attr = principal ? v.p.attr : v.r.attr;
-                return path.size() > 2 ? walk(attr, path, 2) : v64_map(attr);
-            }
-            if (fld == "roles") {
+        uint64_t slot_value(const InputView &v, const std::vector<std::string> &path, SlotSrc src) {
+            switch (src) {
+            case SRC_ERROR: return V_ERROR;
+            case SRC_AUX: return path.size() > 2 ? walk(v.jwt, path, 2) : v64_map(v.jwt);
+            case SRC_P_ATTR: return path.size() > 2 ? walk(v.p.attr, path, 2) : v64_map(v.p.attr);
+            case SRC_R_ATTR: return path.size() > 2 ? walk(v.r.attr, path, 2) : v64_map(v.r.attr);
+            case SRC_P_ROLES: case SRC_R_ROLES: {
                 std::vector<uint64_t> elems;
-                if (principal) for (Span r : v.p.roles) elems.push_back(box(CB_V64_STRING, sid(r)));
+                if (src == SRC_P_ROLES) for (Span r : v.p.roles) elems.push_back(box(CB_V64_STRING, sid(r)));
                 const uint64_t off = heap->size();
                 heap->push_back(elems.size());
                 heap->insert(heap->end(), elems.begin(), elems.end());
                 return box(CB_V64_LIST, off | CB_V64_HEAP_BATCH_BIT);
             }
-            if (fld == "scope") return v64_string(scope_value(str_of(principal ? v.p.scope : v.r.scope)));
-            if (fld == "policy_version") return v64_string(str_of(principal ? v.p.version : v.r.version));
-            if (fld == "id") return v64_string(str_of(principal ? v.p.id : v.r.id));
-            if (fld == "kind") return v64_string(principal ? std::string() : str_of(v.r.kind));
-            return v64_string(std::string());
+            case SRC_P_SCOPE: case SRC_R_SCOPE: return v64_string(scope_value(str_of(src == SRC_P_SCOPE ? v.p.scope : v.r.scope)));
+            case SRC_P_VERSION: case SRC_R_VERSION: return box(CB_V64_STRING, sid(src == SRC_P_VERSION ? v.p.version : v.r.version));
+            case SRC_P_ID: case SRC_R_ID: return box(CB_V64_STRING, sid(src == SRC_P_ID ? v.p.id : v.r.id));
+            case SRC_R_KIND: return box(CB_V64_STRING, sid(v.r.kind));
+            default: return v64_string(std::string());   // SRC_P_KIND, unknown fields: the empty string
+            }
         }
 
         void finish() {
@@ -735,12 +874,12 @@ class Encoder {
                         c->row_am[(ps * n_as + a) * nr + r] = m;
                     }
             // batch string dictionary
-            c->bstr_off.assign(bstr_list.size() + 1, 0);
-            size_t pos = 0;
-            for (size_t j = 0; j < bstr_list.size(); j++) { c->bstr_off[j] = (uint32_t)pos; pos += bstr_list[j].size(); }
-            c->bstr_off[bstr_list.size()] = (uint32_t)pos;
-            c->bstr_bytes.reserve(pos + 16);
-            for (const auto &s : bstr_list) c->bstr_bytes.insert(c->bstr_bytes.end(), s.begin(), s.end());
+            // (entries are stored in order of first appearance and their keys back to back in the arena: that IS the dictionary)
+            c->bstr_off.assign(bstr.size() + 1, 0);
+            for (size_t j = 0; j < bstr.size(); j++) c->bstr_off[j] = bstr.ents[j].off;
+            c->bstr_off[bstr.size()] = (uint32_t)bstr.arena.size();
+            c->bstr_bytes.reserve(bstr.arena.size() + 16);
+            c->bstr_bytes.assign(bstr.arena.begin(), bstr.arena.end());
             c->bstr_bytes.insert(c->bstr_bytes.end(), 16, 0);
         }
     };

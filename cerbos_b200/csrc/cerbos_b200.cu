@@ -1465,12 +1465,12 @@ int cgpu_encode(const cgpu_encoder *e, const void *const *inputs, const size_t *
     *out = nullptr;
     cgpu_encoded *r = new (std::nothrow) cgpu_encoded();
     if (!r) return fail(CGPU_ERR_INVALID, "out of memory");
-    cbenc::Encoder local = e->enc;     // the dictionaries are read-only; only `error` is per call
+    std::string enc_err;               // (the encoder itself is read-only here: concurrent cgpu_encode calls share it)
     // shards of the batch are encoded on host threads and merged in order (CERBOS_B200_ENCODE_THREADS, default: the cores, at most 32)
     unsigned threads = std::thread::hardware_concurrency();
     if (threads > 32) threads = 32;
     if (const char *et = getenv("CERBOS_B200_ENCODE_THREADS")) { const long v = strtol(et, nullptr, 10); if (v >= 1 && v <= 256) threads = (unsigned)v; }
-    if (!local.encode(inputs, input_bytes, n, &r->cols, threads ? threads : 1)) { const std::string why = local.error; delete r; return fail(CGPU_ERR_INVALID, "cgpu_encode: %s", why.c_str()); }
+    if (!e->enc.encode(inputs, input_bytes, n, &r->cols, threads ? threads : 1, &enc_err)) { delete r; return fail(CGPU_ERR_INVALID, "cgpu_encode: %s", enc_err.c_str()); }
     r->flags = e->enc.conf.lenient ? CB_BATCH_FLAG_LENIENT : 0;
     size_t total = 0, offs[CGPU_N_COLUMNS];
     for (int i = 0; i < CGPU_N_COLUMNS; i++) { offs[i] = total; r->bytes[i] = r->cols.bytes(i); total += (r->bytes[i] + 255) & ~(size_t)255; }
