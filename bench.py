@@ -689,11 +689,36 @@ def measure_host_encode(w, blob, table, K, n=1 << 16):
         table.check_encoded(eb, NOW_NS)
         eb.free()
     t_both = (time.perf_counter() - t0) / reps
+    # the same with the native narrowing pass in between: cgpu_encode -> cgpu_narrow_build -> cgpu_check_narrow (no Python on the path)
+    narrow_path = None
+    try:
+        import numpy as _np
+        out = _np.empty((n, K), dtype=_np.uint8)
+        want = None
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            eb = ne.encode_raw(ptrs, lens, n)
+            nz = eb.narrow(2)
+            if nz is None:
+                eb.free()
+                raise RuntimeError("batch not narrowable")
+            b, nr = nz.view(NOW_NS)
+            table.check_narrow_into(b, nr, out.ctypes.data)
+            nz.free()
+            eb.free()
+        t_narrow = (time.perf_counter() - t0) / reps
+        eb = ne.encode_raw(ptrs, lens, n)
+        want = table.check_encoded(eb, NOW_NS)
+        eb.free()
+        narrow_path = {"decisions_per_s": n * K / t_narrow, "equals_canonical_call": bool((_np.asarray(want).reshape(n, -1)[:, :K] == out).all())}
+    except Exception as e:  # noqa: BLE001 -- an optional extra line of the report, never the reason a bench run fails
+        narrow_path = {"error": repr(e)[:200]}
     ne.close()
     threads = int(os.environ.get("CERBOS_B200_ENCODE_THREADS", "0")) or min(32, os.cpu_count() or 1)
     return {"requests_per_s": n / t_enc, "column_gb_per_s": col_bytes / t_enc / 1e9, "wire_bytes_per_request": sum(len(m) for m in msgs) / n,
-            "threads": threads, "encode_plus_check_decisions_per_s": n * K / t_both,
-            "sample": f"{n} serialized CheckInput messages of the workload per call (cgpu_encode, then cgpu_encode + cgpu_check)"}
+            "threads": threads, "encode_plus_check_decisions_per_s": n * K / t_both, "encode_narrow_check": narrow_path,
+            "sample": f"{n} serialized CheckInput messages of the workload per call (cgpu_encode, then cgpu_encode + cgpu_check, then "
+                      "cgpu_encode + cgpu_narrow_build + cgpu_check_narrow)"}
 
 
 WORKLOAD_DOC = {

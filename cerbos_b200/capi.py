@@ -20,6 +20,7 @@ EXPORTS = [
     "cgpu_last_cluster_config", "cgpu_profile", "cgpu_table_wait_ready", "cgpu_table_compile_check", "cgpu_peer_alloc", "cgpu_peer_open", "cgpu_peer_close",
     "cgpu_peer_free", "cgpu_peer_read", "cgpu_check_device_gather", "cgpu_gather_wait", "cgpu_last_error",
     "cgpu_device_count", "cgpu_encoder_create", "cgpu_encoder_destroy", "cgpu_encode", "cgpu_encoded_batch", "cgpu_encoded_free",
+    "cgpu_narrow_build", "cgpu_narrowed_view", "cgpu_narrowed_free",
 ]
 
 
@@ -113,6 +114,12 @@ def lib():
         L.cgpu_encoded_batch.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(_Batch)]
         L.cgpu_encoded_free.restype = None
         L.cgpu_encoded_free.argtypes = [ctypes.c_void_p]
+        L.cgpu_narrow_build.restype = ctypes.c_int
+        L.cgpu_narrow_build.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+        L.cgpu_narrowed_view.restype = ctypes.c_int
+        L.cgpu_narrowed_view.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(_Batch), ctypes.POINTER(_Narrow)]
+        L.cgpu_narrowed_free.restype = None
+        L.cgpu_narrowed_free.argtypes = [ctypes.c_void_p]
         L.cgpu_last_error.restype = ctypes.c_char_p
         L.cgpu_last_error.argtypes = []
         _lib = L
@@ -176,9 +183,37 @@ class EncodedBatch:
         b = self.batch()
         return [np.frombuffer(ctypes.string_at(b.columns[i], b.column_bytes[i]), dtype=np.uint8).copy() for i in range(N_COLUMNS)]
 
+    def narrow(self, form: int = 2):
+        """cgpu_narrow_build: this batch in the narrow wire form (None when an id does not fit its narrow header field).
+        Free the result before this batch."""
+        out = ctypes.c_void_p()
+        rc = lib().cgpu_narrow_build(self._h, form, ctypes.byref(out))
+        if rc == ERR_UNSUPPORTED:
+            return None
+        _check(rc)
+        return NarrowedBatch(out)
+
     def free(self):
         if self._h:
             lib().cgpu_encoded_free(self._h)
+            self._h = None
+
+
+class NarrowedBatch:
+    """cgpu_narrowed: an encoded batch in the narrow wire form, built by the library (cb_narrow.h)."""
+
+    def __init__(self, h):
+        self._h = h
+
+    def view(self, now_ns: int = 0):
+        """-> (cgpu_batch, cgpu_narrow) argument blocks for Table.check_narrow_into; valid until free()"""
+        b, nr = _Batch(), _Narrow()
+        _check(lib().cgpu_narrowed_view(self._h, now_ns, ctypes.byref(b), ctypes.byref(nr)))
+        return b, nr
+
+    def free(self):
+        if self._h:
+            lib().cgpu_narrowed_free(self._h)
             self._h = None
 
 

@@ -23,6 +23,7 @@
 #include "cb_specialize.h"
 #include "cb_uc.h"
 #include "cb_encode.h"
+#include "cb_narrow.h"
 #include "cb_embed.inc"
 #include "cerbos_b200.h"
 
@@ -394,6 +395,17 @@ struct cgpu_encoded {
     const void *ptrs[CGPU_N_COLUMNS] = {};
     size_t bytes[CGPU_N_COLUMNS] = {};
     uint32_t flags = 0;
+    uint32_t n_slots = 0, role_cols = 1;   // of the table / of this batch (cgpu_narrow_build)
+};
+struct cgpu_narrowed {
+    cbnarrow::Narrowed nb;
+    const cgpu_encoded *enc = nullptr;
+    void *pinned = nullptr;                // one page-locked block holding every narrow column (null: no CUDA device, they stay in `nb`)
+    const void *pid = nullptr, *hdr16 = nullptr, *versions = nullptr, *roles = nullptr, *heap = nullptr;
+    std::vector<const void *> slot_ptrs;
+    size_t heap_bytes = 0;
+    const void *cols[CGPU_N_COLUMNS] = {};
+    size_t col_bytes[CGPU_N_COLUMNS] = {};
 };
 
 struct cgpu_table {
@@ -1472,6 +1484,8 @@ int cgpu_encode(const cgpu_encoder *e, const void *const *inputs, const size_t *
     if (const char *et = getenv("CERBOS_B200_ENCODE_THREADS")) { const long v = strtol(et, nullptr, 10); if (v >= 1 && v <= 256) threads = (unsigned)v; }
     if (!e->enc.encode(inputs, input_bytes, n, &r->cols, threads ? threads : 1, &enc_err)) { delete r; return fail(CGPU_ERR_INVALID, "cgpu_encode: %s", enc_err.c_str()); }
     r->flags = e->enc.conf.lenient ? CB_BATCH_FLAG_LENIENT : 0;
+    r->n_slots = (uint32_t)e->enc.slots.size();
+    r->role_cols = r->cols.role_cols;
     size_t total = 0, offs[CGPU_N_COLUMNS];
     for (int i = 0; i < CGPU_N_COLUMNS; i++) { offs[i] = total; r->bytes[i] = r->cols.bytes(i); total += (r->bytes[i] + 255) & ~(size_t)255; }
     // page-locked staging so that cgpu_check's chunked H2D copies run asynchronously; without a CUDA device the columns
@@ -1507,6 +1521,89 @@ int cgpu_encoded_batch(const cgpu_encoded *r, int64_t now_unix_nanos, cgpu_batch
 }
 
 void cgpu_encoded_free(cgpu_encoded *r) {
+    if (!r) return;
+    if (r->pinned) cudaFreeHost(r->pinned);
+    delete r;
+}
+
+int cgpu_narrow_build(const cgpu_encoded *enc, int form, cgpu_narrowed **out) {
+    if (!enc || !out || (form != 1 && form != 2)) return fail(CGPU_ERR_INVALID, "cgpu_narrow_build: null argument, or form not 1 / 2");
+    *out = nullptr;
+    cgpu_narrowed *r = new (std::nothrow) cgpu_narrowed();
+    if (!r) return fail(CGPU_ERR_INVALID, "out of memory");
+    const uint64_t n = enc->cols.n;
+    r->nb = cbnarrow::build(static_cast<const uint32_t *>(enc->ptrs[CGPU_COL_HDR0]), static_cast<const uint8_t *>(enc->ptrs[CGPU_COL_HDR1]),
+                            static_cast<const uint32_t *>(enc->ptrs[CGPU_COL_ROLES]), static_cast<const uint64_t *>(enc->ptrs[CGPU_COL_SLOTS]),
+                            static_cast<const uint64_t *>(enc->ptrs[CGPU_COL_HEAP]), enc->bytes[CGPU_COL_HEAP] / 8, n, enc->role_cols, enc->n_slots, form == 2);
+    if (!r->nb.ok) { delete r; return fail(CGPU_ERR_UNSUPPORTED, "cgpu_narrow_build: an id of this batch does not fit its narrow header field"); }
+    r->enc = enc;
+    cbnarrow::Narrowed &nb = r->nb;
+    // page-locked staging, like cgpu_encode (without a CUDA device the columns stay where they were built)
+    std::vector<std::pair<const void **, std::vector<uint8_t> *>> parts;
+    std::vector<uint8_t> hdr_bytes(reinterpret_cast<const uint8_t *>(nb.hdr16.data()), reinterpret_cast<const uint8_t *>(nb.hdr16.data()) + nb.hdr16.size() * 2);
+    r->slot_ptrs.assign(nb.slot_cols.size() ? nb.slot_cols.size() : 1, nullptr);
+    size_t total = 0;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    total += al(nb.pid.size()) + al(hdr_bytes.size()) + al(nb.versions.size()) + al(nb.roles.size()) + al(nb.heap.size());
+    for (const auto &c : nb.slot_cols) total += al(c.size());
+    uint8_t *base = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void **>(&base), total ? total : 256, cudaHostAllocDefault) == cudaSuccess) r->pinned = base;
+    else cudaGetLastError();
+    size_t at = 0;
+    auto place = [&](const uint8_t *src, size_t bytes) -> const void * {
+        if (!bytes) return nullptr;
+        if (!base) return src;
+        memcpy(base + at, src, bytes);
+        const void *p = base + at;
+        at += al(bytes);
+        return p;
+    };
+    r->pid = place(nb.pid.data(), nb.pid.size());
+    r->hdr16 = place(hdr_bytes.data(), hdr_bytes.size());
+    if (!base && !hdr_bytes.empty()) r->hdr16 = nb.hdr16.data();     // (hdr_bytes is a temporary)
+    r->versions = place(nb.versions.data(), nb.versions.size());
+    r->roles = place(nb.roles.data(), nb.roles.size());
+    r->heap = place(nb.heap.data(), nb.heap.size());
+    r->heap_bytes = nb.heap.size();
+    for (size_t v = 0; v < nb.slot_cols.size(); v++) r->slot_ptrs[v] = place(nb.slot_cols[v].data(), nb.slot_cols[v].size());
+    for (int i = 0; i < CGPU_N_COLUMNS; i++) { r->cols[i] = i < CGPU_COL_HEAP ? nullptr : enc->ptrs[i]; r->col_bytes[i] = i < CGPU_COL_HEAP ? 0 : enc->bytes[i]; }
+    r->cols[CGPU_COL_HEAP] = r->heap; r->col_bytes[CGPU_COL_HEAP] = r->heap_bytes;
+    *out = r;
+    return CGPU_OK;
+}
+
+int cgpu_narrowed_view(const cgpu_narrowed *r, int64_t now_unix_nanos, cgpu_batch *batch_out, cgpu_narrow *narrow_out) {
+    if (!r || !batch_out || !narrow_out) return fail(CGPU_ERR_INVALID, "cgpu_narrowed_view: null argument");
+    const cbnarrow::Narrowed &nb = r->nb;
+    batch_out->n_requests = nb.n;
+    batch_out->max_actions = r->enc->cols.max_actions;
+    batch_out->now_unix_nanos = now_unix_nanos;
+    batch_out->flags = r->enc->flags;
+    batch_out->columns = r->cols;
+    batch_out->column_bytes = r->col_bytes;
+    batch_out->n_columns = CGPU_N_COLUMNS;
+    memset(narrow_out, 0, sizeof(*narrow_out));
+    if (nb.pid16) { narrow_out->principal_id16 = static_cast<const uint16_t *>(r->pid); narrow_out->principal_base = nb.principal_base; }
+    else narrow_out->principal_id = static_cast<const uint32_t *>(r->pid);
+    narrow_out->hdr16 = static_cast<const uint16_t *>(r->hdr16);
+    narrow_out->versions = static_cast<const uint8_t *>(r->versions);
+    narrow_out->roles = static_cast<const uint8_t *>(r->roles);
+    narrow_out->role_cols = nb.role_cols;
+    narrow_out->slot_class = nb.slot_class.data();
+    narrow_out->slot_cols = r->slot_ptrs.data();
+    narrow_out->heap_u32 = nb.heap_u32 ? 1 : 0;
+    narrow_out->slot_base = nb.slot_base.data();
+    narrow_out->slot_base2 = nb.slot_base2.data();
+    narrow_out->hdr_const_mask = nb.hdr_const_mask;
+    for (int f = 0; f < 4; f++) narrow_out->hdr_const[f] = nb.hdr_const[f];
+    narrow_out->versions_const = nb.versions_const ? 1 : 0;
+    narrow_out->versions_value[0] = nb.versions_value[0]; narrow_out->versions_value[1] = nb.versions_value[1];
+    narrow_out->heap_bits = nb.heap_bits;
+    narrow_out->heap_base = nb.heap_base; narrow_out->heap_base2 = nb.heap_base2;
+    return CGPU_OK;
+}
+
+void cgpu_narrowed_free(cgpu_narrowed *r) {
     if (!r) return;
     if (r->pinned) cudaFreeHost(r->pinned);
     delete r;

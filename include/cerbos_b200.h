@@ -165,6 +165,15 @@ int cgpu_encode(const cgpu_encoder *e, const void *const *inputs, const size_t *
 int cgpu_encoded_batch(const cgpu_encoded *r, int64_t now_unix_nanos, cgpu_batch *out);
 void cgpu_encoded_free(cgpu_encoded *r);
 
+/* The encoded batch in the narrow wire form (above), built on the host from the canonical columns: protobuf -> cgpu_encode ->
+ * cgpu_narrow_build -> cgpu_check_narrow needs no other host code.  form: 2 = everything the second half of cgpu_narrow
+ * describes, 1 = the first form only.  Returns CGPU_ERR_UNSUPPORTED when an id of the batch does not fit its 16- / 8-bit
+ * header field (the batch is then checked with cgpu_check).  The result borrows the batch-level tables of `enc`: free it first. */
+typedef struct cgpu_narrowed cgpu_narrowed;
+int cgpu_narrow_build(const cgpu_encoded *enc, int form, cgpu_narrowed **out);
+int cgpu_narrowed_view(const cgpu_narrowed *nb, int64_t now_unix_nanos, cgpu_batch *batch_out, cgpu_narrow *narrow_out);
+void cgpu_narrowed_free(cgpu_narrowed *nb);
+
 /* Decision metadata (the reference's IncludeMeta responses and audit entries: ActionEffect.Policy / Scope and
  * CheckOutput.EffectiveDerivedRoles -- internal/ruletable/ruletable.go:753-782, 913-922, 936-979, 1082-1148;
  * internal/svc/cerbos_svc.go:291-311).  Same inputs as cgpu_check; besides the effect bytes it returns

@@ -102,3 +102,84 @@ def test_encode_then_check_on_gpu():
         eb = ne.encode([wire.check_input(i) for i in inputs])
         assert (t.check_encoded(eb) == want).all(), name
         eb.free(); ne.close(); t.release(); c.close()
+
+
+# ---- native narrowing (cb_narrow.h: cgpu_narrow_build) against its specification, cerbos_b200/narrow.py ------------------
+def _arr(ptr, nbytes, dtype):
+    import ctypes
+    return np.frombuffer(ctypes.string_at(ptr, nbytes), dtype=dtype).copy() if ptr and nbytes else np.zeros(0, dtype=dtype)
+
+
+def _assert_narrowed_equals_spec(eb, want_batch, n_slots, form):
+    """every array and every parameter cgpu_narrow_build produces == narrow.narrow_batch of the same columns"""
+    import ctypes
+    from cerbos_b200 import narrow as NW
+    want = NW.narrow_batch(want_batch, n_slots, v2=(form == 2))
+    got = eb.narrow(form)
+    if want is None:
+        assert got is None
+        return None
+    assert got is not None
+    n = want.n
+    b, nr = got.view(0)
+    if want.principal_base is not None:
+        assert nr.principal_base == want.principal_base and (_arr(nr.principal_id16, n * 2, np.uint16) == want.principal_id).all()
+    else:
+        assert not nr.principal_id16 and (_arr(nr.principal_id, n * 4, np.uint32) == want.principal_id).all()
+    assert nr.hdr_const_mask == want.hdr_const_mask and tuple(nr.hdr_const) == tuple(want.hdr_const)
+    assert (_arr(nr.hdr16, want.hdr16.nbytes, np.uint16) == want.hdr16.reshape(-1)).all()
+    if want.versions is None:
+        assert nr.versions_const == 1 and tuple(nr.versions_value) == tuple(want.versions_value)
+    else:
+        assert nr.versions_const == 0 and (_arr(nr.versions, n * 2, np.uint8) == want.versions.reshape(-1)).all()
+    assert nr.role_cols == want.role_cols and (_arr(nr.roles, want.roles.nbytes, np.uint8) == want.roles.reshape(-1)).all()
+    cls = _arr(nr.slot_class, max(n_slots, 1), np.uint8)
+    assert (cls[:n_slots] == want.slot_class[:n_slots]).all()
+    assert (_arr(nr.slot_base, 4 * max(n_slots, 1), np.uint32)[:n_slots] == want.slot_base[:n_slots]).all()
+    assert (_arr(nr.slot_base2, 4 * max(n_slots, 1), np.uint32)[:n_slots] == want.slot_base2[:n_slots]).all()
+    for v in range(n_slots):
+        assert ctypes.string_at(nr.slot_cols[v], n * NW.ELEM_BYTES[int(cls[v])]) == np.ascontiguousarray(want.slot_cols[v]).tobytes(), v
+    assert (nr.heap_bits, nr.heap_u32, nr.heap_base, nr.heap_base2) == (want.heap_bits, 1 if want.heap_u32 else 0, want.heap_base, want.heap_base2)
+    for i in range(4, 12):
+        tb = np.ascontiguousarray(np.asarray(want.tables[i - 4])).tobytes()
+        assert b.column_bytes[i] == len(tb) and ctypes.string_at(b.columns[i], len(tb)) == tb, i
+    assert all(b.column_bytes[i] == 0 for i in range(4))
+    return got
+
+
+@pytest.mark.parametrize("name,n", [("C1", 300), ("C2", 3000), ("C3", 2500), ("C5", 1500)])
+def test_native_narrowing_equals_narrow_py_on_workloads(name, n):
+    from cerbos_b200 import capi, wire
+    w = W.WORKLOADS[name]()
+    _, ft, enc = W.build(w)
+    inputs = w.inputs(w.fields(n), range(n))
+    ne = capi.NativeEncoder(ft.blob)
+    eb = ne.encode([wire.check_input(i) for i in inputs])
+    want_b = enc.encode(inputs)
+    for form in (2, 1):
+        got = _assert_narrowed_equals_spec(eb, want_b, len(enc.slots), form)
+        got.free()
+    eb.free()
+    ne.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_native_narrowing_equals_narrow_py_on_random_batches(seed):
+    """fuzzed policy sets x requests: mixed-type columns (-> the 8-byte class), nulls, nested values, odd scopes"""
+    import random
+    from cerbos_b200 import capi, wire
+    from cerbos_b200.policy.compile import build_rule_table
+    from fuzzgen import rand_policies, rand_request
+    r = random.Random(8800 + seed)
+    ft = flatten(build_rule_table(rand_policies(r)))
+    enc = Encoder(ft.manifest)
+    inputs = [rand_request(r) for _ in range(300)]
+    ne = capi.NativeEncoder(ft.blob)
+    eb = ne.encode([wire.check_input(i) for i in inputs])
+    want_b = enc.encode(inputs)
+    for form in (2, 1):
+        got = _assert_narrowed_equals_spec(eb, want_b, len(enc.slots), form)
+        if got is not None:
+            got.free()
+    eb.free()
+    ne.close()
