@@ -401,6 +401,7 @@ struct cgpu_narrowed {
     cbnarrow::Narrowed nb;
     const cgpu_encoded *enc = nullptr;
     void *pinned = nullptr;                // one page-locked block holding every narrow column (null: no CUDA device, they stay in `nb`)
+    bool pinned_is_malloc = false;         // tests without a device: the same single-block layout in plain memory (CERBOS_B200_NARROW_BLOCK=1)
     const void *pid = nullptr, *hdr16 = nullptr, *versions = nullptr, *roles = nullptr, *heap = nullptr;
     std::vector<const void *> slot_ptrs;
     size_t heap_bytes = 0;
@@ -1548,7 +1549,12 @@ int cgpu_narrow_build(const cgpu_encoded *enc, int form, cgpu_narrowed **out) {
     for (const auto &c : nb.slot_cols) total += al(c.size());
     uint8_t *base = nullptr;
     if (cudaHostAlloc(reinterpret_cast<void **>(&base), total ? total : 256, cudaHostAllocDefault) == cudaSuccess) r->pinned = base;
-    else cudaGetLastError();
+    else {
+        cudaGetLastError();
+        base = nullptr;
+        const char *tb = getenv("CERBOS_B200_NARROW_BLOCK");
+        if (tb && tb[0] == '1') { base = static_cast<uint8_t *>(malloc(total ? total : 256)); r->pinned = base; r->pinned_is_malloc = base != nullptr; }
+    }
     size_t at = 0;
     auto place = [&](const uint8_t *src, size_t bytes) -> const void * {
         if (!bytes) return nullptr;
@@ -1605,7 +1611,7 @@ int cgpu_narrowed_view(const cgpu_narrowed *r, int64_t now_unix_nanos, cgpu_batc
 
 void cgpu_narrowed_free(cgpu_narrowed *r) {
     if (!r) return;
-    if (r->pinned) cudaFreeHost(r->pinned);
+    if (r->pinned) { if (r->pinned_is_malloc) free(r->pinned); else cudaFreeHost(r->pinned); }
     delete r;
 }
 

@@ -147,9 +147,12 @@ def _assert_narrowed_equals_spec(eb, want_batch, n_slots, form):
     return got
 
 
+@pytest.mark.parametrize("block", ["0", "1"])
 @pytest.mark.parametrize("name,n", [("C1", 300), ("C2", 3000), ("C3", 2500), ("C5", 1500)])
-def test_native_narrowing_equals_narrow_py_on_workloads(name, n):
+def test_native_narrowing_equals_narrow_py_on_workloads(name, n, block, monkeypatch):
+    """block = "1": the single-block layout the library uses for page-locked memory on a GPU host, here in plain memory"""
     from cerbos_b200 import capi, wire
+    monkeypatch.setenv("CERBOS_B200_NARROW_BLOCK", block)
     w = W.WORKLOADS[name]()
     _, ft, enc = W.build(w)
     inputs = w.inputs(w.fields(n), range(n))
