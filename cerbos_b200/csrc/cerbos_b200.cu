@@ -392,6 +392,7 @@ struct cgpu_encoder { cbenc::Encoder enc; };
 struct cgpu_encoded {
     cbenc::Columns cols;
     void *pinned = nullptr;              // one page-locked block holding all twelve columns (null: no CUDA device, columns stay in `cols`)
+    size_t pinned_cap = 0;               // (the block comes from / returns to the staging pool)
     const void *ptrs[CGPU_N_COLUMNS] = {};
     size_t bytes[CGPU_N_COLUMNS] = {};
     uint32_t flags = 0;
@@ -402,6 +403,7 @@ struct cgpu_narrowed {
     const cgpu_encoded *enc = nullptr;
     void *pinned = nullptr;                // one page-locked block holding every narrow column (null: no CUDA device, they stay in `nb`)
     bool pinned_is_malloc = false;         // tests without a device: the same single-block layout in plain memory (CERBOS_B200_NARROW_BLOCK=1)
+    size_t pinned_cap = 0;
     const void *pid = nullptr, *hdr16 = nullptr, *versions = nullptr, *roles = nullptr, *heap = nullptr;
     std::vector<const void *> slot_ptrs;
     size_t heap_bytes = 0;
@@ -1458,6 +1460,43 @@ int cgpu_sync(cgpu_ctx *ctx, void *cuda_stream) {
 }
 
 // ---- native batch encoder (cb_encode.h) ----------------------------------------------------------------------------
+// Page-locked staging blocks of cgpu_encode / cgpu_narrow_build are recycled: cudaHostAlloc costs milliseconds for the tens of
+// megabytes a batch takes, every call.  A block goes back to a small free list (eight blocks) when its batch is freed; blocks
+// are sized in steps so that batches of similar size reuse each other's.  (Without a CUDA device there is nothing to pin: the
+// columns stay in their vectors, or -- CERBOS_B200_NARROW_BLOCK=1, tests -- in plain memory laid out the same way.)
+struct HostBlock { void *p = nullptr; size_t cap = 0; bool is_malloc = false; };
+struct HostBlockPool {
+    std::mutex mu;
+    std::vector<HostBlock> free_list;
+    HostBlock take(size_t bytes, bool allow_malloc) {
+        size_t cap = 1u << 20;                    // powers of two up to 64 MB, then multiples of 64 MB
+        while (cap < bytes && cap < (64u << 20)) cap <<= 1;
+        if (cap < bytes) cap = (bytes + (64u << 20) - 1) / (64u << 20) * (64u << 20);
+        {
+            std::lock_guard<std::mutex> g(mu);
+            size_t best = free_list.size();
+            for (size_t i = 0; i < free_list.size(); i++)
+                if (free_list[i].cap >= bytes && (allow_malloc || !free_list[i].is_malloc) && (best == free_list.size() || free_list[i].cap < free_list[best].cap)) best = i;
+            if (best != free_list.size()) { HostBlock b = free_list[best]; free_list.erase(free_list.begin() + (long)best); return b; }
+        }
+        HostBlock b;
+        if (cudaHostAlloc(&b.p, cap, cudaHostAllocDefault) == cudaSuccess) { b.cap = cap; return b; }
+        cudaGetLastError();
+        b.p = nullptr;
+        if (allow_malloc) { b.p = malloc(cap); b.cap = b.p ? cap : 0; b.is_malloc = b.p != nullptr; }
+        return b;
+    }
+    void give(HostBlock b) {
+        if (!b.p) return;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            if (free_list.size() < 8) { free_list.push_back(b); return; }
+        }
+        if (b.is_malloc) free(b.p); else cudaFreeHost(b.p);
+    }
+};
+static HostBlockPool &host_pool() { static HostBlockPool *p = new HostBlockPool(); return *p; }   // (never destroyed: blocks may outlive static teardown order)
+
 int cgpu_encoder_create(const void *blob, size_t len, const char *default_version, const char *default_scope, int lenient_scope_search, cgpu_encoder **out) {
     if (!blob || !out) return fail(CGPU_ERR_INVALID, "cgpu_encoder_create: null argument");
     *out = nullptr;
@@ -1491,7 +1530,9 @@ int cgpu_encode(const cgpu_encoder *e, const void *const *inputs, const size_t *
     for (int i = 0; i < CGPU_N_COLUMNS; i++) { offs[i] = total; r->bytes[i] = r->cols.bytes(i); total += (r->bytes[i] + 255) & ~(size_t)255; }
     // page-locked staging so that cgpu_check's chunked H2D copies run asynchronously; without a CUDA device the columns
     // simply stay where they were built (host memory either way: this is data marshalling, not evaluation)
-    if (cudaHostAlloc(&r->pinned, total ? total : 256, cudaHostAllocDefault) == cudaSuccess) {
+    const HostBlock hb = host_pool().take(total ? total : 256, false);
+    r->pinned = hb.p; r->pinned_cap = hb.cap;
+    if (r->pinned) {
         for (int i = 0; i < CGPU_N_COLUMNS; i++) {
             if (r->bytes[i]) memcpy(static_cast<uint8_t *>(r->pinned) + offs[i], r->cols.ptr(i), r->bytes[i]);
             r->ptrs[i] = static_cast<uint8_t *>(r->pinned) + offs[i];
@@ -1501,8 +1542,6 @@ int cgpu_encode(const cgpu_encoder *e, const void *const *inputs, const size_t *
         r->cols = cbenc::Columns();
         r->cols.n = nreq; r->cols.max_actions = ma;
     } else {
-        cudaGetLastError();
-        r->pinned = nullptr;
         for (int i = 0; i < CGPU_N_COLUMNS; i++) r->ptrs[i] = r->cols.ptr(i);
     }
     *out = r;
@@ -1523,7 +1562,7 @@ int cgpu_encoded_batch(const cgpu_encoded *r, int64_t now_unix_nanos, cgpu_batch
 
 void cgpu_encoded_free(cgpu_encoded *r) {
     if (!r) return;
-    if (r->pinned) cudaFreeHost(r->pinned);
+    if (r->pinned) { HostBlock hb; hb.p = r->pinned; hb.cap = r->pinned_cap; host_pool().give(hb); }
     delete r;
 }
 
@@ -1548,12 +1587,11 @@ int cgpu_narrow_build(const cgpu_encoded *enc, int form, cgpu_narrowed **out) {
     total += al(nb.pid.size()) + al(hdr_bytes.size()) + al(nb.versions.size()) + al(nb.roles.size()) + al(nb.heap.size());
     for (const auto &c : nb.slot_cols) total += al(c.size());
     uint8_t *base = nullptr;
-    if (cudaHostAlloc(reinterpret_cast<void **>(&base), total ? total : 256, cudaHostAllocDefault) == cudaSuccess) r->pinned = base;
-    else {
-        cudaGetLastError();
-        base = nullptr;
+    {
         const char *tb = getenv("CERBOS_B200_NARROW_BLOCK");
-        if (tb && tb[0] == '1') { base = static_cast<uint8_t *>(malloc(total ? total : 256)); r->pinned = base; r->pinned_is_malloc = base != nullptr; }
+        const HostBlock hb = host_pool().take(total ? total : 256, tb && tb[0] == '1');
+        base = static_cast<uint8_t *>(hb.p);
+        r->pinned = hb.p; r->pinned_cap = hb.cap; r->pinned_is_malloc = hb.is_malloc;
     }
     size_t at = 0;
     auto place = [&](const uint8_t *src, size_t bytes) -> const void * {
@@ -1611,7 +1649,7 @@ int cgpu_narrowed_view(const cgpu_narrowed *r, int64_t now_unix_nanos, cgpu_batc
 
 void cgpu_narrowed_free(cgpu_narrowed *r) {
     if (!r) return;
-    if (r->pinned) { if (r->pinned_is_malloc) free(r->pinned); else cudaFreeHost(r->pinned); }
+    if (r->pinned) { HostBlock hb; hb.p = r->pinned; hb.cap = r->pinned_cap; hb.is_malloc = r->pinned_is_malloc; host_pool().give(hb); }
     delete r;
 }
 
