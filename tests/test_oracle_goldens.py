@@ -69,3 +69,17 @@ def test_engine_goldens_effect_policy_scope():
         wedr = want.get("effectiveDerivedRoles", want.get("effective_derived_roles")) or []
         assert sorted(wedr) == got["effectiveDerivedRoles"], cid
     assert n == 166
+
+
+def test_parent_role_index_known_answers():
+    """internal/ruletable/index/index_test.go:15-60 (TestParentRoleIndex): the transitive closure of parent roles per scope.
+    The hot path always asks for ONE scope (ruletable.go:865, 924: AddParentRoles(ctx, []string{resourceScope}, ...)); the
+    reference's multi-scope case is the union of the per-scope answers."""
+    from cerbos_b200.policy.model import RuleTable
+    rt = RuleTable(rows=[], scope_parent_roles={"acme": {"manager": ["employee"], "employee": ["user"]}, "acme.hr": {"manager": ["contractor"]}})
+    orc = CheckOracle(rt)
+    assert sorted(orc.add_parent_roles("acme", ["manager"])) == sorted(["manager", "employee", "user"])
+    assert sorted(orc.add_parent_roles("acme.hr", ["manager"])) == sorted(["manager", "contractor"])
+    union = set(orc.add_parent_roles("acme", ["manager"])) | set(orc.add_parent_roles("acme.hr", ["manager"]))
+    assert union == {"manager", "employee", "user", "contractor"}
+    assert orc.add_parent_roles("elsewhere", ["manager"]) == ["manager"]          # (an index without the scope: the roles as given)
