@@ -18,7 +18,7 @@ names as in api/public/cerbos/policy/v1/policy.proto:35-318).
 from __future__ import annotations
 
 from ..cel import parser as celparser
-from ..cel.ast import Ident, Select, walk
+from ..cel.ast import Call, Ident, Select, walk
 from . import namer
 from .model import (Cond, DerivedRole, EFFECT_ALLOW, EFFECT_DENY, Expr, KIND_PRINCIPAL, KIND_RESOURCE, Params, Row,
                     RuleTable, SP_OVERRIDE_PARENT, SP_REQUIRE_PARENTAL_CONSENT, SP_UNSPECIFIED, Variable,
@@ -33,11 +33,31 @@ class PolicyCompileError(ValueError):
 
 # ------------------------------------------------------------------ conditions
 
+_DEFS_IDENTS = ("V", "variables", "C", "constants", "G", "globals")
+_CEL_KEYWORDS = ("false", "in", "null", "true")
+
+
+def validate_identifier(kind: str, name) -> None:
+    """conditions.ValidateIdentifier (internal/conditions/identifiers.go:24-34): names of constants and variables."""
+    import re
+    name = str(name)
+    if name in _CEL_KEYWORDS:
+        raise PolicyCompileError(f"invalid {kind} name: \"{name}\" is a reserved keyword and can't be used as an identifier")
+    if not re.match(r"^[_a-zA-Z][_a-zA-Z0-9]*$", name):
+        raise PolicyCompileError(f"invalid {kind} name: \"{name}\" is not a valid identifier")
+
+
 def compile_expr(src: str) -> Expr:
     try:
-        return Expr(original=src, ast=celparser.parse(src))
-    except celparser.CelSyntaxError as e:
-        raise PolicyCompileError(f"invalid expression `{src.strip()}`: {e}") from e
+        e = Expr(original=src, ast=celparser.parse(src))
+    except celparser.CelSyntaxError as ex:
+        raise PolicyCompileError(f"invalid expression `{src.strip()}`: {ex}") from ex
+    # variables / constants / globals are record-like (cerbos.Variables): field selection only -- V["x"] has no overload
+    # and the reference's type checker rejects it (testdata/compile/variables_index_lookup.yaml)
+    for n in walk(e.ast):
+        if isinstance(n, Call) and n.fn == "_[_]" and n.target is None and len(n.args) == 2 and isinstance(n.args[0], Ident) and n.args[0].name in _DEFS_IDENTS:
+            raise PolicyCompileError(f"invalid expression `{src.strip()}`: found no matching overload for '_[_]' applied to '(cerbos.Variables, ...)'")
+    return e
 
 
 def compile_match(m: dict) -> Cond:
@@ -100,12 +120,14 @@ class _Defs:
 
     def add_vars(self, defs: dict, source: str):
         for name, src in (defs or {}).items():
+            validate_identifier("variable", name)
             if name in self.var_defs:
                 raise PolicyCompileError(f"{self.where}: variable '{name}' has multiple definitions ({source})")
             self.var_defs[name] = compile_expr(src)
 
     def add_consts(self, defs: dict, source: str):
         for name, val in (defs or {}).items():
+            validate_identifier("constant", name)
             if name in self.const_defs:
                 raise PolicyCompileError(f"{self.where}: constant '{name}' has multiple definitions ({source})")
             self.const_defs[name] = val

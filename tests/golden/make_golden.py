@@ -220,6 +220,24 @@ def verify_cases():
     print("verify_cases:", len(out), "inputs,", sum(len(o["want"]) for o in out), "decisions")
 
 
+def compile_cases():
+    """internal/test/testdata/compile/*.yaml (+ .input): the compile front-end's own test cases -- a set of policy files
+    and either the errors the reference's compiler reports for it or (no wantErrors) a successful compilation.  Kept: the
+    files as parsed documents and the error kinds; the exact messages and source positions are presentation."""
+    import re
+    src = os.path.join(REF, "test/testdata/compile")
+    out = []
+    for name in sorted({f[:-5] for f in os.listdir(src) if f.endswith(".yaml")}):
+        spec = [x for x in yaml.safe_load_all(open(os.path.join(src, name + ".yaml"))) if x][0]
+        parts = re.split(r"^-- (.+?) --\s*$", open(os.path.join(src, name + ".yaml.input")).read(), flags=re.M)
+        files = {parts[i]: [d for d in yaml.safe_load_all(parts[i + 1]) if d] for i in range(1, len(parts), 2)}
+        out.append({"name": name, "mainDef": spec.get("mainDef"), "files": files,
+                    "wantErrors": [{"file": e.get("file"), "error": e.get("error")} for e in (spec.get("wantErrors") or [])]})
+    with open(os.path.join(OUT, "compile_cases.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True, default=str)
+    print("compile cases:", len(out))
+
+
 def ruletable_bundle():
     """internal/test/testdata/bundle/v2_ruletable/bundle_unencrypted.crrt: the reference compiler's own output for the
     `store` policies as a serialized runtimev1.RuleTable (what OpenRuleTableBundle unmarshals,
@@ -245,3 +263,4 @@ if __name__ == "__main__":
     check_resources_cases()
     verify_cases()
     ruletable_bundle()
+    compile_cases()
