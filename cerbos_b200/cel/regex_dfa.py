@@ -33,10 +33,12 @@ class _NFA:
     def __init__(self):
         self.trans = []   # state -> [(mask, to)]
         self.eps = []     # state -> [to]
+        self.cond = []    # state -> [(BOT | EOT, to)]: zero-width, taken only at the begin / the end of the text
 
     def new(self):
         self.trans.append([])
         self.eps.append([])
+        self.cond.append([])
         return len(self.trans) - 1
 
 
@@ -81,6 +83,12 @@ class _Parser:
     def _eps(self):
         a = self.nfa.new()
         return a, a
+
+    def _assert(self, which):
+        """`^` / `\\A` (which = BOT) and `$` / `\\z` (EOT) consume nothing: `^^a$$`, `$^` on the empty text, `(^|x)^a` all hold"""
+        a, b = self.nfa.new(), self.nfa.new()
+        self.nfa.cond[a].append((which, b))
+        return a, b
 
     def _seq(self, f, g):
         self.nfa.eps[f[1]].append(g[0])
@@ -206,7 +214,17 @@ class _Parser:
             if self.i < len(self.p) and self.p[self.i] == "?":   # lazy: same language
                 self.i += 1
             atom_src = None if atom_src is None else (start, self.i)
+            if self.i < len(self.p) and (self.p[self.i] in "*+?" or self._is_count(self.i)):
+                # Go's regexp (Perl flags) does not stack repetition operators: a**, a*+, a{2}{3}, a??? are errors
+                raise RegexError("invalid nested repetition operator")
         return f
+
+    def _is_count(self, i):
+        if not self.p.startswith("{", i):
+            return False
+        j = self.p.find("}", i)
+        parts = (self.p[i + 1:j] if j > 0 else "").split(",")
+        return j > 0 and parts[0].isdigit() and len(parts) <= 2 and (len(parts) == 1 or not parts[1] or parts[1].isdigit())
 
     def _reparse(self, src):
         """a fresh copy of the fragment whose source is p[src[0]:src[1]] (fragments are not shared)"""
@@ -266,10 +284,10 @@ class _Parser:
             return self._codepoint_set(mask, True)
         if ch == "^":
             self.i += 1
-            return self._sym(1 << BOT)
+            return self._assert(BOT)
         if ch == "$":
             self.i += 1
-            return self._sym(1 << EOT)
+            return self._assert(EOT)
         if ch == "\\":
             return self._escape_atom()
         if ch in "*+?":
@@ -334,7 +352,7 @@ class _Parser:
         if r[0] == "cls":
             return self._codepoint_set(_ASCII_ALL & ~r[1], True) if r[2] else self._sym(r[1])
         if r[0] == "sym":
-            return self._sym(1 << r[1])
+            return self._assert(r[1])
         if r[0] == "lit":
             f = self._eps()
             for ch in r[1]:
@@ -408,9 +426,29 @@ class _Parser:
         return self._sym(mask)
 
 
+def _unquote(p: str) -> str:
+    """\\Q..\\E -> the same text with its metacharacters escaped, so that a repetition operator after \\E binds to the last
+    character only (as in Go's regexp), not to the whole quoted run"""
+    out, i = [], 0
+    while i < len(p):
+        if p[i] == "\\" and i + 1 < len(p):
+            if p[i + 1] == "Q":
+                j = p.find("\\E", i + 2)
+                lit = p[i + 2:] if j < 0 else p[i + 2:j]
+                out.append("".join(c if (c.isalnum() or ord(c) > 127 or c in " _") else "\\" + c for c in lit))
+                i = len(p) if j < 0 else j + 2
+            else:
+                out.append(p[i:i + 2])
+                i += 2
+        else:
+            out.append(p[i])
+            i += 1
+    return "".join(out)
+
+
 def compile_dfa(pattern: str):
     """-> dict(n_states, n_classes, start, classmap (258 ints), accept (list of bool), trans (n_states x n_classes ints))"""
-    ps = _Parser(pattern)
+    ps = _Parser(_unquote(pattern))
     try:
         frag = ps.parse()
     except (IndexError, ValueError) as e:
@@ -423,13 +461,16 @@ def compile_dfa(pattern: str):
     nfa.eps[s0].append(frag[0])
     nfa.eps[frag[1]].append(acc)
     nfa.trans[acc].append((any_mask, acc))
-    # symbol classes: symbols with the same membership in every transition set
+    # symbol classes: symbols with the same membership in every transition set; BOT and EOT each on their own (the
+    # construction treats them specially)
     sig = [0] * NSYM
     masks = sorted({m for st in nfa.trans for m, _ in st})
     for bit, m in enumerate(masks):
         for sym in range(NSYM):
             if (m >> sym) & 1:
                 sig[sym] |= 1 << bit
+    sig[BOT] |= 1 << len(masks)
+    sig[EOT] |= 1 << (len(masks) + 1)
     class_of, reps = {}, []
     classmap = []
     for sym in range(NSYM):
@@ -440,31 +481,47 @@ def compile_dfa(pattern: str):
             reps.append(sym)
         classmap.append(c)
 
-    def closure(states):
+    def closure(states, at_begin, at_end):
         stack, seen = list(states), set(states)
         while stack:
             s = stack.pop()
-            for t in nfa.eps[s]:
+            nxt = list(nfa.eps[s])
+            for which, t in nfa.cond[s]:
+                if (which == BOT and at_begin) or (which == EOT and at_end):
+                    nxt.append(t)
+            for t in nxt:
                 if t not in seen:
                     seen.add(t)
                     stack.append(t)
         return frozenset(seen)
 
-    start = closure({s0})
+    def move(states, sym):
+        nxt = set()
+        for s in states:
+            for m, t in nfa.trans[s]:
+                if (m >> sym) & 1:
+                    nxt.add(t)
+        return nxt
+
+    # a DFA state = (NFA states, "the position is the begin of the text"): `^` edges are followed right after BOT, `$`
+    # edges when EOT arrives -- before and after it is consumed, so that what follows a `$` (another `$`, `\z`, a `^` on
+    # the empty text) is still reached
+    start = (closure({s0}, False, False), False)
     ids = {start: 0}
     order = [start]
     trans = []
     k = 0
     while k < len(order):
-        cur = order[k]
+        cur, cur_begin = order[k]
         row = []
         for rep in reps:
-            nxt = set()
-            for s in cur:
-                for m, t in nfa.trans[s]:
-                    if (m >> rep) & 1:
-                        nxt.add(t)
-            d = closure(nxt)
+            if rep == BOT:
+                d = (closure(move(cur, rep), True, False), True)
+            elif rep == EOT:
+                pre = closure(cur, cur_begin, True)
+                d = (closure(move(pre, rep), cur_begin, True), cur_begin)
+            else:
+                d = (closure(move(cur, rep), False, False), False)
             if d not in ids:
                 if len(ids) >= MAX_STATES:
                     raise RegexUnsupported("pattern needs more than %d DFA states" % MAX_STATES)
@@ -473,7 +530,7 @@ def compile_dfa(pattern: str):
             row.append(ids[d])
         trans.append(row)
         k += 1
-    accept = [acc in st for st in order]
+    accept = [acc in st for st, _ in order]
     return {"n_states": len(order), "n_classes": len(reps), "start": 0, "classmap": classmap, "accept": accept, "trans": trans}
 
 

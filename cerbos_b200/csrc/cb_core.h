@@ -18,6 +18,9 @@
 // host and step through it without a GPU (debug aid only -- the product never runs it on the CPU).
 #pragma once
 #include <stdint.h>
+#if !defined(__CUDACC_RTC__)
+#include <math.h>      // (ceil / floor / round / trunc / fabs / sqrt of ext.Math; built in under NVRTC)
+#endif
 
 #include "cerbos_b200_format.h"
 
@@ -1187,6 +1190,61 @@ CB_HD_NOINLINE Val dyn_strfn(Ctx &c, uint32_t fn, const Val *a, uint32_t argc) {
         return strb_end(s);
     }
     if (fn == CB_FN_TO_BYTES) return (a[0].tag == CB_T_STRING || a[0].tag == CB_T_BYTES) ? mk(CB_T_BYTES, a[0].u) : mk_err();
+    if (fn == CB_FN_TO_STRING) {
+        // cel-go ConvertToType(StringType): string, int, uint, bool, bytes holding valid UTF-8, double.  A double prints by
+        // strconv.FormatFloat(d, 'f', -1, 64): exact here for NaN, the infinities and integral values below 2^53 (JSON
+        // numbers used as ids); shortest-digit printing of the rest, timestamps and durations is flagged, never approximated.
+        const Val &x = a[0];
+        if (x.tag == CB_T_STRING) return x;
+        if (x.tag == CB_T_BYTES) {
+            const uint8_t *q; uint32_t m;
+            str_get(c, x.u, q, m);
+            for (uint32_t i = 0; i < m;) {
+                const uint32_t b0 = ldg(q + i);
+                uint32_t need = 0, lo = 0x80, hi = 0xBF;
+                if (b0 < 0x80) { i++; continue; }
+                if (b0 >= 0xC2 && b0 <= 0xDF) need = 1;
+                else if (b0 >= 0xE0 && b0 <= 0xEF) { need = 2; if (b0 == 0xE0) lo = 0xA0; if (b0 == 0xED) hi = 0x9F; }
+                else if (b0 >= 0xF0 && b0 <= 0xF4) { need = 3; if (b0 == 0xF0) lo = 0x90; if (b0 == 0xF4) hi = 0x8F; }
+                else return mk_err();
+                if (i + need >= m) return mk_err();
+                for (uint32_t k = 1; k <= need; k++) {
+                    const uint32_t bk = ldg(q + i + k);
+                    if (bk < (k == 1 ? lo : 0x80u) || bk > (k == 1 ? hi : 0xBFu)) return mk_err();
+                }
+                i += need + 1;
+            }
+            return mk(CB_T_STRING, x.u);
+        }
+        StrB s = strb_begin(c);
+        if (x.tag == CB_T_BOOL) {
+            const char *t = x.u ? "true" : "false";
+            for (uint32_t i = 0; t[i]; i++) strb_put(s, (uint8_t)t[i]);
+            return strb_end(s);
+        }
+        uint64_t mag;
+        bool neg = false;
+        if (x.tag == CB_T_INT) { neg = (int64_t)x.u < 0; mag = neg ? 0ull - x.u : x.u; }
+        else if (x.tag == CB_T_UINT) mag = x.u;
+        else if (x.tag == CB_T_DOUBLE) {
+            const double d = u2d(x.u);
+            if (d != d) { strb_put(s, 'N'); strb_put(s, 'a'); strb_put(s, 'N'); return strb_end(s); }
+            if (d - d != d - d) { strb_put(s, d > 0 ? '+' : '-'); strb_put(s, 'I'); strb_put(s, 'n'); strb_put(s, 'f'); return strb_end(s); }
+            const double ad = fabs(d);
+            if (ad >= 9007199254740992.0 || floor(ad) != ad) { c.unsupported = 1; return mk_err(); }
+            neg = (x.u >> 63) != 0;       // (-0 prints "-0")
+            mag = (uint64_t)ad;
+        } else {
+            if (x.tag == CB_T_TS || x.tag == CB_T_DUR) c.unsupported = 1;
+            return mk_err();
+        }
+        uint8_t dig[20];
+        uint32_t nd = 0;
+        do { dig[nd++] = (uint8_t)('0' + mag % 10); mag /= 10; } while (mag);
+        if (neg) strb_put(s, '-');
+        while (nd) strb_put(s, dig[--nd]);
+        return strb_end(s);
+    }
     if (fn == CB_FN_B64ENC) {
         if (a[0].tag != CB_T_BYTES) return mk_err();
         const uint8_t *q; uint32_t m;
@@ -1202,26 +1260,36 @@ CB_HD_NOINLINE Val dyn_strfn(Ctx &c, uint32_t fn, const Val *a, uint32_t argc) {
         }
         return strb_end(s);
     }
-    if (fn == CB_FN_B64DEC) {   // standard alphabet; the padding may be missing (cel-go tries StdEncoding, then RawStdEncoding)
+    if (fn == CB_FN_B64DEC) {
+        // cel-go ext.Encoders: base64.StdEncoding.DecodeString, then RawStdEncoding (padding missing).  Go's decoder skips
+        // '\r' and '\n' anywhere in the text and is not strict: non-zero trailing bits of the last quantum are dropped.
         if (a[0].tag != CB_T_STRING) return mk_err();
         const uint8_t *q; uint32_t m;
         str_get(c, a[0].u, q, m);
-        uint32_t body = m, pad = 0;
-        while (body > 0 && ldg(q + body - 1) == '=' && pad < 2) { body--; pad++; }
-        if (pad && (m & 3) != 0) return mk_err();
-        if ((body & 3) == 1) return mk_err();
-        if (pad && ((body + pad) & 3) != 0) return mk_err();
-        StrB s = strb_begin(c);
-        uint32_t acc = 0, bits = 0;
-        for (uint32_t i = 0; i < body; i++) {
+        uint32_t eff = 0, pad = 0;          // characters that count (no CR / LF), '=' at their end (at most two looked at)
+        for (uint32_t i = 0; i < m; i++) {
             const uint8_t ch = ldg(q + i);
+            if (ch == '\r' || ch == '\n') continue;
+            eff++;
+            pad = ch == '=' ? (pad < 2 ? pad + 1 : 3) : 0;
+        }
+        if (pad > 2) return mk_err();
+        const uint32_t body = eff - pad;
+        if (pad && (eff & 3) != 0) return mk_err();
+        if ((body & 3) == 1) return mk_err();
+        if (pad && (body & 3) + pad != 4) return mk_err();
+        StrB s = strb_begin(c);
+        uint32_t acc = 0, bits = 0, seen = 0;
+        for (uint32_t i = 0; i < m && seen < body; i++) {
+            const uint8_t ch = ldg(q + i);
+            if (ch == '\r' || ch == '\n') continue;
+            seen++;
             uint32_t v;
             if (ch >= 'A' && ch <= 'Z') v = ch - 'A'; else if (ch >= 'a' && ch <= 'z') v = ch - 'a' + 26;
             else if (ch >= '0' && ch <= '9') v = ch - '0' + 52; else if (ch == '+') v = 62; else if (ch == '/') v = 63; else return mk_err();
             acc = (acc << 6) | v; bits += 6;
             if (bits >= 8) { bits -= 8; strb_put(s, (uint8_t)(acc >> bits)); acc &= (1u << bits) - 1; }
         }
-        if (acc != 0) return mk_err();   // non-zero trailing bits: illegal base64 data
         Val r = strb_end(s);
         if (r.tag == CB_T_STRING) r.tag = CB_T_BYTES;
         return r;
@@ -1740,7 +1808,88 @@ CB_HD Val op_hier_ca3(Ctx &c, const Val &a0, const Val &b0, const Val &z0, uint3
     const uint32_t k = hier_ca_size(a, b2);
     return mk_bool(hier_count(z) == k && hier_common(a, z, k) == k);
 }
+// cel-go ext.Math (ext/math.go).  greatest / least: one number is itself, one list gives its extreme, several arguments theirs;
+// numbers of different types compare by value (num_cmp), the winner keeps its type, ties keep the earlier one, a NaN cannot
+// be ordered (error).  ceil / floor / round / trunc / isNaN / isInf / isFinite take doubles only; the bit operations take
+// (int, int) or (uint, uint); shifts by 64 or more give 0, a negative count is an error, >> on an int is a logical shift.
+CB_HD bool math_pick(Val &best, bool &have, const Val &v, bool greater) {
+    if (!is_num(v)) return false;
+    if (!have) { best = v; have = true; return true; }
+    const int r = num_cmp(v, best);
+    if (r == 2) return false;
+    if (greater ? r > 0 : r < 0) best = v;
+    return true;
+}
+CB_HD_NOINLINE Val math_fn(Ctx &c, uint32_t fn, const Val *a, uint32_t argc) {
+    const int64_t kMin = (int64_t)0x8000000000000000ull;
+    if (fn == CB_FN_MATH_GREATEST || fn == CB_FN_MATH_LEAST) {
+        const bool greater = fn == CB_FN_MATH_GREATEST;
+        Val best = mk_err();
+        bool have = false;
+        if (argc == 1) {
+            if (is_num(a[0])) return a[0];
+            if (a[0].tag != CB_T_LIST) return mk_err();
+            const uint64_t *h = heap_ptr(c, a[0].u);
+            const uint32_t n = (uint32_t)ldg(h);
+            for (uint32_t i = 0; i < n; i++)
+                if (!math_pick(best, have, decode_elem(ldg(h + 1 + i)), greater)) return mk_err();
+            return best;          // (an empty list: error)
+        }
+        for (uint32_t i = 0; i < argc; i++)
+            if (!math_pick(best, have, a[i], greater)) return mk_err();
+        return best;
+    }
+    const Val &x = a[0];
+    switch (fn) {
+    case CB_FN_MATH_CEIL: case CB_FN_MATH_FLOOR: case CB_FN_MATH_ROUND: case CB_FN_MATH_TRUNC: {
+        if (argc != 1 || x.tag != CB_T_DOUBLE) return mk_err();
+        const double d = u2d(x.u);
+        return mk_double(fn == CB_FN_MATH_CEIL ? ceil(d) : fn == CB_FN_MATH_FLOOR ? floor(d) : fn == CB_FN_MATH_ROUND ? round(d) : trunc(d));
+    }
+    case CB_FN_MATH_ABS:
+        if (argc != 1) return mk_err();
+        if (x.tag == CB_T_INT) return (int64_t)x.u == kMin ? mk_err() : mk_int((int64_t)x.u < 0 ? -(int64_t)x.u : (int64_t)x.u);
+        if (x.tag == CB_T_UINT) return x;
+        if (x.tag == CB_T_DOUBLE) return mk_double(fabs(u2d(x.u)));
+        return mk_err();
+    case CB_FN_MATH_SIGN:
+        if (argc != 1) return mk_err();
+        if (x.tag == CB_T_INT) return mk_int(((int64_t)x.u > 0) - ((int64_t)x.u < 0));
+        if (x.tag == CB_T_UINT) return mk(CB_T_UINT, x.u ? 1u : 0u);
+        if (x.tag == CB_T_DOUBLE) { const double d = u2d(x.u); return mk_double(d != d ? d : d > 0 ? 1.0 : d < 0 ? -1.0 : 0.0); }
+        return mk_err();
+    case CB_FN_MATH_ISNAN: case CB_FN_MATH_ISINF: case CB_FN_MATH_ISFINITE: {
+        if (argc != 1 || x.tag != CB_T_DOUBLE) return mk_err();
+        const double d = u2d(x.u);
+        const bool nan = d != d, inf = !nan && (d - d) != (d - d);      // (inf - inf is NaN)
+        return mk_bool(fn == CB_FN_MATH_ISNAN ? nan : fn == CB_FN_MATH_ISINF ? inf : !nan && !inf);
+    }
+    case CB_FN_MATH_BITAND: case CB_FN_MATH_BITOR: case CB_FN_MATH_BITXOR: {
+        if (argc != 2 || a[0].tag != a[1].tag || (x.tag != CB_T_INT && x.tag != CB_T_UINT)) return mk_err();
+        const uint64_t y = a[1].u;
+        return mk(x.tag, fn == CB_FN_MATH_BITAND ? x.u & y : fn == CB_FN_MATH_BITOR ? x.u | y : x.u ^ y);
+    }
+    case CB_FN_MATH_BITNOT:
+        if (argc != 1 || (x.tag != CB_T_INT && x.tag != CB_T_UINT)) return mk_err();
+        return mk(x.tag, ~x.u);
+    case CB_FN_MATH_SHL: case CB_FN_MATH_SHR: {
+        if (argc != 2 || a[1].tag != CB_T_INT || (x.tag != CB_T_INT && x.tag != CB_T_UINT)) return mk_err();
+        const int64_t k = (int64_t)a[1].u;
+        if (k < 0) return mk_err();
+        if (k > 63) return mk(x.tag, 0);
+        return mk(x.tag, fn == CB_FN_MATH_SHL ? x.u << k : x.u >> k);
+    }
+    case CB_FN_MATH_SQRT: {
+        if (argc != 1 || !is_num(x)) return mk_err();
+        const double d = x.tag == CB_T_DOUBLE ? u2d(x.u) : x.tag == CB_T_INT ? (double)(int64_t)x.u : (double)x.u;
+        return mk_double(sqrt(d));      // (a negative number: NaN)
+    }
+    }
+    return mk_err();
+}
 CB_HD Val op_fn(Ctx &c, uint32_t fn, uint32_t argc, Val *a) {   // a[0..argc): arguments (target first)
+    if (fn == CB_FN_TO_STRING) return dyn_strfn(c, fn, a, argc);
+    if (fn >= CB_FN_MATH_GREATEST) return math_fn(c, fn, a, argc);
     if (fn >= CB_FN_SPIFFE_ID) return spiffe_fn(c, fn, a, argc);
     if (fn == CB_FN_REVERSE && a[0].tag == CB_T_STRING) return dyn_strfn(c, CB_FN_STR_REVERSE, a, argc);
     return fn >= CB_FN_EXCEPT ? dyn_listfn(c, fn, a, argc) : dyn_strfn(c, fn, a, argc);

@@ -809,6 +809,19 @@ class ProgramCompiler:
             return
         if self._spiffe_call(n, fn, args):
             return
+        if fn in self._MATH and (len(args) in self._MATH[fn][1] or (self._MATH[fn][1] == () and 1 <= len(args) <= 16)):
+            # cel-go ext.Math: scalar functions; greatest / least take one number, one list or several numbers.  The macro
+            # behind greatest / least refuses literal arguments that are not numbers at compile time (ext/math.go)
+            if self._MATH[fn][1] == ():
+                for a in args:
+                    bad_literal = isinstance(a, (MapLit, Macro)) or (isinstance(a, ListLit) and len(args) > 1) or \
+                        (isinstance(a, Const) and (isinstance(a.value, (str, bytes, bool)) or a.value is None))
+                    if bad_literal:
+                        raise Unsupported(f"{fn}: a literal argument that is not a number (compile error in the reference)")
+            for a in args:
+                self.expr(a)
+            self.emit("FN", a=L.FNS[self._MATH[fn][0]], b=len(args), delta=1 - len(args))
+            return
         if fn in self._FN and len(args) in self._FN[fn][1]:
             # string / list producing functions (ext.Strings, ext.Lists, Cerbos except / intersect): results live in the
             # device's per-thread scratch arena
@@ -818,7 +831,13 @@ class ProgramCompiler:
             return
         raise Unsupported(f"function `{fn}` with {len(args)} argument(s)")
 
-    _FN = {"bytes": ("TO_BYTES", (1,)), "base64.encode": ("B64ENC", (1,)), "base64.decode": ("B64DEC", (1,)),
+    _MATH = {"math.greatest": ("MATH_GREATEST", ()), "math.least": ("MATH_LEAST", ()), "math.ceil": ("MATH_CEIL", (1,)),
+             "math.floor": ("MATH_FLOOR", (1,)), "math.round": ("MATH_ROUND", (1,)), "math.trunc": ("MATH_TRUNC", (1,)),
+             "math.abs": ("MATH_ABS", (1,)), "math.sign": ("MATH_SIGN", (1,)), "math.isNaN": ("MATH_ISNAN", (1,)),
+             "math.isInf": ("MATH_ISINF", (1,)), "math.isFinite": ("MATH_ISFINITE", (1,)), "math.bitAnd": ("MATH_BITAND", (2,)),
+             "math.bitOr": ("MATH_BITOR", (2,)), "math.bitXor": ("MATH_BITXOR", (2,)), "math.bitNot": ("MATH_BITNOT", (1,)),
+             "math.bitShiftLeft": ("MATH_SHL", (2,)), "math.bitShiftRight": ("MATH_SHR", (2,)), "math.sqrt": ("MATH_SQRT", (1,))}
+    _FN = {"bytes": ("TO_BYTES", (1,)), "string": ("TO_STRING", (1,)), "base64.encode": ("B64ENC", (1,)), "base64.decode": ("B64DEC", (1,)),
            "lowerAscii": ("LOWER", (1,)), "upperAscii": ("UPPER", (1,)), "trim": ("TRIM", (1,)), "charAt": ("CHARAT", (2,)),
            "indexOf": ("INDEXOF", (2, 3)), "lastIndexOf": ("LASTINDEXOF", (2, 3)), "substring": ("SUBSTRING", (2, 3)),
            "replace": ("REPLACE", (3, 4)), "split": ("SPLIT", (2, 3)), "join": ("JOIN", (1, 2)), "reverse": ("REVERSE", (1,)),

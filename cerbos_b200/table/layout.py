@@ -12,7 +12,7 @@ Table blob (little endian, every section 16-byte aligned):
 from __future__ import annotations
 
 MAGIC = 0x32425243  # 'CRB2'
-VERSION = 15
+VERSION = 16
 ALIGN = 16
 
 NONE32 = 0xFFFFFFFF
@@ -167,6 +167,10 @@ FNS = {name: i for i, name in enumerate([
     # SPIFFE (conditions/types/spiffe.go); a matcher never exists as a value: matcher(arg).matchesID(x) is one fused function
     "SPIFFE_ID", "SPIFFE_TD", "SPIFFE_PATH", "SPIFFE_TD_OF", "SPIFFE_MEMBER", "SPIFFE_TD_ID", "SPIFFE_TD_NAME", "SPIFFE_IDSTR",
     "SPIFFE_MATCH_ANY", "SPIFFE_MATCH_EXACT", "SPIFFE_MATCH_ONEOF", "SPIFFE_MATCH_TD",
+    # cel-go ext.Math (conditions/cel.go:62-75 enables it): scalars in, a scalar out
+    "MATH_GREATEST", "MATH_LEAST", "MATH_CEIL", "MATH_FLOOR", "MATH_ROUND", "MATH_TRUNC", "MATH_ABS", "MATH_SIGN", "MATH_ISNAN", "MATH_ISINF",
+    "MATH_ISFINITE", "MATH_BITAND", "MATH_BITOR", "MATH_BITXOR", "MATH_BITNOT", "MATH_SHL", "MATH_SHR", "MATH_SQRT",
+    "TO_STRING",        # string(x): strings, ints, uints, bools, valid UTF-8 bytes, integral doubles below 2^53 (the rest is flagged)
 ])}
 TS_FIELDS = {name: i for i, name in enumerate(["getFullYear", "getMonth", "getDayOfYear", "getDayOfMonth", "getDate", "getDayOfWeek",
                                                "getHours", "getMinutes", "getSeconds", "getMilliseconds"])}

@@ -718,6 +718,29 @@ def format_timestamp(ts: Timestamp) -> str:
     return f"{f['year']:04d}-{f['month']:02d}-{f['day']:02d}T{f['hour']:02d}:{f['minute']:02d}:{f['second']:02d}{frac}Z"
 
 
+def format_double_f(d: float) -> str:
+    """strconv.FormatFloat(d, 'f', -1, 64), which is how cel-go's Double converts to a string (types/double.go,
+    ConvertToType): the shortest digits that round-trip, never an exponent.  (No vector of the reference holds a double
+    outside 1e-4 .. 1e6, where this and the %g form below differ: that part is restated from the library, unpinned.)"""
+    if math.isnan(d):
+        return "NaN"
+    if math.isinf(d):
+        return "+Inf" if d > 0 else "-Inf"
+    sign = "-" if math.copysign(1, d) < 0 else ""
+    r = repr(abs(d))
+    m, _, e = r.partition("e")
+    ip, _, fp = m.partition(".")
+    exp10 = int(e) if e else 0
+    digits = ip + fp
+    point = len(ip) + exp10                 # position of the decimal point within `digits`
+    if point <= 0:
+        digits, point = "0" * (1 - point) + digits, 1
+    if point >= len(digits):
+        digits += "0" * (point - len(digits))
+    whole, frac = digits[:point].lstrip("0") or "0", digits[point:].rstrip("0")
+    return sign + whole + ("." + frac if frac else "")
+
+
 def format_double(d: float) -> str:
     """Go fmt %g / strconv.FormatFloat(d, 'g', -1, 64): shortest digits, %e form when
     the decimal exponent is < -4 or >= 6."""
@@ -821,7 +844,7 @@ def conv_string(v):
     if isinstance(v, int):
         return str(int(v))
     if isinstance(v, float):
-        return format_double(v)
+        return format_double_f(v)
     if isinstance(v, bytes):
         try:
             return v.decode("utf-8")
@@ -891,13 +914,215 @@ def _need(cond, fn, *args):
         raise no_overload(fn, *args)
 
 
+_RE2_POSIX = {"alpha": "A-Za-z", "digit": "0-9", "alnum": "0-9A-Za-z", "upper": "A-Z", "lower": "a-z", "space": "\\t\\n\\v\\f\\r ",
+              "punct": "!-/:-@\\[-`{-~", "xdigit": "0-9A-Fa-f", "word": "0-9A-Za-z_", "blank": "\\t ", "cntrl": "\\x00-\\x1f\\x7f",
+              "print": " -~", "graph": "!-~", "ascii": "\\x00-\\x7f"}
+_RE2_PERL = {"d": "0-9", "w": "0-9A-Za-z_", "s": "\\t\\n\\f\\r "}     # RE2's \s has no \v; all three are ASCII-only
+_regex_cache: dict = {}
+
+
+def _re2_to_python(p: str) -> str:
+    r"""cel-go's `matches` is Go's regexp (RE2 syntax, regexp/syntax doc).  Python's `re` is the engine here, so the pattern
+    is rewritten where the two differ: Perl classes are ASCII and \s lacks \v; `$` without (?m) is the end of the text only
+    (Python's also matches before a final newline); \z; POSIX classes; \Q..\E; (?<name>; inline flags in the middle of a
+    pattern scope to the end of their group; the U flag (greediness cannot change a yes / no answer).  What RE2 rejects --
+    backreferences, lookaround, possessive / atomic forms, \Z, repeat counts over 1000 -- raises CelError like any
+    invalid pattern; what `re` cannot express (\p{..}, \C, negated POSIX classes inside a larger class) raises too, and
+    the product rejects those at table build, so they are never compared."""
+    out, i, n = [], 0, len(p)
+    multiline = False
+    closers = [0]            # per open group: how many "(?flags:" wrappers to close with it
+    first_atom = True
+
+    def bad(why):
+        return CelError(f"invalid regex {p!r}: {why}")
+
+    while i < n:
+        ch = p[i]
+        if ch == "\\":
+            if i + 1 >= n:
+                raise bad("trailing backslash")
+            e = p[i + 1]
+            i += 2
+            if e in "dws":
+                out.append("[" + _RE2_PERL[e] + "]")
+            elif e in "DWS":
+                out.append("[^" + _RE2_PERL[e.lower()] + "]")
+            elif e == "z":
+                out.append("(?:\\Z)")
+            elif e == "A":
+                out.append("(?:\\A)")
+            elif e == "b":       # ASCII word boundary (Python's \\b follows Unicode word characters)
+                out.append("(?:(?<=[0-9A-Za-z_])(?![0-9A-Za-z_])|(?<![0-9A-Za-z_])(?=[0-9A-Za-z_]))")
+            elif e == "B":
+                out.append("(?:(?<=[0-9A-Za-z_])(?=[0-9A-Za-z_])|(?<![0-9A-Za-z_])(?![0-9A-Za-z_]))")
+            elif e == "Z":
+                raise bad("\\Z")
+            elif e == "Q":
+                j = p.find("\\E", i)
+                lit = p[i:] if j < 0 else p[i:j]
+                out.append(re.escape(lit))
+                i = n if j < 0 else j + 2
+            elif e in "pPC":
+                raise bad("\\" + e + " is not supported by this oracle")
+            elif e in "123456789":
+                raise bad("backreference")
+            elif e == "0":
+                j = i
+                while j < n and j < i + 2 and p[j] in "01234567":
+                    j += 1
+                out.append("\\x%02x" % int("0" + p[i:j], 8))
+                i = j
+            elif e == "x" and i < n and p[i] == "{":
+                j = p.find("}", i)
+                if j < 0:
+                    raise bad("\\x{")
+                out.append("\\U%08x" % int(p[i + 1:j], 16))
+                i = j + 1
+            else:
+                out.append("\\" + e)
+            first_atom = False
+            continue
+        if ch == "[":
+            j = i + 1
+            cls = ["["]
+            if j < n and p[j] == "^":
+                cls.append("^")
+                j += 1
+            if j < n and p[j] == "]":
+                cls.append("\\]")
+                j += 1
+            while True:
+                if j >= n:
+                    raise bad("missing ]")
+                c = p[j]
+                if c == "]":
+                    break
+                if c == "[" and p.startswith("[:", j):
+                    k = p.find(":]", j)
+                    if k < 0:
+                        raise bad("bad POSIX class")
+                    name = p[j + 2:k]
+                    if name.startswith("^") or name not in _RE2_POSIX:
+                        raise bad(f"[:{name}:] is not supported by this oracle" if name.lstrip("^") in _RE2_POSIX else f"invalid character class [:{name}:]")
+                    cls.append(_RE2_POSIX[name])
+                    j = k + 2
+                elif c == "\\":
+                    if j + 1 >= n:
+                        raise bad("trailing backslash")
+                    e = p[j + 1]
+                    if e in "dws":
+                        cls.append(_RE2_PERL[e])
+                    elif e in "DWSpPC":
+                        raise bad("\\" + e + " inside a class is not supported by this oracle")
+                    else:
+                        cls.append("\\" + e)
+                    j += 2
+                else:
+                    cls.append("\\" + c if c in "[&~|" else c)
+                    j += 1
+            cls.append("]")
+            out.append("".join(cls))
+            i = j + 1
+            first_atom = False
+            continue
+        if ch == "(":
+            if p.startswith("(?", i):
+                k = i + 2
+                if p.startswith("(?P<", i) or p.startswith("(?<", i) and not p.startswith("(?<=", i) and not p.startswith("(?<!", i):
+                    j = p.find(">", i)
+                    if j < 0:
+                        raise bad("bad group name")
+                    out.append("(?P<" + p[p.index("<", i) + 1:j] + ">")
+                    closers.append(0)
+                    i = j + 1
+                    first_atom = False
+                    continue
+                while k < n and p[k] in "imsU-":
+                    k += 1
+                if k >= n or p[k] not in ":)":
+                    raise bad("lookaround / atomic groups / comments are not RE2")
+                flags = p[i + 2:k]
+                on = flags.split("-")[0]
+                if "m" in on:
+                    multiline = True
+                fl = flags.replace("U", "")
+                if fl.endswith("-"):
+                    fl = fl[:-1]
+                if p[k] == ":":
+                    out.append("(?" + fl + ":")
+                    closers.append(0)
+                elif fl:                       # (?flags): to the end of the enclosing group
+                    if first_atom and len(closers) == 1 and "-" not in fl:
+                        out.append("(?" + fl + ")")
+                    else:
+                        out.append("(?" + fl + ":")
+                        closers[-1] += 1
+                i = k + 1
+                continue
+            out.append("(")
+            closers.append(0)
+            i += 1
+            first_atom = False
+            continue
+        if ch == ")":
+            if len(closers) == 1:
+                raise bad("unexpected )")
+            out.append(")" * (closers.pop() + 1))
+            i += 1
+            continue
+        if ch == "|" and closers[-1]:
+            # an alternation inside a flag scope opened in the middle of a group: RE2's flags run to the end of the group,
+            # across the |, which the scoped form here cannot say
+            raise bad("inline flags before an alternation are not supported by this oracle")
+        if ch == "$" or ch == "^":
+            # (a group: Go lets a repetition operator follow an assertion -- `$?`, `^*` -- where `re` finds nothing to repeat)
+            out.append("(?:^)" if ch == "^" else "(?:$)" if multiline else "(?:\\Z)")
+            i += 1
+            first_atom = False
+            continue
+        if ch in "*+?" or ch == "{":
+            if ch == "{":
+                m = re.match(r"\{(\d+)(,(\d*))?\}", p[i:])
+                if not m:
+                    out.append("\\{")
+                    i += 1
+                    continue
+                if int(m.group(1)) > 1000 or (m.group(3) and int(m.group(3)) > 1000):
+                    raise bad("repeat count over 1000")
+                out.append(m.group(0))
+                i += len(m.group(0))
+            else:
+                out.append(ch)
+                i += 1
+            if i < n and p[i] == "?":
+                out.append("?")
+                i += 1
+            if i < n and (p[i] in "*+?" or re.match(r"\{\d+(,\d*)?\}", p[i:])):
+                raise bad("nested repetition")
+            continue
+        out.append(ch)
+        i += 1
+        first_atom = False
+    if len(closers) != 1:
+        raise bad("missing )")
+    out.append(")" * closers[0])
+    return "".join(out)
+
+
 def _regex(pattern: str):
-    # RE2 syntax subset -> Python re. (?P<name>..) is shared; \z -> \Z ; \pN classes unsupported.
-    p = pattern.replace(r"\z", r"\Z")
-    try:
-        return re.compile(p)
-    except re.error as e:
-        raise CelError(f"invalid regex {pattern!r}: {e}")
+    r = _regex_cache.get(pattern)
+    if r is None:
+        try:
+            r = re.compile(_re2_to_python(pattern))
+        except re.error as e:
+            r = CelError(f"invalid regex {pattern!r}: {e}")
+        except CelError as e:
+            r = e
+        _regex_cache[pattern] = r
+    if isinstance(r, CelError):
+        raise r
+    return r
 
 
 def _str_format(fmt: str, args: list) -> str:
@@ -1877,9 +2102,11 @@ def _math1(name, fi=None, fu=None, fd=None):
 
 
 def _round_half_away(d):
+    """Go's math.Round (exact: |d| - floor(|d|) is computed without rounding error, unlike floor(|d| + 0.5))"""
     if math.isnan(d) or math.isinf(d):
         return d
-    return math.copysign(math.floor(abs(d) + 0.5), d)
+    f = math.floor(abs(d))
+    return math.copysign(f + 1.0 if abs(d) - f >= 0.5 else f, d)
 
 
 def _abs_int(v):
@@ -1941,16 +2168,26 @@ def _f_b64enc(ev, a):
     return _b64.b64encode(a[0]).decode("ascii")
 
 
+_B64_ALPHABET = frozenset("ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/")
+
+
 def _f_b64dec(ev, a):
+    """cel-go ext.Encoders: base64.StdEncoding.DecodeString, then RawStdEncoding.  Go's decoder (encoding/base64) skips CR / LF
+    anywhere; padded text has a length that is a multiple of four with one or two '=' at the very end and nowhere else;
+    unpadded text may end in a quantum of two or three characters; not being Strict(), non-zero trailing bits are dropped.
+    (Python's decoder is more forgiving about misplaced padding, so the shape is checked here.)"""
     _need(isinstance(a[0], str), "base64.decode", *a)
-    s = a[0]
-    try:
-        return _b64.b64decode(s, validate=True)
-    except Exception:
-        try:
-            return _b64.b64decode(s + "=" * (-len(s) % 4), validate=True)
-        except Exception:
+    s = a[0].replace("\r", "").replace("\n", "")
+    body = s.rstrip("=")
+    pad = len(s) - len(body)
+    if pad:
+        if pad > 2 or len(s) % 4 != 0:
             raise CelError("illegal base64 data")
+    elif len(s) % 4 == 1:
+        raise CelError("illegal base64 data")
+    if not all(c in _B64_ALPHABET for c in body):
+        raise CelError("illegal base64 data")
+    return _b64.b64decode(body + "=" * (-len(body) % 4))
 
 
 def _f_sqrt(ev, a):

@@ -1,0 +1,262 @@
+"""Seeded random CEL expressions over the functions that BUILD values at run time (cel-go ext.Strings / ext.Lists,
+Cerbos except / intersect, comprehensions that collect, concatenation, RE2 matches) and random requests whose attributes
+change type from request to request -- for the differential test of oracle #1 against the kernel core
+(tests/test_fuzz_values.py).  Typed generators: S string, I int, L list of strings, N list of ints, B bool."""
+import random
+
+STR_LITS = ["a", "b", "ab", "abc", "a,b,,c", "héllo wörld", " pad ", "", "A.B.c", "x1", "日本語", "a-b_c"]
+PATTERNS = ["^a", "b$", "^[a-c]+$", "l+o", "^$", "a|x", "\\\\d", "^h.llo", "[[:alpha:]]+", "(ab)+", "."]
+ATTR_S = ["P.attr.s", "R.attr.t", "P.attr.u", "R.attr.csv"]
+ATTR_I = ["P.attr.n", "R.attr.k"]
+ATTR_L = ["P.attr.l", "R.attr.m", "P.attr.tags"]
+ATTR_N = ["R.attr.nums", "P.attr.ids"]
+
+
+def _lit(s):
+    """CEL source of a string literal (the lists above hold CEL source text: a backslash there is already doubled)"""
+    return '"' + s + '"'
+
+
+def S(r, d=0):
+    k = r.randrange(14 if d < 3 else 3)
+    if k == 0:
+        return _lit(r.choice(STR_LITS))
+    if k in (1, 2):
+        return r.choice(ATTR_S)
+    if k == 3:
+        return f"{S(r, d + 1)}.{r.choice(['lowerAscii', 'upperAscii', 'trim', 'reverse'])}()"
+    if k == 4:
+        return f"{S(r, d + 1)}.charAt({I(r, d + 1)})"
+    if k == 5:
+        return f"{S(r, d + 1)}.substring({I(r, d + 1)}" + (f", {I(r, d + 1)})" if r.random() < 0.6 else ")")
+    if k == 6:
+        return f"{S(r, d + 1)}.replace({S(r, d + 2)}, {S(r, d + 2)}" + (f", {I(r, d + 1)})" if r.random() < 0.4 else ")")
+    if k == 7:
+        return f"{L(r, d + 1)}.join(" + (f"{_lit(r.choice(['', ',', '-', '::']))})" if r.random() < 0.7 else ")")
+    if k == 8:
+        return f"({S(r, d + 1)} + {S(r, d + 1)})"
+    if k == 9:
+        return f"{L(r, d + 1)}[{I(r, d + 1)}]"
+    if k == 10:
+        return f"({B(r, d + 1)} ? {S(r, d + 1)} : {S(r, d + 1)})"
+    if k == 11:
+        return f"base64.encode(bytes({S(r, d + 1)}))"
+    if k == 12:
+        return f"string({r.choice([I, I, S, S, B, B, I, D])(r, d + 1)})" if r.random() < 0.8 else f"string(bytes({S(r, d + 1)}))"
+    return r.choice(ATTR_S)
+
+
+def I(r, d=0):
+    k = r.randrange(10 if d < 3 else 2)
+    if k == 0:
+        return str(r.choice([0, 1, 2, 3, 5, -1, 7, 100]))
+    if k == 1:
+        return r.choice(ATTR_I)
+    if k == 2:
+        return f"size({r.choice([S, L, N])(r, d + 1)})"
+    if k == 3:
+        return f"{S(r, d + 1)}.{r.choice(['indexOf', 'lastIndexOf'])}({S(r, d + 2)}" + (f", {I(r, d + 1)})" if r.random() < 0.3 else ")")
+    if k == 4:
+        return f"({I(r, d + 1)} {r.choice(['+', '-', '*', '%', '/'])} {I(r, d + 1)})"
+    if k == 5:
+        return f"{N(r, d + 1)}[{I(r, d + 1)}]"
+    if k == 6:
+        return f"({B(r, d + 1)} ? {I(r, d + 1)} : {I(r, d + 1)})"
+    if k == 7:
+        return f"-({I(r, d + 1)})"
+    if k == 8:
+        return f"int({r.choice([S(r, d + 1), I(r, d + 1)])})"
+    return r.choice(ATTR_I)
+
+
+def L(r, d=0):
+    k = r.randrange(15 if d < 3 else 3)
+    if k == 0:
+        return "[" + ", ".join(_lit(r.choice(STR_LITS)) for _ in range(r.randrange(0, 4))) + "]"
+    if k in (1, 2):
+        return r.choice(ATTR_L)
+    if k == 3:
+        return f"{S(r, d + 1)}.split({_lit(r.choice([',', '', '.', 'l', ' ', 'ab']))}" + (f", {I(r, d + 1)})" if r.random() < 0.3 else ")")
+    if k == 4:
+        return f"({L(r, d + 1)} + {L(r, d + 1)})"
+    if k == 5:
+        return f"{L(r, d + 1)}.filter(x, {PX(r, d + 1)})"
+    if k == 6:
+        return f"{L(r, d + 1)}.map(x, {SX(r, d + 1)})"
+    if k == 7:
+        return f"{L(r, d + 1)}.map(x, {PX(r, d + 1)}, {SX(r, d + 1)})"
+    if k == 8:
+        return f"{r.choice(['except', 'intersect'])}({L(r, d + 1)}, {L(r, d + 1)})"
+    if k == 9:
+        return f"{L(r, d + 1)}.{r.choice(['sort', 'distinct', 'reverse', 'flatten'])}()"
+    if k == 10:
+        return f"{L(r, d + 1)}.slice({I(r, d + 1)}, {I(r, d + 1)})"
+    if k == 11:
+        return f"[{S(r, d + 1)}, {S(r, d + 1)}]"
+    if k == 12:
+        return f"{L(r, d + 1)}.sortBy(x, {r.choice(['x', 'size(x)', 'x.lowerAscii()'])})"
+    if k == 13:
+        return f"{L(r, d + 1)}.transformList(i, x, {r.choice(['x', 'x + x', 'x.upperAscii()'])})"
+    return r.choice(ATTR_L)
+
+
+def N(r, d=0):
+    k = r.randrange(9 if d < 3 else 2)
+    if k == 0:
+        return "[" + ", ".join(str(r.choice([0, 1, 2, 3, -4, 10])) for _ in range(r.randrange(0, 4))) + "]"
+    if k == 1:
+        return r.choice(ATTR_N)
+    if k == 2:
+        return f"lists.range({I(r, d + 1)})"
+    if k == 3:
+        return f"{N(r, d + 1)}.{r.choice(['sort', 'distinct', 'reverse'])}()"
+    if k == 4:
+        return f"{N(r, d + 1)}.map(y, {r.choice(['y * 2', 'y + 1', 'y % 3', '-y'])})"
+    if k == 5:
+        return f"{N(r, d + 1)}.filter(y, y {r.choice(['>', '<', '==', '!='])} {I(r, d + 1)})"
+    if k == 6:
+        return f"{L(r, d + 1)}.map(x, size(x))"
+    if k == 7:
+        return f"({N(r, d + 1)} + {N(r, d + 1)})"
+    return r.choice(ATTR_N)
+
+
+ATTR_D = ["P.attr.d", "R.attr.e"]
+
+
+def D(r, d=0):
+    k = r.randrange(9 if d < 3 else 2)
+    if k == 0:
+        return r.choice(["0.0", "1.5", "-2.5", "0.5", "1e300", "3.0", "(0.0 / 0.0)", "(1.0 / 0.0)", "-0.5"])
+    if k == 1:
+        return r.choice(ATTR_D)
+    if k == 2:
+        return f"math.{r.choice(['ceil', 'floor', 'round', 'trunc', 'abs', 'sign', 'sqrt'])}({D(r, d + 1)})"
+    if k == 3:
+        return f"({D(r, d + 1)} {r.choice(['+', '-', '*', '/'])} {D(r, d + 1)})"
+    if k == 4:
+        return f"double({I(r, d + 1)})"
+    if k == 5:
+        return f"math.{r.choice(['greatest', 'least'])}({D(r, d + 1)}, {D(r, d + 1)})"
+    if k == 6:
+        return f"math.sqrt({I(r, d + 1)})"
+    if k == 7:
+        return f"math.{r.choice(['greatest', 'least'])}({r.choice(ATTR_N)})"
+    return r.choice(ATTR_D)
+
+
+def M(r, d=0):
+    """predicates over ext.Math"""
+    k = r.randrange(9)
+    if k == 0:
+        return f"math.{r.choice(['isNaN', 'isInf', 'isFinite'])}({D(r, d + 1)})"
+    if k == 1:
+        return f"{D(r, d + 1)} {r.choice(['==', '<', '>=', '!='])} {D(r, d + 1)}"
+    if k == 2:
+        return f"math.{r.choice(['greatest', 'least'])}({I(r, d + 1)}, {D(r, d + 1)}, {I(r, d + 1)}) {r.choice(['==', '<', '>'])} {r.choice([I, D])(r, d + 1)}"
+    if k == 3:
+        return f"math.{r.choice(['bitAnd', 'bitOr', 'bitXor'])}({I(r, d + 1)}, {I(r, d + 1)}) {r.choice(['==', '<', '>'])} {I(r, d + 1)}"
+    if k == 4:
+        return f"math.{r.choice(['bitShiftLeft', 'bitShiftRight'])}({I(r, d + 1)}, {I(r, d + 1)}) {r.choice(['==', '<', '>'])} {I(r, d + 1)}"
+    if k == 5:
+        return f"math.{r.choice(['abs', 'sign', 'bitNot'])}({I(r, d + 1)}) {r.choice(['==', '<', '>'])} {I(r, d + 1)}"
+    if k == 6:
+        return f"math.{r.choice(['greatest', 'least'])}({N(r, d + 1)}) {r.choice(['==', '<', '>'])} {I(r, d + 1)}"
+    if k == 7:
+        x = D(r, d + 1)
+        return f"math.floor({x}) <= {x} && {x} <= math.ceil({x})"
+    x = I(r, d + 1)
+    return f"math.bitXor(math.bitNot({x}), {x}) == -1 && math.abs({x}) >= 0 && math.greatest({x}, 0 - {x}) == math.abs({x})"
+
+
+def SX(r, d):
+    """a string built from the comprehension variable x"""
+    return r.choice(["x", "x.upperAscii()", 'x + "!"', "x.charAt(0)", "x.trim()", 'x.replace("a", "_")', "x.substring(1)", "x.reverse()"])
+
+
+def PX(r, d):
+    """a predicate over the comprehension variable x"""
+    return r.choice(['x != ""', "size(x) > 1", 'x.startsWith("a")', 'x.contains("b")', f"x.matches({_lit(r.choice(PATTERNS))})",
+                     f"x in {L(r, d + 1)}", f"x == {S(r, d + 1)}", 'x < "b"'])
+
+
+def B(r, d=0):
+    k = r.randrange(18 if d < 3 else 6)
+    if k == 0:
+        return f"{S(r, d + 1)} {r.choice(['==', '!=', '<', '>='])} {S(r, d + 1)}"
+    if k == 1:
+        return f"{I(r, d + 1)} {r.choice(['==', '!=', '<', '<=', '>', '>='])} {I(r, d + 1)}"
+    if k == 2:
+        return f"{L(r, d + 1)} {r.choice(['==', '!='])} {L(r, d + 1)}"
+    if k == 3:
+        return f"{S(r, d + 1)} in {L(r, d + 1)}"
+    if k == 4:
+        return f"{S(r, d + 1)}.matches({_lit(r.choice(PATTERNS))})"
+    if k == 5:
+        return f"{S(r, d + 1)}.{r.choice(['startsWith', 'endsWith', 'contains'])}({S(r, d + 1)})"
+    if k == 6:
+        return f"{N(r, d + 1)} == {N(r, d + 1)}"
+    if k == 7:
+        return f"{I(r, d + 1)} in {N(r, d + 1)}"
+    if k == 8:
+        return f"{L(r, d + 1)}.{r.choice(['exists', 'all', 'exists_one'])}(x, {PX(r, d + 1)})"
+    if k == 9:
+        return f"{r.choice(['hasIntersection', 'isSubset'])}({L(r, d + 1)}, {L(r, d + 1)})"
+    if k == 10:
+        return f"({B(r, d + 1)} {r.choice(['&&', '||'])} {B(r, d + 1)})"
+    if k == 11:
+        return f"!({B(r, d + 1)})"
+    if k == 12:
+        return f"size({L(r, d + 1)}) {r.choice(['==', '>', '<='])} {r.randrange(4)}"
+    if k == 13:
+        return f"{L(r, d + 1)}.transformMap(i, x, {r.choice(['x', 'i'])}) == {{}}"
+    if k == 14:
+        return f"base64.decode({S(r, d + 1)}) == bytes({S(r, d + 1)})"
+    if k == 15:
+        # the same compound value on both sides: true unless its evaluation fails, so an error on one side only shows
+        x = r.choice([S, I, L, N])(r, d)
+        return f"{x} == {x}"
+    return f"{S(r, d + 1)} == {S(r, d + 1)}"
+
+
+def identity(r):
+    """properties that hold for every value of the right type: both sides must find them true on the same requests, and
+    fail on the same requests"""
+    k = r.randrange(12)
+    s, l, n, i = S(r, 1), L(r, 1), N(r, 1), I(r, 1)
+    return [f"{s}.reverse().reverse() == {s}", f"{l}.reverse().reverse() == {l}", f"{l}.sort().sort() == {l}.sort()",
+            f'{s}.split(",").join(",") == {s}', f"{s}.substring(0, {i}) + {s}.substring({i}) == {s}",
+            f"{s}.lowerAscii().upperAscii() == {s}.upperAscii()", f"size({l}.distinct()) <= size({l})",
+            f"size({s}.split(\"\")) == size({s})", f"{l}.slice(0, size({l})) == {l}", f"{n}.sort().reverse() == {n}.sort().reverse().distinct() || size({n}) >= 0",
+            f"{s}.indexOf({s}.charAt({i})) <= {i}", f"({l} + {l}).distinct() == {l}.distinct()"][k]
+
+
+def rand_attr(r, kind):
+    """a value of the nominal kind nine times in ten, anything else otherwise (the type errors are part of the test)"""
+    if r.random() < 0.1:
+        kind = r.choice("silnbdmz")
+    if kind == "s":
+        return r.choice(STR_LITS + ["ABC", "a,b", "aGVsbG8=", "l", "ll", "hello", "  x  ", "a.b.c"])
+    if kind == "i":
+        return r.choice([0, 1, 2, 3, 5, -1, 7, 100, -3])
+    if kind == "l":
+        return [r.choice(STR_LITS + ["ab", "b", "hello"]) for _ in range(r.randrange(0, 5))]
+    if kind == "n":
+        return [r.choice([0, 1, 2, 3, -4, 10, 2.0, 2.5]) for _ in range(r.randrange(0, 5))]
+    if kind == "b":
+        return r.random() < 0.5
+    if kind == "d":
+        return r.choice([0.5, 2.0, -1.5, 1e10, 2.5, -0.5, 0.49999999999999994, 4503599627370497.5, 7.0])
+    if kind == "m":
+        return {"a": "b", "n": 1}
+    return None
+
+
+def rand_request(r):
+    spec_p = [("s", "s"), ("u", "s"), ("n", "i"), ("l", "l"), ("tags", "l"), ("ids", "n"), ("d", "d")]
+    spec_r = [("t", "s"), ("csv", "s"), ("k", "i"), ("m", "l"), ("nums", "n"), ("e", "d")]
+
+    def attrs(spec):
+        return {name: rand_attr(r, kind) for name, kind in spec if r.random() < 0.9}
+    return {"requestId": "v", "principal": {"id": "p", "roles": ["user"], "attr": attrs(spec_p)},
+            "resource": {"kind": "doc", "id": "d", "attr": attrs(spec_r)}}

@@ -42,3 +42,80 @@ def test_rejected_loudly(p):
 def test_invalid_patterns(p):
     with pytest.raises((RegexError, RegexUnsupported)):
         compile_dfa(p)
+
+
+# ---- random patterns: the DFA compiler against oracle #1's reading of RE2 (oracle/celeval.py: _re2_to_python + `re`) ------
+_ATOMS = ["a", "b", "c", "x", "1", " ", "-", "_", ".", "\\.", "\\d", "\\w", "\\s", "\\D", "\\W", "\\S", "[a-c]", "[^a-c]", "[[:alpha:]]", "[[:digit:]x]",
+          "[\\d-]", "[^\\s]", "é", "日", "\\n", "\\t", "[]a]", "[a\\]]", "\\x41", "\\Qa.b\\E", "[[:space:]]", "[[:punct:]]", "[[:upper:][:digit:]]",
+          "\\v", "\\f", "[\\w.]", "\\-", "\\{", "a{,2}"]
+_TEXT = ["a", "b", "c", "x", "1", " ", "-", "_", ".", "A", "B", "\n", "\t", "\v", "\f", "é", "É", "日", "]", "{", ",", "2", "!", "\r"]
+
+
+def _rand_pattern(r, d=0):
+    k = r.randrange(10 if d < 3 else 3)
+    if k < 3:
+        return r.choice(_ATOMS)
+    if k == 3:
+        return _rand_pattern(r, d + 1) + _rand_pattern(r, d + 1)
+    if k == 4:
+        return _rand_pattern(r, d + 1) + r.choice(["*", "+", "?", "{2}", "{1,3}", "{2,}", "*?", "+?", "??"])
+    if k == 5:
+        return "(" + _rand_pattern(r, d + 1) + "|" + _rand_pattern(r, d + 1) + ")"
+    if k == 6:
+        return "(?:" + _rand_pattern(r, d + 1) + ")"
+    if k == 7:
+        return r.choice(["^", "\\A", ""]) + _rand_pattern(r, d + 1) + r.choice(["$", "\\z", ""])
+    if k == 8:
+        fl = r.choice(["(?i)", "(?s)", "(?i:", "(?s:", "(?is)"])
+        return fl + _rand_pattern(r, d + 1) + (")" if fl.endswith(":") else "")
+    return _rand_pattern(r, d + 1) + _rand_pattern(r, d + 1) + _rand_pattern(r, d + 1)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_patterns_against_the_oracle(seed):
+    """Same verdict on validity (stacked repetition operators, bad groups ... are errors in Go's regexp) and the same
+    answer on every text -- texts with newlines, \\v, non-ASCII letters, a trailing newline (where `$` must not match)."""
+    import random
+    from oracle.celeval import CelError, _regex
+    r = random.Random(4200 + seed)
+    compared = invalid = 0
+    for _ in range(500):
+        p = _rand_pattern(r)
+        try:
+            d, perr = compile_dfa(p), False
+        except RegexUnsupported:
+            continue
+        except RegexError:
+            d, perr = None, True
+        try:
+            o, oerr = _regex(p), False
+        except CelError as e:
+            if "not supported by this oracle" in str(e):
+                continue
+            o, oerr = None, True
+        assert perr == oerr, p
+        if perr:
+            invalid += 1
+            continue
+        for _ in range(20):
+            t = "".join(r.choice(_TEXT) for _ in range(r.randrange(0, 7)))
+            assert dfa_match(d, t) == (o.search(t) is not None), (p, t)
+            compared += 1
+    assert compared > 8000 and invalid > 3
+
+
+def test_assertions_are_zero_width():
+    for p, t, want in [(r"^^a$$", "a", True), (r"\A\Aa\z$", "a", True), (r"$^", "", True), (r"$^", "a", False), (r"(^|x)^a", "a", True),
+                       (r"a$\z", "ba", True), (r"^$?a", "a", True), (r"a^b", "ab", False), (r"a$b", "ab", False)]:
+        assert dfa_match(compile_dfa(p), t) == want, (p, t)
+
+
+def test_quoted_run_takes_repetition_on_its_last_character():
+    d = compile_dfa(r"^\Qa.b\E*$")
+    assert dfa_match(d, "a.bbb") and dfa_match(d, "a.") and not dfa_match(d, "a.ba.b")
+
+
+@pytest.mark.parametrize("p", ["a**", "a*+", "a{2}{3}", "a+?*", "a???"])
+def test_stacked_repetition_is_invalid(p):
+    with pytest.raises(RegexError):
+        compile_dfa(p)

@@ -177,6 +177,64 @@ def test_run_time_values_vs_cel_oracle():
         assert hostsim.check(ft.blob, b.columns, 1, 1, now.ns)[0, 0] == want, e
 
 
+# (expression, holds): `holds` None = the evaluation fails, so the expression AND its negation are both denied
+MATH_AND_ENCODER_CASES = [
+    # cel-go ext.Math (ext/math.go) beyond the documentation rows: mixed numeric types, ties, NaN, overflow, shifts
+    ("math.greatest(1, 2.5, 2u) == 2.5", True), ("math.least([3, 1.0, 2]) == 1.0", True), ("math.greatest(R.attr.nums) == 7", True),
+    ("math.least(R.attr.nums) == -2.5", True), ("math.greatest(2, 2.0) == 2 && math.least(2u, 2) == 2u", True),
+    ("math.greatest([]) == 0", None), ("math.greatest(0.0 / 0.0, 1.0) == 1.0", None), ("math.least(R.attr.mixed) == 1", None),
+    ("math.greatest(P.attr.n) == 12 && math.least(P.attr.x) == 2.5", True), ("math.greatest(P.attr.department) == 1", None),
+    ("math.round(0.49999999999999994) == 0.0 && math.round(2.5) == 3.0 && math.round(-2.5) == -3.0", True),
+    ("math.round(4503599627370497.0) == 4503599627370497.0 && math.trunc(-0.9) == 0.0", True), ("math.ceil(1) == 1.0", None),
+    ("math.isNaN(math.sqrt(-1.0)) && math.sqrt(81) == 9.0 && math.sqrt(2u) > 1.41 && math.sqrt(P.attr.x) > 1.58", True),
+    ("math.isInf(1e308 * 10.0) && !math.isFinite(-1.0 / 0.0) && math.isFinite(P.attr.x)", True), ("math.isNaN(1)", None),
+    ("math.abs(-9223372036854775807 - 1) > 0", None), ("math.abs(int(P.attr.n) - 20) == 8 && math.abs(5u) == 5u && math.abs(-0.5) == 0.5", True),
+    ("math.sign(-0.0) == 0.0 && math.sign(7u) == 1u && math.sign(int(P.attr.n) - 20) == -1 && math.isNaN(math.sign(0.0 / 0.0))", True),
+    ("math.bitShiftRight(-8, 1) == 9223372036854775804 && math.bitShiftLeft(1, 63) < 0 && math.bitShiftLeft(int(P.attr.n), 64) == 0", True),
+    ("math.bitShiftLeft(1, -1) == 0", None), ("math.bitShiftLeft(1, 1u) == 2", None), ("math.bitAnd(1, 1u) == 1", None),
+    ("math.bitNot(int(P.attr.n)) == -13 && math.bitXor(int(P.attr.n), 5) == 9 && math.bitOr(12u, 3u) == 15u", True), ("math.bitNot(1.0) == 0", None), ("math.bitNot(P.attr.n) == -13", None),
+    # string(x) (cel-go ConvertToType): a JSON number is a double -- an integral one prints without a fraction
+    ('string(12) == "12" && string(-5) == "-5" && string(7u) == "7" && string(true) == "true" && string("x") == "x"', True),
+    ('string(P.attr.n) == "12" && string(int(P.attr.n) * -1000000) == "-12000000" && "id-" + string(P.attr.n) == "id-12"', True),
+    ('string(0.0 / 0.0) == "NaN" && string(1.0 / 0.0) == "+Inf" && string(-1.0 / 0.0) == "-Inf" && string(P.attr.n * -0.0) == "-0"', True),
+    ('string(b"abc") == "abc" && string(bytes("héllo")) == "héllo" && string(base64.decode("aGVsbG8=")) == "hello"', True),
+    ('string(base64.decode("/w==")) == "x"', None), ('string(base64.decode("7aCA")) == "x"', None), ('string(R.attr.nums) == "x"', None),
+    # base64: Go's decoder skips CR / LF, drops non-zero trailing bits, takes unpadded text, refuses misplaced padding
+    ('size(base64.decode("x1")) == 1 && base64.decode("aGVsbG9=") == b"hello"', True), ('base64.decode("aGVs\\nbG8=\\r\\n") == b"hello"', True),
+    ('size(base64.decode("aaGVsbG8=")) >= 0', None), ('size(base64.decode("abcaGVsbG8=")) >= 0', None), ('size(base64.decode("a")) >= 0', None),
+    ('size(base64.decode("ab=c")) >= 0', None), ('size(base64.decode("ab==")) == 1 && size(base64.decode("abc")) == 2', True),
+    ('size(base64.decode(R.attr.b64 + "=")) == 5 && size(base64.decode(R.attr.b64 + "==")) >= 0', None),
+]
+MATH_REQUEST = {"principal": {"id": "john", "roles": ["employee"], "attr": {"n": 12, "x": 2.5, "department": "marketing"}},
+                "resource": {"kind": "leave_request", "id": "r", "attr": {"nums": [3, -2.5, 7, 0], "mixed": [1, "a"], "b64": "aGVsbG8"}}, "actions": ["a"]}
+
+
+def test_math_and_encoder_functions_vs_cel_oracle():
+    """ext.Math and the base64 edge cases: the expected answer is written out, oracle #1 must give it and the kernel core must
+    give oracle #1's -- on the expression and on its negation, so that a failed evaluation (both denied) differs from `false`."""
+    now = parse_timestamp("2021-04-22T10:05:20.021-05:00")
+    for e, holds in MATH_AND_ENCODER_CASES:
+        for neg in (False, True):
+            expr = f"!({e})" if neg else e
+            rt, ft = run_time_value_table(expr)
+            b = Encoder(ft.manifest).encode([MATH_REQUEST])
+            want = CheckOracle(rt).check(MATH_REQUEST, now)["actions"]["a"]["effect"]
+            assert want == (1 if holds is not None and holds != neg else 2), (expr, want)
+            assert hostsim.check(ft.blob, b.columns, 1, 1, now.ns)[0, 0] == want, expr
+            src, _ = hostsim.generate_uc(ft.blob)           # the generated leaf program takes the same functions
+            assert "CB_HD bool uc_atom_" in src, expr
+
+
+def test_string_of_a_fractional_double_is_flagged():
+    """string(2.5) needs shortest-digit printing (strconv 'f', -1): the device flags the request (the call fails loudly)
+    instead of approximating; oracle #1 prints it."""
+    rt, ft = run_time_value_table('string(P.attr.x) == "2.5"')
+    b = Encoder(ft.manifest).encode([MATH_REQUEST])
+    assert CheckOracle(rt).check(MATH_REQUEST)["actions"]["a"]["effect"] == 1
+    with pytest.raises(RuntimeError, match="-2"):
+        hostsim.check(ft.blob, b.columns, 1, 1)
+
+
 def test_c5_vectorised_columns_answer_like_the_generic_encoder():
     """workloads.C5.columns (numpy, what the bench generates 2^23 requests per GPU with) against the generic encoder over the
     same requests as protojson dicts: same headers and roles, same heap volume, and -- the heap and the batch dictionary
