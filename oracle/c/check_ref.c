@@ -920,7 +920,22 @@ static val_t run_program(ectx_t *c, const cb_instr *code, int64_t now) {
         case CB_OP_IN_CONST_SLOT: { int s; val_t a = load_slot(c, in.b, &s); cb_const k = c->t->consts[in.c]; st[sp++] = do_in(c, mk(k.tag, k.bits), a); break; }
         case CB_OP_IN_IP_RANGE: st[sp - 1] = st[sp - 1].tag == CB_T_ERR ? mk_err() : do_in_ip_range(c, st[sp - 1], c->t->theap + in.c); break;
         case CB_OP_HIER_REL: sp--; st[sp - 1] = do_hier_rel(c, in.a, st[sp - 1], in.b, st[sp], in.c); break;
-        case CB_OP_TS_GET: st[sp - 1] = do_ts_get(in.a, st[sp - 1], in.b, (int32_t)in.c); break;
+        case CB_OP_TS_GET: {
+            int32_t off_s = (int32_t)in.c;
+            if (in.b == 2 && st[sp - 1].tag == CB_T_TS) {
+                /* an IANA zone name: the UTC offset in force at this instant, from the zone's transition records in THEAP
+                 * (table/bytecode.py: iana_zone_words -- [n, first second, end second, n x (from second, offset)]);
+                 * scanned linearly here.  Instants the records do not cover are flagged. */
+                const uint64_t *z = c->t->theap + in.c;
+                const int64_t sec = fdiv((int64_t)st[sp - 1].u, 1000000000ll);
+                if (sec < (int64_t)z[1] || sec >= (int64_t)z[2]) { c->unsupported = 1; st[sp - 1] = mk_err(); break; }
+                off_s = (int32_t)(int64_t)z[4];
+                for (uint64_t k = 0; k < z[0]; k++)
+                    if ((int64_t)z[3 + 2 * k] <= sec) off_s = (int32_t)(int64_t)z[3 + 2 * k + 1];
+            }
+            st[sp - 1] = do_ts_get(in.a, st[sp - 1], in.b, off_s);
+            break;
+        }
         case CB_OP_IN_SPLIT: {   /* x in s.split(sep): ext strings split + the `in` operator over the token list */
             static __thread hier_t toks;
             sp--;

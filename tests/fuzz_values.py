@@ -260,3 +260,121 @@ def rand_request(r):
         return {name: rand_attr(r, kind) for name, kind in spec if r.random() < 0.9}
     return {"requestId": "v", "principal": {"id": "p", "roles": ["user"], "attr": attrs(spec_p)},
             "resource": {"kind": "doc", "id": "d", "attr": attrs(spec_r)}}
+
+
+# ---- timestamps and durations: texts that travel in request attributes (well formed, nearly well formed, malformed) ----------
+ZONES = ["UTC", "+05:30", "-08:00", "America/New_York", "Europe/London", "Asia/Kolkata", "Australia/Lord_Howe", "+00:00", "-00:30", "Mars/Olympus"]
+TS_FIELDS = ["getFullYear", "getMonth", "getDayOfYear", "getDayOfMonth", "getDate", "getDayOfWeek", "getHours", "getMinutes", "getSeconds", "getMilliseconds"]
+
+
+def rand_ts_text(r):
+    y = r.choice([1970, 1999, 2000, 2021, 2024, 2038, 2100, 2200, 1900, 1800, 1700, 1677, 1678, 2262, 2263, 1, 9999, 0])
+    mo, dd = r.randrange(1, 13), r.randrange(1, 29)
+    if r.random() < 0.15:
+        mo, dd = r.choice([(2, 29), (2, 30), (4, 31), (12, 31), (13, 1), (0, 10), (1, 0), (6, 30)])
+    h, mi, s = r.randrange(0, 24), r.randrange(0, 60), r.randrange(0, 60)
+    if r.random() < 0.08:
+        h, mi, s = r.choice([(24, 0, 0), (23, 60, 0), (23, 59, 60), (0, 0, 0)])
+    frac = r.choice(["", "", ".5", ".021", ".123456789", ".000000001", ".1234567891", ".", ",5", ".999999999"])
+    zone = r.choice(["Z", "Z", "+00:00", "-05:00", "+05:30", "+14:00", "-23:59", "+24:00", "z", "", "+0530", "+05", " UTC", "-00:00"])
+    sep = r.choice(["T"] * 8 + ["t", " "])
+    txt = f"{y:04d}-{mo:02d}-{dd:02d}{sep}{h:02d}:{mi:02d}:{s:02d}{frac}{zone}"
+    k = r.random()
+    if k < 0.05:
+        txt = txt.replace("-", "/", 1)
+    elif k < 0.08:
+        txt = txt[: r.randrange(0, len(txt))]
+    elif k < 0.1:
+        txt = " " + txt
+    elif k < 0.12:
+        txt = f"{y}-{mo}-{dd}T{h}:{mi}:{s}Z"
+    return txt
+
+
+def rand_dur_text(r):
+    if r.random() < 0.25:
+        return r.choice(["", "5", "1d", "+3s", ".5s", "1e3s", "-", "1h ", " 1h", "1H", "h", "1.s", "1..5s", "0", "+0", "-0", "1us", "1µs", "1μs",
+                         "9223372036s", "9223372037s", "2562047h47m16.854775807s", "2562047h47m16.854775808s", "-2562047h47m16.854775808s",
+                         "0.000000001s", "0.0000000001s", "1.5h30m", "1ns1ns", "3ms2s", "100000000000000000000h"])
+    parts = []
+    for _ in range(r.randrange(1, 4)):
+        n = r.choice([str(r.randrange(0, 100)), f"{r.randrange(0, 100)}.{r.randrange(0, 1000)}", str(r.randrange(0, 100000))])
+        parts.append(n + r.choice(["h", "m", "s", "ms", "us", "ns"]))
+    return r.choice(["", "", "-", "+"]) + "".join(parts)
+
+
+def TS(r, d=0):
+    k = r.randrange(7 if d < 2 else 2)
+    if k == 0:
+        return f'timestamp("{rand_ts_text(r)}")'
+    if k in (1, 2):
+        return f"timestamp({r.choice(['R.attr.ts', 'P.attr.ts2'])})"
+    if k == 3:
+        return f"({TS(r, d + 1)} {r.choice(['+', '-'])} {DU(r, d + 1)})"
+    if k == 4:
+        return "now()"
+    if k == 5:
+        return f"timestamp({r.choice(['R.attr.secs', '0', '1700000000', '-1', '253402300800', 'int(R.attr.secs)'])})"
+    return f"timestamp({r.choice(['R.attr.ts', 'P.attr.ts2'])})"
+
+
+def DU(r, d=0):
+    k = r.randrange(7 if d < 2 else 2)
+    if k == 0:
+        return f'duration("{rand_dur_text(r)}")'
+    if k == 1:
+        return f"duration({r.choice(['R.attr.dur', 'P.attr.dur2'])})"
+    if k == 2:
+        return f"({TS(r, d + 1)} - {TS(r, d + 1)})"
+    if k == 3:
+        return f"({DU(r, d + 1)} {r.choice(['+', '-'])} {DU(r, d + 1)})"
+    if k == 4:
+        return f"timeSince({TS(r, d + 1)})"
+    if k == 5:
+        return f"duration({r.choice(['R.attr.secs', '5', 'int(R.attr.secs)'])})"
+    return f"duration({r.choice(['R.attr.dur', 'P.attr.dur2'])})"
+
+
+def TB(r):
+    k = r.randrange(8)
+    if k == 0:
+        return f"{TS(r)} {r.choice(['<', '<=', '>', '>=', '==', '!='])} {TS(r)}"
+    if k == 1:
+        return f"{DU(r)} {r.choice(['<', '<=', '>', '>=', '==', '!='])} {DU(r)}"
+    if k == 2:
+        tz = r.choice(ZONES)
+        return f"{TS(r)}.{r.choice(TS_FIELDS)}({'' if r.random() < 0.4 else chr(34) + tz + chr(34)}) {r.choice(['==', '<', '>='])} {r.randrange(0, 32)}"
+    if k == 3:
+        return f"{DU(r)}.{r.choice(['getHours', 'getMinutes', 'getSeconds', 'getMilliseconds'])}() {r.choice(['==', '<', '>='])} {r.choice([0, 1, 59, 60, 3600, -1, 90])}"
+    if k == 4:
+        x = TS(r, 1)
+        return f"({x} + duration(\"1h\")) - {x} == duration(\"60m\")"
+    if k == 5:
+        x = TS(r, 1)
+        return f"{x}.getDayOfWeek() >= 0 && {x}.getDayOfYear() >= {x}.getDayOfMonth() && {x}.getDate() == {x}.getDayOfMonth() + 1"
+    if k == 6:
+        x = DU(r, 1)
+        return f"{x}.getMinutes() == {x}.getSeconds() / 60 && {x}.getHours() == {x}.getMinutes() / 60"
+    return f"int({TS(r)}) {r.choice(['==', '<', '>='])} {r.choice(['0', '1700000000', 'int(R.attr.secs)'])}"
+
+
+def rand_time_request(r):
+    def ts_or_other():
+        k = r.random()
+        return rand_ts_text(r) if k < 0.9 else r.choice([5, None, True, ["x"], "yesterday"])
+
+    def dur_or_other():
+        k = r.random()
+        return rand_dur_text(r) if k < 0.9 else r.choice([5, None, "soon", 1.5])
+    pa, ra = {}, {}
+    if r.random() < 0.95:
+        ra["ts"] = ts_or_other()
+    if r.random() < 0.95:
+        pa["ts2"] = ts_or_other()
+    if r.random() < 0.95:
+        ra["dur"] = dur_or_other()
+    if r.random() < 0.95:
+        pa["dur2"] = dur_or_other()
+    if r.random() < 0.9:
+        ra["secs"] = r.choice([0, 1, 1700000000, -1, 86400, 4102444800, 1.5, 253402300799, 253402300800, -62135596800, -62135596801, 9.3e9, "5"])
+    return {"requestId": "t", "principal": {"id": "p", "roles": ["user"], "attr": pa}, "resource": {"kind": "doc", "id": "d", "attr": ra}}

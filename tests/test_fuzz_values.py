@@ -64,3 +64,57 @@ def test_run_time_values_random(seed):
     mism, flagged, total, allows = run_seed(seed)
     assert not mism, mism[:3]
     assert total >= 200 and flagged <= 20 and allows >= 10     # (an expression or its negation is ALLOWed whenever the evaluation succeeds)
+
+
+def run_time_seed(seed, n_expr=8, n_req=40):
+    """timestamps / durations: oracle #1, oracle #2 (it ports all of this) and the kernel core"""
+    from oracle import cref
+    from oracle.celeval import parse_timestamp
+    now = parse_timestamp("2024-03-10T06:59:59.5Z")      # half a second before the US spring-forward hour
+    r = random.Random(81000 + seed)
+    es = []
+    while len(es) < n_expr:
+        e = FV.TB(r)
+        try:
+            _table([e])
+            es.append(e)
+        except Exception:  # noqa: BLE001
+            pass
+    es = es + [f"!({e})" for e in es]
+    rt, ft = _table(es)
+    orc = CheckOracle(rt)
+    enc = Encoder(ft.manifest)
+    mism, flagged, total, allows = [], 0, 0, 0
+    for _ in range(n_req):
+        inp = dict(FV.rand_time_request(r), actions=[f"a{i}" for i in range(len(es))])
+        want = orc.check(inp, now)["actions"]
+        b = enc.encode([inp])
+        outs = []
+        for fn in (hostsim.check, cref.check):
+            try:
+                outs.append(fn(ft.blob, b.columns, 1, b.max_actions, now.ns))
+            except RuntimeError as x:
+                if "-2" not in str(x):
+                    raise
+                outs.append(None)
+        if outs[0] is None or outs[1] is None:
+            # a value outside the device's exact range (a timestamp beyond 1678..2262 in nanoseconds ...): the call fails
+            # loudly.  The kernel core flags a little more than oracle #2 (which carries wider intermediates); never less.
+            if outs[0] is not None:
+                mism.append(("oracle #2 flags what the kernel core answers", inp))
+            flagged += 1
+            continue
+        for i, e in enumerate(es):
+            total += 1
+            w = want[f"a{i}"]["effect"]
+            allows += w == 1
+            if outs[0][0, i] != w or outs[1][0, i] != w:
+                mism.append((e, inp["principal"]["attr"], inp["resource"]["attr"], int(outs[0][0, i]), int(outs[1][0, i]), w))
+    return mism, flagged, total, allows
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_time_values_random(seed):
+    mism, flagged, total, allows = run_time_seed(seed)
+    assert not mism, mism[:3]
+    assert total >= 100 and allows >= 5
