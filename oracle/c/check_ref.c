@@ -232,10 +232,13 @@ static int list_equal(ectx_t *c, val_t a, val_t b, int depth) {
 static int map_find(ectx_t *c, val_t m, val_t key, val_t *out) {
     const uint64_t *p = heap_ptr(c, m.u);
     uint64_t n = p[0];
-    if (key.tag != CB_T_STRING) return 0;   /* JSON maps: string keys only */
+    /* keys are scalars: strings (JSON maps), ints / uints / bools (map literals); a number finds a numerically equal key of
+     * another numeric type (cel-go maps look a key up across int / uint / double) */
+    if (key.tag != CB_T_STRING && key.tag != CB_T_BOOL && !is_num(key)) return 0;
     for (uint64_t i = 0; i < n; i++) {
         val_t k = decode_v64(p[1 + i], 0);
-        if (k.tag == CB_T_STRING && k.u == key.u) { if (out) *out = decode_v64(p[1 + n + i], 0); return 1; }
+        int same = (is_num(k) && is_num(key)) ? num_cmp(k, key) == 0 : (k.tag == key.tag && k.u == key.u);
+        if (same) { if (out) *out = decode_v64(p[1 + n + i], 0); return 1; }
     }
     return 0;
 }

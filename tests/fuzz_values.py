@@ -378,3 +378,96 @@ def rand_time_request(r):
     if r.random() < 0.9:
         ra["secs"] = r.choice([0, 1, 1700000000, -1, 86400, 4102444800, 1.5, 253402300799, 253402300800, -62135596800, -62135596801, 9.3e9, "5"])
     return {"requestId": "t", "principal": {"id": "p", "roles": ["user"], "attr": pa}, "resource": {"kind": "doc", "id": "d", "attr": ra}}
+
+
+# ---- core semantics: heterogeneous equality, cross-type ordering, conversions and their range errors, arithmetic overflow,
+# ---- maps, has(), index errors, error absorption of && / || -- over attributes whose type changes from request to request
+CORE_ATTRS = ["P.attr.a", "R.attr.b", "P.attr.c", "R.attr.m.k", 'R.attr.m["k2"]', "P.attr.lst[0]", "P.attr.lst[2]", "R.attr.m", "P.attr.lst", "R.attr.nested.x.y"]
+CORE_LITS = ["1", "1u", "1.0", '"1"', "true", "null", "[1, 2.0]", '{"a": 1}', "0", "-1", "2", "9223372036854775807", "-9223372036854775807",
+             "18446744073709551615u", "1e19", "-1e19", "0.5", '""', '"a"', "[]", "{}", "9007199254740993", "2.0", "3u", '["a", "b"]', "false", 'b"a"']
+
+
+def CV(r, d=0):
+    k = r.randrange(12 if d < 3 else 3)
+    if k == 0:
+        return r.choice(CORE_LITS)
+    if k in (1, 2):
+        return r.choice(CORE_ATTRS)
+    if k == 3:
+        return f"{r.choice(['int', 'uint', 'int', 'uint', 'dyn', 'bytes', 'int', 'uint', 'dyn', 'double', 'string'])}({CV(r, d + 1)})"
+    if k == 4:
+        return f"({CV(r, d + 1)} {r.choice(['+', '-', '*', '/', '%'])} {CV(r, d + 1)})"
+    if k == 5:
+        return f"-({CV(r, d + 1)})"
+    if k == 6:
+        return f"size({CV(r, d + 1)})"
+    if k == 7:
+        return f"({CB(r, d + 1)} ? {CV(r, d + 1)} : {CV(r, d + 1)})"
+    if k == 8:
+        return f"{r.choice(['R.attr.m', 'P.attr.lst', 'R.attr.nested.x'])}[{CV(r, d + 1)}]"
+    if k == 9:
+        return f"[{CV(r, d + 1)}, {CV(r, d + 1)}]"
+    if k == 10:
+        return f"{{{r.choice(['1', '\"a\"', 'true', '2u', 'P.attr.c'])}: {CV(r, d + 1)}}}"
+    return r.choice(CORE_ATTRS)
+
+
+def CB(r, d=0):
+    k = r.randrange(13 if d < 3 else 5)
+    if k in (0, 1):
+        return f"{CV(r, d + 1)} {r.choice(['==', '!='])} {CV(r, d + 1)}"
+    if k == 2:
+        return f"{CV(r, d + 1)} {r.choice(['<', '<=', '>', '>='])} {CV(r, d + 1)}"
+    if k == 3:
+        return f"{CV(r, d + 1)} in {CV(r, d + 1)}"
+    if k == 4:
+        return f"has({r.choice(['R.attr.m.k', 'R.attr.m.zz', 'P.attr.a', 'R.attr.q', 'R.attr.nested.x.y', 'R.attr.nested.x.q', 'P.attr.lst', 'R.attr.b.c'])})"
+    if k == 5:
+        return f"({CB(r, d + 1)} {r.choice(['&&', '||'])} {CB(r, d + 1)})"
+    if k == 6:
+        return f"!({CB(r, d + 1)})"
+    if k == 7:
+        return f"R.attr.m.{r.choice(['exists', 'all', 'exists_one'])}(k, {r.choice(['k == \"k\"', 'R.attr.m[k] == 1', 'k != P.attr.c', 'size(k) > 1'])})"
+    if k == 8:
+        return f"R.attr.m.{r.choice(['exists', 'all'])}(k, v, {r.choice(['v == 1', 'k == \"k2\" && v != null', 'v in P.attr.lst', 'v > 0'])})"
+    if k == 9:
+        return f"P.attr.lst.{r.choice(['exists', 'all', 'exists_one'])}(x, {r.choice(['x == 1', 'x > 0', 'x in R.attr.m', 'x == P.attr.a', 'x != null'])})"
+    if k == 10:
+        x = CV(r, d + 1)
+        return f"{x} == {x}"
+    if k == 11:
+        return f"({CB(r, d + 1)} ? {CB(r, d + 1)} : {CB(r, d + 1)})"
+    return f"{CV(r, d + 1)} == {CV(r, d + 1)}"
+
+
+def rand_core_value(r, depth=0):
+    k = r.randrange(12 if depth < 2 else 8)
+    if k == 0:
+        return r.choice([0, 1, 2, -1, 3, 100, 2.0])
+    if k == 1:
+        return r.choice([0.5, -0.5, 1e19, -1e19, 9007199254740993, 9223372036854775807, 9223372036854775808, -9223372036854775808, 1.5, 4294967296, -0.0, 1e-7])
+    if k in (2, 3):
+        return r.choice(["1", "a", "", "k", "k2", "true", "1.5", "abc", "-1", "9223372036854775808", "0x10", " 1", "1e3", "日本"])
+    if k == 4:
+        return r.random() < 0.5
+    if k == 5:
+        return None
+    if k == 6:
+        return 1
+    if k == 7:
+        return "a"
+    if k in (8, 9):
+        return [rand_core_value(r, depth + 1) for _ in range(r.randrange(0, 4))]
+    return {kk: rand_core_value(r, depth + 1) for kk in r.sample(["k", "k2", "a", "1", "x", "y"], r.randrange(0, 4))}
+
+
+def rand_core_request(r):
+    pa = {n: rand_core_value(r) for n in ("a", "c") if r.random() < 0.9}
+    ra = {n: rand_core_value(r) for n in ("b",) if r.random() < 0.9}
+    if r.random() < 0.9:
+        pa["lst"] = [rand_core_value(r, 1) for _ in range(r.randrange(0, 4))] if r.random() < 0.9 else rand_core_value(r)
+    if r.random() < 0.9:
+        ra["m"] = {kk: rand_core_value(r, 1) for kk in r.sample(["k", "k2", "a", "zz"], r.randrange(0, 4))} if r.random() < 0.9 else rand_core_value(r)
+    if r.random() < 0.8:
+        ra["nested"] = {"x": {"y": rand_core_value(r, 1)}} if r.random() < 0.8 else rand_core_value(r)
+    return {"requestId": "c", "principal": {"id": "p", "roles": ["user"], "attr": pa}, "resource": {"kind": "doc", "id": "d", "attr": ra}}
