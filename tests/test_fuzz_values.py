@@ -74,11 +74,14 @@ def run_time_seed(seed, n_expr=8, n_req=40, gen=None, req=None):
     r = random.Random(81000 + seed)
     gen, req = gen or FV.TB, req or FV.rand_time_request
     es = []
+    probe = dict(req(random.Random(seed)), actions=["a0"])
     while len(es) < n_expr:
         e = gen(r)
         try:
-            _table([e])
-            es.append(e)
+            _, ft1 = _table([e])
+            b1 = Encoder(ft1.manifest).encode([probe])
+            hostsim.check(ft1.blob, b1.columns, 1, 1, now.ns)      # (an expression that flags whatever the request holds --
+            es.append(e)                                            # string(0.5) -- would void the whole seed: drawn again)
         except Exception:  # noqa: BLE001
             pass
     es = es + [f"!({e})" for e in es]
