@@ -809,6 +809,8 @@ CB_HD bool digits(const uint8_t *p, int n, int *out) {
     *out = v;
     return true;
 }
+// timestamp(string): Go's time.Parse(time.RFC3339, s) as cel-go calls it -- 'T' and 'Z' in upper case only, a fraction after '.' or
+// ',' of any length (nine digits kept), offsets up to 24:60 -- then cel-go's range check on the instant.
 CB_HD_NOINLINE Val parse_ts(Ctx &c, const Val &s) {
     const uint8_t *p;
     uint32_t n;
@@ -817,7 +819,7 @@ CB_HD_NOINLINE Val parse_ts(Ctx &c, const Val &s) {
     if (n < 20) return mk_err();
     uint8_t tch = ldg(p + 10);
     if (!digits(p, 4, &y) || ldg(p + 4) != '-' || !digits(p + 5, 2, &mo) || ldg(p + 7) != '-' || !digits(p + 8, 2, &d) ||
-        (tch != 'T' && tch != 't') || !digits(p + 11, 2, &h) || ldg(p + 13) != ':' || !digits(p + 14, 2, &mi) ||
+        tch != 'T' || !digits(p + 11, 2, &h) || ldg(p + 13) != ':' || !digits(p + 14, 2, &mi) ||
         ldg(p + 16) != ':' || !digits(p + 17, 2, &se))
         return mk_err();
     uint32_t i = 19;
@@ -839,18 +841,20 @@ CB_HD_NOINLINE Val parse_ts(Ctx &c, const Val &s) {
     if (i >= n) return mk_err();
     int64_t off = 0;
     ch = ldg(p + i);
-    if (ch == 'Z' || ch == 'z') {
+    if (ch == 'Z') {
         if (i + 1 != n) return mk_err();
     } else if (ch == '+' || ch == '-') {
-        int oh, om;
-        if (i + 6 != n || !digits(p + i + 1, 2, &oh) || ldg(p + i + 3) != ':' || !digits(p + i + 4, 2, &om) || oh > 23 || om > 59)
+        int oh, om;     // (Go's range test is `>`: "some people do write offsets of 24 hours or 60 minutes")
+        if (i + 6 != n || !digits(p + i + 1, 2, &oh) || ldg(p + i + 3) != ':' || !digits(p + i + 4, 2, &om) || oh > 24 || om > 60)
             return mk_err();
         off = (int64_t)(oh * 3600 + om * 60) * (ch == '+' ? 1 : -1);
     } else return mk_err();
     bool leap = (y % 4 == 0 && (y % 100 != 0 || y % 400 == 0));
     int dim = (mo == 2) ? (leap ? 29 : 28) : ((mo == 4 || mo == 6 || mo == 9 || mo == 11) ? 30 : 31);
-    if (y < 1 || mo < 1 || mo > 12 || d < 1 || d > dim || h > 23 || mi > 59 || se > 59) return mk_err();
+    if (mo < 1 || mo > 12 || d < 1 || d > dim || h > 23 || mi > 59 || se > 59) return mk_err();
     int64_t secs = days_from_civil(y, mo, d) * 86400 + h * 3600 + mi * 60 + se - off;
+    // cel-go: the INSTANT must lie in 0001-01-01T00:00:00Z .. 9999-12-31T23:59:59Z (year 0000 with a negative offset can)
+    if (secs < -62135596800ll || secs > 253402300799ll) return mk_err();
     int64_t total;
     if (mul_ovf(secs, 1000000000ll, &total) || add_ovf(total, ns, &total)) {
         c.unsupported = 1;  // valid CEL timestamp outside the int64-nanosecond device range

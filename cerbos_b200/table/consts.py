@@ -12,7 +12,7 @@ INT64_MIN = -(1 << 63)
 INT64_MAX = (1 << 63) - 1
 
 _RFC3339 = re.compile(
-    r"^(\d{4})-(\d{2})-(\d{2})[Tt](\d{2}):(\d{2}):(\d{2})(?:[.,](\d{1,9})\d*)?([Zz]|[+-]\d{2}:\d{2})$")
+    r"\A([0-9]{4})-([0-9]{2})-([0-9]{2})T([0-9]{2}):([0-9]{2}):([0-9]{2})(?:[.,]([0-9]{1,9})[0-9]*)?(Z|[+-][0-9]{2}:[0-9]{2})\Z")
 
 
 def days_from_civil(y: int, m: int, d: int) -> int:
@@ -33,16 +33,18 @@ def parse_timestamp_ns(s: str) -> int:
     ns = int((frac + "000000000")[:9]) if frac else 0
     leap = y % 4 == 0 and (y % 100 != 0 or y % 400 == 0)
     dim = [31, 29 if leap else 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31]
-    if not (1 <= mo <= 12 and 1 <= d <= dim[mo - 1] and h < 24 and mi < 60 and sec < 60 and y >= 1):
+    if not (1 <= mo <= 12 and 1 <= d <= dim[mo - 1] and h < 24 and mi < 60 and sec < 60):
         raise ValueError(f"invalid timestamp {s!r}")
     tz = m.group(8)
     off = 0
-    if tz not in ("Z", "z"):
+    if tz != "Z":       # Go's time.Parse(time.RFC3339): 'T' / 'Z' literally; the offset's range test is `>` (24:60 passes)
         oh, om = int(tz[1:3]), int(tz[4:6])
-        if oh > 23 or om > 59:
+        if oh > 24 or om > 60:
             raise ValueError(f"invalid timestamp {s!r}")
         off = (oh * 3600 + om * 60) * (1 if tz[0] == "+" else -1)
     secs = days_from_civil(y, mo, d) * 86400 + h * 3600 + mi * 60 + sec - off
+    if secs < -62135596800 or secs > 253402300799:     # cel-go: the instant within 0001-01-01 .. 9999-12-31
+        raise ValueError(f"timestamp {s!r} out of range")
     total = secs * 1_000_000_000 + ns
     if total < INT64_MIN or total > INT64_MAX:
         from .bytecode import Unsupported

@@ -613,7 +613,7 @@ static val_t parse_ts(ectx_t *c, val_t s) {
     str_get(c, s.u, &p, &n);
     int y, mo, d, h, mi, se;
     if (n < 20) return mk_err();
-    if (!dig(p, 4, &y) || p[4] != '-' || !dig(p + 5, 2, &mo) || p[7] != '-' || !dig(p + 8, 2, &d) || (p[10] != 'T' && p[10] != 't') ||
+    if (!dig(p, 4, &y) || p[4] != '-' || !dig(p + 5, 2, &mo) || p[7] != '-' || !dig(p + 8, 2, &d) || p[10] != 'T' ||
         !dig(p + 11, 2, &h) || p[13] != ':' || !dig(p + 14, 2, &mi) || p[16] != ':' || !dig(p + 17, 2, &se)) return mk_err();
     uint32_t i = 19;
     int64_t ns = 0;
@@ -627,16 +627,17 @@ static val_t parse_ts(ectx_t *c, val_t s) {
     }
     if (i >= n) return mk_err();
     int64_t off = 0;
-    if (p[i] == 'Z' || p[i] == 'z') { if (i + 1 != n) return mk_err(); }
+    if (p[i] == 'Z') { if (i + 1 != n) return mk_err(); }   /* Go's time.Parse: 'T' and 'Z' literally */
     else if (p[i] == '+' || p[i] == '-') {
         int oh, om;
-        if (i + 6 != n || !dig(p + i + 1, 2, &oh) || p[i + 3] != ':' || !dig(p + i + 4, 2, &om) || oh > 23 || om > 59) return mk_err();
+        if (i + 6 != n || !dig(p + i + 1, 2, &oh) || p[i + 3] != ':' || !dig(p + i + 4, 2, &om) || oh > 24 || om > 60) return mk_err();   /* (Go's range test is `>`) */
         off = (oh * 3600 + om * 60) * (p[i] == '+' ? 1 : -1);
     } else return mk_err();
     int leap = (y % 4 == 0 && (y % 100 != 0 || y % 400 == 0));
     static const int dim[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
-    if (y < 1 || mo < 1 || mo > 12 || d < 1 || d > dim[mo - 1] + (mo == 2 && leap) || h > 23 || mi > 59 || se > 59) return mk_err();
+    if (mo < 1 || mo > 12 || d < 1 || d > dim[mo - 1] + (mo == 2 && leap) || h > 23 || mi > 59 || se > 59) return mk_err();
     int64_t secs = days_from_civil(y, mo, d) * 86400 + h * 3600 + mi * 60 + se - off;
+    if (secs < -62135596800ll || secs > 253402300799ll) return mk_err();   /* cel-go: the instant within 0001..9999 */
     int64_t total;
     if (__builtin_mul_overflow(secs, (int64_t)1000000000, &total) || __builtin_add_overflow(total, ns, &total)) {
         c->unsupported = 1;   /* valid CEL timestamp outside the int64-nanosecond device range */

@@ -557,7 +557,7 @@ def op_neg(a):
 # ----------------------------------------------------------------------------- time helpers
 
 _RFC3339 = re.compile(
-    r"^(\d{4})-(\d{2})-(\d{2})[Tt](\d{2}):(\d{2}):(\d{2})(?:[.,](\d{1,9})\d*)?([Zz]|[+-]\d{2}:\d{2})$")
+    r"\A([0-9]{4})-([0-9]{2})-([0-9]{2})T([0-9]{2}):([0-9]{2}):([0-9]{2})(?:[.,]([0-9]{1,9})[0-9]*)?(Z|[+-][0-9]{2}:[0-9]{2})\Z")
 
 
 def _days_from_civil(y, m, d):
@@ -596,12 +596,16 @@ def parse_timestamp(s: str) -> Timestamp:
         raise CelError(f"invalid timestamp {s!r}")
     tz = m.group(8)
     off = 0
-    if tz not in ("Z", "z"):
+    if tz != "Z":
+        # Go's time.Parse (which cel-go calls with time.RFC3339): 'T' and 'Z' literally, and a range test on the offset that
+        # uses `>` ("some people do write offsets of 24 hours or 60 minutes")
         oh, om = int(tz[1:3]), int(tz[4:6])
-        if oh > 23 or om > 59:
+        if oh > 24 or om > 60:
             raise CelError(f"invalid timestamp {s!r}")
         off = (oh * 3600 + om * 60) * (1 if tz[0] == "+" else -1)
     secs = _days_from_civil(y, mo, d) * 86400 + h * 3600 + mi * 60 + sec - off
+    if secs < -62135596800 or secs > 253402300799:      # cel-go (types/string.go): the instant within 0001-01-01 .. 9999-12-31
+        raise CelError("timestamp overflow")
     return Timestamp(secs * 1_000_000_000 + ns)
 
 

@@ -276,7 +276,7 @@ def rand_ts_text(r):
     if r.random() < 0.08:
         h, mi, s = r.choice([(24, 0, 0), (23, 60, 0), (23, 59, 60), (0, 0, 0)])
     frac = r.choice(["", "", ".5", ".021", ".123456789", ".000000001", ".1234567891", ".", ",5", ".999999999"])
-    zone = r.choice(["Z", "Z", "+00:00", "-05:00", "+05:30", "+14:00", "-23:59", "+24:00", "z", "", "+0530", "+05", " UTC", "-00:00"])
+    zone = r.choice(["Z", "Z", "+00:00", "-05:00", "+05:30", "+14:00", "-23:59", "+24:00", "z", "", "+0530", "+05", " UTC", "-00:00", "+23:60", "-24:60", "+25:00", "+00:61"])
     sep = r.choice(["T"] * 8 + ["t", " "])
     txt = f"{y:04d}-{mo:02d}-{dd:02d}{sep}{h:02d}:{mi:02d}:{s:02d}{frac}{zone}"
     k = r.random()
@@ -288,6 +288,10 @@ def rand_ts_text(r):
         txt = " " + txt
     elif k < 0.12:
         txt = f"{y}-{mo}-{dd}T{h}:{mi}:{s}Z"
+    elif k < 0.14:
+        txt = txt + "\n"
+    elif k < 0.16:
+        txt = txt.replace("0", "\u0660", 1)      # an ARABIC-INDIC DIGIT ZERO is a digit to Python's \\d, not to Go
     return txt
 
 

@@ -467,6 +467,52 @@ def test_timestamp_and_duration_accessors():
         assert (hostsim.check(ft.blob, b.columns, b.n, b.max_actions, NOW.ns, mode=mode) == c_out).all(), mode
 
 
+# timestamp(<text>): Go's time.Parse(time.RFC3339, text), then cel-go's range check on the instant.  "ok" = a timestamp,
+# "err" = a failed evaluation, "flag" = a valid CEL timestamp the device's int64 nanoseconds cannot hold (the call fails loudly)
+TIMESTAMP_TEXTS = [
+    ("2021-04-22T10:05:20Z", "ok"), ("2021-04-22T10:05:20.021-05:00", "ok"), ("2021-04-22T10:05:20,5Z", "ok"), ("2021-04-22T10:05:20.1234567891Z", "ok"),
+    ("2021-04-22T10:05:20+24:00", "ok"), ("2021-04-22T10:05:20+23:60", "ok"), ("2021-04-22T10:05:20-24:60", "ok"), ("2024-02-29T23:59:59Z", "ok"),
+    ("2021-04-22t10:05:20Z", "err"), ("2021-04-22T10:05:20z", "err"), ("2021-04-22T10:05:20+25:00", "err"), ("2021-04-22T10:05:20+00:61", "err"),
+    ("2021-04-22T10:05:20Z\n", "err"), (" 2021-04-22T10:05:20Z", "err"), ("2021-04-22T24:00:00Z", "err"), ("2021-04-22T23:59:60Z", "err"),
+    ("2021-02-29T00:00:00Z", "err"), ("2021-04-22 10:05:20Z", "err"), ("2021-04-22T10:05:20.Z", "err"), ("2021-04-22T10:05:20", "err"),
+    ("2021-04-22T10:05:20+0530", "err"), ("2021-4-22T10:05:20Z", "err"), ("2021-04-22T10:05:2\u0660Z", "err"), ("2021-13-01T00:00:00Z", "err"),
+    # the range is on the INSTANT: year 0000 is fine to parse, and fine as a timestamp once the offset moves it into year 1
+    ("0000-06-01T00:00:00Z", "err"), ("0001-01-01T00:00:00+00:01", "err"), ("9999-12-31T23:59:59-00:01", "err"),
+    ("0000-12-31T05:35:43-23:59", "flag"), ("0001-01-01T00:00:00Z", "flag"), ("9999-12-31T23:59:59Z", "flag"), ("1677-09-21T00:12:43Z", "flag"),
+    ("1677-09-21T00:12:44Z", "ok"), ("2262-04-11T23:47:16Z", "ok"), ("2262-04-11T23:47:17Z", "flag"),
+]
+
+
+def test_timestamp_texts_like_go_time_parse():
+    """The expected outcome of each text is written out from Go's parser and cel-go's range check; oracle #1 must give it,
+    oracle #2 and the kernel core must follow -- for texts in request attributes and for the same texts as literals."""
+    rt, ft = run_time_value_table("timestamp(R.attr.ts) <= timestamp(R.attr.ts)")
+    enc = Encoder(ft.manifest)
+    for text, kind in TIMESTAMP_TEXTS:
+        inp = {"principal": {"id": "p", "roles": ["r"]}, "resource": {"kind": "leave_request", "id": "r", "attr": {"ts": text}}, "actions": ["a"]}
+        want = CheckOracle(rt).check(inp)["actions"]["a"]["effect"]
+        assert want == (2 if kind == "err" else 1), (text, want)
+        b = enc.encode([inp])
+        for fn in (hostsim.check, cref.check):
+            if kind == "flag":
+                with pytest.raises(RuntimeError, match="-2"):
+                    fn(ft.blob, b.columns, 1, 1)
+            else:
+                assert fn(ft.blob, b.columns, 1, 1)[0, 0] == want, (text, fn.__module__)
+        if not text.isascii() or not text.isprintable():
+            continue
+        # the same text as a literal: parsed by the table builder (table/consts.py)
+        lit = f'timestamp("{text}") <= timestamp("{text}")'
+        if kind == "flag":
+            with pytest.raises(Unsupported):
+                run_time_value_table(lit)
+            continue
+        rt2, ft2 = run_time_value_table(lit)
+        b2 = Encoder(ft2.manifest).encode([inp])
+        assert CheckOracle(rt2).check(inp)["actions"]["a"]["effect"] == want, text
+        assert hostsim.check(ft2.blob, b2.columns, 1, 1)[0, 0] == want and cref.check(ft2.blob, b2.columns, 1, 1)[0, 0] == want, text
+
+
 def test_duration_of_request_strings():
     """duration(<attribute string>) parsed on the device (Go time.ParseDuration): random and boundary texts (sign, fractions up
     to 22 digits, every unit incl. both micro signs, int64 limits, malformed input => CEL error => no match)."""
