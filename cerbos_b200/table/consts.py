@@ -54,7 +54,7 @@ def parse_timestamp_ns(s: str) -> int:
 
 _DUR_UNITS = {"ns": 1, "us": 1_000, "µs": 1_000, "μs": 1_000, "ms": 1_000_000,
               "s": 1_000_000_000, "m": 60_000_000_000, "h": 3_600_000_000_000}
-_DUR_PART = re.compile(r"(\d*)(?:\.(\d*))?(ns|us|µs|μs|ms|s|m|h)")
+_DUR_PART = re.compile(r"([0-9]*)(?:\.([0-9]*))?(ns|us|µs|μs|ms|s|m|h)")   # (ASCII digits only: \d would take any Unicode digit)
 
 
 def parse_duration_ns(s: str) -> int:

@@ -611,7 +611,7 @@ def parse_timestamp(s: str) -> Timestamp:
 
 _DUR_UNITS = {"ns": 1, "us": 1_000, "µs": 1_000, "μs": 1_000, "ms": 1_000_000,
               "s": 1_000_000_000, "m": 60_000_000_000, "h": 3_600_000_000_000}
-_DUR_PART = re.compile(r"(\d*)(?:\.(\d*))?(ns|us|µs|μs|ms|s|m|h)")
+_DUR_PART = re.compile(r"([0-9]*)(?:\.([0-9]*))?(ns|us|µs|μs|ms|s|m|h)")   # (ASCII digits only: \d would take any Unicode digit)
 
 
 def parse_duration(s: str) -> Duration:
@@ -794,7 +794,7 @@ def conv_int(v):
             raise CelError("integer overflow")
         return int(v)
     if isinstance(v, str):
-        if not re.fullmatch(r"[+-]?\d+", v):
+        if not re.fullmatch(r"[+-]?[0-9]+", v):
             raise CelError(f"cannot convert {v!r} to int")
         return _chk_int(int(v))
     if isinstance(v, Timestamp):
@@ -816,7 +816,7 @@ def conv_uint(v):
             raise CelError("unsigned integer overflow")
         return _chk_uint(int(v))
     if isinstance(v, str):
-        if not re.fullmatch(r"\+?\d+", v):
+        if not re.fullmatch(r"\+?[0-9]+", v):
             raise CelError(f"cannot convert {v!r} to uint")
         return _chk_uint(int(v))
     raise no_overload("uint", v)

@@ -297,7 +297,7 @@ def rand_ts_text(r):
 
 def rand_dur_text(r):
     if r.random() < 0.25:
-        return r.choice(["", "5", "1d", "+3s", ".5s", "1e3s", "-", "1h ", " 1h", "1H", "h", "1.s", "1..5s", "0", "+0", "-0", "1us", "1µs", "1μs",
+        return r.choice(["\u0661s", "1s\n", "", "5", "1d", "+3s", ".5s", "1e3s", "-", "1h ", " 1h", "1H", "h", "1.s", "1..5s", "0", "+0", "-0", "1us", "1µs", "1μs",
                          "9223372036s", "9223372037s", "2562047h47m16.854775807s", "2562047h47m16.854775808s", "-2562047h47m16.854775808s",
                          "0.000000001s", "0.0000000001s", "1.5h30m", "1ns1ns", "3ms2s", "100000000000000000000h"])
     parts = []
@@ -451,7 +451,8 @@ def rand_core_value(r, depth=0):
     if k == 1:
         return r.choice([0.5, -0.5, 1e19, -1e19, 9007199254740993, 9223372036854775807, 9223372036854775808, -9223372036854775808, 1.5, 4294967296, -0.0, 1e-7])
     if k in (2, 3):
-        return r.choice(["1", "a", "", "k", "k2", "true", "1.5", "abc", "-1", "9223372036854775808", "0x10", " 1", "1e3", "日本"])
+        return r.choice(["1", "a", "", "k", "k2", "true", "1.5", "abc", "-1", "9223372036854775808", "0x10", " 1", "1e3", "日本", "\u0661\u0662", "12\n", "+7", "-0",
+                         "1_000", "18446744073709551615", "18446744073709551616", "-9223372036854775808", "007"])
     if k == 4:
         return r.random() < 0.5
     if k == 5:
