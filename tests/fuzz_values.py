@@ -4,7 +4,8 @@ change type from request to request -- for the differential test of oracle #1 ag
 (tests/test_fuzz_values.py).  Typed generators: S string, I int, L list of strings, N list of ints, B bool."""
 import random
 
-STR_LITS = ["a", "b", "ab", "abc", "a,b,,c", "héllo wörld", " pad ", "", "A.B.c", "x1", "日本語", "a-b_c"]
+STR_LITS = ["a", "b", "ab", "abc", "a,b,,c", "héllo wörld", " pad ", "", "A.B.c", "x1", "日本語", "a-b_c", "\u00a0x\u2003", "\u0085a\u3000", "\ufeffb\u200b",
+            "\x1cq\x1f", "e\u0301a", "\U0001F600b", "aaa", "abab", "ÀB"]
 PATTERNS = ["^a", "b$", "^[a-c]+$", "l+o", "^$", "a|x", "\\\\d", "^h.llo", "[[:alpha:]]+", "(ab)+", "."]
 ATTR_S = ["P.attr.s", "R.attr.t", "P.attr.u", "R.attr.csv"]
 ATTR_I = ["P.attr.n", "R.attr.k"]
