@@ -692,6 +692,10 @@ def measure_host_encode(w, blob, table, K, n=1 << 16):
     # the same with the native narrowing pass in between: cgpu_encode -> cgpu_narrow_build -> cgpu_check_narrow (no Python on the path)
     narrow_path = None
     try:
+        if os.environ.get("CERBOS_B200_BENCH_NATIVE_NARROW") != "1":
+            # opt-in: cgpu_narrow_build's output is verified byte for byte against its specification on the CPU, but this leg
+            # (its page-locked block handed to cgpu_check_narrow) has not run on a device yet -- not in the default bench line
+            raise RuntimeError("skipped (set CERBOS_B200_BENCH_NATIVE_NARROW=1)")
         import numpy as _np
         out = None
         want = None
