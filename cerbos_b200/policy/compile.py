@@ -60,6 +60,24 @@ def compile_expr(src: str) -> Expr:
     return e
 
 
+def _compile_output(out, defs):
+    """policy.proto Output -> (when.rule_activated, when.condition_not_met) (compile.go:416-432, 520-536: the deprecated
+    `expr` is the rule_activated expression unless `when.ruleActivated` is given too)"""
+    out = out or {}
+    when = out.get("when") or {}
+    activated = when.get("ruleActivated") or out.get("expr") or None
+    not_met = when.get("conditionNotMet") or None
+    if out.get("expr"):
+        defs.use_expr(compile_expr(out["expr"]))
+    res = []
+    for src in (activated, not_met):
+        e = compile_expr(src) if src else None
+        if e is not None:
+            defs.use_expr(e)
+        res.append(e)
+    return tuple(res)
+
+
 def compile_match(m: dict) -> Cond:
     """policy.proto Match: {expr} | {all|any|none: {of: [...]}} (policy.proto:295-318)."""
     if m is None:
@@ -323,11 +341,7 @@ class PolicySet:
             name = rule.get("name") or f"rule-{i + 1:03d}"
             cond = compile_condition(rule.get("condition"))
             defs.use_cond(cond)
-            out = rule.get("output") or {}
-            for src in (out.get("expr"), (out.get("when") or {}).get("ruleActivated"),
-                        (out.get("when") or {}).get("conditionNotMet")):
-                if src:
-                    defs.use_expr(compile_expr(src))
+            emit = _compile_output(rule.get("output"), defs)
             roles = []
             for r in rule.get("roles") or []:
                 if r == ANY_ROLE:
@@ -337,14 +351,14 @@ class PolicySet:
                     roles.append(r)
             actions = list(dict.fromkeys(rule.get("actions") or []))
             drs = list(dict.fromkeys(rule.get("derivedRoles") or []))
-            rules.append((name, cond, parse_effect(rule["effect"]), roles, actions, drs))
+            rules.append((name, cond, parse_effect(rule["effect"]), roles, actions, drs, emit))
         params = defs.params(fqn)
 
         rows = []
         if not rules:
             rows.append(Row(origin_fqn=fqn, resource=resource, scope=scope, scope_permissions=sp, version=version,
                             policy_kind=KIND_RESOURCE, params=Params(fqn, [], {}), dr_params=Params("", [], {})))
-        for name, cond, effect, roles, actions, drs in rules:
+        for name, cond, effect, roles, actions, drs, emit in rules:
             rule_fqn = f"{where}#{name}"
             eval_key = f"{fqn}#{rule_fqn}"
             for a in actions:
@@ -352,7 +366,7 @@ class PolicySet:
                     rows.append(self._consent_rewrite(Row(
                         origin_fqn=fqn, resource=resource, role=r, action=a, condition=cond, effect=effect,
                         scope=scope, scope_permissions=sp, version=version, name=name, params=params,
-                        evaluation_key=eval_key, policy_kind=KIND_RESOURCE), sp_raw))
+                        evaluation_key=eval_key, policy_kind=KIND_RESOURCE, emit_activated=emit[0], emit_not_met=emit[1]), sp_raw))
                 for dr in drs:
                     rdr = referenced.get(dr)
                     if rdr is None:
@@ -363,7 +377,8 @@ class PolicySet:
                             origin_fqn=fqn, resource=resource, role=pr, action=a, condition=cond,
                             dr_condition=rdr.condition, effect=effect, scope=scope, scope_permissions=sp,
                             version=version, origin_derived_role=dr, name=name, params=params,
-                            dr_params=rdr.params, evaluation_key=dr_key, policy_kind=KIND_RESOURCE), sp_raw))
+                            dr_params=rdr.params, evaluation_key=dr_key, policy_kind=KIND_RESOURCE,
+                            emit_activated=emit[0], emit_not_met=emit[1]), sp_raw))
         return rows
 
     @staticmethod
@@ -393,12 +408,7 @@ class PolicySet:
                 name = act.get("name") or f"{rule['resource']}_rule-{i + 1:03d}"
                 cond = compile_condition(act.get("condition"))
                 defs.use_cond(cond)
-                out = act.get("output") or {}
-                for src in (out.get("expr"), (out.get("when") or {}).get("ruleActivated"),
-                            (out.get("when") or {}).get("conditionNotMet")):
-                    if src:
-                        defs.use_expr(compile_expr(src))
-                ars.append((act["action"], name, parse_effect(act["effect"]), cond))
+                ars.append((act["action"], name, parse_effect(act["effect"]), cond, _compile_output(act.get("output"), defs)))
             resource_rules[rule["resource"]] = ars  # map keyed by resource: later block overwrites (compile.go:505-540)
         params = defs.params(fqn)
 
@@ -407,13 +417,13 @@ class PolicySet:
             rows.append(Row(origin_fqn=fqn, scope=scope, scope_permissions=sp, version=version, principal=principal,
                             policy_kind=KIND_PRINCIPAL, params=Params(fqn, [], {}), dr_params=Params("", [], {})))
         for resource, ars in resource_rules.items():
-            for action, name, effect, cond in ars:
+            for action, name, effect, cond, emit in ars:
                 rule_fqn = f"{where}#{name}"
                 rows.append(self._consent_rewrite(Row(
                     origin_fqn=fqn, resource=namer.sanitize(resource), role=ANY_ROLE, action=action, condition=cond,
                     effect=effect, scope=scope, scope_permissions=sp, version=version, name=name,
                     principal=principal, params=params, evaluation_key=f"{fqn}#{rule_fqn}",
-                    policy_kind=KIND_PRINCIPAL), sp_raw))
+                    policy_kind=KIND_PRINCIPAL, emit_activated=emit[0], emit_not_met=emit[1]), sp_raw))
         return rows
 
     def _role_rows(self, rt: RuleTable, doc: dict) -> list:

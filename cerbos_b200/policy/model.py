@@ -100,6 +100,10 @@ class Row:
     policy_kind: str = KIND_RESOURCE
     from_role_policy: bool = False
     no_match_for_scope_permissions: bool = False
+    # rule outputs (RuleRow.emit_output.when, runtime.proto:260-267): expressions evaluated to a VALUE when the row is visited
+    # and its condition is / is not satisfied (ruletable.go:1065-1106)
+    emit_activated: Optional["Expr"] = None
+    emit_not_met: Optional["Expr"] = None
 
 
 @dataclass

@@ -182,6 +182,14 @@ def decode_rule_row(buf) -> Row:
             r.version = _s(v)
         elif fno == 11:
             r.origin_derived_role = _s(v)
+        elif fno == 12:      # Output emit_output { When when = 1 { Expr rule_activated = 1; Expr condition_not_met = 2 } }
+            for f1, _, w in fields(v):
+                if f1 == 1:
+                    for f2, _, e in fields(w):
+                        if f2 == 1:
+                            r.emit_activated = decode_expr(e)
+                        elif f2 == 2:
+                            r.emit_not_met = decode_expr(e)
         elif fno == 13:
             r.name = _s(v)
         elif fno == 14:

@@ -44,6 +44,26 @@ def native_to_cel(v):
     raise TypeError(type(v))
 
 
+def to_json_value(v):
+    """cel-go ConvertToNative(*structpb.Value): numbers are doubles, bytes base64, map keys their string form, timestamps
+    RFC 3339, durations seconds with an "s"; types without a JSON form fail."""
+    import base64
+    from .celeval import Duration, Timestamp, UInt, conv_string
+    if v is None or isinstance(v, (bool, str)):
+        return v
+    if isinstance(v, (int, UInt, float)):
+        return float(v)
+    if isinstance(v, bytes):
+        return base64.b64encode(v).decode("ascii")
+    if isinstance(v, list):
+        return [to_json_value(x) for x in v]
+    if isinstance(v, CelMap):
+        return {conv_string(k): to_json_value(x) for k, x in v.items()}
+    if isinstance(v, (Timestamp, Duration)):
+        return conv_string(v)
+    raise CelError(f"no protobuf value for {type(v).__name__}")
+
+
 class CheckOracle:
     def __init__(self, rt: RuleTable, globals_=None, default_version="default", default_scope="",
                  lenient_scope_search=False):
@@ -192,8 +212,22 @@ class CheckOracle:
                                runtime=lambda: build_runtime(ctx["edr"]))
         return Evaluator(act, ctx["now"]).eval(expr.ast)
 
+    def _output_value(self, ctx, expr, constants, variables):
+        """evaluateProtobufValueCELExpr (ruletable.go:1443-1465): the expression's value as a protobuf Value (here: its JSON
+        shape).  A CEL evaluation error gives no value at all (evaluateCELExpr returns nil for an error value, :1477-1482)."""
+        try:
+            v = self._eval(ctx, expr, constants or CelMap(), variables or CelMap())
+        except CelError:
+            return None
+        try:
+            return to_json_value(v)
+        except CelError:
+            return "<failed to convert evaluation to protobuf value>"
+
     def satisfies(self, ctx, cond, constants, variables):
-        """SatisfiesCondition (ruletable.go:1346-1441): error / non-bool -> false."""
+        """SatisfiesCondition (ruletable.go:1346-1441): error / non-bool -> false.  (Its `error` return is for failures that are
+        not CEL evaluation errors: evaluateCELExpr turns a CEL error VALUE into nil (:1477-1482), which evaluateBoolCELExpr reads
+        as false (:1431-1433).  Pinned by golden engine/case_20: any(<missing attribute>, true) is satisfied.)"""
         if cond is None:
             return True
         if cond.op == "expr":
@@ -230,7 +264,7 @@ class CheckOracle:
         p_id, p_roles, kind = p.get("id", ""), list(p.get("roles") or []), r.get("kind", "")
 
         effects = {a: {"effect": EFFECT_DENY, "policy": NO_POLICY_MATCH, "scope": ""} for a in actions}
-        out = {"actions": effects, "effectiveDerivedRoles": []}
+        out = {"actions": effects, "effectiveDerivedRoles": [], "outputs": []}
 
         p_scopes, p_key, _ = self.get_all_scopes(KIND_PRINCIPAL, p_scope, p_id, p_ver)
         r_scopes, r_key, _ = self.get_all_scopes(KIND_RESOURCE, r_scope, kind, r_ver)
@@ -310,6 +344,12 @@ class CheckOracle:
                                 if sat is None:
                                     sat = self.satisfies(ctx, row.condition, constants, variables)
                                     cond_cache[row.evaluation_key] = sat
+                            # rule outputs (ruletable.go:1065-1080, 1096-1106): every visit of a row emits its entry -- the
+                            # same rule visited for two roles emits twice
+                            emit = row.emit_activated if sat else row.emit_not_met
+                            if emit is not None:
+                                out["outputs"].append({"action": action, "src": f"{namer.policy_key_from_fqn(row.origin_fqn)}#{row.name}",
+                                                       "val": self._output_value(ctx, emit, constants, variables)})
                             if sat:
                                 role_effects.add(row.effect)
                                 if row.effect == EFFECT_DENY:

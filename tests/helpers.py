@@ -46,6 +46,19 @@ def check_resources_api_cases():
             yield c["file"], ci, want
 
 
+def check_resources_api_outputs():
+    """The rule outputs the same goldens record (results[i].outputs): yields (file, CheckInput, [OutputEntry, ...])."""
+    for c in load_golden("check_resources_cases.json"):
+        if c.get("wantError") or c["file"] == "cr_case_02.yaml":
+            continue
+        inp = c["input"]
+        for i, entry in enumerate(inp["resources"]):
+            ci = {"requestId": inp.get("requestId", ""), "actions": entry["actions"], "principal": inp["principal"], "resource": entry["resource"]}
+            if c.get("jwtClaims"):
+                ci["auxData"] = {"jwt": c["jwtClaims"]}
+            yield c["file"], ci, c["wantResponse"]["results"][i].get("outputs") or []
+
+
 def verify_suite_cases():
     """Engine answers recorded by the reference's policy-test goldens (internal/test/testdata/verify/cases/*.golden, extracted by
     tests/golden/make_golden.py::verify_cases): grouped by engine configuration.

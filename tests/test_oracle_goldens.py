@@ -57,7 +57,7 @@ def test_engine_goldens_effect_policy_scope():
     """166 decisions of internal/test/testdata/engine*, runner internal/engine/engine_test.go:50-234."""
     orc = CheckOracle(store_rule_table(), globals_={"environment": "test"})
     now = parse_timestamp("2024-01-01T00:00:00Z")
-    n = 0
+    n = n_out = 0
     for cid, lenient, inp, want in engine_decisions():
         got = orc.check(inp, now, lenient=lenient)
         for action, w in want["actions"].items():
@@ -68,7 +68,25 @@ def test_engine_goldens_effect_policy_scope():
             n += 1
         wedr = want.get("effectiveDerivedRoles", want.get("effective_derived_roles")) or []
         assert sorted(wedr) == got["effectiveDerivedRoles"], cid
-    assert n == 166
+        # rule outputs (ruletable.go:1065-1106): the engine test compares them as a set (engine_test.go sorts by src / action)
+        key = lambda o: (o["src"], o["action"], repr(o["val"]))  # noqa: E731
+        assert sorted(got["outputs"], key=key) == sorted(want.get("outputs") or [], key=key), cid
+        n_out += len(want.get("outputs") or [])
+    assert n == 166 and n_out == 6
+
+
+def test_rule_outputs_of_the_api_goldens():
+    """Rule outputs recorded by the API-level CheckResources goldens (cr_case_0*.yaml: nested maps and lists, values built
+    from the principal, a principal-policy rule's output): oracle #1, ruletable.go:1065-1106 + :1443-1465."""
+    from helpers import check_resources_api_outputs
+    orc = CheckOracle(store_rule_table(), globals_={"environment": "test"})
+    key = lambda o: (o["src"], o["action"])  # noqa: E731
+    n = 0
+    for f, ci, want in check_resources_api_outputs():
+        got = orc.check(ci)["outputs"]
+        assert sorted(got, key=key) == sorted(want, key=key), f
+        n += len(want)
+    assert n == 5
 
 
 def test_parent_role_index_known_answers():
