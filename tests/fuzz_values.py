@@ -477,3 +477,56 @@ def rand_core_request(r):
     if r.random() < 0.8:
         ra["nested"] = {"x": {"y": rand_core_value(r, 1)}} if r.random() < 0.8 else rand_core_value(r)
     return {"requestId": "c", "principal": {"id": "p", "roles": ["user"], "attr": pa}, "resource": {"kind": "doc", "id": "d", "attr": ra}}
+
+
+# ---- inIPAddrRange (cerbos_lib.go:472-510 over Go's net.ParseIP / ParseCIDR / IPNet.Contains) ------------------------------------
+CIDRS = ["10.0.0.0/8", "10.1.2.0/24", "192.168.0.0/16", "0.0.0.0/0", "10.1.2.3/32", "::/0", "2001:db8::/32", "::ffff:10.0.0.0/104", "::ffff:0:0/96",
+         "fe80::/10", "2001:db8:0:1::/64", "::1/128", "10.0.0.0/33", "10.0.0/8", "2001:db8::/129", "10.0.0.0", "10.0.0.0/08", "::ffff:10.1.2.0/120",
+         "10.0.0.0/ 8", "1.2.3.4/0", "::ffff:10.0.0.0/95"]
+
+
+def rand_ip_text(r):
+    k = r.random()
+    if k < 0.35:
+        parts = [r.choice([0, 1, 2, 3, 10, 168, 192, 255, 256, 127]) for _ in range(4)]
+        if r.random() < 0.5:
+            parts[0:2] = r.choice([[10, 1], [10, 0], [192, 168]])
+        txt = ".".join(str(p) for p in parts)
+        m = r.random()
+        if m < 0.06:
+            txt = txt.replace(".", ".0", 1)
+        elif m < 0.1:
+            txt = txt.rsplit(".", 1)[0]
+        elif m < 0.13:
+            txt += ".1"
+        elif m < 0.16:
+            txt = " " + txt
+        elif m < 0.19:
+            txt = txt.replace("1", "١", 1)
+        return txt
+    if k < 0.55:
+        v4 = ".".join(str(r.choice([10, 1, 2, 3, 0, 255, 192, 168])) for _ in range(4))
+        return r.choice(["::ffff:", "::FFFF:", "0:0:0:0:0:ffff:", "::", "::ffff:0:", "64:ff9b::"]) + v4
+    if k < 0.9:
+        hx = [r.choice(["2001", "db8", "0", "1", "fe80", "ffff", "ABCD", "0001", "00001", "g", ""]) for _ in range(r.choice([8, 8, 8, 7, 9, 4]))]
+        txt = ":".join(hx)
+        m = r.random()
+        if m < 0.4:
+            i = r.randrange(0, 6)
+            txt = ":".join(hx[:i]) + "::" + ":".join(hx[i + 2:])
+        if m > 0.9:
+            txt += "%eth0"
+        return txt
+    return r.choice(["", "::", "::1", "localhost", "1.2.3", "1.2.3.4.5", ":::", "1::2::3", "::ffff:1.2.3", "2001:db8::1", "fe80::1%1", "[::1]", "0x10.1.2.3",
+                     "010.1.2.3", "1.2.3.4/8", "::ffff:10.1.2.3", "2001:DB8:0:1:0:0:0:1"])
+
+
+def IPB(r):
+    ip = r.choice(["R.attr.ip", "P.attr.ip2", "R.attr.ip", f'"{rand_ip_text(r)}"'])
+    return f'{ip}.inIPAddrRange("{r.choice(CIDRS)}")' if r.random() < 0.5 else f'inIPAddrRange({ip}, "{r.choice(CIDRS)}")'
+
+
+def rand_ip_request(r):
+    def v():
+        return rand_ip_text(r) if r.random() < 0.93 else r.choice([5, None, ["10.0.0.1"], True])
+    return {"requestId": "i", "principal": {"id": "p", "roles": ["user"], "attr": {"ip2": v()}}, "resource": {"kind": "doc", "id": "d", "attr": {"ip": v()}}}

@@ -129,3 +129,11 @@ def test_core_semantics_random(seed):
     mism, flagged, total, allows = run_time_seed(5000 + seed, n_expr=10, n_req=40, gen=FV.CB, req=FV.rand_core_request)
     assert not mism, mism[:3]
     assert total >= 100 and allows >= 5
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_ip_ranges_random(seed):
+    """inIPAddrRange over well-formed and malformed IPv4 / IPv6 / IPv4-mapped texts and CIDRs (valid, out of range, malformed) -- three ways"""
+    mism, flagged, total, allows = run_time_seed(9000 + seed, n_expr=10, n_req=60, gen=FV.IPB, req=FV.rand_ip_request)
+    assert not mism, mism[:3]
+    assert total >= 1000 and flagged == 0 and allows >= 20
