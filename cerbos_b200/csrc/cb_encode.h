@@ -297,7 +297,7 @@ struct BytesMap {
             const uint32_t e = tab[i];
             if (!e) return nullptr;
             const Ent &x = ents[e - 1];
-            if (x.h == h && x.len == n && !memcmp(arena.data() + x.off, p, n)) return &x.val;
+            if (x.h == h && x.len == n && (n == 0 || !memcmp(arena.data() + x.off, p, n))) return &x.val;   // (an empty key may come with a null pointer)
         }
     }
     const uint32_t *find(const uint8_t *p, size_t n) const { return find(p, n, hash_bytes(p, n)); }
@@ -769,7 +769,7 @@ class Encoder {
                 const auto &e = ents_in[q];
                 std::pair<Span, Span> *cur = n_in > 12 ? big.data() : small;
                 bool dup = false;
-                for (size_t z = 0; z < ne; z++) if (cur[z].first.n == e.first.n && !memcmp(cur[z].first.p, e.first.p, e.first.n)) { cur[z].second = e.second; dup = true; break; }
+                for (size_t z = 0; z < ne; z++) if (span_eq(cur[z].first, e.first)) { cur[z].second = e.second; dup = true; break; }
                 if (!dup) { if (n_in > 12) big.push_back(e); else small[ne] = e; ne++; }
             }
             ents = n_in > 12 ? big.data() : small;
@@ -790,7 +790,7 @@ class Encoder {
 
         static const Span *find(const std::vector<std::pair<Span, Span>> &ents, const std::string &key) {
             const Span *hit = nullptr;
-            for (const auto &e : ents) if (e.first.n == key.size() && !memcmp(e.first.p, key.data(), key.size())) hit = &e.second;   // last wins
+            for (const auto &e : ents) if (e.first.n == key.size() && (key.empty() || !memcmp(e.first.p, key.data(), key.size()))) hit = &e.second;   // last wins
             return hit;
         }
         // attr[segs[from]] [segs[from + 1]] ...: ABSENT when only the last segment is missing, ERROR when the path leaves the maps
@@ -808,7 +808,7 @@ class Encoder {
                 Span next{};
                 bool found = false;
                 WireIt f(st);
-                while (f.next()) if (f.fno == 1 && f.wt == 2) { Span k, v; if (map_entry(f.s, &k, &v) && k.n == segs[j].size() && !memcmp(k.p, segs[j].data(), k.n)) { next = v; found = true; } }
+                while (f.next()) if (f.fno == 1 && f.wt == 2) { Span k, v; if (map_entry(f.s, &k, &v) && k.n == segs[j].size() && (k.n == 0 || !memcmp(k.p, segs[j].data(), k.n))) { next = v; found = true; } }
                 if (!found) return j + 1 == segs.size() ? V_ABSENT : V_ERROR;
                 val = next;
             }
