@@ -207,3 +207,50 @@ def test_leaf_programs_on_golden_expressions(tmp_path):
                 assert got[0, i] == want[f"a{i}"]["effect"], (f, e)
                 checked += 1
     assert translated >= 60 and checked >= 50, (translated, checked)
+
+
+# ---- the fuzz families of tests/fuzz_values.py through the generated leaf programs ------------------------------------------------
+@pytest.mark.parametrize("family", ["time", "core", "math", "ip"])
+def test_value_families_through_leaf_programs(family, tmp_path):
+    """Random typed expressions (timestamps / durations, core semantics, ext.Math, inIPAddrRange) whose programs the translator
+    takes, each with its negation, in one table; the generated straight-line code (host build) against oracle #1 on requests
+    whose attributes change type.  (The interpreter's run over the same families is tests/test_fuzz_values.py.)"""
+    import fuzz_values as FV
+    from oracle.celeval import parse_timestamp
+    from oracle.check import CheckOracle
+    from test_fuzz_values import _table
+    gen, req = {"time": (FV.TB, FV.rand_time_request), "core": (FV.CB, FV.rand_core_request), "math": (FV.M, FV.rand_request),
+                "ip": (FV.IPB, FV.rand_ip_request)}[family]
+    now = parse_timestamp("2024-03-10T06:59:59.5Z")
+    r = random.Random(91000)
+    es, tries = [], 0
+    while len(es) < 8 and tries < 400:
+        tries += 1
+        e = gen(r)
+        try:
+            _, ft1 = _table([e])
+        except Exception:  # noqa: BLE001 -- a construct the table build refuses: drawn again
+            continue
+        if "CB_HD bool uc_atom_" in hostsim.generate_uc(ft1.blob)[0]:
+            es.append(e)
+    assert len(es) >= 4
+    es = es + [f"!({e})" for e in es]
+    rt, ft = _table(es)
+    src, _ = hostsim.generate_uc(ft.blob)
+    assert src.count("CB_HD bool uc_atom_") >= 4
+    lib = hostsim.build_spec(ft.blob, str(tmp_path), uc=True)
+    orc, enc = CheckOracle(rt), Encoder(ft.manifest)
+    compared = 0
+    for _ in range(40):
+        inp = dict(req(r), actions=[f"a{i}" for i in range(len(es))])
+        want = orc.check(inp, now)["actions"]
+        b = enc.encode([inp])
+        try:
+            got = hostsim.check_spec(lib, ft.blob, b.columns, 1, b.max_actions, now.ns, mode=4)
+        except RuntimeError as x:
+            assert "-2" in str(x), x          # a value outside the device's exact range: the call fails loudly
+            continue
+        for i, e in enumerate(es):
+            assert got[0, i] == want[f"a{i}"]["effect"], (e, inp["principal"]["attr"], inp["resource"]["attr"])
+            compared += 1
+    assert compared >= 200
