@@ -36,3 +36,30 @@ def test_random_tables(seed):
     for mode in (0, 1, 2, 3):
         k_out = hostsim.check(ft.blob, b.columns, b.n, b.max_actions, 0, fl, mode=mode)
         assert (k_out[valid] == c_out[valid]).all(), (seed, mode)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_decision_metadata_on_random_tables(seed):
+    """The metadata body of the kernel core (cb::eval_request_meta behind cgpu_check_meta) against oracle #1 on random policy sets:
+    effect, winning policy and scope of every action, effectiveDerivedRoles of every request (ruletable.go:753-782, 936-979, 1082-1148)."""
+    from cerbos_b200 import meta as M
+    r = random.Random(33000 + seed)
+    docs = rand_policies(r)
+    rt = build_rule_table(docs)
+    ft = flatten(rt)
+    lenient = seed % 4 == 0
+    orc = CheckOracle(rt, lenient_scope_search=lenient)
+    enc = Encoder(ft.manifest, lenient_scope_search=lenient)
+    fl = L.BATCH_FLAG_LENIENT if lenient else 0
+    inputs = [rand_request(r) for _ in range(40)]
+    b = enc.encode(inputs)
+    eff, am, rm = hostsim.check_meta(ft.blob, b.columns, b.n, b.max_actions, 0, fl)
+    for j, inp in enumerate(inputs):
+        py = orc.check(inp)
+        p, rs = inp.get("principal") or {}, inp.get("resource") or {}
+        for k, a in enumerate(inp["actions"]):
+            pol, sc = M.decode_action(int(am[j, k]), rm[j], ft.manifest, p.get("id", ""), rs.get("kind", ""),
+                                      p.get("policyVersion") or "default", rs.get("policyVersion") or "default")
+            w = py["actions"][a]
+            assert (int(eff[j, k]), pol, sc) == (w["effect"], w["policy"], w["scope"]), (seed, j, a)
+        assert M.decode_edr(int(rm[j]["effective_derived_roles"]), ft.manifest) == py["effectiveDerivedRoles"], (seed, j)
