@@ -94,6 +94,32 @@ def rand_policies(r: random.Random):
                     rule["condition"] = {"match": rand_cond(r)}
                 rules.append(rule)
             rp = {"resource": kind, "version": r.choice(["default", "default", "v2"]), "rules": rules}
+            if r.random() < 0.4:
+                # variables and constants (local and imported; a variable may use earlier ones, constants, or fail): the
+                # table builder inlines them, oracle #1 evaluates them eagerly per request (ruletable.go:1319-1344)
+                rp["constants"] = {"local": {"c0": r.choice(STRS), "c1": r.choice([1, 3, 5.5]), "c2": [r.choice(STRS), r.choice(STRS)]}}
+                rp["variables"] = {"local": {
+                    "flag": rand_expr(r, 1), "lvl": "P.attr.level", "who": r.choice(["P.id", "R.attr.owner", "P.attr.nope"]),
+                    "both": f"V.flag || ({rand_expr(r, 1)})", "big": "variables.lvl > C.c1", "inc": "C.c0 in constants.c2 || V.who == R.attr.owner"}}
+                if r.random() < 0.5:
+                    rp["variables"]["import"] = ["shared_vars"]
+                    rp["constants"]["import"] = ["shared_consts"]
+                extra = ["V.flag", "V.both", "V.big", "V.inc", "V.who == P.id", "V.lvl >= 3", "R.attr.dept == C.c0", "V.who in C.c2", "!V.flag"]
+                if "import" in rp["variables"]:
+                    extra += ["V.sv_owner", "V.sv_lvl > C.sk1", "C.sk0 == P.attr.dept"]
+                for rule in rules:
+                    if r.random() < 0.6:
+                        x = r.choice(extra)
+                        if "condition" in rule and r.random() < 0.5:
+                            rule["condition"] = {"match": {r.choice(["all", "any"]): {"of": [rule["condition"]["match"], {"expr": x}]}}}
+                        else:
+                            rule["condition"] = {"match": {"expr": x}}
+            if dr_defs and r.random() < 0.3 and scopes == {""}:
+                # runtime.effectiveDerivedRoles in a condition (ruletable.go:936-979) -- only where the kind has one scope: along
+                # a scope chain the reference's value depends on the order in which actions and roles were walked (the set is
+                # replaced when a scope is FIRST processed and kept afterwards), which the device does not reproduce
+                rules.append({"actions": [r.choice(ACTIONS)], "effect": r.choice(["EFFECT_ALLOW", "EFFECT_DENY"]), "roles": ["*"],
+                              "condition": {"match": {"expr": f'"{r.choice(dr_defs)["name"]}" in runtime.effectiveDerivedRoles'}}})
             if dr_defs:
                 rp["importDerivedRoles"] = ["drs"]
             if s:
@@ -113,6 +139,10 @@ def rand_policies(r: random.Random):
                 continue
         keep.append(d)
     docs = keep
+    if any("import" in (d.get("resourcePolicy", {}).get("variables") or {}) for d in docs):
+        docs.append({"apiVersion": "api.cerbos.dev/v1", "exportVariables": {"name": "shared_vars", "definitions": {
+            "sv_owner": "R.attr.owner == P.id", "sv_lvl": "P.attr.level"}}})
+        docs.append({"apiVersion": "api.cerbos.dev/v1", "exportConstants": {"name": "shared_consts", "definitions": {"sk0": r.choice(STRS), "sk1": 2}}})
     # de-duplicate (kind, version, scope)
     seen, out = set(), []
     for d in docs:

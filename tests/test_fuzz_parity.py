@@ -27,15 +27,22 @@ def test_random_tables(seed):
     inputs = [rand_request(r) for _ in range(60)]
     b = enc.encode(inputs)
     fl = L.BATCH_FLAG_LENIENT if lenient else 0
-    c_out = cref.check(ft.blob, b.columns, b.n, b.max_actions, 0, fl)
+    want = np.zeros((b.n, max(b.max_actions, 1)), dtype=np.uint8)
     for j, inp in enumerate(inputs):
         py = orc.check(inp)
         for k, a in enumerate(inp["actions"]):
-            assert c_out[j, k] == py["actions"][a]["effect"], (seed, j, a, inp)
-    valid = c_out != 0
+            want[j, k] = py["actions"][a]["effect"]
+    try:
+        c_out = cref.check(ft.blob, b.columns, b.n, b.max_actions, 0, fl)
+        valid = c_out != 0
+        assert (c_out[valid] == want[valid]).all() and (want[~valid] == 0).all(), seed
+    except RuntimeError as x:
+        # oracle #2 does not port runtime.effectiveDerivedRoles nor concatenation (it flags them): oracle #1 alone judges
+        assert "-2" in str(x), x
+        valid = want != 0
     for mode in (0, 1, 2, 3):
         k_out = hostsim.check(ft.blob, b.columns, b.n, b.max_actions, 0, fl, mode=mode)
-        assert (k_out[valid] == c_out[valid]).all(), (seed, mode)
+        assert (k_out[valid] == want[valid]).all(), (seed, mode)
 
 
 @pytest.mark.parametrize("seed", range(12))

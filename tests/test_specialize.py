@@ -47,7 +47,7 @@ def test_generated_source_is_straight_line_for_c2():
 def test_random_tables(seed, tmp_path):
     r = random.Random(7000 + seed)
     # resource policies only (the lean body's domain): strip what the generator does not cover
-    docs = [d for d in rand_policies(r) if "resourcePolicy" in d or "derivedRoles" in d]
+    docs = [d for d in rand_policies(r) if "resourcePolicy" in d or "derivedRoles" in d or "exportVariables" in d or "exportConstants" in d]
     rt = build_rule_table(docs)
     ft = flatten(rt)
     src = hostsim.generate(ft.blob)
@@ -117,7 +117,7 @@ def test_unique_condition_body_on_random_tables(seed, tmp_path):
     leaf programs translated from bytecode, leaf programs over one string slot evaluated by the per-string pre-pass --
     against oracle #2."""
     r = random.Random(9100 + seed)
-    docs = [d for d in rand_policies(r) if "resourcePolicy" in d or "derivedRoles" in d]
+    docs = [d for d in rand_policies(r) if "resourcePolicy" in d or "derivedRoles" in d or "exportVariables" in d or "exportConstants" in d]
     rt = build_rule_table(docs)
     ft = flatten(rt)
     enc = Encoder(ft.manifest)
