@@ -985,6 +985,10 @@ class ProgramCompiler:
                  # collecting comprehensions: the result is built in the device's scratch arena
                  "map": (L.LOOP_MAP, 1), "filter": (L.LOOP_FILTER, 1), "transformList": (L.LOOP_MAP, 2),
                  "transformMap": (L.LOOP_TMAP, 2), "transformMapEntry": (L.LOOP_TENTRY, 2), "sortBy": (L.LOOP_SORTBY, 1)}
+        if n.name == "bind":
+            # cel.bind(x, init, body) (ext.Bindings): the expressions are pure, so the body with x replaced by init has the same
+            # value (an init that fails and is never used harms nothing either way)
+            return self.expr(expand_bind(n))
         if n.name not in kinds:
             raise Unsupported(f"macro `{n.name}`")
         kind, nv = kinds[n.name]
@@ -1015,6 +1019,34 @@ class ProgramCompiler:
     def finish(self):
         self.emit("RET")
         return self.code
+
+
+def _substitute(node, name, repl, repl_free):
+    """`node` with every free occurrence of the identifier `name` replaced by `repl`"""
+    if isinstance(node, Ident):
+        return repl if node.name == name else node
+    if isinstance(node, Select):
+        return Select(_substitute(node.operand, name, repl, repl_free), node.field, node.test_only)
+    if isinstance(node, Call):
+        return Call(node.fn, None if node.target is None else _substitute(node.target, name, repl, repl_free),
+                    [_substitute(a, name, repl, repl_free) for a in node.args])
+    if isinstance(node, ListLit):
+        return ListLit([_substitute(e, name, repl, repl_free) for e in node.elems])
+    if isinstance(node, MapLit):
+        return MapLit([(_substitute(k, name, repl, repl_free), _substitute(v, name, repl, repl_free)) for k, v in node.entries])
+    if isinstance(node, Macro):
+        target = _substitute(node.target, name, repl, repl_free)
+        if name in node.vars:
+            return Macro(node.name, target, node.vars, node.args)        # shadowed inside
+        if repl_free & set(node.vars) and any(isinstance(z, Ident) and z.name == name for a in node.args for z in walk_nodes(a)):
+            raise Unsupported("cel.bind: the bound expression mentions a name that a comprehension inside the body redefines")
+        return Macro(node.name, target, node.vars, [_substitute(a, name, repl, repl_free) for a in node.args])
+    return node
+
+
+def expand_bind(n: Macro):
+    free = {z.name for z in walk_nodes(n.target) if isinstance(z, Ident)}
+    return _substitute(n.args[0], n.vars[0], n.target, free)
 
 
 class FlatCompiler:
@@ -1112,6 +1144,8 @@ class FlatCompiler:
 
     # ---- DNF: list of groups, each a list of (term, lit_false)
     def lit(self, n: Node, want_false: bool):
+        if isinstance(n, Macro) and n.name == "bind":
+            n = expand_bind(n)
         if isinstance(n, Call) and n.target is None:
             if n.fn == "!_" and len(n.args) == 1:
                 return self.lit(n.args[0], not want_false)

@@ -213,6 +213,14 @@ def B(r, d=0):
         return f"{L(r, d + 1)}.transformMap(i, x, {r.choice(['x', 'i'])}) == {{}}"
     if k == 14:
         return f"base64.decode({S(r, d + 1)}) == bytes({S(r, d + 1)})"
+    if k == 16:
+        # cel.bind (ext.Bindings): the bound value used twice, once inside a comprehension
+        kind = r.choice("SLI")
+        if kind == "S":
+            return f"cel.bind(bv, {S(r, d + 1)}, bv + bv == {S(r, d + 1)} || {L(r, d + 1)}.exists(x, x == bv) || size(bv) > 2)"
+        if kind == "L":
+            return f"cel.bind(bv, {L(r, d + 1)}, size(bv) > 1 && bv[0] in bv && bv.all(x, x in bv))"
+        return f"cel.bind(bv, {I(r, d + 1)}, cel.bind(bw, bv + 1, bw > bv && bv * 2 - bv == bv))"
     if k == 15:
         # the same compound value on both sides: true unless its evaluation fails, so an error on one side only shows
         x = r.choice([S, I, L, N])(r, d)
