@@ -354,7 +354,7 @@ CB_HD bool scalar_equal(const Ctx &c, const Val &a, const Val &b) {
     if (a.tag != b.tag) return false;
     if (a.tag == CB_T_NULL) return true;
     if (a.tag == CB_T_STRING || a.tag == CB_T_BYTES) return str_equal(c, a.u, b.u);
-    return a.u == b.u;  // BOOL / TS / DUR
+    return a.u == b.u;  // BOOL / TS / DUR / TYPE
 }
 CB_HD bool is_container(const Val &v) { return v.tag == CB_T_LIST || v.tag == CB_T_MAP; }
 
@@ -1194,6 +1194,42 @@ CB_HD_NOINLINE Val dyn_strfn(Ctx &c, uint32_t fn, const Val *a, uint32_t argc) {
         return strb_end(s);
     }
     if (fn == CB_FN_TO_BYTES) return (a[0].tag == CB_T_STRING || a[0].tag == CB_T_BYTES) ? mk(CB_T_BYTES, a[0].u) : mk_err();
+    if (fn == CB_FN_TYPE_OF) {      // type(x): the run-time type as a TYPE value
+        uint32_t code;
+        switch (a[0].tag) {
+        case CB_T_BOOL: code = CB_TYPE_BOOL; break;
+        case CB_T_INT: code = CB_TYPE_INT; break;
+        case CB_T_UINT: code = CB_TYPE_UINT; break;
+        case CB_T_DOUBLE: code = CB_TYPE_DOUBLE; break;
+        case CB_T_STRING: code = CB_TYPE_STRING; break;
+        case CB_T_BYTES: code = CB_TYPE_BYTES; break;
+        case CB_T_LIST: code = CB_TYPE_LIST; break;
+        case CB_T_MAP: code = CB_TYPE_MAP; break;
+        case CB_T_NULL: code = CB_TYPE_NULL_TYPE; break;
+        case CB_T_TS: code = CB_TYPE_TIMESTAMP; break;
+        case CB_T_DUR: code = CB_TYPE_DURATION; break;
+        case CB_T_TYPE: code = CB_TYPE_TYPE; break;
+        case CB_T_ERR: return mk_err();
+        default: c.unsupported = 1; return mk_err();      // SPIFFE ids / trust domains: custom types, not modelled
+        }
+        return mk(CB_T_TYPE, code);
+    }
+    if (fn == CB_FN_TO_BOOL) {      // cel-go ConvertToType(BoolType): strconv.ParseBool on a string
+        if (a[0].tag == CB_T_BOOL) return a[0];
+        if (a[0].tag != CB_T_STRING) return mk_err();
+        const uint8_t *q; uint32_t m;
+        str_get(c, a[0].u, q, m);
+        if (m == 0 || m > 5) return mk_err();
+        uint8_t w[5] = {0, 0, 0, 0, 0};
+        for (uint32_t i = 0; i < m; i++) w[i] = ldg(q + i);
+        const bool rest_t = (w[1] == 'r' && w[2] == 'u' && w[3] == 'e') || (w[0] == 'T' && w[1] == 'R' && w[2] == 'U' && w[3] == 'E');
+        const bool rest_f = (w[1] == 'a' && w[2] == 'l' && w[3] == 's' && w[4] == 'e') || (w[0] == 'F' && w[1] == 'A' && w[2] == 'L' && w[3] == 'S' && w[4] == 'E');
+        if (m == 1 && (w[0] == '1' || w[0] == 't' || w[0] == 'T')) return mk_bool(true);
+        if (m == 1 && (w[0] == '0' || w[0] == 'f' || w[0] == 'F')) return mk_bool(false);
+        if (m == 4 && (w[0] == 't' || w[0] == 'T') && rest_t) return mk_bool(true);
+        if (m == 5 && (w[0] == 'f' || w[0] == 'F') && rest_f) return mk_bool(false);
+        return mk_err();
+    }
     if (fn == CB_FN_TO_STRING) {
         // cel-go ConvertToType(StringType): string, int, uint, bool, bytes holding valid UTF-8, double.  A double prints by
         // strconv.FormatFloat(d, 'f', -1, 64): exact here for NaN, the infinities and integral values below 2^53 (JSON
@@ -1892,7 +1928,7 @@ CB_HD_NOINLINE Val math_fn(Ctx &c, uint32_t fn, const Val *a, uint32_t argc) {
     return mk_err();
 }
 CB_HD Val op_fn(Ctx &c, uint32_t fn, uint32_t argc, Val *a) {   // a[0..argc): arguments (target first)
-    if (fn == CB_FN_TO_STRING) return dyn_strfn(c, fn, a, argc);
+    if (fn == CB_FN_TO_STRING || fn == CB_FN_TO_BOOL || fn == CB_FN_TYPE_OF) return dyn_strfn(c, fn, a, argc);
     if (fn >= CB_FN_MATH_GREATEST) return math_fn(c, fn, a, argc);
     if (fn >= CB_FN_SPIFFE_ID) return spiffe_fn(c, fn, a, argc);
     if (fn == CB_FN_REVERSE && a[0].tag == CB_T_STRING) return dyn_strfn(c, CB_FN_STR_REVERSE, a, argc);

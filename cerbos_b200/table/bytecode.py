@@ -435,6 +435,9 @@ class ProgramCompiler:
                 return
             if n.name in ("runtime",):
                 raise Unsupported("`runtime` (effectiveDerivedRoles) in conditions")
+            if n.name in L.TYPE_CODES:        # a type name as a value: `type(x) == string`
+                self.push_const(ConstVal(T["TYPE"], L.TYPE_CODES[n.name]))
+                return
             st = self._static(n)
             if st is not None:
                 self._push_static(st)
@@ -837,7 +840,7 @@ class ProgramCompiler:
              "math.isInf": ("MATH_ISINF", (1,)), "math.isFinite": ("MATH_ISFINITE", (1,)), "math.bitAnd": ("MATH_BITAND", (2,)),
              "math.bitOr": ("MATH_BITOR", (2,)), "math.bitXor": ("MATH_BITXOR", (2,)), "math.bitNot": ("MATH_BITNOT", (1,)),
              "math.bitShiftLeft": ("MATH_SHL", (2,)), "math.bitShiftRight": ("MATH_SHR", (2,)), "math.sqrt": ("MATH_SQRT", (1,))}
-    _FN = {"bytes": ("TO_BYTES", (1,)), "string": ("TO_STRING", (1,)), "base64.encode": ("B64ENC", (1,)), "base64.decode": ("B64DEC", (1,)),
+    _FN = {"bytes": ("TO_BYTES", (1,)), "string": ("TO_STRING", (1,)), "bool": ("TO_BOOL", (1,)), "type": ("TYPE_OF", (1,)), "base64.encode": ("B64ENC", (1,)), "base64.decode": ("B64DEC", (1,)),
            "lowerAscii": ("LOWER", (1,)), "upperAscii": ("UPPER", (1,)), "trim": ("TRIM", (1,)), "charAt": ("CHARAT", (2,)),
            "indexOf": ("INDEXOF", (2, 3)), "lastIndexOf": ("LASTINDEXOF", (2, 3)), "substring": ("SUBSTRING", (2, 3)),
            "replace": ("REPLACE", (3, 4)), "split": ("SPLIT", (2, 3)), "join": ("JOIN", (1, 2)), "reverse": ("REVERSE", (1,)),

@@ -171,7 +171,12 @@ FNS = {name: i for i, name in enumerate([
     "MATH_GREATEST", "MATH_LEAST", "MATH_CEIL", "MATH_FLOOR", "MATH_ROUND", "MATH_TRUNC", "MATH_ABS", "MATH_SIGN", "MATH_ISNAN", "MATH_ISINF",
     "MATH_ISFINITE", "MATH_BITAND", "MATH_BITOR", "MATH_BITXOR", "MATH_BITNOT", "MATH_SHL", "MATH_SHR", "MATH_SQRT",
     "TO_STRING",        # string(x): strings, ints, uints, bools, valid UTF-8 bytes, integral doubles below 2^53 (the rest is flagged)
+    "TYPE_OF",          # type(x) -> a TYPE value (payload: TYPE_CODES); type names are TYPE constants, compared by payload
+    "TO_BOOL",          # bool(x): a bool, or a string strconv.ParseBool reads ("1" "t" "T" "TRUE" "true" "True" / "0" "f" "F" "FALSE" "false" "False")
 ])}
+# payload of a TYPE value (type(x), the identifiers int / string / ... in an expression)
+TYPE_CODES = {"bool": 1, "int": 2, "uint": 3, "double": 4, "string": 5, "bytes": 6, "list": 7, "map": 8, "null_type": 9,
+              "google.protobuf.Timestamp": 10, "google.protobuf.Duration": 11, "type": 12}
 TS_FIELDS = {name: i for i, name in enumerate(["getFullYear", "getMonth", "getDayOfYear", "getDayOfMonth", "getDate", "getDayOfWeek",
                                                "getHours", "getMinutes", "getSeconds", "getMilliseconds"])}
 HIER_RELS = {name: i for i, name in enumerate(["ancestorOf", "descendentOf", "immediateChildOf", "immediateParentOf", "siblingOf", "overlaps", "equals"])}
@@ -274,6 +279,8 @@ def c_header() -> str:
         d(f"CB_HIER_{k.upper()}", v)
     for k, v in TS_FIELDS.items():
         d(f"CB_TS_{k.upper()}", v)
+    for k, v in TYPE_CODES.items():
+        d("CB_TYPE_" + k.replace("google.protobuf.", "").upper(), v)
     out.append("")
     d("CB_FLAT_DNF", FLAT_DNF)
     for k, v in TERM_OPS.items():

@@ -1387,6 +1387,13 @@ _TYPE_IDENTS = {"int": "int", "uint": "uint", "double": "double", "bool": "bool"
                 "dyn": "dyn"}
 
 
+class _FailedBinding:
+    __slots__ = ("err",)
+
+    def __init__(self, err):
+        self.err = err
+
+
 class Evaluator:
     """Evaluates AST nodes against an activation (dict of top-level identifiers).
 
@@ -1427,6 +1434,8 @@ class Evaluator:
         raise TypeError(f"unknown node {n!r}")
 
     def _ident(self, name, env):
+        if env is not None and isinstance(env.get(name), _FailedBinding):
+            raise env[name].err
         if env is not None and name in env:
             return env[name]
         if name in self.act:
@@ -1510,7 +1519,12 @@ class Evaluator:
         name = n.name
         env = dict(env) if env else {}
         if name == "bind":
-            env[n.vars[0]] = self.eval(n.target, env)
+            # cel.bind is a comprehension whose accumulator starts as `init` (ext/bindings.go): an init that fails is an error
+            # VALUE held by the variable -- it surfaces only if the body reads the variable
+            try:
+                env[n.vars[0]] = self.eval(n.target, env)
+            except CelError as e:
+                env[n.vars[0]] = _FailedBinding(e)
             return self.eval(n.args[0], env)
         rng = self.eval(n.target, env)
         two = len(n.vars) == 2

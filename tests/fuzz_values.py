@@ -426,7 +426,7 @@ def CV(r, d=0):
 
 
 def CB(r, d=0):
-    k = r.randrange(13 if d < 3 else 5)
+    k = r.randrange(14 if d < 3 else 5)
     if k in (0, 1):
         return f"{CV(r, d + 1)} {r.choice(['==', '!='])} {CV(r, d + 1)}"
     if k == 2:
@@ -450,6 +450,9 @@ def CB(r, d=0):
         return f"{x} == {x}"
     if k == 11:
         return f"({CB(r, d + 1)} ? {CB(r, d + 1)} : {CB(r, d + 1)})"
+    if k == 12:
+        tn = r.choice(["string", "int", "uint", "double", "bool", "list", "map", "null_type", "bytes", "type"])
+        return r.choice([f"type({CV(r, d + 1)}) {r.choice(['==', '!='])} {tn}", f"type({CV(r, d + 1)}) == type({CV(r, d + 1)})", f"bool({CV(r, d + 1)})"])
     return f"{CV(r, d + 1)} == {CV(r, d + 1)}"
 
 
@@ -461,7 +464,7 @@ def rand_core_value(r, depth=0):
         return r.choice([0.5, -0.5, 1e19, -1e19, 9007199254740993, 9223372036854775807, 9223372036854775808, -9223372036854775808, 1.5, 4294967296, -0.0, 1e-7])
     if k in (2, 3):
         return r.choice(["1", "a", "", "k", "k2", "true", "1.5", "abc", "-1", "9223372036854775808", "0x10", " 1", "1e3", "日本", "\u0661\u0662", "12\n", "+7", "-0",
-                         "1_000", "18446744073709551615", "18446744073709551616", "-9223372036854775808", "007"])
+                         "1_000", "t", "F", "TRUE", "False", "18446744073709551615", "18446744073709551616", "-9223372036854775808", "007"])
     if k == 4:
         return r.random() < 0.5
     if k == 5:

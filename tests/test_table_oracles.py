@@ -199,6 +199,14 @@ MATH_AND_ENCODER_CASES = [
     ('string(0.0 / 0.0) == "NaN" && string(1.0 / 0.0) == "+Inf" && string(-1.0 / 0.0) == "-Inf" && string(P.attr.n * -0.0) == "-0"', True),
     ('string(b"abc") == "abc" && string(bytes("héllo")) == "héllo" && string(base64.decode("aGVsbG8=")) == "hello"', True),
     ('string(base64.decode("/w==")) == "x"', None), ('string(base64.decode("7aCA")) == "x"', None), ('string(R.attr.nums) == "x"', None),
+    # bool(x) = strconv.ParseBool on strings; type(x) and the type names; cel.bind (ext.Bindings)
+    ('bool("t") && bool("TRUE") && bool("1") && !bool("F") && !bool("false") && !bool("0") && bool(true)', True), ('bool("tRUE")', None),
+    ('bool("yes")', None), ('bool("")', None), ('bool(1)', None), ('bool(P.attr.department)', None), ('bool(R.attr.yes) && !bool(R.attr.no)', True),
+    ('type(P.attr.n) == double && type(P.attr.department) == string && type(R.attr.nums) == list && type(P.attr) == map', True),
+    ('type(1) == int && type(1u) == uint && type(b"a") == bytes && type(null) == null_type && type(type(1)) == type && type(true) == bool', True),
+    ('type(P.attr.n) != int && string != bytes && type(P.attr.nope) == string', None), ('type(P.attr.n) == type(P.attr.x) && type(P.attr.n) != type(1)', True),
+    ('cel.bind(d, P.attr.department, d.startsWith("mark") && d.size() == 9 && cel.bind(e, d + d, e.size() == 18))', True),
+    ('cel.bind(z, P.attr.nope, true)', True), ('cel.bind(z, P.attr.nope, z == 1)', None), ('cel.bind(xs, R.attr.nums, xs.all(v, v in xs) && xs[0] == 3)', True),
     # base64: Go's decoder skips CR / LF, drops non-zero trailing bits, takes unpadded text, refuses misplaced padding
     ('size(base64.decode("x1")) == 1 && base64.decode("aGVsbG9=") == b"hello"', True), ('base64.decode("aGVs\\nbG8=\\r\\n") == b"hello"', True),
     ('size(base64.decode("aaGVsbG8=")) >= 0', None), ('size(base64.decode("abcaGVsbG8=")) >= 0', None), ('size(base64.decode("a")) >= 0', None),
@@ -206,13 +214,14 @@ MATH_AND_ENCODER_CASES = [
     ('size(base64.decode(R.attr.b64 + "=")) == 5 && size(base64.decode(R.attr.b64 + "==")) >= 0', None),
 ]
 MATH_REQUEST = {"principal": {"id": "john", "roles": ["employee"], "attr": {"n": 12, "x": 2.5, "department": "marketing"}},
-                "resource": {"kind": "leave_request", "id": "r", "attr": {"nums": [3, -2.5, 7, 0], "mixed": [1, "a"], "b64": "aGVsbG8"}}, "actions": ["a"]}
+                "resource": {"kind": "leave_request", "id": "r", "attr": {"nums": [3, -2.5, 7, 0], "mixed": [1, "a"], "b64": "aGVsbG8", "yes": "True", "no": "FALSE"}}, "actions": ["a"]}
 
 
 def test_math_and_encoder_functions_vs_cel_oracle():
     """ext.Math and the base64 edge cases: the expected answer is written out, oracle #1 must give it and the kernel core must
     give oracle #1's -- on the expression and on its negation, so that a failed evaluation (both denied) differs from `false`."""
     now = parse_timestamp("2021-04-22T10:05:20.021-05:00")
+    programs = 0
     for e, holds in MATH_AND_ENCODER_CASES:
         for neg in (False, True):
             expr = f"!({e})" if neg else e
@@ -221,8 +230,9 @@ def test_math_and_encoder_functions_vs_cel_oracle():
             want = CheckOracle(rt).check(MATH_REQUEST, now)["actions"]["a"]["effect"]
             assert want == (1 if holds is not None and holds != neg else 2), (expr, want)
             assert hostsim.check(ft.blob, b.columns, 1, 1, now.ns)[0, 0] == want, expr
-            src, _ = hostsim.generate_uc(ft.blob)           # the generated leaf program takes the same functions
-            assert "CB_HD bool uc_atom_" in src, expr
+            src, _ = hostsim.generate_uc(ft.blob)           # the generated leaf programs take the same functions
+            programs += "CB_HD bool uc_atom_" in src        # (a bind whose body has a flat form needs none)
+    assert programs >= 2 * len(MATH_AND_ENCODER_CASES) - 8
 
 
 def test_string_of_a_fractional_double_is_flagged():
