@@ -1691,7 +1691,7 @@ def _f_in(ev, a):
 def _index_or_error(i):
     if _is_int(i) or isinstance(i, UInt):
         return int(i)
-    if isinstance(i, float) and i == math.floor(i) and not math.isinf(i):
+    if isinstance(i, float) and math.isfinite(i) and i == math.floor(i):      # (a NaN or infinite index is no index)
         return int(i)
     raise CelError(f"unsupported index type '{type_name(i)}' in list")
 
